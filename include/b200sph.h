@@ -1,0 +1,205 @@
+/*
+ * b200sph.h -- C-ABI of libb200sph.so: the B200-native (sm_100a) evaluator for
+ * PySPH's per-timestep WCSPH hot path.
+ *
+ * The reference has no FFI for this path: the seam is the set of duck-typed
+ * Python objects SPHCompiler installs.  Each entry point below
+ * names the reference interface it stands behind (file:line under
+ * /root/reference); pysph_b200/ binds them with ctypes and INTEGRATION.md
+ * shows the stub a PySPH maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, <0 on error
+ *     (b200sph_last_error gives the message), unless stated otherwise.
+ *   - the library OWNS device memory.  Host pointers are borrowed for the
+ *     duration of a push/pull call only (ParticleArray storage is re-allocated
+ *     by resize/append, particle_array.pyx:439-700, so callers re-fetch them).
+ *   - one context = one device + one stream; calls on a context are not
+ *     re-entrant.  Multi-GPU = one context per rank/device.
+ *   - host-side floating point properties are fp64 (ParticleArray is fp64);
+ *     on the device the integrated state (x y z u v w rho h m and the *0
+ *     copies) is fp64, derived fields (p cs arho au.. ax.. dt_cfl dt_force)
+ *     are fp32, and the pair kernel works on fp32 cell-relative records.
+ */
+#ifndef B200SPH_H_INCLUDED
+#define B200SPH_H_INCLUDED
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SPH_MAX_ARRAYS 8
+#define B200SPH_ABI_VERSION 1
+
+typedef struct b200sph_ctx b200sph_ctx;
+
+/* smoothing kernels: pysph/base/kernels.py:29 (CubicSpline), :274
+ * (WendlandQuintic), :1050 (QuinticSpline), :830 (Gaussian) */
+enum {
+    B200SPH_KERNEL_CUBIC_SPLINE = 0,
+    B200SPH_KERNEL_WENDLAND_QUINTIC = 1,
+    B200SPH_KERNEL_QUINTIC_SPLINE = 2,
+    B200SPH_KERNEL_GAUSSIAN = 3
+};
+
+/* particle properties: pysph/base/utils.py:41-44,177-178 */
+enum {
+    /* fp64 on device */
+    B200SPH_X = 0, B200SPH_Y, B200SPH_Z, B200SPH_U, B200SPH_V, B200SPH_W,
+    B200SPH_RHO, B200SPH_H, B200SPH_M,
+    B200SPH_X0, B200SPH_Y0, B200SPH_Z0, B200SPH_U0, B200SPH_V0, B200SPH_W0,
+    B200SPH_RHO0,
+    /* fp32 on device */
+    B200SPH_P, B200SPH_CS, B200SPH_ARHO, B200SPH_AU, B200SPH_AV, B200SPH_AW,
+    B200SPH_AX, B200SPH_AY, B200SPH_AZ, B200SPH_DT_CFL, B200SPH_DT_FORCE,
+    B200SPH_NUM_REAL_PROPS,
+    /* 32-bit integer props */
+    B200SPH_GID = 64, B200SPH_TAG = 65, B200SPH_PID = 66
+};
+
+/* pair-equation bits of one (destination array, source array) loop */
+enum {
+    B200SPH_EQ_SUMMATION_DENSITY = 1, /* basic_equations.py:19-29   */
+    B200SPH_EQ_CONTINUITY = 2,        /* basic_equations.py:180-192 */
+    B200SPH_EQ_MOMENTUM = 4,          /* wc/basic.py:129-269        */
+    B200SPH_EQ_XSPH = 8,              /* basic_equations.py:260-300 */
+    B200SPH_EQ_MONAGHAN_AV = 16       /* basic_equations.py:195-257 */
+};
+
+/* One Group's pair loops (acceleration_eval_cython.mako:10-154) after the
+ * MegaGroup regrouping (acceleration_eval.py:127-162): eqmask[d][s] is the OR
+ * of the equations with destination array d and source array s. */
+typedef struct {
+    uint32_t eqmask[B200SPH_MAX_ARRAYS][B200SPH_MAX_ARRAYS];
+    int32_t real_only;          /* Group(real=True): dests = real particles  */
+    int32_t tensile_correction; /* MomentumEquation(tensile_correction=...)  */
+    double c0, alpha, beta;     /* MomentumEquation / MonaghanArtificialViscosity */
+    double gx, gy, gz;          /* MomentumEquation body force               */
+    double eps_xsph;            /* XSPHCorrection(eps=...)                   */
+} b200sph_pair_program;
+
+typedef struct {
+    double cell_size;  /* DomainManager.cell_size  nnps_base.pyx:942-978    */
+    double hmin;       /* radius_scale * min(h)    nnps_base.pyx:970        */
+    double xmin[3];    /* NNPS.xmin                nnps_base.pyx:1520-1575  */
+    double xmax[3];
+    int32_t ncells[3]; /* LinkedListNNPS.ncells_per_dim linked_list_nnps.pyx:293-326 */
+    int64_t n_cells;
+    int64_t n_particles; /* particles binned (all arrays, real + ghost)     */
+} b200sph_grid_info;
+
+typedef struct {
+    double ms_nnps;     /* device time in nnps_update since last reset      */
+    double ms_pair;     /* device time in pair_pass kernels                 */
+    double ms_other;    /* eos / stage / reductions                         */
+    int64_t pair_launches;
+    int64_t kernel_launches; /* every kernel this library launched          */
+    int64_t pairs;      /* directed pair interactions counted (if enabled)  */
+} b200sph_stats;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int b200sph_abi_version(void);
+int b200sph_create(int device, b200sph_ctx **out);
+int b200sph_destroy(b200sph_ctx *ctx);
+const char *b200sph_last_error(b200sph_ctx *ctx);
+/* run on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) so
+ * that torch.distributed collectives order with our kernels; NULL = own stream */
+int b200sph_set_stream(b200sph_ctx *ctx, void *cuda_stream);
+int b200sph_synchronize(b200sph_ctx *ctx);
+
+/* ---- device mirror of the ParticleArrays: DeviceHelper push/pull/resize
+ *      pysph/base/device_helper.py:47-250 --------------------------------- */
+/* returns the array index (>= 0) */
+int b200sph_add_array(b200sph_ctx *ctx, const char *name, int64_t n,
+                      int64_t n_real, int64_t capacity);
+int b200sph_resize_array(b200sph_ctx *ctx, int arr, int64_t n, int64_t n_real);
+int b200sph_get_array_size(b200sph_ctx *ctx, int arr, int64_t *n, int64_t *n_real);
+int b200sph_push_f64(b200sph_ctx *ctx, int arr, int prop, const double *host,
+                     int64_t start, int64_t count);
+int b200sph_pull_f64(b200sph_ctx *ctx, int arr, int prop, double *host,
+                     int64_t start, int64_t count);
+int b200sph_push_u32(b200sph_ctx *ctx, int arr, int prop, const uint32_t *host,
+                     int64_t start, int64_t count);
+int b200sph_pull_u32(b200sph_ctx *ctx, int arr, int prop, uint32_t *host,
+                     int64_t start, int64_t count);
+/* device pointer of a property region of one array (for zero-copy use by
+ * torch / NCCL plumbing); fp64 props -> double*, fp32 props -> float* */
+int b200sph_device_ptr(b200sph_ctx *ctx, int arr, int prop, void **out);
+
+/* ---- NNPS: kernel choice, DomainManager.update, NNPS.update ------------- */
+/* kernel.__dict__ (dim, radius_scale via the kernel id)
+ * acceleration_eval_cython_helper.py:242-246 */
+int b200sph_set_kernel(b200sph_ctx *ctx, int kernel, int dim);
+/* NNPS.update_domain -> CPUDomainManager._compute_cell_size_for_binning
+ * nnps_base.pyx:450-483, :942-978 */
+int b200sph_update_domain(b200sph_ctx *ctx);
+/* NNPS.update nnps_base.pyx:1471-1510: bounds (:1520-1575), cell grid
+ * (linked_list_nnps.pyx:293-343; error if > 2^28 cells), binning (:235-286)
+ * -- here a deterministic counting sort + cell-relative fp32 repack */
+int b200sph_nnps_update(b200sph_ctx *ctx);
+int b200sph_get_grid(b200sph_ctx *ctx, b200sph_grid_info *out);
+/* NNPS.get_nearest_particles(src, dst, d_idx, nbrs) nnps_base.pyx:1268-1290:
+ * runs the SAME accept test as the pair kernel.  Writes up to cap source
+ * indices (ascending); returns the full neighbour count, or <0 on error. */
+int64_t b200sph_get_neighbors(b200sph_ctx *ctx, int dst_arr, int src_arr,
+                              int64_t d_idx, uint32_t *out, int64_t cap);
+
+/* ---- AccelerationEval.compute building blocks --------------------------- */
+/* TaitEOS.loop (hg=0) wc/basic.py:60-65 / TaitEOSHGCorrection.loop (hg=1)
+ * wc/basic.py:118-126 on one array */
+int b200sph_eos(b200sph_ctx *ctx, int arr, int hg, double rho0, double c0,
+                double gamma, double p0, int real_only);
+/* UpdateSmoothingLengthFerrari.loop wc/basic.py:458-463 */
+int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim,
+                      int real_only);
+/* one Group of pair equations: initialize + loop over all sources + post_loop
+ * fused in one kernel.  pairs_out (may be NULL) receives the number of
+ * directed pair interactions (sum of neighbour-list lengths over the enabled
+ * (dest, source) loops); counting costs one extra atomic per warp. */
+int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog,
+                      int64_t *pairs_out);
+
+/* ---- Integrator stages: WCSPHStep integrator_step.py:38-91 -------------- */
+/* which: 0 initialize, 1 stage1, 2 stage2; arr = -1 -> every array */
+int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt);
+/* out = {max dt_cfl, max dt_force (real particles; -1 if none),
+ *        min h (all particles, starting from 1.0)}
+ * Integrator._get_dt_adapt_factors / compute_h_minimum integrator.py:62-81,146-159 */
+int b200sph_dt_factors(b200sph_ctx *ctx, double out[3]);
+
+/* ---- halo exchange helpers (replace ParallelManager.update,
+ *      parallel_manager.pyx:512-632).  Buffers are DEVICE pointers owned by
+ *      the caller (torch tensors handed to NCCL). ------------------------- */
+#define B200SPH_HALO_FIELDS 9 /* x y z u v w rho h m (fp64 each) */
+/* select the real particles of `arr` with lo <= x < hi, write their
+ * B200SPH_HALO_FIELDS doubles field-major into dev_buf (capacity cap
+ * particles); *count = number selected (may exceed cap -> error) */
+int b200sph_halo_pack(b200sph_ctx *ctx, int arr, double lo, double hi,
+                      double *dev_buf, int64_t cap, int64_t *count);
+/* append n particles from dev_buf (same layout, field stride `stride`
+ * particles) after the current particles of `arr` as ghosts (tag Remote);
+ * as_real != 0 appends them as real particles instead (migration) */
+int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf,
+                        int64_t stride, int64_t n, int as_real);
+/* drop every ghost particle of `arr` (n <- n_real)
+ * parallel_manager.pyx:519 remove_remote_particles */
+int b200sph_drop_ghosts(b200sph_ctx *ctx, int arr);
+/* remove the real particles of `arr` with x outside [lo, hi) after packing
+ * their full state (B200SPH_MIGRATE_FIELDS doubles, field-major, stride cap)
+ * into dev_buf; counts: count[0] = moved below lo, count[1] = moved >= hi;
+ * the below-lo block is written first */
+#define B200SPH_MIGRATE_FIELDS 9
+int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi,
+                        double *dev_buf, int64_t cap, int64_t count[2]);
+
+/* ---- bookkeeping -------------------------------------------------------- */
+int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out);
+int b200sph_reset_stats(b200sph_ctx *ctx);
+/* enable (1) / disable (0) per-phase CUDA-event timing (adds syncs) */
+int b200sph_set_profiling(b200sph_ctx *ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

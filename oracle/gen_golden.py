@@ -1,0 +1,367 @@
+"""Generate the golden fixtures in tests/golden/ FROM THE REFERENCE ITSELF.
+
+TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference);
+the fixtures it writes are committed so that the tests can run on the GPU box,
+where the reference does not exist.
+
+What is executed here is the reference's own code, unmodified, loaded by path:
+
+* pysph/base/kernels.py                      (pure Python kernels)
+* oracle/_ref/c_kernels*.so                  (the reference's compiled kernels,
+                                              built by oracle/build_ref.py)
+* pysph/sph/wc/basic.py, pysph/sph/basic_equations.py  -- the equation classes,
+  with ``pysph.sph.equation`` stubbed by a 6-line ``Equation`` base (the real
+  module imports compyle/mako which are not installed) and ``pow/abs/max/sqrt``
+  injected (the transpiler normally supplies them)
+* pysph/sph/integrator_step.py               (WCSPHStep)
+
+Only the loop DRIVER is ours (brute-force neighbours with the criterion of
+pysph/base/nnps_base.pyx:1365, precomputed symbols per
+pysph/sph/equation.py:188-297, loop nest per acceleration_eval_cython.mako).
+
+    python oracle/gen_golden.py          # rewrites tests/golden/*.json
+"""
+import importlib.util
+import inspect
+import json
+import math
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get('PYSPH_REFERENCE', '/root/reference')
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_reference():
+    stub = types.ModuleType('pysph.sph.equation')
+
+    class Equation(object):
+        def __init__(self, dest, sources):
+            self.dest = dest
+            self.sources = sources
+            self.no_source = sources is None
+
+    stub.Equation = Equation
+    for pkg in ('pysph', 'pysph.sph', 'pysph.sph.wc', 'pysph.base'):
+        sys.modules.setdefault(pkg, types.ModuleType(pkg))
+    sys.modules['pysph.sph.equation'] = stub
+    kernels = _load('pysph.base.kernels',
+                    os.path.join(REF, 'pysph/base/kernels.py'))
+    basic = _load('pysph.sph.basic_equations',
+                  os.path.join(REF, 'pysph/sph/basic_equations.py'))
+    wc = _load('pysph.sph.wc.basic', os.path.join(REF, 'pysph/sph/wc/basic.py'))
+    steps = _load('pysph.sph.integrator_step',
+                  os.path.join(REF, 'pysph/sph/integrator_step.py'))
+    for m in (basic, wc, steps):
+        m.pow, m.abs, m.max, m.sqrt = pow, abs, max, math.sqrt
+    sys.path.insert(0, os.path.join(HERE, '_ref'))
+    import c_kernels
+    return kernels, basic, wc, steps, c_kernels
+
+
+def call(method, env):
+    """Call an equation method with the arguments its signature asks for."""
+    names = [a for a in inspect.signature(method).parameters]
+    return method(*[env[a] for a in names])
+
+
+# ---------------------------------------------------------------------------
+def gen_kernels(kernels, c_kernels):
+    out = []
+    rs = np.random.RandomState(7)
+    combos = [('CubicSpline', (1, 2, 3)), ('WendlandQuintic', (2, 3)),
+              ('QuinticSpline', (1, 2, 3)), ('Gaussian', (1, 2, 3))]
+    for name, dims in combos:
+        for dim in dims:
+            k = getattr(kernels, name)(dim=dim)
+            ck = getattr(c_kernels, name)(**k.__dict__)
+            wrap = getattr(c_kernels, name + 'Wrapper')(ck)
+            cases = []
+            h_vals = [1.0, 0.0114, 0.039, 0.5]
+            q_vals = [0.0, 1e-13, 0.25, 0.5, 0.999, 1.0, 1.001, 1.5, 1.999, 2.0,
+                      2.001, 2.5, 2.999, 3.0, 3.5] + list(rs.uniform(0, 3.2, 8))
+            for h in h_vals:
+                for q in q_vals:
+                    d = rs.normal(size=3)
+                    if dim < 3:
+                        d[2] = 0.0
+                    if dim < 2:
+                        d[1] = 0.0
+                    d = d / np.linalg.norm(d) * q * h
+                    rij = float(np.sqrt(np.dot(d, d)))
+                    grad = [0.0, 0.0, 0.0]
+                    k.gradient(list(d), rij, h, grad)
+                    w_py = k.kernel(list(d), rij, h)
+                    w_c = wrap.kernel(d[0], d[1], d[2], 0.0, 0.0, 0.0, h)
+                    g_c = wrap.gradient(d[0], d[1], d[2], 0.0, 0.0, 0.0, h)
+                    # the reference's compiled and Python kernels agree
+                    assert abs(w_py - w_c) <= 1e-12 * max(1.0, abs(w_py)), (name, dim, q)
+                    assert np.allclose(grad, g_c, rtol=1e-11,
+                                       atol=1e-12 * k.fac / h ** (dim + 1)), (name, dim, q)
+                    cases.append(dict(xij=list(map(float, d)), rij=rij, h=h,
+                                      w=float(w_c), grad=list(map(float, g_c))))
+            out.append(dict(kernel=name, dim=dim, fac=k.fac,
+                            radius_scale=k.radius_scale,
+                            deltap=k.get_deltap(), cases=cases))
+    return out
+
+
+def pair_symbols(kernel, d, s, di, si):
+    XIJ = [d['x'][di] - s['x'][si], d['y'][di] - s['y'][si],
+           d['z'][di] - s['z'][si]]
+    VIJ = [d['u'][di] - s['u'][si], d['v'][di] - s['v'][si],
+           d['w'][di] - s['w'][si]]
+    R2IJ = XIJ[0] * XIJ[0] + XIJ[1] * XIJ[1] + XIJ[2] * XIJ[2]
+    RIJ = math.sqrt(R2IJ)
+    HIJ = 0.5 * (d['h'][di] + s['h'][si])
+    EPS = 0.01 * HIJ * HIJ
+    RHOIJ = 0.5 * (d['rho'][di] + s['rho'][si])
+    # only requested by equations that read rho; guard the unused 0/0 case
+    RHOIJ1 = 1.0 / RHOIJ if RHOIJ != 0.0 else float('inf')
+    WIJ = kernel.kernel(XIJ, RIJ, HIJ)
+    DWIJ = [0.0, 0.0, 0.0]
+    kernel.gradient(XIJ, RIJ, HIJ, DWIJ)
+    WDP = kernel.kernel(XIJ, kernel.get_deltap() * HIJ, HIJ)
+    return dict(XIJ=XIJ, VIJ=VIJ, R2IJ=R2IJ, RIJ=RIJ, HIJ=HIJ, EPS=EPS,
+                RHOIJ=RHOIJ, RHOIJ1=RHOIJ1, WIJ=WIJ, DWIJ=DWIJ, WDP=WDP)
+
+
+def evaluate_reference(kernel, arrays, groups):
+    """Our driver (mako:10-154) around the reference's loop bodies.
+    arrays: dict name -> dict prop -> list;  groups: list of (real, [eq])."""
+    k2 = kernel.radius_scale
+    for real, eqs in groups:
+        dests = []
+        for e in eqs:
+            if e.dest not in dests:
+                dests.append(e.dest)
+        for dname in dests:
+            d = arrays[dname]
+            npd = d['_n_real'] if real else len(d['x'])
+            deqs = [e for e in eqs if e.dest == dname]
+            denv = dict(('d_' + k, v) for k, v in d.items() if k[0] != '_')
+            for di in range(npd):
+                for e in deqs:
+                    if hasattr(e, 'initialize'):
+                        call(e.initialize, dict(denv, d_idx=di))
+            for e in deqs:
+                if e.sources is None and hasattr(e, 'loop'):
+                    for di in range(npd):
+                        call(e.loop, dict(denv, d_idx=di))
+            srcs = []
+            for e in deqs:
+                for s in (e.sources or []):
+                    if s not in srcs:
+                        srcs.append(s)
+            for sname in srcs:
+                s = arrays[sname]
+                senv = dict(('s_' + k, v) for k, v in s.items() if k[0] != '_')
+                seqs = [e for e in deqs if e.sources and sname in e.sources]
+                for di in range(npd):
+                    hi = k2 * d['h'][di]
+                    for si in range(len(s['x'])):
+                        hj = k2 * s['h'][si]
+                        xij2 = ((d['x'][di] - s['x'][si]) ** 2 +
+                                (d['y'][di] - s['y'][si]) ** 2 +
+                                (d['z'][di] - s['z'][si]) ** 2)
+                        if xij2 < hi * hi or xij2 < hj * hj:
+                            env = dict(denv)
+                            env.update(senv)
+                            env.update(pair_symbols(kernel, d, s, di, si))
+                            env.update(d_idx=di, s_idx=si)
+                            for e in seqs:
+                                call(e.loop, env)
+            for di in range(npd):
+                for e in deqs:
+                    if hasattr(e, 'post_loop'):
+                        call(e.post_loop, dict(denv, d_idx=di))
+
+
+PROPS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'p', 'cs', 'arho', 'au',
+         'av', 'aw', 'ax', 'ay', 'az', 'dt_cfl', 'dt_force']
+
+
+def make_array(rs, n, lo, hi, dx, dim, rho0, ghost=0, vel=1.0, hvar=0.0):
+    pts = rs.uniform(lo, hi, size=(n, 3))
+    if dim < 3:
+        pts[:, 2] = 0.0
+    if dim < 2:
+        pts[:, 1] = 0.0
+    a = dict((p, [0.0] * n) for p in PROPS)
+    a['x'], a['y'], a['z'] = (list(map(float, pts[:, i])) for i in range(3))
+    v = rs.normal(scale=vel, size=(n, 3))
+    if dim < 3:
+        v[:, 2] = 0.0
+    if dim < 2:
+        v[:, 1] = 0.0
+    a['u'], a['v'], a['w'] = (list(map(float, v[:, i])) for i in range(3))
+    a['h'] = list(map(float, 1.3 * dx * (1.0 + hvar * rs.uniform(-1, 1, n))))
+    a['m'] = [float(rho0 * dx ** dim)] * n
+    a['rho'] = list(map(float, rho0 * (1.0 + 0.02 * rs.uniform(-1, 1, n))))
+    a['_n_real'] = n - ghost
+    return a
+
+
+def gen_wcsph_case(kernels, basic, wc, kernel_name, dim, seed, hvar=0.0,
+                   tensile=False, summation_density=False):
+    """A small 3-array WCSPH evaluation through the reference's bodies."""
+    rs = np.random.RandomState(seed)
+    kernel = getattr(kernels, kernel_name)(dim=dim)
+    dx = 0.1
+    rho0, c0, gamma = 1000.0, 32.85, 7.0
+    nf, nb, no = 90, 60, 12
+    if dim == 3:
+        lo_f, hi_f = [0, 0, 0], [0.5, 0.4, 0.4]
+        lo_b, hi_b = [-0.15, -0.1, -0.15], [0.65, 0.5, 0.0]
+        lo_o, hi_o = [0.5, 0.1, 0.0], [0.6, 0.3, 0.2]
+    else:
+        lo_f, hi_f = [0, 0, 0], [1.0, 0.8, 0.0]
+        lo_b, hi_b = [-0.2, -0.2, 0], [1.2, 0.0, 0.0]
+        lo_o, hi_o = [1.0, 0.0, 0.0], [1.2, 0.4, 0.0]
+    arrays = dict(
+        fluid=make_array(rs, nf, lo_f, hi_f, dx, dim, rho0, ghost=10, hvar=hvar),
+        boundary=make_array(rs, nb, lo_b, hi_b, dx, dim, rho0, ghost=5,
+                            vel=0.0, hvar=hvar),
+        obstacle=make_array(rs, no, lo_o, hi_o, dx, dim, rho0, vel=0.0,
+                            hvar=hvar))
+    inputs = json.loads(json.dumps(arrays))
+    fluids, solids = ['fluid'], ['boundary', 'obstacle']
+    all_ = fluids + solids
+    params = dict(rho0=rho0, c0=c0, gamma=gamma, alpha=0.25, beta=0.1,
+                  gx=0.3, gy=-0.2 if dim > 1 else 0.0,
+                  gz=-9.81 if dim == 3 else 0.0, tensile_correction=tensile,
+                  hg_correction=True, summation_density=summation_density,
+                  dim=dim, hdx=1.3, h0=1.3 * dx)
+    groups = []
+    if summation_density:
+        groups.append((False, [basic.SummationDensity(dest=f, sources=all_)
+                               for f in fluids]))
+    g1 = [wc.TaitEOS(dest=f, sources=None, rho0=rho0, c0=c0, gamma=gamma)
+          for f in fluids]
+    g1 += [wc.TaitEOSHGCorrection(dest=s, sources=None, rho0=rho0, c0=c0,
+                                  gamma=gamma) for s in solids]
+    groups.append((False, g1))
+    g2 = [basic.ContinuityEquation(dest=s, sources=fluids) for s in solids]
+    for f in fluids:
+        if not summation_density:
+            g2.append(basic.ContinuityEquation(dest=f, sources=all_))
+        g2.append(wc.MomentumEquation(
+            dest=f, sources=all_, c0=c0, alpha=params['alpha'],
+            beta=params['beta'], gx=params['gx'], gy=params['gy'],
+            gz=params['gz'], tensile_correction=tensile))
+        g2.append(basic.XSPHCorrection(dest=f, sources=[f]))
+    groups.append((True, g2))
+    evaluate_reference(kernel, arrays, groups)
+    return dict(kernel=kernel_name, dim=dim, params=params, inputs=inputs,
+                outputs=arrays)
+
+
+def gen_steppers(steps):
+    rs = np.random.RandomState(11)
+    n = 7
+    st = steps.WCSPHStep()
+    names = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'x0', 'y0', 'z0', 'u0', 'v0',
+             'w0', 'rho0', 'au', 'av', 'aw', 'ax', 'ay', 'az', 'arho']
+    a = dict((k, list(map(float, rs.normal(size=n)))) for k in names)
+    inputs = json.loads(json.dumps(a))
+    dt = 0.0123
+    res = {}
+    for which, meth in (('initialize', st.initialize), ('stage1', st.stage1),
+                        ('stage2', st.stage2)):
+        b = json.loads(json.dumps(inputs))
+        env = dict(('d_' + k, v) for k, v in b.items())
+        for i in range(n):
+            call(meth, dict(env, d_idx=i, dt=dt))
+        res[which] = b
+    return dict(dt=dt, inputs=inputs, outputs=res)
+
+
+def gen_eos(wc):
+    rs = np.random.RandomState(3)
+    rho = list(map(float, 1000.0 * (1 + 0.03 * rs.uniform(-1, 1, 16))))
+    out = {}
+    for name, cls, kw in (('TaitEOS', wc.TaitEOS, dict(p0=12.5)),
+                          ('TaitEOSHGCorrection', wc.TaitEOSHGCorrection, {})):
+        e = cls(dest='f', sources=None, rho0=1000.0, c0=32.85, gamma=7.0, **kw)
+        r = list(rho)
+        p = [0.0] * len(r)
+        cs = [0.0] * len(r)
+        for i in range(len(r)):
+            e.loop(i, r, p, cs)
+        out[name] = dict(rho_in=rho, rho_out=r, p=p, cs=cs, rho0=1000.0,
+                         c0=32.85, gamma=7.0, p0=kw.get('p0', 0.0))
+    f = wc.UpdateSmoothingLengthFerrari(dest='f', sources=None, dim=2, hdx=1.3)
+    h = [0.0] * len(rho)
+    m = [0.9] * len(rho)
+    for i in range(len(rho)):
+        f.loop(i, rho, h, m)
+    out['UpdateSmoothingLengthFerrari'] = dict(rho=rho, m=m, h=h, dim=2, hdx=1.3)
+    return out
+
+
+def gen_density_1d(kernels, basic):
+    """test_acceleration_eval.py:294-303: 10 points on [0,1], m=1, h=1.05dx."""
+    n = 10
+    dx = 1.0 / (n - 1)
+    x = list(map(float, np.linspace(0, 1, n)))
+    a = dict((p, [0.0] * n) for p in PROPS)
+    a['x'] = x
+    a['m'] = [1.0] * n
+    a['h'] = [1.05 * dx] * n
+    a['_n_real'] = n
+    kernel = kernels.CubicSpline(dim=1)
+    eq = basic.SummationDensity(dest='fluid', sources=['fluid'])
+    arrays = dict(fluid=a)
+    evaluate_reference(kernel, arrays, [(True, [eq])])
+    k2 = 2.0
+    counts = []
+    for i in range(n):
+        c = 0
+        for j in range(n):
+            r2 = (x[i] - x[j]) ** 2
+            if r2 < (k2 * a['h'][i]) ** 2 or r2 < (k2 * a['h'][j]) ** 2:
+                c += 1
+        counts.append(c)
+    return dict(x=x, h=a['h'], m=a['m'], rho=a['rho'], nbr_counts=counts)
+
+
+def main():
+    kernels, basic, wc, steps, c_kernels = load_reference()
+    os.makedirs(GOLD, exist_ok=True)
+
+    def dump(name, obj):
+        with open(os.path.join(GOLD, name), 'w') as f:
+            json.dump(obj, f)
+        print('wrote', name, os.path.getsize(os.path.join(GOLD, name)), 'bytes')
+
+    dump('kernels.json', gen_kernels(kernels, c_kernels))
+    dump('eos.json', gen_eos(wc))
+    dump('steppers.json', gen_steppers(steps))
+    dump('density_1d.json', gen_density_1d(kernels, basic))
+    cases = [
+        gen_wcsph_case(kernels, basic, wc, 'CubicSpline', 3, 101),
+        gen_wcsph_case(kernels, basic, wc, 'WendlandQuintic', 3, 102, hvar=0.15),
+        gen_wcsph_case(kernels, basic, wc, 'WendlandQuintic', 2, 103),
+        gen_wcsph_case(kernels, basic, wc, 'QuinticSpline', 3, 104, tensile=True),
+        gen_wcsph_case(kernels, basic, wc, 'CubicSpline', 2, 105, hvar=0.1,
+                       summation_density=True),
+        gen_wcsph_case(kernels, basic, wc, 'Gaussian', 3, 106),
+    ]
+    dump('wcsph_cases.json', cases)
+
+
+if __name__ == '__main__':
+    main()

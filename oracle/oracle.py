@@ -1,0 +1,356 @@
+"""ctypes wrapper + WCSPH driver for the fp64 CPU oracle (liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  Nothing in pysph_b200/ may
+import this module.
+
+The driver below restates, independently of pysph_b200.program, which loops the
+reference runs for a WCSPHScheme (pysph/sph/scheme.py:388-506), in which order
+(pysph/sph/integrator.py:344-361 PEC, :401-420 EPEC) and how the solver picks
+the time step (pysph/solver/solver.py:454-507, :647-688;
+pysph/sph/integrator.py:161-200).
+"""
+import ctypes as C
+import os
+import subprocess
+from math import sqrt
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, 'liboracle.so')
+
+MAX_ARRAYS = 8
+K_IDS = {'CubicSpline': 0, 'WendlandQuintic': 1, 'QuinticSpline': 2,
+         'Gaussian': 3}
+EQ_SUMDENS, EQ_CONT, EQ_MOM, EQ_XSPH, EQ_AV = 1, 2, 4, 8, 16
+
+_PTR_FIELDS = ['x', 'y', 'z', 'h', 'm', 'rho', 'u', 'v', 'w', 'p', 'cs',
+               'arho', 'au', 'av', 'aw', 'ax', 'ay', 'az', 'dt_cfl',
+               'dt_force', 'x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'rho0']
+
+
+class OrcArray(C.Structure):
+    _fields_ = [('n', C.c_int64), ('n_real', C.c_int64)] + \
+        [(f, C.POINTER(C.c_double)) for f in _PTR_FIELDS]
+
+
+class OrcPairProgram(C.Structure):
+    _fields_ = [('kernel', C.c_int), ('dim', C.c_int),
+                ('c0', C.c_double), ('alpha', C.c_double), ('beta', C.c_double),
+                ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
+                ('tensile_correction', C.c_int),
+                ('eps_xsph', C.c_double),
+                ('real_only', C.c_int),
+                ('eqmask', (C.c_uint32 * MAX_ARRAYS) * MAX_ARRAYS),
+                ('src_order', (C.c_int * MAX_ARRAYS) * MAX_ARRAYS),
+                ('dest_order', C.c_int * MAX_ARRAYS)]
+
+
+def build(force=False):
+    src = os.path.join(HERE, 'sph_oracle.c')
+    if force or not os.path.exists(LIB) or \
+            os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.check_call(['make', '-C', HERE, 'liboracle.so'],
+                              stdout=subprocess.DEVNULL)
+    return LIB
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        lib = C.CDLL(LIB)
+        lib.orc_create.restype = C.c_void_p
+        lib.orc_create.argtypes = [C.c_int, C.c_int, C.c_double]
+        lib.orc_destroy.argtypes = [C.c_void_p]
+        lib.orc_set_array.argtypes = [C.c_void_p, C.c_int, C.POINTER(OrcArray)]
+        lib.orc_set_num_threads.argtypes = [C.c_int]
+        lib.orc_get_max_threads.restype = C.c_int
+        lib.orc_update_domain.argtypes = [C.c_void_p]
+        lib.orc_nnps_update.argtypes = [C.c_void_p]
+        lib.orc_nnps_update.restype = C.c_int
+        lib.orc_get_grid.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        for f in ('orc_find_neighbors', 'orc_brute_neighbors'):
+            getattr(lib, f).restype = C.c_int64
+            getattr(lib, f).argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64,
+                                        C.c_void_p, C.c_int64]
+        lib.orc_eos.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                C.c_double, C.c_double, C.c_double, C.c_int]
+        lib.orc_ferrari_h.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                      C.c_int]
+        lib.orc_pair_pass.restype = C.c_int64
+        lib.orc_pair_pass.argtypes = [C.c_void_p, C.POINTER(OrcPairProgram)]
+        lib.orc_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        lib.orc_dt_factors.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orc_kernel_w.restype = C.c_double
+        lib.orc_kernel_w.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
+        lib.orc_kernel_grad.argtypes = [C.c_int, C.c_int, C.c_void_p,
+                                        C.c_double, C.c_double, C.c_void_p]
+        lib.orc_kernel_deltap.restype = C.c_double
+        lib.orc_kernel_deltap.argtypes = [C.c_int]
+        lib.orc_kernel_radius_scale.restype = C.c_double
+        lib.orc_kernel_radius_scale.argtypes = [C.c_int]
+        _lib = lib
+    return _lib
+
+
+def kernel_w(kernel, dim, rij, h):
+    return load().orc_kernel_w(K_IDS[kernel], dim, rij, h)
+
+
+def kernel_grad(kernel, dim, xij, rij, h):
+    x = (C.c_double * 3)(*xij)
+    g = (C.c_double * 3)()
+    load().orc_kernel_grad(K_IDS[kernel], dim, x, rij, h, g)
+    return np.array(g[:])
+
+
+class Oracle(object):
+    """fp64 evaluator over a list of host particle arrays (any object with
+    ``properties`` dict of float64 numpy arrays, ``get_number_of_particles``
+    and ``num_real_particles``).  Operates IN PLACE on those arrays."""
+
+    def __init__(self, particle_arrays, dim, kernel='CubicSpline',
+                 radius_scale=None, threads=1):
+        self.lib = load()
+        self.pas = list(particle_arrays)
+        self.names = [pa.name for pa in self.pas]
+        self.index = dict((n, i) for i, n in enumerate(self.names))
+        self.dim = dim
+        self.kernel = kernel
+        self.kid = K_IDS[kernel]
+        if radius_scale is None:
+            radius_scale = self.lib.orc_kernel_radius_scale(self.kid)
+        self.radius_scale = radius_scale
+        self.lib.orc_set_num_threads(int(threads))
+        self.h = C.c_void_p(self.lib.orc_create(len(self.pas), dim,
+                                                 radius_scale))
+        self.bind()
+
+    def bind(self):
+        """(Re)bind host pointers -- call after any array was re-allocated."""
+        self._keep = []
+        for i, pa in enumerate(self.pas):
+            oa = OrcArray()
+            oa.n = pa.get_number_of_particles()
+            oa.n_real = pa.get_number_of_particles(real=True)
+            for f in _PTR_FIELDS:
+                if f in pa.properties:
+                    a = pa.properties[f]
+                    assert a.dtype == np.float64 and a.flags.c_contiguous
+                    setattr(oa, f, a.ctypes.data_as(C.POINTER(C.c_double)))
+            self._keep.append(oa)
+            self.lib.orc_set_array(self.h, i, C.byref(oa))
+
+    def __del__(self):
+        try:
+            self.lib.orc_destroy(self.h)
+        except Exception:
+            pass
+
+    # -- NNPS -----------------------------------------------------------------
+    def update_domain(self):
+        self.lib.orc_update_domain(self.h)
+
+    def nnps_update(self):
+        rc = self.lib.orc_nnps_update(self.h)
+        if rc == -1:
+            raise RuntimeError('ERROR: LinkedListNNPS requires too many cells')
+        if rc:
+            raise RuntimeError('oracle nnps_update failed (%d)' % rc)
+
+    def grid(self):
+        cs, hm = C.c_double(), C.c_double()
+        xmin, xmax = (C.c_double * 3)(), (C.c_double * 3)()
+        nc, n = (C.c_int * 3)(), C.c_int64()
+        self.lib.orc_get_grid(self.h, C.byref(cs), C.byref(hm), xmin, xmax, nc,
+                              C.byref(n))
+        return dict(cell_size=cs.value, hmin=hm.value, xmin=np.array(xmin[:]),
+                    xmax=np.array(xmax[:]), ncells=np.array(nc[:]),
+                    n_cells=n.value)
+
+    def _nbrs(self, fn, dst, src, d_idx):
+        cap = 4096
+        while True:
+            buf = np.empty(cap, dtype=np.uint32)
+            n = fn(self.h, dst, src, int(d_idx), buf.ctypes.data, cap)
+            if n <= cap:
+                return buf[:n].copy()
+            cap = int(n)
+
+    def neighbors(self, dst, src, d_idx):
+        return self._nbrs(self.lib.orc_find_neighbors, dst, src, d_idx)
+
+    def brute_neighbors(self, dst, src, d_idx):
+        return self._nbrs(self.lib.orc_brute_neighbors, dst, src, d_idx)
+
+    # -- equations ------------------------------------------------------------
+    def eos(self, arr, hg, rho0, c0, gamma, p0=0.0, real_only=False):
+        self.lib.orc_eos(self.h, arr, int(hg), rho0, c0, gamma, p0,
+                         int(real_only))
+
+    def ferrari_h(self, arr, hdx, dim, real_only=False):
+        self.lib.orc_ferrari_h(self.h, arr, hdx, dim, int(real_only))
+
+    def pair_pass(self, eqs, real_only=True, c0=0.0, alpha=0.0, beta=0.0,
+                  gx=0.0, gy=0.0, gz=0.0, tensile_correction=False,
+                  eps_xsph=0.5):
+        """eqs: list of (bit, dest_index, [source indices]) in user order."""
+        P = OrcPairProgram()
+        P.kernel, P.dim = self.kid, self.dim
+        P.c0, P.alpha, P.beta = c0, alpha, beta
+        P.gx, P.gy, P.gz = gx, gy, gz
+        P.tensile_correction = int(tensile_correction)
+        P.eps_xsph = eps_xsph
+        P.real_only = int(real_only)
+        dests = []
+        orders = {}
+        for bit, d, srcs in eqs:
+            if d not in dests:
+                dests.append(d)
+                orders[d] = []
+            for s in srcs:
+                P.eqmask[d][s] |= bit
+                if s not in orders[d]:
+                    orders[d].append(s)
+        for d in range(MAX_ARRAYS):
+            for k in range(MAX_ARRAYS):
+                P.src_order[d][k] = -1
+            P.dest_order[d] = -1
+        for k, d in enumerate(dests):
+            P.dest_order[k] = d
+            for j, s in enumerate(orders[d]):
+                P.src_order[d][j] = s
+        return self.lib.orc_pair_pass(self.h, C.byref(P))
+
+    def stage(self, arr, which, dt):
+        self.lib.orc_stage(self.h, arr, which, dt)
+
+    def dt_factors(self):
+        out = (C.c_double * 3)()
+        self.lib.orc_dt_factors(self.h, out)
+        return out[0], out[1], out[2]
+
+
+class WCSPHOracleSolver(object):
+    """Runs a WCSPHScheme simulation with the oracle: scheme.py:388-506 for the
+    loops, integrator.py:344-361/401-420 for the stage order, solver.py for the
+    time step.  ``params`` as returned by pysph_b200.geometry.*_params."""
+
+    def __init__(self, particles, params, kernel='CubicSpline', threads=1):
+        p = dict(params)
+        self.p = p
+        self.integrator = p.get('integrator', 'EPEC')
+        self.dim = p['dim']
+        self.o = Oracle(particles, self.dim, kernel, threads=threads)
+        ix = self.o.index
+        self.fluids = [ix[n] for n in p['fluids']]
+        self.solids = [ix[n] for n in p['solids']]
+        self.all = self.fluids + self.solids
+        self.dt = p['dt0']
+        self.cfl = p.get('cfl', 0.3)
+        self.n_damp = p.get('n_damp', 0)
+        self.adaptive = p.get('adaptive_timestep', True)
+        self.t = 0.0
+        self.count = 0
+        self._damping_factor = 1.0
+        self.pairs_last_eval = 0
+        self.pairs_total = 0
+        # NNPS constructor: domain.update(); update()  (linked_list_nnps.pyx:84-88)
+        self.o.update_domain()
+        self.o.nnps_update()
+        self._initialised = False
+
+    # AccelerationEval.compute for the WCSPH groups
+    def evaluate(self):
+        p, o = self.p, self.o
+        pairs = 0
+        if p.get('summation_density', False):
+            pairs += o.pair_pass([(EQ_SUMDENS, f, self.all) for f in self.fluids],
+                                 real_only=False)
+        for f in self.fluids:
+            o.eos(f, 0, p['rho0'], p['c0'], p['gamma'], 0.0, real_only=False)
+        for s in self.solids:
+            o.eos(s, 1 if p.get('hg_correction', False) else 0, p['rho0'],
+                  p['c0'], p['gamma'], 0.0, real_only=False)
+        eqs = [(EQ_CONT, s, self.fluids) for s in self.solids]
+        for f in self.fluids:
+            if not p.get('summation_density', False):
+                eqs.append((EQ_CONT, f, self.all))
+            eqs.append((EQ_MOM, f, self.all))
+            eqs.append((EQ_XSPH, f, [f]))
+        pairs += o.pair_pass(
+            eqs, real_only=True, c0=p['c0'], alpha=p.get('alpha', 0.1),
+            beta=p.get('beta', 0.0), gx=p.get('gx', 0.0), gy=p.get('gy', 0.0),
+            gz=p.get('gz', 0.0),
+            tensile_correction=p.get('tensile_correction', False), eps_xsph=0.5)
+        if p.get('update_h', False):
+            for f in self.fluids:
+                o.ferrari_h(f, p['hdx'], self.dim, real_only=False)
+        self.pairs_last_eval = pairs
+        self.pairs_total += pairs
+        return pairs
+
+    def compute_accelerations(self):
+        self.o.nnps_update()
+        self.evaluate()
+
+    def _stage(self, which, dt):
+        for a in self.all:
+            self.o.stage(a, which, dt)
+
+    def one_timestep(self, dt):
+        self._stage(0, 0.0)
+        if self.integrator == 'EPEC':
+            self.compute_accelerations()
+        self._stage(1, dt)
+        self.o.update_domain()
+        self.compute_accelerations()
+        self._stage(2, dt)
+        self.o.update_domain()
+
+    def _compute_timestep(self):
+        undamped = self.dt / self._damping_factor
+        if not self.adaptive:
+            return undamped
+        f_cfl, f_force, hmin = self.o.dt_factors()
+        dt_cfl = dt_force = np.inf
+        if f_cfl > 0:
+            dt_cfl = hmin / f_cfl
+        if f_force > 0:
+            dt_force = sqrt(hmin / sqrt(f_force))
+        dt_min = min(dt_cfl, dt_force)
+        if dt_min <= 0.0 or np.isinf(dt_min):
+            return undamped
+        return self.cfl * dt_min
+
+    def _get_timestep(self):
+        dt = self._compute_timestep()
+        if self.count < self.n_damp and self.n_damp > 0:
+            frac = (self.count + 1) / float(self.n_damp)
+            self._damping_factor = 0.5 * (np.sin(np.pi * (-0.5 + frac)) + 1.0)
+        else:
+            self._damping_factor = 1.0
+        return dt * self._damping_factor
+
+    def initialise(self):
+        if not self._initialised:
+            self.evaluate()                 # initial_acceleration, no NNPS update
+            self.dt = self._get_timestep()
+            self._initialised = True
+
+    def step(self):
+        self.initialise()
+        self.one_timestep(self.dt)
+        self.t += self.dt
+        self.count += 1
+        self.dt = self._get_timestep()
+
+    def solve(self, max_steps):
+        self.initialise()
+        while self.count < max_steps:
+            self.step()

@@ -1,0 +1,124 @@
+/*
+ * oracle/sph_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * fp64 CPU restatement of the PySPH WCSPH hot path (LinkedListNNPS + the
+ * generated AccelerationEval.compute loop nest + WCSPHStep), used only as the
+ * parity checker in tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs.  Nothing under pysph_b200/ may import,
+ * link or call this.
+ *
+ * Parity pinning: see oracle/README.md -- the restatement is checked against
+ * (a) the reference's own compiled c_kernels.pyx (built into oracle/_ref),
+ * (b) the reference's own Python equation bodies (pysph/sph/wc/basic.py,
+ *     pysph/sph/basic_equations.py, pysph/sph/integrator_step.py) driven
+ *     pair-by-pair, and (c) the known-answer vectors in the reference tests
+ *     (test_acceleration_eval.py, test_nnps.py, test_kernel.py).
+ */
+#ifndef SPH_ORACLE_H
+#define SPH_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_ARRAYS 8
+
+/* smoothing kernels -- pysph/base/kernels.py */
+enum { ORC_K_CUBIC = 0, ORC_K_WENDLAND = 1, ORC_K_QUINTIC = 2, ORC_K_GAUSSIAN = 3 };
+
+/* pair-equation bits (one nibble+ per (dest, source) entry of the program) */
+enum {
+    ORC_EQ_SUMDENS = 1,   /* SummationDensity          basic_equations.py:19-29   */
+    ORC_EQ_CONT    = 2,   /* ContinuityEquation        basic_equations.py:180-192 */
+    ORC_EQ_MOM     = 4,   /* MomentumEquation          wc/basic.py:129-269        */
+    ORC_EQ_XSPH    = 8,   /* XSPHCorrection            basic_equations.py:260-300 */
+    ORC_EQ_AV      = 16   /* MonaghanArtificialViscosity basic_equations.py:195-257 */
+};
+
+/* borrowed host pointers to one ParticleArray's fp64 SoA properties
+ * (pysph/base/utils.py:152-190).  Any pointer an enabled equation does not
+ * touch may be NULL. */
+typedef struct {
+    int64_t n;       /* all particles (real + ghost/remote) */
+    int64_t n_real;  /* real particles come first (particle_array.pyx:1092-1172) */
+    double *x, *y, *z, *h, *m, *rho, *u, *v, *w, *p, *cs;
+    double *arho, *au, *av, *aw, *ax, *ay, *az, *dt_cfl, *dt_force;
+    double *x0, *y0, *z0, *u0, *v0, *w0, *rho0;
+} orc_array;
+
+typedef struct {
+    int kernel;          /* ORC_K_*                                     */
+    int dim;             /* 1, 2, 3                                     */
+    /* MomentumEquation / MonaghanArtificialViscosity */
+    double c0, alpha, beta, gx, gy, gz;
+    int tensile_correction;
+    /* XSPHCorrection */
+    double eps_xsph;
+    /* group flag: real=True -> destinations are the real particles only */
+    int real_only;
+    /* eqmask[d][s]: OR of ORC_EQ_* for dest array d, source array s        */
+    uint32_t eqmask[ORC_MAX_ARRAYS][ORC_MAX_ARRAYS];
+    /* src_order[d][k]: k-th source array visited for dest d (first-mention
+     * order, acceleration_eval.py:139-160); -1 terminates */
+    int src_order[ORC_MAX_ARRAYS][ORC_MAX_ARRAYS];
+    /* dest_order[k]: k-th destination array; -1 terminates */
+    int dest_order[ORC_MAX_ARRAYS];
+} orc_pair_program;
+
+typedef struct orc_ctx orc_ctx;
+
+orc_ctx *orc_create(int narrays, int dim, double radius_scale);
+void orc_destroy(orc_ctx *);
+void orc_set_array(orc_ctx *, int idx, const orc_array *a);
+void orc_set_num_threads(int n);
+int orc_get_max_threads(void);
+
+/* a1: CPUDomainManager._compute_cell_size_for_binning  nnps_base.pyx:942-978 */
+void orc_update_domain(orc_ctx *);
+/* a2-a4: NNPS.update -> _compute_bounds, _refresh, _bin
+ * nnps_base.pyx:1471-1575, linked_list_nnps.pyx:235-382.  returns 0, or -1 if
+ * the grid needs more than 2^28 cells (linked_list_nnps.pyx:336-343) */
+int orc_nnps_update(orc_ctx *);
+void orc_get_grid(orc_ctx *, double *cell_size, double *hmin, double xmin[3],
+                  double xmax[3], int ncells[3], int64_t *n_cells);
+
+/* a5: LinkedListNNPS.find_nearest_neighbors  linked_list_nnps.pyx:92-196.
+ * Writes up to cap indices (linked-list order); returns the full count. */
+int64_t orc_find_neighbors(orc_ctx *, int dst, int src, int64_t d_idx,
+                           uint32_t *out, int64_t cap);
+/* NNPS.brute_force_neighbors  nnps_base.pyx:1325-1366 */
+int64_t orc_brute_neighbors(orc_ctx *, int dst, int src, int64_t d_idx,
+                            uint32_t *out, int64_t cap);
+
+/* a11: TaitEOS (hg=0) / TaitEOSHGCorrection (hg=1)  wc/basic.py:9-126 */
+void orc_eos(orc_ctx *, int arr, int hg, double rho0, double c0, double gamma,
+             double p0, int real_only);
+/* UpdateSmoothingLengthFerrari  wc/basic.py:417-463 */
+void orc_ferrari_h(orc_ctx *, int arr, double hdx, int dim, int real_only);
+
+/* a8-a17: one Group's pair loops (initialize / per-source loop / post_loop)
+ * acceleration_eval_cython.mako:10-154.  returns the number of directed pair
+ * interactions evaluated (sum of neighbour-list lengths over enabled
+ * (dest, source) loops). */
+int64_t orc_pair_pass(orc_ctx *, const orc_pair_program *prog);
+
+/* a18: WCSPHStep.initialize (0) / stage1 (1) / stage2 (2) over real particles
+ * integrator_step.py:38-91 */
+void orc_stage(orc_ctx *, int arr, int which, double dt);
+
+/* a19 inputs: max dt_cfl, max dt_force over real+ghost of all arrays that have
+ * them (integrator.py:62-81), raw min h (integrator.py:146-159, start 1.0) */
+void orc_dt_factors(orc_ctx *, double out[3]);
+
+/* single kernel evaluations for the kernel parity tests */
+double orc_kernel_w(int kernel, int dim, double rij, double h);
+void orc_kernel_grad(int kernel, int dim, const double xij[3], double rij,
+                     double h, double grad[3]);
+double orc_kernel_deltap(int kernel);
+double orc_kernel_radius_scale(int kernel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,164 @@
+"""ctypes binding of libb200sph.so (the C-ABI declared in include/b200sph.h).
+
+Loading fails loudly if the shared library is missing -- there is no CPU or
+PyTorch fallback for any entry point.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libb200sph.so')
+
+MAX_ARRAYS = 8
+
+# property ids (include/b200sph.h)
+PROP_IDS = {}
+for _i, _n in enumerate(['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm',
+                         'x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'rho0',
+                         'p', 'cs', 'arho', 'au', 'av', 'aw', 'ax', 'ay', 'az',
+                         'dt_cfl', 'dt_force']):
+    PROP_IDS[_n] = _i
+INT_PROP_IDS = {'gid': 64, 'tag': 65, 'pid': 66}
+F64_DEVICE_PROPS = ('x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm',
+                    'x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'rho0')
+
+EQ_SUMMATION_DENSITY = 1
+EQ_CONTINUITY = 2
+EQ_MOMENTUM = 4
+EQ_XSPH = 8
+EQ_MONAGHAN_AV = 16
+
+HALO_FIELDS = 9
+HALO_FIELD_NAMES = ('x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm')
+
+
+class PairProgram(C.Structure):
+    _fields_ = [('eqmask', (C.c_uint32 * MAX_ARRAYS) * MAX_ARRAYS),
+                ('real_only', C.c_int32),
+                ('tensile_correction', C.c_int32),
+                ('c0', C.c_double), ('alpha', C.c_double), ('beta', C.c_double),
+                ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
+                ('eps_xsph', C.c_double)]
+
+
+class GridInfo(C.Structure):
+    _fields_ = [('cell_size', C.c_double), ('hmin', C.c_double),
+                ('xmin', C.c_double * 3), ('xmax', C.c_double * 3),
+                ('ncells', C.c_int32 * 3), ('n_cells', C.c_int64),
+                ('n_particles', C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [('ms_nnps', C.c_double), ('ms_pair', C.c_double),
+                ('ms_other', C.c_double), ('pair_launches', C.c_int64),
+                ('kernel_launches', C.c_int64), ('pairs', C.c_int64)]
+
+
+_ctx_p = C.c_void_p
+_i64 = C.c_int64
+_dp = C.POINTER(C.c_double)
+_up = C.POINTER(C.c_uint32)
+
+# name -> (restype, argtypes); must list every function of include/b200sph.h
+SIGNATURES = {
+    'b200sph_abi_version': (C.c_int, []),
+    'b200sph_create': (C.c_int, [C.c_int, C.POINTER(_ctx_p)]),
+    'b200sph_destroy': (C.c_int, [_ctx_p]),
+    'b200sph_last_error': (C.c_char_p, [_ctx_p]),
+    'b200sph_set_stream': (C.c_int, [_ctx_p, C.c_void_p]),
+    'b200sph_synchronize': (C.c_int, [_ctx_p]),
+    'b200sph_add_array': (C.c_int, [_ctx_p, C.c_char_p, _i64, _i64, _i64]),
+    'b200sph_resize_array': (C.c_int, [_ctx_p, C.c_int, _i64, _i64]),
+    'b200sph_get_array_size': (C.c_int, [_ctx_p, C.c_int, C.POINTER(_i64),
+                                         C.POINTER(_i64)]),
+    'b200sph_push_f64': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, _i64, _i64]),
+    'b200sph_pull_f64': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, _i64, _i64]),
+    'b200sph_push_u32': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, _i64, _i64]),
+    'b200sph_pull_u32': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, _i64, _i64]),
+    'b200sph_device_ptr': (C.c_int, [_ctx_p, C.c_int, C.c_int,
+                                     C.POINTER(C.c_void_p)]),
+    'b200sph_set_kernel': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
+    'b200sph_update_domain': (C.c_int, [_ctx_p]),
+    'b200sph_nnps_update': (C.c_int, [_ctx_p]),
+    'b200sph_get_grid': (C.c_int, [_ctx_p, C.POINTER(GridInfo)]),
+    'b200sph_get_neighbors': (_i64, [_ctx_p, C.c_int, C.c_int, _i64, C.c_void_p, _i64]),
+    'b200sph_eos': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                              C.c_double, C.c_double, C.c_int]),
+    'b200sph_ferrari_h': (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_int, C.c_int]),
+    'b200sph_pair_pass': (C.c_int, [_ctx_p, C.POINTER(PairProgram),
+                                    C.POINTER(_i64)]),
+    'b200sph_stage': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
+    'b200sph_dt_factors': (C.c_int, [_ctx_p, _dp]),
+    'b200sph_halo_pack': (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_double,
+                                    C.c_void_p, _i64, C.POINTER(_i64)]),
+    'b200sph_halo_append': (C.c_int, [_ctx_p, C.c_int, C.c_void_p, _i64, _i64,
+                                      C.c_int]),
+    'b200sph_drop_ghosts': (C.c_int, [_ctx_p, C.c_int]),
+    'b200sph_migrate_out': (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_double,
+                                      C.c_void_p, _i64, C.POINTER(_i64)]),
+    'b200sph_get_stats': (C.c_int, [_ctx_p, C.POINTER(Stats)]),
+    'b200sph_reset_stats': (C.c_int, [_ctx_p]),
+    'b200sph_set_profiling': (C.c_int, [_ctx_p, C.c_int]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libb200sph.so (build it with `python -m pysph_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'pysph_b200: %s is missing. Build it with `python -m '
+            'pysph_b200.build` (needs nvcc). There is no CPU fallback.'
+            % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class Context(object):
+    """Thin RAII wrapper over a b200sph_ctx handle."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = _ctx_p()
+        rc = self.lib.b200sph_create(int(device), C.byref(h))
+        if rc != 0 or not h:
+            msg = ''
+            if h:
+                msg = self.lib.b200sph_last_error(h).decode()
+                self.lib.b200sph_destroy(h)
+            raise B200Error(
+                'b200sph_create(device=%d) failed (rc=%d) %s -- a CUDA device '
+                'is required, there is no CPU fallback' % (device, rc, msg))
+        self.h = h
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.b200sph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc < 0:
+            raise B200Error(self.lib.b200sph_last_error(self.h).decode())
+        return rc
+
+    def call(self, name, *args):
+        return self.check(getattr(self.lib, name)(self.h, *args))

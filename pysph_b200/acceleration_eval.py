@@ -1,0 +1,73 @@
+"""B200AccelerationEval: drop-in for the compiled AccelerationEval object.
+
+Stands where ``SPHCompiler`` installs the generated Cython extension
+(pysph/sph/sph_compiler.py:26-58, pysph/sph/acceleration_eval.py:228-248):
+``compute(t, dt)``, ``set_nnps(nnps)``, ``update_particle_arrays(arrays)``.
+The loop nest of acceleration_eval_cython.mako:262-363 becomes the op list
+built by ``pysph_b200.program.build_program``, executed through the C-ABI.
+"""
+import ctypes as C
+
+from . import _lib
+from .kernels import kernel_id
+from .program import build_program
+
+
+class B200AccelerationEval(object):
+    def __init__(self, particle_arrays, equations, kernel, backend=None,
+                 mode='serial', device=0):
+        from .backend import B200Backend
+        self.particle_arrays = list(particle_arrays)
+        self.kernel = kernel
+        self.mode = mode
+        self.backend = backend or B200Backend(self.particle_arrays,
+                                              device=device)
+        self.ctx = self.backend.ctx
+        self.ctx.call('b200sph_set_kernel', kernel_id(kernel), int(kernel.dim))
+        self.equation_groups = equations
+        self.ops = build_program(equations, self.backend.names, kernel.dim)
+        self.nnps = None
+        self.count_pairs = False
+        self.last_pairs = 0
+        # reference API: AccelerationEval.c_acceleration_eval is "the compiled
+        # object"; here the adapter is its own compiled object
+        self.c_acceleration_eval = self
+
+    # -- reference protocol ---------------------------------------------------
+    def set_nnps(self, nnps):
+        self.nnps = nnps
+
+    def set_compiled_object(self, obj):
+        self.c_acceleration_eval = obj
+
+    def update_particle_arrays(self, particle_arrays):
+        by_name = dict((pa.name, pa) for pa in particle_arrays)
+        for i, name in enumerate(self.backend.names):
+            if name in by_name:
+                pa = by_name[name]
+                self.backend.particle_arrays[i] = pa
+                pa.gpu = self.particle_arrays[i].gpu
+                self.particle_arrays[i] = pa
+        self.backend.push_all()
+
+    def compute(self, t, dt):
+        ctx = self.ctx
+        pairs = 0
+        cnt = C.c_int64(0)
+        for op in self.ops:
+            kind = op[0]
+            if kind == 'eos':
+                ctx.call('b200sph_eos', *op[1:])
+            elif kind == 'ferrari':
+                ctx.call('b200sph_ferrari_h', *op[1:])
+            elif kind == 'pair':
+                if self.count_pairs:
+                    ctx.call('b200sph_pair_pass', C.byref(op[1]), C.byref(cnt))
+                    pairs += cnt.value
+                else:
+                    ctx.call('b200sph_pair_pass', C.byref(op[1]), None)
+            elif kind == 'update_nnps':
+                # mako:139-145: nnps.update_domain(); nnps.update()
+                ctx.call('b200sph_update_domain')
+                ctx.call('b200sph_nnps_update')
+        self.last_pairs = pairs

@@ -1,0 +1,167 @@
+"""Device-resident mirror of a list of ParticleArrays on one B200.
+
+``B200Backend`` owns the C-ABI context and plays the role the reference gives
+to ``DeviceHelper`` (pysph/base/device_helper.py:47-250: push / pull / resize /
+get_number_of_particles) for every array at once; ``B200DeviceHelper`` is the
+per-array object installed as ``pa.gpu`` so that reference code paths which go
+through ``pa.gpu`` (output pull particle_array.pyx:377-378, adaptive dt
+integrator.py:62-81,146-159) find what they expect.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import PROP_IDS, INT_PROP_IDS
+
+
+def _host_array(pa, name):
+    """Zero-copy numpy view of ALL particles of a property (real + ghost)."""
+    if hasattr(pa, 'get_carray'):       # real PySPH ParticleArray
+        return pa.get_carray(name).get_npy_array()
+    return pa.properties[name]
+
+
+class _MinMax(object):
+    def __init__(self, minimum, maximum):
+        self.minimum = minimum
+        self.maximum = maximum
+
+
+class B200DeviceHelper(object):
+    """``pa.gpu`` stand-in bound to one array of a B200Backend."""
+
+    def __init__(self, backend, index):
+        self._backend = backend
+        self._index = index
+
+    def push(self, *props):
+        self._backend.push(self._index, props or None)
+
+    def pull(self, *props):
+        self._backend.pull(self._index, props or None)
+
+    def resize(self, n):
+        self._backend.resize(self._index, n)
+
+    def get_number_of_particles(self, real=False):
+        n, n_real = self._backend.sizes(self._index)
+        return n_real if real else n
+
+    def update_minmax_cl(self, props, only_max=False):
+        # integrator.py:69-79 -> per-property maxima over the real particles
+        f = self._backend.dt_factors()
+        for name, val in (('dt_cfl', f[0]), ('dt_force', f[1])):
+            if name in props:
+                setattr(self, name, _MinMax(None, val))
+
+    def get_device_array(self, name):
+        if name != 'h':
+            raise NotImplementedError('get_device_array(%r)' % name)
+        return _MinMax(self._backend.dt_factors()[2], None)
+
+
+class B200Backend(object):
+    def __init__(self, particle_arrays, device=0, capacity_factor=1.0,
+                 extra_capacity=0):
+        if len(particle_arrays) > _lib.MAX_ARRAYS:
+            raise ValueError('at most %d particle arrays' % _lib.MAX_ARRAYS)
+        self.ctx = _lib.Context(device)
+        self.device = device
+        self.particle_arrays = list(particle_arrays)
+        self.names = [pa.name for pa in particle_arrays]
+        self.index = dict((n, i) for i, n in enumerate(self.names))
+        for pa in particle_arrays:
+            n = pa.get_number_of_particles()
+            n_real = pa.get_number_of_particles(real=True)
+            cap = int(n * capacity_factor) + int(extra_capacity)
+            i = self.ctx.call('b200sph_add_array', pa.name.encode(), n, n_real,
+                              cap)
+            assert i == self.index[pa.name]
+            pa.gpu = B200DeviceHelper(self, i)
+        self._dt_cache = None
+        self.push_all()
+
+    # -- sizes ----------------------------------------------------------------
+    def sizes(self, i):
+        n, nr = C.c_int64(), C.c_int64()
+        self.ctx.call('b200sph_get_array_size', i, C.byref(n), C.byref(nr))
+        return n.value, nr.value
+
+    def resize(self, i, n, n_real=None):
+        if n_real is None:
+            n_real = min(self.sizes(i)[1], n)
+        self.ctx.call('b200sph_resize_array', i, int(n), int(n_real))
+
+    # -- host <-> device ------------------------------------------------------
+    def _props_of(self, pa, props):
+        if props is None:
+            props = [p for p in pa.properties
+                     if p in PROP_IDS or p in INT_PROP_IDS]
+        return props
+
+    def push(self, i, props=None):
+        pa = self.particle_arrays[i]
+        n = pa.get_number_of_particles()
+        dn, _ = self.sizes(i)
+        if dn != n:
+            self.resize(i, n, pa.get_number_of_particles(real=True))
+        for name in self._props_of(pa, props):
+            a = _host_array(pa, name)
+            if name in PROP_IDS:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                self.ctx.call('b200sph_push_f64', i, PROP_IDS[name],
+                              a.ctypes.data, 0, n)
+            elif name in INT_PROP_IDS:
+                a = np.ascontiguousarray(a).view(np.uint32)
+                self.ctx.call('b200sph_push_u32', i, INT_PROP_IDS[name],
+                              a.ctypes.data, 0, n)
+            # properties the hot path never touches (div, ...) stay host-only
+        self._dt_cache = None
+
+    def pull(self, i, props=None):
+        pa = self.particle_arrays[i]
+        n, n_real = self.sizes(i)
+        if pa.get_number_of_particles() != n:
+            if hasattr(pa, 'resize'):
+                pa.resize(n)
+            pa.set_num_real_particles(n_real) if hasattr(
+                pa, 'set_num_real_particles') else None
+        for name in self._props_of(pa, props):
+            a = _host_array(pa, name)
+            if name in PROP_IDS:
+                if a.dtype == np.float64 and a.flags.c_contiguous:
+                    self.ctx.call('b200sph_pull_f64', i, PROP_IDS[name],
+                                  a.ctypes.data, 0, n)
+                else:
+                    tmp = np.empty(n, dtype=np.float64)
+                    self.ctx.call('b200sph_pull_f64', i, PROP_IDS[name],
+                                  tmp.ctypes.data, 0, n)
+                    a[:] = tmp
+            elif name in INT_PROP_IDS:
+                tmp = np.empty(n, dtype=np.uint32)
+                self.ctx.call('b200sph_pull_u32', i, INT_PROP_IDS[name],
+                              tmp.ctypes.data, 0, n)
+                a[:] = tmp.view(a.dtype) if a.dtype.itemsize == 4 else tmp
+
+    def push_all(self, props=None):
+        for i in range(len(self.particle_arrays)):
+            self.push(i, props)
+
+    def pull_all(self, props=None):
+        for i in range(len(self.particle_arrays)):
+            self.pull(i, props)
+
+    # -- reductions -----------------------------------------------------------
+    def dt_factors(self):
+        out = (C.c_double * 3)()
+        self.ctx.call('b200sph_dt_factors', out)
+        return out[0], out[1], out[2]
+
+    def stats(self):
+        s = _lib.Stats()
+        self.ctx.call('b200sph_get_stats', C.byref(s))
+        return dict((k, getattr(s, k)) for k, _ in s._fields_)
+
+    def synchronize(self):
+        self.ctx.call('b200sph_synchronize')

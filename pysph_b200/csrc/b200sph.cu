@@ -1,0 +1,1843 @@
+// b200sph.cu -- B200 (sm_100a) evaluator for PySPH's WCSPH per-timestep hot path.
+//
+// What lives here (see DESIGN.md for the data layout and rooflines):
+//   * device mirror of the ParticleArrays: one pool, SoA, fp64 integrated state
+//     + fp32 derived fields            (reference: pysph/base/device_helper.py)
+//   * NNPS build: bounds/h reductions, cell keys, deterministic counting sort,
+//     cell-relative fp32 repack        (reference: pysph/base/nnps_base.pyx:1471-1575,
+//                                       linked_list_nnps.pyx:235-382; GPU precedent
+//                                       z_order_gpu_nnps_kernels.py:7-47)
+//   * fused pair kernel: initialize + loop over all sources + post_loop of
+//     SummationDensity / ContinuityEquation / MomentumEquation(+AV) /
+//     XSPHCorrection / MonaghanArtificialViscosity
+//                                      (reference: acceleration_eval_cython.mako:10-154,
+//                                       equation.py:188-297, wc/basic.py:129-269,
+//                                       basic_equations.py:19-29,180-300)
+//   * TaitEOS / TaitEOSHGCorrection / UpdateSmoothingLengthFerrari, WCSPHStep
+//     stages, adaptive-dt reductions   (wc/basic.py:9-126,417-463,
+//                                       integrator_step.py:38-91, integrator.py:62-81)
+//   * halo pack / append / migrate helpers for the slab decomposition
+//                                      (replaces parallel_manager.pyx:512-632)
+//
+// No CPU fallback: every entry point needs a CUDA device.
+#include "b200sph.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// --------------------------------------------------------------------------
+// small helpers
+// --------------------------------------------------------------------------
+#define N_F64 16
+#define N_F32 11
+#define N_U32 3
+#define PT_INVALID 0xFFu
+#define PT_GHOST 0x08u
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+struct ArrayInfo {
+    std::string name;
+    int64_t off = 0, cap = 0, n = 0, n_real = 0;
+};
+
+struct b200sph_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    int narr = 0;
+    ArrayInfo arr[B200SPH_MAX_ARRAYS];
+    int64_t pool_cap = 0;   // allocated particles in the pool
+    int64_t pool_end = 0;   // off[last] + cap[last]
+    double *f64[N_F64] = {nullptr};
+    float *f32[N_F32] = {nullptr};
+    uint32_t *u32[N_U32] = {nullptr};
+    uint8_t *ptype = nullptr;
+    bool ptype_dirty = true;
+
+    int kernel = 0, dim = 3;
+    double radius_scale = 2.0;
+
+    // domain manager
+    double cell_size = 1.0, hmin_scaled = 1.0;
+    bool domain_valid = false;
+    // grid
+    b200sph_grid_info grid;
+    bool grid_valid = false;
+    double last_domain_size = 0.0;
+
+    // sort / cell list buffers
+    int64_t sort_cap = 0;        // particles
+    int64_t cell_cap = 0;        // cells (+1)
+    uint32_t *key_of = nullptr;  // [pool] cell key per particle
+    uint32_t *off_in = nullptr;  // [pool] arrival rank inside the cell
+    uint32_t *cell_cnt = nullptr;
+    uint32_t *cell_start = nullptr;
+    uint32_t *blk_sums = nullptr;
+    int64_t blk_cap = 0;
+    uint32_t *perm_tmp = nullptr, *perm = nullptr, *skey = nullptr, *rank = nullptr;
+    float4 *A = nullptr, *B = nullptr, *C = nullptr;
+    int64_t n_sorted = 0;
+    bool state_packed = false;
+
+    // scratch
+    long long *red = nullptr;     // 16 ordered-int64 slots
+    long long *red_host = nullptr;  // pinned
+    unsigned long long *counter = nullptr;  // pair counter + misc
+    unsigned long long *counter_host = nullptr;
+    double *stage_buf = nullptr;  // host<->device staging for f32 props
+    int64_t stage_cap = 0;
+    uint32_t *flag_a = nullptr, *flag_b = nullptr;  // [pool+1] scan scratch
+    int64_t flag_cap = 0;
+
+    // stats
+    b200sph_stats stats;
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static int set_err(b200sph_ctx *c, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return -1;
+}
+
+#define CU(call)                                                                    \
+    do {                                                                            \
+        cudaError_t _e = (call);                                                    \
+        if (_e != cudaSuccess)                                                      \
+            return set_err(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                           __FILE__, __LINE__);                                     \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                              \
+    do {                                                                            \
+        ctx->stats.kernel_launches++;                                               \
+        cudaError_t _e = cudaGetLastError();                                        \
+        if (_e != cudaSuccess)                                                      \
+            return set_err(ctx, "kernel launch failed: %s (%s:%d)",                 \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);             \
+    } while (0)
+
+// ordered-int64 image of a double so atomicMin/Max(long long) order like doubles
+__host__ __device__ static inline long long d2o(double d)
+{
+    long long b;
+#ifdef __CUDA_ARCH__
+    b = __double_as_longlong(d);
+#else
+    memcpy(&b, &d, 8);
+#endif
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__host__ __device__ static inline double o2d(long long o)
+{
+    long long b = o ^ ((o >> 63) & 0x7fffffffffffffffLL);
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+
+__device__ __forceinline__ float frcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float frsqrt(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// --------------------------------------------------------------------------
+// elementwise / reduction kernels over the pool
+// --------------------------------------------------------------------------
+struct PoolLayout {
+    int narr;
+    long long off[B200SPH_MAX_ARRAYS], n[B200SPH_MAX_ARRAYS], n_real[B200SPH_MAX_ARRAYS];
+};
+
+__global__ void k_fill_ptype(uint8_t *ptype, long long pool_end, PoolLayout L)
+{
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pool_end) return;
+    uint8_t t = PT_INVALID;
+    for (int a = 0; a < L.narr; a++) {
+        long long i = g - L.off[a];
+        if (i >= 0 && i < L.n[a]) t = (uint8_t)(a | (i >= L.n_real[a] ? PT_GHOST : 0));
+    }
+    ptype[g] = t;
+}
+
+__global__ void k_red_init(long long *red)
+{
+    int i = threadIdx.x;
+    if (i < 16) red[i] = (i & 1) ? d2o(-1e300) : d2o(1e300);  // even: min slots, odd: max slots
+}
+
+// slots: 0 xmin 1 xmax 2 ymin 3 ymax 4 zmin 5 zmax 6 hmin 7 hmax
+__global__ void k_reduce_minmax(const double *__restrict__ x, const double *__restrict__ y,
+                                const double *__restrict__ z, const double *__restrict__ h,
+                                const uint8_t *__restrict__ ptype, long long pool_end,
+                                int do_xyz, int do_h, long long *red)
+{
+    double mn[4] = {1e300, 1e300, 1e300, 1e300}, mx[4] = {-1e300, -1e300, -1e300, -1e300};
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < pool_end;
+         g += (long long)gridDim.x * blockDim.x) {
+        if (ptype[g] == PT_INVALID) continue;
+        if (do_xyz) {
+            double v = x[g]; mn[0] = fmin(mn[0], v); mx[0] = fmax(mx[0], v);
+            v = y[g]; mn[1] = fmin(mn[1], v); mx[1] = fmax(mx[1], v);
+            v = z[g]; mn[2] = fmin(mn[2], v); mx[2] = fmax(mx[2], v);
+        }
+        if (do_h) {
+            double v = h[g]; mn[3] = fmin(mn[3], v); mx[3] = fmax(mx[3], v);
+        }
+    }
+    for (int k = 0; k < 4; k++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 4; k++) {
+            if ((k < 3 && !do_xyz) || (k == 3 && !do_h)) continue;
+            atomicMin(&red[2 * k], d2o(mn[k]));
+            atomicMax(&red[2 * k + 1], d2o(mx[k]));
+        }
+    }
+}
+
+// slots: 9 max dt_cfl, 11 max dt_force (real particles), 12 min h (all)
+__global__ void k_reduce_dt(const float *__restrict__ dt_cfl, const float *__restrict__ dt_force,
+                            const double *__restrict__ h, const uint8_t *__restrict__ ptype,
+                            long long pool_end, long long *red)
+{
+    double mc = -1e300, mf = -1e300, hm = 1e300;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < pool_end;
+         g += (long long)gridDim.x * blockDim.x) {
+        uint8_t t = ptype[g];
+        if (t == PT_INVALID) continue;
+        hm = fmin(hm, h[g]);
+        if (t & PT_GHOST) continue;
+        mc = fmax(mc, (double)dt_cfl[g]);
+        mf = fmax(mf, (double)dt_force[g]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mc = fmax(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+        mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+        hm = fmin(hm, __shfl_xor_sync(0xffffffffu, hm, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&red[9], d2o(mc));
+        atomicMax(&red[11], d2o(mf));
+        atomicMin(&red[12], d2o(hm));
+    }
+}
+
+// TaitEOS.loop wc/basic.py:60-65 ; TaitEOSHGCorrection.loop wc/basic.py:118-126
+__global__ void k_eos(double *__restrict__ rho, float *__restrict__ p, float *__restrict__ cs,
+                      const uint8_t *__restrict__ ptype, long long lo, long long hi, int hg,
+                      double rho0, double c0, double gamma, double p0)
+{
+    long long g = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= hi) return;
+    double r = rho[g];
+    if (hg && r < rho0) {
+        r = rho0;
+        rho[g] = r;
+    }
+    double ratio = r * (1.0 / rho0);
+    double B = rho0 * c0 * c0 / gamma;
+    double tmp = pow(ratio, gamma);
+    p[g] = (float)((hg ? 0.0 : p0) + B * (tmp - 1.0));
+    cs[g] = (float)(c0 * pow(ratio, 0.5 * (gamma - 1.0)));
+}
+
+// UpdateSmoothingLengthFerrari.loop wc/basic.py:458-463
+__global__ void k_ferrari(double *__restrict__ h, const double *__restrict__ m,
+                          const double *__restrict__ rho, long long lo, long long hi, double hdx,
+                          double dim1)
+{
+    long long g = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= hi) return;
+    h[g] = hdx * pow(m[g] / rho[g], dim1);
+}
+
+struct StageArgs {
+    double *x, *y, *z, *u, *v, *w, *rho;
+    double *x0, *y0, *z0, *u0, *v0, *w0, *rho0;
+    const float *au, *av, *aw, *ax, *ay, *az, *arho;
+    const uint8_t *ptype;
+    long long pool_end;
+    int arr, which;
+    double f;
+};
+
+// WCSPHStep.initialize / stage1 / stage2 integrator_step.py:51-91 (real particles only,
+// integrator_cython.mako:97-111)
+__global__ void k_stage(StageArgs a)
+{
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.pool_end) return;
+    uint8_t t = a.ptype[g];
+    if (t == PT_INVALID || (t & PT_GHOST)) return;
+    if (a.arr >= 0 && (t & 7) != a.arr) return;
+    if (a.which == 0) {
+        a.x0[g] = a.x[g]; a.y0[g] = a.y[g]; a.z0[g] = a.z[g];
+        a.u0[g] = a.u[g]; a.v0[g] = a.v[g]; a.w0[g] = a.w[g];
+        a.rho0[g] = a.rho[g];
+    } else {
+        const double f = a.f;
+        a.u[g] = a.u0[g] + f * (double)a.au[g];
+        a.v[g] = a.v0[g] + f * (double)a.av[g];
+        a.w[g] = a.w0[g] + f * (double)a.aw[g];
+        a.x[g] = a.x0[g] + f * (double)a.ax[g];
+        a.y[g] = a.y0[g] + f * (double)a.ay[g];
+        a.z[g] = a.z0[g] + f * (double)a.az[g];
+        a.rho[g] = a.rho0[g] + f * (double)a.arho[g];
+    }
+}
+
+__global__ void k_f64_to_f32(const double *__restrict__ in, float *__restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+__global__ void k_f32_to_f64(const float *__restrict__ in, double *__restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+
+// --------------------------------------------------------------------------
+// exclusive scan (u32), three-phase; n up to 2^28 + 1
+// --------------------------------------------------------------------------
+#define SCAN_THREADS 512
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total)
+{
+    // exclusive scan of one value per thread across the block
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = (lane < SCAN_THREADS / 32) ? wsum[lane] : 0;
+        uint32_t si = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        if (lane < SCAN_THREADS / 32) wsum[lane] = si - s;  // exclusive warp offsets
+        if (lane == SCAN_THREADS / 32 - 1) *total = si;
+    }
+    __syncthreads();
+    uint32_t r = wsum[w] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tiles(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, long long n,
+             uint32_t *__restrict__ blk_sums)
+{
+    __shared__ uint32_t total;
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t ex = block_excl_scan(s, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) blk_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint32_t *blk_sums, long long nb)
+{
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    for (long long b0 = 0; b0 < nb; b0 += SCAN_THREADS) {
+        long long i = b0 + threadIdx.x;
+        uint32_t v = (i < nb) ? blk_sums[i] : 0u;
+        uint32_t ex = block_excl_scan(v, &total);
+        if (i < nb) blk_sums[i] = ex + carry;
+        carry += total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_add(uint32_t *__restrict__ out, long long n, const uint32_t *__restrict__ blk_sums)
+{
+    const uint32_t add = blk_sums[blockIdx.x];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n) out[base + k] += add;
+}
+
+// --------------------------------------------------------------------------
+// NNPS build kernels
+// --------------------------------------------------------------------------
+struct GridDev {
+    double xmin[3];
+    double cell;
+    int nc[3];
+    float cellf;
+};
+
+// cell id = floor((p - xmin)/cell) per axis (find_cell_id_raw, nnps_base.pxd:39-80),
+// flat = cx + ncx*cy + ncx*ncy*cz (flatten_raw, nnps_base.pxd:84-96); the arrival
+// counter replaces the linked-list push (linked_list_nnps.pyx:285-286).
+__global__ void k_cell_count(const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ z, const uint8_t *__restrict__ ptype,
+                             long long pool_end, GridDev G, uint32_t *__restrict__ key_of,
+                             uint32_t *__restrict__ off_in, uint32_t *__restrict__ cell_cnt)
+{
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pool_end) return;
+    if (ptype[g] == PT_INVALID) return;
+    int cx = (int)floor((x[g] - G.xmin[0]) / G.cell);
+    int cy = (int)floor((y[g] - G.xmin[1]) / G.cell);
+    int cz = (int)floor((z[g] - G.xmin[2]) / G.cell);
+    cx = min(max(cx, 0), G.nc[0] - 1);
+    cy = min(max(cy, 0), G.nc[1] - 1);
+    cz = min(max(cz, 0), G.nc[2] - 1);
+    uint32_t key = (uint32_t)cx + (uint32_t)G.nc[0] * ((uint32_t)cy + (uint32_t)G.nc[1] * (uint32_t)cz);
+    key_of[g] = key;
+    off_in[g] = atomicAdd(&cell_cnt[key], 1u);
+}
+
+__global__ void k_scatter(const uint32_t *__restrict__ key_of, const uint32_t *__restrict__ off_in,
+                          const uint8_t *__restrict__ ptype, long long pool_end,
+                          const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ perm_tmp)
+{
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pool_end) return;
+    if (ptype[g] == PT_INVALID) return;
+    perm_tmp[cell_start[key_of[g]] + off_in[g]] = (uint32_t)g;
+}
+
+// make the order inside every cell canonical (ascending pool index) so that the
+// build -- and therefore every fp32 sum downstream -- is run-to-run deterministic.
+__global__ void k_canon(const uint32_t *__restrict__ perm_tmp, const uint32_t *__restrict__ key_of,
+                        const uint32_t *__restrict__ cell_start, long long n,
+                        uint32_t *__restrict__ perm, uint32_t *__restrict__ skey,
+                        uint32_t *__restrict__ rank)
+{
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t g = perm_tmp[s];
+    const uint32_t key = key_of[g];
+    const uint32_t cs = cell_start[key], ce = cell_start[key + 1];
+    uint32_t r = 0;
+    for (uint32_t t = cs; t < ce; t++) r += (perm_tmp[t] < g) ? 1u : 0u;
+    const uint32_t d = cs + r;
+    perm[d] = g;
+    skey[d] = key;
+    rank[g] = d;
+}
+
+// A[s] = (x, y, z relative to the particle's own cell origin, h)
+__global__ void k_pack_pos(const double *__restrict__ x, const double *__restrict__ y,
+                           const double *__restrict__ z, const double *__restrict__ h,
+                           const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skey,
+                           long long n, GridDev G, float4 *__restrict__ A)
+{
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t g = perm[s];
+    uint32_t key = skey[s];
+    const uint32_t cx = key % (uint32_t)G.nc[0];
+    key /= (uint32_t)G.nc[0];
+    const uint32_t cy = key % (uint32_t)G.nc[1];
+    const uint32_t cz = key / (uint32_t)G.nc[1];
+    float4 a;
+    a.x = (float)(x[g] - (G.xmin[0] + (double)cx * G.cell));
+    a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell));
+    a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell));
+    a.w = (float)h[g];
+    A[s] = a;
+}
+
+// B[s] = (u, v, w, m);  C[s] = (rho, p/rho^2, cs, type)
+__global__ void k_pack_state(const double *__restrict__ u, const double *__restrict__ v,
+                             const double *__restrict__ w, const double *__restrict__ m,
+                             const double *__restrict__ rho, const float *__restrict__ p,
+                             const float *__restrict__ cs, const uint8_t *__restrict__ ptype,
+                             const uint32_t *__restrict__ perm, long long n,
+                             float4 *__restrict__ B, float4 *__restrict__ C)
+{
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t g = perm[s];
+    float4 b, c;
+    b.x = (float)u[g]; b.y = (float)v[g]; b.z = (float)w[g]; b.w = (float)m[g];
+    const double r = rho[g];
+    c.x = (float)r;
+    c.y = (float)((double)p[g] / (r * r));
+    c.z = cs[g];
+    c.w = __int_as_float((int)ptype[g]);
+    B[s] = b;
+    C[s] = c;
+}
+
+// --------------------------------------------------------------------------
+// SPH smoothing kernels in fp32 (pysph/base/kernels.py; see oracle for fp64)
+//   returns w = W(q)/sigma-free value * fac  and  dw = dW/dq * fac
+// --------------------------------------------------------------------------
+template <int DIM> __device__ __forceinline__ float hpow(float h1)
+{
+    return DIM == 1 ? h1 : (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
+}
+
+template <int K> __device__ __forceinline__ void sph_kernel(float q, float &w, float &dw);
+
+// CubicSpline kernels.py:69-124
+template <> __device__ __forceinline__ void sph_kernel<0>(float q, float &w, float &dw)
+{
+    const float t2 = 2.0f - q;
+    const float w_in = 1.0f - 1.5f * q * q * (1.0f - 0.5f * q);
+    const float d_in = -3.0f * q * (1.0f - 0.75f * q);
+    const float w_out = 0.25f * t2 * t2 * t2;
+    const float d_out = -0.75f * t2 * t2;
+    w = q > 2.0f ? 0.0f : (q > 1.0f ? w_out : w_in);
+    dw = q > 2.0f ? 0.0f : (q > 1.0f ? d_out : d_in);
+}
+// WendlandQuintic kernels.py:304-343
+template <> __device__ __forceinline__ void sph_kernel<1>(float q, float &w, float &dw)
+{
+    const float t = 1.0f - 0.5f * q;
+    const float t3 = t * t * t;
+    w = q < 2.0f ? t3 * t * (2.0f * q + 1.0f) : 0.0f;
+    dw = q < 2.0f ? -5.0f * q * t3 : 0.0f;
+}
+// QuinticSpline kernels.py:1087-1153
+template <> __device__ __forceinline__ void sph_kernel<2>(float q, float &w, float &dw)
+{
+    const float t3 = 3.0f - q, t2 = 2.0f - q, t1 = 1.0f - q;
+    const float a3 = t3 * t3, a2 = t2 * t2, a1 = t1 * t1;
+    const float p3 = a3 * a3, p2 = a2 * a2, p1 = a1 * a1;  // 4th powers
+    float ww = 0.0f, dd = 0.0f;
+    if (q <= 3.0f) { ww = p3 * t3; dd = -5.0f * p3; }
+    if (q <= 2.0f) { ww -= 6.0f * p2 * t2; dd += 30.0f * p2; }
+    if (q <= 1.0f) { ww += 15.0f * p1 * t1; dd -= 75.0f * p1; }
+    w = ww;
+    dw = dd;
+}
+// Gaussian kernels.py:864-898
+template <> __device__ __forceinline__ void sph_kernel<3>(float q, float &w, float &dw)
+{
+    const float e = __expf(-q * q);
+    w = q < 3.0f ? e : 0.0f;
+    dw = q < 3.0f ? -2.0f * q * e : 0.0f;
+}
+
+// --------------------------------------------------------------------------
+// the fused pair kernel
+// --------------------------------------------------------------------------
+struct PairArgs {
+    const float4 *A, *B, *C;
+    const uint32_t *cell_start, *skey, *perm;
+    float *arho, *au, *av, *aw, *ax, *ay, *az, *dt_cfl, *dt_force;
+    double *rho;  // SummationDensity destination (fp64 state)
+    long long n;
+    int ncx, ncy, ncz;
+    float cell, k2;  // cell size, radius_scale^2
+    float kfac;      // kernel.fac for this dim
+    float deltap;
+    unsigned long long emask[B200SPH_MAX_ARRAYS];  // per dest type: 8 bits per source type
+    float c0, alpha, beta, gx, gy, gz, eps_xsph;
+    int tensile, real_only;
+    unsigned long long *pair_counter;  // may be null
+};
+
+#define PAIR_WARPS 8
+#define PAIR_CHUNK 16
+#define QCAP 64
+
+struct Acc {
+    float arho, au, av, aw, ax, ay, az, cfl, rsum;
+};
+
+template <int K, int DIM>
+__device__ __forceinline__ void pair_body(const PairArgs &a, const float4 qv, const uint32_t t,
+                                          const float4 Ai, const float4 Bi, const float4 Ci,
+                                          const unsigned long long mask_i, const float tmpi,
+                                          Acc &acc, unsigned &npairs)
+{
+    const float4 Cj = a.C[t];
+    const int tj = __float_as_int(Cj.w) & 7;
+    const unsigned bits = (unsigned)(mask_i >> (8 * tj)) & 0xFFu;
+    if (!bits) return;
+    npairs++;
+    const float4 Bj = a.B[t];
+    const float xij = qv.x, yij = qv.y, zij = qv.z, hj = qv.w;
+    // precomputed symbols, equation.py:188-297
+    const float r2 = xij * xij + yij * yij + zij * zij;
+    const bool far = r2 > 1e-24f;          // RIJ > 1e-12 guard of kernels.py:128-132
+    const float rinv = far ? frsqrt(r2) : 0.0f;
+    const float rij = r2 * rinv;
+    const float hij = 0.5f * (Ai.w + hj);
+    const float h1 = frcp(hij);
+    const float q = rij * h1;
+    const float fac = a.kfac * hpow<DIM>(h1);
+    float w, dw;
+    sph_kernel<K>(q, w, dw);
+    const float wij = w * fac;
+    const float gt = dw * fac * h1 * rinv;  // DWIJ = gt * XIJ  (gradient(), kernels.py:126-136)
+    const float mj = Bj.w;
+    const float uij = Bi.x - Bj.x, vij = Bi.y - Bj.y, wwij = Bi.z - Bj.z;
+    const float vdotx = uij * xij + vij * yij + wwij * zij;
+
+    if (bits & B200SPH_EQ_SUMMATION_DENSITY) acc.rsum += mj * wij;  // basic_equations.py:28-29
+    if (bits & B200SPH_EQ_CONTINUITY)                              // basic_equations.py:190-192
+        acc.arho += mj * gt * vdotx;
+    if (bits & (B200SPH_EQ_MOMENTUM | B200SPH_EQ_MONAGHAN_AV | B200SPH_EQ_XSPH)) {
+        const float rhoij1 = frcp(0.5f * (Ci.x + Cj.x));
+        float piij = 0.0f;
+        if (vdotx < 0.0f) {  // wc/basic.py:215-222, basic_equations.py:245-252
+            const float cij = 0.5f * (Ci.z + Cj.z);
+            const float muij = hij * vdotx * frcp(r2 + 0.01f * hij * hij);
+            piij = (-a.alpha * cij * muij + a.beta * muij * muij) * rhoij1;
+        }
+        if (bits & B200SPH_EQ_MOMENTUM) {
+            if (r2 > 1e-12f)  // wc/basic.py:224-228
+                acc.cfl = fmaxf(acc.cfl, fabsf(hij * vdotx * rinv * rinv) + a.c0);
+            const float tmpj = Cj.y;  // p_j / rho_j^2 (precomputed in k_pack_state)
+            float tmp = tmpi + tmpj;
+            if (a.tensile) {  // wc/basic.py:233-248
+                float wdp, dwdp;
+                sph_kernel<K>(a.deltap, wdp, dwdp);
+                float fij = w / wdp;  // WIJ/WDP: the fac*h^-dim normalisation cancels
+                fij = fij * fij;
+                fij = fij * fij;
+                const float Ri = tmpi > 0.0f ? 0.01f * tmpi : 0.2f * fabsf(tmpi);
+                const float Rj = tmpj > 0.0f ? 0.01f * tmpj : 0.2f * fabsf(tmpj);
+                tmp += (Ri + Rj) * fij;
+            }
+            const float f = -mj * (tmp + piij) * gt;  // wc/basic.py:255-257
+            acc.au += f * xij;
+            acc.av += f * yij;
+            acc.aw += f * zij;
+        }
+        if (bits & B200SPH_EQ_MONAGHAN_AV) {  // basic_equations.py:254-257
+            const float f = -mj * piij * gt;
+            acc.au += f * xij;
+            acc.av += f * yij;
+            acc.aw += f * zij;
+        }
+        if (bits & B200SPH_EQ_XSPH) {  // basic_equations.py:290-295
+            const float f = -a.eps_xsph * mj * wij * rhoij1;
+            acc.ax += f * uij;
+            acc.ay += f * vij;
+            acc.az += f * wwij;
+        }
+    }
+}
+
+template <int K, int DIM>
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
+{
+    __shared__ float4 q_v[PAIR_WARPS][QCAP];
+    __shared__ uint32_t q_i[PAIR_WARPS][QCAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const long long first = ((long long)blockIdx.x * PAIR_WARPS + warp) * PAIR_CHUNK;
+
+    uint32_t cur_key = 0xFFFFFFFFu;
+    int cx = 0;
+    // lane r < 9 holds the candidate range of neighbour row r = (dy+1) + 3*(dz+1)
+    uint32_t r_rs = 0, r_b1 = 0, r_b2 = 0, r_re = 0;
+    unsigned npairs = 0;
+
+    for (int kk = 0; kk < PAIR_CHUNK; kk++) {
+        const long long s = first + kk;
+        if (s >= a.n) break;
+        const float4 Ci = a.C[s];
+        const int ti = __float_as_int(Ci.w);
+        if (a.real_only && (ti & PT_GHOST)) continue;
+        const unsigned long long mask_i = a.emask[ti & 7];
+        if (!mask_i) continue;
+        const float4 Ai = a.A[s];
+        const float4 Bi = a.B[s];
+        const uint32_t key = a.skey[s];
+        if (key != cur_key) {
+            cur_key = key;
+            uint32_t kq = key;
+            cx = (int)(kq % (uint32_t)a.ncx);
+            kq /= (uint32_t)a.ncx;
+            const int cy = (int)(kq % (uint32_t)a.ncy);
+            const int cz = (int)(kq / (uint32_t)a.ncy);
+            r_rs = r_b1 = r_b2 = r_re = 0;
+            if (lane < 9) {
+                const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
+                if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
+                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+                    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
+                    r_rs = a.cell_start[base + x0];
+                    r_b1 = a.cell_start[base + cx];
+                    r_b2 = a.cell_start[base + cx + 1];
+                    r_re = a.cell_start[base + x1 + 1];
+                }
+            }
+        }
+        const float hi2 = a.k2 * Ai.w * Ai.w;
+        const float tmpi = Ci.y;  // p_i / rho_i^2
+        Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int qn = 0, qhead = 0;
+
+        for (int r = 0; r < 9; r++) {
+            const uint32_t rs = __shfl_sync(FULL, r_rs, r);
+            const uint32_t re = __shfl_sync(FULL, r_re, r);
+            if (rs >= re) continue;
+            const uint32_t b1 = __shfl_sync(FULL, r_b1, r);
+            const uint32_t b2 = __shfl_sync(FULL, r_b2, r);
+            const float yoff = Ai.y - (float)((r % 3) - 1) * a.cell;
+            const float zoff = Ai.z - (float)((r / 3) - 1) * a.cell;
+            for (uint32_t t0 = rs; t0 < re; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                bool ok = false;
+                float xij = 0.f, yij = 0.f, zij = 0.f, hj = 0.f;
+                if (t < re) {
+                    const float4 Aj = a.A[t];
+                    const int dxc = (int)(t >= b1) + (int)(t >= b2) - 1;
+                    xij = Ai.x - Aj.x - (float)dxc * a.cell;
+                    yij = yoff - Aj.y;
+                    zij = zoff - Aj.z;
+                    hj = Aj.w;
+                    const float r2 = xij * xij + yij * yij + zij * zij;
+                    // linked_list_nnps.pyx:188: (xij2 < hi2) or (xij2 < hj2)
+                    ok = (r2 < hi2) || (r2 < a.k2 * hj * hj);
+                }
+                const unsigned m = __ballot_sync(FULL, ok);
+                if (m) {
+                    if (ok) {
+                        const int pos = (qhead + qn + __popc(m & lt_mask)) & (QCAP - 1);
+                        q_v[warp][pos] = make_float4(xij, yij, zij, hj);
+                        q_i[warp][pos] = t;
+                    }
+                    qn += __popc(m);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        const int e = (qhead + lane) & (QCAP - 1);
+                        pair_body<K, DIM>(a, q_v[warp][e], q_i[warp][e], Ai, Bi, Ci, mask_i, tmpi,
+                                          acc, npairs);
+                        qhead = (qhead + 32) & (QCAP - 1);
+                        qn -= 32;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (lane < qn) {
+            const int e = (qhead + lane) & (QCAP - 1);
+            pair_body<K, DIM>(a, q_v[warp][e], q_i[warp][e], Ai, Bi, Ci, mask_i, tmpi, acc, npairs);
+        }
+        __syncwarp();
+
+        // warp reduction of the per-particle sums
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.arho += __shfl_xor_sync(FULL, acc.arho, o);
+            acc.au += __shfl_xor_sync(FULL, acc.au, o);
+            acc.av += __shfl_xor_sync(FULL, acc.av, o);
+            acc.aw += __shfl_xor_sync(FULL, acc.aw, o);
+            acc.ax += __shfl_xor_sync(FULL, acc.ax, o);
+            acc.ay += __shfl_xor_sync(FULL, acc.ay, o);
+            acc.az += __shfl_xor_sync(FULL, acc.az, o);
+            acc.rsum += __shfl_xor_sync(FULL, acc.rsum, o);
+            acc.cfl = fmaxf(acc.cfl, __shfl_xor_sync(FULL, acc.cfl, o));
+        }
+        if (lane == 0) {
+            unsigned all_bits = 0;
+#pragma unroll
+            for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
+            const uint32_t g = a.perm[s];
+            if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
+            if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
+            if (all_bits & B200SPH_EQ_MOMENTUM) {
+                // post_loop wc/basic.py:259-269
+                const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
+                a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
+                a.dt_cfl[g] = acc.cfl;
+                a.dt_force[g] = fu * fu + fv * fv + fw * fw;
+            } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
+                a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
+            }
+            if (all_bits & B200SPH_EQ_XSPH) {
+                // post_loop basic_equations.py:297-300
+                a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
+            }
+        }
+    }
+    if (a.pair_counter) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
+        if (lane == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
+    }
+}
+
+// neighbour query for one destination particle with the pair kernel's accept test.
+// One warp. flags[t - lo] = 1 for every accepted source of array src_arr.
+__global__ void k_neighbors(const float4 *__restrict__ A, const float4 *__restrict__ C,
+                            const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ skey,
+                            const uint32_t *__restrict__ perm, long long s, int src_arr,
+                            long long src_off, int ncx, int ncy, int ncz, float cell, float k2,
+                            uint32_t *__restrict__ out, long long cap, unsigned long long *count)
+{
+    const int lane = threadIdx.x;
+    const float4 Ai = A[s];
+    uint32_t kq = skey[s];
+    const int cx = (int)(kq % (uint32_t)ncx);
+    kq /= (uint32_t)ncx;
+    const int cy = (int)(kq % (uint32_t)ncy), cz = (int)(kq / (uint32_t)ncy);
+    const float hi2 = k2 * Ai.w * Ai.w;
+    unsigned long long n = 0;
+    for (int r = 0; r < 9; r++) {
+        const int dy = (r % 3) - 1, dz = (r / 3) - 1;
+        const int yy = cy + dy, zz = cz + dz;
+        if (yy < 0 || yy >= ncy || zz < 0 || zz >= ncz) continue;
+        const uint32_t base = ((uint32_t)yy + (uint32_t)ncy * (uint32_t)zz) * (uint32_t)ncx;
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, ncx - 1);
+        const uint32_t rs = cell_start[base + x0], b1 = cell_start[base + cx],
+                       b2 = cell_start[base + cx + 1], re = cell_start[base + x1 + 1];
+        for (uint32_t t0 = rs; t0 < re; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            bool ok = false;
+            if (t < re) {
+                const float4 Aj = A[t];
+                const int dxc = (int)(t >= b1) + (int)(t >= b2) - 1;
+                const float xij = Ai.x - Aj.x - (float)dxc * cell;
+                const float yij = Ai.y - (float)dy * cell - Aj.y;
+                const float zij = Ai.z - (float)dz * cell - Aj.z;
+                const float r2 = xij * xij + yij * yij + zij * zij;
+                ok = ((r2 < hi2) || (r2 < k2 * Aj.w * Aj.w)) &&
+                     ((__float_as_int(C[t].w) & 7) == src_arr);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const unsigned long long pos = n + __popc(m & ((1u << lane) - 1u));
+                if ((long long)pos < cap) out[pos] = (uint32_t)((long long)perm[t] - src_off);
+            }
+            n += __popc(m);
+        }
+    }
+    if (lane == 0) *count = n;
+}
+
+// --------------------------------------------------------------------------
+// halo / migration kernels
+// --------------------------------------------------------------------------
+// mode 0: flag = lo <= x < hi ; mode 1: flag = x < lo ; mode 2: flag = x >= hi ;
+// mode 3: flag = keep (lo <= x < hi)
+__global__ void k_flag_range(const double *__restrict__ x, long long off, long long n, double lo,
+                             double hi, int mode, uint32_t *__restrict__ flag)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint32_t f = 0;
+    if (i < n) {
+        const double v = x[off + i];
+        if (mode == 0 || mode == 3) f = (v >= lo && v < hi);
+        else if (mode == 1) f = v < lo;
+        else f = v >= hi;
+    }
+    flag[i] = f;  // flag[n] = 0 so that scan[n] = total
+}
+
+__global__ void k_gather_f64(const double *__restrict__ src, long long off, long long n,
+                             const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                             double *__restrict__ dst, long long dst_off)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) dst[dst_off + pos[i]] = src[off + i];
+}
+__global__ void k_gather_u32_as_f64(const uint32_t *__restrict__ src, long long off, long long n,
+                                    const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                                    double *__restrict__ dst, long long dst_off)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) dst[dst_off + pos[i]] = (double)src[off + i];
+}
+__global__ void k_gather_u32(const uint32_t *__restrict__ src, long long off, long long n,
+                             const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                             uint32_t *__restrict__ dst)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) dst[pos[i]] = src[off + i];
+}
+__global__ void k_f64_to_u32(const double *__restrict__ in, uint32_t *__restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)in[i];
+}
+__global__ void k_fill_u32(uint32_t *p, long long n, uint32_t v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// --------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------
+static int is_f64_prop(int p) { return p >= 0 && p < N_F64; }
+static int is_f32_prop(int p) { return p >= N_F64 && p < N_F64 + N_F32; }
+static int u32_index(int p) { return (p >= B200SPH_GID && p <= B200SPH_PID) ? p - B200SPH_GID : -1; }
+
+// (re)build the pool so that every array owns [off, off+cap); moves existing data.
+static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
+{
+    int64_t new_off[B200SPH_MAX_ARRAYS], total = 0;
+    for (int a = 0; a < ctx->narr; a++) {
+        new_off[a] = total;
+        total += (new_cap[a] + 31) / 32 * 32;
+    }
+    const int64_t alloc = std::max<int64_t>(total, 32);
+    // allocate new buffers and move array by array
+    for (int k = 0; k < N_F64 + N_F32 + N_U32; k++) {
+        const size_t esz = k < N_F64 ? 8 : 4;
+        void *old = k < N_F64 ? (void *)ctx->f64[k]
+                              : (k < N_F64 + N_F32 ? (void *)ctx->f32[k - N_F64]
+                                                   : (void *)ctx->u32[k - N_F64 - N_F32]);
+        void *nw = nullptr;
+        CU(cudaMalloc(&nw, esz * (size_t)alloc));
+        CU(cudaMemsetAsync(nw, 0, esz * (size_t)alloc, ctx->stream));
+        if (old) {
+            for (int a = 0; a < ctx->narr; a++) {
+                if (ctx->arr[a].n > 0 && ctx->arr[a].cap > 0)
+                    CU(cudaMemcpyAsync((char *)nw + esz * (size_t)new_off[a],
+                                       (char *)old + esz * (size_t)ctx->arr[a].off,
+                                       esz * (size_t)ctx->arr[a].n, cudaMemcpyDeviceToDevice,
+                                       ctx->stream));
+            }
+            CU(cudaStreamSynchronize(ctx->stream));
+            CU(cudaFree(old));
+        }
+        if (k < N_F64) ctx->f64[k] = (double *)nw;
+        else if (k < N_F64 + N_F32) ctx->f32[k - N_F64] = (float *)nw;
+        else ctx->u32[k - N_F64 - N_F32] = (uint32_t *)nw;
+    }
+    if (ctx->ptype) CU(cudaFree(ctx->ptype));
+    CU(cudaMalloc((void **)&ctx->ptype, (size_t)alloc));
+    for (int a = 0; a < ctx->narr; a++) {
+        ctx->arr[a].off = new_off[a];
+        ctx->arr[a].cap = new_cap[a];
+    }
+    ctx->pool_cap = alloc;
+    ctx->pool_end = total;
+    ctx->ptype_dirty = true;
+    ctx->grid_valid = false;
+    // per-particle work buffers
+    if (ctx->key_of) cudaFree(ctx->key_of);
+    if (ctx->off_in) cudaFree(ctx->off_in);
+    if (ctx->perm_tmp) cudaFree(ctx->perm_tmp);
+    if (ctx->perm) cudaFree(ctx->perm);
+    if (ctx->skey) cudaFree(ctx->skey);
+    if (ctx->rank) cudaFree(ctx->rank);
+    if (ctx->A) cudaFree(ctx->A);
+    if (ctx->B) cudaFree(ctx->B);
+    if (ctx->C) cudaFree(ctx->C);
+    if (ctx->flag_a) cudaFree(ctx->flag_a);
+    if (ctx->flag_b) cudaFree(ctx->flag_b);
+    CU(cudaMalloc((void **)&ctx->key_of, 4 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->off_in, 4 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->perm_tmp, 4 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->perm, 4 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->skey, 4 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->rank, 4 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->A, 16 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->B, 16 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->C, 16 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->flag_a, 4 * (size_t)(alloc + 1)));
+    CU(cudaMalloc((void **)&ctx->flag_b, 4 * (size_t)(alloc + 1)));
+    ctx->flag_cap = alloc + 1;
+    ctx->sort_cap = alloc;
+    return 0;
+}
+
+static int ensure_capacity(b200sph_ctx *ctx, int arr, int64_t need)
+{
+    if (need <= ctx->arr[arr].cap && ctx->pool_cap > 0) return 0;
+    int64_t caps[B200SPH_MAX_ARRAYS];
+    for (int a = 0; a < ctx->narr; a++) caps[a] = ctx->arr[a].cap;
+    if (need > caps[arr]) caps[arr] = need + need / 4 + 1024;
+    return pool_layout(ctx, caps);
+}
+
+static int refresh_ptype(b200sph_ctx *ctx)
+{
+    if (!ctx->ptype_dirty) return 0;
+    PoolLayout L;
+    L.narr = ctx->narr;
+    for (int a = 0; a < ctx->narr; a++) {
+        L.off[a] = ctx->arr[a].off;
+        L.n[a] = ctx->arr[a].n;
+        L.n_real[a] = ctx->arr[a].n_real;
+    }
+    if (ctx->pool_end > 0) {
+        k_fill_ptype<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(ctx->ptype,
+                                                                                  ctx->pool_end, L);
+        LAUNCH_CHECK();
+    }
+    ctx->ptype_dirty = false;
+    return 0;
+}
+
+static int ensure_pool(b200sph_ctx *ctx)
+{
+    if (ctx->pool_cap == 0) {
+        int64_t caps[B200SPH_MAX_ARRAYS];
+        for (int a = 0; a < ctx->narr; a++) caps[a] = std::max(ctx->arr[a].cap, ctx->arr[a].n);
+        int rc = pool_layout(ctx, caps);
+        if (rc) return rc;
+    }
+    return refresh_ptype(ctx);
+}
+
+static int device_scan(b200sph_ctx *ctx, const uint32_t *in, uint32_t *out, int64_t n)
+{
+    const int64_t nb = cdiv(n, SCAN_TILE);
+    if (nb > ctx->blk_cap) {
+        if (ctx->blk_sums) CU(cudaFree(ctx->blk_sums));
+        CU(cudaMalloc((void **)&ctx->blk_sums, 4 * (size_t)(nb + 1024)));
+        ctx->blk_cap = nb + 1024;
+    }
+    k_scan_tiles<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, ctx->blk_sums);
+    LAUNCH_CHECK();
+    if (nb > 1) {
+        k_scan_sums<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->blk_sums, nb);
+        LAUNCH_CHECK();
+        k_scan_add<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(out, n, ctx->blk_sums);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+struct PhaseTimer {
+    b200sph_ctx *ctx;
+    double *slot;
+    PhaseTimer(b200sph_ctx *c, double *s) : ctx(c), slot(s)
+    {
+        if (ctx->profiling) cudaEventRecord(ctx->ev0, ctx->stream);
+    }
+    ~PhaseTimer()
+    {
+        if (ctx->profiling) {
+            cudaEventRecord(ctx->ev1, ctx->stream);
+            cudaEventSynchronize(ctx->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            *slot += ms;
+        }
+    }
+};
+
+template <int K> static void launch_pair_dim(int dim, unsigned nb, cudaStream_t st, const PairArgs &pa)
+{
+    if (dim == 1) k_pair<K, 1><<<nb, PAIR_WARPS * 32, 0, st>>>(pa);
+    else if (dim == 2) k_pair<K, 2><<<nb, PAIR_WARPS * 32, 0, st>>>(pa);
+    else k_pair<K, 3><<<nb, PAIR_WARPS * 32, 0, st>>>(pa);
+}
+
+static double kernel_fac(int kernel, int dim)
+{
+    const double pi = 3.14159265358979323846;
+    switch (kernel) {
+    case 0: return dim == 3 ? 1.0 / pi : (dim == 2 ? 10.0 / (7.0 * pi) : 2.0 / 3.0);  // kernels.py:57-65
+    case 1: return dim == 2 ? 7.0 / (4.0 * pi) : 21.0 / (16.0 * pi);                  // kernels.py:291-299
+    case 2: return dim == 1 ? 1.0 / 120.0 : (dim == 2 ? 7.0 / (478.0 * pi) : 1.0 / (120.0 * pi));  // kernels.py:1071-1079
+    default: return std::pow(1.0 / std::sqrt(pi), dim);                                // kernels.py:852-858
+    }
+}
+static double kernel_deltap(int kernel)
+{
+    switch (kernel) {
+    case 0: return 2. / 3;
+    case 1: return 0.5;
+    case 2: return 0.759298480738450;
+    default: return 0.70710678118654746;
+    }
+}
+
+extern "C" {
+
+int b200sph_abi_version(void) { return B200SPH_ABI_VERSION; }
+
+int b200sph_create(int device, b200sph_ctx **out)
+{
+    if (!out) return -1;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) {
+        fprintf(stderr, "b200sph_create: no usable CUDA device %d (found %d) -- this library has "
+                        "no CPU fallback\n", device, ndev);
+        return -2;
+    }
+    b200sph_ctx *ctx = new b200sph_ctx();
+    ctx->device = device;
+    memset(&ctx->grid, 0, sizeof(ctx->grid));
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    *out = ctx;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    CU(cudaMalloc((void **)&ctx->red, 16 * sizeof(long long)));
+    CU(cudaMallocHost((void **)&ctx->red_host, 16 * sizeof(long long)));
+    CU(cudaMalloc((void **)&ctx->counter, 8 * sizeof(unsigned long long)));
+    CU(cudaMallocHost((void **)&ctx->counter_host, 8 * sizeof(unsigned long long)));
+    CU(cudaEventCreate(&ctx->ev0));
+    CU(cudaEventCreate(&ctx->ev1));
+    return 0;
+}
+
+int b200sph_destroy(b200sph_ctx *ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < N_F64; k++) cudaFree(ctx->f64[k]);
+    for (int k = 0; k < N_F32; k++) cudaFree(ctx->f32[k]);
+    for (int k = 0; k < N_U32; k++) cudaFree(ctx->u32[k]);
+    cudaFree(ctx->ptype);
+    cudaFree(ctx->key_of); cudaFree(ctx->off_in); cudaFree(ctx->cell_cnt); cudaFree(ctx->cell_start);
+    cudaFree(ctx->blk_sums); cudaFree(ctx->perm_tmp); cudaFree(ctx->perm); cudaFree(ctx->skey);
+    cudaFree(ctx->rank); cudaFree(ctx->A); cudaFree(ctx->B); cudaFree(ctx->C);
+    cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->counter);
+    cudaFreeHost(ctx->counter_host); cudaFree(ctx->stage_buf); cudaFree(ctx->flag_a);
+    cudaFree(ctx->flag_b);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+const char *b200sph_last_error(b200sph_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int b200sph_set_stream(b200sph_ctx *ctx, void *s)
+{
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) CU(cudaStreamDestroy(ctx->stream));
+    if (s) {
+        ctx->stream = (cudaStream_t)s;
+        ctx->own_stream = false;
+    } else {
+        CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return 0;
+}
+
+int b200sph_synchronize(b200sph_ctx *ctx)
+{
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200sph_add_array(b200sph_ctx *ctx, const char *name, int64_t n, int64_t n_real, int64_t capacity)
+{
+    if (ctx->narr >= B200SPH_MAX_ARRAYS) return set_err(ctx, "too many particle arrays (max %d)", B200SPH_MAX_ARRAYS);
+    if (n < 0 || n_real < 0 || n_real > n) return set_err(ctx, "add_array: bad sizes n=%lld n_real=%lld", (long long)n, (long long)n_real);
+    CU(cudaSetDevice(ctx->device));
+    const int a = ctx->narr;
+    ctx->arr[a].name = name ? name : "";
+    ctx->arr[a].n = n;
+    ctx->arr[a].n_real = n_real;
+    ctx->arr[a].cap = std::max<int64_t>(capacity, n);
+    ctx->arr[a].off = 0;
+    ctx->narr++;
+    if (ctx->pool_cap > 0) {  // pool already built: re-layout, preserving data of older arrays
+        int64_t caps[B200SPH_MAX_ARRAYS];
+        const int64_t n_new = ctx->arr[a].n;
+        ctx->arr[a].n = 0;  // nothing to move for the new array
+        for (int k = 0; k < ctx->narr; k++) caps[k] = ctx->arr[k].cap;
+        int rc = pool_layout(ctx, caps);
+        ctx->arr[a].n = n_new;
+        if (rc) return rc;
+    }
+    ctx->ptype_dirty = true;
+    ctx->grid_valid = false;
+    return a;
+}
+
+int b200sph_resize_array(b200sph_ctx *ctx, int arr, int64_t n, int64_t n_real)
+{
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "resize_array: bad array %d", arr);
+    if (n < 0 || n_real < 0 || n_real > n) return set_err(ctx, "resize_array: bad sizes");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->pool_cap == 0) {
+        ctx->arr[arr].cap = std::max(ctx->arr[arr].cap, n);
+    } else {
+        int rc = ensure_capacity(ctx, arr, n);
+        if (rc) return rc;
+    }
+    ctx->arr[arr].n = n;
+    ctx->arr[arr].n_real = n_real;
+    ctx->ptype_dirty = true;
+    ctx->grid_valid = false;
+    return 0;
+}
+
+int b200sph_get_array_size(b200sph_ctx *ctx, int arr, int64_t *n, int64_t *n_real)
+{
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "get_array_size: bad array %d", arr);
+    if (n) *n = ctx->arr[arr].n;
+    if (n_real) *n_real = ctx->arr[arr].n_real;
+    return 0;
+}
+
+static int check_range(b200sph_ctx *ctx, int arr, int64_t start, int64_t count)
+{
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "bad array index %d", arr);
+    if (start < 0 || count < 0 || start + count > ctx->arr[arr].n)
+        return set_err(ctx, "range [%lld, %lld) outside array '%s' of %lld particles", (long long)start,
+                       (long long)(start + count), ctx->arr[arr].name.c_str(), (long long)ctx->arr[arr].n);
+    return 0;
+}
+
+static int ensure_stage(b200sph_ctx *ctx, int64_t count)
+{
+    if (count > ctx->stage_cap) {
+        if (ctx->stage_buf) CU(cudaFree(ctx->stage_buf));
+        CU(cudaMalloc((void **)&ctx->stage_buf, 8 * (size_t)(count + 1024)));
+        ctx->stage_cap = count + 1024;
+    }
+    return 0;
+}
+
+int b200sph_push_f64(b200sph_ctx *ctx, int arr, int prop, const double *host, int64_t start, int64_t count)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = check_range(ctx, arr, start, count))) return rc;
+    if (count == 0) return 0;
+    const int64_t o = ctx->arr[arr].off + start;
+    if (is_f64_prop(prop)) {
+        CU(cudaMemcpyAsync(ctx->f64[prop] + o, host, 8 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    } else if (is_f32_prop(prop)) {
+        if ((rc = ensure_stage(ctx, count))) return rc;
+        CU(cudaMemcpyAsync(ctx->stage_buf, host, 8 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+        k_f64_to_f32<<<(unsigned)cdiv(count, 256), 256, 0, ctx->stream>>>(ctx->stage_buf, ctx->f32[prop - N_F64] + o, count);
+        LAUNCH_CHECK();
+    } else {
+        return set_err(ctx, "push_f64: property id %d is not a floating point property", prop);
+    }
+    // the host buffer is borrowed only for this call
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (prop == B200SPH_H) ctx->domain_valid = false;
+    if (prop <= B200SPH_Z || prop == B200SPH_H) ctx->grid_valid = false;
+    ctx->state_packed = false;
+    return 0;
+}
+
+int b200sph_pull_f64(b200sph_ctx *ctx, int arr, int prop, double *host, int64_t start, int64_t count)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = check_range(ctx, arr, start, count))) return rc;
+    if (count == 0) return 0;
+    const int64_t o = ctx->arr[arr].off + start;
+    if (is_f64_prop(prop)) {
+        CU(cudaMemcpyAsync(host, ctx->f64[prop] + o, 8 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (is_f32_prop(prop)) {
+        if ((rc = ensure_stage(ctx, count))) return rc;
+        k_f32_to_f64<<<(unsigned)cdiv(count, 256), 256, 0, ctx->stream>>>(ctx->f32[prop - N_F64] + o, ctx->stage_buf, count);
+        LAUNCH_CHECK();
+        CU(cudaMemcpyAsync(host, ctx->stage_buf, 8 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        return set_err(ctx, "pull_f64: property id %d is not a floating point property", prop);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200sph_push_u32(b200sph_ctx *ctx, int arr, int prop, const uint32_t *host, int64_t start, int64_t count)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = check_range(ctx, arr, start, count))) return rc;
+    const int k = u32_index(prop);
+    if (k < 0) return set_err(ctx, "push_u32: property id %d is not an integer property", prop);
+    if (count == 0) return 0;
+    CU(cudaMemcpyAsync(ctx->u32[k] + ctx->arr[arr].off + start, host, 4 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200sph_pull_u32(b200sph_ctx *ctx, int arr, int prop, uint32_t *host, int64_t start, int64_t count)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = check_range(ctx, arr, start, count))) return rc;
+    const int k = u32_index(prop);
+    if (k < 0) return set_err(ctx, "pull_u32: property id %d is not an integer property", prop);
+    if (count == 0) return 0;
+    CU(cudaMemcpyAsync(host, ctx->u32[k] + ctx->arr[arr].off + start, 4 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200sph_device_ptr(b200sph_ctx *ctx, int arr, int prop, void **out)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "device_ptr: bad array %d", arr);
+    const int64_t o = ctx->arr[arr].off;
+    if (is_f64_prop(prop)) *out = ctx->f64[prop] + o;
+    else if (is_f32_prop(prop)) *out = ctx->f32[prop - N_F64] + o;
+    else if (u32_index(prop) >= 0) *out = ctx->u32[u32_index(prop)] + o;
+    else return set_err(ctx, "device_ptr: bad property %d", prop);
+    return 0;
+}
+
+int b200sph_set_kernel(b200sph_ctx *ctx, int kernel, int dim)
+{
+    if (kernel < 0 || kernel > 3) return set_err(ctx, "set_kernel: unknown kernel id %d", kernel);
+    if (dim < 1 || dim > 3) return set_err(ctx, "set_kernel: dim must be 1, 2 or 3");
+    if (kernel == B200SPH_KERNEL_WENDLAND_QUINTIC && dim == 1)
+        return set_err(ctx, "WendlandQuintic: Dim 1 not supported");  // kernels.py:289-290
+    ctx->kernel = kernel;
+    ctx->dim = dim;
+    ctx->radius_scale = (kernel == B200SPH_KERNEL_QUINTIC_SPLINE || kernel == B200SPH_KERNEL_GAUSSIAN) ? 3.0 : 2.0;
+    ctx->domain_valid = false;
+    ctx->grid_valid = false;
+    return 0;
+}
+
+static int run_minmax(b200sph_ctx *ctx, int do_xyz, int do_h)
+{
+    k_red_init<<<1, 32, 0, ctx->stream>>>(ctx->red);
+    LAUNCH_CHECK();
+    if (ctx->pool_end > 0) {
+        const unsigned nb = (unsigned)std::min<int64_t>(cdiv(ctx->pool_end, 256), 148 * 8);
+        k_reduce_minmax<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z],
+                                                     ctx->f64[B200SPH_H], ctx->ptype, ctx->pool_end, do_xyz, do_h, ctx->red);
+        LAUNCH_CHECK();
+    }
+    CU(cudaMemcpyAsync(ctx->red_host, ctx->red, 16 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200sph_update_domain(b200sph_ctx *ctx)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    PhaseTimer pt(ctx, &ctx->stats.ms_other);
+    if ((rc = run_minmax(ctx, 0, 1))) return rc;
+    // nnps_base.pyx:942-978
+    double hmin = o2d(ctx->red_host[6]), hmax = o2d(ctx->red_host[7]);
+    int64_t ntot = 0;
+    for (int a = 0; a < ctx->narr; a++) ntot += ctx->arr[a].n;
+    if (ntot == 0) { hmax = -1.0; hmin = 1.7976931348623157e308; }
+    double cell = ctx->radius_scale * hmax;
+    ctx->hmin_scaled = ctx->radius_scale * hmin;
+    if (cell < 1e-6) cell = 1.0;
+    if (cell != ctx->cell_size) ctx->grid_valid = false;
+    ctx->cell_size = cell;
+    ctx->domain_valid = true;
+    return 0;
+}
+
+int b200sph_nnps_update(b200sph_ctx *ctx)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (!ctx->domain_valid && (rc = b200sph_update_domain(ctx))) return rc;
+    PhaseTimer pt(ctx, &ctx->stats.ms_nnps);
+
+    int64_t ntot = 0;
+    for (int a = 0; a < ctx->narr; a++) ntot += ctx->arr[a].n;
+    if (ntot >= (1LL << 32) - 1) return set_err(ctx, "more than 2^32-2 particles: indices are 32-bit (as in the reference)");
+
+    // _compute_bounds nnps_base.pyx:1520-1575
+    if ((rc = run_minmax(ctx, 1, 0))) return rc;
+    double mn[3], mx[3], l[3];
+    for (int d = 0; d < 3; d++) {
+        mn[d] = ntot ? o2d(ctx->red_host[2 * d]) : 1e100;
+        mx[d] = ntot ? o2d(ctx->red_host[2 * d + 1]) : -1e100;
+        l[d] = mx[d] - mn[d];
+    }
+    for (int d = 0; d < 3; d++) {
+        mn[d] -= l[d] * 0.01;
+        mx[d] += l[d] * 0.01;
+    }
+    const double domain_size = std::max(std::max(l[0], l[1]), l[2]);
+    if (ctx->last_domain_size > 1e-16 && domain_size > 2.0 * ctx->last_domain_size)
+        fprintf(stderr, "b200sph WARNING: Domain size has increased by a large amount. "
+                        "Particles are probably diverging, please check your code!\n");
+    ctx->last_domain_size = domain_size;
+    if (std::fabs(mx[0] - mn[0]) < 1e-12 && std::fabs(mx[1] - mn[1]) < 1e-12 && std::fabs(mx[2] - mn[2]) < 1e-12)
+        for (int d = 0; d < 3; d++) {
+            mn[d] -= 0.5;
+            mx[d] += 0.5;
+        }
+    // _get_number_of_cells / _count_occupied_cells linked_list_nnps.pyx:293-343
+    const double cs1 = 1. / ctx->cell_size;
+    int nc[3];
+    for (int d = 0; d < 3; d++) {
+        const double v = std::ceil(cs1 * (mx[d] - mn[d]));
+        if (!(v < 2147483647.0)) return set_err(ctx, "LinkedListNNPS requires too many cells along axis %d", d);
+        nc[d] = (int)v;
+        if (nc[d] < 0) return set_err(ctx, "LinkedListNNPS: Number of cells is negative");
+        if (nc[d] == 0) nc[d] = 1;
+    }
+    const double ncells_d = (double)nc[0] * (double)nc[1] * (double)nc[2];
+    if (ncells_d > (double)(1LL << 28))
+        return set_err(ctx, "ERROR: LinkedListNNPS requires too many cells (%.0f).", ncells_d);
+    const int64_t ncells = (int64_t)nc[0] * nc[1] * nc[2];
+
+    b200sph_grid_info &gi = ctx->grid;
+    gi.cell_size = ctx->cell_size;
+    gi.hmin = ctx->hmin_scaled;
+    for (int d = 0; d < 3; d++) {
+        gi.xmin[d] = mn[d];
+        gi.xmax[d] = mx[d];
+        gi.ncells[d] = nc[d];
+    }
+    gi.n_cells = ncells;
+    gi.n_particles = ntot;
+
+    if (ncells + 2 > ctx->cell_cap) {
+        if (ctx->cell_cnt) CU(cudaFree(ctx->cell_cnt));
+        if (ctx->cell_start) CU(cudaFree(ctx->cell_start));
+        const int64_t cap = ncells + ncells / 2 + 1024;
+        CU(cudaMalloc((void **)&ctx->cell_cnt, 4 * (size_t)cap));
+        CU(cudaMalloc((void **)&ctx->cell_start, 4 * (size_t)cap));
+        ctx->cell_cap = cap;
+    }
+    GridDev G;
+    for (int d = 0; d < 3; d++) {
+        G.xmin[d] = mn[d];
+        G.nc[d] = nc[d];
+    }
+    G.cell = ctx->cell_size;
+    G.cellf = (float)ctx->cell_size;
+
+    CU(cudaMemsetAsync(ctx->cell_cnt, 0, 4 * (size_t)(ncells + 1), ctx->stream));
+    ctx->n_sorted = ntot;
+    if (ctx->pool_end > 0) {
+        const unsigned nb = (unsigned)cdiv(ctx->pool_end, 256);
+        k_cell_count<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z],
+                                                  ctx->ptype, ctx->pool_end, G, ctx->key_of, ctx->off_in, ctx->cell_cnt);
+        LAUNCH_CHECK();
+    }
+    if ((rc = device_scan(ctx, ctx->cell_cnt, ctx->cell_start, ncells + 1))) return rc;
+    if (ctx->pool_end > 0 && ntot > 0) {
+        const unsigned nb = (unsigned)cdiv(ctx->pool_end, 256);
+        k_scatter<<<nb, 256, 0, ctx->stream>>>(ctx->key_of, ctx->off_in, ctx->ptype, ctx->pool_end, ctx->cell_start, ctx->perm_tmp);
+        LAUNCH_CHECK();
+        const unsigned ns = (unsigned)cdiv(ntot, 256);
+        k_canon<<<ns, 256, 0, ctx->stream>>>(ctx->perm_tmp, ctx->key_of, ctx->cell_start, ntot, ctx->perm, ctx->skey, ctx->rank);
+        LAUNCH_CHECK();
+        k_pack_pos<<<ns, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H],
+                                                ctx->perm, ctx->skey, ntot, G, ctx->A);
+        LAUNCH_CHECK();
+    }
+    ctx->grid_valid = true;
+    ctx->state_packed = false;
+    return 0;
+}
+
+int b200sph_get_grid(b200sph_ctx *ctx, b200sph_grid_info *out)
+{
+    if (!ctx->grid_valid) return set_err(ctx, "get_grid: the NNPS has not been updated");
+    *out = ctx->grid;
+    return 0;
+}
+
+static int pack_state(b200sph_ctx *ctx)
+{
+    if (ctx->n_sorted > 0) {
+        k_pack_state<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
+            ctx->f64[B200SPH_U], ctx->f64[B200SPH_V], ctx->f64[B200SPH_W], ctx->f64[B200SPH_M], ctx->f64[B200SPH_RHO],
+            ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64], ctx->ptype, ctx->perm, ctx->n_sorted, ctx->B, ctx->C);
+        LAUNCH_CHECK();
+    }
+    ctx->state_packed = true;
+    return 0;
+}
+
+int64_t b200sph_get_neighbors(b200sph_ctx *ctx, int dst_arr, int src_arr, int64_t d_idx, uint32_t *out, int64_t cap)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->grid_valid) return set_err(ctx, "get_neighbors: call nnps_update first");
+    if (dst_arr < 0 || dst_arr >= ctx->narr || src_arr < 0 || src_arr >= ctx->narr) return set_err(ctx, "get_neighbors: bad array index");
+    if (d_idx < 0 || d_idx >= ctx->arr[dst_arr].n) return set_err(ctx, "get_neighbors: d_idx out of range");
+    int rc;
+    if (!ctx->state_packed && (rc = pack_state(ctx))) return rc;
+    uint32_t s32 = 0;
+    CU(cudaMemcpyAsync(&s32, ctx->rank + ctx->arr[dst_arr].off + d_idx, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int64_t dcap = std::max<int64_t>(cap, 1);
+    uint32_t *dout = nullptr;
+    CU(cudaMalloc((void **)&dout, 4 * (size_t)dcap));
+    k_neighbors<<<1, 32, 0, ctx->stream>>>(ctx->A, ctx->C, ctx->cell_start, ctx->skey, ctx->perm, (long long)s32, src_arr,
+                                           (long long)ctx->arr[src_arr].off, ctx->grid.ncells[0], ctx->grid.ncells[1], ctx->grid.ncells[2],
+                                           (float)ctx->cell_size, (float)(ctx->radius_scale * ctx->radius_scale), dout, cap, ctx->counter + 1);
+    ctx->stats.kernel_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(dout); return set_err(ctx, "k_neighbors launch failed: %s", cudaGetErrorString(e)); }
+    CU(cudaMemcpyAsync(ctx->counter_host + 1, ctx->counter + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int64_t n = (int64_t)ctx->counter_host[1];
+    const int64_t ncopy = std::min(n, cap);
+    if (ncopy > 0) {
+        CU(cudaMemcpy(out, dout, 4 * (size_t)ncopy, cudaMemcpyDeviceToHost));
+        std::sort(out, out + ncopy);
+    }
+    cudaFree(dout);
+    return n;
+}
+
+static int arr_range(b200sph_ctx *ctx, int arr, int real_only, int64_t *lo, int64_t *hi)
+{
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "bad array index %d", arr);
+    *lo = ctx->arr[arr].off;
+    *hi = ctx->arr[arr].off + (real_only ? ctx->arr[arr].n_real : ctx->arr[arr].n);
+    return 0;
+}
+
+int b200sph_eos(b200sph_ctx *ctx, int arr, int hg, double rho0, double c0, double gamma, double p0, int real_only)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    int64_t lo, hi;
+    if ((rc = arr_range(ctx, arr, real_only, &lo, &hi))) return rc;
+    PhaseTimer pt(ctx, &ctx->stats.ms_other);
+    if (hi > lo) {
+        k_eos<<<(unsigned)cdiv(hi - lo, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_RHO], ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64],
+                                                                    ctx->ptype, lo, hi, hg, rho0, c0, gamma, p0);
+        LAUNCH_CHECK();
+    }
+    ctx->state_packed = false;
+    return 0;
+}
+
+int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim, int real_only)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    int64_t lo, hi;
+    if ((rc = arr_range(ctx, arr, real_only, &lo, &hi))) return rc;
+    PhaseTimer pt(ctx, &ctx->stats.ms_other);
+    if (hi > lo) {
+        k_ferrari<<<(unsigned)cdiv(hi - lo, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_H], ctx->f64[B200SPH_M], ctx->f64[B200SPH_RHO], lo, hi, hdx, 1.0 / dim);
+        LAUNCH_CHECK();
+    }
+    ctx->domain_valid = false;  // h changed: the next update_domain must re-reduce it
+    return 0;
+}
+
+int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_t *pairs_out)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (!ctx->grid_valid) return set_err(ctx, "pair_pass: the NNPS is stale (particles were pushed/resized); call nnps_update first");
+    if (!ctx->state_packed && (rc = pack_state(ctx))) return rc;
+    PhaseTimer pt(ctx, &ctx->stats.ms_pair);
+
+    PairArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.A = ctx->A; pa.B = ctx->B; pa.C = ctx->C;
+    pa.cell_start = ctx->cell_start; pa.skey = ctx->skey; pa.perm = ctx->perm;
+    pa.arho = ctx->f32[B200SPH_ARHO - N_F64];
+    pa.au = ctx->f32[B200SPH_AU - N_F64]; pa.av = ctx->f32[B200SPH_AV - N_F64]; pa.aw = ctx->f32[B200SPH_AW - N_F64];
+    pa.ax = ctx->f32[B200SPH_AX - N_F64]; pa.ay = ctx->f32[B200SPH_AY - N_F64]; pa.az = ctx->f32[B200SPH_AZ - N_F64];
+    pa.dt_cfl = ctx->f32[B200SPH_DT_CFL - N_F64]; pa.dt_force = ctx->f32[B200SPH_DT_FORCE - N_F64];
+    pa.rho = ctx->f64[B200SPH_RHO];
+    pa.n = ctx->n_sorted;
+    pa.ncx = ctx->grid.ncells[0]; pa.ncy = ctx->grid.ncells[1]; pa.ncz = ctx->grid.ncells[2];
+    pa.cell = (float)ctx->cell_size;
+    pa.k2 = (float)(ctx->radius_scale * ctx->radius_scale);
+    pa.kfac = (float)kernel_fac(ctx->kernel, ctx->dim);
+    pa.deltap = (float)kernel_deltap(ctx->kernel);
+    bool sumdens = false;
+    for (int d = 0; d < B200SPH_MAX_ARRAYS; d++) {
+        unsigned long long m = 0;
+        for (int s = 0; s < B200SPH_MAX_ARRAYS; s++) {
+            const uint32_t b = (d < ctx->narr && s < ctx->narr) ? prog->eqmask[d][s] : 0u;
+            if (b > 0xFFu) return set_err(ctx, "pair_pass: unknown equation bits 0x%x", b);
+            m |= (unsigned long long)b << (8 * s);
+            if (b & B200SPH_EQ_SUMMATION_DENSITY) sumdens = true;
+        }
+        pa.emask[d] = m;
+    }
+    pa.c0 = (float)prog->c0; pa.alpha = (float)prog->alpha; pa.beta = (float)prog->beta;
+    pa.gx = (float)prog->gx; pa.gy = (float)prog->gy; pa.gz = (float)prog->gz;
+    pa.eps_xsph = (float)prog->eps_xsph;
+    pa.tensile = prog->tensile_correction;
+    pa.real_only = prog->real_only;
+    pa.pair_counter = nullptr;
+    if (pairs_out) {
+        CU(cudaMemsetAsync(ctx->counter, 0, 8, ctx->stream));
+        pa.pair_counter = ctx->counter;
+    }
+    if (ctx->n_sorted > 0) {
+        const unsigned nb = (unsigned)cdiv(ctx->n_sorted, PAIR_WARPS * PAIR_CHUNK);
+        switch (ctx->kernel) {
+        case 0: launch_pair_dim<0>(ctx->dim, nb, ctx->stream, pa); break;
+        case 1: launch_pair_dim<1>(ctx->dim, nb, ctx->stream, pa); break;
+        case 2: launch_pair_dim<2>(ctx->dim, nb, ctx->stream, pa); break;
+        default: launch_pair_dim<3>(ctx->dim, nb, ctx->stream, pa); break;
+        }
+        LAUNCH_CHECK();
+        ctx->stats.pair_launches++;
+    }
+    if (pairs_out) {
+        CU(cudaMemcpyAsync(ctx->counter_host, ctx->counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *pairs_out = (int64_t)ctx->counter_host[0];
+        ctx->stats.pairs += *pairs_out;
+    }
+    if (sumdens) ctx->state_packed = false;  // rho changed
+    return 0;
+}
+
+int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (arr >= ctx->narr) return set_err(ctx, "stage: bad array %d", arr);
+    if (which < 0 || which > 2) return set_err(ctx, "stage: which must be 0 (initialize), 1 (stage1) or 2 (stage2)");
+    PhaseTimer pt(ctx, &ctx->stats.ms_other);
+    StageArgs sa;
+    sa.x = ctx->f64[B200SPH_X]; sa.y = ctx->f64[B200SPH_Y]; sa.z = ctx->f64[B200SPH_Z];
+    sa.u = ctx->f64[B200SPH_U]; sa.v = ctx->f64[B200SPH_V]; sa.w = ctx->f64[B200SPH_W]; sa.rho = ctx->f64[B200SPH_RHO];
+    sa.x0 = ctx->f64[B200SPH_X0]; sa.y0 = ctx->f64[B200SPH_Y0]; sa.z0 = ctx->f64[B200SPH_Z0];
+    sa.u0 = ctx->f64[B200SPH_U0]; sa.v0 = ctx->f64[B200SPH_V0]; sa.w0 = ctx->f64[B200SPH_W0]; sa.rho0 = ctx->f64[B200SPH_RHO0];
+    sa.au = ctx->f32[B200SPH_AU - N_F64]; sa.av = ctx->f32[B200SPH_AV - N_F64]; sa.aw = ctx->f32[B200SPH_AW - N_F64];
+    sa.ax = ctx->f32[B200SPH_AX - N_F64]; sa.ay = ctx->f32[B200SPH_AY - N_F64]; sa.az = ctx->f32[B200SPH_AZ - N_F64];
+    sa.arho = ctx->f32[B200SPH_ARHO - N_F64];
+    sa.ptype = ctx->ptype;
+    sa.pool_end = ctx->pool_end;
+    sa.arr = arr;
+    sa.which = which;
+    sa.f = which == 1 ? 0.5 * dt : dt;
+    if (ctx->pool_end > 0) {
+        k_stage<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa);
+        LAUNCH_CHECK();
+    }
+    if (which != 0) {
+        ctx->grid_valid = false;  // particles moved: neighbours are stale until nnps_update
+        ctx->state_packed = false;
+    }
+    return 0;
+}
+
+int b200sph_dt_factors(b200sph_ctx *ctx, double out[3])
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    PhaseTimer pt(ctx, &ctx->stats.ms_other);
+    k_red_init<<<1, 32, 0, ctx->stream>>>(ctx->red);
+    LAUNCH_CHECK();
+    if (ctx->pool_end > 0) {
+        const unsigned nb = (unsigned)std::min<int64_t>(cdiv(ctx->pool_end, 256), 148 * 8);
+        k_reduce_dt<<<nb, 256, 0, ctx->stream>>>(ctx->f32[B200SPH_DT_CFL - N_F64], ctx->f32[B200SPH_DT_FORCE - N_F64], ctx->f64[B200SPH_H],
+                                                 ctx->ptype, ctx->pool_end, ctx->red);
+        LAUNCH_CHECK();
+    }
+    CU(cudaMemcpyAsync(ctx->red_host, ctx->red, 16 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const double mc = o2d(ctx->red_host[9]), mf = o2d(ctx->red_host[11]), hm = o2d(ctx->red_host[12]);
+    out[0] = mc < -1e299 ? -1.0 : mc;  // _my_max of an empty property is -1.0, integrator.py:55-59
+    out[1] = mf < -1e299 ? -1.0 : mf;
+    out[2] = std::min(1.0, hm);        // compute_h_minimum starts from 1.0, integrator.py:149
+    return 0;
+}
+
+// ---- halo helpers ------------------------------------------------------------
+static const int halo_fields[9] = {B200SPH_X, B200SPH_Y, B200SPH_Z, B200SPH_U, B200SPH_V, B200SPH_W, B200SPH_RHO, B200SPH_H, B200SPH_M};
+
+int b200sph_halo_pack(b200sph_ctx *ctx, int arr, double lo, double hi, double *dev_buf, int64_t cap, int64_t *count)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "halo_pack: bad array %d", arr);
+    const int64_t n = ctx->arr[arr].n_real, off = ctx->arr[arr].off;
+    *count = 0;
+    if (n == 0) return 0;
+    const unsigned nb = (unsigned)cdiv(n + 1, 256);
+    k_flag_range<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], off, n, lo, hi, 0, ctx->flag_a);
+    LAUNCH_CHECK();
+    if ((rc = device_scan(ctx, ctx->flag_a, ctx->flag_b, n + 1))) return rc;
+    uint32_t tot = 0;
+    CU(cudaMemcpyAsync(&tot, ctx->flag_b + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *count = tot;
+    if ((int64_t)tot > cap) return set_err(ctx, "halo_pack: %u particles selected but the buffer holds %lld", tot, (long long)cap);
+    if (tot == 0) return 0;
+    for (int f = 0; f < 9; f++) {
+        k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[halo_fields[f]], off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)f * cap);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf, int64_t stride, int64_t n, int as_real)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "halo_append: bad array %d", arr);
+    ArrayInfo &ai = ctx->arr[arr];
+    if (as_real && ai.n != ai.n_real) return set_err(ctx, "halo_append(as_real): drop the ghosts of '%s' first (real particles must precede ghosts)", ai.name.c_str());
+    if (n <= 0) return 0;
+    if ((rc = ensure_capacity(ctx, arr, ai.n + n))) return rc;
+    const int64_t o = ai.off + ai.n;
+    for (int f = 0; f < 9; f++)
+        CU(cudaMemcpyAsync(ctx->f64[halo_fields[f]] + o, dev_buf + (size_t)f * stride, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    // every other property of the appended particles starts at zero; tag = Remote (1) for ghosts
+    for (int k = B200SPH_X0; k < N_F64; k++) CU(cudaMemsetAsync(ctx->f64[k] + o, 0, 8 * (size_t)n, ctx->stream));
+    for (int k = 0; k < N_F32; k++) CU(cudaMemsetAsync(ctx->f32[k] + o, 0, 4 * (size_t)n, ctx->stream));
+    k_fill_u32<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->u32[0] + o, n, 0xFFFFFFFFu);
+    LAUNCH_CHECK();
+    k_fill_u32<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->u32[1] + o, n, as_real ? 0u : 1u);
+    LAUNCH_CHECK();
+    CU(cudaMemsetAsync(ctx->u32[2] + o, 0, 4 * (size_t)n, ctx->stream));
+    ai.n += n;
+    if (as_real) ai.n_real += n;
+    ctx->ptype_dirty = true;
+    ctx->grid_valid = false;
+    ctx->domain_valid = false;
+    ctx->state_packed = false;
+    return 0;
+}
+
+int b200sph_drop_ghosts(b200sph_ctx *ctx, int arr)
+{
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "drop_ghosts: bad array %d", arr);
+    if (ctx->arr[arr].n != ctx->arr[arr].n_real) {
+        ctx->arr[arr].n = ctx->arr[arr].n_real;
+        ctx->ptype_dirty = true;
+        ctx->grid_valid = false;
+        ctx->state_packed = false;
+    }
+    return 0;
+}
+
+int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double *dev_buf, int64_t cap, int64_t count[2])
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "migrate_out: bad array %d", arr);
+    ArrayInfo &ai = ctx->arr[arr];
+    if (ai.n != ai.n_real) return set_err(ctx, "migrate_out: drop the ghosts of '%s' first", ai.name.c_str());
+    const int64_t n = ai.n_real, off = ai.off;
+    count[0] = count[1] = 0;
+    if (n == 0) return 0;
+    const unsigned nb = (unsigned)cdiv(n + 1, 256);
+    int64_t base = 0;
+    for (int side = 0; side < 2; side++) {
+        k_flag_range<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], off, n, lo, hi, side == 0 ? 1 : 2, ctx->flag_a);
+        LAUNCH_CHECK();
+        if ((rc = device_scan(ctx, ctx->flag_a, ctx->flag_b, n + 1))) return rc;
+        uint32_t tot = 0;
+        CU(cudaMemcpyAsync(&tot, ctx->flag_b + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        count[side] = tot;
+        if (base + (int64_t)tot > cap) return set_err(ctx, "migrate_out: buffer too small");
+        for (int f = 0; f < 9 && tot; f++) {
+            k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[halo_fields[f]], off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)f * cap + base);
+            LAUNCH_CHECK();
+        }
+        base += tot;
+    }
+    if (count[0] + count[1] == 0) return 0;
+    // stable compaction of the keepers, property by property, through the staging buffer
+    k_flag_range<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], off, n, lo, hi, 3, ctx->flag_a);
+    LAUNCH_CHECK();
+    if ((rc = device_scan(ctx, ctx->flag_a, ctx->flag_b, n + 1))) return rc;
+    const int64_t keep = n - count[0] - count[1];
+    if ((rc = ensure_stage(ctx, n))) return rc;
+    for (int k = 0; k < N_F64; k++) {
+        k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[k], off, n, ctx->flag_a, ctx->flag_b, ctx->stage_buf, 0);
+        LAUNCH_CHECK();
+        CU(cudaMemcpyAsync(ctx->f64[k] + off, ctx->stage_buf, 8 * (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    for (int k = 0; k < N_U32; k++) {
+        k_gather_u32<<<nb, 256, 0, ctx->stream>>>(ctx->u32[k], off, n, ctx->flag_a, ctx->flag_b, (uint32_t *)ctx->stage_buf);
+        LAUNCH_CHECK();
+        CU(cudaMemcpyAsync(ctx->u32[k] + off, ctx->stage_buf, 4 * (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ai.n = ai.n_real = keep;
+    ctx->ptype_dirty = true;
+    ctx->grid_valid = false;
+    ctx->domain_valid = false;
+    ctx->state_packed = false;
+    return 0;
+}
+
+int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out)
+{
+    *out = ctx->stats;
+    return 0;
+}
+int b200sph_reset_stats(b200sph_ctx *ctx)
+{
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    return 0;
+}
+int b200sph_set_profiling(b200sph_ctx *ctx, int on)
+{
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+"""Synthetic inputs for the benchmark configurations (BASELINE.json configs).
+
+The particle lattices of the reference examples, restated with vectorised
+numpy so 1 M / 10 M particle cases build in seconds:
+
+* 3D dam break  -- pysph/examples/_db_geometry.py:250-432 (DamBreak3DGeometry)
+  with the parameters of pysph/examples/dam_break_3d.py:17-31,46-51.
+* 2D dam break  -- pysph/examples/dam_break_2d.py:212-241, using
+  pysph/tools/geometry.py:236-288 (get_2d_tank) and :385-421 (get_2d_block),
+  including the example's quirk that particle h and m stay at the module-level
+  dx = 0.03 constants whatever --dx is (dam_break_2d.py:35,45-47,230-232).
+"""
+import numpy as np
+
+from .particle_array import get_particle_array_wcsph
+
+
+def dam_break_3d_particles(dx=0.02, hdx=1.3, rho0=1000.0, nboundary_layers=1,
+                           with_obstacle=True, xrange=None):
+    """Return [fluid, boundary, obstacle] for the SPHERIC test-2 tank.
+
+    ``xrange=(lo, hi)`` keeps only lattice columns with lo <= x < hi (used by
+    the multi-GPU slab decomposition so that no rank ever materialises the
+    whole lattice).
+    """
+    L, W, H = 3.22, 1.0, 1.0                 # container length, width, height
+    fl, fw, fh = 1.228, 1.0, 0.55            # fluid column
+    ocx, ocy = 2.5, 0.0                      # obstacle centre
+    ol, oh, ow = 0.16, 0.161, 0.4            # obstacle length, height, width
+
+    ghost = nboundary_layers * dx
+    eps = 0.1 * dx
+    xs = np.mgrid[0.0 - ghost:L + ghost + eps:dx]
+    ys = np.mgrid[-0.5 * W - ghost:0.5 * W + ghost + eps:dx]
+    zs = np.mgrid[0.0 - ghost:H + ghost + eps:dx]
+    if xrange is not None:
+        xs = xs[(xs >= xrange[0]) & (xs < xrange[1])]
+    x, y, z = [a.ravel() for a in np.meshgrid(xs, ys, zs, indexing='ij')]
+
+    cw2 = 0.5 * W
+    fluid_mask = ((0 < x) & (x <= fl) & (-cw2 < y) & (y < cw2) &
+                  (0 < z) & (z <= fh))
+    obw2, obl2 = 0.5 * ow, 0.5 * ol
+    obst_mask = ((ocx - obl2 <= x) & (x <= ocx + obl2) &
+                 (ocy - obw2 <= y) & (y <= ocy + obw2) & (0 < z) & (z <= oh))
+    wall_mask = (y <= -cw2) | (y >= cw2) | (x >= L) | (x <= 0) | (z <= 0)
+
+    h0 = hdx * dx
+    m0 = rho0 * dx ** 3
+
+    def make(name, mask):
+        return get_particle_array_wcsph(name=name, x=x[mask], y=y[mask],
+                                        z=z[mask], m=m0, h=h0, rho=rho0)
+
+    arrays = [make('fluid', fluid_mask), make('boundary', wall_mask)]
+    if with_obstacle:
+        arrays.append(make('obstacle', obst_mask))
+    return arrays
+
+
+def dam_break_3d_params(dx, hdx=1.3):
+    """Scheme/solver parameters of pysph/examples/dam_break_3d.py:17-31,54-73."""
+    rho0 = 1000.0
+    c0 = 10.0 * np.sqrt(2.0 * 9.81 * 0.55)
+    h0 = dx * hdx
+    return dict(fluids=['fluid'], solids=['boundary', 'obstacle'], dim=3,
+                rho0=rho0, c0=float(c0), h0=h0, hdx=hdx, gz=-9.81, alpha=0.25,
+                beta=0.0, gamma=7.0, hg_correction=True,
+                tensile_correction=False,
+                dt0=0.25 * h0 / (1.1 * float(c0)), n_damp=50, cfl=0.3,
+                integrator='EPEC')
+
+
+def _tank_2d(dx, length, height, num_layers, base_center):
+    start = (1 - num_layers) * dx
+    end = num_layers * dx
+    x, y = np.mgrid[start:length + end:dx, start:height + end:dx]
+    inside = (x > 0) & (x < length) & (y > 0) & (y < height + 10 * height)
+    keep = ~inside
+    return x[keep] + base_center[0] - length / 2, y[keep] + base_center[1]
+
+
+def _block_2d(dx, length, height, center):
+    n1 = int(length / dx) + 1
+    n2 = int(height / dx) + 1
+    x, y = np.mgrid[-length / 2.:length / 2.:n1 * 1j,
+                    -height / 2.:height / 2.:n2 * 1j]
+    return x.ravel() + center[0], y.ravel() + center[1]
+
+
+def dam_break_2d_particles(dx=0.03):
+    """Return [fluid, boundary] exactly as dam_break_2d.py builds them."""
+    rho0 = 1000.0
+    h = 1.3 * 0.03                 # module constant, NOT 1.3*dx (reference quirk)
+    m = 0.03 ** 2 * rho0           # module constant
+    xt, yt = _tank_2d(dx, 4.0, 4.0, 4, [2, 0])
+    xf, yf = _block_2d(dx, 1.0, 2.0, [0.5, 1])
+    xf = xf + dx
+    yf = yf + dx
+    fluid = get_particle_array_wcsph(name='fluid', x=xf, y=yf, h=h, m=m,
+                                     rho=rho0)
+    boundary = get_particle_array_wcsph(name='boundary', x=xt, y=yt, h=h, m=m,
+                                        rho=rho0)
+    return [fluid, boundary]
+
+
+def dam_break_2d_params(dx=0.03, hdx=1.3):
+    """pysph/examples/dam_break_2d.py:29-47,86-96,146-150."""
+    rho0 = 1000.0
+    c0 = 10.0 * np.sqrt(2 * 9.81 * 2.0)
+    hq = 1.3 * 0.03
+    h_opt = hdx * dx
+    return dict(fluids=['fluid'], solids=['boundary'], dim=2, rho0=rho0,
+                c0=float(c0), h0=hq, hdx=1.3, gy=-9.81, alpha=0.1, beta=0.0,
+                gamma=7.0, hg_correction=True, update_h=True,
+                dt0=0.125 * h_opt / float(c0), n_damp=50, cfl=0.3,
+                integrator='PEC')

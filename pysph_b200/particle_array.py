@@ -1,0 +1,147 @@
+"""Minimal host-side ParticleArray stand-in.
+
+PySPH's real ``ParticleArray`` (pysph/base/particle_array.pyx:68-300) is a
+Cython class over ``cyarray`` buffers and cannot be imported where PySPH is
+not installed.  The B200 adapters in this package are duck-typed against the
+small attribute surface they need (SURVEY.md 8b "Host buffers"):
+
+    pa.name, pa.properties (dict name -> array), pa.constants,
+    pa.num_real_particles, pa.get_number_of_particles(real=False),
+    pa.get(name, only_real_particles=True), pa.add_property(name, ...),
+    pa.gpu  (device helper installed by the backend)
+
+This class provides exactly that over numpy arrays so the package, its tests
+and bench.py run stand-alone; a real PySPH ParticleArray can be passed to
+every adapter instead.
+"""
+import numpy as np
+
+UINT_MAX = (1 << 32) - 1
+
+# pysph/base/particle_array.pxd:24-27
+LOCAL, REMOTE, GHOST = 0, 1, 2
+
+# pysph/base/utils.py:41-44
+DEFAULT_PROPS = ('x', 'y', 'z', 'u', 'v', 'w', 'm', 'h', 'rho', 'p',
+                 'au', 'av', 'aw', 'gid', 'pid', 'tag')
+# pysph/base/utils.py:177-178
+WCSPH_PROPS = ('cs', 'ax', 'ay', 'az', 'arho', 'x0', 'y0', 'z0',
+               'u0', 'v0', 'w0', 'rho0', 'div', 'dt_cfl', 'dt_force')
+
+_INT_PROPS = {'tag': np.int32, 'pid': np.int32, 'gid': np.uint32}
+
+
+class ParticleArray(object):
+    def __init__(self, name='array', constants=None, **props):
+        self.name = name
+        self.properties = {}
+        self.constants = dict(constants or {})
+        self.output_property_arrays = []
+        self.gpu = None
+        self.backend = 'b200'
+        n = 0
+        for v in props.values():
+            n = max(n, np.asarray(v).size)
+        self._n = n
+        self.num_real_particles = n
+        for k, v in props.items():
+            self.add_property(k, data=v)
+
+    # -- sizes ------------------------------------------------------------
+    def get_number_of_particles(self, real=False):
+        return self.num_real_particles if real else self._n
+
+    # -- properties -------------------------------------------------------
+    def add_property(self, name, type=None, default=None, data=None, stride=1):
+        dtype = _INT_PROPS.get(name, np.float64)
+        if default is None:
+            default = UINT_MAX if name == 'gid' else 0
+        arr = np.full(self._n * stride, default, dtype=dtype)
+        if data is not None:
+            d = np.asarray(data)
+            if d.size == 1:
+                arr[:] = d.ravel()[0]
+            else:
+                if d.size != arr.size:
+                    raise ValueError('property %r: size %d != %d' %
+                                     (name, d.size, arr.size))
+                arr[:] = d.ravel()
+        self.properties[name] = arr
+
+    def get(self, *names, **kw):
+        only_real = kw.get('only_real_particles', True)
+        out = []
+        for nme in names:
+            a = self.properties[nme] if nme in self.properties \
+                else self.constants[nme]
+            if only_real and nme in self.properties:
+                a = a[:self.num_real_particles]
+            out.append(a)
+        return out[0] if len(out) == 1 else out
+
+    def set(self, **props):
+        for k, v in props.items():
+            self.properties[k][:] = v
+
+    def __getattr__(self, name):
+        # pa.x style access, like the reference (particle_array.pyx:767-770)
+        props = self.__dict__.get('properties', {})
+        if name in props:
+            return props[name]
+        consts = self.__dict__.get('constants', {})
+        if name in consts:
+            return consts[name]
+        raise AttributeError(name)
+
+    def set_output_arrays(self, names):
+        self.output_property_arrays = list(names)
+
+    def add_constant(self, name, data):
+        self.constants[name] = np.atleast_1d(np.asarray(data, dtype=float))
+
+    def set_num_real_particles(self, n):
+        self.num_real_particles = int(n)
+
+    # -- growth / shrink (used by the halo exchange for Remote particles) --
+    def resize(self, n):
+        n = int(n)
+        for k, a in list(self.properties.items()):
+            stride = a.size // max(self._n, 1) if self._n else 1
+            b = np.zeros(n * stride, dtype=a.dtype)
+            m = min(a.size, b.size)
+            b[:m] = a[:m]
+            self.properties[k] = b
+        self._n = n
+        self.num_real_particles = min(self.num_real_particles, n)
+
+    def extract(self, idx, name=None):
+        idx = np.asarray(idx)
+        pa = ParticleArray(name=name or self.name, constants=self.constants)
+        pa._n = idx.size
+        pa.num_real_particles = idx.size
+        for k, a in self.properties.items():
+            pa.properties[k] = a[idx].copy()
+        pa.output_property_arrays = list(self.output_property_arrays)
+        return pa
+
+
+def get_particle_array(additional_props=None, constants=None, **props):
+    """pysph/base/utils.py:47-146: default SPH property set."""
+    name = props.pop('name', 'array')
+    pa = ParticleArray(name=name, constants=constants, **props)
+    want = list(DEFAULT_PROPS) + list(additional_props or [])
+    for p in want:
+        if p not in pa.properties:
+            pa.add_property(p)
+    pa.set_output_arrays(['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'm', 'h',
+                          'pid', 'gid', 'tag'])
+    return pa
+
+
+def get_particle_array_wcsph(constants=None, **props):
+    """pysph/base/utils.py:152-190: the WCSPH property set."""
+    pa = get_particle_array(additional_props=WCSPH_PROPS, constants=constants,
+                            **props)
+    pa.set_output_arrays(['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'm', 'h',
+                          'pid', 'gid', 'tag', 'p'])
+    return pa
