@@ -1,0 +1,392 @@
+"""bench.py -- particle-pair interactions/s on the 3D WCSPH dam break.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU arm (oracle, all threads)
+
+One "step" = one EPEC time step of pysph/examples/dam_break_3d.py with
+--kernel CubicSpline: 2 x (cell-list build + EOS + fused pair kernel) + the
+WCSPHStep stages + the adaptive-dt reduction.  N = 1 runs BASELINE.json
+configs[1] (dx = 0.00877: ~1.0 M fluid + ~0.23 M wall/obstacle particles);
+N > 1 keeps ~1.2 M particles per GPU (dx = 0.00877 / N^(1/3); N = 8 is
+configs[2], ~10 M) with x-slabs and a NCCL halo exchange before every
+evaluation.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BASE_DX = 0.00877
+BYTES_PER_PAIR = 45.0   # 44 B gathered source state + ~1.1 B dest I/O
+METRIC = 'particle_pair_interactions_per_s'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(np.max(mx)) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def copy_arrays(pas):
+    import pysph_b200 as pb
+    out = []
+    for pa in pas:
+        q = pb.get_particle_array_wcsph(
+            name=pa.name, **dict((k, v.copy()) for k, v in pa.properties.items()))
+        q.set_num_real_particles(pa.num_real_particles)
+        out.append(q)
+    return out
+
+
+def cpu_leg(pas, params, threads, budget_s, max_steps, warmup=0):
+    """Time the fp64 oracle (the CPU restatement of the reference path) on the
+    same workload: EPEC steps until the budget is used.  Returns a dict."""
+    from oracle import oracle as orc
+    s = orc.WCSPHOracleSolver(pas, params, 'CubicSpline', threads=threads)
+    s.initialise()
+    for _ in range(warmup):
+        s.step()
+    s.pairs_total = 0
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_steps:
+        s.step()
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    el = time.perf_counter() - t0
+    return dict(pairs_per_s=s.pairs_total / el, steps=n, seconds=el,
+                pairs_per_step=s.pairs_total / n)
+
+
+def cpu_model():
+    try:
+        for ln in open('/proc/cpuinfo'):
+            if ln.startswith('model name'):
+                return ln.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return 'unknown'
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU arm.  /root/reference cannot be built without
+    cyarray/compyle/mako, so this times the oracle port with all
+    host threads on the same config; rank 0 only."""
+    if rank != 0:
+        return
+    from pysph_b200 import geometry as geo
+    from oracle import oracle as orc
+    dx = BASE_DX / world ** (1.0 / 3.0)
+    pas = geo.dam_break_3d_particles(dx=dx)
+    params = geo.dam_break_3d_params(dx)
+    ncores = os.cpu_count() or 1
+    threads = min(ncores, orc.load().orc_get_max_threads() if True else 1, 64)
+    ntot = sum(pa.get_number_of_particles() for pa in pas)
+    r = cpu_leg(pas, params, threads, budget_s=150.0,
+                max_steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    ms = 1e3 * r['seconds'] / r['steps']
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['pairs_per_s'],
+        'unit': 'pairs/s', 'n_gpus': world, 'steps': r['steps'],
+        'warmup': min(args.warmup, 1), 'ms_per_step': ms,
+        'steps_per_s': 1e3 / ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'dam_break_3d EPEC CubicSpline dx=%.6f' % dx,
+                   'particles': ntot, 'pairs_per_step': r['pairs_per_step']},
+        'cpu_baseline': {'value': r['pairs_per_s'], 'unit': 'pairs/s',
+                         'cores': threads, 'kind': 'port',
+                         'cpu': cpu_model(),
+                         'sample': '%d full EPEC steps of the same %d-particle '
+                                   'state (time budget 150 s)' % (r['steps'], ntot)},
+        'e2e': {'value': r['pairs_per_s'], 'unit': 'pairs/s',
+                'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def pinned_arrays(pas):
+    """Re-home every property of the ParticleArrays in pinned host memory."""
+    import torch
+    keep = []
+    for pa in pas:
+        for k, a in list(pa.properties.items()):
+            t = torch.from_numpy(a.copy()).pin_memory()
+            keep.append(t)
+            pa.properties[k] = t.numpy()
+    return keep
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=50)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--dx', type=float, default=None)
+    ap.add_argument('--e2e-steps', type=int, default=10)
+    ap.add_argument('--cpu-budget', type=float, default=20.0)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world == 1 and args.gpus > 1:
+        print('bench.py: --gpus %d needs torch.distributed.run with '
+              '--nproc-per-node %d' % (args.gpus, args.gpus), file=sys.stderr)
+        sys.exit(2)
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    dx = args.dx or BASE_DX / world ** (1.0 / 3.0)
+    params = geo.dam_break_3d_params(dx)
+    kernel = pb.CubicSpline(dim=3)
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    if world == 1:
+        pas = geo.dam_break_3d_particles(dx=dx)
+        host_copy = copy_arrays(pas) if not args.no_cpu else None
+        keep = pinned_arrays(pas)
+        solver = pb.make_wcsph_solver(pas, dict(params), kernel, device=local_rank)
+        pm = None
+    else:
+        from pysph_b200.parallel import make_slab_solver
+        solver, pm, pas = make_slab_solver(dx, params, kernel, rank, world,
+                                           device=local_rank)
+        host_copy = None
+    be = solver.backend
+    # run on torch's current stream so torch events / NCCL order with our kernels
+    stream = torch.cuda.current_stream()
+    be.ctx.call('b200sph_set_stream', stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_local = sum(be.sizes(i)[1] for i in range(len(pas)))
+
+    # ---- pair count of one step (untimed verification pass) -----------------
+    solver.initialise()
+    for _ in range(W):
+        solver.step()
+    solver.a_eval.count_pairs = True
+    pairs_step = 0
+    orig_compute = solver.a_eval.compute
+
+    def counting_compute(t, dt):
+        nonlocal pairs_step
+        orig_compute(t, dt)
+        pairs_step += solver.a_eval.last_pairs
+    solver.a_eval.compute = counting_compute
+    solver.step()
+    solver.a_eval.compute = orig_compute
+    solver.a_eval.count_pairs = False
+    pairs_local = pairs_step
+    if world > 1:
+        t = torch.tensor([pairs_local], dtype=torch.int64, device='cuda')
+        dist.all_reduce(t)
+        pairs_total = int(t.item())
+    else:
+        pairs_total = pairs_local
+
+    # ---- timed region: exactly K steps, device resident ----------------------
+    be.ctx.call('b200sph_reset_stats')
+    be.ctx.call('b200sph_set_profiling', 1)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(K):
+        solver.step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    st = be.stats()
+    be.ctx.call('b200sph_set_profiling', 0)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = pairs_total / (ms_step * 1e-3)
+
+    # ---- e2e: the same step through the host-buffer API ----------------------
+    e2e = None
+    if world == 1:
+        state = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm']
+        outp = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'p']
+        nall = sum(pa.get_number_of_particles() for pa in pas)
+        for _ in range(2):
+            be.push_all(state)
+            solver.step()
+            be.pull_all(outp)
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.e2e_steps):
+            be.push_all(state)      # H2D from pinned host ParticleArray buffers
+            solver.step()
+            be.pull_all(outp)       # D2H of the step's result
+        ev1.record(stream)
+        barrier()
+        ms_e2e = ev0.elapsed_time(ev1) / args.e2e_steps
+        e2e = {'value': pairs_total / (ms_e2e * 1e-3), 'unit': 'pairs/s',
+               'ms_per_step': ms_e2e, 'steps': args.e2e_steps,
+               'h2d_bytes_per_step': 8 * len(state) * nall,
+               'd2h_bytes_per_step': 8 * len(outp) * nall}
+    else:
+        e2e = {'value': None, 'unit': 'pairs/s', 'note': 'measured at N=1 only',
+               'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+    # ---- roofline of the dominant kernel (k_pair), from the timed region -----
+    peak, peak_src = peaks()
+    ms_pair = st['ms_pair'] / max(st['pair_launches'], 1)
+    pairs_per_launch = pairs_local / 2.0     # EPEC: two evaluations per step
+    achieved = pairs_per_launch * BYTES_PER_PAIR / (ms_pair * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'k_pair<CubicSpline,3>',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None,
+                'peak_source': peak_src,
+                'algorithmic_bytes_per_pair': BYTES_PER_PAIR,
+                'pairs_per_launch': pairs_per_launch,
+                'avg_launch_ms': ms_pair,
+                'share_of_step': st['ms_pair'] / K / ms_step,
+                'ms_nnps_per_step': st['ms_nnps'] / K,
+                'ms_other_per_step': st['ms_other'] / K}
+    prof = os.path.join(ROOT, 'profiles', 'pair_traffic.json')
+    if os.path.exists(prof):
+        try:
+            roofline['traffic'] = json.load(open(prof)).get('dram_bytes_per_launch')
+        except Exception:
+            pass
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (rank 0, N = 1): the oracle on a bounded sample --------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        r = cpu_leg(host_copy, params, 1, budget_s=args.cpu_budget, max_steps=1)
+        cpu = {'value': r['pairs_per_s'], 'unit': 'pairs/s', 'cores': 1,
+               'kind': 'port', 'cpu': cpu_model(),
+               'sample': '%d full EPEC step(s) of the same %d-particle state from '
+                         't=0, fp64 oracle, 1 thread (%.1f s)'
+                         % (r['steps'], sum(p.get_number_of_particles()
+                                            for p in host_copy), r['seconds'])}
+
+    ntot_all = n_local
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
+        'steps': K, 'warmup': W, 'ms_per_step': ms_step,
+        'steps_per_s': 1e3 / ms_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'dam_break_3d (BASELINE configs[%d]) EPEC '
+                               'CubicSpline dx=%.6f hdx=1.3' % (1 if world == 1 else 2, dx),
+                   'particles_rank0': ntot_all,
+                   'pairs_per_step': pairs_total,
+                   'parallelism': 'single GPU' if world == 1 else 'x-slabs x%d + NCCL halo' % world,
+                   'l2': 'no flush: per-step working set (~220 B/particle state '
+                         '+ 48 B/particle packed records, > 126 MB L2 at 1.2 M '
+                         'particles) and the state advances every step',
+                   'precision': 'fp32 pair arithmetic on cell-relative '
+                                'coordinates, fp64 integrated state'},
+        'clocks': clocks,
+        'e2e': e2e,
+        'gpu_launches': int(st['kernel_launches']),
+        'roofline': roofline,
+    }
+    if cpu:
+        line['cpu_baseline'] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

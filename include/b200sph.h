@@ -171,32 +171,35 @@ int b200sph_dt_factors(b200sph_ctx *ctx, double out[3]);
 /* ---- halo exchange helpers (replace ParallelManager.update,
  *      parallel_manager.pyx:512-632).  Buffers are DEVICE pointers owned by
  *      the caller (torch tensors handed to NCCL). ------------------------- */
-#define B200SPH_HALO_FIELDS 9 /* x y z u v w rho h m (fp64 each) */
-/* select the real particles of `arr` with lo <= x < hi, write their
- * B200SPH_HALO_FIELDS doubles field-major into dev_buf (capacity cap
- * particles); *count = number selected (may exceed cap -> error) */
+#define B200SPH_HALO_FIELDS 9     /* x y z u v w rho h m (fp64 each)          */
+#define B200SPH_MIGRATE_FIELDS 17 /* the 16 fp64 state props (x..m, x0..rho0) + gid */
+/* select the real particles of `arr` with lo <= x < hi and write their
+ * B200SPH_HALO_FIELDS doubles field-major and TIGHT (field f of particle k at
+ * dev_buf[f * count + k]); *count = number selected; error if count > cap */
 int b200sph_halo_pack(b200sph_ctx *ctx, int arr, double lo, double hi,
                       double *dev_buf, int64_t cap, int64_t *count);
-/* append n particles from dev_buf (same layout, field stride `stride`
- * particles) after the current particles of `arr` as ghosts (tag Remote);
- * as_real != 0 appends them as real particles instead (migration) */
+/* append n particles from dev_buf (field f of particle k at
+ * dev_buf[f * stride + k]) after the current particles of `arr`.
+ * nfields = B200SPH_HALO_FIELDS: ghosts (tag Remote), other props zeroed;
+ * nfields = B200SPH_MIGRATE_FIELDS with as_real != 0: real particles arriving
+ * by migration (the array must hold no ghosts at that moment) */
 int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf,
-                        int64_t stride, int64_t n, int as_real);
+                        int64_t stride, int64_t n, int nfields, int as_real);
 /* drop every ghost particle of `arr` (n <- n_real)
  * parallel_manager.pyx:519 remove_remote_particles */
 int b200sph_drop_ghosts(b200sph_ctx *ctx, int arr);
 /* remove the real particles of `arr` with x outside [lo, hi) after packing
- * their full state (B200SPH_MIGRATE_FIELDS doubles, field-major, stride cap)
- * into dev_buf; counts: count[0] = moved below lo, count[1] = moved >= hi;
- * the below-lo block is written first */
-#define B200SPH_MIGRATE_FIELDS 9
+ * their B200SPH_MIGRATE_FIELDS doubles into dev_buf: the particles that left
+ * below lo first (field-major, stride count[0]) then those at x >= hi
+ * (field-major, stride count[1], starting at dev_buf + 17 * count[0]) */
 int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi,
                         double *dev_buf, int64_t cap, int64_t count[2]);
 
 /* ---- bookkeeping -------------------------------------------------------- */
 int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out);
 int b200sph_reset_stats(b200sph_ctx *ctx);
-/* enable (1) / disable (0) per-phase CUDA-event timing (adds syncs) */
+/* enable (1) / disable (0) per-phase CUDA-event timing: event pairs are
+ * recorded on the stream (no sync) and resolved by b200sph_get_stats */
 int b200sph_set_profiling(b200sph_ctx *ctx, int on);
 
 #ifdef __cplusplus

@@ -29,6 +29,7 @@ EQ_XSPH = 8
 EQ_MONAGHAN_AV = 16
 
 HALO_FIELDS = 9
+MIGRATE_FIELDS = 17
 HALO_FIELD_NAMES = ('x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm')
 
 
@@ -92,7 +93,7 @@ SIGNATURES = {
     'b200sph_halo_pack': (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_double,
                                     C.c_void_p, _i64, C.POINTER(_i64)]),
     'b200sph_halo_append': (C.c_int, [_ctx_p, C.c_int, C.c_void_p, _i64, _i64,
-                                      C.c_int]),
+                                      C.c_int, C.c_int]),
     'b200sph_drop_ghosts': (C.c_int, [_ctx_p, C.c_int]),
     'b200sph_migrate_out': (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_double,
                                       C.c_void_p, _i64, C.POINTER(_i64)]),

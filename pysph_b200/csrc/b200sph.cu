@@ -48,6 +48,11 @@ struct ArrayInfo {
     int64_t off = 0, cap = 0, n = 0, n_real = 0;
 };
 
+struct PendingEvent {
+    cudaEvent_t e0, e1;
+    int slot;  // 0 nnps, 1 pair, 2 other
+};
+
 struct b200sph_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -102,9 +107,11 @@ struct b200sph_ctx {
     // stats
     b200sph_stats stats;
     bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<PendingEvent> pending;
+    std::vector<cudaEvent_t> ev_pool;
 };
 
+struct PhaseTimer;
 static int set_err(b200sph_ctx *c, const char *fmt, ...)
 {
     char buf[512];
@@ -1053,24 +1060,36 @@ static int device_scan(b200sph_ctx *ctx, const uint32_t *in, uint32_t *out, int6
     return 0;
 }
 
+// Per-phase device timing without host syncs: event pairs are recorded on the
+// context's stream and only resolved (cudaEventElapsedTime) in get_stats.
 struct PhaseTimer {
     b200sph_ctx *ctx;
-    double *slot;
-    PhaseTimer(b200sph_ctx *c, double *s) : ctx(c), slot(s)
-    {
-        if (ctx->profiling) cudaEventRecord(ctx->ev0, ctx->stream);
-    }
-    ~PhaseTimer()
-    {
-        if (ctx->profiling) {
-            cudaEventRecord(ctx->ev1, ctx->stream);
-            cudaEventSynchronize(ctx->ev1);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-            *slot += ms;
+    int slot;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    PhaseTimer(b200sph_ctx *c, int s);
+    ~PhaseTimer();
+};
+
+
+PhaseTimer::PhaseTimer(b200sph_ctx *c, int s) : ctx(c), slot(s)
+{
+    if (!ctx->profiling) return;
+    for (cudaEvent_t *e : {&e0, &e1}) {
+        if (!ctx->ev_pool.empty()) {
+            *e = ctx->ev_pool.back();
+            ctx->ev_pool.pop_back();
+        } else {
+            cudaEventCreate(e);
         }
     }
-};
+    cudaEventRecord(e0, ctx->stream);
+}
+PhaseTimer::~PhaseTimer()
+{
+    if (!e0) return;
+    cudaEventRecord(e1, ctx->stream);
+    ctx->pending.push_back({e0, e1, slot});
+}
 
 template <int K> static void launch_pair_dim(int dim, unsigned nb, cudaStream_t st, const PairArgs &pa)
 {
@@ -1125,8 +1144,6 @@ int b200sph_create(int device, b200sph_ctx **out)
     CU(cudaMallocHost((void **)&ctx->red_host, 16 * sizeof(long long)));
     CU(cudaMalloc((void **)&ctx->counter, 8 * sizeof(unsigned long long)));
     CU(cudaMallocHost((void **)&ctx->counter_host, 8 * sizeof(unsigned long long)));
-    CU(cudaEventCreate(&ctx->ev0));
-    CU(cudaEventCreate(&ctx->ev1));
     return 0;
 }
 
@@ -1145,7 +1162,8 @@ int b200sph_destroy(b200sph_ctx *ctx)
     cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->counter);
     cudaFreeHost(ctx->counter_host); cudaFree(ctx->stage_buf); cudaFree(ctx->flag_a);
     cudaFree(ctx->flag_b);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    for (auto &pe : ctx->pending) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -1370,7 +1388,7 @@ int b200sph_update_domain(b200sph_ctx *ctx)
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
-    PhaseTimer pt(ctx, &ctx->stats.ms_other);
+    PhaseTimer pt(ctx, 2);
     if ((rc = run_minmax(ctx, 0, 1))) return rc;
     // nnps_base.pyx:942-978
     double hmin = o2d(ctx->red_host[6]), hmax = o2d(ctx->red_host[7]);
@@ -1392,7 +1410,7 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     int rc = ensure_pool(ctx);
     if (rc) return rc;
     if (!ctx->domain_valid && (rc = b200sph_update_domain(ctx))) return rc;
-    PhaseTimer pt(ctx, &ctx->stats.ms_nnps);
+    PhaseTimer pt(ctx, 0);
 
     int64_t ntot = 0;
     for (int a = 0; a < ctx->narr; a++) ntot += ctx->arr[a].n;
@@ -1553,7 +1571,7 @@ int b200sph_eos(b200sph_ctx *ctx, int arr, int hg, double rho0, double c0, doubl
     if (rc) return rc;
     int64_t lo, hi;
     if ((rc = arr_range(ctx, arr, real_only, &lo, &hi))) return rc;
-    PhaseTimer pt(ctx, &ctx->stats.ms_other);
+    PhaseTimer pt(ctx, 2);
     if (hi > lo) {
         k_eos<<<(unsigned)cdiv(hi - lo, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_RHO], ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64],
                                                                     ctx->ptype, lo, hi, hg, rho0, c0, gamma, p0);
@@ -1570,7 +1588,7 @@ int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim, int real_o
     if (rc) return rc;
     int64_t lo, hi;
     if ((rc = arr_range(ctx, arr, real_only, &lo, &hi))) return rc;
-    PhaseTimer pt(ctx, &ctx->stats.ms_other);
+    PhaseTimer pt(ctx, 2);
     if (hi > lo) {
         k_ferrari<<<(unsigned)cdiv(hi - lo, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_H], ctx->f64[B200SPH_M], ctx->f64[B200SPH_RHO], lo, hi, hdx, 1.0 / dim);
         LAUNCH_CHECK();
@@ -1586,7 +1604,7 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     if (rc) return rc;
     if (!ctx->grid_valid) return set_err(ctx, "pair_pass: the NNPS is stale (particles were pushed/resized); call nnps_update first");
     if (!ctx->state_packed && (rc = pack_state(ctx))) return rc;
-    PhaseTimer pt(ctx, &ctx->stats.ms_pair);
+    PhaseTimer pt(ctx, 1);
 
     PairArgs pa;
     memset(&pa, 0, sizeof(pa));
@@ -1652,7 +1670,7 @@ int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt)
     if (rc) return rc;
     if (arr >= ctx->narr) return set_err(ctx, "stage: bad array %d", arr);
     if (which < 0 || which > 2) return set_err(ctx, "stage: which must be 0 (initialize), 1 (stage1) or 2 (stage2)");
-    PhaseTimer pt(ctx, &ctx->stats.ms_other);
+    PhaseTimer pt(ctx, 2);
     StageArgs sa;
     sa.x = ctx->f64[B200SPH_X]; sa.y = ctx->f64[B200SPH_Y]; sa.z = ctx->f64[B200SPH_Z];
     sa.u = ctx->f64[B200SPH_U]; sa.v = ctx->f64[B200SPH_V]; sa.w = ctx->f64[B200SPH_W]; sa.rho = ctx->f64[B200SPH_RHO];
@@ -1682,7 +1700,7 @@ int b200sph_dt_factors(b200sph_ctx *ctx, double out[3])
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
-    PhaseTimer pt(ctx, &ctx->stats.ms_other);
+    PhaseTimer pt(ctx, 2);
     k_red_init<<<1, 32, 0, ctx->stream>>>(ctx->red);
     LAUNCH_CHECK();
     if (ctx->pool_end > 0) {
@@ -1722,32 +1740,41 @@ int b200sph_halo_pack(b200sph_ctx *ctx, int arr, double lo, double hi, double *d
     *count = tot;
     if ((int64_t)tot > cap) return set_err(ctx, "halo_pack: %u particles selected but the buffer holds %lld", tot, (long long)cap);
     if (tot == 0) return 0;
-    for (int f = 0; f < 9; f++) {
-        k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[halo_fields[f]], off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)f * cap);
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) {
+        k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[halo_fields[f]], off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)f * tot);
         LAUNCH_CHECK();
     }
     return 0;
 }
 
-int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf, int64_t stride, int64_t n, int as_real)
+int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf, int64_t stride, int64_t n, int nfields, int as_real)
 {
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "halo_append: bad array %d", arr);
+    if (nfields != B200SPH_HALO_FIELDS && nfields != B200SPH_MIGRATE_FIELDS) return set_err(ctx, "halo_append: nfields must be %d or %d", B200SPH_HALO_FIELDS, B200SPH_MIGRATE_FIELDS);
     ArrayInfo &ai = ctx->arr[arr];
     if (as_real && ai.n != ai.n_real) return set_err(ctx, "halo_append(as_real): drop the ghosts of '%s' first (real particles must precede ghosts)", ai.name.c_str());
     if (n <= 0) return 0;
     if ((rc = ensure_capacity(ctx, arr, ai.n + n))) return rc;
     const int64_t o = ai.off + ai.n;
-    for (int f = 0; f < 9; f++)
-        CU(cudaMemcpyAsync(ctx->f64[halo_fields[f]] + o, dev_buf + (size_t)f * stride, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
-    // every other property of the appended particles starts at zero; tag = Remote (1) for ghosts
-    for (int k = B200SPH_X0; k < N_F64; k++) CU(cudaMemsetAsync(ctx->f64[k] + o, 0, 8 * (size_t)n, ctx->stream));
+    const unsigned nb = (unsigned)cdiv(n, 256);
+    if (nfields == B200SPH_HALO_FIELDS) {
+        for (int f = 0; f < 9; f++)
+            CU(cudaMemcpyAsync(ctx->f64[halo_fields[f]] + o, dev_buf + (size_t)f * stride, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        for (int k = B200SPH_X0; k < N_F64; k++) CU(cudaMemsetAsync(ctx->f64[k] + o, 0, 8 * (size_t)n, ctx->stream));
+        k_fill_u32<<<nb, 256, 0, ctx->stream>>>(ctx->u32[0] + o, n, 0xFFFFFFFFu);
+        LAUNCH_CHECK();
+    } else {
+        for (int k = 0; k < N_F64; k++)
+            CU(cudaMemcpyAsync(ctx->f64[k] + o, dev_buf + (size_t)k * stride, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        k_f64_to_u32<<<nb, 256, 0, ctx->stream>>>(dev_buf + (size_t)N_F64 * stride, ctx->u32[0] + o, n);
+        LAUNCH_CHECK();
+    }
+    // derived fields of the appended particles start at zero; tag = Remote (1) for ghosts
     for (int k = 0; k < N_F32; k++) CU(cudaMemsetAsync(ctx->f32[k] + o, 0, 4 * (size_t)n, ctx->stream));
-    k_fill_u32<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->u32[0] + o, n, 0xFFFFFFFFu);
-    LAUNCH_CHECK();
-    k_fill_u32<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->u32[1] + o, n, as_real ? 0u : 1u);
+    k_fill_u32<<<nb, 256, 0, ctx->stream>>>(ctx->u32[1] + o, n, as_real ? 0u : 1u);
     LAUNCH_CHECK();
     CU(cudaMemsetAsync(ctx->u32[2] + o, 0, 4 * (size_t)n, ctx->stream));
     ai.n += n;
@@ -1783,7 +1810,7 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
     count[0] = count[1] = 0;
     if (n == 0) return 0;
     const unsigned nb = (unsigned)cdiv(n + 1, 256);
-    int64_t base = 0;
+    int64_t base = 0;  // doubles written so far
     for (int side = 0; side < 2; side++) {
         k_flag_range<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], off, n, lo, hi, side == 0 ? 1 : 2, ctx->flag_a);
         LAUNCH_CHECK();
@@ -1792,12 +1819,16 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
         CU(cudaMemcpyAsync(&tot, ctx->flag_b + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         count[side] = tot;
-        if (base + (int64_t)tot > cap) return set_err(ctx, "migrate_out: buffer too small");
-        for (int f = 0; f < 9 && tot; f++) {
-            k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[halo_fields[f]], off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)f * cap + base);
+        if (base + (int64_t)tot * B200SPH_MIGRATE_FIELDS > cap * B200SPH_MIGRATE_FIELDS) return set_err(ctx, "migrate_out: buffer too small");
+        if (tot) {
+            for (int k = 0; k < N_F64; k++) {
+                k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[k], off, n, ctx->flag_a, ctx->flag_b, dev_buf, base + (long long)k * tot);
+                LAUNCH_CHECK();
+            }
+            k_gather_u32_as_f64<<<nb, 256, 0, ctx->stream>>>(ctx->u32[0], off, n, ctx->flag_a, ctx->flag_b, dev_buf, base + (long long)N_F64 * tot);
             LAUNCH_CHECK();
         }
-        base += tot;
+        base += (int64_t)tot * B200SPH_MIGRATE_FIELDS;
     }
     if (count[0] + count[1] == 0) return 0;
     // stable compaction of the keepers, property by property, through the staging buffer
@@ -1806,15 +1837,16 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
     if ((rc = device_scan(ctx, ctx->flag_a, ctx->flag_b, n + 1))) return rc;
     const int64_t keep = n - count[0] - count[1];
     if ((rc = ensure_stage(ctx, n))) return rc;
-    for (int k = 0; k < N_F64; k++) {
+    // x is the selection key: compact it last
+    for (int k = N_F64 - 1; k >= 0; k--) {
         k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[k], off, n, ctx->flag_a, ctx->flag_b, ctx->stage_buf, 0);
         LAUNCH_CHECK();
-        CU(cudaMemcpyAsync(ctx->f64[k] + off, ctx->stage_buf, 8 * (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (keep) CU(cudaMemcpyAsync(ctx->f64[k] + off, ctx->stage_buf, 8 * (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     for (int k = 0; k < N_U32; k++) {
         k_gather_u32<<<nb, 256, 0, ctx->stream>>>(ctx->u32[k], off, n, ctx->flag_a, ctx->flag_b, (uint32_t *)ctx->stage_buf);
         LAUNCH_CHECK();
-        CU(cudaMemcpyAsync(ctx->u32[k] + off, ctx->stage_buf, 4 * (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (keep) CU(cudaMemcpyAsync(ctx->u32[k] + off, ctx->stage_buf, 4 * (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     ai.n = ai.n_real = keep;
     ctx->ptype_dirty = true;
@@ -1826,11 +1858,27 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
 
 int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out)
 {
+    if (!ctx->pending.empty()) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (auto &pe : ctx->pending) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pe.e0, pe.e1);
+            if (pe.slot == 0) ctx->stats.ms_nnps += ms;
+            else if (pe.slot == 1) ctx->stats.ms_pair += ms;
+            else ctx->stats.ms_other += ms;
+            ctx->ev_pool.push_back(pe.e0);
+            ctx->ev_pool.push_back(pe.e1);
+        }
+        ctx->pending.clear();
+    }
     *out = ctx->stats;
     return 0;
 }
 int b200sph_reset_stats(b200sph_ctx *ctx)
 {
+    b200sph_stats tmp;
+    b200sph_get_stats(ctx, &tmp);  // drain pending events
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     return 0;
 }

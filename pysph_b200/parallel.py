@@ -1,0 +1,300 @@
+"""Static x-slab decomposition + halo exchange over torch.distributed.
+
+Replaces the reference's Zoltan/MPI ``ParallelManager``
+(pysph/parallel/parallel_manager.pyx:343-1440) for the one-box multi-GPU case:
+
+* partition: 1-D slabs along x (the dam-break tank is 3.22 m long), cut planes
+  at lattice-column boundaries chosen so that every rank gets the same weighted
+  particle count (fluid 1, solids ``solid_weight`` -- the reference weights
+  solids 0.1, scheme.py:523-527);
+* ``update()`` (called from ``Integrator.compute_accelerations`` exactly like
+  parallel_manager.pyx:512-530): drop last evaluation's Remote particles,
+  migrate real particles that left the slab (all 16 fp64 state properties +
+  gid, so that a mid-step migration keeps x0..rho0), then import the
+  neighbours' particles within one kernel support of the cut planes as ghosts
+  (tag Remote, appended after the real particles);
+* ``update_time_steps(dt)``: all-reduce MIN (parallel_manager.pyx:454-465).
+
+Device work (select / pack / append / compact) is done by the C-ABI library
+through ``DeviceHaloOps``; the transport is ``torch.distributed`` point-to-point
+(NCCL over NVLink on GPUs, gloo in the CPU tests) -- plumbing, not product.
+Messages are latency bound (a 10 M-particle fluid cross-section is ~4 MB), so
+each exchange is one count message + one payload message per neighbour.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+HALO_FIELDS = _lib.HALO_FIELDS
+MIGRATE_FIELDS = _lib.MIGRATE_FIELDS
+
+
+# ---------------------------------------------------------------------------
+# partition
+# ---------------------------------------------------------------------------
+def dam_break_column_weights(dx, hdx=1.3, nboundary_layers=1, solid_weight=0.3):
+    """Weighted particle count of every lattice x-column of the 3D dam break
+    (same lattice as geometry.dam_break_3d_particles) without building it."""
+    L, W, H = 3.22, 1.0, 1.0
+    fl, fh = 1.228, 0.55
+    ocx, ocy, ol, oh, ow = 2.5, 0.0, 0.16, 0.161, 0.4
+    ghost = nboundary_layers * dx
+    eps = 0.1 * dx
+    xs = np.mgrid[0.0 - ghost:L + ghost + eps:dx]
+    ys = np.mgrid[-0.5 * W - ghost:0.5 * W + ghost + eps:dx]
+    zs = np.mgrid[0.0 - ghost:H + ghost + eps:dx]
+    Y, Z = np.meshgrid(ys, zs, indexing='ij')
+    cw2 = 0.5 * W
+    n_fluid_yz = np.count_nonzero((-cw2 < Y) & (Y < cw2) & (0 < Z) & (Z <= fh))
+    n_obst_yz = np.count_nonzero((ocy - 0.5 * ow <= Y) & (Y <= ocy + 0.5 * ow) &
+                                 (0 < Z) & (Z <= oh))
+    n_wall_yz = np.count_nonzero((Y <= -cw2) | (Y >= cw2) | (Z <= 0))
+    n_yz = Y.size
+    w = np.zeros(xs.size)
+    is_fluid = (0 < xs) & (xs <= fl)
+    is_obst = (ocx - 0.5 * ol <= xs) & (xs <= ocx + 0.5 * ol)
+    is_endwall = (xs >= L) | (xs <= 0)
+    w += is_fluid * n_fluid_yz
+    w += solid_weight * is_obst * n_obst_yz
+    w += solid_weight * np.where(is_endwall, n_yz, n_wall_yz)
+    return xs, w
+
+
+def balanced_cuts(xs, weights, nparts, dx):
+    """Cut planes (nparts + 1 values, -inf / +inf at the ends) at column
+    boundaries such that the weighted counts per part are as equal as possible."""
+    c = np.cumsum(weights)
+    total = c[-1]
+    cuts = [-np.inf]
+    for k in range(1, nparts):
+        i = int(np.searchsorted(c, total * k / nparts))
+        i = min(max(i, 1), xs.size - 1)
+        cuts.append(float(xs[i] - 0.5 * dx))
+    cuts.append(np.inf)
+    # strictly increasing
+    for k in range(1, nparts):
+        if not cuts[k] > cuts[k - 1]:
+            raise ValueError('slab decomposition: too many parts for this lattice')
+    return cuts
+
+
+# ---------------------------------------------------------------------------
+# device side of the exchange (C-ABI)
+# ---------------------------------------------------------------------------
+class DeviceHaloOps(object):
+    """select/pack/append on the device; buffers are torch CUDA tensors."""
+
+    def __init__(self, backend, device):
+        import torch
+        self.torch = torch
+        self.backend = backend
+        self.ctx = backend.ctx
+        self.narr = len(backend.names)
+        self.device = torch.device('cuda', device)
+
+    def new_buffer(self, ndoubles):
+        return self.torch.empty(max(int(ndoubles), 1), dtype=self.torch.float64,
+                                device=self.device)
+
+    def new_counts(self, values=None, n=0):
+        t = self.torch
+        if values is not None:
+            return t.tensor(values, dtype=t.int64, device=self.device)
+        return t.zeros(n, dtype=t.int64, device=self.device)
+
+    def n_real(self, arr):
+        return self.backend.sizes(arr)[1]
+
+    def drop_ghosts(self, arr):
+        self.ctx.call('b200sph_drop_ghosts', arr)
+
+    def pack(self, arr, lo, hi, buf, offset):
+        """pack into buf[offset:]; returns the particle count."""
+        cnt = C.c_int64()
+        cap = (buf.numel() - offset) // HALO_FIELDS
+        self.ctx.call('b200sph_halo_pack', arr, float(lo), float(hi),
+                      buf.data_ptr() + 8 * offset, cap, C.byref(cnt))
+        return cnt.value
+
+    def append(self, arr, buf, offset, n, nfields, as_real):
+        if n:
+            self.ctx.call('b200sph_halo_append', arr,
+                          buf.data_ptr() + 8 * offset, n, n, nfields,
+                          1 if as_real else 0)
+
+    def migrate_out(self, arr, lo, hi, buf, offset):
+        cnt = (C.c_int64 * 2)()
+        cap = (buf.numel() - offset) // MIGRATE_FIELDS
+        self.ctx.call('b200sph_migrate_out', arr, float(lo), float(hi),
+                      buf.data_ptr() + 8 * offset, cap, cnt)
+        return cnt[0], cnt[1]
+
+
+# ---------------------------------------------------------------------------
+# the parallel manager
+# ---------------------------------------------------------------------------
+class SlabParallelManager(object):
+    def __init__(self, ops, rank, world, cuts, halo_width, dist=None,
+                 migrate=True):
+        """ops: DeviceHaloOps-like object.  cuts: world+1 cut planes.
+        halo_width: ghost_layers * cell_size = radius_scale * hmax
+        (application.py:642, nnps_base.pyx:942-978)."""
+        if dist is None:
+            import torch.distributed as dist
+        self.dist = dist
+        self.ops = ops
+        self.rank, self.world = rank, world
+        self.lo, self.hi = cuts[rank], cuts[rank + 1]
+        self.halo = float(halo_width)
+        self.left = rank - 1 if rank > 0 else None
+        self.right = rank + 1 if rank < world - 1 else None
+        self.migrate = migrate
+        self.narr = ops.narr
+        self.n_exchanges = 0
+        self.bytes_sent = 0
+        self._send = {}
+        self._recv = {}
+
+    # -- transport ------------------------------------------------------------
+    def _exchange(self, send_counts, send_bufs, nfields):
+        """send_counts[nb] = list of per-array counts, send_bufs[nb] = tensor
+        holding the per-array blocks back to back.  Returns the same for the
+        received side."""
+        dist = self.dist
+        nbs = [nb for nb in (self.left, self.right) if nb is not None]
+        if not nbs:
+            return {}, {}
+        # 1. counts
+        ops_list = []
+        cnt_send = {}
+        cnt_recv = {}
+        for nb in nbs:
+            cnt_send[nb] = self.ops.new_counts(send_counts[nb])
+            cnt_recv[nb] = self.ops.new_counts(n=self.narr)
+            ops_list.append(dist.P2POp(dist.isend, cnt_send[nb], nb))
+            ops_list.append(dist.P2POp(dist.irecv, cnt_recv[nb], nb))
+        for w in dist.batch_isend_irecv(ops_list):
+            w.wait()
+        recv_counts = dict((nb, [int(v) for v in cnt_recv[nb].tolist()])
+                           for nb in nbs)
+        # 2. payload
+        ops_list = []
+        recv_bufs = {}
+        for nb in nbs:
+            ns = sum(send_counts[nb]) * nfields
+            nr = sum(recv_counts[nb]) * nfields
+            if nr:
+                recv_bufs[nb] = self.ops.new_buffer(nr)
+                ops_list.append(dist.P2POp(dist.irecv, recv_bufs[nb][:nr], nb))
+            if ns:
+                ops_list.append(dist.P2POp(dist.isend, send_bufs[nb][:ns], nb))
+                self.bytes_sent += 8 * ns
+        if ops_list:
+            for w in dist.batch_isend_irecv(ops_list):
+                w.wait()
+        self.n_exchanges += 1
+        return recv_counts, recv_bufs
+
+    def _capacity(self, nfields):
+        n = sum(self.ops.n_real(a) for a in range(self.narr))
+        return max(n, 1) * nfields
+
+    # -- ParallelManager protocol ----------------------------------------------
+    def update(self):
+        ops = self.ops
+        for a in range(self.narr):
+            ops.drop_ghosts(a)                       # parallel_manager.pyx:519
+        if self.migrate:
+            self._migrate()
+        self._import_ghosts()
+
+    def _migrate(self):
+        ops = self.ops
+        cap = self._capacity(MIGRATE_FIELDS)
+        buf = ops.new_buffer(cap)
+        send_counts = dict((nb, [0] * self.narr) for nb in (self.left, self.right)
+                           if nb is not None)
+        blocks = {self.left: [], self.right: []}
+        off = 0
+        for a in range(self.narr):
+            if ops.n_real(a) == 0:
+                continue
+            n_lo, n_hi = ops.migrate_out(a, self.lo, self.hi, buf, off)
+            for nb, n in ((self.left, n_lo), (self.right, n_hi)):
+                if n:
+                    if nb is None:
+                        raise RuntimeError(
+                            'slab decomposition: %d particles left the global '
+                            'domain through an outer cut plane' % n)
+                    send_counts[nb][a] = n
+                    blocks[nb].append((off, n * MIGRATE_FIELDS))
+                off += n * MIGRATE_FIELDS
+        send_bufs = {}
+        for nb in send_counts:
+            tot = sum(n for _, n in blocks[nb])
+            sb = ops.new_buffer(tot)
+            o = 0
+            for start, n in blocks[nb]:
+                sb[o:o + n] = buf[start:start + n]
+                o += n
+            send_bufs[nb] = sb
+        recv_counts, recv_bufs = self._exchange(send_counts, send_bufs,
+                                                MIGRATE_FIELDS)
+        for nb in sorted(recv_counts):
+            o = 0
+            for a, n in enumerate(recv_counts[nb]):
+                ops.append(a, recv_bufs.get(nb), o, n, MIGRATE_FIELDS, True)
+                o += n * MIGRATE_FIELDS
+
+    def _import_ghosts(self):
+        ops = self.ops
+        send_counts, send_bufs = {}, {}
+        for nb, (lo, hi) in ((self.left, (self.lo, self.lo + self.halo)),
+                             (self.right, (self.hi - self.halo, self.hi))):
+            if nb is None:
+                continue
+            buf = ops.new_buffer(self._capacity(HALO_FIELDS))
+            counts, off = [], 0
+            for a in range(self.narr):
+                n = ops.pack(a, lo, hi, buf, off) if ops.n_real(a) else 0
+                counts.append(n)
+                off += n * HALO_FIELDS
+            send_counts[nb], send_bufs[nb] = counts, buf
+        recv_counts, recv_bufs = self._exchange(send_counts, send_bufs,
+                                                HALO_FIELDS)
+        # deterministic order: left neighbour's ghosts first
+        for nb in sorted(recv_counts):
+            o = 0
+            for a, n in enumerate(recv_counts[nb]):
+                ops.append(a, recv_bufs.get(nb), o, n, HALO_FIELDS, False)
+                o += n * HALO_FIELDS
+
+    def update_time_steps(self, dt):
+        t = self.ops.new_buffer(1)
+        t[0] = dt
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return float(t[0].item())
+
+
+# ---------------------------------------------------------------------------
+def make_slab_solver(dx, params, kernel, rank, world, device=0,
+                     solid_weight=0.3, **solver_kw):
+    """Build this rank's slab of the 3D dam break and a ready solver."""
+    import pysph_b200 as pb
+    from . import geometry as geo
+    xs, w = dam_break_column_weights(dx, solid_weight=solid_weight)
+    cuts = balanced_cuts(xs, w, world, dx)
+    pas = geo.dam_break_3d_particles(dx=dx, xrange=(cuts[rank], cuts[rank + 1]))
+    # global ids so that results can be matched across decompositions
+    halo = kernel.radius_scale * params['hdx'] * dx
+    n_real = [pa.get_number_of_particles() for pa in pas]
+    extra = int(0.35 * max(n_real)) + 4096
+    solver = pb.make_wcsph_solver(pas, dict(params), kernel, device=device,
+                                  capacity_factor=1.05, extra_capacity=extra,
+                                  **solver_kw)
+    ops = DeviceHaloOps(solver.backend, device)
+    pm = SlabParallelManager(ops, rank, world, cuts, halo)
+    solver.set_parallel_manager(pm)
+    return solver, pm, pas

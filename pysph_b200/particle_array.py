@@ -41,7 +41,9 @@ class ParticleArray(object):
         self.backend = 'b200'
         n = 0
         for v in props.values():
-            n = max(n, np.asarray(v).size)
+            v = np.asarray(v)
+            if v.ndim > 0:          # scalars broadcast, they do not size
+                n = max(n, v.size)
         self._n = n
         self.num_real_particles = n
         for k, v in props.items():
@@ -59,7 +61,7 @@ class ParticleArray(object):
         arr = np.full(self._n * stride, default, dtype=dtype)
         if data is not None:
             d = np.asarray(data)
-            if d.size == 1:
+            if d.ndim == 0 or (d.size == 1 and arr.size != 1):
                 arr[:] = d.ravel()[0]
             else:
                 if d.size != arr.size:

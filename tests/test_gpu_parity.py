@@ -1,0 +1,392 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the fp64 oracle
+and the golden fixtures generated from the reference.
+
+Tolerances (fp32 pair arithmetic on cell-relative coordinates, fp64 state):
+every acceleration-like field f is compared as max|f_gpu - f_ref| <= tol *
+max|f_ref| with tol = 2e-5 for single evaluations (stated per test); neighbour
+SETS must be identical except for fp32 knife-edge pairs, which are counted.
+"""
+import numpy as np
+import pytest
+
+from helpers import (ACC_FIELDS, arrays_from_dict, copy_arrays, load_golden,
+                     rel_err, wcsph_params_from_case)
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_EVAL = 2e-5
+
+
+def make_solver(pas, params, kernel_name, **kw):
+    import pysph_b200 as pb
+    kernel = getattr(pb, kernel_name)(dim=params['dim'])
+    p = dict((k, v) for k, v in params.items())
+    return pb.make_wcsph_solver(pas, p, kernel, **kw)
+
+
+def scheme_params(p):
+    keep = ('fluids', 'solids', 'dim', 'rho0', 'c0', 'h0', 'hdx', 'gamma', 'gx',
+            'gy', 'gz', 'alpha', 'beta', 'tensile_correction', 'hg_correction',
+            'update_h', 'summation_density', 'dt0', 'n_damp', 'cfl',
+            'integrator')
+    return dict((k, v) for k, v in p.items() if k in keep)
+
+
+# ---------------------------------------------------------------------------
+def test_kernels_via_two_particle_density(gpu_device):
+    """Every kernel/dim: W from SummationDensity on 2 particles vs the values of
+    the reference's compiled kernels (tests/golden/kernels.json)."""
+    import pysph_b200 as pb
+    for entry in load_golden('kernels.json'):
+        name, dim = entry['kernel'], entry['dim']
+        kernel = getattr(pb, name)(dim=dim)
+        for c in entry['cases'][::3]:
+            if c['rij'] >= kernel.radius_scale * c['h'] or c['rij'] < 1e-9:
+                continue
+            x = np.array([c['xij'][0], 0.0])
+            y = np.array([c['xij'][1], 0.0])
+            z = np.array([c['xij'][2], 0.0])
+            pa = pb.get_particle_array_wcsph(name='f', x=x, y=y, z=z,
+                                             h=np.full(2, c['h']),
+                                             m=np.array([0.0, 1.0]))
+            ae = pb.B200AccelerationEval(
+                [pa], [pb.SummationDensity(dest='f', sources=['f'])], kernel)
+            nn = pb.B200NNPS(dim, [pa], backend=ae.backend, kernel=kernel)
+            ae.set_nnps(nn)
+            ae.compute(0.0, 0.0)
+            ae.backend.pull_all(['rho'])
+            scale = entry['fac'] / c['h'] ** dim
+            # fp32 arithmetic: relative to the kernel's own magnitude
+            assert abs(pa.rho[0] - c['w']) <= 3e-6 * max(scale, abs(c['w'])), \
+                (name, dim, c)
+
+
+def test_density_1d_fixture(gpu_device):
+    # pysph/sph/tests/test_acceleration_eval.py:294-303,341,737-741
+    import pysph_b200 as pb
+    g = load_golden('density_1d.json')
+    pa = pb.get_particle_array_wcsph(name='fluid', x=np.array(g['x']),
+                                     h=np.array(g['h']), m=np.array(g['m']))
+    kernel = pb.CubicSpline(dim=1)
+    ae = pb.B200AccelerationEval(
+        [pa], [pb.SummationDensity(dest='fluid', sources=['fluid'])], kernel)
+    nn = pb.B200NNPS(1, [pa], backend=ae.backend, kernel=kernel)
+    ae.set_nnps(nn)
+    ae.count_pairs = True
+    ae.compute(0.0, 0.1)
+    ae.backend.pull_all(['rho'])
+    assert [len(nn.get_nearest_particles(0, 0, i)) for i in range(10)] == \
+        g['nbr_counts']
+    assert ae.last_pairs == sum(g['nbr_counts'])
+    assert np.allclose(pa.rho, g['rho'], rtol=2e-6)
+    # the reference's own fp32 GPU tolerance for this fixture
+    assert np.allclose(pa.rho, [7.357] + [9.0] * 8 + [7.357], atol=1e-2)
+
+
+@pytest.mark.parametrize('idx', range(6))
+def test_wcsph_evaluation_vs_reference_bodies(gpu_device, idx):
+    """One AccelerationEval.compute on the golden 3-array cases."""
+    case = load_golden('wcsph_cases.json')[idx]
+    pas = arrays_from_dict(case['inputs'])
+    s = make_solver(pas, scheme_params(wcsph_params_from_case(case)),
+                    case['kernel'])
+    s.a_eval.count_pairs = True
+    s.a_eval.compute(0.0, 0.0)
+    s.pull()
+    # pair count == oracle pair count (neighbour sets are identical)
+    opas = arrays_from_dict(case['inputs'])
+    osol = orc.WCSPHOracleSolver(opas, wcsph_params_from_case(case),
+                                 case['kernel'])
+    assert s.a_eval.last_pairs == osol.evaluate()
+    for pa in pas:
+        ref = case['outputs'][pa.name]
+        nr = ref['_n_real']
+        for f in ACC_FIELDS:
+            want = np.array(ref[f])[:nr]
+            got = pa.properties[f][:nr]
+            if np.max(np.abs(want)) == 0.0:
+                assert np.max(np.abs(got)) == 0.0, (pa.name, f)
+                continue
+            assert rel_err(got, want) <= TOL_EVAL, (pa.name, f, rel_err(got, want))
+        assert np.allclose(pa.p, ref['p'], rtol=1e-6, atol=1e-3)
+        assert np.allclose(pa.cs, ref['cs'], rtol=1e-6)
+        assert np.allclose(pa.rho, ref['rho'], rtol=2e-6 if case['params'][
+            'summation_density'] else 1e-15)
+
+
+def _random_arrays(seed=123):
+    import pysph_b200 as pb
+    rs = np.random.RandomState(seed)
+    out = []
+    for name, n, hv in (('a', 2048, 0.0), ('b', 1024, 0.0), ('c', 1024, 1.0)):
+        x, y, z = (rs.uniform(-1, 1, n) for _ in range(3))
+        dx = 2.0 / n ** (1. / 3)
+        h = np.full(n, 1.2 * dx) * (1.0 + hv * rs.uniform(0, 1, n))
+        out.append(pb.get_particle_array_wcsph(name=name, x=x, y=y, z=z, h=h))
+    return out
+
+
+def test_nnps_equals_brute_force(gpu_device):
+    """pysph/base/tests/test_nnps.py:303-474: all (src, dst) pairings, constant
+    and variable h, against the fp64 brute force."""
+    import pysph_b200 as pb
+    pas = _random_arrays()
+    kernel = pb.CubicSpline(dim=3)
+    nn = pb.B200NNPS(3, pas, kernel=kernel)
+    o = orc.Oracle(copy_arrays(pas), 3, 'CubicSpline')
+    g = nn
+    og = None
+    o.update_domain()
+    o.nnps_update()
+    og = o.grid()
+    # the grid follows the reference exactly (fp64 on the host)
+    assert g.cell_size == og['cell_size']
+    assert np.array_equal(g.ncells_per_dim, og['ncells'])
+    assert np.allclose(g.xmin, og['xmin'], rtol=0, atol=0)
+    rs = np.random.RandomState(0)
+    mismatched = 0
+    total = 0
+    for dst in range(3):
+        for src in range(3):
+            n = pas[dst].get_number_of_particles()
+            for i in rs.randint(0, n, 40):
+                a = nn.get_nearest_particles(src, dst, i)
+                b = np.sort(o.brute_neighbors(dst, src, i))
+                total += len(b)
+                mismatched += len(np.setxor1d(a, b))
+    # fp32 knife-edge pairs: |r^2 - (kh)^2| within fp32 rounding
+    assert mismatched <= 2, (mismatched, total)
+
+
+def test_nnps_corner_cases(gpu_device):
+    import pysph_b200 as pb
+    # test_nnps.py:1250-1391
+    rs = np.random.RandomState(1)
+    n = 2 ** 14
+    pb_ = pb.get_particle_array_wcsph(name='b', x=rs.uniform(0, 0.1, n),
+                                      y=rs.uniform(0, 0.1, n),
+                                      z=rs.uniform(0, 0.1, n), h=np.ones(n))
+    nn = pb.B200NNPS(3, [pb_], kernel=pb.CubicSpline(dim=3))
+    assert len(nn.get_nearest_particles(0, 0, 5)) == n
+    # degenerate dimension: only y varies
+    pc = pb.get_particle_array_wcsph(name='c', x=np.zeros(2),
+                                     y=np.array([0.0, 0.5]), z=np.zeros(2),
+                                     h=np.ones(2))
+    for dim in (2, 3):
+        nn = pb.B200NNPS(dim, [pc], kernel=pb.CubicSpline(dim=dim))
+        assert list(nn.get_nearest_particles(0, 0, 0)) == [0, 1]
+    # too many cells -> RuntimeError like linked_list_nnps.pyx:336-343
+    pd = pb.get_particle_array_wcsph(name='d', x=np.array([0.0, 1e6]),
+                                     y=np.array([0.0, 1e6]),
+                                     z=np.array([0.0, 1e6]), h=np.full(2, 0.5))
+    with pytest.raises(RuntimeError):
+        pb.B200NNPS(3, [pd], kernel=pb.CubicSpline(dim=3))
+    # empty + tiny arrays
+    pe = pb.get_particle_array_wcsph(name='e', x=np.zeros(0))
+    pf = pb.get_particle_array_wcsph(name='f', x=np.array([0.25]), h=np.ones(1))
+    nn = pb.B200NNPS(1, [pe, pf], kernel=pb.CubicSpline(dim=1))
+    assert list(nn.get_nearest_particles(1, 1, 0)) == [0]
+    assert len(nn.get_nearest_particles(0, 1, 0)) == 0
+
+
+def test_steppers_and_eos_vs_reference_bodies(gpu_device):
+    import ctypes as C
+    import pysph_b200 as pb
+    g = load_golden('steppers.json')
+    for which, key in ((0, 'initialize'), (1, 'stage1'), (2, 'stage2')):
+        props = dict((k, np.array(v)) for k, v in g['inputs'].items())
+        pa = pb.get_particle_array_wcsph(name='f', **props)
+        be = pb.B200Backend([pa])
+        be.ctx.call('b200sph_stage', -1, which, g['dt'])
+        be.pull_all()
+        for k, v in g['outputs'][key].items():
+            # accelerations are fp32 on the device, the state is fp64
+            assert np.allclose(pa.properties[k], v, rtol=1e-6, atol=1e-7), (key, k)
+    e = load_golden('eos.json')
+    for name, hg in (('TaitEOS', 0), ('TaitEOSHGCorrection', 1)):
+        d = e[name]
+        pa = pb.get_particle_array_wcsph(name='f', x=np.zeros(len(d['rho_in'])),
+                                         rho=np.array(d['rho_in']))
+        be = pb.B200Backend([pa])
+        be.ctx.call('b200sph_eos', 0, hg, d['rho0'], d['c0'], d['gamma'],
+                    d['p0'], 0)
+        be.pull_all()
+        assert np.array_equal(pa.rho, d['rho_out'])
+        assert np.allclose(pa.p, d['p'], rtol=1e-6, atol=1e-3)
+        assert np.allclose(pa.cs, d['cs'], rtol=1e-6)
+    d = e['UpdateSmoothingLengthFerrari']
+    pa = pb.get_particle_array_wcsph(name='f', x=np.zeros(len(d['rho'])),
+                                     rho=np.array(d['rho']), m=np.array(d['m']))
+    be = pb.B200Backend([pa])
+    be.ctx.call('b200sph_ferrari_h', 0, d['hdx'], d['dim'], 0)
+    be.pull_all()
+    assert np.allclose(pa.h, d['h'], rtol=1e-14)
+
+
+def _compare_state(pas, opas, tol_pos, tol_vel, tol_rho, h0, c0, rho0):
+    for pa, oa in zip(pas, opas):
+        nr = oa.num_real_particles
+        for f in ('x', 'y', 'z'):
+            assert np.max(np.abs(pa.properties[f][:nr] - oa.properties[f][:nr])) \
+                <= tol_pos * h0, (pa.name, f)
+        for f in ('u', 'v', 'w'):
+            assert np.max(np.abs(pa.properties[f][:nr] - oa.properties[f][:nr])) \
+                <= tol_vel * c0, (pa.name, f)
+        assert np.max(np.abs(pa.rho[:nr] - oa.rho[:nr])) <= tol_rho * rho0, pa.name
+
+
+def test_dam_break_3d_small_eval_and_steps(gpu_device):
+    """Config 2 at reduced resolution (dx = 0.05: ~5 k fluid): one evaluation
+    and then 20 adaptive EPEC steps against the oracle."""
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo
+    dx = 0.05
+    pas = geo.dam_break_3d_particles(dx=dx)
+    params = geo.dam_break_3d_params(dx)
+    opas = copy_arrays(pas)
+    s = make_solver(pas, scheme_params(params), 'CubicSpline')
+    o = orc.WCSPHOracleSolver(opas, params, 'CubicSpline', threads=4)
+    s.a_eval.count_pairs = True
+    s.initialise()
+    o.initialise()
+    assert s.a_eval.last_pairs == o.pairs_last_eval
+    assert abs(s.dt - o.dt) <= 1e-6 * o.dt
+    s.pull()
+    for pa, oa in zip(pas, opas):
+        nr = oa.num_real_particles
+        for f in ACC_FIELDS:
+            want = oa.properties[f][:nr]
+            got = pa.properties[f][:nr]
+            scale = max(np.max(np.abs(want)), 1e-30)
+            if f in ('au', 'av', 'aw'):
+                scale = max(scale, 9.81)
+            assert np.max(np.abs(got - want)) <= TOL_EVAL * scale, (pa.name, f)
+    for _ in range(20):
+        s.step()
+        o.step()
+    s.pull()
+    assert abs(s.t - o.t) <= 1e-5 * o.t
+    _compare_state(pas, opas, tol_pos=1e-6, tol_vel=1e-6, tol_rho=1e-7,
+                   h0=params['h0'], c0=params['c0'], rho0=params['rho0'])
+
+
+def test_dam_break_2d_gate(gpu_device):
+    """Config 1 (the reference correctness gate): 2D dam break, WendlandQuintic,
+    PEC, update_h, HG correction -- default dx = 0.03, 25 steps."""
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo
+    pas = geo.dam_break_2d_particles(dx=0.03)
+    params = geo.dam_break_2d_params(dx=0.03)
+    opas = copy_arrays(pas)
+    s = make_solver(pas, scheme_params(params), 'WendlandQuintic')
+    o = orc.WCSPHOracleSolver(opas, params, 'WendlandQuintic', threads=4)
+    for _ in range(25):
+        s.step()
+        o.step()
+    s.pull()
+    assert abs(s.t - o.t) <= 1e-5 * o.t
+    _compare_state(pas, opas, tol_pos=1e-6, tol_vel=1e-6, tol_rho=1e-7,
+                   h0=params['h0'], c0=params['c0'], rho0=params['rho0'])
+    assert np.allclose(pas[0].h, opas[0].h, rtol=1e-7)
+
+
+def test_push_pull_roundtrip_and_errors(gpu_device):
+    import pysph_b200 as pb
+    from pysph_b200._lib import B200Error
+    rs = np.random.RandomState(5)
+    n = 1000
+    pa = pb.get_particle_array_wcsph(name='f', x=rs.normal(size=n),
+                                     y=rs.normal(size=n), u=rs.normal(size=n),
+                                     rho=rs.uniform(900, 1100, n),
+                                     h=np.full(n, 0.1))
+    pa.gid[:] = np.arange(n)
+    ref = dict((k, v.copy()) for k, v in pa.properties.items())
+    be = pb.B200Backend([pa])
+    for k in pa.properties:
+        pa.properties[k][:] = 0
+    be.pull_all()
+    for k in ('x', 'y', 'u', 'rho', 'h', 'gid', 'tag'):
+        assert np.array_equal(pa.properties[k], ref[k]), k   # fp64 state is exact
+    with pytest.raises(B200Error):
+        be.ctx.call('b200sph_push_f64', 0, 0, pa.x.ctypes.data, 0, n + 1)
+    with pytest.raises(B200Error):
+        be.ctx.call('b200sph_push_f64', 3, 0, pa.x.ctypes.data, 0, 1)
+    # evaluating before a neighbour build is an error, not a silent stale result
+    ae = pb.B200AccelerationEval(
+        [pa], [pb.SummationDensity(dest='f', sources=['f'])],
+        pb.CubicSpline(dim=2), backend=be)
+    with pytest.raises(B200Error):
+        ae.compute(0.0, 0.0)
+    with pytest.raises(NotImplementedError):
+        class Foo(pb.Equation):
+            pass
+        pb.B200AccelerationEval([pa], [Foo(dest='f', sources=['f'])],
+                                pb.CubicSpline(dim=2), backend=be)
+
+
+def test_determinism(gpu_device):
+    """Two builds + evaluations of the same state give bit-identical results
+    (the counting sort is made canonical inside each cell)."""
+    from pysph_b200 import geometry as geo
+    dx = 0.06
+    res = []
+    for _ in range(2):
+        pas = geo.dam_break_3d_particles(dx=dx)
+        rs = np.random.RandomState(3)
+        for pa in pas[:1]:
+            pa.u[:] = rs.normal(size=pa.u.size)
+            pa.rho[:] *= 1 + 0.01 * rs.uniform(-1, 1, pa.u.size)
+        s = make_solver(pas, scheme_params(geo.dam_break_3d_params(dx)),
+                        'CubicSpline')
+        s.initialise()
+        s.step()
+        s.pull()
+        res.append(np.concatenate([pas[0].au, pas[0].arho, pas[0].x]))
+    assert np.array_equal(res[0], res[1])
+
+
+def test_size_independent_properties_100k(gpu_device):
+    """At a size the oracle would take too long for in CI: lattice symmetry
+    properties of config 2 (dx = 0.018 -> ~117 k fluid particles).
+    * the initial state is mirror symmetric in y: au(y) = au(-y), av(y) = -av(-y)
+    * interior fluid particles at rest: arho = 0, ax = u = 0
+    * pair count is symmetric: #(fluid<-boundary) == #(boundary<-fluid)
+    """
+    import ctypes as C
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo, _lib
+    dx = 0.018
+    pas = geo.dam_break_3d_particles(dx=dx)
+    params = geo.dam_break_3d_params(dx)
+    s = make_solver(pas, scheme_params(params), 'CubicSpline')
+    s.initialise()
+    s.pull()
+    f = pas[0]
+    key = np.lexsort((np.round(f.z / dx), np.round(np.abs(f.y) / dx),
+                      np.round(f.x / dx)))
+    # pair up y-mirror images: particles with equal (x, |y|, z)
+    xs, ys, zs = f.x[key], f.y[key], f.z[key]
+    same = (np.abs(xs[1:] - xs[:-1]) < 1e-9) & (np.abs(zs[1:] - zs[:-1]) < 1e-9) & \
+        (np.abs(ys[1:] + ys[:-1]) < 1e-9)
+    i0, i1 = key[:-1][same], key[1:][same]
+    assert len(i0) > 0.4 * f.x.size
+    g = 9.81
+    assert np.max(np.abs(f.au[i0] - f.au[i1])) <= 2e-4 * g
+    assert np.max(np.abs(f.aw[i0] - f.aw[i1])) <= 2e-4 * g
+    assert np.max(np.abs(f.av[i0] + f.av[i1])) <= 2e-4 * g
+    assert np.max(np.abs(f.arho)) <= 1e-3     # fluid at rest: v_ij = 0 exactly
+    assert np.max(np.abs(f.ax)) == 0.0
+    # pair-count symmetry through two single-loop programs
+    be = s.backend
+    prog = _lib.PairProgram()
+    cnt = C.c_int64()
+    prog.eqmask[0][1] = _lib.EQ_CONTINUITY
+    prog.real_only = 1
+    be.ctx.call('b200sph_pair_pass', C.byref(prog), C.byref(cnt))
+    n_fb = cnt.value
+    prog = _lib.PairProgram()
+    prog.eqmask[1][0] = _lib.EQ_CONTINUITY
+    prog.real_only = 1
+    be.ctx.call('b200sph_pair_pass', C.byref(prog), C.byref(cnt))
+    assert n_fb == cnt.value and n_fb > 0

@@ -1,0 +1,189 @@
+"""CPU-only tests of the host side: C-ABI surface, program translation, scheme
+assembly, geometry, time-step logic.  No compute call needs a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pysph_b200 as pb
+from pysph_b200 import _lib, geometry as geo
+from pysph_b200.program import build_program
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'b200sph.h')).read()
+    declared = set(re.findall(r'\b(b200sph_[a-z0-9_]+)\s*\(', hdr))
+    declared -= {'b200sph_ctx'}
+    assert len(declared) >= 25
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'libb200sph.so does not export %s' % name
+    # and the ctypes table covers exactly the header
+    assert set(_lib.SIGNATURES) == declared
+    assert lib.b200sph_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a GPU the product path must fail loudly, not fall back."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip('GPU present')
+    pa = pb.get_particle_array_wcsph(name='f', x=np.zeros(4))
+    with pytest.raises(_lib.B200Error):
+        pb.B200Backend([pa])
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'pysph_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f
+                assert 'liboracle' not in src, f
+
+
+def test_struct_layouts_match_header():
+    # sizes implied by include/b200sph.h (x86-64 SysV)
+    assert C.sizeof(_lib.PairProgram) == 8 * 8 * 4 + 2 * 4 + 7 * 8
+    assert C.sizeof(_lib.GridInfo) == 8 + 8 + 24 + 24 + 12 + 4 + 8 + 8
+    assert C.sizeof(_lib.Stats) == 3 * 8 + 3 * 8
+    ids = _lib.PROP_IDS
+    assert ids['x'] == 0 and ids['rho'] == 6 and ids['h'] == 7 and ids['m'] == 8
+    assert ids['rho0'] == 15 and ids['p'] == 16 and ids['dt_force'] == 26
+
+
+def test_wcsph_scheme_equations_order():
+    # scheme.py:388-506 for dam_break_3d (hg_correction, no update_h)
+    s = pb.WCSPHScheme(['fluid'], ['boundary', 'obstacle'], dim=3, rho0=1000.0,
+                       c0=32.85, h0=0.026, hdx=1.3, gz=-9.81, alpha=0.25,
+                       beta=0.0, gamma=7.0, hg_correction=True)
+    groups = s.get_equations()
+    assert [g.real for g in groups] == [False, True]
+    g1 = [(e.name, e.dest) for e in groups[0].equations]
+    assert g1 == [('TaitEOS', 'fluid'), ('TaitEOSHGCorrection', 'boundary'),
+                  ('TaitEOSHGCorrection', 'obstacle')]
+    g2 = [(e.name, e.dest, e.sources) for e in groups[1].equations]
+    assert g2 == [
+        ('ContinuityEquation', 'boundary', ['fluid']),
+        ('ContinuityEquation', 'obstacle', ['fluid']),
+        ('ContinuityEquation', 'fluid', ['fluid', 'boundary', 'obstacle']),
+        ('MomentumEquation', 'fluid', ['fluid', 'boundary', 'obstacle']),
+        ('XSPHCorrection', 'fluid', ['fluid'])]
+    with pytest.raises(NotImplementedError):
+        pb.WCSPHScheme(['f'], [], dim=2, rho0=1, c0=1, h0=1, hdx=1, delta_sph=True)
+
+
+def test_program_translation():
+    names = ['fluid', 'boundary', 'obstacle']
+    s = pb.WCSPHScheme(['fluid'], ['boundary', 'obstacle'], dim=2, rho0=1000.0,
+                       c0=62.0, h0=0.039, hdx=1.3, gy=-9.81, alpha=0.1,
+                       hg_correction=True, update_h=True)
+    ops = build_program(s.get_equations(), names, 2)
+    kinds = [o[0] for o in ops]
+    assert kinds == ['eos', 'eos', 'eos', 'pair', 'ferrari']
+    assert ops[0][1:3] == (0, 0) and ops[1][1:3] == (1, 1) and ops[0][-1] == 0
+    prog = ops[3][1]
+    F, B, O = 0, 1, 2
+    CONT, MOM, XSPH = _lib.EQ_CONTINUITY, _lib.EQ_MOMENTUM, _lib.EQ_XSPH
+    assert prog.eqmask[F][F] == CONT | MOM | XSPH
+    assert prog.eqmask[F][B] == CONT | MOM and prog.eqmask[F][O] == CONT | MOM
+    assert prog.eqmask[B][F] == CONT and prog.eqmask[B][B] == 0
+    assert prog.eqmask[O][F] == CONT and prog.eqmask[O][B] == 0
+    assert prog.real_only == 1 and prog.gy == -9.81 and prog.alpha == 0.1
+    assert prog.eps_xsph == 0.5 and prog.c0 == 62.0
+    assert ops[4] == ('ferrari', 0, 1.3, 2, 0)
+
+    # unsupported constructs fail at setup time
+    with pytest.raises(NotImplementedError):
+        build_program([pb.Group([pb.SummationDensity('fluid', ['fluid']),
+                                 pb.XSPHCorrection('fluid', ['fluid'])])],
+                      names, 3)
+    with pytest.raises(NotImplementedError):
+        build_program([pb.Group([pb.SummationDensity('fluid', ['fluid'])],
+                                iterate=True)], names, 3)
+    with pytest.raises(NotImplementedError):
+        build_program([pb.Group([
+            pb.MomentumEquation('fluid', ['fluid'], c0=1.0, alpha=0.1),
+            pb.MomentumEquation('boundary', ['fluid'], c0=1.0, alpha=0.2)])],
+            names, 3)
+    with pytest.raises(ValueError):
+        build_program([pb.SummationDensity('nope', ['fluid'])], names, 3)
+    # a bare list of equations is one Group (equation.py:346-373)
+    ops = build_program([pb.SummationDensity('fluid', ['fluid', 'boundary'])],
+                        names, 3)
+    assert ops[0][0] == 'pair' and ops[0][1].eqmask[0][1] == 1
+    # subgroups are flattened in order, update_nnps is honoured
+    ops = build_program([pb.Group([
+        pb.Group([pb.SummationDensity('fluid', ['fluid'])], update_nnps=True),
+        pb.Group([pb.TaitEOS('fluid', None, rho0=1., c0=1., gamma=7.)])])],
+        names, 3)
+    assert [o[0] for o in ops] == ['pair', 'update_nnps', 'eos']
+
+
+def test_equation_attributes_mirror_reference():
+    e = pb.TaitEOS('f', None, rho0=1000.0, c0=10.0, gamma=7.0)
+    assert e.no_source and e.sources is None
+    assert e.B == 1000.0 * 100.0 / 7.0 and e.gamma1 == 3.0 and e.rho01 == 1e-3
+    m = pb.MomentumEquation('f', ['f', 'b'], c0=10.0)
+    assert (m.alpha, m.beta, m.gx, m.tensile_correction) == (1.0, 1.0, 0.0, False)
+    k = pb.UpdateSmoothingLengthFerrari('f', None, dim=2, hdx=1.3)
+    assert k.dim1 == 0.5
+    with pytest.raises(ValueError):
+        pb.WendlandQuintic(dim=1)
+    assert pb.QuinticSpline(dim=3).radius_scale == 3.0
+    assert abs(pb.Gaussian(dim=2).fac - 1.0 / np.pi) < 1e-15
+    assert abs(pb.CubicSpline(dim=3).fac - 1.0 / np.pi) < 1e-15
+
+
+def test_dam_break_geometry_counts():
+    # _db_geometry.py:284-432 at the example default dx = 0.02, 1 boundary layer:
+    # the docstring of dam_break_3d.py quotes the same lattice
+    fluid, boundary, obstacle = geo.dam_break_3d_particles(dx=0.05)
+    nx = len(np.mgrid[-0.05:3.22 + 0.05 + 0.005:0.05])
+    assert fluid.get_number_of_particles() == 24 * 19 * 11
+    assert obstacle.get_number_of_particles() > 0
+    n_lattice = nx * len(np.mgrid[-0.55:0.55 + 0.005:0.05]) * \
+        len(np.mgrid[-0.05:1.05 + 0.005:0.05])
+    assert boundary.get_number_of_particles() < n_lattice
+    assert np.all(fluid.h == 1.3 * 0.05) and np.all(fluid.m == 1000.0 * 0.05 ** 3)
+    assert fluid.x.min() > 0 and fluid.x.max() <= 1.228 and fluid.z.max() <= 0.55
+    assert np.all((boundary.x <= 0) | (boundary.x >= 3.22) | (boundary.z <= 0) |
+                  (np.abs(boundary.y) >= 0.5))
+    # slab-restricted generation gives the same particles
+    a = geo.dam_break_3d_particles(dx=0.05, xrange=(-1.0, 1.0))
+    b = geo.dam_break_3d_particles(dx=0.05, xrange=(1.0, 9.0))
+    for k in range(3):
+        assert a[k].get_number_of_particles() + b[k].get_number_of_particles() \
+            == [fluid, boundary, obstacle][k].get_number_of_particles()
+    # dam_break_2d.py at its default dx: SURVEY.md 8d quotes 2278 + 1660
+    f2, b2 = geo.dam_break_2d_particles(dx=0.03)
+    assert f2.get_number_of_particles() == 2278
+    assert b2.get_number_of_particles() == 1660
+    assert np.all(f2.h == 1.3 * 0.03) and np.all(f2.m == 0.03 ** 2 * 1000.0)
+    # the reference quirk: h and m do NOT follow --dx
+    f3, b3 = geo.dam_break_2d_particles(dx=0.01)
+    assert f3.get_number_of_particles() == 20301
+    assert b3.get_number_of_particles() == 4852
+    assert np.all(f3.h == 1.3 * 0.03)
+
+
+def test_particle_array_standin():
+    pa = pb.get_particle_array_wcsph(name='f', x=np.arange(5.0), h=0.1)
+    assert set(['x0', 'rho0', 'arho', 'dt_cfl', 'dt_force', 'gid', 'tag']) <= \
+        set(pa.properties)
+    assert pa.gid.dtype == np.uint32 and pa.gid[0] == 2 ** 32 - 1
+    assert pa.tag.dtype == np.int32
+    pa.set_num_real_particles(3)
+    assert pa.get_number_of_particles(real=True) == 3
+    assert pa.get('x').size == 3 and pa.get('x', only_real_particles=False).size == 5
+    pa.resize(8)
+    assert pa.x.size == 8 and pa.x[4] == 4.0 and pa.x[7] == 0.0
