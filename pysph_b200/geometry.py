@@ -33,9 +33,15 @@ def dam_break_3d_particles(dx=0.02, hdx=1.3, rho0=1000.0, nboundary_layers=1,
     xs = np.mgrid[0.0 - ghost:L + ghost + eps:dx]
     ys = np.mgrid[-0.5 * W - ghost:0.5 * W + ghost + eps:dx]
     zs = np.mgrid[0.0 - ghost:H + ghost + eps:dx]
+    ix = np.arange(xs.size)
     if xrange is not None:
-        xs = xs[(xs >= xrange[0]) & (xs < xrange[1])]
+        keep = (xs >= xrange[0]) & (xs < xrange[1])
+        xs, ix = xs[keep], ix[keep]
     x, y, z = [a.ravel() for a in np.meshgrid(xs, ys, zs, indexing='ij')]
+    # global id = lattice index: unique over arrays and independent of how the
+    # lattice is split over ranks (used to match results across decompositions)
+    gid = ((ix[:, None, None] * ys.size + np.arange(ys.size)[None, :, None]) *
+           zs.size + np.arange(zs.size)[None, None, :]).ravel().astype(np.uint32)
 
     cw2 = 0.5 * W
     fluid_mask = ((0 < x) & (x <= fl) & (-cw2 < y) & (y < cw2) &
@@ -50,7 +56,8 @@ def dam_break_3d_particles(dx=0.02, hdx=1.3, rho0=1000.0, nboundary_layers=1,
 
     def make(name, mask):
         return get_particle_array_wcsph(name=name, x=x[mask], y=y[mask],
-                                        z=z[mask], m=m0, h=h0, rho=rho0)
+                                        z=z[mask], m=m0, h=h0, rho=rho0,
+                                        gid=gid[mask])
 
     arrays = [make('fluid', fluid_mask), make('boundary', wall_mask)]
     if with_obstacle:

@@ -109,8 +109,12 @@ def test_wcsph_evaluation_vs_reference_bodies(gpu_device, idx):
                 assert np.max(np.abs(got)) == 0.0, (pa.name, f)
                 continue
             assert rel_err(got, want) <= TOL_EVAL, (pa.name, f, rel_err(got, want))
-        assert np.allclose(pa.p, ref['p'], rtol=1e-6, atol=1e-3)
-        assert np.allclose(pa.cs, ref['cs'], rtol=1e-6)
+        sd = case['params']['summation_density']
+        # with summation density rho itself is an fp32 sum (rel. 2e-7), which the
+        # EOS amplifies by gamma = 7 on top of the B*(ratio^7 - 1) cancellation
+        B = case['params']['rho0'] * case['params']['c0'] ** 2 / case['params']['gamma']
+        assert np.allclose(pa.p, ref['p'], rtol=1e-6, atol=(2e-5 * B) if sd else 1e-3)
+        assert np.allclose(pa.cs, ref['cs'], rtol=2e-6)
         assert np.allclose(pa.rho, ref['rho'], rtol=2e-6 if case['params'][
             'summation_density'] else 1e-15)
 
@@ -348,7 +352,8 @@ def test_determinism(gpu_device):
 
 def test_size_independent_properties_100k(gpu_device):
     """At a size the oracle would take too long for in CI: lattice symmetry
-    properties of config 2 (dx = 0.018 -> ~117 k fluid particles).
+    properties of config 2 at the example's default dx = 0.02 (~81 k fluid, 1/dx
+    integer so that the lattice is mirror symmetric in y).
     * the initial state is mirror symmetric in y: au(y) = au(-y), av(y) = -av(-y)
     * interior fluid particles at rest: arho = 0, ax = u = 0
     * pair count is symmetric: #(fluid<-boundary) == #(boundary<-fluid)
@@ -356,7 +361,7 @@ def test_size_independent_properties_100k(gpu_device):
     import ctypes as C
     import pysph_b200 as pb
     from pysph_b200 import geometry as geo, _lib
-    dx = 0.018
+    dx = 0.02
     pas = geo.dam_break_3d_particles(dx=dx)
     params = geo.dam_break_3d_params(dx)
     s = make_solver(pas, scheme_params(params), 'CubicSpline')
