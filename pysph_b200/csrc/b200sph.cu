@@ -28,6 +28,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -93,6 +94,14 @@ struct b200sph_ctx {
     float4 *A = nullptr, *B = nullptr, *C = nullptr;
     int64_t n_sorted = 0;
     bool state_packed = false;
+    // tile kernel configuration (decided by nnps_update)
+    int tile_R = 1;
+    int tiles_per_row = 1;
+    int64_t ntiles = 0;
+    int64_t tile_maxc = 0;   // max candidates a tile stages
+    bool tile_ok = false;
+    double avg_per_cell = 0.0;  // particles per non-empty cell, from the last build
+    int force_kernel = 0;       // 0 auto, 1 warp kernel, 2 tile kernel (env B200SPH_PAIR_KERNEL)
 
     // scratch
     long long *red = nullptr;     // 16 ordered-int64 slots
@@ -426,6 +435,8 @@ struct GridDev {
     double cell;
     int nc[3];
     float cellf;
+    int R;  // x coordinates of the packed records are relative to the origin of the
+            // R-cell span (cx / R) * R that contains the particle's cell
 };
 
 // cell id = floor((p - xmin)/cell) per axis (find_cell_id_raw, nnps_base.pxd:39-80),
@@ -480,7 +491,8 @@ __global__ void k_canon(const uint32_t *__restrict__ perm_tmp, const uint32_t *_
     rank[g] = d;
 }
 
-// A[s] = (x, y, z relative to the particle's own cell origin, h)
+// A[s] = (x relative to the origin of the particle's R-cell span, y and z relative to
+//         the particle's own cell origin, h)
 __global__ void k_pack_pos(const double *__restrict__ x, const double *__restrict__ y,
                            const double *__restrict__ z, const double *__restrict__ h,
                            const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skey,
@@ -495,7 +507,7 @@ __global__ void k_pack_pos(const double *__restrict__ x, const double *__restric
     const uint32_t cy = key % (uint32_t)G.nc[1];
     const uint32_t cz = key / (uint32_t)G.nc[1];
     float4 a;
-    a.x = (float)(x[g] - (G.xmin[0] + (double)cx * G.cell));
+    a.x = (float)(x[g] - (G.xmin[0] + (double)((cx / (uint32_t)G.R) * (uint32_t)G.R) * G.cell));
     a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell));
     a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell));
     a.w = (float)h[g];
@@ -592,6 +604,8 @@ struct PairArgs {
     float c0, alpha, beta, gx, gy, gz, eps_xsph;
     int tensile, real_only;
     unsigned long long *pair_counter;  // may be null
+    // tile kernel only
+    int R, tiles_per_row, need_type;  // need_type: bit t set if dest type t skips some source type
 };
 
 #define PAIR_WARPS 8
@@ -603,17 +617,15 @@ struct Acc {
 };
 
 template <int K, int DIM>
-__device__ __forceinline__ void pair_body(const PairArgs &a, const float4 qv, const uint32_t t,
-                                          const float4 Ai, const float4 Bi, const float4 Ci,
-                                          const unsigned long long mask_i, const float tmpi,
-                                          Acc &acc, unsigned &npairs)
+__device__ __forceinline__ void pair_body(const PairArgs &a, const float4 qv, const float4 Bj,
+                                          const float4 Cj, const float4 Ai, const float4 Bi,
+                                          const float4 Ci, const unsigned long long mask_i,
+                                          const float tmpi, Acc &acc, unsigned &npairs)
 {
-    const float4 Cj = a.C[t];
     const int tj = __float_as_int(Cj.w) & 7;
     const unsigned bits = (unsigned)(mask_i >> (8 * tj)) & 0xFFu;
     if (!bits) return;
     npairs++;
-    const float4 Bj = a.B[t];
     const float xij = qv.x, yij = qv.y, zij = qv.z, hj = qv.w;
     // precomputed symbols, equation.py:188-297
     const float r2 = xij * xij + yij * yij + zij * zij;
@@ -692,6 +704,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
     int cx = 0;
     // lane r < 9 holds the candidate range of neighbour row r = (dy+1) + 3*(dz+1)
     uint32_t r_rs = 0, r_b1 = 0, r_b2 = 0, r_re = 0;
+    float xo_m = 0.f, xo_p = 0.f;
     unsigned npairs = 0;
 
     for (int kk = 0; kk < PAIR_CHUNK; kk++) {
@@ -712,6 +725,10 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
             kq /= (uint32_t)a.ncx;
             const int cy = (int)(kq % (uint32_t)a.ncy);
             const int cz = (int)(kq / (uint32_t)a.ncy);
+            // x origins differ between R-cell spans: offsets (in cells) of the left /
+            // right neighbour cell's span origin relative to this cell's span origin
+            xo_m = (float)((max(cx - 1, 0) / a.R - cx / a.R) * a.R) * a.cell;
+            xo_p = (float)(((cx + 1) / a.R - cx / a.R) * a.R) * a.cell;
             r_rs = r_b1 = r_b2 = r_re = 0;
             if (lane < 9) {
                 const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
@@ -744,8 +761,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
                 float xij = 0.f, yij = 0.f, zij = 0.f, hj = 0.f;
                 if (t < re) {
                     const float4 Aj = a.A[t];
-                    const int dxc = (int)(t >= b1) + (int)(t >= b2) - 1;
-                    xij = Ai.x - Aj.x - (float)dxc * a.cell;
+                    const float xo = t >= b2 ? xo_p : (t >= b1 ? 0.0f : xo_m);
+                    xij = Ai.x - Aj.x - xo;
                     yij = yoff - Aj.y;
                     zij = zoff - Aj.z;
                     hj = Aj.w;
@@ -764,8 +781,9 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
                     __syncwarp();
                     if (qn >= 32) {
                         const int e = (qhead + lane) & (QCAP - 1);
-                        pair_body<K, DIM>(a, q_v[warp][e], q_i[warp][e], Ai, Bi, Ci, mask_i, tmpi,
-                                          acc, npairs);
+                        const uint32_t tq = q_i[warp][e];
+                        pair_body<K, DIM>(a, q_v[warp][e], a.B[tq], a.C[tq], Ai, Bi, Ci, mask_i,
+                                          tmpi, acc, npairs);
                         qhead = (qhead + 32) & (QCAP - 1);
                         qn -= 32;
                         __syncwarp();
@@ -775,7 +793,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
         }
         if (lane < qn) {
             const int e = (qhead + lane) & (QCAP - 1);
-            pair_body<K, DIM>(a, q_v[warp][e], q_i[warp][e], Ai, Bi, Ci, mask_i, tmpi, acc, npairs);
+            const uint32_t tq = q_i[warp][e];
+            pair_body<K, DIM>(a, q_v[warp][e], a.B[tq], a.C[tq], Ai, Bi, Ci, mask_i, tmpi, acc, npairs);
         }
         __syncwarp();
 
@@ -821,12 +840,238 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
     }
 }
 
+
+// --------------------------------------------------------------------------
+// tile variant of the pair kernel (the fast path)
+//
+// One CTA = one tile = the destination particles of R consecutive cells of one
+// x-row.  The 9 neighbouring rows' candidate ranges (cells cx_lo-1 .. cx_hi+1,
+// contiguous in the sorted arrays) are staged in shared memory once; then every
+// THREAD owns one destination particle: phase 1 walks the staged candidates
+// (every lane reads the same record: a shared-memory broadcast) and appends the
+// accepted ones to a private list; phase 2 runs the pair arithmetic densely over
+// the lists.  No warp reductions, no queue, ~3x fewer executed instructions than
+// the warp-per-destination kernel (profiles/r01a_pair_full_summary.md).
+// --------------------------------------------------------------------------
+#define TILE_NT 128
+#define TILE_CAP 48     // private list entries per thread
+#define TILE_STEP 16    // candidates between two list-overflow checks
+#define TILE_MAXR 12
+
+// candidates a tile must stage; max over non-empty tiles -> stats[0]; number of
+// non-empty cells -> stats[1] (used to choose R for the next build)
+__global__ void k_tile_stats(const uint32_t *__restrict__ cs, int ncx, int ncy, int ncz, int R,
+                             int tiles_per_row, long long ntiles, unsigned long long *stats)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t row = (uint32_t)(t / tiles_per_row);
+    const int chunk = (int)(t % tiles_per_row);
+    const int cx_lo = chunk * R, cx_hi = min(cx_lo + R - 1, ncx - 1);
+    const uint32_t base = row * (uint32_t)ncx;
+    unsigned nonempty = 0;
+    for (int c = cx_lo; c <= cx_hi; c++) nonempty += cs[base + c + 1] > cs[base + c];
+    if (nonempty) atomicAdd(&stats[1], (unsigned long long)nonempty);
+    if (cs[base + cx_hi + 1] == cs[base + cx_lo]) return;
+    const int cy = (int)(row % (uint32_t)ncy), cz = (int)(row / (uint32_t)ncy);
+    unsigned long long cand = 0;
+    for (int r = 0; r < 9; r++) {
+        const int yy = cy + (r % 3) - 1, zz = cz + (r / 3) - 1;
+        if (yy < 0 || yy >= ncy || zz < 0 || zz >= ncz) continue;
+        const uint32_t b = ((uint32_t)yy + (uint32_t)ncy * (uint32_t)zz) * (uint32_t)ncx;
+        cand += cs[b + min(cx_hi + 2, ncx)] - cs[b + max(cx_lo - 1, 0)];
+    }
+    atomicMax(&stats[0], cand);
+    atomicAdd(&stats[2], 1ull);
+}
+
+// phase 2 of the tile kernel: every lane runs the pair arithmetic over its private list
+template <int K, int DIM>
+__device__ __forceinline__ void tile_flush(const PairArgs &a, const float4 *sA, const float4 *sB,
+                                           const float4 *sC, const float4 *s_T, const uint32_t *lst,
+                                           const int tid, int &count, const float4 Ai, const float4 Bi,
+                                           const float4 Ci, const unsigned long long mask_i,
+                                           const float tmpi, Acc &acc, unsigned &npairs)
+{
+    int cmax = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    for (int k = 0; k < cmax; k++) {
+        if (k < count) {
+            const uint32_t e = lst[k * TILE_NT + tid];
+            const uint32_t j = e & 0xFFFFu;
+            const float4 T = s_T[e >> 16];
+            const float4 Aj = sA[j];
+            const float4 qv = make_float4(Ai.x - Aj.x + T.x, Ai.y - Aj.y + T.y, Ai.z - Aj.z + T.z, Aj.w);
+            pair_body<K, DIM>(a, qv, sB[j], sC[j], Ai, Bi, Ci, mask_i, tmpi, acc, npairs);
+        }
+    }
+    count = 0;
+}
+
+template <int K, int DIM>
+__global__ void __launch_bounds__(TILE_NT, 4) k_pair_tile(const PairArgs a)
+{
+    extern __shared__ float4 dyn_smem[];
+    __shared__ uint32_t s_cb[9][TILE_MAXR + 4];  // sorted index where cell (cx_lo - 1 + k) starts, per row
+    __shared__ uint32_t s_lo[9], s_off[10];
+    __shared__ float4 s_T[27];                   // (x, y, z) offset of candidates of row r, segment g
+
+    const int tid = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const int R = a.R;
+    const uint32_t row = blockIdx.x / (uint32_t)a.tiles_per_row;
+    const int chunk = (int)(blockIdx.x % (uint32_t)a.tiles_per_row);
+    const int cx_lo = chunk * R, cx_hi = min(cx_lo + R - 1, a.ncx - 1);
+    const uint32_t base = row * (uint32_t)a.ncx;
+    const uint32_t s0 = a.cell_start[base + cx_lo], s1 = a.cell_start[base + cx_hi + 1];
+    if (s0 == s1) return;  // empty tile (uniform)
+    const int cy = (int)(row % (uint32_t)a.ncy), cz = (int)(row / (uint32_t)a.ncy);
+
+    // cell boundaries of the 9 candidate rows: k = 0 .. R+2  <->  cells cx_lo-1 .. cx_lo+R+1
+    for (int i = tid; i < 9 * (R + 3); i += TILE_NT) {
+        const int r = i / (R + 3), k = i % (R + 3);
+        const int yy = cy + (r % 3) - 1, zz = cz + (r / 3) - 1;
+        uint32_t v = 0;
+        if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
+            const uint32_t b = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+            v = a.cell_start[b + (uint32_t)min(max(cx_lo - 1 + k, 0), a.ncx)];
+        }
+        s_cb[r][k] = v;
+    }
+    if (tid < 27) {
+        const int r = tid / 3, g = tid % 3;
+        // candidates left of the span belong to the previous span (origin - R cells), etc.
+        s_T[tid] = make_float4((float)((1 - g) * R) * a.cell, -(float)((r % 3) - 1) * a.cell,
+                               -(float)((r / 3) - 1) * a.cell, 0.f);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t o = 0;
+        for (int r = 0; r < 9; r++) {
+            s_lo[r] = s_cb[r][0];
+            s_off[r] = o;
+            o += s_cb[r][R + 2] - s_cb[r][0];
+        }
+        s_off[9] = o;
+    }
+    __syncthreads();
+    const uint32_t ncand = s_off[9];
+    float4 *sA = dyn_smem, *sB = dyn_smem + ncand, *sC = dyn_smem + 2 * ncand;
+    uint32_t *lst = (uint32_t *)(dyn_smem + 3 * ncand);  // [TILE_CAP][TILE_NT]
+
+    // stage the candidate rows: contiguous ranges of the sorted records
+    for (int r = 0; r < 9; r++) {
+        const uint32_t n = s_off[r + 1] - s_off[r], lo = s_lo[r], o = s_off[r];
+        for (uint32_t i = tid; i < n; i += TILE_NT) {
+            sA[o + i] = a.A[lo + i];
+            sB[o + i] = a.B[lo + i];
+            sC[o + i] = a.C[lo + i];
+        }
+    }
+    __syncthreads();
+
+    unsigned npairs = 0;
+    for (uint32_t b0 = s0; b0 < s1; b0 += TILE_NT) {
+        const uint32_t s = b0 + tid;
+        bool active = s < s1;
+        float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = Ai;
+        unsigned long long mask_i = 0;
+        int ki = 1;  // own cell as boundary-table slot: cell cx_lo - 1 + ki
+        if (active) {
+            const uint32_t j = s_off[4] + (s - s_lo[4]);
+            Ai = sA[j]; Bi = sB[j]; Ci = sC[j];
+            const int ti = __float_as_int(Ci.w);
+            mask_i = a.emask[ti & 7];
+            if ((a.real_only && (ti & PT_GHOST)) || !mask_i) active = false;
+            ki = (int)(a.skey[s] % (uint32_t)a.ncx) - (cx_lo - 1);
+        }
+        const bool type_chk = active && ((a.need_type >> (__float_as_int(Ci.w) & 7)) & 1);
+        // the warp only walks cells kmin-1 .. kmax+1
+        int kmin = active ? ki : (R + 1), kmax = active ? ki : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(FULL, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(FULL, kmax, o));
+        }
+        if (kmax == 0) continue;  // no active lane in this warp (uniform)
+        const float hi2 = active ? a.k2 * Ai.w * Ai.w : -1.0f;
+        const float tmpi = Ci.y;
+        Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int count = 0;
+
+        for (int r = 0; r < 9; r++) {
+            const uint32_t g0 = s_cb[r][kmin - 1], g1 = s_cb[r][kmax + 2];
+            if (g0 >= g1) continue;
+            const uint32_t b1 = s_cb[r][1], b2 = s_cb[r][R + 1];
+            const uint32_t lo = s_lo[r], off = s_off[r];
+#pragma unroll 1
+            for (int g = 0; g < 3; g++) {
+                const uint32_t ga = g == 0 ? g0 : (g == 1 ? max(g0, b1) : max(g0, b2));
+                const uint32_t gb = g == 0 ? min(g1, b1) : (g == 1 ? min(g1, b2) : g1);
+                if (ga >= gb) continue;
+                const float4 T = s_T[r * 3 + g];
+                const float xo = Ai.x + T.x, yo = Ai.y + T.y, zo = Ai.z + T.z;
+                const uint32_t code = (uint32_t)(r * 3 + g) << 16;
+                const uint32_t ja = off + (ga - lo), jb = off + (gb - lo);
+                for (uint32_t jc = ja; jc < jb; jc += TILE_STEP) {
+                    if (__any_sync(FULL, count > TILE_CAP - TILE_STEP))
+                        tile_flush<K, DIM>(a, sA, sB, sC, s_T, lst, tid, count, Ai, Bi, Ci, mask_i, tmpi, acc, npairs);
+                    const uint32_t je = min(jc + TILE_STEP, jb);
+#pragma unroll 4
+                    for (uint32_t j = jc; j < je; j++) {
+                        const float4 Aj = sA[j];
+                        const float dx = xo - Aj.x, dy = yo - Aj.y, dz = zo - Aj.z;
+                        const float r2 = dx * dx + dy * dy + dz * dz;
+                        // linked_list_nnps.pyx:188: (xij2 < hi2) or (xij2 < hj2)
+                        bool ok = (r2 < hi2) || (active && r2 < a.k2 * Aj.w * Aj.w);
+                        if (type_chk && ok)
+                            ok = ((mask_i >> (8 * (__float_as_int(sC[j].w) & 7))) & 0xFFu) != 0;
+                        if (ok) {
+                            lst[count * TILE_NT + tid] = j | code;
+                            count++;
+                        }
+                    }
+                }
+            }
+        }
+        tile_flush<K, DIM>(a, sA, sB, sC, s_T, lst, tid, count, Ai, Bi, Ci, mask_i, tmpi, acc, npairs);
+
+        if (active) {
+            unsigned all_bits = 0;
+#pragma unroll
+            for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
+            const uint32_t g = a.perm[s];
+            if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
+            if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
+            if (all_bits & B200SPH_EQ_MOMENTUM) {
+                // post_loop wc/basic.py:259-269
+                const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
+                a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
+                a.dt_cfl[g] = acc.cfl;
+                a.dt_force[g] = fu * fu + fv * fv + fw * fw;
+            } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
+                a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
+            }
+            if (all_bits & B200SPH_EQ_XSPH) {
+                // post_loop basic_equations.py:297-300
+                a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
+            }
+        }
+    }
+    if (a.pair_counter) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
+        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
+    }
+}
+
 // neighbour query for one destination particle with the pair kernel's accept test.
 // One warp. flags[t - lo] = 1 for every accepted source of array src_arr.
 __global__ void k_neighbors(const float4 *__restrict__ A, const float4 *__restrict__ C,
                             const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ skey,
                             const uint32_t *__restrict__ perm, long long s, int src_arr,
-                            long long src_off, int ncx, int ncy, int ncz, float cell, float k2,
+                            long long src_off, int ncx, int ncy, int ncz, float cell, float k2, int R,
                             uint32_t *__restrict__ out, long long cap, unsigned long long *count)
 {
     const int lane = threadIdx.x;
@@ -851,7 +1096,8 @@ __global__ void k_neighbors(const float4 *__restrict__ A, const float4 *__restri
             if (t < re) {
                 const float4 Aj = A[t];
                 const int dxc = (int)(t >= b1) + (int)(t >= b2) - 1;
-                const float xij = Ai.x - Aj.x - (float)dxc * cell;
+                const int orgd = ((cx + dxc) / R - cx / R) * R;
+                const float xij = Ai.x - Aj.x - (float)orgd * cell;
                 const float yij = Ai.y - (float)dy * cell - Aj.y;
                 const float zij = Ai.z - (float)dz * cell - Aj.z;
                 const float r2 = xij * xij + yij * yij + zij * zij;
@@ -1091,6 +1337,24 @@ PhaseTimer::~PhaseTimer()
     ctx->pending.push_back({e0, e1, slot});
 }
 
+template <int K, int DIM> static cudaError_t launch_tile_kd(unsigned nb, size_t smem, cudaStream_t st, const PairArgs &pa)
+{
+    static size_t configured = 0;  // per instantiation
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_pair_tile<K, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(208 * 1024));
+        if (e != cudaSuccess) return e;
+        configured = 208 * 1024;
+    }
+    k_pair_tile<K, DIM><<<nb, TILE_NT, smem, st>>>(pa);
+    return cudaSuccess;
+}
+template <int K> static cudaError_t launch_tile_dim(int dim, unsigned nb, size_t smem, cudaStream_t st, const PairArgs &pa)
+{
+    if (dim == 1) return launch_tile_kd<K, 1>(nb, smem, st, pa);
+    if (dim == 2) return launch_tile_kd<K, 2>(nb, smem, st, pa);
+    return launch_tile_kd<K, 3>(nb, smem, st, pa);
+}
+
 template <int K> static void launch_pair_dim(int dim, unsigned nb, cudaStream_t st, const PairArgs &pa)
 {
     if (dim == 1) k_pair<K, 1><<<nb, PAIR_WARPS * 32, 0, st>>>(pa);
@@ -1140,6 +1404,10 @@ int b200sph_create(int device, b200sph_ctx **out)
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
+    if (const char *e = getenv("B200SPH_PAIR_KERNEL")) {
+        if (!strcmp(e, "warp")) ctx->force_kernel = 1;
+        else if (!strcmp(e, "tile")) ctx->force_kernel = 2;
+    }
     CU(cudaMalloc((void **)&ctx->red, 16 * sizeof(long long)));
     CU(cudaMallocHost((void **)&ctx->red_host, 16 * sizeof(long long)));
     CU(cudaMalloc((void **)&ctx->counter, 8 * sizeof(unsigned long long)));
@@ -1496,9 +1764,45 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         const unsigned ns = (unsigned)cdiv(ntot, 256);
         k_canon<<<ns, 256, 0, ctx->stream>>>(ctx->perm_tmp, ctx->key_of, ctx->cell_start, ntot, ctx->perm, ctx->skey, ctx->rank);
         LAUNCH_CHECK();
+        // choose the tile span R (cells per tile) so that a tile holds ~TILE_NT destinations
+        const int64_t nrows = (int64_t)nc[1] * nc[2];
+        if (ctx->avg_per_cell <= 0.0) {  // first build: count the non-empty cells once
+            CU(cudaMemsetAsync(ctx->counter + 2, 0, 3 * sizeof(unsigned long long), ctx->stream));
+            k_tile_stats<<<(unsigned)cdiv(nrows * nc[0], 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], 1, nc[0], nrows * nc[0], ctx->counter + 2);
+            LAUNCH_CHECK();
+            CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            ctx->avg_per_cell = (double)ntot / (double)std::max<unsigned long long>(ctx->counter_host[3], 1ull);
+        }
+        int R = (int)((double)TILE_NT / std::max(ctx->avg_per_cell, 1.0));
+        R = std::min(std::max(R, 1), TILE_MAXR);
+        R = std::min(R, nc[0]);
+        G.R = R;
+        ctx->tile_R = R;
+        ctx->tiles_per_row = (int)cdiv(nc[0], R);
+        ctx->ntiles = nrows * ctx->tiles_per_row;
         k_pack_pos<<<ns, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H],
                                                 ctx->perm, ctx->skey, ntot, G, ctx->A);
         LAUNCH_CHECK();
+        CU(cudaMemsetAsync(ctx->counter + 2, 0, 3 * sizeof(unsigned long long), ctx->stream));
+        k_tile_stats<<<(unsigned)cdiv(ctx->ntiles, 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], R, ctx->tiles_per_row, ctx->ntiles, ctx->counter + 2);
+        LAUNCH_CHECK();
+        CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->tile_maxc = (int64_t)ctx->counter_host[2];
+        ctx->avg_per_cell = (double)ntot / (double)std::max<unsigned long long>(ctx->counter_host[3], 1ull);
+        const int64_t smem_need = ctx->tile_maxc * 48 + (int64_t)TILE_CAP * TILE_NT * 4;
+        ctx->tile_ok = ctx->tile_maxc < 65536 && smem_need <= 200 * 1024 && ctx->ntiles < 2147483647LL;
+        if (getenv("B200SPH_DEBUG")) {
+            static int shown = 0;
+            if (shown++ < 3)
+                fprintf(stderr, "b200sph: tiles R=%d per_row=%d ntiles=%lld nonempty_tiles=%llu max_cands=%lld avg/cell=%.2f smem=%lld B tile_ok=%d\n",
+                        R, ctx->tiles_per_row, (long long)ctx->ntiles, ctx->counter_host[4], (long long)ctx->tile_maxc,
+                        ctx->avg_per_cell, (long long)smem_need, (int)ctx->tile_ok);
+        }
+    } else {
+        ctx->tile_ok = false;
+        ctx->tile_R = 1;
     }
     ctx->grid_valid = true;
     ctx->state_packed = false;
@@ -1540,7 +1844,7 @@ int64_t b200sph_get_neighbors(b200sph_ctx *ctx, int dst_arr, int src_arr, int64_
     CU(cudaMalloc((void **)&dout, 4 * (size_t)dcap));
     k_neighbors<<<1, 32, 0, ctx->stream>>>(ctx->A, ctx->C, ctx->cell_start, ctx->skey, ctx->perm, (long long)s32, src_arr,
                                            (long long)ctx->arr[src_arr].off, ctx->grid.ncells[0], ctx->grid.ncells[1], ctx->grid.ncells[2],
-                                           (float)ctx->cell_size, (float)(ctx->radius_scale * ctx->radius_scale), dout, cap, ctx->counter + 1);
+                                           (float)ctx->cell_size, (float)(ctx->radius_scale * ctx->radius_scale), ctx->tile_R, dout, cap, ctx->counter + 1);
     ctx->stats.kernel_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cudaFree(dout); return set_err(ctx, "k_neighbors launch failed: %s", cudaGetErrorString(e)); }
@@ -1631,7 +1935,12 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
             if (b & B200SPH_EQ_SUMMATION_DENSITY) sumdens = true;
         }
         pa.emask[d] = m;
+        if (m)
+            for (int s2 = 0; s2 < ctx->narr; s2++)
+                if (((m >> (8 * s2)) & 0xFFull) == 0) pa.need_type |= 1 << d;
     }
+    pa.R = ctx->tile_R;
+    pa.tiles_per_row = ctx->tiles_per_row;
     pa.c0 = (float)prog->c0; pa.alpha = (float)prog->alpha; pa.beta = (float)prog->beta;
     pa.gx = (float)prog->gx; pa.gy = (float)prog->gy; pa.gz = (float)prog->gz;
     pa.eps_xsph = (float)prog->eps_xsph;
@@ -1642,7 +1951,22 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
         CU(cudaMemsetAsync(ctx->counter, 0, 8, ctx->stream));
         pa.pair_counter = ctx->counter;
     }
-    if (ctx->n_sorted > 0) {
+    const bool use_tile = ctx->force_kernel == 2 && ctx->tile_ok;  // opt-in while the tile path is slower
+    if (ctx->force_kernel == 2 && !ctx->tile_ok)
+        return set_err(ctx, "B200SPH_PAIR_KERNEL=tile but a tile needs %lld candidates in shared memory", (long long)ctx->tile_maxc);
+    if (ctx->n_sorted > 0 && use_tile) {
+        const size_t smem = (size_t)ctx->tile_maxc * 48 + (size_t)TILE_CAP * TILE_NT * 4;
+        cudaError_t e;
+        switch (ctx->kernel) {
+        case 0: e = launch_tile_dim<0>(ctx->dim, (unsigned)ctx->ntiles, smem, ctx->stream, pa); break;
+        case 1: e = launch_tile_dim<1>(ctx->dim, (unsigned)ctx->ntiles, smem, ctx->stream, pa); break;
+        case 2: e = launch_tile_dim<2>(ctx->dim, (unsigned)ctx->ntiles, smem, ctx->stream, pa); break;
+        default: e = launch_tile_dim<3>(ctx->dim, (unsigned)ctx->ntiles, smem, ctx->stream, pa); break;
+        }
+        if (e != cudaSuccess) return set_err(ctx, "k_pair_tile configuration failed: %s", cudaGetErrorString(e));
+        LAUNCH_CHECK();
+        ctx->stats.pair_launches++;
+    } else if (ctx->n_sorted > 0) {
         const unsigned nb = (unsigned)cdiv(ctx->n_sorted, PAIR_WARPS * PAIR_CHUNK);
         switch (ctx->kernel) {
         case 0: launch_pair_dim<0>(ctx->dim, nb, ctx->stream, pa); break;
