@@ -326,7 +326,7 @@ def main():
     ms_pair = st['ms_pair'] / max(st['pair_launches'], 1)
     pairs_per_launch = pairs_local / 2.0     # EPEC: two evaluations per step
     achieved = pairs_per_launch * BYTES_PER_PAIR / (ms_pair * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'k_pair<CubicSpline,3>',
+    roofline = {'bound': 'hbm', 'kernel': 'k_pair_list<CubicSpline,3>' if st['list_builds'] or st['light_updates'] else 'k_pair<CubicSpline,3>',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': None,
                 'peak_source': peak_src,
@@ -335,7 +335,11 @@ def main():
                 'avg_launch_ms': ms_pair,
                 'share_of_step': st['ms_pair'] / K / ms_step,
                 'ms_nnps_per_step': st['ms_nnps'] / K,
-                'ms_other_per_step': st['ms_other'] / K}
+                'ms_other_per_step': st['ms_other'] / K,
+                'nnps': {'full_builds': st['full_builds'],
+                         'light_updates': st['light_updates'],
+                         'list_builds': st['list_builds'],
+                         'list_entries_per_particle': st['list_entries_per_particle']}}
     prof = os.path.join(ROOT, 'profiles', 'pair_traffic.json')
     if os.path.exists(prof):
         try:

@@ -96,6 +96,11 @@ typedef struct {
     int64_t pair_launches;
     int64_t kernel_launches; /* every kernel this library launched          */
     int64_t pairs;      /* directed pair interactions counted (if enabled)  */
+    int64_t full_builds;   /* nnps_update calls that re-sorted the particles   */
+    int64_t light_updates; /* nnps_update calls that only refreshed positions
+                              (persistent neighbour lists still valid)          */
+    int64_t list_builds;   /* neighbour list (re)builds                         */
+    int64_t list_entries_per_particle; /* list capacity reserved per particle   */
 } b200sph_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */

@@ -52,7 +52,10 @@ class GridInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [('ms_nnps', C.c_double), ('ms_pair', C.c_double),
                 ('ms_other', C.c_double), ('pair_launches', C.c_int64),
-                ('kernel_launches', C.c_int64), ('pairs', C.c_int64)]
+                ('kernel_launches', C.c_int64), ('pairs', C.c_int64),
+                ('full_builds', C.c_int64), ('light_updates', C.c_int64),
+                ('list_builds', C.c_int64),
+                ('list_entries_per_particle', C.c_int64)]
 
 
 _ctx_p = C.c_void_p

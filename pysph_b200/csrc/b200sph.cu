@@ -49,6 +49,15 @@ struct ArrayInfo {
     int64_t off = 0, cap = 0, n = 0, n_real = 0;
 };
 
+struct GridDev {
+    double xmin[3];
+    double cell;
+    int nc[3];
+    float cellf;
+    int R;  // x coordinates of the packed records are relative to the origin of the
+            // R-cell span (cx / R) * R that contains the particle's cell
+};
+
 struct PendingEvent {
     cudaEvent_t e0, e1;
     int slot;  // 0 nnps, 1 pair, 2 other
@@ -101,7 +110,22 @@ struct b200sph_ctx {
     int64_t tile_maxc = 0;   // max candidates a tile stages
     bool tile_ok = false;
     double avg_per_cell = 0.0;  // particles per non-empty cell, from the last build
-    int force_kernel = 0;       // 0 auto, 1 warp kernel, 2 tile kernel (env B200SPH_PAIR_KERNEL)
+    int force_kernel = 0;       // 0 lists (default), 1 warp kernel, 2 tile kernel (env B200SPH_PAIR_KERNEL)
+    // persistent neighbour lists
+    double skin = 0.1;          // S = skin * radius_scale * hmax   (env B200SPH_SKIN)
+    double S_abs = 0.0;         // absolute skin of the current build
+    double cell_int = 1.0;      // internal cell size (cell_size + S)
+    GridDev G;                  // frozen device grid of the current build
+    float4 *A0 = nullptr;       // packed positions at build time
+    uint32_t *lst = nullptr;    // transposed lists: [n/32][capg][32]
+    int64_t lst_cap = 0;        // entries allocated
+    uint32_t *cnt = nullptr;    // [n] list length per destination
+    int capg = 0;               // entries reserved per destination
+    bool lists_valid = false;
+    bool topo_dirty = true;     // particle set / h pushed: a light update is not enough
+    bool h_dirty = true;        // h changed since the last update_domain reduction
+    unsigned *red_u32 = nullptr, *red_u32_host = nullptr;
+    int64_t n_full_builds = 0, n_light_updates = 0, n_list_builds = 0;
 
     // scratch
     long long *red = nullptr;     // 16 ordered-int64 slots
@@ -430,14 +454,6 @@ k_scan_add(uint32_t *__restrict__ out, long long n, const uint32_t *__restrict__
 // --------------------------------------------------------------------------
 // NNPS build kernels
 // --------------------------------------------------------------------------
-struct GridDev {
-    double xmin[3];
-    double cell;
-    int nc[3];
-    float cellf;
-    int R;  // x coordinates of the packed records are relative to the origin of the
-            // R-cell span (cx / R) * R that contains the particle's cell
-};
 
 // cell id = floor((p - xmin)/cell) per axis (find_cell_id_raw, nnps_base.pxd:39-80),
 // flat = cx + ncx*cy + ncx*ncy*cz (flatten_raw, nnps_base.pxd:84-96); the arrival
@@ -842,7 +858,233 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
 
 
 // --------------------------------------------------------------------------
-// tile variant of the pair kernel (the fast path)
+// persistent neighbour lists (the default fast path)
+//
+// k_list_build runs the reference's accept test widened by a skin S
+//   r^2 < (k h_i + S)^2  or  r^2 < (k h_j + S)^2
+// once per (re)build and stores, for every destination, the sorted indices of
+// the candidates that pass, 32 destinations interleaved ("transposed") so that
+// the consumer reads them coalesced.  The lists stay valid while
+//   2 max|x - x_build| + k max(h - h_build) <= S            (checked every update),
+// so an evaluation normally only runs k_pair_list: one THREAD per destination
+// walks its list, re-applies the EXACT accept test of linked_list_nnps.pyx:188
+// on the current positions and evaluates the equations.  Results are identical
+// to rebuilding the neighbours every evaluation; only the cost is amortised.
+// entry = j (26 bits, sorted index) | code << 26, code = (dxc+1) + 4 (dy+1) + 16 (dz+1)
+// --------------------------------------------------------------------------
+#define LIST_JBITS 26
+#define LIST_JMASK 0x03FFFFFFu
+#define LIST_NT 128
+
+struct ListBuildArgs {
+    const float4 *A;
+    const uint32_t *cell_start, *skey;
+    long long n;
+    int ncx, ncy, ncz;
+    float cell;      // internal cell size (>= k hmax + S)
+    float kr, S;     // radius scale, absolute skin
+    uint32_t *cnt;   // [n] neighbours per destination
+    uint32_t *lst;   // null: count only
+    int capg;        // entries reserved per destination
+    unsigned *max_count;
+};
+
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildArgs a)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const long long first = ((long long)blockIdx.x * PAIR_WARPS + warp) * PAIR_CHUNK;
+    uint32_t cur_key = 0xFFFFFFFFu;
+    int cx = 0;
+    uint32_t r_rs = 0, r_b1 = 0, r_b2 = 0, r_re = 0;
+    unsigned wmax = 0;
+    for (int kk = 0; kk < PAIR_CHUNK; kk++) {
+        const long long s = first + kk;
+        if (s >= a.n) break;
+        const float4 Ai = a.A[s];
+        const uint32_t key = a.skey[s];
+        if (key != cur_key) {
+            cur_key = key;
+            uint32_t kq = key;
+            cx = (int)(kq % (uint32_t)a.ncx);
+            kq /= (uint32_t)a.ncx;
+            const int cy = (int)(kq % (uint32_t)a.ncy);
+            const int cz = (int)(kq / (uint32_t)a.ncy);
+            r_rs = r_b1 = r_b2 = r_re = 0;
+            if (lane < 9) {
+                const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
+                if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
+                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+                    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
+                    r_rs = a.cell_start[base + x0];
+                    r_b1 = a.cell_start[base + cx];
+                    r_b2 = a.cell_start[base + cx + 1];
+                    r_re = a.cell_start[base + x1 + 1];
+                }
+            }
+        }
+        float hi = a.kr * Ai.w + a.S;
+        const float hi2 = hi * hi;
+        uint32_t *out = a.lst ? a.lst + ((size_t)(s >> 5) * (size_t)a.capg) * 32u + (uint32_t)(s & 31) : nullptr;
+        unsigned count = 0;
+        for (int r = 0; r < 9; r++) {
+            const uint32_t rs = __shfl_sync(FULL, r_rs, r);
+            const uint32_t re = __shfl_sync(FULL, r_re, r);
+            if (rs >= re) continue;
+            const uint32_t b1 = __shfl_sync(FULL, r_b1, r);
+            const uint32_t b2 = __shfl_sync(FULL, r_b2, r);
+            const float yoff = Ai.y - (float)((r % 3) - 1) * a.cell;
+            const float zoff = Ai.z - (float)((r / 3) - 1) * a.cell;
+            const uint32_t rcode = (uint32_t)(4 * (r % 3) + 16 * (r / 3));
+            for (uint32_t t0 = rs; t0 < re; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                bool ok = false;
+                uint32_t dxc1 = 0;
+                if (t < re) {
+                    const float4 Aj = a.A[t];
+                    dxc1 = (uint32_t)(t >= b1) + (uint32_t)(t >= b2);  // dxc + 1
+                    const float xij = Ai.x - Aj.x - ((float)dxc1 - 1.0f) * a.cell;
+                    const float yij = yoff - Aj.y;
+                    const float zij = zoff - Aj.z;
+                    const float r2 = xij * xij + yij * yij + zij * zij;
+                    const float hj = a.kr * Aj.w + a.S;
+                    ok = (r2 < hi2) || (r2 < hj * hj);
+                }
+                const unsigned m = __ballot_sync(FULL, ok);
+                if (ok && out) {
+                    const unsigned pos = count + __popc(m & lt_mask);
+                    if (pos < (unsigned)a.capg) out[(size_t)pos * 32u] = t | ((rcode + dxc1) << LIST_JBITS);
+                }
+                count += __popc(m);
+            }
+        }
+        if (lane == 0) a.cnt[s] = count;
+        wmax = max(wmax, count);
+    }
+    if (lane == 0 && wmax) atomicMax(a.max_count, wmax);
+}
+
+template <int K, int DIM>
+__global__ void __launch_bounds__(LIST_NT, 4) k_pair_list(const PairArgs a, const uint32_t *__restrict__ cnt,
+                                                         const uint32_t *__restrict__ lst, const int capg)
+{
+    __shared__ float4 s_T[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
+        s_T[tid] = make_float4(-(float)dxc * a.cell, -(float)dy * a.cell, -(float)dz * a.cell, 0.f);
+    }
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const long long s = (long long)blockIdx.x * LIST_NT + tid;
+    bool active = s < a.n;
+    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = Ai;
+    unsigned long long mask_i = 0;
+    int count = 0;
+    if (active) {
+        Ci = a.C[s];
+        const int ti = __float_as_int(Ci.w);
+        mask_i = a.emask[ti & 7];
+        if ((a.real_only && (ti & PT_GHOST)) || !mask_i) active = false;
+    }
+    if (active) {
+        Ai = a.A[s];
+        Bi = a.B[s];
+        count = (int)cnt[s];
+    }
+    int cmax = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
+    const float hi2 = a.k2 * Ai.w * Ai.w;
+    const float tmpi = Ci.y;
+    Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    unsigned npairs = 0;
+    for (int k = 0; k < cmax; k++) {
+        if (k < count) {
+            const uint32_t e = my[(size_t)k * 32u];
+            const uint32_t j = e & LIST_JMASK;
+            const float4 T = s_T[e >> LIST_JBITS];
+            const float4 Aj = a.A[j];
+            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+            const float r2 = xij * xij + yij * yij + zij * zij;
+            // the exact accept test, linked_list_nnps.pyx:188
+            if ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w))
+                pair_body<K, DIM>(a, make_float4(xij, yij, zij, Aj.w), a.B[j], a.C[j], Ai, Bi, Ci, mask_i,
+                                  tmpi, acc, npairs);
+        }
+    }
+    if (active) {
+        unsigned all_bits = 0;
+#pragma unroll
+        for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
+        const uint32_t g = a.perm[s];
+        if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
+        if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
+        if (all_bits & B200SPH_EQ_MOMENTUM) {
+            // post_loop wc/basic.py:259-269
+            const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
+            a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
+            a.dt_cfl[g] = acc.cfl;
+            a.dt_force[g] = fu * fu + fv * fv + fw * fw;
+        } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
+            a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
+        }
+        if (all_bits & B200SPH_EQ_XSPH) {
+            // post_loop basic_equations.py:297-300
+            a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
+        }
+    }
+    if (a.pair_counter) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
+        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
+    }
+}
+
+// refresh the packed positions in the FROZEN sorted order / cell frames of the last
+// build and measure how far particles moved (and h grew) since then.
+// red_u32[0] = max |dx|^2 (float bits), red_u32[1] = max (h - h_build) (float bits, >= 0)
+__global__ void k_pack_pos_light(const double *__restrict__ x, const double *__restrict__ y,
+                                 const double *__restrict__ z, const double *__restrict__ h,
+                                 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skey,
+                                 long long n, GridDev G, const float4 *__restrict__ A0,
+                                 float4 *__restrict__ A, unsigned *__restrict__ red_u32)
+{
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float d2 = 0.f, dh = 0.f;
+    if (s < n) {
+        const uint32_t g = perm[s];
+        uint32_t key = skey[s];
+        const uint32_t cx = key % (uint32_t)G.nc[0];
+        key /= (uint32_t)G.nc[0];
+        const uint32_t cy = key % (uint32_t)G.nc[1];
+        const uint32_t cz = key / (uint32_t)G.nc[1];
+        float4 a;
+        a.x = (float)(x[g] - (G.xmin[0] + (double)((cx / (uint32_t)G.R) * (uint32_t)G.R) * G.cell));
+        a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell));
+        a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell));
+        a.w = (float)h[g];
+        A[s] = a;
+        const float4 b = A0[s];
+        const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+        d2 = dx * dx + dy * dy + dz * dz;
+        dh = fmaxf(a.w - b.w, 0.f);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+        dh = fmaxf(dh, __shfl_xor_sync(0xffffffffu, dh, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (d2 > 0.f) atomicMax(&red_u32[0], __float_as_uint(d2));
+        if (dh > 0.f) atomicMax(&red_u32[1], __float_as_uint(dh));
+    }
+}
+
+
+// --------------------------------------------------------------------------
+// tile variant of the pair kernel (experimental, opt-in)
 //
 // One CTA = one tile = the destination particles of R consecutive cells of one
 // x-row.  The 9 neighbouring rows' candidate ranges (cells cx_lo-1 .. cx_hi+1,
@@ -1230,6 +1472,8 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     if (ctx->A) cudaFree(ctx->A);
     if (ctx->B) cudaFree(ctx->B);
     if (ctx->C) cudaFree(ctx->C);
+    if (ctx->A0) cudaFree(ctx->A0);
+    if (ctx->cnt) cudaFree(ctx->cnt);
     if (ctx->flag_a) cudaFree(ctx->flag_a);
     if (ctx->flag_b) cudaFree(ctx->flag_b);
     CU(cudaMalloc((void **)&ctx->key_of, 4 * (size_t)alloc));
@@ -1241,6 +1485,11 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     CU(cudaMalloc((void **)&ctx->A, 16 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->B, 16 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->C, 16 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->A0, 16 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->cnt, 4 * (size_t)alloc));
+    ctx->lists_valid = false;
+    ctx->topo_dirty = true;
+    ctx->h_dirty = true;
     CU(cudaMalloc((void **)&ctx->flag_a, 4 * (size_t)(alloc + 1)));
     CU(cudaMalloc((void **)&ctx->flag_b, 4 * (size_t)(alloc + 1)));
     ctx->flag_cap = alloc + 1;
@@ -1407,7 +1656,16 @@ int b200sph_create(int device, b200sph_ctx **out)
     if (const char *e = getenv("B200SPH_PAIR_KERNEL")) {
         if (!strcmp(e, "warp")) ctx->force_kernel = 1;
         else if (!strcmp(e, "tile")) ctx->force_kernel = 2;
+        else if (strcmp(e, "list") && e[0]) {
+            fprintf(stderr, "b200sph: B200SPH_PAIR_KERNEL must be list, warp or tile\n");
+            delete ctx;
+            *out = nullptr;
+            return -3;
+        }
     }
+    if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = std::max(0.0, atof(e));
+    CU(cudaMalloc((void **)&ctx->red_u32, 4 * sizeof(unsigned)));
+    CU(cudaMallocHost((void **)&ctx->red_u32_host, 4 * sizeof(unsigned)));
     CU(cudaMalloc((void **)&ctx->red, 16 * sizeof(long long)));
     CU(cudaMallocHost((void **)&ctx->red_host, 16 * sizeof(long long)));
     CU(cudaMalloc((void **)&ctx->counter, 8 * sizeof(unsigned long long)));
@@ -1429,7 +1687,8 @@ int b200sph_destroy(b200sph_ctx *ctx)
     cudaFree(ctx->rank); cudaFree(ctx->A); cudaFree(ctx->B); cudaFree(ctx->C);
     cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->counter);
     cudaFreeHost(ctx->counter_host); cudaFree(ctx->stage_buf); cudaFree(ctx->flag_a);
-    cudaFree(ctx->flag_b);
+    cudaFree(ctx->flag_b); cudaFree(ctx->A0); cudaFree(ctx->lst); cudaFree(ctx->cnt);
+    cudaFree(ctx->red_u32); cudaFreeHost(ctx->red_u32_host);
     for (auto &pe : ctx->pending) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1484,6 +1743,8 @@ int b200sph_add_array(b200sph_ctx *ctx, const char *name, int64_t n, int64_t n_r
     }
     ctx->ptype_dirty = true;
     ctx->grid_valid = false;
+    ctx->topo_dirty = true;
+    ctx->h_dirty = true;
     return a;
 }
 
@@ -1502,6 +1763,8 @@ int b200sph_resize_array(b200sph_ctx *ctx, int arr, int64_t n, int64_t n_real)
     ctx->arr[arr].n_real = n_real;
     ctx->ptype_dirty = true;
     ctx->grid_valid = false;
+    ctx->topo_dirty = true;
+    ctx->h_dirty = true;
     return 0;
 }
 
@@ -1552,8 +1815,8 @@ int b200sph_push_f64(b200sph_ctx *ctx, int arr, int prop, const double *host, in
     }
     // the host buffer is borrowed only for this call
     CU(cudaStreamSynchronize(ctx->stream));
-    if (prop == B200SPH_H) ctx->domain_valid = false;
-    if (prop <= B200SPH_Z || prop == B200SPH_H) ctx->grid_valid = false;
+    if (prop == B200SPH_H) { ctx->domain_valid = false; ctx->h_dirty = true; }
+    if (prop <= B200SPH_Z || prop == B200SPH_H) { ctx->grid_valid = false; ctx->topo_dirty = true; }
     ctx->state_packed = false;
     return 0;
 }
@@ -1633,6 +1896,8 @@ int b200sph_set_kernel(b200sph_ctx *ctx, int kernel, int dim)
     ctx->radius_scale = (kernel == B200SPH_KERNEL_QUINTIC_SPLINE || kernel == B200SPH_KERNEL_GAUSSIAN) ? 3.0 : 2.0;
     ctx->domain_valid = false;
     ctx->grid_valid = false;
+    ctx->topo_dirty = true;
+    ctx->h_dirty = true;
     return 0;
 }
 
@@ -1656,6 +1921,7 @@ int b200sph_update_domain(b200sph_ctx *ctx)
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
+    if (ctx->domain_valid && !ctx->h_dirty) return 0;  // h untouched since the last reduction
     PhaseTimer pt(ctx, 2);
     if ((rc = run_minmax(ctx, 0, 1))) return rc;
     // nnps_base.pyx:942-978
@@ -1669,7 +1935,28 @@ int b200sph_update_domain(b200sph_ctx *ctx)
     if (cell != ctx->cell_size) ctx->grid_valid = false;
     ctx->cell_size = cell;
     ctx->domain_valid = true;
+    ctx->h_dirty = false;
     return 0;
+}
+
+// light path of nnps_update: same sorted order, same cell frames, fresh positions;
+// returns 1 if the persistent lists are still valid, 0 if a full rebuild is needed
+static int nnps_light_update(b200sph_ctx *ctx)
+{
+    if (ctx->n_sorted <= 0) return 1;
+    CU(cudaMemsetAsync(ctx->red_u32, 0, 4 * sizeof(unsigned), ctx->stream));
+    k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
+        ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
+        ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->red_u32);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(ctx->red_u32_host, ctx->red_u32, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float d2, dh;
+    memcpy(&d2, &ctx->red_u32_host[0], 4);
+    memcpy(&dh, &ctx->red_u32_host[1], 4);
+    // 2 |dx|max + k dh <= S, with a 2 % safety margin for the fp32 measurement
+    const double need = 2.0 * std::sqrt((double)d2) + ctx->radius_scale * (double)dh;
+    return need <= 0.98 * ctx->S_abs ? 1 : 0;
 }
 
 int b200sph_nnps_update(b200sph_ctx *ctx)
@@ -1679,6 +1966,20 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     if (rc) return rc;
     if (!ctx->domain_valid && (rc = b200sph_update_domain(ctx))) return rc;
     PhaseTimer pt(ctx, 0);
+
+    const bool use_lists = ctx->force_kernel == 0;
+    if (use_lists && ctx->lists_valid && !ctx->topo_dirty) {
+        rc = nnps_light_update(ctx);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            ctx->n_light_updates++;
+            ctx->grid_valid = true;
+            ctx->state_packed = false;
+            return 0;
+        }
+    }
+    ctx->lists_valid = false;
+    ctx->n_full_builds++;
 
     int64_t ntot = 0;
     for (int a = 0; a < ctx->narr; a++) ntot += ctx->arr[a].n;
@@ -1706,31 +2007,42 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
             mn[d] -= 0.5;
             mx[d] += 0.5;
         }
-    // _get_number_of_cells / _count_occupied_cells linked_list_nnps.pyx:293-343
-    const double cs1 = 1. / ctx->cell_size;
-    int nc[3];
-    for (int d = 0; d < 3; d++) {
-        const double v = std::ceil(cs1 * (mx[d] - mn[d]));
-        if (!(v < 2147483647.0)) return set_err(ctx, "LinkedListNNPS requires too many cells along axis %d", d);
-        nc[d] = (int)v;
-        if (nc[d] < 0) return set_err(ctx, "LinkedListNNPS: Number of cells is negative");
-        if (nc[d] == 0) nc[d] = 1;
+    // the reference's grid: _get_number_of_cells / _count_occupied_cells
+    // linked_list_nnps.pyx:293-343 (reported by get_grid; the 2^28 guard is honoured)
+    int nc_ref[3];
+    {
+        const double cs1 = 1. / ctx->cell_size;
+        for (int d = 0; d < 3; d++) {
+            const double v = std::ceil(cs1 * (mx[d] - mn[d]));
+            if (!(v < 2147483647.0)) return set_err(ctx, "ERROR: LinkedListNNPS requires too many cells along axis %d", d);
+            nc_ref[d] = (int)v;
+            if (nc_ref[d] < 0) return set_err(ctx, "LinkedListNNPS: Number of cells is negative");
+            if (nc_ref[d] == 0) nc_ref[d] = 1;
+        }
+        const double ncells_d = (double)nc_ref[0] * (double)nc_ref[1] * (double)nc_ref[2];
+        if (ncells_d > (double)(1LL << 28))
+            return set_err(ctx, "ERROR: LinkedListNNPS requires too many cells (%.0f).", ncells_d);
     }
-    const double ncells_d = (double)nc[0] * (double)nc[1] * (double)nc[2];
-    if (ncells_d > (double)(1LL << 28))
-        return set_err(ctx, "ERROR: LinkedListNNPS requires too many cells (%.0f).", ncells_d);
-    const int64_t ncells = (int64_t)nc[0] * nc[1] * nc[2];
-
     b200sph_grid_info &gi = ctx->grid;
     gi.cell_size = ctx->cell_size;
     gi.hmin = ctx->hmin_scaled;
     for (int d = 0; d < 3; d++) {
         gi.xmin[d] = mn[d];
         gi.xmax[d] = mx[d];
-        gi.ncells[d] = nc[d];
+        gi.ncells[d] = nc_ref[d];
     }
-    gi.n_cells = ncells;
+    gi.n_cells = (int64_t)nc_ref[0] * nc_ref[1] * nc_ref[2];
     gi.n_particles = ntot;
+
+    // the internal grid: cells widened by the skin when the persistent lists are used
+    ctx->S_abs = use_lists ? ctx->skin * ctx->cell_size : 0.0;
+    ctx->cell_int = ctx->cell_size + ctx->S_abs;
+    int nc[3];
+    for (int d = 0; d < 3; d++) {
+        nc[d] = (int)std::ceil((mx[d] - mn[d]) / ctx->cell_int);
+        if (nc[d] <= 0) nc[d] = 1;
+    }
+    const int64_t ncells = (int64_t)nc[0] * nc[1] * nc[2];
 
     if (ncells + 2 > ctx->cell_cap) {
         if (ctx->cell_cnt) CU(cudaFree(ctx->cell_cnt));
@@ -1740,16 +2052,19 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         CU(cudaMalloc((void **)&ctx->cell_start, 4 * (size_t)cap));
         ctx->cell_cap = cap;
     }
-    GridDev G;
+    GridDev &G = ctx->G;
     for (int d = 0; d < 3; d++) {
         G.xmin[d] = mn[d];
         G.nc[d] = nc[d];
     }
-    G.cell = ctx->cell_size;
-    G.cellf = (float)ctx->cell_size;
+    G.cell = ctx->cell_int;
+    G.cellf = (float)ctx->cell_int;
+    G.R = 1;
 
     CU(cudaMemsetAsync(ctx->cell_cnt, 0, 4 * (size_t)(ncells + 1), ctx->stream));
     ctx->n_sorted = ntot;
+    ctx->tile_ok = false;
+    ctx->tile_R = 1;
     if (ctx->pool_end > 0) {
         const unsigned nb = (unsigned)cdiv(ctx->pool_end, 256);
         k_cell_count<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z],
@@ -1764,49 +2079,94 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         const unsigned ns = (unsigned)cdiv(ntot, 256);
         k_canon<<<ns, 256, 0, ctx->stream>>>(ctx->perm_tmp, ctx->key_of, ctx->cell_start, ntot, ctx->perm, ctx->skey, ctx->rank);
         LAUNCH_CHECK();
-        // choose the tile span R (cells per tile) so that a tile holds ~TILE_NT destinations
-        const int64_t nrows = (int64_t)nc[1] * nc[2];
-        if (ctx->avg_per_cell <= 0.0) {  // first build: count the non-empty cells once
-            CU(cudaMemsetAsync(ctx->counter + 2, 0, 3 * sizeof(unsigned long long), ctx->stream));
-            k_tile_stats<<<(unsigned)cdiv(nrows * nc[0], 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], 1, nc[0], nrows * nc[0], ctx->counter + 2);
-            LAUNCH_CHECK();
-            CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            ctx->avg_per_cell = (double)ntot / (double)std::max<unsigned long long>(ctx->counter_host[3], 1ull);
+        if (ctx->force_kernel == 2) {
+            // tile kernel: choose the span R (cells per tile) so that a tile holds ~TILE_NT destinations
+            const int64_t nrows = (int64_t)nc[1] * nc[2];
+            if (ctx->avg_per_cell <= 0.0) {  // first build: count the non-empty cells once
+                CU(cudaMemsetAsync(ctx->counter + 2, 0, 3 * sizeof(unsigned long long), ctx->stream));
+                k_tile_stats<<<(unsigned)cdiv(nrows * nc[0], 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], 1, nc[0], nrows * nc[0], ctx->counter + 2);
+                LAUNCH_CHECK();
+                CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+                ctx->avg_per_cell = (double)ntot / (double)std::max<unsigned long long>(ctx->counter_host[3], 1ull);
+            }
+            int R = (int)((double)TILE_NT / std::max(ctx->avg_per_cell, 1.0));
+            R = std::min(std::max(R, 1), TILE_MAXR);
+            R = std::min(R, nc[0]);
+            G.R = R;
+            ctx->tile_R = R;
+            ctx->tiles_per_row = (int)cdiv(nc[0], R);
+            ctx->ntiles = nrows * ctx->tiles_per_row;
         }
-        int R = (int)((double)TILE_NT / std::max(ctx->avg_per_cell, 1.0));
-        R = std::min(std::max(R, 1), TILE_MAXR);
-        R = std::min(R, nc[0]);
-        G.R = R;
-        ctx->tile_R = R;
-        ctx->tiles_per_row = (int)cdiv(nc[0], R);
-        ctx->ntiles = nrows * ctx->tiles_per_row;
         k_pack_pos<<<ns, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H],
                                                 ctx->perm, ctx->skey, ntot, G, ctx->A);
         LAUNCH_CHECK();
-        CU(cudaMemsetAsync(ctx->counter + 2, 0, 3 * sizeof(unsigned long long), ctx->stream));
-        k_tile_stats<<<(unsigned)cdiv(ctx->ntiles, 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], R, ctx->tiles_per_row, ctx->ntiles, ctx->counter + 2);
-        LAUNCH_CHECK();
-        CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        ctx->tile_maxc = (int64_t)ctx->counter_host[2];
-        ctx->avg_per_cell = (double)ntot / (double)std::max<unsigned long long>(ctx->counter_host[3], 1ull);
-        const int64_t smem_need = ctx->tile_maxc * 48 + (int64_t)TILE_CAP * TILE_NT * 4;
-        ctx->tile_ok = ctx->tile_maxc < 65536 && smem_need <= 200 * 1024 && ctx->ntiles < 2147483647LL;
-        if (getenv("B200SPH_DEBUG")) {
-            static int shown = 0;
-            if (shown++ < 3)
-                fprintf(stderr, "b200sph: tiles R=%d per_row=%d ntiles=%lld nonempty_tiles=%llu max_cands=%lld avg/cell=%.2f smem=%lld B tile_ok=%d\n",
-                        R, ctx->tiles_per_row, (long long)ctx->ntiles, ctx->counter_host[4], (long long)ctx->tile_maxc,
-                        ctx->avg_per_cell, (long long)smem_need, (int)ctx->tile_ok);
+        if (use_lists)
+            CU(cudaMemcpyAsync(ctx->A0, ctx->A, 16 * (size_t)ntot, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (ctx->force_kernel == 2) {
+            CU(cudaMemsetAsync(ctx->counter + 2, 0, 3 * sizeof(unsigned long long), ctx->stream));
+            k_tile_stats<<<(unsigned)cdiv(ctx->ntiles, 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], ctx->tile_R, ctx->tiles_per_row, ctx->ntiles, ctx->counter + 2);
+            LAUNCH_CHECK();
+            CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            ctx->tile_maxc = (int64_t)ctx->counter_host[2];
+            ctx->avg_per_cell = (double)ntot / (double)std::max<unsigned long long>(ctx->counter_host[3], 1ull);
+            const int64_t smem_need = ctx->tile_maxc * 48 + (int64_t)TILE_CAP * TILE_NT * 4;
+            ctx->tile_ok = ctx->tile_maxc < 65536 && smem_need <= 200 * 1024 && ctx->ntiles < 2147483647LL;
         }
-    } else {
-        ctx->tile_ok = false;
-        ctx->tile_R = 1;
     }
+    ctx->topo_dirty = false;
     ctx->grid_valid = true;
     ctx->state_packed = false;
     return 0;
+}
+
+// (re)build the persistent neighbour lists for the current build
+static int build_lists(b200sph_ctx *ctx)
+{
+    const int64_t n = ctx->n_sorted;
+    if (n >= (1LL << LIST_JBITS)) return set_err(ctx, "neighbour lists hold 26-bit indices: more than %lld particles per GPU need B200SPH_PAIR_KERNEL=warp", (long long)(1LL << LIST_JBITS));
+    ListBuildArgs la;
+    la.A = ctx->A; la.cell_start = ctx->cell_start; la.skey = ctx->skey;
+    la.n = n;
+    la.ncx = ctx->G.nc[0]; la.ncy = ctx->G.nc[1]; la.ncz = ctx->G.nc[2];
+    la.cell = (float)ctx->cell_int;
+    la.kr = (float)ctx->radius_scale;
+    la.S = (float)ctx->S_abs;
+    la.cnt = ctx->cnt;
+    la.max_count = ctx->red_u32 + 2;
+    const unsigned nb = (unsigned)cdiv(n, PAIR_WARPS * PAIR_CHUNK);
+    const int64_t nblk = cdiv(n, 32);
+    for (int attempt = 0; attempt < 4; attempt++) {
+        const bool count_only = ctx->capg == 0;
+        if (!count_only) {
+            const int64_t need = nblk * ctx->capg * 32;
+            if (need > ctx->lst_cap) {
+                if (ctx->lst) CU(cudaFree(ctx->lst));
+                ctx->lst = nullptr;
+                const int64_t cap = need + need / 8;
+                cudaError_t e = cudaMalloc((void **)&ctx->lst, 4 * (size_t)cap);
+                if (e != cudaSuccess) return set_err(ctx, "cannot allocate %.1f GB of neighbour lists: %s", 4e-9 * cap, cudaGetErrorString(e));
+                ctx->lst_cap = cap;
+            }
+        }
+        la.lst = count_only ? nullptr : ctx->lst;
+        la.capg = ctx->capg;
+        CU(cudaMemsetAsync(ctx->red_u32 + 2, 0, sizeof(unsigned), ctx->stream));
+        k_list_build<<<nb, PAIR_WARPS * 32, 0, ctx->stream>>>(la);
+        LAUNCH_CHECK();
+        CU(cudaMemcpyAsync(ctx->red_u32_host + 2, ctx->red_u32 + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        const int maxc = (int)ctx->red_u32_host[2];
+        if (!count_only && maxc <= ctx->capg) {
+            ctx->lists_valid = true;
+            ctx->n_list_builds++;
+            return 0;
+        }
+        // (re)size: a little head-room so that later rebuilds usually fit in one pass
+        ctx->capg = ((int)(maxc * 1.15) + 8 + 7) / 8 * 8;
+    }
+    return set_err(ctx, "neighbour list build did not converge");
 }
 
 int b200sph_get_grid(b200sph_ctx *ctx, b200sph_grid_info *out)
@@ -1843,8 +2203,8 @@ int64_t b200sph_get_neighbors(b200sph_ctx *ctx, int dst_arr, int src_arr, int64_
     uint32_t *dout = nullptr;
     CU(cudaMalloc((void **)&dout, 4 * (size_t)dcap));
     k_neighbors<<<1, 32, 0, ctx->stream>>>(ctx->A, ctx->C, ctx->cell_start, ctx->skey, ctx->perm, (long long)s32, src_arr,
-                                           (long long)ctx->arr[src_arr].off, ctx->grid.ncells[0], ctx->grid.ncells[1], ctx->grid.ncells[2],
-                                           (float)ctx->cell_size, (float)(ctx->radius_scale * ctx->radius_scale), ctx->tile_R, dout, cap, ctx->counter + 1);
+                                           (long long)ctx->arr[src_arr].off, ctx->G.nc[0], ctx->G.nc[1], ctx->G.nc[2],
+                                           (float)ctx->cell_int, (float)(ctx->radius_scale * ctx->radius_scale), ctx->tile_R, dout, cap, ctx->counter + 1);
     ctx->stats.kernel_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cudaFree(dout); return set_err(ctx, "k_neighbors launch failed: %s", cudaGetErrorString(e)); }
@@ -1898,6 +2258,8 @@ int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim, int real_o
         LAUNCH_CHECK();
     }
     ctx->domain_valid = false;  // h changed: the next update_domain must re-reduce it
+    ctx->h_dirty = true;
+    ctx->grid_valid = false;
     return 0;
 }
 
@@ -1908,6 +2270,11 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     if (rc) return rc;
     if (!ctx->grid_valid) return set_err(ctx, "pair_pass: the NNPS is stale (particles were pushed/resized); call nnps_update first");
     if (!ctx->state_packed && (rc = pack_state(ctx))) return rc;
+    const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0;
+    if (use_lists && !ctx->lists_valid) {
+        PhaseTimer pt_build(ctx, 0);  // list builds are part of the neighbour search time
+        if ((rc = build_lists(ctx))) return rc;
+    }
     PhaseTimer pt(ctx, 1);
 
     PairArgs pa;
@@ -1920,8 +2287,8 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     pa.dt_cfl = ctx->f32[B200SPH_DT_CFL - N_F64]; pa.dt_force = ctx->f32[B200SPH_DT_FORCE - N_F64];
     pa.rho = ctx->f64[B200SPH_RHO];
     pa.n = ctx->n_sorted;
-    pa.ncx = ctx->grid.ncells[0]; pa.ncy = ctx->grid.ncells[1]; pa.ncz = ctx->grid.ncells[2];
-    pa.cell = (float)ctx->cell_size;
+    pa.ncx = ctx->G.nc[0]; pa.ncy = ctx->G.nc[1]; pa.ncz = ctx->G.nc[2];
+    pa.cell = (float)ctx->cell_int;
     pa.k2 = (float)(ctx->radius_scale * ctx->radius_scale);
     pa.kfac = (float)kernel_fac(ctx->kernel, ctx->dim);
     pa.deltap = (float)kernel_deltap(ctx->kernel);
@@ -1954,7 +2321,18 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     const bool use_tile = ctx->force_kernel == 2 && ctx->tile_ok;  // opt-in while the tile path is slower
     if (ctx->force_kernel == 2 && !ctx->tile_ok)
         return set_err(ctx, "B200SPH_PAIR_KERNEL=tile but a tile needs %lld candidates in shared memory", (long long)ctx->tile_maxc);
-    if (ctx->n_sorted > 0 && use_tile) {
+    if (use_lists) {
+        const unsigned nb = (unsigned)cdiv(ctx->n_sorted, LIST_NT);
+        switch (ctx->kernel * 4 + ctx->dim) {
+#define LIST_CASE(K, D) case K * 4 + D: k_pair_list<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg); break;
+            LIST_CASE(0, 1) LIST_CASE(0, 2) LIST_CASE(0, 3) LIST_CASE(1, 2) LIST_CASE(1, 3)
+            LIST_CASE(2, 1) LIST_CASE(2, 2) LIST_CASE(2, 3) LIST_CASE(3, 1) LIST_CASE(3, 2) LIST_CASE(3, 3)
+#undef LIST_CASE
+        default: return set_err(ctx, "pair_pass: unsupported kernel/dim combination");
+        }
+        LAUNCH_CHECK();
+        ctx->stats.pair_launches++;
+    } else if (ctx->n_sorted > 0 && use_tile) {
         const size_t smem = (size_t)ctx->tile_maxc * 48 + (size_t)TILE_CAP * TILE_NT * 4;
         cudaError_t e;
         switch (ctx->kernel) {
@@ -2105,6 +2483,8 @@ int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf, int64_
     if (as_real) ai.n_real += n;
     ctx->ptype_dirty = true;
     ctx->grid_valid = false;
+    ctx->topo_dirty = true;
+    ctx->h_dirty = true;
     ctx->domain_valid = false;
     ctx->state_packed = false;
     return 0;
@@ -2117,6 +2497,8 @@ int b200sph_drop_ghosts(b200sph_ctx *ctx, int arr)
         ctx->arr[arr].n = ctx->arr[arr].n_real;
         ctx->ptype_dirty = true;
         ctx->grid_valid = false;
+        ctx->topo_dirty = true;
+        ctx->h_dirty = true;
         ctx->state_packed = false;
     }
     return 0;
@@ -2175,6 +2557,8 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
     ai.n = ai.n_real = keep;
     ctx->ptype_dirty = true;
     ctx->grid_valid = false;
+    ctx->topo_dirty = true;
+    ctx->h_dirty = true;
     ctx->domain_valid = false;
     ctx->state_packed = false;
     return 0;
@@ -2196,6 +2580,10 @@ int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out)
         }
         ctx->pending.clear();
     }
+    ctx->stats.full_builds = ctx->n_full_builds;
+    ctx->stats.light_updates = ctx->n_light_updates;
+    ctx->stats.list_builds = ctx->n_list_builds;
+    ctx->stats.list_entries_per_particle = ctx->capg;
     *out = ctx->stats;
     return 0;
 }
@@ -2204,6 +2592,7 @@ int b200sph_reset_stats(b200sph_ctx *ctx)
     b200sph_stats tmp;
     b200sph_get_stats(ctx, &tmp);  // drain pending events
     memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->n_full_builds = ctx->n_light_updates = ctx->n_list_builds = 0;
     return 0;
 }
 int b200sph_set_profiling(b200sph_ctx *ctx, int on)

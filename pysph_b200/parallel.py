@@ -282,8 +282,13 @@ class SlabParallelManager(object):
 def make_slab_solver(dx, params, kernel, rank, world, device=0,
                      solid_weight=0.3, **solver_kw):
     """Build this rank's slab of the 3D dam break and a ready solver."""
+    import os
     import pysph_b200 as pb
     from . import geometry as geo
+    # the ghost set changes at every exchange, so persistent neighbour lists
+    # would be rebuilt every evaluation: use the list-free kernel (must be set
+    # before the context is created)
+    os.environ.setdefault('B200SPH_PAIR_KERNEL', 'warp')
     xs, w = dam_break_column_weights(dx, solid_weight=solid_weight)
     cuts = balanced_cuts(xs, w, world, dx)
     pas = geo.dam_break_3d_particles(dx=dx, xrange=(cuts[rank], cuts[rank + 1]))

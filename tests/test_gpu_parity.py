@@ -398,25 +398,29 @@ def test_size_independent_properties_100k(gpu_device):
     assert n_fb == cnt.value and n_fb > 0
 
 
-def test_warp_and_tile_kernels_agree(gpu_device, monkeypatch):
-    """Both pair kernels (tile fast path and the warp-per-destination fallback
-    used when a tile's candidates do not fit in shared memory) implement the
-    same accept test and arithmetic: identical pair counts, results within fp32
-    summation-order noise, on a perturbed 3-D dam break (variable velocities)
-    and on the 2-D gate."""
+def _perturbed_dam_break(dx=0.05, vscale=0.5, seed=9):
     from pysph_b200 import geometry as geo
+    pas = geo.dam_break_3d_particles(dx=dx)
+    rs = np.random.RandomState(seed)
+    f = pas[0]
+    for k in ('u', 'v', 'w'):
+        f.properties[k][:] = rs.normal(scale=vscale, size=f.u.size)
+    f.rho[:] *= 1 + 0.01 * rs.uniform(-1, 1, f.u.size)
+    return pas, geo.dam_break_3d_params(dx)
+
+
+def test_all_pair_kernels_agree(gpu_device, monkeypatch):
+    """The three pair-kernel paths -- persistent neighbour lists (default), the
+    warp-per-destination kernel (fallback, also used for > 2^26 particles) and
+    the experimental shared-memory tile kernel -- implement the same accept test
+    and arithmetic: identical pair counts, results within fp32 summation-order
+    noise, on a perturbed 3-D dam break."""
     out = {}
-    for which in ('warp', 'tile'):
+    for which in ('list', 'warp', 'tile'):
         monkeypatch.setenv('B200SPH_PAIR_KERNEL', which)
-        dx = 0.05
-        pas = geo.dam_break_3d_particles(dx=dx)
-        rs = np.random.RandomState(9)
+        pas, params = _perturbed_dam_break()
         f = pas[0]
-        for k in ('u', 'v', 'w'):
-            f.properties[k][:] = rs.normal(scale=0.5, size=f.u.size)
-        f.rho[:] *= 1 + 0.01 * rs.uniform(-1, 1, f.u.size)
-        s = make_solver(pas, scheme_params(geo.dam_break_3d_params(dx)),
-                        'CubicSpline')
+        s = make_solver(pas, scheme_params(params), 'CubicSpline')
         s.a_eval.count_pairs = True
         s.initialise()
         pairs = s.a_eval.last_pairs
@@ -424,8 +428,42 @@ def test_warp_and_tile_kernels_agree(gpu_device, monkeypatch):
         s.pull()
         out[which] = (pairs, dict((k, f.properties[k].copy())
                                   for k in ACC_FIELDS + ['x', 'u', 'rho']))
-    assert out['warp'][0] == out['tile'][0]
-    for k, v in out['warp'][1].items():
-        w = out['tile'][1][k]
-        scale = max(np.max(np.abs(v)), 1e-30)
-        assert np.max(np.abs(v - w)) <= 5e-6 * scale, k
+    for which in ('warp', 'tile'):
+        assert out['list'][0] == out[which][0]
+        for k, v in out['list'][1].items():
+            w = out[which][1][k]
+            scale = max(np.max(np.abs(v)), 1e-30)
+            assert np.max(np.abs(v - w)) <= 5e-6 * scale, (which, k)
+
+
+def test_list_reuse_is_exact(gpu_device, monkeypatch):
+    """Persistent lists with a skin give the same trajectory as rebuilding the
+    neighbours at every evaluation (skin 0), and as the fp64 oracle, over enough
+    fast steps that particles cross the skin several times."""
+    res = {}
+    for skin in ('0.1', '0.0'):
+        monkeypatch.setenv('B200SPH_SKIN', skin)
+        monkeypatch.setenv('B200SPH_PAIR_KERNEL', 'list')
+        pas, params = _perturbed_dam_break(vscale=3.0)
+        s = make_solver(pas, scheme_params(params), 'CubicSpline')
+        for _ in range(40):
+            s.step()
+        s.pull()
+        st = s.backend.stats()
+        res[skin] = (pas, st, s.t)
+    st = res['0.1'][1]
+    assert st['light_updates'] > 20, st          # lists really were reused ...
+    assert st['full_builds'] >= 3, st            # ... and rebuilt when the skin was used up
+    assert res['0.0'][1]['light_updates'] <= 2   # only updates with no motion at all
+    pas_a, pas_b = res['0.1'][0], res['0.0'][0]
+    assert abs(res['0.1'][2] - res['0.0'][2]) <= 1e-6 * res['0.0'][2]
+    params = _perturbed_dam_break()[1]
+    _compare_state(pas_a, pas_b, tol_pos=2e-6, tol_vel=2e-6, tol_rho=2e-7,
+                   h0=params['h0'], c0=params['c0'], rho0=params['rho0'])
+    # and against the oracle
+    opas, _ = _perturbed_dam_break(vscale=3.0)
+    o = orc.WCSPHOracleSolver(opas, params, 'CubicSpline', threads=4)
+    for _ in range(40):
+        o.step()
+    _compare_state(pas_a, opas, tol_pos=2e-6, tol_vel=2e-6, tol_rho=2e-7,
+                   h0=params['h0'], c0=params['c0'], rho0=params['rho0'])
