@@ -128,6 +128,10 @@ int b200sph_push_u32(b200sph_ctx *ctx, int arr, int prop, const uint32_t *host,
                      int64_t start, int64_t count);
 int b200sph_pull_u32(b200sph_ctx *ctx, int arr, int prop, uint32_t *host,
                      int64_t start, int64_t count);
+/* on != 0: push/pull only enqueue the copies on the context's stream and return;
+ * the host buffers (which should be pinned) stay borrowed until the next
+ * b200sph_synchronize.  Default off: every push/pull call is synchronous. */
+int b200sph_set_async_copies(b200sph_ctx *ctx, int on);
 /* device pointer of a property region of one array (for zero-copy use by
  * torch / NCCL plumbing); fp64 props -> double*, fp32 props -> float* */
 int b200sph_device_ptr(b200sph_ctx *ctx, int arr, int prop, void **out);

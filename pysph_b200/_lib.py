@@ -79,6 +79,7 @@ SIGNATURES = {
     'b200sph_pull_f64': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, _i64, _i64]),
     'b200sph_push_u32': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, _i64, _i64]),
     'b200sph_pull_u32': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p, _i64, _i64]),
+    'b200sph_set_async_copies': (C.c_int, [_ctx_p, C.c_int]),
     'b200sph_device_ptr': (C.c_int, [_ctx_p, C.c_int, C.c_int,
                                      C.POINTER(C.c_void_p)]),
     'b200sph_set_kernel': (C.c_int, [_ctx_p, C.c_int, C.c_int]),

@@ -58,6 +58,15 @@ struct GridDev {
             // R-cell span (cx / R) * R that contains the particle's cell
 };
 
+// equation-of-state calls wait here until the next k_pack_state applies them in the
+// same pass that gathers the state into the pair records (saves one launch and one
+// sweep over rho/p/cs per array and evaluation); eos_flush() runs them stand-alone
+// if something reads rho/p/cs before that.
+struct EosTab {
+    int on[B200SPH_MAX_ARRAYS], hg[B200SPH_MAX_ARRAYS], real_only[B200SPH_MAX_ARRAYS];
+    double rho0[B200SPH_MAX_ARRAYS], c0[B200SPH_MAX_ARRAYS], gamma[B200SPH_MAX_ARRAYS], p0[B200SPH_MAX_ARRAYS];
+};
+
 struct PendingEvent {
     cudaEvent_t e0, e1;
     int slot;  // 0 nnps, 1 pair, 2 other
@@ -101,15 +110,19 @@ struct b200sph_ctx {
     int64_t blk_cap = 0;
     uint32_t *perm_tmp = nullptr, *perm = nullptr, *skey = nullptr, *rank = nullptr;
     float4 *A = nullptr, *B = nullptr, *C = nullptr;
+    float4 *BC = nullptr;  // {B, C} interleaved (32 B per particle) for the list consumer's 256-bit gathers
     int64_t n_sorted = 0;
     bool state_packed = false;
     // tile kernel configuration (decided by nnps_update)
     int tile_R = 1;
     int tiles_per_row = 1;
+    int tiles_y = 1, tiles_z = 1;  // 3-D tiles (R x 2 x 2 cells) of the list consumer
+    int tile_nt = 256;             // threads per consumer CTA
     int64_t ntiles = 0;
     int64_t tile_maxc = 0;   // max candidates a tile stages
     bool tile_ok = false;
-    double avg_per_cell = 0.0;  // particles per non-empty cell, from the last build
+    double occ_per_cell = 0.0;  // particle-weighted mean cell occupancy, from the last build
+    int tile_R_env = 0;         // env B200SPH_TILE_R
     int force_kernel = 0;       // 0 lists (default), 1 warp kernel, 2 tile kernel (env B200SPH_PAIR_KERNEL)
     // persistent neighbour lists
     double skin = 0.1;          // S = skin * radius_scale * hmax   (env B200SPH_SKIN)
@@ -137,9 +150,13 @@ struct b200sph_ctx {
     uint32_t *flag_a = nullptr, *flag_b = nullptr;  // [pool+1] scan scratch
     int64_t flag_cap = 0;
 
+    EosTab eos_pending;
+    bool eos_any = false;
+
     // stats
     b200sph_stats stats;
     bool profiling = false;
+    bool async_copies = false;  // push/pull return without waiting (pinned host buffers)
     std::vector<PendingEvent> pending;
     std::vector<cudaEvent_t> ev_pool;
 };
@@ -530,26 +547,49 @@ __global__ void k_pack_pos(const double *__restrict__ x, const double *__restric
     A[s] = a;
 }
 
-// B[s] = (u, v, w, m);  C[s] = (rho, p/rho^2, cs, type)
+// B[s] = (u, v, w, m);  C[s] = (rho, p/rho^2, cs, type); pending TaitEOS /
+// TaitEOSHGCorrection calls (wc/basic.py:60-65,118-126) are applied on the way
 __global__ void k_pack_state(const double *__restrict__ u, const double *__restrict__ v,
                              const double *__restrict__ w, const double *__restrict__ m,
-                             const double *__restrict__ rho, const float *__restrict__ p,
-                             const float *__restrict__ cs, const uint8_t *__restrict__ ptype,
+                             double *__restrict__ rho, float *__restrict__ p,
+                             float *__restrict__ cs, const uint8_t *__restrict__ ptype,
                              const uint32_t *__restrict__ perm, long long n,
-                             float4 *__restrict__ B, float4 *__restrict__ C)
+                             float4 *__restrict__ B, float4 *__restrict__ C,
+                             float4 *__restrict__ BC, const EosTab E, const int eos_any)
 {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const uint32_t g = perm[s];
+    const int t = (int)ptype[g];
     float4 b, c;
     b.x = (float)u[g]; b.y = (float)v[g]; b.z = (float)w[g]; b.w = (float)m[g];
-    const double r = rho[g];
+    double r = rho[g];
+    float pg, csg;
+    const int a = t & 7;
+    if (eos_any && E.on[a] && !(E.real_only[a] && (t & PT_GHOST))) {
+        const double rho0 = E.rho0[a];
+        if (E.hg[a] && r < rho0) {
+            r = rho0;
+            rho[g] = r;
+        }
+        const double ratio = r * (1.0 / rho0);
+        const double Bc = rho0 * E.c0[a] * E.c0[a] / E.gamma[a];
+        pg = (float)((E.hg[a] ? 0.0 : E.p0[a]) + Bc * (pow(ratio, E.gamma[a]) - 1.0));
+        csg = (float)(E.c0[a] * pow(ratio, 0.5 * (E.gamma[a] - 1.0)));
+        p[g] = pg;
+        cs[g] = csg;
+    } else {
+        pg = p[g];
+        csg = cs[g];
+    }
     c.x = (float)r;
-    c.y = (float)((double)p[g] / (r * r));
-    c.z = cs[g];
-    c.w = __int_as_float((int)ptype[g]);
+    c.y = (float)((double)pg / (r * r));
+    c.z = csg;
+    c.w = __int_as_float(t);
     B[s] = b;
     C[s] = c;
+    BC[2 * s] = b;
+    BC[2 * s + 1] = c;
 }
 
 // --------------------------------------------------------------------------
@@ -607,7 +647,7 @@ template <> __device__ __forceinline__ void sph_kernel<3>(float q, float &w, flo
 // the fused pair kernel
 // --------------------------------------------------------------------------
 struct PairArgs {
-    const float4 *A, *B, *C;
+    const float4 *A, *B, *C, *BC;
     const uint32_t *cell_start, *skey, *perm;
     float *arho, *au, *av, *aw, *ax, *ay, *az, *dt_cfl, *dt_force;
     double *rho;  // SummationDensity destination (fp64 state)
@@ -622,6 +662,8 @@ struct PairArgs {
     unsigned long long *pair_counter;  // may be null
     // tile kernel only
     int R, tiles_per_row, need_type;  // need_type: bit t set if dest type t skips some source type
+    int nty;           // 3-D tiles of the list consumer: tiles per row in x = tiles_per_row, in y = nty
+    int frameR;        // span of the x frames of the packed records (GridDev.R)
 };
 
 #define PAIR_WARPS 8
@@ -743,8 +785,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
             const int cz = (int)(kq / (uint32_t)a.ncy);
             // x origins differ between R-cell spans: offsets (in cells) of the left /
             // right neighbour cell's span origin relative to this cell's span origin
-            xo_m = (float)((max(cx - 1, 0) / a.R - cx / a.R) * a.R) * a.cell;
-            xo_p = (float)(((cx + 1) / a.R - cx / a.R) * a.R) * a.cell;
+            xo_m = (float)((max(cx - 1, 0) / a.frameR - cx / a.frameR) * a.frameR) * a.cell;
+            xo_p = (float)(((cx + 1) / a.frameR - cx / a.frameR) * a.frameR) * a.cell;
             r_rs = r_b1 = r_b2 = r_re = 0;
             if (lane < 9) {
                 const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
@@ -887,6 +929,7 @@ struct ListBuildArgs {
     uint32_t *lst;   // null: count only
     int capg;        // entries reserved per destination
     unsigned *max_count;
+    int R;           // cells per tile: entries index the tile's staged candidate rows
 };
 
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildArgs a)
@@ -898,6 +941,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
     uint32_t cur_key = 0xFFFFFFFFu;
     int cx = 0;
     uint32_t r_rs = 0, r_b1 = 0, r_b2 = 0, r_re = 0;
+    uint32_t t_lo = 0, t_off = 0;  // lane q < 16: first sorted index / staged offset of the tile's row q
+    int row0 = 5;
     unsigned wmax = 0;
     for (int kk = 0; kk < PAIR_CHUNK; kk++) {
         const long long s = first + kk;
@@ -923,6 +968,28 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
                     r_re = a.cell_start[base + x1 + 1];
                 }
             }
+            // the 3-D tile (R x 2 x 2 cells) of this destination cell stages 4 x 4 candidate
+            // rows; lane q < 16 holds row q = (yy - (2 ty - 1)) + 4 (zz - (2 tz - 1))
+            t_lo = 0;
+            uint32_t t_n = 0;
+            if (lane < 16) {
+                const int yy = (cy & ~1) - 1 + (lane & 3), zz = (cz & ~1) - 1 + (lane >> 2);
+                if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
+                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+                    const int cx_lo = (cx / a.R) * a.R, cx_hi = min(cx_lo + a.R - 1, a.ncx - 1);
+                    t_lo = a.cell_start[base + max(cx_lo - 1, 0)];
+                    t_n = a.cell_start[base + min(cx_hi + 2, a.ncx)] - t_lo;
+                }
+            }
+            // exclusive prefix of the row sizes = offset of a row in the staged tile
+            uint32_t inc = t_n;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += v;
+            }
+            t_off = inc - t_n;
+            row0 = ((int)(cy & 1) + 1) + 4 * ((int)(cz & 1) + 1);  // tile row of (dy, dz) = (0, 0)
         }
         float hi = a.kr * Ai.w + a.S;
         const float hi2 = hi * hi;
@@ -934,6 +1001,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
             if (rs >= re) continue;
             const uint32_t b1 = __shfl_sync(FULL, r_b1, r);
             const uint32_t b2 = __shfl_sync(FULL, r_b2, r);
+            const int q = row0 + ((r % 3) - 1) + 4 * ((r / 3) - 1);
+            const uint32_t loc = __shfl_sync(FULL, t_off, q) - __shfl_sync(FULL, t_lo, q);  // t -> staged index
             const float yoff = Ai.y - (float)((r % 3) - 1) * a.cell;
             const float zoff = Ai.z - (float)((r / 3) - 1) * a.cell;
             const uint32_t rcode = (uint32_t)(4 * (r % 3) + 16 * (r / 3));
@@ -954,7 +1023,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
                 const unsigned m = __ballot_sync(FULL, ok);
                 if (ok && out) {
                     const unsigned pos = count + __popc(m & lt_mask);
-                    if (pos < (unsigned)a.capg) out[(size_t)pos * 32u] = t | ((rcode + dxc1) << LIST_JBITS);
+                    if (pos < (unsigned)a.capg) out[(size_t)pos * 32u] = (t + loc) | ((rcode + dxc1) << LIST_JBITS);
                 }
                 count += __popc(m);
             }
@@ -965,75 +1034,224 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
     if (lane == 0 && wmax) atomicMax(a.max_count, wmax);
 }
 
-template <int K, int DIM>
-__global__ void __launch_bounds__(LIST_NT, 4) k_pair_list(const PairArgs a, const uint32_t *__restrict__ cnt,
-                                                         const uint32_t *__restrict__ lst, const int capg)
+// one 256-bit read-only load (LDG.E.256 on sm_100a): {B, C} of one candidate
+__device__ __forceinline__ void ld_bc(const float4 *p, float4 &b, float4 &c)
 {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w), "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w)
+                 : "l"(p));
+}
+
+// ---- TMA (cp.async.bulk) + mbarrier helpers ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned done = 0;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// tile geometry shared by the stats kernel, the list builder and the consumer:
+// tile (tx, ty, tz) covers cells [tx R, tx R + R) x {2 ty, 2 ty + 1} x {2 tz, 2 tz + 1}
+// and stages the 4 x 4 candidate rows yy = 2 ty - 1 + (q & 3), zz = 2 tz - 1 + (q >> 2),
+// each the contiguous sorted range of cells cx_lo - 1 .. cx_hi + 1.
+__global__ void k_tile3_stats(const uint32_t *__restrict__ cs, int ncx, int ncy, int ncz, int R,
+                              int ntx, int nty, long long ntiles, unsigned long long *stats)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int tx = (int)(t % ntx), ty = (int)((t / ntx) % nty), tz = (int)(t / ((long long)ntx * nty));
+    const int cx_lo = tx * R, cx_hi = min(cx_lo + R - 1, ncx - 1);
+    unsigned long long nd = 0, cand = 0;
+    for (int q = 0; q < 16; q++) {
+        const int yy = 2 * ty - 1 + (q & 3), zz = 2 * tz - 1 + (q >> 2);
+        if (yy < 0 || yy >= ncy || zz < 0 || zz >= ncz) continue;
+        const uint32_t b = ((uint32_t)yy + (uint32_t)ncy * (uint32_t)zz) * (uint32_t)ncx;
+        cand += cs[b + min(cx_hi + 2, ncx)] - cs[b + max(cx_lo - 1, 0)];
+        if (((q & 3) == 1 || (q & 3) == 2) && ((q >> 2) == 1 || (q >> 2) == 2))
+            nd += cs[b + cx_hi + 1] - cs[b + cx_lo];
+    }
+    if (!nd) return;
+    atomicMax(&stats[0], cand);
+    atomicAdd(&stats[2], 1ull);
+    atomicMax(&stats[4], nd);
+}
+
+// The list consumer with shared-memory staged candidates (the default fast path).
+// One CTA = one 3-D tile.  The 16 candidate rows are contiguous ranges of the sorted
+// SoA records, so one elected thread stages them with up to 48 TMA bulk copies
+// (cp.async.bulk + mbarrier: no per-element instructions); the list entries built by
+// k_list_build index the staged tile, so the scattered 16-byte gathers of the pair
+// loop hit shared memory (a global-gather consumer saturates the L1 tag stage:
+// profiles/r01e).  2 x 2 rows of destinations share the 4 x 4 candidate rows, i.e.
+// ~5.6 staged candidates per destination instead of ~12 with one-row tiles, which is
+// what makes the shared-memory footprint compatible with >= 24 resident warps.
+template <int K, int DIM>
+__global__ void __launch_bounds__(512) k_pair_tlist(const PairArgs a, const uint32_t *__restrict__ cnt,
+                                                   const uint32_t *__restrict__ lst, const int capg)
+{
+    extern __shared__ float4 dyn_smem[];
     __shared__ float4 s_T[64];
-    const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cell, -(float)dy * a.cell, -(float)dz * a.cell, 0.f);
+    __shared__ uint32_t s_lo[16], s_off[17];  // candidate rows: first sorted index, staged offset
+    __shared__ uint32_t s_ds[4], s_dp[5];     // destination segments: first sorted index, prefix count
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const unsigned FULL = 0xffffffffu;
+    const int R = a.R;
+    const int tx = (int)(blockIdx.x % (uint32_t)a.tiles_per_row);
+    const int ty = (int)((blockIdx.x / (uint32_t)a.tiles_per_row) % (uint32_t)a.nty);
+    const int tz = (int)(blockIdx.x / ((uint32_t)a.tiles_per_row * (uint32_t)a.nty));
+    const int cx_lo = tx * R, cx_hi = min(cx_lo + R - 1, a.ncx - 1);
+    if (tid < 16) {
+        const int yy = 2 * ty - 1 + (tid & 3), zz = 2 * tz - 1 + (tid >> 2);
+        uint32_t lo = 0, n = 0, ds = 0, dn = 0;
+        if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
+            const uint32_t b = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+            lo = a.cell_start[b + max(cx_lo - 1, 0)];
+            n = a.cell_start[b + min(cx_hi + 2, a.ncx)] - lo;
+            if (((tid & 3) == 1 || (tid & 3) == 2) && ((tid >> 2) == 1 || (tid >> 2) == 2)) {
+                ds = a.cell_start[b + cx_lo];
+                dn = a.cell_start[b + cx_hi + 1] - ds;
+            }
+        }
+        // exclusive prefixes over the 16 lanes
+        uint32_t inc = n, dinc = dn;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffu, inc, o), dv = __shfl_up_sync(0xffffu, dinc, o);
+            if (tid >= o) { inc += v; dinc += dv; }
+        }
+        s_lo[tid] = lo;
+        s_off[tid] = inc - n;
+        if (tid == 15) s_off[16] = inc;
+        const int dq = ((tid & 3) - 1) + 2 * ((tid >> 2) - 1);  // 0..3 for the destination rows
+        if (((tid & 3) == 1 || (tid & 3) == 2) && ((tid >> 2) == 1 || (tid >> 2) == 2)) {
+            s_ds[dq] = ds;
+            s_dp[dq] = dinc - dn;
+        }
+        if (tid == 15) s_dp[4] = dinc;
+    }
+    if (tid >= 32 && tid < 96) {
+        const int c = tid - 32;
+        const int dxc = (c & 3) - 1, dy = ((c >> 2) & 3) - 1, dz = (c >> 4) - 1;
+        s_T[c] = make_float4(-(float)dxc * a.cell, -(float)dy * a.cell, -(float)dz * a.cell, 0.f);
     }
     __syncthreads();
-    const unsigned FULL = 0xffffffffu;
-    const long long s = (long long)blockIdx.x * LIST_NT + tid;
-    bool active = s < a.n;
-    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = Ai;
-    unsigned long long mask_i = 0;
-    int count = 0;
-    if (active) {
-        Ci = a.C[s];
-        const int ti = __float_as_int(Ci.w);
-        mask_i = a.emask[ti & 7];
-        if ((a.real_only && (ti & PT_GHOST)) || !mask_i) active = false;
+    const uint32_t nd = s_dp[4];
+    if (nd == 0) return;  // empty tile (uniform)
+    const uint32_t ncand = s_off[16];
+    float4 *sA = dyn_smem;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_expect_tx(&s_bar, ncand * 16u);
     }
-    if (active) {
-        Ai = a.A[s];
-        Bi = a.B[s];
-        count = (int)cnt[s];
+    __syncthreads();
+    if (tid < 16) {  // one lane per candidate row issues its bulk copy
+        const uint32_t n = s_off[tid + 1] - s_off[tid];
+        if (n) tma_bulk_g2s(sA + s_off[tid], a.A + s_lo[tid], n * 16u, &s_bar);
     }
-    int cmax = count;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
-    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
-    const float hi2 = a.k2 * Ai.w * Ai.w;
-    const float tmpi = Ci.y;
-    Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    mbar_wait(&s_bar, 0);
+
     unsigned npairs = 0;
-    for (int k = 0; k < cmax; k++) {
-        if (k < count) {
-            const uint32_t e = my[(size_t)k * 32u];
-            const uint32_t j = e & LIST_JMASK;
-            const float4 T = s_T[e >> LIST_JBITS];
-            const float4 Aj = a.A[j];
-            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
-            const float r2 = xij * xij + yij * yij + zij * zij;
-            // the exact accept test, linked_list_nnps.pyx:188
-            if ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w))
-                pair_body<K, DIM>(a, make_float4(xij, yij, zij, Aj.w), a.B[j], a.C[j], Ai, Bi, Ci, mask_i,
-                                  tmpi, acc, npairs);
+    for (uint32_t t0 = 0; t0 < nd; t0 += NT) {
+        const uint32_t t = t0 + tid;
+        bool active = t < nd;
+        uint32_t s = 0, own = 0;
+        int q_own = 5;
+        if (active) {
+            const int dq = (t >= s_dp[1]) + (t >= s_dp[2]) + (t >= s_dp[3]);
+            s = s_ds[dq] + (t - s_dp[dq]);
+            q_own = 5 + (dq & 1) + 4 * (dq >> 1);  // tile row of destination segment dq
+            own = s_off[q_own] + (s - s_lo[q_own]);
         }
-    }
-    if (active) {
-        unsigned all_bits = 0;
+        float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = Ai;
+        unsigned long long mask_i = 0;
+        int count = 0;
+        if (active) {
+            ld_bc(a.BC + 2 * (size_t)s, Bi, Ci);
+            const int ti = __float_as_int(Ci.w);
+            mask_i = a.emask[ti & 7];
+            if ((a.real_only && (ti & PT_GHOST)) || !mask_i) active = false;
+        }
+        if (active) {
+            Ai = sA[own];
+            count = (int)cnt[s];
+        }
+        int cmax = count;
 #pragma unroll
-        for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
-        const uint32_t g = a.perm[s];
-        if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
-        if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
-        if (all_bits & B200SPH_EQ_MOMENTUM) {
-            // post_loop wc/basic.py:259-269
-            const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
-            a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
-            a.dt_cfl[g] = acc.cfl;
-            a.dt_force[g] = fu * fu + fv * fv + fw * fw;
-        } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
-            a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
+        for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+        if (cmax == 0) continue;  // warp-uniform
+        const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
+        const float hi2 = a.k2 * Ai.w * Ai.w;
+        const float tmpi = Ci.y;
+        Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // list entries stream from global memory two iterations ahead
+        uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
+        uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
+        for (int k = 0; k < cmax; k++) {
+            const uint32_t e = e_a;
+            e_a = e_b;
+            if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
+            if (k < count) {
+                const uint32_t j = e & LIST_JMASK;
+                const float4 T = s_T[e >> LIST_JBITS];
+                const float4 Aj = sA[j];
+                const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+                const float r2 = xij * xij + yij * yij + zij * zij;
+                // the exact accept test, linked_list_nnps.pyx:188
+                if ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) {
+                    // staged index -> sorted index: the candidate sits in tile row q
+                    const uint32_t code = e >> LIST_JBITS;
+                    const int q = q_own + (int)((code >> 2) & 3u) - 1 + 4 * ((int)(code >> 4) - 1);
+                    float4 Bj, Cj;
+                    ld_bc(a.BC + 2 * (size_t)(j + s_lo[q] - s_off[q]), Bj, Cj);
+                    pair_body<K, DIM>(a, make_float4(xij, yij, zij, Aj.w), Bj, Cj, Ai, Bi, Ci, mask_i, tmpi,
+                                      acc, npairs);
+                }
+            }
         }
-        if (all_bits & B200SPH_EQ_XSPH) {
-            // post_loop basic_equations.py:297-300
-            a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
+        if (active) {
+            unsigned all_bits = 0;
+#pragma unroll
+            for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
+            const uint32_t g = a.perm[s];
+            if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
+            if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
+            if (all_bits & B200SPH_EQ_MOMENTUM) {
+                // post_loop wc/basic.py:259-269
+                const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
+                a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
+                a.dt_cfl[g] = acc.cfl;
+                a.dt_force[g] = fu * fu + fv * fv + fw * fw;
+            } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
+                a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
+            }
+            if (all_bits & B200SPH_EQ_XSPH) {
+                // post_loop basic_equations.py:297-300
+                a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
+            }
         }
     }
     if (a.pair_counter) {
@@ -1112,8 +1330,16 @@ __global__ void k_tile_stats(const uint32_t *__restrict__ cs, int ncx, int ncy, 
     const int cx_lo = chunk * R, cx_hi = min(cx_lo + R - 1, ncx - 1);
     const uint32_t base = row * (uint32_t)ncx;
     unsigned nonempty = 0;
-    for (int c = cx_lo; c <= cx_hi; c++) nonempty += cs[base + c + 1] > cs[base + c];
-    if (nonempty) atomicAdd(&stats[1], (unsigned long long)nonempty);
+    unsigned long long sq = 0;
+    for (int c = cx_lo; c <= cx_hi; c++) {
+        const unsigned long long nn = cs[base + c + 1] - cs[base + c];
+        nonempty += nn > 0;
+        sq += nn * nn;
+    }
+    if (nonempty) {
+        atomicAdd(&stats[1], (unsigned long long)nonempty);
+        atomicAdd(&stats[3], sq);
+    }
     if (cs[base + cx_hi + 1] == cs[base + cx_lo]) return;
     const int cy = (int)(row % (uint32_t)ncy), cz = (int)(row / (uint32_t)ncy);
     unsigned long long cand = 0;
@@ -1472,6 +1698,7 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     if (ctx->A) cudaFree(ctx->A);
     if (ctx->B) cudaFree(ctx->B);
     if (ctx->C) cudaFree(ctx->C);
+    if (ctx->BC) cudaFree(ctx->BC);
     if (ctx->A0) cudaFree(ctx->A0);
     if (ctx->cnt) cudaFree(ctx->cnt);
     if (ctx->flag_a) cudaFree(ctx->flag_a);
@@ -1485,6 +1712,7 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     CU(cudaMalloc((void **)&ctx->A, 16 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->B, 16 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->C, 16 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->BC, 32 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->A0, 16 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->cnt, 4 * (size_t)alloc));
     ctx->lists_valid = false;
@@ -1633,6 +1861,8 @@ static double kernel_deltap(int kernel)
 
 extern "C" {
 
+static int eos_flush(b200sph_ctx *ctx);
+
 int b200sph_abi_version(void) { return B200SPH_ABI_VERSION; }
 
 int b200sph_create(int device, b200sph_ctx **out)
@@ -1648,6 +1878,7 @@ int b200sph_create(int device, b200sph_ctx **out)
     b200sph_ctx *ctx = new b200sph_ctx();
     ctx->device = device;
     memset(&ctx->grid, 0, sizeof(ctx->grid));
+    memset(&ctx->eos_pending, 0, sizeof(ctx->eos_pending));
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     *out = ctx;
     CU(cudaSetDevice(device));
@@ -1664,6 +1895,7 @@ int b200sph_create(int device, b200sph_ctx **out)
         }
     }
     if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = std::max(0.0, atof(e));
+    if (const char *e = getenv("B200SPH_TILE_R")) ctx->tile_R_env = atoi(e);
     CU(cudaMalloc((void **)&ctx->red_u32, 4 * sizeof(unsigned)));
     CU(cudaMallocHost((void **)&ctx->red_u32_host, 4 * sizeof(unsigned)));
     CU(cudaMalloc((void **)&ctx->red, 16 * sizeof(long long)));
@@ -1684,7 +1916,7 @@ int b200sph_destroy(b200sph_ctx *ctx)
     cudaFree(ctx->ptype);
     cudaFree(ctx->key_of); cudaFree(ctx->off_in); cudaFree(ctx->cell_cnt); cudaFree(ctx->cell_start);
     cudaFree(ctx->blk_sums); cudaFree(ctx->perm_tmp); cudaFree(ctx->perm); cudaFree(ctx->skey);
-    cudaFree(ctx->rank); cudaFree(ctx->A); cudaFree(ctx->B); cudaFree(ctx->C);
+    cudaFree(ctx->rank); cudaFree(ctx->A); cudaFree(ctx->B); cudaFree(ctx->C); cudaFree(ctx->BC);
     cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->counter);
     cudaFreeHost(ctx->counter_host); cudaFree(ctx->stage_buf); cudaFree(ctx->flag_a);
     cudaFree(ctx->flag_b); cudaFree(ctx->A0); cudaFree(ctx->lst); cudaFree(ctx->cnt);
@@ -1753,6 +1985,7 @@ int b200sph_resize_array(b200sph_ctx *ctx, int arr, int64_t n, int64_t n_real)
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "resize_array: bad array %d", arr);
     if (n < 0 || n_real < 0 || n_real > n) return set_err(ctx, "resize_array: bad sizes");
     CU(cudaSetDevice(ctx->device));
+    { int rc0 = eos_flush(ctx); if (rc0) return rc0; }
     if (ctx->pool_cap == 0) {
         ctx->arr[arr].cap = std::max(ctx->arr[arr].cap, n);
     } else {
@@ -1814,7 +2047,7 @@ int b200sph_push_f64(b200sph_ctx *ctx, int arr, int prop, const double *host, in
         return set_err(ctx, "push_f64: property id %d is not a floating point property", prop);
     }
     // the host buffer is borrowed only for this call
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->async_copies) CU(cudaStreamSynchronize(ctx->stream));
     if (prop == B200SPH_H) { ctx->domain_valid = false; ctx->h_dirty = true; }
     if (prop <= B200SPH_Z || prop == B200SPH_H) { ctx->grid_valid = false; ctx->topo_dirty = true; }
     ctx->state_packed = false;
@@ -1826,6 +2059,7 @@ int b200sph_pull_f64(b200sph_ctx *ctx, int arr, int prop, double *host, int64_t 
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
     if ((rc = check_range(ctx, arr, start, count))) return rc;
     if (count == 0) return 0;
     const int64_t o = ctx->arr[arr].off + start;
@@ -1839,7 +2073,7 @@ int b200sph_pull_f64(b200sph_ctx *ctx, int arr, int prop, double *host, int64_t 
     } else {
         return set_err(ctx, "pull_f64: property id %d is not a floating point property", prop);
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->async_copies) CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -1853,7 +2087,7 @@ int b200sph_push_u32(b200sph_ctx *ctx, int arr, int prop, const uint32_t *host, 
     if (k < 0) return set_err(ctx, "push_u32: property id %d is not an integer property", prop);
     if (count == 0) return 0;
     CU(cudaMemcpyAsync(ctx->u32[k] + ctx->arr[arr].off + start, host, 4 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->async_copies) CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -1867,7 +2101,7 @@ int b200sph_pull_u32(b200sph_ctx *ctx, int arr, int prop, uint32_t *host, int64_
     if (k < 0) return set_err(ctx, "pull_u32: property id %d is not an integer property", prop);
     if (count == 0) return 0;
     CU(cudaMemcpyAsync(host, ctx->u32[k] + ctx->arr[arr].off + start, 4 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->async_copies) CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -1964,6 +2198,7 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
     if (!ctx->domain_valid && (rc = b200sph_update_domain(ctx))) return rc;
     PhaseTimer pt(ctx, 0);
 
@@ -2079,40 +2314,64 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         const unsigned ns = (unsigned)cdiv(ntot, 256);
         k_canon<<<ns, 256, 0, ctx->stream>>>(ctx->perm_tmp, ctx->key_of, ctx->cell_start, ntot, ctx->perm, ctx->skey, ctx->rank);
         LAUNCH_CHECK();
-        if (ctx->force_kernel == 2) {
-            // tile kernel: choose the span R (cells per tile) so that a tile holds ~TILE_NT destinations
-            const int64_t nrows = (int64_t)nc[1] * nc[2];
-            if (ctx->avg_per_cell <= 0.0) {  // first build: count the non-empty cells once
-                CU(cudaMemsetAsync(ctx->counter + 2, 0, 3 * sizeof(unsigned long long), ctx->stream));
+        const int64_t nrows = (int64_t)nc[1] * nc[2];
+        if (use_lists || ctx->force_kernel == 2) {
+            if (ctx->occ_per_cell <= 0.0) {  // first build: measure the cell occupancy once
+                CU(cudaMemsetAsync(ctx->counter + 2, 0, 5 * sizeof(unsigned long long), ctx->stream));
                 k_tile_stats<<<(unsigned)cdiv(nrows * nc[0], 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], 1, nc[0], nrows * nc[0], ctx->counter + 2);
                 LAUNCH_CHECK();
-                CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
                 CU(cudaStreamSynchronize(ctx->stream));
-                ctx->avg_per_cell = (double)ntot / (double)std::max<unsigned long long>(ctx->counter_host[3], 1ull);
+                // particle-weighted mean occupancy: what a typical particle's cell holds
+                ctx->occ_per_cell = (double)ctx->counter_host[5] / (double)std::max<int64_t>(ntot, 1);
             }
-            int R = (int)((double)TILE_NT / std::max(ctx->avg_per_cell, 1.0));
-            R = std::min(std::max(R, 1), TILE_MAXR);
-            R = std::min(R, nc[0]);
-            G.R = R;
+        }
+        if (ctx->force_kernel == 2) {
+            // experimental one-row tile kernel: span-relative x frames
+            int R = ctx->tile_R_env > 0 ? ctx->tile_R_env : (int)((double)TILE_NT / std::max(ctx->occ_per_cell, 1.0));
+            R = std::min(std::min(std::max(R, 1), TILE_MAXR), nc[0]);
             ctx->tile_R = R;
             ctx->tiles_per_row = (int)cdiv(nc[0], R);
             ctx->ntiles = nrows * ctx->tiles_per_row;
+            G.R = R;
+        } else if (use_lists) {
+            // 3-D tiles (R x 2 x 2 cells) of the list consumer: aim at ~256 destinations
+            const int dims_yz = (nc[1] > 1 ? 2 : 1) * (nc[2] > 1 ? 2 : 1);
+            int R = ctx->tile_R_env > 0 ? ctx->tile_R_env : (int)(256.0 / (dims_yz * std::max(ctx->occ_per_cell, 1.0)));
+            R = std::min(std::min(std::max(R, 1), 64), nc[0]);
+            ctx->tile_R = R;
+            ctx->tiles_per_row = (int)cdiv(nc[0], R);
+            ctx->tiles_y = (int)cdiv(nc[1], 2);
+            ctx->tiles_z = (int)cdiv(nc[2], 2);
+            ctx->ntiles = (int64_t)ctx->tiles_per_row * ctx->tiles_y * ctx->tiles_z;
         }
         k_pack_pos<<<ns, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H],
                                                 ctx->perm, ctx->skey, ntot, G, ctx->A);
         LAUNCH_CHECK();
         if (use_lists)
             CU(cudaMemcpyAsync(ctx->A0, ctx->A, 16 * (size_t)ntot, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (ctx->force_kernel == 2) {
-            CU(cudaMemsetAsync(ctx->counter + 2, 0, 3 * sizeof(unsigned long long), ctx->stream));
-            k_tile_stats<<<(unsigned)cdiv(ctx->ntiles, 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], ctx->tile_R, ctx->tiles_per_row, ctx->ntiles, ctx->counter + 2);
+        if (use_lists || ctx->force_kernel == 2) {
+            CU(cudaMemsetAsync(ctx->counter + 2, 0, 5 * sizeof(unsigned long long), ctx->stream));
+            if (ctx->force_kernel == 2)
+                k_tile_stats<<<(unsigned)cdiv(ctx->ntiles, 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], ctx->tile_R, ctx->tiles_per_row, ctx->ntiles, ctx->counter + 2);
+            else
+                k_tile3_stats<<<(unsigned)cdiv(ctx->ntiles, 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], ctx->tile_R, ctx->tiles_per_row, ctx->tiles_y, ctx->ntiles, ctx->counter + 2);
             LAUNCH_CHECK();
-            CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             ctx->tile_maxc = (int64_t)ctx->counter_host[2];
-            ctx->avg_per_cell = (double)ntot / (double)std::max<unsigned long long>(ctx->counter_host[3], 1ull);
-            const int64_t smem_need = ctx->tile_maxc * 48 + (int64_t)TILE_CAP * TILE_NT * 4;
+            if (ctx->force_kernel == 2) ctx->occ_per_cell = (double)ctx->counter_host[5] / (double)std::max<int64_t>(ntot, 1);
+            const int64_t maxd = (int64_t)ctx->counter_host[6];
+            ctx->tile_nt = (int)std::min<int64_t>(512, std::max<int64_t>(64, (maxd + 31) / 32 * 32));
+            const int64_t smem_need = ctx->force_kernel == 2 ? ctx->tile_maxc * 48 + (int64_t)TILE_CAP * TILE_NT * 4 : ctx->tile_maxc * 16;
             ctx->tile_ok = ctx->tile_maxc < 65536 && smem_need <= 200 * 1024 && ctx->ntiles < 2147483647LL;
+            if (getenv("B200SPH_DEBUG")) {
+                static int shown = 0;
+                if (shown++ < 3)
+                    fprintf(stderr, "b200sph: tiles R=%d grid=%dx%dx%d ntiles=%lld nonempty=%llu max_cands=%lld max_dests=%lld NT=%d occ/cell=%.2f smem=%lld B tile_ok=%d\n",
+                            ctx->tile_R, ctx->tiles_per_row, ctx->tiles_y, ctx->tiles_z, (long long)ctx->ntiles, ctx->counter_host[4],
+                            (long long)ctx->tile_maxc, (long long)maxd, ctx->tile_nt, ctx->occ_per_cell, (long long)smem_need, (int)ctx->tile_ok);
+            }
         }
     }
     ctx->topo_dirty = false;
@@ -2135,6 +2394,7 @@ static int build_lists(b200sph_ctx *ctx)
     la.S = (float)ctx->S_abs;
     la.cnt = ctx->cnt;
     la.max_count = ctx->red_u32 + 2;
+    la.R = ctx->tile_R;
     const unsigned nb = (unsigned)cdiv(n, PAIR_WARPS * PAIR_CHUNK);
     const int64_t nblk = cdiv(n, 32);
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -2176,13 +2436,35 @@ int b200sph_get_grid(b200sph_ctx *ctx, b200sph_grid_info *out)
     return 0;
 }
 
+// run the pending equation-of-state calls stand-alone (something needs rho/p/cs now)
+static int eos_flush(b200sph_ctx *ctx)
+{
+    if (!ctx->eos_any) return 0;
+    EosTab &E = ctx->eos_pending;
+    for (int a = 0; a < ctx->narr; a++) {
+        if (!E.on[a]) continue;
+        const int64_t lo = ctx->arr[a].off, hi = lo + (E.real_only[a] ? ctx->arr[a].n_real : ctx->arr[a].n);
+        if (hi > lo) {
+            k_eos<<<(unsigned)cdiv(hi - lo, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_RHO], ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64],
+                                                                        ctx->ptype, lo, hi, E.hg[a], E.rho0[a], E.c0[a], E.gamma[a], E.p0[a]);
+            LAUNCH_CHECK();
+        }
+        E.on[a] = 0;
+    }
+    ctx->eos_any = false;
+    return 0;
+}
+
 static int pack_state(b200sph_ctx *ctx)
 {
     if (ctx->n_sorted > 0) {
         k_pack_state<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
             ctx->f64[B200SPH_U], ctx->f64[B200SPH_V], ctx->f64[B200SPH_W], ctx->f64[B200SPH_M], ctx->f64[B200SPH_RHO],
-            ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64], ctx->ptype, ctx->perm, ctx->n_sorted, ctx->B, ctx->C);
+            ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64], ctx->ptype, ctx->perm, ctx->n_sorted, ctx->B, ctx->C, ctx->BC,
+            ctx->eos_pending, ctx->eos_any ? 1 : 0);
         LAUNCH_CHECK();
+        memset(ctx->eos_pending.on, 0, sizeof(ctx->eos_pending.on));
+        ctx->eos_any = false;
     }
     ctx->state_packed = true;
     return 0;
@@ -2204,7 +2486,7 @@ int64_t b200sph_get_neighbors(b200sph_ctx *ctx, int dst_arr, int src_arr, int64_
     CU(cudaMalloc((void **)&dout, 4 * (size_t)dcap));
     k_neighbors<<<1, 32, 0, ctx->stream>>>(ctx->A, ctx->C, ctx->cell_start, ctx->skey, ctx->perm, (long long)s32, src_arr,
                                            (long long)ctx->arr[src_arr].off, ctx->G.nc[0], ctx->G.nc[1], ctx->G.nc[2],
-                                           (float)ctx->cell_int, (float)(ctx->radius_scale * ctx->radius_scale), ctx->tile_R, dout, cap, ctx->counter + 1);
+                                           (float)ctx->cell_int, (float)(ctx->radius_scale * ctx->radius_scale), ctx->G.R, dout, cap, ctx->counter + 1);
     ctx->stats.kernel_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cudaFree(dout); return set_err(ctx, "k_neighbors launch failed: %s", cudaGetErrorString(e)); }
@@ -2233,14 +2515,15 @@ int b200sph_eos(b200sph_ctx *ctx, int arr, int hg, double rho0, double c0, doubl
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
-    int64_t lo, hi;
-    if ((rc = arr_range(ctx, arr, real_only, &lo, &hi))) return rc;
-    PhaseTimer pt(ctx, 2);
-    if (hi > lo) {
-        k_eos<<<(unsigned)cdiv(hi - lo, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_RHO], ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64],
-                                                                    ctx->ptype, lo, hi, hg, rho0, c0, gamma, p0);
-        LAUNCH_CHECK();
-    }
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "bad array index %d", arr);
+    EosTab &E = ctx->eos_pending;
+    // a second call for the same array before the first was applied, or a build that
+    // is not valid (no sorted order to pack): run what is pending now
+    if ((E.on[arr] || !ctx->grid_valid) && (rc = eos_flush(ctx))) return rc;
+    E.on[arr] = 1; E.hg[arr] = hg; E.real_only[arr] = real_only;
+    E.rho0[arr] = rho0; E.c0[arr] = c0; E.gamma[arr] = gamma; E.p0[arr] = p0;
+    ctx->eos_any = true;
+    if (!ctx->grid_valid && (rc = eos_flush(ctx))) return rc;
     ctx->state_packed = false;
     return 0;
 }
@@ -2250,6 +2533,7 @@ int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim, int real_o
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
     int64_t lo, hi;
     if ((rc = arr_range(ctx, arr, real_only, &lo, &hi))) return rc;
     PhaseTimer pt(ctx, 2);
@@ -2270,7 +2554,9 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     if (rc) return rc;
     if (!ctx->grid_valid) return set_err(ctx, "pair_pass: the NNPS is stale (particles were pushed/resized); call nnps_update first");
     if (!ctx->state_packed && (rc = pack_state(ctx))) return rc;
-    const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0;
+    // the list consumer stages each tile's candidates in shared memory; if a tile is
+    // too large for that (degenerate cell occupancies) the warp kernel is used instead
+    const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->tile_ok;
     if (use_lists && !ctx->lists_valid) {
         PhaseTimer pt_build(ctx, 0);  // list builds are part of the neighbour search time
         if ((rc = build_lists(ctx))) return rc;
@@ -2279,7 +2565,7 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
 
     PairArgs pa;
     memset(&pa, 0, sizeof(pa));
-    pa.A = ctx->A; pa.B = ctx->B; pa.C = ctx->C;
+    pa.A = ctx->A; pa.B = ctx->B; pa.C = ctx->C; pa.BC = ctx->BC;
     pa.cell_start = ctx->cell_start; pa.skey = ctx->skey; pa.perm = ctx->perm;
     pa.arho = ctx->f32[B200SPH_ARHO - N_F64];
     pa.au = ctx->f32[B200SPH_AU - N_F64]; pa.av = ctx->f32[B200SPH_AV - N_F64]; pa.aw = ctx->f32[B200SPH_AW - N_F64];
@@ -2308,6 +2594,8 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     }
     pa.R = ctx->tile_R;
     pa.tiles_per_row = ctx->tiles_per_row;
+    pa.nty = ctx->tiles_y;
+    pa.frameR = ctx->G.R;
     pa.c0 = (float)prog->c0; pa.alpha = (float)prog->alpha; pa.beta = (float)prog->beta;
     pa.gx = (float)prog->gx; pa.gy = (float)prog->gy; pa.gz = (float)prog->gz;
     pa.eps_xsph = (float)prog->eps_xsph;
@@ -2322,14 +2610,27 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     if (ctx->force_kernel == 2 && !ctx->tile_ok)
         return set_err(ctx, "B200SPH_PAIR_KERNEL=tile but a tile needs %lld candidates in shared memory", (long long)ctx->tile_maxc);
     if (use_lists) {
-        const unsigned nb = (unsigned)cdiv(ctx->n_sorted, LIST_NT);
+        const size_t smem = (size_t)ctx->tile_maxc * 16;
+        const unsigned nb = (unsigned)ctx->ntiles;
+        cudaError_t e = cudaSuccess;
         switch (ctx->kernel * 4 + ctx->dim) {
-#define LIST_CASE(K, D) case K * 4 + D: k_pair_list<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg); break;
+#define LIST_CASE(K, D)                                                                              \
+    case K * 4 + D: {                                                                                \
+        static bool cfg = false;                                                                     \
+        if (!cfg) {                                                                                  \
+            e = cudaFuncSetAttribute(k_pair_tlist<K, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)(208 * 1024));                                             \
+            cfg = e == cudaSuccess;                                                                  \
+        }                                                                                            \
+        if (e == cudaSuccess)                                                                        \
+            k_pair_tlist<K, D><<<nb, ctx->tile_nt, smem, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg); \
+    } break;
             LIST_CASE(0, 1) LIST_CASE(0, 2) LIST_CASE(0, 3) LIST_CASE(1, 2) LIST_CASE(1, 3)
             LIST_CASE(2, 1) LIST_CASE(2, 2) LIST_CASE(2, 3) LIST_CASE(3, 1) LIST_CASE(3, 2) LIST_CASE(3, 3)
 #undef LIST_CASE
         default: return set_err(ctx, "pair_pass: unsupported kernel/dim combination");
         }
+        if (e != cudaSuccess) return set_err(ctx, "k_pair_tlist configuration failed: %s", cudaGetErrorString(e));
         LAUNCH_CHECK();
         ctx->stats.pair_launches++;
     } else if (ctx->n_sorted > 0 && use_tile) {
@@ -2370,6 +2671,7 @@ int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt)
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
     if (arr >= ctx->narr) return set_err(ctx, "stage: bad array %d", arr);
     if (which < 0 || which > 2) return set_err(ctx, "stage: which must be 0 (initialize), 1 (stage1) or 2 (stage2)");
     PhaseTimer pt(ctx, 2);
@@ -2428,6 +2730,7 @@ int b200sph_halo_pack(b200sph_ctx *ctx, int arr, double lo, double hi, double *d
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "halo_pack: bad array %d", arr);
     const int64_t n = ctx->arr[arr].n_real, off = ctx->arr[arr].off;
     *count = 0;
@@ -2454,6 +2757,7 @@ int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf, int64_
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "halo_append: bad array %d", arr);
     if (nfields != B200SPH_HALO_FIELDS && nfields != B200SPH_MIGRATE_FIELDS) return set_err(ctx, "halo_append: nfields must be %d or %d", B200SPH_HALO_FIELDS, B200SPH_MIGRATE_FIELDS);
     ArrayInfo &ai = ctx->arr[arr];
@@ -2509,6 +2813,7 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "migrate_out: bad array %d", arr);
     ArrayInfo &ai = ctx->arr[arr];
     if (ai.n != ai.n_real) return set_err(ctx, "migrate_out: drop the ghosts of '%s' first", ai.name.c_str());
@@ -2593,6 +2898,12 @@ int b200sph_reset_stats(b200sph_ctx *ctx)
     b200sph_get_stats(ctx, &tmp);  // drain pending events
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     ctx->n_full_builds = ctx->n_light_updates = ctx->n_list_builds = 0;
+    return 0;
+}
+int b200sph_set_async_copies(b200sph_ctx *ctx, int on)
+{
+    ctx->async_copies = on != 0;
+    if (!on) CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 int b200sph_set_profiling(b200sph_ctx *ctx, int on)
