@@ -184,9 +184,24 @@ int b200sph_dt_factors(b200sph_ctx *ctx, double out[3]);
 #define B200SPH_MIGRATE_FIELDS 17 /* the 16 fp64 state props (x..m, x0..rho0) + gid */
 /* select the real particles of `arr` with lo <= x < hi and write their
  * B200SPH_HALO_FIELDS doubles field-major and TIGHT (field f of particle k at
- * dev_buf[f * count + k]); *count = number selected; error if count > cap */
-int b200sph_halo_pack(b200sph_ctx *ctx, int arr, double lo, double hi,
+ * dev_buf[f * count + k]); *count = number selected; error if count > cap.
+ * slot = 0 / 1 (left / right neighbour) also remembers the selection for
+ * b200sph_halo_pack_selected; slot = -1 does not */
+int b200sph_halo_pack(b200sph_ctx *ctx, int arr, int slot, double lo, double hi,
                       double *dev_buf, int64_t cap, int64_t *count);
+/* pack the CURRENT values of the particles remembered by the last
+ * b200sph_halo_pack(arr, slot, ...) -- the per-evaluation ghost refresh that
+ * replaces a full re-import while the neighbour lists stay valid */
+int b200sph_halo_pack_selected(b200sph_ctx *ctx, int arr, int slot, double *dev_buf,
+                               int64_t cap, int64_t *count);
+/* overwrite the B200SPH_HALO_FIELDS of the existing ghosts
+ * [ghost_first, ghost_first + n) of `arr` (indices among the ghosts) */
+int b200sph_halo_overwrite(b200sph_ctx *ctx, int arr, int64_t ghost_first,
+                           const double *dev_buf, int64_t stride, int64_t n);
+/* out[0] = 2 max|x - x_build| + k max(h - h_build) over the particles of the
+ * current neighbour build (-1 if there is no reusable build), out[1] = the skin
+ * S: the build can be reused while out[0] <= out[1] */
+int b200sph_nnps_drift(b200sph_ctx *ctx, double out[2]);
 /* append n particles from dev_buf (field f of particle k at
  * dev_buf[f * stride + k]) after the current particles of `arr`.
  * nfields = B200SPH_HALO_FIELDS: ghosts (tag Remote), other props zeroed;

@@ -110,20 +110,10 @@ struct b200sph_ctx {
     int64_t blk_cap = 0;
     uint32_t *perm_tmp = nullptr, *perm = nullptr, *skey = nullptr, *rank = nullptr;
     float4 *A = nullptr, *B = nullptr, *C = nullptr;
-    float4 *BC = nullptr;  // {B, C} interleaved (32 B per particle) for the list consumer's 256-bit gathers
+    float4 *AB = nullptr;  // {A, B} interleaved (32 B = one sector per particle) for the list consumer's 256-bit gathers
     int64_t n_sorted = 0;
     bool state_packed = false;
-    // tile kernel configuration (decided by nnps_update)
-    int tile_R = 1;
-    int tiles_per_row = 1;
-    int tiles_y = 1, tiles_z = 1;  // 3-D tiles (R x 2 x 2 cells) of the list consumer
-    int tile_nt = 256;             // threads per consumer CTA
-    int64_t ntiles = 0;
-    int64_t tile_maxc = 0;   // max candidates a tile stages
-    bool tile_ok = false;
-    double occ_per_cell = 0.0;  // particle-weighted mean cell occupancy, from the last build
-    int tile_R_env = 0;         // env B200SPH_TILE_R
-    int force_kernel = 0;       // 0 lists (default), 1 warp kernel, 2 tile kernel (env B200SPH_PAIR_KERNEL)
+    int force_kernel = 0;       // 0 lists (default), 1 warp kernel (env B200SPH_PAIR_KERNEL)
     // persistent neighbour lists
     double skin = 0.1;          // S = skin * radius_scale * hmax   (env B200SPH_SKIN)
     double S_abs = 0.0;         // absolute skin of the current build
@@ -149,6 +139,10 @@ struct b200sph_ctx {
     int64_t stage_cap = 0;
     uint32_t *flag_a = nullptr, *flag_b = nullptr;  // [pool+1] scan scratch
     int64_t flag_cap = 0;
+
+    // persistent halo: pool-relative indices of the real particles sent to neighbour `slot`
+    uint32_t *halo_idx[B200SPH_MAX_ARRAYS][2] = {{nullptr}};
+    int64_t halo_cnt[B200SPH_MAX_ARRAYS][2] = {{0}}, halo_cap[B200SPH_MAX_ARRAYS][2] = {{0}};
 
     EosTab eos_pending;
     bool eos_any = false;
@@ -529,7 +523,7 @@ __global__ void k_canon(const uint32_t *__restrict__ perm_tmp, const uint32_t *_
 __global__ void k_pack_pos(const double *__restrict__ x, const double *__restrict__ y,
                            const double *__restrict__ z, const double *__restrict__ h,
                            const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skey,
-                           long long n, GridDev G, float4 *__restrict__ A)
+                           long long n, GridDev G, float4 *__restrict__ A, float4 *__restrict__ AB)
 {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -545,6 +539,7 @@ __global__ void k_pack_pos(const double *__restrict__ x, const double *__restric
     a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell));
     a.w = (float)h[g];
     A[s] = a;
+    AB[2 * s] = a;
 }
 
 // B[s] = (u, v, w, m);  C[s] = (rho, p/rho^2, cs, type); pending TaitEOS /
@@ -555,7 +550,7 @@ __global__ void k_pack_state(const double *__restrict__ u, const double *__restr
                              float *__restrict__ cs, const uint8_t *__restrict__ ptype,
                              const uint32_t *__restrict__ perm, long long n,
                              float4 *__restrict__ B, float4 *__restrict__ C,
-                             float4 *__restrict__ BC, const EosTab E, const int eos_any)
+                             float4 *__restrict__ AB, const EosTab E, const int eos_any)
 {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -588,8 +583,7 @@ __global__ void k_pack_state(const double *__restrict__ u, const double *__restr
     c.w = __int_as_float(t);
     B[s] = b;
     C[s] = c;
-    BC[2 * s] = b;
-    BC[2 * s + 1] = c;
+    AB[2 * s + 1] = b;
 }
 
 // --------------------------------------------------------------------------
@@ -647,7 +641,7 @@ template <> __device__ __forceinline__ void sph_kernel<3>(float q, float &w, flo
 // the fused pair kernel
 // --------------------------------------------------------------------------
 struct PairArgs {
-    const float4 *A, *B, *C, *BC;
+    const float4 *A, *B, *C, *AB;
     const uint32_t *cell_start, *skey, *perm;
     float *arho, *au, *av, *aw, *ax, *ay, *az, *dt_cfl, *dt_force;
     double *rho;  // SummationDensity destination (fp64 state)
@@ -660,10 +654,7 @@ struct PairArgs {
     float c0, alpha, beta, gx, gy, gz, eps_xsph;
     int tensile, real_only;
     unsigned long long *pair_counter;  // may be null
-    // tile kernel only
-    int R, tiles_per_row, need_type;  // need_type: bit t set if dest type t skips some source type
-    int nty;           // 3-D tiles of the list consumer: tiles per row in x = tiles_per_row, in y = nty
-    int frameR;        // span of the x frames of the packed records (GridDev.R)
+    int frameR;        // span of the x frames of the packed records (GridDev.R, always 1 today)
 };
 
 #define PAIR_WARPS 8
@@ -929,7 +920,6 @@ struct ListBuildArgs {
     uint32_t *lst;   // null: count only
     int capg;        // entries reserved per destination
     unsigned *max_count;
-    int R;           // cells per tile: entries index the tile's staged candidate rows
 };
 
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildArgs a)
@@ -941,8 +931,6 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
     uint32_t cur_key = 0xFFFFFFFFu;
     int cx = 0;
     uint32_t r_rs = 0, r_b1 = 0, r_b2 = 0, r_re = 0;
-    uint32_t t_lo = 0, t_off = 0;  // lane q < 16: first sorted index / staged offset of the tile's row q
-    int row0 = 5;
     unsigned wmax = 0;
     for (int kk = 0; kk < PAIR_CHUNK; kk++) {
         const long long s = first + kk;
@@ -968,28 +956,6 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
                     r_re = a.cell_start[base + x1 + 1];
                 }
             }
-            // the 3-D tile (R x 2 x 2 cells) of this destination cell stages 4 x 4 candidate
-            // rows; lane q < 16 holds row q = (yy - (2 ty - 1)) + 4 (zz - (2 tz - 1))
-            t_lo = 0;
-            uint32_t t_n = 0;
-            if (lane < 16) {
-                const int yy = (cy & ~1) - 1 + (lane & 3), zz = (cz & ~1) - 1 + (lane >> 2);
-                if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
-                    const int cx_lo = (cx / a.R) * a.R, cx_hi = min(cx_lo + a.R - 1, a.ncx - 1);
-                    t_lo = a.cell_start[base + max(cx_lo - 1, 0)];
-                    t_n = a.cell_start[base + min(cx_hi + 2, a.ncx)] - t_lo;
-                }
-            }
-            // exclusive prefix of the row sizes = offset of a row in the staged tile
-            uint32_t inc = t_n;
-#pragma unroll
-            for (int o = 1; o < 16; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(FULL, inc, o);
-                if (lane >= o) inc += v;
-            }
-            t_off = inc - t_n;
-            row0 = ((int)(cy & 1) + 1) + 4 * ((int)(cz & 1) + 1);  // tile row of (dy, dz) = (0, 0)
         }
         float hi = a.kr * Ai.w + a.S;
         const float hi2 = hi * hi;
@@ -1001,8 +967,6 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
             if (rs >= re) continue;
             const uint32_t b1 = __shfl_sync(FULL, r_b1, r);
             const uint32_t b2 = __shfl_sync(FULL, r_b2, r);
-            const int q = row0 + ((r % 3) - 1) + 4 * ((r / 3) - 1);
-            const uint32_t loc = __shfl_sync(FULL, t_off, q) - __shfl_sync(FULL, t_lo, q);  // t -> staged index
             const float yoff = Ai.y - (float)((r % 3) - 1) * a.cell;
             const float zoff = Ai.z - (float)((r / 3) - 1) * a.cell;
             const uint32_t rcode = (uint32_t)(4 * (r % 3) + 16 * (r / 3));
@@ -1023,7 +987,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
                 const unsigned m = __ballot_sync(FULL, ok);
                 if (ok && out) {
                     const unsigned pos = count + __popc(m & lt_mask);
-                    if (pos < (unsigned)a.capg) out[(size_t)pos * 32u] = (t + loc) | ((rcode + dxc1) << LIST_JBITS);
+                    if (pos < (unsigned)a.capg) out[(size_t)pos * 32u] = t | ((rcode + dxc1) << LIST_JBITS);
                 }
                 count += __popc(m);
             }
@@ -1034,224 +998,102 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
     if (lane == 0 && wmax) atomicMax(a.max_count, wmax);
 }
 
-// one 256-bit read-only load (LDG.E.256 on sm_100a): {B, C} of one candidate
-__device__ __forceinline__ void ld_bc(const float4 *p, float4 &b, float4 &c)
+// one 256-bit read-only load (LDG.E.ENL2.256 on sm_100a): a whole 32-byte sector
+__device__ __forceinline__ void ld_256(const float4 *p, float4 &b, float4 &c)
 {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w), "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w)
                  : "l"(p));
 }
 
-// ---- TMA (cp.async.bulk) + mbarrier helpers ---------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-    unsigned done = 0;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
-}
-
-// tile geometry shared by the stats kernel, the list builder and the consumer:
-// tile (tx, ty, tz) covers cells [tx R, tx R + R) x {2 ty, 2 ty + 1} x {2 tz, 2 tz + 1}
-// and stages the 4 x 4 candidate rows yy = 2 ty - 1 + (q & 3), zz = 2 tz - 1 + (q >> 2),
-// each the contiguous sorted range of cells cx_lo - 1 .. cx_hi + 1.
-__global__ void k_tile3_stats(const uint32_t *__restrict__ cs, int ncx, int ncy, int ncz, int R,
-                              int ntx, int nty, long long ntiles, unsigned long long *stats)
-{
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
-    const int tx = (int)(t % ntx), ty = (int)((t / ntx) % nty), tz = (int)(t / ((long long)ntx * nty));
-    const int cx_lo = tx * R, cx_hi = min(cx_lo + R - 1, ncx - 1);
-    unsigned long long nd = 0, cand = 0;
-    for (int q = 0; q < 16; q++) {
-        const int yy = 2 * ty - 1 + (q & 3), zz = 2 * tz - 1 + (q >> 2);
-        if (yy < 0 || yy >= ncy || zz < 0 || zz >= ncz) continue;
-        const uint32_t b = ((uint32_t)yy + (uint32_t)ncy * (uint32_t)zz) * (uint32_t)ncx;
-        cand += cs[b + min(cx_hi + 2, ncx)] - cs[b + max(cx_lo - 1, 0)];
-        if (((q & 3) == 1 || (q & 3) == 2) && ((q >> 2) == 1 || (q >> 2) == 2))
-            nd += cs[b + cx_hi + 1] - cs[b + cx_lo];
-    }
-    if (!nd) return;
-    atomicMax(&stats[0], cand);
-    atomicAdd(&stats[2], 1ull);
-    atomicMax(&stats[4], nd);
-}
-
-// The list consumer with shared-memory staged candidates (the default fast path).
-// One CTA = one 3-D tile.  The 16 candidate rows are contiguous ranges of the sorted
-// SoA records, so one elected thread stages them with up to 48 TMA bulk copies
-// (cp.async.bulk + mbarrier: no per-element instructions); the list entries built by
-// k_list_build index the staged tile, so the scattered 16-byte gathers of the pair
-// loop hit shared memory (a global-gather consumer saturates the L1 tag stage:
-// profiles/r01e).  2 x 2 rows of destinations share the 4 x 4 candidate rows, i.e.
-// ~5.6 staged candidates per destination instead of ~12 with one-row tiles, which is
-// what makes the shared-memory footprint compatible with >= 24 resident warps.
+// The list consumer (the default fast path): one THREAD per destination walks its
+// list.  Per entry it gathers {A, B} = (x, y, z, h, u, v, w, m) with ONE 256-bit load
+// (exactly one 32-byte sector) and C = (rho, p/rho^2, cs, type) with one 128-bit load,
+// both issued one iteration ahead of their use; list entries stream in (evict-first)
+// two iterations ahead.  The gathers are what bounds this kernel (L1 tag stage, see
+// profiles/), hence the sector-sized records.
 template <int K, int DIM>
-__global__ void __launch_bounds__(512) k_pair_tlist(const PairArgs a, const uint32_t *__restrict__ cnt,
-                                                   const uint32_t *__restrict__ lst, const int capg)
+__global__ void __launch_bounds__(LIST_NT, 4) k_pair_list(const PairArgs a, const uint32_t *__restrict__ cnt,
+                                                         const uint32_t *__restrict__ lst, const int capg)
 {
-    extern __shared__ float4 dyn_smem[];
     __shared__ float4 s_T[64];
-    __shared__ uint32_t s_lo[16], s_off[17];  // candidate rows: first sorted index, staged offset
-    __shared__ uint32_t s_ds[4], s_dp[5];     // destination segments: first sorted index, prefix count
-    __shared__ __align__(8) uint64_t s_bar;
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
+        s_T[tid] = make_float4(-(float)dxc * a.cell, -(float)dy * a.cell, -(float)dz * a.cell, 0.f);
+    }
+    __syncthreads();
     const unsigned FULL = 0xffffffffu;
-    const int R = a.R;
-    const int tx = (int)(blockIdx.x % (uint32_t)a.tiles_per_row);
-    const int ty = (int)((blockIdx.x / (uint32_t)a.tiles_per_row) % (uint32_t)a.nty);
-    const int tz = (int)(blockIdx.x / ((uint32_t)a.tiles_per_row * (uint32_t)a.nty));
-    const int cx_lo = tx * R, cx_hi = min(cx_lo + R - 1, a.ncx - 1);
-    if (tid < 16) {
-        const int yy = 2 * ty - 1 + (tid & 3), zz = 2 * tz - 1 + (tid >> 2);
-        uint32_t lo = 0, n = 0, ds = 0, dn = 0;
-        if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-            const uint32_t b = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
-            lo = a.cell_start[b + max(cx_lo - 1, 0)];
-            n = a.cell_start[b + min(cx_hi + 2, a.ncx)] - lo;
-            if (((tid & 3) == 1 || (tid & 3) == 2) && ((tid >> 2) == 1 || (tid >> 2) == 2)) {
-                ds = a.cell_start[b + cx_lo];
-                dn = a.cell_start[b + cx_hi + 1] - ds;
-            }
-        }
-        // exclusive prefixes over the 16 lanes
-        uint32_t inc = n, dinc = dn;
+    const long long s = (long long)blockIdx.x * LIST_NT + tid;
+    bool active = s < a.n;
+    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = Ai;
+    unsigned long long mask_i = 0;
+    int count = 0;
+    if (active) {
+        Ci = a.C[s];
+        const int ti = __float_as_int(Ci.w);
+        mask_i = a.emask[ti & 7];
+        if ((a.real_only && (ti & PT_GHOST)) || !mask_i) active = false;
+    }
+    if (active) {
+        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
+        count = (int)cnt[s];
+    }
+    int cmax = count;
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffu, inc, o), dv = __shfl_up_sync(0xffffu, dinc, o);
-            if (tid >= o) { inc += v; dinc += dv; }
-        }
-        s_lo[tid] = lo;
-        s_off[tid] = inc - n;
-        if (tid == 15) s_off[16] = inc;
-        const int dq = ((tid & 3) - 1) + 2 * ((tid >> 2) - 1);  // 0..3 for the destination rows
-        if (((tid & 3) == 1 || (tid & 3) == 2) && ((tid >> 2) == 1 || (tid >> 2) == 2)) {
-            s_ds[dq] = ds;
-            s_dp[dq] = dinc - dn;
-        }
-        if (tid == 15) s_dp[4] = dinc;
-    }
-    if (tid >= 32 && tid < 96) {
-        const int c = tid - 32;
-        const int dxc = (c & 3) - 1, dy = ((c >> 2) & 3) - 1, dz = (c >> 4) - 1;
-        s_T[c] = make_float4(-(float)dxc * a.cell, -(float)dy * a.cell, -(float)dz * a.cell, 0.f);
-    }
-    __syncthreads();
-    const uint32_t nd = s_dp[4];
-    if (nd == 0) return;  // empty tile (uniform)
-    const uint32_t ncand = s_off[16];
-    float4 *sA = dyn_smem;
-    if (tid == 0) {
-        mbar_init(&s_bar, 1);
-        mbar_expect_tx(&s_bar, ncand * 16u);
-    }
-    __syncthreads();
-    if (tid < 16) {  // one lane per candidate row issues its bulk copy
-        const uint32_t n = s_off[tid + 1] - s_off[tid];
-        if (n) tma_bulk_g2s(sA + s_off[tid], a.A + s_lo[tid], n * 16u, &s_bar);
-    }
-    mbar_wait(&s_bar, 0);
-
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
+    const float hi2 = a.k2 * Ai.w * Ai.w;
+    const float tmpi = Ci.y;
+    Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     unsigned npairs = 0;
-    for (uint32_t t0 = 0; t0 < nd; t0 += NT) {
-        const uint32_t t = t0 + tid;
-        bool active = t < nd;
-        uint32_t s = 0, own = 0;
-        int q_own = 5;
-        if (active) {
-            const int dq = (t >= s_dp[1]) + (t >= s_dp[2]) + (t >= s_dp[3]);
-            s = s_ds[dq] + (t - s_dp[dq]);
-            q_own = 5 + (dq & 1) + 4 * (dq >> 1);  // tile row of destination segment dq
-            own = s_off[q_own] + (s - s_lo[q_own]);
+    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
+    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
+    float4 A_a = Ai, B_a = Bi, C_a = Ci;
+    if (count > 0) {
+        const size_t j = e_a & LIST_JMASK;
+        ld_256(a.AB + 2 * j, A_a, B_a);
+        C_a = a.C[j];
+    }
+    for (int k = 0; k < cmax; k++) {
+        const uint32_t e = e_a;
+        const float4 Aj = A_a, Bj = B_a, Cj = C_a;
+        e_a = e_b;
+        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
+        if (k + 1 < count) {
+            const size_t j = e_a & LIST_JMASK;
+            ld_256(a.AB + 2 * j, A_a, B_a);
+            C_a = a.C[j];
         }
-        float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = Ai;
-        unsigned long long mask_i = 0;
-        int count = 0;
-        if (active) {
-            ld_bc(a.BC + 2 * (size_t)s, Bi, Ci);
-            const int ti = __float_as_int(Ci.w);
-            mask_i = a.emask[ti & 7];
-            if ((a.real_only && (ti & PT_GHOST)) || !mask_i) active = false;
+        if (k < count) {
+            const float4 T = s_T[e >> LIST_JBITS];
+            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+            const float r2 = xij * xij + yij * yij + zij * zij;
+            // the exact accept test, linked_list_nnps.pyx:188
+            if ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w))
+                pair_body<K, DIM>(a, make_float4(xij, yij, zij, Aj.w), Bj, Cj, Ai, Bi, Ci, mask_i, tmpi,
+                                  acc, npairs);
         }
-        if (active) {
-            Ai = sA[own];
-            count = (int)cnt[s];
-        }
-        int cmax = count;
+    }
+    if (active) {
+        unsigned all_bits = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
-        if (cmax == 0) continue;  // warp-uniform
-        const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
-        const float hi2 = a.k2 * Ai.w * Ai.w;
-        const float tmpi = Ci.y;
-        Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        // list entries stream from global memory two iterations ahead
-        uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-        uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-        for (int k = 0; k < cmax; k++) {
-            const uint32_t e = e_a;
-            e_a = e_b;
-            if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-            if (k < count) {
-                const uint32_t j = e & LIST_JMASK;
-                const float4 T = s_T[e >> LIST_JBITS];
-                const float4 Aj = sA[j];
-                const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
-                const float r2 = xij * xij + yij * yij + zij * zij;
-                // the exact accept test, linked_list_nnps.pyx:188
-                if ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) {
-                    // staged index -> sorted index: the candidate sits in tile row q
-                    const uint32_t code = e >> LIST_JBITS;
-                    const int q = q_own + (int)((code >> 2) & 3u) - 1 + 4 * ((int)(code >> 4) - 1);
-                    float4 Bj, Cj;
-                    ld_bc(a.BC + 2 * (size_t)(j + s_lo[q] - s_off[q]), Bj, Cj);
-                    pair_body<K, DIM>(a, make_float4(xij, yij, zij, Aj.w), Bj, Cj, Ai, Bi, Ci, mask_i, tmpi,
-                                      acc, npairs);
-                }
-            }
+        for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
+        const uint32_t g = a.perm[s];
+        if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
+        if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
+        if (all_bits & B200SPH_EQ_MOMENTUM) {
+            // post_loop wc/basic.py:259-269
+            const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
+            a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
+            a.dt_cfl[g] = acc.cfl;
+            a.dt_force[g] = fu * fu + fv * fv + fw * fw;
+        } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
+            a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
         }
-        if (active) {
-            unsigned all_bits = 0;
-#pragma unroll
-            for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
-            const uint32_t g = a.perm[s];
-            if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
-            if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
-            if (all_bits & B200SPH_EQ_MOMENTUM) {
-                // post_loop wc/basic.py:259-269
-                const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
-                a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
-                a.dt_cfl[g] = acc.cfl;
-                a.dt_force[g] = fu * fu + fv * fv + fw * fw;
-            } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
-                a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
-            }
-            if (all_bits & B200SPH_EQ_XSPH) {
-                // post_loop basic_equations.py:297-300
-                a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
-            }
+        if (all_bits & B200SPH_EQ_XSPH) {
+            // post_loop basic_equations.py:297-300
+            a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
         }
     }
     if (a.pair_counter) {
@@ -1268,7 +1110,8 @@ __global__ void k_pack_pos_light(const double *__restrict__ x, const double *__r
                                  const double *__restrict__ z, const double *__restrict__ h,
                                  const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skey,
                                  long long n, GridDev G, const float4 *__restrict__ A0,
-                                 float4 *__restrict__ A, unsigned *__restrict__ red_u32)
+                                 float4 *__restrict__ A, float4 *__restrict__ AB,
+                                 unsigned *__restrict__ red_u32)
 {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float d2 = 0.f, dh = 0.f;
@@ -1285,6 +1128,7 @@ __global__ void k_pack_pos_light(const double *__restrict__ x, const double *__r
         a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell));
         a.w = (float)h[g];
         A[s] = a;
+        AB[2 * s] = a;
         const float4 b = A0[s];
         const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
         d2 = dx * dx + dy * dy + dz * dz;
@@ -1300,239 +1144,6 @@ __global__ void k_pack_pos_light(const double *__restrict__ x, const double *__r
     }
 }
 
-
-// --------------------------------------------------------------------------
-// tile variant of the pair kernel (experimental, opt-in)
-//
-// One CTA = one tile = the destination particles of R consecutive cells of one
-// x-row.  The 9 neighbouring rows' candidate ranges (cells cx_lo-1 .. cx_hi+1,
-// contiguous in the sorted arrays) are staged in shared memory once; then every
-// THREAD owns one destination particle: phase 1 walks the staged candidates
-// (every lane reads the same record: a shared-memory broadcast) and appends the
-// accepted ones to a private list; phase 2 runs the pair arithmetic densely over
-// the lists.  No warp reductions, no queue, ~3x fewer executed instructions than
-// the warp-per-destination kernel (profiles/r01a_pair_full_summary.md).
-// --------------------------------------------------------------------------
-#define TILE_NT 128
-#define TILE_CAP 48     // private list entries per thread
-#define TILE_STEP 16    // candidates between two list-overflow checks
-#define TILE_MAXR 12
-
-// candidates a tile must stage; max over non-empty tiles -> stats[0]; number of
-// non-empty cells -> stats[1] (used to choose R for the next build)
-__global__ void k_tile_stats(const uint32_t *__restrict__ cs, int ncx, int ncy, int ncz, int R,
-                             int tiles_per_row, long long ntiles, unsigned long long *stats)
-{
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
-    const uint32_t row = (uint32_t)(t / tiles_per_row);
-    const int chunk = (int)(t % tiles_per_row);
-    const int cx_lo = chunk * R, cx_hi = min(cx_lo + R - 1, ncx - 1);
-    const uint32_t base = row * (uint32_t)ncx;
-    unsigned nonempty = 0;
-    unsigned long long sq = 0;
-    for (int c = cx_lo; c <= cx_hi; c++) {
-        const unsigned long long nn = cs[base + c + 1] - cs[base + c];
-        nonempty += nn > 0;
-        sq += nn * nn;
-    }
-    if (nonempty) {
-        atomicAdd(&stats[1], (unsigned long long)nonempty);
-        atomicAdd(&stats[3], sq);
-    }
-    if (cs[base + cx_hi + 1] == cs[base + cx_lo]) return;
-    const int cy = (int)(row % (uint32_t)ncy), cz = (int)(row / (uint32_t)ncy);
-    unsigned long long cand = 0;
-    for (int r = 0; r < 9; r++) {
-        const int yy = cy + (r % 3) - 1, zz = cz + (r / 3) - 1;
-        if (yy < 0 || yy >= ncy || zz < 0 || zz >= ncz) continue;
-        const uint32_t b = ((uint32_t)yy + (uint32_t)ncy * (uint32_t)zz) * (uint32_t)ncx;
-        cand += cs[b + min(cx_hi + 2, ncx)] - cs[b + max(cx_lo - 1, 0)];
-    }
-    atomicMax(&stats[0], cand);
-    atomicAdd(&stats[2], 1ull);
-}
-
-// phase 2 of the tile kernel: every lane runs the pair arithmetic over its private list
-template <int K, int DIM>
-__device__ __forceinline__ void tile_flush(const PairArgs &a, const float4 *sA, const float4 *sB,
-                                           const float4 *sC, const float4 *s_T, const uint32_t *lst,
-                                           const int tid, int &count, const float4 Ai, const float4 Bi,
-                                           const float4 Ci, const unsigned long long mask_i,
-                                           const float tmpi, Acc &acc, unsigned &npairs)
-{
-    int cmax = count;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-    for (int k = 0; k < cmax; k++) {
-        if (k < count) {
-            const uint32_t e = lst[k * TILE_NT + tid];
-            const uint32_t j = e & 0xFFFFu;
-            const float4 T = s_T[e >> 16];
-            const float4 Aj = sA[j];
-            const float4 qv = make_float4(Ai.x - Aj.x + T.x, Ai.y - Aj.y + T.y, Ai.z - Aj.z + T.z, Aj.w);
-            pair_body<K, DIM>(a, qv, sB[j], sC[j], Ai, Bi, Ci, mask_i, tmpi, acc, npairs);
-        }
-    }
-    count = 0;
-}
-
-template <int K, int DIM>
-__global__ void __launch_bounds__(TILE_NT, 4) k_pair_tile(const PairArgs a)
-{
-    extern __shared__ float4 dyn_smem[];
-    __shared__ uint32_t s_cb[9][TILE_MAXR + 4];  // sorted index where cell (cx_lo - 1 + k) starts, per row
-    __shared__ uint32_t s_lo[9], s_off[10];
-    __shared__ float4 s_T[27];                   // (x, y, z) offset of candidates of row r, segment g
-
-    const int tid = threadIdx.x;
-    const unsigned FULL = 0xffffffffu;
-    const int R = a.R;
-    const uint32_t row = blockIdx.x / (uint32_t)a.tiles_per_row;
-    const int chunk = (int)(blockIdx.x % (uint32_t)a.tiles_per_row);
-    const int cx_lo = chunk * R, cx_hi = min(cx_lo + R - 1, a.ncx - 1);
-    const uint32_t base = row * (uint32_t)a.ncx;
-    const uint32_t s0 = a.cell_start[base + cx_lo], s1 = a.cell_start[base + cx_hi + 1];
-    if (s0 == s1) return;  // empty tile (uniform)
-    const int cy = (int)(row % (uint32_t)a.ncy), cz = (int)(row / (uint32_t)a.ncy);
-
-    // cell boundaries of the 9 candidate rows: k = 0 .. R+2  <->  cells cx_lo-1 .. cx_lo+R+1
-    for (int i = tid; i < 9 * (R + 3); i += TILE_NT) {
-        const int r = i / (R + 3), k = i % (R + 3);
-        const int yy = cy + (r % 3) - 1, zz = cz + (r / 3) - 1;
-        uint32_t v = 0;
-        if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-            const uint32_t b = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
-            v = a.cell_start[b + (uint32_t)min(max(cx_lo - 1 + k, 0), a.ncx)];
-        }
-        s_cb[r][k] = v;
-    }
-    if (tid < 27) {
-        const int r = tid / 3, g = tid % 3;
-        // candidates left of the span belong to the previous span (origin - R cells), etc.
-        s_T[tid] = make_float4((float)((1 - g) * R) * a.cell, -(float)((r % 3) - 1) * a.cell,
-                               -(float)((r / 3) - 1) * a.cell, 0.f);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t o = 0;
-        for (int r = 0; r < 9; r++) {
-            s_lo[r] = s_cb[r][0];
-            s_off[r] = o;
-            o += s_cb[r][R + 2] - s_cb[r][0];
-        }
-        s_off[9] = o;
-    }
-    __syncthreads();
-    const uint32_t ncand = s_off[9];
-    float4 *sA = dyn_smem, *sB = dyn_smem + ncand, *sC = dyn_smem + 2 * ncand;
-    uint32_t *lst = (uint32_t *)(dyn_smem + 3 * ncand);  // [TILE_CAP][TILE_NT]
-
-    // stage the candidate rows: contiguous ranges of the sorted records
-    for (int r = 0; r < 9; r++) {
-        const uint32_t n = s_off[r + 1] - s_off[r], lo = s_lo[r], o = s_off[r];
-        for (uint32_t i = tid; i < n; i += TILE_NT) {
-            sA[o + i] = a.A[lo + i];
-            sB[o + i] = a.B[lo + i];
-            sC[o + i] = a.C[lo + i];
-        }
-    }
-    __syncthreads();
-
-    unsigned npairs = 0;
-    for (uint32_t b0 = s0; b0 < s1; b0 += TILE_NT) {
-        const uint32_t s = b0 + tid;
-        bool active = s < s1;
-        float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = Ai;
-        unsigned long long mask_i = 0;
-        int ki = 1;  // own cell as boundary-table slot: cell cx_lo - 1 + ki
-        if (active) {
-            const uint32_t j = s_off[4] + (s - s_lo[4]);
-            Ai = sA[j]; Bi = sB[j]; Ci = sC[j];
-            const int ti = __float_as_int(Ci.w);
-            mask_i = a.emask[ti & 7];
-            if ((a.real_only && (ti & PT_GHOST)) || !mask_i) active = false;
-            ki = (int)(a.skey[s] % (uint32_t)a.ncx) - (cx_lo - 1);
-        }
-        const bool type_chk = active && ((a.need_type >> (__float_as_int(Ci.w) & 7)) & 1);
-        // the warp only walks cells kmin-1 .. kmax+1
-        int kmin = active ? ki : (R + 1), kmax = active ? ki : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            kmin = min(kmin, __shfl_xor_sync(FULL, kmin, o));
-            kmax = max(kmax, __shfl_xor_sync(FULL, kmax, o));
-        }
-        if (kmax == 0) continue;  // no active lane in this warp (uniform)
-        const float hi2 = active ? a.k2 * Ai.w * Ai.w : -1.0f;
-        const float tmpi = Ci.y;
-        Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int count = 0;
-
-        for (int r = 0; r < 9; r++) {
-            const uint32_t g0 = s_cb[r][kmin - 1], g1 = s_cb[r][kmax + 2];
-            if (g0 >= g1) continue;
-            const uint32_t b1 = s_cb[r][1], b2 = s_cb[r][R + 1];
-            const uint32_t lo = s_lo[r], off = s_off[r];
-#pragma unroll 1
-            for (int g = 0; g < 3; g++) {
-                const uint32_t ga = g == 0 ? g0 : (g == 1 ? max(g0, b1) : max(g0, b2));
-                const uint32_t gb = g == 0 ? min(g1, b1) : (g == 1 ? min(g1, b2) : g1);
-                if (ga >= gb) continue;
-                const float4 T = s_T[r * 3 + g];
-                const float xo = Ai.x + T.x, yo = Ai.y + T.y, zo = Ai.z + T.z;
-                const uint32_t code = (uint32_t)(r * 3 + g) << 16;
-                const uint32_t ja = off + (ga - lo), jb = off + (gb - lo);
-                for (uint32_t jc = ja; jc < jb; jc += TILE_STEP) {
-                    if (__any_sync(FULL, count > TILE_CAP - TILE_STEP))
-                        tile_flush<K, DIM>(a, sA, sB, sC, s_T, lst, tid, count, Ai, Bi, Ci, mask_i, tmpi, acc, npairs);
-                    const uint32_t je = min(jc + TILE_STEP, jb);
-#pragma unroll 4
-                    for (uint32_t j = jc; j < je; j++) {
-                        const float4 Aj = sA[j];
-                        const float dx = xo - Aj.x, dy = yo - Aj.y, dz = zo - Aj.z;
-                        const float r2 = dx * dx + dy * dy + dz * dz;
-                        // linked_list_nnps.pyx:188: (xij2 < hi2) or (xij2 < hj2)
-                        bool ok = (r2 < hi2) || (active && r2 < a.k2 * Aj.w * Aj.w);
-                        if (type_chk && ok)
-                            ok = ((mask_i >> (8 * (__float_as_int(sC[j].w) & 7))) & 0xFFu) != 0;
-                        if (ok) {
-                            lst[count * TILE_NT + tid] = j | code;
-                            count++;
-                        }
-                    }
-                }
-            }
-        }
-        tile_flush<K, DIM>(a, sA, sB, sC, s_T, lst, tid, count, Ai, Bi, Ci, mask_i, tmpi, acc, npairs);
-
-        if (active) {
-            unsigned all_bits = 0;
-#pragma unroll
-            for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
-            const uint32_t g = a.perm[s];
-            if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
-            if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
-            if (all_bits & B200SPH_EQ_MOMENTUM) {
-                // post_loop wc/basic.py:259-269
-                const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
-                a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
-                a.dt_cfl[g] = acc.cfl;
-                a.dt_force[g] = fu * fu + fv * fv + fw * fw;
-            } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
-                a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
-            }
-            if (all_bits & B200SPH_EQ_XSPH) {
-                // post_loop basic_equations.py:297-300
-                a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
-            }
-        }
-    }
-    if (a.pair_counter) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
-        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
-    }
-}
 
 // neighbour query for one destination particle with the pair kernel's accept test.
 // One warp. flags[t - lo] = 1 for every accepted source of array src_arr.
@@ -1627,6 +1238,18 @@ __global__ void k_gather_u32(const uint32_t *__restrict__ src, long long off, lo
     if (i >= n) return;
     if (flag[i]) dst[pos[i]] = src[off + i];
 }
+__global__ void k_save_idx(long long n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                           uint32_t *__restrict__ idx)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) idx[pos[i]] = (uint32_t)i;
+}
+__global__ void k_gather_idx_f64(const double *__restrict__ src, long long off, const uint32_t *__restrict__ idx,
+                                 long long n, double *__restrict__ dst)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst[k] = src[off + idx[k]];
+}
 __global__ void k_f64_to_u32(const double *__restrict__ in, uint32_t *__restrict__ out, long long n)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1698,7 +1321,7 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     if (ctx->A) cudaFree(ctx->A);
     if (ctx->B) cudaFree(ctx->B);
     if (ctx->C) cudaFree(ctx->C);
-    if (ctx->BC) cudaFree(ctx->BC);
+    if (ctx->AB) cudaFree(ctx->AB);
     if (ctx->A0) cudaFree(ctx->A0);
     if (ctx->cnt) cudaFree(ctx->cnt);
     if (ctx->flag_a) cudaFree(ctx->flag_a);
@@ -1712,7 +1335,7 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     CU(cudaMalloc((void **)&ctx->A, 16 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->B, 16 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->C, 16 * (size_t)alloc));
-    CU(cudaMalloc((void **)&ctx->BC, 32 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->AB, 32 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->A0, 16 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->cnt, 4 * (size_t)alloc));
     ctx->lists_valid = false;
@@ -1814,24 +1437,6 @@ PhaseTimer::~PhaseTimer()
     ctx->pending.push_back({e0, e1, slot});
 }
 
-template <int K, int DIM> static cudaError_t launch_tile_kd(unsigned nb, size_t smem, cudaStream_t st, const PairArgs &pa)
-{
-    static size_t configured = 0;  // per instantiation
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_pair_tile<K, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(208 * 1024));
-        if (e != cudaSuccess) return e;
-        configured = 208 * 1024;
-    }
-    k_pair_tile<K, DIM><<<nb, TILE_NT, smem, st>>>(pa);
-    return cudaSuccess;
-}
-template <int K> static cudaError_t launch_tile_dim(int dim, unsigned nb, size_t smem, cudaStream_t st, const PairArgs &pa)
-{
-    if (dim == 1) return launch_tile_kd<K, 1>(nb, smem, st, pa);
-    if (dim == 2) return launch_tile_kd<K, 2>(nb, smem, st, pa);
-    return launch_tile_kd<K, 3>(nb, smem, st, pa);
-}
-
 template <int K> static void launch_pair_dim(int dim, unsigned nb, cudaStream_t st, const PairArgs &pa)
 {
     if (dim == 1) k_pair<K, 1><<<nb, PAIR_WARPS * 32, 0, st>>>(pa);
@@ -1886,16 +1491,14 @@ int b200sph_create(int device, b200sph_ctx **out)
     ctx->own_stream = true;
     if (const char *e = getenv("B200SPH_PAIR_KERNEL")) {
         if (!strcmp(e, "warp")) ctx->force_kernel = 1;
-        else if (!strcmp(e, "tile")) ctx->force_kernel = 2;
         else if (strcmp(e, "list") && e[0]) {
-            fprintf(stderr, "b200sph: B200SPH_PAIR_KERNEL must be list, warp or tile\n");
+            fprintf(stderr, "b200sph: B200SPH_PAIR_KERNEL must be list or warp\n");
             delete ctx;
             *out = nullptr;
             return -3;
         }
     }
     if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = std::max(0.0, atof(e));
-    if (const char *e = getenv("B200SPH_TILE_R")) ctx->tile_R_env = atoi(e);
     CU(cudaMalloc((void **)&ctx->red_u32, 4 * sizeof(unsigned)));
     CU(cudaMallocHost((void **)&ctx->red_u32_host, 4 * sizeof(unsigned)));
     CU(cudaMalloc((void **)&ctx->red, 16 * sizeof(long long)));
@@ -1916,7 +1519,7 @@ int b200sph_destroy(b200sph_ctx *ctx)
     cudaFree(ctx->ptype);
     cudaFree(ctx->key_of); cudaFree(ctx->off_in); cudaFree(ctx->cell_cnt); cudaFree(ctx->cell_start);
     cudaFree(ctx->blk_sums); cudaFree(ctx->perm_tmp); cudaFree(ctx->perm); cudaFree(ctx->skey);
-    cudaFree(ctx->rank); cudaFree(ctx->A); cudaFree(ctx->B); cudaFree(ctx->C); cudaFree(ctx->BC);
+    cudaFree(ctx->rank); cudaFree(ctx->A); cudaFree(ctx->B); cudaFree(ctx->C); cudaFree(ctx->AB);
     cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->counter);
     cudaFreeHost(ctx->counter_host); cudaFree(ctx->stage_buf); cudaFree(ctx->flag_a);
     cudaFree(ctx->flag_b); cudaFree(ctx->A0); cudaFree(ctx->lst); cudaFree(ctx->cnt);
@@ -2181,7 +1784,7 @@ static int nnps_light_update(b200sph_ctx *ctx)
     CU(cudaMemsetAsync(ctx->red_u32, 0, 4 * sizeof(unsigned), ctx->stream));
     k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
         ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
-        ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->red_u32);
+        ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
     LAUNCH_CHECK();
     CU(cudaMemcpyAsync(ctx->red_u32_host, ctx->red_u32, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -2202,7 +1805,9 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     if (!ctx->domain_valid && (rc = b200sph_update_domain(ctx))) return rc;
     PhaseTimer pt(ctx, 0);
 
-    const bool use_lists = ctx->force_kernel == 0;
+    int64_t ntot0 = 0;
+    for (int a = 0; a < ctx->narr; a++) ntot0 += ctx->arr[a].n;
+    const bool use_lists = ctx->force_kernel == 0 && ntot0 < (1LL << LIST_JBITS);
     if (use_lists && ctx->lists_valid && !ctx->topo_dirty) {
         rc = nnps_light_update(ctx);
         if (rc < 0) return rc;
@@ -2298,8 +1903,6 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
 
     CU(cudaMemsetAsync(ctx->cell_cnt, 0, 4 * (size_t)(ncells + 1), ctx->stream));
     ctx->n_sorted = ntot;
-    ctx->tile_ok = false;
-    ctx->tile_R = 1;
     if (ctx->pool_end > 0) {
         const unsigned nb = (unsigned)cdiv(ctx->pool_end, 256);
         k_cell_count<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z],
@@ -2314,65 +1917,11 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         const unsigned ns = (unsigned)cdiv(ntot, 256);
         k_canon<<<ns, 256, 0, ctx->stream>>>(ctx->perm_tmp, ctx->key_of, ctx->cell_start, ntot, ctx->perm, ctx->skey, ctx->rank);
         LAUNCH_CHECK();
-        const int64_t nrows = (int64_t)nc[1] * nc[2];
-        if (use_lists || ctx->force_kernel == 2) {
-            if (ctx->occ_per_cell <= 0.0) {  // first build: measure the cell occupancy once
-                CU(cudaMemsetAsync(ctx->counter + 2, 0, 5 * sizeof(unsigned long long), ctx->stream));
-                k_tile_stats<<<(unsigned)cdiv(nrows * nc[0], 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], 1, nc[0], nrows * nc[0], ctx->counter + 2);
-                LAUNCH_CHECK();
-                CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-                CU(cudaStreamSynchronize(ctx->stream));
-                // particle-weighted mean occupancy: what a typical particle's cell holds
-                ctx->occ_per_cell = (double)ctx->counter_host[5] / (double)std::max<int64_t>(ntot, 1);
-            }
-        }
-        if (ctx->force_kernel == 2) {
-            // experimental one-row tile kernel: span-relative x frames
-            int R = ctx->tile_R_env > 0 ? ctx->tile_R_env : (int)((double)TILE_NT / std::max(ctx->occ_per_cell, 1.0));
-            R = std::min(std::min(std::max(R, 1), TILE_MAXR), nc[0]);
-            ctx->tile_R = R;
-            ctx->tiles_per_row = (int)cdiv(nc[0], R);
-            ctx->ntiles = nrows * ctx->tiles_per_row;
-            G.R = R;
-        } else if (use_lists) {
-            // 3-D tiles (R x 2 x 2 cells) of the list consumer: aim at ~256 destinations
-            const int dims_yz = (nc[1] > 1 ? 2 : 1) * (nc[2] > 1 ? 2 : 1);
-            int R = ctx->tile_R_env > 0 ? ctx->tile_R_env : (int)(256.0 / (dims_yz * std::max(ctx->occ_per_cell, 1.0)));
-            R = std::min(std::min(std::max(R, 1), 64), nc[0]);
-            ctx->tile_R = R;
-            ctx->tiles_per_row = (int)cdiv(nc[0], R);
-            ctx->tiles_y = (int)cdiv(nc[1], 2);
-            ctx->tiles_z = (int)cdiv(nc[2], 2);
-            ctx->ntiles = (int64_t)ctx->tiles_per_row * ctx->tiles_y * ctx->tiles_z;
-        }
         k_pack_pos<<<ns, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H],
-                                                ctx->perm, ctx->skey, ntot, G, ctx->A);
+                                                ctx->perm, ctx->skey, ntot, G, ctx->A, ctx->AB);
         LAUNCH_CHECK();
         if (use_lists)
             CU(cudaMemcpyAsync(ctx->A0, ctx->A, 16 * (size_t)ntot, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (use_lists || ctx->force_kernel == 2) {
-            CU(cudaMemsetAsync(ctx->counter + 2, 0, 5 * sizeof(unsigned long long), ctx->stream));
-            if (ctx->force_kernel == 2)
-                k_tile_stats<<<(unsigned)cdiv(ctx->ntiles, 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], ctx->tile_R, ctx->tiles_per_row, ctx->ntiles, ctx->counter + 2);
-            else
-                k_tile3_stats<<<(unsigned)cdiv(ctx->ntiles, 256), 256, 0, ctx->stream>>>(ctx->cell_start, nc[0], nc[1], nc[2], ctx->tile_R, ctx->tiles_per_row, ctx->tiles_y, ctx->ntiles, ctx->counter + 2);
-            LAUNCH_CHECK();
-            CU(cudaMemcpyAsync(ctx->counter_host + 2, ctx->counter + 2, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            ctx->tile_maxc = (int64_t)ctx->counter_host[2];
-            if (ctx->force_kernel == 2) ctx->occ_per_cell = (double)ctx->counter_host[5] / (double)std::max<int64_t>(ntot, 1);
-            const int64_t maxd = (int64_t)ctx->counter_host[6];
-            ctx->tile_nt = (int)std::min<int64_t>(512, std::max<int64_t>(64, (maxd + 31) / 32 * 32));
-            const int64_t smem_need = ctx->force_kernel == 2 ? ctx->tile_maxc * 48 + (int64_t)TILE_CAP * TILE_NT * 4 : ctx->tile_maxc * 16;
-            ctx->tile_ok = ctx->tile_maxc < 65536 && smem_need <= 200 * 1024 && ctx->ntiles < 2147483647LL;
-            if (getenv("B200SPH_DEBUG")) {
-                static int shown = 0;
-                if (shown++ < 3)
-                    fprintf(stderr, "b200sph: tiles R=%d grid=%dx%dx%d ntiles=%lld nonempty=%llu max_cands=%lld max_dests=%lld NT=%d occ/cell=%.2f smem=%lld B tile_ok=%d\n",
-                            ctx->tile_R, ctx->tiles_per_row, ctx->tiles_y, ctx->tiles_z, (long long)ctx->ntiles, ctx->counter_host[4],
-                            (long long)ctx->tile_maxc, (long long)maxd, ctx->tile_nt, ctx->occ_per_cell, (long long)smem_need, (int)ctx->tile_ok);
-            }
-        }
     }
     ctx->topo_dirty = false;
     ctx->grid_valid = true;
@@ -2384,7 +1933,6 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
 static int build_lists(b200sph_ctx *ctx)
 {
     const int64_t n = ctx->n_sorted;
-    if (n >= (1LL << LIST_JBITS)) return set_err(ctx, "neighbour lists hold 26-bit indices: more than %lld particles per GPU need B200SPH_PAIR_KERNEL=warp", (long long)(1LL << LIST_JBITS));
     ListBuildArgs la;
     la.A = ctx->A; la.cell_start = ctx->cell_start; la.skey = ctx->skey;
     la.n = n;
@@ -2394,7 +1942,6 @@ static int build_lists(b200sph_ctx *ctx)
     la.S = (float)ctx->S_abs;
     la.cnt = ctx->cnt;
     la.max_count = ctx->red_u32 + 2;
-    la.R = ctx->tile_R;
     const unsigned nb = (unsigned)cdiv(n, PAIR_WARPS * PAIR_CHUNK);
     const int64_t nblk = cdiv(n, 32);
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -2460,7 +2007,7 @@ static int pack_state(b200sph_ctx *ctx)
     if (ctx->n_sorted > 0) {
         k_pack_state<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
             ctx->f64[B200SPH_U], ctx->f64[B200SPH_V], ctx->f64[B200SPH_W], ctx->f64[B200SPH_M], ctx->f64[B200SPH_RHO],
-            ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64], ctx->ptype, ctx->perm, ctx->n_sorted, ctx->B, ctx->C, ctx->BC,
+            ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64], ctx->ptype, ctx->perm, ctx->n_sorted, ctx->B, ctx->C, ctx->AB,
             ctx->eos_pending, ctx->eos_any ? 1 : 0);
         LAUNCH_CHECK();
         memset(ctx->eos_pending.on, 0, sizeof(ctx->eos_pending.on));
@@ -2554,9 +2101,8 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     if (rc) return rc;
     if (!ctx->grid_valid) return set_err(ctx, "pair_pass: the NNPS is stale (particles were pushed/resized); call nnps_update first");
     if (!ctx->state_packed && (rc = pack_state(ctx))) return rc;
-    // the list consumer stages each tile's candidates in shared memory; if a tile is
-    // too large for that (degenerate cell occupancies) the warp kernel is used instead
-    const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->tile_ok;
+    // lists hold 26-bit sorted indices: larger particle counts use the warp kernel
+    const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->n_sorted < (1LL << LIST_JBITS);
     if (use_lists && !ctx->lists_valid) {
         PhaseTimer pt_build(ctx, 0);  // list builds are part of the neighbour search time
         if ((rc = build_lists(ctx))) return rc;
@@ -2565,7 +2111,7 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
 
     PairArgs pa;
     memset(&pa, 0, sizeof(pa));
-    pa.A = ctx->A; pa.B = ctx->B; pa.C = ctx->C; pa.BC = ctx->BC;
+    pa.A = ctx->A; pa.B = ctx->B; pa.C = ctx->C; pa.AB = ctx->AB;
     pa.cell_start = ctx->cell_start; pa.skey = ctx->skey; pa.perm = ctx->perm;
     pa.arho = ctx->f32[B200SPH_ARHO - N_F64];
     pa.au = ctx->f32[B200SPH_AU - N_F64]; pa.av = ctx->f32[B200SPH_AV - N_F64]; pa.aw = ctx->f32[B200SPH_AW - N_F64];
@@ -2588,13 +2134,7 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
             if (b & B200SPH_EQ_SUMMATION_DENSITY) sumdens = true;
         }
         pa.emask[d] = m;
-        if (m)
-            for (int s2 = 0; s2 < ctx->narr; s2++)
-                if (((m >> (8 * s2)) & 0xFFull) == 0) pa.need_type |= 1 << d;
     }
-    pa.R = ctx->tile_R;
-    pa.tiles_per_row = ctx->tiles_per_row;
-    pa.nty = ctx->tiles_y;
     pa.frameR = ctx->G.R;
     pa.c0 = (float)prog->c0; pa.alpha = (float)prog->alpha; pa.beta = (float)prog->beta;
     pa.gx = (float)prog->gx; pa.gy = (float)prog->gy; pa.gz = (float)prog->gz;
@@ -2606,43 +2146,15 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
         CU(cudaMemsetAsync(ctx->counter, 0, 8, ctx->stream));
         pa.pair_counter = ctx->counter;
     }
-    const bool use_tile = ctx->force_kernel == 2 && ctx->tile_ok;  // opt-in while the tile path is slower
-    if (ctx->force_kernel == 2 && !ctx->tile_ok)
-        return set_err(ctx, "B200SPH_PAIR_KERNEL=tile but a tile needs %lld candidates in shared memory", (long long)ctx->tile_maxc);
     if (use_lists) {
-        const size_t smem = (size_t)ctx->tile_maxc * 16;
-        const unsigned nb = (unsigned)ctx->ntiles;
-        cudaError_t e = cudaSuccess;
+        const unsigned nb = (unsigned)cdiv(ctx->n_sorted, LIST_NT);
         switch (ctx->kernel * 4 + ctx->dim) {
-#define LIST_CASE(K, D)                                                                              \
-    case K * 4 + D: {                                                                                \
-        static bool cfg = false;                                                                     \
-        if (!cfg) {                                                                                  \
-            e = cudaFuncSetAttribute(k_pair_tlist<K, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)(208 * 1024));                                             \
-            cfg = e == cudaSuccess;                                                                  \
-        }                                                                                            \
-        if (e == cudaSuccess)                                                                        \
-            k_pair_tlist<K, D><<<nb, ctx->tile_nt, smem, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg); \
-    } break;
+#define LIST_CASE(K, D) case K * 4 + D: k_pair_list<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg); break;
             LIST_CASE(0, 1) LIST_CASE(0, 2) LIST_CASE(0, 3) LIST_CASE(1, 2) LIST_CASE(1, 3)
             LIST_CASE(2, 1) LIST_CASE(2, 2) LIST_CASE(2, 3) LIST_CASE(3, 1) LIST_CASE(3, 2) LIST_CASE(3, 3)
 #undef LIST_CASE
         default: return set_err(ctx, "pair_pass: unsupported kernel/dim combination");
         }
-        if (e != cudaSuccess) return set_err(ctx, "k_pair_tlist configuration failed: %s", cudaGetErrorString(e));
-        LAUNCH_CHECK();
-        ctx->stats.pair_launches++;
-    } else if (ctx->n_sorted > 0 && use_tile) {
-        const size_t smem = (size_t)ctx->tile_maxc * 48 + (size_t)TILE_CAP * TILE_NT * 4;
-        cudaError_t e;
-        switch (ctx->kernel) {
-        case 0: e = launch_tile_dim<0>(ctx->dim, (unsigned)ctx->ntiles, smem, ctx->stream, pa); break;
-        case 1: e = launch_tile_dim<1>(ctx->dim, (unsigned)ctx->ntiles, smem, ctx->stream, pa); break;
-        case 2: e = launch_tile_dim<2>(ctx->dim, (unsigned)ctx->ntiles, smem, ctx->stream, pa); break;
-        default: e = launch_tile_dim<3>(ctx->dim, (unsigned)ctx->ntiles, smem, ctx->stream, pa); break;
-        }
-        if (e != cudaSuccess) return set_err(ctx, "k_pair_tile configuration failed: %s", cudaGetErrorString(e));
         LAUNCH_CHECK();
         ctx->stats.pair_launches++;
     } else if (ctx->n_sorted > 0) {
@@ -2725,7 +2237,7 @@ int b200sph_dt_factors(b200sph_ctx *ctx, double out[3])
 // ---- halo helpers ------------------------------------------------------------
 static const int halo_fields[9] = {B200SPH_X, B200SPH_Y, B200SPH_Z, B200SPH_U, B200SPH_V, B200SPH_W, B200SPH_RHO, B200SPH_H, B200SPH_M};
 
-int b200sph_halo_pack(b200sph_ctx *ctx, int arr, double lo, double hi, double *dev_buf, int64_t cap, int64_t *count)
+int b200sph_halo_pack(b200sph_ctx *ctx, int arr, int slot, double lo, double hi, double *dev_buf, int64_t cap, int64_t *count)
 {
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
@@ -2734,6 +2246,7 @@ int b200sph_halo_pack(b200sph_ctx *ctx, int arr, double lo, double hi, double *d
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "halo_pack: bad array %d", arr);
     const int64_t n = ctx->arr[arr].n_real, off = ctx->arr[arr].off;
     *count = 0;
+    if (slot == 0 || slot == 1) ctx->halo_cnt[arr][slot] = 0;
     if (n == 0) return 0;
     const unsigned nb = (unsigned)cdiv(n + 1, 256);
     k_flag_range<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], off, n, lo, hi, 0, ctx->flag_a);
@@ -2744,6 +2257,20 @@ int b200sph_halo_pack(b200sph_ctx *ctx, int arr, double lo, double hi, double *d
     CU(cudaStreamSynchronize(ctx->stream));
     *count = tot;
     if ((int64_t)tot > cap) return set_err(ctx, "halo_pack: %u particles selected but the buffer holds %lld", tot, (long long)cap);
+    if (slot == 0 || slot == 1) {  // remember the selection for halo_pack_selected
+        if ((int64_t)tot > ctx->halo_cap[arr][slot]) {
+            if (ctx->halo_idx[arr][slot]) CU(cudaFree(ctx->halo_idx[arr][slot]));
+            ctx->halo_cap[arr][slot] = (int64_t)tot + tot / 4 + 256;
+            CU(cudaMalloc((void **)&ctx->halo_idx[arr][slot], 4 * (size_t)ctx->halo_cap[arr][slot]));
+        }
+        ctx->halo_cnt[arr][slot] = tot;
+        if (tot) {
+            k_save_idx<<<nb, 256, 0, ctx->stream>>>(n, ctx->flag_a, ctx->flag_b, ctx->halo_idx[arr][slot]);
+            LAUNCH_CHECK();
+        }
+    } else if (slot != -1) {
+        return set_err(ctx, "halo_pack: slot must be -1, 0 or 1");
+    }
     if (tot == 0) return 0;
     for (int f = 0; f < B200SPH_HALO_FIELDS; f++) {
         k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[halo_fields[f]], off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)f * tot);
@@ -2791,6 +2318,66 @@ int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf, int64_
     ctx->h_dirty = true;
     ctx->domain_valid = false;
     ctx->state_packed = false;
+    return 0;
+}
+
+int b200sph_halo_pack_selected(b200sph_ctx *ctx, int arr, int slot, double *dev_buf, int64_t cap, int64_t *count)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
+    if (arr < 0 || arr >= ctx->narr || slot < 0 || slot > 1) return set_err(ctx, "halo_pack_selected: bad array / slot");
+    const int64_t n = ctx->halo_cnt[arr][slot];
+    *count = n;
+    if (n > cap) return set_err(ctx, "halo_pack_selected: buffer too small");
+    if (n == 0) return 0;
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) {
+        k_gather_idx_f64<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->f64[halo_fields[f]], ctx->arr[arr].off, ctx->halo_idx[arr][slot], n, dev_buf + (size_t)f * n);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int b200sph_halo_overwrite(b200sph_ctx *ctx, int arr, int64_t ghost_first, const double *dev_buf, int64_t stride, int64_t n)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "halo_overwrite: bad array %d", arr);
+    const ArrayInfo &ai = ctx->arr[arr];
+    if (ghost_first < 0 || n < 0 || ai.n_real + ghost_first + n > ai.n)
+        return set_err(ctx, "halo_overwrite: ghosts [%lld, %lld) outside the %lld ghosts of '%s'", (long long)ghost_first, (long long)(ghost_first + n), (long long)(ai.n - ai.n_real), ai.name.c_str());
+    if (n == 0) return 0;
+    const int64_t o = ai.off + ai.n_real + ghost_first;
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++)
+        CU(cudaMemcpyAsync(ctx->f64[halo_fields[f]] + o, dev_buf + (size_t)f * stride, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    // values moved, the particle set did not: a light nnps_update is enough
+    ctx->grid_valid = false;
+    ctx->state_packed = false;
+    return 0;
+}
+
+int b200sph_nnps_drift(b200sph_ctx *ctx, double out[2])
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    out[0] = -1.0;
+    out[1] = ctx->S_abs;
+    if (ctx->force_kernel != 0 || !ctx->lists_valid || ctx->topo_dirty) return 0;  // no reusable build
+    if (ctx->n_sorted <= 0) { out[0] = 0.0; return 0; }
+    CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
+    k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
+        ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
+        ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(ctx->red_u32_host, ctx->red_u32, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float d2, dh;
+    memcpy(&d2, &ctx->red_u32_host[0], 4);
+    memcpy(&dh, &ctx->red_u32_host[1], 4);
+    out[0] = 2.0 * std::sqrt((double)d2) + ctx->radius_scale * (double)dh;
     return 0;
 }
 

@@ -110,13 +110,34 @@ class DeviceHaloOps(object):
     def drop_ghosts(self, arr):
         self.ctx.call('b200sph_drop_ghosts', arr)
 
-    def pack(self, arr, lo, hi, buf, offset):
-        """pack into buf[offset:]; returns the particle count."""
+    def pack(self, arr, slot, lo, hi, buf, offset):
+        """select lo <= x < hi (remembered under `slot`), pack into
+        buf[offset:]; returns the particle count."""
         cnt = C.c_int64()
         cap = (buf.numel() - offset) // HALO_FIELDS
-        self.ctx.call('b200sph_halo_pack', arr, float(lo), float(hi),
+        self.ctx.call('b200sph_halo_pack', arr, slot, float(lo), float(hi),
                       buf.data_ptr() + 8 * offset, cap, C.byref(cnt))
         return cnt.value
+
+    def pack_selected(self, arr, slot, buf, offset):
+        """current values of the particles selected by the last pack(slot)."""
+        cnt = C.c_int64()
+        cap = (buf.numel() - offset) // HALO_FIELDS
+        self.ctx.call('b200sph_halo_pack_selected', arr, slot,
+                      buf.data_ptr() + 8 * offset, cap, C.byref(cnt))
+        return cnt.value
+
+    def overwrite(self, arr, ghost_first, buf, offset, n):
+        if n:
+            self.ctx.call('b200sph_halo_overwrite', arr, int(ghost_first),
+                          buf.data_ptr() + 8 * offset, n, n)
+
+    def drift(self):
+        """(need, skin): the neighbour build is reusable while need <= skin;
+        need < 0 means there is no reusable build."""
+        out = (C.c_double * 2)()
+        self.ctx.call('b200sph_nnps_drift', out)
+        return out[0], out[1]
 
     def append(self, arr, buf, offset, n, nfields, as_real):
         if n:
@@ -154,7 +175,11 @@ class SlabParallelManager(object):
         self.narr = ops.narr
         self.n_exchanges = 0
         self.bytes_sent = 0
-        self._send = {}
+        self.n_full = 0
+        self.n_refresh = 0
+        # persistent ghosts: per neighbour, the counts sent / received at the
+        # last full exchange (the refresh path re-sends exactly those particles)
+        self._sent = {}
         self._recv = {}
 
     # -- transport ------------------------------------------------------------
@@ -203,12 +228,61 @@ class SlabParallelManager(object):
 
     # -- ParallelManager protocol ----------------------------------------------
     def update(self):
+        """Called before every evaluation.  While every rank's neighbour build is
+        still valid (max drift <= skin, one scalar all-reduce) only the VALUES of
+        the same ghost particles are refreshed in place; otherwise the full
+        drop / migrate / import path runs and the next NNPS update rebuilds."""
         ops = self.ops
+        if self._recv and hasattr(ops, 'drift'):
+            need, skin = ops.drift()
+            ratio = need / skin if (need >= 0.0 and skin > 0.0) else 2.0
+            t = ops.new_buffer(1)
+            t[0] = ratio
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            if float(t[0].item()) <= 0.9:
+                self._refresh_ghosts()
+                self.n_refresh += 1
+                return
         for a in range(self.narr):
             ops.drop_ghosts(a)                       # parallel_manager.pyx:519
         if self.migrate:
             self._migrate()
         self._import_ghosts()
+        self.n_full += 1
+
+    def _refresh_ghosts(self):
+        ops = self.ops
+        nbs = [nb for nb in (self.left, self.right) if nb is not None]
+        ops_list, recv_bufs, keep = [], {}, []
+        for nb in nbs:
+            slot = 0 if nb == self.left else 1
+            ns = sum(self._sent[nb]) * HALO_FIELDS
+            nr = sum(self._recv[nb]) * HALO_FIELDS
+            if ns:
+                buf = ops.new_buffer(ns)
+                off = 0
+                for a in range(self.narr):
+                    n = ops.pack_selected(a, slot, buf, off) if self._sent[nb][a] else 0
+                    assert n == self._sent[nb][a]
+                    off += n * HALO_FIELDS
+                keep.append(buf)
+                ops_list.append(self.dist.P2POp(self.dist.isend, buf[:ns], nb))
+                self.bytes_sent += 8 * ns
+            if nr:
+                recv_bufs[nb] = ops.new_buffer(nr)
+                ops_list.append(self.dist.P2POp(self.dist.irecv, recv_bufs[nb][:nr], nb))
+        if ops_list:
+            for w in self.dist.batch_isend_irecv(ops_list):
+                w.wait()
+        # ghosts were appended left neighbour first, per array
+        first = [0] * self.narr
+        for nb in sorted(self._recv):
+            o = 0
+            for a, n in enumerate(self._recv[nb]):
+                ops.overwrite(a, first[a], recv_bufs.get(nb), o, n)
+                first[a] += n
+                o += n * HALO_FIELDS
+        self.n_exchanges += 1
 
     def _migrate(self):
         ops = self.ops
@@ -255,15 +329,17 @@ class SlabParallelManager(object):
                              (self.right, (self.hi - self.halo, self.hi))):
             if nb is None:
                 continue
+            slot = 0 if nb == self.left else 1
             buf = ops.new_buffer(self._capacity(HALO_FIELDS))
             counts, off = [], 0
             for a in range(self.narr):
-                n = ops.pack(a, lo, hi, buf, off) if ops.n_real(a) else 0
+                n = ops.pack(a, slot, lo, hi, buf, off) if ops.n_real(a) else 0
                 counts.append(n)
                 off += n * HALO_FIELDS
             send_counts[nb], send_bufs[nb] = counts, buf
         recv_counts, recv_bufs = self._exchange(send_counts, send_bufs,
                                                 HALO_FIELDS)
+        self._sent, self._recv = send_counts, recv_counts
         # deterministic order: left neighbour's ghosts first
         for nb in sorted(recv_counts):
             o = 0
@@ -285,15 +361,14 @@ def make_slab_solver(dx, params, kernel, rank, world, device=0,
     import os
     import pysph_b200 as pb
     from . import geometry as geo
-    # the ghost set changes at every exchange, so persistent neighbour lists
-    # would be rebuilt every evaluation: use the list-free kernel (must be set
-    # before the context is created)
-    os.environ.setdefault('B200SPH_PAIR_KERNEL', 'warp')
     xs, w = dam_break_column_weights(dx, solid_weight=solid_weight)
     cuts = balanced_cuts(xs, w, world, dx)
     pas = geo.dam_break_3d_particles(dx=dx, xrange=(cuts[rank], cuts[rank + 1]))
     # global ids so that results can be matched across decompositions
-    halo = kernel.radius_scale * params['hdx'] * dx
+    # one kernel support plus the neighbour-list skin (ghosts are only re-selected
+    # when the lists are rebuilt, so they must cover the skin as well)
+    skin = float(os.environ.get('B200SPH_SKIN', '0.1'))
+    halo = kernel.radius_scale * params['hdx'] * dx * (1.0 + skin) * 1.0001
     n_real = [pa.get_number_of_particles() for pa in pas]
     extra = int(0.35 * max(n_real)) + 4096
     solver = pb.make_wcsph_solver(pas, dict(params), kernel, device=device,

@@ -410,13 +410,12 @@ def _perturbed_dam_break(dx=0.05, vscale=0.5, seed=9):
 
 
 def test_all_pair_kernels_agree(gpu_device, monkeypatch):
-    """The three pair-kernel paths -- persistent neighbour lists (default), the
-    warp-per-destination kernel (fallback, also used for > 2^26 particles) and
-    the experimental shared-memory tile kernel -- implement the same accept test
-    and arithmetic: identical pair counts, results within fp32 summation-order
-    noise, on a perturbed 3-D dam break."""
+    """The two pair-kernel paths -- persistent neighbour lists (default) and the
+    warp-per-destination kernel (fallback, also used for > 2^26 particles) --
+    implement the same accept test and arithmetic: identical pair counts, results
+    within fp32 summation-order noise, on a perturbed 3-D dam break."""
     out = {}
-    for which in ('list', 'warp', 'tile'):
+    for which in ('list', 'warp'):
         monkeypatch.setenv('B200SPH_PAIR_KERNEL', which)
         pas, params = _perturbed_dam_break()
         f = pas[0]
@@ -428,7 +427,7 @@ def test_all_pair_kernels_agree(gpu_device, monkeypatch):
         s.pull()
         out[which] = (pairs, dict((k, f.properties[k].copy())
                                   for k in ACC_FIELDS + ['x', 'u', 'rho']))
-    for which in ('warp', 'tile'):
+    for which in ('warp',):
         assert out['list'][0] == out[which][0]
         for k, v in out['list'][1].items():
             w = out[which][1][k]

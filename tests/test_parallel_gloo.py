@@ -43,14 +43,35 @@ class NumpyHaloOps(object):
         for k in self.arrays[a]:
             self.arrays[a][k] = self.arrays[a][k][:self.nreal[a]]
 
-    def pack(self, a, lo, hi, buf, off):
+    def pack(self, a, slot, lo, hi, buf, off):
         A = self.arrays[a]
         x = A['x'][:self.nreal[a]]
         sel = np.where((x >= lo) & (x < hi))[0]
+        self.saved = getattr(self, 'saved', {})
+        self.saved[(a, slot)] = sel
+        return self._pack_idx(a, sel, buf, off)
+
+    def _pack_idx(self, a, sel, buf, off):
+        A = self.arrays[a]
         n = sel.size
         for f, name in enumerate(F64[:HALO_FIELDS]):
             buf[off + f * n: off + (f + 1) * n] = self.torch.from_numpy(A[name][sel])
         return n
+
+    def pack_selected(self, a, slot, buf, off):
+        return self._pack_idx(a, self.saved[(a, slot)], buf, off)
+
+    def overwrite(self, a, ghost_first, buf, off, n):
+        if not n:
+            return
+        A = self.arrays[a]
+        blk = buf[off:off + n * HALO_FIELDS].numpy().reshape(HALO_FIELDS, n)
+        lo = self.nreal[a] + ghost_first
+        for f, name in enumerate(F64[:HALO_FIELDS]):
+            A[name][lo:lo + n] = blk[f]
+
+    def drift(self):
+        return getattr(self, 'fake_drift', (0.0, 1.0))
 
     def append(self, a, buf, off, n, nfields, as_real):
         if not n:
@@ -155,10 +176,25 @@ def _worker(rank, world, port, q):
                 j = np.where(a['x'] == xg)[0][0]
                 ok_payload &= (a['rho'][j] == rg)
             res.append((ok_real, ok_props, ok_ghost, bool(ok_payload)))
-        # a second update must be idempotent (ghosts dropped and re-imported)
+        # a second update while the build is valid only REFRESHES the ghost values
         n_before = [ops.arrays[i]['x'].size for i in range(2)]
+        for ai in range(2):
+            nr = ops.nreal[ai]
+            ops.arrays[ai]['rho'][:nr] += 1.0 + rank      # owners move on
         pm.update()
         idem = n_before == [ops.arrays[i]['x'].size for i in range(2)]
+        idem &= pm.n_refresh == 1 and pm.n_full == 1
+        for ai, a in enumerate(glob):
+            got = ops.arrays[ai]
+            nr = ops.nreal[ai]
+            owner = np.searchsorted(cuts, a['x'], side='right') - 1
+            for xg, rg in zip(got['x'][nr:], got['rho'][nr:]):
+                j = np.where(a['x'] == xg)[0][0]
+                idem &= bool(rg == a['rho'][j] + 1.0 + owner[j])
+        # drift beyond the skin on ONE rank forces the full path on all ranks
+        ops.fake_drift = (2.0, 1.0) if rank == 0 else (0.1, 1.0)
+        pm.update()
+        idem &= pm.n_full == 2 and n_before == [ops.arrays[i]['x'].size for i in range(2)]
         dtmin = pm.update_time_steps(0.1 * (rank + 1))
         q.put((rank, res, idem, dtmin))
     finally:
