@@ -237,7 +237,7 @@ def main():
     be = solver.backend
     # run on torch's current stream so torch events / NCCL order with our kernels
     stream = torch.cuda.current_stream()
-    be.ctx.call('b200sph_set_stream', stream.cuda_stream)
+    be.use_torch_stream(stream)
 
     def barrier():
         if world > 1:

@@ -109,7 +109,8 @@ int b200sph_create(int device, b200sph_ctx **out);
 int b200sph_destroy(b200sph_ctx *ctx);
 const char *b200sph_last_error(b200sph_ctx *ctx);
 /* run on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) so
- * that torch.distributed collectives order with our kernels; NULL = own stream */
+ * that torch.distributed collectives order with our kernels; NULL = a private
+ * non-blocking stream.  The legacy default stream is cudaStreamLegacy = (void*)1 */
 int b200sph_set_stream(b200sph_ctx *ctx, void *cuda_stream);
 int b200sph_synchronize(b200sph_ctx *ctx);
 

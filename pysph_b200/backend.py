@@ -165,3 +165,14 @@ class B200Backend(object):
 
     def synchronize(self):
         self.ctx.call('b200sph_synchronize')
+
+    def use_torch_stream(self, stream=None):
+        """Run the library on torch's current (or the given) CUDA stream so that
+        torch.distributed collectives and torch events are ordered with our
+        kernels.  torch's default stream has the handle 0, which the C-ABI reads
+        as "own stream"; CUDA's explicit handle for it is cudaStreamLegacy = 1."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        self.ctx.call('b200sph_set_stream', stream.cuda_stream or 1)
+        return stream

@@ -69,8 +69,7 @@ def _worker(rank, world, port, q):
                                            adaptive_timestep=False, n_damp=0)
         _perturb(pas)
         solver.backend.push_all()
-        solver.backend.ctx.call('b200sph_set_stream',
-                                torch.cuda.current_stream().cuda_stream)
+        solver.backend.use_torch_stream()
         for _ in range(NSTEPS):
             solver.step()
         solver.pull()
