@@ -208,6 +208,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    os.environ['NCCL_DEBUG'] = 'WARN'     # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     import pysph_b200 as pb
@@ -295,36 +296,49 @@ def main():
     value = pairs_total / (ms_step * 1e-3)
 
     # ---- e2e: the same step through the host-buffer API ----------------------
-    e2e = None
-    if world == 1:
-        state = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm']
-        outp = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'p']
-        nall = sum(pa.get_number_of_particles() for pa in pas)
-        # pinned host buffers: enqueue the copies, wait once per step
-        be.ctx.call('b200sph_set_async_copies', 1)
-        for _ in range(2):
-            be.push_all(state)
-            solver.step()
-            be.pull_all(outp)
-            be.synchronize()
-        barrier()
-        ev0.record(stream)
-        for _ in range(args.e2e_steps):
-            be.push_all(state)      # H2D from pinned host ParticleArray buffers
-            solver.step()
-            be.pull_all(outp)       # D2H of the step's result
-            be.synchronize()        # the host sees the result of every step
-        ev1.record(stream)
-        barrier()
-        be.ctx.call('b200sph_set_async_copies', 0)
-        ms_e2e = ev0.elapsed_time(ev1) / args.e2e_steps
-        e2e = {'value': pairs_total / (ms_e2e * 1e-3), 'unit': 'pairs/s',
-               'ms_per_step': ms_e2e, 'steps': args.e2e_steps,
-               'h2d_bytes_per_step': 8 * len(state) * nall,
-               'd2h_bytes_per_step': 8 * len(outp) * nall}
-    else:
-        e2e = {'value': None, 'unit': 'pairs/s', 'note': 'measured at N=1 only',
-               'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    # every step: H2D of the state the step consumes (pinned host ParticleArray
+    # buffers), the step, D2H of the output properties; one wait per step
+    state = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm']
+    outp = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'p']
+    if world > 1:
+        # host mirrors hold this rank's real particles (sizes may have changed by
+        # migration): refresh them once, then pin
+        solver.pull()
+        for pa in pas:
+            nr = pa.get_number_of_particles(real=True)
+            for k in list(pa.properties):
+                pa.properties[k] = pa.properties[k][:nr].copy()
+            pa._n = nr
+        keep = pinned_arrays(pas)
+    nreal = sum(be.sizes(i)[1] for i in range(len(pas)))
+    be.ctx.call('b200sph_set_async_copies', 1)
+
+    def e2e_step():
+        be.push_real(state)      # H2D from pinned host ParticleArray buffers
+        solver.step()
+        be.pull_real(outp)       # D2H of the step's result
+        be.synchronize()         # the host sees the result of every step
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    ev1.record(stream)
+    barrier()
+    be.ctx.call('b200sph_set_async_copies', 0)
+    ms_e2e = ev0.elapsed_time(ev1) / args.e2e_steps
+    h2d, d2h = 8 * len(state) * nreal, 8 * len(outp) * nreal
+    if world > 1:
+        t = torch.tensor([ms_e2e, -float(h2d), -float(d2h)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t[0].item())
+        t2 = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t2)
+        h2d, d2h = int(t2[0].item()), int(t2[1].item())
+    e2e = {'value': pairs_total / (ms_e2e * 1e-3), 'unit': 'pairs/s',
+           'ms_per_step': ms_e2e, 'steps': args.e2e_steps,
+           'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h}
 
     # ---- roofline of the dominant kernel (k_pair), from the timed region -----
     peak, peak_src = peaks()

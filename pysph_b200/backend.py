@@ -144,6 +144,24 @@ class B200Backend(object):
                               tmp.ctypes.data, 0, n)
                 a[:] = tmp.view(a.dtype) if a.dtype.itemsize == 4 else tmp
 
+    def push_real(self, props):
+        """Push the REAL particles' values only (ghosts on the device, if any, keep
+        theirs): the per-step host -> device path of a multi-GPU run."""
+        for i, pa in enumerate(self.particle_arrays):
+            n_real = self.sizes(i)[1]
+            for name in props:
+                a = _host_array(pa, name)
+                self.ctx.call('b200sph_push_f64', i, PROP_IDS[name],
+                              a.ctypes.data, 0, n_real)
+
+    def pull_real(self, props):
+        for i, pa in enumerate(self.particle_arrays):
+            n_real = self.sizes(i)[1]
+            for name in props:
+                a = _host_array(pa, name)
+                self.ctx.call('b200sph_pull_f64', i, PROP_IDS[name],
+                              a.ctypes.data, 0, n_real)
+
     def push_all(self, props=None):
         for i in range(len(self.particle_arrays)):
             self.push(i, props)

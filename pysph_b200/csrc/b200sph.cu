@@ -1651,8 +1651,10 @@ int b200sph_push_f64(b200sph_ctx *ctx, int arr, int prop, const double *host, in
     }
     // the host buffer is borrowed only for this call
     if (!ctx->async_copies) CU(cudaStreamSynchronize(ctx->stream));
+    // new positions / smoothing lengths for the SAME particles: the next nnps_update
+    // measures the drift against the current neighbour build and reuses it if it can
     if (prop == B200SPH_H) { ctx->domain_valid = false; ctx->h_dirty = true; }
-    if (prop <= B200SPH_Z || prop == B200SPH_H) { ctx->grid_valid = false; ctx->topo_dirty = true; }
+    if (prop <= B200SPH_Z || prop == B200SPH_H) ctx->grid_valid = false;
     ctx->state_packed = false;
     return 0;
 }
