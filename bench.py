@@ -208,7 +208,17 @@ def main():
         run_reference(args, rank, world)
         return
 
-    os.environ['NCCL_DEBUG'] = 'WARN'     # keep stdout to the one JSON line
+    # stdout must carry exactly ONE JSON line: NCCL (and anything else native) may
+    # print banners there, so fd 1 points at stderr until the result is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line))
+        sys.stdout.flush()
     import torch
     import torch.distributed as dist
     import pysph_b200 as pb
@@ -406,7 +416,7 @@ def main():
     }
     if cpu:
         line['cpu_baseline'] = cpu
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -203,6 +203,10 @@ int b200sph_halo_overwrite(b200sph_ctx *ctx, int arr, int64_t ghost_first,
  * current neighbour build (-1 if there is no reusable build), out[1] = the skin
  * S: the build can be reused while out[0] <= out[1] */
 int b200sph_nnps_drift(b200sph_ctx *ctx, double out[2]);
+/* the caller decided (collectively, over all ranks) that the current build is
+ * kept for the next nnps_update: that update then only refreshes the packed
+ * positions and does not repeat the drift measurement (saves a host sync) */
+int b200sph_nnps_keep_build(b200sph_ctx *ctx);
 /* append n particles from dev_buf (field f of particle k at
  * dev_buf[f * stride + k]) after the current particles of `arr`.
  * nfields = B200SPH_HALO_FIELDS: ghosts (tag Remote), other props zeroed;

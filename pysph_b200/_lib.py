@@ -102,6 +102,7 @@ SIGNATURES = {
     'b200sph_halo_overwrite': (C.c_int, [_ctx_p, C.c_int, _i64, C.c_void_p, _i64,
                                          _i64]),
     'b200sph_nnps_drift': (C.c_int, [_ctx_p, _dp]),
+    'b200sph_nnps_keep_build': (C.c_int, [_ctx_p]),
     'b200sph_halo_append': (C.c_int, [_ctx_p, C.c_int, C.c_void_p, _i64, _i64,
                                       C.c_int, C.c_int]),
     'b200sph_drop_ghosts': (C.c_int, [_ctx_p, C.c_int]),

@@ -126,6 +126,7 @@ struct b200sph_ctx {
     int capg = 0;               // entries reserved per destination
     bool lists_valid = false;
     bool topo_dirty = true;     // particle set / h pushed: a light update is not enough
+    bool drift_ok = false;      // set by nnps_drift when its caller took the (collective) decision
     bool h_dirty = true;        // h changed since the last update_domain reduction
     unsigned *red_u32 = nullptr, *red_u32_host = nullptr;
     int64_t n_full_builds = 0, n_light_updates = 0, n_list_builds = 0;
@@ -1238,17 +1239,40 @@ __global__ void k_gather_u32(const uint32_t *__restrict__ src, long long off, lo
     if (i >= n) return;
     if (flag[i]) dst[pos[i]] = src[off + i];
 }
+struct HaloPtrs {
+    double *p[B200SPH_HALO_FIELDS];
+};
+// all B200SPH_HALO_FIELDS of the selected particles in one launch (field-major, tight)
+__global__ void k_halo_gather_flag(HaloPtrs P, long long off, long long n, const uint32_t *__restrict__ flag,
+                                   const uint32_t *__restrict__ pos, double *__restrict__ dst, long long tot)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const long long k = pos[i];
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) dst[(long long)f * tot + k] = P.p[f][off + i];
+}
+__global__ void k_halo_gather_idx(HaloPtrs P, long long off, const uint32_t *__restrict__ idx, long long n,
+                                  double *__restrict__ dst)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long i = idx[k];
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) dst[(long long)f * n + k] = P.p[f][off + i];
+}
+__global__ void k_halo_scatter(HaloPtrs P, long long o, const double *__restrict__ src, long long stride, long long n)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) P.p[f][o + k] = src[(long long)f * stride + k];
+}
 __global__ void k_save_idx(long long n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
                            uint32_t *__restrict__ idx)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) idx[pos[i]] = (uint32_t)i;
-}
-__global__ void k_gather_idx_f64(const double *__restrict__ src, long long off, const uint32_t *__restrict__ idx,
-                                 long long n, double *__restrict__ dst)
-{
-    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) dst[k] = src[off + idx[k]];
 }
 __global__ void k_f64_to_u32(const double *__restrict__ in, uint32_t *__restrict__ out, long long n)
 {
@@ -1783,6 +1807,16 @@ int b200sph_update_domain(b200sph_ctx *ctx)
 static int nnps_light_update(b200sph_ctx *ctx)
 {
     if (ctx->n_sorted <= 0) return 1;
+    if (ctx->drift_ok) {
+        // the drift was just measured by b200sph_nnps_drift (multi-GPU: the decision to
+        // keep the build is collective); only refresh the packed positions, no host sync
+        ctx->drift_ok = false;
+        k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
+            ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
+            ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
+        LAUNCH_CHECK();
+        return 1;
+    }
     CU(cudaMemsetAsync(ctx->red_u32, 0, 4 * sizeof(unsigned), ctx->stream));
     k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
         ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
@@ -1821,6 +1855,7 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         }
     }
     ctx->lists_valid = false;
+    ctx->drift_ok = false;
     ctx->n_full_builds++;
 
     int64_t ntot = 0;
@@ -2239,6 +2274,13 @@ int b200sph_dt_factors(b200sph_ctx *ctx, double out[3])
 // ---- halo helpers ------------------------------------------------------------
 static const int halo_fields[9] = {B200SPH_X, B200SPH_Y, B200SPH_Z, B200SPH_U, B200SPH_V, B200SPH_W, B200SPH_RHO, B200SPH_H, B200SPH_M};
 
+static HaloPtrs halo_ptrs(b200sph_ctx *ctx)
+{
+    HaloPtrs P;
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) P.p[f] = ctx->f64[halo_fields[f]];
+    return P;
+}
+
 int b200sph_halo_pack(b200sph_ctx *ctx, int arr, int slot, double lo, double hi, double *dev_buf, int64_t cap, int64_t *count)
 {
     CU(cudaSetDevice(ctx->device));
@@ -2274,10 +2316,8 @@ int b200sph_halo_pack(b200sph_ctx *ctx, int arr, int slot, double lo, double hi,
         return set_err(ctx, "halo_pack: slot must be -1, 0 or 1");
     }
     if (tot == 0) return 0;
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) {
-        k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[halo_fields[f]], off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)f * tot);
-        LAUNCH_CHECK();
-    }
+    k_halo_gather_flag<<<nb, 256, 0, ctx->stream>>>(halo_ptrs(ctx), off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)tot);
+    LAUNCH_CHECK();
     return 0;
 }
 
@@ -2296,8 +2336,8 @@ int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf, int64_
     const int64_t o = ai.off + ai.n;
     const unsigned nb = (unsigned)cdiv(n, 256);
     if (nfields == B200SPH_HALO_FIELDS) {
-        for (int f = 0; f < 9; f++)
-            CU(cudaMemcpyAsync(ctx->f64[halo_fields[f]] + o, dev_buf + (size_t)f * stride, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        k_halo_scatter<<<nb, 256, 0, ctx->stream>>>(halo_ptrs(ctx), o, dev_buf, stride, n);
+        LAUNCH_CHECK();
         for (int k = B200SPH_X0; k < N_F64; k++) CU(cudaMemsetAsync(ctx->f64[k] + o, 0, 8 * (size_t)n, ctx->stream));
         k_fill_u32<<<nb, 256, 0, ctx->stream>>>(ctx->u32[0] + o, n, 0xFFFFFFFFu);
         LAUNCH_CHECK();
@@ -2334,10 +2374,8 @@ int b200sph_halo_pack_selected(b200sph_ctx *ctx, int arr, int slot, double *dev_
     *count = n;
     if (n > cap) return set_err(ctx, "halo_pack_selected: buffer too small");
     if (n == 0) return 0;
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) {
-        k_gather_idx_f64<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->f64[halo_fields[f]], ctx->arr[arr].off, ctx->halo_idx[arr][slot], n, dev_buf + (size_t)f * n);
-        LAUNCH_CHECK();
-    }
+    k_halo_gather_idx<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), ctx->arr[arr].off, ctx->halo_idx[arr][slot], n, dev_buf);
+    LAUNCH_CHECK();
     return 0;
 }
 
@@ -2352,8 +2390,8 @@ int b200sph_halo_overwrite(b200sph_ctx *ctx, int arr, int64_t ghost_first, const
         return set_err(ctx, "halo_overwrite: ghosts [%lld, %lld) outside the %lld ghosts of '%s'", (long long)ghost_first, (long long)(ghost_first + n), (long long)(ai.n - ai.n_real), ai.name.c_str());
     if (n == 0) return 0;
     const int64_t o = ai.off + ai.n_real + ghost_first;
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++)
-        CU(cudaMemcpyAsync(ctx->f64[halo_fields[f]] + o, dev_buf + (size_t)f * stride, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_halo_scatter<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), o, dev_buf, stride, n);
+    LAUNCH_CHECK();
     // values moved, the particle set did not: a light nnps_update is enough
     ctx->grid_valid = false;
     ctx->state_packed = false;
@@ -2380,6 +2418,14 @@ int b200sph_nnps_drift(b200sph_ctx *ctx, double out[2])
     memcpy(&d2, &ctx->red_u32_host[0], 4);
     memcpy(&dh, &ctx->red_u32_host[1], 4);
     out[0] = 2.0 * std::sqrt((double)d2) + ctx->radius_scale * (double)dh;
+    return 0;
+}
+
+int b200sph_nnps_keep_build(b200sph_ctx *ctx)
+{
+    if (ctx->force_kernel != 0 || !ctx->lists_valid || ctx->topo_dirty)
+        return set_err(ctx, "nnps_keep_build: there is no reusable neighbour build");
+    ctx->drift_ok = true;
     return 0;
 }
 

@@ -132,6 +132,9 @@ class DeviceHaloOps(object):
             self.ctx.call('b200sph_halo_overwrite', arr, int(ghost_first),
                           buf.data_ptr() + 8 * offset, n, n)
 
+    def keep_build(self):
+        self.ctx.call('b200sph_nnps_keep_build')
+
     def drift(self):
         """(need, skin): the neighbour build is reusable while need <= skin;
         need < 0 means there is no reusable build."""
@@ -241,6 +244,8 @@ class SlabParallelManager(object):
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             if float(t[0].item()) <= 0.9:
                 self._refresh_ghosts()
+                if hasattr(ops, 'keep_build'):
+                    ops.keep_build()
                 self.n_refresh += 1
                 return
         for a in range(self.narr):
