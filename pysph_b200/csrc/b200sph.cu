@@ -115,7 +115,11 @@ struct b200sph_ctx {
     bool state_packed = false;
     int force_kernel = 0;       // 0 lists (default), 1 warp kernel (env B200SPH_PAIR_KERNEL)
     // persistent neighbour lists
-    double skin = 0.1;          // S = skin * radius_scale * hmax   (env B200SPH_SKIN)
+    double skin = 0.1;          // S = skin * radius_scale * hmax, adapted between skin_min and skin_max
+    double skin_max = 0.1;      // env B200SPH_SKIN (also what a halo exchange must cover)
+    double skin_min = 0.02;
+    bool skin_adapt = true;     // env B200SPH_SKIN_ADAPT=0 switches the controller off
+    int64_t evals_since_build = 0;  // light updates served by the current build
     double S_abs = 0.0;         // absolute skin of the current build
     double cell_int = 1.0;      // internal cell size (cell_size + S)
     GridDev G;                  // frozen device grid of the current build
@@ -909,6 +913,11 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
 #define LIST_JBITS 26
 #define LIST_JMASK 0x03FFFFFFu
 #define LIST_NT 128
+// Skin controller.  Per evaluation a build costs c0 (1+s)^3 (list entries) + R / L(s)
+// (rebuild cost R over a lifetime L that grows linearly with the skin s); the minimum is
+// where L s = R / (3 c0 (1+s)^2) ~ 2 for the measured R / c0 ~ 5.5, i.e. the target
+// lifetime is L* = SKIN_KAPPA / s evaluations.
+#define SKIN_KAPPA 2.0
 
 struct ListBuildArgs {
     const float4 *A;
@@ -1522,7 +1531,9 @@ int b200sph_create(int device, b200sph_ctx **out)
             return -3;
         }
     }
-    if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = std::max(0.0, atof(e));
+    if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = ctx->skin_max = std::max(0.0, atof(e));
+    if (const char *e = getenv("B200SPH_SKIN_ADAPT")) ctx->skin_adapt = atoi(e) != 0;
+    ctx->skin_min = std::min(ctx->skin_min, ctx->skin_max);
     CU(cudaMalloc((void **)&ctx->red_u32, 4 * sizeof(unsigned)));
     CU(cudaMallocHost((void **)&ctx->red_u32_host, 4 * sizeof(unsigned)));
     CU(cudaMalloc((void **)&ctx->red, 16 * sizeof(long long)));
@@ -1844,16 +1855,27 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     int64_t ntot0 = 0;
     for (int a = 0; a < ctx->narr; a++) ntot0 += ctx->arr[a].n;
     const bool use_lists = ctx->force_kernel == 0 && ntot0 < (1LL << LIST_JBITS);
-    if (use_lists && ctx->lists_valid && !ctx->topo_dirty) {
+    if (use_lists && ctx->lists_valid && !ctx->topo_dirty &&
+        !(ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min && !ctx->drift_ok)) {
         rc = nnps_light_update(ctx);
         if (rc < 0) return rc;
         if (rc == 1) {
             ctx->n_light_updates++;
+            ctx->evals_since_build++;
             ctx->grid_valid = true;
             ctx->state_packed = false;
             return 0;
         }
     }
+    // skin controller (see SKIN_KAPPA): a build that outlived 1.5 L* was built with too
+    // generous a skin, one that lasted less than L* / 1.5 with too small a one; builds that
+    // reach 3 L* are retired so that a quiet flow converges to the minimum skin
+    if (use_lists && ctx->skin_adapt && ctx->lists_valid && ctx->evals_since_build > 0) {
+        const double lstar = SKIN_KAPPA / ctx->skin;
+        if (ctx->evals_since_build >= 1.5 * lstar) ctx->skin = std::max(ctx->skin_min, ctx->skin * 0.75);
+        else if (ctx->evals_since_build < lstar / 1.5) ctx->skin = std::min(ctx->skin_max, ctx->skin * 1.33);
+    }
+    ctx->evals_since_build = 0;
     ctx->lists_valid = false;
     ctx->drift_ok = false;
     ctx->n_full_builds++;
@@ -2406,6 +2428,7 @@ int b200sph_nnps_drift(b200sph_ctx *ctx, double out[2])
     out[0] = -1.0;
     out[1] = ctx->S_abs;
     if (ctx->force_kernel != 0 || !ctx->lists_valid || ctx->topo_dirty) return 0;  // no reusable build
+    if (ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min) return 0;  // retire it
     if (ctx->n_sorted <= 0) { out[0] = 0.0; return 0; }
     CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
     k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
