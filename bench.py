@@ -148,7 +148,12 @@ def run_reference(args, rank, world):
     pas = geo.dam_break_3d_particles(dx=dx)
     params = geo.dam_break_3d_params(dx)
     ncores = os.cpu_count() or 1
-    threads = min(ncores, orc.load().orc_get_max_threads() if True else 1, 64)
+    # torchrun exports OMP_NUM_THREADS=1: size the pool from the affinity mask instead
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    threads = max(1, min(ncores, 64))
     ntot = sum(pa.get_number_of_particles() for pa in pas)
     r = cpu_leg(pas, params, threads, budget_s=150.0,
                 max_steps=max(1, args.steps), warmup=min(args.warmup, 1))

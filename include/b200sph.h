@@ -199,10 +199,31 @@ int b200sph_halo_pack_selected(b200sph_ctx *ctx, int arr, int slot, double *dev_
  * [ghost_first, ghost_first + n) of `arr` (indices among the ghosts) */
 int b200sph_halo_overwrite(b200sph_ctx *ctx, int arr, int64_t ghost_first,
                            const double *dev_buf, int64_t stride, int64_t n);
+/* the refresh message of ALL arrays for neighbour `slot` in one kernel: the block
+ * of array a starts at 9 * (count_0 + .. + count_{a-1}) doubles, field-major and
+ * tight.  dev_buf may be a PEER pointer obtained with b200sph_ipc_open (the
+ * neighbour's staging buffer): pack and send are then the same kernel, writing
+ * over NVLink */
+int b200sph_halo_pack_selected_all(b200sph_ctx *ctx, int slot, double *dev_buf,
+                                   int64_t cap_doubles, int64_t *ndoubles);
+/* the inverse on the receiving rank: counts[a] particles of array a (block
+ * layout as above) over the existing ghosts starting at ghost_first[a] */
+int b200sph_halo_overwrite_all(b200sph_ctx *ctx, const int64_t *ghost_first,
+                               const int64_t *counts, const double *dev_buf);
+/* peer-memory staging buffers (ranks of one node): allocate + export a 64-byte
+ * cudaIpcMemHandle_t / map a neighbour's buffer / unmap (owner = 0) or free (1) */
+int b200sph_ipc_alloc(b200sph_ctx *ctx, int64_t bytes, void **dev_ptr, void *handle64);
+int b200sph_ipc_open(b200sph_ctx *ctx, const void *handle64, void **dev_ptr);
+int b200sph_ipc_close(b200sph_ctx *ctx, void *dev_ptr, int owner);
 /* out[0] = 2 max|x - x_build| + k max(h - h_build) over the particles of the
  * current neighbour build (-1 if there is no reusable build), out[1] = the skin
  * S: the build can be reused while out[0] <= out[1] */
 int b200sph_nnps_drift(b200sph_ctx *ctx, double out[2]);
+/* the same measurement without a host round trip: writes out[0] / out[1] (the
+ * fraction of the skin used up) to a DEVICE double, stream ordered, so that a
+ * collective can reduce it directly.  Returns 1 (and writes nothing) if there is
+ * no reusable build, 0 otherwise */
+int b200sph_nnps_drift_device(b200sph_ctx *ctx, double *dev_ratio);
 /* the caller decided (collectively, over all ranks) that the current build is
  * kept for the next nnps_update: that update then only refreshes the packed
  * positions and does not repeat the drift measurement (saves a host sync) */

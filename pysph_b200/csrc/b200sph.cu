@@ -1277,6 +1277,43 @@ __global__ void k_halo_scatter(HaloPtrs P, long long o, const double *__restrict
 #pragma unroll
     for (int f = 0; f < B200SPH_HALO_FIELDS; f++) P.p[f][o + k] = src[(long long)f * stride + k];
 }
+struct HaloAllArgs {
+    int narr;
+    long long prefix[B200SPH_MAX_ARRAYS + 1];  // particles before array a in the message
+    long long off[B200SPH_MAX_ARRAYS];         // pool offset of the first particle addressed
+    const uint32_t *idx[B200SPH_MAX_ARRAYS];   // gather: saved selection (relative to off); scatter: unused
+};
+// the refresh message of ALL arrays in one launch: block of array a starts at
+// 9 * prefix[a] doubles, field-major and tight inside the block.  `dst` may be a peer
+// pointer (the neighbour's staging buffer): then this kernel is pack + send in one.
+__global__ void k_halo_gather_all(HaloPtrs P, HaloAllArgs A, double *__restrict__ dst)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.prefix[A.narr]) return;
+    int a = 0;
+    while (k >= A.prefix[a + 1]) a++;
+    const long long r = k - A.prefix[a], cnt = A.prefix[a + 1] - A.prefix[a];
+    const long long i = A.off[a] + A.idx[a][r];
+    double *out = dst + B200SPH_HALO_FIELDS * A.prefix[a] + r;
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) out[(long long)f * cnt] = P.p[f][i];
+}
+__global__ void k_halo_scatter_all(HaloPtrs P, HaloAllArgs A, const double *__restrict__ src)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.prefix[A.narr]) return;
+    int a = 0;
+    while (k >= A.prefix[a + 1]) a++;
+    const long long r = k - A.prefix[a], cnt = A.prefix[a + 1] - A.prefix[a];
+    const double *in = src + B200SPH_HALO_FIELDS * A.prefix[a] + r;
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) P.p[f][A.off[a] + r] = in[(long long)f * cnt];
+}
+__global__ void k_drift_ratio(const unsigned *__restrict__ red_u32, float kr, float S, double *__restrict__ out)
+{
+    const float need = 2.0f * sqrtf(__uint_as_float(red_u32[0])) + kr * __uint_as_float(red_u32[1]);
+    out[0] = S > 0.f ? (double)(need / S) : 2.0;
+}
 __global__ void k_save_idx(long long n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
                            uint32_t *__restrict__ idx)
 {
@@ -2441,6 +2478,115 @@ int b200sph_nnps_drift(b200sph_ctx *ctx, double out[2])
     memcpy(&d2, &ctx->red_u32_host[0], 4);
     memcpy(&dh, &ctx->red_u32_host[1], 4);
     out[0] = 2.0 * std::sqrt((double)d2) + ctx->radius_scale * (double)dh;
+    return 0;
+}
+
+int b200sph_halo_pack_selected_all(b200sph_ctx *ctx, int slot, double *dev_buf, int64_t cap_doubles, int64_t *ndoubles)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
+    if (slot < 0 || slot > 1) return set_err(ctx, "halo_pack_selected_all: bad slot");
+    HaloAllArgs A;
+    A.narr = ctx->narr;
+    A.prefix[0] = 0;
+    for (int a = 0; a < ctx->narr; a++) {
+        A.prefix[a + 1] = A.prefix[a] + ctx->halo_cnt[a][slot];
+        A.off[a] = ctx->arr[a].off;
+        A.idx[a] = ctx->halo_idx[a][slot];
+    }
+    const int64_t tot = A.prefix[ctx->narr];
+    *ndoubles = tot * B200SPH_HALO_FIELDS;
+    if (*ndoubles > cap_doubles) return set_err(ctx, "halo_pack_selected_all: buffer too small");
+    if (tot == 0) return 0;
+    k_halo_gather_all<<<(unsigned)cdiv(tot, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), A, dev_buf);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int b200sph_halo_overwrite_all(b200sph_ctx *ctx, const int64_t *ghost_first, const int64_t *counts, const double *dev_buf)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    HaloAllArgs A;
+    A.narr = ctx->narr;
+    A.prefix[0] = 0;
+    for (int a = 0; a < ctx->narr; a++) {
+        const ArrayInfo &ai = ctx->arr[a];
+        if (ghost_first[a] < 0 || counts[a] < 0 || ai.n_real + ghost_first[a] + counts[a] > ai.n)
+            return set_err(ctx, "halo_overwrite_all: ghosts [%lld, %lld) outside the %lld ghosts of '%s'", (long long)ghost_first[a],
+                           (long long)(ghost_first[a] + counts[a]), (long long)(ai.n - ai.n_real), ai.name.c_str());
+        A.prefix[a + 1] = A.prefix[a] + counts[a];
+        A.off[a] = ai.off + ai.n_real + ghost_first[a];
+        A.idx[a] = nullptr;
+    }
+    const int64_t tot = A.prefix[ctx->narr];
+    if (tot == 0) return 0;
+    k_halo_scatter_all<<<(unsigned)cdiv(tot, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), A, dev_buf);
+    LAUNCH_CHECK();
+    ctx->grid_valid = false;
+    ctx->state_packed = false;
+    return 0;
+}
+
+// ---- peer memory (same node, NVLink): staging buffers a neighbour rank writes into ----
+int b200sph_ipc_alloc(b200sph_ctx *ctx, int64_t bytes, void **dev_ptr, void *handle64)
+{
+    CU(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    CU(cudaMalloc(&p, (size_t)std::max<int64_t>(bytes, 256)));
+    CU(cudaMemset(p, 0, (size_t)std::max<int64_t>(bytes, 256)));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return set_err(ctx, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return 0;
+}
+
+int b200sph_ipc_open(b200sph_ctx *ctx, const void *handle64, void **dev_ptr)
+{
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return set_err(ctx, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int b200sph_ipc_close(b200sph_ctx *ctx, void *dev_ptr, int owner)
+{
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (owner) CU(cudaFree(dev_ptr));
+    else CU(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+int b200sph_nnps_drift_device(b200sph_ctx *ctx, double *dev_ratio)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (ctx->force_kernel != 0 || !ctx->lists_valid || ctx->topo_dirty) return 1;  // no reusable build
+    if (ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min) return 1;  // retire it
+    if (ctx->n_sorted <= 0) {
+        CU(cudaMemsetAsync(dev_ratio, 0, sizeof(double), ctx->stream));
+        return 0;
+    }
+    CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
+    k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
+        ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
+        ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
+    LAUNCH_CHECK();
+    k_drift_ratio<<<1, 1, 0, ctx->stream>>>(ctx->red_u32, (float)ctx->radius_scale, (float)ctx->S_abs, dev_ratio);
+    LAUNCH_CHECK();
     return 0;
 }
 

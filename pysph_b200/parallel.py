@@ -135,6 +135,43 @@ class DeviceHaloOps(object):
     def keep_build(self):
         self.ctx.call('b200sph_nnps_keep_build')
 
+    # -- all arrays in one kernel; peer (NVLink) staging ------------------------
+    def pack_selected_all(self, slot, ptr, cap_doubles):
+        """Refresh message of every array for neighbour `slot`, written to the
+        raw device pointer `ptr` -- a local buffer or a neighbour's staging
+        buffer mapped with ipc_open (then pack and send are one kernel)."""
+        nd = C.c_int64()
+        self.ctx.call('b200sph_halo_pack_selected_all', slot, ptr, int(cap_doubles),
+                      C.byref(nd))
+        return nd.value
+
+    def overwrite_all(self, ghost_first, counts, ptr):
+        n = self.narr
+        self.ctx.call('b200sph_halo_overwrite_all', (C.c_int64 * n)(*ghost_first),
+                      (C.c_int64 * n)(*counts), ptr)
+
+    def ipc_alloc(self, nbytes):
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self.ctx.call('b200sph_ipc_alloc', int(nbytes), C.byref(ptr), handle)
+        return ptr.value, handle.raw
+
+    def ipc_open(self, handle):
+        ptr = C.c_void_p()
+        self.ctx.call('b200sph_ipc_open', C.create_string_buffer(handle, 64),
+                      C.byref(ptr))
+        return ptr.value
+
+    def ipc_close(self, ptr, owner):
+        self.ctx.call('b200sph_ipc_close', ptr, 1 if owner else 0)
+
+    def drift_to(self, tensor):
+        """Write the used-up fraction of the skin into a 1-element CUDA double
+        tensor (no host sync); 2.0 if there is no reusable build."""
+        rc = self.ctx.call('b200sph_nnps_drift_device', tensor.data_ptr())
+        if rc == 1:
+            tensor.fill_(2.0)
+
     def drift(self):
         """(need, skin): the neighbour build is reusable while need <= skin;
         need < 0 means there is no reusable build."""
@@ -184,6 +221,13 @@ class SlabParallelManager(object):
         # last full exchange (the refresh path re-sends exactly those particles)
         self._sent = {}
         self._recv = {}
+        # peer-memory refresh (GPUs of one node): per neighbour two staging buffers
+        # (double buffered by evaluation parity) that the NEIGHBOUR writes into
+        self.use_peer = bool(int(__import__('os').environ.get('B200SPH_PEER_HALO', '1'))) \
+            and hasattr(ops, 'ipc_alloc')
+        self._peer = None
+        self._parity = 0
+        self.n_peer_refresh = 0
 
     # -- transport ------------------------------------------------------------
     def _exchange(self, send_counts, send_bufs, nfields):
@@ -237,13 +281,38 @@ class SlabParallelManager(object):
         drop / migrate / import path runs and the next NNPS update rebuilds."""
         ops = self.ops
         if self._recv and hasattr(ops, 'drift'):
-            need, skin = ops.drift()
-            ratio = need / skin if (need >= 0.0 and skin > 0.0) else 2.0
-            t = ops.new_buffer(1)
-            t[0] = ratio
+            if getattr(self, '_t1', None) is None:
+                self._t1 = ops.new_buffer(1)
+            t = self._t1
+            if hasattr(ops, 'drift_to'):
+                ops.drift_to(t)           # stays on the device until the all-reduce
+            else:
+                need, skin = ops.drift()
+                t.fill_(need / skin if (need >= 0.0 and skin > 0.0) else 2.0)
+            if self._peer is not None:
+                # speculative pack + send in ONE kernel per neighbour: the values go
+                # straight into the neighbour's staging buffer over NVLink; the
+                # all-reduce below is both the decision and the barrier that makes
+                # them visible (double buffering keeps the previous evaluation's
+                # buffer untouched while a slower neighbour may still read it)
+                self._parity ^= 1
+                for nb in self._peer['nbs']:
+                    slot = 0 if nb == self.left else 1
+                    if sum(self._sent[nb]):
+                        ops.pack_selected_all(slot, self._peer['remote'][nb][self._parity],
+                                              self._peer['cap'])
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-            if float(t[0].item()) <= 0.9:
-                self._refresh_ghosts()
+            if float(t.item()) <= 0.9:
+                if self._peer is not None:
+                    first = [0] * self.narr
+                    for nb in sorted(self._recv):
+                        if sum(self._recv[nb]):
+                            ops.overwrite_all(first, self._recv[nb],
+                                              self._peer['local'][nb][self._parity])
+                        first = [f + n for f, n in zip(first, self._recv[nb])]
+                    self.n_peer_refresh += 1
+                else:
+                    self._refresh_ghosts()
                 if hasattr(ops, 'keep_build'):
                     ops.keep_build()
                 self.n_refresh += 1
@@ -254,6 +323,67 @@ class SlabParallelManager(object):
             self._migrate()
         self._import_ghosts()
         self.n_full += 1
+        if self.use_peer:
+            self._setup_peer()
+
+    def _setup_peer(self):
+        """(Re)allocate the staging buffers when the halo outgrew them and exchange
+        their IPC handles with the slab neighbours.  Collective; full path only."""
+        ops, dist = self.ops, self.dist
+        nbs = [nb for nb in (self.left, self.right) if nb is not None]
+        need = max([sum(self._recv[nb]) for nb in nbs] +
+                   [sum(self._sent[nb]) for nb in nbs] + [1]) * HALO_FIELDS
+        t = ops.new_buffer(1)
+        t.fill_(float(need))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        need = int(t.item())
+        if self._peer is not None and need <= self._peer['cap']:
+            return
+        def all_ok(flag):
+            t.fill_(1.0 if flag else 0.0)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return float(t.item()) > 0.5
+
+        def warn(e):
+            import sys
+            sys.stderr.write('pysph_b200: peer-memory halo disabled (%s)\n' % e)
+
+        if self._peer is not None:      # retire the old buffers (collectively)
+            for nb in self._peer['nbs']:
+                for p in self._peer['remote'][nb]:
+                    ops.ipc_close(p, False)
+            dist.barrier()              # nobody still maps a buffer that is freed next
+            for nb in self._peer['nbs']:
+                for p in self._peer['local'][nb]:
+                    ops.ipc_close(p, True)
+            self._peer = None
+        cap = int(need * 1.5) + 1024
+        local, handles, ok = {}, {}, True
+        try:
+            for nb in nbs:
+                bufs = [ops.ipc_alloc(8 * cap) for _ in range(2)]
+                local[nb] = [b_[0] for b_ in bufs]
+                handles[nb] = [b_[1] for b_ in bufs]
+        except Exception as e:          # e.g. IPC not permitted in this container
+            warn(e)
+            ok = False
+        if not all_ok(ok):
+            self.use_peer = False
+            return
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles)
+        remote = {}
+        try:
+            # the buffer I write into on neighbour nb is the one nb allocated for ME
+            for nb in nbs:
+                remote[nb] = [ops.ipc_open(h) for h in gathered[nb][self.rank]]
+        except Exception as e:
+            warn(e)
+            ok = False
+        if not all_ok(ok):
+            self.use_peer = False
+            return
+        self._peer = dict(nbs=nbs, cap=cap, local=local, remote=remote)
 
     def _refresh_ghosts(self):
         ops = self.ops

@@ -74,7 +74,7 @@ def _worker(rank, world, port, q):
             solver.step()
         solver.pull()
         q.put((rank, _collect(pas), pm.n_full, pm.n_refresh,
-               solver.backend.stats()))
+               solver.backend.stats(), pm.n_peer_refresh))
     finally:
         dist.destroy_process_group()
 
@@ -112,6 +112,8 @@ def test_slab_decomposition_matches_single_gpu(world):
     n_refresh = [o[3] for o in out]
     # the ghost sets were reused (refresh path) and rebuilt (fast particles)
     assert min(n_refresh) > 0 and min(n_full) >= 2, (n_full, n_refresh)
+    # the refreshes went over peer memory (NVLink stores), not NCCL send/recv
+    assert min(o[5] for o in out) > 0, [o[5] for o in out]
     h0, c0 = params['h0'], params['c0']
     for name in ref:
         g_all = np.concatenate([o[1][name]['gid'] for o in out])
