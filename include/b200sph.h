@@ -101,6 +101,7 @@ typedef struct {
                               (persistent neighbour lists still valid)          */
     int64_t list_builds;   /* neighbour list (re)builds                         */
     int64_t list_entries_per_particle; /* list capacity reserved per particle   */
+    int64_t deferred_failed; /* deferred drift checks that forced a repeat      */
 } b200sph_stats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -141,6 +142,13 @@ int b200sph_device_ptr(b200sph_ctx *ctx, int arr, int prop, void **out);
 /* kernel.__dict__ (dim, radius_scale via the kernel id)
  * acceleration_eval_cython_helper.py:242-246 */
 int b200sph_set_kernel(b200sph_ctx *ctx, int kernel, int dim);
+/* DomainManager(xmin.., periodic_in_x..) nnps_base.pyx:226-347: a periodic axis d
+ * wraps positions into [lo[d], hi[d]] at every update_domain (_box_wrap_periodic,
+ * :699-743) and lets particles interact with the periodic images of the others.
+ * Images are NOT materialised as tag=Ghost particles (_create_ghosts_periodic,
+ * :744-940): the cell grid tiles the axis exactly and neighbour cells wrap. */
+int b200sph_set_domain(b200sph_ctx *ctx, const double lo[3], const double hi[3],
+                       const int periodic[3]);
 /* NNPS.update_domain -> CPUDomainManager._compute_cell_size_for_binning
  * nnps_base.pyx:450-483, :942-978 */
 int b200sph_update_domain(b200sph_ctx *ctx);
@@ -148,6 +156,16 @@ int b200sph_update_domain(b200sph_ctx *ctx);
  * (linked_list_nnps.pyx:293-343; error if > 2^28 cells), binning (:235-286)
  * -- here a deterministic counting sort + cell-relative fp32 repack */
 int b200sph_nnps_update(b200sph_ctx *ctx);
+/* The same update, but when the persistent neighbour lists are reused the
+ * measurement that proves them valid (drift <= skin) is only ENQUEUED: the
+ * caller enqueues the evaluation right behind it and then calls
+ * b200sph_nnps_confirm, which waits for the measurement (the GPU is busy with
+ * the evaluation meanwhile).  *redo = 1 means the lists were stale: call
+ * b200sph_nnps_update (it rebuilds) and repeat the evaluation -- every field an
+ * evaluation writes is overwritten by the repeat.  stage / dt_factors / pull /
+ * halo_pack / migrate_out / get_neighbors fail on an unconfirmed stale update. */
+int b200sph_nnps_update_deferred(b200sph_ctx *ctx);
+int b200sph_nnps_confirm(b200sph_ctx *ctx, int *redo);
 int b200sph_get_grid(b200sph_ctx *ctx, b200sph_grid_info *out);
 /* NNPS.get_nearest_particles(src, dst, d_idx, nbrs) nnps_base.pyx:1268-1290:
  * runs the SAME accept test as the pair kernel.  Writes up to cap source

@@ -236,17 +236,80 @@ class Oracle(object):
         return out[0], out[1], out[2]
 
 
+def periodic_box_wrap(pas, lo, hi, periodic):
+    """_box_wrap_periodic, pysph/base/nnps_base.pyx:699-743 (in place)."""
+    for pa in pas:
+        for d, name in enumerate(('x', 'y', 'z')):
+            if not periodic[d]:
+                continue
+            a = pa.properties[name]
+            L = hi[d] - lo[d]
+            a[a < lo[d]] += L
+            a[a > hi[d]] -= L
+
+
+def periodic_ghosts(pas, lo, hi, periodic, cell_size, n_layers=2.0):
+    """_create_ghosts_periodic, pysph/base/nnps_base.pyx:744-940: returns NEW
+    arrays = real particles + their periodic images (tag Ghost = 2) appended,
+    ``num_real_particles`` unchanged.  Images: x first; then y images of the
+    real particles AND of the x images; then z images of everything so far."""
+    from pysph_b200.particle_array import get_particle_array_wcsph
+    width = n_layers * cell_size
+    out = []
+    for pa in pas:
+        nr = pa.get_number_of_particles(real=True)
+        props = dict((k, v[:nr].copy()) for k, v in pa.properties.items())
+        ghosts = dict((k, v[:0].copy()) for k, v in props.items())
+
+        def images(src, name, d):
+            lo_sel = (src[name] - lo[d]) <= width
+            hi_sel = (hi[d] - src[name]) <= width
+            new = []
+            for sel, shift in ((lo_sel, hi[d] - lo[d]), (hi_sel, -(hi[d] - lo[d]))):
+                blk = dict((k, v[sel].copy()) for k, v in src.items())
+                blk[name] = blk[name] + shift
+                new.append(blk)
+            return new
+
+        def cat(parts):
+            return dict((k, np.concatenate([p[k] for p in parts])) for k in props)
+
+        for d, name in enumerate(('x', 'y', 'z')):
+            if not periodic[d]:
+                continue
+            new = images(ghosts, name, d) + images(props, name, d)
+            ghosts = cat([ghosts] + new)
+        allp = cat([props, ghosts])
+        q = get_particle_array_wcsph(name=pa.name, **allp)
+        q.set_num_real_particles(nr)
+        q.tag[nr:] = 2
+        out.append(q)
+    return out
+
+
 class WCSPHOracleSolver(object):
     """Runs a WCSPHScheme simulation with the oracle: scheme.py:388-506 for the
     loops, integrator.py:344-361/401-420 for the stage order, solver.py for the
     time step.  ``params`` as returned by pysph_b200.geometry.*_params."""
 
-    def __init__(self, particles, params, kernel='CubicSpline', threads=1):
+    def __init__(self, particles, params, kernel='CubicSpline', threads=1,
+                 domain=None):
+        """domain = (lo[3], hi[3], periodic[3]) or None.  With a periodic
+        domain every ``update_domain`` re-creates the periodic ghost images
+        (DomainManager.update, nnps_base.pyx:405-433), so ``self.pas`` (the
+        arrays with ghosts) is replaced each time."""
         p = dict(params)
         self.p = p
         self.integrator = p.get('integrator', 'EPEC')
         self.dim = p['dim']
-        self.o = Oracle(particles, self.dim, kernel, threads=threads)
+        self.domain = domain
+        self.kernel = kernel
+        self.threads = threads
+        self.pas = list(particles)
+        if domain is not None:
+            self._reghost()
+        else:
+            self.o = Oracle(particles, self.dim, kernel, threads=threads)
         ix = self.o.index
         self.fluids = [ix[n] for n in p['fluids']]
         self.solids = [ix[n] for n in p['solids']]
@@ -261,9 +324,29 @@ class WCSPHOracleSolver(object):
         self.pairs_last_eval = 0
         self.pairs_total = 0
         # NNPS constructor: domain.update(); update()  (linked_list_nnps.pyx:84-88)
-        self.o.update_domain()
+        self.update_domain()
         self.o.nnps_update()
         self._initialised = False
+
+    def _reghost(self):
+        lo, hi, per = self.domain
+        real = []
+        from pysph_b200.particle_array import get_particle_array_wcsph
+        for pa in self.pas:
+            nr = pa.get_number_of_particles(real=True)
+            q = get_particle_array_wcsph(name=pa.name, **dict(
+                (k, v[:nr].copy()) for k, v in pa.properties.items()))
+            real.append(q)
+        periodic_box_wrap(real, lo, hi, per)
+        k = load().orc_kernel_radius_scale(K_IDS[self.kernel])
+        hmax = max(float(np.max(q.h)) for q in real if len(q.h))
+        self.pas = periodic_ghosts(real, lo, hi, per, k * hmax)
+        self.o = Oracle(self.pas, self.dim, self.kernel, threads=self.threads)
+
+    def update_domain(self):
+        if self.domain is not None:
+            self._reghost()
+        self.o.update_domain()
 
     # AccelerationEval.compute for the WCSPH groups
     def evaluate(self):
@@ -308,10 +391,10 @@ class WCSPHOracleSolver(object):
         if self.integrator == 'EPEC':
             self.compute_accelerations()
         self._stage(1, dt)
-        self.o.update_domain()
+        self.update_domain()
         self.compute_accelerations()
         self._stage(2, dt)
-        self.o.update_domain()
+        self.update_domain()
 
     def _compute_timestep(self):
         undamped = self.dt / self._damping_factor

@@ -29,6 +29,7 @@ from .equations import (Equation, Group, SummationDensity, ContinuityEquation,
                         UpdateSmoothingLengthFerrari)
 from .scheme import WCSPHScheme
 from .backend import B200Backend, B200DeviceHelper
+from .domain import DomainManager
 from .nnps import B200NNPS
 from .acceleration_eval import B200AccelerationEval
 from .integrator import (B200Integrator, PECIntegrator, EPECIntegrator,

@@ -55,7 +55,8 @@ class Stats(C.Structure):
                 ('kernel_launches', C.c_int64), ('pairs', C.c_int64),
                 ('full_builds', C.c_int64), ('light_updates', C.c_int64),
                 ('list_builds', C.c_int64),
-                ('list_entries_per_particle', C.c_int64)]
+                ('list_entries_per_particle', C.c_int64),
+                ('deferred_failed', C.c_int64)]
 
 
 _ctx_p = C.c_void_p
@@ -83,8 +84,11 @@ SIGNATURES = {
     'b200sph_device_ptr': (C.c_int, [_ctx_p, C.c_int, C.c_int,
                                      C.POINTER(C.c_void_p)]),
     'b200sph_set_kernel': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
+    'b200sph_set_domain': (C.c_int, [_ctx_p, _dp, _dp, C.POINTER(C.c_int)]),
     'b200sph_update_domain': (C.c_int, [_ctx_p]),
     'b200sph_nnps_update': (C.c_int, [_ctx_p]),
+    'b200sph_nnps_update_deferred': (C.c_int, [_ctx_p]),
+    'b200sph_nnps_confirm': (C.c_int, [_ctx_p, C.POINTER(C.c_int)]),
     'b200sph_get_grid': (C.c_int, [_ctx_p, C.POINTER(GridInfo)]),
     'b200sph_get_neighbors': (_i64, [_ctx_p, C.c_int, C.c_int, _i64, C.c_void_p, _i64]),
     'b200sph_eos': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double, C.c_double,

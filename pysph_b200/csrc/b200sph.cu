@@ -51,11 +51,9 @@ struct ArrayInfo {
 
 struct GridDev {
     double xmin[3];
-    double cell;
+    double cell[3];   // cell edge per axis (a periodic axis is tiled exactly: L / nc)
     int nc[3];
-    float cellf;
-    int R;  // x coordinates of the packed records are relative to the origin of the
-            // R-cell span (cx / R) * R that contains the particle's cell
+    int periodic[3];
 };
 
 // equation-of-state calls wait here until the next k_pack_state applies them in the
@@ -92,6 +90,8 @@ struct b200sph_ctx {
     double radius_scale = 2.0;
 
     // domain manager
+    bool periodic[3] = {false, false, false};
+    double dom_lo[3] = {0, 0, 0}, dom_hi[3] = {0, 0, 0};
     double cell_size = 1.0, hmin_scaled = 1.0;
     bool domain_valid = false;
     // grid
@@ -131,6 +131,12 @@ struct b200sph_ctx {
     bool lists_valid = false;
     bool topo_dirty = true;     // particle set / h pushed: a light update is not enough
     bool drift_ok = false;      // set by nnps_drift when its caller took the (collective) decision
+    // deferred drift check (b200sph_nnps_update_deferred / b200sph_nnps_confirm)
+    bool defer_check = false;   // the running nnps_update may leave its drift check pending
+    bool check_pending = false; // a light update ran on the assumption that the lists are valid
+    unsigned *drift_host = nullptr;
+    cudaEvent_t drift_evt = nullptr;
+    int64_t n_deferred_failed = 0;
     bool h_dirty = true;        // h changed since the last update_domain reduction
     unsigned *red_u32 = nullptr, *red_u32_host = nullptr;
     int64_t n_full_builds = 0, n_light_updates = 0, n_list_builds = 0;
@@ -376,6 +382,23 @@ __global__ void k_stage(StageArgs a)
     }
 }
 
+// _box_wrap_periodic (nnps_base.pyx:699-743): real and ghost particles alike
+__global__ void k_box_wrap(double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
+                           const uint8_t *__restrict__ ptype, long long pool_end, GridDev D /* xmin = lo, cell = L */)
+{
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pool_end || ptype[g] == PT_INVALID) return;
+    double *p[3] = {x, y, z};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        if (!D.periodic[d]) continue;
+        double v = p[d][g];
+        const double lo = D.xmin[d], L = D.cell[d];
+        if (v < lo) v += L;
+        if (v > lo + L) v -= L;
+        p[d][g] = v;
+    }
+}
 __global__ void k_f64_to_f32(const double *__restrict__ in, float *__restrict__ out, long long n)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -482,9 +505,9 @@ __global__ void k_cell_count(const double *__restrict__ x, const double *__restr
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= pool_end) return;
     if (ptype[g] == PT_INVALID) return;
-    int cx = (int)floor((x[g] - G.xmin[0]) / G.cell);
-    int cy = (int)floor((y[g] - G.xmin[1]) / G.cell);
-    int cz = (int)floor((z[g] - G.xmin[2]) / G.cell);
+    int cx = (int)floor((x[g] - G.xmin[0]) / G.cell[0]);
+    int cy = (int)floor((y[g] - G.xmin[1]) / G.cell[1]);
+    int cz = (int)floor((z[g] - G.xmin[2]) / G.cell[2]);
     cx = min(max(cx, 0), G.nc[0] - 1);
     cy = min(max(cy, 0), G.nc[1] - 1);
     cz = min(max(cz, 0), G.nc[2] - 1);
@@ -523,8 +546,7 @@ __global__ void k_canon(const uint32_t *__restrict__ perm_tmp, const uint32_t *_
     rank[g] = d;
 }
 
-// A[s] = (x relative to the origin of the particle's R-cell span, y and z relative to
-//         the particle's own cell origin, h)
+// A[s] = (x, y, z relative to the particle's own cell origin, h)
 __global__ void k_pack_pos(const double *__restrict__ x, const double *__restrict__ y,
                            const double *__restrict__ z, const double *__restrict__ h,
                            const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skey,
@@ -539,9 +561,9 @@ __global__ void k_pack_pos(const double *__restrict__ x, const double *__restric
     const uint32_t cy = key % (uint32_t)G.nc[1];
     const uint32_t cz = key / (uint32_t)G.nc[1];
     float4 a;
-    a.x = (float)(x[g] - (G.xmin[0] + (double)((cx / (uint32_t)G.R) * (uint32_t)G.R) * G.cell));
-    a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell));
-    a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell));
+    a.x = (float)(x[g] - (G.xmin[0] + (double)cx * G.cell[0]));
+    a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell[1]));
+    a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell[2]));
     a.w = (float)h[g];
     A[s] = a;
     AB[2 * s] = a;
@@ -652,14 +674,14 @@ struct PairArgs {
     double *rho;  // SummationDensity destination (fp64 state)
     long long n;
     int ncx, ncy, ncz;
-    float cell, k2;  // cell size, radius_scale^2
+    float cellx, celly, cellz;  // internal cell edges
+    float k2;                   // radius_scale^2
     float kfac;      // kernel.fac for this dim
     float deltap;
     unsigned long long emask[B200SPH_MAX_ARRAYS];  // per dest type: 8 bits per source type
     float c0, alpha, beta, gx, gy, gz, eps_xsph;
     int tensile, real_only;
     unsigned long long *pair_counter;  // may be null
-    int frameR;        // span of the x frames of the packed records (GridDev.R, always 1 today)
 };
 
 #define PAIR_WARPS 8
@@ -758,7 +780,6 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
     int cx = 0;
     // lane r < 9 holds the candidate range of neighbour row r = (dy+1) + 3*(dz+1)
     uint32_t r_rs = 0, r_b1 = 0, r_b2 = 0, r_re = 0;
-    float xo_m = 0.f, xo_p = 0.f;
     unsigned npairs = 0;
 
     for (int kk = 0; kk < PAIR_CHUNK; kk++) {
@@ -779,10 +800,6 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
             kq /= (uint32_t)a.ncx;
             const int cy = (int)(kq % (uint32_t)a.ncy);
             const int cz = (int)(kq / (uint32_t)a.ncy);
-            // x origins differ between R-cell spans: offsets (in cells) of the left /
-            // right neighbour cell's span origin relative to this cell's span origin
-            xo_m = (float)((max(cx - 1, 0) / a.frameR - cx / a.frameR) * a.frameR) * a.cell;
-            xo_p = (float)(((cx + 1) / a.frameR - cx / a.frameR) * a.frameR) * a.cell;
             r_rs = r_b1 = r_b2 = r_re = 0;
             if (lane < 9) {
                 const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
@@ -807,15 +824,15 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
             if (rs >= re) continue;
             const uint32_t b1 = __shfl_sync(FULL, r_b1, r);
             const uint32_t b2 = __shfl_sync(FULL, r_b2, r);
-            const float yoff = Ai.y - (float)((r % 3) - 1) * a.cell;
-            const float zoff = Ai.z - (float)((r / 3) - 1) * a.cell;
+            const float yoff = Ai.y - (float)((r % 3) - 1) * a.celly;
+            const float zoff = Ai.z - (float)((r / 3) - 1) * a.cellz;
             for (uint32_t t0 = rs; t0 < re; t0 += 32) {
                 const uint32_t t = t0 + lane;
                 bool ok = false;
                 float xij = 0.f, yij = 0.f, zij = 0.f, hj = 0.f;
                 if (t < re) {
                     const float4 Aj = a.A[t];
-                    const float xo = t >= b2 ? xo_p : (t >= b1 ? 0.0f : xo_m);
+                    const float xo = t >= b2 ? a.cellx : (t >= b1 ? 0.0f : -a.cellx);
                     xij = Ai.x - Aj.x - xo;
                     yij = yoff - Aj.y;
                     zij = zoff - Aj.z;
@@ -924,7 +941,8 @@ struct ListBuildArgs {
     const uint32_t *cell_start, *skey;
     long long n;
     int ncx, ncy, ncz;
-    float cell;      // internal cell size (>= k hmax + S)
+    int px, py, pz;                 // periodic axes (cell indices wrap, images shift by nc * cell)
+    float cellx, celly, cellz;      // internal cell edges (>= k hmax + S)
     float kr, S;     // radius scale, absolute skin
     uint32_t *cnt;   // [n] neighbours per destination
     uint32_t *lst;   // null: count only
@@ -932,6 +950,14 @@ struct ListBuildArgs {
     unsigned *max_count;
 };
 
+// PERIODIC = false: 9 candidate rows (3 consecutive cells each, contiguous in the
+// sorted arrays).  PERIODIC = true: 27 single-cell segments with wrapped cell indices;
+// because coordinates are relative to the particle's own cell and a periodic axis is
+// tiled exactly (L = nc * cell), the image shift of a wrapped neighbour cell is the
+// same "- d * cell" offset as for an ordinary neighbour cell -- the consumer kernel does
+// not know about periodicity at all, and no ghost particles are materialised
+// (reference: _create_ghosts_periodic, nnps_base.pyx:744-940, copies the particles).
+template <bool PERIODIC>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildArgs a)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -955,15 +981,27 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
             const int cy = (int)(kq % (uint32_t)a.ncy);
             const int cz = (int)(kq / (uint32_t)a.ncy);
             r_rs = r_b1 = r_b2 = r_re = 0;
-            if (lane < 9) {
-                const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
-                if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
-                    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
-                    r_rs = a.cell_start[base + x0];
-                    r_b1 = a.cell_start[base + cx];
-                    r_b2 = a.cell_start[base + cx + 1];
-                    r_re = a.cell_start[base + x1 + 1];
+            if (!PERIODIC) {
+                if (lane < 9) {
+                    const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
+                    if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
+                        const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+                        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
+                        r_rs = a.cell_start[base + x0];
+                        r_b1 = a.cell_start[base + cx];
+                        r_b2 = a.cell_start[base + cx + 1];
+                        r_re = a.cell_start[base + x1 + 1];
+                    }
+                }
+            } else if (lane < 27) {
+                int xx = cx + (lane % 3) - 1, yy = cy + ((lane / 3) % 3) - 1, zz = cz + (lane / 9) - 1;
+                if (a.px) xx = (xx + a.ncx) % a.ncx;
+                if (a.py) yy = (yy + a.ncy) % a.ncy;
+                if (a.pz) zz = (zz + a.ncz) % a.ncz;
+                if (xx >= 0 && xx < a.ncx && yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
+                    const uint32_t c = (uint32_t)xx + (uint32_t)a.ncx * ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz);
+                    r_rs = a.cell_start[c];
+                    r_re = a.cell_start[c + 1];
                 }
             }
         }
@@ -971,23 +1009,38 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
         const float hi2 = hi * hi;
         uint32_t *out = a.lst ? a.lst + ((size_t)(s >> 5) * (size_t)a.capg) * 32u + (uint32_t)(s & 31) : nullptr;
         unsigned count = 0;
-        for (int r = 0; r < 9; r++) {
+        for (int r = 0; r < (PERIODIC ? 27 : 9); r++) {
             const uint32_t rs = __shfl_sync(FULL, r_rs, r);
             const uint32_t re = __shfl_sync(FULL, r_re, r);
             if (rs >= re) continue;
-            const uint32_t b1 = __shfl_sync(FULL, r_b1, r);
-            const uint32_t b2 = __shfl_sync(FULL, r_b2, r);
-            const float yoff = Ai.y - (float)((r % 3) - 1) * a.cell;
-            const float zoff = Ai.z - (float)((r / 3) - 1) * a.cell;
-            const uint32_t rcode = (uint32_t)(4 * (r % 3) + 16 * (r / 3));
+            uint32_t b1 = 0, b2 = 0, rcode;
+            float xoff, yoff, zoff;
+            if (!PERIODIC) {
+                b1 = __shfl_sync(FULL, r_b1, r);
+                b2 = __shfl_sync(FULL, r_b2, r);
+                xoff = Ai.x;
+                yoff = Ai.y - (float)((r % 3) - 1) * a.celly;
+                zoff = Ai.z - (float)((r / 3) - 1) * a.cellz;
+                rcode = (uint32_t)(4 * (r % 3) + 16 * (r / 3));
+            } else {
+                xoff = Ai.x - (float)((r % 3) - 1) * a.cellx;
+                yoff = Ai.y - (float)(((r / 3) % 3) - 1) * a.celly;
+                zoff = Ai.z - (float)((r / 9) - 1) * a.cellz;
+                rcode = (uint32_t)((r % 3) + 4 * ((r / 3) % 3) + 16 * (r / 9));
+            }
             for (uint32_t t0 = rs; t0 < re; t0 += 32) {
                 const uint32_t t = t0 + lane;
                 bool ok = false;
                 uint32_t dxc1 = 0;
                 if (t < re) {
                     const float4 Aj = a.A[t];
-                    dxc1 = (uint32_t)(t >= b1) + (uint32_t)(t >= b2);  // dxc + 1
-                    const float xij = Ai.x - Aj.x - ((float)dxc1 - 1.0f) * a.cell;
+                    float xij;
+                    if (!PERIODIC) {
+                        dxc1 = (uint32_t)(t >= b1) + (uint32_t)(t >= b2);  // dxc + 1
+                        xij = xoff - Aj.x - ((float)dxc1 - 1.0f) * a.cellx;
+                    } else {
+                        xij = xoff - Aj.x;
+                    }
                     const float yij = yoff - Aj.y;
                     const float zij = zoff - Aj.z;
                     const float r2 = xij * xij + yij * yij + zij * zij;
@@ -1030,7 +1083,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_pair_list(const PairArgs a, cons
     const int tid = threadIdx.x;
     if (tid < 64) {
         const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cell, -(float)dy * a.cell, -(float)dz * a.cell, 0.f);
+        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
     }
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
@@ -1133,9 +1186,9 @@ __global__ void k_pack_pos_light(const double *__restrict__ x, const double *__r
         const uint32_t cy = key % (uint32_t)G.nc[1];
         const uint32_t cz = key / (uint32_t)G.nc[1];
         float4 a;
-        a.x = (float)(x[g] - (G.xmin[0] + (double)((cx / (uint32_t)G.R) * (uint32_t)G.R) * G.cell));
-        a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell));
-        a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell));
+        a.x = (float)(x[g] - (G.xmin[0] + (double)cx * G.cell[0]));
+        a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell[1]));
+        a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell[2]));
         a.w = (float)h[g];
         A[s] = a;
         AB[2 * s] = a;
@@ -1155,15 +1208,16 @@ __global__ void k_pack_pos_light(const double *__restrict__ x, const double *__r
 }
 
 
-// neighbour query for one destination particle with the pair kernel's accept test.
-// One warp. flags[t - lo] = 1 for every accepted source of array src_arr.
+// neighbour query for one destination particle with the pair kernel's accept test
+// (cell by cell; periodic axes wrap).  One warp.
 __global__ void k_neighbors(const float4 *__restrict__ A, const float4 *__restrict__ C,
                             const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ skey,
                             const uint32_t *__restrict__ perm, long long s, int src_arr,
-                            long long src_off, int ncx, int ncy, int ncz, float cell, float k2, int R,
+                            long long src_off, GridDev G, float k2,
                             uint32_t *__restrict__ out, long long cap, unsigned long long *count)
 {
     const int lane = threadIdx.x;
+    const int ncx = G.nc[0], ncy = G.nc[1], ncz = G.nc[2];
     const float4 Ai = A[s];
     uint32_t kq = skey[s];
     const int cx = (int)(kq % (uint32_t)ncx);
@@ -1171,24 +1225,23 @@ __global__ void k_neighbors(const float4 *__restrict__ A, const float4 *__restri
     const int cy = (int)(kq % (uint32_t)ncy), cz = (int)(kq / (uint32_t)ncy);
     const float hi2 = k2 * Ai.w * Ai.w;
     unsigned long long n = 0;
-    for (int r = 0; r < 9; r++) {
-        const int dy = (r % 3) - 1, dz = (r / 3) - 1;
-        const int yy = cy + dy, zz = cz + dz;
-        if (yy < 0 || yy >= ncy || zz < 0 || zz >= ncz) continue;
-        const uint32_t base = ((uint32_t)yy + (uint32_t)ncy * (uint32_t)zz) * (uint32_t)ncx;
-        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, ncx - 1);
-        const uint32_t rs = cell_start[base + x0], b1 = cell_start[base + cx],
-                       b2 = cell_start[base + cx + 1], re = cell_start[base + x1 + 1];
+    for (int r = 0; r < 27; r++) {
+        const int dx = (r % 3) - 1, dy = ((r / 3) % 3) - 1, dz = (r / 9) - 1;
+        int xx = cx + dx, yy = cy + dy, zz = cz + dz;
+        if (G.periodic[0]) xx = (xx + ncx) % ncx;
+        if (G.periodic[1]) yy = (yy + ncy) % ncy;
+        if (G.periodic[2]) zz = (zz + ncz) % ncz;
+        if (xx < 0 || xx >= ncx || yy < 0 || yy >= ncy || zz < 0 || zz >= ncz) continue;
+        const uint32_t c = (uint32_t)xx + (uint32_t)ncx * ((uint32_t)yy + (uint32_t)ncy * (uint32_t)zz);
+        const uint32_t rs = cell_start[c], re = cell_start[c + 1];
         for (uint32_t t0 = rs; t0 < re; t0 += 32) {
             const uint32_t t = t0 + lane;
             bool ok = false;
             if (t < re) {
                 const float4 Aj = A[t];
-                const int dxc = (int)(t >= b1) + (int)(t >= b2) - 1;
-                const int orgd = ((cx + dxc) / R - cx / R) * R;
-                const float xij = Ai.x - Aj.x - (float)orgd * cell;
-                const float yij = Ai.y - (float)dy * cell - Aj.y;
-                const float zij = Ai.z - (float)dz * cell - Aj.z;
+                const float xij = Ai.x - (float)dx * (float)G.cell[0] - Aj.x;
+                const float yij = Ai.y - (float)dy * (float)G.cell[1] - Aj.y;
+                const float zij = Ai.z - (float)dz * (float)G.cell[2] - Aj.z;
                 const float r2 = xij * xij + yij * yij + zij * zij;
                 ok = ((r2 < hi2) || (r2 < k2 * Aj.w * Aj.w)) &&
                      ((__float_as_int(C[t].w) & 7) == src_arr);
@@ -1573,6 +1626,8 @@ int b200sph_create(int device, b200sph_ctx **out)
     ctx->skin_min = std::min(ctx->skin_min, ctx->skin_max);
     CU(cudaMalloc((void **)&ctx->red_u32, 4 * sizeof(unsigned)));
     CU(cudaMallocHost((void **)&ctx->red_u32_host, 4 * sizeof(unsigned)));
+    CU(cudaMallocHost((void **)&ctx->drift_host, 4 * sizeof(unsigned)));
+    CU(cudaEventCreateWithFlags(&ctx->drift_evt, cudaEventDisableTiming));
     CU(cudaMalloc((void **)&ctx->red, 16 * sizeof(long long)));
     CU(cudaMallocHost((void **)&ctx->red_host, 16 * sizeof(long long)));
     CU(cudaMalloc((void **)&ctx->counter, 8 * sizeof(unsigned long long)));
@@ -1596,6 +1651,8 @@ int b200sph_destroy(b200sph_ctx *ctx)
     cudaFreeHost(ctx->counter_host); cudaFree(ctx->stage_buf); cudaFree(ctx->flag_a);
     cudaFree(ctx->flag_b); cudaFree(ctx->A0); cudaFree(ctx->lst); cudaFree(ctx->cnt);
     cudaFree(ctx->red_u32); cudaFreeHost(ctx->red_u32_host);
+    cudaFreeHost(ctx->drift_host);
+    if (ctx->drift_evt) cudaEventDestroy(ctx->drift_evt);
     for (auto &pe : ctx->pending) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -1731,8 +1788,10 @@ int b200sph_push_f64(b200sph_ctx *ctx, int arr, int prop, const double *host, in
     return 0;
 }
 
+static int require_confirmed(b200sph_ctx *ctx, const char *who);
 int b200sph_pull_f64(b200sph_ctx *ctx, int arr, int prop, double *host, int64_t start, int64_t count)
 {
+    if (int rcc = require_confirmed(ctx, "pull_f64")) return rcc;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
@@ -1770,6 +1829,7 @@ int b200sph_push_u32(b200sph_ctx *ctx, int arr, int prop, const uint32_t *host, 
 
 int b200sph_pull_u32(b200sph_ctx *ctx, int arr, int prop, uint32_t *host, int64_t start, int64_t count)
 {
+    if (int rcc = require_confirmed(ctx, "pull_u32")) return rcc;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
@@ -1827,11 +1887,42 @@ static int run_minmax(b200sph_ctx *ctx, int do_xyz, int do_h)
     return 0;
 }
 
+int b200sph_set_domain(b200sph_ctx *ctx, const double lo[3], const double hi[3], const int periodic[3])
+{
+    for (int d = 0; d < 3; d++) {
+        if (periodic[d] && !(hi[d] > lo[d])) return set_err(ctx, "Invalid domain limits!");  // nnps_base.pyx:352-355
+        ctx->periodic[d] = periodic[d] != 0;
+        ctx->dom_lo[d] = lo[d];
+        ctx->dom_hi[d] = hi[d];
+    }
+    ctx->grid_valid = false;
+    ctx->topo_dirty = true;
+    return 0;
+}
+
 int b200sph_update_domain(b200sph_ctx *ctx)
 {
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
+    if (ctx->periodic[0] || ctx->periodic[1] || ctx->periodic[2]) {
+        // _box_wrap_periodic, nnps_base.pyx:699-743 (part of DomainManager.update)
+        if ((rc = eos_flush(ctx))) return rc;
+        GridDev D;
+        for (int d = 0; d < 3; d++) {
+            D.xmin[d] = ctx->dom_lo[d];
+            D.cell[d] = ctx->dom_hi[d] - ctx->dom_lo[d];
+            D.nc[d] = 1;
+            D.periodic[d] = ctx->periodic[d];
+        }
+        if (ctx->pool_end > 0) {
+            k_box_wrap<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z],
+                                                                                   ctx->ptype, ctx->pool_end, D);
+            LAUNCH_CHECK();
+        }
+        ctx->grid_valid = false;
+        ctx->state_packed = false;
+    }
     if (ctx->domain_valid && !ctx->h_dirty) return 0;  // h untouched since the last reduction
     PhaseTimer pt(ctx, 2);
     if ((rc = run_minmax(ctx, 0, 1))) return rc;
@@ -1848,6 +1939,16 @@ int b200sph_update_domain(b200sph_ctx *ctx)
     ctx->domain_valid = true;
     ctx->h_dirty = false;
     return 0;
+}
+
+// 2 |dx|max + k dh <= S, with a 2 % safety margin for the fp32 measurement
+static bool drift_within_skin(b200sph_ctx *ctx, const unsigned *raw)
+{
+    float d2, dh;
+    memcpy(&d2, &raw[0], 4);
+    memcpy(&dh, &raw[1], 4);
+    const double need = 2.0 * std::sqrt((double)d2) + ctx->radius_scale * (double)dh;
+    return need <= 0.98 * ctx->S_abs;
 }
 
 // light path of nnps_update: same sorted order, same cell frames, fresh positions;
@@ -1870,14 +1971,57 @@ static int nnps_light_update(b200sph_ctx *ctx)
         ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
         ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
     LAUNCH_CHECK();
+    if (ctx->defer_check) {
+        // optimistic: carry on as if the lists were valid; b200sph_nnps_confirm reads the
+        // measurement after the evaluation has been enqueued (no idle GPU while we wait)
+        CU(cudaMemcpyAsync(ctx->drift_host, ctx->red_u32, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->drift_evt, ctx->stream));
+        ctx->check_pending = true;
+        return 1;
+    }
     CU(cudaMemcpyAsync(ctx->red_u32_host, ctx->red_u32, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    float d2, dh;
-    memcpy(&d2, &ctx->red_u32_host[0], 4);
-    memcpy(&dh, &ctx->red_u32_host[1], 4);
-    // 2 |dx|max + k dh <= S, with a 2 % safety margin for the fp32 measurement
-    const double need = 2.0 * std::sqrt((double)d2) + ctx->radius_scale * (double)dh;
-    return need <= 0.98 * ctx->S_abs ? 1 : 0;
+    return drift_within_skin(ctx, ctx->red_u32_host) ? 1 : 0;
+}
+
+static int confirm_pending(b200sph_ctx *ctx, int *redo)
+{
+    *redo = 0;
+    if (!ctx->check_pending) return 0;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->drift_evt));
+    ctx->check_pending = false;
+    if (!drift_within_skin(ctx, ctx->drift_host)) {
+        // the evaluation that followed used stale lists: force the full rebuild
+        ctx->topo_dirty = true;
+        ctx->grid_valid = false;
+        ctx->n_light_updates--;
+        ctx->n_deferred_failed++;
+        *redo = 1;
+    }
+    return 0;
+}
+// entry points that consume the results of an evaluation must not run on an
+// unconfirmed deferred update
+static int require_confirmed(b200sph_ctx *ctx, const char *who)
+{
+    if (!ctx->check_pending) return 0;
+    int redo = 0, rc = confirm_pending(ctx, &redo);
+    if (rc) return rc;
+    if (redo)
+        return set_err(ctx, "%s: the deferred drift check of the last nnps_update failed and was never confirmed "
+                            "(call b200sph_nnps_confirm after the evaluation and repeat it when asked to)", who);
+    return 0;
+}
+
+int b200sph_nnps_confirm(b200sph_ctx *ctx, int *redo) { return confirm_pending(ctx, redo); }
+
+int b200sph_nnps_update_deferred(b200sph_ctx *ctx)
+{
+    ctx->defer_check = true;
+    const int rc = b200sph_nnps_update(ctx);
+    ctx->defer_check = false;
+    return rc;
 }
 
 int b200sph_nnps_update(b200sph_ctx *ctx)
@@ -1885,6 +2029,10 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
+    if (ctx->check_pending) {   // update after update without an evaluation in between
+        int redo = 0;
+        if ((rc = confirm_pending(ctx, &redo))) return rc;
+    }
     if ((rc = eos_flush(ctx))) return rc;
     if (!ctx->domain_valid && (rc = b200sph_update_domain(ctx))) return rc;
     PhaseTimer pt(ctx, 0);
@@ -1974,11 +2122,26 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     ctx->S_abs = use_lists ? ctx->skin * ctx->cell_size : 0.0;
     ctx->cell_int = ctx->cell_size + ctx->S_abs;
     int nc[3];
+    double cellv[3];
     for (int d = 0; d < 3; d++) {
-        nc[d] = (int)std::ceil((mx[d] - mn[d]) / ctx->cell_int);
-        if (nc[d] <= 0) nc[d] = 1;
+        if (ctx->periodic[d]) {
+            // a periodic axis is tiled EXACTLY by cells not smaller than the cut-off, so
+            // that the image shift of a wrapped neighbour cell is a whole number of cells
+            const double L = ctx->dom_hi[d] - ctx->dom_lo[d];
+            if (!(L >= ctx->cell_int))
+                return set_err(ctx, "periodic axis %d: the domain (%g) is smaller than the interaction range + skin (%g)", d, L, ctx->cell_int);
+            mn[d] = ctx->dom_lo[d];
+            mx[d] = ctx->dom_hi[d];
+            nc[d] = std::max(1, (int)std::floor(L / ctx->cell_int));
+            cellv[d] = L / nc[d];
+        } else {
+            nc[d] = (int)std::ceil((mx[d] - mn[d]) / ctx->cell_int);
+            if (nc[d] <= 0) nc[d] = 1;
+            cellv[d] = ctx->cell_int;
+        }
     }
     const int64_t ncells = (int64_t)nc[0] * nc[1] * nc[2];
+    if (ncells > (1LL << 28)) return set_err(ctx, "ERROR: LinkedListNNPS requires too many cells (%lld).", (long long)ncells);
 
     if (ncells + 2 > ctx->cell_cap) {
         if (ctx->cell_cnt) CU(cudaFree(ctx->cell_cnt));
@@ -1993,9 +2156,10 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         G.xmin[d] = mn[d];
         G.nc[d] = nc[d];
     }
-    G.cell = ctx->cell_int;
-    G.cellf = (float)ctx->cell_int;
-    G.R = 1;
+    for (int d = 0; d < 3; d++) {
+        G.cell[d] = cellv[d];
+        G.periodic[d] = ctx->periodic[d] ? 1 : 0;
+    }
 
     CU(cudaMemsetAsync(ctx->cell_cnt, 0, 4 * (size_t)(ncells + 1), ctx->stream));
     ctx->n_sorted = ntot;
@@ -2033,7 +2197,9 @@ static int build_lists(b200sph_ctx *ctx)
     la.A = ctx->A; la.cell_start = ctx->cell_start; la.skey = ctx->skey;
     la.n = n;
     la.ncx = ctx->G.nc[0]; la.ncy = ctx->G.nc[1]; la.ncz = ctx->G.nc[2];
-    la.cell = (float)ctx->cell_int;
+    la.cellx = (float)ctx->G.cell[0]; la.celly = (float)ctx->G.cell[1]; la.cellz = (float)ctx->G.cell[2];
+    la.px = ctx->G.periodic[0]; la.py = ctx->G.periodic[1]; la.pz = ctx->G.periodic[2];
+    const bool per = la.px || la.py || la.pz;
     la.kr = (float)ctx->radius_scale;
     la.S = (float)ctx->S_abs;
     la.cnt = ctx->cnt;
@@ -2056,7 +2222,8 @@ static int build_lists(b200sph_ctx *ctx)
         la.lst = count_only ? nullptr : ctx->lst;
         la.capg = ctx->capg;
         CU(cudaMemsetAsync(ctx->red_u32 + 2, 0, sizeof(unsigned), ctx->stream));
-        k_list_build<<<nb, PAIR_WARPS * 32, 0, ctx->stream>>>(la);
+        if (per) k_list_build<true><<<nb, PAIR_WARPS * 32, 0, ctx->stream>>>(la);
+        else k_list_build<false><<<nb, PAIR_WARPS * 32, 0, ctx->stream>>>(la);
         LAUNCH_CHECK();
         CU(cudaMemcpyAsync(ctx->red_u32_host + 2, ctx->red_u32 + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -2115,6 +2282,7 @@ static int pack_state(b200sph_ctx *ctx)
 
 int64_t b200sph_get_neighbors(b200sph_ctx *ctx, int dst_arr, int src_arr, int64_t d_idx, uint32_t *out, int64_t cap)
 {
+    if (int rcc = require_confirmed(ctx, "get_neighbors")) return rcc;
     CU(cudaSetDevice(ctx->device));
     if (!ctx->grid_valid) return set_err(ctx, "get_neighbors: call nnps_update first");
     if (dst_arr < 0 || dst_arr >= ctx->narr || src_arr < 0 || src_arr >= ctx->narr) return set_err(ctx, "get_neighbors: bad array index");
@@ -2128,8 +2296,8 @@ int64_t b200sph_get_neighbors(b200sph_ctx *ctx, int dst_arr, int src_arr, int64_
     uint32_t *dout = nullptr;
     CU(cudaMalloc((void **)&dout, 4 * (size_t)dcap));
     k_neighbors<<<1, 32, 0, ctx->stream>>>(ctx->A, ctx->C, ctx->cell_start, ctx->skey, ctx->perm, (long long)s32, src_arr,
-                                           (long long)ctx->arr[src_arr].off, ctx->G.nc[0], ctx->G.nc[1], ctx->G.nc[2],
-                                           (float)ctx->cell_int, (float)(ctx->radius_scale * ctx->radius_scale), ctx->G.R, dout, cap, ctx->counter + 1);
+                                           (long long)ctx->arr[src_arr].off, ctx->G, (float)(ctx->radius_scale * ctx->radius_scale),
+                                           dout, cap, ctx->counter + 1);
     ctx->stats.kernel_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cudaFree(dout); return set_err(ctx, "k_neighbors launch failed: %s", cudaGetErrorString(e)); }
@@ -2199,6 +2367,8 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     if (!ctx->state_packed && (rc = pack_state(ctx))) return rc;
     // lists hold 26-bit sorted indices: larger particle counts use the warp kernel
     const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->n_sorted < (1LL << LIST_JBITS);
+    if (!use_lists && (ctx->periodic[0] || ctx->periodic[1] || ctx->periodic[2]))
+        return set_err(ctx, "periodic domains need the neighbour-list path (B200SPH_PAIR_KERNEL=list, < 2^26 particles)");
     if (use_lists && !ctx->lists_valid) {
         PhaseTimer pt_build(ctx, 0);  // list builds are part of the neighbour search time
         if ((rc = build_lists(ctx))) return rc;
@@ -2216,7 +2386,7 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     pa.rho = ctx->f64[B200SPH_RHO];
     pa.n = ctx->n_sorted;
     pa.ncx = ctx->G.nc[0]; pa.ncy = ctx->G.nc[1]; pa.ncz = ctx->G.nc[2];
-    pa.cell = (float)ctx->cell_int;
+    pa.cellx = (float)ctx->G.cell[0]; pa.celly = (float)ctx->G.cell[1]; pa.cellz = (float)ctx->G.cell[2];
     pa.k2 = (float)(ctx->radius_scale * ctx->radius_scale);
     pa.kfac = (float)kernel_fac(ctx->kernel, ctx->dim);
     pa.deltap = (float)kernel_deltap(ctx->kernel);
@@ -2231,7 +2401,6 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
         }
         pa.emask[d] = m;
     }
-    pa.frameR = ctx->G.R;
     pa.c0 = (float)prog->c0; pa.alpha = (float)prog->alpha; pa.beta = (float)prog->beta;
     pa.gx = (float)prog->gx; pa.gy = (float)prog->gy; pa.gz = (float)prog->gz;
     pa.eps_xsph = (float)prog->eps_xsph;
@@ -2276,6 +2445,7 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
 
 int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt)
 {
+    if (int rcc = require_confirmed(ctx, "stage")) return rcc;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
@@ -2309,6 +2479,7 @@ int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt)
 
 int b200sph_dt_factors(b200sph_ctx *ctx, double out[3])
 {
+    if (int rcc = require_confirmed(ctx, "dt_factors")) return rcc;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
@@ -2342,6 +2513,7 @@ static HaloPtrs halo_ptrs(b200sph_ctx *ctx)
 
 int b200sph_halo_pack(b200sph_ctx *ctx, int arr, int slot, double lo, double hi, double *dev_buf, int64_t cap, int64_t *count)
 {
+    if (int rcc = require_confirmed(ctx, "halo_pack")) return rcc;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
@@ -2614,6 +2786,7 @@ int b200sph_drop_ghosts(b200sph_ctx *ctx, int arr)
 
 int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double *dev_buf, int64_t cap, int64_t count[2])
 {
+    if (int rcc = require_confirmed(ctx, "migrate_out")) return rcc;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_pool(ctx);
     if (rc) return rc;
@@ -2693,6 +2866,7 @@ int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out)
     ctx->stats.light_updates = ctx->n_light_updates;
     ctx->stats.list_builds = ctx->n_list_builds;
     ctx->stats.list_entries_per_particle = ctx->capg;
+    ctx->stats.deferred_failed = ctx->n_deferred_failed;
     *out = ctx->stats;
     return 0;
 }
@@ -2701,7 +2875,7 @@ int b200sph_reset_stats(b200sph_ctx *ctx)
     b200sph_stats tmp;
     b200sph_get_stats(ctx, &tmp);  // drain pending events
     memset(&ctx->stats, 0, sizeof(ctx->stats));
-    ctx->n_full_builds = ctx->n_light_updates = ctx->n_list_builds = 0;
+    ctx->n_full_builds = ctx->n_light_updates = ctx->n_list_builds = ctx->n_deferred_failed = 0;
     return 0;
 }
 int b200sph_set_async_copies(b200sph_ctx *ctx, int on)

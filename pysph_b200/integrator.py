@@ -102,11 +102,24 @@ class B200Integrator(object):
 
     def compute_accelerations(self, index=0, update_nnps=True):
         # integrator.py:274-286
+        # The decision "are the persistent neighbour lists still valid" (one
+        # rank: a drift measurement; several: an all-reduce of it) is enqueued,
+        # the evaluation is enqueued behind it on that assumption, and only then
+        # does the host wait for the answer -- the GPU never idles on it.  A
+        # "no" (once per list lifetime) repeats update + evaluation; everything
+        # an evaluation writes is overwritten by the repeat.
+        pm = self.parallel_manager
         if update_nnps:
-            if self.parallel_manager:
-                self.parallel_manager.update()
-            self.nnps.update()
+            if pm:
+                pm.update(deferred=True)
+            self.nnps.update(deferred=True)
         self.acceleration_evals[index].compute(self.t, self.dt)
+        if update_nnps:
+            redo = pm.confirm() if pm else False
+            redo = self.nnps.confirm() or redo
+            if redo:
+                self.nnps.update()
+                self.acceleration_evals[index].compute(self.t, self.dt)
 
     def initial_acceleration(self, t, dt):
         # integrator.py:289-297: evaluate once WITHOUT refreshing the NNPS

@@ -23,11 +23,8 @@ class B200NNPS(object):
     def __init__(self, dim, particles, radius_scale=2.0, backend=None,
                  kernel=None, domain=None, cache=False, sort_gids=False):
         from .backend import B200Backend
-        if domain is not None and (getattr(domain, 'is_periodic', False) or
-                                   getattr(domain, 'is_mirror', False)):
-            raise NotImplementedError(
-                'B200 backend: periodic / mirror domains are a "next" row '
-                '(SURVEY.md 8f-1)')
+        if domain is not None and getattr(domain, 'is_mirror', False):
+            raise NotImplementedError('B200 backend: mirror boundaries')
         self.dim = dim
         self.particles = list(particles)
         self.narrays = len(self.particles)
@@ -38,6 +35,14 @@ class B200NNPS(object):
         self.radius_scale = radius_scale if kernel is None \
             else kernel.radius_scale
         self.domain = domain
+        if domain is not None and getattr(domain, 'is_periodic', False):
+            from .domain import DomainManager
+            if not isinstance(domain, DomainManager):   # a PySPH DomainManager
+                m = getattr(domain, 'manager', domain)
+                domain = DomainManager(
+                    m.xmin, m.xmax, m.ymin, m.ymax, m.zmin, m.zmax,
+                    m.periodic_in_x, m.periodic_in_y, m.periodic_in_z)
+            domain.apply(self.ctx)
         self.in_parallel = False
         self.src_index = self.dst_index = 0
         self._grid = None
@@ -53,9 +58,20 @@ class B200NNPS(object):
     def update_domain(self, *args, **kw):
         self.ctx.call('b200sph_update_domain')
 
-    def update(self):
-        self.ctx.call('b200sph_nnps_update')
+    def update(self, deferred=False):
+        """deferred=True (used by the integrator only): when the persistent
+        neighbour lists are reused, the measurement that proves them valid is
+        enqueued but not awaited; ``confirm()`` must follow the evaluation."""
+        self.ctx.call('b200sph_nnps_update_deferred' if deferred
+                      else 'b200sph_nnps_update')
         self._grid = None
+
+    def confirm(self):
+        """True if the evaluation since the last deferred update must be
+        repeated after a plain ``update()`` (the lists turned out stale)."""
+        redo = C.c_int(0)
+        self.ctx.call('b200sph_nnps_confirm', C.byref(redo))
+        return bool(redo.value)
 
     def set_context(self, src_index, dst_index):
         self.src_index, self.dst_index = src_index, dst_index

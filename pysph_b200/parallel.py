@@ -132,8 +132,29 @@ class DeviceHaloOps(object):
             self.ctx.call('b200sph_halo_overwrite', arr, int(ghost_first),
                           buf.data_ptr() + 8 * offset, n, n)
 
-    def keep_build(self):
-        self.ctx.call('b200sph_nnps_keep_build')
+    def keep_build(self, strict=True):
+        try:
+            self.ctx.call('b200sph_nnps_keep_build')
+        except Exception:
+            if strict:
+                raise
+            return False
+        return True
+
+    def read_later(self, tensor):
+        """Enqueue a copy of a 1-element CUDA tensor to pinned host memory;
+        returns a callable that waits for it and returns the value."""
+        torch = self.torch
+        if getattr(self, '_pin', None) is None:
+            self._pin = torch.empty(1, dtype=torch.float64).pin_memory()
+            self._pin_evt = torch.cuda.Event()
+        self._pin.copy_(tensor, non_blocking=True)
+        self._pin_evt.record()
+
+        def get():
+            self._pin_evt.synchronize()
+            return float(self._pin[0])
+        return get
 
     # -- all arrays in one kernel; peer (NVLink) staging ------------------------
     def pack_selected_all(self, slot, ptr, cap_doubles):
@@ -228,6 +249,8 @@ class SlabParallelManager(object):
         self._peer = None
         self._parity = 0
         self.n_peer_refresh = 0
+        self.n_deferred_failed = 0
+        self._pending = None
 
     # -- transport ------------------------------------------------------------
     def _exchange(self, send_counts, send_bufs, nfields):
@@ -274,12 +297,18 @@ class SlabParallelManager(object):
         return max(n, 1) * nfields
 
     # -- ParallelManager protocol ----------------------------------------------
-    def update(self):
+    def update(self, deferred=False):
         """Called before every evaluation.  While every rank's neighbour build is
         still valid (max drift <= skin, one scalar all-reduce) only the VALUES of
         the same ghost particles are refreshed in place; otherwise the full
-        drop / migrate / import path runs and the next NNPS update rebuilds."""
+        drop / migrate / import path runs and the next NNPS update rebuilds.
+
+        deferred=True: the refresh is enqueued on the ASSUMPTION that the
+        all-reduced answer is "valid"; the answer travels to pinned host memory
+        behind it and ``confirm()`` (called after the evaluation was enqueued)
+        reads it.  All ranks read the same number, so they agree."""
         ops = self.ops
+        self._pending = None
         if self._recv and hasattr(ops, 'drift'):
             if getattr(self, '_t1', None) is None:
                 self._t1 = ops.new_buffer(1)
@@ -302,7 +331,12 @@ class SlabParallelManager(object):
                         ops.pack_selected_all(slot, self._peer['remote'][nb][self._parity],
                                               self._peer['cap'])
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-            if float(t.item()) <= 0.9:
+            if deferred and hasattr(ops, 'read_later'):
+                self._pending = ops.read_later(t)
+                ok = True
+            else:
+                ok = float(t.item()) <= 0.9
+            if ok:
                 if self._peer is not None:
                     first = [0] * self.narr
                     for nb in sorted(self._recv):
@@ -314,9 +348,25 @@ class SlabParallelManager(object):
                 else:
                     self._refresh_ghosts()
                 if hasattr(ops, 'keep_build'):
-                    ops.keep_build()
+                    if not ops.keep_build(strict=self._pending is None):
+                        return              # deferred and no local build: confirm() says redo
                 self.n_refresh += 1
                 return
+        self._full_update()
+
+    def confirm(self):
+        """After a deferred update: True if the refresh was not enough -- the full
+        path has then been run and the caller repeats nnps.update + evaluation."""
+        pending, self._pending = self._pending, None
+        if pending is None or pending() <= 0.9:
+            return False
+        self.n_refresh -= 1
+        self.n_deferred_failed += 1
+        self._full_update()
+        return True
+
+    def _full_update(self):
+        ops = self.ops
         for a in range(self.narr):
             ops.drop_ghosts(a)                       # parallel_manager.pyx:519
         if self.migrate:

@@ -18,7 +18,7 @@ class B200Solver(object):
     def __init__(self, particles, equations, kernel, integrator, dt, tf=1.0,
                  adaptive_timestep=False, cfl=0.3, n_damp=0, fixed_h=False,
                  device=0, backend=None, capacity_factor=1.0,
-                 extra_capacity=0):
+                 extra_capacity=0, domain=None):
         self.particles = list(particles)
         self.kernel = kernel
         self.integrator = integrator
@@ -40,7 +40,7 @@ class B200Solver(object):
         self.a_eval = B200AccelerationEval(self.particles, equations, kernel,
                                            backend=self.backend)
         self.nnps = B200NNPS(kernel.dim, self.particles, backend=self.backend,
-                             kernel=kernel)
+                             kernel=kernel, domain=domain)
         self.a_eval.set_nnps(self.nnps)
         integrator.set_acceleration_evals([self.a_eval])
         integrator.set_nnps(self.nnps)
@@ -48,6 +48,10 @@ class B200Solver(object):
         self._initialised = False
 
     def set_parallel_manager(self, pm):
+        dom = self.nnps.domain
+        if pm is not None and dom is not None and getattr(dom, 'is_periodic', False):
+            raise NotImplementedError(
+                'B200 backend: periodic domains with the slab decomposition')
         self.pm = pm
         self.in_parallel = pm is not None
         self.integrator.set_parallel_manager(pm)

@@ -453,6 +453,8 @@ def test_list_reuse_is_exact(gpu_device, monkeypatch):
     st = res['0.1'][1]
     assert st['light_updates'] > 20, st          # lists really were reused ...
     assert st['full_builds'] >= 3, st            # ... and rebuilt when the skin was used up
+    # the integrator defers the drift check: each of those rebuilds was a repeat
+    assert st['deferred_failed'] >= 2, st
     assert res['0.0'][1]['light_updates'] <= 2   # only updates with no motion at all
     pas_a, pas_b = res['0.1'][0], res['0.0'][0]
     assert abs(res['0.1'][2] - res['0.0'][2]) <= 1e-6 * res['0.0'][2]
@@ -466,3 +468,51 @@ def test_list_reuse_is_exact(gpu_device, monkeypatch):
         o.step()
     _compare_state(pas_a, opas, tol_pos=2e-6, tol_vel=2e-6, tol_rho=2e-7,
                    h0=params['h0'], c0=params['c0'], rho0=params['rho0'])
+
+
+def test_deferred_drift_check_protocol(gpu_device):
+    """b200sph_nnps_update_deferred / b200sph_nnps_confirm (include/b200sph.h):
+    a deferred update on stale lists evaluates garbage, confirm() says redo, the
+    repeat equals a fresh evaluation; consuming an unconfirmed stale evaluation
+    is an error, never a silent wrong answer."""
+    import pysph_b200 as pb
+    pas, params = _perturbed_dam_break()
+    s = make_solver(pas, scheme_params(params), 'CubicSpline')
+    s.initialise()                           # builds the lists
+    be, nn, ae = s.backend, s.nnps, s.a_eval
+    f = pas[0]
+    # small motion: deferred update is confirmed
+    f.x[:] += 1e-4 * params['h0']
+    be.push(0, ['x'])
+    nn.update(deferred=True)
+    ae.compute(0.0, 0.0)
+    assert nn.confirm() is False
+    # a jump of one smoothing length: the lists are stale
+    rs = np.random.RandomState(1)
+    f.x[:] += params['h0'] * rs.uniform(-1, 1, f.x.size)
+    be.push(0, ['x'])
+    nn.update(deferred=True)
+    ae.compute(0.0, 0.0)
+    assert nn.confirm() is True
+    assert nn.confirm() is False             # answered once
+    nn.update()
+    ae.compute(0.0, 0.0)
+    be.pull_all(['au', 'arho', 'gid'])
+    got = dict((k, f.properties[k][np.argsort(f.gid)].copy()) for k in ('au', 'arho'))
+    # reference: a fresh context on the same state
+    s.pull()
+    q = copy_arrays(pas)
+    s2 = make_solver(q, scheme_params(params), 'CubicSpline')
+    s2.initialise()
+    s2.pull()
+    for k in ('au', 'arho'):
+        ref = q[0].properties[k][np.argsort(q[0].gid)]
+        assert rel_err(got[k], ref) <= 2e-6, k
+    # unconfirmed stale update: stage / pull / dt_factors refuse
+    f.x[:] += params['h0'] * rs.uniform(-1, 1, f.x.size)
+    be.push(0, ['x'])
+    nn.update(deferred=True)
+    ae.compute(0.0, 0.0)
+    with pytest.raises(RuntimeError, match='never confirmed'):
+        be.pull(0, ['au'])
+    assert be.stats()['deferred_failed'] == 2

@@ -55,7 +55,7 @@ def test_struct_layouts_match_header():
     # sizes implied by include/b200sph.h (x86-64 SysV)
     assert C.sizeof(_lib.PairProgram) == 8 * 8 * 4 + 2 * 4 + 7 * 8
     assert C.sizeof(_lib.GridInfo) == 8 + 8 + 24 + 24 + 12 + 4 + 8 + 8
-    assert C.sizeof(_lib.Stats) == 3 * 8 + 7 * 8
+    assert C.sizeof(_lib.Stats) == 3 * 8 + 8 * 8
     ids = _lib.PROP_IDS
     assert ids['x'] == 0 and ids['rho'] == 6 and ids['h'] == 7 and ids['m'] == 8
     assert ids['rho0'] == 15 and ids['p'] == 16 and ids['dt_force'] == 26
@@ -187,3 +187,16 @@ def test_particle_array_standin():
     assert pa.get('x').size == 3 and pa.get('x', only_real_particles=False).size == 5
     pa.resize(8)
     assert pa.x.size == 8 and pa.x[4] == 4.0 and pa.x[7] == 0.0
+
+
+def test_domain_manager_descriptor():
+    # constructor surface of nnps_base.pyx:226-347 (no device needed)
+    import pysph_b200 as pb
+    dm = pb.DomainManager(xmin=0, xmax=1, ymin=-1, ymax=2, periodic_in_y=True)
+    assert dm.is_periodic and not dm.is_mirror
+    assert (dm.periodic_in_x, dm.periodic_in_y, dm.periodic_in_z) == (False, True, False)
+    assert not pb.DomainManager().is_periodic
+    with pytest.raises(ValueError):
+        pb.DomainManager(xmin=1, xmax=0)
+    with pytest.raises(NotImplementedError):
+        pb.DomainManager(xmin=0, xmax=1, mirror_in_x=True)

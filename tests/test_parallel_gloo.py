@@ -73,6 +73,13 @@ class NumpyHaloOps(object):
     def drift(self):
         return getattr(self, 'fake_drift', (0.0, 1.0))
 
+    def read_later(self, t):          # deferred protocol: the host reads it later
+        return lambda: float(t[0])
+
+    def keep_build(self, strict=True):
+        self.kept = getattr(self, 'kept', 0) + 1
+        return True
+
     def append(self, a, buf, off, n, nfields, as_real):
         if not n:
             return
@@ -195,6 +202,30 @@ def _worker(rank, world, port, q):
         ops.fake_drift = (2.0, 1.0) if rank == 0 else (0.1, 1.0)
         pm.update()
         idem &= pm.n_full == 2 and n_before == [ops.arrays[i]['x'].size for i in range(2)]
+        # deferred protocol (what the integrator uses): the refresh is applied on
+        # the assumption "valid"; confirm() reads the all-reduced answer afterwards
+        ops.fake_drift = (0.1, 1.0)
+        for ai in range(2):
+            ops.arrays[ai]['rho'][:ops.nreal[ai]] += 2.0
+        nf, nr_ = pm.n_full, pm.n_refresh
+        pm.update(deferred=True)
+        idem &= pm._pending is not None and pm.confirm() is False
+        idem &= (pm.n_full, pm.n_refresh) == (nf, nr_ + 1)
+        for ai, a in enumerate(glob):
+            got = ops.arrays[ai]
+            nr = ops.nreal[ai]
+            owner = np.searchsorted(cuts, a['x'], side='right') - 1
+            for xg, rg in zip(got['x'][nr:], got['rho'][nr:]):
+                j = np.where(a['x'] == xg)[0][0]
+                idem &= bool(rg == a['rho'][j] + 3.0 + owner[j])
+        # ... and a "no" from the LAST rank makes every rank run the full path in confirm()
+        ops.fake_drift = (2.0, 1.0) if rank == world - 1 else (0.1, 1.0)
+        pm.update(deferred=True)
+        idem &= pm.n_full == nf                     # nothing happened yet
+        idem &= pm.confirm() is True
+        idem &= (pm.n_full, pm.n_refresh, pm.n_deferred_failed) == (nf + 1, nr_ + 1, 1)
+        idem &= n_before == [ops.arrays[i]['x'].size for i in range(2)]
+        idem &= pm.confirm() is False               # nothing pending any more
         dtmin = pm.update_time_steps(0.1 * (rank + 1))
         q.put((rank, res, idem, dtmin))
     finally:
