@@ -380,6 +380,25 @@ def main():
             roofline['traffic'] = json.load(open(prof)).get('dram_bytes_per_launch')
         except Exception:
             pass
+    if roofline['traffic']:
+        # the per-pair gathers are served by L1/L2 (records of one cell neighbourhood
+        # are re-read ~80x): DRAM moves far fewer bytes than the algorithmic count,
+        # which is why `frac` can exceed 1 -- see DESIGN.md "roofline accounting"
+        roofline['dram_gbs'] = roofline['traffic'] / (ms_pair * 1e-3) / 1e9
+        roofline['dram_frac'] = roofline['dram_gbs'] / peak
+        roofline['note'] = ('achieved = algorithmic gather bytes (45 B/pair, SURVEY 8d) / '
+                            'kernel time; measured DRAM traffic is traffic/launch '
+                            '(ncu, N=1 workload) -- the gathers hit L1/L2, the kernel is '
+                            'LSU/L1-bound, not HBM-bound')
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([st['ms_pair'] / K, st['ms_nnps'] / K, st['ms_other'] / K,
+                             float(n_local), float(pairs_local)],
+                            dtype=torch.float64, device='cuda')
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [dict(zip(('ms_pair', 'ms_nnps', 'ms_other', 'n_real', 'pairs'),
+                             [round(float(v), 4) for v in r.tolist()])) for r in allr]
 
     if rank != 0:
         if world > 1:
@@ -408,6 +427,8 @@ def main():
                                'CubicSpline dx=%.6f hdx=1.3' % (1 if world == 1 else 2, dx),
                    'particles_rank0': ntot_all,
                    'pairs_per_step': pairs_total,
+                   'per_rank': per_rank,
+                   'deferred_failed': int(st['deferred_failed']),
                    'parallelism': 'single GPU' if world == 1 else 'x-slabs x%d + NCCL halo' % world,
                    'l2': 'no flush: per-step working set (~220 B/particle state '
                          '+ 48 B/particle packed records, > 126 MB L2 at 1.2 M '

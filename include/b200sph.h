@@ -196,6 +196,34 @@ int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt);
  * Integrator._get_dt_adapt_factors / compute_h_minimum integrator.py:62-81,146-159 */
 int b200sph_dt_factors(b200sph_ctx *ctx, double out[3]);
 
+/* ---- device-resident time step: the adaptive dt (Integrator.compute_time_step
+ *      integrator.py:161-200), its damping and the t += dt bookkeeping of the solve
+ *      loop (solver.py:478-491, :647-688) without a host round trip per step.
+ * The time-control block is 8 doubles of DEVICE memory:
+ *   [0] dt of the next step (damped)   [1] t   [2] proposed dt (local; the caller may
+ *   MIN-reduce it over ranks between dt_propose and dt_commit)   [3] h_minimum
+ * external_block8 != NULL: use the caller's device memory (e.g. a torch tensor a
+ * collective can reduce in place); NULL: the library's own.  *dev_block = its address */
+int b200sph_time_control(b200sph_ctx *ctx, double *external_block8, double **dev_block);
+int b200sph_time_set(b200sph_ctx *ctx, double t, double dt);
+/* out = {dt, t}; waits for the stream */
+int b200sph_time_get(b200sph_ctx *ctx, double out[2]);
+/* b200sph_stage with dt read from the block (which = 1 uses dt / 2) */
+int b200sph_stage_dev(b200sph_ctx *ctx, int arr, int which);
+/* enqueue: reduce dt_cfl / dt_force / h, then block[2] = cfl * min(hmin / max_cfl,
+ * sqrt(hmin / sqrt(max_force))), or 1e20 when nothing constrains it (solver.py:655-660);
+ * fixed_h keeps the first hmin (integrator.py:170-176) */
+int b200sph_dt_propose(b200sph_ctx *ctx, double cfl, int fixed_h);
+/* enqueue: if (advance) t += dt;  undamped = dt / prev_factor;
+ * dt = new_factor * (adaptive ? (block[2] < 1e20 || in_parallel ? block[2] : undamped)
+ *                             : undamped)                          (solver.py:647-688)
+ * snapshot_slot 0/1: also copy {dt, t} to pinned host memory for b200sph_time_snapshot;
+ * -1: no snapshot */
+int b200sph_dt_commit(b200sph_ctx *ctx, double prev_factor, double new_factor,
+                      int in_parallel, int adaptive, int advance, int snapshot_slot);
+/* wait for the snapshot of `slot` only (not for later work): out = {dt, t} */
+int b200sph_time_snapshot(b200sph_ctx *ctx, int slot, double out[2]);
+
 /* ---- halo exchange helpers (replace ParallelManager.update,
  *      parallel_manager.pyx:512-632).  Buffers are DEVICE pointers owned by
  *      the caller (torch tensors handed to NCCL). ------------------------- */

@@ -98,6 +98,13 @@ SIGNATURES = {
                                     C.POINTER(_i64)]),
     'b200sph_stage': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
     'b200sph_dt_factors': (C.c_int, [_ctx_p, _dp]),
+    'b200sph_time_control': (C.c_int, [_ctx_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    'b200sph_time_set': (C.c_int, [_ctx_p, C.c_double, C.c_double]),
+    'b200sph_time_get': (C.c_int, [_ctx_p, _dp]),
+    'b200sph_stage_dev': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
+    'b200sph_dt_propose': (C.c_int, [_ctx_p, C.c_double, C.c_int]),
+    'b200sph_dt_commit': (C.c_int, [_ctx_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'b200sph_time_snapshot': (C.c_int, [_ctx_p, C.c_int, _dp]),
     'b200sph_halo_pack': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double,
                                     C.c_double, C.c_void_p, _i64,
                                     C.POINTER(_i64)]),

@@ -137,6 +137,11 @@ struct b200sph_ctx {
     unsigned *drift_host = nullptr;
     cudaEvent_t drift_evt = nullptr;
     int64_t n_deferred_failed = 0;
+    // device-resident time control block: [0] dt, [1] t, [2] proposed dt, [3] h_minimum
+    double *tc = nullptr;
+    bool tc_owned = false;
+    double *tc_host = nullptr;          // pinned: 2 snapshot slots x 2 doubles
+    cudaEvent_t tc_evt[2] = {nullptr, nullptr};
     bool h_dirty = true;        // h changed since the last update_domain reduction
     unsigned *red_u32 = nullptr, *red_u32_host = nullptr;
     int64_t n_full_builds = 0, n_light_updates = 0, n_list_builds = 0;
@@ -318,6 +323,35 @@ __global__ void k_reduce_dt(const float *__restrict__ dt_cfl, const float *__res
     }
 }
 
+// Integrator.compute_time_step (integrator.py:161-200) on the reduced factors: the local
+// proposal cfl * dt_min, or 1e20 when no factor constrains it (solver.py:655-660)
+__global__ void k_dt_propose(const long long *__restrict__ red, double *__restrict__ tc, double cfl, int fixed_h)
+{
+    const double mc = o2d(red[9]), mf = o2d(red[11]);
+    const double f_cfl = mc < -1e299 ? -1.0 : mc, f_force = mf < -1e299 ? -1.0 : mf;
+    double hmin = fmin(1.0, o2d(red[12]));
+    if (!fixed_h || tc[3] < 0.0) tc[3] = hmin;
+    hmin = tc[3];
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double dt_cfl = inf, dt_force = inf;
+    if (f_cfl > 0.0) dt_cfl = hmin / f_cfl;
+    if (f_force > 0.0) dt_force = sqrt(hmin / sqrt(f_force));
+    const double dt_min = fmin(dt_cfl, dt_force);
+    tc[2] = (dt_min <= 0.0 || isinf(dt_min)) ? 1e20 : cfl * dt_min;
+}
+// Solver loop bookkeeping (solver.py:478-491, :647-688): t += dt; dt = damp(new dt)
+__global__ void k_dt_commit(double *__restrict__ tc, double prev_factor, double new_factor, int in_parallel, int adaptive, int advance)
+{
+    const double dt_old = tc[0];
+    if (advance) tc[1] += dt_old;
+    const double undamped = dt_old / prev_factor;
+    double dt = undamped;
+    if (adaptive) {
+        dt = tc[2];
+        if (!in_parallel && dt >= 1e20) dt = undamped;
+    }
+    tc[0] = dt * new_factor;
+}
 // TaitEOS.loop wc/basic.py:60-65 ; TaitEOSHGCorrection.loop wc/basic.py:118-126
 __global__ void k_eos(double *__restrict__ rho, float *__restrict__ p, float *__restrict__ cs,
                       const uint8_t *__restrict__ ptype, long long lo, long long hi, int hg,
@@ -359,7 +393,15 @@ struct StageArgs {
 
 // WCSPHStep.initialize / stage1 / stage2 integrator_step.py:51-91 (real particles only,
 // integrator_cython.mako:97-111)
-__global__ void k_stage(StageArgs a)
+__device__ __forceinline__ void stage_body(const StageArgs &a);
+__global__ void k_stage(StageArgs a) { stage_body(a); }
+__global__ void k_stage_devdt(StageArgs a, const double *__restrict__ tc)
+{
+    const double dt = tc[0];
+    a.f = a.which == 1 ? 0.5 * dt : dt;
+    stage_body(a);
+}
+__device__ __forceinline__ void stage_body(const StageArgs &a)
 {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= a.pool_end) return;
@@ -1652,6 +1694,10 @@ int b200sph_destroy(b200sph_ctx *ctx)
     cudaFree(ctx->flag_b); cudaFree(ctx->A0); cudaFree(ctx->lst); cudaFree(ctx->cnt);
     cudaFree(ctx->red_u32); cudaFreeHost(ctx->red_u32_host);
     cudaFreeHost(ctx->drift_host);
+    if (ctx->tc_owned) cudaFree(ctx->tc);
+    if (ctx->tc_host) cudaFreeHost(ctx->tc_host);
+    for (int i = 0; i < 2; i++)
+        if (ctx->tc_evt[i]) cudaEventDestroy(ctx->tc_evt[i]);
     if (ctx->drift_evt) cudaEventDestroy(ctx->drift_evt);
     for (auto &pe : ctx->pending) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -2443,7 +2489,17 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     return 0;
 }
 
-int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt)
+static int ensure_tc(b200sph_ctx *ctx)
+{
+    if (ctx->tc) return 0;
+    CU(cudaMalloc((void **)&ctx->tc, 8 * sizeof(double)));
+    ctx->tc_owned = true;
+    const double init[8] = {0.0, 0.0, 1e20, -1.0, 0.0, 0.0, 0.0, 0.0};
+    CU(cudaMemcpy(ctx->tc, init, sizeof(init), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int stage_impl(b200sph_ctx *ctx, int arr, int which, double dt, bool devdt)
 {
     if (int rcc = require_confirmed(ctx, "stage")) return rcc;
     CU(cudaSetDevice(ctx->device));
@@ -2452,6 +2508,7 @@ int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt)
     if ((rc = eos_flush(ctx))) return rc;
     if (arr >= ctx->narr) return set_err(ctx, "stage: bad array %d", arr);
     if (which < 0 || which > 2) return set_err(ctx, "stage: which must be 0 (initialize), 1 (stage1) or 2 (stage2)");
+    if (devdt && (rc = ensure_tc(ctx))) return rc;
     PhaseTimer pt(ctx, 2);
     StageArgs sa;
     sa.x = ctx->f64[B200SPH_X]; sa.y = ctx->f64[B200SPH_Y]; sa.z = ctx->f64[B200SPH_Z];
@@ -2467,13 +2524,108 @@ int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt)
     sa.which = which;
     sa.f = which == 1 ? 0.5 * dt : dt;
     if (ctx->pool_end > 0) {
-        k_stage<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa);
+        if (devdt) k_stage_devdt<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa, ctx->tc);
+        else k_stage<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa);
         LAUNCH_CHECK();
     }
     if (which != 0) {
         ctx->grid_valid = false;  // particles moved: neighbours are stale until nnps_update
         ctx->state_packed = false;
     }
+    return 0;
+}
+
+int b200sph_stage(b200sph_ctx *ctx, int arr, int which, double dt) { return stage_impl(ctx, arr, which, dt, false); }
+int b200sph_stage_dev(b200sph_ctx *ctx, int arr, int which) { return stage_impl(ctx, arr, which, 0.0, true); }
+
+// ---- device-resident time step ------------------------------------------------
+int b200sph_time_control(b200sph_ctx *ctx, double *external_block8, double **dev_block)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (external_block8) {
+        if (ctx->tc_owned) CU(cudaFree(ctx->tc));
+        ctx->tc = external_block8;
+        ctx->tc_owned = false;
+        const double init[8] = {0.0, 0.0, 1e20, -1.0, 0.0, 0.0, 0.0, 0.0};
+        CU(cudaMemcpyAsync(ctx->tc, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    } else if (int rc = ensure_tc(ctx)) return rc;
+    if (!ctx->tc_host) {
+        CU(cudaMallocHost((void **)&ctx->tc_host, 4 * sizeof(double)));
+        for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&ctx->tc_evt[i], cudaEventDisableTiming));
+    }
+    if (dev_block) *dev_block = ctx->tc;
+    return 0;
+}
+
+int b200sph_time_set(b200sph_ctx *ctx, double t, double dt)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = b200sph_time_control(ctx, nullptr, nullptr);
+    if (rc) return rc;
+    const double v[2] = {dt, t};
+    CU(cudaMemcpyAsync(ctx->tc, v, sizeof(v), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200sph_dt_propose(b200sph_ctx *ctx, double cfl, int fixed_h)
+{
+    if (int rcc = require_confirmed(ctx, "dt_propose")) return rcc;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = b200sph_time_control(ctx, nullptr, nullptr))) return rc;
+    PhaseTimer pt(ctx, 2);
+    k_red_init<<<1, 32, 0, ctx->stream>>>(ctx->red);
+    LAUNCH_CHECK();
+    if (ctx->pool_end > 0) {
+        const unsigned nb = (unsigned)std::min<int64_t>(cdiv(ctx->pool_end, 256), 148 * 8);
+        k_reduce_dt<<<nb, 256, 0, ctx->stream>>>(ctx->f32[B200SPH_DT_CFL - N_F64], ctx->f32[B200SPH_DT_FORCE - N_F64], ctx->f64[B200SPH_H],
+                                                 ctx->ptype, ctx->pool_end, ctx->red);
+        LAUNCH_CHECK();
+    }
+    k_dt_propose<<<1, 1, 0, ctx->stream>>>(ctx->red, ctx->tc, cfl, fixed_h);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int b200sph_dt_commit(b200sph_ctx *ctx, double prev_factor, double new_factor, int in_parallel, int adaptive, int advance, int snapshot_slot)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = b200sph_time_control(ctx, nullptr, nullptr);
+    if (rc) return rc;
+    if (!(prev_factor > 0.0) || !(new_factor > 0.0)) return set_err(ctx, "dt_commit: damping factors must be positive");
+    k_dt_commit<<<1, 1, 0, ctx->stream>>>(ctx->tc, prev_factor, new_factor, in_parallel, adaptive, advance);
+    LAUNCH_CHECK();
+    if (snapshot_slot >= 0) {
+        if (snapshot_slot > 1) return set_err(ctx, "dt_commit: snapshot slot must be 0 or 1");
+        CU(cudaMemcpyAsync(ctx->tc_host + 2 * snapshot_slot, ctx->tc, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->tc_evt[snapshot_slot], ctx->stream));
+    }
+    return 0;
+}
+
+int b200sph_time_snapshot(b200sph_ctx *ctx, int slot, double out[2])
+{
+    if (slot < 0 || slot > 1 || !ctx->tc_host) return set_err(ctx, "time_snapshot: no snapshot in slot %d", slot);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->tc_evt[slot]));
+    out[0] = ctx->tc_host[2 * slot];      // dt of the step that follows the snapshot
+    out[1] = ctx->tc_host[2 * slot + 1];  // t at the snapshot
+    return 0;
+}
+
+int b200sph_time_get(b200sph_ctx *ctx, double out[2])
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = b200sph_time_control(ctx, nullptr, nullptr);
+    if (rc) return rc;
+    double v[2];
+    CU(cudaMemcpyAsync(v, ctx->tc, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    out[0] = v[0];
+    out[1] = v[1];
     return 0;
 }
 

@@ -45,6 +45,7 @@ class B200Integrator(object):
         self.t = 0.0
         self.dt = 0.0
         self._post_stage_callback = None
+        self.device_dt = False      # set by B200Solver: dt lives in device memory
         self._stage_arrays = None
         # the adapter is its own "compiled object" (integrator.py:244-247)
         self.c_integrator = self
@@ -81,7 +82,10 @@ class B200Integrator(object):
     # -- stages ---------------------------------------------------------------
     def _stage(self, which, dt):
         for arr in self._stage_arrays:
-            self.ctx.call('b200sph_stage', arr, which, float(dt))
+            if self.device_dt and which != 0:
+                self.ctx.call('b200sph_stage_dev', arr, which)   # dt read on the device
+            else:
+                self.ctx.call('b200sph_stage', arr, which, float(dt))
 
     def initialize(self):
         self._stage(0, 0.0)

@@ -532,6 +532,11 @@ class SlabParallelManager(object):
                 ops.append(a, recv_bufs.get(nb), o, n, HALO_FIELDS, False)
                 o += n * HALO_FIELDS
 
+    def reduce_dt_device(self, view):
+        """MIN over ranks of a 1-element device tensor, in place, no host sync
+        (parallel_manager.pyx:454-465 on the device-resident time step)."""
+        self.dist.all_reduce(view, op=self.dist.ReduceOp.MIN)
+
     def update_time_steps(self, dt):
         t = self.ops.new_buffer(1)
         t[0] = dt
@@ -541,7 +546,7 @@ class SlabParallelManager(object):
 
 # ---------------------------------------------------------------------------
 def make_slab_solver(dx, params, kernel, rank, world, device=0,
-                     solid_weight=0.3, **solver_kw):
+                     solid_weight=0.45, **solver_kw):
     """Build this rank's slab of the 3D dam break and a ready solver."""
     import os
     import pysph_b200 as pb

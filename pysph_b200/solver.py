@@ -18,13 +18,19 @@ class B200Solver(object):
     def __init__(self, particles, equations, kernel, integrator, dt, tf=1.0,
                  adaptive_timestep=False, cfl=0.3, n_damp=0, fixed_h=False,
                  device=0, backend=None, capacity_factor=1.0,
-                 extra_capacity=0, domain=None):
+                 extra_capacity=0, domain=None, device_dt=True):
+        """device_dt=True keeps dt and t on the device (include/b200sph.h
+        "device-resident time step"): the host enqueues step n+1 while step n
+        runs and never waits for the adaptive time step; ``solver.t`` /
+        ``solver.dt`` read it back on demand.  The arithmetic is the same fp64
+        sequence as the host path (device_dt=False), so both give bitwise the
+        same trajectory."""
         self.particles = list(particles)
         self.kernel = kernel
         self.integrator = integrator
-        self.dt = dt
+        self._dt = dt
         self.tf = tf
-        self.t = 0.0
+        self._t = 0.0
         self.count = 0
         self.adaptive_timestep = adaptive_timestep
         self.cfl = cfl
@@ -32,6 +38,10 @@ class B200Solver(object):
         self._damping_factor = 1.0
         self.pm = None
         self.in_parallel = False
+        self.device_dt = bool(device_dt)
+        self.fixed_h = fixed_h
+        self._commits = 0            # snapshots written: commit k -> slot k % 2
+        self._tc = None
 
         self.backend = backend or B200Backend(
             self.particles, device=device, capacity_factor=capacity_factor,
@@ -58,7 +68,7 @@ class B200Solver(object):
 
     # -- time step (solver.py:647-688, 756-779) -------------------------------
     def _compute_timestep(self):
-        undamped = self.dt / self._damping_factor
+        undamped = self._dt / self._damping_factor
         if not self.adaptive_timestep:
             return undamped
         dt = self.integrator.compute_time_step(undamped, self.cfl)
@@ -68,16 +78,85 @@ class B200Solver(object):
             dt = undamped
         return dt
 
-    def _damp_timestep(self, dt):
+    def _next_damping_factor(self):
         if self.count < self.n_damp and self.n_damp > 0:
             frac = (self.count + 1) / float(self.n_damp)
-            self._damping_factor = 0.5 * (np.sin(np.pi * (-0.5 + frac)) + 1.0)
-        else:
-            self._damping_factor = 1.0
+            return 0.5 * (np.sin(np.pi * (-0.5 + frac)) + 1.0)
+        return 1.0
+
+    def _damp_timestep(self, dt):
+        self._damping_factor = self._next_damping_factor()
         return dt * self._damping_factor
 
     def _get_timestep(self):
         return self._damp_timestep(self._compute_timestep())
+
+    # -- device-resident dt ---------------------------------------------------
+    def _use_device_dt(self):
+        return self.device_dt and self.integrator._post_stage_callback is None
+
+    def _device_dt_begin(self):
+        import ctypes as C
+        ctx = self.backend.ctx
+        if self.pm is not None and hasattr(self.pm.ops, 'new_buffer') and \
+                hasattr(self.pm, 'reduce_dt_device'):
+            self._tc = self.pm.ops.new_buffer(8)     # torch owns it: NCCL reduces in place
+            ctx.call('b200sph_time_control', self._tc.data_ptr(), None)
+        else:
+            ctx.call('b200sph_time_control', None, None)
+        ctx.call('b200sph_time_set', float(self._t), float(self._dt))
+        self.integrator.device_dt = True
+
+    def _device_dt_advance(self, advance):
+        """compute / reduce / damp the next dt and (advance) t += dt, all enqueued."""
+        ctx = self.backend.ctx
+        prev = self._damping_factor
+        new = self._next_damping_factor()
+        if self.adaptive_timestep:
+            ctx.call('b200sph_dt_propose', float(self.cfl), int(bool(self.fixed_h)))
+            if self._tc is not None:
+                self.pm.reduce_dt_device(self._tc[2:3])
+        ctx.call('b200sph_dt_commit', float(prev), float(new),
+                 int(self._tc is not None), int(bool(self.adaptive_timestep)),
+                 int(bool(advance)), self._commits % 2)
+        self._commits += 1
+        self._damping_factor = new
+
+    def _snapshot(self, back=0):
+        """(dt, t) written by the latest commit (back=0, waits for the current
+        step) or the one before it (back=1, normally complete already)."""
+        import ctypes as C
+        out = (C.c_double * 2)()
+        self.backend.ctx.call('b200sph_time_snapshot',
+                              (self._commits - 1 - back) % 2, out)
+        return out[0], out[1]
+
+    def _on_device(self):
+        return self._initialised and self.integrator.device_dt
+
+    @property
+    def t(self):
+        return self._snapshot()[1] if self._on_device() else self._t
+
+    @t.setter
+    def t(self, value):
+        self._t = value
+
+    @property
+    def dt(self):
+        return self._snapshot()[0] if self._on_device() else self._dt
+
+    @dt.setter
+    def dt(self, value):
+        self._dt = value
+
+    def _t_without_waiting(self):
+        """t after the step enqueued last, from the PREVIOUS snapshot: t_n =
+        t_(n-1) + dt_n (the same fp64 addition the device performs)."""
+        if self._commits < 2:
+            return self._snapshot()[1]
+        dt_n, t_prev = self._snapshot(back=1)
+        return t_prev + dt_n
 
     # -- stepping -------------------------------------------------------------
     def initialise(self):
@@ -86,21 +165,35 @@ class B200Solver(object):
                 self.pm.update()
                 self.nnps.update_domain()
                 self.nnps.update()
-            self.integrator.initial_acceleration(self.t, self.dt)  # solver.py:454
-            self.dt = self._get_timestep()                          # solver.py:458
+            self.integrator.initial_acceleration(self._t, self._dt)  # solver.py:454
+            if self._use_device_dt():
+                self._device_dt_begin()
+                self._device_dt_advance(advance=False)               # solver.py:458
+            else:
+                self._dt = self._get_timestep()
             self._initialised = True
 
     def step(self):
         """One iteration of the solve loop (solver.py:460-491)."""
         self.initialise()
-        self.integrator.step(self.t, self.dt)
-        self.t += self.dt
+        if self.integrator.device_dt:
+            self.integrator.step(self._t, self._dt)      # dt, t live on the device
+            self.count += 1
+            self._device_dt_advance(advance=True)
+            return
+        self.integrator.step(self._t, self._dt)
+        self._t += self._dt
         self.count += 1
-        self.dt = self._get_timestep()
+        self._dt = self._get_timestep()
 
     def solve(self, max_steps):
         self.initialise()
-        while self.count < max_steps and (self.tf - self.t) > 1e-15:
+        if self.integrator.device_dt:
+            while self.count < max_steps and \
+                    (self.tf - self._t_without_waiting()) > 1e-15:
+                self.step()
+            return
+        while self.count < max_steps and (self.tf - self._t) > 1e-15:
             self.step()
 
     def pull(self, props=None):

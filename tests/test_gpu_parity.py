@@ -516,3 +516,34 @@ def test_deferred_drift_check_protocol(gpu_device):
     with pytest.raises(RuntimeError, match='never confirmed'):
         be.pull(0, ['au'])
     assert be.stats()['deferred_failed'] == 2
+
+
+def test_device_resident_dt_is_bitwise_the_host_path(gpu_device):
+    """include/b200sph.h "device-resident time step": dt_propose / dt_commit /
+    stage_dev perform the fp64 arithmetic of Integrator.compute_time_step and
+    Solver._get_timestep (integrator.py:161-200, solver.py:647-688) on the
+    device; with deterministic kernels the trajectory, t and dt are bitwise
+    those of the host path, through the damped start-up and a tf-limited
+    solve()."""
+    out = {}
+    for mode in (True, False):
+        pas, params = _perturbed_dam_break(vscale=1.0)
+        p = scheme_params(params)
+        p['n_damp'] = 10
+        s = make_solver(pas, p, 'CubicSpline', device_dt=mode)
+        s.initialise()
+        assert s.integrator.device_dt is mode
+        dt0 = s.dt
+        for _ in range(25):
+            s.step()
+        t25, dt25 = s.t, s.dt
+        s.tf = t25 + 4.5 * dt25             # ends by time, not by count
+        s.solve(1000)
+        s.pull()
+        out[mode] = (dt0, t25, dt25, s.count, s.t,
+                     dict((k, pas[0].properties[k].copy()) for k in ('x', 'y', 'z', 'u', 'rho')))
+    a, b = out[True], out[False]
+    assert a[:5] == b[:5], (a[:5], b[:5])
+    assert 27 <= a[3] <= 40
+    for k, v in a[5].items():
+        assert np.array_equal(v, b[5][k]), k
