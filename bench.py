@@ -55,7 +55,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -66,9 +66,17 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, first=0):
+        """first: number of lines printed before the timed region began; the line
+        in flight then (index first - 1) is kept when the region was shorter than
+        one sampling period."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        time.sleep(0.06)                     # let the sample covering the region's end arrive
+        if len(self.lines) > first:
+            self.lines = self.lines[first:]
+        else:
+            self.lines = self.lines[-1:]
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -263,20 +271,29 @@ def main():
     n_local = sum(be.sizes(i)[1] for i in range(len(pas)))
 
     # ---- pair count of one step (untimed verification pass) -----------------
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML init over every GPU
+    # of the box) perturbs running kernels for tens of ms; only the lines it prints
+    # during the timed region are used
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     solver.initialise()
     for _ in range(W):
         solver.step()
     solver.a_eval.count_pairs = True
     pairs_step = 0
-    orig_compute = solver.a_eval.compute
+    integ = solver.integrator
+    orig_ca = integ.compute_accelerations
 
-    def counting_compute(t, dt):
+    def counting_ca(*a, **kw):
+        # one count per evaluation of the integrator: an evaluation that had to be
+        # repeated after a failed deferred drift check counts once (the repeat)
         nonlocal pairs_step
-        orig_compute(t, dt)
+        orig_ca(*a, **kw)
         pairs_step += solver.a_eval.last_pairs
-    solver.a_eval.compute = counting_compute
+    integ.compute_accelerations = counting_ca
     solver.step()
-    solver.a_eval.compute = orig_compute
+    del integ.compute_accelerations
     solver.a_eval.count_pairs = False
     pairs_local = pairs_step
     if world > 1:
@@ -289,17 +306,27 @@ def main():
     # ---- timed region: exactly K steps, device resident ----------------------
     be.ctx.call('b200sph_reset_stats')
     be.ctx.call('b200sph_set_profiling', 1)
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    n_s0 = len(sampler.lines)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if pm is not None and getattr(pm, '_prof', None) is not None:
+        pm.profile_summary()
+    import time as _time
+    cpu_t0 = _time.perf_counter()
     ev0.record(stream)
     for _ in range(K):
         solver.step()
     ev1.record(stream)
+    cpu_enqueue_ms = 1e3 * (_time.perf_counter() - cpu_t0)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(n_s0) if rank == 0 else None
+    if os.environ.get('B200SPH_PM_PROFILE') and pm is None:
+        sys.stderr.write('[pm-profile rank 0] per step: cpu_loop %.3f ms\n' % (cpu_enqueue_ms / K))
+    if pm is not None and getattr(pm, '_prof', None) is not None:
+        ps = pm.profile_summary()
+        sys.stderr.write('[pm-profile rank %d] per step: cpu_loop %.3f ms; %s\n' % (
+            rank, cpu_enqueue_ms / K,
+            ', '.join('%s %.3f' % (k, v / K) for k, v in sorted(ps.items()))))
     ms_total = ev0.elapsed_time(ev1)
     st = be.stats()
     be.ctx.call('b200sph_set_profiling', 0)

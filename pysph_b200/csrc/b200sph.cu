@@ -97,6 +97,7 @@ struct b200sph_ctx {
     // grid
     b200sph_grid_info grid;
     bool grid_valid = false;
+    bool packed_valid = false;  // A / AB hold the CURRENT positions (set by nnps_drift_device, kept by halo_overwrite_all)
     double last_domain_size = 0.0;
 
     // sort / cell list buffers
@@ -1393,7 +1394,14 @@ __global__ void k_halo_gather_all(HaloPtrs P, HaloAllArgs A, double *__restrict_
 #pragma unroll
     for (int f = 0; f < B200SPH_HALO_FIELDS; f++) out[(long long)f * cnt] = P.p[f][i];
 }
-__global__ void k_halo_scatter_all(HaloPtrs P, HaloAllArgs A, const double *__restrict__ src)
+struct RepackArgs {
+    const uint32_t *rank, *skey;   // rank == nullptr: no repack
+    float4 *A, *AB;
+    GridDev G;
+};
+// ghost values refreshed in place; with a valid neighbour build the ghosts' packed
+// cell-relative positions are refreshed in the same pass (x, y, z, h are fields 0, 1, 2, 7)
+__global__ void k_halo_scatter_all(HaloPtrs P, HaloAllArgs A, const double *__restrict__ src, RepackArgs R)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= A.prefix[A.narr]) return;
@@ -1401,8 +1409,27 @@ __global__ void k_halo_scatter_all(HaloPtrs P, HaloAllArgs A, const double *__re
     while (k >= A.prefix[a + 1]) a++;
     const long long r = k - A.prefix[a], cnt = A.prefix[a + 1] - A.prefix[a];
     const double *in = src + B200SPH_HALO_FIELDS * A.prefix[a] + r;
+    double v[B200SPH_HALO_FIELDS];
 #pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) P.p[f][A.off[a] + r] = in[(long long)f * cnt];
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) {
+        v[f] = in[(long long)f * cnt];
+        P.p[f][A.off[a] + r] = v[f];
+    }
+    if (R.rank) {
+        const uint32_t s = R.rank[A.off[a] + r];
+        uint32_t key = R.skey[s];
+        const uint32_t cx = key % (uint32_t)R.G.nc[0];
+        key /= (uint32_t)R.G.nc[0];
+        const uint32_t cy = key % (uint32_t)R.G.nc[1];
+        const uint32_t cz = key / (uint32_t)R.G.nc[1];
+        float4 q;
+        q.x = (float)(v[0] - (R.G.xmin[0] + (double)cx * R.G.cell[0]));
+        q.y = (float)(v[1] - (R.G.xmin[1] + (double)cy * R.G.cell[1]));
+        q.z = (float)(v[2] - (R.G.xmin[2] + (double)cz * R.G.cell[2]));
+        q.w = (float)v[7];
+        R.A[s] = q;
+        R.AB[2 * s] = q;
+    }
 }
 __global__ void k_drift_ratio(const unsigned *__restrict__ red_u32, float kr, float S, double *__restrict__ out)
 {
@@ -1475,7 +1502,7 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     ctx->pool_cap = alloc;
     ctx->pool_end = total;
     ctx->ptype_dirty = true;
-    ctx->grid_valid = false;
+    ctx->grid_valid = false, ctx->packed_valid = false;
     // per-particle work buffers
     if (ctx->key_of) cudaFree(ctx->key_of);
     if (ctx->off_in) cudaFree(ctx->off_in);
@@ -1752,7 +1779,7 @@ int b200sph_add_array(b200sph_ctx *ctx, const char *name, int64_t n, int64_t n_r
         if (rc) return rc;
     }
     ctx->ptype_dirty = true;
-    ctx->grid_valid = false;
+    ctx->grid_valid = false, ctx->packed_valid = false;
     ctx->topo_dirty = true;
     ctx->h_dirty = true;
     return a;
@@ -1773,7 +1800,7 @@ int b200sph_resize_array(b200sph_ctx *ctx, int arr, int64_t n, int64_t n_real)
     ctx->arr[arr].n = n;
     ctx->arr[arr].n_real = n_real;
     ctx->ptype_dirty = true;
-    ctx->grid_valid = false;
+    ctx->grid_valid = false, ctx->packed_valid = false;
     ctx->topo_dirty = true;
     ctx->h_dirty = true;
     return 0;
@@ -1829,7 +1856,7 @@ int b200sph_push_f64(b200sph_ctx *ctx, int arr, int prop, const double *host, in
     // new positions / smoothing lengths for the SAME particles: the next nnps_update
     // measures the drift against the current neighbour build and reuses it if it can
     if (prop == B200SPH_H) { ctx->domain_valid = false; ctx->h_dirty = true; }
-    if (prop <= B200SPH_Z || prop == B200SPH_H) ctx->grid_valid = false;
+    if (prop <= B200SPH_Z || prop == B200SPH_H) ctx->grid_valid = false, ctx->packed_valid = false;
     ctx->state_packed = false;
     return 0;
 }
@@ -1912,7 +1939,7 @@ int b200sph_set_kernel(b200sph_ctx *ctx, int kernel, int dim)
     ctx->dim = dim;
     ctx->radius_scale = (kernel == B200SPH_KERNEL_QUINTIC_SPLINE || kernel == B200SPH_KERNEL_GAUSSIAN) ? 3.0 : 2.0;
     ctx->domain_valid = false;
-    ctx->grid_valid = false;
+    ctx->grid_valid = false, ctx->packed_valid = false;
     ctx->topo_dirty = true;
     ctx->h_dirty = true;
     return 0;
@@ -1941,7 +1968,7 @@ int b200sph_set_domain(b200sph_ctx *ctx, const double lo[3], const double hi[3],
         ctx->dom_lo[d] = lo[d];
         ctx->dom_hi[d] = hi[d];
     }
-    ctx->grid_valid = false;
+    ctx->grid_valid = false, ctx->packed_valid = false;
     ctx->topo_dirty = true;
     return 0;
 }
@@ -1966,7 +1993,7 @@ int b200sph_update_domain(b200sph_ctx *ctx)
                                                                                    ctx->ptype, ctx->pool_end, D);
             LAUNCH_CHECK();
         }
-        ctx->grid_valid = false;
+        ctx->grid_valid = false, ctx->packed_valid = false;
         ctx->state_packed = false;
     }
     if (ctx->domain_valid && !ctx->h_dirty) return 0;  // h untouched since the last reduction
@@ -1980,7 +2007,7 @@ int b200sph_update_domain(b200sph_ctx *ctx)
     double cell = ctx->radius_scale * hmax;
     ctx->hmin_scaled = ctx->radius_scale * hmin;
     if (cell < 1e-6) cell = 1.0;
-    if (cell != ctx->cell_size) ctx->grid_valid = false;
+    if (cell != ctx->cell_size) ctx->grid_valid = false, ctx->packed_valid = false;
     ctx->cell_size = cell;
     ctx->domain_valid = true;
     ctx->h_dirty = false;
@@ -2006,6 +2033,7 @@ static int nnps_light_update(b200sph_ctx *ctx)
         // the drift was just measured by b200sph_nnps_drift (multi-GPU: the decision to
         // keep the build is collective); only refresh the packed positions, no host sync
         ctx->drift_ok = false;
+        if (ctx->packed_valid) return 1;   // nnps_drift_device packed them, halo_overwrite_all kept the ghosts current
         k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
             ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
             ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
@@ -2040,7 +2068,7 @@ static int confirm_pending(b200sph_ctx *ctx, int *redo)
     if (!drift_within_skin(ctx, ctx->drift_host)) {
         // the evaluation that followed used stale lists: force the full rebuild
         ctx->topo_dirty = true;
-        ctx->grid_valid = false;
+        ctx->grid_valid = false, ctx->packed_valid = false;
         ctx->n_light_updates--;
         ctx->n_deferred_failed++;
         *redo = 1;
@@ -2400,7 +2428,7 @@ int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim, int real_o
     }
     ctx->domain_valid = false;  // h changed: the next update_domain must re-reduce it
     ctx->h_dirty = true;
-    ctx->grid_valid = false;
+    ctx->grid_valid = false, ctx->packed_valid = false;
     return 0;
 }
 
@@ -2529,7 +2557,7 @@ static int stage_impl(b200sph_ctx *ctx, int arr, int which, double dt, bool devd
         LAUNCH_CHECK();
     }
     if (which != 0) {
-        ctx->grid_valid = false;  // particles moved: neighbours are stale until nnps_update
+        ctx->grid_valid = false, ctx->packed_valid = false;  // particles moved: neighbours are stale until nnps_update
         ctx->state_packed = false;
     }
     return 0;
@@ -2738,7 +2766,7 @@ int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf, int64_
     ai.n += n;
     if (as_real) ai.n_real += n;
     ctx->ptype_dirty = true;
-    ctx->grid_valid = false;
+    ctx->grid_valid = false, ctx->packed_valid = false;
     ctx->topo_dirty = true;
     ctx->h_dirty = true;
     ctx->domain_valid = false;
@@ -2776,7 +2804,7 @@ int b200sph_halo_overwrite(b200sph_ctx *ctx, int arr, int64_t ghost_first, const
     k_halo_scatter<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), o, dev_buf, stride, n);
     LAUNCH_CHECK();
     // values moved, the particle set did not: a light nnps_update is enough
-    ctx->grid_valid = false;
+    ctx->grid_valid = false, ctx->packed_valid = false;
     ctx->state_packed = false;
     return 0;
 }
@@ -2848,9 +2876,19 @@ int b200sph_halo_overwrite_all(b200sph_ctx *ctx, const int64_t *ghost_first, con
     }
     const int64_t tot = A.prefix[ctx->narr];
     if (tot == 0) return 0;
-    k_halo_scatter_all<<<(unsigned)cdiv(tot, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), A, dev_buf);
+    // with a reusable build whose packed positions are current (nnps_drift_device just
+    // ran) only the ghosts moved: refresh their packed records here and keep the flag
+    const bool repack = ctx->packed_valid && ctx->lists_valid && !ctx->topo_dirty && ctx->force_kernel == 0 && ctx->n_sorted > 0;
+    RepackArgs R;
+    R.rank = repack ? ctx->rank : nullptr;
+    R.skey = ctx->skey;
+    R.A = ctx->A;
+    R.AB = ctx->AB;
+    R.G = ctx->G;
+    k_halo_scatter_all<<<(unsigned)cdiv(tot, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), A, dev_buf, R);
     LAUNCH_CHECK();
     ctx->grid_valid = false;
+    ctx->packed_valid = repack;
     ctx->state_packed = false;
     return 0;
 }
@@ -2911,6 +2949,7 @@ int b200sph_nnps_drift_device(b200sph_ctx *ctx, double *dev_ratio)
     LAUNCH_CHECK();
     k_drift_ratio<<<1, 1, 0, ctx->stream>>>(ctx->red_u32, (float)ctx->radius_scale, (float)ctx->S_abs, dev_ratio);
     LAUNCH_CHECK();
+    ctx->packed_valid = true;
     return 0;
 }
 
@@ -2928,7 +2967,7 @@ int b200sph_drop_ghosts(b200sph_ctx *ctx, int arr)
     if (ctx->arr[arr].n != ctx->arr[arr].n_real) {
         ctx->arr[arr].n = ctx->arr[arr].n_real;
         ctx->ptype_dirty = true;
-        ctx->grid_valid = false;
+        ctx->grid_valid = false, ctx->packed_valid = false;
         ctx->topo_dirty = true;
         ctx->h_dirty = true;
         ctx->state_packed = false;
@@ -2990,7 +3029,7 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
     }
     ai.n = ai.n_real = keep;
     ctx->ptype_dirty = true;
-    ctx->grid_valid = false;
+    ctx->grid_valid = false, ctx->packed_valid = false;
     ctx->topo_dirty = true;
     ctx->h_dirty = true;
     ctx->domain_valid = false;

@@ -251,6 +251,42 @@ class SlabParallelManager(object):
         self.n_peer_refresh = 0
         self.n_deferred_failed = 0
         self._pending = None
+        self._prof_init()
+
+    # -- optional timeline (B200SPH_PM_PROFILE=1): CPU seconds per phase and CUDA
+    #    event pairs around the collective / the halo kernels -------------------
+    def _prof_init(self):
+        import os
+        self._prof = None
+        if os.environ.get('B200SPH_PM_PROFILE') and hasattr(self.ops, 'torch'):
+            self._prof = dict(cpu={}, ev={}, n=0)
+
+    def _cpu(self, key, t0):
+        import time
+        if self._prof is not None:
+            self._prof['cpu'][key] = self._prof['cpu'].get(key, 0.0) + time.perf_counter() - t0
+
+    def _ev(self, key=None):
+        """record an event; with key, close the pair opened by the previous call"""
+        if self._prof is None:
+            return
+        e = self.ops.torch.cuda.Event(enable_timing=True)
+        e.record()
+        if key is not None:
+            self._prof['ev'].setdefault(key, []).append((self._ev_last, e))
+        self._ev_last = e
+
+    def profile_summary(self, reset=True):
+        if self._prof is None:
+            return None
+        self.ops.torch.cuda.synchronize()
+        out = dict(('cpu_ms_' + k, 1e3 * v) for k, v in self._prof['cpu'].items())
+        for k, pairs in self._prof['ev'].items():
+            out['gpu_ms_' + k] = sum(a.elapsed_time(b) for a, b in pairs)
+        out['updates'] = self._prof['n']
+        if reset:
+            self._prof = dict(cpu={}, ev={}, n=0)
+        return out
 
     # -- transport ------------------------------------------------------------
     def _exchange(self, send_counts, send_bufs, nfields):
@@ -307,12 +343,17 @@ class SlabParallelManager(object):
         all-reduced answer is "valid"; the answer travels to pinned host memory
         behind it and ``confirm()`` (called after the evaluation was enqueued)
         reads it.  All ranks read the same number, so they agree."""
+        import time
         ops = self.ops
         self._pending = None
+        t_begin = time.perf_counter()
+        if self._prof is not None:
+            self._prof['n'] += 1
         if self._recv and hasattr(ops, 'drift'):
             if getattr(self, '_t1', None) is None:
                 self._t1 = ops.new_buffer(1)
             t = self._t1
+            self._ev()
             if hasattr(ops, 'drift_to'):
                 ops.drift_to(t)           # stays on the device until the all-reduce
             else:
@@ -330,7 +371,11 @@ class SlabParallelManager(object):
                     if sum(self._sent[nb]):
                         ops.pack_selected_all(slot, self._peer['remote'][nb][self._parity],
                                               self._peer['cap'])
+            self._ev('drift+send')
+            t_ar = time.perf_counter()
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            self._cpu('all_reduce_call', t_ar)
+            self._ev('all_reduce')
             if deferred and hasattr(ops, 'read_later'):
                 self._pending = ops.read_later(t)
                 ok = True
@@ -347,18 +392,27 @@ class SlabParallelManager(object):
                     self.n_peer_refresh += 1
                 else:
                     self._refresh_ghosts()
+                self._ev('overwrite')
                 if hasattr(ops, 'keep_build'):
                     if not ops.keep_build(strict=self._pending is None):
                         return              # deferred and no local build: confirm() says redo
                 self.n_refresh += 1
+                self._cpu('update', t_begin)
                 return
         self._full_update()
+        self._cpu('update_full', t_begin)
 
     def confirm(self):
         """After a deferred update: True if the refresh was not enough -- the full
         path has then been run and the caller repeats nnps.update + evaluation."""
+        import time
         pending, self._pending = self._pending, None
-        if pending is None or pending() <= 0.9:
+        if pending is None:
+            return False
+        t0 = time.perf_counter()
+        v = pending()
+        self._cpu('confirm_wait', t0)
+        if v <= 0.9:
             return False
         self.n_refresh -= 1
         self.n_deferred_failed += 1
