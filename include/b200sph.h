@@ -294,8 +294,10 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi,
 /* ---- bookkeeping -------------------------------------------------------- */
 int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out);
 int b200sph_reset_stats(b200sph_ctx *ctx);
-/* enable (1) / disable (0) per-phase CUDA-event timing: event pairs are
- * recorded on the stream (no sync) and resolved by b200sph_get_stats */
+/* per-phase CUDA-event timing: 0 off, 1 every phase (ms_nnps, ms_pair, ms_other),
+ * 2 the pair kernels only (ms_pair; two events per pair pass instead of ~25 per
+ * step).  Event pairs are recorded on the stream (no sync) and resolved by
+ * b200sph_get_stats */
 int b200sph_set_profiling(b200sph_ctx *ctx, int on);
 
 #ifdef __cplusplus

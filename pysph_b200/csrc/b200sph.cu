@@ -166,7 +166,7 @@ struct b200sph_ctx {
 
     // stats
     b200sph_stats stats;
-    bool profiling = false;
+    int profiling = 0;          // 0 off, 1 every phase, 2 the pair kernels only
     bool async_copies = false;  // push/pull return without waiting (pinned host buffers)
     std::vector<PendingEvent> pending;
     std::vector<cudaEvent_t> ev_pool;
@@ -1611,7 +1611,7 @@ struct PhaseTimer {
 
 PhaseTimer::PhaseTimer(b200sph_ctx *c, int s) : ctx(c), slot(s)
 {
-    if (!ctx->profiling) return;
+    if (!ctx->profiling || (ctx->profiling == 2 && slot != 1)) return;
     for (cudaEvent_t *e : {&e0, &e1}) {
         if (!ctx->ev_pool.empty()) {
             *e = ctx->ev_pool.back();
@@ -3077,7 +3077,7 @@ int b200sph_set_async_copies(b200sph_ctx *ctx, int on)
 }
 int b200sph_set_profiling(b200sph_ctx *ctx, int on)
 {
-    ctx->profiling = on != 0;
+    ctx->profiling = on < 0 ? 0 : (on > 2 ? 1 : on);
     return 0;
 }
 
