@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define B200SPH_MAX_ARRAYS 8
-#define B200SPH_ABI_VERSION 1
+#define B200SPH_ABI_VERSION 2
 
 typedef struct b200sph_ctx b200sph_ctx;
 
@@ -54,6 +54,13 @@ enum {
     B200SPH_P, B200SPH_CS, B200SPH_ARHO, B200SPH_AU, B200SPH_AV, B200SPH_AW,
     B200SPH_AX, B200SPH_AY, B200SPH_AZ, B200SPH_DT_CFL, B200SPH_DT_FORCE,
     B200SPH_NUM_REAL_PROPS,
+    /* transport-velocity / EDAC extension (wc/edac.py:724-730).  fp64: advection
+     * velocity and the EVOLVED pressure of the EDAC scheme (B200SPH_P above is the
+     * fp32 pressure an equation of state derives); fp32: derived fields */
+    B200SPH_UHAT = 27, B200SPH_VHAT, B200SPH_WHAT, B200SPH_PF, B200SPH_PF0,
+    B200SPH_VOL = 32, B200SPH_PAVG, B200SPH_AUHAT, B200SPH_AVHAT, B200SPH_AWHAT,
+    B200SPH_AP,
+    B200SPH_NUM_PROPS = 38,
     /* 32-bit integer props */
     B200SPH_GID = 64, B200SPH_TAG = 65, B200SPH_PID = 66
 };
@@ -78,6 +85,28 @@ typedef struct {
     double gx, gy, gz;          /* MomentumEquation body force               */
     double eps_xsph;            /* XSPHCorrection(eps=...)                   */
 } b200sph_pair_program;
+
+/* pair-equation bits of the EDAC scheme's momentum group */
+enum {
+    B200SPH_TVF_PGRAD = 1,   /* MomentumEquationPressureGradient   wc/edac.py:389-488 */
+    B200SPH_TVF_AV = 2,      /* MomentumEquationArtificialViscosity transport_velocity.py:389-448 */
+    B200SPH_TVF_VISC = 4,    /* MomentumEquationViscosity          transport_velocity.py:328-386 */
+    B200SPH_TVF_ASTRESS = 8, /* MomentumEquationArtificialStress   transport_velocity.py:451-545 */
+    B200SPH_TVF_EDAC = 16    /* EDACEquation                       wc/edac.py:354-386 */
+};
+
+/* The two Groups EDACScheme._get_internal_flow_equations (wc/edac.py:776-880) emits
+ * for fluids without solids: every fluid array is a destination and a source. */
+typedef struct {
+    uint32_t fluid_mask; /* bit a: array a is a fluid                           */
+    int32_t bql;         /* ComputeAveragePressure (wc/edac.py:62-79) in group 1 */
+    uint32_t eqbits;     /* B200SPH_TVF_* of group 2                            */
+    int32_t passes;      /* bit 0: group 1 (TVF SummationDensity [+ average p],
+                          * real=False), bit 1: group 2 (real=True)              */
+    double pb, nu, edac_nu, c0, rho0, alpha;
+    double gx, gy, gz;   /* body force; damped by tdamp at time t (:483-488)     */
+    double tdamp, t;
+} b200sph_tvf_program;
 
 typedef struct {
     double cell_size;  /* DomainManager.cell_size  nnps_base.pyx:942-978    */
@@ -187,6 +216,17 @@ int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim,
  * (dest, source) loops); counting costs one extra atomic per warp. */
 int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog,
                       int64_t *pairs_out);
+
+/* The EDAC scheme's evaluation (transport-velocity branch): group 1 computes
+ * V = sum W, rho = m V (transport_velocity.py:24-58) and the neighbour-average
+ * pressure; group 2 the momentum terms (au.., auhat..) and ap.  Both walk the same
+ * persistent neighbour lists as pair_pass.  pairs_out may be NULL. */
+int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog,
+                     int64_t *pairs_out);
+/* EDACTVFStep wc/edac.py:491-540; which: 0 initialize, 1 stage1, 2 stage2 */
+int b200sph_stage_tvf(b200sph_ctx *ctx, int arr, int which, double dt);
+/* the same with dt read from the device-resident time-control block */
+int b200sph_stage_tvf_dev(b200sph_ctx *ctx, int arr, int which);
 
 /* ---- Integrator stages: WCSPHStep integrator_step.py:38-91 -------------- */
 /* which: 0 initialize, 1 stage1, 2 stage2; arr = -1 -> every array */

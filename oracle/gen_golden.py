@@ -54,10 +54,26 @@ def load_reference():
             self.sources = sources
             self.no_source = sources is None
 
+    class Group(object):
+        def __init__(self, equations, real=True, **kw):
+            self.equations = equations
+            self.real = real
+
     stub.Equation = Equation
+    stub.Group = Group
     for pkg in ('pysph', 'pysph.sph', 'pysph.sph.wc', 'pysph.base'):
         sys.modules.setdefault(pkg, types.ModuleType(pkg))
     sys.modules['pysph.sph.equation'] = stub
+    # what wc/edac.py imports besides the equations: a Scheme base and two helpers
+    # it only uses in methods that are not called here
+    utils = types.ModuleType('pysph.base.utils')
+    utils.get_particle_array = None
+    utils.DEFAULT_PROPS = set()
+    sys.modules['pysph.base.utils'] = utils
+    scheme = types.ModuleType('pysph.sph.scheme')
+    scheme.Scheme = type('Scheme', (object,), {})
+    scheme.add_bool_argument = None
+    sys.modules['pysph.sph.scheme'] = scheme
     kernels = _load('pysph.base.kernels',
                     os.path.join(REF, 'pysph/base/kernels.py'))
     basic = _load('pysph.sph.basic_equations',
@@ -70,6 +86,14 @@ def load_reference():
     sys.path.insert(0, os.path.join(HERE, '_ref'))
     import c_kernels
     return kernels, basic, wc, steps, c_kernels
+
+
+def load_reference_edac():
+    """wc/transport_velocity.py and wc/edac.py, unmodified (after load_reference)."""
+    tvf = _load('pysph.sph.wc.transport_velocity',
+                os.path.join(REF, 'pysph/sph/wc/transport_velocity.py'))
+    edac = _load('pysph.sph.wc.edac', os.path.join(REF, 'pysph/sph/wc/edac.py'))
+    return tvf, edac
 
 
 def call(method, env):
@@ -139,7 +163,7 @@ def pair_symbols(kernel, d, s, di, si):
                 RHOIJ=RHOIJ, RHOIJ1=RHOIJ1, WIJ=WIJ, DWIJ=DWIJ, WDP=WDP)
 
 
-def evaluate_reference(kernel, arrays, groups):
+def evaluate_reference(kernel, arrays, groups, t=0.0):
     """Our driver (mako:10-154) around the reference's loop bodies.
     arrays: dict name -> dict prop -> list;  groups: list of (real, [eq])."""
     k2 = kernel.radius_scale
@@ -153,6 +177,7 @@ def evaluate_reference(kernel, arrays, groups):
             npd = d['_n_real'] if real else len(d['x'])
             deqs = [e for e in eqs if e.dest == dname]
             denv = dict(('d_' + k, v) for k, v in d.items() if k[0] != '_')
+            denv['t'] = t
             for di in range(npd):
                 for e in deqs:
                     if hasattr(e, 'initialize'):
@@ -269,6 +294,76 @@ def gen_wcsph_case(kernels, basic, wc, kernel_name, dim, seed, hvar=0.0,
                 outputs=arrays)
 
 
+EDAC_PROPS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'p', 'au', 'av', 'aw',
+              'uhat', 'vhat', 'what', 'auhat', 'avhat', 'awhat', 'ap', 'V', 'pavg',
+              'nnbr']
+
+
+def gen_edac_case(kernels, edac, kernel_name, dim, seed, nfluids=1, alpha=0.0,
+                  nu=0.01, bql=True, hvar=0.0, gx=0.0, tdamp=0.0, t=0.0):
+    """One evaluation of EDACScheme(fluids, solids=[], pb != 0).get_equations() --
+    the reference's own scheme method AND equation bodies -- on random particles."""
+    rs = np.random.RandomState(seed)
+    kernel = getattr(kernels, kernel_name)(dim=dim)
+    dx = 0.1
+    rho0, c0 = 1.0, 10.0
+    p0 = rho0 * c0 * c0
+    names = ['fluid', 'fluid2'][:nfluids]
+    arrays = {}
+    for k, name in enumerate(names):
+        n = 70 if k == 0 else 30
+        hi = [0.5, 0.5, 0.4 if dim == 3 else 0.0]
+        pts = rs.uniform(0.0, 1.0, size=(n, 3)) * np.array(hi)
+        a = dict((q, [0.0] * n) for q in EDAC_PROPS)
+        a['x'], a['y'], a['z'] = (list(map(float, pts[:, i])) for i in range(3))
+        v = rs.normal(size=(n, 3))
+        if dim < 3:
+            v[:, 2] = 0.0
+        a['u'], a['v'], a['w'] = (list(map(float, v[:, i])) for i in range(3))
+        vh = v + 0.05 * rs.normal(size=(n, 3)) * (np.arange(3) < dim)
+        a['uhat'], a['vhat'], a['what'] = (list(map(float, vh[:, i])) for i in range(3))
+        a['h'] = list(map(float, 1.0 * dx * (1.0 + hvar * rs.uniform(-1, 1, n))))
+        a['m'] = [float(rho0 * dx ** dim * (1.0 + 0.5 * k))] * n
+        a['p'] = list(map(float, rs.normal(scale=2.0, size=n)))
+        a['_n_real'] = n - (6 if k == 0 else 0)     # some trailing ghosts
+        arrays[name] = a
+    inputs = json.loads(json.dumps(arrays))
+    h0 = dx
+    scheme = edac.EDACScheme(names, [], dim=dim, c0=c0, nu=nu, rho0=rho0, pb=p0,
+                             gx=gx, tdamp=tdamp, h=h0, alpha=alpha, bql=bql)
+    eqs = scheme.get_equations()
+    groups = [(g.real, g.equations) for g in eqs]
+    evaluate_reference(kernel, arrays, groups, t=t)
+    params = dict(dim=dim, c0=c0, rho0=rho0, nu=nu, pb=p0, h=h0, alpha=alpha,
+                  edac_alpha=0.5, bql=bql, gx=gx, gy=0.0, gz=0.0, tdamp=tdamp, t=t,
+                  fluids=names,
+                  groups=[[type(e).__name__ for e in g.equations] for g in eqs],
+                  group_real=[bool(g.real) for g in eqs])
+    return dict(kernel=kernel_name, dim=dim, params=params, inputs=inputs,
+                outputs=arrays)
+
+
+def gen_edac_stepper(edac):
+    rs = np.random.RandomState(12)
+    n = 7
+    st = edac.EDACTVFStep()
+    names = ['x', 'y', 'z', 'u', 'v', 'w', 'p', 'x0', 'y0', 'z0', 'u0', 'v0', 'w0',
+             'p0', 'au', 'av', 'aw', 'auhat', 'avhat', 'awhat', 'uhat', 'vhat',
+             'what', 'ap']
+    a = dict((k, list(map(float, rs.normal(size=n)))) for k in names)
+    inputs = json.loads(json.dumps(a))
+    dt = 0.0123
+    res = {}
+    for which, meth in (('initialize', st.initialize), ('stage1', st.stage1),
+                        ('stage2', st.stage2)):
+        b = json.loads(json.dumps(inputs))
+        env = dict(('d_' + k, v) for k, v in b.items())
+        for i in range(n):
+            call(meth, dict(env, d_idx=i, dt=dt))
+        res[which] = b
+    return dict(dt=dt, inputs=inputs, outputs=res)
+
+
 def gen_steppers(steps):
     rs = np.random.RandomState(11)
     n = 7
@@ -361,6 +456,16 @@ def main():
         gen_wcsph_case(kernels, basic, wc, 'Gaussian', 3, 106),
     ]
     dump('wcsph_cases.json', cases)
+    tvf, edac = load_reference_edac()
+    ecases = [
+        gen_edac_case(kernels, edac, 'QuinticSpline', 2, 201),
+        gen_edac_case(kernels, edac, 'QuinticSpline', 3, 202, hvar=0.1),
+        gen_edac_case(kernels, edac, 'CubicSpline', 3, 203, nfluids=2, alpha=0.2,
+                      gx=0.7, tdamp=1.0, t=0.3),
+        gen_edac_case(kernels, edac, 'WendlandQuintic', 2, 204, nu=0.0, bql=False),
+    ]
+    dump('edac_cases.json', ecases)
+    dump('edac_stepper.json', gen_edac_stepper(edac))
 
 
 if __name__ == '__main__':

@@ -27,7 +27,10 @@ EQ_SUMDENS, EQ_CONT, EQ_MOM, EQ_XSPH, EQ_AV = 1, 2, 4, 8, 16
 
 _PTR_FIELDS = ['x', 'y', 'z', 'h', 'm', 'rho', 'u', 'v', 'w', 'p', 'cs',
                'arho', 'au', 'av', 'aw', 'ax', 'ay', 'az', 'dt_cfl',
-               'dt_force', 'x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'rho0']
+               'dt_force', 'x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'rho0',
+               'uhat', 'vhat', 'what', 'V', 'pavg', 'nnbr', 'auhat', 'avhat',
+               'awhat', 'ap', 'p0']
+TVF_PGRAD, TVF_AV, TVF_VISC, TVF_ASTRESS, TVF_EDAC = 1, 2, 4, 8, 16
 
 
 class OrcArray(C.Structure):
@@ -45,6 +48,16 @@ class OrcPairProgram(C.Structure):
                 ('eqmask', (C.c_uint32 * MAX_ARRAYS) * MAX_ARRAYS),
                 ('src_order', (C.c_int * MAX_ARRAYS) * MAX_ARRAYS),
                 ('dest_order', C.c_int * MAX_ARRAYS)]
+
+
+class OrcTvfProgram(C.Structure):
+    _fields_ = [('kernel', C.c_int), ('dim', C.c_int),
+                ('fluid_mask', C.c_uint32), ('bql', C.c_int),
+                ('eqbits', C.c_uint32),
+                ('pb', C.c_double), ('nu', C.c_double), ('edac_nu', C.c_double),
+                ('c0', C.c_double), ('rho0', C.c_double), ('alpha', C.c_double),
+                ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
+                ('tdamp', C.c_double), ('t', C.c_double)]
 
 
 def build(force=False):
@@ -86,6 +99,10 @@ def load():
         lib.orc_pair_pass.argtypes = [C.c_void_p, C.POINTER(OrcPairProgram)]
         lib.orc_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         lib.orc_dt_factors.argtypes = [C.c_void_p, C.c_void_p]
+        for f in ('orc_tvf_pass1', 'orc_tvf_pass2'):
+            getattr(lib, f).restype = C.c_int64
+            getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(OrcTvfProgram)]
+        lib.orc_stage_tvf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         lib.orc_kernel_w.restype = C.c_double
         lib.orc_kernel_w.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
         lib.orc_kernel_grad.argtypes = [C.c_int, C.c_int, C.c_void_p,
@@ -230,6 +247,27 @@ class Oracle(object):
     def stage(self, arr, which, dt):
         self.lib.orc_stage(self.h, arr, which, dt)
 
+    # -- EDAC, transport-velocity branch ---------------------------------------
+    def tvf_program(self, fluids, eqbits, bql=True, pb=0.0, nu=0.0, edac_nu=0.0,
+                    c0=0.0, rho0=0.0, alpha=0.0, gx=0.0, gy=0.0, gz=0.0,
+                    tdamp=0.0, t=0.0):
+        P = OrcTvfProgram()
+        P.kernel, P.dim = self.kid, self.dim
+        P.fluid_mask = sum(1 << f for f in fluids)
+        P.bql, P.eqbits = int(bql), eqbits
+        P.pb, P.nu, P.edac_nu, P.c0, P.rho0, P.alpha = pb, nu, edac_nu, c0, rho0, alpha
+        P.gx, P.gy, P.gz, P.tdamp, P.t = gx, gy, gz, tdamp, t
+        return P
+
+    def tvf_pass1(self, P):
+        return self.lib.orc_tvf_pass1(self.h, C.byref(P))
+
+    def tvf_pass2(self, P):
+        return self.lib.orc_tvf_pass2(self.h, C.byref(P))
+
+    def stage_tvf(self, arr, which, dt):
+        self.lib.orc_stage_tvf(self.h, arr, which, dt)
+
     def dt_factors(self):
         out = (C.c_double * 3)()
         self.lib.orc_dt_factors(self.h, out)
@@ -248,7 +286,7 @@ def periodic_box_wrap(pas, lo, hi, periodic):
             a[a > hi[d]] -= L
 
 
-def periodic_ghosts(pas, lo, hi, periodic, cell_size, n_layers=2.0):
+def periodic_ghosts(pas, lo, hi, periodic, cell_size, n_layers=2.0, factory=None):
     """_create_ghosts_periodic, pysph/base/nnps_base.pyx:744-940: returns NEW
     arrays = real particles + their periodic images (tag Ghost = 2) appended,
     ``num_real_particles`` unchanged.  Images: x first; then y images of the
@@ -280,7 +318,7 @@ def periodic_ghosts(pas, lo, hi, periodic, cell_size, n_layers=2.0):
             new = images(ghosts, name, d) + images(props, name, d)
             ghosts = cat([ghosts] + new)
         allp = cat([props, ghosts])
-        q = get_particle_array_wcsph(name=pa.name, **allp)
+        q = (factory or get_particle_array_wcsph)(name=pa.name, **allp)
         q.set_num_real_particles(nr)
         q.tag[nr:] = 2
         out.append(q)
@@ -437,3 +475,103 @@ class WCSPHOracleSolver(object):
         self.initialise()
         while self.count < max_steps:
             self.step()
+
+
+def edac_eqbits(p):
+    """Which equations EDACScheme._get_internal_flow_equations emits for fluids
+    without solids (wc/edac.py:842-878)."""
+    bits = TVF_PGRAD | TVF_ASTRESS | TVF_EDAC
+    if p.get('alpha', 0.0) > 0.0:
+        bits |= TVF_AV
+    if p.get('nu', 0.0) > 0.0:
+        bits |= TVF_VISC
+    return bits
+
+
+def edac_nu(p):
+    """EDACScheme._get_edac_nu / attributes_changed, wc/edac.py:651-655, :766-774."""
+    art_nu = p.get('edac_alpha', 0.5) * p.get('h', 0.0) * p['c0'] / 8
+    return art_nu if art_nu > 0 else p.get('nu', 0.0)
+
+
+class EDACOracleSolver(object):
+    """EDACScheme(fluids, solids=[], pb != 0) with PECIntegrator + EDACTVFStep and a
+    fixed time step (the Taylor-Green set-up, pysph/examples/taylor_green.py:
+    190-203): wc/edac.py:776-880 for the groups, integrator.py:344-361 for the
+    stage order.  ``params``: dim, c0, rho0, nu, pb, h (for edac_alpha), alpha,
+    edac_alpha, bql, gx.., tdamp, dt."""
+
+    def __init__(self, particles, params, kernel='QuinticSpline', threads=1,
+                 domain=None):
+        self.p = dict(params)
+        self.dim = self.p['dim']
+        self.domain = domain
+        self.kernel = kernel
+        self.threads = threads
+        self.pas = list(particles)
+        self.dt = self.p['dt']
+        self.t = 0.0
+        self.count = 0
+        self.pairs_last_eval = 0
+        if domain is not None:
+            self._reghost()
+        else:
+            self.o = Oracle(self.pas, self.dim, kernel, threads=threads)
+        self.update_domain()
+        self.o.nnps_update()
+        self._initialised = False
+
+    def _reghost(self):
+        lo, hi, per = self.domain
+        from pysph_b200.particle_array import get_particle_array_edac
+        real = []
+        for pa in self.pas:
+            nr = pa.get_number_of_particles(real=True)
+            real.append(get_particle_array_edac(name=pa.name, **dict(
+                (k, v[:nr].copy()) for k, v in pa.properties.items())))
+        periodic_box_wrap(real, lo, hi, per)
+        k = load().orc_kernel_radius_scale(K_IDS[self.kernel])
+        hmax = max(float(np.max(q.h)) for q in real if len(q.h))
+        self.pas = periodic_ghosts(real, lo, hi, per, k * hmax,
+                                   factory=get_particle_array_edac)
+        self.o = Oracle(self.pas, self.dim, self.kernel, threads=self.threads)
+
+    def update_domain(self):
+        if self.domain is not None:
+            self._reghost()
+        self.o.update_domain()
+
+    def evaluate(self, t=None):
+        p, o = self.p, self.o
+        fl = list(range(len(self.pas)))
+        P = o.tvf_program(fl, edac_eqbits(p), bql=p.get('bql', True), pb=p['pb'],
+                          nu=p.get('nu', 0.0), edac_nu=edac_nu(p), c0=p['c0'],
+                          rho0=p['rho0'], alpha=p.get('alpha', 0.0),
+                          gx=p.get('gx', 0.0), gy=p.get('gy', 0.0), gz=p.get('gz', 0.0),
+                          tdamp=p.get('tdamp', 0.0), t=self.t if t is None else t)
+        pairs = o.tvf_pass1(P)
+        pairs += o.tvf_pass2(P)
+        self.pairs_last_eval = pairs
+        return pairs
+
+    def initialise(self):
+        if not self._initialised:
+            self.evaluate()                 # Solver.solve -> initial_acceleration
+            self._initialised = True
+
+    def step(self):
+        # PECIntegrator.one_timestep integrator.py:344-361
+        self.initialise()
+        n = len(self.pas)
+        for a in range(n):
+            self.o.stage_tvf(a, 0, 0.0)
+        for a in range(n):
+            self.o.stage_tvf(a, 1, self.dt)
+        self.update_domain()
+        self.o.nnps_update()
+        self.evaluate(self.t)               # a_eval.compute(c_integrator.t, ...) integrator.py:286
+        for a in range(n):
+            self.o.stage_tvf(a, 2, self.dt)
+        self.update_domain()
+        self.t += self.dt
+        self.count += 1

@@ -746,3 +746,218 @@ void orc_dt_factors(orc_ctx *c, double out[3])
     out[1] = f_force;
     out[2] = hmin;
 }
+
+
+/* ------------------------------------------------------------------------ */
+/* EDAC scheme, transport-velocity branch (fluids only)                       */
+/* ------------------------------------------------------------------------ */
+
+int64_t orc_tvf_pass1(orc_ctx *c, const orc_tvf_program *P)
+{
+    const int kernel = P->kernel, dim = P->dim;
+    const double kfac = k_fac(kernel, dim);
+    int64_t total = 0;
+    for (int dst = 0; dst < c->narr; dst++) {
+        if (!(P->fluid_mask >> dst & 1u)) continue;
+        orc_array *D = &c->arr[dst];
+        const int64_t np = D->n; /* Group(real=False), wc/edac.py:838 */
+        /* initialize: transport_velocity.py:52-54, wc/edac.py:69-71 */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++) {
+            D->V[i] = 0.0;
+            D->rho[i] = 0.0;
+            if (P->bql) {
+                D->pavg[i] = 0.0;
+                D->nnbr[i] = 0.0;
+            }
+        }
+        for (int src = 0; src < c->narr; src++) {
+            if (!(P->fluid_mask >> src & 1u)) continue;
+            const orc_array *S = &c->arr[src];
+            int64_t pairs = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : pairs)
+            for (int64_t d_idx = 0; d_idx < np; d_idx++) {
+                ORC_FOR_NEIGHBORS(c, dst, src, d_idx, s_idx, {
+                    pairs++;
+                    double XIJ[3];
+                    XIJ[0] = D->x[d_idx] - S->x[s_idx];
+                    XIJ[1] = D->y[d_idx] - S->y[s_idx];
+                    XIJ[2] = D->z[d_idx] - S->z[s_idx];
+                    const double RIJ = sqrt(XIJ[0] * XIJ[0] + XIJ[1] * XIJ[1] + XIJ[2] * XIJ[2]);
+                    const double HIJ = 0.5 * (D->h[d_idx] + S->h[s_idx]);
+                    const double WIJ = k_w(kernel, dim, kfac, RIJ, HIJ);
+                    /* transport_velocity.py:56-58 */
+                    D->V[d_idx] += WIJ;
+                    D->rho[d_idx] += D->m[d_idx] * WIJ;
+                    if (P->bql) { /* wc/edac.py:73-75 */
+                        D->pavg[d_idx] += S->p[s_idx];
+                        D->nnbr[d_idx] += 1.0;
+                    }
+                });
+            }
+            total += pairs;
+        }
+        if (P->bql) { /* post_loop wc/edac.py:77-79 */
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < np; i++)
+                if (D->nnbr[i] > 0) D->pavg[i] /= D->nnbr[i];
+        }
+    }
+    return total;
+}
+
+int64_t orc_tvf_pass2(orc_ctx *c, const orc_tvf_program *P)
+{
+    const int kernel = P->kernel, dim = P->dim;
+    const double kfac = k_fac(kernel, dim);
+    const uint32_t bits = P->eqbits;
+    int64_t total = 0;
+    for (int dst = 0; dst < c->narr; dst++) {
+        if (!(P->fluid_mask >> dst & 1u)) continue;
+        orc_array *D = &c->arr[dst];
+        const int64_t np = D->n_real; /* Group(real=True) default, wc/edac.py:880 */
+        /* initialize of every equation: wc/edac.py:362-363, :438-445 */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++) {
+            D->au[i] = D->av[i] = D->aw[i] = 0.0;
+            if (bits & ORC_TVF_PGRAD) D->auhat[i] = D->avhat[i] = D->awhat[i] = 0.0;
+            if (bits & ORC_TVF_EDAC) D->ap[i] = 0.0;
+        }
+        for (int src = 0; src < c->narr; src++) {
+            if (!(P->fluid_mask >> src & 1u)) continue;
+            const orc_array *S = &c->arr[src];
+            int64_t pairs = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : pairs)
+            for (int64_t d_idx = 0; d_idx < np; d_idx++) {
+                ORC_FOR_NEIGHBORS(c, dst, src, d_idx, s_idx, {
+                    pairs++;
+                    double XIJ[3], VIJ[3], DWIJ[3] = {0, 0, 0};
+                    XIJ[0] = D->x[d_idx] - S->x[s_idx];
+                    XIJ[1] = D->y[d_idx] - S->y[s_idx];
+                    XIJ[2] = D->z[d_idx] - S->z[s_idx];
+                    VIJ[0] = D->u[d_idx] - S->u[s_idx];
+                    VIJ[1] = D->v[d_idx] - S->v[s_idx];
+                    VIJ[2] = D->w[d_idx] - S->w[s_idx];
+                    const double R2IJ = XIJ[0] * XIJ[0] + XIJ[1] * XIJ[1] + XIJ[2] * XIJ[2];
+                    const double RIJ = sqrt(R2IJ);
+                    const double HIJ = 0.5 * (D->h[d_idx] + S->h[s_idx]);
+                    const double EPS = 0.01 * HIJ * HIJ;
+                    k_grad(kernel, dim, kfac, XIJ, RIJ, HIJ, DWIJ);
+                    const double rhoi = D->rho[d_idx], rhoj = S->rho[s_idx];
+                    const double Vi = 1.0 / D->V[d_idx], Vj = 1.0 / S->V[s_idx];
+                    const double Vi2 = Vi * Vi, Vj2 = Vj * Vj;
+                    const double mi1 = 1.0 / D->m[d_idx];
+                    if (bits & ORC_TVF_PGRAD) { /* wc/edac.py:447-481 */
+                        const double pavg = D->pavg[d_idx];
+                        const double pi = D->p[d_idx], pj = S->p[s_idx];
+                        double pij = rhoj * (pi - pavg) + rhoi * (pj - pavg);
+                        pij /= (rhoj + rhoi);
+                        double tmp = -pij * mi1 * (Vi2 + Vj2);
+                        D->au[d_idx] += tmp * DWIJ[0];
+                        D->av[d_idx] += tmp * DWIJ[1];
+                        D->aw[d_idx] += tmp * DWIJ[2];
+                        tmp = -P->pb * mi1 * (Vi2 + Vj2);
+                        D->auhat[d_idx] += tmp * DWIJ[0];
+                        D->avhat[d_idx] += tmp * DWIJ[1];
+                        D->awhat[d_idx] += tmp * DWIJ[2];
+                    }
+                    if (bits & ORC_TVF_AV) { /* transport_velocity.py:432-448 */
+                        const double RHOIJ1 = 1.0 / (0.5 * (rhoi + rhoj));
+                        const double vijdotrij = VIJ[0] * XIJ[0] + VIJ[1] * XIJ[1] + VIJ[2] * XIJ[2];
+                        double piij = 0.0;
+                        if (vijdotrij < 0) {
+                            const double muij = (HIJ * vijdotrij) / (R2IJ + EPS);
+                            piij = -P->alpha * P->c0 * muij;
+                            piij = S->m[s_idx] * piij * RHOIJ1;
+                        }
+                        D->au[d_idx] += -piij * DWIJ[0];
+                        D->av[d_idx] += -piij * DWIJ[1];
+                        D->aw[d_idx] += -piij * DWIJ[2];
+                    }
+                    if (bits & ORC_TVF_VISC) { /* transport_velocity.py:362-386 */
+                        const double etai = P->nu * rhoi, etaj = P->nu * rhoj;
+                        const double etaij = 2 * (etai * etaj) / (etai + etaj);
+                        const double Fij = DWIJ[0] * XIJ[0] + DWIJ[1] * XIJ[1] + DWIJ[2] * XIJ[2];
+                        const double tmp = mi1 * (Vi2 + Vj2) * etaij * Fij / (R2IJ + EPS);
+                        D->au[d_idx] += tmp * VIJ[0];
+                        D->av[d_idx] += tmp * VIJ[1];
+                        D->aw[d_idx] += tmp * VIJ[2];
+                    }
+                    if (bits & ORC_TVF_ASTRESS) { /* transport_velocity.py:473-545 */
+                        const double ui = D->u[d_idx], vi = D->v[d_idx], wi = D->w[d_idx];
+                        const double uj = S->u[s_idx], vj = S->v[s_idx], wj = S->w[s_idx];
+                        const double dui = D->uhat[d_idx] - ui, dvi = D->vhat[d_idx] - vi, dwi = D->what[d_idx] - wi;
+                        const double duj = S->uhat[s_idx] - uj, dvj = S->vhat[s_idx] - vj, dwj = S->what[s_idx] - wj;
+                        const double Ax = 0.5 * ((rhoi * ui * dui + rhoj * uj * duj) * DWIJ[0] +
+                                                 (rhoi * ui * dvi + rhoj * uj * dvj) * DWIJ[1] +
+                                                 (rhoi * ui * dwi + rhoj * uj * dwj) * DWIJ[2]);
+                        const double Ay = 0.5 * ((rhoi * vi * dui + rhoj * vj * duj) * DWIJ[0] +
+                                                 (rhoi * vi * dvi + rhoj * vj * dvj) * DWIJ[1] +
+                                                 (rhoi * vi * dwi + rhoj * vj * dwj) * DWIJ[2]);
+                        const double Az = 0.5 * ((rhoi * wi * dui + rhoj * wj * duj) * DWIJ[0] +
+                                                 (rhoi * wi * dvi + rhoj * wj * dvj) * DWIJ[1] +
+                                                 (rhoi * wi * dwi + rhoj * wj * dwj) * DWIJ[2]);
+                        const double tmp = mi1 * (Vi2 + Vj2);
+                        D->au[d_idx] += tmp * Ax;
+                        D->av[d_idx] += tmp * Ay;
+                        D->aw[d_idx] += tmp * Az;
+                    }
+                    if (bits & ORC_TVF_EDAC) { /* wc/edac.py:365-386 */
+                        const double etaij = 2 * P->edac_nu * (rhoi * rhoj) / (rhoi + rhoj);
+                        const double vijdotdwij = DWIJ[0] * VIJ[0] + DWIJ[1] * VIJ[1] + DWIJ[2] * VIJ[2];
+                        D->ap[d_idx] += rhoi / rhoj * P->c0 * P->c0 * S->m[s_idx] * vijdotdwij;
+                        const double xijdotdwij = DWIJ[0] * XIJ[0] + DWIJ[1] * XIJ[1] + DWIJ[2] * XIJ[2];
+                        const double tmp = mi1 * (Vi2 + Vj2) * etaij * xijdotdwij / (R2IJ + EPS);
+                        D->ap[d_idx] += tmp * (D->p[d_idx] - S->p[s_idx]);
+                    }
+                });
+            }
+            total += pairs;
+        }
+        if (bits & ORC_TVF_PGRAD) { /* post_loop wc/edac.py:483-488 */
+            double damp = 1.0;
+            if (P->t < P->tdamp) damp = 0.5 * (sin((-0.5 + P->t / P->tdamp) * M_PI) + 1.0);
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < np; i++) {
+                D->au[i] += P->gx * damp;
+                D->av[i] += P->gy * damp;
+                D->aw[i] += P->gz * damp;
+            }
+        }
+    }
+    return total;
+}
+
+/* EDACTVFStep wc/edac.py:491-540 (real particles, integrator_cython.mako:97-111) */
+void orc_stage_tvf(orc_ctx *c, int arr, int which, double dt)
+{
+    orc_array *A = &c->arr[arr];
+    const int64_t n = A->n_real;
+    if (which == 0) {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; i++) {
+            A->x0[i] = A->x[i];
+            A->y0[i] = A->y[i];
+            A->z0[i] = A->z[i];
+            A->u0[i] = A->u[i];
+            A->v0[i] = A->v[i];
+            A->w0[i] = A->w[i];
+            A->p0[i] = A->p[i];
+        }
+        return;
+    }
+    const double f = (which == 1) ? 0.5 * dt : dt;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        A->u[i] = A->u0[i] + f * A->au[i];
+        A->v[i] = A->v0[i] + f * A->av[i];
+        A->w[i] = A->w0[i] + f * A->aw[i];
+        A->uhat[i] = A->u[i] + f * A->auhat[i];
+        A->vhat[i] = A->v[i] + f * A->avhat[i];
+        A->what[i] = A->w[i] + f * A->awhat[i];
+        A->x[i] = A->x0[i] + f * A->uhat[i];
+        A->y[i] = A->y0[i] + f * A->vhat[i];
+        A->z[i] = A->z0[i] + f * A->what[i];
+        A->p[i] = A->p0[i] + f * A->ap[i];
+    }
+}

@@ -45,6 +45,8 @@ typedef struct {
     double *x, *y, *z, *h, *m, *rho, *u, *v, *w, *p, *cs;
     double *arho, *au, *av, *aw, *ax, *ay, *az, *dt_cfl, *dt_force;
     double *x0, *y0, *z0, *u0, *v0, *w0, *rho0;
+    /* transport-velocity / EDAC properties (wc/edac.py:724-730); may be NULL */
+    double *uhat, *vhat, *what, *V, *pavg, *nnbr, *auhat, *avhat, *awhat, *ap, *p0;
 } orc_array;
 
 typedef struct {
@@ -65,6 +67,24 @@ typedef struct {
     /* dest_order[k]: k-th destination array; -1 terminates */
     int dest_order[ORC_MAX_ARRAYS];
 } orc_pair_program;
+
+/* EDAC scheme, internal-flow (transport velocity) branch for fluid arrays without
+ * solids: EDACScheme._get_internal_flow_equations wc/edac.py:776-870 */
+enum {
+    ORC_TVF_PGRAD   = 1,  /* MomentumEquationPressureGradient  wc/edac.py:389-488 */
+    ORC_TVF_AV      = 2,  /* MomentumEquationArtificialViscosity transport_velocity.py:389-448 */
+    ORC_TVF_VISC    = 4,  /* MomentumEquationViscosity         transport_velocity.py:328-386 */
+    ORC_TVF_ASTRESS = 8,  /* MomentumEquationArtificialStress  transport_velocity.py:451-545 */
+    ORC_TVF_EDAC    = 16  /* EDACEquation                      wc/edac.py:354-386 */
+};
+typedef struct {
+    int kernel, dim;
+    uint32_t fluid_mask; /* bit a: array a is a fluid; every fluid is a destination and a source */
+    int bql;             /* ComputeAveragePressure wc/edac.py:62-79 in the first group */
+    uint32_t eqbits;     /* ORC_TVF_* of the second group */
+    double pb, nu, edac_nu, c0, rho0, alpha;
+    double gx, gy, gz, tdamp, t;
+} orc_tvf_program;
 
 typedef struct orc_ctx orc_ctx;
 
@@ -110,6 +130,14 @@ void orc_stage(orc_ctx *, int arr, int which, double dt);
 /* a19 inputs: max dt_cfl, max dt_force over real+ghost of all arrays that have
  * them (integrator.py:62-81), raw min h (integrator.py:146-159, start 1.0) */
 void orc_dt_factors(orc_ctx *, double out[3]);
+
+/* group 1 (real=False): TVF SummationDensity transport_velocity.py:24-58 and
+ * ComputeAveragePressure wc/edac.py:62-79.  Returns the pairs visited. */
+int64_t orc_tvf_pass1(orc_ctx *, const orc_tvf_program *);
+/* group 2 (real=True): the momentum terms and the EDAC pressure evolution */
+int64_t orc_tvf_pass2(orc_ctx *, const orc_tvf_program *);
+/* EDACTVFStep wc/edac.py:491-540: which = 0 initialize, 1 stage1, 2 stage2 */
+void orc_stage_tvf(orc_ctx *, int arr, int which, double dt);
 
 /* single kernel evaluations for the kernel parity tests */
 double orc_kernel_w(int kernel, int dim, double rij, double h);

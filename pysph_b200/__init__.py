@@ -21,7 +21,7 @@ There is no CPU fallback: importing the adapters is cheap, but creating a
 backend needs the built library and a CUDA device.
 """
 from .particle_array import (ParticleArray, get_particle_array,
-                             get_particle_array_wcsph)
+                             get_particle_array_wcsph, get_particle_array_edac)
 from .kernels import CubicSpline, WendlandQuintic, QuinticSpline, Gaussian
 from .equations import (Equation, Group, SummationDensity, ContinuityEquation,
                         MonaghanArtificialViscosity, XSPHCorrection, TaitEOS,
@@ -35,6 +35,7 @@ from .acceleration_eval import B200AccelerationEval
 from .integrator import (B200Integrator, PECIntegrator, EPECIntegrator,
                          WCSPHStep)
 from .solver import B200Solver
+from .edac import EDACScheme, EDACTVFStep
 
 __version__ = '0.1.0'
 
@@ -56,3 +57,15 @@ def make_wcsph_solver(particles, params, kernel, device=0, **solver_kw):
     kw.update(solver_kw)
     return B200Solver(particles, scheme.get_equations(), kernel, integrator,
                       dt=dt0, **kw)
+
+
+def make_edac_solver(particles, scheme, kernel, dt, domain=None, integrator='PEC',
+                     device=0, **solver_kw):
+    """Fixed-dt solver for an :class:`EDACScheme` (the reference's configure_solver
+    default is PECIntegrator + EDACTVFStep, wc/edac.py:657-702)."""
+    cls = {'EPEC': EPECIntegrator, 'PEC': PECIntegrator}[integrator]
+    integ = cls(**scheme.get_steppers())
+    kw = dict(adaptive_timestep=False, tf=1e9, fixed_h=True, device=device,
+              domain=domain)
+    kw.update(solver_kw)
+    return B200Solver(particles, scheme.get_equations(), kernel, integ, dt=dt, **kw)

@@ -18,6 +18,12 @@ for _i, _n in enumerate(['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm',
                          'p', 'cs', 'arho', 'au', 'av', 'aw', 'ax', 'ay', 'az',
                          'dt_cfl', 'dt_force']):
     PROP_IDS[_n] = _i
+# transport-velocity / EDAC extension (B200SPH_UHAT ...)
+PROP_IDS.update(uhat=27, vhat=28, what=29, V=32, pavg=33, auhat=34, avhat=35,
+                awhat=36, ap=37)
+# arrays of the EDAC scheme (they own 'ap') integrate p: it lives in the fp64
+# B200SPH_PF / B200SPH_PF0 instead of the derived fp32 B200SPH_P
+EDAC_PROP_IDS = dict(PROP_IDS, p=30, p0=31)
 INT_PROP_IDS = {'gid': 64, 'tag': 65, 'pid': 66}
 F64_DEVICE_PROPS = ('x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm',
                     'x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'rho0')
@@ -40,6 +46,18 @@ class PairProgram(C.Structure):
                 ('c0', C.c_double), ('alpha', C.c_double), ('beta', C.c_double),
                 ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
                 ('eps_xsph', C.c_double)]
+
+
+TVF_PGRAD, TVF_AV, TVF_VISC, TVF_ASTRESS, TVF_EDAC = 1, 2, 4, 8, 16
+
+
+class TvfProgram(C.Structure):
+    _fields_ = [('fluid_mask', C.c_uint32), ('bql', C.c_int32),
+                ('eqbits', C.c_uint32), ('passes', C.c_int32),
+                ('pb', C.c_double), ('nu', C.c_double), ('edac_nu', C.c_double),
+                ('c0', C.c_double), ('rho0', C.c_double), ('alpha', C.c_double),
+                ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
+                ('tdamp', C.c_double), ('t', C.c_double)]
 
 
 class GridInfo(C.Structure):
@@ -96,6 +114,9 @@ SIGNATURES = {
     'b200sph_ferrari_h': (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_int, C.c_int]),
     'b200sph_pair_pass': (C.c_int, [_ctx_p, C.POINTER(PairProgram),
                                     C.POINTER(_i64)]),
+    'b200sph_tvf_pass': (C.c_int, [_ctx_p, C.POINTER(TvfProgram), C.POINTER(_i64)]),
+    'b200sph_stage_tvf': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
+    'b200sph_stage_tvf_dev': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
     'b200sph_stage': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
     'b200sph_dt_factors': (C.c_int, [_ctx_p, _dp]),
     'b200sph_time_control': (C.c_int, [_ctx_p, C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -66,6 +66,13 @@ class B200AccelerationEval(object):
                     pairs += cnt.value
                 else:
                     ctx.call('b200sph_pair_pass', C.byref(op[1]), None)
+            elif kind == 'tvf':
+                op[1].t = float(t)          # body-force damping, wc/edac.py:483-488
+                if self.count_pairs:
+                    ctx.call('b200sph_tvf_pass', C.byref(op[1]), C.byref(cnt))
+                    pairs += cnt.value
+                else:
+                    ctx.call('b200sph_tvf_pass', C.byref(op[1]), None)
             elif kind == 'update_nnps':
                 # mako:139-145: nnps.update_domain(); nnps.update()
                 ctx.call('b200sph_update_domain')

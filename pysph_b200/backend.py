@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import PROP_IDS, INT_PROP_IDS
+from ._lib import PROP_IDS, INT_PROP_IDS, EDAC_PROP_IDS
 
 
 def _host_array(pa, name):
@@ -71,6 +71,9 @@ class B200Backend(object):
         self.particle_arrays = list(particle_arrays)
         self.names = [pa.name for pa in particle_arrays]
         self.index = dict((n, i) for i, n in enumerate(self.names))
+        # name -> device property id, per array: EDAC arrays evolve p (fp64 PF)
+        self.prop_ids = [EDAC_PROP_IDS if 'ap' in pa.properties else PROP_IDS
+                         for pa in particle_arrays]
         for pa in particle_arrays:
             n = pa.get_number_of_particles()
             n_real = pa.get_number_of_particles(real=True)
@@ -94,10 +97,10 @@ class B200Backend(object):
         self.ctx.call('b200sph_resize_array', i, int(n), int(n_real))
 
     # -- host <-> device ------------------------------------------------------
-    def _props_of(self, pa, props):
+    def _props_of(self, pa, props, ids=PROP_IDS):
         if props is None:
             props = [p for p in pa.properties
-                     if p in PROP_IDS or p in INT_PROP_IDS]
+                     if p in ids or p in INT_PROP_IDS]
         return props
 
     def push(self, i, props=None):
@@ -106,11 +109,12 @@ class B200Backend(object):
         dn, _ = self.sizes(i)
         if dn != n:
             self.resize(i, n, pa.get_number_of_particles(real=True))
-        for name in self._props_of(pa, props):
+        ids = self.prop_ids[i]
+        for name in self._props_of(pa, props, ids):
             a = _host_array(pa, name)
-            if name in PROP_IDS:
+            if name in ids:
                 a = np.ascontiguousarray(a, dtype=np.float64)
-                self.ctx.call('b200sph_push_f64', i, PROP_IDS[name],
+                self.ctx.call('b200sph_push_f64', i, ids[name],
                               a.ctypes.data, 0, n)
             elif name in INT_PROP_IDS:
                 a = np.ascontiguousarray(a).view(np.uint32)
@@ -127,15 +131,16 @@ class B200Backend(object):
                 pa.resize(n)
             pa.set_num_real_particles(n_real) if hasattr(
                 pa, 'set_num_real_particles') else None
-        for name in self._props_of(pa, props):
+        ids = self.prop_ids[i]
+        for name in self._props_of(pa, props, ids):
             a = _host_array(pa, name)
-            if name in PROP_IDS:
+            if name in ids:
                 if a.dtype == np.float64 and a.flags.c_contiguous:
-                    self.ctx.call('b200sph_pull_f64', i, PROP_IDS[name],
+                    self.ctx.call('b200sph_pull_f64', i, ids[name],
                                   a.ctypes.data, 0, n)
                 else:
                     tmp = np.empty(n, dtype=np.float64)
-                    self.ctx.call('b200sph_pull_f64', i, PROP_IDS[name],
+                    self.ctx.call('b200sph_pull_f64', i, ids[name],
                                   tmp.ctypes.data, 0, n)
                     a[:] = tmp
             elif name in INT_PROP_IDS:
@@ -151,7 +156,7 @@ class B200Backend(object):
             n_real = self.sizes(i)[1]
             for name in props:
                 a = _host_array(pa, name)
-                self.ctx.call('b200sph_push_f64', i, PROP_IDS[name],
+                self.ctx.call('b200sph_push_f64', i, self.prop_ids[i][name],
                               a.ctypes.data, 0, n_real)
 
     def pull_real(self, props):
@@ -159,7 +164,7 @@ class B200Backend(object):
             n_real = self.sizes(i)[1]
             for name in props:
                 a = _host_array(pa, name)
-                self.ctx.call('b200sph_pull_f64', i, PROP_IDS[name],
+                self.ctx.call('b200sph_pull_f64', i, self.prop_ids[i][name],
                               a.ctypes.data, 0, n_real)
 
     def push_all(self, props=None):

@@ -39,6 +39,8 @@
 #define N_F64 16
 #define N_F32 11
 #define N_U32 3
+#define N_F64X 5   // UHAT VHAT WHAT PF PF0 (ids 27..31)
+#define N_F32X 6   // VOL PAVG AUHAT AVHAT AWHAT AP (ids 32..37)
 #define PT_INVALID 0xFFu
 #define PT_GHOST 0x08u
 
@@ -83,6 +85,10 @@ struct b200sph_ctx {
     double *f64[N_F64] = {nullptr};
     float *f32[N_F32] = {nullptr};
     uint32_t *u32[N_U32] = {nullptr};
+    double *f64x[N_F64X] = {nullptr};   // transport-velocity / EDAC extension
+    float *f32x[N_F32X] = {nullptr};
+    float4 *Dv = nullptr;               // sorted: (uhat-u, vhat-v, what-w, pavg)
+    float2 *PT = nullptr;               // sorted: (p, type)
     uint8_t *ptype = nullptr;
     bool ptype_dirty = true;
 
@@ -1209,6 +1215,305 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_pair_list(const PairArgs a, cons
     }
 }
 
+// --------------------------------------------------------------------------
+// EDAC scheme, transport-velocity branch (wc/edac.py:776-880): two passes over the same
+// persistent neighbour lists.  Sorted records: AB = {A, B} as for k_pair_list,
+// C2 = (rho, p, V, type) [ctx->C], Dv = (uhat-u, vhat-v, what-w, pavg), PT = (p, type)
+// --------------------------------------------------------------------------
+struct TvfArgs {
+    const float4 *AB;
+    float4 *C2, *Dv;
+    const float2 *PT;
+    const uint32_t *perm;
+    double *rho;
+    float *V, *pavg, *au, *av, *aw, *auhat, *avhat, *awhat, *ap;
+    long long n;
+    float cellx, celly, cellz, k2, kfac;
+    unsigned fluid_mask, eqbits;
+    int bql;
+    float pb, nu, edac_nu, c0, alpha, gx, gy, gz;  // gx.. already damped
+    unsigned long long *pair_counter;
+};
+
+__global__ void k_pack_tvf(const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
+                           const double *__restrict__ m, const double *__restrict__ uh, const double *__restrict__ vh,
+                           const double *__restrict__ wh, const double *__restrict__ pf, const float *__restrict__ pavg,
+                           const uint8_t *__restrict__ ptype, const uint32_t *__restrict__ perm, long long n,
+                           float4 *__restrict__ B, float4 *__restrict__ AB, float4 *__restrict__ C2,
+                           float4 *__restrict__ Dv, float2 *__restrict__ PT)
+{
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t g = perm[s];
+    const int t = (int)ptype[g];
+    const double ug = u[g], vg = v[g], wg = w[g];
+    float4 b;
+    b.x = (float)ug; b.y = (float)vg; b.z = (float)wg; b.w = (float)m[g];
+    B[s] = b;
+    AB[2 * s + 1] = b;
+    // differences of nearly equal numbers: formed in fp64, then rounded
+    Dv[s] = make_float4((float)(uh[g] - ug), (float)(vh[g] - vg), (float)(wh[g] - wg), pavg[g]);
+    const float p = (float)pf[g];
+    PT[s] = make_float2(p, __int_as_float(t));
+    C2[s] = make_float4(0.f, p, 1.f, __int_as_float(t));   // rho, V filled in by pass 1
+}
+
+// group 1 (real=False): V_i = sum_j W_ij, rho_i = m_i V_i (transport_velocity.py:52-58) and the
+// neighbour-average pressure (wc/edac.py:69-79), every fluid particle incl. ghosts
+template <int K, int DIM>
+__global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const uint32_t *__restrict__ cnt,
+                                                         const uint32_t *__restrict__ lst, const int capg)
+{
+    __shared__ float4 s_T[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
+        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
+    }
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const long long s = (long long)blockIdx.x * LIST_NT + tid;
+    bool active = s < a.n;
+    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai;
+    int count = 0;
+    if (active) {
+        const int ti = __float_as_int(a.PT[s].y);
+        if (!((a.fluid_mask >> (ti & 7)) & 1u)) active = false;
+    }
+    if (active) {
+        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
+        count = (int)cnt[s];
+    }
+    int cmax = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
+    const float hi2 = a.k2 * Ai.w * Ai.w;
+    float wsum = 0.f, psum = 0.f, nn = 0.f;
+    unsigned npairs = 0;
+    for (int k = 0; k < cmax; k++) {
+        if (k < count) {
+            const uint32_t e = __ldcs(my + (size_t)k * 32u);
+            const size_t j = e & LIST_JMASK;
+            const float4 Aj = a.AB[2 * j];
+            const float2 Pj = a.PT[j];
+            const float4 T = s_T[e >> LIST_JBITS];
+            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+            const float r2 = xij * xij + yij * yij + zij * zij;
+            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Pj.y) & 7)) & 1u)) {
+                npairs++;
+                const float rij = sqrtf(r2);
+                const float h1 = frcp(0.5f * (Ai.w + Aj.w));
+                float w, dw;
+                sph_kernel<K>(rij * h1, w, dw);
+                wsum += w * a.kfac * hpow<DIM>(h1);
+                psum += Pj.x;
+                nn += 1.0f;
+            }
+        }
+    }
+    if (active) {
+        const uint32_t g = a.perm[s];
+        const float rho = Bi.w * wsum;
+        a.V[g] = wsum;
+        a.rho[g] = (double)rho;
+        float4 *c2 = a.C2 + s;
+        c2->x = rho;          // .y (p) and .w (type) were written by k_pack_tvf; other
+        c2->z = wsum;         // threads read only those two while this kernel runs
+        if (a.bql) {
+            const float pv = nn > 0.f ? psum / nn : 0.f;
+            a.pavg[g] = pv;
+            a.Dv[s].w = pv;
+        }
+    }
+    if (a.pair_counter) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
+        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
+    }
+}
+
+// group 2 (real=True): pressure gradient with the background-pressure term, artificial /
+// physical viscosity, artificial stress and the EDAC pressure evolution, fused
+template <int K, int DIM>
+__global__ void __launch_bounds__(LIST_NT, 3) k_tvf_pass2(const TvfArgs a, const uint32_t *__restrict__ cnt,
+                                                         const uint32_t *__restrict__ lst, const int capg)
+{
+    __shared__ float4 s_T[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
+        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
+    }
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const long long s = (long long)blockIdx.x * LIST_NT + tid;
+    bool active = s < a.n;
+    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = make_float4(1.f, 0.f, 1.f, 0.f), Di = Ai;
+    int count = 0;
+    if (active) {
+        Ci = a.C2[s];
+        const int ti = __float_as_int(Ci.w);
+        if ((ti & PT_GHOST) || !((a.fluid_mask >> (ti & 7)) & 1u)) active = false;
+    }
+    if (active) {
+        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
+        Di = a.Dv[s];
+        count = (int)cnt[s];
+    }
+    int cmax = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
+    const float hi2 = a.k2 * Ai.w * Ai.w;
+    const float rhoi = Ci.x, pi = Ci.y, pavg = Di.w;
+    const float Vi1 = frcp(Ci.z);
+    const float Vi2 = Vi1 * Vi1;
+    const float mi1 = frcp(Bi.w);
+    const float cs2 = a.c0 * a.c0;
+    float au = 0.f, av = 0.f, aw = 0.f, auh = 0.f, avh = 0.f, awh = 0.f, ap = 0.f;
+    unsigned npairs = 0;
+    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
+    float4 A_a = Ai, B_a = Bi, C_a = Ci, D_a = Di;
+    if (count > 0) {
+        const size_t j = e_a & LIST_JMASK;
+        ld_256(a.AB + 2 * j, A_a, B_a);
+        C_a = a.C2[j];
+        D_a = a.Dv[j];
+    }
+    for (int k = 0; k < cmax; k++) {
+        const uint32_t e = e_a;
+        const float4 Aj = A_a, Bj = B_a, Cj = C_a, Dj = D_a;
+        if (k + 1 < count) {
+            e_a = __ldcs(my + (size_t)(k + 1) * 32u);
+            const size_t j = e_a & LIST_JMASK;
+            ld_256(a.AB + 2 * j, A_a, B_a);
+            C_a = a.C2[j];
+            D_a = a.Dv[j];
+        }
+        if (k < count) {
+            const float4 T = s_T[e >> LIST_JBITS];
+            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+            const float r2 = xij * xij + yij * yij + zij * zij;
+            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
+                npairs++;
+                const bool far = r2 > 1e-24f;
+                const float rinv = far ? frsqrt(r2) : 0.0f;
+                const float rij = r2 * rinv;
+                const float hij = 0.5f * (Ai.w + Aj.w);
+                const float h1 = frcp(hij);
+                float w, dw;
+                sph_kernel<K>(rij * h1, w, dw);
+                const float gt = dw * a.kfac * hpow<DIM>(h1) * h1 * rinv;   // DWIJ = gt * XIJ
+                const float eps = 0.01f * hij * hij;
+                const float rhoj = Cj.x, pj = Cj.y;
+                const float Vj1 = frcp(Cj.z);
+                const float common = mi1 * (Vi2 + Vj1 * Vj1);
+                const float uij = Bi.x - Bj.x, vij = Bi.y - Bj.y, wij = Bi.z - Bj.z;
+                const float vdotx = uij * xij + vij * yij + wij * zij;
+                const float rsum1 = frcp(rhoi + rhoj);
+                const float r2e1 = frcp(r2 + eps);
+                float fx = 0.f;   // multiplies XIJ in au
+                if (a.eqbits & B200SPH_TVF_PGRAD) {   // wc/edac.py:447-481
+                    const float pij = (rhoj * (pi - pavg) + rhoi * (pj - pavg)) * rsum1;
+                    fx += -pij * common * gt;
+                    const float fh = -a.pb * common * gt;
+                    auh += fh * xij;
+                    avh += fh * yij;
+                    awh += fh * zij;
+                }
+                if ((a.eqbits & B200SPH_TVF_AV) && vdotx < 0.f) {   // transport_velocity.py:432-448
+                    const float muij = hij * vdotx * r2e1;
+                    const float piij = Bj.w * (-a.alpha * a.c0 * muij) * (2.0f * rsum1);
+                    fx += -piij * gt;
+                }
+                au += fx * xij;
+                av += fx * yij;
+                aw += fx * zij;
+                if (a.eqbits & B200SPH_TVF_VISC) {   // transport_velocity.py:362-386
+                    const float etaij = 2.0f * a.nu * rhoi * rhoj * rsum1;
+                    const float tmp = common * etaij * (gt * r2) * r2e1;
+                    au += tmp * uij;
+                    av += tmp * vij;
+                    aw += tmp * wij;
+                }
+                if (a.eqbits & B200SPH_TVF_ASTRESS) {   // transport_velocity.py:473-545
+                    const float si = rhoi * gt * (Di.x * xij + Di.y * yij + Di.z * zij);
+                    const float sj = rhoj * gt * (Dj.x * xij + Dj.y * yij + Dj.z * zij);
+                    const float c = 0.5f * common;
+                    au += c * (Bi.x * si + Bj.x * sj);
+                    av += c * (Bi.y * si + Bj.y * sj);
+                    aw += c * (Bi.z * si + Bj.z * sj);
+                }
+                if (a.eqbits & B200SPH_TVF_EDAC) {   // wc/edac.py:365-386
+                    const float etaij = 2.0f * a.edac_nu * rhoi * rhoj * rsum1;
+                    ap += rhoi * frcp(rhoj) * cs2 * Bj.w * (gt * vdotx);
+                    ap += common * etaij * (gt * r2) * r2e1 * (pi - pj);
+                }
+            }
+        }
+    }
+    if (active) {
+        const uint32_t g = a.perm[s];
+        if (a.eqbits & B200SPH_TVF_PGRAD) {   // post_loop wc/edac.py:483-488
+            au += a.gx; av += a.gy; aw += a.gz;
+            a.auhat[g] = auh; a.avhat[g] = avh; a.awhat[g] = awh;
+        }
+        a.au[g] = au; a.av[g] = av; a.aw[g] = aw;
+        if (a.eqbits & B200SPH_TVF_EDAC) a.ap[g] = ap;
+    }
+    if (a.pair_counter) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
+        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
+    }
+}
+
+struct StageTvfArgs {
+    double *x, *y, *z, *u, *v, *w, *pf, *uh, *vh, *wh;
+    double *x0, *y0, *z0, *u0, *v0, *w0, *pf0;
+    const float *au, *av, *aw, *auh, *avh, *awh, *ap;
+    const uint8_t *ptype;
+    long long pool_end;
+    int arr, which;
+    double f;
+};
+// EDACTVFStep wc/edac.py:491-540 (real particles)
+__device__ __forceinline__ void stage_tvf_body(const StageTvfArgs &a)
+{
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.pool_end) return;
+    uint8_t t = a.ptype[g];
+    if (t == PT_INVALID || (t & PT_GHOST)) return;
+    if (a.arr >= 0 && (t & 7) != a.arr) return;
+    if (a.which == 0) {
+        a.x0[g] = a.x[g]; a.y0[g] = a.y[g]; a.z0[g] = a.z[g];
+        a.u0[g] = a.u[g]; a.v0[g] = a.v[g]; a.w0[g] = a.w[g];
+        a.pf0[g] = a.pf[g];
+        return;
+    }
+    const double f = a.f;
+    const double u = a.u0[g] + f * (double)a.au[g];
+    const double v = a.v0[g] + f * (double)a.av[g];
+    const double w = a.w0[g] + f * (double)a.aw[g];
+    const double uh = u + f * (double)a.auh[g];
+    const double vh = v + f * (double)a.avh[g];
+    const double wh = w + f * (double)a.awh[g];
+    a.u[g] = u; a.v[g] = v; a.w[g] = w;
+    a.uh[g] = uh; a.vh[g] = vh; a.wh[g] = wh;
+    a.x[g] = a.x0[g] + f * uh;
+    a.y[g] = a.y0[g] + f * vh;
+    a.z[g] = a.z0[g] + f * wh;
+    a.pf[g] = a.pf0[g] + f * (double)a.ap[g];
+}
+__global__ void k_stage_tvf(StageTvfArgs a) { stage_tvf_body(a); }
+__global__ void k_stage_tvf_devdt(StageTvfArgs a, const double *__restrict__ tc)
+{
+    const double dt = tc[0];
+    a.f = a.which == 1 ? 0.5 * dt : dt;
+    stage_tvf_body(a);
+}
+
 // refresh the packed positions in the FROZEN sorted order / cell frames of the last
 // build and measure how far particles moved (and h grew) since then.
 // red_u32[0] = max |dx|^2 (float bits), red_u32[1] = max (h - h_build) (float bits, >= 0)
@@ -1456,8 +1761,10 @@ __global__ void k_fill_u32(uint32_t *p, long long n, uint32_t v)
 // --------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------
-static int is_f64_prop(int p) { return p >= 0 && p < N_F64; }
-static int is_f32_prop(int p) { return p >= N_F64 && p < N_F64 + N_F32; }
+static int is_f64_prop(int p) { return (p >= 0 && p < N_F64) || (p >= B200SPH_UHAT && p <= B200SPH_PF0); }
+static int is_f32_prop(int p) { return (p >= N_F64 && p < N_F64 + N_F32) || (p >= B200SPH_VOL && p <= B200SPH_AP); }
+static double *f64_ptr(b200sph_ctx *ctx, int p) { return p < N_F64 ? ctx->f64[p] : ctx->f64x[p - B200SPH_UHAT]; }
+static float *f32_ptr(b200sph_ctx *ctx, int p) { return p < N_F64 + N_F32 ? ctx->f32[p - N_F64] : ctx->f32x[p - B200SPH_VOL]; }
 static int u32_index(int p) { return (p >= B200SPH_GID && p <= B200SPH_PID) ? p - B200SPH_GID : -1; }
 
 // (re)build the pool so that every array owns [off, off+cap); moves existing data.
@@ -1470,11 +1777,14 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     }
     const int64_t alloc = std::max<int64_t>(total, 32);
     // allocate new buffers and move array by array
-    for (int k = 0; k < N_F64 + N_F32 + N_U32; k++) {
-        const size_t esz = k < N_F64 ? 8 : 4;
+    const int NB = N_F64 + N_F32 + N_U32;
+    for (int k = 0; k < NB + N_F64X + N_F32X; k++) {
+        const size_t esz = (k < N_F64 || (k >= NB && k < NB + N_F64X)) ? 8 : 4;
         void *old = k < N_F64 ? (void *)ctx->f64[k]
-                              : (k < N_F64 + N_F32 ? (void *)ctx->f32[k - N_F64]
-                                                   : (void *)ctx->u32[k - N_F64 - N_F32]);
+                  : k < N_F64 + N_F32 ? (void *)ctx->f32[k - N_F64]
+                  : k < NB ? (void *)ctx->u32[k - N_F64 - N_F32]
+                  : k < NB + N_F64X ? (void *)ctx->f64x[k - NB]
+                                    : (void *)ctx->f32x[k - NB - N_F64X];
         void *nw = nullptr;
         CU(cudaMalloc(&nw, esz * (size_t)alloc));
         CU(cudaMemsetAsync(nw, 0, esz * (size_t)alloc, ctx->stream));
@@ -1491,7 +1801,9 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
         }
         if (k < N_F64) ctx->f64[k] = (double *)nw;
         else if (k < N_F64 + N_F32) ctx->f32[k - N_F64] = (float *)nw;
-        else ctx->u32[k - N_F64 - N_F32] = (uint32_t *)nw;
+        else if (k < NB) ctx->u32[k - N_F64 - N_F32] = (uint32_t *)nw;
+        else if (k < NB + N_F64X) ctx->f64x[k - NB] = (double *)nw;
+        else ctx->f32x[k - NB - N_F64X] = (float *)nw;
     }
     if (ctx->ptype) CU(cudaFree(ctx->ptype));
     CU(cudaMalloc((void **)&ctx->ptype, (size_t)alloc));
@@ -1515,6 +1827,8 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     if (ctx->C) cudaFree(ctx->C);
     if (ctx->AB) cudaFree(ctx->AB);
     if (ctx->A0) cudaFree(ctx->A0);
+    if (ctx->Dv) cudaFree(ctx->Dv);
+    if (ctx->PT) cudaFree(ctx->PT);
     if (ctx->cnt) cudaFree(ctx->cnt);
     if (ctx->flag_a) cudaFree(ctx->flag_a);
     if (ctx->flag_b) cudaFree(ctx->flag_b);
@@ -1529,6 +1843,8 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     CU(cudaMalloc((void **)&ctx->C, 16 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->AB, 32 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->A0, 16 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->Dv, 16 * (size_t)alloc));
+    CU(cudaMalloc((void **)&ctx->PT, 8 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->cnt, 4 * (size_t)alloc));
     ctx->lists_valid = false;
     ctx->topo_dirty = true;
@@ -1712,6 +2028,9 @@ int b200sph_destroy(b200sph_ctx *ctx)
     for (int k = 0; k < N_F64; k++) cudaFree(ctx->f64[k]);
     for (int k = 0; k < N_F32; k++) cudaFree(ctx->f32[k]);
     for (int k = 0; k < N_U32; k++) cudaFree(ctx->u32[k]);
+    for (int k = 0; k < N_F64X; k++) cudaFree(ctx->f64x[k]);
+    for (int k = 0; k < N_F32X; k++) cudaFree(ctx->f32x[k]);
+    cudaFree(ctx->Dv); cudaFree(ctx->PT);
     cudaFree(ctx->ptype);
     cudaFree(ctx->key_of); cudaFree(ctx->off_in); cudaFree(ctx->cell_cnt); cudaFree(ctx->cell_start);
     cudaFree(ctx->blk_sums); cudaFree(ctx->perm_tmp); cudaFree(ctx->perm); cudaFree(ctx->skey);
@@ -1842,11 +2161,11 @@ int b200sph_push_f64(b200sph_ctx *ctx, int arr, int prop, const double *host, in
     if (count == 0) return 0;
     const int64_t o = ctx->arr[arr].off + start;
     if (is_f64_prop(prop)) {
-        CU(cudaMemcpyAsync(ctx->f64[prop] + o, host, 8 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(f64_ptr(ctx, prop) + o, host, 8 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
     } else if (is_f32_prop(prop)) {
         if ((rc = ensure_stage(ctx, count))) return rc;
         CU(cudaMemcpyAsync(ctx->stage_buf, host, 8 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
-        k_f64_to_f32<<<(unsigned)cdiv(count, 256), 256, 0, ctx->stream>>>(ctx->stage_buf, ctx->f32[prop - N_F64] + o, count);
+        k_f64_to_f32<<<(unsigned)cdiv(count, 256), 256, 0, ctx->stream>>>(ctx->stage_buf, f32_ptr(ctx, prop) + o, count);
         LAUNCH_CHECK();
     } else {
         return set_err(ctx, "push_f64: property id %d is not a floating point property", prop);
@@ -1873,10 +2192,10 @@ int b200sph_pull_f64(b200sph_ctx *ctx, int arr, int prop, double *host, int64_t 
     if (count == 0) return 0;
     const int64_t o = ctx->arr[arr].off + start;
     if (is_f64_prop(prop)) {
-        CU(cudaMemcpyAsync(host, ctx->f64[prop] + o, 8 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(host, f64_ptr(ctx, prop) + o, 8 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
     } else if (is_f32_prop(prop)) {
         if ((rc = ensure_stage(ctx, count))) return rc;
-        k_f32_to_f64<<<(unsigned)cdiv(count, 256), 256, 0, ctx->stream>>>(ctx->f32[prop - N_F64] + o, ctx->stage_buf, count);
+        k_f32_to_f64<<<(unsigned)cdiv(count, 256), 256, 0, ctx->stream>>>(f32_ptr(ctx, prop) + o, ctx->stage_buf, count);
         LAUNCH_CHECK();
         CU(cudaMemcpyAsync(host, ctx->stage_buf, 8 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
@@ -1922,8 +2241,8 @@ int b200sph_device_ptr(b200sph_ctx *ctx, int arr, int prop, void **out)
     if (rc) return rc;
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "device_ptr: bad array %d", arr);
     const int64_t o = ctx->arr[arr].off;
-    if (is_f64_prop(prop)) *out = ctx->f64[prop] + o;
-    else if (is_f32_prop(prop)) *out = ctx->f32[prop - N_F64] + o;
+    if (is_f64_prop(prop)) *out = f64_ptr(ctx, prop) + o;
+    else if (is_f32_prop(prop)) *out = f32_ptr(ctx, prop) + o;
     else if (u32_index(prop) >= 0) *out = ctx->u32[u32_index(prop)] + o;
     else return set_err(ctx, "device_ptr: bad property %d", prop);
     return 0;
@@ -2516,6 +2835,124 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     if (sumdens) ctx->state_packed = false;  // rho changed
     return 0;
 }
+
+int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog, int64_t *pairs_out)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
+    if (!ctx->grid_valid) return set_err(ctx, "tvf_pass: the NNPS is stale (particles were pushed/resized); call nnps_update first");
+    if (!(prog->passes & 3)) return set_err(ctx, "tvf_pass: passes must select group 1 and/or group 2");
+    if (prog->eqbits > 31u) return set_err(ctx, "tvf_pass: unknown equation bits 0x%x", prog->eqbits);
+    if (prog->fluid_mask == 0 || prog->fluid_mask >= (1u << ctx->narr)) return set_err(ctx, "tvf_pass: bad fluid mask 0x%x", prog->fluid_mask);
+    const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->n_sorted < (1LL << LIST_JBITS);
+    if (ctx->n_sorted == 0) return 0;
+    if (!use_lists) return set_err(ctx, "tvf_pass: the EDAC kernels need the neighbour-list path (B200SPH_PAIR_KERNEL=list, < 2^26 particles)");
+    if (!ctx->lists_valid) {
+        PhaseTimer pt_build(ctx, 0);
+        if ((rc = build_lists(ctx))) return rc;
+    }
+    PhaseTimer pt(ctx, 1);
+    const unsigned nbp = (unsigned)cdiv(ctx->n_sorted, 256);
+    k_pack_tvf<<<nbp, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_U], ctx->f64[B200SPH_V], ctx->f64[B200SPH_W], ctx->f64[B200SPH_M],
+                                             ctx->f64x[B200SPH_UHAT - B200SPH_UHAT], ctx->f64x[B200SPH_VHAT - B200SPH_UHAT],
+                                             ctx->f64x[B200SPH_WHAT - B200SPH_UHAT], ctx->f64x[B200SPH_PF - B200SPH_UHAT],
+                                             ctx->f32x[B200SPH_PAVG - B200SPH_VOL], ctx->ptype, ctx->perm, ctx->n_sorted,
+                                             ctx->B, ctx->AB, ctx->C, ctx->Dv, ctx->PT);
+    LAUNCH_CHECK();
+    ctx->state_packed = false;   // B / C no longer hold the WCSPH records
+
+    TvfArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.AB = ctx->AB; ta.C2 = ctx->C; ta.Dv = ctx->Dv; ta.PT = ctx->PT; ta.perm = ctx->perm;
+    ta.rho = ctx->f64[B200SPH_RHO];
+    ta.V = ctx->f32x[B200SPH_VOL - B200SPH_VOL]; ta.pavg = ctx->f32x[B200SPH_PAVG - B200SPH_VOL];
+    ta.au = ctx->f32[B200SPH_AU - N_F64]; ta.av = ctx->f32[B200SPH_AV - N_F64]; ta.aw = ctx->f32[B200SPH_AW - N_F64];
+    ta.auhat = ctx->f32x[B200SPH_AUHAT - B200SPH_VOL]; ta.avhat = ctx->f32x[B200SPH_AVHAT - B200SPH_VOL];
+    ta.awhat = ctx->f32x[B200SPH_AWHAT - B200SPH_VOL]; ta.ap = ctx->f32x[B200SPH_AP - B200SPH_VOL];
+    ta.n = ctx->n_sorted;
+    ta.cellx = (float)ctx->G.cell[0]; ta.celly = (float)ctx->G.cell[1]; ta.cellz = (float)ctx->G.cell[2];
+    ta.k2 = (float)(ctx->radius_scale * ctx->radius_scale);
+    ta.kfac = (float)kernel_fac(ctx->kernel, ctx->dim);
+    ta.fluid_mask = prog->fluid_mask;
+    ta.eqbits = prog->eqbits;
+    ta.bql = prog->bql;
+    ta.pb = (float)prog->pb; ta.nu = (float)prog->nu; ta.edac_nu = (float)prog->edac_nu;
+    ta.c0 = (float)prog->c0; ta.alpha = (float)prog->alpha;
+    double damp = 1.0;   // wc/edac.py:483-488
+    if (prog->t < prog->tdamp) damp = 0.5 * (std::sin((-0.5 + prog->t / prog->tdamp) * 3.14159265358979323846) + 1.0);
+    ta.gx = (float)(prog->gx * damp); ta.gy = (float)(prog->gy * damp); ta.gz = (float)(prog->gz * damp);
+    if (pairs_out) {
+        CU(cudaMemsetAsync(ctx->counter, 0, 8, ctx->stream));
+        ta.pair_counter = ctx->counter;
+    }
+    const unsigned nb = (unsigned)cdiv(ctx->n_sorted, LIST_NT);
+    for (int pass = 1; pass <= 2; pass++) {
+        if (!(prog->passes & pass)) continue;
+        switch (ctx->kernel * 4 + ctx->dim) {
+#define TVF_CASE(K, D)                                                                                   \
+    case K * 4 + D:                                                                                      \
+        if (pass == 1) k_tvf_pass1<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg); \
+        else k_tvf_pass2<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg);            \
+        break;
+            TVF_CASE(0, 1) TVF_CASE(0, 2) TVF_CASE(0, 3) TVF_CASE(1, 2) TVF_CASE(1, 3)
+            TVF_CASE(2, 1) TVF_CASE(2, 2) TVF_CASE(2, 3) TVF_CASE(3, 1) TVF_CASE(3, 2) TVF_CASE(3, 3)
+#undef TVF_CASE
+        default: return set_err(ctx, "tvf_pass: unsupported kernel/dim combination");
+        }
+        LAUNCH_CHECK();
+        ctx->stats.pair_launches++;
+    }
+    if (pairs_out) {
+        CU(cudaMemcpyAsync(ctx->counter_host, ctx->counter, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *pairs_out = (int64_t)ctx->counter_host[0];
+        ctx->stats.pairs += *pairs_out;
+    }
+    return 0;
+}
+
+static int ensure_tc(b200sph_ctx *ctx);
+static int stage_tvf_impl(b200sph_ctx *ctx, int arr, int which, double dt, bool devdt)
+{
+    if (int rcc = require_confirmed(ctx, "stage_tvf")) return rcc;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (arr >= ctx->narr) return set_err(ctx, "stage_tvf: bad array %d", arr);
+    if (which < 0 || which > 2) return set_err(ctx, "stage_tvf: which must be 0 (initialize), 1 (stage1) or 2 (stage2)");
+    if (devdt && (rc = ensure_tc(ctx))) return rc;
+    PhaseTimer pt(ctx, 2);
+    StageTvfArgs sa;
+    sa.x = ctx->f64[B200SPH_X]; sa.y = ctx->f64[B200SPH_Y]; sa.z = ctx->f64[B200SPH_Z];
+    sa.u = ctx->f64[B200SPH_U]; sa.v = ctx->f64[B200SPH_V]; sa.w = ctx->f64[B200SPH_W];
+    sa.x0 = ctx->f64[B200SPH_X0]; sa.y0 = ctx->f64[B200SPH_Y0]; sa.z0 = ctx->f64[B200SPH_Z0];
+    sa.u0 = ctx->f64[B200SPH_U0]; sa.v0 = ctx->f64[B200SPH_V0]; sa.w0 = ctx->f64[B200SPH_W0];
+    sa.uh = ctx->f64x[B200SPH_UHAT - B200SPH_UHAT]; sa.vh = ctx->f64x[B200SPH_VHAT - B200SPH_UHAT];
+    sa.wh = ctx->f64x[B200SPH_WHAT - B200SPH_UHAT];
+    sa.pf = ctx->f64x[B200SPH_PF - B200SPH_UHAT]; sa.pf0 = ctx->f64x[B200SPH_PF0 - B200SPH_UHAT];
+    sa.au = ctx->f32[B200SPH_AU - N_F64]; sa.av = ctx->f32[B200SPH_AV - N_F64]; sa.aw = ctx->f32[B200SPH_AW - N_F64];
+    sa.auh = ctx->f32x[B200SPH_AUHAT - B200SPH_VOL]; sa.avh = ctx->f32x[B200SPH_AVHAT - B200SPH_VOL];
+    sa.awh = ctx->f32x[B200SPH_AWHAT - B200SPH_VOL]; sa.ap = ctx->f32x[B200SPH_AP - B200SPH_VOL];
+    sa.ptype = ctx->ptype;
+    sa.pool_end = ctx->pool_end;
+    sa.arr = arr;
+    sa.which = which;
+    sa.f = which == 1 ? 0.5 * dt : dt;
+    if (ctx->pool_end > 0) {
+        if (devdt) k_stage_tvf_devdt<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa, ctx->tc);
+        else k_stage_tvf<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa);
+        LAUNCH_CHECK();
+    }
+    if (which != 0) {
+        ctx->grid_valid = false, ctx->packed_valid = false;
+        ctx->state_packed = false;
+    }
+    return 0;
+}
+int b200sph_stage_tvf(b200sph_ctx *ctx, int arr, int which, double dt) { return stage_tvf_impl(ctx, arr, which, dt, false); }
+int b200sph_stage_tvf_dev(b200sph_ctx *ctx, int arr, int which) { return stage_tvf_impl(ctx, arr, which, 0.0, true); }
 
 static int ensure_tc(b200sph_ctx *ctx)
 {

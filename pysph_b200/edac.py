@@ -1,0 +1,118 @@
+"""EDAC scheme, internal-flow (transport-velocity) branch, for fluids without solids.
+
+Mirrors pysph/sph/wc/edac.py for the Taylor-Green configuration (BASELINE configs[3],
+pysph/examples/taylor_green.py:190-203): ``ComputeAveragePressure`` (:62-79),
+``EDACEquation`` (:354-386), ``MomentumEquationPressureGradient`` (:389-488),
+``EDACTVFStep`` (:491-540) and ``EDACScheme`` (:543-880, ``get_equations`` for
+``pb != 0`` and ``solids == []``).  Everything else of that module (external flows,
+solid walls, inlet/outlet) raises NotImplementedError.
+"""
+from .equations import Equation, Group
+from .integrator import IntegratorStep
+from .transport_velocity import (MomentumEquationArtificialStress,
+                                 MomentumEquationArtificialViscosity,
+                                 MomentumEquationViscosity, SummationDensity)
+
+
+class ComputeAveragePressure(Equation):
+    """wc/edac.py:62-79"""
+
+
+class EDACEquation(Equation):
+    """wc/edac.py:354-386"""
+
+    def __init__(self, dest, sources, cs, nu, rho0):
+        self.cs = cs
+        self.nu = nu
+        self.rho0 = rho0
+        super(EDACEquation, self).__init__(dest, sources)
+
+
+class MomentumEquationPressureGradient(Equation):
+    """wc/edac.py:389-488 (the variant that subtracts the average pressure)"""
+
+    def __init__(self, dest, sources, pb, gx=0., gy=0., gz=0., tdamp=0.0):
+        self.pb = pb
+        self.gx = gx
+        self.gy = gy
+        self.gz = gz
+        self.tdamp = tdamp
+        super(MomentumEquationPressureGradient, self).__init__(dest, sources)
+
+
+class EDACTVFStep(IntegratorStep):
+    """wc/edac.py:491-540 (device kernel: k_stage_tvf)"""
+
+
+class EDACScheme(object):
+    def __init__(self, fluids, solids, dim, c0, nu, rho0, pb=0.0, gx=0.0, gy=0.0,
+                 gz=0.0, tdamp=0.0, eps=0.0, h=0.0, edac_alpha=0.5, alpha=0.0,
+                 bql=True, clamp_p=False, inlet_outlet_manager=None,
+                 inviscid_solids=None):
+        self.c0 = c0
+        self.nu = nu
+        self.rho0 = rho0
+        self.gx, self.gy, self.gz = gx, gy, gz
+        self.tdamp = tdamp
+        self.dim = dim
+        self.eps = eps
+        self.fluids = list(fluids)
+        self.solids = list(solids)
+        self.pb = pb
+        self.bql = bql
+        self.clamp_p = clamp_p
+        self.edac_alpha = edac_alpha
+        self.alpha = alpha
+        self.h = h
+        self.inlet_outlet_manager = inlet_outlet_manager
+        self.inviscid_solids = [] if inviscid_solids is None else inviscid_solids
+        self.attributes_changed()
+
+    def attributes_changed(self):                      # wc/edac.py:651-655
+        if self.pb is not None:
+            self.use_tvf = abs(self.pb) > 1e-14
+        if self.h is not None and self.c0 is not None:
+            self.art_nu = self.edac_alpha * self.h * self.c0 / 8
+
+    def configure(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise RuntimeError('Parameter {param} not defined for {scheme}.'
+                                   .format(param=k, scheme=self.__class__.__name__))
+            setattr(self, k, v)
+        self.attributes_changed()
+
+    def _get_edac_nu(self):                            # wc/edac.py:766-774
+        return self.art_nu if self.art_nu > 0 else self.nu
+
+    def get_steppers(self):
+        return dict((f, EDACTVFStep()) for f in self.fluids)
+
+    def get_equations(self):                           # wc/edac.py:704-708, :776-880
+        if not self.use_tvf:
+            raise NotImplementedError('B200 backend: EDAC external-flow branch (pb == 0)')
+        if self.solids or self.inviscid_solids or self.inlet_outlet_manager is not None:
+            raise NotImplementedError('B200 backend: EDAC with solids / inlet-outlet')
+        edac_nu = self._get_edac_nu()
+        all_ = self.fluids
+        group1 = []
+        for fluid in self.fluids:
+            group1.append(SummationDensity(dest=fluid, sources=all_))
+            if self.bql:
+                group1.append(ComputeAveragePressure(dest=fluid, sources=all_))
+        group2 = []
+        for fluid in self.fluids:
+            group2.append(MomentumEquationPressureGradient(
+                dest=fluid, sources=all_, pb=self.pb, gx=self.gx, gy=self.gy,
+                gz=self.gz, tdamp=self.tdamp))
+            if self.alpha > 0.0:
+                group2.append(MomentumEquationArtificialViscosity(
+                    dest=fluid, sources=self.fluids, alpha=self.alpha, c0=self.c0))
+            if self.nu > 0.0:
+                group2.append(MomentumEquationViscosity(
+                    dest=fluid, sources=self.fluids, nu=self.nu))
+            group2.extend([
+                MomentumEquationArtificialStress(dest=fluid, sources=self.fluids),
+                EDACEquation(dest=fluid, sources=all_, nu=edac_nu, cs=self.c0,
+                             rho0=self.rho0)])
+        return [Group(equations=group1, real=False), Group(equations=group2)]

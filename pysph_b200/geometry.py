@@ -122,3 +122,57 @@ def dam_break_2d_params(dx=0.03, hdx=1.3):
                 gamma=7.0, hg_correction=True, update_h=True,
                 dt0=0.125 * h_opt / float(c0), n_damp=50, cfl=0.3,
                 integrator='PEC')
+
+
+# ---------------------------------------------------------------------------
+# Taylor-Green vortex (pysph/examples/taylor_green.py:30-35, :146-166, :268-297)
+# ---------------------------------------------------------------------------
+def taylor_green_params(nx, dim=2, re=100.0, hdx=1.0, L=1.0, U=1.0, rho0=1.0):
+    """Parameters of the reference example (EDAC branch, :197-203).  The example is
+    2-D; the 3-D variant (BASELINE configs[3]) keeps every parameter and uses the
+    classical 3-D Taylor-Green initial field (ours to define)."""
+    c0 = 10.0 * U
+    p0 = c0 ** 2 * rho0
+    nu = U * L / re
+    dx = L / nx
+    h0 = hdx * dx
+    dt = min(0.25 * h0 / (c0 + U), 0.125 * h0 ** 2 / nu, 0.25)
+    return dict(dim=dim, c0=c0, rho0=rho0, nu=nu, pb=p0, h=h0, hdx=hdx, dx=dx, dt=dt,
+                L=L, U=U, re=re, nx=nx, alpha=0.0, edac_alpha=0.5, bql=True)
+
+
+def taylor_green_particles(nx, dim=2, re=100.0, hdx=1.0, L=1.0, U=1.0, rho0=1.0,
+                           perturb=0.0, seed=1):
+    from .particle_array import get_particle_array_edac
+    dx = L / nx
+    ax = np.arange(dx / 2, L, dx)
+    g = np.meshgrid(*([ax] * dim), indexing='ij')
+    x = g[0].ravel().copy()
+    y = g[1].ravel().copy()
+    z = g[2].ravel().copy() if dim == 3 else np.zeros_like(x)
+    if perturb > 0:
+        rs = np.random.RandomState(seed)
+        x += rs.random_sample(x.shape) * dx * perturb
+        y += rs.random_sample(x.shape) * dx * perturb
+        if dim == 3:
+            z += rs.random_sample(x.shape) * dx * perturb
+    k = 2 * np.pi / L
+    if dim == 2:           # exact_solution(t=0), taylor_green.py:63-70
+        u = -U * np.cos(k * x) * np.sin(k * y)
+        v = U * np.sin(k * x) * np.cos(k * y)
+        w = np.zeros_like(x)
+        p = -0.25 * U * U * (np.cos(2 * k * x) + np.cos(2 * k * y))
+    else:
+        u = U * np.sin(k * x) * np.cos(k * y) * np.cos(k * z)
+        v = -U * np.cos(k * x) * np.sin(k * y) * np.cos(k * z)
+        w = np.zeros_like(x)
+        p = rho0 * U * U / 16.0 * (np.cos(2 * k * x) + np.cos(2 * k * y)) * \
+            (np.cos(2 * k * z) + 2.0)
+    pa = get_particle_array_edac(name='fluid', x=x, y=y, z=z, u=u, v=v, w=w, p=p,
+                                 m=rho0 * dx ** dim, h=hdx * dx, rho=rho0)
+    pa.uhat[:] = u
+    pa.vhat[:] = v
+    pa.what[:] = w
+    pa.V[:] = 1.0 / dx ** dim
+    pa.gid[:] = np.arange(x.size)
+    return pa

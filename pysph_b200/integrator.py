@@ -25,7 +25,11 @@ class WCSPHStep(IntegratorStep):
     pysph/sph/integrator_step.py:38-91 (device kernel: k_stage)."""
 
 
-_SUPPORTED_STEPPERS = ('WCSPHStep',)
+# stepper class name -> (C-ABI stage call, the same with dt read on the device)
+_SUPPORTED_STEPPERS = {
+    'WCSPHStep': ('b200sph_stage', 'b200sph_stage_dev'),
+    'EDACTVFStep': ('b200sph_stage_tvf', 'b200sph_stage_tvf_dev'),   # wc/edac.py:491-540
+}
 
 
 class B200Integrator(object):
@@ -35,7 +39,7 @@ class B200Integrator(object):
             if cls not in _SUPPORTED_STEPPERS:
                 raise NotImplementedError(
                     'B200 backend: no device kernel for stepper %r of array '
-                    '%r (supported: %s)' % (cls, name, _SUPPORTED_STEPPERS))
+                    '%r (supported: %s)' % (cls, name, tuple(_SUPPORTED_STEPPERS)))
         self.steppers = kw
         self.acceleration_evals = None
         self.nnps = None
@@ -59,10 +63,14 @@ class B200Integrator(object):
         missing = [n for n in self.steppers if n not in backend.index]
         if missing:
             raise ValueError('steppers given for unknown arrays %r' % missing)
-        if set(self.steppers) == set(backend.names):
-            self._stage_arrays = [-1]          # one launch for every array
+        kinds = set(s.__class__.__name__ for s in self.steppers.values())
+        if set(self.steppers) == set(backend.names) and len(kinds) == 1:
+            # one launch for every array
+            self._stage_arrays = [(-1,) + _SUPPORTED_STEPPERS[kinds.pop()]]
         else:
-            self._stage_arrays = [backend.index[n] for n in self.steppers]
+            self._stage_arrays = [
+                (backend.index[n],) + _SUPPORTED_STEPPERS[s.__class__.__name__]
+                for n, s in self.steppers.items()]
 
     def set_compiled_object(self, c_integrator):
         self.c_integrator = c_integrator
@@ -81,11 +89,11 @@ class B200Integrator(object):
 
     # -- stages ---------------------------------------------------------------
     def _stage(self, which, dt):
-        for arr in self._stage_arrays:
+        for arr, fn, fn_dev in self._stage_arrays:
             if self.device_dt and which != 0:
-                self.ctx.call('b200sph_stage_dev', arr, which)   # dt read on the device
+                self.ctx.call(fn_dev, arr, which)        # dt read on the device
             else:
-                self.ctx.call('b200sph_stage', arr, which, float(dt))
+                self.ctx.call(fn, arr, which, float(dt))
 
     def initialize(self):
         self._stage(0, 0.0)

@@ -28,6 +28,11 @@ DEFAULT_PROPS = ('x', 'y', 'z', 'u', 'v', 'w', 'm', 'h', 'rho', 'p',
 WCSPH_PROPS = ('cs', 'ax', 'ay', 'az', 'arho', 'x0', 'y0', 'z0',
                'u0', 'v0', 'w0', 'rho0', 'div', 'dt_cfl', 'dt_force')
 
+# EDACScheme.setup_properties, internal-flow branch (wc/edac.py:724-735): what the
+# transport-velocity EDAC equations and EDACTVFStep read and write
+EDAC_TVF_PROPS = ('uhat', 'vhat', 'what', 'ap', 'auhat', 'avhat', 'awhat', 'V',
+                  'p0', 'u0', 'v0', 'w0', 'x0', 'y0', 'z0', 'pavg', 'nnbr')
+
 _INT_PROPS = {'tag': np.int32, 'pid': np.int32, 'gid': np.uint32}
 
 
@@ -146,4 +151,14 @@ def get_particle_array_wcsph(constants=None, **props):
                             **props)
     pa.set_output_arrays(['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'm', 'h',
                           'pid', 'gid', 'tag', 'p'])
+    return pa
+
+
+def get_particle_array_edac(constants=None, **props):
+    """A fluid array with the property set ``EDACScheme.setup_properties`` gives it
+    for internal flows (wc/edac.py:709-741)."""
+    pa = get_particle_array(additional_props=EDAC_TVF_PROPS, constants=constants,
+                            **props)
+    pa.set_output_arrays(['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'p', 'm', 'h',
+                          'V', 'pavg'])
     return pa

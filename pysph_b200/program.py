@@ -25,6 +25,121 @@ PAIR_EQUATIONS = {
 NO_SOURCE_EQUATIONS = ('TaitEOS', 'TaitEOSHGCorrection',
                        'UpdateSmoothingLengthFerrari')
 
+# EDAC scheme, transport-velocity branch (wc/edac.py:776-880): two Groups that
+# become ('tvf', TvfProgram) ops (merged into one when they follow each other)
+TVF_GROUP1 = ('SummationDensity', 'ComputeAveragePressure')
+TVF_GROUP2 = {
+    'MomentumEquationPressureGradient': _lib.TVF_PGRAD,
+    'MomentumEquationArtificialViscosity': _lib.TVF_AV,
+    'MomentumEquationViscosity': _lib.TVF_VISC,
+    'MomentumEquationArtificialStress': _lib.TVF_ASTRESS,
+    'EDACEquation': _lib.TVF_EDAC,
+}
+
+
+def _is_tvf_summation(eq):
+    return _eq_name(eq) == 'SummationDensity' and \
+        'transport_velocity' in eq.__class__.__module__
+
+
+def _tvf_group_kind(g):
+    names = [_eq_name(e) for e in g.equations]
+    if any(n == 'ComputeAveragePressure' for n in names) or \
+            any(_is_tvf_summation(e) for e in g.equations):
+        return 1
+    if any(n in TVF_GROUP2 for n in names):
+        return 2
+    return 0
+
+
+def _build_tvf(g, kind, index):
+    names = [_eq_name(e) for e in g.equations]
+    prog = _lib.TvfProgram()
+    params = {}
+    fluids = []
+    for eq in g.equations:
+        name = _eq_name(eq)
+        ok = (name in TVF_GROUP1 and (name != 'SummationDensity' or
+                                      _is_tvf_summation(eq))) if kind == 1 \
+            else name in TVF_GROUP2
+        if not ok:
+            raise NotImplementedError(
+                'B200 backend: equation %r cannot share a Group with the EDAC '
+                'scheme\'s %s' % (name, names))
+        if eq.dest not in index:
+            raise ValueError('equation %s: unknown destination array %r'
+                             % (name, eq.dest))
+        if eq.dest not in fluids:
+            fluids.append(eq.dest)
+    mask = sum(1 << index[f] for f in fluids)
+    for eq in g.equations:
+        name = _eq_name(eq)
+        if sorted(index[s] for s in (eq.sources or [])) != sorted(index[f] for f in fluids):
+            raise NotImplementedError(
+                'B200 backend: EDAC kernels take every fluid as a source of every '
+                'fluid (no solids); %s(dest=%r, sources=%r)' % (name, eq.dest, eq.sources))
+        if name == 'MomentumEquationPressureGradient':
+            if 'edac' not in eq.__class__.__module__:
+                raise NotImplementedError(
+                    'B200 backend: transport_velocity.MomentumEquationPressureGradient '
+                    '(use the EDAC variant, wc/edac.py:389)')
+            for k in ('pb', 'gx', 'gy', 'gz', 'tdamp'):
+                _set_once(params, k, float(getattr(eq, k)), eq)
+        elif name == 'MomentumEquationArtificialViscosity':
+            _set_once(params, 'alpha', float(eq.alpha), eq)
+            _set_once(params, 'c0', float(eq.c0), eq)
+        elif name == 'MomentumEquationViscosity':
+            _set_once(params, 'nu', float(eq.nu), eq)
+        elif name == 'EDACEquation':
+            _set_once(params, 'edac_nu', float(eq.nu), eq)
+            _set_once(params, 'c0', float(eq.cs), eq)
+            _set_once(params, 'rho0', float(eq.rho0), eq)
+    real = getattr(g, 'real', True)
+    if kind == 1:
+        if real:
+            raise NotImplementedError(
+                'B200 backend: the EDAC density / average-pressure Group must be '
+                'real=False (wc/edac.py:838)')
+        if 'SummationDensity' not in names:
+            raise NotImplementedError(
+                'B200 backend: ComputeAveragePressure without the TVF SummationDensity')
+        prog.bql = int('ComputeAveragePressure' in names)
+        prog.passes = 1
+    else:
+        if not real:
+            raise NotImplementedError(
+                'B200 backend: the EDAC momentum Group must be real=True')
+        for f in fluids:
+            mine = [_eq_name(e) for e in g.equations if e.dest == f]
+            if sorted(mine) != sorted(set(names)):
+                raise NotImplementedError(
+                    'B200 backend: every fluid needs the same EDAC equations')
+        bits = 0
+        for n in set(names):
+            bits |= TVF_GROUP2[n]
+        prog.eqbits = bits
+        prog.passes = 2
+    prog.fluid_mask = mask
+    for k, v in params.items():
+        setattr(prog, k, v)
+    return prog
+
+
+def _merge_tvf(ops):
+    """group 1 directly followed by group 2 over the same fluids: one call, one pack."""
+    out = []
+    for op in ops:
+        if out and op[0] == 'tvf' and out[-1][0] == 'tvf' and \
+                out[-1][1].passes == 1 and op[1].passes == 2 and \
+                out[-1][1].fluid_mask == op[1].fluid_mask:
+            op[1].passes = 3
+            op[1].bql = out[-1][1].bql
+            out[-1] = op
+        else:
+            out.append(op)
+    return out
+
+
 # properties each pair equation needs on dest / source arrays (checked like
 # check_equation_array_properties, pysph/sph/acceleration_eval.py:32-73)
 _REQUIRED = ('x', 'y', 'z', 'h', 'm', 'rho')
@@ -86,6 +201,12 @@ def build_program(groups, array_names, dim):
                 raise NotImplementedError(
                     'B200 backend: Group(%s=%r) is not supported'
                     % (attr, getattr(g, attr)))
+        kind = _tvf_group_kind(g)
+        if kind:
+            ops.append(('tvf', _build_tvf(g, kind, index)))
+            if getattr(g, 'update_nnps', False):
+                ops.append(('update_nnps',))
+            continue
         real_only = 1 if getattr(g, 'real', True) else 0
         pair_eqs = []
         nosrc_ops = []
@@ -161,4 +282,4 @@ def build_program(groups, array_names, dim):
             ops.append(('pair', prog))
         if getattr(g, 'update_nnps', False):
             ops.append(('update_nnps',))
-    return ops
+    return _merge_tvf(ops)

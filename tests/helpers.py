@@ -60,3 +60,22 @@ def rel_err(a, b, scale=None):
         return 0.0
     s = scale if scale is not None else scale_of(b, 1e-300)
     return float(np.max(np.abs(a - b)) / s)
+
+
+def edac_arrays_from_dict(d, order=('fluid', 'fluid2')):
+    """golden 'inputs' dict of an EDAC case -> list of stand-in ParticleArrays."""
+    from pysph_b200.particle_array import get_particle_array_edac
+    pas = []
+    for name in order:
+        if name not in d:
+            continue
+        a = d[name]
+        props = dict((k, np.array(v, dtype=float)) for k, v in a.items()
+                     if k[0] != '_')
+        pa = get_particle_array_edac(name=name, **props)
+        pa.set_num_real_particles(a.get('_n_real', len(a['x'])))
+        pas.append(pa)
+    return pas
+
+
+EDAC_FIELDS = ['V', 'rho', 'pavg', 'au', 'av', 'aw', 'auhat', 'avhat', 'awhat', 'ap']

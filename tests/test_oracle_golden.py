@@ -262,3 +262,46 @@ def test_dt_rules():
     assert abs(s._compute_timestep() - 0.3 * 0.1 / 4.0) < 1e-16
     pa.dt_force[:] = 1e6   # sqrt(h / sqrt(f)) = sqrt(0.1/1000) = 0.01 < 0.025
     assert abs(s._compute_timestep() - 0.3 * math.sqrt(0.1 / 1000.0)) < 1e-16
+
+
+# ---------------------------------------------------------------------------
+# EDAC scheme, transport-velocity branch: the oracle against the
+# reference's EDACScheme.get_equations() + equation bodies (oracle/gen_golden.py)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('idx', range(4))
+def test_edac_evaluation_matches_reference_bodies(idx):
+    from helpers import EDAC_FIELDS, edac_arrays_from_dict
+    case = load_golden('edac_cases.json')[idx]
+    p = case['params']
+    # the equations the reference scheme emitted are the ones the oracle driver assumes
+    want = ['MomentumEquationPressureGradient']
+    if p['alpha'] > 0:
+        want.append('MomentumEquationArtificialViscosity')
+    if p['nu'] > 0:
+        want.append('MomentumEquationViscosity')
+    want += ['MomentumEquationArtificialStress', 'EDACEquation']
+    assert p['groups'][1] == want * len(p['fluids'])
+    assert p['groups'][0] == (['SummationDensity'] + (['ComputeAveragePressure'] if p['bql'] else [])) * len(p['fluids'])
+    assert p['group_real'] == [False, True]
+    pas = edac_arrays_from_dict(case['inputs'])
+    s = orc.EDACOracleSolver(pas, dict(p, dt=1e-3), case['kernel'])
+    s.t = p['t']
+    s.evaluate()
+    for pa in pas:
+        ref = case['outputs'][pa.name]
+        for f in EDAC_FIELDS:
+            got, wantv = pa.properties[f], np.array(ref[f])
+            scale = max(np.max(np.abs(wantv)), 1e-300)
+            assert np.max(np.abs(got - wantv)) <= 5e-12 * scale, (pa.name, f)
+
+
+def test_edac_tvf_step_matches_reference_bodies():
+    from pysph_b200.particle_array import get_particle_array_edac
+    g = load_golden('edac_stepper.json')
+    for which, key in ((0, 'initialize'), (1, 'stage1'), (2, 'stage2')):
+        props = dict((k, np.array(v)) for k, v in g['inputs'].items())
+        pa = get_particle_array_edac(name='f', **props)
+        o = orc.Oracle([pa], 3)
+        o.stage_tvf(0, which, g['dt'])
+        for k, v in g['outputs'][key].items():
+            assert np.allclose(pa.properties[k], v, rtol=1e-15, atol=0), (key, k)
