@@ -185,6 +185,136 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_taylor_green(args, emit):
+    """--workload taylor_green: BASELINE configs[3] -- 3-D Taylor-Green vortex, EDAC
+    scheme (transport-velocity branch), QuinticSpline, 126^3 = 2.0 M particles in the
+    periodic unit cube, PEC + EDACTVFStep at the example's fixed dt, one B200.  Same
+    JSON line as the default workload; one step = one evaluation = two pair passes."""
+    import torch
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo
+    torch.cuda.set_device(0)
+    nx = args.nx
+    p = geo.taylor_green_params(nx, dim=3)
+    pa = geo.taylor_green_particles(nx, dim=3)
+    host_copy = None
+    if not args.no_cpu:
+        host_copy = pb.get_particle_array_edac(
+            name='fluid', **dict((k, v.copy()) for k, v in pa.properties.items()))
+    keep = pinned_arrays([pa])
+    dm = pb.DomainManager(xmin=0, xmax=1, ymin=0, ymax=1, zmin=0, zmax=1,
+                          periodic_in_x=True, periodic_in_y=True, periodic_in_z=True)
+    sch = pb.EDACScheme(['fluid'], [], dim=3, c0=p['c0'], nu=p['nu'], rho0=p['rho0'],
+                        pb=p['pb'], h=p['h'])
+    solver = pb.make_edac_solver([pa], sch, pb.QuinticSpline(dim=3), dt=p['dt'], domain=dm)
+    be = solver.backend
+    stream = torch.cuda.current_stream()
+    be.use_torch_stream(stream)
+    W, K = max(args.warmup, 3), args.steps
+    sampler = ClockSampler(0)
+    sampler.start()
+    solver.initialise()
+    for _ in range(W):
+        solver.step()
+    solver.a_eval.count_pairs = True
+    solver.step()
+    pairs_step = solver.a_eval.last_pairs          # both passes
+    solver.a_eval.count_pairs = False
+    be.ctx.call('b200sph_reset_stats')
+    be.ctx.call('b200sph_set_profiling', 2)
+    torch.cuda.synchronize()
+    n_s0 = len(sampler.lines)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(K):
+        solver.step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop(n_s0)
+    ms_step = ev0.elapsed_time(ev1) / K
+    st = be.stats()
+    DIAG = 20
+    be.ctx.call('b200sph_reset_stats')
+    be.ctx.call('b200sph_set_profiling', 1)
+    for _ in range(DIAG):
+        solver.step()
+    torch.cuda.synchronize()
+    st_diag = be.stats()
+    be.ctx.call('b200sph_set_profiling', 0)
+    # e2e: host state in, result out, every step
+    state = ['x', 'y', 'z', 'u', 'v', 'w', 'p', 'h', 'm']
+    outp = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'p']
+    n = pa.get_number_of_particles()
+    be.ctx.call('b200sph_set_async_copies', 1)
+
+    def e2e_step():
+        be.push_real(state)
+        solver.step()
+        be.pull_real(outp)
+        be.synchronize()
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    be.ctx.call('b200sph_set_async_copies', 0)
+    ms_e2e = ev0.elapsed_time(ev1) / args.e2e_steps
+    peak, peak_src = peaks()
+    ms_p2 = st['ms_pair'] / max(st['pair_launches'], 1)
+    pairs_p2 = pairs_step / 2.0
+    B2 = 64.0        # group 2 gathers {A,B} 32 B + C2 16 B + Dv 16 B per pair
+    achieved = pairs_p2 * B2 / (ms_p2 * 1e-3) / 1e9
+    cpu = None
+    if host_copy is not None:
+        from oracle import oracle as orc
+        o = orc.EDACOracleSolver([host_copy], p, 'QuinticSpline', threads=1,
+                                 domain=([0, 0, 0], [1, 1, 1], [1, 1, 1]))
+        t0 = time.perf_counter()
+        pairs_cpu = o.evaluate()
+        el = time.perf_counter() - t0
+        cpu = {'value': pairs_cpu / el, 'unit': 'pairs/s', 'cores': 1, 'kind': 'port',
+               'cpu': cpu_model(),
+               'sample': 'one full evaluation (both EDAC groups) of the same %d-particle '
+                         'state with materialised periodic ghosts, fp64 oracle, 1 thread '
+                         '(%.1f s)' % (n, el)}
+    emit({
+        'metric': METRIC, 'value': pairs_step / (ms_step * 1e-3), 'unit': 'pairs/s',
+        'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': ms_step,
+        'steps_per_s': 1e3 / ms_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'taylor_green 3-D (BASELINE configs[3]) EDAC/TVF PEC '
+                               'QuinticSpline nx=%d hdx=1.0 periodic' % nx,
+                   'particles_rank0': n, 'pairs_per_step': pairs_step,
+                   'parallelism': 'single GPU', 'dt': p['dt'],
+                   'l2': 'no flush: > 126 MB working set per step, state advances',
+                   'precision': 'fp32 pair arithmetic on cell-relative coordinates, '
+                                'fp64 integrated state (x u p uhat)'},
+        'clocks': clocks,
+        'e2e': {'value': pairs_step / (ms_e2e * 1e-3), 'unit': 'pairs/s',
+                'ms_per_step': ms_e2e, 'steps': args.e2e_steps,
+                'h2d_bytes_per_step': 8 * len(state) * n,
+                'd2h_bytes_per_step': 8 * len(outp) * n},
+        'gpu_launches': int(st['kernel_launches']),
+        'roofline': {'bound': 'hbm', 'kernel': 'k_tvf_pass2<QuinticSpline,3>',
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_pair': B2, 'pairs_per_launch': pairs_p2,
+                     'avg_launch_ms': ms_p2,
+                     'share_of_step': st['ms_pair'] / K / ms_step,
+                     'ms_nnps_per_step': st_diag['ms_nnps'] / DIAG,
+                     'ms_other_per_step': st_diag['ms_other'] / DIAG,
+                     'note': 'other = k_pack_tvf + k_tvf_pass1 + stages',
+                     'nnps': {'full_builds': st['full_builds'],
+                              'light_updates': st['light_updates'],
+                              'list_builds': st['list_builds'],
+                              'list_entries_per_particle': st['list_entries_per_particle']}},
+        'cpu_baseline': cpu,
+    })
+
+
 def pinned_arrays(pas):
     """Re-home every property of the ParticleArrays in pinned host memory."""
     import torch
@@ -207,6 +337,9 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=10)
     ap.add_argument('--cpu-budget', type=float, default=20.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--workload', default='dam_break',
+                    choices=['dam_break', 'taylor_green'])
+    ap.add_argument('--nx', type=int, default=126)
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -232,6 +365,13 @@ def main():
         os.dup2(saved_stdout, 1)
         print(json.dumps(line))
         sys.stdout.flush()
+    if args.workload == 'taylor_green':
+        if world > 1:
+            print('bench.py: --workload taylor_green is a single-GPU workload',
+                  file=sys.stderr)
+            sys.exit(2)
+        run_taylor_green(args, emit)
+        return
     import torch
     import torch.distributed as dist
     import pysph_b200 as pb
