@@ -1292,12 +1292,28 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
     const float hi2 = a.k2 * Ai.w * Ai.w;
     float wsum = 0.f, psum = 0.f, nn = 0.f;
     unsigned npairs = 0;
+    // entries two iterations ahead, records one iteration ahead (as in k_pair_list)
+    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
+    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
+    float4 A_a = Ai;
+    float2 P_a = make_float2(0.f, 0.f);
+    if (count > 0) {
+        const size_t j = e_a & LIST_JMASK;
+        A_a = a.AB[2 * j];
+        P_a = a.PT[j];
+    }
     for (int k = 0; k < cmax; k++) {
+        const uint32_t e = e_a;
+        const float4 Aj = A_a;
+        const float2 Pj = P_a;
+        e_a = e_b;
+        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
+        if (k + 1 < count) {
+            const size_t j = e_a & LIST_JMASK;
+            A_a = a.AB[2 * j];
+            P_a = a.PT[j];
+        }
         if (k < count) {
-            const uint32_t e = __ldcs(my + (size_t)k * 32u);
-            const size_t j = e & LIST_JMASK;
-            const float4 Aj = a.AB[2 * j];
-            const float2 Pj = a.PT[j];
             const float4 T = s_T[e >> LIST_JBITS];
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
@@ -1337,7 +1353,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
 // group 2 (real=True): pressure gradient with the background-pressure term, artificial /
 // physical viscosity, artificial stress and the EDAC pressure evolution, fused
 template <int K, int DIM>
-__global__ void __launch_bounds__(LIST_NT, 3) k_tvf_pass2(const TvfArgs a, const uint32_t *__restrict__ cnt,
+__global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const uint32_t *__restrict__ cnt,
                                                          const uint32_t *__restrict__ lst, const int capg)
 {
     __shared__ float4 s_T[64];
@@ -1374,7 +1390,10 @@ __global__ void __launch_bounds__(LIST_NT, 3) k_tvf_pass2(const TvfArgs a, const
     const float cs2 = a.c0 * a.c0;
     float au = 0.f, av = 0.f, aw = 0.f, auh = 0.f, avh = 0.f, awh = 0.f, ap = 0.f;
     unsigned npairs = 0;
+    // entries two iterations ahead, records one iteration ahead (as in k_pair_list):
+    // a record load never waits for the entry load of the same iteration
     uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
+    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
     float4 A_a = Ai, B_a = Bi, C_a = Ci, D_a = Di;
     if (count > 0) {
         const size_t j = e_a & LIST_JMASK;
@@ -1385,8 +1404,9 @@ __global__ void __launch_bounds__(LIST_NT, 3) k_tvf_pass2(const TvfArgs a, const
     for (int k = 0; k < cmax; k++) {
         const uint32_t e = e_a;
         const float4 Aj = A_a, Bj = B_a, Cj = C_a, Dj = D_a;
+        e_a = e_b;
+        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
         if (k + 1 < count) {
-            e_a = __ldcs(my + (size_t)(k + 1) * 32u);
             const size_t j = e_a & LIST_JMASK;
             ld_256(a.AB + 2 * j, A_a, B_a);
             C_a = a.C2[j];
