@@ -200,3 +200,64 @@ def test_domain_manager_descriptor():
         pb.DomainManager(xmin=1, xmax=0)
     with pytest.raises(NotImplementedError):
         pb.DomainManager(xmin=0, xmax=1, mirror_in_x=True)
+
+
+def test_edac_program_and_scheme():
+    """EDACScheme.get_equations (wc/edac.py:776-880, fluids only) -> one fused
+    ('tvf', program) op; what the kernels cannot do is refused at setup."""
+    from pysph_b200 import _lib as L
+    from pysph_b200 import edac, transport_velocity as tv
+    from pysph_b200.equations import Group, SummationDensity
+    sch = pb.EDACScheme(['f1', 'f2'], [], dim=3, c0=10., nu=0.01, rho0=1., pb=100.,
+                        h=0.02, alpha=0.3, gx=1.0, tdamp=2.0)
+    groups = sch.get_equations()
+    assert [g.real for g in groups] == [False, True]
+    assert [type(e).__name__ for e in groups[1].equations][:5] == [
+        'MomentumEquationPressureGradient', 'MomentumEquationArtificialViscosity',
+        'MomentumEquationViscosity', 'MomentumEquationArtificialStress', 'EDACEquation']
+    ops = build_program(groups, ['f1', 'f2'], 3)
+    assert [o[0] for o in ops] == ['tvf']
+    P = ops[0][1]
+    assert (P.passes, P.fluid_mask, P.bql) == (3, 3, 1)
+    assert P.eqbits == L.TVF_PGRAD | L.TVF_AV | L.TVF_VISC | L.TVF_ASTRESS | L.TVF_EDAC
+    assert (P.pb, P.nu, P.c0, P.alpha, P.gx, P.tdamp) == (100., 0.01, 10., 0.3, 1.0, 2.0)
+    assert abs(P.edac_nu - 0.5 * 0.02 * 10. / 8) < 1e-15       # art_nu, wc/edac.py:651-655
+    # the groups alone: two ops, not merged across an unrelated group
+    ops = build_program([groups[0]], ['f1', 'f2'], 3)
+    assert ops[0][1].passes == 1
+    ops = build_program([groups[1]], ['f1', 'f2'], 3)
+    assert ops[0][1].passes == 2 and ops[0][1].bql == 0
+    # refused: basic SummationDensity mixed in, a fluid that is not a source, real=True density
+    with pytest.raises(NotImplementedError):
+        build_program([Group([tv.SummationDensity('f1', ['f1']),
+                              SummationDensity('f1', ['f1'])], real=False)], ['f1'], 2)
+    with pytest.raises(NotImplementedError):
+        build_program([Group([tv.SummationDensity('f1', ['f1']),
+                              tv.SummationDensity('f2', ['f1', 'f2'])], real=False)],
+                      ['f1', 'f2'], 2)
+    with pytest.raises(NotImplementedError):
+        build_program([Group([tv.SummationDensity('f1', ['f1'])], real=True)], ['f1'], 2)
+    with pytest.raises(NotImplementedError):
+        pb.EDACScheme(['f'], ['wall'], dim=2, c0=10., nu=0.01, rho0=1., pb=100.,
+                      h=0.01).get_equations()
+    # steppers: EDACTVFStep is accepted, unknown ones are not
+    pb.PECIntegrator(f1=pb.EDACTVFStep(), f2=pb.EDACTVFStep())
+    with pytest.raises(NotImplementedError):
+        pb.PECIntegrator(f1=type('EulerStep', (), {})())
+
+
+def test_taylor_green_geometry():
+    # pysph/examples/taylor_green.py:146-166 (dt), :268-297 (lattice, exact solution)
+    p = geo.taylor_green_params(50, dim=2)
+    assert abs(p['dt'] - min(0.25 * 0.02 / 11.0, 0.125 * 0.02 ** 2 / 0.01, 0.25)) < 1e-15
+    pa = geo.taylor_green_particles(50, dim=2)
+    assert pa.get_number_of_particles() == 2500
+    assert abs(np.sum(pa.m) - 1.0) < 1e-12
+    i = 7 * 50 + 3
+    assert abs(pa.u[i] + np.cos(2 * np.pi * pa.x[i]) * np.sin(2 * np.pi * pa.y[i])) < 1e-15
+    assert abs(pa.p[i] + 0.25 * (np.cos(4 * np.pi * pa.x[i]) + np.cos(4 * np.pi * pa.y[i]))) < 1e-15
+    assert set(('uhat', 'V', 'pavg', 'ap', 'p0', 'auhat')) <= set(pa.properties)
+    pa3 = geo.taylor_green_particles(8, dim=3)
+    assert pa3.get_number_of_particles() == 512 and np.all(pa3.w == 0.0)
+    # divergence-free initial field: sum of u over a periodic lattice vanishes
+    assert abs(np.sum(pa3.u)) < 1e-10 and abs(np.sum(pa3.v)) < 1e-10
