@@ -364,6 +364,64 @@ def gen_edac_stepper(edac):
     return dict(dt=dt, inputs=inputs, outputs=res)
 
 
+def gen_output_fixture():
+    """pysph/solver/output.py (unmodified, loaded by path) writes the fixture and reads
+    back a file written by pysph_b200.output.  Its three imports are satisfied by the
+    stand-in ParticleArray of pysph_b200 and by pysph_b200.output.get_particles_info
+    (a restatement of pysph/base/utils.py:466-497, the one part that needs cyarray)."""
+    import tempfile
+    sys.path.insert(0, ROOT)
+    from pysph_b200 import output as ours
+    from pysph_b200 import particle_array as ppa
+    m_pa = types.ModuleType('pysph.base.particle_array')
+    m_pa.ParticleArray = ppa.ParticleArray
+    sys.modules['pysph.base.particle_array'] = m_pa
+    utils = sys.modules['pysph.base.utils']
+    utils.get_particles_info = ours.get_particles_info
+    utils.get_particle_array = ppa.get_particle_array
+    sys.modules['pysph'].has_h5py = lambda: False
+    ref = _load('pysph.solver.output', os.path.join(REF, 'pysph/solver/output.py'))
+
+    rs = np.random.RandomState(5)
+
+    def arrays():
+        f = ppa.get_particle_array_wcsph(
+            name='fluid', x=rs.uniform(size=9), y=rs.uniform(size=9),
+            u=rs.normal(size=9), rho=1000.0 + rs.normal(size=9), h=0.013, m=0.7,
+            p=rs.normal(size=9))
+        f.set_num_real_particles(7)                   # 2 trailing ghosts
+        f.gid[:] = np.arange(9) + 100
+        f.tag[7:] = 1
+        b = ppa.get_particle_array_wcsph(name='boundary', x=rs.uniform(size=4),
+                                         h=0.013, m=0.7, rho=1000.0)
+        b.add_constant('total_mass', [2.8])
+        return [f, b]
+    pas = arrays()
+    solver_data = {'dt': 1.25e-4, 't': 0.0375, 'count': 300}
+    # (a) the reference's dump() writes the committed fixture
+    ref.dump(os.path.join(GOLD, 'ref_dump'), pas, solver_data, detailed_output=False,
+             only_real=True)
+    assert os.path.exists(os.path.join(GOLD, 'ref_dump.npz'))
+    # (b) the reference's load() reads OUR dump
+    tmp = tempfile.mkdtemp()
+    mine = ours.dump(os.path.join(tmp, 'ours_00300'), pas, solver_data)
+    back = ref.load(mine)
+    assert dict(back['solver_data']) == solver_data
+    for pa in pas:
+        q = back['arrays'][pa.name]
+        assert q.get_number_of_particles() == pa.get_number_of_particles(real=True)
+        for k in pa.output_property_arrays:
+            assert np.array_equal(q.properties[k],
+                                  pa.properties[k][:pa.num_real_particles]), k
+    expect = dict((pa.name, dict((k, list(map(float, pa.properties[k][:pa.num_real_particles])))
+                                 for k in pa.output_property_arrays)) for pa in pas)
+    return dict(solver_data=solver_data, arrays=expect,
+                output_property_arrays=dict((pa.name, pa.output_property_arrays)
+                                            for pa in pas),
+                all_properties=dict((pa.name, sorted(pa.properties)) for pa in pas),
+                constants={'boundary': {'total_mass': [2.8]}})
+
+
 def gen_steppers(steps):
     rs = np.random.RandomState(11)
     n = 7
@@ -466,6 +524,7 @@ def main():
     ]
     dump('edac_cases.json', ecases)
     dump('edac_stepper.json', gen_edac_stepper(edac))
+    dump('ref_dump_expect.json', gen_output_fixture())
 
 
 if __name__ == '__main__':

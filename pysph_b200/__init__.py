@@ -36,6 +36,7 @@ from .integrator import (B200Integrator, PECIntegrator, EPECIntegrator,
                          WCSPHStep)
 from .solver import B200Solver
 from .edac import EDACScheme, EDACTVFStep
+from .output import dump, load
 
 __version__ = '0.1.0'
 

@@ -46,13 +46,21 @@ class ParticleArray(object):
         self.backend = 'b200'
         n = 0
         for v in props.values():
+            if isinstance(v, dict):     # {'data':.., 'type':.., 'default':.., 'stride':..}
+                v = v.get('data')       # (particle_array.pyx:150-175)
+                if v is None:
+                    continue
             v = np.asarray(v)
             if v.ndim > 0:          # scalars broadcast, they do not size
                 n = max(n, v.size)
         self._n = n
         self.num_real_particles = n
         for k, v in props.items():
-            self.add_property(k, data=v)
+            if isinstance(v, dict):
+                self.add_property(k, type=v.get('type'), default=v.get('default'),
+                                  data=v.get('data'))
+            else:
+                self.add_property(k, data=v)
 
     # -- sizes ------------------------------------------------------------
     def get_number_of_particles(self, real=False):
@@ -61,6 +69,10 @@ class ParticleArray(object):
     # -- properties -------------------------------------------------------
     def add_property(self, name, type=None, default=None, data=None, stride=1):
         dtype = _INT_PROPS.get(name, np.float64)
+        if type is not None:            # C type names, as get_c_type() returns them
+            dtype = {'double': np.float64, 'float': np.float32, 'int': np.int32,
+                     'unsigned int': np.uint32, 'long': np.int64,
+                     'unsigned long': np.uint64}.get(type, dtype)
         if default is None:
             default = UINT_MAX if name == 'gid' else 0
         arr = np.full(self._n * stride, default, dtype=dtype)
@@ -102,6 +114,27 @@ class ParticleArray(object):
 
     def set_output_arrays(self, names):
         self.output_property_arrays = list(names)
+
+    # -- what the output path reads (particle_array.pyx:344-386, :414-421;
+    #    utils.py:466-497) -----------------------------------------------------
+    stride = {}
+    lb_props = None
+
+    @property
+    def default_values(self):
+        return dict((k, UINT_MAX if k == 'gid' else 0) for k in self.properties)
+
+    def get_lb_props(self):
+        return list(self.properties.keys()) if self.lb_props is None else self.lb_props
+
+    def get_property_arrays(self, all=True, only_real=True):
+        props = self.output_property_arrays
+        if all or len(props) == 0:
+            props = list(self.properties.keys())
+        if self.gpu is not None:
+            self.gpu.pull(*props)            # only what is written travels D2H
+        n = self.get_number_of_particles(only_real)
+        return dict((p, self.properties[p][:n]) for p in props)
 
     def add_constant(self, name, data):
         self.constants[name] = np.atleast_1d(np.asarray(data, dtype=float))

@@ -166,7 +166,19 @@ class B200Solver(object):
                 self.nnps.update_domain()
                 self.nnps.update()
             self.integrator.initial_acceleration(self._t, self._dt)  # solver.py:454
-            if self._use_device_dt():
+            restart_dt = getattr(self, '_restart_dt', None)
+            if restart_dt is not None:
+                # restart: the file's dt is already the damped dt of the next step
+                self._restart_dt = None
+                self._damping_factor = self._next_damping_factor()
+                self._dt = restart_dt
+                if self._use_device_dt():
+                    self._device_dt_begin()
+                    self.backend.ctx.call('b200sph_dt_commit', 1.0, 1.0,
+                                          int(self._tc is not None), 0, 0,
+                                          self._commits % 2)
+                    self._commits += 1
+            elif self._use_device_dt():
                 self._device_dt_begin()
                 self._device_dt_advance(advance=False)               # solver.py:458
             else:
@@ -198,3 +210,48 @@ class B200Solver(object):
 
     def pull(self, props=None):
         self.backend.pull_all(props)
+
+    # -- output / restart (solver.py:520-624) ---------------------------------
+    def _get_solver_data(self):
+        return {'dt': self.dt, 't': self.t, 'count': self.count}
+
+    def dump_output(self, output_directory='.', fname='b200', detailed_output=False,
+                    only_real=True, compress=False):
+        """<dir>/<fname>_<count:05d>.npz in PySPH's format; only the output
+        properties of the real particles leave the device."""
+        import os
+        from .output import dump
+        os.makedirs(output_directory, exist_ok=True)
+        base = os.path.join(output_directory, '%s_%05d' % (fname, self.count))
+        return dump(base, self.particles, self._get_solver_data(),
+                    detailed_output=detailed_output, only_real=only_real,
+                    compress=compress)
+
+    def load_output(self, path):
+        """Restart: take the properties a dump holds (same arrays, same particle
+        counts), push them and continue from its t, dt and count."""
+        from .output import load
+        data = load(path)
+        for i, pa in enumerate(self.particles):
+            src = data['arrays'][pa.name]
+            n = src.get_number_of_particles()
+            if n != pa.get_number_of_particles(real=True):
+                raise ValueError('%s: %d particles in the file, %d real particles '
+                                 'in the solver' % (pa.name, n,
+                                                    pa.get_number_of_particles(real=True)))
+            names = [k for k in src.output_property_arrays or src.properties
+                     if k in pa.properties]
+            for k in names:
+                pa.properties[k][:n] = src.properties[k]
+            self.backend.push(i, names)
+        # the reference builds a fresh NNPS at a restart (application.py:1681-1700)
+        self.nnps.update_domain()
+        self.nnps.update()
+        sd = data['solver_data']
+        self._t, self._dt, self.count = float(sd['t']), float(sd['dt']), int(sd['count'])
+        self._initialised = False          # re-evaluate and re-seed the device clock
+        self.integrator.device_dt = False
+        self._commits = 0
+        # dt in the file is the damped dt the next step uses: keep it across the
+        # re-initialisation (solver.py:616-624 restores dt the same way)
+        self._restart_dt = self._dt

@@ -1,0 +1,119 @@
+"""Output / restart files: pysph_b200.output against a fixture that
+the REFERENCE's own pysph/solver/output.py wrote (tests/golden/ref_dump.npz, made by
+oracle/gen_golden.py, which also checks that the reference's load() reads our dump)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLD, load_golden
+import pysph_b200 as pb
+from pysph_b200 import output
+
+
+def _structure(d, depth=0):
+    """nested key / type skeleton of a dumped dictionary"""
+    if isinstance(d, dict):
+        return dict((k, _structure(v, depth + 1)) for k, v in sorted(d.items()))
+    if isinstance(d, np.ndarray):
+        return ('ndarray', str(d.dtype))
+    if isinstance(d, (list, tuple)):
+        return 'list'
+    return type(d).__name__
+
+
+def test_load_reads_the_reference_dump():
+    exp = load_golden('ref_dump_expect.json')
+    r = output.load(os.path.join(GOLD, 'ref_dump.npz'))
+    sd = r['solver_data']
+    assert (float(sd['dt']), float(sd['t']), int(sd['count'])) == \
+        (exp['solver_data']['dt'], exp['solver_data']['t'], exp['solver_data']['count'])
+    assert sorted(r['arrays']) == ['boundary', 'fluid']
+    for name, props in exp['arrays'].items():
+        pa = r['arrays'][name]
+        assert pa.output_property_arrays == exp['output_property_arrays'][name]
+        assert sorted(pa.properties) == exp['all_properties'][name]
+        n = len(props['x'])
+        assert pa.get_number_of_particles() == n          # only_real=True: ghosts dropped
+        for k, v in props.items():
+            assert np.array_equal(pa.properties[k], np.array(v)), (name, k)
+        assert pa.gid.dtype == np.uint32 and pa.tag.dtype == np.int32
+        assert np.all(pa.au == 0.0)                       # not written: default
+    assert np.array_equal(r['arrays']['boundary'].constants['total_mass'], [2.8])
+
+
+def test_dump_writes_the_reference_layout(tmp_path):
+    ref = np.load(os.path.join(GOLD, 'ref_dump.npz'), allow_pickle=True)
+    back = output.load(os.path.join(GOLD, 'ref_dump.npz'))
+    pas = [back['arrays']['fluid'], back['arrays']['boundary']]
+    f = output.dump(str(tmp_path / 'mine_00300.npz'), pas, back['solver_data'])
+    assert f.endswith('mine_00300.npz')
+    mine = np.load(f, allow_pickle=True)
+    assert sorted(mine.files) == sorted(ref.files) == ['particles', 'solver_data', 'version']
+    assert int(mine['version']) == int(ref['version']) == 2
+    for key in ('particles', 'solver_data'):
+        a, b = mine[key].reshape(1)[0], ref[key].reshape(1)[0]
+        assert _structure(a) == _structure(b), key
+    a, b = mine['particles'].reshape(1)[0], ref['particles'].reshape(1)[0]
+    for name in a:
+        for k, v in b[name]['arrays'].items():
+            assert np.array_equal(a[name]['arrays'][k], v), (name, k)
+        assert a[name]['properties']['gid'] == b[name]['properties']['gid']
+    # '.hdf5' without h5py falls back to npz (output.py:403-412)
+    g = output.dump(str(tmp_path / 'x.hdf5'), pas, back['solver_data'], compress=True)
+    assert g.endswith('x.npz') and output.load(g)['arrays']['fluid'].x.size == 7
+    with pytest.raises(RuntimeError):
+        output.load(str(tmp_path / 'missing.npz'))
+
+
+def test_detailed_output_and_ghosts(tmp_path):
+    pa = pb.get_particle_array_wcsph(name='f', x=np.arange(6.0), h=1.0, m=1.0)
+    pa.set_num_real_particles(4)
+    pa.au[:] = 3.0
+    f = output.dump(str(tmp_path / 'd'), [pa], {'dt': 1.0, 't': 2.0, 'count': 3},
+                    detailed_output=True, only_real=False)
+    q = output.load(f)['arrays']['f']
+    assert q.get_number_of_particles() == 6 and np.all(q.au == 3.0)
+    assert set(q.properties) == set(pa.properties)
+
+
+@pytest.mark.gpu
+def test_dump_and_restart_on_device(gpu_device, tmp_path):
+    """Solver.dump_output / load_output (solver.py:520-624): only the output
+    properties of the real particles leave the device; a run restarted from the
+    file continues like the uninterrupted one (neighbour lists are rebuilt at the
+    restart, so sums are re-ordered: fp32 noise only)."""
+    from pysph_b200 import geometry as geo
+    dx = 0.05
+
+    def make():
+        pas = geo.dam_break_3d_particles(dx=dx)
+        rs = np.random.RandomState(2)
+        pas[0].u[:] = rs.normal(scale=0.3, size=pas[0].u.size)
+        return pas, pb.make_wcsph_solver(pas, geo.dam_break_3d_params(dx),
+                                         pb.CubicSpline(dim=3))
+    pas, s = make()
+    for _ in range(12):
+        s.step()
+    f = s.dump_output(str(tmp_path), 'db')
+    assert os.path.basename(f) == 'db_00012.npz'
+    data = output.load(f)
+    assert int(data['solver_data']['count']) == 12
+    assert abs(float(data['solver_data']['t']) - s.t) == 0.0
+    assert data['arrays']['fluid'].get_number_of_particles() == pas[0].num_real_particles
+    t12, dt12 = s.t, s.dt
+    for _ in range(8):
+        s.step()
+    s.pull()
+    pas2, s2 = make()
+    s2.load_output(f)
+    assert (s2.count, s2.t, s2.dt) == (12, t12, dt12)
+    for _ in range(8):
+        s2.step()
+    s2.pull()
+    assert s2.count == 20 and abs(s2.t - s.t) <= 1e-9 * s.t
+    for a, b in zip(pas, pas2):
+        for k in ('x', 'y', 'z', 'u', 'v', 'w', 'rho'):
+            scale = max(np.max(np.abs(a.properties[k])), 1e-12)
+            assert np.max(np.abs(a.properties[k] - b.properties[k])) <= 5e-6 * scale, \
+                (a.name, k)
