@@ -1001,7 +1001,8 @@ struct ListBuildArgs {
 };
 
 // PERIODIC = false: 9 candidate rows (3 consecutive cells each, contiguous in the
-// sorted arrays).  PERIODIC = true: 27 single-cell segments with wrapped cell indices;
+// sorted arrays).  PERIODIC = true: the same 9 rows with wrapped y / z indices plus, on a
+// periodic x axis, up to 2 single-cell segments per row for the cells that wrap;
 // because coordinates are relative to the particle's own cell and a periodic axis is
 // tiled exactly (L = nc * cell), the image shift of a wrapped neighbour cell is the
 // same "- d * cell" offset as for an ordinary neighbour cell -- the consumer kernel does
@@ -1044,14 +1045,28 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
                     }
                 }
             } else if (lane < 27) {
-                int xx = cx + (lane % 3) - 1, yy = cy + ((lane / 3) % 3) - 1, zz = cz + (lane / 9) - 1;
-                if (a.px) xx = (xx + a.ncx) % a.ncx;
+                // 9 (dy, dz) rows with wrapped y / z (segments 0..8: the x-contiguous part of
+                // the row, clipped to the grid) + for a periodic x axis the wrapped cell that
+                // is missing at cx = 0 (segments 9..17, dxc = -1) / cx = ncx - 1 (18..26, +1)
+                const int q = lane % 9, kind = lane / 9;
+                int yy = cy + (q % 3) - 1, zz = cz + (q / 3) - 1;
                 if (a.py) yy = (yy + a.ncy) % a.ncy;
                 if (a.pz) zz = (zz + a.ncz) % a.ncz;
-                if (xx >= 0 && xx < a.ncx && yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                    const uint32_t c = (uint32_t)xx + (uint32_t)a.ncx * ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz);
-                    r_rs = a.cell_start[c];
-                    r_re = a.cell_start[c + 1];
+                if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
+                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+                    if (kind == 0) {
+                        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
+                        r_rs = a.cell_start[base + x0];
+                        r_b1 = a.cell_start[base + cx];
+                        r_b2 = a.cell_start[base + cx + 1];
+                        r_re = a.cell_start[base + x1 + 1];
+                    } else if (kind == 1 && a.px && cx == 0) {
+                        r_rs = a.cell_start[base + a.ncx - 1];
+                        r_re = a.cell_start[base + a.ncx];
+                    } else if (kind == 2 && a.px && cx == a.ncx - 1) {
+                        r_rs = a.cell_start[base];
+                        r_re = a.cell_start[base + 1];
+                    }
                 }
             }
         }
@@ -1073,24 +1088,24 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
                 zoff = Ai.z - (float)((r / 3) - 1) * a.cellz;
                 rcode = (uint32_t)(4 * (r % 3) + 16 * (r / 3));
             } else {
-                xoff = Ai.x - (float)((r % 3) - 1) * a.cellx;
-                yoff = Ai.y - (float)(((r / 3) % 3) - 1) * a.celly;
-                zoff = Ai.z - (float)((r / 9) - 1) * a.cellz;
-                rcode = (uint32_t)((r % 3) + 4 * ((r / 3) % 3) + 16 * (r / 9));
+                const int q = r % 9;
+                b1 = __shfl_sync(FULL, r_b1, r);
+                b2 = __shfl_sync(FULL, r_b2, r);
+                xoff = Ai.x;
+                yoff = Ai.y - (float)((q % 3) - 1) * a.celly;
+                zoff = Ai.z - (float)((q / 3) - 1) * a.cellz;
+                rcode = (uint32_t)(4 * (q % 3) + 16 * (q / 3));
             }
+            const int kind = PERIODIC ? r / 9 : 0;
             for (uint32_t t0 = rs; t0 < re; t0 += 32) {
                 const uint32_t t = t0 + lane;
                 bool ok = false;
                 uint32_t dxc1 = 0;
                 if (t < re) {
                     const float4 Aj = a.A[t];
-                    float xij;
-                    if (!PERIODIC) {
-                        dxc1 = (uint32_t)(t >= b1) + (uint32_t)(t >= b2);  // dxc + 1
-                        xij = xoff - Aj.x - ((float)dxc1 - 1.0f) * a.cellx;
-                    } else {
-                        xij = xoff - Aj.x;
-                    }
+                    // dxc + 1: position inside the row, or the wrapped cell's fixed offset
+                    dxc1 = kind == 0 ? (uint32_t)(t >= b1) + (uint32_t)(t >= b2) : (kind == 1 ? 0u : 2u);
+                    const float xij = xoff - Aj.x - ((float)dxc1 - 1.0f) * a.cellx;
                     const float yij = yoff - Aj.y;
                     const float zij = zoff - Aj.z;
                     const float r2 = xij * xij + yij * yij + zij * zij;
