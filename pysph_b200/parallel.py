@@ -8,18 +8,27 @@ Replaces the reference's Zoltan/MPI ``ParallelManager``
   particle count (fluid 1, solids ``solid_weight`` -- the reference weights
   solids 0.1, scheme.py:523-527);
 * ``update()`` (called from ``Integrator.compute_accelerations`` exactly like
-  parallel_manager.pyx:512-530): drop last evaluation's Remote particles,
-  migrate real particles that left the slab (all 16 fp64 state properties +
-  gid, so that a mid-step migration keeps x0..rho0), then import the
-  neighbours' particles within one kernel support of the cut planes as ghosts
-  (tag Remote, appended after the real particles);
-* ``update_time_steps(dt)``: all-reduce MIN (parallel_manager.pyx:454-465).
+  parallel_manager.pyx:512-530).  While every rank's neighbour lists are still
+  valid (one scalar all-reduce of the drift) only the VALUES of the same ghost
+  particles are refreshed: pack + send is one kernel per neighbour that writes
+  into the neighbour's cudaIpc staging buffer over NVLink (``_setup_peer``), the
+  all-reduce is the barrier, one kernel scatters.  Otherwise the full path runs:
+  drop last build's Remote particles, migrate real particles that left the slab
+  (all 16 fp64 state properties + gid, so that a mid-step migration keeps
+  x0..rho0), import the neighbours' particles within one kernel support + skin of
+  the cut planes as ghosts (tag Remote, appended after the real particles).
+  ``update(deferred=True)`` + ``confirm()`` let the host read the all-reduced
+  decision after the evaluation has been enqueued;
+* ``update_time_steps(dt)`` / ``reduce_dt_device(view)``: all-reduce MIN
+  (parallel_manager.pyx:454-465), the latter in place on the device-resident
+  time-control block.
 
 Device work (select / pack / append / compact) is done by the C-ABI library
-through ``DeviceHaloOps``; the transport is ``torch.distributed`` point-to-point
-(NCCL over NVLink on GPUs, gloo in the CPU tests) -- plumbing, not product.
-Messages are latency bound (a 10 M-particle fluid cross-section is ~4 MB), so
-each exchange is one count message + one payload message per neighbour.
+through ``DeviceHaloOps``; collectives and the full path's point-to-point
+messages go through ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests)
+-- plumbing, not product.  Messages are latency bound (a 10 M-particle fluid
+cross-section is ~6 MB), so the design removes launches and host waits rather
+than bytes.
 """
 import ctypes as C
 
