@@ -133,7 +133,9 @@ typedef struct {
     int64_t deferred_failed; /* deferred drift checks that forced a repeat      */
 } b200sph_stats;
 
-/* ---- lifecycle ---------------------------------------------------------- */
+/* ---- lifecycle: what selecting a backend does in the reference
+ *      (get_config().use_cuda / use_opencl -> a compyle context,
+ *      pysph/sph/acceleration_eval.py:214-223, pysph/base/device_helper.py:52-60) */
 int b200sph_abi_version(void);
 int b200sph_create(int device, b200sph_ctx **out);
 int b200sph_destroy(b200sph_ctx *ctx);
@@ -195,6 +197,8 @@ int b200sph_nnps_update(b200sph_ctx *ctx);
  * halo_pack / migrate_out / get_neighbors fail on an unconfirmed stale update. */
 int b200sph_nnps_update_deferred(b200sph_ctx *ctx);
 int b200sph_nnps_confirm(b200sph_ctx *ctx, int *redo);
+/* the attributes NNPS exposes after update(): cell_size, hmin, xmin, xmax,
+ * ncells_per_dim, n_cells (nnps_base.pxd:279-371, linked_list_nnps.pyx:293-343) */
 int b200sph_get_grid(b200sph_ctx *ctx, b200sph_grid_info *out);
 /* NNPS.get_nearest_particles(src, dst, d_idx, nbrs) nnps_base.pyx:1268-1290:
  * runs the SAME accept test as the pair kernel.  Writes up to cap source
@@ -217,7 +221,8 @@ int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim,
 int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog,
                       int64_t *pairs_out);
 
-/* The EDAC scheme's evaluation (transport-velocity branch): group 1 computes
+/* The two Groups of EDACScheme._get_internal_flow_equations (wc/edac.py:776-880) in
+ * the generated AccelerationEval.compute (acceleration_eval_cython.mako:10-154): group 1 computes
  * V = sum W, rho = m V (transport_velocity.py:24-58) and the neighbour-average
  * pressure; group 2 the momentum terms (au.., auhat..) and ap.  Both walk the same
  * persistent neighbour lists as pair_pass.  pairs_out may be NULL. */
