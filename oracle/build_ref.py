@@ -19,18 +19,28 @@ OUT = os.path.join(HERE, '_ref')
 
 
 def build():
-    pyx = os.path.join(REF, 'pysph', 'base', 'c_kernels.pyx')
+    """c_kernels (smoothing kernels) and linalg3 (the 3x3 symmetric eigen solver the
+    solid-mechanics equations call, pysph/base/linalg3.pyx: libc + numpy only)."""
+    out = None
+    for mod in ('c_kernels', 'linalg3'):
+        out = _build_one(mod) or out
+    return out
+
+
+def _build_one(mod):
+    pyx = os.path.join(REF, 'pysph', 'base', mod + '.pyx')
     if not os.path.exists(pyx):
         print('build_ref: %s not found, nothing to do' % pyx)
         return None
     os.makedirs(OUT, exist_ok=True)
     ext = sysconfig.get_config_var('EXT_SUFFIX')
-    so = os.path.join(OUT, 'c_kernels' + ext)
+    so = os.path.join(OUT, mod + ext)
     if os.path.exists(so) and os.path.getmtime(so) > os.path.getmtime(pyx):
         return so
     import numpy
-    cpp = os.path.join(OUT, 'c_kernels.cpp')
+    cpp = os.path.join(OUT, mod + '.cpp')
     subprocess.check_call([sys.executable, '-m', 'cython', '-3', '--cplus',
+                           '-I', os.path.join(REF, 'pysph', 'base'),
                            pyx, '-o', cpp])
     cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
     subprocess.check_call([

@@ -364,6 +364,135 @@ def gen_edac_stepper(edac):
     return dict(dt=dt, inputs=inputs, outputs=res)
 
 
+SOLID_PROPS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'p', 'cs', 'e', 'arho',
+               'au', 'av', 'aw', 'ax', 'ay', 'az', 'ae'] + \
+    ['v%d%d' % (i, j) for i in range(3) for j in range(3)] + \
+    [pre + k for pre in ('s', 'as', 'r') for k in ('00', '01', '02', '11', '12', '22')]
+
+
+class _Ref(float):
+    """V[0] as the reference body writes it: a float that remembers where it lives, so
+    that cython.address(V[0]) can hand the whole vector to the compiled routine."""
+    def __new__(cls, value, parent):
+        o = float.__new__(cls, value)
+        o.parent = parent
+        return o
+
+
+class _Mat(list):
+    def __getitem__(self, i):
+        v = list.__getitem__(self, i)
+        return _Ref(v, self) if isinstance(v, (int, float)) else v
+
+
+def load_reference_solid():
+    """solid_mech/basic.py, unmodified.  MonaghanArtificialStress.loop is written for
+    Cython (declare('matrix'), cython.address, cimported eigen_decomposition): the four
+    names are provided here, the last two backed by the reference's OWN compiled
+    pysph/base/linalg3.pyx (oracle/_ref/linalg3*.so)."""
+    import linalg3
+    mod = _load('pysph.sph.solid_mech.basic',
+                os.path.join(REF, 'pysph/sph/solid_mech/basic.py'))
+
+    def declare(spec):
+        if '(3,3)' in spec.replace(' ', ''):
+            return [_Mat([0.0, 0.0, 0.0]) for _ in range(3)]
+        return _Mat([0.0, 0.0, 0.0])
+
+    def eigen_decomposition(S, R, v_addr):
+        d, v = linalg3.py_eigen_decompose_eispack(np.array(S, dtype=float))
+        for i in range(3):
+            list.__setitem__(v_addr, i, float(d[i]))
+            for j in range(3):
+                list.__setitem__(R[i], j, float(v[i, j]))
+
+    def transform_diag_inv(rd_addr, R, Rab):
+        res = linalg3.py_transform_diag_inv(np.array(list(rd_addr), dtype=float),
+                                            np.array(R, dtype=float))
+        for i in range(3):
+            for j in range(3):
+                list.__setitem__(Rab[i], j, float(res[i, j]))
+
+    cython = types.SimpleNamespace(address=lambda ref: ref.parent)
+    mod.declare, mod.cython = declare, cython
+    mod.eigen_decomposition, mod.transform_diag_inv = eigen_decomposition, transform_diag_inv
+    mod.pow = pow
+    return mod
+
+
+def gen_solid_case(kernels, solid, kernel_name, dim, seed, wdeltap=True, two=False):
+    """One evaluation of ElasticSolidsScheme(...).get_equations() (the reference's scheme
+    method and equation bodies) on random particles with random stresses."""
+    rs = np.random.RandomState(seed)
+    kernel = getattr(kernels, kernel_name)(dim=dim)
+    dx = 0.1
+    rho_ref, E, nu = 1.2, 1e3, 0.3975
+    G = E / (2.0 * (1.0 + nu))
+    c0 = math.sqrt(E / (3 * (1.0 - 2 * nu)) / rho_ref)      # get_speed_of_sound, :19-29
+    names = ['ring', 'ring2'][:2 if two else 1]
+    arrays, consts = {}, {}
+    for k, name in enumerate(names):
+        n = 60 if k == 0 else 25
+        hi = [0.5, 0.5, 0.4 if dim == 3 else 0.0]
+        pts = rs.uniform(0.0, 1.0, size=(n, 3)) * np.array(hi) + 0.3 * k
+        a = dict((q, [0.0] * n) for q in SOLID_PROPS)
+        a['x'], a['y'], a['z'] = (list(map(float, pts[:, i])) for i in range(3))
+        v = rs.normal(size=(n, 3)) * (np.arange(3) < dim)
+        a['u'], a['v'], a['w'] = (list(map(float, v[:, i])) for i in range(3))
+        a['h'] = [1.3 * dx] * n
+        a['m'] = [float(rho_ref * dx ** dim)] * n
+        a['rho'] = list(map(float, rho_ref * (1 + 0.05 * rs.uniform(-1, 1, n))))
+        a['cs'] = [c0] * n
+        for key in ('s00', 's01', 's11') + (('s02', 's12', 's22') if dim == 3 else ()):
+            a[key] = list(map(float, 20.0 * rs.normal(size=n)))
+        a['_n_real'] = n - (5 if k == 0 else 0)
+        arrays[name] = a
+        wd = kernel.kernel([0, 0, 0], dx, 1.3 * dx) if wdeltap else -1.0
+        consts[name] = dict(wdeltap=[wd], n=[4.0], G=[G], rho_ref=[rho_ref],
+                            c0_ref=[c0])
+    inputs = json.loads(json.dumps(arrays))
+    scheme = solid.ElasticSolidsScheme(names, [], dim=dim, artificial_stress_eps=0.3,
+                                       xsph_eps=0.5, alpha=1.0, beta=1.5)
+    eqs = scheme.get_equations()
+    # array constants are seen by the bodies as d_<name> / s_<name>
+    for name in names:
+        for ck, cv in consts[name].items():
+            arrays[name][ck] = cv
+    groups = [(g.real, g.equations) for g in eqs]
+    evaluate_reference(kernel, arrays, groups)
+    for name in names:
+        for ck in consts[name]:
+            del arrays[name][ck]
+    params = dict(dim=dim, eps=0.3, eps_xsph=0.5, alpha=1.0, beta=1.5, names=names,
+                  constants=consts,
+                  groups=[[type(e).__name__ for e in g.equations] for g in eqs],
+                  group_real=[bool(g.real) for g in eqs])
+    return dict(kernel=kernel_name, dim=dim, params=params, inputs=inputs,
+                outputs=arrays)
+
+
+def gen_solid_stepper(steps):
+    rs = np.random.RandomState(13)
+    n = 6
+    st = steps.SolidMechStep()
+    sym = ['00', '01', '02', '11', '12', '22']
+    names = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'e', 'x0', 'y0', 'z0', 'u0', 'v0', 'w0',
+             'rho0', 'e0', 'au', 'av', 'aw', 'ax', 'ay', 'az', 'arho', 'ae'] + \
+        ['s' + k for k in sym] + ['s' + k + '0' for k in sym] + ['as' + k for k in sym]
+    a = dict((k, list(map(float, rs.normal(size=n)))) for k in names)
+    inputs = json.loads(json.dumps(a))
+    dt = 0.0123
+    res = {}
+    for which, meth in (('initialize', st.initialize), ('stage1', st.stage1),
+                        ('stage2', st.stage2)):
+        b = json.loads(json.dumps(inputs))
+        env = dict(('d_' + k, v) for k, v in b.items())
+        for i in range(n):
+            call(meth, dict(env, d_idx=i, dt=dt))
+        res[which] = b
+    return dict(dt=dt, inputs=inputs, outputs=res)
+
+
 def gen_output_fixture():
     """pysph/solver/output.py (unmodified, loaded by path) writes the fixture and reads
     back a file written by pysph_b200.output.  Its three imports are satisfied by the
@@ -524,6 +653,14 @@ def main():
     ]
     dump('edac_cases.json', ecases)
     dump('edac_stepper.json', gen_edac_stepper(edac))
+    solid = load_reference_solid()
+    scases = [
+        gen_solid_case(kernels, solid, 'CubicSpline', 2, 301),
+        gen_solid_case(kernels, solid, 'CubicSpline', 3, 302, two=True),
+        gen_solid_case(kernels, solid, 'WendlandQuintic', 2, 303, wdeltap=False),
+    ]
+    dump('solid_cases.json', scases)
+    dump('solid_stepper.json', gen_solid_stepper(steps))
     dump('ref_dump_expect.json', gen_output_fixture())
 
 

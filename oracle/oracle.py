@@ -31,6 +31,11 @@ _PTR_FIELDS = ['x', 'y', 'z', 'h', 'm', 'rho', 'u', 'v', 'w', 'p', 'cs',
                'uhat', 'vhat', 'what', 'V', 'pavg', 'nnbr', 'auhat', 'avhat',
                'awhat', 'ap', 'p0']
 TVF_PGRAD, TVF_AV, TVF_VISC, TVF_ASTRESS, TVF_EDAC = 1, 2, 4, 8, 16
+# elastic dynamics (solid_mech/basic.py:52-59), in the order of orc_array
+_SYM = ['00', '01', '02', '11', '12', '22']
+_PTR_FIELDS += ['v%d%d' % (i, j) for i in range(3) for j in range(3)] + \
+    ['s' + k for k in _SYM] + ['as' + k for k in _SYM] + ['r' + k for k in _SYM] + \
+    ['s' + k + '0' for k in _SYM] + ['e', 'e0', 'ae']
 
 
 class OrcArray(C.Structure):
@@ -58,6 +63,16 @@ class OrcTvfProgram(C.Structure):
                 ('c0', C.c_double), ('rho0', C.c_double), ('alpha', C.c_double),
                 ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
                 ('tdamp', C.c_double), ('t', C.c_double)]
+
+
+class OrcSolidProgram(C.Structure):
+    _fields_ = [('kernel', C.c_int), ('dim', C.c_int),
+                ('elastic_mask', C.c_uint32), ('source_mask', C.c_uint32),
+                ('grad3d', C.c_int), ('eps', C.c_double),
+                ('alpha', C.c_double), ('beta', C.c_double), ('eps_xsph', C.c_double),
+                ('c0_ref', C.c_double * MAX_ARRAYS), ('rho_ref', C.c_double * MAX_ARRAYS),
+                ('wdeltap', C.c_double * MAX_ARRAYS), ('n', C.c_double * MAX_ARRAYS),
+                ('G', C.c_double * MAX_ARRAYS)]
 
 
 def build(force=False):
@@ -103,6 +118,11 @@ def load():
             getattr(lib, f).restype = C.c_int64
             getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(OrcTvfProgram)]
         lib.orc_stage_tvf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        for f in ('orc_solid_group1', 'orc_solid_group2'):
+            getattr(lib, f).restype = C.c_int64
+            getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(OrcSolidProgram)]
+        lib.orc_stage_solid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        lib.orc_eigen_sym3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_kernel_w.restype = C.c_double
         lib.orc_kernel_w.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
         lib.orc_kernel_grad.argtypes = [C.c_int, C.c_int, C.c_void_p,
@@ -113,6 +133,15 @@ def load():
         lib.orc_kernel_radius_scale.argtypes = [C.c_int]
         _lib = lib
     return _lib
+
+
+def eigen_sym3(a):
+    """(eigenvalues[3], eigenvectors as columns [3,3]) of a symmetric 3x3 matrix."""
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(9)
+    v = np.zeros(9)
+    d = np.zeros(3)
+    load().orc_eigen_sym3(a.ctypes.data, v.ctypes.data, d.ctypes.data)
+    return d, v.reshape(3, 3)
 
 
 def kernel_w(kernel, dim, rij, h):
@@ -267,6 +296,31 @@ class Oracle(object):
 
     def stage_tvf(self, arr, which, dt):
         self.lib.orc_stage_tvf(self.h, arr, which, dt)
+
+    # -- elastic dynamics (oracle only so far) ----------------------------------
+    def solid_program(self, elastic, sources, eps=0.3, alpha=1.0, beta=1.0,
+                      eps_xsph=0.5, grad3d=False):
+        P = OrcSolidProgram()
+        P.kernel, P.dim = self.kid, self.dim
+        P.elastic_mask = sum(1 << a for a in elastic)
+        P.source_mask = sum(1 << a for a in sources)
+        P.grad3d, P.eps = int(grad3d), eps
+        P.alpha, P.beta, P.eps_xsph = alpha, beta, eps_xsph
+        for a, pa in enumerate(self.pas):
+            c = getattr(pa, 'constants', {})
+            for k in ('c0_ref', 'rho_ref', 'wdeltap', 'n', 'G'):
+                if k in c:
+                    getattr(P, k)[a] = float(np.ravel(c[k])[0])
+        return P
+
+    def solid_group1(self, P):
+        return self.lib.orc_solid_group1(self.h, C.byref(P))
+
+    def solid_group2(self, P):
+        return self.lib.orc_solid_group2(self.h, C.byref(P))
+
+    def stage_solid(self, arr, which, dt):
+        self.lib.orc_stage_solid(self.h, arr, which, dt)
 
     def dt_factors(self):
         out = (C.c_double * 3)()

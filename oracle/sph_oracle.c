@@ -961,3 +961,288 @@ void orc_stage_tvf(orc_ctx *c, int arr, int which, double dt)
         A->p[i] = A->p0[i] + f * A->ap[i];
     }
 }
+
+
+/* ------------------------------------------------------------------------ */
+/* elastic dynamics: oracle only                             */
+/* ------------------------------------------------------------------------ */
+
+/* cyclic Jacobi; converges to machine precision in < 10 sweeps for 3x3 */
+void orc_eigen_sym3(const double a_in[9], double v[9], double d[3])
+{
+    double a[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            a[i][j] = a_in[3 * i + j];
+            v[3 * i + j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 60; sweep++) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+        if (off <= 1e-32 * diag || off == 0.0) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (a[p][q] == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; k++) { /* A <- A J */
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - sn * akq;
+                    a[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 3; k++) { /* A <- J^T A */
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - sn * aqk;
+                    a[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; k++) { /* V <- V J */
+                    const double vkp = v[3 * k + p], vkq = v[3 * k + q];
+                    v[3 * k + p] = c * vkp - sn * vkq;
+                    v[3 * k + q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    d[0] = a[0][0];
+    d[1] = a[1][1];
+    d[2] = a[2][2];
+}
+
+static const int VG_I[9] = {0, 0, 0, 1, 1, 1, 2, 2, 2}; /* velocity component of vg[k] */
+static const int VG_J[9] = {0, 1, 2, 0, 1, 2, 0, 1, 2}; /* spatial component           */
+
+int64_t orc_solid_group1(orc_ctx *c, const orc_solid_program *P)
+{
+    const int kernel = P->kernel, dim = P->dim;
+    const double kfac = k_fac(kernel, dim);
+    int64_t total = 0;
+    for (int dst = 0; dst < c->narr; dst++) {
+        if (!(P->elastic_mask >> dst & 1u)) continue;
+        orc_array *D = &c->arr[dst];
+        const int64_t np = D->n_real; /* Group(real=True) default */
+        /* initialize: VelocityGradient2D basic_equations.py:82-86 / 3D :115-125 */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++)
+            for (int k = 0; k < 9; k++)
+                if (P->grad3d || (VG_I[k] < 2 && VG_J[k] < 2)) D->vg[k][i] = 0.0;
+        /* no-source loops, in the order of the equation list */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++) {
+            /* IsothermalEOS solid_mech/basic.py:100-101 */
+            D->p[i] = P->c0_ref[dst] * P->c0_ref[dst] * (D->rho[i] - P->rho_ref[dst]);
+            /* MonaghanArtificialStress :170-242 */
+            const double rhoi21 = 1.0 / (D->rho[i] * D->rho[i]);
+            double S[9], R[9], V[3], rd[3];
+            S[0] = D->s[0][i] - D->p[i];
+            S[4] = D->s[3][i] - D->p[i];
+            S[8] = D->s[5][i] - D->p[i];
+            S[5] = S[7] = D->s[4][i];
+            S[2] = S[6] = D->s[2][i];
+            S[1] = S[3] = D->s[1][i];
+            orc_eigen_sym3(S, R, V);
+            for (int k = 0; k < 3; k++) rd[k] = V[k] > 0 ? -P->eps * V[k] * rhoi21 : 0.0;
+            /* transform_diag_inv: Rab = R diag(rd) R^T  (linalg3.pyx:220-233) */
+            double Rab[9];
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) {
+                    double sum = 0.0;
+                    for (int k = 0; k < 3; k++) sum += R[3 * a + k] * rd[k] * R[3 * b + k];
+                    Rab[3 * a + b] = sum;
+                }
+            D->r[0][i] = Rab[0];
+            D->r[3][i] = Rab[4];
+            D->r[5][i] = Rab[8];
+            D->r[4][i] = Rab[5];
+            D->r[2][i] = Rab[2];
+            D->r[1][i] = Rab[1];
+        }
+        for (int src = 0; src < c->narr; src++) {
+            if (!(P->source_mask >> src & 1u)) continue;
+            const orc_array *S_ = &c->arr[src];
+            int64_t pairs = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : pairs)
+            for (int64_t d_idx = 0; d_idx < np; d_idx++) {
+                ORC_FOR_NEIGHBORS(c, dst, src, d_idx, s_idx, {
+                    pairs++;
+                    double XIJ[3], VIJ[3], DWIJ[3] = {0, 0, 0};
+                    XIJ[0] = D->x[d_idx] - S_->x[s_idx];
+                    XIJ[1] = D->y[d_idx] - S_->y[s_idx];
+                    XIJ[2] = D->z[d_idx] - S_->z[s_idx];
+                    VIJ[0] = D->u[d_idx] - S_->u[s_idx];
+                    VIJ[1] = D->v[d_idx] - S_->v[s_idx];
+                    VIJ[2] = D->w[d_idx] - S_->w[s_idx];
+                    const double RIJ = sqrt(XIJ[0] * XIJ[0] + XIJ[1] * XIJ[1] + XIJ[2] * XIJ[2]);
+                    const double HIJ = 0.5 * (D->h[d_idx] + S_->h[s_idx]);
+                    k_grad(kernel, dim, kfac, XIJ, RIJ, HIJ, DWIJ);
+                    const double tmp = S_->m[s_idx] / S_->rho[s_idx];
+                    for (int k = 0; k < 9; k++)
+                        if (P->grad3d || (VG_I[k] < 2 && VG_J[k] < 2))
+                            D->vg[k][d_idx] += tmp * -VIJ[VG_I[k]] * DWIJ[VG_J[k]];
+                });
+            }
+            total += pairs;
+        }
+    }
+    return total;
+}
+
+int64_t orc_solid_group2(orc_ctx *c, const orc_solid_program *P)
+{
+    const int kernel = P->kernel, dim = P->dim;
+    const double kfac = k_fac(kernel, dim);
+    /* symmetric index: (a,b) -> 00 01 02 11 12 22 */
+    static const int SYM[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    int64_t total = 0;
+    for (int dst = 0; dst < c->narr; dst++) {
+        if (!(P->elastic_mask >> dst & 1u)) continue;
+        orc_array *D = &c->arr[dst];
+        const int64_t np = D->n_real;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++) {
+            D->arho[i] = 0.0;
+            D->au[i] = D->av[i] = D->aw[i] = 0.0;
+            D->ax[i] = D->ay[i] = D->az[i] = 0.0;
+            for (int k = 0; k < 6; k++) D->as[k][i] = 0.0;
+        }
+        /* HookesDeviatoricStressRate (no source) solid_mech/basic.py:420-505 */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++) {
+            double v[3][3], s[3][3], eps[3][3], om[3][3];
+            for (int k = 0; k < 9; k++) v[VG_I[k]][VG_J[k]] = D->vg[k][i];
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) {
+                    s[a][b] = D->s[SYM[a][b]][i];
+                    eps[a][b] = 0.5 * (v[a][b] + v[b][a]);
+                    om[a][b] = 0.5 * (v[a][b] - v[b][a]);
+                }
+            const double tmp = 2.0 * P->G[dst];
+            const double trace = 1.0 / 3.0 * (eps[0][0] + eps[1][1] + eps[2][2]);
+            for (int a = 0; a < 3; a++)
+                for (int b = a; b < 3; b++) {
+                    /* as_ab = 2G (eps_ab - delta_ab trace) + s_ak om_bk + s_kb om_ak
+                     * (the reference writes out s_ak*omega_bk + s_kb*omega_ak term by term) */
+                    double t1 = 0.0, t2 = 0.0;
+                    for (int k = 0; k < 3; k++) {
+                        t1 += s[a][k] * om[b][k];
+                        t2 += s[k][b] * om[a][k];
+                    }
+                    D->as[SYM[a][b]][i] = tmp * (eps[a][b] - (a == b ? trace : 0.0)) + t1 + t2;
+                }
+        }
+        for (int src = 0; src < c->narr; src++) {
+            if (!(P->source_mask >> src & 1u)) continue;
+            const orc_array *S_ = &c->arr[src];
+            const int xsph = (src == dst);
+            int64_t pairs = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : pairs)
+            for (int64_t d_idx = 0; d_idx < np; d_idx++) {
+                ORC_FOR_NEIGHBORS(c, dst, src, d_idx, s_idx, {
+                    pairs++;
+                    double XIJ[3], VIJ[3], DWIJ[3] = {0, 0, 0};
+                    XIJ[0] = D->x[d_idx] - S_->x[s_idx];
+                    XIJ[1] = D->y[d_idx] - S_->y[s_idx];
+                    XIJ[2] = D->z[d_idx] - S_->z[s_idx];
+                    VIJ[0] = D->u[d_idx] - S_->u[s_idx];
+                    VIJ[1] = D->v[d_idx] - S_->v[s_idx];
+                    VIJ[2] = D->w[d_idx] - S_->w[s_idx];
+                    const double R2IJ = XIJ[0] * XIJ[0] + XIJ[1] * XIJ[1] + XIJ[2] * XIJ[2];
+                    const double RIJ = sqrt(R2IJ);
+                    const double HIJ = 0.5 * (D->h[d_idx] + S_->h[s_idx]);
+                    const double EPS = 0.01 * HIJ * HIJ;
+                    const double WIJ = k_w(kernel, dim, kfac, RIJ, HIJ);
+                    k_grad(kernel, dim, kfac, XIJ, RIJ, HIJ, DWIJ);
+                    const double mb = S_->m[s_idx];
+                    const double rhoa = D->rho[d_idx], rhob = S_->rho[s_idx];
+                    const double RHOIJ1 = 1.0 / (0.5 * (rhoa + rhob));
+                    /* ContinuityEquation basic_equations.py:190-192 */
+                    const double vijdotdwij = DWIJ[0] * VIJ[0] + DWIJ[1] * VIJ[1] + DWIJ[2] * VIJ[2];
+                    D->arho[d_idx] += mb * vijdotdwij;
+                    /* MomentumEquationWithStress solid_mech/basic.py:267-387 */
+                    const double rhoa21 = 1.0 / (rhoa * rhoa), rhob21 = 1.0 / (rhob * rhob);
+                    double fab = 0.0;
+                    const int art = P->wdeltap[dst] > 0.0;
+                    if (art) fab = pow(WIJ / P->wdeltap[dst], P->n[dst]);
+                    double acc[3] = {0, 0, 0};
+                    for (int a = 0; a < 3; a++)
+                        for (int b = 0; b < 3; b++) {
+                            const int k = SYM[a][b];
+                            double sa = D->s[k][d_idx], sb = S_->s[k][s_idx];
+                            if (a == b) {
+                                sa -= D->p[d_idx];
+                                sb -= S_->p[s_idx];
+                            }
+                            const double arts = art ? fab * (D->r[k][d_idx] + S_->r[k][s_idx]) : 0.0;
+                            acc[a] += mb * (sa * rhoa21 + sb * rhob21 + arts) * DWIJ[b];
+                        }
+                    D->au[d_idx] += acc[0];
+                    D->av[d_idx] += acc[1];
+                    D->aw[d_idx] += acc[2];
+                    /* MonaghanArtificialViscosity basic_equations.py:240-257 */
+                    {
+                        const double vijdotxij = VIJ[0] * XIJ[0] + VIJ[1] * XIJ[1] + VIJ[2] * XIJ[2];
+                        double piij = 0.0;
+                        if (vijdotxij < 0) {
+                            const double cij = 0.5 * (D->cs[d_idx] + S_->cs[s_idx]);
+                            const double muij = (HIJ * vijdotxij) / (R2IJ + EPS);
+                            piij = -P->alpha * cij * muij + P->beta * muij * muij;
+                            piij = piij * RHOIJ1;
+                        }
+                        D->au[d_idx] += -mb * piij * DWIJ[0];
+                        D->av[d_idx] += -mb * piij * DWIJ[1];
+                        D->aw[d_idx] += -mb * piij * DWIJ[2];
+                    }
+                    if (xsph) { /* XSPHCorrection(sources=[dest]) basic_equations.py:290-295 */
+                        const double tmp = -P->eps_xsph * mb * WIJ * RHOIJ1;
+                        D->ax[d_idx] += tmp * VIJ[0];
+                        D->ay[d_idx] += tmp * VIJ[1];
+                        D->az[d_idx] += tmp * VIJ[2];
+                    }
+                });
+            }
+            total += pairs;
+        }
+        /* XSPHCorrection.post_loop basic_equations.py:297-300 */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++) {
+            D->ax[i] += D->u[i];
+            D->ay[i] += D->v[i];
+            D->az[i] += D->w[i];
+        }
+    }
+    return total;
+}
+
+/* SolidMechStep integrator_step.py:173-252 */
+void orc_stage_solid(orc_ctx *c, int arr, int which, double dt)
+{
+    orc_array *A = &c->arr[arr];
+    const int64_t n = A->n_real;
+    if (which == 0) {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; i++) {
+            A->x0[i] = A->x[i];
+            A->y0[i] = A->y[i];
+            A->z0[i] = A->z[i];
+            A->u0[i] = A->u[i];
+            A->v0[i] = A->v[i];
+            A->w0[i] = A->w[i];
+            A->rho0[i] = A->rho[i];
+            A->e0[i] = A->e[i];
+            for (int k = 0; k < 6; k++) A->s0[k][i] = A->s[k][i];
+        }
+        return;
+    }
+    const double f = (which == 1) ? 0.5 * dt : dt;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        A->u[i] = A->u0[i] + f * A->au[i];
+        A->v[i] = A->v0[i] + f * A->av[i];
+        A->w[i] = A->w0[i] + f * A->aw[i];
+        A->x[i] = A->x0[i] + f * A->ax[i];
+        A->y[i] = A->y0[i] + f * A->ay[i];
+        A->z[i] = A->z0[i] + f * A->az[i];
+        A->rho[i] = A->rho0[i] + f * A->arho[i];
+        A->e[i] = A->e0[i] + f * A->ae[i];
+        for (int k = 0; k < 6; k++) A->s[k][i] = A->s0[k][i] + f * A->as[k][i];
+    }
+}

@@ -47,6 +47,9 @@ typedef struct {
     double *x0, *y0, *z0, *u0, *v0, *w0, *rho0;
     /* transport-velocity / EDAC properties (wc/edac.py:724-730); may be NULL */
     double *uhat, *vhat, *what, *V, *pavg, *nnbr, *auhat, *avhat, *awhat, *ap, *p0;
+    /* elastic dynamics (solid_mech/basic.py:52-59); may be NULL.  Symmetric tensors
+     * are stored as 00 01 02 11 12 22, the velocity gradient as 00 01 02 10 .. 22 */
+    double *vg[9], *s[6], *as[6], *r[6], *s0[6], *e, *e0, *ae;
 } orc_array;
 
 typedef struct {
@@ -85,6 +88,21 @@ typedef struct {
     double pb, nu, edac_nu, c0, rho0, alpha;
     double gx, gy, gz, tdamp, t;
 } orc_tvf_program;
+
+/* ElasticSolidsScheme.get_equations, solid_mech/basic.py:604-651 */
+typedef struct {
+    int kernel, dim;
+    uint32_t elastic_mask; /* destinations (elastic solids)                        */
+    uint32_t source_mask;  /* sources = solids + elastic solids                    */
+    int grad3d;            /* 0: VelocityGradient2D (what the reference scheme emits),
+                            * 1: VelocityGradient3D (basic_equations.py:101-148)   */
+    double eps;            /* MonaghanArtificialStress(eps)                        */
+    double alpha, beta;    /* MonaghanArtificialViscosity                          */
+    double eps_xsph;       /* XSPHCorrection                                       */
+    /* the array constants of get_particle_array_elastic_dynamics (:61-83) */
+    double c0_ref[ORC_MAX_ARRAYS], rho_ref[ORC_MAX_ARRAYS], wdeltap[ORC_MAX_ARRAYS],
+        n[ORC_MAX_ARRAYS], G[ORC_MAX_ARRAYS];
+} orc_solid_program;
 
 typedef struct orc_ctx orc_ctx;
 
@@ -138,6 +156,20 @@ int64_t orc_tvf_pass1(orc_ctx *, const orc_tvf_program *);
 int64_t orc_tvf_pass2(orc_ctx *, const orc_tvf_program *);
 /* EDACTVFStep wc/edac.py:491-540: which = 0 initialize, 1 stage1, 2 stage2 */
 void orc_stage_tvf(orc_ctx *, int arr, int which, double dt);
+
+/* elastic dynamics (Gray et al.), SURVEY.md 8f-2 -- ORACLE ONLY so far, no CUDA yet.
+ * group 1: IsothermalEOS (solid_mech/basic.py:93-101), VelocityGradient2D/3D
+ * (basic_equations.py:67-148), MonaghanArtificialStress (:104-242);
+ * group 2: ContinuityEquation, MomentumEquationWithStress (:245-387),
+ * MonaghanArtificialViscosity, HookesDeviatoricStressRate (:390-505), XSPHCorrection */
+int64_t orc_solid_group1(orc_ctx *, const orc_solid_program *);
+int64_t orc_solid_group2(orc_ctx *, const orc_solid_program *);
+/* SolidMechStep integrator_step.py:173-252 */
+void orc_stage_solid(orc_ctx *, int arr, int which, double dt);
+/* eigen decomposition of a symmetric 3x3 matrix (row-major a[9]): eigenvalues d[3],
+ * eigenvectors as the COLUMNS of v[9] (what pysph/base/linalg3.pyx:503-529 returns;
+ * order and signs are not specified and do not matter for R = V diag V^T) */
+void orc_eigen_sym3(const double a[9], double v[9], double d[3]);
 
 /* single kernel evaluations for the kernel parity tests */
 double orc_kernel_w(int kernel, int dim, double rij, double h);

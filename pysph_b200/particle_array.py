@@ -195,3 +195,34 @@ def get_particle_array_edac(constants=None, **props):
     pa.set_output_arrays(['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'p', 'm', 'h',
                           'V', 'pavg'])
     return pa
+
+
+# pysph/sph/solid_mech/basic.py:52-59
+ELASTIC_PROPS = ['cs', 'e', 'v00', 'v01', 'v02', 'v10', 'v11', 'v12', 'v20', 'v21',
+                 'v22', 'r00', 'r01', 'r02', 'r11', 'r12', 'r22', 's00', 's01', 's02',
+                 's11', 's12', 's22', 'as00', 'as01', 'as02', 'as11', 'as12', 'as22',
+                 's000', 's010', 's020', 's110', 's120', 's220', 'arho', 'au', 'av',
+                 'aw', 'ax', 'ay', 'az', 'ae', 'rho0', 'u0', 'v0', 'w0', 'x0', 'y0',
+                 'z0', 'e0']
+
+
+def get_particle_array_elastic_dynamics(constants=None, **props):
+    """pysph/sph/solid_mech/basic.py:32-90 (host side only: the B200 backend has no
+    kernels for the elastic-dynamics equations yet)."""
+    consts = {'wdeltap': -1., 'n': 4, 'G': 0.0, 'E': 0.0, 'nu': 0.0,
+              'rho_ref': 1000.0, 'c0_ref': 0.0}
+    given = dict(constants or {})
+    consts.update(given)
+    pa = get_particle_array(additional_props=ELASTIC_PROPS, **props)
+    for k, v in consts.items():
+        pa.add_constant(k, v)
+    E, nu, rho_ref = pa.E[0], pa.nu[0], pa.rho_ref[0]
+    if 'G' not in given:
+        pa.G[0] = E / (2.0 * (1.0 + nu))                   # get_shear_modulus, :26-29
+    if E > 0 and 'c0_ref' not in given:
+        c0 = np.sqrt(E / (3 * (1.0 - 2 * nu)) / rho_ref)   # get_speed_of_sound, :19-23
+        pa.cs[:] = c0
+        pa.c0_ref[0] = c0
+    pa.set_output_arrays(['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'm', 'h', 'pid', 'gid',
+                          'tag', 'p'])
+    return pa

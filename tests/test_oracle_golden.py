@@ -305,3 +305,83 @@ def test_edac_tvf_step_matches_reference_bodies():
         o.stage_tvf(0, which, g['dt'])
         for k, v in g['outputs'][key].items():
             assert np.allclose(pa.properties[k], v, rtol=1e-15, atol=0), (key, k)
+
+
+# ---------------------------------------------------------------------------
+# elastic dynamics: ORACLE ONLY so far -- the restatement of
+# ElasticSolidsScheme's loops against the reference's scheme method + bodies, with the
+# reference's own compiled linalg3 eigen solver behind MonaghanArtificialStress
+# ---------------------------------------------------------------------------
+SOLID_FIELDS = ['p', 'arho', 'au', 'av', 'aw', 'ax', 'ay', 'az'] + \
+    ['v%d%d' % (i, j) for i in range(3) for j in range(3)] + \
+    [pre + k for pre in ('r', 'as') for k in ('00', '01', '02', '11', '12', '22')]
+
+
+def _solid_arrays(case):
+    from pysph_b200.particle_array import get_particle_array_elastic_dynamics
+    pas = []
+    for name in case['params']['names']:
+        a = case['inputs'][name]
+        props = dict((k, np.array(v, dtype=float)) for k, v in a.items() if k[0] != '_')
+        consts = dict((k, v[0]) for k, v in case['params']['constants'][name].items())
+        pa = get_particle_array_elastic_dynamics(name=name, constants=consts, **props)
+        pa.set_num_real_particles(a['_n_real'])
+        pas.append(pa)
+    return pas
+
+
+@pytest.mark.parametrize('idx', range(3))
+def test_elastic_dynamics_matches_reference_bodies(idx):
+    case = load_golden('solid_cases.json')[idx]
+    p = case['params']
+    assert p['groups'][0][:3] == ['IsothermalEOS', 'VelocityGradient2D',
+                                  'MonaghanArtificialStress']
+    assert p['groups'][1][:5] == ['ContinuityEquation', 'MomentumEquationWithStress',
+                                  'MonaghanArtificialViscosity',
+                                  'HookesDeviatoricStressRate', 'XSPHCorrection']
+    assert p['group_real'] == [True, True]
+    pas = _solid_arrays(case)
+    o = orc.Oracle(pas, p['dim'], case['kernel'])
+    o.update_domain()
+    o.nnps_update()
+    idxs = list(range(len(pas)))
+    P = o.solid_program(idxs, idxs, eps=p['eps'], alpha=p['alpha'], beta=p['beta'],
+                        eps_xsph=p['eps_xsph'], grad3d=False)
+    o.solid_group1(P)
+    o.solid_group2(P)
+    for pa in pas:
+        ref = case['outputs'][pa.name]
+        nr = ref['_n_real']
+        for f in SOLID_FIELDS:
+            want = np.array(ref[f])[:nr]
+            got = pa.properties[f][:nr]
+            scale = max(np.max(np.abs(want)), 1e-300)
+            assert np.max(np.abs(got - want)) <= 1e-10 * scale, (pa.name, f)
+        # destinations are the real particles only: ghosts untouched
+        assert np.all(pa.properties['au'][nr:] == 0.0)
+
+
+def test_solid_mech_step_matches_reference_bodies():
+    from pysph_b200.particle_array import get_particle_array_elastic_dynamics
+    g = load_golden('solid_stepper.json')
+    for which, key in ((0, 'initialize'), (1, 'stage1'), (2, 'stage2')):
+        props = dict((k, np.array(v)) for k, v in g['inputs'].items())
+        pa = get_particle_array_elastic_dynamics(name='f', **props)
+        o = orc.Oracle([pa], 3)
+        o.stage_solid(0, which, g['dt'])
+        for k, v in g['outputs'][key].items():
+            assert np.allclose(pa.properties[k], v, rtol=1e-15, atol=0), (key, k)
+
+
+def test_eigen_sym3_against_numpy():
+    rs = np.random.RandomState(4)
+    for t in range(50):
+        a = rs.normal(size=(3, 3)) * 10.0 ** rs.randint(-6, 6)
+        a = a + a.T
+        if t % 10 == 0:
+            a = np.diag([2.0, 2.0, -1.0]) * a[0, 0]          # repeated eigenvalue
+        d, v = orc.eigen_sym3(a)
+        s = max(np.max(np.abs(a)), 1e-300)
+        assert np.max(np.abs(v @ np.diag(d) @ v.T - a)) <= 1e-13 * s
+        assert np.max(np.abs(v.T @ v - np.eye(3))) <= 1e-14
+        assert np.max(np.abs(np.sort(d) - np.linalg.eigvalsh(a))) <= 1e-13 * s
