@@ -61,6 +61,19 @@ enum {
     B200SPH_VOL = 32, B200SPH_PAVG, B200SPH_AUHAT, B200SPH_AVHAT, B200SPH_AWHAT,
     B200SPH_AP,
     B200SPH_NUM_PROPS = 38,
+    /* elastic-dynamics extension (solid_mech/basic.py:52-59), device memory allocated
+     * on first use.  Symmetric tensors as 00 01 02 11 12 22, the velocity gradient as
+     * 00 01 02 10 11 12 20 21 22.  fp64: deviatoric stress (integrated) and its copy;
+     * fp32: velocity gradient, artificial stress, stress rate.
+     * NOTE: written after this round's GPU budget was spent -- compiled, not yet run on
+     * hardware (tests/test_zz_gpu_solid_unvalidated.py) */
+    B200SPH_S00 = 70, B200SPH_S01, B200SPH_S02, B200SPH_S11, B200SPH_S12, B200SPH_S22,
+    B200SPH_S000 = 76, B200SPH_S010, B200SPH_S020, B200SPH_S110, B200SPH_S120, B200SPH_S220,
+    B200SPH_V00 = 82, B200SPH_V01, B200SPH_V02, B200SPH_V10, B200SPH_V11, B200SPH_V12,
+    B200SPH_V20, B200SPH_V21, B200SPH_V22,
+    B200SPH_R00 = 91, B200SPH_R01, B200SPH_R02, B200SPH_R11, B200SPH_R12, B200SPH_R22,
+    B200SPH_AS00 = 97, B200SPH_AS01, B200SPH_AS02, B200SPH_AS11, B200SPH_AS12, B200SPH_AS22,
+    B200SPH_SOLID_PROPS_END = 103,
     /* 32-bit integer props */
     B200SPH_GID = 64, B200SPH_TAG = 65, B200SPH_PID = 66
 };
@@ -107,6 +120,25 @@ typedef struct {
     double gx, gy, gz;   /* body force; damped by tdamp at time t (:483-488)     */
     double tdamp, t;
 } b200sph_tvf_program;
+
+/* The two Groups of ElasticSolidsScheme.get_equations (solid_mech/basic.py:604-651) for
+ * elastic solids without rigid `solids`: every elastic array is a destination and a
+ * source.  Group 1: IsothermalEOS (:93-101), VelocityGradient2D/3D
+ * (basic_equations.py:67-148), MonaghanArtificialStress (:104-242); group 2:
+ * ContinuityEquation, MomentumEquationWithStress (:245-387),
+ * MonaghanArtificialViscosity, HookesDeviatoricStressRate (:390-505), XSPHCorrection. */
+typedef struct {
+    uint32_t elastic_mask; /* bit a: array a is an elastic solid                    */
+    int32_t grad3d;        /* 0 VelocityGradient2D (what the scheme emits), 1 ..3D  */
+    int32_t passes;        /* bit 0: group 1, bit 1: group 2                        */
+    int32_t reserved;
+    double eps;            /* MonaghanArtificialStress(eps)                         */
+    double alpha, beta;    /* MonaghanArtificialViscosity                           */
+    double eps_xsph;       /* XSPHCorrection(eps)                                   */
+    /* the array constants of get_particle_array_elastic_dynamics (:61-83), per array */
+    double c0_ref[B200SPH_MAX_ARRAYS], rho_ref[B200SPH_MAX_ARRAYS],
+        wdeltap[B200SPH_MAX_ARRAYS], n[B200SPH_MAX_ARRAYS], G[B200SPH_MAX_ARRAYS];
+} b200sph_solid_program;
 
 typedef struct {
     double cell_size;  /* DomainManager.cell_size  nnps_base.pyx:942-978    */
@@ -232,6 +264,15 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog,
 int b200sph_stage_tvf(b200sph_ctx *ctx, int arr, int which, double dt);
 /* the same with dt read from the device-resident time-control block */
 int b200sph_stage_tvf_dev(b200sph_ctx *ctx, int arr, int which);
+
+/* The elastic-dynamics evaluation (see b200sph_solid_program); same neighbour lists as
+ * pair_pass.  NOT YET RUN ON HARDWARE (see the property block above). */
+int b200sph_solid_pass(b200sph_ctx *ctx, const b200sph_solid_program *prog,
+                       int64_t *pairs_out);
+/* SolidMechStep integrator_step.py:173-252 (e / ae are not mirrored: the scheme has no
+ * energy equation, so e stays what it is) */
+int b200sph_stage_solid(b200sph_ctx *ctx, int arr, int which, double dt);
+int b200sph_stage_solid_dev(b200sph_ctx *ctx, int arr, int which);
 
 /* ---- Integrator stages: WCSPHStep integrator_step.py:38-91 -------------- */
 /* which: 0 initialize, 1 stage1, 2 stage2; arr = -1 -> every array */

@@ -629,3 +629,56 @@ class EDACOracleSolver(object):
         self.update_domain()
         self.t += self.dt
         self.count += 1
+
+
+class ElasticOracleSolver(object):
+    """ElasticSolidsScheme(elastic_solids, solids=[]) with SolidMechStep and a fixed
+    time step (pysph/examples/solid_mech/rings.py:80-84: the scheme's default
+    EPECIntegrator): solid_mech/basic.py:604-651 for the groups,
+    integrator.py:401-420 for the stage order."""
+
+    def __init__(self, particles, params, kernel='CubicSpline', threads=1):
+        self.p = dict(params)
+        self.pas = list(particles)
+        self.o = Oracle(self.pas, self.p['dim'], kernel, threads=threads)
+        self.dt = self.p['dt']
+        self.t = 0.0
+        self.count = 0
+        self.integrator = self.p.get('integrator', 'EPEC')
+        self.pairs_last_eval = 0
+        self.o.update_domain()
+        self.o.nnps_update()
+        self._initialised = False
+
+    def evaluate(self):
+        p = self.p
+        idx = list(range(len(self.pas)))
+        P = self.o.solid_program(idx, idx, eps=p.get('eps', 0.3), alpha=p.get('alpha', 1.0),
+                                 beta=p.get('beta', 1.0), eps_xsph=p.get('eps_xsph', 0.5),
+                                 grad3d=p.get('grad3d', False))
+        self.pairs_last_eval = self.o.solid_group1(P) + self.o.solid_group2(P)
+        return self.pairs_last_eval
+
+    def initialise(self):
+        if not self._initialised:
+            self.evaluate()
+            self._initialised = True
+
+    def _stage(self, which, dt):
+        for a in range(len(self.pas)):
+            self.o.stage_solid(a, which, dt)
+
+    def step(self):
+        self.initialise()
+        self._stage(0, 0.0)
+        if self.integrator == 'EPEC':
+            self.o.nnps_update()
+            self.evaluate()
+        self._stage(1, self.dt)
+        self.o.update_domain()
+        self.o.nnps_update()
+        self.evaluate()
+        self._stage(2, self.dt)
+        self.o.update_domain()
+        self.t += self.dt
+        self.count += 1

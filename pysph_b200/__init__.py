@@ -21,7 +21,8 @@ There is no CPU fallback: importing the adapters is cheap, but creating a
 backend needs the built library and a CUDA device.
 """
 from .particle_array import (ParticleArray, get_particle_array,
-                             get_particle_array_wcsph, get_particle_array_edac)
+                             get_particle_array_wcsph, get_particle_array_edac,
+                             get_particle_array_elastic_dynamics)
 from .kernels import CubicSpline, WendlandQuintic, QuinticSpline, Gaussian
 from .equations import (Equation, Group, SummationDensity, ContinuityEquation,
                         MonaghanArtificialViscosity, XSPHCorrection, TaitEOS,
@@ -37,6 +38,7 @@ from .integrator import (B200Integrator, PECIntegrator, EPECIntegrator,
 from .solver import B200Solver
 from .edac import EDACScheme, EDACTVFStep
 from .output import dump, load
+from .solid_mech import ElasticSolidsScheme, SolidMechStep
 
 __version__ = '0.1.0'
 
@@ -68,5 +70,16 @@ def make_edac_solver(particles, scheme, kernel, dt, domain=None, integrator='PEC
     integ = cls(**scheme.get_steppers())
     kw = dict(adaptive_timestep=False, tf=1e9, fixed_h=True, device=device,
               domain=domain)
+    kw.update(solver_kw)
+    return B200Solver(particles, scheme.get_equations(), kernel, integ, dt=dt, **kw)
+
+
+def make_elastic_solver(particles, scheme, kernel, dt, integrator='EPEC', device=0,
+                        **solver_kw):
+    """Fixed-dt solver for an :class:`ElasticSolidsScheme` (configure_solver's default
+    is EPECIntegrator + SolidMechStep, solid_mech/basic.py:653-684)."""
+    cls = {'EPEC': EPECIntegrator, 'PEC': PECIntegrator}[integrator]
+    integ = cls(**scheme.get_steppers())
+    kw = dict(adaptive_timestep=False, tf=1e9, fixed_h=True, device=device)
     kw.update(solver_kw)
     return B200Solver(particles, scheme.get_equations(), kernel, integ, dt=dt, **kw)

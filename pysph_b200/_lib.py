@@ -24,6 +24,14 @@ PROP_IDS.update(uhat=27, vhat=28, what=29, V=32, pavg=33, auhat=34, avhat=35,
 # arrays of the EDAC scheme (they own 'ap') integrate p: it lives in the fp64
 # B200SPH_PF / B200SPH_PF0 instead of the derived fp32 B200SPH_P
 EDAC_PROP_IDS = dict(PROP_IDS, p=30, p0=31)
+# elastic-dynamics extension (B200SPH_S00 ...); arrays that own 's00' use these
+_SYM = ('00', '01', '02', '11', '12', '22')
+ELASTIC_PROP_IDS = dict(PROP_IDS)
+ELASTIC_PROP_IDS.update(('s' + k, 70 + i) for i, k in enumerate(_SYM))
+ELASTIC_PROP_IDS.update(('s' + k + '0', 76 + i) for i, k in enumerate(_SYM))
+ELASTIC_PROP_IDS.update(('v%d%d' % (i, j), 82 + 3 * i + j) for i in range(3) for j in range(3))
+ELASTIC_PROP_IDS.update(('r' + k, 91 + i) for i, k in enumerate(_SYM))
+ELASTIC_PROP_IDS.update(('as' + k, 97 + i) for i, k in enumerate(_SYM))
 INT_PROP_IDS = {'gid': 64, 'tag': 65, 'pid': 66}
 F64_DEVICE_PROPS = ('x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm',
                     'x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'rho0')
@@ -58,6 +66,16 @@ class TvfProgram(C.Structure):
                 ('c0', C.c_double), ('rho0', C.c_double), ('alpha', C.c_double),
                 ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
                 ('tdamp', C.c_double), ('t', C.c_double)]
+
+
+class SolidProgram(C.Structure):
+    _fields_ = [('elastic_mask', C.c_uint32), ('grad3d', C.c_int32),
+                ('passes', C.c_int32), ('reserved', C.c_int32),
+                ('eps', C.c_double), ('alpha', C.c_double), ('beta', C.c_double),
+                ('eps_xsph', C.c_double),
+                ('c0_ref', C.c_double * MAX_ARRAYS), ('rho_ref', C.c_double * MAX_ARRAYS),
+                ('wdeltap', C.c_double * MAX_ARRAYS), ('n', C.c_double * MAX_ARRAYS),
+                ('G', C.c_double * MAX_ARRAYS)]
 
 
 class GridInfo(C.Structure):
@@ -117,6 +135,9 @@ SIGNATURES = {
     'b200sph_tvf_pass': (C.c_int, [_ctx_p, C.POINTER(TvfProgram), C.POINTER(_i64)]),
     'b200sph_stage_tvf': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
     'b200sph_stage_tvf_dev': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
+    'b200sph_solid_pass': (C.c_int, [_ctx_p, C.POINTER(SolidProgram), C.POINTER(_i64)]),
+    'b200sph_stage_solid': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
+    'b200sph_stage_solid_dev': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
     'b200sph_stage': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
     'b200sph_dt_factors': (C.c_int, [_ctx_p, _dp]),
     'b200sph_time_control': (C.c_int, [_ctx_p, C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -25,7 +25,8 @@ class B200AccelerationEval(object):
         self.ctx = self.backend.ctx
         self.ctx.call('b200sph_set_kernel', kernel_id(kernel), int(kernel.dim))
         self.equation_groups = equations
-        self.ops = build_program(equations, self.backend.names, kernel.dim)
+        self.ops = build_program(equations, self.backend.names, kernel.dim,
+                                 particle_arrays=self.particle_arrays)
         self.nnps = None
         self.count_pairs = False
         self.last_pairs = 0
@@ -73,6 +74,12 @@ class B200AccelerationEval(object):
                     pairs += cnt.value
                 else:
                     ctx.call('b200sph_tvf_pass', C.byref(op[1]), None)
+            elif kind == 'solid':
+                if self.count_pairs:
+                    ctx.call('b200sph_solid_pass', C.byref(op[1]), C.byref(cnt))
+                    pairs += cnt.value
+                else:
+                    ctx.call('b200sph_solid_pass', C.byref(op[1]), None)
             elif kind == 'update_nnps':
                 # mako:139-145: nnps.update_domain(); nnps.update()
                 ctx.call('b200sph_update_domain')

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import PROP_IDS, INT_PROP_IDS, EDAC_PROP_IDS
+from ._lib import PROP_IDS, INT_PROP_IDS, EDAC_PROP_IDS, ELASTIC_PROP_IDS
 
 
 def _host_array(pa, name):
@@ -72,7 +72,8 @@ class B200Backend(object):
         self.names = [pa.name for pa in particle_arrays]
         self.index = dict((n, i) for i, n in enumerate(self.names))
         # name -> device property id, per array: EDAC arrays evolve p (fp64 PF)
-        self.prop_ids = [EDAC_PROP_IDS if 'ap' in pa.properties else PROP_IDS
+        self.prop_ids = [EDAC_PROP_IDS if 'ap' in pa.properties else
+                         (ELASTIC_PROP_IDS if 's00' in pa.properties else PROP_IDS)
                          for pa in particle_arrays]
         for pa in particle_arrays:
             n = pa.get_number_of_particles()

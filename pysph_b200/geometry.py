@@ -176,3 +176,32 @@ def taylor_green_particles(nx, dim=2, re=100.0, hdx=1.0, L=1.0, U=1.0, rho0=1.0,
     pa.V[:] = 1.0 / dx ** dim
     pa.gid[:] = np.arange(x.size)
     return pa
+
+
+# ---------------------------------------------------------------------------
+# Colliding elastic rings (pysph/examples/solid_mech/rings.py:18-84)
+# ---------------------------------------------------------------------------
+def rings_particles(dx=0.0005, hdx=1.5, ri=0.03, ro=0.04, spacing=0.041, E=1e7,
+                    nu=0.3975, rho0=1.0, u_f=0.059):
+    """One elastic array 'solid' holding both rings, approaching each other at
+    u_f * c0 (rings.py:40-78).  The 2-D CubicSpline value W(dx, h) is ``wdeltap``."""
+    from .particle_array import get_particle_array_elastic_dynamics
+    n = int(round(2 * ro / dx))
+    ax = -ro + dx * np.arange(n)                      # numpy.mgrid[-ro:ro:dx]
+    x, y = np.meshgrid(ax, ax, indexing='ij')
+    x, y = x.ravel(), y.ravel()
+    d = x * x + y * y
+    keep = np.flatnonzero((ri * ri <= d) * (d < ro * ro))
+    x, y = x[keep], y[keep]
+    x = np.concatenate([x - spacing, x + spacing])
+    y = np.concatenate([y, y])
+    h = hdx * dx
+    q = dx / h                                         # CubicSpline(dim=2).kernel(rij=dx, h)
+    fac = 10.0 / (7.0 * np.pi) / (h * h)
+    w = 1.0 - 1.5 * q * q * (1.0 - 0.5 * q) if q <= 1.0 else 0.25 * (2.0 - q) ** 3
+    pa = get_particle_array_elastic_dynamics(
+        name='solid', x=x + spacing, y=y, m=dx * dx, rho=rho0, h=h,
+        constants=dict(wdeltap=fac * w, n=4, rho_ref=rho0, E=E, nu=nu))
+    pa.u[:] = pa.cs * u_f * (2 * (x < 0) - 1)
+    pa.gid[:] = np.arange(x.size)
+    return pa

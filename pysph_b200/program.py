@@ -37,6 +37,122 @@ TVF_GROUP2 = {
 }
 
 
+# elastic dynamics (solid_mech/basic.py:604-651): two Groups -> ('solid', SolidProgram)
+SOLID_GROUP1 = ('IsothermalEOS', 'VelocityGradient2D', 'VelocityGradient3D',
+                'MonaghanArtificialStress')
+SOLID_GROUP2 = ('ContinuityEquation', 'MomentumEquationWithStress',
+                'MonaghanArtificialViscosity', 'HookesDeviatoricStressRate',
+                'XSPHCorrection')
+
+
+def _solid_group_kind(g):
+    names = [_eq_name(e) for e in g.equations]
+    if any(n in ('IsothermalEOS', 'MonaghanArtificialStress') for n in names):
+        return 1
+    if 'MomentumEquationWithStress' in names:
+        return 2
+    return 0
+
+
+def _const(pa, name):
+    c = getattr(pa, 'constants', {}) or {}
+    if name not in c:
+        raise ValueError('array %r lacks the constant %r the elastic-dynamics '
+                         'equations read (get_particle_array_elastic_dynamics)'
+                         % (pa.name, name))
+    v = c[name]
+    v = v.get_npy_array() if hasattr(v, 'get_npy_array') else v
+    return float(list(v)[0])
+
+
+def _build_solid(g, kind, index, particle_arrays):
+    if particle_arrays is None:
+        raise ValueError('the elastic-dynamics equations read array constants: pass '
+                         'particle_arrays to build_program')
+    if not getattr(g, 'real', True):
+        raise NotImplementedError('B200 backend: elastic-dynamics Groups are real=True')
+    names = [_eq_name(e) for e in g.equations]
+    allowed = SOLID_GROUP1 if kind == 1 else SOLID_GROUP2
+    prog = _lib.SolidProgram()
+    params = {}
+    dests = []
+    for eq in g.equations:
+        name = _eq_name(eq)
+        if name not in allowed:
+            raise NotImplementedError(
+                'B200 backend: equation %r cannot share a Group with %s' % (name, names))
+        if eq.dest not in index:
+            raise ValueError('equation %s: unknown destination array %r' % (name, eq.dest))
+        if eq.dest not in dests:
+            dests.append(eq.dest)
+    want = sorted(index[d] for d in dests)
+    for eq in g.equations:
+        name = _eq_name(eq)
+        if eq.sources is None:
+            continue
+        src = sorted(index[s] for s in eq.sources)
+        if name == 'XSPHCorrection':
+            if src != [index[eq.dest]]:
+                raise NotImplementedError('B200 backend: XSPHCorrection(sources=[dest]) '
+                                          'is what the elastic-dynamics kernel does')
+        elif src != want:
+            raise NotImplementedError(
+                'B200 backend: elastic-dynamics kernels take every elastic array as a '
+                'source of every elastic array (no rigid solids); %s(dest=%r, sources=%r)'
+                % (name, eq.dest, eq.sources))
+        if name == 'MonaghanArtificialViscosity':
+            _set_once(params, 'alpha', float(eq.alpha), eq)
+            _set_once(params, 'beta', float(eq.beta), eq)
+        elif name == 'XSPHCorrection':
+            _set_once(params, 'eps_xsph', float(eq.eps), eq)
+    for eq in g.equations:
+        if _eq_name(eq) == 'MonaghanArtificialStress':
+            _set_once(params, 'eps', float(eq.eps), eq)
+    for d in dests:
+        mine = sorted(_eq_name(e) for e in g.equations if e.dest == d)
+        need = sorted(set(names))
+        if mine != need:
+            raise NotImplementedError('B200 backend: every elastic array needs the same '
+                                      'equations (%s vs %s)' % (mine, need))
+    if kind == 1:
+        grads = [n for n in set(names) if n.startswith('VelocityGradient')]
+        if sorted(set(names) - set(grads)) != ['IsothermalEOS', 'MonaghanArtificialStress'] \
+                or len(grads) != 1:
+            raise NotImplementedError('B200 backend: group 1 must be IsothermalEOS + one '
+                                      'VelocityGradient + MonaghanArtificialStress')
+        prog.grad3d = int(grads[0] == 'VelocityGradient3D')
+        prog.passes = 1
+    else:
+        if sorted(set(names)) != sorted(SOLID_GROUP2):
+            raise NotImplementedError('B200 backend: group 2 must hold exactly %s'
+                                      % (SOLID_GROUP2,))
+        prog.passes = 2
+    prog.elastic_mask = sum(1 << index[d] for d in dests)
+    by_name = dict((pa.name, pa) for pa in particle_arrays)
+    for d in dests:
+        a = index[d]
+        for k in ('c0_ref', 'rho_ref', 'wdeltap', 'n', 'G'):
+            getattr(prog, k)[a] = _const(by_name[d], k)
+    for k, v in params.items():
+        setattr(prog, k, v)
+    return prog
+
+
+def _merge_solid(ops):
+    out = []
+    for op in ops:
+        if out and op[0] == 'solid' and out[-1][0] == 'solid' and \
+                out[-1][1].passes == 1 and op[1].passes == 2 and \
+                out[-1][1].elastic_mask == op[1].elastic_mask:
+            op[1].passes = 3
+            op[1].grad3d = out[-1][1].grad3d
+            op[1].eps = out[-1][1].eps
+            out[-1] = op
+        else:
+            out.append(op)
+    return out
+
+
 def _is_tvf_summation(eq):
     return _eq_name(eq) == 'SummationDensity' and \
         'transport_velocity' in eq.__class__.__module__
@@ -186,7 +302,7 @@ def group_equations(equations):
     return [Group(equations=list(equations))]
 
 
-def build_program(groups, array_names, dim):
+def build_program(groups, array_names, dim, particle_arrays=None):
     """groups: list of Group objects (ours or PySPH's)."""
     index = dict((n, i) for i, n in enumerate(array_names))
     ops = []
@@ -201,6 +317,12 @@ def build_program(groups, array_names, dim):
                 raise NotImplementedError(
                     'B200 backend: Group(%s=%r) is not supported'
                     % (attr, getattr(g, attr)))
+        kind = _solid_group_kind(g)
+        if kind:
+            ops.append(('solid', _build_solid(g, kind, index, particle_arrays)))
+            if getattr(g, 'update_nnps', False):
+                ops.append(('update_nnps',))
+            continue
         kind = _tvf_group_kind(g)
         if kind:
             ops.append(('tvf', _build_tvf(g, kind, index)))
@@ -282,4 +404,4 @@ def build_program(groups, array_names, dim):
             ops.append(('pair', prog))
         if getattr(g, 'update_nnps', False):
             ops.append(('update_nnps',))
-    return _merge_tvf(ops)
+    return _merge_solid(_merge_tvf(ops))

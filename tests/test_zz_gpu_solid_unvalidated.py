@@ -1,0 +1,105 @@
+"""FIRST HARDWARE CONTACT of the elastic-dynamics kernels (BASELINE
+configs[4]): `k_solid_pass1/2` and `k_stage_solid` were written after this round's GPU
+budget was spent, so nothing in this file has ever run on a B200.  The oracle they are
+compared with IS pinned to the reference (tests/test_oracle_golden.py:
+test_elastic_dynamics_matches_reference_bodies).  The tests are expected-to-pass but
+marked xfail(strict=False) so that a defect shows up as XFAIL here instead of turning
+the validated suite red; the file name sorts last for the same reason."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, rel_err
+from oracle import oracle as orc
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(reason='elastic-dynamics kernels: not yet validated on '
+                                       'hardware (written without GPU budget)',
+                                strict=False)]
+
+SOLID_FIELDS = ['p', 'arho', 'au', 'av', 'aw', 'ax', 'ay', 'az'] + \
+    ['v%d%d' % (i, j) for i in range(3) for j in range(3)] + \
+    [pre + k for pre in ('r', 'as') for k in ('00', '01', '02', '11', '12', '22')]
+
+
+def _arrays(case):
+    import pysph_b200 as pb
+    pas = []
+    for name in case['params']['names']:
+        a = case['inputs'][name]
+        props = dict((k, np.array(v, dtype=float)) for k, v in a.items() if k[0] != '_')
+        consts = dict((k, v[0]) for k, v in case['params']['constants'][name].items())
+        pa = pb.get_particle_array_elastic_dynamics(name=name, constants=consts, **props)
+        pa.set_num_real_particles(a['_n_real'])
+        pas.append(pa)
+    return pas
+
+
+@pytest.mark.parametrize('idx', range(3))
+def test_elastic_evaluation_matches_reference_bodies(gpu_device, idx):
+    import pysph_b200 as pb
+    case = load_golden('solid_cases.json')[idx]
+    p = case['params']
+    pas = _arrays(case)
+    kernel = getattr(pb, case['kernel'])(dim=p['dim'])
+    sch = pb.ElasticSolidsScheme(p['names'], [], dim=p['dim'], artificial_stress_eps=p['eps'],
+                                 xsph_eps=p['eps_xsph'], alpha=p['alpha'], beta=p['beta'],
+                                 use_3d_gradient=False)     # what the reference scheme emits
+    ae = pb.B200AccelerationEval(pas, sch.get_equations(), kernel)
+    nn = pb.B200NNPS(p['dim'], pas, backend=ae.backend, kernel=kernel)
+    ae.set_nnps(nn)
+    ae.compute(0.0, 1e-6)
+    ae.backend.pull_all()
+    for pa in pas:
+        ref = case['outputs'][pa.name]
+        nr = ref['_n_real']
+        for f in SOLID_FIELDS:
+            want = np.array(ref[f])[:nr]
+            assert rel_err(pa.properties[f][:nr], want) <= 5e-5, (pa.name, f)
+        assert np.all(pa.au[nr:] == 0.0)
+
+
+def test_solid_mech_step_matches_reference_bodies(gpu_device):
+    import pysph_b200 as pb
+    g = load_golden('solid_stepper.json')
+    for which, key in ((0, 'initialize'), (1, 'stage1'), (2, 'stage2')):
+        props = dict((k, np.array(v)) for k, v in g['inputs'].items())
+        pa = pb.get_particle_array_elastic_dynamics(name='f', **props)
+        be = pb.B200Backend([pa])
+        be.ctx.call('b200sph_stage_solid', 0, which, g['dt'])
+        be.pull_all()
+        for k, v in g['outputs'][key].items():
+            if k in ('e', 'e0', 'ae'):
+                continue                  # not mirrored on the device (no energy equation)
+            assert np.allclose(pa.properties[k], v, rtol=0, atol=1e-6), (key, k)
+
+
+def test_rings_steps_vs_oracle(gpu_device):
+    """Colliding rings (rings.py) at dx = 0.002 (1.1 k particles), EPEC + SolidMechStep,
+    30 fixed steps (the rings touch after ~10) against the oracle."""
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo
+    dx, dt = 0.002, 1e-7
+    pa = geo.rings_particles(dx=dx)
+    ref = geo.rings_particles(dx=dx)
+    sch = pb.ElasticSolidsScheme(['solid'], [], dim=2)
+    s = pb.make_elastic_solver([pa], sch, pb.CubicSpline(dim=2), dt=dt)
+    o = orc.ElasticOracleSolver([ref], dict(dim=2, dt=dt, eps=0.3, alpha=1.0, beta=1.0,
+                                            eps_xsph=0.5), 'CubicSpline')
+    s.initialise()
+    o.initialise()
+    s.pull()
+    for f in ('p', 'au', 'av', 'arho', 'as00', 'as01', 'as11', 'v00', 'v01', 'v10', 'v11'):
+        want = ref.properties[f]
+        if np.max(np.abs(want)) == 0.0:
+            continue
+        assert rel_err(pa.properties[f], want) <= 5e-5, f
+    for _ in range(30):
+        s.step()
+        o.step()
+    s.pull()
+    assert np.max(np.abs(ref.s00)) > 1.0          # the rings are in contact
+    for f, tol in (('x', 1e-7), ('y', 1e-7), ('u', 1e-5), ('v', 1e-5), ('rho', 1e-6),
+                   ('s00', 1e-4), ('s01', 1e-4), ('s11', 1e-4)):
+        want = ref.properties[f]
+        scale = max(np.max(np.abs(want)), 1e-12)
+        assert np.max(np.abs(pa.properties[f] - want)) <= tol * scale, f
