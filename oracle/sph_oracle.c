@@ -367,6 +367,14 @@ int orc_nnps_update(orc_ctx *c)
     /* _count_occupied_cells  linked_list_nnps.pyx:336-343 */
     if (ncells < 0 || ncells > (1LL << 28)) return -1;
     c->n_cells = ncells;
+    /* The reference sizes head[] by the dim-dependent count above but flattens cell ids
+     * with all three indices (flatten_raw ignores `dim`, nnps_base.pxd:84-96), so a 1-D /
+     * 2-D problem whose particles spread along an unused axis -- e.g. the +-0.5 padding
+     * of a degenerate box, nnps_base.pyx:1565-1572 -- writes past its table there.  The
+     * oracle keeps the reported n_cells and the lookup bound, but owns enough storage. */
+    const int64_t storage = (int64_t)nc[0] * nc[1] * nc[2];
+    if (storage < 0 || storage > (1LL << 28)) return -1;
+    if (storage > ncells) ncells = storage;
 
     /* _refresh  linked_list_nnps.pyx:345-382 and _bin :235-286 */
     for (int a = 0; a < c->narr; a++) {
