@@ -12,6 +12,7 @@ from helpers import load_golden, rel_err
 from oracle import oracle as orc
 
 pytestmark = [pytest.mark.gpu,
+              pytest.mark.timeout(180),
               pytest.mark.xfail(reason='elastic-dynamics kernels: not yet validated on '
                                        'hardware (written without GPU budget)',
                                 strict=False)]
