@@ -261,3 +261,48 @@ def test_taylor_green_geometry():
     assert pa3.get_number_of_particles() == 512 and np.all(pa3.w == 0.0)
     # divergence-free initial field: sum of u over a periodic lattice vanishes
     assert abs(np.sum(pa3.u)) < 1e-10 and abs(np.sum(pa3.v)) < 1e-10
+
+
+def test_elastic_program_and_scheme():
+    """ElasticSolidsScheme.get_equations (solid_mech/basic.py:604-651) -> one fused
+    ('solid', program) op carrying the array constants; what the kernels cannot do is
+    refused at setup.  (The kernels themselves are not validated on hardware yet.)"""
+    from pysph_b200 import solid_mech as sm
+    from pysph_b200.equations import Group
+    pa = pb.get_particle_array_elastic_dynamics(
+        name='ring', x=np.arange(4.) * 0.1, h=0.13, m=1.0, rho=1.2,
+        constants=dict(E=1e3, nu=0.3975, rho_ref=1.2, wdeltap=0.5))
+    # get_shear_modulus / get_speed_of_sound, solid_mech/basic.py:19-29,77-83
+    assert abs(pa.G[0] - 1e3 / (2 * 1.3975)) < 1e-12
+    c0 = np.sqrt(1e3 / (3 * (1 - 2 * 0.3975) * 1.2))
+    assert abs(pa.c0_ref[0] - c0) < 1e-12 and np.all(pa.cs == c0)
+    assert set(('s00', 's220', 'as12', 'r01', 'v21', 'e0')) <= set(pa.properties)
+    sch = pb.ElasticSolidsScheme(['ring'], [], dim=2, alpha=1.0, beta=1.5)
+    groups = sch.get_equations()
+    assert [type(e).__name__ for e in groups[0].equations] == [
+        'IsothermalEOS', 'VelocityGradient2D', 'MonaghanArtificialStress']
+    assert [type(e).__name__ for e in groups[1].equations] == [
+        'ContinuityEquation', 'MomentumEquationWithStress', 'MonaghanArtificialViscosity',
+        'HookesDeviatoricStressRate', 'XSPHCorrection']
+    ops = build_program(groups, ['ring'], 2, particle_arrays=[pa])
+    assert [o[0] for o in ops] == ['solid']
+    P = ops[0][1]
+    assert (P.passes, P.grad3d, P.elastic_mask) == (3, 0, 1)
+    assert (P.eps, P.alpha, P.beta, P.eps_xsph) == (0.3, 1.0, 1.5, 0.5)
+    assert (P.rho_ref[0], P.wdeltap[0], P.n[0]) == (1.2, 0.5, 4.0)
+    assert abs(P.c0_ref[0] - c0) < 1e-12 and abs(P.G[0] - pa.G[0]) < 1e-12
+    assert pb.ElasticSolidsScheme(['ring'], [], dim=3).use_3d_gradient
+    with pytest.raises(ValueError):          # constants are needed
+        build_program(groups, ['ring'], 2)
+    with pytest.raises(NotImplementedError):
+        pb.ElasticSolidsScheme(['ring'], ['wall'], dim=2).get_equations()
+    with pytest.raises(NotImplementedError):  # a group 2 without the stress rate
+        build_program([groups[0], Group(groups[1].equations[:3])], ['ring'], 2,
+                      particle_arrays=[pa])
+    pb.EPECIntegrator(ring=pb.SolidMechStep())
+    # rings.py:40-78: two rings of the same size approaching each other
+    r = geo.rings_particles(dx=0.004)
+    assert r.get_number_of_particles() % 2 == 0
+    n2 = r.get_number_of_particles() // 2
+    assert np.all(r.u[:n2] > 0) and np.all(r.u[n2:] < 0)
+    assert abs(abs(r.u[0]) - 0.059 * r.cs[0]) < 1e-9
