@@ -1,0 +1,263 @@
+// Host-side emulation harness for the list-consumer kernels of csrc/b200sph.cu.
+// TEST INFRASTRUCTURE: the KERNEL SOURCE ITSELF (extracted verbatim from b200sph.cu into
+// kernels_extract.inc by tests/test_kernel_source_on_cpu.py) is compiled with g++ against
+// the tiny CUDA shim below and run thread by thread, so that the arithmetic, the record
+// layouts, the type masks and the output indexing of a kernel can be checked against the
+// golden fixtures without a GPU.  It says nothing about launch configuration, memory
+// spaces or performance.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "b200sph.h"
+
+struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+struct idx3 { unsigned x, y, z; };
+static idx3 threadIdx, blockIdx, blockDim, gridDim;
+
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+static inline void __syncthreads() {}
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+static inline uint32_t __ldcs(const uint32_t *p) { return *p; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+// glibc declares __expf(float) but does not export it: route the CUDA intrinsic to expf
+#define __expf(x) expf(x)
+static inline float frcp(float x) { return 1.0f / x; }
+static inline float frsqrt(float x) { return 1.0f / sqrtf(x); }
+static inline void ld_256(const float4 *p, float4 &b, float4 &c) { b = p[0]; c = p[1]; }
+static inline void atomicAdd(unsigned long long *p, unsigned long long v) { *p += v; }
+using std::max;
+using std::min;
+
+#define PT_INVALID 0xFFu
+#define PT_GHOST 0x08u
+#define LIST_JBITS 26
+#define LIST_JMASK 0x03FFFFFFu
+#define LIST_NT 128
+
+#include "kernels_extract.inc"
+
+// run one "launch": every block twice, so that the shared cell-offset table a block's
+// first 64 threads fill is complete when the threads are executed for real
+template <class F> static void launch(long long n, int nt, F body)
+{
+    const unsigned nb = (unsigned)((n + nt - 1) / nt);
+    blockDim = idx3{(unsigned)nt, 1, 1};
+    gridDim = idx3{nb, 1, 1};
+    for (unsigned b = 0; b < nb; b++) {
+        blockIdx = idx3{b, 0, 0};
+        for (int rep = 0; rep < 2; rep++)
+            for (int t = 0; t < nt; t++) {
+                threadIdx = idx3{(unsigned)t, 0, 0};
+                body();
+            }
+    }
+}
+
+template <int K, int D> static void run_tvf(const TvfArgs &a, const uint32_t *cnt, const uint32_t *lst, int capg, int passes)
+{
+    if (passes & 1) launch(a.n, LIST_NT, [&] { k_tvf_pass1<K, D>(a, cnt, lst, capg); });
+    if (passes & 2) launch(a.n, LIST_NT, [&] { k_tvf_pass2<K, D>(a, cnt, lst, capg); });
+}
+template <int K, int D> static void run_solid(const SolidArgs &a, const uint32_t *cnt, const uint32_t *lst, int capg, int passes)
+{
+    if (passes & 1) launch(a.n, LIST_NT, [&] { k_solid_pass1<K, D>(a, cnt, lst, capg); });
+    if (passes & 2) launch(a.n, LIST_NT, [&] { k_solid_pass2<K, D>(a, cnt, lst, capg); });
+}
+
+#define DISPATCH(fn, ...)                                                        \
+    switch (kernel * 4 + dim) {                                                  \
+    case 0 * 4 + 2: fn<0, 2>(__VA_ARGS__); break;                                \
+    case 0 * 4 + 3: fn<0, 3>(__VA_ARGS__); break;                                \
+    case 1 * 4 + 2: fn<1, 2>(__VA_ARGS__); break;                                \
+    case 1 * 4 + 3: fn<1, 3>(__VA_ARGS__); break;                                \
+    case 2 * 4 + 2: fn<2, 2>(__VA_ARGS__); break;                                \
+    case 2 * 4 + 3: fn<2, 3>(__VA_ARGS__); break;                                \
+    default: return -1;                                                          \
+    }
+
+extern "C" {
+
+// Everything lives in one "cell": positions are used as they are, every list entry carries the
+// zero cell-offset code (dx = dy = dz = 0  ->  1 + 4 + 16 = 21) and every particle is a
+// candidate of every particle (the kernels re-apply the exact accept test).
+struct emul_common {
+    long long n;            // particles (pool order == sorted order)
+    int kernel, dim;
+    double radius_scale, kfac;
+    const double *x, *y, *z, *h, *u, *v, *w, *m;
+    double *rho;
+    const uint8_t *ptype;
+};
+
+static void make_lists(long long n, std::vector<uint32_t> &cnt, std::vector<uint32_t> &lst, int &capg)
+{
+    capg = (int)n;
+    cnt.assign((size_t)n, (uint32_t)n);
+    lst.assign((size_t)((n + 31) / 32) * (size_t)capg * 32u, 0u);
+    for (long long s = 0; s < n; s++)
+        for (long long k = 0; k < n; k++) lst[((size_t)(s >> 5) * capg + (size_t)k) * 32u + (size_t)(s & 31)] = (uint32_t)k | (21u << LIST_JBITS);
+}
+
+static void pack_A(const emul_common &c, std::vector<float4> &AB)
+{
+    AB.assign(2 * (size_t)c.n, float4{0, 0, 0, 0});
+    for (long long s = 0; s < c.n; s++) AB[2 * s] = make_float4((float)c.x[s], (float)c.y[s], (float)c.z[s], (float)c.h[s]);
+}
+
+// one WCSPH Group: [pending EOS calls applied by k_pack_state] + k_pair_list.
+// eos: per array {on, hg, real_only} and {rho0, c0, gamma, p0}; emask[d] = 8 bits per source
+int emul_wcsph(const emul_common *c, const int *eos_i, const double *eos_d, const unsigned long long *emask,
+               const double *params /* c0 alpha beta gx gy gz eps_xsph */, int tensile, int real_only, double deltap,
+               float *p, float *cs, float *arho, float *au, float *av, float *aw, float *ax, float *ay, float *az,
+               float *dt_cfl, float *dt_force, unsigned long long *pairs)
+{
+    const long long n = c->n;
+    std::vector<uint32_t> cnt, lst, perm((size_t)n);
+    int capg;
+    make_lists(n, cnt, lst, capg);
+    for (long long i = 0; i < n; i++) perm[i] = (uint32_t)i;
+    std::vector<float4> AB, B((size_t)n), Cc((size_t)n);
+    pack_A(*c, AB);
+    EosTab E;
+    memset(&E, 0, sizeof(E));
+    int any = 0;
+    for (int a = 0; a < B200SPH_MAX_ARRAYS; a++) {
+        E.on[a] = eos_i[3 * a]; E.hg[a] = eos_i[3 * a + 1]; E.real_only[a] = eos_i[3 * a + 2];
+        E.rho0[a] = eos_d[4 * a]; E.c0[a] = eos_d[4 * a + 1]; E.gamma[a] = eos_d[4 * a + 2]; E.p0[a] = eos_d[4 * a + 3];
+        any |= E.on[a];
+    }
+    launch(n, 256, [&] { k_pack_state(c->u, c->v, c->w, c->m, c->rho, p, cs, c->ptype, perm.data(), n, B.data(), Cc.data(), AB.data(), E, any); });
+    PairArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.A = nullptr; pa.B = B.data(); pa.C = Cc.data(); pa.AB = AB.data();
+    pa.perm = perm.data();
+    pa.arho = arho; pa.au = au; pa.av = av; pa.aw = aw; pa.ax = ax; pa.ay = ay; pa.az = az;
+    pa.dt_cfl = dt_cfl; pa.dt_force = dt_force;
+    pa.rho = c->rho;
+    pa.n = n;
+    pa.cellx = pa.celly = pa.cellz = 1.0f;
+    pa.k2 = (float)(c->radius_scale * c->radius_scale);
+    pa.kfac = (float)c->kfac;
+    pa.deltap = (float)deltap;
+    for (int a = 0; a < B200SPH_MAX_ARRAYS; a++) pa.emask[a] = emask[a];
+    pa.c0 = (float)params[0]; pa.alpha = (float)params[1]; pa.beta = (float)params[2];
+    pa.gx = (float)params[3]; pa.gy = (float)params[4]; pa.gz = (float)params[5]; pa.eps_xsph = (float)params[6];
+    pa.tensile = tensile;
+    pa.real_only = real_only;
+    unsigned long long counter = 0;
+    pa.pair_counter = nullptr;
+    const int kernel = c->kernel, dim = c->dim;
+    switch (kernel * 4 + dim) {
+#define PL(K, D) case K * 4 + D: launch(n, LIST_NT, [&] { k_pair_list<K, D>(pa, cnt.data(), lst.data(), capg); }); break;
+        PL(0, 2) PL(0, 3) PL(1, 2) PL(1, 3) PL(2, 2) PL(2, 3) PL(3, 2) PL(3, 3)
+#undef PL
+    default: return -1;
+    }
+    if (pairs) *pairs = counter;
+    return 0;
+}
+
+int emul_tvf(const emul_common *c, const b200sph_tvf_program *prog, const double *uh, const double *vh, const double *wh,
+             const double *pf, float *V, float *pavg, float *au, float *av, float *aw, float *auhat, float *avhat,
+             float *awhat, float *ap, unsigned long long *pairs)
+{
+    const long long n = c->n;
+    std::vector<uint32_t> cnt, lst, perm((size_t)n);
+    int capg;
+    make_lists(n, cnt, lst, capg);
+    for (long long i = 0; i < n; i++) perm[i] = (uint32_t)i;
+    std::vector<float4> AB, B((size_t)n), C2((size_t)n), Dv((size_t)n);
+    std::vector<float2> PT((size_t)n);
+    pack_A(*c, AB);
+    launch(n, 256, [&] { k_pack_tvf(c->u, c->v, c->w, c->m, uh, vh, wh, pf, pavg, c->ptype, perm.data(), n, B.data(), AB.data(), C2.data(), Dv.data(), PT.data()); });
+    TvfArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.AB = AB.data(); ta.C2 = C2.data(); ta.Dv = Dv.data(); ta.PT = PT.data(); ta.perm = perm.data();
+    ta.rho = c->rho; ta.V = V; ta.pavg = pavg;
+    ta.au = au; ta.av = av; ta.aw = aw; ta.auhat = auhat; ta.avhat = avhat; ta.awhat = awhat; ta.ap = ap;
+    ta.n = n;
+    ta.cellx = ta.celly = ta.cellz = 1.0f;
+    ta.k2 = (float)(c->radius_scale * c->radius_scale);
+    ta.kfac = (float)c->kfac;
+    ta.fluid_mask = prog->fluid_mask; ta.eqbits = prog->eqbits; ta.bql = prog->bql;
+    ta.pb = (float)prog->pb; ta.nu = (float)prog->nu; ta.edac_nu = (float)prog->edac_nu;
+    ta.c0 = (float)prog->c0; ta.alpha = (float)prog->alpha;
+    double damp = 1.0;
+    if (prog->t < prog->tdamp) damp = 0.5 * (sin((-0.5 + prog->t / prog->tdamp) * 3.14159265358979323846) + 1.0);
+    ta.gx = (float)(prog->gx * damp); ta.gy = (float)(prog->gy * damp); ta.gz = (float)(prog->gz * damp);
+    ta.pair_counter = nullptr;
+    const int kernel = c->kernel, dim = c->dim;
+    DISPATCH(run_tvf, ta, cnt.data(), lst.data(), capg, prog->passes)
+    (void)pairs;
+    return 0;
+}
+
+// k_stage_solid over n real particles of array 0: f64 = x y z u v w rho s[6], then the
+// *0 copies in the same order; f32 = au av aw ax ay az arho as[6]
+int emul_stage_solid(long long n, int which, double dt, double *const f64[26], const float *const f32[13])
+{
+    std::vector<uint8_t> ptype((size_t)n, 0);
+    StageSolidArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = f64[0]; a.y = f64[1]; a.z = f64[2]; a.u = f64[3]; a.v = f64[4]; a.w = f64[5]; a.rho = f64[6];
+    for (int k = 0; k < 6; k++) a.s[k] = f64[7 + k];
+    a.x0 = f64[13]; a.y0 = f64[14]; a.z0 = f64[15]; a.u0 = f64[16]; a.v0 = f64[17]; a.w0 = f64[18]; a.rho0 = f64[19];
+    for (int k = 0; k < 6; k++) a.s0[k] = f64[20 + k];
+    a.au = f32[0]; a.av = f32[1]; a.aw = f32[2]; a.ax = f32[3]; a.ay = f32[4]; a.az = f32[5]; a.arho = f32[6];
+    for (int k = 0; k < 6; k++) a.as[k] = f32[7 + k];
+    a.ptype = ptype.data();
+    a.pool_end = n;
+    a.arr = -1;
+    a.which = which;
+    a.f = which == 1 ? 0.5 * dt : dt;
+    launch(n, 256, [&] { k_stage_solid(a); });
+    return 0;
+}
+
+int emul_solid(const emul_common *c, const b200sph_solid_program *prog, double *const s[6], float *p, const float *cs,
+               float *const vg[9], float *const r[6], float *const as[6], float *arho, float *au, float *av, float *aw,
+               float *ax, float *ay, float *az)
+{
+    const long long n = c->n;
+    std::vector<uint32_t> cnt, lst, perm((size_t)n);
+    int capg;
+    make_lists(n, cnt, lst, capg);
+    for (long long i = 0; i < n; i++) perm[i] = (uint32_t)i;
+    std::vector<float4> AB, B((size_t)n), C3((size_t)n), T01((size_t)n), T2R((size_t)n), R2((size_t)n);
+    pack_A(*c, AB);
+    launch(n, 256, [&] { k_pack_solid(c->u, c->v, c->w, c->m, c->rho, p, cs, c->ptype, perm.data(), n, B.data(), AB.data(), C3.data()); });
+    SolidArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.AB = AB.data(); sa.C3 = C3.data(); sa.T01 = T01.data(); sa.T2R = T2R.data(); sa.R2 = R2.data(); sa.perm = perm.data();
+    sa.rho = c->rho;
+    for (int k = 0; k < 6; k++) { sa.s[k] = s[k]; sa.r[k] = r[k]; sa.as[k] = as[k]; }
+    for (int k = 0; k < 9; k++) sa.vg[k] = vg[k];
+    sa.p = p;
+    sa.arho = arho; sa.au = au; sa.av = av; sa.aw = aw; sa.ax = ax; sa.ay = ay; sa.az = az;
+    sa.n = n;
+    sa.cellx = sa.celly = sa.cellz = 1.0f;
+    sa.k2 = (float)(c->radius_scale * c->radius_scale);
+    sa.kfac = (float)c->kfac;
+    sa.elastic_mask = prog->elastic_mask; sa.grad3d = prog->grad3d;
+    sa.eps = (float)prog->eps; sa.alpha = (float)prog->alpha; sa.beta = (float)prog->beta; sa.eps_xsph = (float)prog->eps_xsph;
+    for (int a = 0; a < B200SPH_MAX_ARRAYS; a++) {
+        sa.c0_ref[a] = prog->c0_ref[a]; sa.rho_ref[a] = prog->rho_ref[a]; sa.G[a] = prog->G[a];
+        sa.wdeltap[a] = (float)prog->wdeltap[a]; sa.nexp[a] = (float)prog->n[a];
+    }
+    const int kernel = c->kernel, dim = c->dim;
+    DISPATCH(run_solid, sa, cnt.data(), lst.data(), capg, prog->passes)
+    return 0;
+}
+}
