@@ -420,7 +420,8 @@ def load_reference_solid():
     return mod
 
 
-def gen_solid_case(kernels, solid, kernel_name, dim, seed, wdeltap=True, two=False):
+def gen_solid_case(kernels, solid, kernel_name, dim, seed, wdeltap=True, two=False,
+                   grad3d=False):
     """One evaluation of ElasticSolidsScheme(...).get_equations() (the reference's scheme
     method and equation bodies) on random particles with random stresses."""
     rs = np.random.RandomState(seed)
@@ -454,6 +455,14 @@ def gen_solid_case(kernels, solid, kernel_name, dim, seed, wdeltap=True, two=Fal
     scheme = solid.ElasticSolidsScheme(names, [], dim=dim, artificial_stress_eps=0.3,
                                        xsph_eps=0.5, alpha=1.0, beta=1.5)
     eqs = scheme.get_equations()
+    if grad3d:
+        # the scheme always emits VelocityGradient2D (solid_mech/basic.py:620-623); a 3-D
+        # run needs the reference's VelocityGradient3D (basic_equations.py:101-148) in its place
+        basic = sys.modules['pysph.sph.basic_equations']
+        g1 = eqs[0].equations
+        for k, e in enumerate(g1):
+            if type(e).__name__ == 'VelocityGradient2D':
+                g1[k] = basic.VelocityGradient3D(dest=e.dest, sources=e.sources)
     # array constants are seen by the bodies as d_<name> / s_<name>
     for name in names:
         for ck, cv in consts[name].items():
@@ -464,7 +473,7 @@ def gen_solid_case(kernels, solid, kernel_name, dim, seed, wdeltap=True, two=Fal
         for ck in consts[name]:
             del arrays[name][ck]
     params = dict(dim=dim, eps=0.3, eps_xsph=0.5, alpha=1.0, beta=1.5, names=names,
-                  constants=consts,
+                  constants=consts, grad3d=bool(grad3d),
                   groups=[[type(e).__name__ for e in g.equations] for g in eqs],
                   group_real=[bool(g.real) for g in eqs])
     return dict(kernel=kernel_name, dim=dim, params=params, inputs=inputs,
@@ -658,6 +667,7 @@ def main():
         gen_solid_case(kernels, solid, 'CubicSpline', 2, 301),
         gen_solid_case(kernels, solid, 'CubicSpline', 3, 302, two=True),
         gen_solid_case(kernels, solid, 'WendlandQuintic', 2, 303, wdeltap=False),
+        gen_solid_case(kernels, solid, 'CubicSpline', 3, 304, grad3d=True),
     ]
     dump('solid_cases.json', scases)
     dump('solid_stepper.json', gen_solid_stepper(steps))

@@ -330,12 +330,12 @@ def _solid_arrays(case):
     return pas
 
 
-@pytest.mark.parametrize('idx', range(3))
+@pytest.mark.parametrize('idx', range(4))
 def test_elastic_dynamics_matches_reference_bodies(idx):
     case = load_golden('solid_cases.json')[idx]
     p = case['params']
-    assert p['groups'][0][:3] == ['IsothermalEOS', 'VelocityGradient2D',
-                                  'MonaghanArtificialStress']
+    assert p['groups'][0][:3] == ['IsothermalEOS', 'VelocityGradient3D' if p.get('grad3d')
+                                  else 'VelocityGradient2D', 'MonaghanArtificialStress']
     assert p['groups'][1][:5] == ['ContinuityEquation', 'MomentumEquationWithStress',
                                   'MonaghanArtificialViscosity',
                                   'HookesDeviatoricStressRate', 'XSPHCorrection']
@@ -346,7 +346,7 @@ def test_elastic_dynamics_matches_reference_bodies(idx):
     o.nnps_update()
     idxs = list(range(len(pas)))
     P = o.solid_program(idxs, idxs, eps=p['eps'], alpha=p['alpha'], beta=p['beta'],
-                        eps_xsph=p['eps_xsph'], grad3d=False)
+                        eps_xsph=p['eps_xsph'], grad3d=p.get('grad3d', False))
     o.solid_group1(P)
     o.solid_group2(P)
     for pa in pas:

@@ -35,7 +35,7 @@ def _arrays(case):
     return pas
 
 
-@pytest.mark.parametrize('idx', range(3))
+@pytest.mark.parametrize('idx', range(4))
 def test_elastic_evaluation_matches_reference_bodies(gpu_device, idx):
     import pysph_b200 as pb
     case = load_golden('solid_cases.json')[idx]
@@ -44,7 +44,7 @@ def test_elastic_evaluation_matches_reference_bodies(gpu_device, idx):
     kernel = getattr(pb, case['kernel'])(dim=p['dim'])
     sch = pb.ElasticSolidsScheme(p['names'], [], dim=p['dim'], artificial_stress_eps=p['eps'],
                                  xsph_eps=p['eps_xsph'], alpha=p['alpha'], beta=p['beta'],
-                                 use_3d_gradient=False)     # what the reference scheme emits
+                                 use_3d_gradient=p.get('grad3d', False))   # 2-D: what the reference scheme emits
     ae = pb.B200AccelerationEval(pas, sch.get_equations(), kernel)
     nn = pb.B200NNPS(p['dim'], pas, backend=ae.backend, kernel=kernel)
     ae.set_nnps(nn)
