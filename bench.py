@@ -55,7 +55,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '50'],
+                 '--format=csv,noheader,nounits', '-lms', '100'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -72,7 +72,7 @@ class ClockSampler(object):
         one sampling period."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        time.sleep(0.06)                     # let the sample covering the region's end arrive
+        time.sleep(0.11)                     # let the sample covering the region's end arrive
         if len(self.lines) > first:
             self.lines = self.lines[first:]
         else:
