@@ -12,7 +12,11 @@
  * (b) the reference's own Python equation bodies (pysph/sph/wc/basic.py,
  *     pysph/sph/basic_equations.py, pysph/sph/integrator_step.py) driven
  *     pair-by-pair, and (c) the known-answer vectors in the reference tests
- *     (test_acceleration_eval.py, test_nnps.py, test_kernel.py).
+ *     (test_acceleration_eval.py, test_nnps.py, test_kernel.py),
+ * (d) the reference's own EDACScheme / ElasticSolidsScheme get_equations() and the
+ *     bodies of wc/edac.py, wc/transport_velocity.py, solid_mech/basic.py (with the
+ *     reference's compiled linalg3.pyx eigen solver), and
+ * (e) for periodic domains, the reference's lattice fixtures (test_domain_manager.py).
  */
 #ifndef SPH_ORACLE_H
 #define SPH_ORACLE_H
