@@ -18,7 +18,41 @@ struct float2 { float x, y; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct idx3 { unsigned x, y, z; };
-static idx3 threadIdx, blockIdx, blockDim, gridDim;
+static thread_local idx3 threadIdx, blockIdx, blockDim, gridDim;
+
+// Warp lockstep for warp-synchronous kernels (k_list_build): the 32 lanes of a warp run as
+// 32 OS threads; every __shfl_sync / __ballot_sync is "publish, barrier, read, barrier".
+// Kernels launched thread by thread (g_warp == nullptr) see the identity shuffle.
+#include <atomic>
+#include <thread>
+struct WarpCtx {
+    std::atomic<int> arrived{0};
+    std::atomic<int> phase{0};
+    unsigned long long slot[32];
+    void barrier()
+    {
+        const int ph = phase.load(std::memory_order_acquire);
+        if (arrived.fetch_add(1, std::memory_order_acq_rel) == 31) {
+            arrived.store(0, std::memory_order_relaxed);
+            phase.store(ph + 1, std::memory_order_release);
+        } else {
+            while (phase.load(std::memory_order_acquire) == ph) std::this_thread::yield();
+        }
+    }
+};
+static thread_local WarpCtx *g_warp = nullptr;
+static thread_local int g_lane = 0;
+template <class T> static inline unsigned long long to_bits(T v) { unsigned long long b = 0; memcpy(&b, &v, sizeof(T)); return b; }
+template <class T> static inline T from_bits(unsigned long long b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+template <class T> static inline T warp_read(T v, int src)
+{
+    if (!g_warp) return v;
+    g_warp->slot[g_lane] = to_bits(v);
+    g_warp->barrier();
+    const T r = from_bits<T>(g_warp->slot[src & 31]);
+    g_warp->barrier();
+    return r;
+}
 
 #define __global__
 #define __device__
@@ -27,7 +61,29 @@ static idx3 threadIdx, blockIdx, blockDim, gridDim;
 #define __launch_bounds__(...)
 #define __shared__ static
 static inline void __syncthreads() {}
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int o) { return warp_read(v, g_lane ^ o); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return warp_read(v, src); }
+static inline unsigned __ballot_sync(unsigned, bool pred)
+{
+    if (!g_warp) return pred ? 1u : 0u;
+    g_warp->slot[g_lane] = pred ? 1ull : 0ull;
+    g_warp->barrier();
+    unsigned m = 0;
+    for (int l = 0; l < 32; l++) m |= (unsigned)g_warp->slot[l] << l;
+    g_warp->barrier();
+    return m;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
+static std::atomic_flag g_atomic_lock = ATOMIC_FLAG_INIT;
+static inline unsigned atomicMax(unsigned *p, unsigned v)
+{
+    while (g_atomic_lock.test_and_set(std::memory_order_acquire)) {}
+    const unsigned o = *p;
+    if (v > o) *p = v;
+    g_atomic_lock.clear(std::memory_order_release);
+    return o;
+}
 static inline uint32_t __ldcs(const uint32_t *p) { return *p; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
@@ -48,21 +104,64 @@ using std::min;
 
 #include "kernels_extract.inc"
 
-// run one "launch": every block twice, so that the shared cell-offset table a block's
-// first 64 threads fill is complete when the threads are executed for real
-template <class F> static void launch(long long n, int nt, F body)
+// run one "launch" thread by thread.  Kernels that fill a block-shared table in their first
+// 64 threads (the cell-offset table: identical for every block, and `static` here) get one
+// warm-up execution of block 0 first, so that the table is complete when threads run for
+// real; `after_warm` undoes whatever the warm-up must not leave behind (pair counters).
+template <class F, class R> static void launch(long long n, int nt, F body, R after_warm)
+{
+    const unsigned nb = (unsigned)((n + nt - 1) / nt);
+    blockDim = idx3{(unsigned)nt, 1, 1};
+    gridDim = idx3{nb, 1, 1};
+    blockIdx = idx3{0, 0, 0};
+    for (int t = 0; t < nt && nb > 0; t++) {
+        threadIdx = idx3{(unsigned)t, 0, 0};
+        body();
+    }
+    after_warm();
+    for (unsigned b = 0; b < nb; b++) {
+        blockIdx = idx3{b, 0, 0};
+        for (int t = 0; t < nt; t++) {
+            threadIdx = idx3{(unsigned)t, 0, 0};
+            body();
+        }
+    }
+}
+template <class F> static void launch(long long n, int nt, F body) { launch(n, nt, body, [] {}); }
+// one execution per thread (kernels without block-shared state, e.g. with atomics)
+template <class F> static void launch1(long long n, int nt, F body)
 {
     const unsigned nb = (unsigned)((n + nt - 1) / nt);
     blockDim = idx3{(unsigned)nt, 1, 1};
     gridDim = idx3{nb, 1, 1};
     for (unsigned b = 0; b < nb; b++) {
         blockIdx = idx3{b, 0, 0};
-        for (int rep = 0; rep < 2; rep++)
-            for (int t = 0; t < nt; t++) {
-                threadIdx = idx3{(unsigned)t, 0, 0};
-                body();
-            }
+        for (int t = 0; t < nt; t++) {
+            threadIdx = idx3{(unsigned)t, 0, 0};
+            body();
+        }
     }
+}
+// warp-synchronous kernels: every warp of every block as 32 lock-stepped OS threads
+template <class F> static void launch_warps(unsigned nb, int nt, F body)
+{
+    for (unsigned b = 0; b < nb; b++)
+        for (int w = 0; w < nt / 32; w++) {
+            WarpCtx ctx;
+            std::vector<std::thread> lanes;
+            for (int l = 0; l < 32; l++)
+                lanes.emplace_back([&, l] {
+                    g_warp = &ctx;
+                    g_lane = l;
+                    blockDim = idx3{(unsigned)nt, 1, 1};
+                    gridDim = idx3{nb, 1, 1};
+                    blockIdx = idx3{b, 0, 0};
+                    threadIdx = idx3{(unsigned)(w * 32 + l), 0, 0};
+                    body();
+                    g_warp = nullptr;
+                });
+            for (auto &t : lanes) t.join();
+        }
 }
 
 template <int K, int D> static void run_tvf(const TvfArgs &a, const uint32_t *cnt, const uint32_t *lst, int capg, int passes)
@@ -161,6 +260,95 @@ int emul_wcsph(const emul_common *c, const int *eos_i, const double *eos_d, cons
     const int kernel = c->kernel, dim = c->dim;
     switch (kernel * 4 + dim) {
 #define PL(K, D) case K * 4 + D: launch(n, LIST_NT, [&] { k_pair_list<K, D>(pa, cnt.data(), lst.data(), capg); }); break;
+        PL(0, 2) PL(0, 3) PL(1, 2) PL(1, 3) PL(2, 2) PL(2, 3) PL(3, 2) PL(3, 3)
+#undef PL
+    default: return -1;
+    }
+    if (pairs) *pairs = counter;
+    return 0;
+}
+
+// The whole neighbour + pair pipeline of one WCSPH Group on a real cell grid: k_cell_count,
+// (host prefix sum instead of the 3-phase scan), k_scatter, k_canon, k_pack_pos, k_list_build
+// (count pass + fill pass, like build_lists), k_pack_state, k_pair_list.  Outputs in POOL order.
+int emul_pipeline(const emul_common *c, const double *gxmin, const double *gcell, const int *gnc, const int *gper,
+                  double skin_abs, const int *eos_i, const double *eos_d, const unsigned long long *emask,
+                  const double *params, int tensile, int real_only, double deltap, float *p, float *cs, float *arho,
+                  float *au, float *av, float *aw, float *ax, float *ay, float *az, float *dt_cfl, float *dt_force,
+                  unsigned long long *pairs, int *capg_out)
+{
+    const long long n = c->n;
+    GridDev G;
+    for (int d = 0; d < 3; d++) { G.xmin[d] = gxmin[d]; G.cell[d] = gcell[d]; G.nc[d] = gnc[d]; G.periodic[d] = gper[d]; }
+    const long long ncells = (long long)G.nc[0] * G.nc[1] * G.nc[2];
+    std::vector<uint32_t> key_of((size_t)n), off_in((size_t)n), cell_cnt((size_t)ncells + 1, 0u), cell_start((size_t)ncells + 2, 0u);
+    std::vector<uint32_t> perm_tmp((size_t)n), perm((size_t)n), skey((size_t)n), rank((size_t)n);
+    launch1(n, 256, [&] { k_cell_count(c->x, c->y, c->z, c->ptype, n, G, key_of.data(), off_in.data(), cell_cnt.data()); });
+    for (long long k = 0; k < ncells + 1; k++) cell_start[k + 1] = cell_start[k] + cell_cnt[k];   // exclusive scan
+    launch1(n, 256, [&] { k_scatter(key_of.data(), off_in.data(), c->ptype, n, cell_start.data(), perm_tmp.data()); });
+    launch1(n, 256, [&] { k_canon(perm_tmp.data(), key_of.data(), cell_start.data(), n, perm.data(), skey.data(), rank.data()); });
+    std::vector<float4> A((size_t)n), AB(2 * (size_t)n), B((size_t)n), Cc((size_t)n);
+    launch1(n, 256, [&] { k_pack_pos(c->x, c->y, c->z, c->h, perm.data(), skey.data(), n, G, A.data(), AB.data()); });
+    // neighbour lists
+    std::vector<uint32_t> cnt((size_t)n, 0u), lst;
+    unsigned max_count = 0;
+    ListBuildArgs la;
+    la.A = A.data(); la.cell_start = cell_start.data(); la.skey = skey.data();
+    la.n = n;
+    la.ncx = G.nc[0]; la.ncy = G.nc[1]; la.ncz = G.nc[2];
+    la.px = G.periodic[0]; la.py = G.periodic[1]; la.pz = G.periodic[2];
+    la.cellx = (float)G.cell[0]; la.celly = (float)G.cell[1]; la.cellz = (float)G.cell[2];
+    la.kr = (float)c->radius_scale;
+    la.S = (float)skin_abs;
+    la.cnt = cnt.data();
+    la.max_count = &max_count;
+    const bool per = la.px || la.py || la.pz;
+    const unsigned nbw = (unsigned)((n + PAIR_WARPS * PAIR_CHUNK - 1) / (PAIR_WARPS * PAIR_CHUNK));
+    int capg = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        la.lst = pass == 0 ? nullptr : lst.data();
+        la.capg = capg;
+        max_count = 0;
+        if (per) launch_warps(nbw, PAIR_WARPS * 32, [&] { k_list_build<true>(la); });
+        else launch_warps(nbw, PAIR_WARPS * 32, [&] { k_list_build<false>(la); });
+        if (pass == 0) {
+            capg = ((int)(max_count * 1.15) + 8 + 7) / 8 * 8;
+            lst.assign((size_t)((n + 31) / 32) * (size_t)capg * 32u, 0u);
+        }
+    }
+    if ((int)max_count > capg) return -2;
+    *capg_out = capg;
+    // state records + the pair kernel, outputs scattered back through perm by the kernel itself
+    EosTab E;
+    memset(&E, 0, sizeof(E));
+    int any = 0;
+    for (int a = 0; a < B200SPH_MAX_ARRAYS; a++) {
+        E.on[a] = eos_i[3 * a]; E.hg[a] = eos_i[3 * a + 1]; E.real_only[a] = eos_i[3 * a + 2];
+        E.rho0[a] = eos_d[4 * a]; E.c0[a] = eos_d[4 * a + 1]; E.gamma[a] = eos_d[4 * a + 2]; E.p0[a] = eos_d[4 * a + 3];
+        any |= E.on[a];
+    }
+    launch1(n, 256, [&] { k_pack_state(c->u, c->v, c->w, c->m, c->rho, p, cs, c->ptype, perm.data(), n, B.data(), Cc.data(), AB.data(), E, any); });
+    PairArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.B = B.data(); pa.C = Cc.data(); pa.AB = AB.data(); pa.perm = perm.data();
+    pa.arho = arho; pa.au = au; pa.av = av; pa.aw = aw; pa.ax = ax; pa.ay = ay; pa.az = az;
+    pa.dt_cfl = dt_cfl; pa.dt_force = dt_force;
+    pa.rho = c->rho;
+    pa.n = n;
+    pa.cellx = la.cellx; pa.celly = la.celly; pa.cellz = la.cellz;
+    pa.k2 = (float)(c->radius_scale * c->radius_scale);
+    pa.kfac = (float)c->kfac;
+    pa.deltap = (float)deltap;
+    for (int a = 0; a < B200SPH_MAX_ARRAYS; a++) pa.emask[a] = emask[a];
+    pa.c0 = (float)params[0]; pa.alpha = (float)params[1]; pa.beta = (float)params[2];
+    pa.gx = (float)params[3]; pa.gy = (float)params[4]; pa.gz = (float)params[5]; pa.eps_xsph = (float)params[6];
+    pa.tensile = tensile;
+    pa.real_only = real_only;
+    unsigned long long counter = 0;
+    pa.pair_counter = pairs ? &counter : nullptr;
+    const int kernel = c->kernel, dim = c->dim;
+    switch (kernel * 4 + dim) {
+#define PL(K, D) case K * 4 + D: launch(n, LIST_NT, [&] { k_pair_list<K, D>(pa, cnt.data(), lst.data(), capg); }, [&] { counter = 0; }); break;
         PL(0, 2) PL(0, 3) PL(1, 2) PL(1, 3) PL(2, 2) PL(2, 3) PL(3, 2) PL(3, 3)
 #undef PL
     default: return -1;

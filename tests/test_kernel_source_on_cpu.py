@@ -20,7 +20,7 @@ import pytest
 
 from helpers import EDAC_FIELDS, load_golden, rel_err
 import pysph_b200 as pb
-from pysph_b200 import _lib
+from pysph_b200 import _lib, geometry as geo
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -30,11 +30,15 @@ BUILD = os.path.join(EMUL, '_build')
 
 BLOCKS = [
     # (first line of the block, first line AFTER the block)
+    ('struct GridDev {', '// equation-of-state calls wait here until the next k_pack_state'),
     ('struct EosTab {', 'struct PendingEvent {'),
+    ('// cell id = floor((p - xmin)/cell) per axis (find_cell_id_raw',
+     '// B[s] = (u, v, w, m);  C[s] = (rho, p/rho^2, cs, type); pending TaitEOS'),
     ('// B[s] = (u, v, w, m);  C[s] = (rho, p/rho^2, cs, type); pending TaitEOS',
      '// SPH smoothing kernels in fp32'),
     ('// SPH smoothing kernels in fp32', '// the fused pair kernel'),
     ('// the fused pair kernel', '__global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair('),
+    ('struct ListBuildArgs {', '// one 256-bit read-only load (LDG.E.ENL2.256'),
     ('// The list consumer (the default fast path)', '// EDAC scheme, transport-velocity branch'),
     ('// EDAC scheme, transport-velocity branch (wc/edac.py:776-880): two passes',
      'struct StageTvfArgs {'),
@@ -57,7 +61,7 @@ def _extract():
         out.append('// ---- b200sph.cu lines %d-%d, verbatim ----' % (i + 1, j))
         out.extend(src[i:j])
     text = '\n'.join(out) + '\n'
-    for name in ('k_pack_state', 'pair_body', 'k_pair_list', 'k_pack_tvf', 'k_tvf_pass1', 'k_tvf_pass2', 'k_pack_solid', 'k_solid_pass1',
+    for name in ('k_cell_count', 'k_scatter', 'k_canon', 'k_pack_pos', 'k_list_build', 'k_pack_state', 'pair_body', 'k_pair_list', 'k_pack_tvf', 'k_tvf_pass1', 'k_tvf_pass2', 'k_pack_solid', 'k_solid_pass1',
                  'k_solid_pass2', 'eigen_sym3', 'sph_kernel<2>'):
         assert name in text, name
     # the constants the shim re-defines are the ones of the CUDA file
@@ -79,7 +83,7 @@ def emul():
     srcs = [inc, os.path.join(EMUL, 'emul.cpp'), os.path.join(ROOT, 'include', 'b200sph.h')]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
-        subprocess.check_call([cxx, '-O1', '-std=c++17', '-shared', '-fPIC', '-w',
+        subprocess.check_call([cxx, '-O1', '-std=c++17', '-shared', '-fPIC', '-w', '-pthread',
                                '-I', os.path.join(ROOT, 'include'), '-I', BUILD,
                                os.path.join(EMUL, 'emul.cpp'), '-o', so])
     return C.CDLL(so)
@@ -277,3 +281,111 @@ def test_wcsph_pair_kernel_on_cpu(emul, idx):
             if f == 'arho' and name == 'fluid' and p['summation_density']:
                 continue                                     # not computed in that scheme
             assert rel_err(out[f][off:off + k], want) <= 2e-5, (name, f)
+
+
+# ---------------------------------------------------------------------------
+# the whole neighbour + pair pipeline on a real cell grid (k_cell_count, k_scatter,
+# k_canon, k_pack_pos, k_list_build with warp lockstep, k_pack_state, k_pair_list)
+# against the fp64 oracle: 3-D dam break and periodic boxes
+# ---------------------------------------------------------------------------
+def _run_pipeline(emul, pas, names, kernel_name, dim, p, eqs, eos, real_only, domain=None,
+                  skin=0.1):
+    from helpers import ACC_FIELDS
+    kernel = getattr(pb, kernel_name)(dim=dim)
+    cols = dict((k, np.ascontiguousarray(np.concatenate([pa.properties[k] for pa in pas])))
+                for k in ('x', 'y', 'z', 'h', 'u', 'v', 'w', 'm', 'rho'))
+    ptype = np.concatenate([np.where(np.arange(pa.get_number_of_particles()) <
+                                     pa.num_real_particles, a, a | 8)
+                            for a, pa in enumerate(pas)]).astype(np.uint8)
+    keep = []
+    c = _common(cols, ptype, kernel_name, dim, keep)
+    n = c.n
+    # the grid b200sph_nnps_update would make (nnps_base.pyx:1520-1575 + skin)
+    cell = kernel.radius_scale * float(np.max(cols['h'])) * (1.0 + skin)
+    xmin, cellv, nc, per = [], [], [], []
+    for d, k in enumerate(('x', 'y', 'z')):
+        if domain is not None and domain[2][d]:
+            lo, hi = domain[0][d], domain[1][d]
+            m = max(1, int(np.floor((hi - lo) / cell)))
+            xmin.append(lo); nc.append(m); cellv.append((hi - lo) / m); per.append(1)
+        else:
+            mn, mx = float(cols[k].min()), float(cols[k].max())
+            ext = mx - mn
+            mn -= 0.01 * ext
+            mx += 0.01 * ext
+            xmin.append(mn); nc.append(max(1, int(np.ceil((mx - mn) / cell))))
+            cellv.append(cell); per.append(0)
+    out = dict((k, _f32(n)) for k in ['p', 'cs'] + ACC_FIELDS)
+    ei = (C.c_int * 24)(*([0] * 24))
+    ed = (C.c_double * 32)(*([0.0] * 32))
+    for a, (on, hg) in eos.items():
+        ei[3 * a], ei[3 * a + 1] = on, hg
+        ed[4 * a], ed[4 * a + 1], ed[4 * a + 2] = p['rho0'], p['c0'], p['gamma']
+    params = (C.c_double * 7)(p['c0'], p.get('alpha', 0.0), p.get('beta', 0.0), p.get('gx', 0.0),
+                              p.get('gy', 0.0), p.get('gz', 0.0), 0.5)
+    pairs = C.c_ulonglong(0)
+    capg = C.c_int(0)
+    rc = emul.emul_pipeline(
+        C.byref(c), (C.c_double * 3)(*xmin), (C.c_double * 3)(*cellv), (C.c_int * 3)(*nc),
+        (C.c_int * 3)(*per), C.c_double(skin * kernel.radius_scale * float(np.max(cols['h']))),
+        ei, ed, _emask(eqs, names), params, int(p.get('tensile_correction', False)),
+        int(real_only), C.c_double(kernel.get_deltap()),
+        *[out[k].ctypes.data_as(C.c_void_p) for k in ('p', 'cs', 'arho', 'au', 'av', 'aw', 'ax',
+                                                        'ay', 'az', 'dt_cfl', 'dt_force')],
+        C.byref(pairs), C.byref(capg))
+    assert rc == 0
+    out['rho'] = cols['rho']
+    return out, pairs.value, capg.value, nc
+
+
+def test_whole_pipeline_dam_break_on_cpu(emul):
+    from helpers import ACC_FIELDS, copy_arrays
+    from oracle import oracle as orc
+    dx = 0.09
+    pas = geo.dam_break_3d_particles(dx=dx)
+    params = geo.dam_break_3d_params(dx)
+    rs = np.random.RandomState(5)
+    f = pas[0]
+    for k in ('u', 'v', 'w'):
+        f.properties[k][:] = rs.normal(scale=0.5, size=f.u.size)
+    f.rho[:] *= 1 + 0.01 * rs.uniform(-1, 1, f.u.size)
+    opas = copy_arrays(pas)
+    o = orc.WCSPHOracleSolver(opas, params, 'CubicSpline')
+    want_pairs = o.evaluate()
+    names = [pa.name for pa in pas]
+    fluids, solids = ['fluid'], ['boundary', 'obstacle']
+    eqs = [(_lib.EQ_CONTINUITY, s_, fluids) for s_ in solids] + \
+        [(_lib.EQ_CONTINUITY, 'fluid', names), (_lib.EQ_MOMENTUM, 'fluid', names),
+         (_lib.EQ_XSPH, 'fluid', ['fluid'])]
+    out, pairs, capg, nc = _run_pipeline(emul, pas, names, 'CubicSpline', 3, params, eqs,
+                                         {0: (1, 0), 1: (1, 1), 2: (1, 1)}, True)
+    assert pairs == want_pairs and min(nc) >= 3 and capg >= 64
+    off = 0
+    for pa, oa in zip(pas, opas):
+        n = pa.get_number_of_particles()
+        for k in ACC_FIELDS + ['p', 'cs']:
+            assert rel_err(out[k][off:off + n], oa.properties[k]) <= 2e-5, (pa.name, k)
+        off += n
+
+
+@pytest.mark.parametrize('pattern', [(1, 1, 1), (1, 0, 1), (0, 1, 0)])
+def test_whole_pipeline_periodic_on_cpu(emul, pattern):
+    """the wrapped rows / wrapped x cells of k_list_build<true> and the cell-offset codes,
+    against the oracle that materialises the periodic ghosts"""
+    from helpers import ACC_FIELDS
+    from oracle import oracle as orc
+    import test_gpu_periodic as T
+    pa, params = T._periodic_case(3, 9)
+    ref, _ = T._periodic_case(3, 9)
+    dom = ([0.0, 0.0, 0.0], [1.0, 1.0, 1.0], list(pattern))
+    o = orc.WCSPHOracleSolver([ref], dict(params), 'CubicSpline', domain=dom)
+    want_pairs = o.evaluate()
+    eqs = [(_lib.EQ_CONTINUITY, 'fluid', ['fluid']), (_lib.EQ_MOMENTUM, 'fluid', ['fluid']),
+           (_lib.EQ_XSPH, 'fluid', ['fluid'])]
+    out, pairs, capg, nc = _run_pipeline(emul, [pa], ['fluid'], 'CubicSpline', 3, params, eqs,
+                                         {0: (1, 0)}, True, domain=dom)
+    assert pairs == want_pairs
+    r = o.pas[0]
+    n = r.num_real_particles
+    for k in ACC_FIELDS + ['p', 'cs']:
+        assert rel_err(out[k], r.properties[k][:n]) <= 2e-5, k
