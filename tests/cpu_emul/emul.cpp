@@ -92,7 +92,7 @@ static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; 
 static inline float frcp(float x) { return 1.0f / x; }
 static inline float frsqrt(float x) { return 1.0f / sqrtf(x); }
 static inline void ld_256(const float4 *p, float4 &b, float4 &c) { b = p[0]; c = p[1]; }
-static inline void atomicAdd(unsigned long long *p, unsigned long long v) { *p += v; }
+static inline void atomicAdd(unsigned long long *p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 using std::max;
 using std::min;
 
@@ -347,12 +347,24 @@ int emul_pipeline(const emul_common *c, const double *gxmin, const double *gcell
     unsigned long long counter = 0;
     pa.pair_counter = pairs ? &counter : nullptr;
     const int kernel = c->kernel, dim = c->dim;
+    // thread by thread for the results; when pairs are counted, once more with real warps:
+    // the kernel sums its per-thread counts with warp shuffles, which the thread-by-thread
+    // mode cannot reproduce (identity shuffle)
+    const unsigned nbl = (unsigned)((n + LIST_NT - 1) / LIST_NT);
+#define PL(K, D)                                                                                          \
+    case K * 4 + D:                                                                                       \
+        pa.pair_counter = nullptr;                                                                        \
+        launch(n, LIST_NT, [&] { k_pair_list<K, D>(pa, cnt.data(), lst.data(), capg); });                 \
+        if (pairs) {                                                                                      \
+            pa.pair_counter = &counter;                                                                   \
+            launch_warps(nbl, LIST_NT, [&] { k_pair_list<K, D>(pa, cnt.data(), lst.data(), capg); });     \
+        }                                                                                                 \
+        break;
     switch (kernel * 4 + dim) {
-#define PL(K, D) case K * 4 + D: launch(n, LIST_NT, [&] { k_pair_list<K, D>(pa, cnt.data(), lst.data(), capg); }, [&] { counter = 0; }); break;
         PL(0, 2) PL(0, 3) PL(1, 2) PL(1, 3) PL(2, 2) PL(2, 3) PL(3, 2) PL(3, 3)
-#undef PL
     default: return -1;
     }
+#undef PL
     if (pairs) *pairs = counter;
     return 0;
 }
