@@ -1,0 +1,268 @@
+"""The WHOLE library on the CPU (no GPU): pysph_b200/csrc/b200sph.cu -- host C-ABI code and
+kernels -- is transformed (tests/cpu_emul/transform.py: kernel launches become emu::launch
+calls, nothing else changes), compiled with g++ against a host stand-in for the CUDA runtime and
+device intrinsics (tests/cpu_emul/cuda_shim.h: blocks run in order; threads of a block in order,
+or as lock-stepped OS threads with real __syncthreads / shuffles / ballots / atomics) and loaded
+in place of libb200sph.so.  The GPU parity tests of this repository are then run against it.
+
+This is TEST INFRASTRUCTURE: the product never loads this library (pysph_b200/_lib.py knows only
+libb200sph.so and raises without it); it exists so that the host logic -- pool layout, list
+builds and rebuilds, deferred drift checks, device-resident dt, periodic wrap, EDAC and
+elastic-dynamics entry points -- can be exercised where no GPU is available, with the same
+tests and tolerances.  It proves nothing about performance or about GPU-specific behaviour
+(memory spaces, launch limits, real concurrency).
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EMUL = os.path.join(HERE, 'cpu_emul')
+BUILD = os.path.join(EMUL, '_build')
+sys.path.insert(0, EMUL)
+
+
+def _build():
+    import transform
+    os.makedirs(BUILD, exist_ok=True)
+    cu = os.path.join(ROOT, 'pysph_b200', 'csrc', 'b200sph.cu')
+    cpp = os.path.join(BUILD, 'b200sph_emul.cpp')
+    text, modes = transform.transform(open(cu).read())
+    assert modes['k_list_build'] == 'emu::WARP' and modes['k_pair_list'] == 'emu::BLOCK' \
+        and modes['k_stage'] == 'emu::SEQ'
+    if not os.path.exists(cpp) or open(cpp).read() != text:
+        open(cpp, 'w').write(text)
+    so = os.path.join(BUILD, 'libb200sph_emul.so')
+    deps = [cpp, os.path.join(EMUL, 'cuda_shim.h'), os.path.join(EMUL, 'cuda_shim.cpp'),
+            os.path.join(ROOT, 'include', 'b200sph.h')]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        cxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+        subprocess.check_call([cxx, '-O1', '-std=c++17', '-shared', '-fPIC', '-w', '-pthread',
+                               '-I', os.path.join(ROOT, 'include'), '-I', EMUL, cpp,
+                               os.path.join(EMUL, 'cuda_shim.cpp'), '-o', so])
+    return so
+
+
+@pytest.fixture(scope='module')
+def emulated_library():
+    """libb200sph_emul.so stands in for libb200sph.so while this module runs."""
+    from pysph_b200 import _lib
+    so = _build()
+    saved = (_lib.LIB_PATH, _lib._lib)
+    _lib.LIB_PATH, _lib._lib = so, None
+    _lib.load()
+    yield 0
+    _lib.LIB_PATH, _lib._lib = saved
+
+
+def test_every_entry_point_is_exported(emulated_library):
+    from pysph_b200 import _lib
+    lib = _lib.load()
+    for name in _lib.SIGNATURES:
+        assert hasattr(lib, name), name
+    assert lib.b200sph_abi_version() == 2
+
+
+# ---- the GPU tests of this repository, run against the emulated library --------------------
+# (module, test, kwargs, approx seconds).  The default selection takes ~2 minutes; the rest runs
+# with B200SPH_EMUL_FULL=1 (another ~12 minutes: hundreds of steps of 14 k particles with every
+# thread of the list kernels a real OS thread).
+FAST = [
+    ('test_gpu_parity', 'test_density_1d_fixture', {}),
+    ('test_gpu_parity', 'test_nnps_equals_brute_force', {}),
+    ('test_gpu_parity', 'test_nnps_corner_cases', {}),
+    ('test_gpu_parity', 'test_steppers_and_eos_vs_reference_bodies', {}),
+    ('test_gpu_parity', 'test_push_pull_roundtrip_and_errors', {}),
+] + [('test_gpu_parity', 'test_wcsph_evaluation_vs_reference_bodies', {'idx': i}) for i in range(6)] + [
+    ('test_gpu_periodic', 'test_periodic_lattice_density', {'dim': d, 'n': n, 'shift': sh})
+    for d, n in ((1, 20), (2, 10), (3, 5)) for sh in (0.0, 0.35)
+] + [
+    ('test_gpu_periodic', 'test_sph_evaluator_periodic_fixture', {}),
+    ('test_gpu_periodic', 'test_periodic_errors', {}),
+    ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 2, 'n': 24, 'pattern': (1, 1, 0)}),
+    ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 0, 1)}),
+] + [('test_gpu_edac', 'test_edac_evaluation_matches_reference_bodies', {'idx': i}) for i in range(4)] + [
+    ('test_gpu_edac', 'test_edac_tvf_step_matches_reference_bodies', {}),
+    ('test_gpu_edac', 'test_taylor_green_steps_vs_oracle', {'dim': 2, 'nx': 32, 'kernel': 'QuinticSpline'}),
+    ('test_gpu_edac', 'test_edac_setup_errors', {}),
+] + [('test_zz_gpu_solid_unvalidated', 'test_elastic_evaluation_matches_reference_bodies', {'idx': i})
+     for i in range(4)] + [
+    ('test_zz_gpu_solid_unvalidated', 'test_solid_mech_step_matches_reference_bodies', {}),
+    ('test_zz_gpu_solid_unvalidated', 'test_rings_steps_vs_oracle', {}),
+]
+FULL = [
+    ('test_gpu_parity', 'test_kernels_via_two_particle_density', {}),
+    ('test_gpu_parity', 'test_dam_break_3d_small_eval_and_steps', {}),
+    ('test_gpu_parity', 'test_dam_break_2d_gate', {}),
+    ('test_gpu_parity', 'test_determinism', {}),
+    ('test_gpu_parity', 'test_deferred_drift_check_protocol', {}),
+    ('test_gpu_parity', 'test_device_resident_dt_is_bitwise_the_host_path', {}),
+    ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
+    ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 2, 'n': 24, 'pattern': (0, 1, 0)}),
+]
+
+
+def _id(t):
+    return t[1].replace('test_', '') + ''.join('-%s' % (v,) for v in t[2].values()).replace(' ', '')
+
+
+def _call(t, emulated_library):
+    mod = __import__(t[0])
+    fn = getattr(mod, t[1])
+    fn = getattr(fn, '__wrapped__', fn)
+    return fn(emulated_library, **t[2])
+
+
+@pytest.mark.parametrize('t', FAST, ids=_id)
+def test_gpu_test_on_the_emulated_library(emulated_library, t):
+    _call(t, emulated_library)
+
+
+@pytest.mark.skipif(not os.environ.get('B200SPH_EMUL_FULL'),
+                    reason='long (minutes each): set B200SPH_EMUL_FULL=1')
+@pytest.mark.parametrize('t', FULL, ids=_id)
+def test_gpu_test_on_the_emulated_library_full(emulated_library, t):
+    _call(t, emulated_library)
+
+
+@pytest.mark.skipif(not os.environ.get('B200SPH_EMUL_FULL'),
+                    reason='long: set B200SPH_EMUL_FULL=1')
+def test_pair_kernel_variants_on_the_emulated_library(emulated_library, monkeypatch):
+    import test_gpu_parity
+    test_gpu_parity.test_all_pair_kernels_agree(emulated_library, monkeypatch)
+
+
+def _small_dam_break(dx=0.08, vscale=1.0):
+    from pysph_b200 import geometry as geo
+    pas = geo.dam_break_3d_particles(dx=dx)
+    rs = np.random.RandomState(9)
+    f = pas[0]
+    for k in ('u', 'v', 'w'):
+        f.properties[k][:] = rs.normal(scale=vscale, size=f.u.size)
+    f.rho[:] *= 1 + 0.01 * rs.uniform(-1, 1, f.u.size)
+    return pas, geo.dam_break_3d_params(dx)
+
+
+def test_small_dam_break_host_logic(emulated_library):
+    """What the long tests check, on a 3.5 k-particle dam break: adaptive EPEC steps against
+    the oracle (pair counts equal), device-resident dt bitwise == the host path, the deferred
+    drift check forces repeats (fast particles use up the skin)."""
+    import pysph_b200 as pb
+    from helpers import copy_arrays
+    from oracle import oracle as orc
+    out = {}
+    for mode in (True, False):
+        pas, params = _small_dam_break(vscale=3.0)
+        params = dict(params, n_damp=4)
+        if mode:
+            opas = copy_arrays(pas)
+            o = orc.WCSPHOracleSolver(opas, params, 'CubicSpline', threads=2)
+        s = pb.make_wcsph_solver(pas, dict(params), pb.CubicSpline(dim=3), device_dt=mode)
+        s.a_eval.count_pairs = True
+        s.initialise()
+        if mode:
+            o.initialise()
+            assert s.a_eval.last_pairs == o.pairs_last_eval
+        s.a_eval.count_pairs = False
+        for _ in range(14):
+            s.step()
+        for _ in range(4):
+            s.step()
+        s.pull()
+        st = s.backend.stats()
+        out[mode] = (s.t, s.dt, dict((k, pas[0].properties[k].copy()) for k in ('x', 'u', 'rho')), st)
+        if mode:
+            for _ in range(18):
+                o.step()
+            assert abs(s.t - o.t) <= 1e-5 * o.t
+            for k, tol in (('x', 2e-6), ('u', 2e-5), ('rho', 1e-6)):
+                want = opas[0].properties[k]
+                scale = max(np.max(np.abs(want)), 1.0 if k == 'x' else 1e-12)
+                assert np.max(np.abs(pas[0].properties[k] - want)) <= tol * scale, k
+    a, b = out[True], out[False]
+    assert a[:2] == b[:2]
+    for k in a[2]:
+        assert np.array_equal(a[2][k], b[2][k]), k
+    st = a[3]
+    assert st['light_updates'] > 10 and st['deferred_failed'] >= 1 and st['list_builds'] >= 2, st
+
+
+def test_deferred_protocol_small(emulated_library):
+    """nnps_update_deferred / nnps_confirm on the small case (the GPU version of this check is
+    tests/test_gpu_parity.py::test_deferred_drift_check_protocol)."""
+    import pysph_b200 as pb
+    pas, params = _small_dam_break(vscale=0.5)
+    s = pb.make_wcsph_solver(pas, dict(params), pb.CubicSpline(dim=3))
+    s.initialise()
+    be, nn, ae = s.backend, s.nnps, s.a_eval
+    f = pas[0]
+    f.x[:] += 1e-4 * params['h0']
+    be.push(0, ['x'])
+    nn.update(deferred=True)
+    ae.compute(0.0, 0.0)
+    assert nn.confirm() is False
+    rs = np.random.RandomState(1)
+    f.x[:] += params['h0'] * rs.uniform(-1, 1, f.x.size)
+    be.push(0, ['x'])
+    nn.update(deferred=True)
+    ae.compute(0.0, 0.0)
+    assert nn.confirm() is True and nn.confirm() is False
+    nn.update()
+    ae.compute(0.0, 0.0)
+    f.x[:] += params['h0'] * rs.uniform(-1, 1, f.x.size)
+    be.push(0, ['x'])
+    nn.update(deferred=True)
+    ae.compute(0.0, 0.0)
+    with pytest.raises(RuntimeError, match='never confirmed'):
+        be.pull(0, ['au'])
+    assert be.stats()['deferred_failed'] == 2
+
+
+def test_dump_and_restart_small(emulated_library, tmp_path):
+    """Solver.dump_output / load_output on the small case (GPU version:
+    tests/test_output.py::test_dump_and_restart_on_device).  A restart re-runs
+    initial_acceleration (solver.py:454), whose TaitEOSHGCorrection clamps the solids'
+    density IN PLACE (wc/basic.py:119-120): like in the reference, a restarted run is therefore
+    not bitwise the uninterrupted one -- it is compared with the oracle restarted the same way."""
+    import pysph_b200 as pb
+    from helpers import copy_arrays
+    from oracle import oracle as orc
+    from pysph_b200 import output
+    pas, params = _small_dam_break(vscale=0.2)
+    params = dict(params, n_damp=4)
+    s = pb.make_wcsph_solver(pas, dict(params), pb.CubicSpline(dim=3))
+    for _ in range(6):
+        s.step()
+    f = s.dump_output(str(tmp_path), 'db')
+    data = output.load(f)
+    assert int(data['solver_data']['count']) == 6 and float(data['solver_data']['t']) == s.t
+    t6, dt6 = s.t, s.dt
+    # the restarted run ...
+    pas2, _ = _small_dam_break(vscale=0.2)
+    s2 = pb.make_wcsph_solver(pas2, dict(params), pb.CubicSpline(dim=3))
+    s2.load_output(f)
+    assert (s2.count, s2.t, s2.dt) == (6, t6, dt6)
+    # ... and the oracle, started from the same file the same way
+    opas = [data['arrays'][pa.name] for pa in pas]
+    for q, pa in zip(opas, pas):                 # the oracle wants every WCSPH property
+        for k in pa.properties:
+            if k not in q.properties:
+                q.add_property(k)
+    o = orc.WCSPHOracleSolver(opas, dict(params, n_damp=0), 'CubicSpline', threads=2)
+    o.initialise()
+    o.t, o.dt, o.count = t6, dt6, 6
+    for _ in range(4):
+        s2.step()
+        o.step()
+    s2.pull()
+    assert s2.count == 10 and abs(s2.t - o.t) <= 1e-6 * o.t
+    for a, b in zip(pas2, opas):
+        for k, tol in (('x', 2e-6), ('y', 2e-6), ('z', 2e-6), ('u', 2e-5), ('v', 2e-5),
+                       ('w', 2e-5), ('rho', 1e-6)):
+            scale = max(np.max(np.abs(b.properties[k])), 1.0 if k in 'xyz' else 1e-3)
+            assert np.max(np.abs(a.properties[k] - b.properties[k])) <= tol * scale, (a.name, k)

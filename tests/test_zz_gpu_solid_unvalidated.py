@@ -1,8 +1,10 @@
 """FIRST HARDWARE CONTACT of the elastic-dynamics kernels (BASELINE
 configs[4]): `k_solid_pass1/2` and `k_stage_solid` were written after this round's GPU
-budget was spent, so nothing in this file has ever run on a B200.  The oracle they are
-compared with IS pinned to the reference (tests/test_oracle_golden.py:
-test_elastic_dynamics_matches_reference_bodies).  The tests are expected-to-pass but
+budget was spent, so nothing in this file has ever run on a B200 -- it HAS run, and passes,
+against the host emulation of the whole library (tests/test_library_on_cpu.py), and the
+kernel source compiled for the host reproduces the goldens
+(tests/test_kernel_source_on_cpu.py).  The oracle they are compared with IS pinned to the
+reference (tests/test_oracle_golden.py: test_elastic_dynamics_matches_reference_bodies).  The tests are expected-to-pass but
 marked xfail(strict=False) so that a defect shows up as XFAIL here instead of turning
 the validated suite red; the file name sorts last for the same reason."""
 import numpy as np
