@@ -266,3 +266,104 @@ def test_dump_and_restart_small(emulated_library, tmp_path):
                        ('w', 2e-5), ('rho', 1e-6)):
             scale = max(np.max(np.abs(b.properties[k])), 1.0 if k in 'xyz' else 1e-3)
             assert np.max(np.abs(a.properties[k] - b.properties[k])) <= tol * scale, (a.name, k)
+
+
+# ---- the slab decomposition: real halo / migration kernels of the (emulated) library, the
+#      real SlabParallelManager, gloo instead of NCCL, host tensors as "device" buffers ---------
+SLAB_DX, SLAB_STEPS = 0.07, 8
+
+
+def _slab_worker(rank, world, port, so, q):
+    import torch
+    import torch.distributed as dist
+    from pysph_b200 import _lib
+    _lib.LIB_PATH, _lib._lib = so, None
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo, parallel
+    import test_gpu_multi as M
+
+    Base = parallel.DeviceHaloOps
+
+    class HostHaloOps(Base):
+        """DeviceHaloOps with CPU tensors: under the emulation device memory IS host memory"""
+
+        def __init__(self, backend, device):
+            Base.__init__(self, backend, 0)
+            self.device = torch.device('cpu')
+
+        def read_later(self, tensor):
+            v = float(tensor[0])
+            return lambda: v
+    parallel.DeviceHaloOps = HostHaloOps
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        params = geo.dam_break_3d_params(SLAB_DX)
+        solver, pm, pas = parallel.make_slab_solver(SLAB_DX, params, pb.CubicSpline(dim=3),
+                                                    rank, world, device=0, n_damp=0)
+        M._perturb(pas)
+        solver.backend.push_all()
+        for _ in range(SLAB_STEPS):
+            solver.step()
+        t, dt = solver.t, solver.dt
+        solver.pull()
+        q.put((rank, M._collect(pas), pm.n_full, pm.n_refresh, pm.n_deferred_failed, t, dt,
+               pm.use_peer))
+    except Exception:
+        import traceback
+        q.put(('error', rank, traceback.format_exc()))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [
+    3, pytest.param(2, marks=pytest.mark.skipif(not os.environ.get('B200SPH_EMUL_FULL'),
+                                                reason='set B200SPH_EMUL_FULL=1'))])
+def test_slab_decomposition_on_the_emulated_library(emulated_library, world):
+    """tests/test_gpu_multi.py without GPUs: x-slabs with ADAPTIVE dt (device-resident dt +
+    all-reduce MIN on the time-control block), deferred refresh / confirm, full path with
+    migration; world 3 has a rank with two neighbours.  Matches the one-process run by gid."""
+    import socket
+    import torch.multiprocessing as mp
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo, _lib
+    import test_gpu_multi as M
+    params = geo.dam_break_3d_params(SLAB_DX)
+    pas = geo.dam_break_3d_particles(dx=SLAB_DX)
+    M._perturb(pas)
+    s = pb.make_wcsph_solver(pas, dict(params, n_damp=0), pb.CubicSpline(dim=3))
+    for _ in range(SLAB_STEPS):
+        s.step()
+    t_ref, dt_ref = s.t, s.dt
+    s.pull()
+    ref = M._collect(pas)
+    sock = socket.socket()
+    sock.bind(('127.0.0.1', 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, _lib.LIB_PATH, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=900) for _ in range(world)]
+    assert not any(o[0] == 'error' for o in out), [o[2] for o in out if o[0] == 'error'][:1]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert min(o[3] for o in out) > 0 and min(o[2] for o in out) >= 1      # refreshes and full paths
+    assert not any(o[7] for o in out)           # no cudaIpc here: refresh went through send/recv
+    for o in out:
+        assert abs(o[5] - t_ref) <= 1e-6 * t_ref and abs(o[6] - dt_ref) <= 1e-5 * dt_ref
+    h0, c0 = params['h0'], params['c0']
+    for name in ref:
+        g_all = np.concatenate([o[1][name]['gid'] for o in out])
+        assert np.array_equal(np.sort(g_all), np.sort(ref[name]['gid'])), name
+        order_ref, order = np.argsort(ref[name]['gid']), np.argsort(g_all)
+        for k, tol in (('x', 5e-6 * h0), ('y', 5e-6 * h0), ('z', 5e-6 * h0), ('u', 5e-6 * c0),
+                       ('v', 5e-6 * c0), ('w', 5e-6 * c0), ('rho', 5e-4)):
+            a = np.concatenate([o[1][name][k] for o in out])[order]
+            assert np.max(np.abs(a - ref[name][k][order_ref])) <= tol, (name, k)
