@@ -377,6 +377,14 @@ int b200sph_drop_ghosts(b200sph_ctx *ctx, int arr);
 int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi,
                         double *dev_buf, int64_t cap, int64_t count[2]);
 
+/* load re-balancing (parallel_manager.pyx:512-530 lb_count/lb_freq, :532-613
+ * update_partition): add the number of REAL particles of `arr` per x column
+ * [x0 + k / inv_width, x0 + (k + 1) / inv_width), k clamped to 0..nbins-1, to the
+ * device counters dev_counts[0..nbins).  The caller zeroes them, weights the arrays
+ * (scheme.py:523-527 weights solids lower), sums over ranks and moves the cut planes */
+int b200sph_column_counts(b200sph_ctx *ctx, int arr, double x0, double inv_width, int nbins,
+                          unsigned long long *dev_counts);
+
 /* ---- bookkeeping -------------------------------------------------------- */
 int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out);
 int b200sph_reset_stats(b200sph_ctx *ctx);

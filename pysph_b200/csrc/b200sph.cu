@@ -4066,6 +4066,46 @@ int b200sph_drop_ghosts(b200sph_ctx *ctx, int arr)
     return 0;
 }
 
+// Per-column particle counts for the slab re-cut.  Every thread walks COLUMN_RUN
+// consecutive particles and merges equal bins before the atomic: particles are stored
+// in cell order, so a run mostly stays in one column and the counters see ~n/32 atomics.
+#define COLUMN_RUN 32
+__global__ void k_column_counts(const double *__restrict__ x, long long off, long long n, double x0, double inv_w, int nbins,
+                                unsigned long long *__restrict__ counts)
+{
+    const long long first = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * COLUMN_RUN;
+    if (first >= n) return;
+    const long long last = first + COLUMN_RUN < n ? first + COLUMN_RUN : n;
+    int cur = -1;
+    unsigned long long run = 0;
+    for (long long i = first; i < last; i++) {
+        int b = (int)floor((x[off + i] - x0) * inv_w);
+        b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);
+        if (b != cur) {
+            if (run) atomicAdd(&counts[cur], run);
+            cur = b, run = 0;
+        }
+        run++;
+    }
+    if (run) atomicAdd(&counts[cur], run);
+}
+
+int b200sph_column_counts(b200sph_ctx *ctx, int arr, double x0, double inv_width, int nbins, unsigned long long *dev_counts)
+{
+    if (int rcc = require_confirmed(ctx, "column_counts")) return rcc;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "column_counts: bad array %d", arr);
+    if (nbins < 1 || !(inv_width > 0.0) || !dev_counts) return set_err(ctx, "column_counts: bad bins");
+    const ArrayInfo &ai = ctx->arr[arr];
+    if (ai.n_real == 0) return 0;
+    const unsigned nb = (unsigned)cdiv(cdiv(ai.n_real, COLUMN_RUN), 256);
+    k_column_counts<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ai.off, ai.n_real, x0, inv_width, nbins, dev_counts);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double *dev_buf, int64_t cap, int64_t count[2])
 {
     if (int rcc = require_confirmed(ctx, "migrate_out")) return rcc;

@@ -215,6 +215,18 @@ class DeviceHaloOps(object):
                           buf.data_ptr() + 8 * offset, n, n, nfields,
                           1 if as_real else 0)
 
+    def column_weights(self, x0, width, nbins, weights):
+        """Weighted number of real particles per x column as a float64 CUDA tensor
+        (nbins,): sum over arrays of weights[arr] * count (for the slab re-cut)."""
+        t = self.torch
+        out = t.zeros(nbins, dtype=t.float64, device=self.device)
+        for a in range(self.narr):
+            cnt = t.zeros(nbins, dtype=t.int64, device=self.device)
+            self.ctx.call('b200sph_column_counts', a, float(x0), 1.0 / float(width),
+                          int(nbins), cnt.data_ptr())
+            out += float(weights[a]) * cnt.to(t.float64)
+        return out
+
     def migrate_out(self, arr, lo, hi, buf, offset):
         cnt = (C.c_int64 * 2)()
         cap = (buf.numel() - offset) // MIGRATE_FIELDS
@@ -228,10 +240,18 @@ class DeviceHaloOps(object):
 # ---------------------------------------------------------------------------
 class SlabParallelManager(object):
     def __init__(self, ops, rank, world, cuts, halo_width, dist=None,
-                 migrate=True):
+                 migrate=True, lb_freq=0, lb_columns=None, lb_weights=None):
         """ops: DeviceHaloOps-like object.  cuts: world+1 cut planes.
         halo_width: ghost_layers * cell_size = radius_scale * hmax
-        (application.py:642, nnps_base.pyx:942-978)."""
+        (application.py:642, nnps_base.pyx:942-978).
+
+        lb_freq > 0 turns the re-cut on (the reference's --lb-freq,
+        application.py:650, :1347-1351; parallel_manager.pyx:512-530): once at least
+        lb_freq evaluations have passed since the last one, the next FULL update (the
+        neighbour lists are rebuilt then anyway) first moves the cut planes so that the
+        weighted particle counts are equal again.  lb_columns = (x0, width, n): the x
+        columns the counts are taken on (cut planes sit on column boundaries);
+        lb_weights: one weight per particle array."""
         if dist is None:
             import torch.distributed as dist
         self.dist = dist
@@ -260,6 +280,14 @@ class SlabParallelManager(object):
         self.n_peer_refresh = 0
         self.n_deferred_failed = 0
         self._pending = None
+        self.cuts = [float(c) for c in cuts]
+        self.lb_freq = int(lb_freq)
+        self.lb_columns = lb_columns
+        self.lb_weights = list(lb_weights) if lb_weights is not None else [1.0] * self.narr
+        if self.lb_freq > 0 and (lb_columns is None or not hasattr(ops, 'column_weights')):
+            raise ValueError('lb_freq > 0 needs lb_columns and ops.column_weights')
+        self.lb_count = 0
+        self.n_recut = 0
         self._prof_init()
 
     # -- optional timeline (B200SPH_PM_PROFILE=1): CPU seconds per phase and CUDA
@@ -356,6 +384,7 @@ class SlabParallelManager(object):
         ops = self.ops
         self._pending = None
         t_begin = time.perf_counter()
+        self.lb_count += 1
         if self._prof is not None:
             self._prof['n'] += 1
         if self._recv and hasattr(ops, 'drift'):
@@ -432,12 +461,62 @@ class SlabParallelManager(object):
         ops = self.ops
         for a in range(self.narr):
             ops.drop_ghosts(a)                       # parallel_manager.pyx:519
+        if self.lb_freq > 0 and self.lb_count >= self.lb_freq and self.migrate \
+                and self.world > 1 and self.n_full > 0:
+            self._recut()                            # parallel_manager.pyx:522-526
         if self.migrate:
             self._migrate()
         self._import_ghosts()
         self.n_full += 1
         if self.use_peer:
             self._setup_peer()
+
+    def _recut(self):
+        """Move the cut planes to re-balance the weighted particle counts
+        (parallel_manager.pyx:532-613 update_partition; the reference hands the cell
+        list to Zoltan, here the partition stays a set of x slabs).  Collective; every
+        rank computes the same planes from the same all-reduced column weights.
+        The migration that follows only talks to the slab neighbours, so a plane moves
+        at most to within one halo width of the neighbouring OLD planes, and no slab
+        becomes narrower than two halo widths (its ghosts come from one neighbour)."""
+        x0, width, nbins = self.lb_columns
+        hist = self.ops.column_weights(x0, width, nbins, self.lb_weights)
+        self.dist.all_reduce(hist, op=self.dist.ReduceOp.SUM)
+        w = np.asarray(hist.tolist(), dtype=float)
+        self.lb_count = 0
+        total = w.sum()
+        if not total > 0.0:
+            return
+        c = np.cumsum(w)
+        old = self.cuts
+        new = [-np.inf]
+        for k in range(1, self.world):
+            i = int(np.searchsorted(c, total * k / self.world))
+            i = min(max(i, 1), nbins - 1)
+            cut = x0 + i * width
+            # neighbour-only migration: stay clear of the adjacent old planes
+            lo = old[k - 1] + self.halo if k > 1 else -np.inf
+            hi = old[k + 1] - self.halo if k < self.world - 1 else np.inf
+            if lo > hi:
+                return
+            cut = min(max(cut, lo), hi)
+            # ... on a column boundary, rounded towards the allowed side
+            j = (cut - x0) / width
+            cut = x0 + (np.ceil(j - 1e-9) if cut == lo else np.floor(j + 1e-9)) * width
+            if cut < lo or cut > hi:
+                return
+            new.append(float(cut))
+        new.append(np.inf)
+        for k in range(1, self.world):
+            wide_enough = new[k + 1] - new[k] >= 2.0 * self.halo and \
+                new[k] - new[k - 1] >= 2.0 * self.halo
+            if not wide_enough:
+                return
+        if new == old:
+            return
+        self.cuts = new
+        self.lo, self.hi = new[self.rank], new[self.rank + 1]
+        self.n_recut += 1
 
     def _setup_peer(self):
         """(Re)allocate the staging buffers when the halo outgrew them and exchange
@@ -609,8 +688,10 @@ class SlabParallelManager(object):
 
 # ---------------------------------------------------------------------------
 def make_slab_solver(dx, params, kernel, rank, world, device=0,
-                     solid_weight=0.45, **solver_kw):
-    """Build this rank's slab of the 3D dam break and a ready solver."""
+                     solid_weight=0.45, lb_freq=None, **solver_kw):
+    """Build this rank's slab of the 3D dam break and a ready solver.
+    lb_freq: evaluations between re-cuts of the slabs (None: B200SPH_LB_FREQ, default
+    0 = static slabs)."""
     import os
     import pysph_b200 as pb
     from . import geometry as geo
@@ -628,6 +709,12 @@ def make_slab_solver(dx, params, kernel, rank, world, device=0,
                                   capacity_factor=1.05, extra_capacity=extra,
                                   **solver_kw)
     ops = DeviceHaloOps(solver.backend, device)
-    pm = SlabParallelManager(ops, rank, world, cuts, halo)
+    if lb_freq is None:
+        lb_freq = int(os.environ.get('B200SPH_LB_FREQ', '0'))
+    # the lattice columns the initial cuts were chosen on; fluid 1, solids solid_weight
+    pm = SlabParallelManager(ops, rank, world, cuts, halo, lb_freq=lb_freq,
+                             lb_columns=(float(xs[0] - 0.5 * dx), dx, int(xs.size)),
+                             lb_weights=[1.0 if pa.name == 'fluid' else solid_weight
+                                         for pa in pas])
     solver.set_parallel_manager(pm)
     return solver, pm, pas

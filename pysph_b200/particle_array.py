@@ -207,8 +207,8 @@ ELASTIC_PROPS = ['cs', 'e', 'v00', 'v01', 'v02', 'v10', 'v11', 'v12', 'v20', 'v2
 
 
 def get_particle_array_elastic_dynamics(constants=None, **props):
-    """pysph/sph/solid_mech/basic.py:32-90 (host side only: the B200 backend has no
-    kernels for the elastic-dynamics equations yet)."""
+    """pysph/sph/solid_mech/basic.py:32-90: the property set and constants of an
+    elastic solid (device kernels: k_solid_pass1/2, k_stage_solid)."""
     consts = {'wdeltap': -1., 'n': 4, 'G': 0.0, 'E': 0.0, 'nu': 0.0,
               'rho_ref': 1000.0, 'c0_ref': 0.0}
     given = dict(constants or {})

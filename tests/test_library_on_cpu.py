@@ -270,10 +270,30 @@ def test_dump_and_restart_small(emulated_library, tmp_path):
 
 # ---- the slab decomposition: real halo / migration kernels of the (emulated) library, the
 #      real SlabParallelManager, gloo instead of NCCL, host tensors as "device" buffers ---------
+def test_column_counts_on_the_emulated_library(emulated_library):
+    """b200sph_column_counts (the slab re-cut's histogram) against numpy: clamped end
+    bins, real particles only, run-merged atomics."""
+    import pysph_b200 as pb
+    rs = np.random.RandomState(3)
+    x = np.sort(rs.uniform(-0.2, 3.4, 5001))
+    pa = pb.get_particle_array_wcsph(name='fluid', x=x, y=x * 0, z=x * 0, h=0.1, m=1.0, rho=1.0)
+    pb2 = pb.get_particle_array_wcsph(name='wall', x=rs.uniform(-0.2, 3.4, 777), h=0.1, m=1.0,
+                                      rho=1.0)
+    pb2.set_num_real_particles(700)              # 77 ghosts at the end: not counted
+    pb2.tag[700:] = 1
+    be = pb.B200Backend([pa, pb2])
+    for arr, p, n in ((0, pa, 5001), (1, pb2, 700)):
+        cnt = np.zeros(64, dtype=np.uint64)
+        be.ctx.call('b200sph_column_counts', arr, 0.0, 1.0 / 0.05, 64, cnt.ctypes.data)
+        b = np.clip(np.floor(p.x[:n] / 0.05).astype(int), 0, 63)
+        assert np.array_equal(cnt.astype(np.int64), np.bincount(b, minlength=64)), arr
+        assert cnt.sum() == n
+
+
 SLAB_DX, SLAB_STEPS = 0.07, 8
 
 
-def _slab_worker(rank, world, port, so, q):
+def _slab_worker(rank, world, port, so, q, lb_freq=0):
     import torch
     import torch.distributed as dist
     from pysph_b200 import _lib
@@ -301,7 +321,10 @@ def _slab_worker(rank, world, port, so, q):
     try:
         params = geo.dam_break_3d_params(SLAB_DX)
         solver, pm, pas = parallel.make_slab_solver(SLAB_DX, params, pb.CubicSpline(dim=3),
-                                                    rank, world, device=0, n_damp=0)
+                                                    rank, world, device=0, n_damp=0,
+                                                    lb_freq=lb_freq)
+        if lb_freq:         # the planes were balanced with solids at 0.45: re-cut with the
+            pm.lb_weights = [1.0] + [0.1] * (len(pas) - 1)     # reference's 0.1 moves them
         M._perturb(pas)
         solver.backend.push_all()
         for _ in range(SLAB_STEPS):
@@ -309,7 +332,7 @@ def _slab_worker(rank, world, port, so, q):
         t, dt = solver.t, solver.dt
         solver.pull()
         q.put((rank, M._collect(pas), pm.n_full, pm.n_refresh, pm.n_deferred_failed, t, dt,
-               pm.use_peer))
+               pm.use_peer, pm.n_recut, list(pm.cuts)))
     except Exception:
         import traceback
         q.put(('error', rank, traceback.format_exc()))
@@ -318,17 +341,18 @@ def _slab_worker(rank, world, port, so, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world', [
-    3, pytest.param(2, marks=pytest.mark.skipif(not os.environ.get('B200SPH_EMUL_FULL'),
+@pytest.mark.parametrize('world,lb_freq', [
+    (3, 0), (3, 2),
+    pytest.param(2, 0, marks=pytest.mark.skipif(not os.environ.get('B200SPH_EMUL_FULL'),
                                                 reason='set B200SPH_EMUL_FULL=1'))])
-def test_slab_decomposition_on_the_emulated_library(emulated_library, world):
+def test_slab_decomposition_on_the_emulated_library(emulated_library, world, lb_freq):
     """tests/test_gpu_multi.py without GPUs: x-slabs with ADAPTIVE dt (device-resident dt +
     all-reduce MIN on the time-control block), deferred refresh / confirm, full path with
     migration; world 3 has a rank with two neighbours.  Matches the one-process run by gid."""
     import socket
     import torch.multiprocessing as mp
     import pysph_b200 as pb
-    from pysph_b200 import geometry as geo, _lib
+    from pysph_b200 import geometry as geo, _lib, parallel
     import test_gpu_multi as M
     params = geo.dam_break_3d_params(SLAB_DX)
     pas = geo.dam_break_3d_particles(dx=SLAB_DX)
@@ -345,7 +369,7 @@ def test_slab_decomposition_on_the_emulated_library(emulated_library, world):
     sock.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, _lib.LIB_PATH, q))
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, _lib.LIB_PATH, q, lb_freq))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -356,6 +380,11 @@ def test_slab_decomposition_on_the_emulated_library(emulated_library, world):
         assert p.exitcode == 0
     assert min(o[3] for o in out) > 0 and min(o[2] for o in out) >= 1      # refreshes and full paths
     assert not any(o[7] for o in out)           # no cudaIpc here: refresh went through send/recv
+    if lb_freq:         # the slabs were re-cut on the way (k_column_counts + migration)
+        static = parallel.balanced_cuts(*parallel.dam_break_column_weights(
+            SLAB_DX, solid_weight=0.45), world, SLAB_DX)
+        assert all(o[8] >= 1 for o in out) and all(o[9] == out[0][9] for o in out)
+        assert out[0][9] != static, (out[0][9], static)
     for o in out:
         assert abs(o[5] - t_ref) <= 1e-6 * t_ref and abs(o[6] - dt_ref) <= 1e-5 * dt_ref
     h0, c0 = params['h0'], params['c0']

@@ -96,6 +96,14 @@ class NumpyHaloOps(object):
             assert A['x'].size - n == self.nreal[a]
             self.nreal[a] += n
 
+    def column_weights(self, x0, width, nbins, weights):
+        out = np.zeros(nbins)
+        for a, A in enumerate(self.arrays):
+            b = np.clip(np.floor((A['x'][:self.nreal[a]] - x0) / width).astype(int),
+                        0, nbins - 1)
+            out += weights[a] * np.bincount(b, minlength=nbins)
+        return self.torch.from_numpy(out)
+
     def migrate_out(self, a, lo, hi, buf, off):
         A = self.arrays[a]
         x = A['x']
@@ -250,6 +258,105 @@ def test_slab_exchange_gloo(world):
         assert all(all(r) for r in res), (rank, res)
         assert idem
         assert abs(dtmin - 0.1) < 1e-15
+
+
+def _recut_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        # equal-width slabs over [0, 3) but the particles crowd towards x = 0
+        cuts = [-np.inf] + [3.0 * k / world for k in range(1, world)] + [np.inf]
+        halo = 0.1
+        rs = np.random.RandomState(5)
+        glob = []
+        for n in (3000, 900):
+            a = dict((k, rs.uniform(0, 1, n)) for k in F64)
+            a['x'] = 3.0 * rs.uniform(0, 1, n) ** 2.0
+            a['gid'] = np.arange(n, dtype=float) + 10000 * len(glob)
+            glob.append(a)
+        weights = [1.0, 0.5]
+        mine = []
+        for a in glob:
+            owner = np.searchsorted(cuts, a['x'], side='right') - 1
+            mine.append(dict((k, v[owner == rank].copy()) for k, v in a.items()))
+        ops = NumpyHaloOps(mine)
+        pm = SlabParallelManager(ops, rank, world, cuts, halo, dist=dist, lb_freq=3,
+                                 lb_columns=(0.0, 0.05, 60), lb_weights=weights)
+        history = []
+        ok = True
+
+        def load():
+            return sum(wt * ops.nreal[i] for i, wt in enumerate(weights))
+
+        def check(cuts_now):
+            good = True
+            for ai, a in enumerate(glob):
+                owner = np.searchsorted(cuts_now, a['x'], side='right') - 1
+                nr = ops.nreal[ai]
+                got = ops.arrays[ai]
+                good &= np.array_equal(np.sort(got['gid'][:nr]), np.sort(a['gid'][owner == rank]))
+                order = np.argsort(got['gid'][:nr])
+                src = np.argsort(a['gid'])
+                src = src[owner[src] == rank]
+                good &= all(np.array_equal(got[k][:nr][order], a[k][src]) for k in F64)
+                lo, hi = cuts_now[rank], cuts_now[rank + 1]
+                want = a['x'][((a['x'] >= lo - halo) & (a['x'] < lo)) |
+                              ((a['x'] >= hi) & (a['x'] < hi + halo))]
+                good &= np.array_equal(np.sort(got['x'][nr:]), np.sort(want))
+            return bool(good)
+
+        pm.update()                                  # first build: the given planes
+        ok &= pm.n_recut == 0 and check(cuts)
+        history.append(load())
+        ops.fake_drift = (2.0, 1.0)                  # every update takes the full path
+        for it in range(12):
+            before = pm.n_recut
+            old = list(pm.cuts)
+            pm.update()
+            # a re-cut happens on a full update once lb_freq evaluations have passed
+            ok &= (pm.n_recut > before) <= (it % 3 == 1)
+            # planes stay on column boundaries, in order, clear of the old neighbours
+            for k in range(1, world):
+                ok &= abs(pm.cuts[k] / 0.05 - round(pm.cuts[k] / 0.05)) < 1e-9
+                ok &= pm.cuts[k] - pm.cuts[k - 1] >= 2 * halo
+                if k > 1:
+                    ok &= pm.cuts[k] >= old[k - 1] + halo - 1e-12
+                if k < world - 1:
+                    ok &= pm.cuts[k] <= old[k + 1] - halo + 1e-12
+            ok &= check(pm.cuts)
+            history.append(load())
+        q.put((rank, bool(ok), history, pm.cuts, pm.n_recut))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_slab_recut_gloo(world):
+    """lb_freq re-cut (parallel_manager.pyx:512-530): the planes move towards equal
+    weighted counts through neighbour-only migration, nothing is lost or duplicated."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_recut_worker, args=(r, world, port, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(o[1] for o in out), [o[1] for o in out]
+    assert all(o[3] == out[0][3] for o in out)              # same planes everywhere
+    assert out[0][4] >= (2 if world > 2 else 1)
+    first = [o[2][0] for o in out]
+    last = [o[2][-1] for o in out]
+    assert abs(sum(first) - sum(last)) < 1e-9               # weighted total conserved
+    imb0 = max(first) / (sum(first) / world)
+    imb1 = max(last) / (sum(last) / world)
+    assert imb0 > 1.4 and imb1 < 1.15, (imb0, imb1)
 
 
 def test_partition_matches_geometry():
