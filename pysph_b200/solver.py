@@ -166,19 +166,7 @@ class B200Solver(object):
                 self.nnps.update_domain()
                 self.nnps.update()
             self.integrator.initial_acceleration(self._t, self._dt)  # solver.py:454
-            restart_dt = getattr(self, '_restart_dt', None)
-            if restart_dt is not None:
-                # restart: the file's dt is already the damped dt of the next step
-                self._restart_dt = None
-                self._damping_factor = self._next_damping_factor()
-                self._dt = restart_dt
-                if self._use_device_dt():
-                    self._device_dt_begin()
-                    self.backend.ctx.call('b200sph_dt_commit', 1.0, 1.0,
-                                          int(self._tc is not None), 0, 0,
-                                          self._commits % 2)
-                    self._commits += 1
-            elif self._use_device_dt():
+            if self._use_device_dt():
                 self._device_dt_begin()
                 self._device_dt_advance(advance=False)               # solver.py:458
             else:
@@ -213,7 +201,9 @@ class B200Solver(object):
 
     # -- output / restart (solver.py:520-624) ---------------------------------
     def _get_solver_data(self):
-        return {'dt': self.dt, 't': self.t, 'count': self.count}
+        # the file holds the UNDAMPED time step (solver.py:747-753): a restart divides
+        # by a damping factor of 1 and damps again for its own count (:647-688)
+        return {'dt': self.dt / self._damping_factor, 't': self.t, 'count': self.count}
 
     def dump_output(self, output_directory='.', fname='b200', detailed_output=False,
                     only_real=True, compress=False):
@@ -249,9 +239,10 @@ class B200Solver(object):
         self.nnps.update()
         sd = data['solver_data']
         self._t, self._dt, self.count = float(sd['t']), float(sd['dt']), int(sd['count'])
+        # like a fresh reference Solver that loaded the file (solver.py:616-624) and
+        # entered solve(): initial_acceleration, then _get_timestep() from the file's
+        # undamped dt with the damping factor of the restored count (:454-458)
         self._initialised = False          # re-evaluate and re-seed the device clock
+        self._damping_factor = 1.0
         self.integrator.device_dt = False
         self._commits = 0
-        # dt in the file is the damped dt the next step uses: keep it across the
-        # re-initialisation (solver.py:616-624 restores dt the same way)
-        self._restart_dt = self._dt

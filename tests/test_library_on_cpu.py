@@ -234,14 +234,16 @@ def test_dump_and_restart_small(emulated_library, tmp_path):
     from oracle import oracle as orc
     from pysph_b200 import output
     pas, params = _small_dam_break(vscale=0.2)
-    params = dict(params, n_damp=4)
+    params = dict(params, n_damp=8)          # the dump falls INTO the damping window
     s = pb.make_wcsph_solver(pas, dict(params), pb.CubicSpline(dim=3))
     for _ in range(6):
         s.step()
     f = s.dump_output(str(tmp_path), 'db')
     data = output.load(f)
     assert int(data['solver_data']['count']) == 6 and float(data['solver_data']['t']) == s.t
-    t6, dt6 = s.t, s.dt
+    t6, dt6 = s.t, float(data['solver_data']['dt'])
+    # the file holds the undamped dt (solver.py:747-753)
+    assert abs(dt6 - s.dt / s._damping_factor) <= 1e-15 * dt6 and 0.9 < s._damping_factor < 1.0
     # the restarted run ...
     pas2, _ = _small_dam_break(vscale=0.2)
     s2 = pb.make_wcsph_solver(pas2, dict(params), pb.CubicSpline(dim=3))
@@ -253,9 +255,11 @@ def test_dump_and_restart_small(emulated_library, tmp_path):
         for k in pa.properties:
             if k not in q.properties:
                 q.add_property(k)
-    o = orc.WCSPHOracleSolver(opas, dict(params, n_damp=0), 'CubicSpline', threads=2)
-    o.initialise()
+    o = orc.WCSPHOracleSolver(opas, dict(params), 'CubicSpline', threads=2)
     o.t, o.dt, o.count = t6, dt6, 6
+    o.initialise()
+    s2.initialise()
+    assert abs(s2.dt - o.dt) <= 1e-6 * o.dt
     for _ in range(4):
         s2.step()
         o.step()
