@@ -377,6 +377,22 @@ int b200sph_drop_ghosts(b200sph_ctx *ctx, int arr);
 int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi,
                         double *dev_buf, int64_t cap, int64_t count[2]);
 
+/* ---- asynchronous output (Solver.dump_output at pfreq, solver.py:520-560; the
+ * reference's GPU arrays copy every property back with the loop stopped) ------------
+ * take: snapshot `nseg` (array, property) segments of count[i] leading particles each
+ *   (count = n_real drops the ghosts) into a library-owned device buffer, in stream
+ *   order: fp64 properties as they are, fp32 ones widened to double, integer ones as
+ *   4-byte values; arr[i] = -1 snapshots the first count[i] doubles {dt, t, ...} of the
+ *   time-control block.  Returns at once; the time loop continues.
+ * fetch: copy segment `seg` to host memory (8 * count bytes, 4 * count for integers) on
+ *   a private stream and wait for THAT copy only; may be called from another host
+ *   thread while the owner keeps stepping.
+ * release: the buffer may be overwritten by the next take.  One snapshot at a time. */
+int b200sph_snapshot_take(b200sph_ctx *ctx, int nseg, const int *arr, const int *prop,
+                          const int64_t *count);
+int b200sph_snapshot_fetch(b200sph_ctx *ctx, int seg, void *host, int64_t count);
+int b200sph_snapshot_release(b200sph_ctx *ctx);
+
 /* load re-balancing (parallel_manager.pyx:512-530 lb_count/lb_freq, :532-613
  * update_partition): add the number of REAL particles of `arr` per x column
  * [x0 + k / inv_width, x0 + (k + 1) / inv_width), k clamped to 0..nbins-1, to the

@@ -154,6 +154,14 @@ struct b200sph_ctx {
     double *tc = nullptr;
     bool tc_owned = false;
     double *tc_host = nullptr;          // pinned: 2 snapshot slots x 2 doubles
+    // asynchronous output snapshot (b200sph_snapshot_*): one in flight
+    double *snap_buf = nullptr;         // device staging, 8-byte slots
+    int64_t snap_cap = 0;               // in doubles
+    std::vector<int64_t> snap_off, snap_len;   // per segment: offset (doubles) / elements
+    std::vector<int> snap_u32;          // per segment: 1 = 4-byte integers
+    cudaStream_t snap_stream = nullptr; // the D2H copies run here, beside the time loop
+    cudaEvent_t snap_ready = nullptr, snap_done = nullptr;
+    bool snap_open = false;
     cudaEvent_t tc_evt[2] = {nullptr, nullptr};
     bool h_dirty = true;        // h changed since the last update_domain reduction
     unsigned *red_u32 = nullptr, *red_u32_host = nullptr;
@@ -2544,6 +2552,10 @@ int b200sph_destroy(b200sph_ctx *ctx)
     if (ctx->drift_evt) cudaEventDestroy(ctx->drift_evt);
     for (auto &pe : ctx->pending) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->snap_stream) { cudaStreamSynchronize(ctx->snap_stream); cudaStreamDestroy(ctx->snap_stream); }
+    if (ctx->snap_ready) cudaEventDestroy(ctx->snap_ready);
+    if (ctx->snap_done) cudaEventDestroy(ctx->snap_done);
+    cudaFree(ctx->snap_buf);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -2763,6 +2775,95 @@ int b200sph_device_ptr(b200sph_ctx *ctx, int arr, int prop, void **out)
     else if (is_f32_prop(prop)) *out = f32_ptr(ctx, prop) + o;
     else if (u32_index(prop) >= 0) *out = ctx->u32[u32_index(prop)] + o;
     else return set_err(ctx, "device_ptr: bad property %d", prop);
+    return 0;
+}
+
+// ---- asynchronous output snapshot ---------------------------------------------------
+// take: device-to-device copies (fp32 properties widened) into a private buffer, in stream
+// order -- the time loop goes on at once; fetch: device-to-host on a second stream, from
+// any host thread; release: lets the next take overwrite the buffer.
+int b200sph_snapshot_take(b200sph_ctx *ctx, int nseg, const int *arr, const int *prop, const int64_t *count)
+{
+    if (int rcc = require_confirmed(ctx, "snapshot_take")) return rcc;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = eos_flush(ctx))) return rc;
+    if (ctx->snap_open) return set_err(ctx, "snapshot_take: the previous snapshot was not released");
+    if (nseg < 1) return set_err(ctx, "snapshot_take: no segments");
+    if (!ctx->snap_stream) {
+        CU(cudaStreamCreateWithFlags(&ctx->snap_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->snap_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->snap_done, cudaEventDisableTiming));
+    } else {
+        // the copies of the previous snapshot must have left the buffer
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->snap_done, 0));
+    }
+    int64_t total = 0;
+    for (int i = 0; i < nseg; i++) {
+        if (arr[i] == -1) {  // the time-control block {dt, t, ...}
+            if (!ctx->tc) return set_err(ctx, "snapshot_take: no time-control block");
+            if (count[i] < 1 || count[i] > 8) return set_err(ctx, "snapshot_take: the time-control block has 8 doubles");
+        } else if ((rc = check_range(ctx, arr[i], 0, count[i]))) return rc;
+        total += std::max<int64_t>(count[i], 1);
+    }
+    if (total > ctx->snap_cap) {
+        if (ctx->snap_buf) CU(cudaFree(ctx->snap_buf));
+        CU(cudaMalloc((void **)&ctx->snap_buf, 8 * (size_t)(total + total / 8 + 1024)));
+        ctx->snap_cap = total + total / 8 + 1024;
+    }
+    ctx->snap_off.assign(nseg, 0), ctx->snap_len.assign(nseg, 0), ctx->snap_u32.assign(nseg, 0);
+    int64_t at = 0;
+    for (int i = 0; i < nseg; i++) {
+        const int64_t n = count[i];
+        ctx->snap_off[i] = at, ctx->snap_len[i] = n;
+        double *dst = ctx->snap_buf + at;
+        at += std::max<int64_t>(n, 1);
+        if (n == 0) continue;
+        if (arr[i] == -1) {
+            CU(cudaMemcpyAsync(dst, ctx->tc, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+            continue;
+        }
+        const int64_t o = ctx->arr[arr[i]].off;
+        const int pr = prop[i];
+        if (is_solid_prop(pr) && (rc = ensure_solid(ctx))) return rc;
+        if (is_f64_prop(pr)) {
+            CU(cudaMemcpyAsync(dst, f64_ptr(ctx, pr) + o, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else if (is_f32_prop(pr)) {
+            k_f32_to_f64<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(f32_ptr(ctx, pr) + o, dst, n);
+            LAUNCH_CHECK();
+        } else if (u32_index(pr) >= 0) {
+            ctx->snap_u32[i] = 1;
+            CU(cudaMemcpyAsync(dst, ctx->u32[u32_index(pr)] + o, 4 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            return set_err(ctx, "snapshot_take: bad property %d", pr);
+        }
+    }
+    CU(cudaEventRecord(ctx->snap_ready, ctx->stream));
+    ctx->snap_open = true;
+    return 0;
+}
+
+int b200sph_snapshot_fetch(b200sph_ctx *ctx, int seg, void *host, int64_t count)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->snap_open) return set_err(ctx, "snapshot_fetch: no snapshot");
+    if (seg < 0 || seg >= (int)ctx->snap_len.size() || count != ctx->snap_len[seg])
+        return set_err(ctx, "snapshot_fetch: segment %d does not hold %lld elements", seg, (long long)count);
+    if (count == 0) return 0;
+    CU(cudaStreamWaitEvent(ctx->snap_stream, ctx->snap_ready, 0));
+    CU(cudaMemcpyAsync(host, ctx->snap_buf + ctx->snap_off[seg], (ctx->snap_u32[seg] ? 4 : 8) * (size_t)count,
+                       cudaMemcpyDeviceToHost, ctx->snap_stream));
+    CU(cudaStreamSynchronize(ctx->snap_stream));
+    return 0;
+}
+
+int b200sph_snapshot_release(b200sph_ctx *ctx)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->snap_open) return 0;
+    CU(cudaEventRecord(ctx->snap_done, ctx->snap_stream));
+    ctx->snap_open = false;
     return 0;
 }
 

@@ -57,23 +57,33 @@ def get_particles_info(particles):
     return info
 
 
+def npz_name(filename):
+    fname = os.path.splitext(filename)[0] if filename.endswith(output_formats) \
+        else filename
+    return fname + '.npz'
+
+
+def write_npz(filename, particle_data, solver_data, compress=False):
+    """The file itself: particle_data = get_particles_info(...) with every array's
+    'arrays' dict filled in (pysph/solver/output.py:246-262)."""
+    save = np.savez_compressed if compress else np.savez
+    save(filename, version=2, particles=particle_data, solver_data=dict(solver_data))
+    return filename
+
+
 def dump(filename, particles, solver_data, detailed_output=False, only_real=True,
          mpi_comm=None, compress=False):
     """pysph/solver/output.py:364-415 (the npz branch)."""
     if mpi_comm is not None:
         raise NotImplementedError('B200 backend: collected parallel output (every '
                                   'rank writes its own file, solver.py:569-571)')
-    fname = os.path.splitext(filename)[0] if filename.endswith(output_formats) \
-        else filename
-    filename = fname + '.npz'
+    filename = npz_name(filename)
     particle_data = get_particles_info(particles)
     for pa in particles:
         arrays = pa.get_property_arrays(all=detailed_output, only_real=only_real)
         particle_data[pa.name]['arrays'] = dict(
             (k, np.array(v, copy=True)) for k, v in arrays.items())
-    save = np.savez_compressed if compress else np.savez
-    save(filename, version=2, particles=particle_data, solver_data=dict(solver_data))
-    return filename
+    return write_npz(filename, particle_data, solver_data, compress)
 
 
 def _to_str(s):

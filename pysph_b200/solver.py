@@ -186,15 +186,31 @@ class B200Solver(object):
         self.count += 1
         self._dt = self._get_timestep()
 
-    def solve(self, max_steps):
+    def solve(self, max_steps, pfreq=0, output_directory=None, fname='b200',
+              asynchronous=True, **dump_kw):
+        """The solve loop (solver.py:425-507).  With pfreq > 0 and an output
+        directory it writes the initial state, every pfreq-th iteration and the
+        final state (solver.py:445, :689-704, :505-507) -- asynchronously by
+        default, so the time loop does not wait for the copy or the file."""
+        dumping = pfreq > 0 and output_directory is not None
+
+        def dump():
+            if dumping:
+                self.dump_output(output_directory, fname, asynchronous=asynchronous,
+                                 **dump_kw)
+        if not self._initialised:
+            dump()                                   # initial solution, solver.py:445
         self.initialise()
-        if self.integrator.device_dt:
-            while self.count < max_steps and \
-                    (self.tf - self._t_without_waiting()) > 1e-15:
-                self.step()
-            return
-        while self.count < max_steps and (self.tf - self._t) > 1e-15:
+
+        def running():
+            t = self._t_without_waiting() if self.integrator.device_dt else self._t
+            return self.count < max_steps and (self.tf - t) > 1e-15
+        while running():
             self.step()
+            if dumping and self.count % pfreq == 0 and running():
+                dump()                               # solver.py:689-704
+        dump()                                       # final output, solver.py:505-507
+        self.wait_for_output()
 
     def pull(self, props=None):
         self.backend.pull_all(props)
@@ -206,16 +222,91 @@ class B200Solver(object):
         return {'dt': self.dt / self._damping_factor, 't': self.t, 'count': self.count}
 
     def dump_output(self, output_directory='.', fname='b200', detailed_output=False,
-                    only_real=True, compress=False):
+                    only_real=True, compress=False, asynchronous=False):
         """<dir>/<fname>_<count:05d>.npz in PySPH's format; only the output
-        properties of the real particles leave the device."""
+        properties of the real particles leave the device.
+
+        asynchronous=True: the properties are snapshotted on the device in stream
+        order (b200sph_snapshot_take) and this call returns; a host thread copies
+        the snapshot back on a second stream and writes the file while the time
+        loop goes on.  ``wait_for_output()`` joins it (the next dump does too)."""
         import os
         from .output import dump
         os.makedirs(output_directory, exist_ok=True)
         base = os.path.join(output_directory, '%s_%05d' % (fname, self.count))
+        self.wait_for_output()
+        if asynchronous:
+            return self._dump_async(base, detailed_output, only_real, compress)
         return dump(base, self.particles, self._get_solver_data(),
                     detailed_output=detailed_output, only_real=only_real,
                     compress=compress)
+
+    def wait_for_output(self):
+        """Block until the file of the last asynchronous dump is on disk."""
+        th, self._out_thread = getattr(self, '_out_thread', None), None
+        if th is not None:
+            th.join()
+            err, self._out_error = getattr(self, '_out_error', None), None
+            if err is not None:
+                raise err
+
+    def _dump_async(self, base, detailed_output, only_real, compress):
+        import ctypes as C
+        import threading
+        from . import output
+        from .backend import INT_PROP_IDS
+        be, ctx = self.backend, self.backend.ctx
+        filename = output.npz_name(base)
+        particle_data = output.get_particles_info(self.particles)
+        segs, host_side = [], []           # (array, prop id, count, name, dtype, is_int)
+        for i, pa in enumerate(self.particles):
+            n, n_real = be.sizes(i)
+            cnt = n_real if only_real else n
+            names = list(pa.output_property_arrays)
+            if detailed_output or not names:
+                names = list(pa.properties.keys())
+            ids = be.prop_ids[i]
+            particle_data[pa.name]['arrays'] = {}
+            for k in names:
+                dt = pa.properties[k].dtype
+                if k in ids:
+                    segs.append((i, ids[k], cnt, pa.name, k, dt, False))
+                elif k in INT_PROP_IDS:
+                    segs.append((i, INT_PROP_IDS[k], cnt, pa.name, k, dt, True))
+                else:                      # never on the device: the host copy is current
+                    particle_data[pa.name]['arrays'][k] = \
+                        np.array(pa.properties[k][:cnt], copy=True)
+        on_device = self._on_device()
+        if on_device:
+            segs.append((-1, 0, 2, None, None, None, False))
+        nseg = len(segs)
+        ctx.call('b200sph_snapshot_take', nseg,
+                 (C.c_int * nseg)(*[sg[0] for sg in segs]),
+                 (C.c_int * nseg)(*[sg[1] for sg in segs]),
+                 (C.c_int64 * nseg)(*[sg[2] for sg in segs]))
+        count, damping = self.count, self._damping_factor
+        host_time = None if on_device else (self._dt, self._t)
+
+        def work():
+            try:
+                dt_t = host_time
+                for j, (a, pid, cnt, aname, k, dtype, is_int) in enumerate(segs):
+                    buf = np.empty(cnt, dtype=np.uint32 if is_int else np.float64)
+                    ctx.call('b200sph_snapshot_fetch', j, buf.ctypes.data, cnt)
+                    if a == -1:
+                        dt_t = (float(buf[0]), float(buf[1]))
+                    else:
+                        particle_data[aname]['arrays'][k] = \
+                            buf.view(dtype) if is_int else buf.astype(dtype, copy=False)
+                ctx.call('b200sph_snapshot_release')
+                sd = {'dt': dt_t[0] / damping, 't': dt_t[1], 'count': count}
+                output.write_npz(filename, particle_data, sd, compress)
+            except Exception as e:         # surfaces in wait_for_output()
+                self._out_error = e
+        self._out_error = None
+        self._out_thread = threading.Thread(target=work, name='b200sph-output')
+        self._out_thread.start()
+        return filename
 
     def load_output(self, path):
         """Restart: take the properties a dump holds (same arrays, same particle

@@ -272,6 +272,61 @@ def test_dump_and_restart_small(emulated_library, tmp_path):
             assert np.max(np.abs(a.properties[k] - b.properties[k])) <= tol * scale, (a.name, k)
 
 
+def test_async_output_small(emulated_library, tmp_path):
+    """solve(pfreq=...) with asynchronous dumps (b200sph_snapshot_take / fetch / release +
+    the writer thread) writes the same files as synchronous dumps, for the device-resident
+    and the host-side time step; a file written asynchronously restarts."""
+    import pysph_b200 as pb
+    from pysph_b200 import output
+    files = {}
+    for mode, asyn, device_dt in (('async', True, True), ('sync', False, True),
+                                  ('async_host_dt', True, False)):
+        pas, params = _small_dam_break(vscale=0.5)
+        s = pb.make_wcsph_solver(pas, dict(params, n_damp=5), pb.CubicSpline(dim=3),
+                                 device_dt=device_dt)
+        d = tmp_path / mode
+        s.solve(7, pfreq=3, output_directory=str(d), fname='db', asynchronous=asyn,
+                detailed_output=(mode != 'async_host_dt'))
+        assert sorted(os.listdir(str(d))) == ['db_00000.npz', 'db_00003.npz', 'db_00006.npz',
+                                              'db_00007.npz']
+        files[mode] = dict((f, output.load(str(d / f))) for f in os.listdir(str(d)))
+        assert s.count == 7
+    for f, want in files['sync'].items():
+        for mode in ('async', 'async_host_dt'):
+            got = files[mode][f]
+            for k in ('t', 'dt', 'count'):
+                assert float(got['solver_data'][k]) == float(want['solver_data'][k]), (f, k)
+            for name, pa in want['arrays'].items():
+                q = got['arrays'][name]
+                assert q.get_number_of_particles() == pa.get_number_of_particles()
+                props = q.output_property_arrays if mode == 'async_host_dt' else pa.properties
+                assert len(props) > 10
+                for k in props:
+                    assert q.properties[k].dtype == pa.properties[k].dtype, (f, name, k)
+                    assert np.array_equal(q.properties[k], pa.properties[k]), (f, name, k)
+    # something moved between the dumps, and integer properties came through
+    a, b = files['async']['db_00003.npz'], files['async']['db_00006.npz']
+    assert np.max(np.abs(a['arrays']['fluid'].x - b['arrays']['fluid'].x)) > 0
+    assert np.array_equal(a['arrays']['fluid'].gid, b['arrays']['fluid'].gid)
+    assert a['arrays']['fluid'].gid.dtype == np.uint32 and len(set(a['arrays']['fluid'].gid)) > 100
+    # misuse: a second snapshot while one is open
+    pas, params = _small_dam_break()
+    s = pb.make_wcsph_solver(pas, dict(params), pb.CubicSpline(dim=3))
+    s.initialise()
+    import ctypes as C
+    args = (1, (C.c_int * 1)(0), (C.c_int * 1)(0), (C.c_int64 * 1)(10))
+    s.backend.ctx.call('b200sph_snapshot_take', *args)
+    with pytest.raises(Exception, match='not released'):
+        s.backend.ctx.call('b200sph_snapshot_take', *args)
+    buf = np.empty(10)
+    with pytest.raises(Exception, match='does not hold'):
+        s.backend.ctx.call('b200sph_snapshot_fetch', 0, buf.ctypes.data, 11)
+    s.backend.ctx.call('b200sph_snapshot_fetch', 0, buf.ctypes.data, 10)
+    s.pull()
+    assert np.array_equal(buf, pas[0].x[:10])
+    s.backend.ctx.call('b200sph_snapshot_release')
+
+
 # ---- the slab decomposition: real halo / migration kernels of the (emulated) library, the
 #      real SlabParallelManager, gloo instead of NCCL, host tensors as "device" buffers ---------
 def test_column_counts_on_the_emulated_library(emulated_library):
