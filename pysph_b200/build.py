@@ -33,11 +33,32 @@ def find_nvcc():
     raise RuntimeError('nvcc not found: cannot build libb200sph.so')
 
 
+def sources():
+    """b200sph.cu and the kernel files it includes (one translation unit)."""
+    d = os.path.dirname(SRC)
+    return [SRC] + sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith('.cuh'))
+
+
+def read_source():
+    """The translation unit as one text: b200sph.cu with its own `#include "x.cuh"`
+    lines replaced by the files (what the compiler sees; the CPU tests that compile
+    the kernel source for the host read it through this)."""
+    d = os.path.dirname(SRC)
+    out = []
+    for line in open(SRC).read().split('\n'):
+        name = line[len('#include "'):-1] if line.startswith('#include "') else ''
+        if name.endswith('.cuh') and os.path.exists(os.path.join(d, name)):
+            out.append(open(os.path.join(d, name)).read().rstrip('\n'))
+        else:
+            out.append(line)
+    return '\n'.join(out)
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(p) > t for p in (SRC, HDR, __file__))
+    return any(os.path.getmtime(p) > t for p in sources() + [HDR, __file__])
 
 
 def build(force=False, verbose=False):

@@ -19,6 +19,10 @@
 //   * halo pack / append / migrate helpers for the slab decomposition
 //                                      (replaces parallel_manager.pyx:512-632)
 //
+// One translation unit: this file holds the context, the pool and every C-ABI entry
+// point; the kernels are included below by family (pool_kernels, scan, nnps_kernels,
+// sph_kernels, pair_kernel, pair_list, tvf_kernels, solid_kernels, halo_kernels .cuh).
+//
 // No CPU fallback: every entry point needs a CUDA device.
 #include "b200sph.h"
 
@@ -257,1972 +261,15 @@ __device__ __forceinline__ float frsqrt(float x)
     return r;
 }
 
-// --------------------------------------------------------------------------
-// elementwise / reduction kernels over the pool
-// --------------------------------------------------------------------------
-struct PoolLayout {
-    int narr;
-    long long off[B200SPH_MAX_ARRAYS], n[B200SPH_MAX_ARRAYS], n_real[B200SPH_MAX_ARRAYS];
-};
-
-__global__ void k_fill_ptype(uint8_t *ptype, long long pool_end, PoolLayout L)
-{
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= pool_end) return;
-    uint8_t t = PT_INVALID;
-    for (int a = 0; a < L.narr; a++) {
-        long long i = g - L.off[a];
-        if (i >= 0 && i < L.n[a]) t = (uint8_t)(a | (i >= L.n_real[a] ? PT_GHOST : 0));
-    }
-    ptype[g] = t;
-}
-
-__global__ void k_red_init(long long *red)
-{
-    int i = threadIdx.x;
-    if (i < 16) red[i] = (i & 1) ? d2o(-1e300) : d2o(1e300);  // even: min slots, odd: max slots
-}
-
-// slots: 0 xmin 1 xmax 2 ymin 3 ymax 4 zmin 5 zmax 6 hmin 7 hmax
-__global__ void k_reduce_minmax(const double *__restrict__ x, const double *__restrict__ y,
-                                const double *__restrict__ z, const double *__restrict__ h,
-                                const uint8_t *__restrict__ ptype, long long pool_end,
-                                int do_xyz, int do_h, long long *red)
-{
-    double mn[4] = {1e300, 1e300, 1e300, 1e300}, mx[4] = {-1e300, -1e300, -1e300, -1e300};
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < pool_end;
-         g += (long long)gridDim.x * blockDim.x) {
-        if (ptype[g] == PT_INVALID) continue;
-        if (do_xyz) {
-            double v = x[g]; mn[0] = fmin(mn[0], v); mx[0] = fmax(mx[0], v);
-            v = y[g]; mn[1] = fmin(mn[1], v); mx[1] = fmax(mx[1], v);
-            v = z[g]; mn[2] = fmin(mn[2], v); mx[2] = fmax(mx[2], v);
-        }
-        if (do_h) {
-            double v = h[g]; mn[3] = fmin(mn[3], v); mx[3] = fmax(mx[3], v);
-        }
-    }
-    for (int k = 0; k < 4; k++) {
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-        }
-    }
-    if ((threadIdx.x & 31) == 0) {
-        for (int k = 0; k < 4; k++) {
-            if ((k < 3 && !do_xyz) || (k == 3 && !do_h)) continue;
-            atomicMin(&red[2 * k], d2o(mn[k]));
-            atomicMax(&red[2 * k + 1], d2o(mx[k]));
-        }
-    }
-}
-
-// slots: 9 max dt_cfl, 11 max dt_force (real particles), 12 min h (all)
-__global__ void k_reduce_dt(const float *__restrict__ dt_cfl, const float *__restrict__ dt_force,
-                            const double *__restrict__ h, const uint8_t *__restrict__ ptype,
-                            long long pool_end, long long *red)
-{
-    double mc = -1e300, mf = -1e300, hm = 1e300;
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < pool_end;
-         g += (long long)gridDim.x * blockDim.x) {
-        uint8_t t = ptype[g];
-        if (t == PT_INVALID) continue;
-        hm = fmin(hm, h[g]);
-        if (t & PT_GHOST) continue;
-        mc = fmax(mc, (double)dt_cfl[g]);
-        mf = fmax(mf, (double)dt_force[g]);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        mc = fmax(mc, __shfl_xor_sync(0xffffffffu, mc, o));
-        mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
-        hm = fmin(hm, __shfl_xor_sync(0xffffffffu, hm, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(&red[9], d2o(mc));
-        atomicMax(&red[11], d2o(mf));
-        atomicMin(&red[12], d2o(hm));
-    }
-}
-
-// Integrator.compute_time_step (integrator.py:161-200) on the reduced factors: the local
-// proposal cfl * dt_min, or 1e20 when no factor constrains it (solver.py:655-660)
-__global__ void k_dt_propose(const long long *__restrict__ red, double *__restrict__ tc, double cfl, int fixed_h)
-{
-    const double mc = o2d(red[9]), mf = o2d(red[11]);
-    const double f_cfl = mc < -1e299 ? -1.0 : mc, f_force = mf < -1e299 ? -1.0 : mf;
-    double hmin = fmin(1.0, o2d(red[12]));
-    if (!fixed_h || tc[3] < 0.0) tc[3] = hmin;
-    hmin = tc[3];
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    double dt_cfl = inf, dt_force = inf;
-    if (f_cfl > 0.0) dt_cfl = hmin / f_cfl;
-    if (f_force > 0.0) dt_force = sqrt(hmin / sqrt(f_force));
-    const double dt_min = fmin(dt_cfl, dt_force);
-    tc[2] = (dt_min <= 0.0 || isinf(dt_min)) ? 1e20 : cfl * dt_min;
-}
-// Solver loop bookkeeping (solver.py:478-491, :647-688): t += dt; dt = damp(new dt)
-__global__ void k_dt_commit(double *__restrict__ tc, double prev_factor, double new_factor, int in_parallel, int adaptive, int advance)
-{
-    const double dt_old = tc[0];
-    if (advance) tc[1] += dt_old;
-    const double undamped = dt_old / prev_factor;
-    double dt = undamped;
-    if (adaptive) {
-        dt = tc[2];
-        if (!in_parallel && dt >= 1e20) dt = undamped;
-    }
-    tc[0] = dt * new_factor;
-}
-// TaitEOS.loop wc/basic.py:60-65 ; TaitEOSHGCorrection.loop wc/basic.py:118-126
-__global__ void k_eos(double *__restrict__ rho, float *__restrict__ p, float *__restrict__ cs,
-                      const uint8_t *__restrict__ ptype, long long lo, long long hi, int hg,
-                      double rho0, double c0, double gamma, double p0)
-{
-    long long g = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= hi) return;
-    double r = rho[g];
-    if (hg && r < rho0) {
-        r = rho0;
-        rho[g] = r;
-    }
-    double ratio = r * (1.0 / rho0);
-    double B = rho0 * c0 * c0 / gamma;
-    double tmp = pow(ratio, gamma);
-    p[g] = (float)((hg ? 0.0 : p0) + B * (tmp - 1.0));
-    cs[g] = (float)(c0 * pow(ratio, 0.5 * (gamma - 1.0)));
-}
-
-// UpdateSmoothingLengthFerrari.loop wc/basic.py:458-463
-__global__ void k_ferrari(double *__restrict__ h, const double *__restrict__ m,
-                          const double *__restrict__ rho, long long lo, long long hi, double hdx,
-                          double dim1)
-{
-    long long g = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= hi) return;
-    h[g] = hdx * pow(m[g] / rho[g], dim1);
-}
-
-struct StageArgs {
-    double *x, *y, *z, *u, *v, *w, *rho;
-    double *x0, *y0, *z0, *u0, *v0, *w0, *rho0;
-    const float *au, *av, *aw, *ax, *ay, *az, *arho;
-    const uint8_t *ptype;
-    long long pool_end;
-    int arr, which;
-    double f;
-};
-
-// WCSPHStep.initialize / stage1 / stage2 integrator_step.py:51-91 (real particles only,
-// integrator_cython.mako:97-111)
-__device__ __forceinline__ void stage_body(const StageArgs &a);
-__global__ void k_stage(StageArgs a) { stage_body(a); }
-__global__ void k_stage_devdt(StageArgs a, const double *__restrict__ tc)
-{
-    const double dt = tc[0];
-    a.f = a.which == 1 ? 0.5 * dt : dt;
-    stage_body(a);
-}
-__device__ __forceinline__ void stage_body(const StageArgs &a)
-{
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.pool_end) return;
-    uint8_t t = a.ptype[g];
-    if (t == PT_INVALID || (t & PT_GHOST)) return;
-    if (a.arr >= 0 && (t & 7) != a.arr) return;
-    if (a.which == 0) {
-        a.x0[g] = a.x[g]; a.y0[g] = a.y[g]; a.z0[g] = a.z[g];
-        a.u0[g] = a.u[g]; a.v0[g] = a.v[g]; a.w0[g] = a.w[g];
-        a.rho0[g] = a.rho[g];
-    } else {
-        const double f = a.f;
-        a.u[g] = a.u0[g] + f * (double)a.au[g];
-        a.v[g] = a.v0[g] + f * (double)a.av[g];
-        a.w[g] = a.w0[g] + f * (double)a.aw[g];
-        a.x[g] = a.x0[g] + f * (double)a.ax[g];
-        a.y[g] = a.y0[g] + f * (double)a.ay[g];
-        a.z[g] = a.z0[g] + f * (double)a.az[g];
-        a.rho[g] = a.rho0[g] + f * (double)a.arho[g];
-    }
-}
-
-// _box_wrap_periodic (nnps_base.pyx:699-743): real and ghost particles alike
-__global__ void k_box_wrap(double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
-                           const uint8_t *__restrict__ ptype, long long pool_end, GridDev D /* xmin = lo, cell = L */)
-{
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= pool_end || ptype[g] == PT_INVALID) return;
-    double *p[3] = {x, y, z};
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        if (!D.periodic[d]) continue;
-        double v = p[d][g];
-        const double lo = D.xmin[d], L = D.cell[d];
-        if (v < lo) v += L;
-        if (v > lo + L) v -= L;
-        p[d][g] = v;
-    }
-}
-__global__ void k_f64_to_f32(const double *__restrict__ in, float *__restrict__ out, long long n)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (float)in[i];
-}
-__global__ void k_f32_to_f64(const float *__restrict__ in, double *__restrict__ out, long long n)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (double)in[i];
-}
-
-// --------------------------------------------------------------------------
-// exclusive scan (u32), three-phase; n up to 2^28 + 1
-// --------------------------------------------------------------------------
-#define SCAN_THREADS 512
-#define SCAN_ITEMS 4
-#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
-
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total)
-{
-    // exclusive scan of one value per thread across the block
-    __shared__ uint32_t wsum[SCAN_THREADS / 32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t inc = v;
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        uint32_t s = (lane < SCAN_THREADS / 32) ? wsum[lane] : 0;
-        uint32_t si = s;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
-            if (lane >= o) si += t;
-        }
-        if (lane < SCAN_THREADS / 32) wsum[lane] = si - s;  // exclusive warp offsets
-        if (lane == SCAN_THREADS / 32 - 1) *total = si;
-    }
-    __syncthreads();
-    uint32_t r = wsum[w] + inc - v;
-    __syncthreads();
-    return r;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_tiles(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, long long n,
-             uint32_t *__restrict__ blk_sums)
-{
-    __shared__ uint32_t total;
-    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS], s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        v[k] = (base + k < n) ? in[base + k] : 0u;
-        s += v[k];
-    }
-    uint32_t ex = block_excl_scan(s, &total);
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        if (base + k < n) out[base + k] = ex;
-        ex += v[k];
-    }
-    if (threadIdx.x == 0) blk_sums[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint32_t *blk_sums, long long nb)
-{
-    __shared__ uint32_t total;
-    uint32_t carry = 0;
-    for (long long b0 = 0; b0 < nb; b0 += SCAN_THREADS) {
-        long long i = b0 + threadIdx.x;
-        uint32_t v = (i < nb) ? blk_sums[i] : 0u;
-        uint32_t ex = block_excl_scan(v, &total);
-        if (i < nb) blk_sums[i] = ex + carry;
-        carry += total;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_add(uint32_t *__restrict__ out, long long n, const uint32_t *__restrict__ blk_sums)
-{
-    const uint32_t add = blk_sums[blockIdx.x];
-    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++)
-        if (base + k < n) out[base + k] += add;
-}
-
-// --------------------------------------------------------------------------
-// NNPS build kernels
-// --------------------------------------------------------------------------
-
-// cell id = floor((p - xmin)/cell) per axis (find_cell_id_raw, nnps_base.pxd:39-80),
-// flat = cx + ncx*cy + ncx*ncy*cz (flatten_raw, nnps_base.pxd:84-96); the arrival
-// counter replaces the linked-list push (linked_list_nnps.pyx:285-286).
-__global__ void k_cell_count(const double *__restrict__ x, const double *__restrict__ y,
-                             const double *__restrict__ z, const uint8_t *__restrict__ ptype,
-                             long long pool_end, GridDev G, uint32_t *__restrict__ key_of,
-                             uint32_t *__restrict__ off_in, uint32_t *__restrict__ cell_cnt)
-{
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= pool_end) return;
-    if (ptype[g] == PT_INVALID) return;
-    int cx = (int)floor((x[g] - G.xmin[0]) / G.cell[0]);
-    int cy = (int)floor((y[g] - G.xmin[1]) / G.cell[1]);
-    int cz = (int)floor((z[g] - G.xmin[2]) / G.cell[2]);
-    cx = min(max(cx, 0), G.nc[0] - 1);
-    cy = min(max(cy, 0), G.nc[1] - 1);
-    cz = min(max(cz, 0), G.nc[2] - 1);
-    uint32_t key = (uint32_t)cx + (uint32_t)G.nc[0] * ((uint32_t)cy + (uint32_t)G.nc[1] * (uint32_t)cz);
-    key_of[g] = key;
-    off_in[g] = atomicAdd(&cell_cnt[key], 1u);
-}
-
-__global__ void k_scatter(const uint32_t *__restrict__ key_of, const uint32_t *__restrict__ off_in,
-                          const uint8_t *__restrict__ ptype, long long pool_end,
-                          const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ perm_tmp)
-{
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= pool_end) return;
-    if (ptype[g] == PT_INVALID) return;
-    perm_tmp[cell_start[key_of[g]] + off_in[g]] = (uint32_t)g;
-}
-
-// make the order inside every cell canonical (ascending pool index) so that the
-// build -- and therefore every fp32 sum downstream -- is run-to-run deterministic.
-__global__ void k_canon(const uint32_t *__restrict__ perm_tmp, const uint32_t *__restrict__ key_of,
-                        const uint32_t *__restrict__ cell_start, long long n,
-                        uint32_t *__restrict__ perm, uint32_t *__restrict__ skey,
-                        uint32_t *__restrict__ rank)
-{
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const uint32_t g = perm_tmp[s];
-    const uint32_t key = key_of[g];
-    const uint32_t cs = cell_start[key], ce = cell_start[key + 1];
-    uint32_t r = 0;
-    for (uint32_t t = cs; t < ce; t++) r += (perm_tmp[t] < g) ? 1u : 0u;
-    const uint32_t d = cs + r;
-    perm[d] = g;
-    skey[d] = key;
-    rank[g] = d;
-}
-
-// A[s] = (x, y, z relative to the particle's own cell origin, h)
-__global__ void k_pack_pos(const double *__restrict__ x, const double *__restrict__ y,
-                           const double *__restrict__ z, const double *__restrict__ h,
-                           const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skey,
-                           long long n, GridDev G, float4 *__restrict__ A, float4 *__restrict__ AB)
-{
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const uint32_t g = perm[s];
-    uint32_t key = skey[s];
-    const uint32_t cx = key % (uint32_t)G.nc[0];
-    key /= (uint32_t)G.nc[0];
-    const uint32_t cy = key % (uint32_t)G.nc[1];
-    const uint32_t cz = key / (uint32_t)G.nc[1];
-    float4 a;
-    a.x = (float)(x[g] - (G.xmin[0] + (double)cx * G.cell[0]));
-    a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell[1]));
-    a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell[2]));
-    a.w = (float)h[g];
-    A[s] = a;
-    AB[2 * s] = a;
-}
-
-// B[s] = (u, v, w, m);  C[s] = (rho, p/rho^2, cs, type); pending TaitEOS /
-// TaitEOSHGCorrection calls (wc/basic.py:60-65,118-126) are applied on the way
-__global__ void k_pack_state(const double *__restrict__ u, const double *__restrict__ v,
-                             const double *__restrict__ w, const double *__restrict__ m,
-                             double *__restrict__ rho, float *__restrict__ p,
-                             float *__restrict__ cs, const uint8_t *__restrict__ ptype,
-                             const uint32_t *__restrict__ perm, long long n,
-                             float4 *__restrict__ B, float4 *__restrict__ C,
-                             float4 *__restrict__ AB, const EosTab E, const int eos_any)
-{
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const uint32_t g = perm[s];
-    const int t = (int)ptype[g];
-    float4 b, c;
-    b.x = (float)u[g]; b.y = (float)v[g]; b.z = (float)w[g]; b.w = (float)m[g];
-    double r = rho[g];
-    float pg, csg;
-    const int a = t & 7;
-    if (eos_any && E.on[a] && !(E.real_only[a] && (t & PT_GHOST))) {
-        const double rho0 = E.rho0[a];
-        if (E.hg[a] && r < rho0) {
-            r = rho0;
-            rho[g] = r;
-        }
-        const double ratio = r * (1.0 / rho0);
-        const double Bc = rho0 * E.c0[a] * E.c0[a] / E.gamma[a];
-        pg = (float)((E.hg[a] ? 0.0 : E.p0[a]) + Bc * (pow(ratio, E.gamma[a]) - 1.0));
-        csg = (float)(E.c0[a] * pow(ratio, 0.5 * (E.gamma[a] - 1.0)));
-        p[g] = pg;
-        cs[g] = csg;
-    } else {
-        pg = p[g];
-        csg = cs[g];
-    }
-    c.x = (float)r;
-    c.y = (float)((double)pg / (r * r));
-    c.z = csg;
-    c.w = __int_as_float(t);
-    B[s] = b;
-    C[s] = c;
-    AB[2 * s + 1] = b;
-}
-
-// --------------------------------------------------------------------------
-// SPH smoothing kernels in fp32 (pysph/base/kernels.py; see oracle for fp64)
-//   returns w = W(q)/sigma-free value * fac  and  dw = dW/dq * fac
-// --------------------------------------------------------------------------
-template <int DIM> __device__ __forceinline__ float hpow(float h1)
-{
-    return DIM == 1 ? h1 : (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
-}
-
-template <int K> __device__ __forceinline__ void sph_kernel(float q, float &w, float &dw);
-
-// CubicSpline kernels.py:69-124
-template <> __device__ __forceinline__ void sph_kernel<0>(float q, float &w, float &dw)
-{
-    const float t2 = 2.0f - q;
-    const float w_in = 1.0f - 1.5f * q * q * (1.0f - 0.5f * q);
-    const float d_in = -3.0f * q * (1.0f - 0.75f * q);
-    const float w_out = 0.25f * t2 * t2 * t2;
-    const float d_out = -0.75f * t2 * t2;
-    w = q > 2.0f ? 0.0f : (q > 1.0f ? w_out : w_in);
-    dw = q > 2.0f ? 0.0f : (q > 1.0f ? d_out : d_in);
-}
-// WendlandQuintic kernels.py:304-343
-template <> __device__ __forceinline__ void sph_kernel<1>(float q, float &w, float &dw)
-{
-    const float t = 1.0f - 0.5f * q;
-    const float t3 = t * t * t;
-    w = q < 2.0f ? t3 * t * (2.0f * q + 1.0f) : 0.0f;
-    dw = q < 2.0f ? -5.0f * q * t3 : 0.0f;
-}
-// QuinticSpline kernels.py:1087-1153
-template <> __device__ __forceinline__ void sph_kernel<2>(float q, float &w, float &dw)
-{
-    const float t3 = 3.0f - q, t2 = 2.0f - q, t1 = 1.0f - q;
-    const float a3 = t3 * t3, a2 = t2 * t2, a1 = t1 * t1;
-    const float p3 = a3 * a3, p2 = a2 * a2, p1 = a1 * a1;  // 4th powers
-    float ww = 0.0f, dd = 0.0f;
-    if (q <= 3.0f) { ww = p3 * t3; dd = -5.0f * p3; }
-    if (q <= 2.0f) { ww -= 6.0f * p2 * t2; dd += 30.0f * p2; }
-    if (q <= 1.0f) { ww += 15.0f * p1 * t1; dd -= 75.0f * p1; }
-    w = ww;
-    dw = dd;
-}
-// Gaussian kernels.py:864-898
-template <> __device__ __forceinline__ void sph_kernel<3>(float q, float &w, float &dw)
-{
-    const float e = __expf(-q * q);
-    w = q < 3.0f ? e : 0.0f;
-    dw = q < 3.0f ? -2.0f * q * e : 0.0f;
-}
-
-// --------------------------------------------------------------------------
-// the fused pair kernel
-// --------------------------------------------------------------------------
-struct PairArgs {
-    const float4 *A, *B, *C, *AB;
-    const uint32_t *cell_start, *skey, *perm;
-    float *arho, *au, *av, *aw, *ax, *ay, *az, *dt_cfl, *dt_force;
-    double *rho;  // SummationDensity destination (fp64 state)
-    long long n;
-    int ncx, ncy, ncz;
-    float cellx, celly, cellz;  // internal cell edges
-    float k2;                   // radius_scale^2
-    float kfac;      // kernel.fac for this dim
-    float deltap;
-    unsigned long long emask[B200SPH_MAX_ARRAYS];  // per dest type: 8 bits per source type
-    float c0, alpha, beta, gx, gy, gz, eps_xsph;
-    int tensile, real_only;
-    unsigned long long *pair_counter;  // may be null
-};
-
-#define PAIR_WARPS 8
-#define PAIR_CHUNK 16
-#define QCAP 64
-
-struct Acc {
-    float arho, au, av, aw, ax, ay, az, cfl, rsum;
-};
-
-template <int K, int DIM>
-__device__ __forceinline__ void pair_body(const PairArgs &a, const float4 qv, const float4 Bj,
-                                          const float4 Cj, const float4 Ai, const float4 Bi,
-                                          const float4 Ci, const unsigned long long mask_i,
-                                          const float tmpi, Acc &acc, unsigned &npairs)
-{
-    const int tj = __float_as_int(Cj.w) & 7;
-    const unsigned bits = (unsigned)(mask_i >> (8 * tj)) & 0xFFu;
-    if (!bits) return;
-    npairs++;
-    const float xij = qv.x, yij = qv.y, zij = qv.z, hj = qv.w;
-    // precomputed symbols, equation.py:188-297
-    const float r2 = xij * xij + yij * yij + zij * zij;
-    const bool far = r2 > 1e-24f;          // RIJ > 1e-12 guard of kernels.py:128-132
-    const float rinv = far ? frsqrt(r2) : 0.0f;
-    const float rij = r2 * rinv;
-    const float hij = 0.5f * (Ai.w + hj);
-    const float h1 = frcp(hij);
-    const float q = rij * h1;
-    const float fac = a.kfac * hpow<DIM>(h1);
-    float w, dw;
-    sph_kernel<K>(q, w, dw);
-    const float wij = w * fac;
-    const float gt = dw * fac * h1 * rinv;  // DWIJ = gt * XIJ  (gradient(), kernels.py:126-136)
-    const float mj = Bj.w;
-    const float uij = Bi.x - Bj.x, vij = Bi.y - Bj.y, wwij = Bi.z - Bj.z;
-    const float vdotx = uij * xij + vij * yij + wwij * zij;
-
-    if (bits & B200SPH_EQ_SUMMATION_DENSITY) acc.rsum += mj * wij;  // basic_equations.py:28-29
-    if (bits & B200SPH_EQ_CONTINUITY)                              // basic_equations.py:190-192
-        acc.arho += mj * gt * vdotx;
-    if (bits & (B200SPH_EQ_MOMENTUM | B200SPH_EQ_MONAGHAN_AV | B200SPH_EQ_XSPH)) {
-        const float rhoij1 = frcp(0.5f * (Ci.x + Cj.x));
-        float piij = 0.0f;
-        if (vdotx < 0.0f) {  // wc/basic.py:215-222, basic_equations.py:245-252
-            const float cij = 0.5f * (Ci.z + Cj.z);
-            const float muij = hij * vdotx * frcp(r2 + 0.01f * hij * hij);
-            piij = (-a.alpha * cij * muij + a.beta * muij * muij) * rhoij1;
-        }
-        if (bits & B200SPH_EQ_MOMENTUM) {
-            if (r2 > 1e-12f)  // wc/basic.py:224-228
-                acc.cfl = fmaxf(acc.cfl, fabsf(hij * vdotx * rinv * rinv) + a.c0);
-            const float tmpj = Cj.y;  // p_j / rho_j^2 (precomputed in k_pack_state)
-            float tmp = tmpi + tmpj;
-            if (a.tensile) {  // wc/basic.py:233-248
-                float wdp, dwdp;
-                sph_kernel<K>(a.deltap, wdp, dwdp);
-                float fij = w / wdp;  // WIJ/WDP: the fac*h^-dim normalisation cancels
-                fij = fij * fij;
-                fij = fij * fij;
-                const float Ri = tmpi > 0.0f ? 0.01f * tmpi : 0.2f * fabsf(tmpi);
-                const float Rj = tmpj > 0.0f ? 0.01f * tmpj : 0.2f * fabsf(tmpj);
-                tmp += (Ri + Rj) * fij;
-            }
-            const float f = -mj * (tmp + piij) * gt;  // wc/basic.py:255-257
-            acc.au += f * xij;
-            acc.av += f * yij;
-            acc.aw += f * zij;
-        }
-        if (bits & B200SPH_EQ_MONAGHAN_AV) {  // basic_equations.py:254-257
-            const float f = -mj * piij * gt;
-            acc.au += f * xij;
-            acc.av += f * yij;
-            acc.aw += f * zij;
-        }
-        if (bits & B200SPH_EQ_XSPH) {  // basic_equations.py:290-295
-            const float f = -a.eps_xsph * mj * wij * rhoij1;
-            acc.ax += f * uij;
-            acc.ay += f * vij;
-            acc.az += f * wwij;
-        }
-    }
-}
-
-template <int K, int DIM>
-__global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
-{
-    __shared__ float4 q_v[PAIR_WARPS][QCAP];
-    __shared__ uint32_t q_i[PAIR_WARPS][QCAP];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const long long first = ((long long)blockIdx.x * PAIR_WARPS + warp) * PAIR_CHUNK;
-
-    uint32_t cur_key = 0xFFFFFFFFu;
-    int cx = 0;
-    // lane r < 9 holds the candidate range of neighbour row r = (dy+1) + 3*(dz+1)
-    uint32_t r_rs = 0, r_b1 = 0, r_b2 = 0, r_re = 0;
-    unsigned npairs = 0;
-
-    for (int kk = 0; kk < PAIR_CHUNK; kk++) {
-        const long long s = first + kk;
-        if (s >= a.n) break;
-        const float4 Ci = a.C[s];
-        const int ti = __float_as_int(Ci.w);
-        if (a.real_only && (ti & PT_GHOST)) continue;
-        const unsigned long long mask_i = a.emask[ti & 7];
-        if (!mask_i) continue;
-        const float4 Ai = a.A[s];
-        const float4 Bi = a.B[s];
-        const uint32_t key = a.skey[s];
-        if (key != cur_key) {
-            cur_key = key;
-            uint32_t kq = key;
-            cx = (int)(kq % (uint32_t)a.ncx);
-            kq /= (uint32_t)a.ncx;
-            const int cy = (int)(kq % (uint32_t)a.ncy);
-            const int cz = (int)(kq / (uint32_t)a.ncy);
-            r_rs = r_b1 = r_b2 = r_re = 0;
-            if (lane < 9) {
-                const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
-                if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
-                    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
-                    r_rs = a.cell_start[base + x0];
-                    r_b1 = a.cell_start[base + cx];
-                    r_b2 = a.cell_start[base + cx + 1];
-                    r_re = a.cell_start[base + x1 + 1];
-                }
-            }
-        }
-        const float hi2 = a.k2 * Ai.w * Ai.w;
-        const float tmpi = Ci.y;  // p_i / rho_i^2
-        Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int qn = 0, qhead = 0;
-
-        for (int r = 0; r < 9; r++) {
-            const uint32_t rs = __shfl_sync(FULL, r_rs, r);
-            const uint32_t re = __shfl_sync(FULL, r_re, r);
-            if (rs >= re) continue;
-            const uint32_t b1 = __shfl_sync(FULL, r_b1, r);
-            const uint32_t b2 = __shfl_sync(FULL, r_b2, r);
-            const float yoff = Ai.y - (float)((r % 3) - 1) * a.celly;
-            const float zoff = Ai.z - (float)((r / 3) - 1) * a.cellz;
-            for (uint32_t t0 = rs; t0 < re; t0 += 32) {
-                const uint32_t t = t0 + lane;
-                bool ok = false;
-                float xij = 0.f, yij = 0.f, zij = 0.f, hj = 0.f;
-                if (t < re) {
-                    const float4 Aj = a.A[t];
-                    const float xo = t >= b2 ? a.cellx : (t >= b1 ? 0.0f : -a.cellx);
-                    xij = Ai.x - Aj.x - xo;
-                    yij = yoff - Aj.y;
-                    zij = zoff - Aj.z;
-                    hj = Aj.w;
-                    const float r2 = xij * xij + yij * yij + zij * zij;
-                    // linked_list_nnps.pyx:188: (xij2 < hi2) or (xij2 < hj2)
-                    ok = (r2 < hi2) || (r2 < a.k2 * hj * hj);
-                }
-                const unsigned m = __ballot_sync(FULL, ok);
-                if (m) {
-                    if (ok) {
-                        const int pos = (qhead + qn + __popc(m & lt_mask)) & (QCAP - 1);
-                        q_v[warp][pos] = make_float4(xij, yij, zij, hj);
-                        q_i[warp][pos] = t;
-                    }
-                    qn += __popc(m);
-                    __syncwarp();
-                    if (qn >= 32) {
-                        const int e = (qhead + lane) & (QCAP - 1);
-                        const uint32_t tq = q_i[warp][e];
-                        pair_body<K, DIM>(a, q_v[warp][e], a.B[tq], a.C[tq], Ai, Bi, Ci, mask_i,
-                                          tmpi, acc, npairs);
-                        qhead = (qhead + 32) & (QCAP - 1);
-                        qn -= 32;
-                        __syncwarp();
-                    }
-                }
-            }
-        }
-        if (lane < qn) {
-            const int e = (qhead + lane) & (QCAP - 1);
-            const uint32_t tq = q_i[warp][e];
-            pair_body<K, DIM>(a, q_v[warp][e], a.B[tq], a.C[tq], Ai, Bi, Ci, mask_i, tmpi, acc, npairs);
-        }
-        __syncwarp();
-
-        // warp reduction of the per-particle sums
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc.arho += __shfl_xor_sync(FULL, acc.arho, o);
-            acc.au += __shfl_xor_sync(FULL, acc.au, o);
-            acc.av += __shfl_xor_sync(FULL, acc.av, o);
-            acc.aw += __shfl_xor_sync(FULL, acc.aw, o);
-            acc.ax += __shfl_xor_sync(FULL, acc.ax, o);
-            acc.ay += __shfl_xor_sync(FULL, acc.ay, o);
-            acc.az += __shfl_xor_sync(FULL, acc.az, o);
-            acc.rsum += __shfl_xor_sync(FULL, acc.rsum, o);
-            acc.cfl = fmaxf(acc.cfl, __shfl_xor_sync(FULL, acc.cfl, o));
-        }
-        if (lane == 0) {
-            unsigned all_bits = 0;
-#pragma unroll
-            for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
-            const uint32_t g = a.perm[s];
-            if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
-            if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
-            if (all_bits & B200SPH_EQ_MOMENTUM) {
-                // post_loop wc/basic.py:259-269
-                const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
-                a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
-                a.dt_cfl[g] = acc.cfl;
-                a.dt_force[g] = fu * fu + fv * fv + fw * fw;
-            } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
-                a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
-            }
-            if (all_bits & B200SPH_EQ_XSPH) {
-                // post_loop basic_equations.py:297-300
-                a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
-            }
-        }
-    }
-    if (a.pair_counter) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
-        if (lane == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
-    }
-}
-
-
-// --------------------------------------------------------------------------
-// persistent neighbour lists (the default fast path)
-//
-// k_list_build runs the reference's accept test widened by a skin S
-//   r^2 < (k h_i + S)^2  or  r^2 < (k h_j + S)^2
-// once per (re)build and stores, for every destination, the sorted indices of
-// the candidates that pass, 32 destinations interleaved ("transposed") so that
-// the consumer reads them coalesced.  The lists stay valid while
-//   2 max|x - x_build| + k max(h - h_build) <= S            (checked every update),
-// so an evaluation normally only runs k_pair_list: one THREAD per destination
-// walks its list, re-applies the EXACT accept test of linked_list_nnps.pyx:188
-// on the current positions and evaluates the equations.  Results are identical
-// to rebuilding the neighbours every evaluation; only the cost is amortised.
-// entry = j (26 bits, sorted index) | code << 26, code = (dxc+1) + 4 (dy+1) + 16 (dz+1)
-// --------------------------------------------------------------------------
-#define LIST_JBITS 26
-#define LIST_JMASK 0x03FFFFFFu
-#define LIST_NT 128
-// Skin controller.  Per evaluation a build costs c0 (1+s)^3 (list entries) + R / L(s)
-// (rebuild cost R over a lifetime L that grows linearly with the skin s); the minimum is
-// where L s = R / (3 c0 (1+s)^2) ~ 2 for the measured R / c0 ~ 5.5, i.e. the target
-// lifetime is L* = SKIN_KAPPA / s evaluations.
-#define SKIN_KAPPA 2.0
-
-struct ListBuildArgs {
-    const float4 *A;
-    const uint32_t *cell_start, *skey;
-    long long n;
-    int ncx, ncy, ncz;
-    int px, py, pz;                 // periodic axes (cell indices wrap, images shift by nc * cell)
-    float cellx, celly, cellz;      // internal cell edges (>= k hmax + S)
-    float kr, S;     // radius scale, absolute skin
-    uint32_t *cnt;   // [n] neighbours per destination
-    uint32_t *lst;   // null: count only
-    int capg;        // entries reserved per destination
-    unsigned *max_count;
-};
-
-// PERIODIC = false: 9 candidate rows (3 consecutive cells each, contiguous in the
-// sorted arrays).  PERIODIC = true: the same 9 rows with wrapped y / z indices plus, on a
-// periodic x axis, up to 2 single-cell segments per row for the cells that wrap;
-// because coordinates are relative to the particle's own cell and a periodic axis is
-// tiled exactly (L = nc * cell), the image shift of a wrapped neighbour cell is the
-// same "- d * cell" offset as for an ordinary neighbour cell -- the consumer kernel does
-// not know about periodicity at all, and no ghost particles are materialised
-// (reference: _create_ghosts_periodic, nnps_base.pyx:744-940, copies the particles).
-template <bool PERIODIC>
-__global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildArgs a)
-{
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const long long first = ((long long)blockIdx.x * PAIR_WARPS + warp) * PAIR_CHUNK;
-    uint32_t cur_key = 0xFFFFFFFFu;
-    int cx = 0;
-    uint32_t r_rs = 0, r_b1 = 0, r_b2 = 0, r_re = 0;
-    unsigned wmax = 0;
-    for (int kk = 0; kk < PAIR_CHUNK; kk++) {
-        const long long s = first + kk;
-        if (s >= a.n) break;
-        const float4 Ai = a.A[s];
-        const uint32_t key = a.skey[s];
-        if (key != cur_key) {
-            cur_key = key;
-            uint32_t kq = key;
-            cx = (int)(kq % (uint32_t)a.ncx);
-            kq /= (uint32_t)a.ncx;
-            const int cy = (int)(kq % (uint32_t)a.ncy);
-            const int cz = (int)(kq / (uint32_t)a.ncy);
-            r_rs = r_b1 = r_b2 = r_re = 0;
-            if (!PERIODIC) {
-                if (lane < 9) {
-                    const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
-                    if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                        const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
-                        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
-                        r_rs = a.cell_start[base + x0];
-                        r_b1 = a.cell_start[base + cx];
-                        r_b2 = a.cell_start[base + cx + 1];
-                        r_re = a.cell_start[base + x1 + 1];
-                    }
-                }
-            } else if (lane < 27) {
-                // 9 (dy, dz) rows with wrapped y / z (segments 0..8: the x-contiguous part of
-                // the row, clipped to the grid) + for a periodic x axis the wrapped cell that
-                // is missing at cx = 0 (segments 9..17, dxc = -1) / cx = ncx - 1 (18..26, +1)
-                const int q = lane % 9, kind = lane / 9;
-                int yy = cy + (q % 3) - 1, zz = cz + (q / 3) - 1;
-                if (a.py) yy = (yy + a.ncy) % a.ncy;
-                if (a.pz) zz = (zz + a.ncz) % a.ncz;
-                if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
-                    if (kind == 0) {
-                        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
-                        r_rs = a.cell_start[base + x0];
-                        r_b1 = a.cell_start[base + cx];
-                        r_b2 = a.cell_start[base + cx + 1];
-                        r_re = a.cell_start[base + x1 + 1];
-                    } else if (kind == 1 && a.px && cx == 0) {
-                        r_rs = a.cell_start[base + a.ncx - 1];
-                        r_re = a.cell_start[base + a.ncx];
-                    } else if (kind == 2 && a.px && cx == a.ncx - 1) {
-                        r_rs = a.cell_start[base];
-                        r_re = a.cell_start[base + 1];
-                    }
-                }
-            }
-        }
-        float hi = a.kr * Ai.w + a.S;
-        const float hi2 = hi * hi;
-        uint32_t *out = a.lst ? a.lst + ((size_t)(s >> 5) * (size_t)a.capg) * 32u + (uint32_t)(s & 31) : nullptr;
-        unsigned count = 0;
-        for (int r = 0; r < (PERIODIC ? 27 : 9); r++) {
-            const uint32_t rs = __shfl_sync(FULL, r_rs, r);
-            const uint32_t re = __shfl_sync(FULL, r_re, r);
-            if (rs >= re) continue;
-            uint32_t b1 = 0, b2 = 0, rcode;
-            float xoff, yoff, zoff;
-            if (!PERIODIC) {
-                b1 = __shfl_sync(FULL, r_b1, r);
-                b2 = __shfl_sync(FULL, r_b2, r);
-                xoff = Ai.x;
-                yoff = Ai.y - (float)((r % 3) - 1) * a.celly;
-                zoff = Ai.z - (float)((r / 3) - 1) * a.cellz;
-                rcode = (uint32_t)(4 * (r % 3) + 16 * (r / 3));
-            } else {
-                const int q = r % 9;
-                b1 = __shfl_sync(FULL, r_b1, r);
-                b2 = __shfl_sync(FULL, r_b2, r);
-                xoff = Ai.x;
-                yoff = Ai.y - (float)((q % 3) - 1) * a.celly;
-                zoff = Ai.z - (float)((q / 3) - 1) * a.cellz;
-                rcode = (uint32_t)(4 * (q % 3) + 16 * (q / 3));
-            }
-            const int kind = PERIODIC ? r / 9 : 0;
-            for (uint32_t t0 = rs; t0 < re; t0 += 32) {
-                const uint32_t t = t0 + lane;
-                bool ok = false;
-                uint32_t dxc1 = 0;
-                if (t < re) {
-                    const float4 Aj = a.A[t];
-                    // dxc + 1: position inside the row, or the wrapped cell's fixed offset
-                    dxc1 = kind == 0 ? (uint32_t)(t >= b1) + (uint32_t)(t >= b2) : (kind == 1 ? 0u : 2u);
-                    const float xij = xoff - Aj.x - ((float)dxc1 - 1.0f) * a.cellx;
-                    const float yij = yoff - Aj.y;
-                    const float zij = zoff - Aj.z;
-                    const float r2 = xij * xij + yij * yij + zij * zij;
-                    const float hj = a.kr * Aj.w + a.S;
-                    ok = (r2 < hi2) || (r2 < hj * hj);
-                }
-                const unsigned m = __ballot_sync(FULL, ok);
-                if (ok && out) {
-                    const unsigned pos = count + __popc(m & lt_mask);
-                    if (pos < (unsigned)a.capg) out[(size_t)pos * 32u] = t | ((rcode + dxc1) << LIST_JBITS);
-                }
-                count += __popc(m);
-            }
-        }
-        if (lane == 0) a.cnt[s] = count;
-        wmax = max(wmax, count);
-    }
-    if (lane == 0 && wmax) atomicMax(a.max_count, wmax);
-}
-
-// one 256-bit read-only load (LDG.E.ENL2.256 on sm_100a): a whole 32-byte sector
-__device__ __forceinline__ void ld_256(const float4 *p, float4 &b, float4 &c)
-{
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w), "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w)
-                 : "l"(p));
-}
-
-// The list consumer (the default fast path): one THREAD per destination walks its
-// list.  Per entry it gathers {A, B} = (x, y, z, h, u, v, w, m) with ONE 256-bit load
-// (exactly one 32-byte sector) and C = (rho, p/rho^2, cs, type) with one 128-bit load,
-// both issued one iteration ahead of their use; list entries stream in (evict-first)
-// two iterations ahead.  The gathers are what bounds this kernel (L1 tag stage, see
-// profiles/), hence the sector-sized records.
-template <int K, int DIM>
-__global__ void __launch_bounds__(LIST_NT, 4) k_pair_list(const PairArgs a, const uint32_t *__restrict__ cnt,
-                                                         const uint32_t *__restrict__ lst, const int capg)
-{
-    __shared__ float4 s_T[64];
-    const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
-    }
-    __syncthreads();
-    const unsigned FULL = 0xffffffffu;
-    const long long s = (long long)blockIdx.x * LIST_NT + tid;
-    bool active = s < a.n;
-    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = Ai;
-    unsigned long long mask_i = 0;
-    int count = 0;
-    if (active) {
-        Ci = a.C[s];
-        const int ti = __float_as_int(Ci.w);
-        mask_i = a.emask[ti & 7];
-        if ((a.real_only && (ti & PT_GHOST)) || !mask_i) active = false;
-    }
-    if (active) {
-        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
-        count = (int)cnt[s];
-    }
-    int cmax = count;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
-    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
-    const float hi2 = a.k2 * Ai.w * Ai.w;
-    const float tmpi = Ci.y;
-    Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    unsigned npairs = 0;
-    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-    float4 A_a = Ai, B_a = Bi, C_a = Ci;
-    if (count > 0) {
-        const size_t j = e_a & LIST_JMASK;
-        ld_256(a.AB + 2 * j, A_a, B_a);
-        C_a = a.C[j];
-    }
-    for (int k = 0; k < cmax; k++) {
-        const uint32_t e = e_a;
-        const float4 Aj = A_a, Bj = B_a, Cj = C_a;
-        e_a = e_b;
-        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-        if (k + 1 < count) {
-            const size_t j = e_a & LIST_JMASK;
-            ld_256(a.AB + 2 * j, A_a, B_a);
-            C_a = a.C[j];
-        }
-        if (k < count) {
-            const float4 T = s_T[e >> LIST_JBITS];
-            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
-            const float r2 = xij * xij + yij * yij + zij * zij;
-            // the exact accept test, linked_list_nnps.pyx:188
-            if ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w))
-                pair_body<K, DIM>(a, make_float4(xij, yij, zij, Aj.w), Bj, Cj, Ai, Bi, Ci, mask_i, tmpi,
-                                  acc, npairs);
-        }
-    }
-    if (active) {
-        unsigned all_bits = 0;
-#pragma unroll
-        for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
-        const uint32_t g = a.perm[s];
-        if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
-        if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
-        if (all_bits & B200SPH_EQ_MOMENTUM) {
-            // post_loop wc/basic.py:259-269
-            const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
-            a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
-            a.dt_cfl[g] = acc.cfl;
-            a.dt_force[g] = fu * fu + fv * fv + fw * fw;
-        } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
-            a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
-        }
-        if (all_bits & B200SPH_EQ_XSPH) {
-            // post_loop basic_equations.py:297-300
-            a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
-        }
-    }
-    if (a.pair_counter) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
-        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
-    }
-}
-
-// --------------------------------------------------------------------------
-// EDAC scheme, transport-velocity branch (wc/edac.py:776-880): two passes over the same
-// persistent neighbour lists.  Sorted records: AB = {A, B} as for k_pair_list,
-// C2 = (rho, p, V, type) [ctx->C], Dv = (uhat-u, vhat-v, what-w, pavg), PT = (p, type)
-// --------------------------------------------------------------------------
-struct TvfArgs {
-    const float4 *AB;
-    float4 *C2, *Dv;
-    const float2 *PT;
-    const uint32_t *perm;
-    double *rho;
-    float *V, *pavg, *au, *av, *aw, *auhat, *avhat, *awhat, *ap;
-    long long n;
-    float cellx, celly, cellz, k2, kfac;
-    unsigned fluid_mask, eqbits;
-    int bql;
-    float pb, nu, edac_nu, c0, alpha, gx, gy, gz;  // gx.. already damped
-    unsigned long long *pair_counter;
-};
-
-__global__ void k_pack_tvf(const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
-                           const double *__restrict__ m, const double *__restrict__ uh, const double *__restrict__ vh,
-                           const double *__restrict__ wh, const double *__restrict__ pf, const float *__restrict__ pavg,
-                           const uint8_t *__restrict__ ptype, const uint32_t *__restrict__ perm, long long n,
-                           float4 *__restrict__ B, float4 *__restrict__ AB, float4 *__restrict__ C2,
-                           float4 *__restrict__ Dv, float2 *__restrict__ PT)
-{
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const uint32_t g = perm[s];
-    const int t = (int)ptype[g];
-    const double ug = u[g], vg = v[g], wg = w[g];
-    float4 b;
-    b.x = (float)ug; b.y = (float)vg; b.z = (float)wg; b.w = (float)m[g];
-    B[s] = b;
-    AB[2 * s + 1] = b;
-    // differences of nearly equal numbers: formed in fp64, then rounded
-    Dv[s] = make_float4((float)(uh[g] - ug), (float)(vh[g] - vg), (float)(wh[g] - wg), pavg[g]);
-    const float p = (float)pf[g];
-    PT[s] = make_float2(p, __int_as_float(t));
-    C2[s] = make_float4(0.f, p, 1.f, __int_as_float(t));   // rho, V filled in by pass 1
-}
-
-// group 1 (real=False): V_i = sum_j W_ij, rho_i = m_i V_i (transport_velocity.py:52-58) and the
-// neighbour-average pressure (wc/edac.py:69-79), every fluid particle incl. ghosts
-template <int K, int DIM>
-__global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const uint32_t *__restrict__ cnt,
-                                                         const uint32_t *__restrict__ lst, const int capg)
-{
-    __shared__ float4 s_T[64];
-    const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
-    }
-    __syncthreads();
-    const unsigned FULL = 0xffffffffu;
-    const long long s = (long long)blockIdx.x * LIST_NT + tid;
-    bool active = s < a.n;
-    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai;
-    int count = 0;
-    if (active) {
-        const int ti = __float_as_int(a.PT[s].y);
-        if (!((a.fluid_mask >> (ti & 7)) & 1u)) active = false;
-    }
-    if (active) {
-        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
-        count = (int)cnt[s];
-    }
-    int cmax = count;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
-    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
-    const float hi2 = a.k2 * Ai.w * Ai.w;
-    float wsum = 0.f, psum = 0.f, nn = 0.f;
-    unsigned npairs = 0;
-    // entries two iterations ahead, records one iteration ahead (as in k_pair_list)
-    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-    float4 A_a = Ai;
-    float2 P_a = make_float2(0.f, 0.f);
-    if (count > 0) {
-        const size_t j = e_a & LIST_JMASK;
-        A_a = a.AB[2 * j];
-        P_a = a.PT[j];
-    }
-    for (int k = 0; k < cmax; k++) {
-        const uint32_t e = e_a;
-        const float4 Aj = A_a;
-        const float2 Pj = P_a;
-        e_a = e_b;
-        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-        if (k + 1 < count) {
-            const size_t j = e_a & LIST_JMASK;
-            A_a = a.AB[2 * j];
-            P_a = a.PT[j];
-        }
-        if (k < count) {
-            const float4 T = s_T[e >> LIST_JBITS];
-            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
-            const float r2 = xij * xij + yij * yij + zij * zij;
-            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Pj.y) & 7)) & 1u)) {
-                npairs++;
-                const float rij = sqrtf(r2);
-                const float h1 = frcp(0.5f * (Ai.w + Aj.w));
-                float w, dw;
-                sph_kernel<K>(rij * h1, w, dw);
-                wsum += w * a.kfac * hpow<DIM>(h1);
-                psum += Pj.x;
-                nn += 1.0f;
-            }
-        }
-    }
-    if (active) {
-        const uint32_t g = a.perm[s];
-        const float rho = Bi.w * wsum;
-        a.V[g] = wsum;
-        a.rho[g] = (double)rho;
-        float4 *c2 = a.C2 + s;
-        c2->x = rho;          // .y (p) and .w (type) were written by k_pack_tvf; other
-        c2->z = wsum;         // threads read only those two while this kernel runs
-        if (a.bql) {
-            const float pv = nn > 0.f ? psum / nn : 0.f;
-            a.pavg[g] = pv;
-            a.Dv[s].w = pv;
-        }
-    }
-    if (a.pair_counter) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
-        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
-    }
-}
-
-// group 2 (real=True): pressure gradient with the background-pressure term, artificial /
-// physical viscosity, artificial stress and the EDAC pressure evolution, fused
-template <int K, int DIM>
-__global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const uint32_t *__restrict__ cnt,
-                                                         const uint32_t *__restrict__ lst, const int capg)
-{
-    __shared__ float4 s_T[64];
-    const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
-    }
-    __syncthreads();
-    const unsigned FULL = 0xffffffffu;
-    const long long s = (long long)blockIdx.x * LIST_NT + tid;
-    bool active = s < a.n;
-    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = make_float4(1.f, 0.f, 1.f, 0.f), Di = Ai;
-    int count = 0;
-    if (active) {
-        Ci = a.C2[s];
-        const int ti = __float_as_int(Ci.w);
-        if ((ti & PT_GHOST) || !((a.fluid_mask >> (ti & 7)) & 1u)) active = false;
-    }
-    if (active) {
-        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
-        Di = a.Dv[s];
-        count = (int)cnt[s];
-    }
-    int cmax = count;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
-    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
-    const float hi2 = a.k2 * Ai.w * Ai.w;
-    const float rhoi = Ci.x, pi = Ci.y, pavg = Di.w;
-    const float Vi1 = frcp(Ci.z);
-    const float Vi2 = Vi1 * Vi1;
-    const float mi1 = frcp(Bi.w);
-    const float cs2 = a.c0 * a.c0;
-    float au = 0.f, av = 0.f, aw = 0.f, auh = 0.f, avh = 0.f, awh = 0.f, ap = 0.f;
-    unsigned npairs = 0;
-    // entries two iterations ahead, records one iteration ahead (as in k_pair_list):
-    // a record load never waits for the entry load of the same iteration
-    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-    float4 A_a = Ai, B_a = Bi, C_a = Ci, D_a = Di;
-    if (count > 0) {
-        const size_t j = e_a & LIST_JMASK;
-        ld_256(a.AB + 2 * j, A_a, B_a);
-        C_a = a.C2[j];
-        D_a = a.Dv[j];
-    }
-    for (int k = 0; k < cmax; k++) {
-        const uint32_t e = e_a;
-        const float4 Aj = A_a, Bj = B_a, Cj = C_a, Dj = D_a;
-        e_a = e_b;
-        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-        if (k + 1 < count) {
-            const size_t j = e_a & LIST_JMASK;
-            ld_256(a.AB + 2 * j, A_a, B_a);
-            C_a = a.C2[j];
-            D_a = a.Dv[j];
-        }
-        if (k < count) {
-            const float4 T = s_T[e >> LIST_JBITS];
-            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
-            const float r2 = xij * xij + yij * yij + zij * zij;
-            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
-                npairs++;
-                const bool far = r2 > 1e-24f;
-                const float rinv = far ? frsqrt(r2) : 0.0f;
-                const float rij = r2 * rinv;
-                const float hij = 0.5f * (Ai.w + Aj.w);
-                const float h1 = frcp(hij);
-                float w, dw;
-                sph_kernel<K>(rij * h1, w, dw);
-                const float gt = dw * a.kfac * hpow<DIM>(h1) * h1 * rinv;   // DWIJ = gt * XIJ
-                const float eps = 0.01f * hij * hij;
-                const float rhoj = Cj.x, pj = Cj.y;
-                const float Vj1 = frcp(Cj.z);
-                const float common = mi1 * (Vi2 + Vj1 * Vj1);
-                const float uij = Bi.x - Bj.x, vij = Bi.y - Bj.y, wij = Bi.z - Bj.z;
-                const float vdotx = uij * xij + vij * yij + wij * zij;
-                const float rsum1 = frcp(rhoi + rhoj);
-                const float r2e1 = frcp(r2 + eps);
-                float fx = 0.f;   // multiplies XIJ in au
-                if (a.eqbits & B200SPH_TVF_PGRAD) {   // wc/edac.py:447-481
-                    const float pij = (rhoj * (pi - pavg) + rhoi * (pj - pavg)) * rsum1;
-                    fx += -pij * common * gt;
-                    const float fh = -a.pb * common * gt;
-                    auh += fh * xij;
-                    avh += fh * yij;
-                    awh += fh * zij;
-                }
-                if ((a.eqbits & B200SPH_TVF_AV) && vdotx < 0.f) {   // transport_velocity.py:432-448
-                    const float muij = hij * vdotx * r2e1;
-                    const float piij = Bj.w * (-a.alpha * a.c0 * muij) * (2.0f * rsum1);
-                    fx += -piij * gt;
-                }
-                au += fx * xij;
-                av += fx * yij;
-                aw += fx * zij;
-                if (a.eqbits & B200SPH_TVF_VISC) {   // transport_velocity.py:362-386
-                    const float etaij = 2.0f * a.nu * rhoi * rhoj * rsum1;
-                    const float tmp = common * etaij * (gt * r2) * r2e1;
-                    au += tmp * uij;
-                    av += tmp * vij;
-                    aw += tmp * wij;
-                }
-                if (a.eqbits & B200SPH_TVF_ASTRESS) {   // transport_velocity.py:473-545
-                    const float si = rhoi * gt * (Di.x * xij + Di.y * yij + Di.z * zij);
-                    const float sj = rhoj * gt * (Dj.x * xij + Dj.y * yij + Dj.z * zij);
-                    const float c = 0.5f * common;
-                    au += c * (Bi.x * si + Bj.x * sj);
-                    av += c * (Bi.y * si + Bj.y * sj);
-                    aw += c * (Bi.z * si + Bj.z * sj);
-                }
-                if (a.eqbits & B200SPH_TVF_EDAC) {   // wc/edac.py:365-386
-                    const float etaij = 2.0f * a.edac_nu * rhoi * rhoj * rsum1;
-                    ap += rhoi * frcp(rhoj) * cs2 * Bj.w * (gt * vdotx);
-                    ap += common * etaij * (gt * r2) * r2e1 * (pi - pj);
-                }
-            }
-        }
-    }
-    if (active) {
-        const uint32_t g = a.perm[s];
-        if (a.eqbits & B200SPH_TVF_PGRAD) {   // post_loop wc/edac.py:483-488
-            au += a.gx; av += a.gy; aw += a.gz;
-            a.auhat[g] = auh; a.avhat[g] = avh; a.awhat[g] = awh;
-        }
-        a.au[g] = au; a.av[g] = av; a.aw[g] = aw;
-        if (a.eqbits & B200SPH_TVF_EDAC) a.ap[g] = ap;
-    }
-    if (a.pair_counter) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
-        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
-    }
-}
-
-struct StageTvfArgs {
-    double *x, *y, *z, *u, *v, *w, *pf, *uh, *vh, *wh;
-    double *x0, *y0, *z0, *u0, *v0, *w0, *pf0;
-    const float *au, *av, *aw, *auh, *avh, *awh, *ap;
-    const uint8_t *ptype;
-    long long pool_end;
-    int arr, which;
-    double f;
-};
-// EDACTVFStep wc/edac.py:491-540 (real particles)
-__device__ __forceinline__ void stage_tvf_body(const StageTvfArgs &a)
-{
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.pool_end) return;
-    uint8_t t = a.ptype[g];
-    if (t == PT_INVALID || (t & PT_GHOST)) return;
-    if (a.arr >= 0 && (t & 7) != a.arr) return;
-    if (a.which == 0) {
-        a.x0[g] = a.x[g]; a.y0[g] = a.y[g]; a.z0[g] = a.z[g];
-        a.u0[g] = a.u[g]; a.v0[g] = a.v[g]; a.w0[g] = a.w[g];
-        a.pf0[g] = a.pf[g];
-        return;
-    }
-    const double f = a.f;
-    const double u = a.u0[g] + f * (double)a.au[g];
-    const double v = a.v0[g] + f * (double)a.av[g];
-    const double w = a.w0[g] + f * (double)a.aw[g];
-    const double uh = u + f * (double)a.auh[g];
-    const double vh = v + f * (double)a.avh[g];
-    const double wh = w + f * (double)a.awh[g];
-    a.u[g] = u; a.v[g] = v; a.w[g] = w;
-    a.uh[g] = uh; a.vh[g] = vh; a.wh[g] = wh;
-    a.x[g] = a.x0[g] + f * uh;
-    a.y[g] = a.y0[g] + f * vh;
-    a.z[g] = a.z0[g] + f * wh;
-    a.pf[g] = a.pf0[g] + f * (double)a.ap[g];
-}
-__global__ void k_stage_tvf(StageTvfArgs a) { stage_tvf_body(a); }
-__global__ void k_stage_tvf_devdt(StageTvfArgs a, const double *__restrict__ tc)
-{
-    const double dt = tc[0];
-    a.f = a.which == 1 ? 0.5 * dt : dt;
-    stage_tvf_body(a);
-}
-
-// --------------------------------------------------------------------------
-// Elastic dynamics (solid_mech/basic.py:604-651), elastic arrays only.  NOT YET RUN ON
-// HARDWARE.  Sorted records: AB = {A, B}, C3 = (rho, p, cs, type) [ctx->C], and the
-// stress records T = (s - p I) / rho^2 and R (artificial stress), 6 components each:
-//   T01 = (T00, T01, T02, T11)   T2R = (T12, T22, R00, R01)   R2 = (R02, R11, R12, R22)
-// --------------------------------------------------------------------------
-struct SolidArgs {
-    const float4 *AB;
-    float4 *C3, *T01, *T2R, *R2;
-    const uint32_t *perm;
-    const double *rho;
-    const double *s[6];
-    float *p, *vg[9], *r[6], *as[6];
-    float *arho, *au, *av, *aw, *ax, *ay, *az;
-    long long n;
-    float cellx, celly, cellz, k2, kfac;
-    unsigned elastic_mask;
-    int grad3d;
-    float eps, alpha, beta, eps_xsph;
-    double c0_ref[B200SPH_MAX_ARRAYS], rho_ref[B200SPH_MAX_ARRAYS], G[B200SPH_MAX_ARRAYS];
-    float wdeltap[B200SPH_MAX_ARRAYS], nexp[B200SPH_MAX_ARRAYS];
-    unsigned long long *pair_counter;
-};
-
-__global__ void k_pack_solid(const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
-                             const double *__restrict__ m, const double *__restrict__ rho, const float *__restrict__ p,
-                             const float *__restrict__ cs, const uint8_t *__restrict__ ptype,
-                             const uint32_t *__restrict__ perm, long long n, float4 *__restrict__ B,
-                             float4 *__restrict__ AB, float4 *__restrict__ C3)
-{
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const uint32_t g = perm[s];
-    float4 b;
-    b.x = (float)u[g]; b.y = (float)v[g]; b.z = (float)w[g]; b.w = (float)m[g];
-    B[s] = b;
-    AB[2 * s + 1] = b;
-    C3[s] = make_float4((float)rho[g], p[g], cs[g], __int_as_float((int)ptype[g]));
-}
-
-// cyclic Jacobi for a symmetric 3x3 matrix (fp64): eigenvalues d, eigenvectors = columns of v
-__device__ __forceinline__ void eigen_sym3(double a[3][3], double v[3][3], double d[3])
-{
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) v[i][j] = (i == j) ? 1.0 : 0.0;
-    for (int sweep = 0; sweep < 30; sweep++) {
-        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
-        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
-        if (off <= 1e-30 * diag || off == 0.0) break;
-#pragma unroll
-        for (int pq = 0; pq < 3; pq++) {
-            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
-            if (a[p][q] == 0.0) continue;
-            const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
-            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const double akp = a[k][p], akq = a[k][q];
-                a[k][p] = c * akp - sn * akq;
-                a[k][q] = sn * akp + c * akq;
-            }
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const double apk = a[p][k], aqk = a[q][k];
-                a[p][k] = c * apk - sn * aqk;
-                a[q][k] = sn * apk + c * aqk;
-            }
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const double vkp = v[k][p], vkq = v[k][q];
-                v[k][p] = c * vkp - sn * vkq;
-                v[k][q] = sn * vkp + c * vkq;
-            }
-        }
-    }
-    d[0] = a[0][0];
-    d[1] = a[1][1];
-    d[2] = a[2][2];
-}
-
-// group 1: IsothermalEOS, VelocityGradient2D/3D (the pair loop), MonaghanArtificialStress and
-// -- it needs only this particle's gradient -- HookesDeviatoricStressRate of group 2; writes
-// the stress records group 2 gathers
-template <int K, int DIM>
-__global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, const uint32_t *__restrict__ cnt,
-                                                           const uint32_t *__restrict__ lst, const int capg)
-{
-    __shared__ float4 s_T[64];
-    const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
-    }
-    __syncthreads();
-    const unsigned FULL = 0xffffffffu;
-    const long long s = (long long)blockIdx.x * LIST_NT + tid;
-    bool active = s < a.n, ghost_src = false;
-    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai;
-    int ti = 0, count = 0;
-    if (active) {
-        ti = __float_as_int(a.C3[s].w);
-        const bool elastic = (a.elastic_mask >> (ti & 7)) & 1u;
-        ghost_src = elastic && (ti & PT_GHOST);
-        if ((ti & PT_GHOST) || !elastic) active = false;
-    }
-    if (ghost_src) {
-        // a ghost is a source of group 2 with the values it carries (group 1 is real=True)
-        const uint32_t g = a.perm[s];
-        const double rho = a.rho[g], p = (double)a.p[g], rho21 = 1.0 / (rho * rho);
-        a.T01[s] = make_float4((float)((a.s[0][g] - p) * rho21), (float)(a.s[1][g] * rho21), (float)(a.s[2][g] * rho21),
-                               (float)((a.s[3][g] - p) * rho21));
-        a.T2R[s] = make_float4((float)(a.s[4][g] * rho21), (float)((a.s[5][g] - p) * rho21), a.r[0][g], a.r[1][g]);
-        a.R2[s] = make_float4(a.r[2][g], a.r[3][g], a.r[4][g], a.r[5][g]);
-    }
-    if (active) {
-        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
-        count = (int)cnt[s];
-    }
-    int cmax = count;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
-    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
-    const float hi2 = a.k2 * Ai.w * Ai.w;
-    float g00 = 0.f, g01 = 0.f, g02 = 0.f, g10 = 0.f, g11 = 0.f, g12 = 0.f, g20 = 0.f, g21 = 0.f, g22 = 0.f;
-    unsigned npairs = 0;
-    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-    float4 A_a = Ai, B_a = Bi, C_a = make_float4(1.f, 0.f, 0.f, 0.f);
-    if (count > 0) {
-        const size_t j = e_a & LIST_JMASK;
-        ld_256(a.AB + 2 * j, A_a, B_a);
-        C_a = a.C3[j];
-    }
-    for (int k = 0; k < cmax; k++) {
-        const uint32_t e = e_a;
-        const float4 Aj = A_a, Bj = B_a, Cj = C_a;
-        e_a = e_b;
-        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-        if (k + 1 < count) {
-            const size_t j = e_a & LIST_JMASK;
-            ld_256(a.AB + 2 * j, A_a, B_a);
-            C_a = a.C3[j];
-        }
-        if (k < count) {
-            const float4 T = s_T[e >> LIST_JBITS];
-            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
-            const float r2 = xij * xij + yij * yij + zij * zij;
-            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.elastic_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
-                npairs++;
-                const float rinv = r2 > 1e-24f ? frsqrt(r2) : 0.0f;
-                const float h1 = frcp(0.5f * (Ai.w + Aj.w));
-                float w, dw;
-                sph_kernel<K>(r2 * rinv * h1, w, dw);
-                const float gt = dw * a.kfac * hpow<DIM>(h1) * h1 * rinv;   // DWIJ = gt * XIJ
-                const float tmp = -Bj.w * frcp(Cj.x) * gt;                 // basic_equations.py:88-98
-                const float du = tmp * (Bi.x - Bj.x), dv = tmp * (Bi.y - Bj.y), dwv = tmp * (Bi.z - Bj.z);
-                g00 += du * xij; g01 += du * yij;
-                g10 += dv * xij; g11 += dv * yij;
-                if (a.grad3d) {
-                    g02 += du * zij; g12 += dv * zij;
-                    g20 += dwv * xij; g21 += dwv * yij; g22 += dwv * zij;
-                }
-            }
-        }
-    }
-    if (active) {
-        const uint32_t g = a.perm[s];
-        const int arr = ti & 7;
-        const double rho = a.rho[g];
-        const double p = a.c0_ref[arr] * a.c0_ref[arr] * (rho - a.rho_ref[arr]);   // solid_mech/basic.py:100-101
-        a.p[g] = (float)p;
-        double sd[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) sd[k] = a.s[k][g];
-        // velocity gradient: the 2-D equation leaves the other five components alone
-        float vgl[9];
-        if (a.grad3d) {
-            vgl[0] = g00; vgl[1] = g01; vgl[2] = g02; vgl[3] = g10; vgl[4] = g11; vgl[5] = g12;
-            vgl[6] = g20; vgl[7] = g21; vgl[8] = g22;
-#pragma unroll
-            for (int k = 0; k < 9; k++) a.vg[k][g] = vgl[k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < 9; k++) vgl[k] = a.vg[k][g];
-            vgl[0] = g00; vgl[1] = g01; vgl[3] = g10; vgl[4] = g11;
-            a.vg[0][g] = g00; a.vg[1][g] = g01; a.vg[3][g] = g10; a.vg[4][g] = g11;
-        }
-        // MonaghanArtificialStress solid_mech/basic.py:170-242
-        double S[3][3], Rv[3][3], ev[3], rd[3];
-        S[0][0] = sd[0] - p; S[1][1] = sd[3] - p; S[2][2] = sd[5] - p;
-        S[0][1] = S[1][0] = sd[1];
-        S[0][2] = S[2][0] = sd[2];
-        S[1][2] = S[2][1] = sd[4];
-        eigen_sym3(S, Rv, ev);
-        const double rho21 = 1.0 / (rho * rho);
-#pragma unroll
-        for (int k = 0; k < 3; k++) rd[k] = ev[k] > 0.0 ? -(double)a.eps * ev[k] * rho21 : 0.0;
-        float rr[6];
-        {
-            const int IA[6] = {0, 0, 0, 1, 1, 2}, IB[6] = {0, 1, 2, 1, 2, 2};
-#pragma unroll
-            for (int q = 0; q < 6; q++) {
-                double sum = 0.0;
-#pragma unroll
-                for (int k = 0; k < 3; k++) sum += Rv[IA[q]][k] * rd[k] * Rv[IB[q]][k];
-                rr[q] = (float)sum;
-                a.r[q][g] = rr[q];
-            }
-        }
-        // HookesDeviatoricStressRate solid_mech/basic.py:420-505
-        {
-            double vv[3][3], ss[3][3], ep[3][3], om[3][3];
-#pragma unroll
-            for (int k = 0; k < 9; k++) vv[k / 3][k % 3] = (double)vgl[k];
-            ss[0][0] = sd[0]; ss[0][1] = ss[1][0] = sd[1]; ss[0][2] = ss[2][0] = sd[2];
-            ss[1][1] = sd[3]; ss[1][2] = ss[2][1] = sd[4]; ss[2][2] = sd[5];
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    ep[i][j] = 0.5 * (vv[i][j] + vv[j][i]);
-                    om[i][j] = 0.5 * (vv[i][j] - vv[j][i]);
-                }
-            const double tmp = 2.0 * a.G[arr];
-            const double trace = (1.0 / 3.0) * (ep[0][0] + ep[1][1] + ep[2][2]);
-            const int IA[6] = {0, 0, 0, 1, 1, 2}, IB[6] = {0, 1, 2, 1, 2, 2};
-#pragma unroll
-            for (int q = 0; q < 6; q++) {
-                const int i = IA[q], j = IB[q];
-                double t1 = 0.0, t2 = 0.0;
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    t1 += ss[i][k] * om[j][k];
-                    t2 += ss[k][j] * om[i][k];
-                }
-                a.as[q][g] = (float)(tmp * (ep[i][j] - (i == j ? trace : 0.0)) + t1 + t2);
-            }
-        }
-        // records for group 2
-        const float T00 = (float)((sd[0] - p) * rho21), T11 = (float)((sd[3] - p) * rho21), T22 = (float)((sd[5] - p) * rho21);
-        const float T01 = (float)(sd[1] * rho21), T02 = (float)(sd[2] * rho21), T12 = (float)(sd[4] * rho21);
-        a.T01[s] = make_float4(T00, T01, T02, T11);
-        a.T2R[s] = make_float4(T12, T22, rr[0], rr[1]);
-        a.R2[s] = make_float4(rr[2], rr[3], rr[4], rr[5]);
-        a.C3[s].y = (float)p;
-    }
-    if (a.pair_counter) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
-        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
-    }
-}
-
-// group 2: ContinuityEquation, MomentumEquationWithStress, MonaghanArtificialViscosity, XSPHCorrection
-template <int K, int DIM>
-__global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass2(const SolidArgs a, const uint32_t *__restrict__ cnt,
-                                                           const uint32_t *__restrict__ lst, const int capg)
-{
-    __shared__ float4 s_T[64];
-    const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
-    }
-    __syncthreads();
-    const unsigned FULL = 0xffffffffu;
-    const long long s = (long long)blockIdx.x * LIST_NT + tid;
-    bool active = s < a.n;
-    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = make_float4(1.f, 0.f, 0.f, 0.f), Ti1 = Ai, Ti2 = Ai, Ti3 = Ai;
-    int ti = 0, count = 0;
-    if (active) {
-        Ci = a.C3[s];
-        ti = __float_as_int(Ci.w);
-        if ((ti & PT_GHOST) || !((a.elastic_mask >> (ti & 7)) & 1u)) active = false;
-    }
-    if (active) {
-        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
-        Ti1 = a.T01[s]; Ti2 = a.T2R[s]; Ti3 = a.R2[s];
-        count = (int)cnt[s];
-    }
-    int cmax = count;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
-    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
-    const float hi2 = a.k2 * Ai.w * Ai.w;
-    const float wdp = a.wdeltap[ti & 7], nexp = a.nexp[ti & 7];
-    const float wdp1 = wdp > 0.f ? frcp(wdp) : 0.f;
-    float arho = 0.f, au = 0.f, av = 0.f, aw = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-    unsigned npairs = 0;
-    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-    float4 A_a = Ai, B_a = Bi, C_a = Ci, T1_a = Ti1, T2_a = Ti2, T3_a = Ti3;
-    if (count > 0) {
-        const size_t j = e_a & LIST_JMASK;
-        ld_256(a.AB + 2 * j, A_a, B_a);
-        C_a = a.C3[j]; T1_a = a.T01[j]; T2_a = a.T2R[j]; T3_a = a.R2[j];
-    }
-    for (int k = 0; k < cmax; k++) {
-        const uint32_t e = e_a;
-        const float4 Aj = A_a, Bj = B_a, Cj = C_a, Tj1 = T1_a, Tj2 = T2_a, Tj3 = T3_a;
-        e_a = e_b;
-        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-        if (k + 1 < count) {
-            const size_t j = e_a & LIST_JMASK;
-            ld_256(a.AB + 2 * j, A_a, B_a);
-            C_a = a.C3[j]; T1_a = a.T01[j]; T2_a = a.T2R[j]; T3_a = a.R2[j];
-        }
-        if (k < count) {
-            const float4 T = s_T[e >> LIST_JBITS];
-            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
-            const float r2 = xij * xij + yij * yij + zij * zij;
-            const int tj = __float_as_int(Cj.w) & 7;
-            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.elastic_mask >> tj) & 1u)) {
-                npairs++;
-                const float rinv = r2 > 1e-24f ? frsqrt(r2) : 0.0f;
-                const float hij = 0.5f * (Ai.w + Aj.w);
-                const float h1 = frcp(hij);
-                float w, dw;
-                sph_kernel<K>(r2 * rinv * h1, w, dw);
-                const float fac = a.kfac * hpow<DIM>(h1);
-                const float wij = w * fac;
-                const float gt = dw * fac * h1 * rinv;
-                const float dwx = gt * xij, dwy = gt * yij, dwz = gt * zij;
-                const float mb = Bj.w;
-                const float uij = Bi.x - Bj.x, vij = Bi.y - Bj.y, wwij = Bi.z - Bj.z;
-                const float vdotx = uij * xij + vij * yij + wwij * zij;
-                arho += mb * (uij * dwx + vij * dwy + wwij * dwz);   // basic_equations.py:190-192
-                // MomentumEquationWithStress solid_mech/basic.py:267-387
-                float fab = 0.f;
-                if (wdp > 0.f) fab = powf(wij * wdp1, nexp);
-                const float m00 = Ti1.x + Tj1.x + fab * (Ti2.z + Tj2.z);
-                const float m01 = Ti1.y + Tj1.y + fab * (Ti2.w + Tj2.w);
-                const float m02 = Ti1.z + Tj1.z + fab * (Ti3.x + Tj3.x);
-                const float m11 = Ti1.w + Tj1.w + fab * (Ti3.y + Tj3.y);
-                const float m12 = Ti2.x + Tj2.x + fab * (Ti3.z + Tj3.z);
-                const float m22 = Ti2.y + Tj2.y + fab * (Ti3.w + Tj3.w);
-                float fu = mb * (m00 * dwx + m01 * dwy + m02 * dwz);
-                float fv = mb * (m01 * dwx + m11 * dwy + m12 * dwz);
-                float fw = mb * (m02 * dwx + m12 * dwy + m22 * dwz);
-                // MonaghanArtificialViscosity basic_equations.py:240-257
-                const float rhoij1 = 2.0f * frcp(Ci.x + Cj.x);
-                if (vdotx < 0.f) {
-                    const float cij = 0.5f * (Ci.z + Cj.z);
-                    const float muij = hij * vdotx * frcp(r2 + 0.01f * hij * hij);
-                    const float piij = (-a.alpha * cij * muij + a.beta * muij * muij) * rhoij1;
-                    fu -= mb * piij * dwx;
-                    fv -= mb * piij * dwy;
-                    fw -= mb * piij * dwz;
-                }
-                au += fu; av += fv; aw += fw;
-                if (tj == (ti & 7)) {   // XSPHCorrection(sources=[dest]) basic_equations.py:290-295
-                    const float f = -a.eps_xsph * mb * wij * rhoij1;
-                    ax += f * uij; ay += f * vij; az += f * wwij;
-                }
-            }
-        }
-    }
-    if (active) {
-        const uint32_t g = a.perm[s];
-        a.arho[g] = arho;
-        a.au[g] = au; a.av[g] = av; a.aw[g] = aw;
-        a.ax[g] = ax + Bi.x; a.ay[g] = ay + Bi.y; a.az[g] = az + Bi.z;   // post_loop :297-300
-    }
-    if (a.pair_counter) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
-        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
-    }
-}
-
-struct StageSolidArgs {
-    double *x, *y, *z, *u, *v, *w, *rho, *s[6];
-    double *x0, *y0, *z0, *u0, *v0, *w0, *rho0, *s0[6];
-    const float *au, *av, *aw, *ax, *ay, *az, *arho, *as[6];
-    const uint8_t *ptype;
-    long long pool_end;
-    int arr, which;
-    double f;
-};
-// SolidMechStep integrator_step.py:173-252 (real particles)
-__device__ __forceinline__ void stage_solid_body(const StageSolidArgs &a)
-{
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.pool_end) return;
-    uint8_t t = a.ptype[g];
-    if (t == PT_INVALID || (t & PT_GHOST)) return;
-    if (a.arr >= 0 && (t & 7) != a.arr) return;
-    if (a.which == 0) {
-        a.x0[g] = a.x[g]; a.y0[g] = a.y[g]; a.z0[g] = a.z[g];
-        a.u0[g] = a.u[g]; a.v0[g] = a.v[g]; a.w0[g] = a.w[g];
-        a.rho0[g] = a.rho[g];
-#pragma unroll
-        for (int k = 0; k < 6; k++) a.s0[k][g] = a.s[k][g];
-        return;
-    }
-    const double f = a.f;
-    a.u[g] = a.u0[g] + f * (double)a.au[g];
-    a.v[g] = a.v0[g] + f * (double)a.av[g];
-    a.w[g] = a.w0[g] + f * (double)a.aw[g];
-    a.x[g] = a.x0[g] + f * (double)a.ax[g];
-    a.y[g] = a.y0[g] + f * (double)a.ay[g];
-    a.z[g] = a.z0[g] + f * (double)a.az[g];
-    a.rho[g] = a.rho0[g] + f * (double)a.arho[g];
-#pragma unroll
-    for (int k = 0; k < 6; k++) a.s[k][g] = a.s0[k][g] + f * (double)a.as[k][g];
-}
-__global__ void k_stage_solid(StageSolidArgs a) { stage_solid_body(a); }
-__global__ void k_stage_solid_devdt(StageSolidArgs a, const double *__restrict__ tc)
-{
-    const double dt = tc[0];
-    a.f = a.which == 1 ? 0.5 * dt : dt;
-    stage_solid_body(a);
-}
-
-// refresh the packed positions in the FROZEN sorted order / cell frames of the last
-// build and measure how far particles moved (and h grew) since then.
-// red_u32[0] = max |dx|^2 (float bits), red_u32[1] = max (h - h_build) (float bits, >= 0)
-__global__ void k_pack_pos_light(const double *__restrict__ x, const double *__restrict__ y,
-                                 const double *__restrict__ z, const double *__restrict__ h,
-                                 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skey,
-                                 long long n, GridDev G, const float4 *__restrict__ A0,
-                                 float4 *__restrict__ A, float4 *__restrict__ AB,
-                                 unsigned *__restrict__ red_u32)
-{
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    float d2 = 0.f, dh = 0.f;
-    if (s < n) {
-        const uint32_t g = perm[s];
-        uint32_t key = skey[s];
-        const uint32_t cx = key % (uint32_t)G.nc[0];
-        key /= (uint32_t)G.nc[0];
-        const uint32_t cy = key % (uint32_t)G.nc[1];
-        const uint32_t cz = key / (uint32_t)G.nc[1];
-        float4 a;
-        a.x = (float)(x[g] - (G.xmin[0] + (double)cx * G.cell[0]));
-        a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell[1]));
-        a.z = (float)(z[g] - (G.xmin[2] + (double)cz * G.cell[2]));
-        a.w = (float)h[g];
-        A[s] = a;
-        AB[2 * s] = a;
-        const float4 b = A0[s];
-        const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
-        d2 = dx * dx + dy * dy + dz * dz;
-        dh = fmaxf(a.w - b.w, 0.f);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-        dh = fmaxf(dh, __shfl_xor_sync(0xffffffffu, dh, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (d2 > 0.f) atomicMax(&red_u32[0], __float_as_uint(d2));
-        if (dh > 0.f) atomicMax(&red_u32[1], __float_as_uint(dh));
-    }
-}
-
-
-// neighbour query for one destination particle with the pair kernel's accept test
-// (cell by cell; periodic axes wrap).  One warp.
-__global__ void k_neighbors(const float4 *__restrict__ A, const float4 *__restrict__ C,
-                            const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ skey,
-                            const uint32_t *__restrict__ perm, long long s, int src_arr,
-                            long long src_off, GridDev G, float k2,
-                            uint32_t *__restrict__ out, long long cap, unsigned long long *count)
-{
-    const int lane = threadIdx.x;
-    const int ncx = G.nc[0], ncy = G.nc[1], ncz = G.nc[2];
-    const float4 Ai = A[s];
-    uint32_t kq = skey[s];
-    const int cx = (int)(kq % (uint32_t)ncx);
-    kq /= (uint32_t)ncx;
-    const int cy = (int)(kq % (uint32_t)ncy), cz = (int)(kq / (uint32_t)ncy);
-    const float hi2 = k2 * Ai.w * Ai.w;
-    unsigned long long n = 0;
-    for (int r = 0; r < 27; r++) {
-        const int dx = (r % 3) - 1, dy = ((r / 3) % 3) - 1, dz = (r / 9) - 1;
-        int xx = cx + dx, yy = cy + dy, zz = cz + dz;
-        if (G.periodic[0]) xx = (xx + ncx) % ncx;
-        if (G.periodic[1]) yy = (yy + ncy) % ncy;
-        if (G.periodic[2]) zz = (zz + ncz) % ncz;
-        if (xx < 0 || xx >= ncx || yy < 0 || yy >= ncy || zz < 0 || zz >= ncz) continue;
-        const uint32_t c = (uint32_t)xx + (uint32_t)ncx * ((uint32_t)yy + (uint32_t)ncy * (uint32_t)zz);
-        const uint32_t rs = cell_start[c], re = cell_start[c + 1];
-        for (uint32_t t0 = rs; t0 < re; t0 += 32) {
-            const uint32_t t = t0 + lane;
-            bool ok = false;
-            if (t < re) {
-                const float4 Aj = A[t];
-                const float xij = Ai.x - (float)dx * (float)G.cell[0] - Aj.x;
-                const float yij = Ai.y - (float)dy * (float)G.cell[1] - Aj.y;
-                const float zij = Ai.z - (float)dz * (float)G.cell[2] - Aj.z;
-                const float r2 = xij * xij + yij * yij + zij * zij;
-                ok = ((r2 < hi2) || (r2 < k2 * Aj.w * Aj.w)) &&
-                     ((__float_as_int(C[t].w) & 7) == src_arr);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const unsigned long long pos = n + __popc(m & ((1u << lane) - 1u));
-                if ((long long)pos < cap) out[pos] = (uint32_t)((long long)perm[t] - src_off);
-            }
-            n += __popc(m);
-        }
-    }
-    if (lane == 0) *count = n;
-}
-
-// --------------------------------------------------------------------------
-// halo / migration kernels
-// --------------------------------------------------------------------------
-// mode 0: flag = lo <= x < hi ; mode 1: flag = x < lo ; mode 2: flag = x >= hi ;
-// mode 3: flag = keep (lo <= x < hi)
-__global__ void k_flag_range(const double *__restrict__ x, long long off, long long n, double lo,
-                             double hi, int mode, uint32_t *__restrict__ flag)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    uint32_t f = 0;
-    if (i < n) {
-        const double v = x[off + i];
-        if (mode == 0 || mode == 3) f = (v >= lo && v < hi);
-        else if (mode == 1) f = v < lo;
-        else f = v >= hi;
-    }
-    flag[i] = f;  // flag[n] = 0 so that scan[n] = total
-}
-
-__global__ void k_gather_f64(const double *__restrict__ src, long long off, long long n,
-                             const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
-                             double *__restrict__ dst, long long dst_off)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (flag[i]) dst[dst_off + pos[i]] = src[off + i];
-}
-__global__ void k_gather_u32_as_f64(const uint32_t *__restrict__ src, long long off, long long n,
-                                    const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
-                                    double *__restrict__ dst, long long dst_off)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (flag[i]) dst[dst_off + pos[i]] = (double)src[off + i];
-}
-__global__ void k_gather_u32(const uint32_t *__restrict__ src, long long off, long long n,
-                             const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
-                             uint32_t *__restrict__ dst)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (flag[i]) dst[pos[i]] = src[off + i];
-}
-struct HaloPtrs {
-    double *p[B200SPH_HALO_FIELDS];
-};
-// all B200SPH_HALO_FIELDS of the selected particles in one launch (field-major, tight)
-__global__ void k_halo_gather_flag(HaloPtrs P, long long off, long long n, const uint32_t *__restrict__ flag,
-                                   const uint32_t *__restrict__ pos, double *__restrict__ dst, long long tot)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !flag[i]) return;
-    const long long k = pos[i];
-#pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) dst[(long long)f * tot + k] = P.p[f][off + i];
-}
-__global__ void k_halo_gather_idx(HaloPtrs P, long long off, const uint32_t *__restrict__ idx, long long n,
-                                  double *__restrict__ dst)
-{
-    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const long long i = idx[k];
-#pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) dst[(long long)f * n + k] = P.p[f][off + i];
-}
-__global__ void k_halo_scatter(HaloPtrs P, long long o, const double *__restrict__ src, long long stride, long long n)
-{
-    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-#pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) P.p[f][o + k] = src[(long long)f * stride + k];
-}
-struct HaloAllArgs {
-    int narr;
-    long long prefix[B200SPH_MAX_ARRAYS + 1];  // particles before array a in the message
-    long long off[B200SPH_MAX_ARRAYS];         // pool offset of the first particle addressed
-    const uint32_t *idx[B200SPH_MAX_ARRAYS];   // gather: saved selection (relative to off); scatter: unused
-};
-// the refresh message of ALL arrays in one launch: block of array a starts at
-// 9 * prefix[a] doubles, field-major and tight inside the block.  `dst` may be a peer
-// pointer (the neighbour's staging buffer): then this kernel is pack + send in one.
-__global__ void k_halo_gather_all(HaloPtrs P, HaloAllArgs A, double *__restrict__ dst)
-{
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= A.prefix[A.narr]) return;
-    int a = 0;
-    while (k >= A.prefix[a + 1]) a++;
-    const long long r = k - A.prefix[a], cnt = A.prefix[a + 1] - A.prefix[a];
-    const long long i = A.off[a] + A.idx[a][r];
-    double *out = dst + B200SPH_HALO_FIELDS * A.prefix[a] + r;
-#pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) out[(long long)f * cnt] = P.p[f][i];
-}
-struct RepackArgs {
-    const uint32_t *rank, *skey;   // rank == nullptr: no repack
-    float4 *A, *AB;
-    GridDev G;
-};
-// ghost values refreshed in place; with a valid neighbour build the ghosts' packed
-// cell-relative positions are refreshed in the same pass (x, y, z, h are fields 0, 1, 2, 7)
-__global__ void k_halo_scatter_all(HaloPtrs P, HaloAllArgs A, const double *__restrict__ src, RepackArgs R)
-{
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= A.prefix[A.narr]) return;
-    int a = 0;
-    while (k >= A.prefix[a + 1]) a++;
-    const long long r = k - A.prefix[a], cnt = A.prefix[a + 1] - A.prefix[a];
-    const double *in = src + B200SPH_HALO_FIELDS * A.prefix[a] + r;
-    double v[B200SPH_HALO_FIELDS];
-#pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) {
-        v[f] = in[(long long)f * cnt];
-        P.p[f][A.off[a] + r] = v[f];
-    }
-    if (R.rank) {
-        const uint32_t s = R.rank[A.off[a] + r];
-        uint32_t key = R.skey[s];
-        const uint32_t cx = key % (uint32_t)R.G.nc[0];
-        key /= (uint32_t)R.G.nc[0];
-        const uint32_t cy = key % (uint32_t)R.G.nc[1];
-        const uint32_t cz = key / (uint32_t)R.G.nc[1];
-        float4 q;
-        q.x = (float)(v[0] - (R.G.xmin[0] + (double)cx * R.G.cell[0]));
-        q.y = (float)(v[1] - (R.G.xmin[1] + (double)cy * R.G.cell[1]));
-        q.z = (float)(v[2] - (R.G.xmin[2] + (double)cz * R.G.cell[2]));
-        q.w = (float)v[7];
-        R.A[s] = q;
-        R.AB[2 * s] = q;
-    }
-}
-__global__ void k_drift_ratio(const unsigned *__restrict__ red_u32, float kr, float S, double *__restrict__ out)
-{
-    const float need = 2.0f * sqrtf(__uint_as_float(red_u32[0])) + kr * __uint_as_float(red_u32[1]);
-    out[0] = S > 0.f ? (double)(need / S) : 2.0;
-}
-__global__ void k_save_idx(long long n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
-                           uint32_t *__restrict__ idx)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && flag[i]) idx[pos[i]] = (uint32_t)i;
-}
-__global__ void k_f64_to_u32(const double *__restrict__ in, uint32_t *__restrict__ out, long long n)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (uint32_t)in[i];
-}
-__global__ void k_fill_u32(uint32_t *p, long long n, uint32_t v)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
+#include "pool_kernels.cuh"
+#include "scan.cuh"
+#include "nnps_kernels.cuh"
+#include "sph_kernels.cuh"
+#include "pair_kernel.cuh"
+#include "pair_list.cuh"
+#include "tvf_kernels.cuh"
+#include "solid_kernels.cuh"
+#include "halo_kernels.cuh"
 
 // --------------------------------------------------------------------------
 // host side

@@ -1,0 +1,156 @@
+// halo_kernels.cuh -- halo / migration kernels of the slab decomposition.
+// Part of the single translation unit b200sph.cu (included there, in this order; not a
+// stand-alone header).
+
+// --------------------------------------------------------------------------
+// halo / migration kernels
+// --------------------------------------------------------------------------
+// mode 0: flag = lo <= x < hi ; mode 1: flag = x < lo ; mode 2: flag = x >= hi ;
+// mode 3: flag = keep (lo <= x < hi)
+__global__ void k_flag_range(const double *__restrict__ x, long long off, long long n, double lo,
+                             double hi, int mode, uint32_t *__restrict__ flag)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint32_t f = 0;
+    if (i < n) {
+        const double v = x[off + i];
+        if (mode == 0 || mode == 3) f = (v >= lo && v < hi);
+        else if (mode == 1) f = v < lo;
+        else f = v >= hi;
+    }
+    flag[i] = f;  // flag[n] = 0 so that scan[n] = total
+}
+
+__global__ void k_gather_f64(const double *__restrict__ src, long long off, long long n,
+                             const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                             double *__restrict__ dst, long long dst_off)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) dst[dst_off + pos[i]] = src[off + i];
+}
+__global__ void k_gather_u32_as_f64(const uint32_t *__restrict__ src, long long off, long long n,
+                                    const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                                    double *__restrict__ dst, long long dst_off)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) dst[dst_off + pos[i]] = (double)src[off + i];
+}
+__global__ void k_gather_u32(const uint32_t *__restrict__ src, long long off, long long n,
+                             const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                             uint32_t *__restrict__ dst)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) dst[pos[i]] = src[off + i];
+}
+struct HaloPtrs {
+    double *p[B200SPH_HALO_FIELDS];
+};
+// all B200SPH_HALO_FIELDS of the selected particles in one launch (field-major, tight)
+__global__ void k_halo_gather_flag(HaloPtrs P, long long off, long long n, const uint32_t *__restrict__ flag,
+                                   const uint32_t *__restrict__ pos, double *__restrict__ dst, long long tot)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const long long k = pos[i];
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) dst[(long long)f * tot + k] = P.p[f][off + i];
+}
+__global__ void k_halo_gather_idx(HaloPtrs P, long long off, const uint32_t *__restrict__ idx, long long n,
+                                  double *__restrict__ dst)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long i = idx[k];
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) dst[(long long)f * n + k] = P.p[f][off + i];
+}
+__global__ void k_halo_scatter(HaloPtrs P, long long o, const double *__restrict__ src, long long stride, long long n)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) P.p[f][o + k] = src[(long long)f * stride + k];
+}
+struct HaloAllArgs {
+    int narr;
+    long long prefix[B200SPH_MAX_ARRAYS + 1];  // particles before array a in the message
+    long long off[B200SPH_MAX_ARRAYS];         // pool offset of the first particle addressed
+    const uint32_t *idx[B200SPH_MAX_ARRAYS];   // gather: saved selection (relative to off); scatter: unused
+};
+// the refresh message of ALL arrays in one launch: block of array a starts at
+// 9 * prefix[a] doubles, field-major and tight inside the block.  `dst` may be a peer
+// pointer (the neighbour's staging buffer): then this kernel is pack + send in one.
+__global__ void k_halo_gather_all(HaloPtrs P, HaloAllArgs A, double *__restrict__ dst)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.prefix[A.narr]) return;
+    int a = 0;
+    while (k >= A.prefix[a + 1]) a++;
+    const long long r = k - A.prefix[a], cnt = A.prefix[a + 1] - A.prefix[a];
+    const long long i = A.off[a] + A.idx[a][r];
+    double *out = dst + B200SPH_HALO_FIELDS * A.prefix[a] + r;
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) out[(long long)f * cnt] = P.p[f][i];
+}
+struct RepackArgs {
+    const uint32_t *rank, *skey;   // rank == nullptr: no repack
+    float4 *A, *AB;
+    GridDev G;
+};
+// ghost values refreshed in place; with a valid neighbour build the ghosts' packed
+// cell-relative positions are refreshed in the same pass (x, y, z, h are fields 0, 1, 2, 7)
+__global__ void k_halo_scatter_all(HaloPtrs P, HaloAllArgs A, const double *__restrict__ src, RepackArgs R)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.prefix[A.narr]) return;
+    int a = 0;
+    while (k >= A.prefix[a + 1]) a++;
+    const long long r = k - A.prefix[a], cnt = A.prefix[a + 1] - A.prefix[a];
+    const double *in = src + B200SPH_HALO_FIELDS * A.prefix[a] + r;
+    double v[B200SPH_HALO_FIELDS];
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) {
+        v[f] = in[(long long)f * cnt];
+        P.p[f][A.off[a] + r] = v[f];
+    }
+    if (R.rank) {
+        const uint32_t s = R.rank[A.off[a] + r];
+        uint32_t key = R.skey[s];
+        const uint32_t cx = key % (uint32_t)R.G.nc[0];
+        key /= (uint32_t)R.G.nc[0];
+        const uint32_t cy = key % (uint32_t)R.G.nc[1];
+        const uint32_t cz = key / (uint32_t)R.G.nc[1];
+        float4 q;
+        q.x = (float)(v[0] - (R.G.xmin[0] + (double)cx * R.G.cell[0]));
+        q.y = (float)(v[1] - (R.G.xmin[1] + (double)cy * R.G.cell[1]));
+        q.z = (float)(v[2] - (R.G.xmin[2] + (double)cz * R.G.cell[2]));
+        q.w = (float)v[7];
+        R.A[s] = q;
+        R.AB[2 * s] = q;
+    }
+}
+__global__ void k_drift_ratio(const unsigned *__restrict__ red_u32, float kr, float S, double *__restrict__ out)
+{
+    const float need = 2.0f * sqrtf(__uint_as_float(red_u32[0])) + kr * __uint_as_float(red_u32[1]);
+    out[0] = S > 0.f ? (double)(need / S) : 2.0;
+}
+__global__ void k_save_idx(long long n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                           uint32_t *__restrict__ idx)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) idx[pos[i]] = (uint32_t)i;
+}
+__global__ void k_f64_to_u32(const double *__restrict__ in, uint32_t *__restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)in[i];
+}
+__global__ void k_fill_u32(uint32_t *p, long long n, uint32_t v)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}

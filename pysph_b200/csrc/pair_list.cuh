@@ -1,0 +1,272 @@
+// pair_list.cuh -- persistent neighbour lists: k_list_build and the dominant kernel k_pair_list.
+// Part of the single translation unit b200sph.cu (included there, in this order; not a
+// stand-alone header).
+
+// --------------------------------------------------------------------------
+// persistent neighbour lists (the default fast path)
+//
+// k_list_build runs the reference's accept test widened by a skin S
+//   r^2 < (k h_i + S)^2  or  r^2 < (k h_j + S)^2
+// once per (re)build and stores, for every destination, the sorted indices of
+// the candidates that pass, 32 destinations interleaved ("transposed") so that
+// the consumer reads them coalesced.  The lists stay valid while
+//   2 max|x - x_build| + k max(h - h_build) <= S            (checked every update),
+// so an evaluation normally only runs k_pair_list: one THREAD per destination
+// walks its list, re-applies the EXACT accept test of linked_list_nnps.pyx:188
+// on the current positions and evaluates the equations.  Results are identical
+// to rebuilding the neighbours every evaluation; only the cost is amortised.
+// entry = j (26 bits, sorted index) | code << 26, code = (dxc+1) + 4 (dy+1) + 16 (dz+1)
+// --------------------------------------------------------------------------
+#define LIST_JBITS 26
+#define LIST_JMASK 0x03FFFFFFu
+#define LIST_NT 128
+// Skin controller.  Per evaluation a build costs c0 (1+s)^3 (list entries) + R / L(s)
+// (rebuild cost R over a lifetime L that grows linearly with the skin s); the minimum is
+// where L s = R / (3 c0 (1+s)^2) ~ 2 for the measured R / c0 ~ 5.5, i.e. the target
+// lifetime is L* = SKIN_KAPPA / s evaluations.
+#define SKIN_KAPPA 2.0
+
+struct ListBuildArgs {
+    const float4 *A;
+    const uint32_t *cell_start, *skey;
+    long long n;
+    int ncx, ncy, ncz;
+    int px, py, pz;                 // periodic axes (cell indices wrap, images shift by nc * cell)
+    float cellx, celly, cellz;      // internal cell edges (>= k hmax + S)
+    float kr, S;     // radius scale, absolute skin
+    uint32_t *cnt;   // [n] neighbours per destination
+    uint32_t *lst;   // null: count only
+    int capg;        // entries reserved per destination
+    unsigned *max_count;
+};
+
+// PERIODIC = false: 9 candidate rows (3 consecutive cells each, contiguous in the
+// sorted arrays).  PERIODIC = true: the same 9 rows with wrapped y / z indices plus, on a
+// periodic x axis, up to 2 single-cell segments per row for the cells that wrap;
+// because coordinates are relative to the particle's own cell and a periodic axis is
+// tiled exactly (L = nc * cell), the image shift of a wrapped neighbour cell is the
+// same "- d * cell" offset as for an ordinary neighbour cell -- the consumer kernel does
+// not know about periodicity at all, and no ghost particles are materialised
+// (reference: _create_ghosts_periodic, nnps_base.pyx:744-940, copies the particles).
+template <bool PERIODIC>
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildArgs a)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const long long first = ((long long)blockIdx.x * PAIR_WARPS + warp) * PAIR_CHUNK;
+    uint32_t cur_key = 0xFFFFFFFFu;
+    int cx = 0;
+    uint32_t r_rs = 0, r_b1 = 0, r_b2 = 0, r_re = 0;
+    unsigned wmax = 0;
+    for (int kk = 0; kk < PAIR_CHUNK; kk++) {
+        const long long s = first + kk;
+        if (s >= a.n) break;
+        const float4 Ai = a.A[s];
+        const uint32_t key = a.skey[s];
+        if (key != cur_key) {
+            cur_key = key;
+            uint32_t kq = key;
+            cx = (int)(kq % (uint32_t)a.ncx);
+            kq /= (uint32_t)a.ncx;
+            const int cy = (int)(kq % (uint32_t)a.ncy);
+            const int cz = (int)(kq / (uint32_t)a.ncy);
+            r_rs = r_b1 = r_b2 = r_re = 0;
+            if (!PERIODIC) {
+                if (lane < 9) {
+                    const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
+                    if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
+                        const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+                        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
+                        r_rs = a.cell_start[base + x0];
+                        r_b1 = a.cell_start[base + cx];
+                        r_b2 = a.cell_start[base + cx + 1];
+                        r_re = a.cell_start[base + x1 + 1];
+                    }
+                }
+            } else if (lane < 27) {
+                // 9 (dy, dz) rows with wrapped y / z (segments 0..8: the x-contiguous part of
+                // the row, clipped to the grid) + for a periodic x axis the wrapped cell that
+                // is missing at cx = 0 (segments 9..17, dxc = -1) / cx = ncx - 1 (18..26, +1)
+                const int q = lane % 9, kind = lane / 9;
+                int yy = cy + (q % 3) - 1, zz = cz + (q / 3) - 1;
+                if (a.py) yy = (yy + a.ncy) % a.ncy;
+                if (a.pz) zz = (zz + a.ncz) % a.ncz;
+                if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
+                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+                    if (kind == 0) {
+                        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
+                        r_rs = a.cell_start[base + x0];
+                        r_b1 = a.cell_start[base + cx];
+                        r_b2 = a.cell_start[base + cx + 1];
+                        r_re = a.cell_start[base + x1 + 1];
+                    } else if (kind == 1 && a.px && cx == 0) {
+                        r_rs = a.cell_start[base + a.ncx - 1];
+                        r_re = a.cell_start[base + a.ncx];
+                    } else if (kind == 2 && a.px && cx == a.ncx - 1) {
+                        r_rs = a.cell_start[base];
+                        r_re = a.cell_start[base + 1];
+                    }
+                }
+            }
+        }
+        float hi = a.kr * Ai.w + a.S;
+        const float hi2 = hi * hi;
+        uint32_t *out = a.lst ? a.lst + ((size_t)(s >> 5) * (size_t)a.capg) * 32u + (uint32_t)(s & 31) : nullptr;
+        unsigned count = 0;
+        for (int r = 0; r < (PERIODIC ? 27 : 9); r++) {
+            const uint32_t rs = __shfl_sync(FULL, r_rs, r);
+            const uint32_t re = __shfl_sync(FULL, r_re, r);
+            if (rs >= re) continue;
+            uint32_t b1 = 0, b2 = 0, rcode;
+            float xoff, yoff, zoff;
+            if (!PERIODIC) {
+                b1 = __shfl_sync(FULL, r_b1, r);
+                b2 = __shfl_sync(FULL, r_b2, r);
+                xoff = Ai.x;
+                yoff = Ai.y - (float)((r % 3) - 1) * a.celly;
+                zoff = Ai.z - (float)((r / 3) - 1) * a.cellz;
+                rcode = (uint32_t)(4 * (r % 3) + 16 * (r / 3));
+            } else {
+                const int q = r % 9;
+                b1 = __shfl_sync(FULL, r_b1, r);
+                b2 = __shfl_sync(FULL, r_b2, r);
+                xoff = Ai.x;
+                yoff = Ai.y - (float)((q % 3) - 1) * a.celly;
+                zoff = Ai.z - (float)((q / 3) - 1) * a.cellz;
+                rcode = (uint32_t)(4 * (q % 3) + 16 * (q / 3));
+            }
+            const int kind = PERIODIC ? r / 9 : 0;
+            for (uint32_t t0 = rs; t0 < re; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                bool ok = false;
+                uint32_t dxc1 = 0;
+                if (t < re) {
+                    const float4 Aj = a.A[t];
+                    // dxc + 1: position inside the row, or the wrapped cell's fixed offset
+                    dxc1 = kind == 0 ? (uint32_t)(t >= b1) + (uint32_t)(t >= b2) : (kind == 1 ? 0u : 2u);
+                    const float xij = xoff - Aj.x - ((float)dxc1 - 1.0f) * a.cellx;
+                    const float yij = yoff - Aj.y;
+                    const float zij = zoff - Aj.z;
+                    const float r2 = xij * xij + yij * yij + zij * zij;
+                    const float hj = a.kr * Aj.w + a.S;
+                    ok = (r2 < hi2) || (r2 < hj * hj);
+                }
+                const unsigned m = __ballot_sync(FULL, ok);
+                if (ok && out) {
+                    const unsigned pos = count + __popc(m & lt_mask);
+                    if (pos < (unsigned)a.capg) out[(size_t)pos * 32u] = t | ((rcode + dxc1) << LIST_JBITS);
+                }
+                count += __popc(m);
+            }
+        }
+        if (lane == 0) a.cnt[s] = count;
+        wmax = max(wmax, count);
+    }
+    if (lane == 0 && wmax) atomicMax(a.max_count, wmax);
+}
+
+// one 256-bit read-only load (LDG.E.ENL2.256 on sm_100a): a whole 32-byte sector
+__device__ __forceinline__ void ld_256(const float4 *p, float4 &b, float4 &c)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w), "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w)
+                 : "l"(p));
+}
+
+// The list consumer (the default fast path): one THREAD per destination walks its
+// list.  Per entry it gathers {A, B} = (x, y, z, h, u, v, w, m) with ONE 256-bit load
+// (exactly one 32-byte sector) and C = (rho, p/rho^2, cs, type) with one 128-bit load,
+// both issued one iteration ahead of their use; list entries stream in (evict-first)
+// two iterations ahead.  The gathers are what bounds this kernel (L1 tag stage, see
+// profiles/), hence the sector-sized records.
+template <int K, int DIM>
+__global__ void __launch_bounds__(LIST_NT, 4) k_pair_list(const PairArgs a, const uint32_t *__restrict__ cnt,
+                                                         const uint32_t *__restrict__ lst, const int capg)
+{
+    __shared__ float4 s_T[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
+        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
+    }
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const long long s = (long long)blockIdx.x * LIST_NT + tid;
+    bool active = s < a.n;
+    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = Ai;
+    unsigned long long mask_i = 0;
+    int count = 0;
+    if (active) {
+        Ci = a.C[s];
+        const int ti = __float_as_int(Ci.w);
+        mask_i = a.emask[ti & 7];
+        if ((a.real_only && (ti & PT_GHOST)) || !mask_i) active = false;
+    }
+    if (active) {
+        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
+        count = (int)cnt[s];
+    }
+    int cmax = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
+    const float hi2 = a.k2 * Ai.w * Ai.w;
+    const float tmpi = Ci.y;
+    Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    unsigned npairs = 0;
+    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
+    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
+    float4 A_a = Ai, B_a = Bi, C_a = Ci;
+    if (count > 0) {
+        const size_t j = e_a & LIST_JMASK;
+        ld_256(a.AB + 2 * j, A_a, B_a);
+        C_a = a.C[j];
+    }
+    for (int k = 0; k < cmax; k++) {
+        const uint32_t e = e_a;
+        const float4 Aj = A_a, Bj = B_a, Cj = C_a;
+        e_a = e_b;
+        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
+        if (k + 1 < count) {
+            const size_t j = e_a & LIST_JMASK;
+            ld_256(a.AB + 2 * j, A_a, B_a);
+            C_a = a.C[j];
+        }
+        if (k < count) {
+            const float4 T = s_T[e >> LIST_JBITS];
+            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+            const float r2 = xij * xij + yij * yij + zij * zij;
+            // the exact accept test, linked_list_nnps.pyx:188
+            if ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w))
+                pair_body<K, DIM>(a, make_float4(xij, yij, zij, Aj.w), Bj, Cj, Ai, Bi, Ci, mask_i, tmpi,
+                                  acc, npairs);
+        }
+    }
+    if (active) {
+        unsigned all_bits = 0;
+#pragma unroll
+        for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
+        const uint32_t g = a.perm[s];
+        if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
+        if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;
+        if (all_bits & B200SPH_EQ_MOMENTUM) {
+            // post_loop wc/basic.py:259-269
+            const float fu = acc.au + a.gx, fv = acc.av + a.gy, fw = acc.aw + a.gz;
+            a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
+            a.dt_cfl[g] = acc.cfl;
+            a.dt_force[g] = fu * fu + fv * fv + fw * fw;
+        } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
+            a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
+        }
+        if (all_bits & B200SPH_EQ_XSPH) {
+            // post_loop basic_equations.py:297-300
+            a.ax[g] = acc.ax + Bi.x; a.ay[g] = acc.ay + Bi.y; a.az[g] = acc.az + Bi.z;
+        }
+    }
+    if (a.pair_counter) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
+        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
+    }
+}

@@ -1,0 +1,322 @@
+// tvf_kernels.cuh -- EDAC / transport-velocity passes.
+// Part of the single translation unit b200sph.cu (included there, in this order; not a
+// stand-alone header).
+
+// --------------------------------------------------------------------------
+// EDAC scheme, transport-velocity branch (wc/edac.py:776-880): two passes over the same
+// persistent neighbour lists.  Sorted records: AB = {A, B} as for k_pair_list,
+// C2 = (rho, p, V, type) [ctx->C], Dv = (uhat-u, vhat-v, what-w, pavg), PT = (p, type)
+// --------------------------------------------------------------------------
+struct TvfArgs {
+    const float4 *AB;
+    float4 *C2, *Dv;
+    const float2 *PT;
+    const uint32_t *perm;
+    double *rho;
+    float *V, *pavg, *au, *av, *aw, *auhat, *avhat, *awhat, *ap;
+    long long n;
+    float cellx, celly, cellz, k2, kfac;
+    unsigned fluid_mask, eqbits;
+    int bql;
+    float pb, nu, edac_nu, c0, alpha, gx, gy, gz;  // gx.. already damped
+    unsigned long long *pair_counter;
+};
+
+__global__ void k_pack_tvf(const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
+                           const double *__restrict__ m, const double *__restrict__ uh, const double *__restrict__ vh,
+                           const double *__restrict__ wh, const double *__restrict__ pf, const float *__restrict__ pavg,
+                           const uint8_t *__restrict__ ptype, const uint32_t *__restrict__ perm, long long n,
+                           float4 *__restrict__ B, float4 *__restrict__ AB, float4 *__restrict__ C2,
+                           float4 *__restrict__ Dv, float2 *__restrict__ PT)
+{
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t g = perm[s];
+    const int t = (int)ptype[g];
+    const double ug = u[g], vg = v[g], wg = w[g];
+    float4 b;
+    b.x = (float)ug; b.y = (float)vg; b.z = (float)wg; b.w = (float)m[g];
+    B[s] = b;
+    AB[2 * s + 1] = b;
+    // differences of nearly equal numbers: formed in fp64, then rounded
+    Dv[s] = make_float4((float)(uh[g] - ug), (float)(vh[g] - vg), (float)(wh[g] - wg), pavg[g]);
+    const float p = (float)pf[g];
+    PT[s] = make_float2(p, __int_as_float(t));
+    C2[s] = make_float4(0.f, p, 1.f, __int_as_float(t));   // rho, V filled in by pass 1
+}
+
+// group 1 (real=False): V_i = sum_j W_ij, rho_i = m_i V_i (transport_velocity.py:52-58) and the
+// neighbour-average pressure (wc/edac.py:69-79), every fluid particle incl. ghosts
+template <int K, int DIM>
+__global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const uint32_t *__restrict__ cnt,
+                                                         const uint32_t *__restrict__ lst, const int capg)
+{
+    __shared__ float4 s_T[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
+        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
+    }
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const long long s = (long long)blockIdx.x * LIST_NT + tid;
+    bool active = s < a.n;
+    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai;
+    int count = 0;
+    if (active) {
+        const int ti = __float_as_int(a.PT[s].y);
+        if (!((a.fluid_mask >> (ti & 7)) & 1u)) active = false;
+    }
+    if (active) {
+        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
+        count = (int)cnt[s];
+    }
+    int cmax = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
+    const float hi2 = a.k2 * Ai.w * Ai.w;
+    float wsum = 0.f, psum = 0.f, nn = 0.f;
+    unsigned npairs = 0;
+    // entries two iterations ahead, records one iteration ahead (as in k_pair_list)
+    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
+    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
+    float4 A_a = Ai;
+    float2 P_a = make_float2(0.f, 0.f);
+    if (count > 0) {
+        const size_t j = e_a & LIST_JMASK;
+        A_a = a.AB[2 * j];
+        P_a = a.PT[j];
+    }
+    for (int k = 0; k < cmax; k++) {
+        const uint32_t e = e_a;
+        const float4 Aj = A_a;
+        const float2 Pj = P_a;
+        e_a = e_b;
+        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
+        if (k + 1 < count) {
+            const size_t j = e_a & LIST_JMASK;
+            A_a = a.AB[2 * j];
+            P_a = a.PT[j];
+        }
+        if (k < count) {
+            const float4 T = s_T[e >> LIST_JBITS];
+            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+            const float r2 = xij * xij + yij * yij + zij * zij;
+            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Pj.y) & 7)) & 1u)) {
+                npairs++;
+                const float rij = sqrtf(r2);
+                const float h1 = frcp(0.5f * (Ai.w + Aj.w));
+                float w, dw;
+                sph_kernel<K>(rij * h1, w, dw);
+                wsum += w * a.kfac * hpow<DIM>(h1);
+                psum += Pj.x;
+                nn += 1.0f;
+            }
+        }
+    }
+    if (active) {
+        const uint32_t g = a.perm[s];
+        const float rho = Bi.w * wsum;
+        a.V[g] = wsum;
+        a.rho[g] = (double)rho;
+        float4 *c2 = a.C2 + s;
+        c2->x = rho;          // .y (p) and .w (type) were written by k_pack_tvf; other
+        c2->z = wsum;         // threads read only those two while this kernel runs
+        if (a.bql) {
+            const float pv = nn > 0.f ? psum / nn : 0.f;
+            a.pavg[g] = pv;
+            a.Dv[s].w = pv;
+        }
+    }
+    if (a.pair_counter) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
+        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
+    }
+}
+
+// group 2 (real=True): pressure gradient with the background-pressure term, artificial /
+// physical viscosity, artificial stress and the EDAC pressure evolution, fused
+template <int K, int DIM>
+__global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const uint32_t *__restrict__ cnt,
+                                                         const uint32_t *__restrict__ lst, const int capg)
+{
+    __shared__ float4 s_T[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
+        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
+    }
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const long long s = (long long)blockIdx.x * LIST_NT + tid;
+    bool active = s < a.n;
+    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = make_float4(1.f, 0.f, 1.f, 0.f), Di = Ai;
+    int count = 0;
+    if (active) {
+        Ci = a.C2[s];
+        const int ti = __float_as_int(Ci.w);
+        if ((ti & PT_GHOST) || !((a.fluid_mask >> (ti & 7)) & 1u)) active = false;
+    }
+    if (active) {
+        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
+        Di = a.Dv[s];
+        count = (int)cnt[s];
+    }
+    int cmax = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
+    const float hi2 = a.k2 * Ai.w * Ai.w;
+    const float rhoi = Ci.x, pi = Ci.y, pavg = Di.w;
+    const float Vi1 = frcp(Ci.z);
+    const float Vi2 = Vi1 * Vi1;
+    const float mi1 = frcp(Bi.w);
+    const float cs2 = a.c0 * a.c0;
+    float au = 0.f, av = 0.f, aw = 0.f, auh = 0.f, avh = 0.f, awh = 0.f, ap = 0.f;
+    unsigned npairs = 0;
+    // entries two iterations ahead, records one iteration ahead (as in k_pair_list):
+    // a record load never waits for the entry load of the same iteration
+    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
+    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
+    float4 A_a = Ai, B_a = Bi, C_a = Ci, D_a = Di;
+    if (count > 0) {
+        const size_t j = e_a & LIST_JMASK;
+        ld_256(a.AB + 2 * j, A_a, B_a);
+        C_a = a.C2[j];
+        D_a = a.Dv[j];
+    }
+    for (int k = 0; k < cmax; k++) {
+        const uint32_t e = e_a;
+        const float4 Aj = A_a, Bj = B_a, Cj = C_a, Dj = D_a;
+        e_a = e_b;
+        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
+        if (k + 1 < count) {
+            const size_t j = e_a & LIST_JMASK;
+            ld_256(a.AB + 2 * j, A_a, B_a);
+            C_a = a.C2[j];
+            D_a = a.Dv[j];
+        }
+        if (k < count) {
+            const float4 T = s_T[e >> LIST_JBITS];
+            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+            const float r2 = xij * xij + yij * yij + zij * zij;
+            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
+                npairs++;
+                const bool far = r2 > 1e-24f;
+                const float rinv = far ? frsqrt(r2) : 0.0f;
+                const float rij = r2 * rinv;
+                const float hij = 0.5f * (Ai.w + Aj.w);
+                const float h1 = frcp(hij);
+                float w, dw;
+                sph_kernel<K>(rij * h1, w, dw);
+                const float gt = dw * a.kfac * hpow<DIM>(h1) * h1 * rinv;   // DWIJ = gt * XIJ
+                const float eps = 0.01f * hij * hij;
+                const float rhoj = Cj.x, pj = Cj.y;
+                const float Vj1 = frcp(Cj.z);
+                const float common = mi1 * (Vi2 + Vj1 * Vj1);
+                const float uij = Bi.x - Bj.x, vij = Bi.y - Bj.y, wij = Bi.z - Bj.z;
+                const float vdotx = uij * xij + vij * yij + wij * zij;
+                const float rsum1 = frcp(rhoi + rhoj);
+                const float r2e1 = frcp(r2 + eps);
+                float fx = 0.f;   // multiplies XIJ in au
+                if (a.eqbits & B200SPH_TVF_PGRAD) {   // wc/edac.py:447-481
+                    const float pij = (rhoj * (pi - pavg) + rhoi * (pj - pavg)) * rsum1;
+                    fx += -pij * common * gt;
+                    const float fh = -a.pb * common * gt;
+                    auh += fh * xij;
+                    avh += fh * yij;
+                    awh += fh * zij;
+                }
+                if ((a.eqbits & B200SPH_TVF_AV) && vdotx < 0.f) {   // transport_velocity.py:432-448
+                    const float muij = hij * vdotx * r2e1;
+                    const float piij = Bj.w * (-a.alpha * a.c0 * muij) * (2.0f * rsum1);
+                    fx += -piij * gt;
+                }
+                au += fx * xij;
+                av += fx * yij;
+                aw += fx * zij;
+                if (a.eqbits & B200SPH_TVF_VISC) {   // transport_velocity.py:362-386
+                    const float etaij = 2.0f * a.nu * rhoi * rhoj * rsum1;
+                    const float tmp = common * etaij * (gt * r2) * r2e1;
+                    au += tmp * uij;
+                    av += tmp * vij;
+                    aw += tmp * wij;
+                }
+                if (a.eqbits & B200SPH_TVF_ASTRESS) {   // transport_velocity.py:473-545
+                    const float si = rhoi * gt * (Di.x * xij + Di.y * yij + Di.z * zij);
+                    const float sj = rhoj * gt * (Dj.x * xij + Dj.y * yij + Dj.z * zij);
+                    const float c = 0.5f * common;
+                    au += c * (Bi.x * si + Bj.x * sj);
+                    av += c * (Bi.y * si + Bj.y * sj);
+                    aw += c * (Bi.z * si + Bj.z * sj);
+                }
+                if (a.eqbits & B200SPH_TVF_EDAC) {   // wc/edac.py:365-386
+                    const float etaij = 2.0f * a.edac_nu * rhoi * rhoj * rsum1;
+                    ap += rhoi * frcp(rhoj) * cs2 * Bj.w * (gt * vdotx);
+                    ap += common * etaij * (gt * r2) * r2e1 * (pi - pj);
+                }
+            }
+        }
+    }
+    if (active) {
+        const uint32_t g = a.perm[s];
+        if (a.eqbits & B200SPH_TVF_PGRAD) {   // post_loop wc/edac.py:483-488
+            au += a.gx; av += a.gy; aw += a.gz;
+            a.auhat[g] = auh; a.avhat[g] = avh; a.awhat[g] = awh;
+        }
+        a.au[g] = au; a.av[g] = av; a.aw[g] = aw;
+        if (a.eqbits & B200SPH_TVF_EDAC) a.ap[g] = ap;
+    }
+    if (a.pair_counter) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
+        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
+    }
+}
+
+struct StageTvfArgs {
+    double *x, *y, *z, *u, *v, *w, *pf, *uh, *vh, *wh;
+    double *x0, *y0, *z0, *u0, *v0, *w0, *pf0;
+    const float *au, *av, *aw, *auh, *avh, *awh, *ap;
+    const uint8_t *ptype;
+    long long pool_end;
+    int arr, which;
+    double f;
+};
+// EDACTVFStep wc/edac.py:491-540 (real particles)
+__device__ __forceinline__ void stage_tvf_body(const StageTvfArgs &a)
+{
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.pool_end) return;
+    uint8_t t = a.ptype[g];
+    if (t == PT_INVALID || (t & PT_GHOST)) return;
+    if (a.arr >= 0 && (t & 7) != a.arr) return;
+    if (a.which == 0) {
+        a.x0[g] = a.x[g]; a.y0[g] = a.y[g]; a.z0[g] = a.z[g];
+        a.u0[g] = a.u[g]; a.v0[g] = a.v[g]; a.w0[g] = a.w[g];
+        a.pf0[g] = a.pf[g];
+        return;
+    }
+    const double f = a.f;
+    const double u = a.u0[g] + f * (double)a.au[g];
+    const double v = a.v0[g] + f * (double)a.av[g];
+    const double w = a.w0[g] + f * (double)a.aw[g];
+    const double uh = u + f * (double)a.auh[g];
+    const double vh = v + f * (double)a.avh[g];
+    const double wh = w + f * (double)a.awh[g];
+    a.u[g] = u; a.v[g] = v; a.w[g] = w;
+    a.uh[g] = uh; a.vh[g] = vh; a.wh[g] = wh;
+    a.x[g] = a.x0[g] + f * uh;
+    a.y[g] = a.y0[g] + f * vh;
+    a.z[g] = a.z0[g] + f * wh;
+    a.pf[g] = a.pf0[g] + f * (double)a.ap[g];
+}
+__global__ void k_stage_tvf(StageTvfArgs a) { stage_tvf_body(a); }
+__global__ void k_stage_tvf_devdt(StageTvfArgs a, const double *__restrict__ tc)
+{
+    const double dt = tc[0];
+    a.f = a.which == 1 ? 0.5 * dt : dt;
+    stage_tvf_body(a);
+}

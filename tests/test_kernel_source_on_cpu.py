@@ -25,6 +25,7 @@ from pysph_b200 import _lib, geometry as geo
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CU = os.path.join(ROOT, 'pysph_b200', 'csrc', 'b200sph.cu')
+from pysph_b200.build import read_source  # noqa: E402  (b200sph.cu with its .cuh files inlined)
 EMUL = os.path.join(HERE, 'cpu_emul')
 BUILD = os.path.join(EMUL, '_build')
 
@@ -49,7 +50,7 @@ BLOCKS = [
 
 
 def _extract():
-    src = open(CU).read().split('\n')
+    src = read_source().split('\n')
     out = []
     for first, after in BLOCKS:
         i = next(k for k, ln in enumerate(src) if ln.startswith(first))
@@ -58,14 +59,14 @@ def _extract():
         while src[j - 1].startswith('//') or src[j - 1].startswith('template <') or \
                 src[j - 1].strip() == '':
             j -= 1
-        out.append('// ---- b200sph.cu lines %d-%d, verbatim ----' % (i + 1, j))
+        out.append('// ---- b200sph.cu + *.cuh (as one text) lines %d-%d, verbatim ----' % (i + 1, j))
         out.extend(src[i:j])
     text = '\n'.join(out) + '\n'
     for name in ('k_cell_count', 'k_scatter', 'k_canon', 'k_pack_pos', 'k_list_build', 'k_pack_state', 'pair_body', 'k_pair_list', 'k_pack_tvf', 'k_tvf_pass1', 'k_tvf_pass2', 'k_pack_solid', 'k_solid_pass1',
                  'k_solid_pass2', 'eigen_sym3', 'sph_kernel<2>'):
         assert name in text, name
     # the constants the shim re-defines are the ones of the CUDA file
-    cu = open(CU).read()
+    cu = read_source()
     for d in ('#define PT_GHOST 0x08u', '#define LIST_JBITS 26', '#define LIST_JMASK 0x03FFFFFFu',
               '#define LIST_NT 128'):
         assert d in cu, d

@@ -30,9 +30,9 @@ sys.path.insert(0, EMUL)
 def _build():
     import transform
     os.makedirs(BUILD, exist_ok=True)
-    cu = os.path.join(ROOT, 'pysph_b200', 'csrc', 'b200sph.cu')
+    from pysph_b200 import build as lib_build
     cpp = os.path.join(BUILD, 'b200sph_emul.cpp')
-    text, modes = transform.transform(open(cu).read())
+    text, modes = transform.transform(lib_build.read_source())
     assert modes['k_list_build'] == 'emu::WARP' and modes['k_pair_list'] == 'emu::BLOCK' \
         and modes['k_stage'] == 'emu::SEQ'
     if not os.path.exists(cpp) or open(cpp).read() != text:
