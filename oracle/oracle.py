@@ -206,6 +206,8 @@ class Oracle(object):
         rc = self.lib.orc_nnps_update(self.h)
         if rc == -1:
             raise RuntimeError('ERROR: LinkedListNNPS requires too many cells')
+        if rc == -3:
+            raise FloatingPointError('oracle: non-finite particle positions (the run blew up)')
         if rc:
             raise RuntimeError('oracle nnps_update failed (%d)' % rc)
 

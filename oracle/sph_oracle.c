@@ -356,7 +356,9 @@ int orc_nnps_update(orc_ctx *c)
     double cs1 = 1. / c->cell_size;
     int nc[3];
     for (int d = 0; d < 3; d++) {
-        nc[d] = (int)ceil(cs1 * (c->xmax[d] - c->xmin[d]));
+        const double extent = cs1 * (c->xmax[d] - c->xmin[d]);
+        if (!(extent >= 0.0 && extent < 2147483647.0)) return -3; /* NaN / inf positions: a blown-up run */
+        nc[d] = (int)ceil(extent);
         if (nc[d] < 0) return -2;
         if (nc[d] == 0) nc[d] = 1;
         c->nc[d] = nc[d];
@@ -396,6 +398,7 @@ int orc_nnps_update(orc_ctx *c)
             int cy = real_to_int(pa->y[i] - c->xmin[1], c->cell_size);
             int cz = real_to_int(pa->z[i] - c->xmin[2], c->cell_size);
             int64_t cid = flatten_raw(cx, cy, cz, nc);
+            if (cid < 0 || cid >= ncells) return -3; /* a non-finite position */
             next[i] = head[cid];
             head[cid] = (uint32_t)i;
         }
