@@ -104,6 +104,8 @@ FULL = [
     ('test_gpu_parity', 'test_device_resident_dt_is_bitwise_the_host_path', {}),
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 2, 'n': 24, 'pattern': (0, 1, 0)}),
+    ('test_zz_gpu_gate_25k_unvalidated', 'test_dam_break_2d_gate_25k', {}),
+    ('test_output', 'test_dump_and_restart_on_device', {'tmp_path': None}),
 ]
 
 
@@ -115,7 +117,12 @@ def _call(t, emulated_library):
     mod = __import__(t[0])
     fn = getattr(mod, t[1])
     fn = getattr(fn, '__wrapped__', fn)
-    return fn(emulated_library, **t[2])
+    kw = dict(t[2])
+    if 'tmp_path' in kw:
+        import pathlib
+        import tempfile
+        kw['tmp_path'] = pathlib.Path(tempfile.mkdtemp())
+    return fn(emulated_library, **kw)
 
 
 @pytest.mark.parametrize('t', FAST, ids=_id)
