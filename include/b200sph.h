@@ -309,6 +309,12 @@ int b200sph_dt_commit(b200sph_ctx *ctx, double prev_factor, double new_factor,
                       int in_parallel, int adaptive, int advance, int snapshot_slot);
 /* wait for the snapshot of `slot` only (not for later work): out = {dt, t} */
 int b200sph_time_snapshot(b200sph_ctx *ctx, int slot, double out[2]);
+/* the final time of the run and the tolerance it is compared with (solver.py:757-760,
+ * :771-773; the reference's eps grows with the iteration count, :488, so the caller sets
+ * it before every commit): dt_commit then makes the last step land on t_final --
+ * dt = t_final - t when t + dt > t_final - eps -- and leaves dt alone once
+ * |t_final - t| < eps.  Default: +inf (never). */
+int b200sph_time_final(b200sph_ctx *ctx, double t_final, double eps);
 
 /* ---- halo exchange helpers (replace ParallelManager.update,
  *      parallel_manager.pyx:512-632).  Buffers are DEVICE pointers owned by

@@ -506,13 +506,21 @@ class WCSPHOracleSolver(object):
         return self.cfl * dt_min
 
     def _get_timestep(self):
+        # solver.py:756-776 (tf: the final time the last step lands on; eps :441, :488)
+        tf = self.p.get('tf', np.inf)
+        eps = np.finfo(float).eps * 2 * tf * max(self.count, 1) if np.isfinite(tf) else 0.0
+        if abs(tf - self.t) < eps:
+            return self.dt
         dt = self._compute_timestep()
         if self.count < self.n_damp and self.n_damp > 0:
             frac = (self.count + 1) / float(self.n_damp)
             self._damping_factor = 0.5 * (np.sin(np.pi * (-0.5 + frac)) + 1.0)
         else:
             self._damping_factor = 1.0
-        return dt * self._damping_factor
+        dt = dt * self._damping_factor
+        if (self.t + dt) > (tf - eps):
+            dt = tf - self.t
+        return dt
 
     def initialise(self):
         if not self._initialised:

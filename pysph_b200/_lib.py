@@ -170,6 +170,7 @@ SIGNATURES = {
     'b200sph_drop_ghosts': (C.c_int, [_ctx_p, C.c_int]),
     'b200sph_migrate_out': (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_double,
                                       C.c_void_p, _i64, C.POINTER(_i64)]),
+    'b200sph_time_final': (C.c_int, [_ctx_p, C.c_double, C.c_double]),
     'b200sph_snapshot_take': (C.c_int, [_ctx_p, C.c_int, C.POINTER(C.c_int),
                                         C.POINTER(C.c_int), C.POINTER(_i64)]),
     'b200sph_snapshot_fetch': (C.c_int, [_ctx_p, C.c_int, C.c_void_p, _i64]),

@@ -158,6 +158,7 @@ struct b200sph_ctx {
     double *tc = nullptr;
     bool tc_owned = false;
     double *tc_host = nullptr;          // pinned: 2 snapshot slots x 2 doubles
+    double t_final = INFINITY, t_eps = 0.0;  // b200sph_time_final: the last dt lands on t_final
     // asynchronous output snapshot (b200sph_snapshot_*): one in flight
     double *snap_buf = nullptr;         // device staging, 8-byte slots
     int64_t snap_cap = 0;               // in doubles
@@ -1863,13 +1864,21 @@ int b200sph_dt_commit(b200sph_ctx *ctx, double prev_factor, double new_factor, i
     int rc = b200sph_time_control(ctx, nullptr, nullptr);
     if (rc) return rc;
     if (!(prev_factor > 0.0) || !(new_factor > 0.0)) return set_err(ctx, "dt_commit: damping factors must be positive");
-    k_dt_commit<<<1, 1, 0, ctx->stream>>>(ctx->tc, prev_factor, new_factor, in_parallel, adaptive, advance);
+    k_dt_commit<<<1, 1, 0, ctx->stream>>>(ctx->tc, prev_factor, new_factor, in_parallel, adaptive, advance, ctx->t_final, ctx->t_eps);
     LAUNCH_CHECK();
     if (snapshot_slot >= 0) {
         if (snapshot_slot > 1) return set_err(ctx, "dt_commit: snapshot slot must be 0 or 1");
         CU(cudaMemcpyAsync(ctx->tc_host + 2 * snapshot_slot, ctx->tc, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaEventRecord(ctx->tc_evt[snapshot_slot], ctx->stream));
     }
+    return 0;
+}
+
+int b200sph_time_final(b200sph_ctx *ctx, double t_final, double eps)
+{
+    if (!(eps >= 0.0) || t_final != t_final) return set_err(ctx, "time_final: bad final time / tolerance");
+    ctx->t_final = t_final;
+    ctx->t_eps = eps;
     return 0;
 }
 

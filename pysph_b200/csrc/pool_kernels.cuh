@@ -106,17 +106,23 @@ __global__ void k_dt_propose(const long long *__restrict__ red, double *__restri
     tc[2] = (dt_min <= 0.0 || isinf(dt_min)) ? 1e20 : cfl * dt_min;
 }
 // Solver loop bookkeeping (solver.py:478-491, :647-688): t += dt; dt = damp(new dt)
-__global__ void k_dt_commit(double *__restrict__ tc, double prev_factor, double new_factor, int in_parallel, int adaptive, int advance)
+// and the last step lands on the final time (solver.py:757-760, :771-773)
+__global__ void k_dt_commit(double *__restrict__ tc, double prev_factor, double new_factor, int in_parallel, int adaptive, int advance,
+                            double t_final, double t_eps)
 {
     const double dt_old = tc[0];
     if (advance) tc[1] += dt_old;
+    const double t = tc[1];
+    if (fabs(t_final - t) < t_eps) return;  // reached the end: dt stays
     const double undamped = dt_old / prev_factor;
     double dt = undamped;
     if (adaptive) {
         dt = tc[2];
         if (!in_parallel && dt >= 1e20) dt = undamped;
     }
-    tc[0] = dt * new_factor;
+    dt *= new_factor;
+    if (t + dt > t_final - t_eps) dt = t_final - t;
+    tc[0] = dt;
 }
 // TaitEOS.loop wc/basic.py:60-65 ; TaitEOSHGCorrection.loop wc/basic.py:118-126
 __global__ void k_eos(double *__restrict__ rho, float *__restrict__ p, float *__restrict__ cs,

@@ -13,6 +13,8 @@ from .acceleration_eval import B200AccelerationEval
 from .backend import B200Backend
 from .nnps import B200NNPS
 
+EPSILON = np.finfo(float).eps * 2        # solver.py:18
+
 
 class B200Solver(object):
     def __init__(self, particles, equations, kernel, integrator, dt, tf=1.0,
@@ -88,8 +90,21 @@ class B200Solver(object):
         self._damping_factor = self._next_damping_factor()
         return dt * self._damping_factor
 
+    def _eps(self):
+        """solver.py:441, :488: the tolerance the final time is compared with."""
+        if not np.isfinite(self.tf):
+            return 0.0
+        return EPSILON * self.tf * max(self.count, 1)
+
     def _get_timestep(self):
-        return self._damp_timestep(self._compute_timestep())
+        # solver.py:756-776
+        eps = self._eps()
+        if abs(self.tf - self._t) < eps:
+            return self._dt                  # reached the end
+        dt = self._damp_timestep(self._compute_timestep())
+        if (self._t + dt) > (self.tf - eps):
+            dt = self.tf - self._t           # land exactly on the final time
+        return dt
 
     # -- device-resident dt ---------------------------------------------------
     def _use_device_dt(self):
@@ -112,6 +127,7 @@ class B200Solver(object):
         ctx = self.backend.ctx
         prev = self._damping_factor
         new = self._next_damping_factor()
+        ctx.call('b200sph_time_final', float(self.tf), float(self._eps()))
         if self.adaptive_timestep:
             ctx.call('b200sph_dt_propose', float(self.cfl), int(bool(self.fixed_h)))
             if self._tc is not None:
@@ -204,7 +220,7 @@ class B200Solver(object):
 
         def running():
             t = self._t_without_waiting() if self.integrator.device_dt else self._t
-            return self.count < max_steps and (self.tf - t) > 1e-15
+            return self.count < max_steps and (self.tf - t) > self._eps()
         while running():
             self.step()
             if dumping and self.count % pfreq == 0 and running():

@@ -199,6 +199,43 @@ def test_small_dam_break_host_logic(emulated_library):
     assert st['light_updates'] > 10 and st['deferred_failed'] >= 1 and st['list_builds'] >= 2, st
 
 
+def test_final_time_small(emulated_library):
+    """The last step lands on the final time (solver.py:756-776): dt = tf - t when the next
+    step would overshoot, the loop stops within the reference's tolerance; device-resident
+    clock (k_dt_commit) == host clock bitwise == the oracle's step count and time."""
+    import pysph_b200 as pb
+    from helpers import copy_arrays
+    from oracle import oracle as orc
+    pas, params = _small_dam_break(vscale=0.3)
+    params = dict(params, n_damp=3)
+    probe = pb.make_wcsph_solver(pas, dict(params), pb.CubicSpline(dim=3))
+    for _ in range(5):
+        probe.step()
+    tf = probe.t + 0.4 * probe.dt             # inside the 6th step
+    out = {}
+    for mode in (True, False):
+        pas, _ = _small_dam_break(vscale=0.3)
+        if mode:
+            opas = copy_arrays(pas)
+            o = orc.WCSPHOracleSolver(opas, dict(params, tf=tf), 'CubicSpline', threads=2)
+            o.initialise()
+            while (tf - o.t) > np.finfo(float).eps * 2 * tf * max(o.count, 1):
+                o.step()
+        s = pb.make_wcsph_solver(pas, dict(params), pb.CubicSpline(dim=3), device_dt=mode,
+                                 tf=tf)
+        s.solve(100)
+        s.pull()
+        assert s.count == 6 and abs(s.t - tf) <= 4 * np.finfo(float).eps * tf, (s.count, s.t, tf)
+        out[mode] = (s.t, s.dt, pas[0].x.copy(), pas[0].u.copy())
+        s.solve(100)                           # nothing left to do
+        assert s.count == 6
+        if mode:
+            assert o.count == 6 and abs(o.t - s.t) <= 1e-12 * tf and abs(o.dt - s.dt) <= 1e-5 * o.dt
+            assert np.max(np.abs(pas[0].x - opas[0].x)) <= 2e-6
+    a, b = out[True], out[False]
+    assert a[:2] == b[:2] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+
+
 def test_deferred_protocol_small(emulated_library):
     """nnps_update_deferred / nnps_confirm on the small case (the GPU version of this check is
     tests/test_gpu_parity.py::test_deferred_drift_check_protocol)."""
