@@ -44,6 +44,18 @@ class B200Solver(object):
         self.fixed_h = fixed_h
         self._commits = 0            # snapshots written: commit k -> slot k % 2
         self._tc = None
+        # what Solver.__init__ keeps for the loop and the output (solver.py:120-180)
+        self.pre_step_callbacks = []
+        self.post_step_callbacks = []
+        self.post_stage_callbacks = []
+        self.max_steps = 1 << 31
+        self.pfreq = 100
+        self.disable_output = True   # nothing is written unless a directory is set
+        self.output_directory = None
+        self.fname = 'b200'
+        self.detailed_output = False
+        self.output_only_real = True
+        self.compress_output = False
 
         self.backend = backend or B200Backend(
             self.particles, device=device, capacity_factor=capacity_factor,
@@ -58,6 +70,77 @@ class B200Solver(object):
         integrator.set_nnps(self.nnps)
         integrator.set_fixed_h(fixed_h)
         self._initialised = False
+
+    # -- the reference Solver's configuration surface (solver.py:231-384) --------
+    def add_pre_step_callback(self, callback):
+        """callback(solver) before every time step (solver.py:264-278)."""
+        self.pre_step_callbacks.append(callback)
+
+    def add_post_step_callback(self, callback):
+        """callback(solver) after every time step, before t advances (:248-262)."""
+        self.post_step_callbacks.append(callback)
+
+    def add_post_stage_callback(self, callback):
+        """callback(t, dt, stage) after every integrator stage (:231-246).  The host
+        then needs t and dt at every stage: the time step stays on the host."""
+        self.post_stage_callbacks.append(callback)
+        self.integrator.set_post_stage_callback(self._post_stage_callback)
+
+    def _post_stage_callback(self, time, dt, stage):     # solver.py:781-785
+        for callback in self.post_stage_callbacks:
+            callback(time, dt, stage)
+
+    def set_adaptive_timestep(self, value):
+        self.adaptive_timestep = value
+
+    def set_cfl(self, value):
+        self.cfl = value
+
+    def set_final_time(self, tf):
+        self.tf = tf
+
+    def set_n_damp(self, ndamp):
+        self.n_damp = ndamp
+
+    def set_time_step(self, dt):
+        self.dt = dt
+
+    def set_max_steps(self, max_steps):
+        self.max_steps = max_steps
+
+    def set_print_freq(self, n):
+        self.pfreq = n
+
+    def set_disable_output(self, value):
+        self.disable_output = value
+
+    def set_output_directory(self, path):
+        self.output_directory = path
+        self.disable_output = path is None
+
+    def set_output_fname(self, fname):
+        self.fname = fname
+
+    def set_output_printing_level(self, detailed_output):
+        self.detailed_output = detailed_output
+
+    def set_output_only_real(self, output_only_real):
+        self.output_only_real = output_only_real
+
+    def set_compress_output(self, compress):
+        self.compress_output = compress
+
+    def set_arrays_to_print(self, array_names=None):
+        """solver.py:340-357 (the reference's dump_output writes every array all the
+        same, :563-566; the per-array property lists are ``pa.set_output_arrays``)."""
+        by_name = dict((pa.name, pa) for pa in self.particles)
+        if array_names:
+            for name in array_names:
+                if name not in by_name:
+                    raise RuntimeError('Array %s not availabe' % name)
+            self.arrays_to_print = [by_name[n] for n in array_names]
+        else:
+            self.arrays_to_print = self.particles
 
     def set_parallel_manager(self, pm):
         dom = self.nnps.domain
@@ -192,22 +275,37 @@ class B200Solver(object):
     def step(self):
         """One iteration of the solve loop (solver.py:460-491)."""
         self.initialise()
+        for callback in self.pre_step_callbacks:         # solver.py:464-467
+            callback(self)
         if self.integrator.device_dt:
             self.integrator.step(self._t, self._dt)      # dt, t live on the device
+            for callback in self.post_step_callbacks:
+                callback(self)
             self.count += 1
             self._device_dt_advance(advance=True)
             return
         self.integrator.step(self._t, self._dt)
+        for callback in self.post_step_callbacks:        # solver.py:480-483
+            callback(self)
         self._t += self._dt
         self.count += 1
         self._dt = self._get_timestep()
 
-    def solve(self, max_steps, pfreq=0, output_directory=None, fname='b200',
+    def solve(self, max_steps=None, pfreq=None, output_directory=None, fname=None,
               asynchronous=True, **dump_kw):
         """The solve loop (solver.py:425-507).  With pfreq > 0 and an output
         directory it writes the initial state, every pfreq-th iteration and the
         final state (solver.py:445, :689-704, :505-507) -- asynchronously by
-        default, so the time loop does not wait for the copy or the file."""
+        default, so the time loop does not wait for the copy or the file.
+        Arguments left out come from the set_* methods."""
+        max_steps = self.max_steps if max_steps is None else max_steps
+        if output_directory is None and not self.disable_output:
+            output_directory = self.output_directory
+        pfreq = (self.pfreq if output_directory is not None else 0) if pfreq is None else pfreq
+        fname = self.fname if fname is None else fname
+        dump_kw.setdefault('detailed_output', self.detailed_output)
+        dump_kw.setdefault('only_real', self.output_only_real)
+        dump_kw.setdefault('compress', self.compress_output)
         dumping = pfreq > 0 and output_directory is not None
 
         def dump():

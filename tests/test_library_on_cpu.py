@@ -499,3 +499,47 @@ def test_slab_decomposition_on_the_emulated_library(emulated_library, world, lb_
                        ('v', 5e-6 * c0), ('w', 5e-6 * c0), ('rho', 5e-4)):
             a = np.concatenate([o[1][name][k] for o in out])[order]
             assert np.max(np.abs(a - ref[name][k][order_ref])) <= tol, (name, k)
+
+
+def test_solver_configuration_surface(emulated_library, tmp_path):
+    """The reference Solver's set_* / add_*_callback methods (solver.py:231-384) drive the
+    same loop: callbacks see the solver before / after every step (t not yet advanced in the
+    post-step callback, solver.py:480-487), a post-stage callback moves the clock to the
+    host, solve() without arguments uses what was configured."""
+    import pysph_b200 as pb
+    from pysph_b200 import output
+    seen = {'pre': [], 'post': [], 'stage': []}
+    pas, params = _small_dam_break(vscale=0.3)
+    s = pb.make_wcsph_solver(pas, dict(params, n_damp=2), pb.CubicSpline(dim=3))
+    s.add_pre_step_callback(lambda sv: seen['pre'].append((sv.count, sv.t, sv.dt)))
+    s.add_post_step_callback(lambda sv: seen['post'].append((sv.count, sv.t, sv.dt)))
+    s.set_max_steps(4)
+    s.set_print_freq(2)
+    s.set_output_directory(str(tmp_path))
+    s.set_output_fname('cfg')
+    s.set_output_printing_level(True)
+    s.set_arrays_to_print(['fluid'])
+    with pytest.raises(RuntimeError, match='not availabe'):
+        s.set_arrays_to_print(['nope'])
+    s.solve()
+    assert s.count == 4 and s.integrator.device_dt
+    assert sorted(os.listdir(str(tmp_path))) == ['cfg_%05d.npz' % k for k in (0, 2, 4)]
+    assert 'au' in output.load(str(tmp_path / 'cfg_00004.npz'))['arrays']['fluid'].properties
+    assert [c for c, _, _ in seen['pre']] == [0, 1, 2, 3] == [c for c, _, _ in seen['post']]
+    for (c0, t0, d0), (c1, t1, d1) in zip(seen['pre'], seen['post']):
+        assert (t0, d0) == (t1, d1)                      # t advances after the callbacks
+    ts = [t for _, t, _ in seen['pre']] + [s.t]
+    for k in range(4):
+        assert abs(ts[k] + seen['pre'][k][2] - ts[k + 1]) <= 1e-15
+    # the same run with a post-stage callback: host clock, same trajectory
+    pas2, _ = _small_dam_break(vscale=0.3)
+    s2 = pb.make_wcsph_solver(pas2, dict(params, n_damp=2), pb.CubicSpline(dim=3))
+    s2.add_post_stage_callback(lambda t, dt, stage: seen['stage'].append((t, dt, stage)))
+    s2.set_final_time(1e9)
+    s2.solve(4)
+    assert not s2.integrator.device_dt and (s2.t, s2.dt) == (s.t, s.dt)
+    assert [st for _, _, st in seen['stage']] == [1, 2] * 4
+    s.pull()
+    s2.pull()
+    assert np.array_equal(pas[0].x, pas2[0].x)
+    assert not os.path.exists(str(tmp_path / 'b200_00000.npz'))      # s2 wrote nothing
