@@ -56,6 +56,8 @@ class B200Solver(object):
         self.detailed_output = False
         self.output_only_real = True
         self.compress_output = False
+        self.output_at_times = np.array([])
+        self._prev_dt = None
 
         self.backend = backend or B200Backend(
             self.particles, device=device, capacity_factor=capacity_factor,
@@ -130,6 +132,11 @@ class B200Solver(object):
     def set_compress_output(self, compress):
         self.compress_output = compress
 
+    def set_output_at_times(self, output_at_times):
+        """Also dump at these times; dt is cut so that steps land on them
+        (solver.py:375-377, :706-742).  Keeps the time step on the host."""
+        self.output_at_times = np.asarray(output_at_times, dtype=float)
+
     def set_arrays_to_print(self, array_names=None):
         """solver.py:340-357 (the reference's dump_output writes every array all the
         same, :563-566; the per-array property lists are ``pa.set_output_arrays``)."""
@@ -184,14 +191,44 @@ class B200Solver(object):
         eps = self._eps()
         if abs(self.tf - self._t) < eps:
             return self._dt                  # reached the end
+        if self._prev_dt is not None and abs(self._prev_dt - self._dt) > eps:
+            # the last dt was cut to reach an output time: go on from the one before
+            self._dt = self._prev_dt
+            self._prev_dt = None
         dt = self._damp_timestep(self._compute_timestep())
         if (self._t + dt) > (self.tf - eps):
             dt = self.tf - self._t           # land exactly on the final time
         return dt
 
+    def _dump_output_if_needed(self, pfreq, dump):
+        """solver.py:689-745: dump at multiples of pfreq and at the requested output
+        times; cuts dt so that the next step lands on the next output time."""
+        eps = self._eps()
+        if abs(self._t - self.tf) < eps:
+            return
+        do = pfreq > 0 and self.count % pfreq == 0
+        times = self.output_at_times
+        if len(times) > 0:
+            tdiff = times - self._t
+            if np.any(np.abs(tdiff) < eps):
+                do = True
+            too_big = (tdiff > 0.0) & (tdiff < self._dt)
+            if np.any(too_big):
+                indices = np.where(too_big)[0]
+                output_time = times[indices[0]]
+                if abs(output_time - self._t) < eps and len(indices) > 1:
+                    output_time = times[indices[1]]
+                if abs(output_time - self._t) > eps:
+                    self._prev_dt = self._dt
+                    self._dt = float(output_time - self._t)
+        if do:
+            dump()
+
     # -- device-resident dt ---------------------------------------------------
     def _use_device_dt(self):
-        return self.device_dt and self.integrator._post_stage_callback is None
+        # output times and stage callbacks need t and dt on the host at every step
+        return self.device_dt and self.integrator._post_stage_callback is None and \
+            len(self.output_at_times) == 0
 
     def _device_dt_begin(self):
         import ctypes as C
@@ -306,7 +343,8 @@ class B200Solver(object):
         dump_kw.setdefault('detailed_output', self.detailed_output)
         dump_kw.setdefault('only_real', self.output_only_real)
         dump_kw.setdefault('compress', self.compress_output)
-        dumping = pfreq > 0 and output_directory is not None
+        dumping = output_directory is not None and \
+            (pfreq > 0 or len(self.output_at_times) > 0)
 
         def dump():
             if dumping:
@@ -321,7 +359,9 @@ class B200Solver(object):
             return self.count < max_steps and (self.tf - t) > self._eps()
         while running():
             self.step()
-            if dumping and self.count % pfreq == 0 and running():
+            if len(self.output_at_times) > 0:        # host clock
+                self._dump_output_if_needed(pfreq, dump)
+            elif dumping and pfreq > 0 and self.count % pfreq == 0 and running():
                 dump()                               # solver.py:689-704
         dump()                                       # final output, solver.py:505-507
         self.wait_for_output()
@@ -333,7 +373,8 @@ class B200Solver(object):
     def _get_solver_data(self):
         # the file holds the UNDAMPED time step (solver.py:747-753): a restart divides
         # by a damping factor of 1 and damps again for its own count (:647-688)
-        return {'dt': self.dt / self._damping_factor, 't': self.t, 'count': self.count}
+        dt = self.dt if self._prev_dt is None else self._prev_dt
+        return {'dt': dt / self._damping_factor, 't': self.t, 'count': self.count}
 
     def dump_output(self, output_directory='.', fname='b200', detailed_output=False,
                     only_real=True, compress=False, asynchronous=False):
@@ -399,7 +440,8 @@ class B200Solver(object):
                  (C.c_int * nseg)(*[sg[1] for sg in segs]),
                  (C.c_int64 * nseg)(*[sg[2] for sg in segs]))
         count, damping = self.count, self._damping_factor
-        host_time = None if on_device else (self._dt, self._t)
+        host_time = None if on_device else \
+            (self._dt if self._prev_dt is None else self._prev_dt, self._t)
 
         def work():
             try:

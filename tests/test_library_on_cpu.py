@@ -543,3 +543,44 @@ def test_solver_configuration_surface(emulated_library, tmp_path):
     s2.pull()
     assert np.array_equal(pas[0].x, pas2[0].x)
     assert not os.path.exists(str(tmp_path / 'b200_00000.npz'))      # s2 wrote nothing
+
+
+def test_output_at_times_small(emulated_library, tmp_path):
+    """set_output_at_times (solver.py:706-742): a step is cut so that it lands on each
+    requested time, a file is written there, and the time step resumes from the uncut one."""
+    import pysph_b200 as pb
+    from pysph_b200 import output
+    pas, params = _small_dam_break(vscale=0.3)
+    probe = pb.make_wcsph_solver(pas, dict(params, n_damp=0), pb.CubicSpline(dim=3))
+    for _ in range(8):
+        probe.step()
+    dt_typ = probe.dt
+    times = [2.5 * dt_typ, 4.2 * dt_typ]
+    log = []
+    pas, _ = _small_dam_break(vscale=0.3)
+    s = pb.make_wcsph_solver(pas, dict(params, n_damp=0), pb.CubicSpline(dim=3),
+                             tf=6.1 * dt_typ)
+    s.set_output_at_times(times)
+    s.set_output_directory(str(tmp_path))
+    s.set_print_freq(1000)
+    s.add_pre_step_callback(lambda sv: log.append((sv.count, sv.t, sv.dt)))
+    s.solve(asynchronous=False)
+    assert not s.integrator.device_dt                      # host clock
+    ts = [t for _, t, _ in log] + [s.t]
+    eps = 4 * np.finfo(float).eps * s.tf * s.count
+    for want in times + [s.tf]:
+        assert min(abs(t - want) for t in ts) <= eps, (want, ts)
+    # a cut step is shorter than its neighbours, the one after it is a full step again
+    dts = [d for _, _, d in log]
+    cut = [k for k in range(len(ts) - 1) if any(abs(ts[k + 1] - w) <= eps for w in times)]
+    assert len(cut) == 2
+    for k in cut:
+        assert dts[k] < 0.9 * dts[k - 1] and dts[k + 1] > 0.9 * dts[k - 1]
+    files = sorted(os.listdir(str(tmp_path)))
+    assert len(files) == 4                                 # initial, two output times, final
+    got = sorted(float(output.load(str(tmp_path / f))['solver_data']['t']) for f in files)
+    for want, t in zip([0.0] + times + [s.tf], got):
+        assert abs(t - want) <= eps
+    # the file at an output time holds the UNCUT dt (solver.py:747-750)
+    d1 = output.load(str(tmp_path / files[1]))['solver_data']
+    assert abs(float(d1['dt']) - dts[cut[0] - 1]) <= 0.2 * dts[cut[0] - 1]
