@@ -584,3 +584,41 @@ def test_output_at_times_small(emulated_library, tmp_path):
     # the file at an output time holds the UNCUT dt (solver.py:747-750)
     d1 = output.load(str(tmp_path / files[1]))['solver_data']
     assert abs(float(d1['dt']) - dts[cut[0] - 1]) <= 0.2 * dts[cut[0] - 1]
+
+
+@pytest.mark.parametrize('empty', ['obstacle', 'fluid', 'boundary'])
+def test_empty_arrays_small(emulated_library, empty):
+    """Ragged inputs: a whole particle array with zero particles (as a source only, as the
+    only fluid, as the only wall) goes through NNPS, evaluation, EPEC steps and the adaptive
+    time step like in the oracle."""
+    import pysph_b200 as pb
+    from helpers import copy_arrays
+    from oracle import oracle as orc
+    pas, params = _small_dam_break(vscale=0.5)
+    keep = []
+    for pa in pas:
+        if pa.name == empty:
+            pa = pb.get_particle_array_wcsph(name=pa.name, x=np.zeros(0))
+        keep.append(pa)
+    pas = keep
+    assert [pa.name for pa in pas] == ['fluid', 'boundary', 'obstacle']
+    opas = copy_arrays(pas)
+    params = dict(params, n_damp=2)
+    s = pb.make_wcsph_solver(pas, dict(params), pb.CubicSpline(dim=3))
+    o = orc.WCSPHOracleSolver(opas, params, 'CubicSpline', threads=2)
+    s.a_eval.count_pairs = True
+    s.initialise()
+    o.initialise()
+    assert s.a_eval.last_pairs == o.pairs_last_eval
+    for _ in range(5):
+        s.step()
+        o.step()
+    s.pull()
+    assert abs(s.t - o.t) <= 1e-6 * o.t
+    for a, b in zip(pas, opas):
+        assert a.get_number_of_particles() == b.get_number_of_particles()
+        for k, tol in (('x', 2e-6), ('u', 2e-5), ('rho', 1e-6), ('au', 1e-4), ('arho', 1e-4)):
+            want = b.properties[k]
+            if want.size:
+                scale = max(np.max(np.abs(want)), 1.0 if k == 'x' else 1e-3)
+                assert np.max(np.abs(a.properties[k] - want)) <= tol * scale, (a.name, k)
