@@ -315,6 +315,135 @@ def run_taylor_green(args, emit):
     })
 
 
+def run_rings(args, emit):
+    """--workload rings: BASELINE configs[4] -- 3-D elastic dynamics (Gray, Monaghan &
+    Swift), the colliding rings of rings.py extruded along z, CubicSpline hdx=1.5,
+    EPEC + SolidMechStep at a fixed dt.  One GPU's share of the 4 M / 4 GPU case:
+    dx = 0.00028, lz = 0.005 (1.0 M particles).  One step = two evaluations = four pair
+    passes (velocity gradient; continuity + momentum with stress + AV + XSPH)."""
+    import torch
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo
+    torch.cuda.set_device(0)
+    dx = args.dx or 0.00028
+    lz = args.lz
+    dt = args.dt or 1e-8 * dx / 0.0005      # rings.py:36 (dt = 1e-8 at dx = 0.0005), same dt / h
+    pa = geo.rings_3d_particles(dx=dx, lz=lz)
+    host_copy = None
+    if not args.no_cpu:
+        host_copy = geo.rings_3d_particles(dx=dx, lz=lz)
+    keep = pinned_arrays([pa])
+    sch = pb.ElasticSolidsScheme(['solid'], [], dim=3)
+    solver = pb.make_elastic_solver([pa], sch, pb.CubicSpline(dim=3), dt=dt)
+    be = solver.backend
+    stream = torch.cuda.current_stream()
+    be.use_torch_stream(stream)
+    W, K = max(args.warmup, 3), args.steps
+    sampler = ClockSampler(0)
+    sampler.start()
+    solver.initialise()
+    for _ in range(W):
+        solver.step()
+    solver.a_eval.count_pairs = True
+    solver.step()
+    pairs_eval = solver.a_eval.last_pairs          # both passes of the step's last evaluation
+    solver.a_eval.count_pairs = False
+    pairs_step = 2 * pairs_eval                    # EPEC: two evaluations per step
+    be.ctx.call('b200sph_reset_stats')
+    be.ctx.call('b200sph_set_profiling', 2)
+    torch.cuda.synchronize()
+    n_s0 = len(sampler.lines)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(K):
+        solver.step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop(n_s0)
+    ms_step = ev0.elapsed_time(ev1) / K
+    st = be.stats()
+    DIAG = 20
+    be.ctx.call('b200sph_reset_stats')
+    be.ctx.call('b200sph_set_profiling', 1)
+    for _ in range(DIAG):
+        solver.step()
+    torch.cuda.synchronize()
+    st_diag = be.stats()
+    be.ctx.call('b200sph_set_profiling', 0)
+    state = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm',
+             's00', 's01', 's02', 's11', 's12', 's22']
+    outp = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'p']
+    n = pa.get_number_of_particles()
+    be.ctx.call('b200sph_set_async_copies', 1)
+
+    def e2e_step():
+        be.push_real(state)
+        solver.step()
+        be.pull_real(outp)
+        be.synchronize()
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    be.ctx.call('b200sph_set_async_copies', 0)
+    ms_e2e = ev0.elapsed_time(ev1) / args.e2e_steps
+    peak, peak_src = peaks()
+    ms_p2 = st['ms_pair'] / max(st['pair_launches'], 1)
+    pairs_p2 = pairs_eval / 2.0
+    B2 = 96.0        # pass 2 gathers {A,B} 32 B + C 16 B + stress records 48 B per pair
+    achieved = pairs_p2 * B2 / (ms_p2 * 1e-3) / 1e9
+    cpu = None
+    if host_copy is not None:
+        from oracle import oracle as orc
+        o = orc.ElasticOracleSolver([host_copy], dict(dim=3, dt=dt, eps=0.3, alpha=1.0,
+                                                      beta=1.0, eps_xsph=0.5, grad3d=True),
+                                    'CubicSpline', threads=1)
+        t0 = time.perf_counter()
+        pairs_cpu = o.evaluate()
+        el = time.perf_counter() - t0
+        cpu = {'value': pairs_cpu / el, 'unit': 'pairs/s', 'cores': 1, 'kind': 'port',
+               'cpu': cpu_model(),
+               'sample': 'one full evaluation (both elastic-dynamics groups) of the same '
+                         '%d-particle initial state, fp64 oracle, 1 thread (%.1f s)' % (n, el)}
+    emit({
+        'metric': METRIC, 'value': pairs_step / (ms_step * 1e-3), 'unit': 'pairs/s',
+        'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': ms_step,
+        'steps_per_s': 1e3 / ms_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'rings 3-D (BASELINE configs[4], one GPU\'s share) elastic '
+                               'dynamics EPEC CubicSpline hdx=1.5 dx=%g lz=%g' % (dx, lz),
+                   'particles_rank0': n, 'pairs_per_step': pairs_step,
+                   'parallelism': 'single GPU', 'dt': dt,
+                   'l2': 'no flush: > 126 MB working set per step, state advances',
+                   'precision': 'fp32 pair arithmetic on cell-relative coordinates, '
+                                'fp64 integrated state (x u rho s)'},
+        'clocks': clocks,
+        'e2e': {'value': pairs_step / (ms_e2e * 1e-3), 'unit': 'pairs/s',
+                'ms_per_step': ms_e2e, 'steps': args.e2e_steps,
+                'h2d_bytes_per_step': 8 * len(state) * n,
+                'd2h_bytes_per_step': 8 * len(outp) * n},
+        'gpu_launches': int(st['kernel_launches']),
+        'roofline': {'bound': 'hbm', 'kernel': 'k_solid_pass2<CubicSpline,3>',
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_pair': B2, 'pairs_per_launch': pairs_p2,
+                     'avg_launch_ms': ms_p2,
+                     'share_of_step': st['ms_pair'] / K / ms_step,
+                     'ms_nnps_per_step': st_diag['ms_nnps'] / DIAG,
+                     'ms_other_per_step': st_diag['ms_other'] / DIAG,
+                     'note': 'other = k_pack_solid + k_solid_pass1 + stages',
+                     'nnps': {'full_builds': st['full_builds'],
+                              'light_updates': st['light_updates'],
+                              'list_builds': st['list_builds'],
+                              'list_entries_per_particle': st['list_entries_per_particle']}},
+        'cpu_baseline': cpu,
+    })
+
+
 def pinned_arrays(pas):
     """Re-home every property of the ParticleArrays in pinned host memory."""
     import torch
@@ -338,8 +467,10 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=20.0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--workload', default='dam_break',
-                    choices=['dam_break', 'taylor_green'])
+                    choices=['dam_break', 'taylor_green', 'rings'])
     ap.add_argument('--nx', type=int, default=126)
+    ap.add_argument('--lz', type=float, default=0.005)
+    ap.add_argument('--dt', type=float, default=None)
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -371,6 +502,13 @@ def main():
                   file=sys.stderr)
             sys.exit(2)
         run_taylor_green(args, emit)
+        return
+    if args.workload == 'rings':
+        if world > 1:
+            print('bench.py: --workload rings is a single-GPU workload so far (the slab '
+                  'halo does not carry the stress fields yet)', file=sys.stderr)
+            sys.exit(2)
+        run_rings(args, emit)
         return
     import torch
     import torch.distributed as dist

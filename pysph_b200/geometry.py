@@ -205,3 +205,44 @@ def rings_particles(dx=0.0005, hdx=1.5, ri=0.03, ro=0.04, spacing=0.041, E=1e7,
     pa.u[:] = pa.cs * u_f * (2 * (x < 0) - 1)
     pa.gid[:] = np.arange(x.size)
     return pa
+
+
+def rings_3d_particles(dx=0.0005, lz=0.01, hdx=1.5, ri=0.03, ro=0.04, spacing=0.041,
+                       E=1e7, nu=0.3975, rho0=1.0, u_f=0.059, x_range=None):
+    """BASELINE configs[4]: the colliding rings of rings.py:18-84 extruded along z into
+    two thick-walled tubes of length ``lz`` with free end faces (the reference example is
+    2-D only; everything but the third lattice axis, the 3-D mass ``dx^3`` and the 3-D
+    CubicSpline value ``wdeltap = W(dx, h)`` follows rings.py:40-78).  4 M particles is
+    ``dx = 0.00028, lz = 0.02``.  ``x_range = (lo, hi)`` keeps only the lattice columns
+    with ``lo <= x < hi`` (a rank's slab) so that no rank builds the whole body."""
+    from .particle_array import get_particle_array_elastic_dynamics
+    n = int(round(2 * ro / dx))
+    ax = -ro + dx * np.arange(n)                      # numpy.mgrid[-ro:ro:dx]
+    x, y = np.meshgrid(ax, ax, indexing='ij')
+    x, y = x.ravel(), y.ravel()
+    d = x * x + y * y
+    keep = np.flatnonzero((ri * ri <= d) * (d < ro * ro))
+    x, y = x[keep], y[keep]
+    sign = np.concatenate([np.ones(x.size), -np.ones(x.size)])    # left ring moves right
+    x = np.concatenate([x - spacing, x + spacing]) + spacing
+    y = np.concatenate([y, y])
+    gid2 = np.arange(x.size)
+    if x_range is not None:
+        sel = np.flatnonzero((x >= x_range[0]) * (x < x_range[1]))
+        x, y, sign, gid2 = x[sel], y[sel], sign[sel], gid2[sel]
+    nz = max(int(round(lz / dx)), 1)
+    z = dx * (np.arange(nz) + 0.5)
+    X = np.repeat(x, nz)
+    Y = np.repeat(y, nz)
+    Z = np.tile(z, x.size)
+    h = hdx * dx
+    q = dx / h                                         # CubicSpline(dim=3).kernel(rij=dx, h)
+    fac = 1.0 / (np.pi * h * h * h)
+    w = 1.0 - 1.5 * q * q * (1.0 - 0.5 * q) if q <= 1.0 else 0.25 * (2.0 - q) ** 3
+    pa = get_particle_array_elastic_dynamics(
+        name='solid', x=X, y=Y, z=Z, m=dx * dx * dx, rho=rho0, h=h,
+        constants=dict(wdeltap=fac * w, n=4, rho_ref=rho0, E=E, nu=nu))
+    pa.u[:] = pa.cs * u_f * np.repeat(sign, nz)
+    pa.gid[:] = np.repeat(gid2, nz) * nz + np.tile(np.arange(nz), x.size)
+    return pa
+

@@ -94,6 +94,7 @@ FAST = [
      for i in range(4)] + [
     ('test_zz_gpu_solid_unvalidated', 'test_solid_mech_step_matches_reference_bodies', {}),
     ('test_zz_gpu_solid_unvalidated', 'test_rings_steps_vs_oracle', {}),
+    ('test_zz_gpu_solid_unvalidated', 'test_rings_3d_steps_vs_oracle', {}),
 ]
 FULL = [
     ('test_gpu_parity', 'test_kernels_via_two_particle_density', {}),
