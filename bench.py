@@ -315,32 +315,56 @@ def run_taylor_green(args, emit):
     })
 
 
-def run_rings(args, emit):
+def run_rings(args, emit, rank=0, local_rank=0, world=1):
     """--workload rings: BASELINE configs[4] -- 3-D elastic dynamics (Gray, Monaghan &
     Swift), the colliding rings of rings.py extruded along z, CubicSpline hdx=1.5,
-    EPEC + SolidMechStep at a fixed dt.  One GPU's share of the 4 M / 4 GPU case:
-    dx = 0.00028, lz = 0.005 (1.0 M particles).  One step = two evaluations = four pair
-    passes (velocity gradient; continuity + momentum with stress + AV + XSPH)."""
+    EPEC + SolidMechStep at a fixed dt.  dx = 0.00028; lz = 0.005 per GPU (1.0 M particles
+    per GPU, 4 GPUs = the 4 M case: weak scaling along z, x-slabs with a two-support halo
+    that carries the deviatoric stress).  One step = two evaluations = four pair passes
+    (velocity gradient; continuity + momentum with stress + AV + XSPH)."""
     import torch
+    import torch.distributed as dist
     import pysph_b200 as pb
     from pysph_b200 import geometry as geo
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     dx = args.dx or 0.00028
-    lz = args.lz
+    lz = args.lz * world
     dt = args.dt or 1e-8 * dx / 0.0005      # rings.py:36 (dt = 1e-8 at dx = 0.0005), same dt / h
-    pa = geo.rings_3d_particles(dx=dx, lz=lz)
     host_copy = None
-    if not args.no_cpu:
-        host_copy = geo.rings_3d_particles(dx=dx, lz=lz)
-    keep = pinned_arrays([pa])
-    sch = pb.ElasticSolidsScheme(['solid'], [], dim=3)
-    solver = pb.make_elastic_solver([pa], sch, pb.CubicSpline(dim=3), dt=dt)
+    if world == 1:
+        pa = geo.rings_3d_particles(dx=dx, lz=lz)
+        if not args.no_cpu:
+            host_copy = geo.rings_3d_particles(dx=dx, lz=lz)
+        keep = pinned_arrays([pa])
+        sch = pb.ElasticSolidsScheme(['solid'], [], dim=3)
+        solver = pb.make_elastic_solver([pa], sch, pb.CubicSpline(dim=3), dt=dt,
+                                        device=local_rank)
+        pm = None
+    else:
+        from pysph_b200.parallel import make_rings_slab_solver
+        solver, pm, pas = make_rings_slab_solver(dx, lz, rank, world, device=local_rank, dt=dt)
+        pa = pas[0]
     be = solver.backend
     stream = torch.cuda.current_stream()
     be.use_torch_stream(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=op)
+        return float(t.item())
     W, K = max(args.warmup, 3), args.steps
-    sampler = ClockSampler(0)
-    sampler.start()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     solver.initialise()
     for _ in range(W):
         solver.step()
@@ -348,19 +372,19 @@ def run_rings(args, emit):
     solver.step()
     pairs_eval = solver.a_eval.last_pairs          # both passes of the step's last evaluation
     solver.a_eval.count_pairs = False
-    pairs_step = 2 * pairs_eval                    # EPEC: two evaluations per step
+    pairs_step = int(reduce(2 * pairs_eval, dist.ReduceOp.SUM))   # EPEC: two evaluations per step
     be.ctx.call('b200sph_reset_stats')
     be.ctx.call('b200sph_set_profiling', 2)
-    torch.cuda.synchronize()
+    barrier()
     n_s0 = len(sampler.lines)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(K):
         solver.step()
     ev1.record(stream)
-    torch.cuda.synchronize()
-    clocks = sampler.stop(n_s0)
-    ms_step = ev0.elapsed_time(ev1) / K
+    barrier()
+    clocks = sampler.stop(n_s0) if rank == 0 else None
+    ms_step = reduce(ev0.elapsed_time(ev1), dist.ReduceOp.MAX) / K
     st = be.stats()
     DIAG = 20
     be.ctx.call('b200sph_reset_stats')
@@ -373,7 +397,17 @@ def run_rings(args, emit):
     state = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm',
              's00', 's01', 's02', 's11', 's12', 's22']
     outp = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'p']
-    n = pa.get_number_of_particles()
+    if world > 1:
+        # host mirrors hold this rank's real particles (migration may have changed the
+        # count): refresh them once, then pin
+        solver.pull()
+        nr = pa.get_number_of_particles(real=True)
+        for k in list(pa.properties):
+            pa.properties[k] = pa.properties[k][:nr].copy()
+        pa._n = nr
+        keep = pinned_arrays([pa])
+    n = be.sizes(0)[1]
+    n_total = int(reduce(n, dist.ReduceOp.SUM))
     be.ctx.call('b200sph_set_async_copies', 1)
 
     def e2e_step():
@@ -383,14 +417,14 @@ def run_rings(args, emit):
         be.synchronize()
     for _ in range(2):
         e2e_step()
-    torch.cuda.synchronize()
+    barrier()
     ev0.record(stream)
     for _ in range(args.e2e_steps):
         e2e_step()
     ev1.record(stream)
-    torch.cuda.synchronize()
+    barrier()
     be.ctx.call('b200sph_set_async_copies', 0)
-    ms_e2e = ev0.elapsed_time(ev1) / args.e2e_steps
+    ms_e2e = reduce(ev0.elapsed_time(ev1), dist.ReduceOp.MAX) / args.e2e_steps
     peak, peak_src = peaks()
     ms_p2 = st['ms_pair'] / max(st['pair_launches'], 1)
     pairs_p2 = pairs_eval / 2.0
@@ -409,23 +443,30 @@ def run_rings(args, emit):
                'cpu': cpu_model(),
                'sample': 'one full evaluation (both elastic-dynamics groups) of the same '
                          '%d-particle initial state, fp64 oracle, 1 thread (%.1f s)' % (n, el)}
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     emit({
         'metric': METRIC, 'value': pairs_step / (ms_step * 1e-3), 'unit': 'pairs/s',
-        'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': ms_step,
+        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_step,
         'steps_per_s': 1e3 / ms_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'rings 3-D (BASELINE configs[4], one GPU\'s share) elastic '
-                               'dynamics EPEC CubicSpline hdx=1.5 dx=%g lz=%g' % (dx, lz),
-                   'particles_rank0': n, 'pairs_per_step': pairs_step,
-                   'parallelism': 'single GPU', 'dt': dt,
+        'config': {'workload': 'rings 3-D (BASELINE configs[4]) elastic dynamics EPEC '
+                               'CubicSpline hdx=1.5 dx=%g lz=%g' % (dx, lz),
+                   'particles': n_total, 'particles_rank0': n, 'pairs_per_step': pairs_step,
+                   'parallelism': 'single GPU' if world == 1 else
+                                  'x-slabs x%d, two-support halo (16 fields), peer-memory '
+                                  'refresh' % world,
+                   'dt': dt,
                    'l2': 'no flush: > 126 MB working set per step, state advances',
                    'precision': 'fp32 pair arithmetic on cell-relative coordinates, '
                                 'fp64 integrated state (x u rho s)'},
         'clocks': clocks,
         'e2e': {'value': pairs_step / (ms_e2e * 1e-3), 'unit': 'pairs/s',
                 'ms_per_step': ms_e2e, 'steps': args.e2e_steps,
-                'h2d_bytes_per_step': 8 * len(state) * n,
-                'd2h_bytes_per_step': 8 * len(outp) * n},
+                'h2d_bytes_per_step': 8 * len(state) * n_total,
+                'd2h_bytes_per_step': 8 * len(outp) * n_total},
         'gpu_launches': int(st['kernel_launches']),
         'roofline': {'bound': 'hbm', 'kernel': 'k_solid_pass2<CubicSpline,3>',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
@@ -435,12 +476,14 @@ def run_rings(args, emit):
                      'share_of_step': st['ms_pair'] / K / ms_step,
                      'ms_nnps_per_step': st_diag['ms_nnps'] / DIAG,
                      'ms_other_per_step': st_diag['ms_other'] / DIAG,
-                     'note': 'other = k_pack_solid + k_solid_pass1 + stages',
+                     'note': 'rank 0; other = k_pack_solid + k_solid_pass1 + stages',
                      'nnps': {'full_builds': st['full_builds'],
                               'light_updates': st['light_updates'],
                               'list_builds': st['list_builds'],
                               'list_entries_per_particle': st['list_entries_per_particle']}},
         'cpu_baseline': cpu,
+        'halo': None if pm is None else {'full_updates': pm.n_full, 'refreshes': pm.n_refresh,
+                                         'peer_refreshes': pm.n_peer_refresh},
     })
 
 
@@ -504,11 +547,7 @@ def main():
         run_taylor_green(args, emit)
         return
     if args.workload == 'rings':
-        if world > 1:
-            print('bench.py: --workload rings is a single-GPU workload so far (the slab '
-                  'halo does not carry the stress fields yet)', file=sys.stderr)
-            sys.exit(2)
-        run_rings(args, emit)
+        run_rings(args, emit, rank, local_rank, world)
         return
     import torch
     import torch.distributed as dist

@@ -131,7 +131,11 @@ typedef struct {
     uint32_t elastic_mask; /* bit a: array a is an elastic solid                    */
     int32_t grad3d;        /* 0 VelocityGradient2D (what the scheme emits), 1 ..3D  */
     int32_t passes;        /* bit 0: group 1, bit 1: group 2                        */
-    int32_t reserved;
+    int32_t ghost_group1;  /* != 0: group 1 also runs on ghosts (like Group(real=False));
+                            * the slab decomposition then imports two kernel supports so
+                            * that a ghost's p and artificial stress are THIS evaluation's,
+                            * as in a serial run, instead of the carried values a
+                            * reference Remote particle has (parallel_manager.pyx:512-530) */
     double eps;            /* MonaghanArtificialStress(eps)                         */
     double alpha, beta;    /* MonaghanArtificialViscosity                           */
     double eps_xsph;       /* XSPHCorrection(eps)                                   */
@@ -321,6 +325,15 @@ int b200sph_time_final(b200sph_ctx *ctx, double t_final, double eps);
  *      the caller (torch tensors handed to NCCL). ------------------------- */
 #define B200SPH_HALO_FIELDS 9     /* x y z u v w rho h m (fp64 each)          */
 #define B200SPH_MIGRATE_FIELDS 17 /* the 16 fp64 state props (x..m, x0..rho0) + gid */
+/* once an elastic-dynamics property has been named (solid_mech/basic.py:32-90) the
+ * deviatoric stress travels too, and cs (which no equation of that scheme recomputes):
+ * ghosts carry s00 s01 s02 s11 s12 s22 cs after the 9 fields, migrating particles
+ * s00..s22, the stage copies s000..s220 and cs after the 17 */
+#define B200SPH_HALO_FIELDS_SOLID 16
+#define B200SPH_MIGRATE_FIELDS_SOLID 30
+/* the field counts of THIS context's messages (9 / 17, or 16 / 30): what the caller sizes
+ * its buffers with and passes to b200sph_halo_append as nfields */
+int b200sph_halo_layout(b200sph_ctx *ctx, int *halo_fields, int *migrate_fields);
 /* select the real particles of `arr` with lo <= x < hi and write their
  * B200SPH_HALO_FIELDS doubles field-major and TIGHT (field f of particle k at
  * dev_buf[f * count + k]); *count = number selected; error if count > cap.

@@ -70,7 +70,7 @@ class TvfProgram(C.Structure):
 
 class SolidProgram(C.Structure):
     _fields_ = [('elastic_mask', C.c_uint32), ('grad3d', C.c_int32),
-                ('passes', C.c_int32), ('reserved', C.c_int32),
+                ('passes', C.c_int32), ('ghost_group1', C.c_int32),
                 ('eps', C.c_double), ('alpha', C.c_double), ('beta', C.c_double),
                 ('eps_xsph', C.c_double),
                 ('c0_ref', C.c_double * MAX_ARRAYS), ('rho_ref', C.c_double * MAX_ARRAYS),
@@ -175,6 +175,7 @@ SIGNATURES = {
                                         C.POINTER(C.c_int), C.POINTER(_i64)]),
     'b200sph_snapshot_fetch': (C.c_int, [_ctx_p, C.c_int, C.c_void_p, _i64]),
     'b200sph_snapshot_release': (C.c_int, [_ctx_p]),
+    'b200sph_halo_layout': (C.c_int, [_ctx_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'b200sph_column_counts': (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_double, C.c_int,
                                         C.c_void_p]),
     'b200sph_get_stats': (C.c_int, [_ctx_p, C.POINTER(Stats)]),

@@ -1623,6 +1623,7 @@ int b200sph_solid_pass(b200sph_ctx *ctx, const b200sph_solid_program *prog, int6
     sa.kfac = (float)kernel_fac(ctx->kernel, ctx->dim);
     sa.elastic_mask = prog->elastic_mask;
     sa.grad3d = prog->grad3d;
+    sa.ghost_group1 = prog->ghost_group1;
     sa.eps = (float)prog->eps; sa.alpha = (float)prog->alpha; sa.beta = (float)prog->beta; sa.eps_xsph = (float)prog->eps_xsph;
     for (int a = 0; a < B200SPH_MAX_ARRAYS; a++) {
         sa.c0_ref[a] = prog->c0_ref[a]; sa.rho_ref[a] = prog->rho_ref[a]; sa.G[a] = prog->G[a];
@@ -1932,11 +1933,26 @@ int b200sph_dt_factors(b200sph_ctx *ctx, double out[3])
 // ---- halo helpers ------------------------------------------------------------
 static const int halo_fields[9] = {B200SPH_X, B200SPH_Y, B200SPH_Z, B200SPH_U, B200SPH_V, B200SPH_W, B200SPH_RHO, B200SPH_H, B200SPH_M};
 
+// with the elastic-dynamics arrays allocated the deviatoric stress travels too: a ghost is a
+// source of group 2 (and, with SolidProgram.ghost_group1, a destination of group 1), and a
+// migrating particle takes s and its stage copy s0 along
+static inline int halo_nf(const b200sph_ctx *ctx) { return ctx->solid_alloc ? B200SPH_HALO_FIELDS_SOLID : B200SPH_HALO_FIELDS; }
+static inline int migrate_nf(const b200sph_ctx *ctx) { return ctx->solid_alloc ? B200SPH_MIGRATE_FIELDS_SOLID : B200SPH_MIGRATE_FIELDS; }
+
 static HaloPtrs halo_ptrs(b200sph_ctx *ctx)
 {
     HaloPtrs P;
     for (int f = 0; f < B200SPH_HALO_FIELDS; f++) P.p[f] = ctx->f64[halo_fields[f]];
+    for (int f = B200SPH_HALO_FIELDS; f < B200SPH_HALO_FIELDS_SOLID - 1; f++) P.p[f] = ctx->f64s[f - B200SPH_HALO_FIELDS];
+    P.cs = ctx->f32[B200SPH_CS - N_F64];
     return P;
+}
+
+int b200sph_halo_layout(b200sph_ctx *ctx, int *halo_fields_out, int *migrate_fields_out)
+{
+    if (halo_fields_out) *halo_fields_out = halo_nf(ctx);
+    if (migrate_fields_out) *migrate_fields_out = migrate_nf(ctx);
+    return 0;
 }
 
 int b200sph_halo_pack(b200sph_ctx *ctx, int arr, int slot, double lo, double hi, double *dev_buf, int64_t cap, int64_t *count)
@@ -1975,7 +1991,8 @@ int b200sph_halo_pack(b200sph_ctx *ctx, int arr, int slot, double lo, double hi,
         return set_err(ctx, "halo_pack: slot must be -1, 0 or 1");
     }
     if (tot == 0) return 0;
-    k_halo_gather_flag<<<nb, 256, 0, ctx->stream>>>(halo_ptrs(ctx), off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)tot);
+    if (halo_nf(ctx) == B200SPH_HALO_FIELDS) k_halo_gather_flag<B200SPH_HALO_FIELDS><<<nb, 256, 0, ctx->stream>>>(halo_ptrs(ctx), off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)tot);
+    else k_halo_gather_flag<B200SPH_HALO_FIELDS_SOLID><<<nb, 256, 0, ctx->stream>>>(halo_ptrs(ctx), off, n, ctx->flag_a, ctx->flag_b, dev_buf, (long long)tot);
     LAUNCH_CHECK();
     return 0;
 }
@@ -1987,17 +2004,26 @@ int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf, int64_
     if (rc) return rc;
     if ((rc = eos_flush(ctx))) return rc;
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "halo_append: bad array %d", arr);
-    if (nfields != B200SPH_HALO_FIELDS && nfields != B200SPH_MIGRATE_FIELDS) return set_err(ctx, "halo_append: nfields must be %d or %d", B200SPH_HALO_FIELDS, B200SPH_MIGRATE_FIELDS);
+    const int hnf = halo_nf(ctx), mnf = migrate_nf(ctx);
+    if (nfields != hnf && nfields != mnf) return set_err(ctx, "halo_append: nfields must be %d or %d", hnf, mnf);
     ArrayInfo &ai = ctx->arr[arr];
     if (as_real && ai.n != ai.n_real) return set_err(ctx, "halo_append(as_real): drop the ghosts of '%s' first (real particles must precede ghosts)", ai.name.c_str());
     if (n <= 0) return 0;
     if ((rc = ensure_capacity(ctx, arr, ai.n + n))) return rc;
     const int64_t o = ai.off + ai.n;
     const unsigned nb = (unsigned)cdiv(n, 256);
-    if (nfields == B200SPH_HALO_FIELDS) {
-        k_halo_scatter<<<nb, 256, 0, ctx->stream>>>(halo_ptrs(ctx), o, dev_buf, stride, n);
+    // derived fields of the appended particles start at zero (cs of an elastic array is then
+    // filled from the message)
+    for (int k = 0; k < N_F32; k++) CU(cudaMemsetAsync(ctx->f32[k] + o, 0, 4 * (size_t)n, ctx->stream));
+    if (ctx->solid_alloc)
+        for (int k = 0; k < 21; k++) CU(cudaMemsetAsync(ctx->f32s[k] + o, 0, 4 * (size_t)n, ctx->stream));
+    if (nfields == hnf) {
+        if (hnf == B200SPH_HALO_FIELDS) k_halo_scatter<B200SPH_HALO_FIELDS><<<nb, 256, 0, ctx->stream>>>(halo_ptrs(ctx), o, dev_buf, stride, n);
+        else k_halo_scatter<B200SPH_HALO_FIELDS_SOLID><<<nb, 256, 0, ctx->stream>>>(halo_ptrs(ctx), o, dev_buf, stride, n);
         LAUNCH_CHECK();
         for (int k = B200SPH_X0; k < N_F64; k++) CU(cudaMemsetAsync(ctx->f64[k] + o, 0, 8 * (size_t)n, ctx->stream));
+        if (ctx->solid_alloc)
+            for (int k = 6; k < 12; k++) CU(cudaMemsetAsync(ctx->f64s[k] + o, 0, 8 * (size_t)n, ctx->stream));
         k_fill_u32<<<nb, 256, 0, ctx->stream>>>(ctx->u32[0] + o, n, 0xFFFFFFFFu);
         LAUNCH_CHECK();
     } else {
@@ -2005,9 +2031,14 @@ int b200sph_halo_append(b200sph_ctx *ctx, int arr, const double *dev_buf, int64_
             CU(cudaMemcpyAsync(ctx->f64[k] + o, dev_buf + (size_t)k * stride, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
         k_f64_to_u32<<<nb, 256, 0, ctx->stream>>>(dev_buf + (size_t)N_F64 * stride, ctx->u32[0] + o, n);
         LAUNCH_CHECK();
+        if (ctx->solid_alloc) {  // fields 17..28: s00..s22, s000..s220; field 29: cs
+            for (int k = 0; k < 12; k++)
+                CU(cudaMemcpyAsync(ctx->f64s[k] + o, dev_buf + (size_t)(B200SPH_MIGRATE_FIELDS + k) * stride, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+            k_f64_to_f32<<<nb, 256, 0, ctx->stream>>>(dev_buf + (size_t)(B200SPH_MIGRATE_FIELDS + 12) * stride, ctx->f32[B200SPH_CS - N_F64] + o, n);
+            LAUNCH_CHECK();
+        }
     }
-    // derived fields of the appended particles start at zero; tag = Remote (1) for ghosts
-    for (int k = 0; k < N_F32; k++) CU(cudaMemsetAsync(ctx->f32[k] + o, 0, 4 * (size_t)n, ctx->stream));
+    // tag = Remote (1) for ghosts
     k_fill_u32<<<nb, 256, 0, ctx->stream>>>(ctx->u32[1] + o, n, as_real ? 0u : 1u);
     LAUNCH_CHECK();
     CU(cudaMemsetAsync(ctx->u32[2] + o, 0, 4 * (size_t)n, ctx->stream));
@@ -2033,7 +2064,8 @@ int b200sph_halo_pack_selected(b200sph_ctx *ctx, int arr, int slot, double *dev_
     *count = n;
     if (n > cap) return set_err(ctx, "halo_pack_selected: buffer too small");
     if (n == 0) return 0;
-    k_halo_gather_idx<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), ctx->arr[arr].off, ctx->halo_idx[arr][slot], n, dev_buf);
+    if (halo_nf(ctx) == B200SPH_HALO_FIELDS) k_halo_gather_idx<B200SPH_HALO_FIELDS><<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), ctx->arr[arr].off, ctx->halo_idx[arr][slot], n, dev_buf);
+    else k_halo_gather_idx<B200SPH_HALO_FIELDS_SOLID><<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), ctx->arr[arr].off, ctx->halo_idx[arr][slot], n, dev_buf);
     LAUNCH_CHECK();
     return 0;
 }
@@ -2049,7 +2081,8 @@ int b200sph_halo_overwrite(b200sph_ctx *ctx, int arr, int64_t ghost_first, const
         return set_err(ctx, "halo_overwrite: ghosts [%lld, %lld) outside the %lld ghosts of '%s'", (long long)ghost_first, (long long)(ghost_first + n), (long long)(ai.n - ai.n_real), ai.name.c_str());
     if (n == 0) return 0;
     const int64_t o = ai.off + ai.n_real + ghost_first;
-    k_halo_scatter<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), o, dev_buf, stride, n);
+    if (halo_nf(ctx) == B200SPH_HALO_FIELDS) k_halo_scatter<B200SPH_HALO_FIELDS><<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), o, dev_buf, stride, n);
+    else k_halo_scatter<B200SPH_HALO_FIELDS_SOLID><<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), o, dev_buf, stride, n);
     LAUNCH_CHECK();
     // values moved, the particle set did not: a light nnps_update is enough
     ctx->grid_valid = false, ctx->packed_valid = false;
@@ -2097,10 +2130,11 @@ int b200sph_halo_pack_selected_all(b200sph_ctx *ctx, int slot, double *dev_buf, 
         A.idx[a] = ctx->halo_idx[a][slot];
     }
     const int64_t tot = A.prefix[ctx->narr];
-    *ndoubles = tot * B200SPH_HALO_FIELDS;
+    *ndoubles = tot * halo_nf(ctx);
     if (*ndoubles > cap_doubles) return set_err(ctx, "halo_pack_selected_all: buffer too small");
     if (tot == 0) return 0;
-    k_halo_gather_all<<<(unsigned)cdiv(tot, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), A, dev_buf);
+    if (halo_nf(ctx) == B200SPH_HALO_FIELDS) k_halo_gather_all<B200SPH_HALO_FIELDS><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), A, dev_buf);
+    else k_halo_gather_all<B200SPH_HALO_FIELDS_SOLID><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), A, dev_buf);
     LAUNCH_CHECK();
     return 0;
 }
@@ -2133,7 +2167,8 @@ int b200sph_halo_overwrite_all(b200sph_ctx *ctx, const int64_t *ghost_first, con
     R.A = ctx->A;
     R.AB = ctx->AB;
     R.G = ctx->G;
-    k_halo_scatter_all<<<(unsigned)cdiv(tot, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), A, dev_buf, R);
+    if (halo_nf(ctx) == B200SPH_HALO_FIELDS) k_halo_scatter_all<B200SPH_HALO_FIELDS><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), A, dev_buf, R);
+    else k_halo_scatter_all<B200SPH_HALO_FIELDS_SOLID><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->stream>>>(halo_ptrs(ctx), A, dev_buf, R);
     LAUNCH_CHECK();
     ctx->grid_valid = false;
     ctx->packed_valid = repack;
@@ -2277,6 +2312,7 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
     count[0] = count[1] = 0;
     if (n == 0) return 0;
     const unsigned nb = (unsigned)cdiv(n + 1, 256);
+    const int mnf = migrate_nf(ctx);
     int64_t base = 0;  // doubles written so far
     for (int side = 0; side < 2; side++) {
         k_flag_range<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], off, n, lo, hi, side == 0 ? 1 : 2, ctx->flag_a);
@@ -2286,7 +2322,7 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
         CU(cudaMemcpyAsync(&tot, ctx->flag_b + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         count[side] = tot;
-        if (base + (int64_t)tot * B200SPH_MIGRATE_FIELDS > cap * B200SPH_MIGRATE_FIELDS) return set_err(ctx, "migrate_out: buffer too small");
+        if (base + (int64_t)tot * mnf > cap * mnf) return set_err(ctx, "migrate_out: buffer too small");
         if (tot) {
             for (int k = 0; k < N_F64; k++) {
                 k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64[k], off, n, ctx->flag_a, ctx->flag_b, dev_buf, base + (long long)k * tot);
@@ -2294,8 +2330,16 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
             }
             k_gather_u32_as_f64<<<nb, 256, 0, ctx->stream>>>(ctx->u32[0], off, n, ctx->flag_a, ctx->flag_b, dev_buf, base + (long long)N_F64 * tot);
             LAUNCH_CHECK();
+            if (ctx->solid_alloc) {
+                for (int k = 0; k < 12; k++) {
+                    k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64s[k], off, n, ctx->flag_a, ctx->flag_b, dev_buf, base + (long long)(B200SPH_MIGRATE_FIELDS + k) * tot);
+                    LAUNCH_CHECK();
+                }
+                k_gather_f32_as_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f32[B200SPH_CS - N_F64], off, n, ctx->flag_a, ctx->flag_b, dev_buf, base + (long long)(B200SPH_MIGRATE_FIELDS + 12) * tot);
+                LAUNCH_CHECK();
+            }
         }
-        base += (int64_t)tot * B200SPH_MIGRATE_FIELDS;
+        base += (int64_t)tot * mnf;
     }
     if (count[0] + count[1] == 0) return 0;
     // stable compaction of the keepers, property by property, through the staging buffer
@@ -2314,6 +2358,16 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi, double 
         k_gather_u32<<<nb, 256, 0, ctx->stream>>>(ctx->u32[k], off, n, ctx->flag_a, ctx->flag_b, (uint32_t *)ctx->stage_buf);
         LAUNCH_CHECK();
         if (keep) CU(cudaMemcpyAsync(ctx->u32[k] + off, ctx->stage_buf, 4 * (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (ctx->solid_alloc) {  // the keepers' stress state and cs move with them (the other fp32 fields are recomputed)
+        for (int k = 0; k < 12; k++) {
+            k_gather_f64<<<nb, 256, 0, ctx->stream>>>(ctx->f64s[k], off, n, ctx->flag_a, ctx->flag_b, ctx->stage_buf, 0);
+            LAUNCH_CHECK();
+            if (keep) CU(cudaMemcpyAsync(ctx->f64s[k] + off, ctx->stage_buf, 8 * (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        k_gather_u32<<<nb, 256, 0, ctx->stream>>>((const uint32_t *)ctx->f32[B200SPH_CS - N_F64], off, n, ctx->flag_a, ctx->flag_b, (uint32_t *)ctx->stage_buf);
+        LAUNCH_CHECK();
+        if (keep) CU(cudaMemcpyAsync(ctx->f32[B200SPH_CS - N_F64] + off, ctx->stage_buf, 4 * (size_t)keep, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     ai.n = ai.n_real = keep;
     ctx->ptype_dirty = true;

@@ -46,10 +46,17 @@ __global__ void k_gather_u32(const uint32_t *__restrict__ src, long long off, lo
     if (i >= n) return;
     if (flag[i]) dst[pos[i]] = src[off + i];
 }
+// the ghost message: B200SPH_HALO_FIELDS (x y z u v w rho h m), or with the elastic-dynamics
+// arrays allocated B200SPH_HALO_FIELDS_SOLID (+ s00 s01 s02 s11 s12 s22 and, last, the fp32
+// property cs widened to a double: no equation of that scheme recomputes it); NF is a
+// template parameter so that the 9-field kernels stay the unrolled ones that were measured
+#define HALO_ND(NF) ((NF) == B200SPH_HALO_FIELDS ? B200SPH_HALO_FIELDS : B200SPH_HALO_FIELDS_SOLID - 1)
 struct HaloPtrs {
-    double *p[B200SPH_HALO_FIELDS];
+    double *p[B200SPH_HALO_FIELDS_SOLID - 1];
+    float *cs;
 };
-// all B200SPH_HALO_FIELDS of the selected particles in one launch (field-major, tight)
+// all NF fields of the selected particles in one launch (field-major, tight)
+template <int NF>
 __global__ void k_halo_gather_flag(HaloPtrs P, long long off, long long n, const uint32_t *__restrict__ flag,
                                    const uint32_t *__restrict__ pos, double *__restrict__ dst, long long tot)
 {
@@ -57,8 +64,10 @@ __global__ void k_halo_gather_flag(HaloPtrs P, long long off, long long n, const
     if (i >= n || !flag[i]) return;
     const long long k = pos[i];
 #pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) dst[(long long)f * tot + k] = P.p[f][off + i];
+    for (int f = 0; f < HALO_ND(NF); f++) dst[(long long)f * tot + k] = P.p[f][off + i];
+    if (NF != B200SPH_HALO_FIELDS) dst[(long long)(NF - 1) * tot + k] = (double)P.cs[off + i];
 }
+template <int NF>
 __global__ void k_halo_gather_idx(HaloPtrs P, long long off, const uint32_t *__restrict__ idx, long long n,
                                   double *__restrict__ dst)
 {
@@ -66,14 +75,17 @@ __global__ void k_halo_gather_idx(HaloPtrs P, long long off, const uint32_t *__r
     if (k >= n) return;
     const long long i = idx[k];
 #pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) dst[(long long)f * n + k] = P.p[f][off + i];
+    for (int f = 0; f < HALO_ND(NF); f++) dst[(long long)f * n + k] = P.p[f][off + i];
+    if (NF != B200SPH_HALO_FIELDS) dst[(long long)(NF - 1) * n + k] = (double)P.cs[off + i];
 }
+template <int NF>
 __global__ void k_halo_scatter(HaloPtrs P, long long o, const double *__restrict__ src, long long stride, long long n)
 {
     long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
 #pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) P.p[f][o + k] = src[(long long)f * stride + k];
+    for (int f = 0; f < HALO_ND(NF); f++) P.p[f][o + k] = src[(long long)f * stride + k];
+    if (NF != B200SPH_HALO_FIELDS) P.cs[o + k] = (float)src[(long long)(NF - 1) * stride + k];
 }
 struct HaloAllArgs {
     int narr;
@@ -82,8 +94,9 @@ struct HaloAllArgs {
     const uint32_t *idx[B200SPH_MAX_ARRAYS];   // gather: saved selection (relative to off); scatter: unused
 };
 // the refresh message of ALL arrays in one launch: block of array a starts at
-// 9 * prefix[a] doubles, field-major and tight inside the block.  `dst` may be a peer
+// NF * prefix[a] doubles, field-major and tight inside the block.  `dst` may be a peer
 // pointer (the neighbour's staging buffer): then this kernel is pack + send in one.
+template <int NF>
 __global__ void k_halo_gather_all(HaloPtrs P, HaloAllArgs A, double *__restrict__ dst)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,9 +105,10 @@ __global__ void k_halo_gather_all(HaloPtrs P, HaloAllArgs A, double *__restrict_
     while (k >= A.prefix[a + 1]) a++;
     const long long r = k - A.prefix[a], cnt = A.prefix[a + 1] - A.prefix[a];
     const long long i = A.off[a] + A.idx[a][r];
-    double *out = dst + B200SPH_HALO_FIELDS * A.prefix[a] + r;
+    double *out = dst + NF * A.prefix[a] + r;
 #pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) out[(long long)f * cnt] = P.p[f][i];
+    for (int f = 0; f < HALO_ND(NF); f++) out[(long long)f * cnt] = P.p[f][i];
+    if (NF != B200SPH_HALO_FIELDS) out[(long long)(NF - 1) * cnt] = (double)P.cs[i];
 }
 struct RepackArgs {
     const uint32_t *rank, *skey;   // rank == nullptr: no repack
@@ -103,6 +117,7 @@ struct RepackArgs {
 };
 // ghost values refreshed in place; with a valid neighbour build the ghosts' packed
 // cell-relative positions are refreshed in the same pass (x, y, z, h are fields 0, 1, 2, 7)
+template <int NF>
 __global__ void k_halo_scatter_all(HaloPtrs P, HaloAllArgs A, const double *__restrict__ src, RepackArgs R)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,13 +125,14 @@ __global__ void k_halo_scatter_all(HaloPtrs P, HaloAllArgs A, const double *__re
     int a = 0;
     while (k >= A.prefix[a + 1]) a++;
     const long long r = k - A.prefix[a], cnt = A.prefix[a + 1] - A.prefix[a];
-    const double *in = src + B200SPH_HALO_FIELDS * A.prefix[a] + r;
-    double v[B200SPH_HALO_FIELDS];
+    const double *in = src + NF * A.prefix[a] + r;
+    double v[HALO_ND(NF)];
 #pragma unroll
-    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) {
+    for (int f = 0; f < HALO_ND(NF); f++) {
         v[f] = in[(long long)f * cnt];
         P.p[f][A.off[a] + r] = v[f];
     }
+    if (NF != B200SPH_HALO_FIELDS) P.cs[A.off[a] + r] = (float)in[(long long)(NF - 1) * cnt];
     if (R.rank) {
         const uint32_t s = R.rank[A.off[a] + r];
         uint32_t key = R.skey[s];
@@ -148,6 +164,14 @@ __global__ void k_f64_to_u32(const double *__restrict__ in, uint32_t *__restrict
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint32_t)in[i];
+}
+__global__ void k_gather_f32_as_f64(const float *__restrict__ src, long long off, long long n,
+                                    const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                                    double *__restrict__ dst, long long dst_off)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) dst[dst_off + pos[i]] = (double)src[off + i];
 }
 __global__ void k_fill_u32(uint32_t *p, long long n, uint32_t v)
 {

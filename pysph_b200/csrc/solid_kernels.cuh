@@ -19,7 +19,7 @@ struct SolidArgs {
     long long n;
     float cellx, celly, cellz, k2, kfac;
     unsigned elastic_mask;
-    int grad3d;
+    int grad3d, ghost_group1;
     float eps, alpha, beta, eps_xsph;
     double c0_ref[B200SPH_MAX_ARRAYS], rho_ref[B200SPH_MAX_ARRAYS], G[B200SPH_MAX_ARRAYS];
     float wdeltap[B200SPH_MAX_ARRAYS], nexp[B200SPH_MAX_ARRAYS];
@@ -107,8 +107,9 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, c
     if (active) {
         ti = __float_as_int(a.C3[s].w);
         const bool elastic = (a.elastic_mask >> (ti & 7)) & 1u;
-        ghost_src = elastic && (ti & PT_GHOST);
-        if ((ti & PT_GHOST) || !elastic) active = false;
+        // ghost_group1: ghosts are destinations of group 1 like everyone else (real=False)
+        ghost_src = elastic && (ti & PT_GHOST) && !a.ghost_group1;
+        if (ghost_src || !elastic) active = false;
     }
     if (ghost_src) {
         // a ghost is a source of group 2 with the values it carries (group 1 is real=True)
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, c
         a.C3[s].y = (float)p;
     }
     if (a.pair_counter) {
+        if (ti & PT_GHOST) npairs = 0;   // ghost destinations (ghost_group1) are the owner's pairs
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
         if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);

@@ -103,6 +103,21 @@ class DeviceHaloOps(object):
         self.narr = len(backend.names)
         self.device = torch.device('cuda', device)
 
+    def _layout(self):
+        h, m = C.c_int(), C.c_int()
+        self.ctx.call('b200sph_halo_layout', C.byref(h), C.byref(m))
+        return h.value, m.value
+
+    @property
+    def halo_nf(self):
+        """doubles per ghost in this context's messages: 9, or 16 with elastic arrays"""
+        return self._layout()[0]
+
+    @property
+    def migrate_nf(self):
+        """doubles per migrating particle: 17, or 30 with elastic arrays"""
+        return self._layout()[1]
+
     def new_buffer(self, ndoubles):
         return self.torch.empty(max(int(ndoubles), 1), dtype=self.torch.float64,
                                 device=self.device)
@@ -123,7 +138,7 @@ class DeviceHaloOps(object):
         """select lo <= x < hi (remembered under `slot`), pack into
         buf[offset:]; returns the particle count."""
         cnt = C.c_int64()
-        cap = (buf.numel() - offset) // HALO_FIELDS
+        cap = (buf.numel() - offset) // self.halo_nf
         self.ctx.call('b200sph_halo_pack', arr, slot, float(lo), float(hi),
                       buf.data_ptr() + 8 * offset, cap, C.byref(cnt))
         return cnt.value
@@ -131,7 +146,7 @@ class DeviceHaloOps(object):
     def pack_selected(self, arr, slot, buf, offset):
         """current values of the particles selected by the last pack(slot)."""
         cnt = C.c_int64()
-        cap = (buf.numel() - offset) // HALO_FIELDS
+        cap = (buf.numel() - offset) // self.halo_nf
         self.ctx.call('b200sph_halo_pack_selected', arr, slot,
                       buf.data_ptr() + 8 * offset, cap, C.byref(cnt))
         return cnt.value
@@ -229,7 +244,7 @@ class DeviceHaloOps(object):
 
     def migrate_out(self, arr, lo, hi, buf, offset):
         cnt = (C.c_int64 * 2)()
-        cap = (buf.numel() - offset) // MIGRATE_FIELDS
+        cap = (buf.numel() - offset) // self.migrate_nf
         self.ctx.call('b200sph_migrate_out', arr, float(lo), float(hi),
                       buf.data_ptr() + 8 * offset, cap, cnt)
         return cnt[0], cnt[1]
@@ -364,6 +379,14 @@ class SlabParallelManager(object):
                 w.wait()
         self.n_exchanges += 1
         return recv_counts, recv_bufs
+
+    @property
+    def _hnf(self):
+        return getattr(self.ops, 'halo_nf', HALO_FIELDS)
+
+    @property
+    def _mnf(self):
+        return getattr(self.ops, 'migrate_nf', MIGRATE_FIELDS)
 
     def _capacity(self, nfields):
         n = sum(self.ops.n_real(a) for a in range(self.narr))
@@ -524,7 +547,7 @@ class SlabParallelManager(object):
         ops, dist = self.ops, self.dist
         nbs = [nb for nb in (self.left, self.right) if nb is not None]
         need = max([sum(self._recv[nb]) for nb in nbs] +
-                   [sum(self._sent[nb]) for nb in nbs] + [1]) * HALO_FIELDS
+                   [sum(self._sent[nb]) for nb in nbs] + [1]) * self._hnf
         t = ops.new_buffer(1)
         t.fill_(float(need))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -583,15 +606,15 @@ class SlabParallelManager(object):
         ops_list, recv_bufs, keep = [], {}, []
         for nb in nbs:
             slot = 0 if nb == self.left else 1
-            ns = sum(self._sent[nb]) * HALO_FIELDS
-            nr = sum(self._recv[nb]) * HALO_FIELDS
+            ns = sum(self._sent[nb]) * self._hnf
+            nr = sum(self._recv[nb]) * self._hnf
             if ns:
                 buf = ops.new_buffer(ns)
                 off = 0
                 for a in range(self.narr):
                     n = ops.pack_selected(a, slot, buf, off) if self._sent[nb][a] else 0
                     assert n == self._sent[nb][a]
-                    off += n * HALO_FIELDS
+                    off += n * self._hnf
                 keep.append(buf)
                 ops_list.append(self.dist.P2POp(self.dist.isend, buf[:ns], nb))
                 self.bytes_sent += 8 * ns
@@ -608,12 +631,12 @@ class SlabParallelManager(object):
             for a, n in enumerate(self._recv[nb]):
                 ops.overwrite(a, first[a], recv_bufs.get(nb), o, n)
                 first[a] += n
-                o += n * HALO_FIELDS
+                o += n * self._hnf
         self.n_exchanges += 1
 
     def _migrate(self):
         ops = self.ops
-        cap = self._capacity(MIGRATE_FIELDS)
+        cap = self._capacity(self._mnf)
         buf = ops.new_buffer(cap)
         send_counts = dict((nb, [0] * self.narr) for nb in (self.left, self.right)
                            if nb is not None)
@@ -630,8 +653,8 @@ class SlabParallelManager(object):
                             'slab decomposition: %d particles left the global '
                             'domain through an outer cut plane' % n)
                     send_counts[nb][a] = n
-                    blocks[nb].append((off, n * MIGRATE_FIELDS))
-                off += n * MIGRATE_FIELDS
+                    blocks[nb].append((off, n * self._mnf))
+                off += n * self._mnf
         send_bufs = {}
         for nb in send_counts:
             tot = sum(n for _, n in blocks[nb])
@@ -642,12 +665,12 @@ class SlabParallelManager(object):
                 o += n
             send_bufs[nb] = sb
         recv_counts, recv_bufs = self._exchange(send_counts, send_bufs,
-                                                MIGRATE_FIELDS)
+                                                self._mnf)
         for nb in sorted(recv_counts):
             o = 0
             for a, n in enumerate(recv_counts[nb]):
-                ops.append(a, recv_bufs.get(nb), o, n, MIGRATE_FIELDS, True)
-                o += n * MIGRATE_FIELDS
+                ops.append(a, recv_bufs.get(nb), o, n, self._mnf, True)
+                o += n * self._mnf
 
     def _import_ghosts(self):
         ops = self.ops
@@ -657,22 +680,22 @@ class SlabParallelManager(object):
             if nb is None:
                 continue
             slot = 0 if nb == self.left else 1
-            buf = ops.new_buffer(self._capacity(HALO_FIELDS))
+            buf = ops.new_buffer(self._capacity(self._hnf))
             counts, off = [], 0
             for a in range(self.narr):
                 n = ops.pack(a, slot, lo, hi, buf, off) if ops.n_real(a) else 0
                 counts.append(n)
-                off += n * HALO_FIELDS
+                off += n * self._hnf
             send_counts[nb], send_bufs[nb] = counts, buf
         recv_counts, recv_bufs = self._exchange(send_counts, send_bufs,
-                                                HALO_FIELDS)
+                                                self._hnf)
         self._sent, self._recv = send_counts, recv_counts
         # deterministic order: left neighbour's ghosts first
         for nb in sorted(recv_counts):
             o = 0
             for a, n in enumerate(recv_counts[nb]):
-                ops.append(a, recv_bufs.get(nb), o, n, HALO_FIELDS, False)
-                o += n * HALO_FIELDS
+                ops.append(a, recv_bufs.get(nb), o, n, self._hnf, False)
+                o += n * self._hnf
 
     def reduce_dt_device(self, view):
         """MIN over ranks of a 1-element device tensor, in place, no host sync
@@ -718,3 +741,63 @@ def make_slab_solver(dx, params, kernel, rank, world, device=0,
                                          for pa in pas])
     solver.set_parallel_manager(pm)
     return solver, pm, pas
+
+
+def rings_column_weights(dx, ri=0.03, ro=0.04, spacing=0.041):
+    """x columns of geometry.rings_3d_particles and the particles per unit z-layer in
+    each (the cut planes are balanced on these)."""
+    n = int(round(2 * ro / dx))
+    ax = -ro + dx * np.arange(n)
+    x, y = np.meshgrid(ax, ax, indexing='ij')
+    d = x * x + y * y
+    cnt = np.count_nonzero((ri * ri <= d) * (d < ro * ro), axis=1).astype(float)
+    xs = np.concatenate([ax - spacing, ax + spacing]) + spacing
+    w = np.concatenate([cnt, cnt])
+    order = np.argsort(xs, kind='stable')
+    xs, w = xs[order], w[order]
+    # the two rings' lattices interleave where they overlap in x: merge equal columns
+    keep = np.concatenate([[True], np.diff(xs) > 1e-9 * dx])
+    idx = np.cumsum(keep) - 1
+    return xs[keep], np.bincount(idx, weights=w)
+
+
+def make_rings_slab_solver(dx, lz, rank, world, device=0, dt=None, lb_freq=0,
+                           geometry_kw=None, **solver_kw):
+    """This rank's x-slab of the 3-D colliding rings (BASELINE configs[4]) and a ready
+    EPEC + SolidMechStep solver.  Differences from the WCSPH slabs: the ghost message
+    carries the deviatoric stress (16 fields, migration 30), and the halo is TWO kernel
+    supports (+ skin) wide with group 1 a ``Group(real=False)``: pressure, velocity
+    gradient and artificial stress of the inner ghost layer are recomputed locally from
+    the same neighbours their owner sees, so N ranks reproduce the one-process result
+    (a reference Remote particle carries the values of the previous evaluation instead,
+    parallel_manager.pyx:512-530) -- without a second exchange in the middle of an
+    evaluation."""
+    import os
+    import pysph_b200 as pb
+    from . import geometry as geo
+    gkw = dict(geometry_kw or {})
+    xs, w = rings_column_weights(dx, **dict((k, gkw[k]) for k in ('ri', 'ro', 'spacing')
+                                            if k in gkw))
+    # columns of the two lattices need not be dx apart where the rings overlap in x:
+    # cut half a lattice spacing to the left of a column, never through one
+    cuts = balanced_cuts(xs, w, world, min(dx, float(np.min(np.diff(xs)))))
+    pa = geo.rings_3d_particles(dx=dx, lz=lz, x_range=(cuts[rank], cuts[rank + 1]), **gkw)
+    hdx = gkw.get('hdx', 1.5)
+    kernel = pb.CubicSpline(dim=3)
+    skin = float(os.environ.get('B200SPH_SKIN', '0.1'))
+    halo = 2.0 * kernel.radius_scale * hdx * dx * (1.0 + skin) * 1.0001
+    n_real = pa.get_number_of_particles()
+    extra = int(1.0 * n_real) + 4096
+    sch = pb.ElasticSolidsScheme(['solid'], [], dim=3, ghost_group1=True)
+    if dt is None:
+        dt = 1e-8 * dx / 0.0005                 # rings.py:36, same dt / h
+    solver = pb.make_elastic_solver([pa], sch, kernel, dt=dt, device=device,
+                                    capacity_factor=1.05, extra_capacity=extra, **solver_kw)
+    ops = DeviceHaloOps(solver.backend, device)
+    width = float(np.min(np.diff(xs)))
+    pm = SlabParallelManager(ops, rank, world, cuts, halo, lb_freq=lb_freq,
+                             lb_columns=(float(xs[0] - 0.5 * width), width,
+                                         int(round((xs[-1] - xs[0]) / width)) + 1),
+                             lb_weights=[1.0])
+    solver.set_parallel_manager(pm)
+    return solver, pm, [pa]

@@ -69,11 +69,14 @@ def _build_solid(g, kind, index, particle_arrays):
     if particle_arrays is None:
         raise ValueError('the elastic-dynamics equations read array constants: pass '
                          'particle_arrays to build_program')
-    if not getattr(g, 'real', True):
-        raise NotImplementedError('B200 backend: elastic-dynamics Groups are real=True')
+    if not getattr(g, 'real', True) and kind != 1:
+        raise NotImplementedError('B200 backend: elastic-dynamics group 2 is real=True')
     names = [_eq_name(e) for e in g.equations]
     allowed = SOLID_GROUP1 if kind == 1 else SOLID_GROUP2
     prog = _lib.SolidProgram()
+    # Group(real=False) (equation.py:452-560): group 1 also runs on the ghosts -- what the
+    # slab decomposition asks for so that a ghost's p / artificial stress are current
+    prog.ghost_group1 = int(kind == 1 and not getattr(g, 'real', True))
     params = {}
     dests = []
     for eq in g.equations:
@@ -147,6 +150,7 @@ def _merge_solid(ops):
             op[1].passes = 3
             op[1].grad3d = out[-1][1].grad3d
             op[1].eps = out[-1][1].eps
+            op[1].ghost_group1 = out[-1][1].ghost_group1
             out[-1] = op
         else:
             out.append(op)

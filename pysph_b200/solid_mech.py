@@ -46,10 +46,15 @@ class SolidMechStep(IntegratorStep):
 
 class ElasticSolidsScheme(object):
     """solid_mech/basic.py:592-651; ``use_3d_gradient`` swaps VelocityGradient2D (what
-    the reference scheme always emits) for VelocityGradient3D, which a 3-D run needs."""
+    the reference scheme always emits) for VelocityGradient3D, which a 3-D run needs.
+    ``ghost_group1`` makes group 1 a ``Group(real=False)``: with the slab decomposition
+    importing two kernel supports of ghosts (parallel.make_rings_slab_solver) the ghosts'
+    p and artificial stress are then this evaluation's, and N ranks reproduce one."""
 
     def __init__(self, elastic_solids, solids, dim, artificial_stress_eps=0.3,
-                 xsph_eps=0.5, alpha=1.0, beta=1.0, use_3d_gradient=None):
+                 xsph_eps=0.5, alpha=1.0, beta=1.0, use_3d_gradient=None,
+                 ghost_group1=False):
+        self.ghost_group1 = bool(ghost_group1)
         self.elastic_solids = list(elastic_solids)
         self.solids = list(solids)
         self.dim = dim
@@ -80,4 +85,4 @@ class ElasticSolidsScheme(object):
                                                   alpha=self.alpha, beta=self.beta))
             g2.append(HookesDeviatoricStressRate(dest=es, sources=None))
             g2.append(XSPHCorrection(dest=es, sources=[es], eps=self.xsph_eps))
-        return [Group(equations=g1), Group(g2)]
+        return [Group(equations=g1, real=not self.ghost_group1), Group(g2)]

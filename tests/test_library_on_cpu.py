@@ -502,6 +502,115 @@ def test_slab_decomposition_on_the_emulated_library(emulated_library, world, lb_
             assert np.max(np.abs(a - ref[name][k][order_ref])) <= tol, (name, k)
 
 
+RINGS = dict(dx=0.0025, lz=0.0075, dt=2e-7, steps=10, u_f=0.25)
+RING_FIELDS = ('x', 'y', 'z', 'u', 'v', 'w', 'rho', 's00', 's01', 's02', 's11', 's12', 's22')
+
+
+def _rings_perturb(pa):
+    """pressure and shear everywhere (not only at the contact), the same function of
+    position whatever the decomposition"""
+    pa.rho[:] *= 1.0 + 0.01 * np.sin(300.0 * pa.x + 170.0 * pa.y + 90.0 * pa.z)
+    pa.v[:] += 0.02 * pa.cs * np.sin(250.0 * pa.x)
+    pa.w[:] += 0.02 * pa.cs * np.cos(200.0 * pa.y)
+
+
+def _rings_collect(pa):
+    nr = pa.get_number_of_particles(real=True)
+    return dict((k, pa.properties[k][:nr].copy()) for k in ('gid',) + RING_FIELDS)
+
+
+def _rings_worker(rank, world, port, so, q):
+    import torch
+    import torch.distributed as dist
+    from pysph_b200 import _lib
+    _lib.LIB_PATH, _lib._lib = so, None
+    from pysph_b200 import parallel
+
+    Base = parallel.DeviceHaloOps
+
+    class HostHaloOps(Base):
+        def __init__(self, backend, device):
+            Base.__init__(self, backend, 0)
+            self.device = torch.device('cpu')
+
+        def read_later(self, tensor):
+            v = float(tensor[0])
+            return lambda: v
+    parallel.DeviceHaloOps = HostHaloOps
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        solver, pm, pas = parallel.make_rings_slab_solver(
+            RINGS['dx'], RINGS['lz'], rank, world, dt=RINGS['dt'],
+            geometry_kw=dict(u_f=RINGS['u_f']))
+        assert pm.ops.halo_nf == 16 and pm.ops.migrate_nf == 30
+        _rings_perturb(pas[0])
+        solver.backend.push_all()
+        n0 = pas[0].get_number_of_particles()
+        for _ in range(RINGS['steps']):
+            solver.step()
+        solver.pull()
+        q.put((rank, _rings_collect(pas[0]), pm.n_full, pm.n_refresh, n0,
+               pas[0].get_number_of_particles(real=True)))
+    except Exception:
+        import traceback
+        q.put(('error', rank, traceback.format_exc()))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rings_slab_decomposition_on_the_emulated_library(emulated_library):
+    """BASELINE configs[4] across ranks, without GPUs: the 3-D colliding rings cut into 3
+    x-slabs (the ghost message carries the deviatoric stress, migration the stress and its
+    stage copy, group 1 runs on a two-support halo) against the one-process run, by gid.
+    The rings move fast enough (u_f = 0.25) that lists are rebuilt, particles migrate
+    and the bodies are in contact within the 10 steps."""
+    import socket
+    import torch.multiprocessing as mp
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo, _lib
+    world = 3
+    pa = geo.rings_3d_particles(dx=RINGS['dx'], lz=RINGS['lz'], u_f=RINGS['u_f'])
+    _rings_perturb(pa)
+    s = pb.make_elastic_solver([pa], pb.ElasticSolidsScheme(['solid'], [], dim=3),
+                               pb.CubicSpline(dim=3), dt=RINGS['dt'])
+    for _ in range(RINGS['steps']):
+        s.step()
+    s.pull()
+    ref = _rings_collect(pa)
+    assert np.max(np.abs(ref['s00'])) > 1.0
+    sock = socket.socket()
+    sock.bind(('127.0.0.1', 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rings_worker, args=(r, world, port, _lib.LIB_PATH, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=900) for _ in range(world)]
+    assert not any(o[0] == 'error' for o in out), [o[2] for o in out if o[0] == 'error'][:1]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert min(o[2] for o in out) >= 2                  # full paths (rebuild + migration)
+    assert any(o[4] != o[5] for o in out)               # somebody gained / lost particles
+    g_all = np.concatenate([o[1]['gid'] for o in out])
+    assert np.array_equal(np.sort(g_all), np.sort(ref['gid']))
+    order_ref, order = np.argsort(ref['gid']), np.argsort(g_all)
+    c0 = pa.cs[0]
+    smax = np.max(np.abs(ref['s00']))
+    tols = dict(x=1e-7 * 0.08, y=1e-7 * 0.08, z=1e-7 * 0.08, u=2e-6 * c0, v=2e-6 * c0,
+                w=2e-6 * c0, rho=5e-6)
+    for k in RING_FIELDS:
+        a = np.concatenate([o[1][k] for o in out])[order]
+        tol = tols.get(k, 2e-4 * smax)
+        assert np.max(np.abs(a - ref[k][order_ref])) <= tol, (k, np.max(np.abs(a - ref[k][order_ref])), tol)
+
+
 def test_solver_configuration_surface(emulated_library, tmp_path):
     """The reference Solver's set_* / add_*_callback methods (solver.py:231-384) drive the
     same loop: callbacks see the solver before / after every step (t not yet advanced in the
