@@ -33,6 +33,7 @@ struct idx3 { unsigned x, y, z; };
 #define __shared__ static
 
 namespace emu {
+void yield();   // cuda_shim.cpp: hand the core to the next lock-stepped lane
 struct Barrier {
     int n;
     std::atomic<int> arrived{0};
@@ -45,7 +46,7 @@ struct Barrier {
             arrived.store(0, std::memory_order_relaxed);
             phase.store(ph + 1, std::memory_order_release);
         } else {
-            while (phase.load(std::memory_order_acquire) == ph) std::this_thread::yield();
+            while (phase.load(std::memory_order_acquire) == ph) emu::yield();
         }
     }
 };
@@ -59,8 +60,8 @@ struct BlockCtx {
     explicit BlockCtx(int nt) : bar(nt), warps((size_t)(nt + 31) / 32) {}
 };
 extern thread_local idx3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
-extern thread_local WarpCtx *t_warp;     // non-null: lanes are real threads
-extern thread_local BlockCtx *t_block;   // non-null: block threads are real threads
+extern thread_local WarpCtx *t_warp;     // non-null: lanes run in lock step (fibers, or real threads)
+extern thread_local BlockCtx *t_block;   // non-null: the block's threads run in lock step
 extern thread_local int t_lane;
 enum Mode { SEQ = 0, WARP = 1, BLOCK = 2 };
 void launch(long long grid, long long block, int mode, const std::function<void()> &body);

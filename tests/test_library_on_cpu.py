@@ -2,7 +2,7 @@
 kernels -- is transformed (tests/cpu_emul/transform.py: kernel launches become emu::launch
 calls, nothing else changes), compiled with g++ against a host stand-in for the CUDA runtime and
 device intrinsics (tests/cpu_emul/cuda_shim.h: blocks run in order; threads of a block in order,
-or as lock-stepped OS threads with real __syncthreads / shuffles / ballots / atomics) and loaded
+or lock-stepped -- as fibers, or with B200SPH_EMUL_THREADS=1 as OS threads -- with real __syncthreads / shuffles / ballots / atomics) and loaded
 in place of libb200sph.so.  The GPU parity tests of this repository are then run against it.
 
 This is TEST INFRASTRUCTURE: the product never loads this library (pysph_b200/_lib.py knows only
@@ -69,9 +69,9 @@ def test_every_entry_point_is_exported(emulated_library):
 
 
 # ---- the GPU tests of this repository, run against the emulated library --------------------
-# (module, test, kwargs, approx seconds).  The default selection takes ~2 minutes; the rest runs
-# with B200SPH_EMUL_FULL=1 (another ~12 minutes: hundreds of steps of 14 k particles with every
-# thread of the list kernels a real OS thread).
+# (module, test, kwargs).  The default selection takes ~1.5 minutes (lock-stepped lanes are
+# fibers, cuda_shim.cpp); the rest runs with B200SPH_EMUL_FULL=1 (another ~2 minutes).
+# B200SPH_EMUL_THREADS=1 makes every lane a real OS thread instead (the cross-check: ~5x slower).
 FAST = [
     ('test_gpu_parity', 'test_density_1d_fixture', {}),
     ('test_gpu_parity', 'test_nnps_equals_brute_force', {}),
@@ -95,18 +95,18 @@ FAST = [
     ('test_zz_gpu_solid_unvalidated', 'test_solid_mech_step_matches_reference_bodies', {}),
     ('test_zz_gpu_solid_unvalidated', 'test_rings_steps_vs_oracle', {}),
     ('test_zz_gpu_solid_unvalidated', 'test_rings_3d_steps_vs_oracle', {}),
-]
-FULL = [
     ('test_gpu_parity', 'test_kernels_via_two_particle_density', {}),
     ('test_gpu_parity', 'test_dam_break_3d_small_eval_and_steps', {}),
     ('test_gpu_parity', 'test_dam_break_2d_gate', {}),
     ('test_gpu_parity', 'test_determinism', {}),
     ('test_gpu_parity', 'test_deferred_drift_check_protocol', {}),
-    ('test_gpu_parity', 'test_device_resident_dt_is_bitwise_the_host_path', {}),
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 2, 'n': 24, 'pattern': (0, 1, 0)}),
-    ('test_zz_gpu_gate_25k_unvalidated', 'test_dam_break_2d_gate_25k', {}),
     ('test_output', 'test_dump_and_restart_on_device', {'tmp_path': None}),
+]
+FULL = [
+    ('test_gpu_parity', 'test_device_resident_dt_is_bitwise_the_host_path', {}),
+    ('test_zz_gpu_gate_25k_unvalidated', 'test_dam_break_2d_gate_25k', {}),
 ]
 
 
