@@ -1,0 +1,25 @@
+#!/bin/bash
+# First hardware contact of everything that was written without GPU time:
+# ONE gpurun call on ONE GPU.  Each step has its own timeout so that a defect in one does
+# not cost the others; outputs land in gpurun_out/first_contact/.
+#   gpurun --timeout 1500 -- 'bash profiles/first_contact.sh'
+# The 2-GPU items (tests/test_zz_gpu_recut_unvalidated.py, test_zz_gpu_rings_multi_unvalidated.py,
+# `torchrun --nproc-per-node 4 bench.py --gpus 4 --workload rings`) need `gpurun --gpus N`.
+O=gpurun_out/first_contact
+mkdir -p $O
+run() { name=$1; shift; echo "== $name" | tee -a $O/summary.txt; timeout 420 "$@" > $O/$name.log 2>&1; echo "exit $?" | tee -a $O/summary.txt; tail -3 $O/$name.log >> $O/summary.txt; }
+# 1. the validated suite first (must stay green), then the unvalidated files with xfail lifted
+run validated python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_multi.py -k "not unvalidated"
+run solid python -m pytest tests/test_zz_gpu_solid_unvalidated.py -m gpu -q --runxfail
+run async_output python -m pytest tests/test_zz_gpu_async_output_unvalidated.py -m gpu -q --runxfail
+run gate25k python -m pytest tests/test_zz_gpu_gate_25k_unvalidated.py -m gpu -q --runxfail
+# 2. the three bench workloads
+run bench_dam python bench.py
+run bench_tg python bench.py --workload taylor_green
+run bench_rings python bench.py --workload rings
+# 3. launch list + one full capture of the elastic-dynamics kernels
+run ncu_rings_launches ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
+    --log-file $O/launches_rings.csv python bench.py --workload rings --steps 3 --warmup 3 --no-cpu --e2e-steps 1
+run ncu_rings_full ncu --set full --clock-control none --import-source on -k regex:k_solid_pass -s 4 -c 2 \
+    -f -o $O/solid python bench.py --workload rings --steps 1 --warmup 3 --no-cpu --e2e-steps 1
+cat $O/summary.txt
