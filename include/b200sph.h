@@ -216,6 +216,16 @@ int b200sph_set_kernel(b200sph_ctx *ctx, int kernel, int dim);
  * :744-940): the cell grid tiles the axis exactly and neighbour cells wrap. */
 int b200sph_set_domain(b200sph_ctx *ctx, const double lo[3], const double hi[3],
                        const int periodic[3]);
+/* DomainManager(mirror_in_x ...) nnps_base.pyx:329-335, _create_ghosts_mirror :506-689
+ * (after b200sph_set_domain, which gives the planes lo / hi): every particle within
+ * n_layers cells (+ the list skin) of a mirror plane gets an image with tag = Ghost on the
+ * other side -- position reflected, the normal velocity component negated, x y z u v w
+ * rho h m copied (p, cs follow from the EOS) -- and images of images at the corners in the
+ * reference's order (x, then y of real + x images, then z of everything).  The reference
+ * re-selects at every update_domain; here the selection is made when the neighbour lists
+ * are built and b200sph_nnps_update refreshes the images' values before every evaluation.
+ * WCSPH arrays, one GPU (no slab decomposition). */
+int b200sph_set_mirror(b200sph_ctx *ctx, const int mirror[3], double n_layers);
 /* NNPS.update_domain -> CPUDomainManager._compute_cell_size_for_binning
  * nnps_base.pyx:450-483, :942-978 */
 int b200sph_update_domain(b200sph_ctx *ctx);

@@ -381,6 +381,50 @@ def periodic_ghosts(pas, lo, hi, periodic, cell_size, n_layers=2.0, factory=None
     return out
 
 
+def mirror_ghosts(pas, lo, hi, mirror, cell_size, n_layers=2.0, factory=None):
+    """_create_ghosts_mirror, pysph/base/nnps_base.pyx:506-689: returns NEW arrays = real
+    particles + their mirror images (tag Ghost = 2) appended.  Selection: (x - min) <=
+    n_layers * cell_size / (max - x) <= n_layers * cell_size (:568-590); image position
+    x + (-2 (x - min)) / x + 2 (max - x), normal velocity times -1 (:598-611); x images of
+    the real particles first, then y images of the images so far (low, high) followed by
+    the y images of the real particles (high, low) (:613-652), then z likewise (:654-689)."""
+    from pysph_b200.particle_array import get_particle_array_wcsph
+    width = n_layers * cell_size
+    vel = ('u', 'v', 'w')
+    out = []
+    for pa in pas:
+        nr = pa.get_number_of_particles(real=True)
+        props = dict((k, v[:nr].copy()) for k, v in pa.properties.items())
+        added = dict((k, v[:0].copy()) for k, v in props.items())
+
+        def image(src, name, d, low):
+            sel = ((src[name] - lo[d]) <= width) if low else ((hi[d] - src[name]) <= width)
+            blk = dict((k, v[sel].copy()) for k, v in src.items())
+            blk[name] = blk[name] + (-2.0 * (blk[name] - lo[d]) if low else 2.0 * (hi[d] - blk[name]))
+            blk[vel[d]] = -1.0 * blk[vel[d]]
+            return blk
+
+        def cat(parts):
+            return dict((k, np.concatenate([p[k] for p in parts])) for k in props)
+
+        for d, name in enumerate(('x', 'y', 'z')):
+            if not mirror[d]:
+                continue
+            if d == 0:
+                new = [image(props, name, d, True), image(props, name, d, False)]
+            else:
+                # both corner blocks select from `added` as it was before this axis
+                new = [image(added, name, d, True), image(added, name, d, False),
+                       image(props, name, d, False), image(props, name, d, True)]
+            added = cat([added] + new)
+        allp = cat([props, added])
+        q = (factory or get_particle_array_wcsph)(name=pa.name, **allp)
+        q.set_num_real_particles(nr)
+        q.tag[nr:] = 2
+        out.append(q)
+    return out
+
+
 class WCSPHOracleSolver(object):
     """Runs a WCSPHScheme simulation with the oracle: scheme.py:388-506 for the
     loops, integrator.py:344-361/401-420 for the stage order, solver.py for the
@@ -388,8 +432,8 @@ class WCSPHOracleSolver(object):
 
     def __init__(self, particles, params, kernel='CubicSpline', threads=1,
                  domain=None):
-        """domain = (lo[3], hi[3], periodic[3]) or None.  With a periodic
-        domain every ``update_domain`` re-creates the periodic ghost images
+        """domain = (lo[3], hi[3], periodic[3][, mirror[3]]) or None.  With a periodic
+        or mirror domain every ``update_domain`` re-creates the periodic ghost images
         (DomainManager.update, nnps_base.pyx:405-433), so ``self.pas`` (the
         arrays with ghosts) is replaced each time."""
         p = dict(params)
@@ -423,18 +467,24 @@ class WCSPHOracleSolver(object):
         self._initialised = False
 
     def _reghost(self):
-        lo, hi, per = self.domain
+        lo, hi, per = self.domain[:3]
+        mir = self.domain[3] if len(self.domain) > 3 else (0, 0, 0)
         real = []
         from pysph_b200.particle_array import get_particle_array_wcsph
         for pa in self.pas:
             nr = pa.get_number_of_particles(real=True)
             q = get_particle_array_wcsph(name=pa.name, **dict(
                 (k, v[:nr].copy()) for k, v in pa.properties.items()))
+            q.set_num_real_particles(nr)
             real.append(q)
-        periodic_box_wrap(real, lo, hi, per)
         k = load().orc_kernel_radius_scale(K_IDS[self.kernel])
         hmax = max(float(np.max(q.h)) for q in real if len(q.h))
-        self.pas = periodic_ghosts(real, lo, hi, per, k * hmax)
+        if any(per):
+            periodic_box_wrap(real, lo, hi, per)
+            real = periodic_ghosts(real, lo, hi, per, k * hmax)
+        if any(mir):                       # DomainManager.update, nnps_base.pyx:471-480
+            real = mirror_ghosts(real, lo, hi, mir, k * hmax)
+        self.pas = real
         self.o = Oracle(self.pas, self.dim, self.kernel, threads=self.threads)
 
     def update_domain(self):

@@ -12,6 +12,7 @@ run() { name=$1; shift; echo "== $name" | tee -a $O/summary.txt; timeout 420 "$@
 run validated python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_multi.py -k "not unvalidated"
 run solid python -m pytest tests/test_zz_gpu_solid_unvalidated.py -m gpu -q --runxfail
 run async_output python -m pytest tests/test_zz_gpu_async_output_unvalidated.py -m gpu -q --runxfail
+run mirror python -m pytest tests/test_zz_gpu_mirror_unvalidated.py -m gpu -q --runxfail
 run gate25k python -m pytest tests/test_zz_gpu_gate_25k_unvalidated.py -m gpu -q --runxfail
 # 2. the three bench workloads
 run bench_dam python bench.py

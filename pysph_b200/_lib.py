@@ -121,6 +121,7 @@ SIGNATURES = {
                                      C.POINTER(C.c_void_p)]),
     'b200sph_set_kernel': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
     'b200sph_set_domain': (C.c_int, [_ctx_p, _dp, _dp, C.POINTER(C.c_int)]),
+    'b200sph_set_mirror': (C.c_int, [_ctx_p, C.POINTER(C.c_int), C.c_double]),
     'b200sph_update_domain': (C.c_int, [_ctx_p]),
     'b200sph_nnps_update': (C.c_int, [_ctx_p]),
     'b200sph_nnps_update_deferred': (C.c_int, [_ctx_p]),

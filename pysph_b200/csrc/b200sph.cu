@@ -108,6 +108,16 @@ struct b200sph_ctx {
     // domain manager
     bool periodic[3] = {false, false, false};
     double dom_lo[3] = {0, 0, 0}, dom_hi[3] = {0, 0, 0};
+    // mirror boundaries (b200sph_set_mirror): images are materialised as tag=Ghost particles
+    bool mirror[3] = {false, false, false};
+    double mirror_layers = 2.0;
+    struct MirrorSeg {
+        int arr, axis, side;
+        int64_t count = 0, cap = 0, ghost_first = 0;   // ghost_first: relative to the array's first ghost
+        uint32_t *idx = nullptr;                        // sources, relative to the array's offset
+    };
+    std::vector<MirrorSeg> mirror_segs;                 // in creation order (corner images read earlier ones)
+    bool mirror_built = false;
     double cell_size = 1.0, hmin_scaled = 1.0;
     bool domain_valid = false;
     // grid
@@ -581,6 +591,7 @@ int b200sph_destroy(b200sph_ctx *ctx)
     for (int k = 0; k < N_F64X; k++) cudaFree(ctx->f64x[k]);
     for (int k = 0; k < N_F32X; k++) cudaFree(ctx->f32x[k]);
     cudaFree(ctx->Dv); cudaFree(ctx->PT);
+    for (auto &sg : ctx->mirror_segs) cudaFree(sg.idx);
     for (int k = 0; k < 12; k++) cudaFree(ctx->f64s[k]);
     for (int k = 0; k < 21; k++) cudaFree(ctx->f32s[k]);
     cudaFree(ctx->T01); cudaFree(ctx->T2R); cudaFree(ctx->R2);
@@ -959,6 +970,25 @@ int b200sph_set_domain(b200sph_ctx *ctx, const double lo[3], const double hi[3],
     return 0;
 }
 
+static inline bool mirror_any(const b200sph_ctx *ctx) { return ctx->mirror[0] || ctx->mirror[1] || ctx->mirror[2]; }
+static int mirror_create(b200sph_ctx *ctx);
+static int mirror_refresh(b200sph_ctx *ctx);
+
+int b200sph_set_mirror(b200sph_ctx *ctx, const int mirror[3], double n_layers)
+{
+    if (!(n_layers >= 1.0)) return set_err(ctx, "set_mirror: n_layers must be >= 1 (the images must cover one kernel support)");
+    for (int d = 0; d < 3; d++) {
+        if (mirror[d] && !(ctx->dom_hi[d] > ctx->dom_lo[d])) return set_err(ctx, "Invalid domain limits!");
+        if (mirror[d] && ctx->periodic[d]) return set_err(ctx, "set_mirror: axis %d is periodic", d);
+    }
+    for (int d = 0; d < 3; d++) ctx->mirror[d] = mirror[d] != 0;
+    ctx->mirror_layers = n_layers;
+    ctx->mirror_built = false;
+    ctx->grid_valid = false, ctx->packed_valid = false;
+    ctx->topo_dirty = true;
+    return 0;
+}
+
 int b200sph_update_domain(b200sph_ctx *ctx)
 {
     CU(cudaSetDevice(ctx->device));
@@ -1102,6 +1132,8 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     const bool use_lists = ctx->force_kernel == 0 && ntot0 < (1LL << LIST_JBITS);
     if (use_lists && ctx->lists_valid && !ctx->topo_dirty &&
         !(ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min && !ctx->drift_ok)) {
+        // mirror images: the same ghosts, current values (the set is re-selected with the lists)
+        if (mirror_any(ctx) && ctx->mirror_built && (rc = mirror_refresh(ctx))) return rc;
         rc = nnps_light_update(ctx);
         if (rc < 0) return rc;
         if (rc == 1) {
@@ -1124,6 +1156,11 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     ctx->lists_valid = false;
     ctx->drift_ok = false;
     ctx->n_full_builds++;
+    if (mirror_any(ctx)) {
+        // _create_ghosts_mirror (nnps_base.pyx:506-689) -- here once per list build, not per update
+        if ((rc = mirror_create(ctx))) return rc;
+        if (!ctx->domain_valid && (rc = b200sph_update_domain(ctx))) return rc;
+    }
 
     int64_t ntot = 0;
     for (int a = 0; a < ctx->narr; a++) ntot += ctx->arr[a].n;
@@ -1946,6 +1983,97 @@ static HaloPtrs halo_ptrs(b200sph_ctx *ctx)
     for (int f = B200SPH_HALO_FIELDS; f < B200SPH_HALO_FIELDS_SOLID - 1; f++) P.p[f] = ctx->f64s[f - B200SPH_HALO_FIELDS];
     P.cs = ctx->f32[B200SPH_CS - N_F64];
     return P;
+}
+
+// ---- mirror boundaries ----------------------------------------------------------------
+// DomainManager(mirror_in_x ...) nnps_base.pyx:506-689: every particle within n_layers cells
+// of a mirror plane gets an image on the other side (position reflected, the normal velocity
+// component negated, everything else copied), images of images at the corners: x images
+// first, then y images of the real particles AND of the x images, then z images of
+// everything.  The reference re-selects at every update_domain; here the selection lives as
+// long as the neighbour lists (its width covers the skin) and nnps_update refreshes the
+// images' values in creation order before every evaluation.
+static int mirror_refresh(b200sph_ctx *ctx)
+{
+    const HaloPtrs P = halo_ptrs(ctx);
+    for (const auto &sg : ctx->mirror_segs) {
+        if (sg.count == 0) continue;
+        const ArrayInfo &ai = ctx->arr[sg.arr];
+        const double plane2 = 2.0 * (sg.side == 0 ? ctx->dom_lo[sg.axis] : ctx->dom_hi[sg.axis]);
+        k_mirror_copy<<<(unsigned)cdiv(sg.count, 256), 256, 0, ctx->stream>>>(P, ai.off, sg.idx, sg.count, ai.off + ai.n_real + sg.ghost_first, sg.axis, plane2);
+        LAUNCH_CHECK();
+    }
+    ctx->grid_valid = false, ctx->packed_valid = false;
+    ctx->state_packed = false;
+    return 0;
+}
+
+static int mirror_create(b200sph_ctx *ctx)
+{
+    int rc;
+    if (ctx->solid_alloc) return set_err(ctx, "mirror boundaries: images carry the WCSPH fields only (x y z u v w rho h m), not the elastic-dynamics state");
+    if ((rc = eos_flush(ctx))) return rc;
+    // the cell size of the REAL particles decides the width (images have their sources' h)
+    for (int a = 0; a < ctx->narr; a++) ctx->arr[a].n = ctx->arr[a].n_real;
+    ctx->domain_valid = false;
+    ctx->mirror_built = false;
+    if ((rc = b200sph_update_domain(ctx))) return rc;
+    const double width = ctx->mirror_layers * ctx->cell_size * (1.0 + (ctx->force_kernel == 0 ? ctx->skin : 0.0));
+    size_t nseg = 0;
+    for (int a = 0; a < ctx->narr; a++) {
+        for (int axis = 0; axis < 3; axis++) {
+            if (!ctx->mirror[axis]) continue;
+            // both sides select from the particles present BEFORE this axis (real + earlier axes' images)
+            const int64_t n_sel = ctx->arr[a].n;
+            for (int side = 0; side < 2; side++) {
+                if (nseg == ctx->mirror_segs.size()) ctx->mirror_segs.emplace_back();
+                b200sph_ctx::MirrorSeg &sg = ctx->mirror_segs[nseg++];
+                sg.arr = a, sg.axis = axis, sg.side = side, sg.count = 0;
+                ArrayInfo &ai = ctx->arr[a];
+                sg.ghost_first = ai.n - ai.n_real;
+                if (n_sel == 0) continue;
+                const unsigned nb = (unsigned)cdiv(n_sel + 1, 256);
+                k_flag_mirror<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X + axis], ai.off, n_sel, side == 0 ? ctx->dom_lo[axis] : ctx->dom_hi[axis], width, side, ctx->flag_a);
+                LAUNCH_CHECK();
+                if ((rc = device_scan(ctx, ctx->flag_a, ctx->flag_b, n_sel + 1))) return rc;
+                uint32_t tot = 0;
+                CU(cudaMemcpyAsync(&tot, ctx->flag_b + n_sel, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+                if (tot == 0) continue;
+                if ((int64_t)tot > sg.cap) {
+                    if (sg.idx) CU(cudaFree(sg.idx));
+                    sg.cap = (int64_t)tot + tot / 4 + 256;
+                    CU(cudaMalloc((void **)&sg.idx, 4 * (size_t)sg.cap));
+                }
+                k_save_idx<<<nb, 256, 0, ctx->stream>>>(n_sel, ctx->flag_a, ctx->flag_b, sg.idx);
+                LAUNCH_CHECK();
+                if ((rc = ensure_capacity(ctx, a, ai.n + tot))) return rc;   // may move the pool
+                const int64_t o = ai.off + ai.n;
+                const unsigned nbt = (unsigned)cdiv((int64_t)tot, 256);
+                k_mirror_copy<<<nbt, 256, 0, ctx->stream>>>(halo_ptrs(ctx), ai.off, sg.idx, (long long)tot, o, axis, 2.0 * (side == 0 ? ctx->dom_lo[axis] : ctx->dom_hi[axis]));
+                LAUNCH_CHECK();
+                // like halo_append for ghosts: stage copies and derived fields zero, no gid, tag = Ghost (2)
+                for (int k = B200SPH_X0; k < N_F64; k++) CU(cudaMemsetAsync(ctx->f64[k] + o, 0, 8 * (size_t)tot, ctx->stream));
+                for (int k = 0; k < N_F32; k++) CU(cudaMemsetAsync(ctx->f32[k] + o, 0, 4 * (size_t)tot, ctx->stream));
+                k_fill_u32<<<nbt, 256, 0, ctx->stream>>>(ctx->u32[0] + o, tot, 0xFFFFFFFFu);
+                LAUNCH_CHECK();
+                k_fill_u32<<<nbt, 256, 0, ctx->stream>>>(ctx->u32[1] + o, tot, 2u);
+                LAUNCH_CHECK();
+                CU(cudaMemsetAsync(ctx->u32[2] + o, 0, 4 * (size_t)tot, ctx->stream));
+                sg.count = tot;
+                ai.n += tot;
+            }
+        }
+    }
+    ctx->mirror_segs.resize(nseg);   // (a shrinking narr never happens; keeps the vector tidy)
+    ctx->mirror_built = true;
+    ctx->ptype_dirty = true;
+    ctx->grid_valid = false, ctx->packed_valid = false;
+    ctx->topo_dirty = true;
+    ctx->h_dirty = true;
+    ctx->domain_valid = false;
+    ctx->state_packed = false;
+    return 0;
 }
 
 int b200sph_halo_layout(b200sph_ctx *ctx, int *halo_fields_out, int *migrate_fields_out)

@@ -87,6 +87,35 @@ __global__ void k_halo_scatter(HaloPtrs P, long long o, const double *__restrict
     for (int f = 0; f < HALO_ND(NF); f++) P.p[f][o + k] = src[(long long)f * stride + k];
     if (NF != B200SPH_HALO_FIELDS) P.cs[o + k] = (float)src[(long long)(NF - 1) * stride + k];
 }
+// mirror images (nnps_base.pyx:506-689): side 0: (v - plane) <= width, side 1: (plane - v) <= width
+__global__ void k_flag_mirror(const double *__restrict__ v, long long off, long long n, double plane, double width, int side,
+                              uint32_t *__restrict__ flag)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint32_t f = 0;
+    if (i < n) {
+        const double x = v[off + i];
+        f = side == 0 ? ((x - plane) <= width) : ((plane - x) <= width);
+    }
+    flag[i] = f;  // flag[n] = 0 so that scan[n] = total
+}
+// image k = source idx[k] reflected in the plane normal to `axis`: position 2 plane - x, the
+// normal velocity component negated, the other fields of the ghost message copied
+__global__ void k_mirror_copy(HaloPtrs P, long long off, const uint32_t *__restrict__ idx, long long n, long long dst,
+                              int axis, double plane2)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long i = off + idx[k];
+#pragma unroll
+    for (int f = 0; f < B200SPH_HALO_FIELDS; f++) {
+        double v = P.p[f][i];
+        if (f == axis) v = plane2 - v;
+        else if (f == 3 + axis) v = -v;
+        P.p[f][dst + k] = v;
+    }
+}
 struct HaloAllArgs {
     int narr;
     long long prefix[B200SPH_MAX_ARRAYS + 1];  // particles before array a in the message

@@ -6,8 +6,15 @@ into the box at every ``update_domain`` (``_box_wrap_periodic``, :699-743) and
 particles interact with the periodic images of the others, but the images are
 NOT materialised as ``tag = Ghost`` particles (``_create_ghosts_periodic``,
 :744-940): the cell grid tiles the axis exactly and neighbour cells wrap, see
-``k_list_build<true>`` in csrc/b200sph.cu.  ``n_layers`` is therefore accepted
-and ignored.  Mirror boundaries are not supported.
+``k_list_build<true>`` in csrc/b200sph.cu; ``n_layers`` plays no role there.
+
+A mirror axis (``mirror_in_x`` ..., nnps_base.pyx:329-335, ``_create_ghosts_mirror``
+:506-689) DOES materialise its images as ``tag = Ghost`` particles appended after the
+real ones -- every particle within ``n_layers`` cells of a plane, reflected, with the
+normal velocity component negated, corner images in the reference's order.  The
+reference re-selects them at every ``update_domain``; here the selection is made when the
+neighbour lists are built (its width covers the list skin) and the images' values are
+refreshed before every evaluation (``b200sph_set_mirror``).  WCSPH arrays, one GPU.
 """
 import ctypes as C
 
@@ -17,8 +24,6 @@ class DomainManager(object):
                  periodic_in_x=False, periodic_in_y=False, periodic_in_z=False,
                  n_layers=2.0, backend=None, props=None, mirror_in_x=False,
                  mirror_in_y=False, mirror_in_z=False):
-        if mirror_in_x or mirror_in_y or mirror_in_z:
-            raise NotImplementedError('B200 backend: mirror boundaries')
         if xmax < xmin or ymax < ymin or zmax < zmin:
             raise ValueError("Invalid domain limits!")     # nnps_base.pyx:352-355
         self.xmin, self.xmax = float(xmin), float(xmax)
@@ -29,7 +34,10 @@ class DomainManager(object):
         self.periodic_in_z = bool(periodic_in_z)
         self.is_periodic = (self.periodic_in_x or self.periodic_in_y or
                             self.periodic_in_z)
-        self.is_mirror = False
+        self.mirror_in_x = bool(mirror_in_x)
+        self.mirror_in_y = bool(mirror_in_y)
+        self.mirror_in_z = bool(mirror_in_z)
+        self.is_mirror = self.mirror_in_x or self.mirror_in_y or self.mirror_in_z
         self.n_layers = n_layers
         self.manager = self
 
@@ -39,3 +47,7 @@ class DomainManager(object):
         per = (C.c_int * 3)(int(self.periodic_in_x), int(self.periodic_in_y),
                             int(self.periodic_in_z))
         ctx.call('b200sph_set_domain', lo, hi, per)
+        if self.is_mirror:
+            mir = (C.c_int * 3)(int(self.mirror_in_x), int(self.mirror_in_y),
+                                int(self.mirror_in_z))
+            ctx.call('b200sph_set_mirror', mir, float(self.n_layers))

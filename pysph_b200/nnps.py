@@ -23,8 +23,6 @@ class B200NNPS(object):
     def __init__(self, dim, particles, radius_scale=2.0, backend=None,
                  kernel=None, domain=None, cache=False, sort_gids=False):
         from .backend import B200Backend
-        if domain is not None and getattr(domain, 'is_mirror', False):
-            raise NotImplementedError('B200 backend: mirror boundaries')
         self.dim = dim
         self.particles = list(particles)
         self.narrays = len(self.particles)
@@ -35,13 +33,18 @@ class B200NNPS(object):
         self.radius_scale = radius_scale if kernel is None \
             else kernel.radius_scale
         self.domain = domain
-        if domain is not None and getattr(domain, 'is_periodic', False):
+        if domain is not None and (getattr(domain, 'is_periodic', False) or
+                                   getattr(domain, 'is_mirror', False)):
             from .domain import DomainManager
             if not isinstance(domain, DomainManager):   # a PySPH DomainManager
                 m = getattr(domain, 'manager', domain)
                 domain = DomainManager(
                     m.xmin, m.xmax, m.ymin, m.ymax, m.zmin, m.zmax,
-                    m.periodic_in_x, m.periodic_in_y, m.periodic_in_z)
+                    m.periodic_in_x, m.periodic_in_y, m.periodic_in_z,
+                    n_layers=getattr(m, 'n_layers', 2.0),
+                    mirror_in_x=getattr(m, 'mirror_in_x', False),
+                    mirror_in_y=getattr(m, 'mirror_in_y', False),
+                    mirror_in_z=getattr(m, 'mirror_in_z', False))
             domain.apply(self.ctx)
         self.in_parallel = False
         self.src_index = self.dst_index = 0

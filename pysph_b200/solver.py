@@ -151,9 +151,10 @@ class B200Solver(object):
 
     def set_parallel_manager(self, pm):
         dom = self.nnps.domain
-        if pm is not None and dom is not None and getattr(dom, 'is_periodic', False):
+        if pm is not None and dom is not None and (getattr(dom, 'is_periodic', False) or
+                                                   getattr(dom, 'is_mirror', False)):
             raise NotImplementedError(
-                'B200 backend: periodic domains with the slab decomposition')
+                'B200 backend: periodic / mirror domains with the slab decomposition')
         self.pm = pm
         self.in_parallel = pm is not None
         self.integrator.set_parallel_manager(pm)

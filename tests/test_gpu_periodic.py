@@ -224,7 +224,6 @@ def test_periodic_errors(gpu_device):
     be = pb.B200Backend([pa2])
     with pytest.raises(RuntimeError):
         pb.B200NNPS(2, [pa2], backend=be, kernel=kernel, domain=dm)
-    with pytest.raises(NotImplementedError):
-        pb.DomainManager(xmin=0, xmax=1, mirror_in_x=True)
     with pytest.raises(ValueError):
         pb.DomainManager(xmin=1, xmax=0)
+

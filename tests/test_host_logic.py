@@ -198,8 +198,9 @@ def test_domain_manager_descriptor():
     assert not pb.DomainManager().is_periodic
     with pytest.raises(ValueError):
         pb.DomainManager(xmin=1, xmax=0)
-    with pytest.raises(NotImplementedError):
-        pb.DomainManager(xmin=0, xmax=1, mirror_in_x=True)
+    dm = pb.DomainManager(xmin=0, xmax=1, mirror_in_x=True, n_layers=3.0)
+    assert dm.is_mirror and not dm.is_periodic and dm.n_layers == 3.0
+    assert (dm.mirror_in_x, dm.mirror_in_y, dm.mirror_in_z) == (True, False, False)
 
 
 def test_edac_program_and_scheme():

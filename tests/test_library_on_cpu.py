@@ -103,6 +103,10 @@ FAST = [
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 2, 'n': 24, 'pattern': (0, 1, 0)}),
     ('test_output', 'test_dump_and_restart_on_device', {'tmp_path': None}),
+    ('test_zz_gpu_mirror_unvalidated', 'test_mirror_wcsph_steps_vs_oracle', {'dim': 2, 'n': 24, 'pattern': (1, 1, 0)}),
+    ('test_zz_gpu_mirror_unvalidated', 'test_mirror_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 0, 1)}),
+    ('test_zz_gpu_mirror_unvalidated', 'test_mirror_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
+    ('test_zz_gpu_mirror_unvalidated', 'test_mirror_errors', {}),
 ]
 FULL = [
     ('test_gpu_parity', 'test_device_resident_dt_is_bitwise_the_host_path', {}),
