@@ -2015,6 +2015,7 @@ static int mirror_create(b200sph_ctx *ctx)
     if ((rc = eos_flush(ctx))) return rc;
     // the cell size of the REAL particles decides the width (images have their sources' h)
     for (int a = 0; a < ctx->narr; a++) ctx->arr[a].n = ctx->arr[a].n_real;
+    ctx->ptype_dirty = true;
     ctx->domain_valid = false;
     ctx->mirror_built = false;
     if ((rc = b200sph_update_domain(ctx))) return rc;
