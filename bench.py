@@ -144,6 +144,32 @@ def cpu_model():
     return 'unknown'
 
 
+def _oracle_steps(solver, budget_s, max_steps, warmup):
+    """EPEC / PEC steps of an oracle solver until the budget is used; pairs counted per
+    evaluation through pairs_last_eval (one evaluate() call = every group once)."""
+    total = [0]
+    orig = solver.evaluate
+
+    def counting(*a, **kw):
+        r = orig(*a, **kw)
+        total[0] += solver.pairs_last_eval
+        return r
+    solver.evaluate = counting
+    solver.initialise()
+    for _ in range(warmup):
+        solver.step()
+    total[0] = 0
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_steps:
+        solver.step()
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    el = time.perf_counter() - t0
+    return dict(pairs_per_s=total[0] / el, steps=n, seconds=el, pairs_per_step=total[0] / n)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU arm.  /root/reference cannot be built without
     cyarray/compyle/mako, so this times the oracle port with all
@@ -152,9 +178,6 @@ def run_reference(args, rank, world):
         return
     from pysph_b200 import geometry as geo
     from oracle import oracle as orc
-    dx = BASE_DX / world ** (1.0 / 3.0)
-    pas = geo.dam_break_3d_particles(dx=dx)
-    params = geo.dam_break_3d_params(dx)
     ncores = os.cpu_count() or 1
     # torchrun exports OMP_NUM_THREADS=1: size the pool from the affinity mask instead
     try:
@@ -162,9 +185,37 @@ def run_reference(args, rank, world):
     except Exception:
         pass
     threads = max(1, min(ncores, 64))
-    ntot = sum(pa.get_number_of_particles() for pa in pas)
-    r = cpu_leg(pas, params, threads, budget_s=150.0,
-                max_steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    budget = args.cpu_budget if args.cpu_budget != 20.0 else 150.0
+    if args.workload == 'rings':
+        dx = args.dx or 0.00028
+        lz = args.lz * world
+        dt = args.dt or 1e-8 * dx / 0.0005
+        pas = [geo.rings_3d_particles(dx=dx, lz=lz)]
+        o = orc.ElasticOracleSolver(pas, dict(dim=3, dt=dt, eps=0.3, alpha=1.0, beta=1.0,
+                                              eps_xsph=0.5, grad3d=True),
+                                    'CubicSpline', threads=threads)
+        r = _oracle_steps(o, budget, max(1, args.steps), min(args.warmup, 1))
+        workload = 'rings 3-D (BASELINE configs[4]) elastic dynamics EPEC CubicSpline ' \
+                   'hdx=1.5 dx=%g lz=%g' % (dx, lz)
+        what = 'full EPEC steps (two evaluations of both elastic-dynamics groups)'
+    elif args.workload == 'taylor_green':
+        p = geo.taylor_green_params(args.nx, dim=3)
+        pas = [geo.taylor_green_particles(args.nx, dim=3)]
+        o = orc.EDACOracleSolver(pas, p, 'QuinticSpline', threads=threads,
+                                 domain=([0, 0, 0], [1, 1, 1], [1, 1, 1]))
+        r = _oracle_steps(o, budget, max(1, args.steps), min(args.warmup, 1))
+        workload = 'taylor_green 3-D (BASELINE configs[3]) EDAC/TVF PEC QuinticSpline ' \
+                   'nx=%d hdx=1.0 periodic' % args.nx
+        what = 'full PEC steps (one evaluation of both EDAC groups, materialised periodic ghosts)'
+    else:
+        dx = args.dx or BASE_DX / world ** (1.0 / 3.0)
+        pas = geo.dam_break_3d_particles(dx=dx)
+        params = geo.dam_break_3d_params(dx)
+        r = cpu_leg(pas, params, threads, budget_s=budget,
+                    max_steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        workload = 'dam_break_3d EPEC CubicSpline dx=%.6f' % dx
+        what = 'full EPEC steps'
+    ntot = sum(pa.get_number_of_particles(real=True) for pa in pas)
     ms = 1e3 * r['seconds'] / r['steps']
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': r['pairs_per_s'],
@@ -172,13 +223,14 @@ def run_reference(args, rank, world):
         'warmup': min(args.warmup, 1), 'ms_per_step': ms,
         'steps_per_s': 1e3 / ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'dam_break_3d EPEC CubicSpline dx=%.6f' % dx,
+        'config': {'workload': workload,
                    'particles': ntot, 'pairs_per_step': r['pairs_per_step']},
         'cpu_baseline': {'value': r['pairs_per_s'], 'unit': 'pairs/s',
                          'cores': threads, 'kind': 'port',
                          'cpu': cpu_model(),
-                         'sample': '%d full EPEC steps of the same %d-particle '
-                                   'state (time budget 150 s)' % (r['steps'], ntot)},
+                         'sample': '%d %s of the same %d-particle '
+                                   'state (time budget %.0f s)' % (r['steps'], what, ntot,
+                                                                   budget)},
         'e2e': {'value': r['pairs_per_s'], 'unit': 'pairs/s',
                 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }

@@ -307,3 +307,29 @@ def test_elastic_program_and_scheme():
     n2 = r.get_number_of_particles() // 2
     assert np.all(r.u[:n2] > 0) and np.all(r.u[n2:] < 0)
     assert abs(abs(r.u[0]) - 0.059 * r.cs[0]) < 1e-9
+
+
+@pytest.mark.parametrize('extra', [['--dx', '0.07'],
+                                   ['--workload', 'rings', '--dx', '0.0025', '--lz', '0.0075'],
+                                   ['--workload', 'taylor_green', '--nx', '10']])
+def test_bench_reference_arm_contract(extra):
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON
+    line with the contract's keys, for every workload, at a size that takes seconds."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference',
+                          '--steps', '2', '--warmup', '1'] + extra, capture_output=True,
+                         text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'pairs/s' and d['higher_is_better'] is True
+    assert d['metric'] == 'particle_pair_interactions_per_s' and d['value'] > 0
+    assert d['steps'] == 2 and d['n_gpus'] == 1 and d['ms_per_step'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['value'] == d['value'] == d['e2e']['value']
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    assert d['config']['pairs_per_step'] > 0 and 'workload' in d['config']
