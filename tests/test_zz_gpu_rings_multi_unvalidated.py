@@ -77,3 +77,71 @@ def test_rings_slabs_match_single_gpu():
     for k in RING_FIELDS:
         a = np.concatenate([o[1][k] for o in out])[order]
         assert np.max(np.abs(a - ref[k][order_ref])) <= tols.get(k, 2e-4 * smax), k
+
+
+S6 = ['s00', 's01', 's02', 's11', 's12', 's22']
+F9 = ['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm']
+F16 = F9 + ['x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'rho0']
+
+
+def test_elastic_halo_and_migration_layout(gpu_device):
+    """One GPU: with elastic-dynamics arrays b200sph_halo_layout reports 16 / 30 fields, the
+    ghost message is x y z u v w rho h m s00 s01 s02 s11 s12 s22 cs, the migration message
+    the 16 fp64 state properties, gid, s00..s22, s000..s220, cs -- field-major, exact."""
+    import torch
+    import pysph_b200 as pb
+    from pysph_b200.parallel import DeviceHaloOps
+    rs = np.random.RandomState(5)
+    n = 400
+    props = dict((k, rs.uniform(0.1, 1.0, n)) for k in F16 + S6 + [k + '0' for k in S6])
+    props['x'] = rs.uniform(0.0, 3.0, n)
+    props['cs'] = rs.uniform(10.0, 20.0, n)
+    mk = lambda name: pb.get_particle_array_elastic_dynamics(
+        name=name, constants=dict(E=1e7, nu=0.3, rho_ref=1.0, c0_ref=5.0), **props)
+    a, b = mk('solid'), mk('other')
+    a.gid[:] = np.arange(n) + 7
+    ref = dict((k, v.copy()) for k, v in a.properties.items())
+    cs32 = ref['cs'].astype(np.float32).astype(np.float64)      # cs is fp32 on the device
+    be = pb.B200Backend([a, b], extra_capacity=2000)
+    ops = DeviceHaloOps(be, 0)
+    if not torch.cuda.is_available():          # the library emulation: device memory is host memory
+        ops.device = torch.device('cpu')
+    assert (ops.halo_nf, ops.migrate_nf) == (16, 30)
+    lo, hi = 1.0, 1.6
+    buf = ops.new_buffer(16 * n)
+    cnt = ops.pack(0, 1, lo, hi, buf, 0)
+    sel = np.where((ref['x'] >= lo) & (ref['x'] < hi))[0]
+    assert cnt == sel.size and cnt > 20
+    got = buf[:16 * cnt].cpu().numpy().reshape(16, cnt)
+    for f, k in enumerate(F9 + S6):
+        assert np.array_equal(got[f], ref[k][sel]), k
+    assert np.array_equal(got[15], cs32[sel])
+    ops.append(1, buf, 0, cnt, 16, False)
+    assert be.sizes(1) == (n + cnt, n)
+    be.pull(1)
+    for k in F9 + S6:
+        assert np.array_equal(b.properties[k][n:], ref[k][sel]), k
+    assert np.array_equal(b.cs[n:], cs32[sel]) and np.all(b.s000[n:] == 0.0)
+    assert np.all(b.tag[n:] == 1)
+    ops.drop_ghosts(1)
+    mbuf = ops.new_buffer(30 * n)
+    n_lo, n_hi = ops.migrate_out(0, 0.5, 2.5, mbuf, 0)
+    s_lo = np.where(ref['x'] < 0.5)[0]
+    keep = np.where((ref['x'] >= 0.5) & (ref['x'] < 2.5))[0]
+    assert n_lo == s_lo.size > 0 and n_hi > 0
+    blk = mbuf[:30 * n_lo].cpu().numpy().reshape(30, n_lo)
+    names = F16 + ['gid'] + S6 + [k + '0' for k in S6]
+    for f, k in enumerate(names):
+        assert np.array_equal(blk[f], ref[k][s_lo].astype(float)), k
+    assert np.array_equal(blk[29], cs32[s_lo])
+    be.pull(0)
+    for k in F16 + S6 + [k + '0' for k in S6]:
+        assert np.array_equal(a.properties[k], ref[k][keep]), k
+    assert np.array_equal(a.cs, cs32[keep]) and np.array_equal(a.gid, ref['gid'][keep])
+    ops.append(1, mbuf, 0, n_lo, 30, True)
+    assert be.sizes(1) == (n + n_lo, n + n_lo)
+    be.pull(1)
+    for k in F16 + S6 + [k + '0' for k in S6]:
+        assert np.array_equal(b.properties[k][n:], ref[k][s_lo]), k
+    assert np.array_equal(b.cs[n:], cs32[s_lo]) and np.array_equal(b.gid[n:], ref['gid'][s_lo])
+    assert np.all(b.tag[n:] == 0)
