@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define B200SPH_MAX_ARRAYS 8
-#define B200SPH_ABI_VERSION 2
+#define B200SPH_ABI_VERSION 3
 
 typedef struct b200sph_ctx b200sph_ctx;
 
@@ -122,8 +122,7 @@ typedef struct {
 } b200sph_tvf_program;
 
 /* The two Groups of ElasticSolidsScheme.get_equations (solid_mech/basic.py:604-651) for
- * elastic solids without rigid `solids`: every elastic array is a destination and a
- * source.  Group 1: IsothermalEOS (:93-101), VelocityGradient2D/3D
+ * elastic solids (destinations and sources) and rigid `solids` (sources only).  Group 1: IsothermalEOS (:93-101), VelocityGradient2D/3D
  * (basic_equations.py:67-148), MonaghanArtificialStress (:104-242); group 2:
  * ContinuityEquation, MomentumEquationWithStress (:245-387),
  * MonaghanArtificialViscosity, HookesDeviatoricStressRate (:390-505), XSPHCorrection. */
@@ -142,6 +141,11 @@ typedef struct {
     /* the array constants of get_particle_array_elastic_dynamics (:61-83), per array */
     double c0_ref[B200SPH_MAX_ARRAYS], rho_ref[B200SPH_MAX_ARRAYS],
         wdeltap[B200SPH_MAX_ARRAYS], n[B200SPH_MAX_ARRAYS], G[B200SPH_MAX_ARRAYS];
+    uint32_t source_mask;  /* bit a: array a is a source of the pair equations: the elastic
+                            * arrays plus the scheme's rigid `solids` (all = solids +
+                            * elastic_solids, :613), which are destinations of nothing and
+                            * contribute with the p / s / r they carry.  0 = elastic_mask */
+    uint32_t reserved;
 } b200sph_solid_program;
 
 typedef struct {

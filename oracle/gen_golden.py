@@ -421,9 +421,11 @@ def load_reference_solid():
 
 
 def gen_solid_case(kernels, solid, kernel_name, dim, seed, wdeltap=True, two=False,
-                   grad3d=False):
+                   grad3d=False, wall=False):
     """One evaluation of ElasticSolidsScheme(...).get_equations() (the reference's scheme
-    method and equation bodies) on random particles with random stresses."""
+    method and equation bodies) on random particles with random stresses.  wall=True adds a
+    rigid `solids` array: a source of every pair equation, a destination of none -- it
+    contributes with whatever p / s / r it carries (solid_mech/basic.py:613-648)."""
     rs = np.random.RandomState(seed)
     kernel = getattr(kernels, kernel_name)(dim=dim)
     dx = 0.1
@@ -451,9 +453,34 @@ def gen_solid_case(kernels, solid, kernel_name, dim, seed, wdeltap=True, two=Fal
         wd = kernel.kernel([0, 0, 0], dx, 1.3 * dx) if wdeltap else -1.0
         consts[name] = dict(wdeltap=[wd], n=[4.0], G=[G], rho_ref=[rho_ref],
                             c0_ref=[c0])
+    solids = []
+    if wall:
+        n = 30
+        hi = [0.5, 0.5, 0.4 if dim == 3 else 0.0]
+        pts = rs.uniform(0.0, 1.0, size=(n, 3)) * np.array(hi) + np.array([0.25, 0.0, 0.0])
+        a = dict((q, [0.0] * n) for q in SOLID_PROPS)
+        a['x'], a['y'], a['z'] = (list(map(float, pts[:, i])) for i in range(3))
+        v = 0.3 * rs.normal(size=(n, 3)) * (np.arange(3) < dim)
+        a['u'], a['v'], a['w'] = (list(map(float, v[:, i])) for i in range(3))
+        a['h'] = [1.2 * dx] * n
+        a['m'] = [float(1.5 * rho_ref * dx ** dim)] * n
+        a['rho'] = list(map(float, 1.5 * rho_ref * (1 + 0.02 * rs.uniform(-1, 1, n))))
+        a['cs'] = [1.3 * c0] * n
+        a['p'] = list(map(float, 15.0 * rs.normal(size=n)))
+        for key in ('s00', 's01', 's11') + (('s02', 's12', 's22') if dim == 3 else ()):
+            a[key] = list(map(float, 10.0 * rs.normal(size=n)))
+        for key in ('r00', 'r01', 'r11') + (('r02', 'r12', 'r22') if dim == 3 else ()):
+            a[key] = list(map(float, 0.5 * rs.normal(size=n)))
+        a['_n_real'] = n
+        arrays['wall'] = a
+        consts['wall'] = dict(wdeltap=[-1.0], n=[4.0], G=[0.0], rho_ref=[1.5 * rho_ref],
+                              c0_ref=[1.3 * c0])
+        solids = ['wall']
     inputs = json.loads(json.dumps(arrays))
-    scheme = solid.ElasticSolidsScheme(names, [], dim=dim, artificial_stress_eps=0.3,
+    scheme = solid.ElasticSolidsScheme(names, solids, dim=dim, artificial_stress_eps=0.3,
                                        xsph_eps=0.5, alpha=1.0, beta=1.5)
+    elastic = list(names)
+    names = names + solids
     eqs = scheme.get_equations()
     if grad3d:
         # the scheme always emits VelocityGradient2D (solid_mech/basic.py:620-623); a 3-D
@@ -473,6 +500,7 @@ def gen_solid_case(kernels, solid, kernel_name, dim, seed, wdeltap=True, two=Fal
         for ck in consts[name]:
             del arrays[name][ck]
     params = dict(dim=dim, eps=0.3, eps_xsph=0.5, alpha=1.0, beta=1.5, names=names,
+                  elastic=elastic, solids=solids,
                   constants=consts, grad3d=bool(grad3d),
                   groups=[[type(e).__name__ for e in g.equations] for g in eqs],
                   group_real=[bool(g.real) for g in eqs])
@@ -668,6 +696,8 @@ def main():
         gen_solid_case(kernels, solid, 'CubicSpline', 3, 302, two=True),
         gen_solid_case(kernels, solid, 'WendlandQuintic', 2, 303, wdeltap=False),
         gen_solid_case(kernels, solid, 'CubicSpline', 3, 304, grad3d=True),
+        gen_solid_case(kernels, solid, 'CubicSpline', 2, 305, wall=True),
+        gen_solid_case(kernels, solid, 'CubicSpline', 3, 306, two=True, grad3d=True, wall=True),
     ]
     dump('solid_cases.json', scases)
     dump('solid_stepper.json', gen_solid_stepper(steps))

@@ -710,10 +710,17 @@ class ElasticOracleSolver(object):
         self.o.nnps_update()
         self._initialised = False
 
+    def _elastic(self):
+        """indices of the elastic arrays; params['solids'] names the rigid ones (sources of
+        every pair equation, destinations of none, never stepped: solid_mech/basic.py:613,
+        :653-684)"""
+        rigid = set(self.p.get('solids', ()))
+        return [a for a, pa in enumerate(self.pas) if pa.name not in rigid]
+
     def evaluate(self):
         p = self.p
         idx = list(range(len(self.pas)))
-        P = self.o.solid_program(idx, idx, eps=p.get('eps', 0.3), alpha=p.get('alpha', 1.0),
+        P = self.o.solid_program(self._elastic(), idx, eps=p.get('eps', 0.3), alpha=p.get('alpha', 1.0),
                                  beta=p.get('beta', 1.0), eps_xsph=p.get('eps_xsph', 0.5),
                                  grad3d=p.get('grad3d', False))
         self.pairs_last_eval = self.o.solid_group1(P) + self.o.solid_group2(P)
@@ -725,7 +732,7 @@ class ElasticOracleSolver(object):
             self._initialised = True
 
     def _stage(self, which, dt):
-        for a in range(len(self.pas)):
+        for a in self._elastic():
             self.o.stage_solid(a, which, dt)
 
     def step(self):

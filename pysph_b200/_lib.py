@@ -75,7 +75,8 @@ class SolidProgram(C.Structure):
                 ('eps_xsph', C.c_double),
                 ('c0_ref', C.c_double * MAX_ARRAYS), ('rho_ref', C.c_double * MAX_ARRAYS),
                 ('wdeltap', C.c_double * MAX_ARRAYS), ('n', C.c_double * MAX_ARRAYS),
-                ('G', C.c_double * MAX_ARRAYS)]
+                ('G', C.c_double * MAX_ARRAYS),
+                ('source_mask', C.c_uint32), ('reserved', C.c_uint32)]
 
 
 class GridInfo(C.Structure):

@@ -1659,6 +1659,8 @@ int b200sph_solid_pass(b200sph_ctx *ctx, const b200sph_solid_program *prog, int6
     sa.k2 = (float)(ctx->radius_scale * ctx->radius_scale);
     sa.kfac = (float)kernel_fac(ctx->kernel, ctx->dim);
     sa.elastic_mask = prog->elastic_mask;
+    sa.source_mask = prog->source_mask ? prog->source_mask : prog->elastic_mask;
+    if ((sa.source_mask & sa.elastic_mask) != sa.elastic_mask) return set_err(ctx, "solid_pass: every elastic array must be a source");
     sa.grad3d = prog->grad3d;
     sa.ghost_group1 = prog->ghost_group1;
     sa.eps = (float)prog->eps; sa.alpha = (float)prog->alpha; sa.beta = (float)prog->beta; sa.eps_xsph = (float)prog->eps_xsph;

@@ -18,7 +18,7 @@ struct SolidArgs {
     float *arho, *au, *av, *aw, *ax, *ay, *az;
     long long n;
     float cellx, celly, cellz, k2, kfac;
-    unsigned elastic_mask;
+    unsigned elastic_mask, source_mask;   // destinations (and sources); all sources (+ rigid solids)
     int grad3d, ghost_group1;
     float eps, alpha, beta, eps_xsph;
     double c0_ref[B200SPH_MAX_ARRAYS], rho_ref[B200SPH_MAX_ARRAYS], G[B200SPH_MAX_ARRAYS];
@@ -108,11 +108,12 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, c
         ti = __float_as_int(a.C3[s].w);
         const bool elastic = (a.elastic_mask >> (ti & 7)) & 1u;
         // ghost_group1: ghosts are destinations of group 1 like everyone else (real=False)
-        ghost_src = elastic && (ti & PT_GHOST) && !a.ghost_group1;
+        ghost_src = elastic ? ((ti & PT_GHOST) && !a.ghost_group1) : (((a.source_mask >> (ti & 7)) & 1u) != 0);
         if (ghost_src || !elastic) active = false;
     }
     if (ghost_src) {
-        // a ghost is a source of group 2 with the values it carries (group 1 is real=True)
+        // a ghost (group 1 is real=True) or a particle of a rigid solid (a destination of
+        // nothing) is a source of group 2 with the values it carries
         const uint32_t g = a.perm[s];
         const double rho = a.rho[g], p = (double)a.p[g], rho21 = 1.0 / (rho * rho);
         a.T01[s] = make_float4((float)((a.s[0][g] - p) * rho21), (float)(a.s[1][g] * rho21), (float)(a.s[2][g] * rho21),
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, c
             const float4 T = s_T[e >> LIST_JBITS];
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
-            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.elastic_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
+            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.source_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
                 npairs++;
                 const float rinv = r2 > 1e-24f ? frsqrt(r2) : 0.0f;
                 const float h1 = frcp(0.5f * (Ai.w + Aj.w));
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass2(const SolidArgs a, c
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
             const int tj = __float_as_int(Cj.w) & 7;
-            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.elastic_mask >> tj) & 1u)) {
+            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.source_mask >> tj) & 1u)) {
                 npairs++;
                 const float rinv = r2 > 1e-24f ? frsqrt(r2) : 0.0f;
                 const float hij = 0.5f * (Ai.w + Aj.w);

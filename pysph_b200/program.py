@@ -89,20 +89,30 @@ def _build_solid(g, kind, index, particle_arrays):
         if eq.dest not in dests:
             dests.append(eq.dest)
     want = sorted(index[d] for d in dests)
+    all_src = None          # all = solids + elastic_solids (solid_mech/basic.py:613)
     for eq in g.equations:
         name = _eq_name(eq)
         if eq.sources is None:
             continue
+        for s_ in eq.sources:
+            if s_ not in index:
+                raise ValueError('equation %s: unknown source array %r' % (name, s_))
         src = sorted(index[s] for s in eq.sources)
         if name == 'XSPHCorrection':
             if src != [index[eq.dest]]:
                 raise NotImplementedError('B200 backend: XSPHCorrection(sources=[dest]) '
                                           'is what the elastic-dynamics kernel does')
-        elif src != want:
+            continue
+        if all_src is None:
+            all_src = src
+        if src != all_src or not set(want) <= set(src):
             raise NotImplementedError(
-                'B200 backend: elastic-dynamics kernels take every elastic array as a '
-                'source of every elastic array (no rigid solids); %s(dest=%r, sources=%r)'
-                % (name, eq.dest, eq.sources))
+                'B200 backend: elastic-dynamics kernels take ONE source set (the rigid '
+                'solids + every elastic array) for all pair equations; %s(dest=%r, '
+                'sources=%r)' % (name, eq.dest, eq.sources))
+    prog.source_mask = sum(1 << a for a in (all_src if all_src is not None else want))
+    for eq in g.equations:
+        name = _eq_name(eq)
         if name == 'MonaghanArtificialViscosity':
             _set_once(params, 'alpha', float(eq.alpha), eq)
             _set_once(params, 'beta', float(eq.beta), eq)
@@ -146,7 +156,8 @@ def _merge_solid(ops):
     for op in ops:
         if out and op[0] == 'solid' and out[-1][0] == 'solid' and \
                 out[-1][1].passes == 1 and op[1].passes == 2 and \
-                out[-1][1].elastic_mask == op[1].elastic_mask:
+                out[-1][1].elastic_mask == op[1].elastic_mask and \
+                out[-1][1].source_mask == op[1].source_mask:
             op[1].passes = 3
             op[1].grad3d = out[-1][1].grad3d
             op[1].eps = out[-1][1].eps

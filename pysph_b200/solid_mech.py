@@ -1,5 +1,6 @@
-"""Elastic dynamics (Gray, Monaghan & Swift 2001), mirroring pysph/sph/solid_mech/basic.py
-for elastic solids without rigid ``solids`` (BASELINE configs[4]).
+"""Elastic dynamics (Gray, Monaghan & Swift 2001), mirroring pysph/sph/solid_mech/basic.py:
+elastic solids, optionally with rigid ``solids`` as sources (BASELINE configs[4],
+SURVEY.md 8f-2).
 
 STATUS: the CUDA kernels behind these descriptors (``k_solid_pass1/2``,
 ``k_stage_solid``) were written after this round's GPU budget was spent.  They
@@ -68,8 +69,6 @@ class ElasticSolidsScheme(object):
         return dict((n, SolidMechStep()) for n in self.elastic_solids)
 
     def get_equations(self):
-        if self.solids:
-            raise NotImplementedError('B200 backend: elastic dynamics with rigid solids')
         all_ = self.solids + self.elastic_solids
         grad = VelocityGradient3D if self.use_3d_gradient else VelocityGradient2D
         g1, g2 = [], []

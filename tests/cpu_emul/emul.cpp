@@ -451,6 +451,7 @@ int emul_solid(const emul_common *c, const b200sph_solid_program *prog, double *
     sa.k2 = (float)(c->radius_scale * c->radius_scale);
     sa.kfac = (float)c->kfac;
     sa.elastic_mask = prog->elastic_mask; sa.grad3d = prog->grad3d;
+    sa.source_mask = prog->source_mask ? prog->source_mask : prog->elastic_mask; sa.ghost_group1 = prog->ghost_group1;
     sa.eps = (float)prog->eps; sa.alpha = (float)prog->alpha; sa.beta = (float)prog->beta; sa.eps_xsph = (float)prog->eps_xsph;
     for (int a = 0; a < B200SPH_MAX_ARRAYS; a++) {
         sa.c0_ref[a] = prog->c0_ref[a]; sa.rho_ref[a] = prog->rho_ref[a]; sa.G[a] = prog->G[a];

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), 'libb200sph.so does not export %s' % name
     # and the ctypes table covers exactly the header
     assert set(_lib.SIGNATURES) == declared
-    assert lib.b200sph_abi_version() == 2
+    assert lib.b200sph_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_device():
@@ -295,8 +295,19 @@ def test_elastic_program_and_scheme():
     assert pb.ElasticSolidsScheme(['ring'], [], dim=3).use_3d_gradient
     with pytest.raises(ValueError):          # constants are needed
         build_program(groups, ['ring'], 2)
-    with pytest.raises(NotImplementedError):
-        pb.ElasticSolidsScheme(['ring'], ['wall'], dim=2).get_equations()
+    # rigid `solids` (all = solids + elastic_solids, solid_mech/basic.py:613): sources only
+    wall = pb.get_particle_array_elastic_dynamics(name='wall', x=np.zeros(2), rho=1.0, m=1.0,
+                                                  h=0.1)
+    gw = pb.ElasticSolidsScheme(['ring'], ['wall'], dim=2).get_equations()
+    assert gw[1].equations[0].sources == ['wall', 'ring']
+    assert gw[1].equations[4].sources == ['ring']                # XSPH: own array only
+    Pw = build_program(gw, ['ring', 'wall'], 2, particle_arrays=[pa, wall])[0][1]
+    assert (Pw.passes, Pw.elastic_mask, Pw.source_mask) == (3, 1, 3)
+    assert P.source_mask == 1
+    with pytest.raises(NotImplementedError):  # ONE source set for all pair equations
+        bad = pb.ElasticSolidsScheme(['ring'], ['wall'], dim=2).get_equations()
+        bad[1].equations[0].sources = ['ring']
+        build_program(bad, ['ring', 'wall'], 2, particle_arrays=[pa, wall])
     with pytest.raises(NotImplementedError):  # a group 2 without the stress rate
         build_program([groups[0], Group(groups[1].equations[:3])], ['ring'], 2,
                       particle_arrays=[pa])

@@ -168,7 +168,7 @@ SYM = ['00', '01', '02', '11', '12', '22']
 VG = ['v%d%d' % (i, j) for i in range(3) for j in range(3)]
 
 
-@pytest.mark.parametrize('idx', range(4))
+@pytest.mark.parametrize('idx', range(6))      # 4, 5: a rigid `solids` array among the sources
 def test_elastic_kernels_on_cpu(emul, idx):
     case = load_golden('solid_cases.json')[idx]
     p = case['params']
@@ -177,7 +177,8 @@ def test_elastic_kernels_on_cpu(emul, idx):
     c = _common(cols, ptype, case['kernel'], p['dim'], keep)
     n = c.n
     P = _lib.SolidProgram()
-    P.elastic_mask = (1 << len(p['names'])) - 1
+    P.elastic_mask = sum(1 << a for a, name in enumerate(p['names']) if name in p['elastic'])
+    P.source_mask = (1 << len(p['names'])) - 1
     P.grad3d, P.passes = int(p.get('grad3d', False)), 3
     P.eps, P.alpha, P.beta, P.eps_xsph = p['eps'], p['alpha'], p['beta'], p['eps_xsph']
     for a, name in enumerate(p['names']):

@@ -65,7 +65,7 @@ def test_every_entry_point_is_exported(emulated_library):
     lib = _lib.load()
     for name in _lib.SIGNATURES:
         assert hasattr(lib, name), name
-    assert lib.b200sph_abi_version() == 2
+    assert lib.b200sph_abi_version() == 3
 
 
 # ---- the GPU tests of this repository, run against the emulated library --------------------
@@ -91,10 +91,11 @@ FAST = [
     ('test_gpu_edac', 'test_taylor_green_steps_vs_oracle', {'dim': 2, 'nx': 32, 'kernel': 'QuinticSpline'}),
     ('test_gpu_edac', 'test_edac_setup_errors', {}),
 ] + [('test_zz_gpu_solid_unvalidated', 'test_elastic_evaluation_matches_reference_bodies', {'idx': i})
-     for i in range(4)] + [
+     for i in range(6)] + [
     ('test_zz_gpu_solid_unvalidated', 'test_solid_mech_step_matches_reference_bodies', {}),
     ('test_zz_gpu_solid_unvalidated', 'test_rings_steps_vs_oracle', {}),
     ('test_zz_gpu_solid_unvalidated', 'test_rings_3d_steps_vs_oracle', {}),
+    ('test_zz_gpu_solid_unvalidated', 'test_bar_hits_rigid_wall_vs_oracle', {}),
     ('test_gpu_parity', 'test_kernels_via_two_particle_density', {}),
     ('test_gpu_parity', 'test_dam_break_3d_small_eval_and_steps', {}),
     ('test_gpu_parity', 'test_dam_break_2d_gate', {}),

@@ -330,7 +330,7 @@ def _solid_arrays(case):
     return pas
 
 
-@pytest.mark.parametrize('idx', range(4))
+@pytest.mark.parametrize('idx', range(6))
 def test_elastic_dynamics_matches_reference_bodies(idx):
     case = load_golden('solid_cases.json')[idx]
     p = case['params']
@@ -344,8 +344,9 @@ def test_elastic_dynamics_matches_reference_bodies(idx):
     o = orc.Oracle(pas, p['dim'], case['kernel'])
     o.update_domain()
     o.nnps_update()
-    idxs = list(range(len(pas)))
-    P = o.solid_program(idxs, idxs, eps=p['eps'], alpha=p['alpha'], beta=p['beta'],
+    idxs = list(range(len(pas)))                 # sources: rigid solids + elastic solids
+    elastic = [i for i, pa in enumerate(pas) if pa.name in p['elastic']]
+    P = o.solid_program(elastic, idxs, eps=p['eps'], alpha=p['alpha'], beta=p['beta'],
                         eps_xsph=p['eps_xsph'], grad3d=p.get('grad3d', False))
     o.solid_group1(P)
     o.solid_group2(P)
@@ -355,6 +356,10 @@ def test_elastic_dynamics_matches_reference_bodies(idx):
         for f in SOLID_FIELDS:
             want = np.array(ref[f])[:nr]
             got = pa.properties[f][:nr]
+            if pa.name in p['solids']:           # a rigid solid is a destination of nothing
+                assert np.array_equal(got, want) and \
+                    np.array_equal(want, np.array(case['inputs'][pa.name][f])[:nr]), (pa.name, f)
+                continue
             scale = max(np.max(np.abs(want)), 1e-300)
             assert np.max(np.abs(got - want)) <= 1e-10 * scale, (pa.name, f)
         # destinations are the real particles only: ghosts untouched
