@@ -508,6 +508,24 @@ def test_slab_decomposition_on_the_emulated_library(emulated_library, world, lb_
             assert np.max(np.abs(a - ref[name][k][order_ref])) <= tol, (name, k)
 
 
+@pytest.mark.parametrize('name', ['test_halo_pack_append_overwrite_migrate',
+                                  'test_evaluation_with_ghosts_equals_one_array'])
+def test_halo_entry_points_on_the_emulated_library(emulated_library, monkeypatch, name):
+    """tests/test_gpu_halo.py (pack / append / overwrite / migrate through the C-ABI, and an
+    evaluation with imported ghosts) with the buffers in host memory -- under the emulation
+    device memory IS host memory; the product's DeviceHaloOps knows only CUDA tensors."""
+    import torch
+    import test_gpu_halo
+    from pysph_b200 import parallel
+    init = parallel.DeviceHaloOps.__init__
+
+    def host_init(self, backend, device):
+        init(self, backend, 0)
+        self.device = torch.device('cpu')
+    monkeypatch.setattr(parallel.DeviceHaloOps, '__init__', host_init)
+    getattr(test_gpu_halo, name)(emulated_library)
+
+
 RINGS = dict(dx=0.0025, lz=0.0075, dt=2e-7, steps=10, u_f=0.25)
 RING_FIELDS = ('x', 'y', 'z', 'u', 'v', 'w', 'rho', 's00', 's01', 's02', 's11', 's12', 's22')
 
