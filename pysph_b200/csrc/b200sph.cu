@@ -744,9 +744,11 @@ int b200sph_push_f64(b200sph_ctx *ctx, int arr, int prop, const double *host, in
     int rc = ensure_pool(ctx);
     if (rc) return rc;
     if ((rc = check_range(ctx, arr, start, count))) return rc;
+    // naming an elastic-dynamics property allocates that pool even for an empty array: every
+    // rank of a slab decomposition must agree on the message layout (b200sph_halo_layout)
+    if (is_solid_prop(prop) && (rc = ensure_solid(ctx))) return rc;
     if (count == 0) return 0;
     const int64_t o = ctx->arr[arr].off + start;
-    if (is_solid_prop(prop) && (rc = ensure_solid(ctx))) return rc;
     if (is_f64_prop(prop)) {
         CU(cudaMemcpyAsync(f64_ptr(ctx, prop) + o, host, 8 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
     } else if (is_f32_prop(prop)) {

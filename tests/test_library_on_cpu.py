@@ -109,6 +109,7 @@ FAST = [
     ('test_zz_gpu_mirror_unvalidated', 'test_mirror_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
     ('test_zz_gpu_mirror_unvalidated', 'test_mirror_errors', {}),
     ('test_zz_gpu_rings_multi_unvalidated', 'test_elastic_halo_and_migration_layout', {}),
+    ('test_zz_gpu_rings_multi_unvalidated', 'test_empty_elastic_array_agrees_on_the_message_layout', {}),
 ]
 FULL = [
     ('test_gpu_parity', 'test_device_resident_dt_is_bitwise_the_host_path', {}),

@@ -145,3 +145,22 @@ def test_elastic_halo_and_migration_layout(gpu_device):
         assert np.array_equal(b.properties[k][n:], ref[k][s_lo]), k
     assert np.array_equal(b.cs[n:], cs32[s_lo]) and np.array_equal(b.gid[n:], ref['gid'][s_lo])
     assert np.all(b.tag[n:] == 0)
+
+
+def test_empty_elastic_array_agrees_on_the_message_layout(gpu_device):
+    """A rank whose slab holds no particle must still report the 16 / 30-field layout (its
+    neighbours size their messages with it): pushing an EMPTY elastic array allocates the
+    elastic-dynamics pool."""
+    import ctypes as C
+    import pysph_b200 as pb
+    pa = pb.get_particle_array_elastic_dynamics(name='solid', x=np.zeros(0))
+    be = pb.B200Backend([pa], extra_capacity=64)
+    be.push_all()
+    h, m = C.c_int(), C.c_int()
+    be.ctx.call('b200sph_halo_layout', C.byref(h), C.byref(m))
+    assert (h.value, m.value) == (16, 30)
+    q = pb.get_particle_array_wcsph(name='fluid', x=np.zeros(0))
+    be2 = pb.B200Backend([q], extra_capacity=64)
+    be2.push_all()
+    be2.ctx.call('b200sph_halo_layout', C.byref(h), C.byref(m))
+    assert (h.value, m.value) == (9, 17)
