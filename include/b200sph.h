@@ -228,7 +228,7 @@ int b200sph_set_domain(b200sph_ctx *ctx, const double lo[3], const double hi[3],
  * reference's order (x, then y of real + x images, then z of everything).  The reference
  * re-selects at every update_domain; here the selection is made when the neighbour lists
  * are built and b200sph_nnps_update refreshes the images' values before every evaluation.
- * WCSPH arrays, one GPU (no slab decomposition). */
+ * WCSPH arrays, one GPU (no slab decomposition), no periodic axis in the same domain. */
 int b200sph_set_mirror(b200sph_ctx *ctx, const int mirror[3], double n_layers);
 /* NNPS.update_domain -> CPUDomainManager._compute_cell_size_for_binning
  * nnps_base.pyx:450-483, :942-978 */

@@ -479,6 +479,8 @@ class WCSPHOracleSolver(object):
             real.append(q)
         k = load().orc_kernel_radius_scale(K_IDS[self.kernel])
         hmax = max(float(np.max(q.h)) for q in real if len(q.h))
+        if any(per) and any(mir):
+            raise NotImplementedError('oracle: mirror planes in a periodic domain')
         if any(per):
             periodic_box_wrap(real, lo, hi, per)
             real = periodic_ghosts(real, lo, hi, per, k * hmax)

@@ -961,6 +961,8 @@ static int run_minmax(b200sph_ctx *ctx, int do_xyz, int do_h)
 
 int b200sph_set_domain(b200sph_ctx *ctx, const double lo[3], const double hi[3], const int periodic[3])
 {
+    if ((periodic[0] || periodic[1] || periodic[2]) && (ctx->mirror[0] || ctx->mirror[1] || ctx->mirror[2]))
+        return set_err(ctx, "set_domain: mirror planes in a periodic domain are not supported");
     for (int d = 0; d < 3; d++) {
         if (periodic[d] && !(hi[d] > lo[d])) return set_err(ctx, "Invalid domain limits!");  // nnps_base.pyx:352-355
         ctx->periodic[d] = periodic[d] != 0;
@@ -981,8 +983,11 @@ int b200sph_set_mirror(b200sph_ctx *ctx, const int mirror[3], double n_layers)
     if (!(n_layers >= 1.0)) return set_err(ctx, "set_mirror: n_layers must be >= 1 (the images must cover one kernel support)");
     for (int d = 0; d < 3; d++) {
         if (mirror[d] && !(ctx->dom_hi[d] > ctx->dom_lo[d])) return set_err(ctx, "Invalid domain limits!");
-        if (mirror[d] && ctx->periodic[d]) return set_err(ctx, "set_mirror: axis %d is periodic", d);
     }
+    // the reference mirrors the periodic ghosts it has just created as well (nnps_base.pyx:471-480);
+    // here periodic images are never materialised, so the combination is refused
+    if ((mirror[0] || mirror[1] || mirror[2]) && (ctx->periodic[0] || ctx->periodic[1] || ctx->periodic[2]))
+        return set_err(ctx, "set_mirror: mirror planes in a periodic domain are not supported");
     for (int d = 0; d < 3; d++) ctx->mirror[d] = mirror[d] != 0;
     ctx->mirror_layers = n_layers;
     ctx->mirror_built = false;

@@ -76,8 +76,8 @@ def test_mirror_wcsph_steps_vs_oracle(gpu_device, dim, n, pattern):
 def test_mirror_errors(gpu_device):
     import pysph_b200 as pb
     pa, params = _periodic_case(2, 8)
-    with pytest.raises(Exception):                  # periodic and mirror on the same axis
-        dm = pb.DomainManager(xmin=0, xmax=1, ymin=0, ymax=1, periodic_in_x=True,
+    with pytest.raises(Exception):                  # mirror planes in a periodic domain
+        dm = pb.DomainManager(xmin=0, xmax=1, ymin=0, ymax=1, periodic_in_y=True,
                               mirror_in_x=True)
         pb.make_wcsph_solver([pa], dict(params), pb.CubicSpline(dim=2), domain=dm).initialise()
     with pytest.raises(Exception):                  # fewer layers than one kernel support
