@@ -96,6 +96,8 @@ FAST = [
     ('test_zz_gpu_solid_unvalidated', 'test_rings_steps_vs_oracle', {}),
     ('test_zz_gpu_solid_unvalidated', 'test_rings_3d_steps_vs_oracle', {}),
     ('test_zz_gpu_solid_unvalidated', 'test_bar_hits_rigid_wall_vs_oracle', {}),
+    ('test_zz_gpu_solid_unvalidated', 'test_rings_3d_momentum_and_symmetry_at_size',
+     {'dx': 0.0025, 'lz': 0.01, 'steps': 6, 'min_particles': 1000}),
     ('test_gpu_parity', 'test_kernels_via_two_particle_density', {}),
     ('test_gpu_parity', 'test_dam_break_3d_small_eval_and_steps', {}),
     ('test_gpu_parity', 'test_dam_break_2d_gate', {}),

@@ -188,3 +188,37 @@ def test_bar_hits_rigid_wall_vs_oracle(gpu_device):
         assert np.max(np.abs(bar.properties[f] - want)) <= tol * scale, f
     for f in ('x', 'y', 'u', 'rho', 's00', 'p'):
         assert np.array_equal(pas[1].properties[f], ref[1].properties[f]), f
+
+
+def test_rings_3d_momentum_and_symmetry_at_size(gpu_device, dx=0.0008, lz=0.024, steps=25,
+                                                min_particles=150000):
+    """Size-independent properties at a size the oracle does not reach in seconds (3-D rings,
+    ~200 k particles): the pair forces of MomentumEquationWithStress + artificial viscosity
+    are antisymmetric, so total linear momentum stays what it was (zero: the rings approach
+    each other with equal speeds) over EPEC steps; the tubes stay mirror symmetric about
+    their mid-plane in z and about the contact plane x = spacing."""
+    import pysph_b200 as pb
+    from pysph_b200 import geometry as geo
+    pa = geo.rings_3d_particles(dx=dx, lz=lz, u_f=0.2)
+    n = pa.get_number_of_particles()
+    assert n > min_particles
+    sch = pb.ElasticSolidsScheme(['solid'], [], dim=3)
+    s = pb.make_elastic_solver([pa], sch, pb.CubicSpline(dim=3), dt=2e-8 * dx / 0.0005)
+    z0 = pa.z.copy()
+    for _ in range(steps):
+        s.step()
+    s.pull()
+    scale = np.sum(pa.m * np.abs(pa.u))
+    for k in ('u', 'v', 'w'):
+        assert abs(np.sum(pa.m * pa.properties[k])) <= 2e-6 * scale, k
+    assert np.max(np.abs(pa.s00)) > 0.0
+    # z mirror symmetry: particle (column, layer j) <-> (column, layer nz-1-j)
+    nz = int(round(lz / dx))
+    g = pa.gid.astype(np.int64)
+    order = np.argsort(g)
+    col, lay = g[order] // nz, g[order] % nz
+    partner = np.argsort(col * nz + (nz - 1 - lay))
+    zs, ws, us = pa.z[order], pa.w[order], pa.u[order]
+    assert np.max(np.abs((zs - z0[order]) + (zs[partner] - z0[order][partner]))) <= 1e-9 * lz
+    assert np.max(np.abs(ws + ws[partner])) <= 1e-5 * np.max(np.abs(us))
+    assert np.max(np.abs(us - us[partner])) <= 1e-5 * np.max(np.abs(us))
