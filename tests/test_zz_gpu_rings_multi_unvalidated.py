@@ -123,6 +123,25 @@ def test_elastic_halo_and_migration_layout(gpu_device):
         assert np.array_equal(b.properties[k][n:], ref[k][sel]), k
     assert np.array_equal(b.cs[n:], cs32[sel]) and np.all(b.s000[n:] == 0.0)
     assert np.all(b.tag[n:] == 1)
+    # the refresh message of ALL arrays in one kernel (what the peer-memory path sends) and
+    # its scatter onto the existing ghosts: same layout, current values
+    a.s01[:] = ref['s01'] + 3.0
+    a.cs[:] = ref['cs'] * 2.0
+    be.push(0, ['s01', 'cs'])
+    buf2 = ops.new_buffer(16 * n)
+    nd = ops.pack_selected_all(1, buf2.data_ptr(), buf2.numel())
+    assert nd == 16 * cnt
+    got2 = buf2[:nd].cpu().numpy().reshape(16, cnt)
+    assert np.array_equal(got2[10], ref['s01'][sel] + 3.0) and np.array_equal(got2[0], ref['x'][sel])
+    assert np.array_equal(got2[15], (ref['cs'] * 2.0).astype(np.float32).astype(np.float64)[sel])
+    ops.overwrite_all([0, 0], [0, cnt], buf2.data_ptr())
+    be.pull(1, ['s01', 'cs', 'x'])
+    assert np.array_equal(b.s01[n:], ref['s01'][sel] + 3.0)
+    assert np.array_equal(b.cs[n:], (ref['cs'] * 2.0).astype(np.float32).astype(np.float64)[sel])
+    assert np.array_equal(b.x[n:], ref['x'][sel])
+    a.s01[:] = ref['s01']
+    a.cs[:] = ref['cs']
+    be.push(0, ['s01', 'cs'])
     ops.drop_ghosts(1)
     mbuf = ops.new_buffer(30 * n)
     n_lo, n_hi = ops.migrate_out(0, 0.5, 2.5, mbuf, 0)
