@@ -8,10 +8,100 @@
 // then really run concurrently, atomics included.
 #include "cuda_shim.h"
 
+#include <cstdio>
 #include <cstdlib>
+#include <fcntl.h>
+#include <map>
 #include <memory>
+#include <mutex>
+#include <sys/mman.h>
+#include <unistd.h>
 
 namespace emu {
+// ---- "device" allocations and the cudaIpc stand-in ------------------------------------------
+struct Block { size_t size; int kind; int fd; };   // kind 0 malloc, 1 anonymous mmap, 2 shared (memfd), 3 imported
+static std::map<void *, Block> g_blocks;
+static std::mutex g_blocks_mu;
+static size_t page_round(size_t n) { const size_t pg = (size_t)sysconf(_SC_PAGESIZE); return (n + pg - 1) / pg * pg; }
+
+int dev_alloc(void **p, size_t n)
+{
+    if (n == 0) n = 1;
+    Block b{n, 0, -1};
+    if (n >= 4096) {
+        b.size = page_round(n);
+        b.kind = 1;
+        *p = mmap(nullptr, b.size, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (*p == MAP_FAILED) { *p = nullptr; return 2; }
+    } else {
+        *p = malloc(n);
+        if (!*p) return 2;
+    }
+    std::lock_guard<std::mutex> g(g_blocks_mu);
+    g_blocks[*p] = b;
+    return 0;
+}
+
+int dev_free(void *p)
+{
+    if (!p) return 0;
+    Block b{0, 0, -1};
+    {
+        std::lock_guard<std::mutex> g(g_blocks_mu);
+        auto it = g_blocks.find(p);
+        if (it == g_blocks.end()) { free(p); return 0; }
+        b = it->second;
+        g_blocks.erase(it);
+    }
+    if (b.kind == 0) free(p);
+    else munmap(p, b.size);
+    if (b.fd >= 0) close(b.fd);
+    return 0;
+}
+
+struct IpcHandle { int magic, pid, fd; unsigned long long size; };
+
+// make the block a shared mapping of a memfd at the SAME address; the handle names the fd
+int ipc_export(void *handle64, void *p)
+{
+    std::lock_guard<std::mutex> g(g_blocks_mu);
+    auto it = g_blocks.find(p);
+    if (it == g_blocks.end() || it->second.kind == 0 || it->second.kind == 3) return 3;
+    Block &b = it->second;
+    if (b.kind == 1) {
+        const int fd = memfd_create("b200sph_emul_ipc", 0);
+        if (fd < 0) return 3;
+        if (ftruncate(fd, (off_t)b.size) != 0 || pwrite(fd, p, b.size, 0) != (ssize_t)b.size) { close(fd); return 3; }
+        if (mmap(p, b.size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0) != p) { close(fd); return 3; }
+        b.kind = 2;
+        b.fd = fd;
+    }
+    IpcHandle h{0x1bc, (int)getpid(), b.fd, (unsigned long long)b.size};
+    memset(handle64, 0, 64);
+    memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+
+int ipc_import(void **p, const void *handle64)
+{
+    IpcHandle h;
+    memcpy(&h, handle64, sizeof(h));
+    if (h.magic != 0x1bc) return 3;
+    char path[64];
+    snprintf(path, sizeof(path), "/proc/%d/fd/%d", h.pid, h.fd);
+    const int fd = open(path, O_RDWR);
+    if (fd < 0) return 3;
+    void *q = mmap(nullptr, (size_t)h.size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) return 3;
+    std::lock_guard<std::mutex> g(g_blocks_mu);
+    g_blocks[q] = Block{(size_t)h.size, 3, -1};
+    *p = q;
+    return 0;
+}
+
+int ipc_release(void *p) { return dev_free(p); }
+
 thread_local idx3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
 thread_local WarpCtx *t_warp = nullptr;
 thread_local BlockCtx *t_block = nullptr;

@@ -144,10 +144,21 @@ static inline const char *cudaGetErrorString(cudaError_t e) { return e ? "emulat
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
-static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+// "device" memory: malloc for small blocks, anonymous mmap for >= 4 KiB so that a block can be
+// turned into a shared mapping IN PLACE when another process asks for it (cudaIpc emulation,
+// cuda_shim.cpp: memfd + /proc/<pid>/fd/<fd>) -- the slab decomposition's peer-memory halo
+// then runs across the worker processes of the tests exactly as over NVLink
+namespace emu {
+int dev_alloc(void **p, size_t n);
+int dev_free(void *p);
+int ipc_export(void *handle64, void *p);
+int ipc_import(void **p, const void *handle64);
+int ipc_release(void *p);
+}
+static inline cudaError_t cudaMalloc(void **p, size_t n) { return emu::dev_alloc(p, n); }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
-static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
-static inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
+static inline cudaError_t cudaFree(void *p) { return emu::dev_free(p); }
+static inline cudaError_t cudaFreeHost(void *p) { return emu::dev_free(p); }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return 0; }
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return 0; }
@@ -162,6 +173,6 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) {
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return 3; }
-static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return 3; }
-static inline cudaError_t cudaIpcCloseMemHandle(void *) { return 3; }
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { return emu::ipc_export(h->reserved, p); }
+static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { return emu::ipc_import(p, h.reserved); }
+static inline cudaError_t cudaIpcCloseMemHandle(void *p) { return emu::ipc_release(p); }

@@ -430,6 +430,9 @@ def _slab_worker(rank, world, port, so, q, lb_freq=0):
     parallel.DeviceHaloOps = HostHaloOps
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
+    # lb_freq runs take the send / recv refresh, the others the peer-memory refresh (the shim
+    # emulates cudaIpc with shared memory between the worker processes)
+    os.environ['B200SPH_PEER_HALO'] = '0' if lb_freq else '1'
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         params = geo.dam_break_3d_params(SLAB_DX)
@@ -445,7 +448,7 @@ def _slab_worker(rank, world, port, so, q, lb_freq=0):
         t, dt = solver.t, solver.dt
         solver.pull()
         q.put((rank, M._collect(pas), pm.n_full, pm.n_refresh, pm.n_deferred_failed, t, dt,
-               pm.use_peer, pm.n_recut, list(pm.cuts)))
+               pm.use_peer, pm.n_recut, list(pm.cuts), pm.n_peer_refresh))
     except Exception:
         import traceback
         q.put(('error', rank, traceback.format_exc()))
@@ -492,7 +495,10 @@ def test_slab_decomposition_on_the_emulated_library(emulated_library, world, lb_
         p.join(timeout=120)
         assert p.exitcode == 0
     assert min(o[3] for o in out) > 0 and min(o[2] for o in out) >= 1      # refreshes and full paths
-    assert not any(o[7] for o in out)           # no cudaIpc here: refresh went through send/recv
+    if lb_freq:         # refresh through send / recv (B200SPH_PEER_HALO=0)
+        assert not any(o[7] for o in out) and not any(o[10] for o in out)
+    else:               # refresh through the neighbours' staging buffers ("NVLink stores")
+        assert all(o[7] for o in out) and min(o[10] for o in out) > 0
     if lb_freq:         # the slabs were re-cut on the way (k_column_counts + migration)
         static = parallel.balanced_cuts(*parallel.dam_break_column_weights(
             SLAB_DX, solid_weight=0.45), world, SLAB_DX)
@@ -579,7 +585,7 @@ def _rings_worker(rank, world, port, so, q):
             solver.step()
         solver.pull()
         q.put((rank, _rings_collect(pas[0]), pm.n_full, pm.n_refresh, n0,
-               pas[0].get_number_of_particles(real=True)))
+               pas[0].get_number_of_particles(real=True), pm.use_peer, pm.n_peer_refresh))
     except Exception:
         import traceback
         q.put(('error', rank, traceback.format_exc()))
@@ -625,6 +631,8 @@ def test_rings_slab_decomposition_on_the_emulated_library(emulated_library):
         assert p.exitcode == 0
     assert min(o[2] for o in out) >= 2                  # full paths (rebuild + migration)
     assert any(o[4] != o[5] for o in out)               # somebody gained / lost particles
+    # refreshes went through the neighbours' staging buffers (k_halo_gather_all / scatter_all<16>)
+    assert all(o[6] for o in out) and min(o[7] for o in out) > 0, [(o[6], o[7]) for o in out]
     g_all = np.concatenate([o[1]['gid'] for o in out])
     assert np.array_equal(np.sort(g_all), np.sort(ref['gid']))
     order_ref, order = np.argsort(ref['gid']), np.argsort(g_all)
