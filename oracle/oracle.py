@@ -9,6 +9,10 @@ reference runs for a WCSPHScheme (pysph/sph/scheme.py:388-506), in which order
 (pysph/sph/integrator.py:344-361 PEC, :401-420 EPEC) and how the solver picks
 the time step (pysph/solver/solver.py:454-507, :647-688;
 pysph/sph/integrator.py:161-200).
+
+Pinned to the reference: see oracle/README.md and DESIGN.md section 5.  One function is
+NOT: ``mirror_ghosts`` (a restatement of nnps_base.pyx:506-689; parity unpinned -- the
+reference holds no mirror fixture and its DomainManager cannot be executed here).
 """
 import ctypes as C
 import os
