@@ -89,3 +89,95 @@ def test_bench_gpu_arm_on_the_emulated_library(emulated_library, fake_cuda, monk
     assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and r['peak'] > 0
     c = d['cpu_baseline']
     assert c['kind'] == 'port' and c['cores'] == 1 and c['value'] > 0 and c['sample']
+
+
+def _rank_main(rank, world, port, so, argv, q):
+    """one rank of `torchrun bench.py --gpus N` without GPUs: gloo for nccl, host tensors
+    for device tensors, the library emulation for libb200sph.so"""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from pysph_b200 import _lib, parallel
+    _lib.LIB_PATH, _lib._lib = so, None
+    torch.cuda.Event = _Event
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.set_device = lambda *a, **k: None
+    torch.cuda.current_stream = lambda *a, **k: _Stream()
+    torch.Tensor.pin_memory = lambda self, *a, **k: self
+    real_tensor, real_init = torch.tensor, dist.init_process_group
+
+    def tensor(*a, **k):
+        if str(k.get('device', 'cpu')).startswith('cuda'):
+            k['device'] = 'cpu'
+        return real_tensor(*a, **k)
+    torch.tensor = tensor
+    dist.init_process_group = lambda backend=None, **k: real_init(
+        'gloo', rank=rank, world_size=world)
+    init = parallel.DeviceHaloOps.__init__
+
+    def host_init(self, backend, device):
+        init(self, backend, 0)
+        self.device = torch.device('cpu')
+
+    def read_later(self, t):
+        v = float(t[0])
+        return lambda: v
+    parallel.DeviceHaloOps.__init__ = host_init
+    parallel.DeviceHaloOps.read_later = read_later
+    os.environ.update(RANK=str(rank), LOCAL_RANK='0', WORLD_SIZE=str(world),  # one emulated device per process
+                      MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    sys.argv = ['bench.py', '--gpus', str(world), '--steps', '3', '--warmup', '3',
+                '--e2e-steps', '2', '--no-cpu'] + argv
+    import tempfile
+    tmp = tempfile.TemporaryFile()
+    saved = os.dup(1)
+    os.dup2(tmp.fileno(), 1)        # what bench prints on fd 1 (it parks fd 1 on stderr itself)
+    try:
+        bench = importlib.import_module('bench')
+        bench.main()
+        sys.stdout.flush()
+    except BaseException:
+        import traceback
+        os.dup2(saved, 1)
+        q.put((rank, 'error', traceback.format_exc()))
+        raise
+    os.dup2(saved, 1)
+    tmp.seek(0)
+    q.put((rank, 'ok', tmp.read().decode()))
+
+
+@pytest.mark.timeout(400)
+@pytest.mark.parametrize('argv', [['--dx', '0.07'],
+                                  ['--workload', 'rings', '--dx', '0.0025', '--lz', '0.005']],
+                         ids=['dam_break', 'rings'])
+def test_bench_two_ranks_on_the_emulated_library(emulated_library, argv):  # noqa: F811
+    """`torchrun --nproc-per-node 2 bench.py --gpus 2 ...` on the CPU: rank 0 prints ONE line
+    with the whole-job aggregate, the other rank prints nothing."""
+    import socket
+    import torch.multiprocessing as mp
+    from pysph_b200 import _lib
+    sock = socket.socket()
+    sock.bind(('127.0.0.1', 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, _lib.LIB_PATH, argv, q))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict()
+    for _ in range(2):
+        rank, status, text = q.get(timeout=240)
+        assert status == 'ok', text[-3000:]
+        out[rank] = text
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    lines = [ln for ln in out[0].splitlines() if ln.startswith('{')]
+    assert len(lines) == 1 and not [ln for ln in out[1].splitlines() if ln.startswith('{')]
+    d = json.loads(lines[0])
+    assert d['n_gpus'] == 2 and d['scaling'] == 'weak' and d['value'] > 0
+    assert d['e2e']['value'] > 0 and d['e2e']['h2d_bytes_per_step'] > 0
+    assert d['gpu_launches'] > 0 and d['roofline']['frac'] > 0
