@@ -294,6 +294,39 @@ def gen_wcsph_case(kernels, basic, wc, kernel_name, dim, seed, hvar=0.0,
                 outputs=arrays)
 
 
+def gen_monaghan_av_case(kernels, basic, wc, kernel_name, dim, seed, hvar=0.0):
+    """The stand-alone artificial viscosity (basic_equations.py:195-257): a Group in which
+    the fluid's velocity change comes from MonaghanArtificialViscosity alone (no
+    MomentumEquation) next to ContinuityEquation and XSPHCorrection -- the branch of the
+    device's pair body that the WCSPH scheme never takes."""
+    rs = np.random.RandomState(seed)
+    kernel = getattr(kernels, kernel_name)(dim=dim)
+    dx = 0.1
+    rho0, c0, gamma = 1000.0, 32.85, 7.0
+    if dim == 3:
+        lo_f, hi_f = [0, 0, 0], [0.5, 0.4, 0.4]
+        lo_b, hi_b = [-0.15, -0.1, -0.15], [0.65, 0.5, 0.0]
+    else:
+        lo_f, hi_f = [0, 0, 0], [1.0, 0.8, 0.0]
+        lo_b, hi_b = [-0.2, -0.2, 0], [1.2, 0.0, 0.0]
+    arrays = dict(
+        fluid=make_array(rs, 90, lo_f, hi_f, dx, dim, rho0, ghost=10, hvar=hvar),
+        boundary=make_array(rs, 60, lo_b, hi_b, dx, dim, rho0, ghost=5, vel=0.3,
+                            hvar=hvar))
+    inputs = json.loads(json.dumps(arrays))
+    all_ = ['fluid', 'boundary']
+    params = dict(rho0=rho0, c0=c0, gamma=gamma, alpha=0.7, beta=1.3, dim=dim,
+                  eps_xsph=0.4, names=all_)
+    g1 = [wc.TaitEOS(dest=a, sources=None, rho0=rho0, c0=c0, gamma=gamma) for a in all_]
+    g2 = [basic.ContinuityEquation(dest='fluid', sources=all_),
+          basic.MonaghanArtificialViscosity(dest='fluid', sources=all_,
+                                            alpha=params['alpha'], beta=params['beta']),
+          basic.XSPHCorrection(dest='fluid', sources=['fluid'], eps=params['eps_xsph'])]
+    evaluate_reference(kernel, arrays, [(False, g1), (True, g2)])
+    return dict(kernel=kernel_name, dim=dim, params=params, inputs=inputs,
+                outputs=arrays)
+
+
 EDAC_PROPS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'p', 'au', 'av', 'aw',
               'uhat', 'vhat', 'what', 'auhat', 'avhat', 'awhat', 'ap', 'V', 'pavg',
               'nnbr']
@@ -680,6 +713,10 @@ def main():
         gen_wcsph_case(kernels, basic, wc, 'Gaussian', 3, 106),
     ]
     dump('wcsph_cases.json', cases)
+    dump('monaghan_av_cases.json', [
+        gen_monaghan_av_case(kernels, basic, wc, 'CubicSpline', 3, 111),
+        gen_monaghan_av_case(kernels, basic, wc, 'WendlandQuintic', 2, 112, hvar=0.1),
+    ])
     tvf, edac = load_reference_edac()
     ecases = [
         gen_edac_case(kernels, edac, 'QuinticSpline', 2, 201),

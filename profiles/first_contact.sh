@@ -3,17 +3,17 @@
 # ONE gpurun call on ONE GPU.  Each step has its own timeout so that a defect in one does
 # not cost the others; outputs land in gpurun_out/first_contact/.
 #   gpurun --timeout 1500 -- 'bash profiles/first_contact.sh'
-# The 2-GPU items (tests/test_zz_gpu_recut_unvalidated.py, test_zz_gpu_rings_multi_unvalidated.py,
+# The 2-GPU items (tests/test_gpu_recut.py, test_gpu_rings_multi.py,
 # `torchrun --nproc-per-node 4 bench.py --gpus 4 --workload rings`) need `gpurun --gpus N`.
 O=gpurun_out/first_contact
 mkdir -p $O
 run() { name=$1; shift; echo "== $name" | tee -a $O/summary.txt; timeout 420 "$@" > $O/$name.log 2>&1; echo "exit $?" | tee -a $O/summary.txt; tail -3 $O/$name.log >> $O/summary.txt; }
 # 1. the validated suite first (must stay green), then the unvalidated files with xfail lifted
 run validated python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_multi.py -k "not unvalidated"
-run solid python -m pytest tests/test_zz_gpu_solid_unvalidated.py -m gpu -q --runxfail
-run async_output python -m pytest tests/test_zz_gpu_async_output_unvalidated.py -m gpu -q --runxfail
-run mirror python -m pytest tests/test_zz_gpu_mirror_unvalidated.py -m gpu -q --runxfail
-run gate25k python -m pytest tests/test_zz_gpu_gate_25k_unvalidated.py -m gpu -q --runxfail
+run solid python -m pytest tests/test_gpu_solid.py -m gpu -q --runxfail
+run async_output python -m pytest tests/test_gpu_async_output.py -m gpu -q --runxfail
+run mirror python -m pytest tests/test_gpu_mirror.py -m gpu -q --runxfail
+run gate25k python -m pytest tests/test_gpu_gate_25k.py -m gpu -q --runxfail
 # 2. the three bench workloads
 run bench_dam python bench.py
 run bench_tg python bench.py --workload taylor_green

@@ -127,11 +127,12 @@ class B200Backend(object):
     def pull(self, i, props=None):
         pa = self.particle_arrays[i]
         n, n_real = self.sizes(i)
-        if pa.get_number_of_particles() != n:
-            if hasattr(pa, 'resize'):
-                pa.resize(n)
-            pa.set_num_real_particles(n_real) if hasattr(
-                pa, 'set_num_real_particles') else None
+        if pa.get_number_of_particles() != n and hasattr(pa, 'resize'):
+            pa.resize(n)
+        # the real / ghost split can change while n stays the same (one particle
+        # migrates out, one more ghost arrives): always take it from the device
+        if hasattr(pa, 'set_num_real_particles'):
+            pa.set_num_real_particles(n_real)
         ids = self.prop_ids[i]
         for name in self._props_of(pa, props, ids):
             a = _host_array(pa, name)
@@ -150,21 +151,40 @@ class B200Backend(object):
                               tmp.ctypes.data, 0, n)
                 a[:] = tmp.view(a.dtype) if a.dtype.itemsize == 4 else tmp
 
+    def _real_view(self, pa, name, n_real, who):
+        """A contiguous fp64 host buffer of at least n_real elements, or an error: the
+        C-ABI takes a raw pointer and a count, so a host mirror shorter than the
+        device's real-particle count (particles migrated in since it was sized) would
+        be read / written past its end."""
+        a = _host_array(pa, name)
+        if a.dtype != np.float64 or not a.flags.c_contiguous:
+            raise TypeError('%s: %s.%s must be a contiguous float64 array'
+                            % (who, pa.name, name))
+        if a.size < n_real:
+            raise ValueError(
+                '%s: the host mirror of %s.%s holds %d values but the device has %d '
+                'real particles (migration changed the count): pull() / resize the '
+                'host array first' % (who, pa.name, name, a.size, n_real))
+        return a
+
     def push_real(self, props):
         """Push the REAL particles' values only (ghosts on the device, if any, keep
-        theirs): the per-step host -> device path of a multi-GPU run."""
+        theirs): the per-step host -> device path of a multi-GPU run.  The host
+        mirrors must be in the device's particle order (true until a migration
+        compacts the arrays: re-pull then)."""
         for i, pa in enumerate(self.particle_arrays):
             n_real = self.sizes(i)[1]
             for name in props:
-                a = _host_array(pa, name)
+                a = self._real_view(pa, name, n_real, 'push_real')
                 self.ctx.call('b200sph_push_f64', i, self.prop_ids[i][name],
                               a.ctypes.data, 0, n_real)
+        self._dt_cache = None
 
     def pull_real(self, props):
         for i, pa in enumerate(self.particle_arrays):
             n_real = self.sizes(i)[1]
             for name in props:
-                a = _host_array(pa, name)
+                a = self._real_view(pa, name, n_real, 'pull_real')
                 self.ctx.call('b200sph_pull_f64', i, self.prop_ids[i][name],
                               a.ctypes.data, 0, n_real)
 

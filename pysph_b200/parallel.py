@@ -102,6 +102,17 @@ class DeviceHaloOps(object):
         self.ctx = backend.ctx
         self.narr = len(backend.names)
         self.device = torch.device('cuda', device)
+        # torch.distributed collectives and P2P only order against torch's current
+        # stream; the library's own stream is a cudaStreamNonBlocking one.  Everything
+        # this class enqueues (drift_to, packs into peer staging, appends that read
+        # receive buffers, the dt block NCCL reduces in place) must therefore run on
+        # torch's stream -- adopt it here instead of trusting the caller to.
+        # (no CUDA in the process = the host emulation of the library used by the CPU
+        # tests, where streams are no-ops; a real backend cannot exist without a device)
+        self.stream = None
+        if torch.cuda.is_available():
+            with torch.cuda.device(self.device):
+                self.stream = backend.use_torch_stream()
 
     def _layout(self):
         h, m = C.c_int(), C.c_int()

@@ -155,6 +155,16 @@ class B200Solver(object):
                                                    getattr(dom, 'is_mirror', False)):
             raise NotImplementedError(
                 'B200 backend: periodic / mirror domains with the slab decomposition')
+        if pm is not None:
+            from ._lib import EDAC_PROP_IDS
+            edac = any(s.__class__.__name__ == 'EDACTVFStep'
+                       for s in self.integrator.steppers.values()) or \
+                any(ids is EDAC_PROP_IDS for ids in self.backend.prop_ids)
+            if edac:
+                # uhat vhat what p p0 are in neither the halo nor the migration message
+                raise NotImplementedError(
+                    'B200 backend: the EDAC / transport-velocity scheme with the slab '
+                    'decomposition (its evolved p and transport velocity do not travel)')
         self.pm = pm
         self.in_parallel = pm is not None
         self.integrator.set_parallel_manager(pm)

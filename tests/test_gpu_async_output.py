@@ -1,19 +1,16 @@
-"""FIRST HARDWARE CONTACT of the asynchronous output path (SURVEY.md 8f-4 "async D2H of
-only output props at pfreq"): `b200sph_snapshot_take / fetch / release` and
-`B200Solver.solve(pfreq=..., asynchronous=True)` were written after this round's GPU budget
-was spent.  They pass on the host emulation of the library
-(tests/test_library_on_cpu.py::test_async_output_small), where streams are no-ops -- the
-ordering between the time loop's stream and the copy stream is what only a GPU can show.
-xfail(strict=False) and sorted last so a defect cannot turn the validated suite red."""
+"""Asynchronous output path (SURVEY.md 8f-4 "async D2H of only output props at pfreq"):
+`b200sph_snapshot_take / fetch / release` and `B200Solver.solve(pfreq=..., asynchronous=True)`.
+The ordering between the time loop's stream and the copy stream is what only a GPU can
+show; the same comparison also runs on the host emulation of the library
+(tests/test_library_on_cpu.py::test_async_output_small).  First passed on a B200 in the
+driver's round-1 run (GPUTEST_r01.json)."""
 import os
 
 import numpy as np
 import pytest
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.timeout(300),
-              pytest.mark.xfail(reason='asynchronous output: not yet validated on hardware '
-                                       '(written without GPU budget)', strict=False)]
+              pytest.mark.timeout(300)]
 
 
 def test_async_dumps_equal_sync_dumps(gpu_device, tmp_path):

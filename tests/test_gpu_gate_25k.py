@@ -4,10 +4,9 @@ adaptive damped dt -- including the reference's quirk that the particles keep th
 module-level h = 0.039 and m = 0.9 (dam_break_2d.py:35,45-47,230-232):
 ~183 neighbours per particle and 9x over-heavy particles, so the run is a parity gate, not
 physics -- it blows up (dt -> 1e-8, in the oracle and on the device alike) after ~33 steps,
-and the comparison stops at 30.  The validated gate (tests/test_gpu_parity.py::
-test_dam_break_2d_gate) runs the same path at the example's default dx = 0.03; this size
-was added after the GPU budget was spent and has only run on the library emulation (max
-relative error 2.5e-8 after 30 steps), hence xfail(strict=False) and the zz name."""
+and the comparison stops at 30.  tests/test_gpu_parity.py::test_dam_break_2d_gate runs the
+same path at the example's default dx = 0.03.  First passed on a B200 in the driver's
+round-1 run (GPUTEST_r01.json)."""
 import numpy as np
 import pytest
 
@@ -15,9 +14,7 @@ from helpers import copy_arrays
 from oracle import oracle as orc
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.timeout(300),
-              pytest.mark.xfail(reason='25 k-particle gate: not yet run on hardware',
-                                strict=False)]
+              pytest.mark.timeout(300)]
 
 
 def test_dam_break_2d_gate_25k(gpu_device):

@@ -1,8 +1,7 @@
-"""FIRST HARDWARE CONTACT of the mirror boundaries (DomainManager(mirror_in_x ...),
-nnps_base.pyx:506-689; `b200sph_set_mirror`, `k_flag_mirror`, `k_mirror_copy`): written in a
-session without GPU time.  The tests pass on the library emulation
-(tests/test_library_on_cpu.py); xfail(strict=False) and a file name that sorts last until
-they have run on a B200."""
+"""Mirror boundaries (DomainManager(mirror_in_x ...), nnps_base.pyx:506-689;
+`b200sph_set_mirror`, `k_flag_mirror`, `k_mirror_copy`).  Also run on the library emulation
+(tests/test_library_on_cpu.py).  First passed on a B200 in the driver's round-1 run
+(GPUTEST_r01.json)."""
 import numpy as np
 import pytest
 
@@ -10,9 +9,7 @@ from helpers import rel_err
 from oracle import oracle as orc
 from test_gpu_periodic import _dom_tuple, _periodic_case
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180),
-              pytest.mark.xfail(reason='mirror boundaries: not yet validated on hardware',
-                                strict=False)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
 
 
 def _mirror_tuple(dm):

@@ -547,3 +547,41 @@ def test_device_resident_dt_is_bitwise_the_host_path(gpu_device):
     assert 27 <= a[3] <= 40
     for k, v in a[5].items():
         assert np.array_equal(v, b[5][k]), k
+
+
+@pytest.mark.parametrize('idx', range(2))
+def test_monaghan_av_vs_reference_bodies(gpu_device, idx):
+    """The B200SPH_EQ_MONAGHAN_AV branch of pair_body: a Group with ContinuityEquation,
+    stand-alone MonaghanArtificialViscosity (basic_equations.py:195-257) and
+    XSPHCorrection, against the values the reference's own bodies produced
+    (tests/golden/monaghan_av_cases.json, oracle/gen_golden.py)."""
+    import pysph_b200 as pb
+    from test_oracle_golden import run_oracle_monaghan_case
+    case = load_golden('monaghan_av_cases.json')[idx]
+    p = case['params']
+    names = p['names']
+    pas = arrays_from_dict(case['inputs'], order=tuple(names))
+    kernel = getattr(pb, case['kernel'])(dim=case['dim'])
+    groups = [
+        pb.Group(equations=[pb.TaitEOS(dest=a, sources=None, rho0=p['rho0'], c0=p['c0'],
+                                       gamma=p['gamma']) for a in names], real=False),
+        pb.Group(equations=[
+            pb.ContinuityEquation(dest='fluid', sources=names),
+            pb.MonaghanArtificialViscosity(dest='fluid', sources=names, alpha=p['alpha'],
+                                           beta=p['beta']),
+            pb.XSPHCorrection(dest='fluid', sources=['fluid'], eps=p['eps_xsph'])],
+            real=True)]
+    ae = pb.B200AccelerationEval(pas, groups, kernel)
+    nn = pb.B200NNPS(case['dim'], pas, backend=ae.backend, kernel=kernel)
+    ae.set_nnps(nn)
+    ae.count_pairs = True
+    ae.compute(0.0, 0.0)
+    ae.backend.pull_all()
+    _, pairs = run_oracle_monaghan_case(case)
+    assert ae.last_pairs == pairs
+    ref = case['outputs']['fluid']
+    nr = ref['_n_real']
+    for f in ('arho', 'au', 'av', 'aw', 'ax', 'ay', 'az'):
+        want = np.array(ref[f])[:nr]
+        assert rel_err(pas[0].properties[f][:nr], want) <= TOL_EVAL, f
+    assert np.max(np.abs(ref['au'])) > 1.0

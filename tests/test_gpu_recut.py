@@ -1,16 +1,13 @@
-"""FIRST HARDWARE CONTACT of the slab re-cut (SURVEY.md 8e "re-cut every K steps"):
-`b200sph_column_counts` / `k_column_counts` and `SlabParallelManager._recut` were written
-after this round's GPU budget was spent.  They HAVE run, and pass, on the host emulation of
+"""Slab re-cut (SURVEY.md 8e "re-cut every K steps"): `b200sph_column_counts` /
+`k_column_counts` and `SlabParallelManager._recut`.  Also covered on the host emulation of
 the library (tests/test_library_on_cpu.py: slab decomposition with lb_freq=2 on 3 ranks)
-and with the numpy test double (tests/test_parallel_gloo.py: test_slab_recut_gloo).  Marked
-xfail(strict=False) and sorted last so a defect cannot turn the validated suite red."""
+and with the numpy test double (tests/test_parallel_gloo.py: test_slab_recut_gloo).  The
+2-GPU test needs `gpurun --gpus 2` (skipped on a 1-GPU lease)."""
 import numpy as np
 import pytest
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.timeout(300),
-              pytest.mark.xfail(reason='slab re-cut: not yet validated on hardware '
-                                       '(written without GPU budget)', strict=False)]
+              pytest.mark.timeout(300)]
 
 
 def test_column_counts_match_numpy(gpu_device):

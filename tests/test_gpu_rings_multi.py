@@ -1,10 +1,9 @@
-"""FIRST HARDWARE CONTACT of the elastic-dynamics slab decomposition (BASELINE configs[4]
-is a 4-GPU case): the 16-field ghost message, the 30-field migration message and group 1 on
-a two-support halo were written after this round's GPU budget was spent.  The same
-comparison passes on the library emulation over gloo with 3 ranks
+"""Elastic-dynamics slab decomposition (BASELINE configs[4] is a 4-GPU case): the
+16-field ghost message, the 30-field migration message and group 1 on a two-support halo.
+The same comparison runs on the library emulation over gloo with 3 ranks
 (tests/test_library_on_cpu.py::test_rings_slab_decomposition_on_the_emulated_library);
-here it runs on 2 GPUs with NCCL and the peer-memory refresh.  xfail(strict=False) until
-it has run on hardware; needs >= 2 GPUs (gpurun --gpus 2)."""
+here it runs on 2 GPUs with the peer-memory refresh; needs >= 2 GPUs (gpurun --gpus 2),
+the layout tests run on one."""
 import os
 
 import numpy as np
@@ -13,9 +12,7 @@ import pytest
 from test_gpu_multi import _free_port, _ngpus
 from test_library_on_cpu import RINGS, RING_FIELDS, _rings_collect, _rings_perturb
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(reason='elastic-dynamics slab decomposition: not yet '
-                                       'validated on hardware', strict=False)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 def _worker(rank, world, port, q):

@@ -1,12 +1,9 @@
-"""FIRST HARDWARE CONTACT of the elastic-dynamics kernels (BASELINE
-configs[4]): `k_solid_pass1/2` and `k_stage_solid` were written after this round's GPU
-budget was spent, so nothing in this file has ever run on a B200 -- it HAS run, and passes,
-against the host emulation of the whole library (tests/test_library_on_cpu.py), and the
-kernel source compiled for the host reproduces the goldens
-(tests/test_kernel_source_on_cpu.py).  The oracle they are compared with IS pinned to the
-reference (tests/test_oracle_golden.py: test_elastic_dynamics_matches_reference_bodies).  The tests are expected-to-pass but
-marked xfail(strict=False) so that a defect shows up as XFAIL here instead of turning
-the validated suite red; the file name sorts last for the same reason."""
+"""Elastic-dynamics kernels (BASELINE configs[4]): `k_solid_pass1/2` and
+`k_stage_solid` against the reference-generated goldens and the oracle, which IS pinned to
+the reference (tests/test_oracle_golden.py: test_elastic_dynamics_matches_reference_bodies).
+Also run against the host emulation of the whole library (tests/test_library_on_cpu.py) and
+with the kernel source compiled for the host (tests/test_kernel_source_on_cpu.py).  First
+passed on a B200 in the driver's round-1 run (GPUTEST_r01.json: 11 tests)."""
 import numpy as np
 import pytest
 
@@ -14,10 +11,7 @@ from helpers import load_golden, rel_err
 from oracle import oracle as orc
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.timeout(180),
-              pytest.mark.xfail(reason='elastic-dynamics kernels: not yet validated on '
-                                       'hardware (written without GPU budget)',
-                                strict=False)]
+              pytest.mark.timeout(180)]
 
 SOLID_FIELDS = ['p', 'arho', 'au', 'av', 'aw', 'ax', 'ay', 'az'] + \
     ['v%d%d' % (i, j) for i in range(3) for j in range(3)] + \

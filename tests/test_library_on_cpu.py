@@ -79,6 +79,7 @@ FAST = [
     ('test_gpu_parity', 'test_steppers_and_eos_vs_reference_bodies', {}),
     ('test_gpu_parity', 'test_push_pull_roundtrip_and_errors', {}),
 ] + [('test_gpu_parity', 'test_wcsph_evaluation_vs_reference_bodies', {'idx': i}) for i in range(6)] + [
+    ('test_gpu_parity', 'test_monaghan_av_vs_reference_bodies', {'idx': i}) for i in range(2)] + [
     ('test_gpu_periodic', 'test_periodic_lattice_density', {'dim': d, 'n': n, 'shift': sh})
     for d, n in ((1, 20), (2, 10), (3, 5)) for sh in (0.0, 0.35)
 ] + [
@@ -90,13 +91,13 @@ FAST = [
     ('test_gpu_edac', 'test_edac_tvf_step_matches_reference_bodies', {}),
     ('test_gpu_edac', 'test_taylor_green_steps_vs_oracle', {'dim': 2, 'nx': 32, 'kernel': 'QuinticSpline'}),
     ('test_gpu_edac', 'test_edac_setup_errors', {}),
-] + [('test_zz_gpu_solid_unvalidated', 'test_elastic_evaluation_matches_reference_bodies', {'idx': i})
+] + [('test_gpu_solid', 'test_elastic_evaluation_matches_reference_bodies', {'idx': i})
      for i in range(6)] + [
-    ('test_zz_gpu_solid_unvalidated', 'test_solid_mech_step_matches_reference_bodies', {}),
-    ('test_zz_gpu_solid_unvalidated', 'test_rings_steps_vs_oracle', {}),
-    ('test_zz_gpu_solid_unvalidated', 'test_rings_3d_steps_vs_oracle', {}),
-    ('test_zz_gpu_solid_unvalidated', 'test_bar_hits_rigid_wall_vs_oracle', {}),
-    ('test_zz_gpu_solid_unvalidated', 'test_rings_3d_momentum_and_symmetry_at_size',
+    ('test_gpu_solid', 'test_solid_mech_step_matches_reference_bodies', {}),
+    ('test_gpu_solid', 'test_rings_steps_vs_oracle', {}),
+    ('test_gpu_solid', 'test_rings_3d_steps_vs_oracle', {}),
+    ('test_gpu_solid', 'test_bar_hits_rigid_wall_vs_oracle', {}),
+    ('test_gpu_solid', 'test_rings_3d_momentum_and_symmetry_at_size',
      {'dx': 0.0025, 'lz': 0.01, 'steps': 6, 'min_particles': 1000}),
     ('test_gpu_parity', 'test_kernels_via_two_particle_density', {}),
     ('test_gpu_parity', 'test_dam_break_3d_small_eval_and_steps', {}),
@@ -106,16 +107,16 @@ FAST = [
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 2, 'n': 24, 'pattern': (0, 1, 0)}),
     ('test_output', 'test_dump_and_restart_on_device', {'tmp_path': None}),
-    ('test_zz_gpu_mirror_unvalidated', 'test_mirror_wcsph_steps_vs_oracle', {'dim': 2, 'n': 24, 'pattern': (1, 1, 0)}),
-    ('test_zz_gpu_mirror_unvalidated', 'test_mirror_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 0, 1)}),
-    ('test_zz_gpu_mirror_unvalidated', 'test_mirror_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
-    ('test_zz_gpu_mirror_unvalidated', 'test_mirror_errors', {}),
-    ('test_zz_gpu_rings_multi_unvalidated', 'test_elastic_halo_and_migration_layout', {}),
-    ('test_zz_gpu_rings_multi_unvalidated', 'test_empty_elastic_array_agrees_on_the_message_layout', {}),
+    ('test_gpu_mirror', 'test_mirror_wcsph_steps_vs_oracle', {'dim': 2, 'n': 24, 'pattern': (1, 1, 0)}),
+    ('test_gpu_mirror', 'test_mirror_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 0, 1)}),
+    ('test_gpu_mirror', 'test_mirror_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
+    ('test_gpu_mirror', 'test_mirror_errors', {}),
+    ('test_gpu_rings_multi', 'test_elastic_halo_and_migration_layout', {}),
+    ('test_gpu_rings_multi', 'test_empty_elastic_array_agrees_on_the_message_layout', {}),
 ]
 FULL = [
     ('test_gpu_parity', 'test_device_resident_dt_is_bitwise_the_host_path', {}),
-    ('test_zz_gpu_gate_25k_unvalidated', 'test_dam_break_2d_gate_25k', {}),
+    ('test_gpu_gate_25k', 'test_dam_break_2d_gate_25k', {}),
 ]
 
 

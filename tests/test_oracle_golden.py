@@ -390,3 +390,34 @@ def test_eigen_sym3_against_numpy():
         assert np.max(np.abs(v @ np.diag(d) @ v.T - a)) <= 1e-13 * s
         assert np.max(np.abs(v.T @ v - np.eye(3))) <= 1e-14
         assert np.max(np.abs(np.sort(d) - np.linalg.eigvalsh(a))) <= 1e-13 * s
+
+
+# ---------------------------------------------------------------------------
+# stand-alone MonaghanArtificialViscosity (basic_equations.py:195-257): the ORC_EQ_AV
+# branch, which the WCSPH scheme never takes (its MomentumEquation carries the AV)
+# ---------------------------------------------------------------------------
+def run_oracle_monaghan_case(case):
+    p = case['params']
+    pas = arrays_from_dict(case['inputs'], order=tuple(p['names']))
+    o = orc.Oracle(pas, case['dim'], case['kernel'])
+    o.update_domain()
+    o.nnps_update()
+    for a in range(len(pas)):
+        o.eos(a, 0, p['rho0'], p['c0'], p['gamma'], 0.0, real_only=False)
+    pairs = o.pair_pass([(orc.EQ_CONT, 0, [0, 1]), (orc.EQ_AV, 0, [0, 1]),
+                         (orc.EQ_XSPH, 0, [0])], real_only=True, alpha=p['alpha'],
+                        beta=p['beta'], eps_xsph=p['eps_xsph'])
+    return pas, pairs
+
+
+@pytest.mark.parametrize('idx', range(2))
+def test_monaghan_av_matches_reference_bodies(idx):
+    case = load_golden('monaghan_av_cases.json')[idx]
+    pas, pairs = run_oracle_monaghan_case(case)
+    assert pairs > 0
+    ref = case['outputs']['fluid']
+    for f in ('arho', 'au', 'av', 'aw', 'ax', 'ay', 'az', 'p', 'cs'):
+        got, want = pas[0].properties[f], np.array(ref[f])
+        scale = max(np.max(np.abs(want)), 1e-300)
+        assert np.max(np.abs(got - want)) <= 2e-12 * scale, f
+    assert np.max(np.abs(ref['au'])) > 1.0       # the AV term is active in the fixture
