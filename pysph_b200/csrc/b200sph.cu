@@ -141,6 +141,7 @@ struct b200sph_ctx {
     int64_t n_sorted = 0;
     bool state_packed = false;
     int force_kernel = 0;       // 0 lists (default), 1 warp kernel (env B200SPH_PAIR_KERNEL)
+    int pair_minb = 6;          // resident CTAs per SM k_pair_list is compiled for (env B200SPH_PAIR_MINB: 6, 7, 8)
     // persistent neighbour lists
     double skin = 0.1;          // S = skin * radius_scale * hmax, adapted between skin_min and skin_max
     double skin_max = 0.1;      // env B200SPH_SKIN (also what a halo exchange must cover)
@@ -271,6 +272,25 @@ __device__ __forceinline__ float frsqrt(float x)
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+
+// A float4 table in shared memory read through an opaque 32-bit shared address: the
+// compiler otherwise re-derives the CTA's shared window base (three uniform instructions)
+// at every use inside the pair loops.  (The host emulation of the tests supplies its own.)
+#ifndef B200SPH_HOST_EMULATION
+typedef uint32_t smem_tab_t;
+__device__ __forceinline__ smem_tab_t smem_tab(const float4 *table)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(table);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ float4 lds_T(const smem_tab_t t, const uint32_t index)
+{
+    float4 v;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(t + (index << 4)));
+    return v;
+}
+#endif
 
 #include "pool_kernels.cuh"
 #include "scan.cuh"
@@ -566,6 +586,7 @@ int b200sph_create(int device, b200sph_ctx **out)
             return -3;
         }
     }
+    if (const char *e = getenv("B200SPH_PAIR_MINB")) ctx->pair_minb = atoi(e);
     if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = ctx->skin_max = std::max(0.0, atof(e));
     if (const char *e = getenv("B200SPH_SKIN_ADAPT")) ctx->skin_adapt = atoi(e) != 0;
     ctx->skin_min = std::min(ctx->skin_min, ctx->skin_max);
@@ -1518,7 +1539,12 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     if (use_lists) {
         const unsigned nb = (unsigned)cdiv(ctx->n_sorted, LIST_NT);
         switch (ctx->kernel * 4 + ctx->dim) {
-#define LIST_CASE(K, D) case K * 4 + D: k_pair_list<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg); break;
+#define LIST_CASE(K, D)                                                                                          \
+    case K * 4 + D:                                                                                              \
+        if (ctx->pair_minb >= 8) k_pair_list<K, D, 8><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg);      \
+        else if (ctx->pair_minb == 7) k_pair_list<K, D, 7><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg); \
+        else k_pair_list<K, D, 6><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg);                         \
+        break;
             LIST_CASE(0, 1) LIST_CASE(0, 2) LIST_CASE(0, 3) LIST_CASE(1, 2) LIST_CASE(1, 3)
             LIST_CASE(2, 1) LIST_CASE(2, 2) LIST_CASE(2, 3) LIST_CASE(3, 1) LIST_CASE(3, 2) LIST_CASE(3, 3)
 #undef LIST_CASE

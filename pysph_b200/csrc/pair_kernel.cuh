@@ -63,12 +63,12 @@ __device__ __forceinline__ void pair_body(const PairArgs &a, const float4 qv, co
         acc.arho += mj * gt * vdotx;
     if (bits & (B200SPH_EQ_MOMENTUM | B200SPH_EQ_MONAGHAN_AV | B200SPH_EQ_XSPH)) {
         const float rhoij1 = frcp(0.5f * (Ci.x + Cj.x));
-        float piij = 0.0f;
-        if (vdotx < 0.0f) {  // wc/basic.py:215-222, basic_equations.py:245-252
-            const float cij = 0.5f * (Ci.z + Cj.z);
-            const float muij = hij * vdotx * frcp(r2 + 0.01f * hij * hij);
-            piij = (-a.alpha * cij * muij + a.beta * muij * muij) * rhoij1;
-        }
+        // wc/basic.py:215-222, basic_equations.py:245-252 (vdotx < 0 only); branch-free: in a
+        // warp some lane almost always takes it, and a select is cheaper than a
+        // reconvergence scope
+        const float cij = 0.5f * (Ci.z + Cj.z);
+        const float muij = hij * vdotx * frcp(r2 + 0.01f * hij * hij);
+        const float piij = vdotx < 0.0f ? (-a.alpha * cij * muij + a.beta * muij * muij) * rhoij1 : 0.0f;
         if (bits & B200SPH_EQ_MOMENTUM) {
             if (r2 > 1e-12f)  // wc/basic.py:224-228
                 acc.cfl = fmaxf(acc.cfl, fabsf(hij * vdotx * rinv * rinv) + a.c0);

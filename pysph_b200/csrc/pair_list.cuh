@@ -15,10 +15,15 @@
 // walks its list, re-applies the EXACT accept test of linked_list_nnps.pyx:188
 // on the current positions and evaluates the equations.  Results are identical
 // to rebuilding the neighbours every evaluation; only the cost is amortised.
-// entry = j (26 bits, sorted index) | code << 26, code = (dxc+1) + 4 (dy+1) + 16 (dz+1)
+// entry = j << 6 | code: j = sorted index (26 bits), code = (dxc+1) + 4 (dy+1) + 16 (dz+1).
+// The index sits in the HIGH bits so that a consumer gets it with one shift and both record
+// addresses with one IMAD.WIDE each (no mask), the code with one AND.
 // --------------------------------------------------------------------------
 #define LIST_JBITS 26
-#define LIST_JMASK 0x03FFFFFFu
+#define LIST_CBITS 6
+#define LIST_ENTRY(j, code) (((uint32_t)(j) << LIST_CBITS) | (uint32_t)(code))
+#define LIST_J(e) ((uint32_t)(e) >> LIST_CBITS)
+#define LIST_CODE(e) ((uint32_t)(e) & 63u)
 #define LIST_NT 128
 // Skin controller.  Per evaluation a build costs c0 (1+s)^3 (list entries) + R / L(s)
 // (rebuild cost R over a lifetime L that grows linearly with the skin s); the minimum is
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
                 const unsigned m = __ballot_sync(FULL, ok);
                 if (ok && out) {
                     const unsigned pos = count + __popc(m & lt_mask);
-                    if (pos < (unsigned)a.capg) out[(size_t)pos * 32u] = t | ((rcode + dxc1) << LIST_JBITS);
+                    if (pos < (unsigned)a.capg) out[(size_t)pos * 32u] = LIST_ENTRY(t, rcode + dxc1);
                 }
                 count += __popc(m);
             }
@@ -177,11 +182,37 @@ __device__ __forceinline__ void ld_256(const float4 *p, float4 &b, float4 &c)
 // The list consumer (the default fast path): one THREAD per destination walks its
 // list.  Per entry it gathers {A, B} = (x, y, z, h, u, v, w, m) with ONE 256-bit load
 // (exactly one 32-byte sector) and C = (rho, p/rho^2, cs, type) with one 128-bit load,
-// both issued one iteration ahead of their use; list entries stream in (evict-first)
-// two iterations ahead.  The gathers are what bounds this kernel (L1 tag stage, see
-// profiles/), hence the sector-sized records.
+// both issued one entry ahead of their use; list entries stream in (evict-first) two
+// entries ahead.  The gathers and instruction issue bound this kernel at the same time
+// (profiles/), hence the sector-sized records and the hand-scheduled loop: two entries
+// per trip with ping-pong record registers (no register-rotation moves), 32-bit record
+// indices (one IMAD.WIDE per address).
+__device__ __forceinline__ void ld_rec(const PairArgs &a, const uint32_t e, float4 &A, float4 &B, float4 &C)
+{
+    const uint32_t j = LIST_J(e);
+    ld_256(a.AB + 2u * j, A, B);
+    C = __ldg(a.C + j);
+}
+
+// one list entry: cell-offset lookup, distance, the exact accept test, the equations.  `live`
+// is false for the lanes whose list is shorter than the warp's longest (their entry reads
+// as 0 and their record as record 0, so everything up to the test is harmless to execute).
 template <int K, int DIM>
-__global__ void __launch_bounds__(LIST_NT, 4) k_pair_list(const PairArgs a, const uint32_t *__restrict__ cnt,
+__device__ __forceinline__ void pair_entry(const PairArgs &a, const smem_tab_t sT, const bool live, const uint32_t e,
+                                           const float4 Aj, const float4 Bj, const float4 Cj, const float4 Ai,
+                                           const float4 Bi, const float4 Ci, const float hi2,
+                                           const unsigned long long mask_i, Acc &acc, unsigned &npairs)
+{
+    const float4 T = lds_T(sT, LIST_CODE(e));
+    const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+    const float r2 = xij * xij + yij * yij + zij * zij;
+    // the exact accept test, linked_list_nnps.pyx:188
+    if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)))
+        pair_body<K, DIM>(a, make_float4(xij, yij, zij, Aj.w), Bj, Cj, Ai, Bi, Ci, mask_i, Ci.y, acc, npairs);
+}
+
+template <int K, int DIM, int MINB>
+__global__ void __launch_bounds__(LIST_NT, MINB) k_pair_list(const PairArgs a, const uint32_t *__restrict__ cnt,
                                                          const uint32_t *__restrict__ lst, const int capg)
 {
     __shared__ float4 s_T[64];
@@ -191,6 +222,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_pair_list(const PairArgs a, cons
         s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
     }
     __syncthreads();
+    const smem_tab_t sT = smem_tab(s_T);
     const unsigned FULL = 0xffffffffu;
     const long long s = (long long)blockIdx.x * LIST_NT + tid;
     bool active = s < a.n;
@@ -210,38 +242,29 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_pair_list(const PairArgs a, cons
     int cmax = count;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
-    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
+    const uint32_t *nxt = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
     const float hi2 = a.k2 * Ai.w * Ai.w;
-    const float tmpi = Ci.y;
     Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     unsigned npairs = 0;
-    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-    float4 A_a = Ai, B_a = Bi, C_a = Ci;
-    if (count > 0) {
-        const size_t j = e_a & LIST_JMASK;
-        ld_256(a.AB + 2 * j, A_a, B_a);
-        C_a = a.C[j];
-    }
-    for (int k = 0; k < cmax; k++) {
-        const uint32_t e = e_a;
-        const float4 Aj = A_a, Bj = B_a, Cj = C_a;
-        e_a = e_b;
-        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-        if (k + 1 < count) {
-            const size_t j = e_a & LIST_JMASK;
-            ld_256(a.AB + 2 * j, A_a, B_a);
-            C_a = a.C[j];
-        }
-        if (k < count) {
-            const float4 T = s_T[e >> LIST_JBITS];
-            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
-            const float r2 = xij * xij + yij * yij + zij * zij;
-            // the exact accept test, linked_list_nnps.pyx:188
-            if ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w))
-                pair_body<K, DIM>(a, make_float4(xij, yij, zij, Aj.w), Bj, Cj, Ai, Bi, Ci, mask_i, tmpi,
-                                  acc, npairs);
-        }
+    // entries beyond a lane's own count read as 0 = "record 0, same cell": the record loads
+    // below are unconditional (a predicated 256-bit gather costs the compiler a branch),
+    // the pair itself is skipped
+    uint32_t e0 = count > 0 ? __ldcs(nxt) : 0u;
+    uint32_t e1 = count > 1 ? __ldcs(nxt + 32) : 0u;
+    nxt += 64;
+    float4 A0r, B0r, C0r, A1r, B1r, C1r;
+    ld_rec(a, e0, A0r, B0r, C0r);
+    for (int rem = count; cmax > 0; cmax -= 2, rem -= 2, nxt += 64) {
+        // entry k (registers 0) while record k + 1 (registers 1) and entry k + 2 are in flight
+        const uint32_t e2 = rem > 2 ? __ldcs(nxt) : 0u;
+        ld_rec(a, e1, A1r, B1r, C1r);
+        pair_entry<K, DIM>(a, sT, rem > 0, e0, A0r, B0r, C0r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
+        // entry k + 1 (registers 1) while record k + 2 (registers 0) and entry k + 3 are in flight
+        const uint32_t e3 = rem > 3 ? __ldcs(nxt + 32) : 0u;
+        ld_rec(a, e2, A0r, B0r, C0r);
+        pair_entry<K, DIM>(a, sT, rem > 1, e1, A1r, B1r, C1r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
+        e0 = e2;
+        e1 = e3;
     }
     if (active) {
         unsigned all_bits = 0;

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, c
     uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
     float4 A_a = Ai, B_a = Bi, C_a = make_float4(1.f, 0.f, 0.f, 0.f);
     if (count > 0) {
-        const size_t j = e_a & LIST_JMASK;
+        const size_t j = LIST_J(e_a);
         ld_256(a.AB + 2 * j, A_a, B_a);
         C_a = a.C3[j];
     }
@@ -146,12 +146,12 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, c
         e_a = e_b;
         if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
         if (k + 1 < count) {
-            const size_t j = e_a & LIST_JMASK;
+            const size_t j = LIST_J(e_a);
             ld_256(a.AB + 2 * j, A_a, B_a);
             C_a = a.C3[j];
         }
         if (k < count) {
-            const float4 T = s_T[e >> LIST_JBITS];
+            const float4 T = s_T[LIST_CODE(e)];
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
             if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.source_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass2(const SolidArgs a, c
     uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
     float4 A_a = Ai, B_a = Bi, C_a = Ci, T1_a = Ti1, T2_a = Ti2, T3_a = Ti3;
     if (count > 0) {
-        const size_t j = e_a & LIST_JMASK;
+        const size_t j = LIST_J(e_a);
         ld_256(a.AB + 2 * j, A_a, B_a);
         C_a = a.C3[j]; T1_a = a.T01[j]; T2_a = a.T2R[j]; T3_a = a.R2[j];
     }
@@ -311,12 +311,12 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass2(const SolidArgs a, c
         e_a = e_b;
         if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
         if (k + 1 < count) {
-            const size_t j = e_a & LIST_JMASK;
+            const size_t j = LIST_J(e_a);
             ld_256(a.AB + 2 * j, A_a, B_a);
             C_a = a.C3[j]; T1_a = a.T01[j]; T2_a = a.T2R[j]; T3_a = a.R2[j];
         }
         if (k < count) {
-            const float4 T = s_T[e >> LIST_JBITS];
+            const float4 T = s_T[LIST_CODE(e)];
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
             const int tj = __float_as_int(Cj.w) & 7;

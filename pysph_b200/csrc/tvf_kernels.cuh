@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
     float4 A_a = Ai;
     float2 P_a = make_float2(0.f, 0.f);
     if (count > 0) {
-        const size_t j = e_a & LIST_JMASK;
+        const size_t j = LIST_J(e_a);
         A_a = a.AB[2 * j];
         P_a = a.PT[j];
     }
@@ -95,12 +95,12 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
         e_a = e_b;
         if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
         if (k + 1 < count) {
-            const size_t j = e_a & LIST_JMASK;
+            const size_t j = LIST_J(e_a);
             A_a = a.AB[2 * j];
             P_a = a.PT[j];
         }
         if (k < count) {
-            const float4 T = s_T[e >> LIST_JBITS];
+            const float4 T = s_T[LIST_CODE(e)];
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
             if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Pj.y) & 7)) & 1u)) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const
     uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
     float4 A_a = Ai, B_a = Bi, C_a = Ci, D_a = Di;
     if (count > 0) {
-        const size_t j = e_a & LIST_JMASK;
+        const size_t j = LIST_J(e_a);
         ld_256(a.AB + 2 * j, A_a, B_a);
         C_a = a.C2[j];
         D_a = a.Dv[j];
@@ -193,13 +193,13 @@ __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const
         e_a = e_b;
         if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
         if (k + 1 < count) {
-            const size_t j = e_a & LIST_JMASK;
+            const size_t j = LIST_J(e_a);
             ld_256(a.AB + 2 * j, A_a, B_a);
             C_a = a.C2[j];
             D_a = a.Dv[j];
         }
         if (k < count) {
-            const float4 T = s_T[e >> LIST_JBITS];
+            const float4 T = s_T[LIST_CODE(e)];
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
             if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {

@@ -92,6 +92,13 @@ static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; 
 static inline float frcp(float x) { return 1.0f / x; }
 static inline float frsqrt(float x) { return 1.0f / sqrtf(x); }
 static inline void ld_256(const float4 *p, float4 &b, float4 &c) { b = p[0]; c = p[1]; }
+
+// smem_tab_t / smem_tab / lds_T: inline PTX in the CUDA build
+#define B200SPH_HOST_EMULATION 1
+typedef const float4 *smem_tab_t;
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline smem_tab_t smem_tab(const float4 *table) { return table; }
+static inline float4 lds_T(smem_tab_t t, uint32_t index) { return t[index]; }
 static inline void atomicAdd(unsigned long long *p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 using std::max;
 using std::min;
@@ -99,7 +106,10 @@ using std::min;
 #define PT_INVALID 0xFFu
 #define PT_GHOST 0x08u
 #define LIST_JBITS 26
-#define LIST_JMASK 0x03FFFFFFu
+#define LIST_CBITS 6
+#define LIST_ENTRY(j, code) (((uint32_t)(j) << LIST_CBITS) | (uint32_t)(code))
+#define LIST_J(e) ((uint32_t)(e) >> LIST_CBITS)
+#define LIST_CODE(e) ((uint32_t)(e) & 63u)
 #define LIST_NT 128
 
 #include "kernels_extract.inc"
@@ -206,7 +216,7 @@ static void make_lists(long long n, std::vector<uint32_t> &cnt, std::vector<uint
     cnt.assign((size_t)n, (uint32_t)n);
     lst.assign((size_t)((n + 31) / 32) * (size_t)capg * 32u, 0u);
     for (long long s = 0; s < n; s++)
-        for (long long k = 0; k < n; k++) lst[((size_t)(s >> 5) * capg + (size_t)k) * 32u + (size_t)(s & 31)] = (uint32_t)k | (21u << LIST_JBITS);
+        for (long long k = 0; k < n; k++) lst[((size_t)(s >> 5) * capg + (size_t)k) * 32u + (size_t)(s & 31)] = LIST_ENTRY(k, 21u);
 }
 
 static void pack_A(const emul_common &c, std::vector<float4> &AB)
@@ -259,7 +269,7 @@ int emul_wcsph(const emul_common *c, const int *eos_i, const double *eos_d, cons
     pa.pair_counter = nullptr;
     const int kernel = c->kernel, dim = c->dim;
     switch (kernel * 4 + dim) {
-#define PL(K, D) case K * 4 + D: launch(n, LIST_NT, [&] { k_pair_list<K, D>(pa, cnt.data(), lst.data(), capg); }); break;
+#define PL(K, D) case K * 4 + D: launch(n, LIST_NT, [&] { k_pair_list<K, D, 6>(pa, cnt.data(), lst.data(), capg); }); break;
         PL(0, 2) PL(0, 3) PL(1, 2) PL(1, 3) PL(2, 2) PL(2, 3) PL(3, 2) PL(3, 3)
 #undef PL
     default: return -1;
@@ -354,10 +364,10 @@ int emul_pipeline(const emul_common *c, const double *gxmin, const double *gcell
 #define PL(K, D)                                                                                          \
     case K * 4 + D:                                                                                       \
         pa.pair_counter = nullptr;                                                                        \
-        launch(n, LIST_NT, [&] { k_pair_list<K, D>(pa, cnt.data(), lst.data(), capg); });                 \
+        launch(n, LIST_NT, [&] { k_pair_list<K, D, 6>(pa, cnt.data(), lst.data(), capg); });                 \
         if (pairs) {                                                                                      \
             pa.pair_counter = &counter;                                                                   \
-            launch_warps(nbl, LIST_NT, [&] { k_pair_list<K, D>(pa, cnt.data(), lst.data(), capg); });     \
+            launch_warps(nbl, LIST_NT, [&] { k_pair_list<K, D, 6>(pa, cnt.data(), lst.data(), capg); });     \
         }                                                                                                 \
         break;
     switch (kernel * 4 + dim) {

@@ -67,7 +67,7 @@ def _extract():
         assert name in text, name
     # the constants the shim re-defines are the ones of the CUDA file
     cu = read_source()
-    for d in ('#define PT_GHOST 0x08u', '#define LIST_JBITS 26', '#define LIST_JMASK 0x03FFFFFFu',
+    for d in ('#define PT_GHOST 0x08u', '#define LIST_JBITS 26', '#define LIST_CBITS 6',
               '#define LIST_NT 128'):
         assert d in cu, d
     return text
