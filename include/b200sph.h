@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define B200SPH_MAX_ARRAYS 8
-#define B200SPH_ABI_VERSION 3
+#define B200SPH_ABI_VERSION 4
 
 typedef struct b200sph_ctx b200sph_ctx;
 
@@ -171,6 +171,7 @@ typedef struct {
     int64_t list_builds;   /* neighbour list (re)builds                         */
     int64_t list_entries_per_particle; /* list capacity reserved per particle   */
     int64_t deferred_failed; /* deferred drift checks that forced a repeat      */
+    int64_t fused_stages;  /* stage calls served by the fused stage + pack kernel      */
 } b200sph_stats;
 
 /* ---- lifecycle: what selecting a backend does in the reference
@@ -312,7 +313,15 @@ int b200sph_time_control(b200sph_ctx *ctx, double *external_block8, double **dev
 int b200sph_time_set(b200sph_ctx *ctx, double t, double dt);
 /* out = {dt, t}; waits for the stream */
 int b200sph_time_get(b200sph_ctx *ctx, double out[2]);
-/* b200sph_stage with dt read from the block (which = 1 uses dt / 2) */
+/* b200sph_stage with dt read from the block (which = 1 uses dt / 2).
+ * Fast path (both b200sph_stage and b200sph_stage_dev, arr = -1, which = 1 or 2, a reusable
+ * neighbour build, no periodic / mirror domain; B200SPH_FUSE=0 switches it off): ONE kernel
+ * does the stage, refreshes the packed pair records of the real particles for the next
+ * evaluation (positions, drift of the build, state with the equation-of-state calls of
+ * the last evaluation applied to the records) and, after stage2, reduces the adaptive-dt
+ * factors -- the work of k_stage + k_pack_pos_light + k_pack_state + k_reduce_dt in one
+ * sweep over the state.  Results are bitwise those of the separate kernels; the pool's
+ * rho / p / cs change only when the next evaluation issues its b200sph_eos calls. */
 int b200sph_stage_dev(b200sph_ctx *ctx, int arr, int which);
 /* enqueue: reduce dt_cfl / dt_force / h, then block[2] = cfl * min(hmin / max_cfl,
  * sqrt(hmin / sqrt(max_force))), or 1e20 when nothing constrains it (solver.py:655-660);
@@ -325,6 +334,13 @@ int b200sph_dt_propose(b200sph_ctx *ctx, double cfl, int fixed_h);
  * -1: no snapshot */
 int b200sph_dt_commit(b200sph_ctx *ctx, double prev_factor, double new_factor,
                       int in_parallel, int adaptive, int advance, int snapshot_slot);
+/* b200sph_dt_propose + b200sph_dt_commit in one launch for a run on ONE rank (nothing to
+ * reduce between them): the whole of Solver._get_timestep + `t += dt` (solver.py:478-491,
+ * :647-688, :756-776) is one tiny kernel per step.  When the fused stage kernel has left the
+ * factors of the last evaluation in the reduction slots (see b200sph_stage_dev) no
+ * reduction runs here. */
+int b200sph_dt_advance(b200sph_ctx *ctx, double cfl, int fixed_h, double prev_factor,
+                       double new_factor, int adaptive, int advance, int snapshot_slot);
 /* wait for the snapshot of `slot` only (not for later work): out = {dt, t} */
 int b200sph_time_snapshot(b200sph_ctx *ctx, int slot, double out[2]);
 /* the final time of the run and the tolerance it is compared with (solver.py:757-760,

@@ -93,7 +93,7 @@ class Stats(C.Structure):
                 ('full_builds', C.c_int64), ('light_updates', C.c_int64),
                 ('list_builds', C.c_int64),
                 ('list_entries_per_particle', C.c_int64),
-                ('deferred_failed', C.c_int64)]
+                ('deferred_failed', C.c_int64), ('fused_stages', C.c_int64)]
 
 
 _ctx_p = C.c_void_p
@@ -148,6 +148,7 @@ SIGNATURES = {
     'b200sph_stage_dev': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
     'b200sph_dt_propose': (C.c_int, [_ctx_p, C.c_double, C.c_int]),
     'b200sph_dt_commit': (C.c_int, [_ctx_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'b200sph_dt_advance': (C.c_int, [_ctx_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
     'b200sph_time_snapshot': (C.c_int, [_ctx_p, C.c_int, _dp]),
     'b200sph_halo_pack': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double,
                                     C.c_double, C.c_void_p, _i64,

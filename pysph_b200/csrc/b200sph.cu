@@ -199,6 +199,17 @@ struct b200sph_ctx {
 
     EosTab eos_pending;
     bool eos_any = false;
+    // ---- fused stage kernel (k_stage_pack) bookkeeping ---------------------------------
+    bool fuse = true;            // env B200SPH_FUSE=0: the unfused kernels only
+    EosTab eos_last;             // the equation-of-state calls of the last evaluation ...
+    bool eos_last_valid = false;
+    bool spec_records = false;   // ... were applied to the packed records speculatively
+    unsigned spec_confirmed = 0; // arrays whose b200sph_eos call has matched the speculation
+    bool drift_measured = false; // red_u32 holds the drift of the CURRENT packed positions
+    bool red_armed = false;      // red[9,11,12] hold their neutral values
+    bool dt_reduced = false;     // ... hold the factors of the last evaluation (fused stage2)
+    bool dt_adaptive_seen = false;  // a dt proposal followed the last stage2: reduce in the next one
+    int64_t n_fused = 0;
 
     // stats
     b200sph_stats stats;
@@ -572,6 +583,7 @@ int b200sph_create(int device, b200sph_ctx **out)
     ctx->device = device;
     memset(&ctx->grid, 0, sizeof(ctx->grid));
     memset(&ctx->eos_pending, 0, sizeof(ctx->eos_pending));
+    memset(&ctx->eos_last, 0, sizeof(ctx->eos_last));
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     *out = ctx;
     CU(cudaSetDevice(device));
@@ -587,6 +599,7 @@ int b200sph_create(int device, b200sph_ctx **out)
         }
     }
     if (const char *e = getenv("B200SPH_PAIR_MINB")) ctx->pair_minb = atoi(e);
+    if (const char *e = getenv("B200SPH_FUSE")) ctx->fuse = atoi(e) != 0;
     if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = ctx->skin_max = std::max(0.0, atof(e));
     if (const char *e = getenv("B200SPH_SKIN_ADAPT")) ctx->skin_adapt = atoi(e) != 0;
     ctx->skin_min = std::min(ctx->skin_min, ctx->skin_max);
@@ -969,6 +982,8 @@ static int run_minmax(b200sph_ctx *ctx, int do_xyz, int do_h)
 {
     k_red_init<<<1, 32, 0, ctx->stream>>>(ctx->red);
     LAUNCH_CHECK();
+    ctx->red_armed = true;   // (slots 9, 11, 12 are not touched by k_reduce_minmax)
+    ctx->dt_reduced = false;
     if (ctx->pool_end > 0) {
         const unsigned nb = (unsigned)std::min<int64_t>(cdiv(ctx->pool_end, 256), 148 * 8);
         k_reduce_minmax<<<nb, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z],
@@ -1077,6 +1092,7 @@ static int nnps_light_update(b200sph_ctx *ctx)
         // the drift was just measured by b200sph_nnps_drift (multi-GPU: the decision to
         // keep the build is collective); only refresh the packed positions, no host sync
         ctx->drift_ok = false;
+        ctx->drift_measured = false;
         if (ctx->packed_valid) return 1;   // nnps_drift_device packed them, halo_overwrite_all kept the ghosts current
         k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
             ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
@@ -1084,11 +1100,15 @@ static int nnps_light_update(b200sph_ctx *ctx)
         LAUNCH_CHECK();
         return 1;
     }
-    CU(cudaMemsetAsync(ctx->red_u32, 0, 4 * sizeof(unsigned), ctx->stream));
-    k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
-        ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
-        ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
-    LAUNCH_CHECK();
+    if (!(ctx->packed_valid && ctx->drift_measured)) {   // (the fused stage kernel packs and measures)
+        CU(cudaMemsetAsync(ctx->red_u32, 0, 4 * sizeof(unsigned), ctx->stream));
+        k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
+            ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
+            ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
+        LAUNCH_CHECK();
+    }
+    ctx->drift_measured = false;
+    ctx->packed_valid = true;
     if (ctx->defer_check) {
         // optimistic: carry on as if the lists were valid; b200sph_nnps_confirm reads the
         // measurement after the evaluation has been enqueued (no idle GPU while we wait)
@@ -1167,8 +1187,7 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         if (rc == 1) {
             ctx->n_light_updates++;
             ctx->evals_since_build++;
-            ctx->grid_valid = true;
-            ctx->state_packed = false;
+            ctx->grid_valid = true;   // (state_packed is left alone: whatever changed the state cleared it)
             return 0;
         }
     }
@@ -1371,21 +1390,18 @@ int b200sph_get_grid(b200sph_ctx *ctx, b200sph_grid_info *out)
     return 0;
 }
 
-// run the pending equation-of-state calls stand-alone (something needs rho/p/cs now)
+// run the pending equation-of-state calls stand-alone (something needs rho/p/cs now, or the
+// packed records already hold them: the pool side of a speculated EOS) -- one launch
 static int eos_flush(b200sph_ctx *ctx)
 {
     if (!ctx->eos_any) return 0;
     EosTab &E = ctx->eos_pending;
-    for (int a = 0; a < ctx->narr; a++) {
-        if (!E.on[a]) continue;
-        const int64_t lo = ctx->arr[a].off, hi = lo + (E.real_only[a] ? ctx->arr[a].n_real : ctx->arr[a].n);
-        if (hi > lo) {
-            k_eos<<<(unsigned)cdiv(hi - lo, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_RHO], ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64],
-                                                                        ctx->ptype, lo, hi, E.hg[a], E.rho0[a], E.c0[a], E.gamma[a], E.p0[a]);
-            LAUNCH_CHECK();
-        }
-        E.on[a] = 0;
+    if (ctx->pool_end > 0) {
+        k_eos_tab<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_RHO], ctx->f32[B200SPH_P - N_F64],
+                                                                              ctx->f32[B200SPH_CS - N_F64], ctx->ptype, ctx->pool_end, E);
+        LAUNCH_CHECK();
     }
+    memset(E.on, 0, sizeof(E.on));
     ctx->eos_any = false;
     return 0;
 }
@@ -1402,6 +1418,7 @@ static int pack_state(b200sph_ctx *ctx)
         ctx->eos_any = false;
     }
     ctx->state_packed = true;
+    ctx->spec_records = false;
     return 0;
 }
 
@@ -1420,7 +1437,7 @@ int64_t b200sph_get_neighbors(b200sph_ctx *ctx, int dst_arr, int src_arr, int64_
     const int64_t dcap = std::max<int64_t>(cap, 1);
     uint32_t *dout = nullptr;
     CU(cudaMalloc((void **)&dout, 4 * (size_t)dcap));
-    k_neighbors<<<1, 32, 0, ctx->stream>>>(ctx->A, ctx->C, ctx->cell_start, ctx->skey, ctx->perm, (long long)s32, src_arr,
+    k_neighbors<<<1, 32, 0, ctx->stream>>>(ctx->AB, ctx->C, ctx->cell_start, ctx->skey, ctx->perm, (long long)s32, src_arr,
                                            (long long)ctx->arr[src_arr].off, ctx->G, (float)(ctx->radius_scale * ctx->radius_scale),
                                            dout, cap, ctx->counter + 1);
     ctx->stats.kernel_launches++;
@@ -1460,7 +1477,17 @@ int b200sph_eos(b200sph_ctx *ctx, int arr, int hg, double rho0, double c0, doubl
     E.rho0[arr] = rho0; E.c0[arr] = c0; E.gamma[arr] = gamma; E.p0[arr] = p0;
     ctx->eos_any = true;
     if (!ctx->grid_valid && (rc = eos_flush(ctx))) return rc;
-    ctx->state_packed = false;
+    // the fused stage kernel may have applied exactly this call to the packed records
+    // already (it repeats the last evaluation's calls); pair_pass checks that ALL of them
+    // were confirmed before it trusts the records
+    const EosTab &L = ctx->eos_last;
+    if (ctx->spec_records && ctx->state_packed && ctx->eos_last_valid && L.on[arr] && L.hg[arr] == hg &&
+        L.real_only[arr] == real_only && L.rho0[arr] == rho0 && L.c0[arr] == c0 && L.gamma[arr] == gamma && L.p0[arr] == p0) {
+        ctx->spec_confirmed |= 1u << arr;
+    } else {
+        ctx->state_packed = false;
+        ctx->spec_records = false;
+    }
     return 0;
 }
 
@@ -1489,7 +1516,30 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     int rc = ensure_pool(ctx);
     if (rc) return rc;
     if (!ctx->grid_valid) return set_err(ctx, "pair_pass: the NNPS is stale (particles were pushed/resized); call nnps_update first");
-    if (!ctx->state_packed && (rc = pack_state(ctx))) return rc;
+    if (ctx->spec_records && ctx->state_packed) {
+        // records packed by the fused stage kernel: valid only if this evaluation issued
+        // exactly the equation-of-state calls that were applied speculatively
+        unsigned want = 0, pending = 0;
+        for (int a = 0; a < ctx->narr; a++) {
+            if (ctx->eos_last_valid && ctx->eos_last.on[a]) want |= 1u << a;
+            if (ctx->eos_any && ctx->eos_pending.on[a]) pending |= 1u << a;
+        }
+        if (pending != want || ctx->spec_confirmed != want) ctx->state_packed = false;
+    }
+    ctx->spec_records = false;
+    ctx->spec_confirmed = 0;
+    ctx->dt_reduced = false;   // this pass writes new dt_cfl / dt_force
+    if (ctx->eos_any) {
+        ctx->eos_last = ctx->eos_pending;
+        ctx->eos_last_valid = true;
+    } else {
+        ctx->eos_last_valid = false;
+    }
+    if (!ctx->state_packed) {
+        if ((rc = pack_state(ctx))) return rc;
+    } else if ((rc = eos_flush(ctx))) {   // the records have them; now the pool's rho / p / cs
+        return rc;
+    }
     // lists hold 26-bit sorted indices: larger particle counts use the warp kernel
     const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->n_sorted < (1LL << LIST_JBITS);
     if (!use_lists && (ctx->periodic[0] || ctx->periodic[1] || ctx->periodic[2]))
@@ -1840,6 +1890,19 @@ static int ensure_tc(b200sph_ctx *ctx)
     return 0;
 }
 
+// the fused stage kernel applies when one launch steps every array (arr == -1) and the
+// neighbour lists of the current build can be reused: then the records of the next
+// evaluation can be written at the particles' frozen sorted slots
+static bool can_fuse_stage(const b200sph_ctx *ctx, int arr)
+{
+    if (!ctx->fuse || arr != -1 || ctx->force_kernel != 0) return false;
+    if (!ctx->lists_valid || ctx->topo_dirty || ctx->n_sorted <= 0) return false;
+    if (ctx->periodic[0] || ctx->periodic[1] || ctx->periodic[2] || mirror_any(ctx)) return false;
+    int64_t ntot = 0;
+    for (int a = 0; a < ctx->narr; a++) ntot += ctx->arr[a].n;
+    return ntot == ctx->n_sorted && ntot < (1LL << LIST_JBITS);
+}
+
 static int stage_impl(b200sph_ctx *ctx, int arr, int which, double dt, bool devdt)
 {
     if (int rcc = require_confirmed(ctx, "stage")) return rcc;
@@ -1864,6 +1927,41 @@ static int stage_impl(b200sph_ctx *ctx, int arr, int which, double dt, bool devd
     sa.arr = arr;
     sa.which = which;
     sa.f = which == 1 ? 0.5 * dt : dt;
+    if (which != 0 && ctx->pool_end > 0 && can_fuse_stage(ctx, arr)) {
+        // stage + records of the next evaluation (+ the dt factors after stage2) in one pass
+        FusePackArgs q;
+        memset(&q, 0, sizeof(q));
+        q.h = ctx->f64[B200SPH_H]; q.m = ctx->f64[B200SPH_M];
+        q.p = ctx->f32[B200SPH_P - N_F64]; q.cs = ctx->f32[B200SPH_CS - N_F64];
+        q.rank = ctx->rank; q.key_of = ctx->key_of;
+        q.A0 = ctx->A0; q.AB = ctx->AB; q.C = ctx->C;
+        q.G = ctx->G;
+        q.red_u32 = ctx->red_u32;
+        q.dt_cfl = ctx->f32[B200SPH_DT_CFL - N_F64]; q.dt_force = ctx->f32[B200SPH_DT_FORCE - N_F64];
+        q.red = ctx->red;
+        q.tc = devdt ? ctx->tc : nullptr;
+        q.do_init = 0;
+        q.reduce_dt = (which == 2 && ctx->dt_adaptive_seen) ? 1 : 0;
+        q.eos_any = ctx->eos_last_valid ? 1 : 0;
+        q.E = ctx->eos_last;
+        if (q.reduce_dt && !ctx->red_armed) {
+            k_red_init<<<1, 32, 0, ctx->stream>>>(ctx->red);
+            LAUNCH_CHECK();
+        }
+        CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
+        k_stage_pack<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa, q);
+        LAUNCH_CHECK();
+        ctx->n_fused++;
+        if (q.reduce_dt) ctx->red_armed = false;
+        if (which == 2) ctx->dt_reduced = q.reduce_dt != 0, ctx->dt_adaptive_seen = false;
+        ctx->grid_valid = false;       // particles moved: nnps_update must decide about the lists
+        ctx->packed_valid = true;      // ... but their packed positions are current,
+        ctx->drift_measured = true;    // the drift of the build is in red_u32,
+        ctx->state_packed = true;      // and so is their packed state,
+        ctx->spec_records = ctx->eos_last_valid;   // with last evaluation's EOS calls applied
+        ctx->spec_confirmed = 0;
+        return 0;
+    }
     if (ctx->pool_end > 0) {
         if (devdt) k_stage_devdt<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa, ctx->tc);
         else k_stage<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa);
@@ -1872,6 +1970,7 @@ static int stage_impl(b200sph_ctx *ctx, int arr, int which, double dt, bool devd
     if (which != 0) {
         ctx->grid_valid = false, ctx->packed_valid = false;  // particles moved: neighbours are stale until nnps_update
         ctx->state_packed = false;
+        if (which == 2) ctx->dt_adaptive_seen = false, ctx->dt_reduced = false;
     }
     return 0;
 }
@@ -1910,14 +2009,11 @@ int b200sph_time_set(b200sph_ctx *ctx, double t, double dt)
     return 0;
 }
 
-int b200sph_dt_propose(b200sph_ctx *ctx, double cfl, int fixed_h)
+// max dt_cfl, max dt_force, min h into red[9,11,12] -- unless the fused stage2 kernel has
+// just left them there
+static int reduce_dt_factors(b200sph_ctx *ctx)
 {
-    if (int rcc = require_confirmed(ctx, "dt_propose")) return rcc;
-    CU(cudaSetDevice(ctx->device));
-    int rc = ensure_pool(ctx);
-    if (rc) return rc;
-    if ((rc = b200sph_time_control(ctx, nullptr, nullptr))) return rc;
-    PhaseTimer pt(ctx, 2);
+    if (ctx->dt_reduced) return 0;
     k_red_init<<<1, 32, 0, ctx->stream>>>(ctx->red);
     LAUNCH_CHECK();
     if (ctx->pool_end > 0) {
@@ -1926,8 +2022,48 @@ int b200sph_dt_propose(b200sph_ctx *ctx, double cfl, int fixed_h)
                                                  ctx->ptype, ctx->pool_end, ctx->red);
         LAUNCH_CHECK();
     }
+    ctx->red_armed = false;
+    return 0;
+}
+
+int b200sph_dt_propose(b200sph_ctx *ctx, double cfl, int fixed_h)
+{
+    if (int rcc = require_confirmed(ctx, "dt_propose")) return rcc;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = b200sph_time_control(ctx, nullptr, nullptr))) return rc;
+    PhaseTimer pt(ctx, 2);
+    if ((rc = reduce_dt_factors(ctx))) return rc;
     k_dt_propose<<<1, 1, 0, ctx->stream>>>(ctx->red, ctx->tc, cfl, fixed_h);
     LAUNCH_CHECK();
+    ctx->red_armed = true;
+    ctx->dt_reduced = false;
+    ctx->dt_adaptive_seen = true;
+    return 0;
+}
+
+int b200sph_dt_advance(b200sph_ctx *ctx, double cfl, int fixed_h, double prev_factor, double new_factor, int adaptive, int advance,
+                       int snapshot_slot)
+{
+    if (int rcc = require_confirmed(ctx, "dt_advance")) return rcc;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if ((rc = b200sph_time_control(ctx, nullptr, nullptr))) return rc;
+    if (!(prev_factor > 0.0) || !(new_factor > 0.0)) return set_err(ctx, "dt_advance: damping factors must be positive");
+    if (snapshot_slot > 1) return set_err(ctx, "dt_advance: snapshot slot must be 0 or 1");
+    PhaseTimer pt(ctx, 2);
+    if (adaptive && (rc = reduce_dt_factors(ctx))) return rc;
+    k_dt_advance<<<1, 1, 0, ctx->stream>>>(ctx->red, ctx->tc, cfl, fixed_h, prev_factor, new_factor, adaptive, advance, ctx->t_final, ctx->t_eps);
+    LAUNCH_CHECK();
+    ctx->red_armed = true;
+    ctx->dt_reduced = false;
+    ctx->dt_adaptive_seen = adaptive != 0;
+    if (snapshot_slot >= 0) {
+        CU(cudaMemcpyAsync(ctx->tc_host + 2 * snapshot_slot, ctx->tc, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->tc_evt[snapshot_slot], ctx->stream));
+    }
     return 0;
 }
 
@@ -1985,14 +2121,8 @@ int b200sph_dt_factors(b200sph_ctx *ctx, double out[3])
     int rc = ensure_pool(ctx);
     if (rc) return rc;
     PhaseTimer pt(ctx, 2);
-    k_red_init<<<1, 32, 0, ctx->stream>>>(ctx->red);
-    LAUNCH_CHECK();
-    if (ctx->pool_end > 0) {
-        const unsigned nb = (unsigned)std::min<int64_t>(cdiv(ctx->pool_end, 256), 148 * 8);
-        k_reduce_dt<<<nb, 256, 0, ctx->stream>>>(ctx->f32[B200SPH_DT_CFL - N_F64], ctx->f32[B200SPH_DT_FORCE - N_F64], ctx->f64[B200SPH_H],
-                                                 ctx->ptype, ctx->pool_end, ctx->red);
-        LAUNCH_CHECK();
-    }
+    if ((rc = reduce_dt_factors(ctx))) return rc;
+    ctx->dt_adaptive_seen = true;
     CU(cudaMemcpyAsync(ctx->red_host, ctx->red, 16 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const double mc = o2d(ctx->red_host[9]), mf = o2d(ctx->red_host[11]), hm = o2d(ctx->red_host[12]);
@@ -2264,11 +2394,13 @@ int b200sph_nnps_drift(b200sph_ctx *ctx, double out[2])
     if (ctx->force_kernel != 0 || !ctx->lists_valid || ctx->topo_dirty) return 0;  // no reusable build
     if (ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min) return 0;  // retire it
     if (ctx->n_sorted <= 0) { out[0] = 0.0; return 0; }
-    CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
-    k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
-        ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
-        ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
-    LAUNCH_CHECK();
+    if (!(ctx->packed_valid && ctx->drift_measured)) {
+        CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
+        k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
+            ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
+            ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
+        LAUNCH_CHECK();
+    }
     CU(cudaMemcpyAsync(ctx->red_u32_host, ctx->red_u32, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float d2, dh;
@@ -2389,14 +2521,17 @@ int b200sph_nnps_drift_device(b200sph_ctx *ctx, double *dev_ratio)
         CU(cudaMemsetAsync(dev_ratio, 0, sizeof(double), ctx->stream));
         return 0;
     }
-    CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
-    k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
-        ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
-        ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
-    LAUNCH_CHECK();
+    if (!(ctx->packed_valid && ctx->drift_measured)) {   // (the fused stage kernel packs and measures)
+        CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
+        k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
+            ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
+            ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
+        LAUNCH_CHECK();
+    }
     k_drift_ratio<<<1, 1, 0, ctx->stream>>>(ctx->red_u32, (float)ctx->radius_scale, (float)ctx->S_abs, dev_ratio);
     LAUNCH_CHECK();
     ctx->packed_valid = true;
+    ctx->drift_measured = true;
     return 0;
 }
 
@@ -2564,6 +2699,7 @@ int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out)
     ctx->stats.list_builds = ctx->n_list_builds;
     ctx->stats.list_entries_per_particle = ctx->capg;
     ctx->stats.deferred_failed = ctx->n_deferred_failed;
+    ctx->stats.fused_stages = ctx->n_fused;
     *out = ctx->stats;
     return 0;
 }
@@ -2572,7 +2708,7 @@ int b200sph_reset_stats(b200sph_ctx *ctx)
     b200sph_stats tmp;
     b200sph_get_stats(ctx, &tmp);  // drain pending events
     memset(&ctx->stats, 0, sizeof(ctx->stats));
-    ctx->n_full_builds = ctx->n_light_updates = ctx->n_list_builds = ctx->n_deferred_failed = 0;
+    ctx->n_full_builds = ctx->n_light_updates = ctx->n_list_builds = ctx->n_deferred_failed = ctx->n_fused = 0;
     return 0;
 }
 int b200sph_set_async_copies(b200sph_ctx *ctx, int on)

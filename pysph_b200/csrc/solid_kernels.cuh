@@ -466,7 +466,7 @@ __global__ void k_pack_pos_light(const double *__restrict__ x, const double *__r
 
 // neighbour query for one destination particle with the pair kernel's accept test
 // (cell by cell; periodic axes wrap).  One warp.
-__global__ void k_neighbors(const float4 *__restrict__ A, const float4 *__restrict__ C,
+__global__ void k_neighbors(const float4 *__restrict__ A /* {A,B} interleaved: A of particle s at [2 s] */, const float4 *__restrict__ C,
                             const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ skey,
                             const uint32_t *__restrict__ perm, long long s, int src_arr,
                             long long src_off, GridDev G, float k2,
@@ -474,7 +474,7 @@ __global__ void k_neighbors(const float4 *__restrict__ A, const float4 *__restri
 {
     const int lane = threadIdx.x;
     const int ncx = G.nc[0], ncy = G.nc[1], ncz = G.nc[2];
-    const float4 Ai = A[s];
+    const float4 Ai = A[2 * (size_t)s];
     uint32_t kq = skey[s];
     const int cx = (int)(kq % (uint32_t)ncx);
     kq /= (uint32_t)ncx;
@@ -494,7 +494,7 @@ __global__ void k_neighbors(const float4 *__restrict__ A, const float4 *__restri
             const uint32_t t = t0 + lane;
             bool ok = false;
             if (t < re) {
-                const float4 Aj = A[t];
+                const float4 Aj = A[2 * (size_t)t];
                 const float xij = Ai.x - (float)dx * (float)G.cell[0] - Aj.x;
                 const float yij = Ai.y - (float)dy * (float)G.cell[1] - Aj.y;
                 const float zij = Ai.z - (float)dz * (float)G.cell[2] - Aj.z;

@@ -259,13 +259,18 @@ class B200Solver(object):
         prev = self._damping_factor
         new = self._next_damping_factor()
         ctx.call('b200sph_time_final', float(self.tf), float(self._eps()))
-        if self.adaptive_timestep:
-            ctx.call('b200sph_dt_propose', float(self.cfl), int(bool(self.fixed_h)))
-            if self._tc is not None:
+        if self._tc is None:
+            # one rank: proposal and commit are one kernel
+            ctx.call('b200sph_dt_advance', float(self.cfl), int(bool(self.fixed_h)),
+                     float(prev), float(new), int(bool(self.adaptive_timestep)),
+                     int(bool(advance)), self._commits % 2)
+        else:
+            if self.adaptive_timestep:
+                ctx.call('b200sph_dt_propose', float(self.cfl), int(bool(self.fixed_h)))
                 self.pm.reduce_dt_device(self._tc[2:3])
-        ctx.call('b200sph_dt_commit', float(prev), float(new),
-                 int(self._tc is not None), int(bool(self.adaptive_timestep)),
-                 int(bool(advance)), self._commits % 2)
+            ctx.call('b200sph_dt_commit', float(prev), float(new), 1,
+                     int(bool(self.adaptive_timestep)), int(bool(advance)),
+                     self._commits % 2)
         self._commits += 1
         self._damping_factor = new
 

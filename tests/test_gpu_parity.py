@@ -585,3 +585,37 @@ def test_monaghan_av_vs_reference_bodies(gpu_device, idx):
         want = np.array(ref[f])[:nr]
         assert rel_err(pas[0].properties[f][:nr], want) <= TOL_EVAL, f
     assert np.max(np.abs(ref['au'])) > 1.0
+
+
+@pytest.mark.parametrize('device_dt', [True, False])
+def test_fused_stage_kernel_is_bitwise_the_separate_kernels(gpu_device, monkeypatch, device_dt, dx=0.05):
+    """include/b200sph.h "Fast path" of b200sph_stage / b200sph_stage_dev: k_stage_pack (stage
+    + packed records of the next evaluation with the last evaluation's EOS calls applied
+    speculatively + drift of the build + dt factors) against k_stage, k_pack_pos_light,
+    k_pack_state and k_reduce_dt run one after the other (B200SPH_FUSE=0): every property
+    the host can pull -- including p / cs / rho of the HG-corrected solids and the stage
+    copies x0 .. rho0 -- t, dt and the rebuild count must be bitwise equal through list
+    rebuilds (3 m/s random velocities use up the skin in a few steps)."""
+    out = {}
+    for fuse in ('1', '0'):
+        monkeypatch.setenv('B200SPH_FUSE', fuse)
+        pas, params = _perturbed_dam_break(dx=dx, vscale=3.0)
+        p = scheme_params(params)
+        p['n_damp'] = 6
+        s = make_solver(pas, p, 'CubicSpline', device_dt=device_dt)
+        for _ in range(22):
+            s.step()
+        st = s.backend.stats()
+        s.pull()
+        out[fuse] = (s.t, s.dt, st['full_builds'],
+                     [dict((k, v.copy()) for k, v in pa.properties.items()) for pa in pas])
+        if fuse == '1':
+            assert st['full_builds'] >= 2          # the lists were rebuilt on the way
+            assert st['fused_stages'] >= 30        # ... and the fused kernel served the stages
+        else:
+            assert st['fused_stages'] == 0
+    a, b = out['1'], out['0']
+    assert a[:3] == b[:3], (a[:3], b[:3])
+    for pa, pb_ in zip(a[3], b[3]):
+        for k, v in pa.items():
+            assert np.array_equal(v, pb_[k]), k

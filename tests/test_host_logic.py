@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), 'libb200sph.so does not export %s' % name
     # and the ctypes table covers exactly the header
     assert set(_lib.SIGNATURES) == declared
-    assert lib.b200sph_abi_version() == 3
+    assert lib.b200sph_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_device():
@@ -55,7 +55,7 @@ def test_struct_layouts_match_header():
     # sizes implied by include/b200sph.h (x86-64 SysV)
     assert C.sizeof(_lib.PairProgram) == 8 * 8 * 4 + 2 * 4 + 7 * 8
     assert C.sizeof(_lib.GridInfo) == 8 + 8 + 24 + 24 + 12 + 4 + 8 + 8
-    assert C.sizeof(_lib.Stats) == 3 * 8 + 8 * 8
+    assert C.sizeof(_lib.Stats) == 3 * 8 + 9 * 8
     ids = _lib.PROP_IDS
     assert ids['x'] == 0 and ids['rho'] == 6 and ids['h'] == 7 and ids['m'] == 8
     assert ids['rho0'] == 15 and ids['p'] == 16 and ids['dt_force'] == 26

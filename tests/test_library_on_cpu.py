@@ -65,7 +65,7 @@ def test_every_entry_point_is_exported(emulated_library):
     lib = _lib.load()
     for name in _lib.SIGNATURES:
         assert hasattr(lib, name), name
-    assert lib.b200sph_abi_version() == 3
+    assert lib.b200sph_abi_version() == 4
 
 
 # ---- the GPU tests of this repository, run against the emulated library --------------------
@@ -104,6 +104,8 @@ FAST = [
     ('test_gpu_parity', 'test_dam_break_2d_gate', {}),
     ('test_gpu_parity', 'test_determinism', {}),
     ('test_gpu_parity', 'test_deferred_drift_check_protocol', {}),
+    ('test_gpu_parity', 'test_fused_stage_kernel_is_bitwise_the_separate_kernels', {'monkeypatch': None, 'device_dt': True, 'dx': 0.08}),
+    ('test_gpu_parity', 'test_fused_stage_kernel_is_bitwise_the_separate_kernels', {'monkeypatch': None, 'device_dt': False, 'dx': 0.08}),
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 2, 'n': 24, 'pattern': (0, 1, 0)}),
     ('test_output', 'test_dump_and_restart_on_device', {'tmp_path': None}),
@@ -121,7 +123,8 @@ FULL = [
 
 
 def _id(t):
-    return t[1].replace('test_', '') + ''.join('-%s' % (v,) for v in t[2].values()).replace(' ', '')
+    return t[1].replace('test_', '') + ''.join('-%s' % (v,) for v in t[2].values()
+                                               if v is not None).replace(' ', '')
 
 
 def _call(t, emulated_library):
@@ -133,6 +136,10 @@ def _call(t, emulated_library):
         import pathlib
         import tempfile
         kw['tmp_path'] = pathlib.Path(tempfile.mkdtemp())
+    if 'monkeypatch' in kw:
+        with pytest.MonkeyPatch.context() as mp:
+            kw['monkeypatch'] = mp
+            return fn(emulated_library, **kw)
     return fn(emulated_library, **kw)
 
 
