@@ -30,6 +30,7 @@ extern "C" {
 #endif
 
 #define B200SPH_MAX_ARRAYS 8
+#define B200SPH_MAX_RANKS 16   /* ranks of one node in the peer protocol (b200sph_peer_*) */
 #define B200SPH_ABI_VERSION 4
 
 typedef struct b200sph_ctx b200sph_ctx;
@@ -172,6 +173,10 @@ typedef struct {
     int64_t list_entries_per_particle; /* list capacity reserved per particle   */
     int64_t deferred_failed; /* deferred drift checks that forced a repeat      */
     int64_t fused_stages;  /* stage calls served by the fused stage + pack kernel      */
+    int64_t overlapped;    /* pair passes that ran their ghost-free CTAs under the halo  */
+    int64_t chunks_interior, chunks_boundary; /* CTAs of the list consumers without / with a
+                              ghost among their destinations or neighbours (current build;
+                              0 / 0 without ghosts)                                          */
 } b200sph_stats;
 
 /* ---- lifecycle: what selecting a backend does in the reference
@@ -409,6 +414,53 @@ int b200sph_nnps_drift_device(b200sph_ctx *ctx, double *dev_ratio);
  * kept for the next nnps_update: that update then only refreshes the packed
  * positions and does not repeat the drift measurement (saves a host sync) */
 int b200sph_nnps_keep_build(b200sph_ctx *ctx);
+
+/* ---- peer protocol: the ghost refresh of an evaluation, overlapped with the interior
+ *      pair work, and the scalar agreements that go with it -- no library collective.
+ * Replaces, for the ranks of ONE node, what the reference does serially in front of every
+ * evaluation (ParallelManager.update, parallel_manager.pyx:512-530, called from
+ * Integrator.compute_accelerations, integrator.py:274-286) and its dt all-reduce
+ * (update_time_steps, parallel_manager.pyx:454-465).
+ * Every rank owns a small mailbox in device memory that the other ranks write into over
+ * NVLink (cudaIpc); payload, __threadfence_system(), then an epoch word the reader polls.
+ *   peer_init     allocate + export this rank's mailbox (handle64: 64 bytes)
+ *   peer_connect  map every rank's mailbox (handles: world x 64 bytes, rank order)
+ * One refresh epoch, every call only ENQUEUES work (on a second, high-priority stream):
+ *   peer_begin    measure the drift of the neighbour build if the fused stage kernel has
+ *                 not, then let the communication stream wait for the main stream;
+ *                 returns 1 if there is no reusable build (publish says so to everyone)
+ *   peer_publish  {used-up fraction of the list skin, dt proposal | +inf} to every rank
+ *   peer_send     b200sph_halo_pack_selected_all into the neighbour's staging buffer
+ *                 (remote_staging: its buffer mapped with b200sph_ipc_open) + the
+ *                 data-ready flag in its mailbox; side = 0: I am its RIGHT neighbour's
+ *                 left... precisely: side is the slot the RECEIVER reads, 0 = message from
+ *                 its left neighbour, 1 = from its right neighbour
+ *   peer_reduce   wait for every rank's scalars: MAX fraction -> the decision (device,
+ *                 and pinned host memory for peer_decision), MIN dt -> block[2]
+ *   peer_recv     wait for the data-ready flag `side`, then b200sph_halo_overwrite_all
+ *                 from the local staging buffer, including the ghosts' packed pair
+ *                 records (position + state with the last evaluation's EOS calls)
+ *   peer_end      from here b200sph_pair_pass may run the destinations that do not
+ *                 depend on ghosts while the above is still in flight; every other entry
+ *                 point that touches particle data first waits for it
+ *   peer_decision (host) wait for the decision of the current epoch only: *ratio_max > 0.9
+ *                 means some rank's lists have expired -- discard the evaluation, run the
+ *                 full exchange (the caller's protocol, as with b200sph_nnps_confirm)
+ *   peer_allreduce_dt  the stand-alone agreement on the time step: block[2] = MIN over
+ *                 ranks of block[2], enqueued on the main stream (between b200sph_dt_propose
+ *                 and b200sph_dt_commit) */
+int b200sph_peer_init(b200sph_ctx *ctx, int rank, int world, void *handle64);
+int b200sph_peer_connect(b200sph_ctx *ctx, const void *handles);
+int b200sph_peer_begin(b200sph_ctx *ctx);
+int b200sph_peer_publish(b200sph_ctx *ctx, int have_build, int with_dt);
+int b200sph_peer_send(b200sph_ctx *ctx, int slot, int nb_rank, int side, double *remote_staging,
+                      int64_t cap_doubles);
+int b200sph_peer_reduce(b200sph_ctx *ctx, int with_dt);
+int b200sph_peer_recv(b200sph_ctx *ctx, int side, const int64_t *ghost_first, const int64_t *counts,
+                      const double *local_staging);
+int b200sph_peer_end(b200sph_ctx *ctx);
+int b200sph_peer_decision(b200sph_ctx *ctx, double *ratio_max);
+int b200sph_peer_allreduce_dt(b200sph_ctx *ctx);
 /* append n particles from dev_buf (field f of particle k at
  * dev_buf[f * stride + k]) after the current particles of `arr`.
  * nfields = B200SPH_HALO_FIELDS: ghosts (tag Remote), other props zeroed;

@@ -93,7 +93,9 @@ class Stats(C.Structure):
                 ('full_builds', C.c_int64), ('light_updates', C.c_int64),
                 ('list_builds', C.c_int64),
                 ('list_entries_per_particle', C.c_int64),
-                ('deferred_failed', C.c_int64), ('fused_stages', C.c_int64)]
+                ('deferred_failed', C.c_int64), ('fused_stages', C.c_int64),
+                ('overlapped', C.c_int64), ('chunks_interior', C.c_int64),
+                ('chunks_boundary', C.c_int64)]
 
 
 _ctx_p = C.c_void_p
@@ -149,6 +151,16 @@ SIGNATURES = {
     'b200sph_dt_propose': (C.c_int, [_ctx_p, C.c_double, C.c_int]),
     'b200sph_dt_commit': (C.c_int, [_ctx_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
     'b200sph_dt_advance': (C.c_int, [_ctx_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
+    'b200sph_peer_init': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_void_p]),
+    'b200sph_peer_connect': (C.c_int, [_ctx_p, C.c_void_p]),
+    'b200sph_peer_begin': (C.c_int, [_ctx_p]),
+    'b200sph_peer_publish': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
+    'b200sph_peer_send': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_int, C.c_void_p, _i64]),
+    'b200sph_peer_reduce': (C.c_int, [_ctx_p, C.c_int]),
+    'b200sph_peer_recv': (C.c_int, [_ctx_p, C.c_int, C.POINTER(_i64), C.POINTER(_i64), C.c_void_p]),
+    'b200sph_peer_end': (C.c_int, [_ctx_p]),
+    'b200sph_peer_decision': (C.c_int, [_ctx_p, _dp]),
+    'b200sph_peer_allreduce_dt': (C.c_int, [_ctx_p]),
     'b200sph_time_snapshot': (C.c_int, [_ctx_p, C.c_int, _dp]),
     'b200sph_halo_pack': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double,
                                     C.c_double, C.c_void_p, _i64,

@@ -180,6 +180,16 @@ class B200Backend(object):
                               a.ctypes.data, 0, n_real)
         self._dt_cache = None
 
+    def push_real_array(self, i, props):
+        """push_real for one array"""
+        pa = self.particle_arrays[i]
+        n_real = self.sizes(i)[1]
+        for name in props:
+            a = self._real_view(pa, name, n_real, 'push_real_array')
+            self.ctx.call('b200sph_push_f64', i, self.prop_ids[i][name],
+                          a.ctypes.data, 0, n_real)
+        self._dt_cache = None
+
     def pull_real(self, props):
         for i, pa in enumerate(self.particle_arrays):
             n_real = self.sizes(i)[1]

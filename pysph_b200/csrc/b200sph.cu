@@ -72,6 +72,23 @@ struct EosTab {
     double rho0[B200SPH_MAX_ARRAYS], c0[B200SPH_MAX_ARRAYS], gamma[B200SPH_MAX_ARRAYS], p0[B200SPH_MAX_ARRAYS];
 };
 
+// ratio^gamma and ratio^((gamma - 1) / 2) of the Tait equation of state (wc/basic.py:60-65,
+// :118-126).  Water's gamma = 7 -- every WCSPH example of the reference -- needs no pow():
+// five fp64 multiplications, within 3 ulp of pow() (the results are stored as fp32); any
+// other exponent takes the library route.  ONE function for every kernel that evaluates
+// the EOS, so that they all produce the same bits.
+__host__ __device__ static inline void tait_powers(const double ratio, const double gamma, double &rg, double &rh)
+{
+    if (gamma == 7.0) {
+        const double r2 = ratio * ratio;
+        rh = r2 * ratio;
+        rg = rh * rh * ratio;
+    } else {
+        rg = pow(ratio, gamma);
+        rh = pow(ratio, 0.5 * (gamma - 1.0));
+    }
+}
+
 struct PendingEvent {
     cudaEvent_t e0, e1;
     int slot;  // 0 nnps, 1 pair, 2 other
@@ -141,7 +158,8 @@ struct b200sph_ctx {
     int64_t n_sorted = 0;
     bool state_packed = false;
     int force_kernel = 0;       // 0 lists (default), 1 warp kernel (env B200SPH_PAIR_KERNEL)
-    int pair_minb = 6;          // resident CTAs per SM k_pair_list is compiled for (env B200SPH_PAIR_MINB: 6, 7, 8)
+    int pair_minb = 7;          // resident CTAs per SM k_pair_list is compiled for (env B200SPH_PAIR_MINB: 6, 7, 8)
+    bool pair_spec = true;      // use the WCSPH-only variant of k_pair_list when the program allows (env B200SPH_PAIR_SPEC)
     // persistent neighbour lists
     double skin = 0.1;          // S = skin * radius_scale * hmax, adapted between skin_min and skin_max
     double skin_max = 0.1;      // env B200SPH_SKIN (also what a halo exchange must cover)
@@ -199,6 +217,23 @@ struct b200sph_ctx {
 
     EosTab eos_pending;
     bool eos_any = false;
+    // ---- peer protocol (b200sph_peer_*) + interior / boundary split of the list consumer --
+    int peer_rank = -1, peer_world = 0;
+    struct PeerBox *peer_box = nullptr;          // this rank's mailbox
+    struct PeerBox *peer_boxes[B200SPH_MAX_RANKS] = {nullptr};   // every rank's (own: the local one)
+    bool peer_connected = false;
+    unsigned long long peer_epoch = 0, peer_dt_epoch = 0;
+    unsigned *peer_done = nullptr;               // "blocks finished" counter of k_peer_send
+    double *peer_dec_dev = nullptr;
+    struct PeerDecision *peer_dec_host = nullptr, *peer_dec_hostdev = nullptr;   // pinned + its device alias
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool comm_pending = false;                   // work on comm_stream that the main stream has not waited for
+    uint8_t *sflag = nullptr;                    // [sorted] 1 = ghost
+    uint32_t *chunk_boundary = nullptr, *chunk_interior = nullptr;
+    int64_t n_chunk_boundary = 0, n_chunk_interior = 0, chunk_cap = 0;
+    bool chunks_valid = false;
+    int64_t n_overlapped = 0;
     // ---- fused stage kernel (k_stage_pack) bookkeeping ---------------------------------
     bool fuse = true;            // env B200SPH_FUSE=0: the unfused kernels only
     EosTab eos_last;             // the equation-of-state calls of the last evaluation ...
@@ -300,6 +335,13 @@ __device__ __forceinline__ float4 lds_T(const smem_tab_t t, const uint32_t index
     float4 v;
     asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(t + (index << 4)));
     return v;
+}
+// nanosecond clock shared by every SM (bounds the spin waits of the peer protocol)
+__device__ __forceinline__ unsigned long long peer_now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 #endif
 
@@ -475,8 +517,21 @@ static int refresh_ptype(b200sph_ctx *ctx)
     return 0;
 }
 
-static int ensure_pool(b200sph_ctx *ctx)
+// the main stream waits for what the peer protocol left running on the communication stream
+static int sync_comm(b200sph_ctx *ctx)
 {
+    if (!ctx->comm_pending) return 0;
+    ctx->comm_pending = false;
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return 0;
+}
+
+static int ensure_pool(b200sph_ctx *ctx, bool join = true)
+{
+    if (join) {
+        int rc0 = sync_comm(ctx);
+        if (rc0) return rc0;
+    }
     if (ctx->pool_cap == 0) {
         int64_t caps[B200SPH_MAX_ARRAYS];
         for (int a = 0; a < ctx->narr; a++) caps[a] = std::max(ctx->arr[a].cap, ctx->arr[a].n);
@@ -600,6 +655,7 @@ int b200sph_create(int device, b200sph_ctx **out)
     }
     if (const char *e = getenv("B200SPH_PAIR_MINB")) ctx->pair_minb = atoi(e);
     if (const char *e = getenv("B200SPH_FUSE")) ctx->fuse = atoi(e) != 0;
+    if (const char *e = getenv("B200SPH_PAIR_SPEC")) ctx->pair_spec = atoi(e) != 0;
     if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = ctx->skin_max = std::max(0.0, atof(e));
     if (const char *e = getenv("B200SPH_SKIN_ADAPT")) ctx->skin_adapt = atoi(e) != 0;
     ctx->skin_min = std::min(ctx->skin_min, ctx->skin_max);
@@ -649,6 +705,14 @@ int b200sph_destroy(b200sph_ctx *ctx)
     if (ctx->snap_ready) cudaEventDestroy(ctx->snap_ready);
     if (ctx->snap_done) cudaEventDestroy(ctx->snap_done);
     cudaFree(ctx->snap_buf);
+    for (int r = 0; r < ctx->peer_world; r++)
+        if (r != ctx->peer_rank && ctx->peer_boxes[r]) cudaIpcCloseMemHandle(ctx->peer_boxes[r]);
+    cudaFree(ctx->peer_box); cudaFree(ctx->peer_done); cudaFree(ctx->peer_dec_dev);
+    if (ctx->peer_dec_host) cudaFreeHost(ctx->peer_dec_host);
+    if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    cudaFree(ctx->sflag); cudaFree(ctx->chunk_boundary); cudaFree(ctx->chunk_interior);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -674,6 +738,7 @@ int b200sph_set_stream(b200sph_ctx *ctx, void *s)
 int b200sph_synchronize(b200sph_ctx *ctx)
 {
     CU(cudaSetDevice(ctx->device));
+    if (int rcj = sync_comm(ctx)) return rcj;
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -1165,7 +1230,10 @@ int b200sph_nnps_update_deferred(b200sph_ctx *ctx)
 int b200sph_nnps_update(b200sph_ctx *ctx)
 {
     CU(cudaSetDevice(ctx->device));
-    int rc = ensure_pool(ctx);
+    // with the peer protocol's refresh in flight the only thing this call may do without
+    // waiting for it is to accept the build the ranks have (speculatively) agreed to keep
+    int rc = ensure_pool(ctx, !(ctx->comm_pending && ctx->drift_ok && ctx->packed_valid && ctx->lists_valid &&
+                                !ctx->topo_dirty && !ctx->eos_any && ctx->domain_valid && !ctx->check_pending));
     if (rc) return rc;
     if (ctx->check_pending) {   // update after update without an evaluation in between
         int redo = 0;
@@ -1333,9 +1401,47 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     return 0;
 }
 
+// With ghosts in the build (slab decomposition) the CTAs of the list consumers are split
+// into the ones that do not depend on a ghost -- they may run while the halo of the
+// evaluation is still in flight -- and the rest (k_chunk_classify).
+static int split_chunks(b200sph_ctx *ctx)
+{
+    ctx->chunks_valid = false;
+    int64_t nghost = 0;
+    for (int a = 0; a < ctx->narr; a++) nghost += ctx->arr[a].n - ctx->arr[a].n_real;
+    const int64_t n = ctx->n_sorted, nchunks = cdiv(n, LIST_NT);
+    if (nghost == 0 || n <= 0 || nchunks + 1 > ctx->flag_cap) return 0;
+    if (nchunks > ctx->chunk_cap) {
+        if (ctx->chunk_boundary) CU(cudaFree(ctx->chunk_boundary));
+        if (ctx->chunk_interior) CU(cudaFree(ctx->chunk_interior));
+        if (ctx->sflag) CU(cudaFree(ctx->sflag));
+        ctx->chunk_cap = nchunks + nchunks / 4 + 64;
+        CU(cudaMalloc((void **)&ctx->chunk_boundary, 4 * (size_t)ctx->chunk_cap));
+        CU(cudaMalloc((void **)&ctx->chunk_interior, 4 * (size_t)ctx->chunk_cap));
+        CU(cudaMalloc((void **)&ctx->sflag, (size_t)ctx->chunk_cap * LIST_NT));
+    }
+    int rc = refresh_ptype(ctx);
+    if (rc) return rc;
+    k_sorted_ghost_flag<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->ptype, ctx->perm, n, ctx->sflag);
+    LAUNCH_CHECK();
+    k_chunk_classify<<<(unsigned)nchunks, LIST_NT, 0, ctx->stream>>>(ctx->cnt, ctx->lst, ctx->capg, ctx->sflag, n, ctx->flag_a);
+    LAUNCH_CHECK();
+    if ((rc = device_scan(ctx, ctx->flag_a, ctx->flag_b, nchunks + 1))) return rc;
+    uint32_t nb = 0;
+    CU(cudaMemcpyAsync(&nb, ctx->flag_b + nchunks, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    k_chunk_split<<<(unsigned)cdiv(nchunks, 256), 256, 0, ctx->stream>>>(nchunks, ctx->flag_a, ctx->flag_b, ctx->chunk_boundary, ctx->chunk_interior);
+    LAUNCH_CHECK();
+    ctx->n_chunk_boundary = nb;
+    ctx->n_chunk_interior = nchunks - nb;
+    ctx->chunks_valid = true;
+    return 0;
+}
+
 // (re)build the persistent neighbour lists for the current build
 static int build_lists(b200sph_ctx *ctx)
 {
+    ctx->chunks_valid = false;
     const int64_t n = ctx->n_sorted;
     ListBuildArgs la;
     la.A = ctx->A; la.cell_start = ctx->cell_start; la.skey = ctx->skey;
@@ -1375,7 +1481,7 @@ static int build_lists(b200sph_ctx *ctx)
         if (!count_only && maxc <= ctx->capg) {
             ctx->lists_valid = true;
             ctx->n_list_builds++;
-            return 0;
+            return split_chunks(ctx);
         }
         // (re)size: a little head-room so that later rebuilds usually fit in one pass
         ctx->capg = ((int)(maxc * 1.15) + 8 + 7) / 8 * 8;
@@ -1395,6 +1501,7 @@ int b200sph_get_grid(b200sph_ctx *ctx, b200sph_grid_info *out)
 static int eos_flush(b200sph_ctx *ctx)
 {
     if (!ctx->eos_any) return 0;
+    if (int rcj = sync_comm(ctx)) return rcj;   // (ghost rho is being refreshed)
     EosTab &E = ctx->eos_pending;
     if (ctx->pool_end > 0) {
         k_eos_tab<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_RHO], ctx->f32[B200SPH_P - N_F64],
@@ -1466,7 +1573,7 @@ static int arr_range(b200sph_ctx *ctx, int arr, int real_only, int64_t *lo, int6
 int b200sph_eos(b200sph_ctx *ctx, int arr, int hg, double rho0, double c0, double gamma, double p0, int real_only)
 {
     CU(cudaSetDevice(ctx->device));
-    int rc = ensure_pool(ctx);
+    int rc = ensure_pool(ctx, false);   // only book-keeping here: a halo in flight stays in flight
     if (rc) return rc;
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "bad array index %d", arr);
     EosTab &E = ctx->eos_pending;
@@ -1513,7 +1620,7 @@ int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim, int real_o
 int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_t *pairs_out)
 {
     CU(cudaSetDevice(ctx->device));
-    int rc = ensure_pool(ctx);
+    int rc = ensure_pool(ctx, false);   // a halo in flight is waited for below, as late as possible
     if (rc) return rc;
     if (!ctx->grid_valid) return set_err(ctx, "pair_pass: the NNPS is stale (particles were pushed/resized); call nnps_update first");
     if (ctx->spec_records && ctx->state_packed) {
@@ -1535,13 +1642,18 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     } else {
         ctx->eos_last_valid = false;
     }
-    if (!ctx->state_packed) {
-        if ((rc = pack_state(ctx))) return rc;
-    } else if ((rc = eos_flush(ctx))) {   // the records have them; now the pool's rho / p / cs
-        return rc;
-    }
     // lists hold 26-bit sorted indices: larger particle counts use the warp kernel
     const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->n_sorted < (1LL << LIST_JBITS);
+    // the peer protocol's refresh is still in flight and every record a ghost-free CTA
+    // reads is in place: those CTAs go first, the main stream waits for the halo only then
+    const bool overlap = ctx->comm_pending && use_lists && ctx->lists_valid && ctx->chunks_valid && ctx->state_packed &&
+                         ctx->n_chunk_interior > 0 && !pairs_out;
+    if (!overlap && (rc = sync_comm(ctx))) return rc;
+    if (!ctx->state_packed) {
+        if ((rc = pack_state(ctx))) return rc;
+    } else if (!overlap && (rc = eos_flush(ctx))) {   // the records have them; now the pool's rho / p / cs
+        return rc;
+    }
     if (!use_lists && (ctx->periodic[0] || ctx->periodic[1] || ctx->periodic[2]))
         return set_err(ctx, "periodic domains need the neighbour-list path (B200SPH_PAIR_KERNEL=list, < 2^26 particles)");
     if (use_lists && !ctx->lists_valid) {
@@ -1581,26 +1693,45 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     pa.eps_xsph = (float)prog->eps_xsph;
     pa.tensile = prog->tensile_correction;
     pa.real_only = prog->real_only;
+    // the WCSPH scheme's Group (continuity + momentum + XSPH, no tensile correction) has a
+    // leaner kernel variant (B200SPH_PAIR_SPEC=0: always the generic one)
+    unsigned prog_bits = 0;
+    for (int d = 0; d < ctx->narr; d++)
+        for (int sx = 0; sx < ctx->narr; sx++) prog_bits |= prog->eqmask[d][sx];
+    const bool wcsph_only = ctx->pair_spec && !(prog_bits & ~(unsigned)PAIR_EQS_WCSPH) && !prog->tensile_correction;
     pa.pair_counter = nullptr;
     if (pairs_out) {
         CU(cudaMemsetAsync(ctx->counter, 0, 8, ctx->stream));
         pa.pair_counter = ctx->counter;
     }
     if (use_lists) {
-        const unsigned nb = (unsigned)cdiv(ctx->n_sorted, LIST_NT);
-        switch (ctx->kernel * 4 + ctx->dim) {
-#define LIST_CASE(K, D)                                                                                          \
-    case K * 4 + D:                                                                                              \
-        if (ctx->pair_minb >= 8) k_pair_list<K, D, 8><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg);      \
-        else if (ctx->pair_minb == 7) k_pair_list<K, D, 7><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg); \
-        else k_pair_list<K, D, 6><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg);                         \
+        // phase 0: every CTA, or (overlap) the ghost-free CTAs; phase 1: the others, behind the halo
+        for (int phase = 0; phase < (overlap ? 2 : 1); phase++) {
+            const uint32_t *ids = !overlap ? nullptr : (phase == 0 ? ctx->chunk_interior : ctx->chunk_boundary);
+            const unsigned nb = (unsigned)(!overlap ? cdiv(ctx->n_sorted, LIST_NT) : (phase == 0 ? ctx->n_chunk_interior : ctx->n_chunk_boundary));
+            if (phase == 1) {
+                if ((rc = sync_comm(ctx))) return rc;
+                if ((rc = eos_flush(ctx))) return rc;   // pool side of the speculated EOS, ghosts included
+                ctx->n_overlapped++;
+            }
+            if (nb == 0) continue;
+            switch (ctx->kernel * 4 + ctx->dim) {
+#define LIST_LAUNCH(K, D, M, Q) k_pair_list<K, D, M, Q><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg, ids)
+#define LIST_CASE(K, D)                                                          \
+    case K * 4 + D:                                                              \
+        if (wcsph_only && ctx->pair_minb >= 8) LIST_LAUNCH(K, D, 8, PAIR_EQS_WCSPH); \
+        else if (wcsph_only && ctx->pair_minb == 7) LIST_LAUNCH(K, D, 7, PAIR_EQS_WCSPH); \
+        else if (ctx->pair_minb >= 7) LIST_LAUNCH(K, D, 7, PAIR_EQS_ALL);          \
+        else LIST_LAUNCH(K, D, 6, PAIR_EQS_ALL);                                  \
         break;
-            LIST_CASE(0, 1) LIST_CASE(0, 2) LIST_CASE(0, 3) LIST_CASE(1, 2) LIST_CASE(1, 3)
-            LIST_CASE(2, 1) LIST_CASE(2, 2) LIST_CASE(2, 3) LIST_CASE(3, 1) LIST_CASE(3, 2) LIST_CASE(3, 3)
+                LIST_CASE(0, 1) LIST_CASE(0, 2) LIST_CASE(0, 3) LIST_CASE(1, 2) LIST_CASE(1, 3)
+                LIST_CASE(2, 1) LIST_CASE(2, 2) LIST_CASE(2, 3) LIST_CASE(3, 1) LIST_CASE(3, 2) LIST_CASE(3, 3)
+#undef LIST_LAUNCH
 #undef LIST_CASE
-        default: return set_err(ctx, "pair_pass: unsupported kernel/dim combination");
+            default: return set_err(ctx, "pair_pass: unsupported kernel/dim combination");
+            }
+            LAUNCH_CHECK();
         }
-        LAUNCH_CHECK();
         ctx->stats.pair_launches++;
     } else if (ctx->n_sorted > 0) {
         const unsigned nb = (unsigned)cdiv(ctx->n_sorted, PAIR_WARPS * PAIR_CHUNK);
@@ -2543,6 +2674,233 @@ int b200sph_nnps_keep_build(b200sph_ctx *ctx)
     return 0;
 }
 
+// ---- peer protocol (include/b200sph.h "peer protocol") ---------------------------------
+static int peer_streams(b200sph_ctx *ctx)
+{
+    if (ctx->comm_stream) return 0;
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = the numerically lowest = highest priority
+    CU(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+    CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    return 0;
+}
+
+int b200sph_peer_init(b200sph_ctx *ctx, int rank, int world, void *handle64)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (world < 1 || world > B200SPH_MAX_RANKS || rank < 0 || rank >= world)
+        return set_err(ctx, "peer_init: rank %d of %d (at most %d ranks)", rank, world, B200SPH_MAX_RANKS);
+    if (ctx->peer_box) return set_err(ctx, "peer_init: already initialised");
+    int rc = peer_streams(ctx);
+    if (rc) return rc;
+    const size_t box_bytes = std::max<size_t>(sizeof(PeerBox), 4096);
+    CU(cudaMalloc((void **)&ctx->peer_box, box_bytes));
+    CU(cudaMemset(ctx->peer_box, 0, box_bytes));
+    CU(cudaMalloc((void **)&ctx->peer_done, 2 * sizeof(unsigned)));
+    CU(cudaMemset(ctx->peer_done, 0, 2 * sizeof(unsigned)));
+    CU(cudaMalloc((void **)&ctx->peer_dec_dev, sizeof(double)));
+    CU(cudaHostAlloc((void **)&ctx->peer_dec_host, sizeof(PeerDecision), cudaHostAllocMapped));
+    memset(ctx->peer_dec_host, 0, sizeof(PeerDecision));
+    CU(cudaHostGetDevicePointer((void **)&ctx->peer_dec_hostdev, ctx->peer_dec_host, 0));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ctx->peer_box);
+    if (e != cudaSuccess) return set_err(ctx, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    memcpy(handle64, &h, 64);
+    ctx->peer_rank = rank;
+    ctx->peer_world = world;
+    ctx->peer_boxes[rank] = ctx->peer_box;
+    return 0;
+}
+
+int b200sph_peer_connect(b200sph_ctx *ctx, const void *handles)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->peer_box) return set_err(ctx, "peer_connect: call peer_init first");
+    if (ctx->peer_connected) return 0;
+    for (int r = 0; r < ctx->peer_world; r++) {
+        if (r == ctx->peer_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)r, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return set_err(ctx, "peer_connect: cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+        ctx->peer_boxes[r] = (PeerBox *)p;
+    }
+    ctx->peer_connected = true;
+    return 0;
+}
+
+static PeerPtrs peer_ptrs(const b200sph_ctx *ctx)
+{
+    PeerPtrs R;
+    for (int r = 0; r < B200SPH_MAX_RANKS; r++) R.box[r] = ctx->peer_boxes[r];
+    return R;
+}
+
+int b200sph_peer_begin(b200sph_ctx *ctx)
+{
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (!ctx->peer_connected) return set_err(ctx, "peer_begin: the mailboxes are not connected");
+    if ((rc = eos_flush(ctx))) return rc;
+    int no_build = 0;
+    if (ctx->force_kernel != 0 || !ctx->lists_valid || ctx->topo_dirty) no_build = 1;
+    else if (ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min) no_build = 1;  // retire it
+    if (!no_build && ctx->n_sorted > 0 && !(ctx->packed_valid && ctx->drift_measured)) {
+        CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
+        k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
+            ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H], ctx->perm, ctx->skey,
+            ctx->n_sorted, ctx->G, ctx->A0, ctx->A, ctx->AB, ctx->red_u32);
+        LAUNCH_CHECK();
+    }
+    if (!no_build) ctx->packed_valid = true, ctx->drift_measured = true;
+    ctx->peer_epoch++;
+    CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+    return no_build;
+}
+
+int b200sph_peer_publish(b200sph_ctx *ctx, int have_build, int with_dt)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->peer_connected) return set_err(ctx, "peer_publish: the mailboxes are not connected");
+    if (with_dt && !ctx->tc) return set_err(ctx, "peer_publish: no time-control block");
+    k_peer_publish<<<1, 32, 0, ctx->comm_stream>>>(peer_ptrs(ctx), ctx->peer_rank, ctx->peer_world, ctx->peer_epoch, 0, ctx->red_u32,
+                                                    (float)ctx->radius_scale, (float)ctx->S_abs, have_build && ctx->n_sorted > 0 ? 1 : (have_build ? 2 : 0),
+                                                    ctx->tc, with_dt);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int b200sph_peer_send(b200sph_ctx *ctx, int slot, int nb_rank, int side, double *remote_staging, int64_t cap_doubles)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->peer_connected) return set_err(ctx, "peer_send: the mailboxes are not connected");
+    if (slot < -1 || slot > 1 || side < 0 || side > 1 || nb_rank < 0 || nb_rank >= ctx->peer_world || nb_rank == ctx->peer_rank)
+        return set_err(ctx, "peer_send: bad slot / side / neighbour");
+    HaloAllArgs A;
+    A.narr = ctx->narr;
+    A.prefix[0] = 0;
+    for (int a = 0; a < ctx->narr; a++) {
+        // slot -1: the flag alone (this rank has no reusable build: the neighbour must not wait)
+        A.prefix[a + 1] = A.prefix[a] + (slot < 0 ? 0 : ctx->halo_cnt[a][slot]);
+        A.off[a] = ctx->arr[a].off;
+        A.idx[a] = slot < 0 ? nullptr : ctx->halo_idx[a][slot];
+    }
+    const int64_t tot = A.prefix[ctx->narr];
+    if (tot * halo_nf(ctx) > cap_doubles) return set_err(ctx, "peer_send: staging buffer too small");
+    unsigned long long *flag = &ctx->peer_boxes[nb_rank]->data_seq[ctx->peer_epoch & 1][side];
+    if (tot == 0) {
+        k_peer_flag<<<1, 1, 0, ctx->comm_stream>>>(flag, ctx->peer_epoch);
+    } else if (halo_nf(ctx) == B200SPH_HALO_FIELDS) {
+        k_peer_send<B200SPH_HALO_FIELDS><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->comm_stream>>>(halo_ptrs(ctx), A, remote_staging, ctx->peer_done, flag, ctx->peer_epoch);
+    } else {
+        k_peer_send<B200SPH_HALO_FIELDS_SOLID><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->comm_stream>>>(halo_ptrs(ctx), A, remote_staging, ctx->peer_done, flag, ctx->peer_epoch);
+    }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int b200sph_peer_reduce(b200sph_ctx *ctx, int with_dt)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->peer_connected) return set_err(ctx, "peer_reduce: the mailboxes are not connected");
+    k_peer_reduce<<<1, 32, 0, ctx->comm_stream>>>(ctx->peer_box, ctx->peer_world, ctx->peer_epoch, 0, ctx->peer_dec_dev, ctx->peer_dec_hostdev,
+                                                   ctx->tc, with_dt && ctx->tc ? 1 : 0);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int b200sph_peer_recv(b200sph_ctx *ctx, int side, const int64_t *ghost_first, const int64_t *counts, const double *local_staging)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->peer_connected) return set_err(ctx, "peer_recv: the mailboxes are not connected");
+    if (side < 0 || side > 1) return set_err(ctx, "peer_recv: bad side");
+    HaloAllArgs A;
+    A.narr = ctx->narr;
+    A.prefix[0] = 0;
+    for (int a = 0; a < ctx->narr; a++) {
+        const ArrayInfo &ai = ctx->arr[a];
+        if (ghost_first[a] < 0 || counts[a] < 0 || ai.n_real + ghost_first[a] + counts[a] > ai.n)
+            return set_err(ctx, "peer_recv: ghosts [%lld, %lld) outside the %lld ghosts of '%s'", (long long)ghost_first[a],
+                           (long long)(ghost_first[a] + counts[a]), (long long)(ai.n - ai.n_real), ai.name.c_str());
+        A.prefix[a + 1] = A.prefix[a] + counts[a];
+        A.off[a] = ai.off + ai.n_real + ghost_first[a];
+        A.idx[a] = nullptr;
+    }
+    const int64_t tot = A.prefix[ctx->narr];
+    if (tot == 0) return 0;
+    int rc = refresh_ptype(ctx);
+    if (rc) return rc;
+    const bool repack = ctx->packed_valid && ctx->lists_valid && !ctx->topo_dirty && ctx->force_kernel == 0 && ctx->n_sorted > 0;
+    // the ghosts' state records too when the real particles' are in place (fused stage kernel)
+    const bool records = repack && ctx->state_packed && halo_nf(ctx) == B200SPH_HALO_FIELDS;
+    GhostPackArgs R;
+    memset(&R, 0, sizeof(R));
+    R.rank = repack ? ctx->rank : nullptr;
+    R.skey = ctx->skey;
+    R.A = ctx->A; R.AB = ctx->AB;
+    R.C = records ? ctx->C : nullptr;
+    R.G = ctx->G;
+    R.ptype = ctx->ptype;
+    R.p = ctx->f32[B200SPH_P - N_F64]; R.cs = ctx->f32[B200SPH_CS - N_F64];
+    R.eos_any = ctx->spec_records && ctx->eos_last_valid ? 1 : 0;
+    R.E = ctx->eos_last;
+    const unsigned long long *flag = &ctx->peer_box->data_seq[ctx->peer_epoch & 1][side];
+    if (halo_nf(ctx) == B200SPH_HALO_FIELDS)
+        k_peer_recv<B200SPH_HALO_FIELDS><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->comm_stream>>>(halo_ptrs(ctx), A, local_staging, R, flag, ctx->peer_epoch, ctx->peer_dec_hostdev);
+    else
+        k_peer_recv<B200SPH_HALO_FIELDS_SOLID><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->comm_stream>>>(halo_ptrs(ctx), A, local_staging, R, flag, ctx->peer_epoch, ctx->peer_dec_hostdev);
+    LAUNCH_CHECK();
+    ctx->grid_valid = false;
+    ctx->packed_valid = repack;
+    if (!records) ctx->state_packed = false;
+    return 0;
+}
+
+int b200sph_peer_end(b200sph_ctx *ctx)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->comm_stream) return set_err(ctx, "peer_end: no epoch in flight");
+    CU(cudaEventRecord(ctx->ev_join, ctx->comm_stream));
+    ctx->comm_pending = true;
+    return 0;
+}
+
+int b200sph_peer_decision(b200sph_ctx *ctx, double *ratio_max)
+{
+    if (!ctx->peer_dec_host) return set_err(ctx, "peer_decision: no peer protocol");
+    volatile PeerDecision *d = ctx->peer_dec_host;
+    const unsigned long long want = ctx->peer_epoch;
+    // the kernel that writes it is on the communication stream and needs no help from the host
+    for (long long spin = 0; d->seq != want; spin++) {
+        if ((spin & 0xFFFF) == 0xFFFF) {
+            // nothing enqueued can be stuck for half a minute unless a peer died
+            cudaError_t e = cudaStreamQuery(ctx->comm_stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return set_err(ctx, "peer_decision: %s", cudaGetErrorString(e));
+            if (e == cudaSuccess && d->seq != want) return set_err(ctx, "peer_decision: epoch %llu was never decided", want);
+        }
+    }
+    if (d->error == want) return set_err(ctx, "peer protocol: a rank did not answer within %.0f s (epoch %llu)", PEER_TIMEOUT_NS * 1e-9, want);
+    *ratio_max = d->value;
+    return 0;
+}
+
+int b200sph_peer_allreduce_dt(b200sph_ctx *ctx)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->peer_connected) return set_err(ctx, "peer_allreduce_dt: the mailboxes are not connected");
+    if (!ctx->tc) return set_err(ctx, "peer_allreduce_dt: no time-control block");
+    ctx->peer_dt_epoch++;
+    k_peer_publish<<<1, 32, 0, ctx->stream>>>(peer_ptrs(ctx), ctx->peer_rank, ctx->peer_world, ctx->peer_dt_epoch, 1, ctx->red_u32, 0.f, 0.f, 0, ctx->tc, 1);
+    LAUNCH_CHECK();
+    k_peer_reduce<<<1, 32, 0, ctx->stream>>>(ctx->peer_box, ctx->peer_world, ctx->peer_dt_epoch, 1, nullptr, nullptr, ctx->tc, 1);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 int b200sph_drop_ghosts(b200sph_ctx *ctx, int arr)
 {
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "drop_ghosts: bad array %d", arr);
@@ -2700,6 +3058,9 @@ int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out)
     ctx->stats.list_entries_per_particle = ctx->capg;
     ctx->stats.deferred_failed = ctx->n_deferred_failed;
     ctx->stats.fused_stages = ctx->n_fused;
+    ctx->stats.overlapped = ctx->n_overlapped;
+    ctx->stats.chunks_interior = ctx->chunks_valid ? ctx->n_chunk_interior : 0;
+    ctx->stats.chunks_boundary = ctx->chunks_valid ? ctx->n_chunk_boundary : 0;
     *out = ctx->stats;
     return 0;
 }
@@ -2708,7 +3069,7 @@ int b200sph_reset_stats(b200sph_ctx *ctx)
     b200sph_stats tmp;
     b200sph_get_stats(ctx, &tmp);  // drain pending events
     memset(&ctx->stats, 0, sizeof(ctx->stats));
-    ctx->n_full_builds = ctx->n_light_updates = ctx->n_list_builds = ctx->n_deferred_failed = ctx->n_fused = 0;
+    ctx->n_full_builds = ctx->n_light_updates = ctx->n_list_builds = ctx->n_deferred_failed = ctx->n_fused = ctx->n_overlapped = 0;
     return 0;
 }
 int b200sph_set_async_copies(b200sph_ctx *ctx, int on)

@@ -108,8 +108,9 @@ __global__ void k_pack_state(const double *__restrict__ u, const double *__restr
         }
         const double ratio = r * (1.0 / rho0);
         const double Bc = rho0 * E.c0[a] * E.c0[a] / E.gamma[a];
-        pg = (float)((E.hg[a] ? 0.0 : E.p0[a]) + Bc * (pow(ratio, E.gamma[a]) - 1.0));
-        csg = (float)(E.c0[a] * pow(ratio, 0.5 * (E.gamma[a] - 1.0)));
+{ double rg_, rh_; tait_powers(ratio, E.gamma[a], rg_, rh_);
+        pg = (float)((E.hg[a] ? 0.0 : E.p0[a]) + Bc * (rg_ - 1.0));
+        csg = (float)(E.c0[a] * rh_); }
         p[g] = pg;
         cs[g] = csg;
     } else {

@@ -30,14 +30,21 @@ struct Acc {
     float arho, au, av, aw, ax, ay, az, cfl, rsum;
 };
 
-template <int K, int DIM>
+// EQS: what the Group can contain, known when the kernel is chosen -- the low 8 bits are the
+// equation bits that may occur, PAIR_EQS_TENSILE that the tensile correction may be on.
+// The default admits everything; a narrower set lets the compiler drop the other
+// equations' code and registers (k_pair_list has a variant for the WCSPH scheme's Group).
+#define PAIR_EQS_TENSILE 0x100
+#define PAIR_EQS_ALL 0x1FF
+#define PAIR_EQS_WCSPH (B200SPH_EQ_CONTINUITY | B200SPH_EQ_MOMENTUM | B200SPH_EQ_XSPH)
+template <int K, int DIM, int EQS = PAIR_EQS_ALL>
 __device__ __forceinline__ void pair_body(const PairArgs &a, const float4 qv, const float4 Bj,
                                           const float4 Cj, const float4 Ai, const float4 Bi,
                                           const float4 Ci, const unsigned long long mask_i,
                                           const float tmpi, Acc &acc, unsigned &npairs)
 {
     const int tj = __float_as_int(Cj.w) & 7;
-    const unsigned bits = (unsigned)(mask_i >> (8 * tj)) & 0xFFu;
+    const unsigned bits = (unsigned)(mask_i >> (8 * tj)) & (unsigned)(EQS & 0xFF);
     if (!bits) return;
     npairs++;
     const float xij = qv.x, yij = qv.y, zij = qv.z, hj = qv.w;
@@ -74,7 +81,7 @@ __device__ __forceinline__ void pair_body(const PairArgs &a, const float4 qv, co
                 acc.cfl = fmaxf(acc.cfl, fabsf(hij * vdotx * rinv * rinv) + a.c0);
             const float tmpj = Cj.y;  // p_j / rho_j^2 (precomputed in k_pack_state)
             float tmp = tmpi + tmpj;
-            if (a.tensile) {  // wc/basic.py:233-248
+            if ((EQS & PAIR_EQS_TENSILE) && a.tensile) {  // wc/basic.py:233-248
                 float wdp, dwdp;
                 sph_kernel<K>(a.deltap, wdp, dwdp);
                 float fij = w / wdp;  // WIJ/WDP: the fac*h^-dim normalisation cancels

@@ -197,7 +197,7 @@ __device__ __forceinline__ void ld_rec(const PairArgs &a, const uint32_t e, floa
 // one list entry: cell-offset lookup, distance, the exact accept test, the equations.  `live`
 // is false for the lanes whose list is shorter than the warp's longest (their entry reads
 // as 0 and their record as record 0, so everything up to the test is harmless to execute).
-template <int K, int DIM>
+template <int K, int DIM, int EQS>
 __device__ __forceinline__ void pair_entry(const PairArgs &a, const smem_tab_t sT, const bool live, const uint32_t e,
                                            const float4 Aj, const float4 Bj, const float4 Cj, const float4 Ai,
                                            const float4 Bi, const float4 Ci, const float hi2,
@@ -208,12 +208,13 @@ __device__ __forceinline__ void pair_entry(const PairArgs &a, const smem_tab_t s
     const float r2 = xij * xij + yij * yij + zij * zij;
     // the exact accept test, linked_list_nnps.pyx:188
     if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)))
-        pair_body<K, DIM>(a, make_float4(xij, yij, zij, Aj.w), Bj, Cj, Ai, Bi, Ci, mask_i, Ci.y, acc, npairs);
+        pair_body<K, DIM, EQS>(a, make_float4(xij, yij, zij, Aj.w), Bj, Cj, Ai, Bi, Ci, mask_i, Ci.y, acc, npairs);
 }
 
-template <int K, int DIM, int MINB>
+template <int K, int DIM, int MINB, int EQS>
 __global__ void __launch_bounds__(LIST_NT, MINB) k_pair_list(const PairArgs a, const uint32_t *__restrict__ cnt,
-                                                         const uint32_t *__restrict__ lst, const int capg)
+                                                            const uint32_t *__restrict__ lst, const int capg,
+                                                            const uint32_t *__restrict__ chunk_ids)
 {
     __shared__ float4 s_T[64];
     const int tid = threadIdx.x;
@@ -224,7 +225,9 @@ __global__ void __launch_bounds__(LIST_NT, MINB) k_pair_list(const PairArgs a, c
     __syncthreads();
     const smem_tab_t sT = smem_tab(s_T);
     const unsigned FULL = 0xffffffffu;
-    const long long s = (long long)blockIdx.x * LIST_NT + tid;
+    // chunk_ids: this launch covers a subset of the CTA-sized chunks (the interior /
+    // boundary split of the slab decomposition, k_chunk_classify)
+    const long long s = (long long)(chunk_ids ? chunk_ids[blockIdx.x] : blockIdx.x) * LIST_NT + tid;
     bool active = s < a.n;
     float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai, Ci = Ai;
     unsigned long long mask_i = 0;
@@ -258,18 +261,18 @@ __global__ void __launch_bounds__(LIST_NT, MINB) k_pair_list(const PairArgs a, c
         // entry k (registers 0) while record k + 1 (registers 1) and entry k + 2 are in flight
         const uint32_t e2 = rem > 2 ? __ldcs(nxt) : 0u;
         ld_rec(a, e1, A1r, B1r, C1r);
-        pair_entry<K, DIM>(a, sT, rem > 0, e0, A0r, B0r, C0r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
+        pair_entry<K, DIM, EQS>(a, sT, rem > 0, e0, A0r, B0r, C0r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
         // entry k + 1 (registers 1) while record k + 2 (registers 0) and entry k + 3 are in flight
         const uint32_t e3 = rem > 3 ? __ldcs(nxt + 32) : 0u;
         ld_rec(a, e2, A0r, B0r, C0r);
-        pair_entry<K, DIM>(a, sT, rem > 1, e1, A1r, B1r, C1r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
+        pair_entry<K, DIM, EQS>(a, sT, rem > 1, e1, A1r, B1r, C1r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
         e0 = e2;
         e1 = e3;
     }
     if (active) {
         unsigned all_bits = 0;
 #pragma unroll
-        for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & 0xFFu;
+        for (int j = 0; j < B200SPH_MAX_ARRAYS; j++) all_bits |= (unsigned)(mask_i >> (8 * j)) & (unsigned)(EQS & 0xFF);
         const uint32_t g = a.perm[s];
         if (all_bits & B200SPH_EQ_SUMMATION_DENSITY) a.rho[g] = (double)acc.rsum;
         if (all_bits & B200SPH_EQ_CONTINUITY) a.arho[g] = acc.arho;

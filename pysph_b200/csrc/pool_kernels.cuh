@@ -126,25 +126,6 @@ __global__ void k_dt_commit(double *__restrict__ tc, double prev_factor, double 
     if (t + dt > t_final - t_eps) dt = t_final - t;
     tc[0] = dt;
 }
-// TaitEOS.loop wc/basic.py:60-65 ; TaitEOSHGCorrection.loop wc/basic.py:118-126
-__global__ void k_eos(double *__restrict__ rho, float *__restrict__ p, float *__restrict__ cs,
-                      const uint8_t *__restrict__ ptype, long long lo, long long hi, int hg,
-                      double rho0, double c0, double gamma, double p0)
-{
-    long long g = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= hi) return;
-    double r = rho[g];
-    if (hg && r < rho0) {
-        r = rho0;
-        rho[g] = r;
-    }
-    double ratio = r * (1.0 / rho0);
-    double B = rho0 * c0 * c0 / gamma;
-    double tmp = pow(ratio, gamma);
-    p[g] = (float)((hg ? 0.0 : p0) + B * (tmp - 1.0));
-    cs[g] = (float)(c0 * pow(ratio, 0.5 * (gamma - 1.0)));
-}
-
 // UpdateSmoothingLengthFerrari.loop wc/basic.py:458-463
 __global__ void k_ferrari(double *__restrict__ h, const double *__restrict__ m,
                           const double *__restrict__ rho, long long lo, long long hi, double hdx,
@@ -230,7 +211,7 @@ struct FusePackArgs {
     EosTab E;
 };
 
-__global__ void __launch_bounds__(256) k_stage_pack(const StageArgs a, const FusePackArgs q)
+__global__ void __launch_bounds__(256, 5) k_stage_pack(const StageArgs a, const FusePackArgs q)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float d2 = 0.f, dh = 0.f;
@@ -292,8 +273,9 @@ __global__ void __launch_bounds__(256) k_stage_pack(const StageArgs a, const Fus
                 if (q.E.hg[ar] && r < rho0) r = rho0;   // the record only: the pool keeps rho
                 const double ratio = r * (1.0 / rho0);
                 const double Bc = rho0 * q.E.c0[ar] * q.E.c0[ar] / q.E.gamma[ar];
-                pg = (float)((q.E.hg[ar] ? 0.0 : q.E.p0[ar]) + Bc * (pow(ratio, q.E.gamma[ar]) - 1.0));
-                csg = (float)(q.E.c0[ar] * pow(ratio, 0.5 * (q.E.gamma[ar] - 1.0)));
+{ double rg_, rh_; tait_powers(ratio, q.E.gamma[ar], rg_, rh_);
+                pg = (float)((q.E.hg[ar] ? 0.0 : q.E.p0[ar]) + Bc * (rg_ - 1.0));
+                csg = (float)(q.E.c0[ar] * rh_); }
             } else {
                 pg = q.p[g];
                 csg = q.cs[g];
@@ -348,8 +330,9 @@ __global__ void __launch_bounds__(256) k_stage_pack(const StageArgs a, const Fus
     }
 }
 
-// the pending equation-of-state calls of every array in one launch (pool side: rho clamp of
-// the HG variant, p, cs); same arithmetic as k_eos / k_pack_state
+// TaitEOS.loop wc/basic.py:60-65 ; TaitEOSHGCorrection.loop wc/basic.py:118-126: the pending
+// equation-of-state calls of every array in one launch (pool side: rho clamp of the HG
+// variant, p, cs); same arithmetic as k_pack_state
 __global__ void k_eos_tab(double *__restrict__ rho, float *__restrict__ p, float *__restrict__ cs,
                           const uint8_t *__restrict__ ptype, long long pool_end, const EosTab E)
 {
@@ -367,8 +350,9 @@ __global__ void k_eos_tab(double *__restrict__ rho, float *__restrict__ p, float
     }
     const double ratio = r * (1.0 / rho0);
     const double Bc = rho0 * E.c0[a] * E.c0[a] / E.gamma[a];
-    p[g] = (float)((E.hg[a] ? 0.0 : E.p0[a]) + Bc * (pow(ratio, E.gamma[a]) - 1.0));
-    cs[g] = (float)(E.c0[a] * pow(ratio, 0.5 * (E.gamma[a] - 1.0)));
+{ double rg_, rh_; tait_powers(ratio, E.gamma[a], rg_, rh_);
+    p[g] = (float)((E.hg[a] ? 0.0 : E.p0[a]) + Bc * (rg_ - 1.0));
+    cs[g] = (float)(E.c0[a] * rh_); }
 }
 
 // k_dt_propose + k_dt_commit in one launch (one rank: nothing to reduce in between), and

@@ -221,6 +221,45 @@ class DeviceHaloOps(object):
     def ipc_close(self, ptr, owner):
         self.ctx.call('b200sph_ipc_close', ptr, 1 if owner else 0)
 
+    # -- peer protocol (include/b200sph.h): refresh + scalar agreement without NCCL ------
+    def peer_init(self, rank, world):
+        handle = C.create_string_buffer(64)
+        self.ctx.call('b200sph_peer_init', int(rank), int(world), handle)
+        return handle.raw
+
+    def peer_connect(self, handles):
+        self.ctx.call('b200sph_peer_connect', C.create_string_buffer(b''.join(handles),
+                                                                     64 * len(handles)))
+
+    def peer_begin(self):
+        """-> True if this rank has a reusable neighbour build"""
+        return self.ctx.call('b200sph_peer_begin') == 0
+
+    def peer_publish(self, have_build, with_dt=False):
+        self.ctx.call('b200sph_peer_publish', int(bool(have_build)), int(bool(with_dt)))
+
+    def peer_send(self, slot, nb_rank, side, remote_ptr, cap_doubles):
+        self.ctx.call('b200sph_peer_send', slot, nb_rank, side, remote_ptr, int(cap_doubles))
+
+    def peer_reduce(self, with_dt=False):
+        self.ctx.call('b200sph_peer_reduce', int(bool(with_dt)))
+
+    def peer_recv(self, side, ghost_first, counts, local_ptr):
+        n = self.narr
+        self.ctx.call('b200sph_peer_recv', side, (C.c_int64 * n)(*ghost_first),
+                      (C.c_int64 * n)(*counts), local_ptr)
+
+    def peer_end(self):
+        self.ctx.call('b200sph_peer_end')
+
+    def peer_decision(self):
+        out = C.c_double()
+        self.ctx.call('b200sph_peer_decision', C.byref(out))
+        return out.value
+
+    def peer_allreduce_dt(self):
+        self.ctx.call('b200sph_peer_allreduce_dt')
+
     def drift_to(self, tensor):
         """Write the used-up fraction of the skin into a 1-element CUDA double
         tensor (no host sync); 2.0 if there is no reusable build."""
@@ -303,6 +342,11 @@ class SlabParallelManager(object):
             and hasattr(ops, 'ipc_alloc')
         self._peer = None
         self._parity = 0
+        # peer protocol: the scalar agreements go through mailboxes in peer memory too and
+        # the refresh runs on a second stream under the interior pair work
+        self.use_peer_sync = self.use_peer and hasattr(ops, 'peer_begin') and \
+            bool(int(__import__('os').environ.get('B200SPH_PEER_SYNC', '1')))
+        self._peer_sync = False
         self.n_peer_refresh = 0
         self.n_deferred_failed = 0
         self._pending = None
@@ -421,6 +465,10 @@ class SlabParallelManager(object):
         self.lb_count += 1
         if self._prof is not None:
             self._prof['n'] += 1
+        if self._recv and self._peer is not None and self._peer_sync:
+            self._update_peer_sync(deferred)
+            self._cpu('update', t_begin)
+            return
         if self._recv and hasattr(ops, 'drift'):
             if getattr(self, '_t1', None) is None:
                 self._t1 = ops.new_buffer(1)
@@ -474,6 +522,48 @@ class SlabParallelManager(object):
         self._full_update()
         self._cpu('update_full', t_begin)
 
+    def _update_peer_sync(self, deferred):
+        """The refresh path on the peer protocol: everything below only ENQUEUES work on the
+        library's communication stream -- publish the drift, pack + send into the
+        neighbours' staging buffers (flag in their mailbox), agree on MAX drift over all
+        ranks, scatter the ghosts behind the neighbours' flags -- and pair_pass runs the
+        ghost-free destinations while it is in flight."""
+        ops = self.ops
+        self._ev()
+        have = ops.peer_begin()
+        self._parity ^= 1
+        ops.peer_publish(have)
+        for nb in self._peer['nbs']:
+            slot = 0 if nb == self.left else 1
+            # the receiver reads the flag of the side the message comes FROM; without a
+            # reusable build only the flag goes out (slot -1): the neighbour must not wait
+            side = 1 if nb == self.left else 0
+            ops.peer_send(slot if have else -1, nb, side,
+                          self._peer['remote'][nb][self._parity], self._peer['cap'])
+        self._ev('drift+send')
+        ops.peer_reduce()
+        self._ev('all_reduce')
+        if have:
+            first = [0] * self.narr
+            for nb in sorted(self._recv):
+                ops.peer_recv(0 if nb == self.left else 1, first, self._recv[nb],
+                              self._peer['local'][nb][self._parity])
+                first = [f_ + n for f_, n in zip(first, self._recv[nb])]
+        ops.peer_end()
+        self._ev('overwrite')
+        if deferred:
+            self._pending = ops.peer_decision
+            ok = have
+        else:
+            ok = ops.peer_decision() <= 0.9 and have
+        if ok and ops.keep_build(strict=not deferred):
+            self.n_peer_refresh += 1
+            self.n_refresh += 1
+            return
+        if deferred:
+            return                      # confirm() reads the decision and runs the full path
+        self._full_update()
+
     def confirm(self):
         """After a deferred update: True if the refresh was not enough -- the full
         path has then been run and the caller repeats nnps.update + evaluation."""
@@ -486,7 +576,7 @@ class SlabParallelManager(object):
         self._cpu('confirm_wait', t0)
         if v <= 0.9:
             return False
-        self.n_refresh -= 1
+        self.n_refresh = max(self.n_refresh - 1, 0)
         self.n_deferred_failed += 1
         self._full_update()
         return True
@@ -610,6 +700,35 @@ class SlabParallelManager(object):
             self.use_peer = False
             return
         self._peer = dict(nbs=nbs, cap=cap, local=local, remote=remote)
+        self._setup_peer_sync()
+
+    def _setup_peer_sync(self):
+        """Once: every rank maps every rank's mailbox (collective)."""
+        if not self.use_peer_sync or self._peer_sync:
+            return
+        ops, dist = self.ops, self.dist
+        ok, handle = True, None
+        try:
+            handle = ops.peer_init(self.rank, self.world)
+        except Exception as e:
+            __import__('sys').stderr.write('pysph_b200: peer protocol disabled (%s)\n' % e)
+            ok = False
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handle)
+        ok = ok and all(h is not None for h in gathered)
+        if ok:
+            try:
+                ops.peer_connect(gathered)
+            except Exception as e:
+                __import__('sys').stderr.write('pysph_b200: peer protocol disabled (%s)\n' % e)
+                ok = False
+        t = ops.new_buffer(1)
+        t.fill_(1.0 if ok else 0.0)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if float(t.item()) > 0.5:
+            self._peer_sync = True
+        else:
+            self.use_peer_sync = False
 
     def _refresh_ghosts(self):
         ops = self.ops
@@ -711,7 +830,10 @@ class SlabParallelManager(object):
     def reduce_dt_device(self, view):
         """MIN over ranks of a 1-element device tensor, in place, no host sync
         (parallel_manager.pyx:454-465 on the device-resident time step)."""
-        self.dist.all_reduce(view, op=self.dist.ReduceOp.MIN)
+        if self._peer_sync:
+            self.ops.peer_allreduce_dt()      # the library's time-control block[2], in place
+        else:
+            self.dist.all_reduce(view, op=self.dist.ReduceOp.MIN)
 
     def update_time_steps(self, dt):
         t = self.ops.new_buffer(1)

@@ -183,3 +183,23 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent
 static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { return emu::ipc_export(h->reserved, p); }
 static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { return emu::ipc_import(p, h.reserved); }
 static inline cudaError_t cudaIpcCloseMemHandle(void *p) { return emu::ipc_release(p); }
+// ---- what the peer protocol (b200sph_peer_*) needs: priorities and mapped pinned memory are
+//      no-ops / plain memory here, fences are real (the ranks are concurrent OS processes) ----
+#include <sched.h>
+#include <time.h>
+#define cudaHostAllocMapped 2
+#define cudaErrorNotReady 600
+static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned) { *d = h; return 0; }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -1; return 0; }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = (void *)0x11; return 0; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { return 0; }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __nanosleep(unsigned) { sched_yield(); }
+template <class T> static inline T __ldcg(const T *p) { return *(const volatile T *)p; }
+static inline unsigned long long peer_now_ns()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}

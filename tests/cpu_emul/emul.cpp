@@ -56,6 +56,7 @@ template <class T> static inline T warp_read(T v, int src)
 
 #define __global__
 #define __device__
+#define __host__
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
@@ -269,7 +270,7 @@ int emul_wcsph(const emul_common *c, const int *eos_i, const double *eos_d, cons
     pa.pair_counter = nullptr;
     const int kernel = c->kernel, dim = c->dim;
     switch (kernel * 4 + dim) {
-#define PL(K, D) case K * 4 + D: launch(n, LIST_NT, [&] { k_pair_list<K, D, 6>(pa, cnt.data(), lst.data(), capg); }); break;
+#define PL(K, D) case K * 4 + D: launch(n, LIST_NT, [&] { k_pair_list<K, D, 6, PAIR_EQS_ALL>(pa, cnt.data(), lst.data(), capg, nullptr); }); break;
         PL(0, 2) PL(0, 3) PL(1, 2) PL(1, 3) PL(2, 2) PL(2, 3) PL(3, 2) PL(3, 3)
 #undef PL
     default: return -1;
@@ -364,10 +365,10 @@ int emul_pipeline(const emul_common *c, const double *gxmin, const double *gcell
 #define PL(K, D)                                                                                          \
     case K * 4 + D:                                                                                       \
         pa.pair_counter = nullptr;                                                                        \
-        launch(n, LIST_NT, [&] { k_pair_list<K, D, 6>(pa, cnt.data(), lst.data(), capg); });                 \
+        launch(n, LIST_NT, [&] { k_pair_list<K, D, 6, PAIR_EQS_ALL>(pa, cnt.data(), lst.data(), capg, nullptr); });                 \
         if (pairs) {                                                                                      \
             pa.pair_counter = &counter;                                                                   \
-            launch_warps(nbl, LIST_NT, [&] { k_pair_list<K, D, 6>(pa, cnt.data(), lst.data(), capg); });     \
+            launch_warps(nbl, LIST_NT, [&] { k_pair_list<K, D, 6, PAIR_EQS_ALL>(pa, cnt.data(), lst.data(), capg, nullptr); });     \
         }                                                                                                 \
         break;
     switch (kernel * 4 + dim) {

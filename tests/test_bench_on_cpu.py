@@ -181,3 +181,20 @@ def test_bench_two_ranks_on_the_emulated_library(emulated_library, argv):  # noq
     assert d['n_gpus'] == 2 and d['scaling'] == 'weak' and d['value'] > 0
     assert d['e2e']['value'] > 0 and d['e2e']['h2d_bytes_per_step'] > 0
     assert d['gpu_launches'] > 0 and d['roofline']['frac'] > 0
+    if argv[0] == '--dx':
+        # the slab run inside the bench reproduced one process (by gid), the peer protocol
+        # carried the refreshes and pair passes ran their ghost-free CTAs under the halo
+        par = d['config']['multi_gpu_parity']
+        assert par['ok'] is True and max(par['max_scaled_error'].values()) <= 1e-9, par
+        # ... on a problem where pair passes DID run ghost-free CTAs under the halo in flight
+        assert par['halo']['overlapped_evaluations'] > 0 and par['halo']['ctas_interior'] > 0 \
+            and par['halo']['fused_stages'] > 0, par
+        halo = d['config']['halo']
+        assert halo['peer_sync'] is True and halo['peer_refreshes'] > 0, halo
+        # (slabs this thin have a ghost in every CTA's neighbourhood: the overlap needs
+        # ghost-free CTAs, which the bench's own parity problem at dx = 0.03 has)
+        assert halo['ctas_boundary'] > 0 and (halo['overlapped_evaluations'] > 0) == \
+            (halo['ctas_interior'] > 0), halo
+        dev = d['developed']
+        assert dev['value'] > 0 and dev['full_builds'] >= 1, dev
+        assert d['launches_per_step'] > 0
