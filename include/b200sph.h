@@ -458,6 +458,11 @@ int b200sph_peer_send(b200sph_ctx *ctx, int slot, int nb_rank, int side, double 
 int b200sph_peer_reduce(b200sph_ctx *ctx, int with_dt);
 int b200sph_peer_recv(b200sph_ctx *ctx, int side, const int64_t *ghost_first, const int64_t *counts,
                       const double *local_staging);
+/* b200sph_dt_commit on the communication stream, between peer_reduce(with_dt = 1) and
+ * peer_end: the time-step agreement of the step that has just ended rides on the refresh of
+ * the next step's first evaluation (the new dt is first needed by its stage1) */
+int b200sph_peer_commit_dt(b200sph_ctx *ctx, double prev_factor, double new_factor, int adaptive,
+                           int advance, int snapshot_slot);
 int b200sph_peer_end(b200sph_ctx *ctx);
 int b200sph_peer_decision(b200sph_ctx *ctx, double *ratio_max);
 int b200sph_peer_allreduce_dt(b200sph_ctx *ctx);

@@ -158,6 +158,7 @@ SIGNATURES = {
     'b200sph_peer_send': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_int, C.c_void_p, _i64]),
     'b200sph_peer_reduce': (C.c_int, [_ctx_p, C.c_int]),
     'b200sph_peer_recv': (C.c_int, [_ctx_p, C.c_int, C.POINTER(_i64), C.POINTER(_i64), C.c_void_p]),
+    'b200sph_peer_commit_dt': (C.c_int, [_ctx_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
     'b200sph_peer_end': (C.c_int, [_ctx_p]),
     'b200sph_peer_decision': (C.c_int, [_ctx_p, _dp]),
     'b200sph_peer_allreduce_dt': (C.c_int, [_ctx_p]),

@@ -61,7 +61,50 @@ struct GridDev {
     double cell[3];   // cell edge per axis (a periodic axis is tiled exactly: L / nc)
     int nc[3];
     int periodic[3];
+    int zorder;       // 1: cell ROWS are ordered along the Z-curve of (cy, cz), see grid_row
 };
+
+// Cell key = row(cy, cz) * ncx + cx.  x is always the fastest axis, so the 27 neighbour
+// cells of a cell are 9 contiguous ranges of the sorted arrays (what the list builder
+// streams); the ROWS are ordered row-major (cy + ncy cz) or, zorder, along the Z-curve
+// (Morton code) of (cy, cz) -- rows that are close in space are then close in memory
+// whatever the aspect ratio of the grid (the reference's GPU NNPS sorts particles by the
+// 3-D Morton key of their cell, z_order_nnps.pyx:252-355, z_order.h:24-46).
+__host__ __device__ static inline uint32_t part1by1(uint32_t v)
+{
+    v &= 0x0000ffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+__host__ __device__ static inline uint32_t compact1by1(uint32_t v)
+{
+    v &= 0x55555555u;
+    v = (v | (v >> 1)) & 0x33333333u;
+    v = (v | (v >> 2)) & 0x0f0f0f0fu;
+    v = (v | (v >> 4)) & 0x00ff00ffu;
+    v = (v | (v >> 8)) & 0x0000ffffu;
+    return v;
+}
+__host__ __device__ static inline uint32_t grid_row(const int zorder, const uint32_t ncy, const uint32_t cy, const uint32_t cz)
+{
+    return zorder ? (part1by1(cy) | (part1by1(cz) << 1)) : cy + ncy * cz;
+}
+__host__ __device__ static inline void grid_decode(const int zorder, const uint32_t ncx, const uint32_t ncy, const uint32_t key,
+                                                   uint32_t &cx, uint32_t &cy, uint32_t &cz)
+{
+    cx = key % ncx;
+    const uint32_t row = key / ncx;
+    if (zorder) {
+        cy = compact1by1(row);
+        cz = compact1by1(row >> 1);
+    } else {
+        cy = row % ncy;
+        cz = row / ncy;
+    }
+}
 
 // equation-of-state calls wait here until the next k_pack_state applies them in the
 // same pass that gathers the state into the pair records (saves one launch and one
@@ -159,6 +202,7 @@ struct b200sph_ctx {
     bool state_packed = false;
     int force_kernel = 0;       // 0 lists (default), 1 warp kernel (env B200SPH_PAIR_KERNEL)
     int pair_minb = 7;          // resident CTAs per SM k_pair_list is compiled for (env B200SPH_PAIR_MINB: 6, 7, 8)
+    bool zorder = false;        // cell rows along the Z-curve of (cy, cz) (env B200SPH_ZORDER; measured: profiles/)
     bool pair_spec = true;      // use the WCSPH-only variant of k_pair_list when the program allows (env B200SPH_PAIR_SPEC)
     // persistent neighbour lists
     double skin = 0.1;          // S = skin * radius_scale * hmax, adapted between skin_min and skin_max
@@ -620,7 +664,7 @@ static double kernel_deltap(int kernel)
 
 extern "C" {
 
-static int eos_flush(b200sph_ctx *ctx);
+static int eos_flush(b200sph_ctx *ctx, cudaStream_t on_comm_stream = nullptr);
 
 int b200sph_abi_version(void) { return B200SPH_ABI_VERSION; }
 
@@ -656,6 +700,7 @@ int b200sph_create(int device, b200sph_ctx **out)
     if (const char *e = getenv("B200SPH_PAIR_MINB")) ctx->pair_minb = atoi(e);
     if (const char *e = getenv("B200SPH_FUSE")) ctx->fuse = atoi(e) != 0;
     if (const char *e = getenv("B200SPH_PAIR_SPEC")) ctx->pair_spec = atoi(e) != 0;
+    if (const char *e = getenv("B200SPH_ZORDER")) ctx->zorder = atoi(e) != 0;
     if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = ctx->skin_max = std::max(0.0, atof(e));
     if (const char *e = getenv("B200SPH_SKIN_ADAPT")) ctx->skin_adapt = atoi(e) != 0;
     ctx->skin_min = std::min(ctx->skin_min, ctx->skin_max);
@@ -1112,6 +1157,7 @@ int b200sph_update_domain(b200sph_ctx *ctx)
             D.nc[d] = 1;
             D.periodic[d] = ctx->periodic[d];
         }
+        D.zorder = 0;
         if (ctx->pool_end > 0) {
             k_box_wrap<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z],
                                                                                    ctx->ptype, ctx->pool_end, D);
@@ -1352,8 +1398,20 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
             cellv[d] = ctx->cell_int;
         }
     }
-    const int64_t ncells = (int64_t)nc[0] * nc[1] * nc[2];
+    int64_t ncells = (int64_t)nc[0] * nc[1] * nc[2];
     if (ncells > (1LL << 28)) return set_err(ctx, "ERROR: LinkedListNNPS requires too many cells (%lld).", (long long)ncells);
+    // Z-curve over the cell rows: the row table is padded to a power of two per axis (the
+    // unused rows are empty cells); a grid whose padding would be excessive stays row-major
+    int zorder = 0;
+    if (ctx->zorder) {
+        int bits = 0;
+        while ((1 << bits) < std::max(nc[1], nc[2])) bits++;
+        const int64_t padded = ((int64_t)1 << (2 * bits)) * nc[0];
+        if (bits <= 15 && padded <= (1LL << 27) && padded <= 8 * ncells + (1 << 20)) {
+            zorder = 1;
+            ncells = padded;
+        }
+    }
 
     if (ncells + 2 > ctx->cell_cap) {
         if (ctx->cell_cnt) CU(cudaFree(ctx->cell_cnt));
@@ -1372,6 +1430,7 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         G.cell[d] = cellv[d];
         G.periodic[d] = ctx->periodic[d] ? 1 : 0;
     }
+    G.zorder = zorder;
 
     CU(cudaMemsetAsync(ctx->cell_cnt, 0, 4 * (size_t)(ncells + 1), ctx->stream));
     ctx->n_sorted = ntot;
@@ -1448,6 +1507,7 @@ static int build_lists(b200sph_ctx *ctx)
     la.n = n;
     la.ncx = ctx->G.nc[0]; la.ncy = ctx->G.nc[1]; la.ncz = ctx->G.nc[2];
     la.cellx = (float)ctx->G.cell[0]; la.celly = (float)ctx->G.cell[1]; la.cellz = (float)ctx->G.cell[2];
+    la.zorder = ctx->G.zorder;
     la.px = ctx->G.periodic[0]; la.py = ctx->G.periodic[1]; la.pz = ctx->G.periodic[2];
     const bool per = la.px || la.py || la.pz;
     la.kr = (float)ctx->radius_scale;
@@ -1498,14 +1558,17 @@ int b200sph_get_grid(b200sph_ctx *ctx, b200sph_grid_info *out)
 
 // run the pending equation-of-state calls stand-alone (something needs rho/p/cs now, or the
 // packed records already hold them: the pool side of a speculated EOS) -- one launch
-static int eos_flush(b200sph_ctx *ctx)
+static int eos_flush(b200sph_ctx *ctx, cudaStream_t on_comm_stream)
 {
     if (!ctx->eos_any) return 0;
-    if (int rcj = sync_comm(ctx)) return rcj;   // (ghost rho is being refreshed)
+    // ghost rho may be in the middle of a refresh: wait for it -- unless the caller puts
+    // this launch on the communication stream itself, behind the scatter
+    if (!on_comm_stream)
+        if (int rcj = sync_comm(ctx)) return rcj;
     EosTab &E = ctx->eos_pending;
     if (ctx->pool_end > 0) {
-        k_eos_tab<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(ctx->f64[B200SPH_RHO], ctx->f32[B200SPH_P - N_F64],
-                                                                              ctx->f32[B200SPH_CS - N_F64], ctx->ptype, ctx->pool_end, E);
+        k_eos_tab<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, on_comm_stream ? on_comm_stream : ctx->stream>>>(
+            ctx->f64[B200SPH_RHO], ctx->f32[B200SPH_P - N_F64], ctx->f32[B200SPH_CS - N_F64], ctx->ptype, ctx->pool_end, E);
         LAUNCH_CHECK();
     }
     memset(E.on, 0, sizeof(E.on));
@@ -1673,6 +1736,7 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     pa.rho = ctx->f64[B200SPH_RHO];
     pa.n = ctx->n_sorted;
     pa.ncx = ctx->G.nc[0]; pa.ncy = ctx->G.nc[1]; pa.ncz = ctx->G.nc[2];
+    pa.zorder = ctx->G.zorder;
     pa.cellx = (float)ctx->G.cell[0]; pa.celly = (float)ctx->G.cell[1]; pa.cellz = (float)ctx->G.cell[2];
     pa.k2 = (float)(ctx->radius_scale * ctx->radius_scale);
     pa.kfac = (float)kernel_fac(ctx->kernel, ctx->dim);
@@ -1705,18 +1769,23 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
         pa.pair_counter = ctx->counter;
     }
     if (use_lists) {
-        // phase 0: every CTA, or (overlap) the ghost-free CTAs; phase 1: the others, behind the halo
+        // phase 0: every CTA, or (overlap) the ghost-free CTAs on the main stream; phase 1: the
+        // others on the COMMUNICATION stream, in order behind the halo scatter -- the two
+        // launches run side by side, the boundary CTAs (higher stream priority) take the SM
+        // slots the interior CTAs free, and there is one tail instead of two.  The main
+        // stream joins when the next entry point needs the results (sync_comm).
         for (int phase = 0; phase < (overlap ? 2 : 1); phase++) {
             const uint32_t *ids = !overlap ? nullptr : (phase == 0 ? ctx->chunk_interior : ctx->chunk_boundary);
             const unsigned nb = (unsigned)(!overlap ? cdiv(ctx->n_sorted, LIST_NT) : (phase == 0 ? ctx->n_chunk_interior : ctx->n_chunk_boundary));
+            cudaStream_t lst_stream = ctx->stream;
             if (phase == 1) {
-                if ((rc = sync_comm(ctx))) return rc;
-                if ((rc = eos_flush(ctx))) return rc;   // pool side of the speculated EOS, ghosts included
+                lst_stream = ctx->comm_stream;
+                if ((rc = eos_flush(ctx, ctx->comm_stream))) return rc;   // pool side of the speculated EOS, ghosts included
                 ctx->n_overlapped++;
             }
             if (nb == 0) continue;
             switch (ctx->kernel * 4 + ctx->dim) {
-#define LIST_LAUNCH(K, D, M, Q) k_pair_list<K, D, M, Q><<<nb, LIST_NT, 0, ctx->stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg, ids)
+#define LIST_LAUNCH(K, D, M, Q) k_pair_list<K, D, M, Q><<<nb, LIST_NT, 0, lst_stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg, ids)
 #define LIST_CASE(K, D)                                                          \
     case K * 4 + D:                                                              \
         if (wcsph_only && ctx->pair_minb >= 8) LIST_LAUNCH(K, D, 8, PAIR_EQS_WCSPH); \
@@ -1731,6 +1800,10 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
             default: return set_err(ctx, "pair_pass: unsupported kernel/dim combination");
             }
             LAUNCH_CHECK();
+        }
+        if (overlap) {   // the join point moves behind the boundary launch
+            CU(cudaEventRecord(ctx->ev_join, ctx->comm_stream));
+            ctx->comm_pending = true;
         }
         ctx->stats.pair_launches++;
     } else if (ctx->n_sorted > 0) {
@@ -2857,6 +2930,21 @@ int b200sph_peer_recv(b200sph_ctx *ctx, int side, const int64_t *ghost_first, co
     ctx->grid_valid = false;
     ctx->packed_valid = repack;
     if (!records) ctx->state_packed = false;
+    return 0;
+}
+
+int b200sph_peer_commit_dt(b200sph_ctx *ctx, double prev_factor, double new_factor, int adaptive, int advance, int snapshot_slot)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->comm_stream || !ctx->tc) return set_err(ctx, "peer_commit_dt: no epoch in flight / no time-control block");
+    if (!(prev_factor > 0.0) || !(new_factor > 0.0)) return set_err(ctx, "peer_commit_dt: damping factors must be positive");
+    if (snapshot_slot > 1) return set_err(ctx, "peer_commit_dt: snapshot slot must be 0 or 1");
+    k_dt_commit<<<1, 1, 0, ctx->comm_stream>>>(ctx->tc, prev_factor, new_factor, 1, adaptive, advance, ctx->t_final, ctx->t_eps);
+    LAUNCH_CHECK();
+    if (snapshot_slot >= 0) {
+        CU(cudaMemcpyAsync(ctx->tc_host + 2 * snapshot_slot, ctx->tc, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->comm_stream));
+        CU(cudaEventRecord(ctx->tc_evt[snapshot_slot], ctx->comm_stream));
+    }
     return 0;
 }
 

@@ -165,10 +165,8 @@ __global__ void k_halo_scatter_all(HaloPtrs P, HaloAllArgs A, const double *__re
     if (R.rank) {
         const uint32_t s = R.rank[A.off[a] + r];
         uint32_t key = R.skey[s];
-        const uint32_t cx = key % (uint32_t)R.G.nc[0];
-        key /= (uint32_t)R.G.nc[0];
-        const uint32_t cy = key % (uint32_t)R.G.nc[1];
-        const uint32_t cz = key / (uint32_t)R.G.nc[1];
+        uint32_t cx, cy, cz;
+        grid_decode(R.G.zorder, (uint32_t)R.G.nc[0], (uint32_t)R.G.nc[1], key, cx, cy, cz);
         float4 q;
         q.x = (float)(v[0] - (R.G.xmin[0] + (double)cx * R.G.cell[0]));
         q.y = (float)(v[1] - (R.G.xmin[1] + (double)cy * R.G.cell[1]));
@@ -388,10 +386,8 @@ __global__ void k_peer_recv(HaloPtrs P, HaloAllArgs A, const double *__restrict_
     if (R.rank) {
         const uint32_t s = R.rank[g];
         uint32_t key = R.skey[s];
-        const uint32_t cx = key % (uint32_t)R.G.nc[0];
-        key /= (uint32_t)R.G.nc[0];
-        const uint32_t cy = key % (uint32_t)R.G.nc[1];
-        const uint32_t cz = key / (uint32_t)R.G.nc[1];
+        uint32_t cx, cy, cz;
+        grid_decode(R.G.zorder, (uint32_t)R.G.nc[0], (uint32_t)R.G.nc[1], key, cx, cy, cz);
         float4 q;
         q.x = (float)(v[0] - (R.G.xmin[0] + (double)cx * R.G.cell[0]));
         q.y = (float)(v[1] - (R.G.xmin[1] + (double)cy * R.G.cell[1]));

@@ -7,7 +7,8 @@
 // --------------------------------------------------------------------------
 
 // cell id = floor((p - xmin)/cell) per axis (find_cell_id_raw, nnps_base.pxd:39-80),
-// flat = cx + ncx*cy + ncx*ncy*cz (flatten_raw, nnps_base.pxd:84-96); the arrival
+// flat = cx + ncx*cy + ncx*ncy*cz (flatten_raw, nnps_base.pxd:84-96) or, zorder, cx + ncx *
+// morton(cy, cz) (z_order.h:24-46 interleaves all three; see grid_row); the arrival
 // counter replaces the linked-list push (linked_list_nnps.pyx:285-286).
 __global__ void k_cell_count(const double *__restrict__ x, const double *__restrict__ y,
                              const double *__restrict__ z, const uint8_t *__restrict__ ptype,
@@ -23,7 +24,7 @@ __global__ void k_cell_count(const double *__restrict__ x, const double *__restr
     cx = min(max(cx, 0), G.nc[0] - 1);
     cy = min(max(cy, 0), G.nc[1] - 1);
     cz = min(max(cz, 0), G.nc[2] - 1);
-    uint32_t key = (uint32_t)cx + (uint32_t)G.nc[0] * ((uint32_t)cy + (uint32_t)G.nc[1] * (uint32_t)cz);
+    uint32_t key = (uint32_t)cx + (uint32_t)G.nc[0] * grid_row(G.zorder, (uint32_t)G.nc[1], (uint32_t)cy, (uint32_t)cz);
     key_of[g] = key;
     off_in[g] = atomicAdd(&cell_cnt[key], 1u);
 }
@@ -68,10 +69,8 @@ __global__ void k_pack_pos(const double *__restrict__ x, const double *__restric
     if (s >= n) return;
     const uint32_t g = perm[s];
     uint32_t key = skey[s];
-    const uint32_t cx = key % (uint32_t)G.nc[0];
-    key /= (uint32_t)G.nc[0];
-    const uint32_t cy = key % (uint32_t)G.nc[1];
-    const uint32_t cz = key / (uint32_t)G.nc[1];
+    uint32_t cx, cy, cz;
+    grid_decode(G.zorder, (uint32_t)G.nc[0], (uint32_t)G.nc[1], key, cx, cy, cz);
     float4 a;
     a.x = (float)(x[g] - (G.xmin[0] + (double)cx * G.cell[0]));
     a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell[1]));

@@ -12,6 +12,7 @@ struct PairArgs {
     double *rho;  // SummationDensity destination (fp64 state)
     long long n;
     int ncx, ncy, ncz;
+    int zorder;                 // rows along the Z-curve of (cy, cz), see grid_row
     float cellx, celly, cellz;  // internal cell edges
     float k2;                   // radius_scale^2
     float kfac;      // kernel.fac for this dim
@@ -140,16 +141,15 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
         const uint32_t key = a.skey[s];
         if (key != cur_key) {
             cur_key = key;
-            uint32_t kq = key;
-            cx = (int)(kq % (uint32_t)a.ncx);
-            kq /= (uint32_t)a.ncx;
-            const int cy = (int)(kq % (uint32_t)a.ncy);
-            const int cz = (int)(kq / (uint32_t)a.ncy);
+            uint32_t ucx, ucy, ucz;
+            grid_decode(a.zorder, (uint32_t)a.ncx, (uint32_t)a.ncy, key, ucx, ucy, ucz);
+            cx = (int)ucx;
+            const int cy = (int)ucy, cz = (int)ucz;
             r_rs = r_b1 = r_b2 = r_re = 0;
             if (lane < 9) {
                 const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
                 if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+                    const uint32_t base = grid_row(a.zorder, (uint32_t)a.ncy, (uint32_t)yy, (uint32_t)zz) * (uint32_t)a.ncx;
                     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
                     r_rs = a.cell_start[base + x0];
                     r_b1 = a.cell_start[base + cx];

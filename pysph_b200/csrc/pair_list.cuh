@@ -36,6 +36,7 @@ struct ListBuildArgs {
     const uint32_t *cell_start, *skey;
     long long n;
     int ncx, ncy, ncz;
+    int zorder;                     // rows along the Z-curve of (cy, cz), see grid_row
     int px, py, pz;                 // periodic axes (cell indices wrap, images shift by nc * cell)
     float cellx, celly, cellz;      // internal cell edges (>= k hmax + S)
     float kr, S;     // radius scale, absolute skin
@@ -71,17 +72,16 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
         const uint32_t key = a.skey[s];
         if (key != cur_key) {
             cur_key = key;
-            uint32_t kq = key;
-            cx = (int)(kq % (uint32_t)a.ncx);
-            kq /= (uint32_t)a.ncx;
-            const int cy = (int)(kq % (uint32_t)a.ncy);
-            const int cz = (int)(kq / (uint32_t)a.ncy);
+            uint32_t ucx, ucy, ucz;
+            grid_decode(a.zorder, (uint32_t)a.ncx, (uint32_t)a.ncy, key, ucx, ucy, ucz);
+            cx = (int)ucx;
+            const int cy = (int)ucy, cz = (int)ucz;
             r_rs = r_b1 = r_b2 = r_re = 0;
             if (!PERIODIC) {
                 if (lane < 9) {
                     const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
                     if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                        const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+                        const uint32_t base = grid_row(a.zorder, (uint32_t)a.ncy, (uint32_t)yy, (uint32_t)zz) * (uint32_t)a.ncx;
                         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
                         r_rs = a.cell_start[base + x0];
                         r_b1 = a.cell_start[base + cx];
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildA
                 if (a.py) yy = (yy + a.ncy) % a.ncy;
                 if (a.pz) zz = (zz + a.ncz) % a.ncz;
                 if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                    const uint32_t base = ((uint32_t)yy + (uint32_t)a.ncy * (uint32_t)zz) * (uint32_t)a.ncx;
+                    const uint32_t base = grid_row(a.zorder, (uint32_t)a.ncy, (uint32_t)yy, (uint32_t)zz) * (uint32_t)a.ncx;
                     if (kind == 0) {
                         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
                         r_rs = a.cell_start[base + x0];

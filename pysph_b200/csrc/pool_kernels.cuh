@@ -255,11 +255,9 @@ __global__ void __launch_bounds__(256, 5) k_stage_pack(const StageArgs a, const 
             }
             // ---- records of the next evaluation ---------------------------------------
             const uint32_t s = q.rank[g];
-            uint32_t key = q.key_of[g];
-            const uint32_t cx = key % (uint32_t)q.G.nc[0];
-            key /= (uint32_t)q.G.nc[0];
-            const uint32_t cy = key % (uint32_t)q.G.nc[1];
-            const uint32_t cz = key / (uint32_t)q.G.nc[1];
+            const uint32_t key = q.key_of[g];
+            uint32_t cx, cy, cz;
+            grid_decode(q.G.zorder, (uint32_t)q.G.nc[0], (uint32_t)q.G.nc[1], key, cx, cy, cz);
             float4 A, B, C;
             A.x = (float)(xn - (q.G.xmin[0] + (double)cx * q.G.cell[0]));
             A.y = (float)(yn - (q.G.xmin[1] + (double)cy * q.G.cell[1]));

@@ -437,10 +437,8 @@ __global__ void k_pack_pos_light(const double *__restrict__ x, const double *__r
     if (s < n) {
         const uint32_t g = perm[s];
         uint32_t key = skey[s];
-        const uint32_t cx = key % (uint32_t)G.nc[0];
-        key /= (uint32_t)G.nc[0];
-        const uint32_t cy = key % (uint32_t)G.nc[1];
-        const uint32_t cz = key / (uint32_t)G.nc[1];
+        uint32_t cx, cy, cz;
+        grid_decode(G.zorder, (uint32_t)G.nc[0], (uint32_t)G.nc[1], key, cx, cy, cz);
         float4 a;
         a.x = (float)(x[g] - (G.xmin[0] + (double)cx * G.cell[0]));
         a.y = (float)(y[g] - (G.xmin[1] + (double)cy * G.cell[1]));
@@ -476,9 +474,9 @@ __global__ void k_neighbors(const float4 *__restrict__ A /* {A,B} interleaved: A
     const int ncx = G.nc[0], ncy = G.nc[1], ncz = G.nc[2];
     const float4 Ai = A[2 * (size_t)s];
     uint32_t kq = skey[s];
-    const int cx = (int)(kq % (uint32_t)ncx);
-    kq /= (uint32_t)ncx;
-    const int cy = (int)(kq % (uint32_t)ncy), cz = (int)(kq / (uint32_t)ncy);
+    uint32_t ucx, ucy, ucz;
+    grid_decode(G.zorder, (uint32_t)ncx, (uint32_t)ncy, kq, ucx, ucy, ucz);
+    const int cx = (int)ucx, cy = (int)ucy, cz = (int)ucz;
     const float hi2 = k2 * Ai.w * Ai.w;
     unsigned long long n = 0;
     for (int r = 0; r < 27; r++) {
@@ -488,7 +486,7 @@ __global__ void k_neighbors(const float4 *__restrict__ A /* {A,B} interleaved: A
         if (G.periodic[1]) yy = (yy + ncy) % ncy;
         if (G.periodic[2]) zz = (zz + ncz) % ncz;
         if (xx < 0 || xx >= ncx || yy < 0 || yy >= ncy || zz < 0 || zz >= ncz) continue;
-        const uint32_t c = (uint32_t)xx + (uint32_t)ncx * ((uint32_t)yy + (uint32_t)ncy * (uint32_t)zz);
+        const uint32_t c = (uint32_t)xx + (uint32_t)ncx * grid_row(G.zorder, (uint32_t)ncy, (uint32_t)yy, (uint32_t)zz);
         const uint32_t rs = cell_start[c], re = cell_start[c + 1];
         for (uint32_t t0 = rs; t0 < re; t0 += 32) {
             const uint32_t t = t0 + lane;

@@ -249,6 +249,14 @@ class DeviceHaloOps(object):
         self.ctx.call('b200sph_peer_recv', side, (C.c_int64 * n)(*ghost_first),
                       (C.c_int64 * n)(*counts), local_ptr)
 
+    def peer_commit_dt(self, prev, new, adaptive, advance, slot):
+        self.ctx.call('b200sph_peer_commit_dt', float(prev), float(new), int(adaptive),
+                      int(advance), int(slot))
+
+    def dt_commit(self, prev, new, adaptive, advance, slot):
+        self.ctx.call('b200sph_dt_commit', float(prev), float(new), 1, int(adaptive),
+                      int(advance), int(slot))
+
     def peer_end(self):
         self.ctx.call('b200sph_peer_end')
 
@@ -347,6 +355,7 @@ class SlabParallelManager(object):
         self.use_peer_sync = self.use_peer and hasattr(ops, 'peer_begin') and \
             bool(int(__import__('os').environ.get('B200SPH_PEER_SYNC', '1')))
         self._peer_sync = False
+        self._dt_pending = None       # (prev, new, adaptive, advance, slot): agreement + commit deferred
         self.n_peer_refresh = 0
         self.n_deferred_failed = 0
         self._pending = None
@@ -469,6 +478,7 @@ class SlabParallelManager(object):
             self._update_peer_sync(deferred)
             self._cpu('update', t_begin)
             return
+        self.flush_dt()
         if self._recv and hasattr(ops, 'drift'):
             if getattr(self, '_t1', None) is None:
                 self._t1 = ops.new_buffer(1)
@@ -532,7 +542,8 @@ class SlabParallelManager(object):
         self._ev()
         have = ops.peer_begin()
         self._parity ^= 1
-        ops.peer_publish(have)
+        dt_args, self._dt_pending = self._dt_pending, None
+        ops.peer_publish(have, with_dt=dt_args is not None)
         for nb in self._peer['nbs']:
             slot = 0 if nb == self.left else 1
             # the receiver reads the flag of the side the message comes FROM; without a
@@ -541,7 +552,9 @@ class SlabParallelManager(object):
             ops.peer_send(slot if have else -1, nb, side,
                           self._peer['remote'][nb][self._parity], self._peer['cap'])
         self._ev('drift+send')
-        ops.peer_reduce()
+        ops.peer_reduce(with_dt=dt_args is not None)
+        if dt_args is not None:
+            ops.peer_commit_dt(*dt_args)      # the step's new dt: MIN over ranks, damped, t += dt
         self._ev('all_reduce')
         if have:
             first = [0] * self.narr
@@ -583,6 +596,7 @@ class SlabParallelManager(object):
 
     def _full_update(self):
         ops = self.ops
+        self.flush_dt()
         for a in range(self.narr):
             ops.drop_ghosts(a)                       # parallel_manager.pyx:519
         if self.lb_freq > 0 and self.lb_count >= self.lb_freq and self.migrate \
@@ -826,6 +840,24 @@ class SlabParallelManager(object):
             for a, n in enumerate(recv_counts[nb]):
                 ops.append(a, recv_bufs.get(nb), o, n, self._hnf, False)
                 o += n * self._hnf
+
+    def defer_dt(self, prev, new, adaptive, advance, slot):
+        """The time-step agreement (MIN over ranks of the proposal in block[2]) and its
+        commit ride on the refresh of the next evaluation instead of being a collective of
+        their own -- the new dt is first needed by that step's stage1.  False: not on the
+        peer protocol, the caller does it now."""
+        if not self._peer_sync:
+            return False
+        self.flush_dt()
+        self._dt_pending = (prev, new, adaptive, advance, slot)
+        return True
+
+    def flush_dt(self):
+        """Run a deferred agreement + commit now (a full update, or somebody reads t / dt)."""
+        args, self._dt_pending = self._dt_pending, None
+        if args is not None:
+            self.ops.peer_allreduce_dt()
+            self.ops.dt_commit(*args)
 
     def reduce_dt_device(self, view):
         """MIN over ranks of a 1-element device tensor, in place, no host sync

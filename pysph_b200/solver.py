@@ -267,10 +267,15 @@ class B200Solver(object):
         else:
             if self.adaptive_timestep:
                 ctx.call('b200sph_dt_propose', float(self.cfl), int(bool(self.fixed_h)))
-                self.pm.reduce_dt_device(self._tc[2:3])
-            ctx.call('b200sph_dt_commit', float(prev), float(new), 1,
-                     int(bool(self.adaptive_timestep)), int(bool(advance)),
-                     self._commits % 2)
+            cargs = (float(prev), float(new), int(bool(self.adaptive_timestep)),
+                     int(bool(advance)), self._commits % 2)
+            # on the peer protocol the MIN over ranks and the commit ride on the next
+            # evaluation's refresh (SlabParallelManager.defer_dt)
+            defer = getattr(self.pm, 'defer_dt', None)
+            if not (self.adaptive_timestep and defer is not None and defer(*cargs)):
+                if self.adaptive_timestep:
+                    self.pm.reduce_dt_device(self._tc[2:3])
+                ctx.call('b200sph_dt_commit', cargs[0], cargs[1], 1, cargs[2], cargs[3], cargs[4])
         self._commits += 1
         self._damping_factor = new
 
@@ -278,6 +283,8 @@ class B200Solver(object):
         """(dt, t) written by the latest commit (back=0, waits for the current
         step) or the one before it (back=1, normally complete already)."""
         import ctypes as C
+        if self.pm is not None and getattr(self.pm, '_dt_pending', None) is not None:
+            self.pm.flush_dt()          # a deferred time-step agreement: the host asks for t / dt now
         out = (C.c_double * 2)()
         self.backend.ctx.call('b200sph_time_snapshot',
                               (self._commits - 1 - back) % 2, out)

@@ -291,7 +291,14 @@ int emul_pipeline(const emul_common *c, const double *gxmin, const double *gcell
     const long long n = c->n;
     GridDev G;
     for (int d = 0; d < 3; d++) { G.xmin[d] = gxmin[d]; G.cell[d] = gcell[d]; G.nc[d] = gnc[d]; G.periodic[d] = gper[d]; }
-    const long long ncells = (long long)G.nc[0] * G.nc[1] * G.nc[2];
+    // B200SPH_ZORDER=1: the cell rows along the Z-curve of (cy, cz), row table padded as in b200sph.cu
+    G.zorder = getenv("B200SPH_ZORDER") ? atoi(getenv("B200SPH_ZORDER")) != 0 : 0;
+    long long ncells = (long long)G.nc[0] * G.nc[1] * G.nc[2];
+    if (G.zorder) {
+        int bits = 0;
+        while ((1 << bits) < std::max(G.nc[1], G.nc[2])) bits++;
+        ncells = ((long long)1 << (2 * bits)) * G.nc[0];
+    }
     std::vector<uint32_t> key_of((size_t)n), off_in((size_t)n), cell_cnt((size_t)ncells + 1, 0u), cell_start((size_t)ncells + 2, 0u);
     std::vector<uint32_t> perm_tmp((size_t)n), perm((size_t)n), skey((size_t)n), rank((size_t)n);
     launch1(n, 256, [&] { k_cell_count(c->x, c->y, c->z, c->ptype, n, G, key_of.data(), off_in.data(), cell_cnt.data()); });
@@ -307,6 +314,7 @@ int emul_pipeline(const emul_common *c, const double *gxmin, const double *gcell
     la.A = A.data(); la.cell_start = cell_start.data(); la.skey = skey.data();
     la.n = n;
     la.ncx = G.nc[0]; la.ncy = G.nc[1]; la.ncz = G.nc[2];
+    la.zorder = G.zorder;
     la.px = G.periodic[0]; la.py = G.periodic[1]; la.pz = G.periodic[2];
     la.cellx = (float)G.cell[0]; la.celly = (float)G.cell[1]; la.cellz = (float)G.cell[2];
     la.kr = (float)c->radius_scale;

@@ -619,3 +619,35 @@ def test_fused_stage_kernel_is_bitwise_the_separate_kernels(gpu_device, monkeypa
     for pa, pb_ in zip(a[3], b[3]):
         for k, v in pa.items():
             assert np.array_equal(v, pb_[k]), k
+
+
+def test_zorder_rows_give_the_same_neighbours_and_fields(gpu_device, monkeypatch):
+    """B200SPH_ZORDER=1 orders the cell rows along the Z-curve of (cy, cz) (north_star's
+    "Z-curve cell list"; z_order_nnps.pyx:252-355 sorts by the 3-D Morton key): only the
+    order in which neighbours are visited changes -- identical pair counts, neighbour sets
+    and (to fp32 summation order) fields, through list rebuilds."""
+    import pysph_b200 as pb
+    out = {}
+    for z in ('0', '1'):
+        monkeypatch.setenv('B200SPH_ZORDER', z)
+        pas, params = _perturbed_dam_break(vscale=3.0)
+        s = make_solver(pas, scheme_params(params), 'CubicSpline')
+        s.a_eval.count_pairs = True
+        s.initialise()
+        pairs = s.a_eval.last_pairs
+        nn = s.nnps
+        nb = [np.sort(nn.get_nearest_particles(0, d, i)) for d in range(3)
+              for i in (0, pas[d].get_number_of_particles() // 2, pas[d].get_number_of_particles() - 1)]
+        s.a_eval.count_pairs = False
+        for _ in range(22):
+            s.step()
+        st = s.backend.stats()
+        s.pull()
+        out[z] = (pairs, nb, st['full_builds'],
+                  dict((k, pas[0].properties[k].copy()) for k in ACC_FIELDS + ['x', 'u', 'rho']))
+    assert out['0'][0] == out['1'][0] and out['0'][2] == out['1'][2] >= 2
+    for a, b in zip(out['0'][1], out['1'][1]):
+        assert np.array_equal(a, b)
+    for k, v in out['0'][3].items():
+        w = out['1'][3][k]
+        assert np.max(np.abs(v - w)) <= 5e-6 * max(np.max(np.abs(v)), 1e-30), k

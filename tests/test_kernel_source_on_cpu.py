@@ -340,9 +340,13 @@ def _run_pipeline(emul, pas, names, kernel_name, dim, p, eqs, eos, real_only, do
     return out, pairs.value, capg.value, nc
 
 
-def test_whole_pipeline_dam_break_on_cpu(emul):
+@pytest.mark.parametrize('zorder', ['0', '1'])
+def test_whole_pipeline_dam_break_on_cpu(emul, monkeypatch, zorder):
+    """zorder = 1: the cell rows along the Z-curve of (cy, cz) (grid_row / grid_decode) --
+    same neighbours, same fields"""
     from helpers import ACC_FIELDS, copy_arrays
     from oracle import oracle as orc
+    monkeypatch.setenv('B200SPH_ZORDER', zorder)
     dx = 0.09
     pas = geo.dam_break_3d_particles(dx=dx)
     params = geo.dam_break_3d_params(dx)
@@ -370,13 +374,15 @@ def test_whole_pipeline_dam_break_on_cpu(emul):
         off += n
 
 
-@pytest.mark.parametrize('pattern', [(1, 1, 1), (1, 0, 1), (0, 1, 0)])
-def test_whole_pipeline_periodic_on_cpu(emul, pattern):
+@pytest.mark.parametrize('pattern,zorder', [((1, 1, 1), '0'), ((1, 0, 1), '0'), ((0, 1, 0), '0'),
+                                            ((1, 1, 1), '1'), ((0, 1, 0), '1')])
+def test_whole_pipeline_periodic_on_cpu(emul, monkeypatch, pattern, zorder):
     """the wrapped rows / wrapped x cells of k_list_build<true> and the cell-offset codes,
     against the oracle that materialises the periodic ghosts"""
     from helpers import ACC_FIELDS
     from oracle import oracle as orc
     import test_gpu_periodic as T
+    monkeypatch.setenv('B200SPH_ZORDER', zorder)
     pa, params = T._periodic_case(3, 9)
     ref, _ = T._periodic_case(3, 9)
     dom = ([0.0, 0.0, 0.0], [1.0, 1.0, 1.0], list(pattern))

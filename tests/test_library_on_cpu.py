@@ -104,6 +104,7 @@ FAST = [
     ('test_gpu_parity', 'test_dam_break_2d_gate', {}),
     ('test_gpu_parity', 'test_determinism', {}),
     ('test_gpu_parity', 'test_deferred_drift_check_protocol', {}),
+    ('test_gpu_parity', 'test_zorder_rows_give_the_same_neighbours_and_fields', {'monkeypatch': None}),
     ('test_gpu_parity', 'test_fused_stage_kernel_is_bitwise_the_separate_kernels', {'monkeypatch': None, 'device_dt': True, 'dx': 0.08}),
     ('test_gpu_parity', 'test_fused_stage_kernel_is_bitwise_the_separate_kernels', {'monkeypatch': None, 'device_dt': False, 'dx': 0.08}),
     ('test_gpu_periodic', 'test_periodic_wcsph_steps_vs_oracle', {'dim': 3, 'n': 10, 'pattern': (1, 1, 1)}),
