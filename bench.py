@@ -951,6 +951,7 @@ def run_dam_break(args, rank, local_rank, world):
             'full_builds': int(std['full_builds']), 'list_builds': int(std['list_builds']),
             'light_updates': int(std['light_updates']),
             'deferred_failed': int(std['deferred_failed']),
+            'proactive_builds': int(std.get('proactive_builds', 0) or 0),
             'ms_nnps_per_step': std['ms_nnps'] / Kd,
             'ms_per_rebuild': (std['ms_nnps'] / max(int(std['full_builds']), 1))
             if std['full_builds'] else None,
@@ -960,6 +961,7 @@ def run_dam_break(args, rank, local_rank, world):
         if pm is not None:
             developed['halo_full_updates'] = pm.n_full - pm_full0
             developed['halo_deferred_failed'] = pm.n_deferred_failed - pm_fail0
+            developed['halo_proactive'] = pm.n_proactive
 
     # ---- roofline of the dominant kernel (k_pair_list), from the timed region -----
     peak, peak_src = peaks()

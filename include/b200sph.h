@@ -174,6 +174,8 @@ typedef struct {
     int64_t deferred_failed; /* deferred drift checks that forced a repeat      */
     int64_t fused_stages;  /* stage calls served by the fused stage + pack kernel      */
     int64_t overlapped;    /* pair passes that ran their ghost-free CTAs under the halo  */
+    int64_t proactive_builds; /* list rebuilds done one evaluation early: the extrapolated drift
+                              said the deferred check of that evaluation would fail        */
     int64_t chunks_interior, chunks_boundary; /* CTAs of the list consumers without / with a
                               ghost among their destinations or neighbours (current build;
                               0 / 0 without ghosts)                                          */

@@ -94,7 +94,8 @@ class Stats(C.Structure):
                 ('list_builds', C.c_int64),
                 ('list_entries_per_particle', C.c_int64),
                 ('deferred_failed', C.c_int64), ('fused_stages', C.c_int64),
-                ('overlapped', C.c_int64), ('chunks_interior', C.c_int64),
+                ('overlapped', C.c_int64), ('proactive_builds', C.c_int64),
+                ('chunks_interior', C.c_int64),
                 ('chunks_boundary', C.c_int64)]
 
 

@@ -227,6 +227,12 @@ struct b200sph_ctx {
     unsigned *drift_host = nullptr;
     cudaEvent_t drift_evt = nullptr;
     int64_t n_deferred_failed = 0;
+    // proactive rebuild: the used-up fraction of the skin at the last two confirmed deferred
+    // checks of the current build; when their extrapolation says the NEXT evaluation would
+    // fail its check, the lists are rebuilt before it instead of after a wasted evaluation
+    double drift_hist[2] = {-1.0, -1.0};
+    bool proactive = true;      // env B200SPH_PROACTIVE=0
+    int64_t n_proactive = 0;
     // device-resident time control block: [0] dt, [1] t, [2] proposed dt, [3] h_minimum
     double *tc = nullptr;
     bool tc_owned = false;
@@ -701,6 +707,7 @@ int b200sph_create(int device, b200sph_ctx **out)
     if (const char *e = getenv("B200SPH_FUSE")) ctx->fuse = atoi(e) != 0;
     if (const char *e = getenv("B200SPH_PAIR_SPEC")) ctx->pair_spec = atoi(e) != 0;
     if (const char *e = getenv("B200SPH_ZORDER")) ctx->zorder = atoi(e) != 0;
+    if (const char *e = getenv("B200SPH_PROACTIVE")) ctx->proactive = atoi(e) != 0;
     if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = ctx->skin_max = std::max(0.0, atof(e));
     if (const char *e = getenv("B200SPH_SKIN_ADAPT")) ctx->skin_adapt = atoi(e) != 0;
     ctx->skin_min = std::min(ctx->skin_min, ctx->skin_max);
@@ -1240,6 +1247,13 @@ static int confirm_pending(b200sph_ctx *ctx, int *redo)
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventSynchronize(ctx->drift_evt));
     ctx->check_pending = false;
+    {
+        float d2, dh;
+        memcpy(&d2, &ctx->drift_host[0], 4);
+        memcpy(&dh, &ctx->drift_host[1], 4);
+        ctx->drift_hist[0] = ctx->drift_hist[1];
+        ctx->drift_hist[1] = ctx->S_abs > 0.0 ? (2.0 * std::sqrt((double)d2) + ctx->radius_scale * (double)dh) / ctx->S_abs : 2.0;
+    }
     if (!drift_within_skin(ctx, ctx->drift_host)) {
         // the evaluation that followed used stale lists: force the full rebuild
         ctx->topo_dirty = true;
@@ -1292,7 +1306,16 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     int64_t ntot0 = 0;
     for (int a = 0; a < ctx->narr; a++) ntot0 += ctx->arr[a].n;
     const bool use_lists = ctx->force_kernel == 0 && ntot0 < (1LL << LIST_JBITS);
-    if (use_lists && ctx->lists_valid && !ctx->topo_dirty &&
+    // deferred check + a build whose drift, extrapolated by its last increment, would exceed
+    // the skin at THIS evaluation: rebuild now rather than after an evaluation on stale lists
+    bool expiring = false;
+    if (ctx->proactive && ctx->defer_check && !ctx->drift_ok && ctx->drift_hist[1] >= 0.0) {
+        const double r1 = ctx->drift_hist[1], r0 = ctx->drift_hist[0];
+        const double step = r0 >= 0.0 ? std::max(r1 - r0, 0.0) : r1;
+        expiring = r1 + step > 0.98;
+        if (expiring && use_lists && ctx->lists_valid && !ctx->topo_dirty) ctx->n_proactive++;
+    }
+    if (use_lists && ctx->lists_valid && !ctx->topo_dirty && !expiring &&
         !(ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min && !ctx->drift_ok)) {
         // mirror images: the same ghosts, current values (the set is re-selected with the lists)
         if (mirror_any(ctx) && ctx->mirror_built && (rc = mirror_refresh(ctx))) return rc;
@@ -1316,6 +1339,7 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     ctx->evals_since_build = 0;
     ctx->lists_valid = false;
     ctx->drift_ok = false;
+    ctx->drift_hist[0] = ctx->drift_hist[1] = -1.0;
     ctx->n_full_builds++;
     if (mirror_any(ctx)) {
         // _create_ghosts_mirror (nnps_base.pyx:506-689) -- here once per list build, not per update
@@ -3147,6 +3171,7 @@ int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out)
     ctx->stats.deferred_failed = ctx->n_deferred_failed;
     ctx->stats.fused_stages = ctx->n_fused;
     ctx->stats.overlapped = ctx->n_overlapped;
+    ctx->stats.proactive_builds = ctx->n_proactive;
     ctx->stats.chunks_interior = ctx->chunks_valid ? ctx->n_chunk_interior : 0;
     ctx->stats.chunks_boundary = ctx->chunks_valid ? ctx->n_chunk_boundary : 0;
     *out = ctx->stats;
@@ -3157,7 +3182,7 @@ int b200sph_reset_stats(b200sph_ctx *ctx)
     b200sph_stats tmp;
     b200sph_get_stats(ctx, &tmp);  // drain pending events
     memset(&ctx->stats, 0, sizeof(ctx->stats));
-    ctx->n_full_builds = ctx->n_light_updates = ctx->n_list_builds = ctx->n_deferred_failed = ctx->n_fused = ctx->n_overlapped = 0;
+    ctx->n_full_builds = ctx->n_light_updates = ctx->n_list_builds = ctx->n_deferred_failed = ctx->n_fused = ctx->n_overlapped = ctx->n_proactive = 0;
     return 0;
 }
 int b200sph_set_async_copies(b200sph_ctx *ctx, int on)

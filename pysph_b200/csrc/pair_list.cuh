@@ -198,13 +198,21 @@ __device__ __forceinline__ void ld_rec(const PairArgs &a, const uint32_t e, floa
 // is false for the lanes whose list is shorter than the warp's longest (their entry reads
 // as 0 and their record as record 0, so everything up to the test is harmless to execute).
 template <int K, int DIM, int EQS>
-__device__ __forceinline__ void pair_entry(const PairArgs &a, const smem_tab_t sT, const bool live, const uint32_t e,
+__device__ __forceinline__ void pair_entry(const PairArgs &a, const bool live, const uint32_t e,
                                            const float4 Aj, const float4 Bj, const float4 Cj, const float4 Ai,
                                            const float4 Bi, const float4 Ci, const float hi2,
                                            const unsigned long long mask_i, Acc &acc, unsigned &npairs)
 {
-    const float4 T = lds_T(sT, LIST_CODE(e));
-    const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+    // cell offset of the neighbour's cell relative to the destination's, decoded arithmetically:
+    // (code field | 0x4B000000) as a float is 2^23 + field, exactly, so field - 1 costs one
+    // LOP3 and one FADD per axis.  (A shared-memory table of the 64 offset vectors was the
+    // alternative: its divergent 128-bit reads were 16 % of the LSU data-pipe wavefronts,
+    // the pipe that bounds this kernel -- profiles/r02a_ncu_summary.md.)
+    const float dxc = __uint_as_float((e & 3u) | 0x4B000000u) - 8388609.0f;
+    const float dyc = __uint_as_float(((e >> 2) & 3u) | 0x4B000000u) - 8388609.0f;
+    const float dzc = __uint_as_float(((e >> 4) & 3u) | 0x4B000000u) - 8388609.0f;
+    const float xij = fmaf(-dxc, a.cellx, Ai.x - Aj.x), yij = fmaf(-dyc, a.celly, Ai.y - Aj.y),
+                zij = fmaf(-dzc, a.cellz, Ai.z - Aj.z);
     const float r2 = xij * xij + yij * yij + zij * zij;
     // the exact accept test, linked_list_nnps.pyx:188
     if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)))
@@ -216,14 +224,7 @@ __global__ void __launch_bounds__(LIST_NT, MINB) k_pair_list(const PairArgs a, c
                                                             const uint32_t *__restrict__ lst, const int capg,
                                                             const uint32_t *__restrict__ chunk_ids)
 {
-    __shared__ float4 s_T[64];
     const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
-    }
-    __syncthreads();
-    const smem_tab_t sT = smem_tab(s_T);
     const unsigned FULL = 0xffffffffu;
     // chunk_ids: this launch covers a subset of the CTA-sized chunks (the interior /
     // boundary split of the slab decomposition, k_chunk_classify)
@@ -261,11 +262,11 @@ __global__ void __launch_bounds__(LIST_NT, MINB) k_pair_list(const PairArgs a, c
         // entry k (registers 0) while record k + 1 (registers 1) and entry k + 2 are in flight
         const uint32_t e2 = rem > 2 ? __ldcs(nxt) : 0u;
         ld_rec(a, e1, A1r, B1r, C1r);
-        pair_entry<K, DIM, EQS>(a, sT, rem > 0, e0, A0r, B0r, C0r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
+        pair_entry<K, DIM, EQS>(a, rem > 0, e0, A0r, B0r, C0r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
         // entry k + 1 (registers 1) while record k + 2 (registers 0) and entry k + 3 are in flight
         const uint32_t e3 = rem > 3 ? __ldcs(nxt + 32) : 0u;
         ld_rec(a, e2, A0r, B0r, C0r);
-        pair_entry<K, DIM, EQS>(a, sT, rem > 1, e1, A1r, B1r, C1r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
+        pair_entry<K, DIM, EQS>(a, rem > 1, e1, A1r, B1r, C1r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
         e0 = e2;
         e1 = e3;
     }

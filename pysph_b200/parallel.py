@@ -356,6 +356,11 @@ class SlabParallelManager(object):
             bool(int(__import__('os').environ.get('B200SPH_PEER_SYNC', '1')))
         self._peer_sync = False
         self._dt_pending = None       # (prev, new, adaptive, advance, slot): agreement + commit deferred
+        # proactive full update: the global used-up fraction of the skin at the last two
+        # confirmed refreshes; every rank sees the same numbers, hence takes the same decision
+        self._ratio_hist = [-1.0, -1.0]
+        self.proactive = bool(int(__import__('os').environ.get('B200SPH_PROACTIVE', '1')))
+        self.n_proactive = 0
         self.n_peer_refresh = 0
         self.n_deferred_failed = 0
         self._pending = None
@@ -475,6 +480,15 @@ class SlabParallelManager(object):
         if self._prof is not None:
             self._prof['n'] += 1
         if self._recv and self._peer is not None and self._peer_sync:
+            r0, r1 = self._ratio_hist
+            if deferred and self.proactive and r1 >= 0.0 and \
+                    r1 + (max(r1 - r0, 0.0) if r0 >= 0.0 else r1) > 0.9:
+                # the extrapolated drift says this refresh would be rejected: exchange and
+                # rebuild now instead of after an evaluation on expired lists
+                self.n_proactive += 1
+                self._full_update()
+                self._cpu('update_full', t_begin)
+                return
             self._update_peer_sync(deferred)
             self._cpu('update', t_begin)
             return
@@ -588,6 +602,7 @@ class SlabParallelManager(object):
         v = pending()
         self._cpu('confirm_wait', t0)
         if v <= 0.9:
+            self._ratio_hist = [self._ratio_hist[1], v]
             return False
         self.n_refresh = max(self.n_refresh - 1, 0)
         self.n_deferred_failed += 1
@@ -597,6 +612,7 @@ class SlabParallelManager(object):
     def _full_update(self):
         ops = self.ops
         self.flush_dt()
+        self._ratio_hist = [-1.0, -1.0]
         for a in range(self.narr):
             ops.drop_ghosts(a)                       # parallel_manager.pyx:519
         if self.lb_freq > 0 and self.lb_count >= self.lb_freq and self.migrate \

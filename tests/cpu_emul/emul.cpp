@@ -88,6 +88,7 @@ static inline unsigned atomicMax(unsigned *p, unsigned v)
 static inline uint32_t __ldcs(const uint32_t *p) { return *p; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
 // glibc declares __expf(float) but does not export it: route the CUDA intrinsic to expf
 #define __expf(x) expf(x)
 static inline float frcp(float x) { return 1.0f / x; }

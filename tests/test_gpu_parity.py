@@ -453,8 +453,10 @@ def test_list_reuse_is_exact(gpu_device, monkeypatch):
     st = res['0.1'][1]
     assert st['light_updates'] > 20, st          # lists really were reused ...
     assert st['full_builds'] >= 3, st            # ... and rebuilt when the skin was used up
-    # the integrator defers the drift check: each of those rebuilds was a repeat
-    assert st['deferred_failed'] >= 2, st
+    # the integrator defers the drift check: each of those rebuilds followed a failed
+    # check (evaluation repeated) or, when the extrapolated drift announced the failure, was
+    # done one evaluation early
+    assert st['deferred_failed'] + st['proactive_builds'] >= 2, st
     assert res['0.0'][1]['light_updates'] <= 2   # only updates with no motion at all
     pas_a, pas_b = res['0.1'][0], res['0.0'][0]
     assert abs(res['0.1'][2] - res['0.0'][2]) <= 1e-6 * res['0.0'][2]

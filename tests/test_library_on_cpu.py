@@ -33,8 +33,8 @@ def _build():
     from pysph_b200 import build as lib_build
     cpp = os.path.join(BUILD, 'b200sph_emul.cpp')
     text, modes = transform.transform(lib_build.read_source())
-    assert modes['k_list_build'] == 'emu::WARP' and modes['k_pair_list'] == 'emu::BLOCK' \
-        and modes['k_stage'] == 'emu::SEQ'
+    assert modes['k_list_build'] == 'emu::WARP' and modes['k_pair_list'] == 'emu::WARP' \
+        and modes['k_stage'] == 'emu::SEQ' and modes['k_stage_pack'] == 'emu::BLOCK'
     if not os.path.exists(cpp) or open(cpp).read() != text:
         open(cpp, 'w').write(text)
     so = os.path.join(BUILD, 'libb200sph_emul.so')
@@ -215,7 +215,10 @@ def test_small_dam_break_host_logic(emulated_library):
     for k in a[2]:
         assert np.array_equal(a[2][k], b[2][k]), k
     st = a[3]
-    assert st['light_updates'] > 10 and st['deferred_failed'] >= 1 and st['list_builds'] >= 2, st
+    # the skin was used up on the way: either a deferred check failed (evaluation repeated)
+    # or the extrapolated drift made the library rebuild one evaluation early
+    assert st['light_updates'] > 10 and st['deferred_failed'] + st['proactive_builds'] >= 1 \
+        and st['list_builds'] >= 2, st
 
 
 def test_final_time_small(emulated_library):
