@@ -1538,7 +1538,7 @@ static int build_lists(b200sph_ctx *ctx)
     la.S = (float)ctx->S_abs;
     la.cnt = ctx->cnt;
     la.max_count = ctx->red_u32 + 2;
-    const unsigned nb = (unsigned)cdiv(n, PAIR_WARPS * PAIR_CHUNK);
+    const unsigned nb = (unsigned)cdiv(n, LB_WARPS * 32);
     const int64_t nblk = cdiv(n, 32);
     for (int attempt = 0; attempt < 4; attempt++) {
         const bool count_only = ctx->capg == 0;
@@ -1556,8 +1556,8 @@ static int build_lists(b200sph_ctx *ctx)
         la.lst = count_only ? nullptr : ctx->lst;
         la.capg = ctx->capg;
         CU(cudaMemsetAsync(ctx->red_u32 + 2, 0, sizeof(unsigned), ctx->stream));
-        if (per) k_list_build<true><<<nb, PAIR_WARPS * 32, 0, ctx->stream>>>(la);
-        else k_list_build<false><<<nb, PAIR_WARPS * 32, 0, ctx->stream>>>(la);
+        if (per) k_list_build<true><<<nb, LB_WARPS * 32, 0, ctx->stream>>>(la);
+        else k_list_build<false><<<nb, LB_WARPS * 32, 0, ctx->stream>>>(la);
         LAUNCH_CHECK();
         CU(cudaMemcpyAsync(ctx->red_u32_host + 2, ctx->red_u32 + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));

@@ -46,128 +46,122 @@ struct ListBuildArgs {
     unsigned *max_count;
 };
 
-// PERIODIC = false: 9 candidate rows (3 consecutive cells each, contiguous in the
-// sorted arrays).  PERIODIC = true: the same 9 rows with wrapped y / z indices plus, on a
-// periodic x axis, up to 2 single-cell segments per row for the cells that wrap;
-// because coordinates are relative to the particle's own cell and a periodic axis is
-// tiled exactly (L = nc * cell), the image shift of a wrapped neighbour cell is the
-// same "- d * cell" offset as for an ordinary neighbour cell -- the consumer kernel does
-// not know about periodicity at all, and no ghost particles are materialised
-// (reference: _create_ghosts_periodic, nnps_base.pyx:744-940, copies the particles).
+// One THREAD per destination, one warp per 32 consecutive destinations of the sorted order
+// (normally 1-2 cells of one cell row).  For each of the 9 neighbour rows (dy, dz) the warp
+// stages the candidates of the cells [cx_min - 1, cx_max + 1] -- one contiguous range of
+// the sorted arrays -- tile by tile into shared memory with coalesced loads; every lane
+// then walks the tile (broadcast reads), keeps the candidates of ITS three cells, applies
+// the skin-widened accept test and appends to its own list.  Entries come out in the order
+// "row (dy, dz), then ascending sorted index", which is also the order the pair kernels
+// sum in.  (The first builder of this file put a warp on ONE destination with the lanes
+// across candidates: 1.4 G warp instructions at 1.2 M particles, 91 % issue-bound,
+// profiles/r02a_ncu_summary.md; this one executes about a third of that.)
+// PERIODIC: y / z row indices wrap; on a periodic x axis the cells that wrap (cx = -1 seen
+// from cx = 0, cx = ncx seen from ncx - 1) are staged as extra segments after the 9 rows,
+// first all "left" wraps then all "right" wraps.  Because coordinates are relative to the
+// particle's own cell and a periodic axis is tiled exactly (L = nc * cell), the image shift
+// of a wrapped neighbour cell is the same "- d * cell" offset as for an ordinary neighbour
+// cell -- the consumer kernels do not know about periodicity at all, and no ghost
+// particles are materialised (reference: _create_ghosts_periodic, nnps_base.pyx:744-940).
+#define LB_WARPS 4
+#define LB_TILE 128
 template <bool PERIODIC>
-__global__ void __launch_bounds__(PAIR_WARPS * 32) k_list_build(const ListBuildArgs a)
+__global__ void __launch_bounds__(LB_WARPS * 32) k_list_build(const ListBuildArgs a)
 {
+    __shared__ float4 s_A[LB_WARPS][LB_TILE];
+    __shared__ int s_cx[LB_WARPS][LB_TILE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const long long first = ((long long)blockIdx.x * PAIR_WARPS + warp) * PAIR_CHUNK;
-    uint32_t cur_key = 0xFFFFFFFFu;
-    int cx = 0;
-    uint32_t r_rs = 0, r_b1 = 0, r_b2 = 0, r_re = 0;
-    unsigned wmax = 0;
-    for (int kk = 0; kk < PAIR_CHUNK; kk++) {
-        const long long s = first + kk;
-        if (s >= a.n) break;
-        const float4 Ai = a.A[s];
-        const uint32_t key = a.skey[s];
-        if (key != cur_key) {
-            cur_key = key;
-            uint32_t ucx, ucy, ucz;
-            grid_decode(a.zorder, (uint32_t)a.ncx, (uint32_t)a.ncy, key, ucx, ucy, ucz);
-            cx = (int)ucx;
-            const int cy = (int)ucy, cz = (int)ucz;
-            r_rs = r_b1 = r_b2 = r_re = 0;
-            if (!PERIODIC) {
-                if (lane < 9) {
-                    const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
-                    if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                        const uint32_t base = grid_row(a.zorder, (uint32_t)a.ncy, (uint32_t)yy, (uint32_t)zz) * (uint32_t)a.ncx;
-                        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
-                        r_rs = a.cell_start[base + x0];
-                        r_b1 = a.cell_start[base + cx];
-                        r_b2 = a.cell_start[base + cx + 1];
-                        r_re = a.cell_start[base + x1 + 1];
-                    }
-                }
-            } else if (lane < 27) {
-                // 9 (dy, dz) rows with wrapped y / z (segments 0..8: the x-contiguous part of
-                // the row, clipped to the grid) + for a periodic x axis the wrapped cell that
-                // is missing at cx = 0 (segments 9..17, dxc = -1) / cx = ncx - 1 (18..26, +1)
-                const int q = lane % 9, kind = lane / 9;
-                int yy = cy + (q % 3) - 1, zz = cz + (q / 3) - 1;
+    const long long s = ((long long)blockIdx.x * LB_WARPS + warp) * 32 + lane;
+    const bool valid = s < a.n;
+    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t cxi = 0, cyi = 0, czi = 0, row_i = 0xFFFFFFFFu;
+    if (valid) {
+        Ai = a.A[s];
+        grid_decode(a.zorder, (uint32_t)a.ncx, (uint32_t)a.ncy, a.skey[s], cxi, cyi, czi);
+        row_i = cyi + (uint32_t)a.ncy * czi;
+    }
+    const float hi = a.kr * Ai.w + a.S;
+    const float hi2 = hi * hi;
+    uint32_t *out = (a.lst && valid) ? a.lst + ((size_t)(s >> 5) * (size_t)a.capg) * 32u + (uint32_t)(s & 31) : nullptr;
+    unsigned count = 0;
+    // the lanes of a warp usually share one cell row; at a row end they are served row by row
+    unsigned todo = __ballot_sync(FULL, valid);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const uint32_t row = __shfl_sync(FULL, row_i, leader);
+        const bool mine = valid && row_i == row;
+        const unsigned group = __ballot_sync(FULL, mine);
+        todo &= ~group;
+        const int cy = (int)__shfl_sync(FULL, cyi, leader), cz = (int)__shfl_sync(FULL, czi, leader);
+        int cxa = mine ? (int)cxi : 0x7fffffff, cxb = mine ? (int)cxi : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cxa = min(cxa, __shfl_xor_sync(FULL, cxa, o));
+            cxb = max(cxb, __shfl_xor_sync(FULL, cxb, o));
+        }
+        // segments: 0..8 the rows (dy, dz); PERIODIC in x: 9..17 the cell ncx - 1 seen as cx = -1,
+        // 18..26 the cell 0 seen as cx = ncx
+        for (int seg = 0; seg < (PERIODIC ? 27 : 9); seg++) {
+            const int q = seg % 9, kind = seg / 9;
+            if (PERIODIC && kind == 1 && !(a.px && cxa == 0)) continue;
+            if (PERIODIC && kind == 2 && !(a.px && cxb == a.ncx - 1)) continue;
+            int yy = cy + (q % 3) - 1, zz = cz + (q / 3) - 1;
+            if (PERIODIC) {
                 if (a.py) yy = (yy + a.ncy) % a.ncy;
                 if (a.pz) zz = (zz + a.ncz) % a.ncz;
-                if (yy >= 0 && yy < a.ncy && zz >= 0 && zz < a.ncz) {
-                    const uint32_t base = grid_row(a.zorder, (uint32_t)a.ncy, (uint32_t)yy, (uint32_t)zz) * (uint32_t)a.ncx;
-                    if (kind == 0) {
-                        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.ncx - 1);
-                        r_rs = a.cell_start[base + x0];
-                        r_b1 = a.cell_start[base + cx];
-                        r_b2 = a.cell_start[base + cx + 1];
-                        r_re = a.cell_start[base + x1 + 1];
-                    } else if (kind == 1 && a.px && cx == 0) {
-                        r_rs = a.cell_start[base + a.ncx - 1];
-                        r_re = a.cell_start[base + a.ncx];
-                    } else if (kind == 2 && a.px && cx == a.ncx - 1) {
-                        r_rs = a.cell_start[base];
-                        r_re = a.cell_start[base + 1];
+            }
+            if (yy < 0 || yy >= a.ncy || zz < 0 || zz >= a.ncz) continue;
+            const uint32_t base = grid_row(a.zorder, (uint32_t)a.ncy, (uint32_t)yy, (uint32_t)zz) * (uint32_t)a.ncx;
+            uint32_t rs, re;
+            int cx_fixed = 0;                       // kind 1 / 2: the apparent cell index of the wrapped cell
+            if (kind == 0) {
+                rs = a.cell_start[base + max(cxa - 1, 0)];
+                re = a.cell_start[base + min(cxb + 1, a.ncx - 1) + 1];
+            } else if (kind == 1) {
+                rs = a.cell_start[base + a.ncx - 1];
+                re = a.cell_start[base + a.ncx];
+                cx_fixed = -1;
+            } else {
+                rs = a.cell_start[base];
+                re = a.cell_start[base + 1];
+                cx_fixed = a.ncx;
+            }
+            if (rs >= re) continue;
+            const float yoff = Ai.y - (float)((q % 3) - 1) * a.celly;
+            const float zoff = Ai.z - (float)((q / 3) - 1) * a.cellz;
+            const uint32_t rcode = (uint32_t)(4 * (q % 3) + 16 * (q / 3));
+            for (uint32_t t0 = rs; t0 < re; t0 += LB_TILE) {
+                const int tn = (int)min((uint32_t)LB_TILE, re - t0);
+                __syncwarp();
+                for (int k = lane; k < tn; k += 32) {
+                    s_A[warp][k] = a.A[t0 + k];
+                    s_cx[warp][k] = kind == 0 ? (int)(a.skey[t0 + k] - base) : cx_fixed;
+                }
+                __syncwarp();
+                if (mine) {
+                    for (int k = 0; k < tn; k++) {
+                        const int dxc1 = s_cx[warp][k] - (int)cxi + 1;     // dxc + 1
+                        if ((unsigned)dxc1 > 2u) continue;                 // not one of this lane's three cells
+                        const float4 Aj = s_A[warp][k];
+                        const float xij = Ai.x - Aj.x - ((float)dxc1 - 1.0f) * a.cellx;
+                        const float yij = yoff - Aj.y;
+                        const float zij = zoff - Aj.z;
+                        const float r2 = xij * xij + yij * yij + zij * zij;
+                        const float hj = a.kr * Aj.w + a.S;
+                        if ((r2 < hi2) || (r2 < hj * hj)) {
+                            if (out && count < (unsigned)a.capg) out[(size_t)count * 32u] = LIST_ENTRY(t0 + (uint32_t)k, rcode + (uint32_t)dxc1);
+                            count++;
+                        }
                     }
                 }
             }
         }
-        float hi = a.kr * Ai.w + a.S;
-        const float hi2 = hi * hi;
-        uint32_t *out = a.lst ? a.lst + ((size_t)(s >> 5) * (size_t)a.capg) * 32u + (uint32_t)(s & 31) : nullptr;
-        unsigned count = 0;
-        for (int r = 0; r < (PERIODIC ? 27 : 9); r++) {
-            const uint32_t rs = __shfl_sync(FULL, r_rs, r);
-            const uint32_t re = __shfl_sync(FULL, r_re, r);
-            if (rs >= re) continue;
-            uint32_t b1 = 0, b2 = 0, rcode;
-            float xoff, yoff, zoff;
-            if (!PERIODIC) {
-                b1 = __shfl_sync(FULL, r_b1, r);
-                b2 = __shfl_sync(FULL, r_b2, r);
-                xoff = Ai.x;
-                yoff = Ai.y - (float)((r % 3) - 1) * a.celly;
-                zoff = Ai.z - (float)((r / 3) - 1) * a.cellz;
-                rcode = (uint32_t)(4 * (r % 3) + 16 * (r / 3));
-            } else {
-                const int q = r % 9;
-                b1 = __shfl_sync(FULL, r_b1, r);
-                b2 = __shfl_sync(FULL, r_b2, r);
-                xoff = Ai.x;
-                yoff = Ai.y - (float)((q % 3) - 1) * a.celly;
-                zoff = Ai.z - (float)((q / 3) - 1) * a.cellz;
-                rcode = (uint32_t)(4 * (q % 3) + 16 * (q / 3));
-            }
-            const int kind = PERIODIC ? r / 9 : 0;
-            for (uint32_t t0 = rs; t0 < re; t0 += 32) {
-                const uint32_t t = t0 + lane;
-                bool ok = false;
-                uint32_t dxc1 = 0;
-                if (t < re) {
-                    const float4 Aj = a.A[t];
-                    // dxc + 1: position inside the row, or the wrapped cell's fixed offset
-                    dxc1 = kind == 0 ? (uint32_t)(t >= b1) + (uint32_t)(t >= b2) : (kind == 1 ? 0u : 2u);
-                    const float xij = xoff - Aj.x - ((float)dxc1 - 1.0f) * a.cellx;
-                    const float yij = yoff - Aj.y;
-                    const float zij = zoff - Aj.z;
-                    const float r2 = xij * xij + yij * yij + zij * zij;
-                    const float hj = a.kr * Aj.w + a.S;
-                    ok = (r2 < hi2) || (r2 < hj * hj);
-                }
-                const unsigned m = __ballot_sync(FULL, ok);
-                if (ok && out) {
-                    const unsigned pos = count + __popc(m & lt_mask);
-                    if (pos < (unsigned)a.capg) out[(size_t)pos * 32u] = LIST_ENTRY(t, rcode + dxc1);
-                }
-                count += __popc(m);
-            }
-        }
-        if (lane == 0) a.cnt[s] = count;
-        wmax = max(wmax, count);
     }
+    if (valid) a.cnt[s] = count;
+    unsigned wmax = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(FULL, wmax, o));
     if (lane == 0 && wmax) atomicMax(a.max_count, wmax);
 }
 
@@ -192,6 +186,18 @@ __device__ __forceinline__ void ld_rec(const PairArgs &a, const uint32_t e, floa
     const uint32_t j = LIST_J(e);
     ld_256(a.AB + 2u * j, A, B);
     C = __ldg(a.C + j);
+}
+
+// the cell offset a list entry carries, as the vector to ADD to (x_i - x_j) of cell-relative
+// coordinates: -(d - 1) * cell per axis, d the 2-bit code field.  (code field | 0x4B000000) as a
+// float is 2^23 + field exactly, so the decode is one LOP3 + one FADD per axis; a shared-memory
+// table of the 64 vectors cost 16 % of the LSU data-pipe wavefronts in k_pair_list.
+__device__ __forceinline__ float4 list_cell_offset(const uint32_t e, const float cellx, const float celly, const float cellz)
+{
+    const float dxc = __uint_as_float((e & 3u) | 0x4B000000u) - 8388609.0f;
+    const float dyc = __uint_as_float(((e >> 2) & 3u) | 0x4B000000u) - 8388609.0f;
+    const float dzc = __uint_as_float(((e >> 4) & 3u) | 0x4B000000u) - 8388609.0f;
+    return make_float4(-dxc * cellx, -dyc * celly, -dzc * cellz, 0.f);
 }
 
 // one list entry: cell-offset lookup, distance, the exact accept test, the equations.  `live`

@@ -92,13 +92,7 @@ template <int K, int DIM>
 __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, const uint32_t *__restrict__ cnt,
                                                            const uint32_t *__restrict__ lst, const int capg)
 {
-    __shared__ float4 s_T[64];
     const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
-    }
-    __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const long long s = (long long)blockIdx.x * LIST_NT + tid;
     bool active = s < a.n, ghost_src = false;
@@ -151,7 +145,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, c
             C_a = a.C3[j];
         }
         if (k < count) {
-            const float4 T = s_T[LIST_CODE(e)];
+            const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
             if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.source_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
@@ -266,13 +260,7 @@ template <int K, int DIM>
 __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass2(const SolidArgs a, const uint32_t *__restrict__ cnt,
                                                            const uint32_t *__restrict__ lst, const int capg)
 {
-    __shared__ float4 s_T[64];
     const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
-    }
-    __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const long long s = (long long)blockIdx.x * LIST_NT + tid;
     bool active = s < a.n;
@@ -316,7 +304,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass2(const SolidArgs a, c
             C_a = a.C3[j]; T1_a = a.T01[j]; T2_a = a.T2R[j]; T3_a = a.R2[j];
         }
         if (k < count) {
-            const float4 T = s_T[LIST_CODE(e)];
+            const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
             const int tj = __float_as_int(Cj.w) & 7;

@@ -51,13 +51,7 @@ template <int K, int DIM>
 __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const uint32_t *__restrict__ cnt,
                                                          const uint32_t *__restrict__ lst, const int capg)
 {
-    __shared__ float4 s_T[64];
     const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
-    }
-    __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const long long s = (long long)blockIdx.x * LIST_NT + tid;
     bool active = s < a.n;
@@ -100,7 +94,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
             P_a = a.PT[j];
         }
         if (k < count) {
-            const float4 T = s_T[LIST_CODE(e)];
+            const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
             if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Pj.y) & 7)) & 1u)) {
@@ -142,13 +136,7 @@ template <int K, int DIM>
 __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const uint32_t *__restrict__ cnt,
                                                          const uint32_t *__restrict__ lst, const int capg)
 {
-    __shared__ float4 s_T[64];
     const int tid = threadIdx.x;
-    if (tid < 64) {
-        const int dxc = (tid & 3) - 1, dy = ((tid >> 2) & 3) - 1, dz = (tid >> 4) - 1;
-        s_T[tid] = make_float4(-(float)dxc * a.cellx, -(float)dy * a.celly, -(float)dz * a.cellz, 0.f);
-    }
-    __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const long long s = (long long)blockIdx.x * LIST_NT + tid;
     bool active = s < a.n;
@@ -199,7 +187,7 @@ __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const
             D_a = a.Dv[j];
         }
         if (k < count) {
-            const float4 T = s_T[LIST_CODE(e)];
+            const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
             if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {

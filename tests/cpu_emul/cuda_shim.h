@@ -99,6 +99,7 @@ static inline unsigned __ballot_sync(unsigned, bool pred)
     return m;
 }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 
 // ---- bit casts, loads, math -----------------------------------------------------------------
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }

@@ -75,6 +75,8 @@ static inline unsigned __ballot_sync(unsigned, bool pred)
     return m;
 }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { if (g_warp) g_warp->barrier(); }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 static std::atomic_flag g_atomic_lock = ATOMIC_FLAG_INIT;
 static inline unsigned atomicMax(unsigned *p, unsigned v)
@@ -323,14 +325,14 @@ int emul_pipeline(const emul_common *c, const double *gxmin, const double *gcell
     la.cnt = cnt.data();
     la.max_count = &max_count;
     const bool per = la.px || la.py || la.pz;
-    const unsigned nbw = (unsigned)((n + PAIR_WARPS * PAIR_CHUNK - 1) / (PAIR_WARPS * PAIR_CHUNK));
+    const unsigned nbw = (unsigned)((n + LB_WARPS * 32 - 1) / (LB_WARPS * 32));
     int capg = 0;
     for (int pass = 0; pass < 2; pass++) {
         la.lst = pass == 0 ? nullptr : lst.data();
         la.capg = capg;
         max_count = 0;
-        if (per) launch_warps(nbw, PAIR_WARPS * 32, [&] { k_list_build<true>(la); });
-        else launch_warps(nbw, PAIR_WARPS * 32, [&] { k_list_build<false>(la); });
+        if (per) launch_warps(nbw, LB_WARPS * 32, [&] { k_list_build<true>(la); });
+        else launch_warps(nbw, LB_WARPS * 32, [&] { k_list_build<false>(la); });
         if (pass == 0) {
             capg = ((int)(max_count * 1.15) + 8 + 7) / 8 * 8;
             lst.assign((size_t)((n + 31) / 32) * (size_t)capg * 32u, 0u);

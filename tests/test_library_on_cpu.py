@@ -33,7 +33,7 @@ def _build():
     from pysph_b200 import build as lib_build
     cpp = os.path.join(BUILD, 'b200sph_emul.cpp')
     text, modes = transform.transform(lib_build.read_source())
-    assert modes['k_list_build'] == 'emu::WARP' and modes['k_pair_list'] == 'emu::WARP' \
+    assert modes['k_list_build'] == 'emu::BLOCK' and modes['k_pair_list'] == 'emu::WARP' \
         and modes['k_stage'] == 'emu::SEQ' and modes['k_stage_pack'] == 'emu::BLOCK'
     if not os.path.exists(cpp) or open(cpp).read() != text:
         open(cpp, 'w').write(text)
