@@ -51,7 +51,11 @@ struct ListBuildArgs {
 // stages the candidates of the cells [cx_min - 1, cx_max + 1] -- one contiguous range of
 // the sorted arrays -- tile by tile into shared memory with coalesced loads; every lane
 // then walks the tile (broadcast reads), keeps the candidates of ITS three cells, applies
-// the skin-widened accept test and appends to its own list.  Entries come out in the order
+// the skin-widened accept test (on x coordinates relative to the segment's first cell, the
+// widened radius squared once per candidate at staging time) and appends to its own list.
+// The list only has to CONTAIN every pair the exact test can accept while the build is valid
+// (there is a 2 % margin on the skin for the fp32 drift measurement); which candidates of the
+// skin shell it holds beyond that is immaterial.  Entries come out in the order
 // "row (dy, dz), then ascending sorted index", which is also the order the pair kernels
 // sum in.  (The first builder of this file put a warp on ONE destination with the lanes
 // across candidates: 1.4 G warp instructions at 1.2 M particles, 91 % issue-bound,
@@ -128,6 +132,11 @@ __global__ void __launch_bounds__(LB_WARPS * 32) k_list_build(const ListBuildArg
                 cx_fixed = a.ncx;
             }
             if (rs >= re) continue;
+            // x relative to the cell cxa - 1 for the lane and for every candidate of the segment:
+            // no per-candidate cell arithmetic in the loop below, and a candidate two or more
+            // cells away in x cannot pass the distance test (the cell edge is the widened cut-off)
+            const int x0c = cxa - 1;
+            const float xoff = Ai.x + (float)((int)cxi - x0c) * a.cellx;
             const float yoff = Ai.y - (float)((q % 3) - 1) * a.celly;
             const float zoff = Ai.z - (float)((q / 3) - 1) * a.cellz;
             const uint32_t rcode = (uint32_t)(4 * (q % 3) + 16 * (q / 3));
@@ -135,23 +144,27 @@ __global__ void __launch_bounds__(LB_WARPS * 32) k_list_build(const ListBuildArg
                 const int tn = (int)min((uint32_t)LB_TILE, re - t0);
                 __syncwarp();
                 for (int k = lane; k < tn; k += 32) {
-                    s_A[warp][k] = a.A[t0 + k];
-                    s_cx[warp][k] = kind == 0 ? (int)(a.skey[t0 + k] - base) : cx_fixed;
+                    float4 Aj = a.A[t0 + k];
+                    const int cxj = kind == 0 ? (int)(a.skey[t0 + k] - base) : cx_fixed;
+                    const float hj = a.kr * Aj.w + a.S;
+                    Aj.x += (float)(cxj - x0c) * a.cellx;
+                    Aj.w = hj * hj;
+                    s_A[warp][k] = Aj;
+                    s_cx[warp][k] = cxj;
                 }
                 __syncwarp();
                 if (mine) {
+#pragma unroll 4
                     for (int k = 0; k < tn; k++) {
-                        const int dxc1 = s_cx[warp][k] - (int)cxi + 1;     // dxc + 1
-                        if ((unsigned)dxc1 > 2u) continue;                 // not one of this lane's three cells
                         const float4 Aj = s_A[warp][k];
-                        const float xij = Ai.x - Aj.x - ((float)dxc1 - 1.0f) * a.cellx;
-                        const float yij = yoff - Aj.y;
-                        const float zij = zoff - Aj.z;
+                        const float xij = xoff - Aj.x, yij = yoff - Aj.y, zij = zoff - Aj.z;
                         const float r2 = xij * xij + yij * yij + zij * zij;
-                        const float hj = a.kr * Aj.w + a.S;
-                        if ((r2 < hi2) || (r2 < hj * hj)) {
-                            if (out && count < (unsigned)a.capg) out[(size_t)count * 32u] = LIST_ENTRY(t0 + (uint32_t)k, rcode + (uint32_t)dxc1);
-                            count++;
+                        if ((r2 < hi2) || (r2 < Aj.w)) {
+                            const int dxc1 = s_cx[warp][k] - (int)cxi + 1;     // dxc + 1
+                            if ((unsigned)dxc1 <= 2u) {
+                                if (out && count < (unsigned)a.capg) out[(size_t)count * 32u] = LIST_ENTRY(t0 + (uint32_t)k, rcode + (uint32_t)dxc1);
+                                count++;
+                            }
                         }
                     }
                 }
