@@ -892,13 +892,19 @@ class SlabParallelManager(object):
 
 # ---------------------------------------------------------------------------
 def make_slab_solver(dx, params, kernel, rank, world, device=0,
-                     solid_weight=0.45, lb_freq=None, **solver_kw):
+                     solid_weight=None, lb_freq=None, **solver_kw):
     """Build this rank's slab of the 3D dam break and a ready solver.
     lb_freq: evaluations between re-cuts of the slabs (None: B200SPH_LB_FREQ, default
     0 = static slabs)."""
     import os
     import pysph_b200 as pb
     from . import geometry as geo
+    if solid_weight is None:
+        # cost of a wall / obstacle particle relative to a fluid particle.  Measured (B200,
+        # round 2): a step costs 6.3e-9 ms per directed pair (~163 per fluid particle and
+        # step, the walls' own pair loops included) + 2.0e-7 ms per particle of any kind,
+        # i.e. 1.22e-6 ms per fluid and 0.2e-6 ms per solid particle
+        solid_weight = float(os.environ.get('B200SPH_SOLID_WEIGHT', '0.2'))
     xs, w = dam_break_column_weights(dx, solid_weight=solid_weight)
     cuts = balanced_cuts(xs, w, world, dx)
     pas = geo.dam_break_3d_particles(dx=dx, xrange=(cuts[rank], cuts[rank + 1]))
