@@ -210,6 +210,7 @@ struct b200sph_ctx {
     double skin_min = 0.02;
     bool skin_adapt = true;     // env B200SPH_SKIN_ADAPT=0 switches the controller off
     int64_t evals_since_build = 0;  // light updates served by the current build
+    double skin_next = -1.0;        // set by retire_build: the skin of the next build (else the geometric rule)
     double S_abs = 0.0;         // absolute skin of the current build
     double cell_int = 1.0;      // internal cell size (cell_size + S)
     GridDev G;                  // frozen device grid of the current build
@@ -1201,6 +1202,31 @@ static bool drift_within_skin(b200sph_ctx *ctx, const unsigned *raw)
     return need <= 0.98 * ctx->S_abs;
 }
 
+// Skin controller, part 2 (part 1 adapts the skin geometrically from the lifetime of the build
+// that has just ended, see nnps_update).  A build is RETIRED -- rebuilt although it is valid --
+//  * when it has lived 3 L* evaluations with more than the minimum skin (a quiet flow must
+//    converge to the minimum skin), or
+//  * early, after SKIN_PROBE evaluations, when the drift measured so far says the skin is far too
+//    generous: with d = drift per evaluation, a skin s lives L(s) = 0.98 s cell / d evaluations,
+//    and L(s) = L*(s) = kappa / s gives s* = sqrt(kappa d / (0.98 cell)).  s* < 0.7 s: rebuild
+//    now with s* (a rebuild costs ~3 evaluations' worth of the list entries it removes per
+//    evaluation; the first build of a run is always made blind, with the maximum skin).
+#define SKIN_PROBE 6
+static bool retire_build(b200sph_ctx *ctx)
+{
+    if (!ctx->skin_adapt || !(ctx->skin > ctx->skin_min)) return false;
+    if (ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin) return true;
+    if (ctx->evals_since_build == SKIN_PROBE && ctx->drift_hist[1] >= 0.0 && ctx->cell_size > 0.0) {
+        const double d = ctx->drift_hist[1] * ctx->S_abs / (double)SKIN_PROBE;
+        const double s_opt = std::min(ctx->skin_max, std::max(ctx->skin_min, std::sqrt(SKIN_KAPPA * d / (0.98 * ctx->cell_size))));
+        if (s_opt < 0.7 * ctx->skin) {
+            ctx->skin_next = s_opt;
+            return true;
+        }
+    }
+    return false;
+}
+
 // light path of nnps_update: same sorted order, same cell frames, fresh positions;
 // returns 1 if the persistent lists are still valid, 0 if a full rebuild is needed
 static int nnps_light_update(b200sph_ctx *ctx)
@@ -1316,7 +1342,7 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         if (expiring && use_lists && ctx->lists_valid && !ctx->topo_dirty) ctx->n_proactive++;
     }
     if (use_lists && ctx->lists_valid && !ctx->topo_dirty && !expiring &&
-        !(ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min && !ctx->drift_ok)) {
+        !(!ctx->drift_ok && retire_build(ctx))) {
         // mirror images: the same ghosts, current values (the set is re-selected with the lists)
         if (mirror_any(ctx) && ctx->mirror_built && (rc = mirror_refresh(ctx))) return rc;
         rc = nnps_light_update(ctx);
@@ -1333,9 +1359,11 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
     // reach 3 L* are retired so that a quiet flow converges to the minimum skin
     if (use_lists && ctx->skin_adapt && ctx->lists_valid && ctx->evals_since_build > 0) {
         const double lstar = SKIN_KAPPA / ctx->skin;
-        if (ctx->evals_since_build >= 1.5 * lstar) ctx->skin = std::max(ctx->skin_min, ctx->skin * 0.75);
+        if (ctx->skin_next > 0.0) ctx->skin = ctx->skin_next;     // measured (retire_build)
+        else if (ctx->evals_since_build >= 1.5 * lstar) ctx->skin = std::max(ctx->skin_min, ctx->skin * 0.75);
         else if (ctx->evals_since_build < lstar / 1.5) ctx->skin = std::min(ctx->skin_max, ctx->skin * 1.33);
     }
+    ctx->skin_next = -1.0;
     ctx->evals_since_build = 0;
     ctx->lists_valid = false;
     ctx->drift_ok = false;
@@ -2620,7 +2648,7 @@ int b200sph_nnps_drift(b200sph_ctx *ctx, double out[2])
     out[0] = -1.0;
     out[1] = ctx->S_abs;
     if (ctx->force_kernel != 0 || !ctx->lists_valid || ctx->topo_dirty) return 0;  // no reusable build
-    if (ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min) return 0;  // retire it
+    if (retire_build(ctx)) return 0;
     if (ctx->n_sorted <= 0) { out[0] = 0.0; return 0; }
     if (!(ctx->packed_valid && ctx->drift_measured)) {
         CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
@@ -2744,7 +2772,7 @@ int b200sph_nnps_drift_device(b200sph_ctx *ctx, double *dev_ratio)
     int rc = ensure_pool(ctx);
     if (rc) return rc;
     if (ctx->force_kernel != 0 || !ctx->lists_valid || ctx->topo_dirty) return 1;  // no reusable build
-    if (ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min) return 1;  // retire it
+    if (retire_build(ctx)) return 1;
     if (ctx->n_sorted <= 0) {
         CU(cudaMemsetAsync(dev_ratio, 0, sizeof(double), ctx->stream));
         return 0;
@@ -2844,7 +2872,7 @@ int b200sph_peer_begin(b200sph_ctx *ctx)
     if ((rc = eos_flush(ctx))) return rc;
     int no_build = 0;
     if (ctx->force_kernel != 0 || !ctx->lists_valid || ctx->topo_dirty) no_build = 1;
-    else if (ctx->skin_adapt && ctx->evals_since_build >= 3.0 * SKIN_KAPPA / ctx->skin && ctx->skin > ctx->skin_min) no_build = 1;  // retire it
+    else if (retire_build(ctx)) no_build = 1;
     if (!no_build && ctx->n_sorted > 0 && !(ctx->packed_valid && ctx->drift_measured)) {
         CU(cudaMemsetAsync(ctx->red_u32, 0, 2 * sizeof(unsigned), ctx->stream));
         k_pack_pos_light<<<(unsigned)cdiv(ctx->n_sorted, 256), 256, 0, ctx->stream>>>(
@@ -2997,6 +3025,10 @@ int b200sph_peer_decision(b200sph_ctx *ctx, double *ratio_max)
     }
     if (d->error == want) return set_err(ctx, "peer protocol: a rank did not answer within %.0f s (epoch %llu)", PEER_TIMEOUT_NS * 1e-9, want);
     *ratio_max = d->value;
+    if (d->value <= 1.0) {   // the skin controller's view of the build: the all-rank maximum (the same on every rank)
+        ctx->drift_hist[0] = ctx->drift_hist[1];
+        ctx->drift_hist[1] = d->value;
+    }
     return 0;
 }
 
