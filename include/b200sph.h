@@ -495,7 +495,10 @@ int b200sph_migrate_out(b200sph_ctx *ctx, int arr, double lo, double hi,
  * fetch: copy segment `seg` to host memory (8 * count bytes, 4 * count for integers) on
  *   a private stream and wait for THAT copy only; may be called from another host
  *   thread while the owner keeps stepping.
- * release: the buffer may be overwritten by the next take.  One snapshot at a time. */
+ * release: the buffer may be overwritten by the next take.  One snapshot at a time.
+ * Threading: only snapshot_fetch / snapshot_release (and b200sph_last_error) may be called
+ * from a second host thread; the error message and the "snapshot open" flag they share
+ * with the time loop's thread are guarded. */
 int b200sph_snapshot_take(b200sph_ctx *ctx, int nseg, const int *arr, const int *prop,
                           const int64_t *count);
 int b200sph_snapshot_fetch(b200sph_ctx *ctx, int seg, void *host, int64_t count);

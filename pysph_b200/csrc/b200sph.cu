@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -36,6 +37,7 @@
 #include <cstring>
 #include <string>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 // --------------------------------------------------------------------------
@@ -141,7 +143,9 @@ struct b200sph_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    std::string err;
+    std::string err;            // last error of the calling threads' entry points ...
+    std::string err_out;        // ... and the copy b200sph_last_error hands out
+    std::mutex err_mu;          // the output thread (snapshot_fetch / release) reports errors too
 
     int narr = 0;
     ArrayInfo arr[B200SPH_MAX_ARRAYS];
@@ -246,7 +250,7 @@ struct b200sph_ctx {
     std::vector<int> snap_u32;          // per segment: 1 = 4-byte integers
     cudaStream_t snap_stream = nullptr; // the D2H copies run here, beside the time loop
     cudaEvent_t snap_ready = nullptr, snap_done = nullptr;
-    bool snap_open = false;
+    std::atomic<bool> snap_open{false};   // taken by the time loop, released by the output thread
     cudaEvent_t tc_evt[2] = {nullptr, nullptr};
     bool h_dirty = true;        // h changed since the last update_domain reduction
     unsigned *red_u32 = nullptr, *red_u32_host = nullptr;
@@ -313,7 +317,10 @@ static int set_err(b200sph_ctx *c, const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (c) c->err = buf;
+    if (c) {
+        std::lock_guard<std::mutex> lk(c->err_mu);
+        c->err = buf;
+    }
     return -1;
 }
 
@@ -771,7 +778,13 @@ int b200sph_destroy(b200sph_ctx *ctx)
     return 0;
 }
 
-const char *b200sph_last_error(b200sph_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char *b200sph_last_error(b200sph_ctx *ctx)
+{
+    if (!ctx) return "null context";
+    std::lock_guard<std::mutex> lk(ctx->err_mu);
+    ctx->err_out = ctx->err;     // a stable copy: another thread may be writing the next message
+    return ctx->err_out.c_str();
+}
 
 int b200sph_set_stream(b200sph_ctx *ctx, void *s)
 {
