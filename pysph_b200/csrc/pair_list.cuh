@@ -201,6 +201,32 @@ __device__ __forceinline__ void ld_rec(const PairArgs &a, const uint32_t e, floa
     C = __ldg(a.C + j);
 }
 
+// The software-pipelined walk over one destination's list that every list consumer shares:
+// two entries per trip with ping-pong record registers; entries stream in (evict-first) two
+// entries ahead, the record of an entry is loaded one entry ahead of its use.  `load(e, rec)`
+// gathers the records entry e names -- unconditionally: an entry past the lane's own count
+// reads as 0 = "record 0, same cell" -- and `body(live, e, rec)` does the work, live = false
+// for the lanes whose list is shorter than the warp's longest.
+template <class Rec, class Load, class Body>
+__device__ __forceinline__ void list_walk(const uint32_t *nxt, const int count, int cmax, Load load, Body body)
+{
+    uint32_t e0 = count > 0 ? __ldcs(nxt) : 0u;
+    uint32_t e1 = count > 1 ? __ldcs(nxt + 32) : 0u;
+    nxt += 64;
+    Rec r0, r1;
+    load(e0, r0);
+    for (int rem = count; cmax > 0; cmax -= 2, rem -= 2, nxt += 64) {
+        const uint32_t e2 = rem > 2 ? __ldcs(nxt) : 0u;
+        load(e1, r1);
+        body(rem > 0, e0, r0);
+        const uint32_t e3 = rem > 3 ? __ldcs(nxt + 32) : 0u;
+        load(e2, r0);
+        body(rem > 1, e1, r1);
+        e0 = e2;
+        e1 = e3;
+    }
+}
+
 // the cell offset a list entry carries, as the vector to ADD to (x_i - x_j) of cell-relative
 // coordinates: -(d - 1) * cell per axis, d the 2-bit code field.  (code field | 0x4B000000) as a
 // float is 2^23 + field exactly, so the decode is one LOP3 + one FADD per axis; a shared-memory
@@ -269,26 +295,12 @@ __global__ void __launch_bounds__(LIST_NT, MINB) k_pair_list(const PairArgs a, c
     const float hi2 = a.k2 * Ai.w * Ai.w;
     Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     unsigned npairs = 0;
-    // entries beyond a lane's own count read as 0 = "record 0, same cell": the record loads
-    // below are unconditional (a predicated 256-bit gather costs the compiler a branch),
-    // the pair itself is skipped
-    uint32_t e0 = count > 0 ? __ldcs(nxt) : 0u;
-    uint32_t e1 = count > 1 ? __ldcs(nxt + 32) : 0u;
-    nxt += 64;
-    float4 A0r, B0r, C0r, A1r, B1r, C1r;
-    ld_rec(a, e0, A0r, B0r, C0r);
-    for (int rem = count; cmax > 0; cmax -= 2, rem -= 2, nxt += 64) {
-        // entry k (registers 0) while record k + 1 (registers 1) and entry k + 2 are in flight
-        const uint32_t e2 = rem > 2 ? __ldcs(nxt) : 0u;
-        ld_rec(a, e1, A1r, B1r, C1r);
-        pair_entry<K, DIM, EQS>(a, rem > 0, e0, A0r, B0r, C0r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
-        // entry k + 1 (registers 1) while record k + 2 (registers 0) and entry k + 3 are in flight
-        const uint32_t e3 = rem > 3 ? __ldcs(nxt + 32) : 0u;
-        ld_rec(a, e2, A0r, B0r, C0r);
-        pair_entry<K, DIM, EQS>(a, rem > 1, e1, A1r, B1r, C1r, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
-        e0 = e2;
-        e1 = e3;
-    }
+    struct Rec { float4 A, B, C; };
+    list_walk<Rec>(nxt, count, cmax,
+        [&](const uint32_t e, Rec &r) { ld_rec(a, e, r.A, r.B, r.C); },
+        [&](const bool live, const uint32_t e, const Rec &r) {
+            pair_entry<K, DIM, EQS>(a, live, e, r.A, r.B, r.C, Ai, Bi, Ci, hi2, mask_i, acc, npairs);
+        });
     if (active) {
         unsigned all_bits = 0;
 #pragma unroll

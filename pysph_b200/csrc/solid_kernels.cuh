@@ -126,29 +126,19 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, c
     const float hi2 = a.k2 * Ai.w * Ai.w;
     float g00 = 0.f, g01 = 0.f, g02 = 0.f, g10 = 0.f, g11 = 0.f, g12 = 0.f, g20 = 0.f, g21 = 0.f, g22 = 0.f;
     unsigned npairs = 0;
-    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-    float4 A_a = Ai, B_a = Bi, C_a = make_float4(1.f, 0.f, 0.f, 0.f);
-    if (count > 0) {
-        const size_t j = LIST_J(e_a);
-        ld_256(a.AB + 2 * j, A_a, B_a);
-        C_a = a.C3[j];
-    }
-    for (int k = 0; k < cmax; k++) {
-        const uint32_t e = e_a;
-        const float4 Aj = A_a, Bj = B_a, Cj = C_a;
-        e_a = e_b;
-        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-        if (k + 1 < count) {
-            const size_t j = LIST_J(e_a);
-            ld_256(a.AB + 2 * j, A_a, B_a);
-            C_a = a.C3[j];
-        }
-        if (k < count) {
+    struct Rec { float4 A, B, C; };
+    list_walk<Rec>(my, count, cmax,
+        [&](const uint32_t e, Rec &r) {
+            const uint32_t j = LIST_J(e);
+            ld_256(a.AB + 2u * j, r.A, r.B);
+            r.C = a.C3[j];
+        },
+        [&](const bool live, const uint32_t e, const Rec &r) {
+            const float4 Aj = r.A, Bj = r.B, Cj = r.C;
             const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
-            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.source_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
+            if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.source_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
                 npairs++;
                 const float rinv = r2 > 1e-24f ? frsqrt(r2) : 0.0f;
                 const float h1 = frcp(0.5f * (Ai.w + Aj.w));
@@ -164,8 +154,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass1(const SolidArgs a, c
                     g20 += dwv * xij; g21 += dwv * yij; g22 += dwv * zij;
                 }
             }
-        }
-    }
+        });
     if (active) {
         const uint32_t g = a.perm[s];
         const int arr = ti & 7;
@@ -285,30 +274,20 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass2(const SolidArgs a, c
     const float wdp1 = wdp > 0.f ? frcp(wdp) : 0.f;
     float arho = 0.f, au = 0.f, av = 0.f, aw = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
     unsigned npairs = 0;
-    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-    float4 A_a = Ai, B_a = Bi, C_a = Ci, T1_a = Ti1, T2_a = Ti2, T3_a = Ti3;
-    if (count > 0) {
-        const size_t j = LIST_J(e_a);
-        ld_256(a.AB + 2 * j, A_a, B_a);
-        C_a = a.C3[j]; T1_a = a.T01[j]; T2_a = a.T2R[j]; T3_a = a.R2[j];
-    }
-    for (int k = 0; k < cmax; k++) {
-        const uint32_t e = e_a;
-        const float4 Aj = A_a, Bj = B_a, Cj = C_a, Tj1 = T1_a, Tj2 = T2_a, Tj3 = T3_a;
-        e_a = e_b;
-        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-        if (k + 1 < count) {
-            const size_t j = LIST_J(e_a);
-            ld_256(a.AB + 2 * j, A_a, B_a);
-            C_a = a.C3[j]; T1_a = a.T01[j]; T2_a = a.T2R[j]; T3_a = a.R2[j];
-        }
-        if (k < count) {
+    struct Rec { float4 A, B, C, T1, T2, T3; };
+    list_walk<Rec>(my, count, cmax,
+        [&](const uint32_t e, Rec &r) {
+            const uint32_t j = LIST_J(e);
+            ld_256(a.AB + 2u * j, r.A, r.B);
+            r.C = a.C3[j]; r.T1 = a.T01[j]; r.T2 = a.T2R[j]; r.T3 = a.R2[j];
+        },
+        [&](const bool live, const uint32_t e, const Rec &r) {
+            const float4 Aj = r.A, Bj = r.B, Cj = r.C, Tj1 = r.T1, Tj2 = r.T2, Tj3 = r.T3;
             const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
             const int tj = __float_as_int(Cj.w) & 7;
-            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.source_mask >> tj) & 1u)) {
+            if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.source_mask >> tj) & 1u)) {
                 npairs++;
                 const float rinv = r2 > 1e-24f ? frsqrt(r2) : 0.0f;
                 const float hij = 0.5f * (Ai.w + Aj.w);
@@ -351,8 +330,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_solid_pass2(const SolidArgs a, c
                     ax += f * uij; ay += f * vij; az += f * wwij;
                 }
             }
-        }
-    }
+        });
     if (active) {
         const uint32_t g = a.perm[s];
         a.arho[g] = arho;

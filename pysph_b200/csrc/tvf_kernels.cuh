@@ -72,32 +72,20 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
     const float hi2 = a.k2 * Ai.w * Ai.w;
     float wsum = 0.f, psum = 0.f, nn = 0.f;
     unsigned npairs = 0;
-    // entries two iterations ahead, records one iteration ahead (as in k_pair_list)
-    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-    float4 A_a = Ai;
-    float2 P_a = make_float2(0.f, 0.f);
-    if (count > 0) {
-        const size_t j = LIST_J(e_a);
-        A_a = a.AB[2 * j];
-        P_a = a.PT[j];
-    }
-    for (int k = 0; k < cmax; k++) {
-        const uint32_t e = e_a;
-        const float4 Aj = A_a;
-        const float2 Pj = P_a;
-        e_a = e_b;
-        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-        if (k + 1 < count) {
-            const size_t j = LIST_J(e_a);
-            A_a = a.AB[2 * j];
-            P_a = a.PT[j];
-        }
-        if (k < count) {
+    struct Rec { float4 A; float2 P; };
+    list_walk<Rec>(my, count, cmax,
+        [&](const uint32_t e, Rec &r) {
+            const uint32_t j = LIST_J(e);
+            r.A = a.AB[2u * j];
+            r.P = a.PT[j];
+        },
+        [&](const bool live, const uint32_t e, const Rec &r) {
+            const float4 Aj = r.A;
+            const float2 Pj = r.P;
             const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
-            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Pj.y) & 7)) & 1u)) {
+            if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Pj.y) & 7)) & 1u)) {
                 npairs++;
                 const float rij = sqrtf(r2);
                 const float h1 = frcp(0.5f * (Ai.w + Aj.w));
@@ -107,8 +95,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
                 psum += Pj.x;
                 nn += 1.0f;
             }
-        }
-    }
+        });
     if (active) {
         const uint32_t g = a.perm[s];
         const float rho = Bi.w * wsum;
@@ -164,33 +151,20 @@ __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const
     const float cs2 = a.c0 * a.c0;
     float au = 0.f, av = 0.f, aw = 0.f, auh = 0.f, avh = 0.f, awh = 0.f, ap = 0.f;
     unsigned npairs = 0;
-    // entries two iterations ahead, records one iteration ahead (as in k_pair_list):
-    // a record load never waits for the entry load of the same iteration
-    uint32_t e_a = count > 0 ? __ldcs(my) : 0u;
-    uint32_t e_b = count > 1 ? __ldcs(my + 32) : 0u;
-    float4 A_a = Ai, B_a = Bi, C_a = Ci, D_a = Di;
-    if (count > 0) {
-        const size_t j = LIST_J(e_a);
-        ld_256(a.AB + 2 * j, A_a, B_a);
-        C_a = a.C2[j];
-        D_a = a.Dv[j];
-    }
-    for (int k = 0; k < cmax; k++) {
-        const uint32_t e = e_a;
-        const float4 Aj = A_a, Bj = B_a, Cj = C_a, Dj = D_a;
-        e_a = e_b;
-        if (k + 2 < count) e_b = __ldcs(my + (size_t)(k + 2) * 32u);
-        if (k + 1 < count) {
-            const size_t j = LIST_J(e_a);
-            ld_256(a.AB + 2 * j, A_a, B_a);
-            C_a = a.C2[j];
-            D_a = a.Dv[j];
-        }
-        if (k < count) {
+    struct Rec { float4 A, B, C, D; };
+    list_walk<Rec>(my, count, cmax,
+        [&](const uint32_t e, Rec &r) {
+            const uint32_t j = LIST_J(e);
+            ld_256(a.AB + 2u * j, r.A, r.B);
+            r.C = a.C2[j];
+            r.D = a.Dv[j];
+        },
+        [&](const bool live, const uint32_t e, const Rec &r) {
+            const float4 Aj = r.A, Bj = r.B, Cj = r.C, Dj = r.D;
             const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
-            if (((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
+            if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
                 npairs++;
                 const bool far = r2 > 1e-24f;
                 const float rinv = far ? frsqrt(r2) : 0.0f;
@@ -246,8 +220,7 @@ __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const
                     ap += common * etaij * (gt * r2) * r2e1 * (pi - pj);
                 }
             }
-        }
-    }
+        });
     if (active) {
         const uint32_t g = a.perm[s];
         if (a.eqbits & B200SPH_TVF_PGRAD) {   // post_loop wc/edac.py:483-488
