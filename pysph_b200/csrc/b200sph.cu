@@ -285,6 +285,8 @@ struct b200sph_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool comm_pending = false;                   // work on comm_stream that the main stream has not waited for
     uint8_t *sflag = nullptr;                    // [sorted] 1 = ghost
+    uint8_t *stype = nullptr;                    // [sorted] particle type byte (array id | ghost bit), written by k_pack_pos
+    unsigned long long list_mask[B200SPH_MAX_ARRAYS] = {0};   // the equation mask the current lists were filtered with
     uint32_t *chunk_boundary = nullptr, *chunk_interior = nullptr;
     int64_t n_chunk_boundary = 0, n_chunk_interior = 0, chunk_cap = 0;
     bool chunks_valid = false;
@@ -537,6 +539,8 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
     CU(cudaMalloc((void **)&ctx->Dv, 16 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->PT, 8 * (size_t)alloc));
     CU(cudaMalloc((void **)&ctx->cnt, 4 * (size_t)alloc));
+    if (ctx->stype) cudaFree(ctx->stype);
+    CU(cudaMalloc((void **)&ctx->stype, (size_t)alloc));
     ctx->lists_valid = false;
     ctx->topo_dirty = true;
     ctx->h_dirty = true;
@@ -772,7 +776,7 @@ int b200sph_destroy(b200sph_ctx *ctx)
     if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    cudaFree(ctx->sflag); cudaFree(ctx->chunk_boundary); cudaFree(ctx->chunk_interior);
+    cudaFree(ctx->sflag); cudaFree(ctx->stype); cudaFree(ctx->chunk_boundary); cudaFree(ctx->chunk_interior);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -1514,7 +1518,7 @@ int b200sph_nnps_update(b200sph_ctx *ctx)
         k_canon<<<ns, 256, 0, ctx->stream>>>(ctx->perm_tmp, ctx->key_of, ctx->cell_start, ntot, ctx->perm, ctx->skey, ctx->rank);
         LAUNCH_CHECK();
         k_pack_pos<<<ns, 256, 0, ctx->stream>>>(ctx->f64[B200SPH_X], ctx->f64[B200SPH_Y], ctx->f64[B200SPH_Z], ctx->f64[B200SPH_H],
-                                                ctx->perm, ctx->skey, ntot, G, ctx->A, ctx->AB);
+                                                ctx->perm, ctx->skey, ntot, G, ctx->A, ctx->AB, ctx->ptype, ctx->stype);
         LAUNCH_CHECK();
         if (use_lists)
             CU(cudaMemcpyAsync(ctx->A0, ctx->A, 16 * (size_t)ntot, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1562,10 +1566,29 @@ static int split_chunks(b200sph_ctx *ctx)
     return 0;
 }
 
-// (re)build the persistent neighbour lists for the current build
-static int build_lists(b200sph_ctx *ctx)
+// (re)build the persistent neighbour lists for the current build.  want[d] (8 bits per source
+// type; null: everything) = the (destination, source) type pairs the caller has equations for:
+// the lists are filtered with the union of what has been asked for since the particle set last
+// changed, so that e.g. a wall particle's wall neighbours -- for which the WCSPH Group has no
+// equation -- are never stored, gathered or tested (they were a quarter of the list entries of
+// a wall-heavy slab).
+static bool lists_cover(const b200sph_ctx *ctx, const unsigned long long *want)
+{
+    for (int d = 0; d < B200SPH_MAX_ARRAYS; d++) {
+        const unsigned long long w = want ? want[d] : ~0ull;
+        for (int sx = 0; sx < B200SPH_MAX_ARRAYS; sx++)
+            if (((w >> (8 * sx)) & 0xFFull) && !((ctx->list_mask[d] >> (8 * sx)) & 0xFFull)) return false;
+    }
+    return true;
+}
+static int build_lists(b200sph_ctx *ctx, const unsigned long long *want)
 {
     ctx->chunks_valid = false;
+    for (int d = 0; d < B200SPH_MAX_ARRAYS; d++) {
+        const unsigned long long w = want ? want[d] : ~0ull;
+        for (int sx = 0; sx < B200SPH_MAX_ARRAYS; sx++)
+            if ((w >> (8 * sx)) & 0xFFull) ctx->list_mask[d] |= 0xFFull << (8 * sx);
+    }
     const int64_t n = ctx->n_sorted;
     ListBuildArgs la;
     la.A = ctx->A; la.cell_start = ctx->cell_start; la.skey = ctx->skey;
@@ -1579,6 +1602,8 @@ static int build_lists(b200sph_ctx *ctx)
     la.S = (float)ctx->S_abs;
     la.cnt = ctx->cnt;
     la.max_count = ctx->red_u32 + 2;
+    for (int d = 0; d < B200SPH_MAX_ARRAYS; d++) la.emask[d] = ctx->list_mask[d];
+    la.stype = ctx->stype;
     const unsigned nb = (unsigned)cdiv(n, LB_WARPS * 32);
     const int64_t nblk = cdiv(n, 32);
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -1772,6 +1797,15 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     }
     // lists hold 26-bit sorted indices: larger particle counts use the warp kernel
     const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->n_sorted < (1LL << LIST_JBITS);
+    // the (destination, source) type pairs this Group has equations for; lists that were
+    // filtered with a narrower set are rebuilt with the union
+    unsigned long long want[B200SPH_MAX_ARRAYS];
+    for (int d = 0; d < B200SPH_MAX_ARRAYS; d++) {
+        want[d] = 0;
+        for (int sx = 0; sx < B200SPH_MAX_ARRAYS; sx++)
+            if (d < ctx->narr && sx < ctx->narr && prog->eqmask[d][sx]) want[d] |= 0xFFull << (8 * sx);
+    }
+    if (use_lists && ctx->lists_valid && !lists_cover(ctx, want)) ctx->lists_valid = false;
     // the peer protocol's refresh is still in flight and every record a ghost-free CTA
     // reads is in place: those CTAs go first, the main stream waits for the halo only then
     const bool overlap = ctx->comm_pending && use_lists && ctx->lists_valid && ctx->chunks_valid && ctx->state_packed &&
@@ -1786,7 +1820,7 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
         return set_err(ctx, "periodic domains need the neighbour-list path (B200SPH_PAIR_KERNEL=list, < 2^26 particles)");
     if (use_lists && !ctx->lists_valid) {
         PhaseTimer pt_build(ctx, 0);  // list builds are part of the neighbour search time
-        if ((rc = build_lists(ctx))) return rc;
+        if ((rc = build_lists(ctx, want))) return rc;
     }
     PhaseTimer pt(ctx, 1);
 
@@ -1905,9 +1939,10 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog, int64_t 
     const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->n_sorted < (1LL << LIST_JBITS);
     if (ctx->n_sorted == 0) return 0;
     if (!use_lists) return set_err(ctx, "tvf_pass: the EDAC kernels need the neighbour-list path (B200SPH_PAIR_KERNEL=list, < 2^26 particles)");
+    if (ctx->lists_valid && !lists_cover(ctx, nullptr)) ctx->lists_valid = false;   // (these passes take unfiltered lists)
     if (!ctx->lists_valid) {
         PhaseTimer pt_build(ctx, 0);
-        if ((rc = build_lists(ctx))) return rc;
+        if ((rc = build_lists(ctx, nullptr))) return rc;
     }
     // timing slots: pack + group 1 count as "other", group 2 (the dominant kernel) as "pair"
     std::unique_ptr<PhaseTimer> pt(new PhaseTimer(ctx, 2));
@@ -1988,9 +2023,10 @@ int b200sph_solid_pass(b200sph_ctx *ctx, const b200sph_solid_program *prog, int6
     if (ctx->n_sorted == 0) return 0;
     const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted < (1LL << LIST_JBITS);
     if (!use_lists) return set_err(ctx, "solid_pass: the elastic-dynamics kernels need the neighbour-list path");
+    if (ctx->lists_valid && !lists_cover(ctx, nullptr)) ctx->lists_valid = false;   // (these passes take unfiltered lists)
     if (!ctx->lists_valid) {
         PhaseTimer pt_build(ctx, 0);
-        if ((rc = build_lists(ctx))) return rc;
+        if ((rc = build_lists(ctx, nullptr))) return rc;
     }
     SolidArgs sa;
     memset(&sa, 0, sizeof(sa));

@@ -63,11 +63,13 @@ __global__ void k_canon(const uint32_t *__restrict__ perm_tmp, const uint32_t *_
 __global__ void k_pack_pos(const double *__restrict__ x, const double *__restrict__ y,
                            const double *__restrict__ z, const double *__restrict__ h,
                            const uint32_t *__restrict__ perm, const uint32_t *__restrict__ skey,
-                           long long n, GridDev G, float4 *__restrict__ A, float4 *__restrict__ AB)
+                           long long n, GridDev G, float4 *__restrict__ A, float4 *__restrict__ AB,
+                           const uint8_t *__restrict__ ptype, uint8_t *__restrict__ stype)
 {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const uint32_t g = perm[s];
+    if (stype) stype[s] = ptype[g];
     uint32_t key = skey[s];
     uint32_t cx, cy, cz;
     grid_decode(G.zorder, (uint32_t)G.nc[0], (uint32_t)G.nc[1], key, cx, cy, cz);

@@ -44,6 +44,12 @@ struct ListBuildArgs {
     uint32_t *lst;   // null: count only
     int capg;        // entries reserved per destination
     unsigned *max_count;
+    // the (destination type, source type) pairs for which some equation of the Group exists
+    // (8 bits per source type, as PairArgs.emask; all ones: no filter): an entry the pair
+    // kernel would gather only to find no equation for it is not stored.  stype[s] = particle
+    // type byte (array id | ghost bit) in sorted order.
+    unsigned long long emask[B200SPH_MAX_ARRAYS];
+    const uint8_t *stype;
 };
 
 // One THREAD per destination, one warp per 32 consecutive destinations of the sorted order
@@ -73,17 +79,19 @@ template <bool PERIODIC>
 __global__ void __launch_bounds__(LB_WARPS * 32) k_list_build(const ListBuildArgs a)
 {
     __shared__ float4 s_A[LB_WARPS][LB_TILE];
-    __shared__ int s_cx[LB_WARPS][LB_TILE];
+    __shared__ int s_cx[LB_WARPS][LB_TILE];     // cell x index | source type << 24
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     const long long s = ((long long)blockIdx.x * LB_WARPS + warp) * 32 + lane;
     const bool valid = s < a.n;
     float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t cxi = 0, cyi = 0, czi = 0, row_i = 0xFFFFFFFFu;
+    unsigned long long mask_i = 0;
     if (valid) {
         Ai = a.A[s];
         grid_decode(a.zorder, (uint32_t)a.ncx, (uint32_t)a.ncy, a.skey[s], cxi, cyi, czi);
         row_i = cyi + (uint32_t)a.ncy * czi;
+        mask_i = a.emask[a.stype[s] & 7];
     }
     const float hi = a.kr * Ai.w + a.S;
     const float hi2 = hi * hi;
@@ -150,18 +158,19 @@ __global__ void __launch_bounds__(LB_WARPS * 32) k_list_build(const ListBuildArg
                     Aj.x += (float)(cxj - x0c) * a.cellx;
                     Aj.w = hj * hj;
                     s_A[warp][k] = Aj;
-                    s_cx[warp][k] = cxj;
+                    s_cx[warp][k] = (cxj + 1) | ((int)(a.stype[t0 + k] & 7) << 24);   // cxj >= -1
                 }
                 __syncwarp();
-                if (mine) {
+                if (mine && mask_i) {
 #pragma unroll 4
                     for (int k = 0; k < tn; k++) {
                         const float4 Aj = s_A[warp][k];
                         const float xij = xoff - Aj.x, yij = yoff - Aj.y, zij = zoff - Aj.z;
                         const float r2 = xij * xij + yij * yij + zij * zij;
                         if ((r2 < hi2) || (r2 < Aj.w)) {
-                            const int dxc1 = s_cx[warp][k] - (int)cxi + 1;     // dxc + 1
-                            if ((unsigned)dxc1 <= 2u) {
+                            const int cj = s_cx[warp][k];
+                            const int dxc1 = (cj & 0xFFFFFF) - 1 - (int)cxi + 1;     // dxc + 1
+                            if ((unsigned)dxc1 <= 2u && ((mask_i >> (8 * (cj >> 24))) & 0xFFull)) {
                                 if (out && count < (unsigned)a.capg) out[(size_t)count * 32u] = LIST_ENTRY(t0 + (uint32_t)k, rcode + (uint32_t)dxc1);
                                 count++;
                             }

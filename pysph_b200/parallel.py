@@ -900,11 +900,14 @@ def make_slab_solver(dx, params, kernel, rank, world, device=0,
     import pysph_b200 as pb
     from . import geometry as geo
     if solid_weight is None:
-        # cost of a wall / obstacle particle relative to a fluid particle.  Measured (B200,
-        # round 2): a step costs 6.3e-9 ms per directed pair (~163 per fluid particle and
-        # step, the walls' own pair loops included) + 2.0e-7 ms per particle of any kind,
-        # i.e. 1.22e-6 ms per fluid and 0.2e-6 ms per solid particle
-        solid_weight = float(os.environ.get('B200SPH_SOLID_WEIGHT', '0.2'))
+        # cost of a wall / obstacle particle relative to a fluid particle.  A step costs
+        # ~5.7e-9 ms per list entry and evaluation + 2.0e-7 ms per particle of any kind; a
+        # wall particle far from the fluid still walks ~22 entries (its in-plane wall
+        # neighbours, rejected by the equation mask after the gather), one under the fluid
+        # ~57.  Measured on 8 B200 (round 2): with 0.45 the last, wall-heavy slab idles
+        # (0.73 of the others' time), with 0.2 it is the straggler (1.35 vs 1.22 ms / step);
+        # the crossing of the two lines is at 0.25
+        solid_weight = float(os.environ.get('B200SPH_SOLID_WEIGHT', '0.26'))
     xs, w = dam_break_column_weights(dx, solid_weight=solid_weight)
     cuts = balanced_cuts(xs, w, world, dx)
     pas = geo.dam_break_3d_particles(dx=dx, xrange=(cuts[rank], cuts[rank + 1]))

@@ -309,7 +309,8 @@ int emul_pipeline(const emul_common *c, const double *gxmin, const double *gcell
     launch1(n, 256, [&] { k_scatter(key_of.data(), off_in.data(), c->ptype, n, cell_start.data(), perm_tmp.data()); });
     launch1(n, 256, [&] { k_canon(perm_tmp.data(), key_of.data(), cell_start.data(), n, perm.data(), skey.data(), rank.data()); });
     std::vector<float4> A((size_t)n), AB(2 * (size_t)n), B((size_t)n), Cc((size_t)n);
-    launch1(n, 256, [&] { k_pack_pos(c->x, c->y, c->z, c->h, perm.data(), skey.data(), n, G, A.data(), AB.data()); });
+    std::vector<uint8_t> stype((size_t)n);
+    launch1(n, 256, [&] { k_pack_pos(c->x, c->y, c->z, c->h, perm.data(), skey.data(), n, G, A.data(), AB.data(), c->ptype, stype.data()); });
     // neighbour lists
     std::vector<uint32_t> cnt((size_t)n, 0u), lst;
     unsigned max_count = 0;
@@ -324,6 +325,8 @@ int emul_pipeline(const emul_common *c, const double *gxmin, const double *gcell
     la.S = (float)skin_abs;
     la.cnt = cnt.data();
     la.max_count = &max_count;
+    for (int d = 0; d < B200SPH_MAX_ARRAYS; d++) la.emask[d] = emask[d];   // the Group's (dest, source) pairs
+    la.stype = stype.data();
     const bool per = la.px || la.py || la.pz;
     const unsigned nbw = (unsigned)((n + LB_WARPS * 32 - 1) / (LB_WARPS * 32));
     int capg = 0;
