@@ -179,6 +179,10 @@ typedef struct {
     int64_t chunks_interior, chunks_boundary; /* CTAs of the list consumers without / with a
                               ghost among their destinations or neighbours (current build;
                               0 / 0 without ghosts)                                          */
+    double ms_halo_chain;  /* overlapped evaluations (profiling on): device time from the fork of the
+                              communication stream to the end of the ghost scatter, summed      */
+    double ms_pair_wall;   /* ... and to the end of BOTH pair launches (what the evaluation's
+                              pair work costs in wall time, protocol included)                  */
 } b200sph_stats;
 
 /* ---- lifecycle: what selecting a backend does in the reference

@@ -96,7 +96,8 @@ class Stats(C.Structure):
                 ('deferred_failed', C.c_int64), ('fused_stages', C.c_int64),
                 ('overlapped', C.c_int64), ('proactive_builds', C.c_int64),
                 ('chunks_interior', C.c_int64),
-                ('chunks_boundary', C.c_int64)]
+                ('chunks_boundary', C.c_int64), ('ms_halo_chain', C.c_double),
+                ('ms_pair_wall', C.c_double)]
 
 
 _ctx_p = C.c_void_p

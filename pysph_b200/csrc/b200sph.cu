@@ -283,6 +283,11 @@ struct b200sph_ctx {
     struct PeerDecision *peer_dec_host = nullptr, *peer_dec_hostdev = nullptr;   // pinned + its device alias
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // profiling of the overlapped evaluation (b200sph_set_profiling != 0): per pair pass an event
+    // triple {fork of the communication stream, scatter done, boundary launch done}
+    struct HaloEvents { cudaEvent_t fork, chain, end; };
+    std::vector<HaloEvents> halo_pending;
+    cudaEvent_t halo_ev_fork = nullptr, halo_ev_chain = nullptr;
     bool comm_pending = false;                   // work on comm_stream that the main stream has not waited for
     uint8_t *sflag = nullptr;                    // [sorted] 1 = ghost
     uint8_t *stype = nullptr;                    // [sorted] particle type byte (array id | ghost bit), written by k_pack_pos
@@ -1903,6 +1908,14 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
         if (overlap) {   // the join point moves behind the boundary launch
             CU(cudaEventRecord(ctx->ev_join, ctx->comm_stream));
             ctx->comm_pending = true;
+            if (ctx->profiling && ctx->halo_ev_fork && ctx->halo_ev_chain) {
+                cudaEvent_t e_end = nullptr;
+                if (!ctx->ev_pool.empty()) { e_end = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+                else CU(cudaEventCreate(&e_end));
+                CU(cudaEventRecord(e_end, ctx->comm_stream));
+                ctx->halo_pending.push_back({ctx->halo_ev_fork, ctx->halo_ev_chain, e_end});
+                ctx->halo_ev_fork = ctx->halo_ev_chain = nullptr;
+            }
         }
         ctx->stats.pair_launches++;
     } else if (ctx->n_sorted > 0) {
@@ -2933,6 +2946,14 @@ int b200sph_peer_begin(b200sph_ctx *ctx)
     ctx->peer_epoch++;
     CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+    if (ctx->profiling) {
+        for (cudaEvent_t *e : {&ctx->halo_ev_fork, &ctx->halo_ev_chain})
+            if (!*e) {
+                if (!ctx->ev_pool.empty()) { *e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+                else CU(cudaEventCreate(e));
+            }
+        CU(cudaEventRecord(ctx->halo_ev_fork, ctx->stream));
+    }
     return no_build;
 }
 
@@ -3053,6 +3074,7 @@ int b200sph_peer_end(b200sph_ctx *ctx)
 {
     CU(cudaSetDevice(ctx->device));
     if (!ctx->comm_stream) return set_err(ctx, "peer_end: no epoch in flight");
+    if (ctx->profiling && ctx->halo_ev_chain) CU(cudaEventRecord(ctx->halo_ev_chain, ctx->comm_stream));
     CU(cudaEventRecord(ctx->ev_join, ctx->comm_stream));
     ctx->comm_pending = true;
     return 0;
@@ -3244,6 +3266,20 @@ int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out)
             ctx->ev_pool.push_back(pe.e1);
         }
         ctx->pending.clear();
+    }
+    if (!ctx->halo_pending.empty()) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->comm_stream) CU(cudaStreamSynchronize(ctx->comm_stream));
+        for (auto &h : ctx->halo_pending) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, h.fork, h.chain);
+            cudaEventElapsedTime(&b, h.fork, h.end);
+            ctx->stats.ms_halo_chain += a;
+            ctx->stats.ms_pair_wall += b;
+            ctx->ev_pool.push_back(h.fork); ctx->ev_pool.push_back(h.chain); ctx->ev_pool.push_back(h.end);
+        }
+        ctx->halo_pending.clear();
     }
     ctx->stats.full_builds = ctx->n_full_builds;
     ctx->stats.light_updates = ctx->n_light_updates;
