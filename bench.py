@@ -1010,7 +1010,8 @@ def run_dam_break(args, rank, local_rank, world):
         nov = max(int(st.get('overlapped', 0) or 0), 1)
         mine = torch.tensor([st['ms_pair'] / K, st_diag['ms_nnps'] / DIAG, st_diag['ms_other'] / DIAG,
                              float(n_local), float(pairs_local),
-                             float(st.get('ms_halo_chain', 0.0)) / nov, float(st.get('ms_pair_wall', 0.0)) / nov],
+                             float(st.get('ms_halo_chain', 0.0)) / nov, float(st.get('ms_pair_wall', 0.0)) / nov,
+                             float(st.get('ms_halo_sent', 0.0)) / nov, float(st.get('ms_halo_reduced', 0.0)) / nov],
                             dtype=torch.float64, device='cuda')
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
@@ -1018,7 +1019,7 @@ def run_dam_break(args, rank, local_rank, world):
         # ms_pair_wall: per EVALUATION, from the fork of the communication stream to the end of
         # the ghost scatter / to the end of both pair launches
         per_rank = [dict(zip(('ms_pair', 'ms_nnps', 'ms_other', 'n_real', 'pairs', 'ms_halo_chain',
-                              'ms_pair_wall'),
+                              'ms_pair_wall', 'ms_halo_sent', 'ms_halo_reduced'),
                              [round(float(v), 4) for v in r.tolist()])) for r in allr]
     n_total = int(reduce(n_local, dist.ReduceOp.SUM)) if world > 1 else n_local
     halo = None

@@ -183,6 +183,7 @@ typedef struct {
                               communication stream to the end of the ghost scatter, summed      */
     double ms_pair_wall;   /* ... and to the end of BOTH pair launches (what the evaluation's
                               pair work costs in wall time, protocol included)                  */
+    double ms_halo_sent, ms_halo_reduced; /* ... to the end of the sends / of the all-rank agreement */
 } b200sph_stats;
 
 /* ---- lifecycle: what selecting a backend does in the reference

@@ -17,7 +17,7 @@ for tag in ('weak', 'strong'):
         print('   halo', d['config']['halo'])
         p = d['config'].get('multi_gpu_parity')
         if p: print('   parity', p['ok'], max(p['max_scaled_error'].values()))
-        print('   per_rank (ms_pair, ms_other, n_real, pairs, chain, pair_wall)', [(r['ms_pair'], r['ms_other'], int(r['n_real']), int(r['pairs']), r.get('ms_halo_chain'), r.get('ms_pair_wall')) for r in d['config']['per_rank']])
+        print('   per_rank (ms_pair, ms_other, n_real, pairs, sent, reduced, chain, pair_wall)', [(r['ms_pair'], r['ms_other'], int(r['n_real']), int(r['pairs']), r.get('ms_halo_sent'), r.get('ms_halo_reduced'), r.get('ms_halo_chain'), r.get('ms_pair_wall')) for r in d['config']['per_rank']])
         if d.get('developed'): print('   developed ms/step %.4f halo_full %s proactive %s failed %s' % (d['developed']['ms_per_step'], d['developed'].get('halo_full_updates'), d['developed'].get('halo_proactive'), d['developed'].get('halo_deferred_failed')))
         if d.get('configs2_as_quoted'): print('   configs2_as_quoted ms/step %.4f value %.4g' % (d['configs2_as_quoted']['ms_per_step'], d['configs2_as_quoted']['value']))
         for k, v in (d.get('extra') or {}).items():

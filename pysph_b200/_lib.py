@@ -97,7 +97,8 @@ class Stats(C.Structure):
                 ('overlapped', C.c_int64), ('proactive_builds', C.c_int64),
                 ('chunks_interior', C.c_int64),
                 ('chunks_boundary', C.c_int64), ('ms_halo_chain', C.c_double),
-                ('ms_pair_wall', C.c_double)]
+                ('ms_pair_wall', C.c_double), ('ms_halo_sent', C.c_double),
+                ('ms_halo_reduced', C.c_double)]
 
 
 _ctx_p = C.c_void_p

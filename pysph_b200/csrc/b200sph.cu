@@ -285,9 +285,9 @@ struct b200sph_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // profiling of the overlapped evaluation (b200sph_set_profiling != 0): per pair pass an event
     // triple {fork of the communication stream, scatter done, boundary launch done}
-    struct HaloEvents { cudaEvent_t fork, chain, end; };
+    struct HaloEvents { cudaEvent_t fork, chain, end, sent, reduced; };
     std::vector<HaloEvents> halo_pending;
-    cudaEvent_t halo_ev_fork = nullptr, halo_ev_chain = nullptr;
+    cudaEvent_t halo_ev_fork = nullptr, halo_ev_chain = nullptr, halo_ev_sent = nullptr, halo_ev_reduced = nullptr;
     bool comm_pending = false;                   // work on comm_stream that the main stream has not waited for
     uint8_t *sflag = nullptr;                    // [sorted] 1 = ghost
     uint8_t *stype = nullptr;                    // [sorted] particle type byte (array id | ghost bit), written by k_pack_pos
@@ -1913,8 +1913,8 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
                 if (!ctx->ev_pool.empty()) { e_end = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
                 else CU(cudaEventCreate(&e_end));
                 CU(cudaEventRecord(e_end, ctx->comm_stream));
-                ctx->halo_pending.push_back({ctx->halo_ev_fork, ctx->halo_ev_chain, e_end});
-                ctx->halo_ev_fork = ctx->halo_ev_chain = nullptr;
+                ctx->halo_pending.push_back({ctx->halo_ev_fork, ctx->halo_ev_chain, e_end, ctx->halo_ev_sent, ctx->halo_ev_reduced});
+                ctx->halo_ev_fork = ctx->halo_ev_chain = ctx->halo_ev_sent = ctx->halo_ev_reduced = nullptr;
             }
         }
         ctx->stats.pair_launches++;
@@ -2947,7 +2947,7 @@ int b200sph_peer_begin(b200sph_ctx *ctx)
     CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
     if (ctx->profiling) {
-        for (cudaEvent_t *e : {&ctx->halo_ev_fork, &ctx->halo_ev_chain})
+        for (cudaEvent_t *e : {&ctx->halo_ev_fork, &ctx->halo_ev_chain, &ctx->halo_ev_sent, &ctx->halo_ev_reduced})
             if (!*e) {
                 if (!ctx->ev_pool.empty()) { *e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
                 else CU(cudaEventCreate(e));
@@ -3002,9 +3002,11 @@ int b200sph_peer_reduce(b200sph_ctx *ctx, int with_dt)
 {
     CU(cudaSetDevice(ctx->device));
     if (!ctx->peer_connected) return set_err(ctx, "peer_reduce: the mailboxes are not connected");
+    if (ctx->profiling && ctx->halo_ev_sent) CU(cudaEventRecord(ctx->halo_ev_sent, ctx->comm_stream));
     k_peer_reduce<<<1, 32, 0, ctx->comm_stream>>>(ctx->peer_box, ctx->peer_world, ctx->peer_epoch, 0, ctx->peer_dec_dev, ctx->peer_dec_hostdev,
                                                    ctx->tc, with_dt && ctx->tc ? 1 : 0);
     LAUNCH_CHECK();
+    if (ctx->profiling && ctx->halo_ev_reduced) CU(cudaEventRecord(ctx->halo_ev_reduced, ctx->comm_stream));
     return 0;
 }
 
@@ -3277,6 +3279,12 @@ int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out)
             cudaEventElapsedTime(&b, h.fork, h.end);
             ctx->stats.ms_halo_chain += a;
             ctx->stats.ms_pair_wall += b;
+            if (h.sent && h.reduced) {
+                float c = 0.f, d = 0.f;
+                if (cudaEventElapsedTime(&c, h.fork, h.sent) == cudaSuccess) ctx->stats.ms_halo_sent += c;
+                if (cudaEventElapsedTime(&d, h.fork, h.reduced) == cudaSuccess) ctx->stats.ms_halo_reduced += d;
+                ctx->ev_pool.push_back(h.sent); ctx->ev_pool.push_back(h.reduced);
+            }
             ctx->ev_pool.push_back(h.fork); ctx->ev_pool.push_back(h.chain); ctx->ev_pool.push_back(h.end);
         }
         ctx->halo_pending.clear();

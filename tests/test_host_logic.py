@@ -55,7 +55,7 @@ def test_struct_layouts_match_header():
     # sizes implied by include/b200sph.h (x86-64 SysV)
     assert C.sizeof(_lib.PairProgram) == 8 * 8 * 4 + 2 * 4 + 7 * 8
     assert C.sizeof(_lib.GridInfo) == 8 + 8 + 24 + 24 + 12 + 4 + 8 + 8
-    assert C.sizeof(_lib.Stats) == 3 * 8 + 15 * 8
+    assert C.sizeof(_lib.Stats) == 3 * 8 + 17 * 8
     ids = _lib.PROP_IDS
     assert ids['x'] == 0 and ids['rho'] == 6 and ids['h'] == 7 and ids['m'] == 8
     assert ids['rho0'] == 15 and ids['p'] == 16 and ids['dt_force'] == 26
