@@ -432,7 +432,10 @@ int b200sph_nnps_keep_build(b200sph_ctx *ctx);
  * NVLink (cudaIpc); payload, __threadfence_system(), then an epoch word the reader polls.
  *   peer_init     allocate + export this rank's mailbox (handle64: 64 bytes)
  *   peer_connect  map every rank's mailbox (handles: world x 64 bytes, rank order)
- * One refresh epoch, every call only ENQUEUES work (on a second, high-priority stream):
+ * One refresh epoch, in THIS order; every call only enqueues work on two further
+ * high-priority streams (communication, agreement).  publish + send are merged into ONE
+ * launch at peer_reduce and the recv calls into one at peer_end; the agreement has its own
+ * stream because a rank's ghosts need its two neighbours only, the decision every rank:
  *   peer_begin    measure the drift of the neighbour build if the fused stage kernel has
  *                 not, then let the communication stream wait for the main stream;
  *                 returns 1 if there is no reusable build (publish says so to everyone)
@@ -465,8 +468,8 @@ int b200sph_peer_send(b200sph_ctx *ctx, int slot, int nb_rank, int side, double 
 int b200sph_peer_reduce(b200sph_ctx *ctx, int with_dt);
 int b200sph_peer_recv(b200sph_ctx *ctx, int side, const int64_t *ghost_first, const int64_t *counts,
                       const double *local_staging);
-/* b200sph_dt_commit on the communication stream, between peer_reduce(with_dt = 1) and
- * peer_end: the time-step agreement of the step that has just ended rides on the refresh of
+/* b200sph_dt_commit behind the agreement (on its stream), between peer_reduce(with_dt = 1)
+ * and peer_end: the time-step agreement of the step that has just ended rides on the refresh of
  * the next step's first evaluation (the new dt is first needed by its stage1) */
 int b200sph_peer_commit_dt(b200sph_ctx *ctx, double prev_factor, double new_factor, int adaptive,
                            int advance, int snapshot_slot);

@@ -278,7 +278,7 @@ struct b200sph_ctx {
     struct PeerBox *peer_boxes[B200SPH_MAX_RANKS] = {nullptr};   // every rank's (own: the local one)
     bool peer_connected = false;
     unsigned long long peer_epoch = 0, peer_dt_epoch = 0;
-    unsigned *peer_done = nullptr;               // "blocks finished" counter of k_peer_send
+    unsigned *peer_done = nullptr;               // "blocks finished" counters of k_peer_push, one per direction
     double *peer_dec_dev = nullptr;
     struct PeerDecision *peer_dec_host = nullptr, *peer_dec_hostdev = nullptr;   // pinned + its device alias
     cudaStream_t comm_stream = nullptr;
@@ -289,6 +289,13 @@ struct b200sph_ctx {
     std::vector<HaloEvents> halo_pending;
     cudaEvent_t halo_ev_fork = nullptr, halo_ev_chain = nullptr, halo_ev_sent = nullptr, halo_ev_reduced = nullptr;
     bool comm_pending = false;                   // work on comm_stream that the main stream has not waited for
+    // The scalar agreement runs on its own stream: a rank's ghosts only need its two neighbours,
+    // the decision needs every rank, and the boundary launch must not wait for the slowest one.
+    cudaStream_t red_stream = nullptr;
+    cudaEvent_t ev_pushed = nullptr, ev_red = nullptr;
+    // peer_publish / peer_send / peer_recv only RECORD: the launches are merged into one
+    // k_peer_push (at peer_reduce) and one k_peer_pull (at peer_end)
+    struct PeerPending *pend = nullptr;
     uint8_t *sflag = nullptr;                    // [sorted] 1 = ghost
     uint8_t *stype = nullptr;                    // [sorted] particle type byte (array id | ghost bit), written by k_pack_pos
     unsigned long long list_mask[B200SPH_MAX_ARRAYS] = {0};   // the equation mask the current lists were filtered with
@@ -590,6 +597,7 @@ static int sync_comm(b200sph_ctx *ctx)
     if (!ctx->comm_pending) return 0;
     ctx->comm_pending = false;
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_red, 0));
     return 0;
 }
 
@@ -688,6 +696,7 @@ static double kernel_deltap(int kernel)
 extern "C" {
 
 static int eos_flush(b200sph_ctx *ctx, cudaStream_t on_comm_stream = nullptr);
+static void free_peer_pending(b200sph_ctx *ctx);
 
 int b200sph_abi_version(void) { return B200SPH_ABI_VERSION; }
 
@@ -779,6 +788,10 @@ int b200sph_destroy(b200sph_ctx *ctx)
     cudaFree(ctx->peer_box); cudaFree(ctx->peer_done); cudaFree(ctx->peer_dec_dev);
     if (ctx->peer_dec_host) cudaFreeHost(ctx->peer_dec_host);
     if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
+    if (ctx->red_stream) { cudaStreamSynchronize(ctx->red_stream); cudaStreamDestroy(ctx->red_stream); }
+    if (ctx->ev_pushed) cudaEventDestroy(ctx->ev_pushed);
+    if (ctx->ev_red) cudaEventDestroy(ctx->ev_red);
+    free_peer_pending(ctx);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     cudaFree(ctx->sflag); cudaFree(ctx->stype); cudaFree(ctx->chunk_boundary); cudaFree(ctx->chunk_interior);
@@ -2862,6 +2875,23 @@ int b200sph_nnps_keep_build(b200sph_ctx *ctx)
 }
 
 // ---- peer protocol (include/b200sph.h "peer protocol") ---------------------------------
+// peer_publish / peer_send / peer_recv only RECORD what the epoch carries; peer_reduce
+// launches the outgoing half as one k_peer_push and peer_end the incoming half as one
+// k_peer_pull (seven dependent launches on a busy GPU cost 0.1 ms per evaluation, the two
+// merged ones a third of that: profiles/r02k_chain.md).
+struct PeerPending {
+    struct Dir { HaloAllArgs A; double *buf; unsigned long long *flag; long long tot; };
+    Dir send[2], recv[2];
+    int n_send = 0, n_recv = 0;
+    int have_build = 0, with_dt = 0;
+    bool publish = false;
+    GhostPackArgs pack;
+};
+static void free_peer_pending(b200sph_ctx *ctx)
+{
+    delete ctx->pend;
+    ctx->pend = nullptr;
+}
 static int peer_streams(b200sph_ctx *ctx)
 {
     if (ctx->comm_stream) return 0;
@@ -2870,6 +2900,11 @@ static int peer_streams(b200sph_ctx *ctx)
     CU(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
     CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithPriority(&ctx->red_stream, cudaStreamNonBlocking, hi));
+    CU(cudaEventCreateWithFlags(&ctx->ev_pushed, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_red, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ev_red, ctx->red_stream));
+    ctx->pend = new PeerPending();
     return 0;
 }
 
@@ -2962,10 +2997,10 @@ int b200sph_peer_publish(b200sph_ctx *ctx, int have_build, int with_dt)
     CU(cudaSetDevice(ctx->device));
     if (!ctx->peer_connected) return set_err(ctx, "peer_publish: the mailboxes are not connected");
     if (with_dt && !ctx->tc) return set_err(ctx, "peer_publish: no time-control block");
-    k_peer_publish<<<1, 32, 0, ctx->comm_stream>>>(peer_ptrs(ctx), ctx->peer_rank, ctx->peer_world, ctx->peer_epoch, 0, ctx->red_u32,
-                                                    (float)ctx->radius_scale, (float)ctx->S_abs, have_build && ctx->n_sorted > 0 ? 1 : (have_build ? 2 : 0),
-                                                    ctx->tc, with_dt);
-    LAUNCH_CHECK();
+    ctx->pend->publish = true;
+    ctx->pend->have_build = have_build && ctx->n_sorted > 0 ? 1 : (have_build ? 2 : 0);
+    ctx->pend->with_dt = with_dt;
+    ctx->pend->n_send = ctx->pend->n_recv = 0;
     return 0;
 }
 
@@ -2986,14 +3021,67 @@ int b200sph_peer_send(b200sph_ctx *ctx, int slot, int nb_rank, int side, double 
     }
     const int64_t tot = A.prefix[ctx->narr];
     if (tot * halo_nf(ctx) > cap_doubles) return set_err(ctx, "peer_send: staging buffer too small");
-    unsigned long long *flag = &ctx->peer_boxes[nb_rank]->data_seq[ctx->peer_epoch & 1][side];
-    if (tot == 0) {
-        k_peer_flag<<<1, 1, 0, ctx->comm_stream>>>(flag, ctx->peer_epoch);
-    } else if (halo_nf(ctx) == B200SPH_HALO_FIELDS) {
-        k_peer_send<B200SPH_HALO_FIELDS><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->comm_stream>>>(halo_ptrs(ctx), A, remote_staging, ctx->peer_done, flag, ctx->peer_epoch);
-    } else {
-        k_peer_send<B200SPH_HALO_FIELDS_SOLID><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->comm_stream>>>(halo_ptrs(ctx), A, remote_staging, ctx->peer_done, flag, ctx->peer_epoch);
-    }
+    if (!ctx->pend->publish) return set_err(ctx, "peer_send: peer_publish opens the outgoing half of an epoch");
+    if (ctx->pend->n_send >= 2) return set_err(ctx, "peer_send: a slab has two neighbours");
+    PeerPending::Dir &D = ctx->pend->send[ctx->pend->n_send++];
+    D.A = A;
+    D.buf = remote_staging;
+    D.flag = &ctx->peer_boxes[nb_rank]->data_seq[ctx->peer_epoch & 1][side];
+    D.tot = tot;
+    return 0;
+}
+
+static void peer_dir(PeerDir &d, const PeerPending::Dir &p, unsigned *done)
+{
+    d.A = p.A;
+    d.buf = p.buf;
+    d.flag = p.flag;
+    d.done = done;
+    d.nblocks = (unsigned)cdiv(p.tot, PEER_NT);
+}
+
+// the outgoing half of the epoch: scalars + both messages, one launch
+static int peer_push(b200sph_ctx *ctx)
+{
+    PeerPending &Q = *ctx->pend;
+    if (!Q.publish) return set_err(ctx, "peer_reduce: nothing was published for this epoch");
+    Q.publish = false;
+    PeerPushArgs X;
+    memset(&X, 0, sizeof(X));
+    X.ndir = Q.n_send;
+    for (int d = 0; d < Q.n_send; d++) peer_dir(X.d[d], Q.send[d], ctx->peer_done + d);
+    X.rank = ctx->peer_rank;
+    X.world = ctx->peer_world;
+    X.have_build = Q.have_build;
+    X.with_dt = Q.with_dt;
+    X.kr = (float)ctx->radius_scale;
+    X.S = (float)ctx->S_abs;
+    X.red_u32 = ctx->red_u32;
+    X.tc = ctx->tc;
+    const unsigned blocks = 1 + X.d[0].nblocks + X.d[1].nblocks;
+    if (halo_nf(ctx) == B200SPH_HALO_FIELDS)
+        k_peer_push<B200SPH_HALO_FIELDS><<<blocks, PEER_NT, 0, ctx->comm_stream>>>(halo_ptrs(ctx), X, peer_ptrs(ctx), ctx->peer_epoch);
+    else
+        k_peer_push<B200SPH_HALO_FIELDS_SOLID><<<blocks, PEER_NT, 0, ctx->comm_stream>>>(halo_ptrs(ctx), X, peer_ptrs(ctx), ctx->peer_epoch);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// the incoming half: both neighbours' messages scattered (and packed) by one launch
+static int peer_pull(b200sph_ctx *ctx)
+{
+    PeerPending &Q = *ctx->pend;
+    if (Q.n_recv == 0) return 0;
+    PeerPullArgs X;
+    memset(&X, 0, sizeof(X));
+    X.ndir = Q.n_recv;
+    for (int d = 0; d < Q.n_recv; d++) peer_dir(X.d[d], Q.recv[d], nullptr);
+    Q.n_recv = 0;
+    const unsigned blocks = X.d[0].nblocks + X.d[1].nblocks;
+    if (halo_nf(ctx) == B200SPH_HALO_FIELDS)
+        k_peer_pull<B200SPH_HALO_FIELDS><<<blocks, PEER_NT, 0, ctx->comm_stream>>>(halo_ptrs(ctx), X, Q.pack, ctx->peer_epoch, ctx->peer_dec_hostdev);
+    else
+        k_peer_pull<B200SPH_HALO_FIELDS_SOLID><<<blocks, PEER_NT, 0, ctx->comm_stream>>>(halo_ptrs(ctx), X, Q.pack, ctx->peer_epoch, ctx->peer_dec_hostdev);
     LAUNCH_CHECK();
     return 0;
 }
@@ -3002,11 +3090,16 @@ int b200sph_peer_reduce(b200sph_ctx *ctx, int with_dt)
 {
     CU(cudaSetDevice(ctx->device));
     if (!ctx->peer_connected) return set_err(ctx, "peer_reduce: the mailboxes are not connected");
+    int rc = peer_push(ctx);
+    if (rc) return rc;
     if (ctx->profiling && ctx->halo_ev_sent) CU(cudaEventRecord(ctx->halo_ev_sent, ctx->comm_stream));
-    k_peer_reduce<<<1, 32, 0, ctx->comm_stream>>>(ctx->peer_box, ctx->peer_world, ctx->peer_epoch, 0, ctx->peer_dec_dev, ctx->peer_dec_hostdev,
-                                                   ctx->tc, with_dt && ctx->tc ? 1 : 0);
+    CU(cudaEventRecord(ctx->ev_pushed, ctx->comm_stream));
+    CU(cudaStreamWaitEvent(ctx->red_stream, ctx->ev_pushed, 0));   // my scalars are out before I wait for the others'
+    k_peer_reduce<<<1, 32, 0, ctx->red_stream>>>(ctx->peer_box, ctx->peer_world, ctx->peer_epoch, 0, ctx->peer_dec_dev, ctx->peer_dec_hostdev,
+                                                  ctx->tc, with_dt && ctx->tc ? 1 : 0);
     LAUNCH_CHECK();
-    if (ctx->profiling && ctx->halo_ev_reduced) CU(cudaEventRecord(ctx->halo_ev_reduced, ctx->comm_stream));
+    if (ctx->profiling && ctx->halo_ev_reduced) CU(cudaEventRecord(ctx->halo_ev_reduced, ctx->red_stream));
+    CU(cudaEventRecord(ctx->ev_red, ctx->red_stream));
     return 0;
 }
 
@@ -3045,12 +3138,13 @@ int b200sph_peer_recv(b200sph_ctx *ctx, int side, const int64_t *ghost_first, co
     R.p = ctx->f32[B200SPH_P - N_F64]; R.cs = ctx->f32[B200SPH_CS - N_F64];
     R.eos_any = ctx->spec_records && ctx->eos_last_valid ? 1 : 0;
     R.E = ctx->eos_last;
-    const unsigned long long *flag = &ctx->peer_box->data_seq[ctx->peer_epoch & 1][side];
-    if (halo_nf(ctx) == B200SPH_HALO_FIELDS)
-        k_peer_recv<B200SPH_HALO_FIELDS><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->comm_stream>>>(halo_ptrs(ctx), A, local_staging, R, flag, ctx->peer_epoch, ctx->peer_dec_hostdev);
-    else
-        k_peer_recv<B200SPH_HALO_FIELDS_SOLID><<<(unsigned)cdiv(tot, 256), 256, 0, ctx->comm_stream>>>(halo_ptrs(ctx), A, local_staging, R, flag, ctx->peer_epoch, ctx->peer_dec_hostdev);
-    LAUNCH_CHECK();
+    if (ctx->pend->n_recv >= 2) return set_err(ctx, "peer_recv: a slab has two neighbours");
+    PeerPending::Dir &D = ctx->pend->recv[ctx->pend->n_recv++];
+    D.A = A;
+    D.buf = const_cast<double *>(local_staging);
+    D.flag = &ctx->peer_box->data_seq[ctx->peer_epoch & 1][side];
+    D.tot = tot;
+    ctx->pend->pack = R;          // the same for both sides: it describes the receiver
     ctx->grid_valid = false;
     ctx->packed_valid = repack;
     if (!records) ctx->state_packed = false;
@@ -3063,12 +3157,14 @@ int b200sph_peer_commit_dt(b200sph_ctx *ctx, double prev_factor, double new_fact
     if (!ctx->comm_stream || !ctx->tc) return set_err(ctx, "peer_commit_dt: no epoch in flight / no time-control block");
     if (!(prev_factor > 0.0) || !(new_factor > 0.0)) return set_err(ctx, "peer_commit_dt: damping factors must be positive");
     if (snapshot_slot > 1) return set_err(ctx, "peer_commit_dt: snapshot slot must be 0 or 1");
-    k_dt_commit<<<1, 1, 0, ctx->comm_stream>>>(ctx->tc, prev_factor, new_factor, 1, adaptive, advance, ctx->t_final, ctx->t_eps);
+    // behind the agreement (k_peer_reduce left the MIN in tc[2]), on its stream
+    k_dt_commit<<<1, 1, 0, ctx->red_stream>>>(ctx->tc, prev_factor, new_factor, 1, adaptive, advance, ctx->t_final, ctx->t_eps);
     LAUNCH_CHECK();
     if (snapshot_slot >= 0) {
-        CU(cudaMemcpyAsync(ctx->tc_host + 2 * snapshot_slot, ctx->tc, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->comm_stream));
-        CU(cudaEventRecord(ctx->tc_evt[snapshot_slot], ctx->comm_stream));
+        CU(cudaMemcpyAsync(ctx->tc_host + 2 * snapshot_slot, ctx->tc, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->red_stream));
+        CU(cudaEventRecord(ctx->tc_evt[snapshot_slot], ctx->red_stream));
     }
+    CU(cudaEventRecord(ctx->ev_red, ctx->red_stream));
     return 0;
 }
 
@@ -3076,6 +3172,8 @@ int b200sph_peer_end(b200sph_ctx *ctx)
 {
     CU(cudaSetDevice(ctx->device));
     if (!ctx->comm_stream) return set_err(ctx, "peer_end: no epoch in flight");
+    if (ctx->pend->publish) return set_err(ctx, "peer_end: peer_reduce closes the outgoing half of an epoch");
+    if (int rc = peer_pull(ctx)) return rc;
     if (ctx->profiling && ctx->halo_ev_chain) CU(cudaEventRecord(ctx->halo_ev_chain, ctx->comm_stream));
     CU(cudaEventRecord(ctx->ev_join, ctx->comm_stream));
     ctx->comm_pending = true;
@@ -3091,7 +3189,7 @@ int b200sph_peer_decision(b200sph_ctx *ctx, double *ratio_max)
     for (long long spin = 0; d->seq != want; spin++) {
         if ((spin & 0xFFFF) == 0xFFFF) {
             // nothing enqueued can be stuck for half a minute unless a peer died
-            cudaError_t e = cudaStreamQuery(ctx->comm_stream);
+            cudaError_t e = cudaStreamQuery(ctx->red_stream);
             if (e != cudaSuccess && e != cudaErrorNotReady) return set_err(ctx, "peer_decision: %s", cudaGetErrorString(e));
             if (e == cudaSuccess && d->seq != want) return set_err(ctx, "peer_decision: epoch %llu was never decided", want);
         }
@@ -3273,6 +3371,7 @@ int b200sph_get_stats(b200sph_ctx *ctx, b200sph_stats *out)
         CU(cudaSetDevice(ctx->device));
         CU(cudaStreamSynchronize(ctx->stream));
         if (ctx->comm_stream) CU(cudaStreamSynchronize(ctx->comm_stream));
+        if (ctx->red_stream) CU(cudaStreamSynchronize(ctx->red_stream));
         for (auto &h : ctx->halo_pending) {
             float a = 0.f, b = 0.f;
             cudaEventElapsedTime(&a, h.fork, h.chain);

@@ -312,19 +312,65 @@ __global__ void k_peer_reduce(PeerBox *mine, int world, unsigned long long epoch
     }
 }
 
-// k_halo_gather_all into a neighbour's staging buffer + the data-ready flag in its mailbox,
-// raised by whichever block finishes last (every block fences its stores first)
+// One direction of the fused push / pull kernels below.
+struct PeerDir {
+    HaloAllArgs A;
+    double *buf;                 // push: the neighbour's staging buffer (peer pointer); pull: mine
+    unsigned long long *flag;    // push: data_seq in the neighbour's mailbox; pull: in mine
+    unsigned *done;              // push: block counter of this direction
+    unsigned nblocks;            // blocks of PEER_NT messages entries (0: the flag alone)
+};
+#define PEER_NT 256
+struct PeerPushArgs {
+    PeerDir d[2];
+    int ndir;
+    // the scalars of k_peer_publish, sent by block 0
+    int rank, world, have_build, with_dt;
+    float kr, S;
+    const unsigned *red_u32;
+    const double *tc;
+};
+
+// The outgoing half of a refresh epoch in ONE launch: block 0 publishes this rank's scalars
+// to every mailbox (k_peer_publish's body) and raises the flag of a direction that has
+// nothing to carry; the other blocks are k_halo_gather_all into the neighbours' staging
+// buffers, and whichever block of a direction finishes last raises that neighbour's
+// data-ready flag (every block fences its stores first).
 template <int NF>
-__global__ void k_peer_send(HaloPtrs P, HaloAllArgs A, double *__restrict__ dst, unsigned *done,
-                            unsigned long long *remote_flag, unsigned long long epoch)
+__global__ void __launch_bounds__(PEER_NT) k_peer_push(HaloPtrs P, PeerPushArgs X, PeerPtrs R, unsigned long long epoch)
 {
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < A.prefix[A.narr]) {
+    if (blockIdx.x == 0) {
+        const int r = threadIdx.x;
+        if (r < X.world) {
+            double v0 = 2.0;
+            if (X.have_build == 1) {
+                const float need = 2.0f * sqrtf(__uint_as_float(X.red_u32[0])) + X.kr * __uint_as_float(X.red_u32[1]);
+                v0 = X.S > 0.f ? (double)(need / X.S) : 2.0;
+            } else if (X.have_build == 2) {
+                v0 = 0.0;
+            }
+            const double v1 = X.with_dt ? X.tc[2] : __longlong_as_double(0x7ff0000000000000LL);
+            PeerSlot *sl = &R.box[r]->scal[epoch & 1][X.rank];
+            sl->v[0] = v0;
+            sl->v[1] = v1;
+            __threadfence_system();
+            *(volatile unsigned long long *)&sl->seq = epoch;
+        } else if (r >= 32 && r < 32 + X.ndir && X.d[r - 32].nblocks == 0) {
+            __threadfence_system();
+            *(volatile unsigned long long *)X.d[r - 32].flag = epoch;
+        }
+        return;
+    }
+    const unsigned b = blockIdx.x - 1;
+    const int d = b >= X.d[0].nblocks ? 1 : 0;
+    const PeerDir &D = X.d[d];
+    const long long k = (long long)(b - (d ? X.d[0].nblocks : 0u)) * PEER_NT + threadIdx.x;
+    if (k < D.A.prefix[D.A.narr]) {
         int a = 0;
-        while (k >= A.prefix[a + 1]) a++;
-        const long long r = k - A.prefix[a], cnt = A.prefix[a + 1] - A.prefix[a];
-        const long long i = A.off[a] + A.idx[a][r];
-        double *out = dst + NF * A.prefix[a] + r;
+        while (k >= D.A.prefix[a + 1]) a++;
+        const long long r = k - D.A.prefix[a], cnt = D.A.prefix[a + 1] - D.A.prefix[a];
+        const long long i = D.A.off[a] + D.A.idx[a][r];
+        double *out = D.buf + NF * D.A.prefix[a] + r;
 #pragma unroll
         for (int f = 0; f < HALO_ND(NF); f++) out[(long long)f * cnt] = P.p[f][i];
         if (NF != B200SPH_HALO_FIELDS) out[(long long)(NF - 1) * cnt] = (double)P.cs[i];
@@ -332,11 +378,11 @@ __global__ void k_peer_send(HaloPtrs P, HaloAllArgs A, double *__restrict__ dst,
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned prev = atomicAdd(done, 1u);
-        if (prev == gridDim.x - 1) {
-            *done = 0;                       // re-armed for the next launch on this stream
+        const unsigned prev = atomicAdd(D.done, 1u);
+        if (prev == D.nblocks - 1) {
+            *D.done = 0;                     // re-armed for the next launch on this stream
             __threadfence_system();
-            *(volatile unsigned long long *)remote_flag = epoch;
+            *(volatile unsigned long long *)D.flag = epoch;
         }
     }
 }
@@ -354,22 +400,32 @@ struct GhostPackArgs {
     EosTab E;
 };
 
-// k_halo_scatter_all behind the neighbour's data-ready flag
+struct PeerPullArgs {
+    PeerDir d[2];
+    int ndir;
+};
+// The incoming half in ONE launch: k_halo_scatter_all of both neighbours' messages, every
+// block behind the data-ready flag of its own direction (a block of the left message does
+// not wait for the right neighbour).
 template <int NF>
-__global__ void k_peer_recv(HaloPtrs P, HaloAllArgs A, const double *__restrict__ src, GhostPackArgs R,
-                            const unsigned long long *flag, unsigned long long epoch, PeerDecision *dec_host)
+__global__ void __launch_bounds__(PEER_NT) k_peer_pull(HaloPtrs P, PeerPullArgs X, GhostPackArgs R, unsigned long long epoch,
+                                                       PeerDecision *dec_host)
 {
     __shared__ int s_ok;
+    const int d = blockIdx.x >= X.d[0].nblocks ? 1 : 0;
+    const PeerDir &D = X.d[d];
+    const HaloAllArgs &A = D.A;
+    const double *src = D.buf;
     if (threadIdx.x == 0) {
-        s_ok = peer_wait((const volatile unsigned long long *)flag, epoch) ? 1 : 0;
+        s_ok = peer_wait((const volatile unsigned long long *)D.flag, epoch) ? 1 : 0;
         __threadfence_system();
     }
     __syncthreads();
     if (!s_ok) {
-        if (threadIdx.x == 0 && blockIdx.x == 0 && dec_host) dec_host->error = epoch;
+        if (threadIdx.x == 0 && dec_host) dec_host->error = epoch;
         return;
     }
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long k = (long long)(blockIdx.x - (d ? X.d[0].nblocks : 0u)) * PEER_NT + threadIdx.x;
     if (k >= A.prefix[A.narr]) return;
     int a = 0;
     while (k >= A.prefix[a + 1]) a++;
@@ -423,13 +479,6 @@ __global__ void k_peer_recv(HaloPtrs P, HaloAllArgs A, const double *__restrict_
             R.C[s] = c;
         }
     }
-}
-
-// the flag alone (nothing to send to that neighbour this build)
-__global__ void k_peer_flag(unsigned long long *remote_flag, unsigned long long epoch)
-{
-    __threadfence_system();
-    *(volatile unsigned long long *)remote_flag = epoch;
 }
 
 // ---- interior / boundary split of the list consumer ---------------------------------------
