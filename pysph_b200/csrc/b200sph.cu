@@ -292,6 +292,7 @@ struct b200sph_ctx {
     // The scalar agreement runs on its own stream: a rank's ghosts only need its two neighbours,
     // the decision needs every rank, and the boundary launch must not wait for the slowest one.
     cudaStream_t red_stream = nullptr;
+    int push_first = 1;                          // B200SPH_PUSH_FIRST
     cudaEvent_t ev_pushed = nullptr, ev_red = nullptr;
     // peer_publish / peer_send / peer_recv only RECORD: the launches are merged into one
     // k_peer_push (at peer_reduce) and one k_peer_pull (at peer_end)
@@ -734,6 +735,7 @@ int b200sph_create(int device, b200sph_ctx **out)
     if (const char *e = getenv("B200SPH_PAIR_SPEC")) ctx->pair_spec = atoi(e) != 0;
     if (const char *e = getenv("B200SPH_ZORDER")) ctx->zorder = atoi(e) != 0;
     if (const char *e = getenv("B200SPH_PROACTIVE")) ctx->proactive = atoi(e) != 0;
+    if (const char *e = getenv("B200SPH_PUSH_FIRST")) ctx->push_first = atoi(e) != 0;
     if (const char *e = getenv("B200SPH_SKIN")) ctx->skin = ctx->skin_max = std::max(0.0, atof(e));
     if (const char *e = getenv("B200SPH_SKIN_ADAPT")) ctx->skin_adapt = atoi(e) != 0;
     ctx->skin_min = std::min(ctx->skin_min, ctx->skin_max);
@@ -1901,6 +1903,10 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
                 ctx->n_overlapped++;
             }
             if (nb == 0) continue;
+            // The interior CTAs of the first wave hold every SM slot for a whole CTA lifetime
+            // (~50 us): the outgoing messages go first, and the receiving CTAs (next on the
+            // communication stream, higher priority) get their slots before the wave does.
+            if (overlap && phase == 0 && ctx->push_first) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_pushed, 0));
             switch (ctx->kernel * 4 + ctx->dim) {
 #define LIST_LAUNCH(K, D, M, Q) k_pair_list<K, D, M, Q><<<nb, LIST_NT, 0, lst_stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg, ids)
 #define LIST_CASE(K, D)                                                          \
