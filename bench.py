@@ -970,8 +970,9 @@ def run_dam_break(args, rank, local_rank, world):
     achieved = pairs_per_launch * BYTES_PER_PAIR / (ms_pair * 1e-3) / 1e9
     lists = bool(st['list_builds'] or st['light_updates'])
     roofline = {'bound': 'hbm',      # the contract's class (memory, not tensor) = the denominator used
-                'limiter_ncu': 'L1/TEX gather path 82 % + long-scoreboard latency (issue 64 %); DRAM at '
-                               '11 % of peak -- NOT HBM-bound: "achieved" charges every gathered '
+                'limiter_ncu': 'L1/TEX gather path 85 % (LSU data-pipe wavefronts) + long-scoreboard latency '
+                               '(issue active 73 %, 41 % warps active; profiles/r02e_lb_raw.csv); DRAM at '
+                               '15 % of peak -- NOT HBM-bound: "achieved" charges every gathered '
                                'record to HBM as SURVEY 8d defines it, the records are served by L1/L2',
                 'kernel': 'k_pair_list<CubicSpline,3>' if lists else 'k_pair<CubicSpline,3>',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

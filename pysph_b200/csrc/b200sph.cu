@@ -292,7 +292,7 @@ struct b200sph_ctx {
     // The scalar agreement runs on its own stream: a rank's ghosts only need its two neighbours,
     // the decision needs every rank, and the boundary launch must not wait for the slowest one.
     cudaStream_t red_stream = nullptr;
-    int push_first = 1;                          // B200SPH_PUSH_FIRST
+    int push_first = 0;                          // B200SPH_PUSH_FIRST (measured: profiles/r02k_chain.md)
     cudaEvent_t ev_pushed = nullptr, ev_red = nullptr;
     // peer_publish / peer_send / peer_recv only RECORD: the launches are merged into one
     // k_peer_push (at peer_reduce) and one k_peer_pull (at peer_end)
