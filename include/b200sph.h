@@ -31,7 +31,7 @@ extern "C" {
 
 #define B200SPH_MAX_ARRAYS 8
 #define B200SPH_MAX_RANKS 16   /* ranks of one node in the peer protocol (b200sph_peer_*) */
-#define B200SPH_ABI_VERSION 4
+#define B200SPH_ABI_VERSION 5
 
 typedef struct b200sph_ctx b200sph_ctx;
 
@@ -283,6 +283,12 @@ int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim,
  * (dest, source) loops); counting costs one extra atomic per warp. */
 int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog,
                       int64_t *pairs_out);
+/* Group(start_idx, stop_idx) (equation.py:448-520; D_START_IDX / NP_DEST of the generated
+ * loop, acceleration_eval_cython_helper.py:259-284): the NEXT b200sph_pair_pass only touches
+ * the destinations [start, stop) of array `arr` (indices into the array; stop = -1: to the end,
+ * i.e. what real_only admits); arrays not named keep all their destinations.  One-shot: the
+ * pass clears it. */
+int b200sph_set_dest_range(b200sph_ctx *ctx, int arr, int64_t start, int64_t stop);
 
 /* The two Groups of EDACScheme._get_internal_flow_equations (wc/edac.py:776-880) in
  * the generated AccelerationEval.compute (acceleration_eval_cython.mako:10-154): group 1 computes

@@ -139,6 +139,7 @@ SIGNATURES = {
     'b200sph_ferrari_h': (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_int, C.c_int]),
     'b200sph_pair_pass': (C.c_int, [_ctx_p, C.POINTER(PairProgram),
                                     C.POINTER(_i64)]),
+    'b200sph_set_dest_range': (C.c_int, [_ctx_p, C.c_int, _i64, _i64]),
     'b200sph_tvf_pass': (C.c_int, [_ctx_p, C.POINTER(TvfProgram), C.POINTER(_i64)]),
     'b200sph_stage_tvf': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
     'b200sph_stage_tvf_dev': (C.c_int, [_ctx_p, C.c_int, C.c_int]),

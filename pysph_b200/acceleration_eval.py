@@ -10,7 +10,7 @@ import ctypes as C
 
 from . import _lib
 from .kernels import kernel_id
-from .program import build_program
+from .program import build_program, index_value, _converged
 
 
 class B200AccelerationEval(object):
@@ -52,36 +52,59 @@ class B200AccelerationEval(object):
         self.backend.push_all()
 
     def compute(self, t, dt):
+        self._pairs = 0
+        self._run(self.ops, t, dt)
+        self.last_pairs = self._pairs
+
+    def _run(self, ops, t, dt):
+        """The loop nest of acceleration_eval_cython.mako:262-363 over the op list."""
         ctx = self.ctx
-        pairs = 0
         cnt = C.c_int64(0)
-        for op in self.ops:
+        for op in ops:
             kind = op[0]
-            if kind == 'eos':
+            if kind == 'cond':
+                if op[1](t, dt):
+                    self._run(op[2], t, dt)
+            elif kind == 'iterate':
+                # helper:320-340: at least min_iterations, stop when every equation has
+                # converged or after max_iterations
+                _, min_it, max_it, group, body = op
+                it = 1
+                while True:
+                    self._run(body, t, dt)
+                    if it >= min_it and (_converged(group) or it == max_it):
+                        break
+                    it += 1
+            elif kind == 'call':
+                op[1]()
+            elif kind == 'range':
+                for d, (lo, hi, pa) in op[1].items():
+                    ctx.call('b200sph_set_dest_range', d, index_value(lo, pa),
+                             -1 if hi is None else index_value(hi, pa))
+            elif kind == 'eos':
                 ctx.call('b200sph_eos', *op[1:])
             elif kind == 'ferrari':
                 ctx.call('b200sph_ferrari_h', *op[1:])
             elif kind == 'pair':
                 if self.count_pairs:
                     ctx.call('b200sph_pair_pass', C.byref(op[1]), C.byref(cnt))
-                    pairs += cnt.value
+                    self._pairs += cnt.value
                 else:
                     ctx.call('b200sph_pair_pass', C.byref(op[1]), None)
             elif kind == 'tvf':
                 op[1].t = float(t)          # body-force damping, wc/edac.py:483-488
                 if self.count_pairs:
                     ctx.call('b200sph_tvf_pass', C.byref(op[1]), C.byref(cnt))
-                    pairs += cnt.value
+                    self._pairs += cnt.value
                 else:
                     ctx.call('b200sph_tvf_pass', C.byref(op[1]), None)
             elif kind == 'solid':
                 if self.count_pairs:
                     ctx.call('b200sph_solid_pass', C.byref(op[1]), C.byref(cnt))
-                    pairs += cnt.value
+                    self._pairs += cnt.value
                 else:
                     ctx.call('b200sph_solid_pass', C.byref(op[1]), None)
             elif kind == 'update_nnps':
                 # mako:139-145: nnps.update_domain(); nnps.update()
                 ctx.call('b200sph_update_domain')
                 ctx.call('b200sph_nnps_update')
-        self.last_pairs = pairs

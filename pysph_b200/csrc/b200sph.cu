@@ -292,6 +292,9 @@ struct b200sph_ctx {
     // The scalar agreement runs on its own stream: a rank's ghosts only need its two neighbours,
     // the decision needs every rank, and the boundary launch must not wait for the slowest one.
     cudaStream_t red_stream = nullptr;
+    // Group(start_idx, stop_idx): one-shot destination ranges of the next pair pass
+    int64_t dst_lo[B200SPH_MAX_ARRAYS] = {0}, dst_hi[B200SPH_MAX_ARRAYS] = {0};
+    bool dst_ranged = false;
     int push_first = 0;                          // B200SPH_PUSH_FIRST (measured: profiles/r02k_chain.md)
     cudaEvent_t ev_pushed = nullptr, ev_red = nullptr;
     // peer_publish / peer_send / peer_recv only RECORD: the launches are merged into one
@@ -1790,6 +1793,18 @@ int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim, int real_o
     return 0;
 }
 
+int b200sph_set_dest_range(b200sph_ctx *ctx, int arr, int64_t start, int64_t stop)
+{
+    if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "set_dest_range: bad array index %d", arr);
+    if (start < 0 || stop < -1) return set_err(ctx, "set_dest_range: start >= 0 and stop >= 0 (or -1: no limit), got [%lld, %lld)", (long long)start, (long long)stop);
+    if (!ctx->dst_ranged)
+        for (int d = 0; d < B200SPH_MAX_ARRAYS; d++) ctx->dst_lo[d] = 0, ctx->dst_hi[d] = -1;
+    ctx->dst_lo[arr] = start;
+    ctx->dst_hi[arr] = stop;
+    ctx->dst_ranged = true;
+    return 0;
+}
+
 int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_t *pairs_out)
 {
     CU(cudaSetDevice(ctx->device));
@@ -1817,6 +1832,10 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     }
     // lists hold 26-bit sorted indices: larger particle counts use the warp kernel
     const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->n_sorted < (1LL << LIST_JBITS);
+    const bool ranged = ctx->dst_ranged;
+    ctx->dst_ranged = false;
+    if (ranged && !use_lists && ctx->n_sorted > 0)
+        return set_err(ctx, "pair_pass: destination ranges (Group start_idx / stop_idx) need the neighbour-list path");
     // the (destination, source) type pairs this Group has equations for; lists that were
     // filtered with a narrower set are rebuilt with the union
     unsigned long long want[B200SPH_MAX_ARRAYS];
@@ -1829,7 +1848,7 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     // the peer protocol's refresh is still in flight and every record a ghost-free CTA
     // reads is in place: those CTAs go first, the main stream waits for the halo only then
     const bool overlap = ctx->comm_pending && use_lists && ctx->lists_valid && ctx->chunks_valid && ctx->state_packed &&
-                         ctx->n_chunk_interior > 0 && !pairs_out;
+                         ctx->n_chunk_interior > 0 && !pairs_out && !ranged;
     if (!overlap && (rc = sync_comm(ctx))) return rc;
     if (!ctx->state_packed) {
         if ((rc = pack_state(ctx))) return rc;
@@ -1882,6 +1901,12 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     for (int d = 0; d < ctx->narr; d++)
         for (int sx = 0; sx < ctx->narr; sx++) prog_bits |= prog->eqmask[d][sx];
     const bool wcsph_only = ctx->pair_spec && !(prog_bits & ~(unsigned)PAIR_EQS_WCSPH) && !prog->tensile_correction;
+    if (ranged)
+        for (int d = 0; d < ctx->narr; d++) {
+            pa.doff[d] = ctx->arr[d].off;
+            pa.dlo[d] = ctx->dst_lo[d];
+            pa.dhi[d] = ctx->dst_hi[d] < 0 ? (int64_t)1 << 62 : ctx->dst_hi[d];
+        }
     pa.pair_counter = nullptr;
     if (pairs_out) {
         CU(cudaMemsetAsync(ctx->counter, 0, 8, ctx->stream));
@@ -1911,7 +1936,8 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
 #define LIST_LAUNCH(K, D, M, Q) k_pair_list<K, D, M, Q><<<nb, LIST_NT, 0, lst_stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg, ids)
 #define LIST_CASE(K, D)                                                          \
     case K * 4 + D:                                                              \
-        if (wcsph_only && ctx->pair_minb >= 8) LIST_LAUNCH(K, D, 8, PAIR_EQS_WCSPH); \
+        if (ranged) k_pair_list<K, D, 6, PAIR_EQS_ALL, true><<<nb, LIST_NT, 0, lst_stream>>>(pa, ctx->cnt, ctx->lst, ctx->capg, ids); \
+        else if (wcsph_only && ctx->pair_minb >= 8) LIST_LAUNCH(K, D, 8, PAIR_EQS_WCSPH); \
         else if (wcsph_only && ctx->pair_minb == 7) LIST_LAUNCH(K, D, 7, PAIR_EQS_WCSPH); \
         else if (ctx->pair_minb >= 7) LIST_LAUNCH(K, D, 7, PAIR_EQS_ALL);          \
         else LIST_LAUNCH(K, D, 6, PAIR_EQS_ALL);                                  \

@@ -21,6 +21,9 @@ struct PairArgs {
     float c0, alpha, beta, gx, gy, gz, eps_xsph;
     int tensile, real_only;
     unsigned long long *pair_counter;  // may be null
+    // Group(start_idx, stop_idx): destinations [dlo, dhi) of every array, as indices INTO the
+    // array (equation.py:448-520); read by the RANGED instantiations of k_pair_list only
+    long long doff[B200SPH_MAX_ARRAYS], dlo[B200SPH_MAX_ARRAYS], dhi[B200SPH_MAX_ARRAYS];
 };
 
 #define PAIR_WARPS 8

@@ -273,7 +273,7 @@ __device__ __forceinline__ void pair_entry(const PairArgs &a, const bool live, c
         pair_body<K, DIM, EQS>(a, make_float4(xij, yij, zij, Aj.w), Bj, Cj, Ai, Bi, Ci, mask_i, Ci.y, acc, npairs);
 }
 
-template <int K, int DIM, int MINB, int EQS>
+template <int K, int DIM, int MINB, int EQS, bool RANGED = false>
 __global__ void __launch_bounds__(LIST_NT, MINB) k_pair_list(const PairArgs a, const uint32_t *__restrict__ cnt,
                                                             const uint32_t *__restrict__ lst, const int capg,
                                                             const uint32_t *__restrict__ chunk_ids)
@@ -292,6 +292,10 @@ __global__ void __launch_bounds__(LIST_NT, MINB) k_pair_list(const PairArgs a, c
         const int ti = __float_as_int(Ci.w);
         mask_i = a.emask[ti & 7];
         if ((a.real_only && (ti & PT_GHOST)) || !mask_i) active = false;
+        if (RANGED && active) {   // Group(start_idx, stop_idx): only these destinations of the array
+            const long long li = (long long)a.perm[s] - a.doff[ti & 7];
+            if (li < a.dlo[ti & 7] || li >= a.dhi[ti & 7]) active = false;
+        }
     }
     if (active) {
         ld_256(a.AB + 2 * (size_t)s, Ai, Bi);

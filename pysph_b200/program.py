@@ -289,20 +289,14 @@ def _set_once(params, key, value, eq):
     params[key] = value
 
 
-def _flatten(groups):
-    """Group(subgroups) -> sequence of plain groups (mako:320-343)."""
-    out = []
-    for g in groups:
-        if getattr(g, 'has_subgroups', False):
-            if getattr(g, 'iterate', False):
-                raise NotImplementedError(
-                    'B200 backend: iterated groups are not supported')
-            out.extend(_flatten(g.equations))
-            if getattr(g, 'update_nnps', False):
-                out.append('update_nnps')
-        else:
-            out.append(g)
-    return out
+def _converged(group):
+    """Group.get_converged_condition (equation.py:656-667): every equation's converged() is
+    called (no short circuit) and all must return > 0."""
+    if getattr(group, 'has_subgroups', False):
+        res = [_converged(g) for g in group.equations]
+    else:
+        res = [getattr(eq, 'converged', lambda: 1.0)() > 0 for eq in group.equations]
+    return all(res)
 
 
 def group_equations(equations):
@@ -318,105 +312,188 @@ def group_equations(equations):
 
 
 def build_program(groups, array_names, dim, particle_arrays=None):
-    """groups: list of Group objects (ours or PySPH's)."""
+    """groups: list of Group objects (ours or PySPH's) -> nested op list, the loop nest of
+    acceleration_eval_cython.mako:262-363:
+
+        ('cond', callable, body)              Group(condition=...): body runs if callable(t, dt)
+        ('iterate', min, max, group, body)    Group(iterate=True): repeat body until every
+                                              equation's converged() > 0 (mako + helper:320-340)
+        ('call', callable)                    Group(pre=..., post=...)
+        ('range', {array: (start, stop)})     Group(start_idx=..., stop_idx=...): destinations
+                                              of the NEXT pair op
+        ('eos' | 'ferrari' | 'pair' | 'tvf' | 'solid' | 'update_nnps', ...)   device calls
+    """
     index = dict((n, i) for i, n in enumerate(array_names))
+    arrays = dict((pa.name, pa) for pa in (particle_arrays or []))
     ops = []
-    for g in _flatten(group_equations(groups)):
-        if g == 'update_nnps':
-            ops.append(('update_nnps',))
-            continue
-        for attr, default in (('iterate', False), ('condition', None),
-                              ('pre', None), ('post', None), ('start_idx', 0),
-                              ('stop_idx', None)):
-            if getattr(g, attr, default) not in (default,):
-                raise NotImplementedError(
-                    'B200 backend: Group(%s=%r) is not supported'
-                    % (attr, getattr(g, attr)))
-        kind = _solid_group_kind(g)
-        if kind:
-            ops.append(('solid', _build_solid(g, kind, index, particle_arrays)))
-            if getattr(g, 'update_nnps', False):
-                ops.append(('update_nnps',))
-            continue
-        kind = _tvf_group_kind(g)
-        if kind:
-            ops.append(('tvf', _build_tvf(g, kind, index)))
-            if getattr(g, 'update_nnps', False):
-                ops.append(('update_nnps',))
-            continue
-        real_only = 1 if getattr(g, 'real', True) else 0
-        pair_eqs = []
-        nosrc_ops = []
-        for eq in g.equations:
-            name = _eq_name(eq)
-            if eq.dest not in index:
-                raise ValueError('equation %s: unknown destination array %r'
-                                 % (name, eq.dest))
-            d = index[eq.dest]
-            if name in PAIR_EQUATIONS:
-                if not eq.sources:
-                    raise ValueError('%s needs sources' % name)
-                pair_eqs.append(eq)
-            elif name in ('TaitEOS', 'TaitEOSHGCorrection'):
-                hg = 1 if name == 'TaitEOSHGCorrection' else 0
-                nosrc_ops.append(('eos', d, hg, float(eq.rho0), float(eq.c0),
-                                  float(eq.gamma),
-                                  float(getattr(eq, 'p0', 0.0)), real_only))
-            elif name == 'UpdateSmoothingLengthFerrari':
-                nosrc_ops.append(('ferrari', d, float(eq.hdx),
-                                  int(round(1.0 / eq.dim1)), real_only))
-            else:
-                raise NotImplementedError(
-                    'B200 backend: no CUDA kernel for equation %r (supported: '
-                    '%s)' % (name, ', '.join(sorted(list(PAIR_EQUATIONS) +
-                                                    list(NO_SOURCE_EQUATIONS)))))
-        if pair_eqs and nosrc_ops:
-            raise NotImplementedError(
-                'B200 backend: a Group mixing no-source equations and pair '
-                'equations is not supported; put them in separate Groups '
-                '(as WCSPHScheme does, scheme.py:414-483)')
-        ops.extend(nosrc_ops)
-        if pair_eqs:
-            prog = _lib.PairProgram()
-            params = {}
-            all_bits = 0
-            for eq in pair_eqs:
-                name = _eq_name(eq)
-                bit = PAIR_EQUATIONS[name]
-                all_bits |= bit
-                d = index[eq.dest]
-                for s in eq.sources:
-                    if s not in index:
-                        raise ValueError('equation %s: unknown source array %r'
-                                         % (name, s))
-                    prog.eqmask[d][index[s]] |= bit
-                if name == 'MomentumEquation':
-                    for k in ('c0', 'alpha', 'beta', 'gx', 'gy', 'gz'):
-                        _set_once(params, k, float(getattr(eq, k)), eq)
-                    _set_once(params, 'tensile_correction',
-                              int(bool(eq.tensile_correction)), eq)
-                elif name == 'MonaghanArtificialViscosity':
-                    for k in ('alpha', 'beta'):
-                        _set_once(params, k, float(getattr(eq, k)), eq)
-                elif name == 'XSPHCorrection':
-                    _set_once(params, 'eps_xsph', float(eq.eps), eq)
-            if (all_bits & _lib.EQ_SUMMATION_DENSITY) and (
-                    all_bits & (_lib.EQ_MOMENTUM | _lib.EQ_XSPH |
-                                _lib.EQ_MONAGHAN_AV)):
-                raise NotImplementedError(
-                    'B200 backend: SummationDensity (writes rho) cannot share a '
-                    'Group with equations that read rho; the reference '
-                    'evaluates destinations one after another there '
-                    '(mako:20-135) -- use separate Groups')
-            if (all_bits & _lib.EQ_MOMENTUM) and (all_bits & _lib.EQ_MONAGHAN_AV):
-                raise NotImplementedError(
-                    'B200 backend: MomentumEquation already contains the '
-                    'artificial viscosity; combining it with '
-                    'MonaghanArtificialViscosity in one Group is not supported')
-            prog.real_only = real_only
-            for k, v in params.items():
-                setattr(prog, k, v)
-            ops.append(('pair', prog))
-        if getattr(g, 'update_nnps', False):
-            ops.append(('update_nnps',))
+    for g in group_equations(groups):
+        ops.extend(_mega_group(g, index, arrays, particle_arrays))
     return _merge_solid(_merge_tvf(ops))
+
+
+def _wrap(g, body, top):
+    # iteration is a property of the mega group only: do_group (mako:10-155), which runs the
+    # sub-groups, never looks at `iterate`
+    if top and getattr(g, 'iterate', False):
+        body = [('iterate', int(getattr(g, 'min_iterations', 0)),
+                 int(getattr(g, 'max_iterations', 1)), g, body)]
+    if getattr(g, 'condition', None) is not None:
+        body = [('cond', g.condition, body)]
+    return body
+
+
+def _mega_group(g, index, arrays, particle_arrays):
+    if getattr(g, 'has_subgroups', False):
+        body = []
+        if getattr(g, 'pre', None):
+            body.append(('call', g.pre))
+        inner = []
+        for sg in g.equations:
+            if getattr(sg, 'has_subgroups', False):
+                raise NotImplementedError(
+                    'B200 backend: Groups nest one level deep (as in the reference, '
+                    'acceleration_eval.py:293-300)')
+            inner.extend(_wrap(sg, _leaf_group(sg, index, arrays, particle_arrays), False))
+        body.extend(_merge_solid(_merge_tvf(inner)))
+        if getattr(g, 'update_nnps', False):
+            body.append(('update_nnps',))
+        if getattr(g, 'post', None):
+            body.append(('call', g.post))
+    else:
+        body = _leaf_group(g, index, arrays, particle_arrays)
+    return _wrap(g, body, True)
+
+
+def index_value(v, pa):
+    """start_idx / stop_idx: a number, or the name of a property / constant of the
+    destination whose first value is the index (helper:265-278)."""
+    if isinstance(v, str):
+        holder = getattr(pa, 'constants', {})
+        if v in holder:
+            return int(holder[v][0])
+        return int(getattr(pa, v)[0])
+    return int(v)
+
+
+def _no_range(g, ranged, what):
+    if ranged:
+        raise NotImplementedError(
+            'B200 backend: Group(start_idx / stop_idx) is supported for the WCSPH pair '
+            'equations only, not for the %s groups' % what)
+
+
+def _leaf_group(g, index, arrays, particle_arrays):
+    """do_group (mako:10-155): pre, the destination loops, update_nnps, post."""
+    ops = []
+    if getattr(g, 'pre', None):
+        ops.append(('call', g.pre))
+    ops.extend(_leaf_body(g, index, arrays, particle_arrays))
+    if getattr(g, 'update_nnps', False):
+        ops.append(('update_nnps',))
+    if getattr(g, 'post', None):
+        ops.append(('call', g.post))
+    return ops
+
+
+def _leaf_body(g, index, arrays, particle_arrays):
+    ops = []
+    start, stop = getattr(g, 'start_idx', 0), getattr(g, 'stop_idx', None)
+    ranged = (stop is not None) or (start not in (0, None))
+    kind = _solid_group_kind(g)
+    if kind:
+        _no_range(g, ranged, 'elastic-dynamics')
+        ops.append(('solid', _build_solid(g, kind, index, particle_arrays)))
+        return ops
+    kind = _tvf_group_kind(g)
+    if kind:
+        _no_range(g, ranged, 'EDAC')
+        ops.append(('tvf', _build_tvf(g, kind, index)))
+        return ops
+    real_only = 1 if getattr(g, 'real', True) else 0
+    pair_eqs = []
+    nosrc_ops = []
+    for eq in g.equations:
+        name = _eq_name(eq)
+        if eq.dest not in index:
+            raise ValueError('equation %s: unknown destination array %r'
+                             % (name, eq.dest))
+        d = index[eq.dest]
+        if name in PAIR_EQUATIONS:
+            if not eq.sources:
+                raise ValueError('%s needs sources' % name)
+            pair_eqs.append(eq)
+        elif name in ('TaitEOS', 'TaitEOSHGCorrection'):
+            hg = 1 if name == 'TaitEOSHGCorrection' else 0
+            nosrc_ops.append(('eos', d, hg, float(eq.rho0), float(eq.c0),
+                              float(eq.gamma),
+                              float(getattr(eq, 'p0', 0.0)), real_only))
+        elif name == 'UpdateSmoothingLengthFerrari':
+            nosrc_ops.append(('ferrari', d, float(eq.hdx),
+                              int(round(1.0 / eq.dim1)), real_only))
+        else:
+            raise NotImplementedError(
+                'B200 backend: no CUDA kernel for equation %r (supported: '
+                '%s)' % (name, ', '.join(sorted(list(PAIR_EQUATIONS) +
+                                                list(NO_SOURCE_EQUATIONS)))))
+    if pair_eqs and nosrc_ops:
+        raise NotImplementedError(
+            'B200 backend: a Group mixing no-source equations and pair '
+            'equations is not supported; put them in separate Groups '
+            '(as WCSPHScheme does, scheme.py:414-483)')
+    if nosrc_ops:
+        _no_range(g, ranged, 'equation-of-state / smoothing-length')
+    ops.extend(nosrc_ops)
+    if pair_eqs:
+        if ranged:
+            # resolved at every compute(): a str names a property / constant of the
+            # destination that may change between calls (helper:265-278)
+            rng = {}
+            for eq in pair_eqs:
+                pa = arrays.get(eq.dest)
+                if pa is None and (isinstance(start, str) or isinstance(stop, str)):
+                    raise ValueError('Group(start_idx=%r, stop_idx=%r) needs the particle '
+                                     'arrays' % (start, stop))
+                rng[index[eq.dest]] = (start or 0, stop, pa)
+            ops.append(('range', rng))
+        prog = _lib.PairProgram()
+        params = {}
+        all_bits = 0
+        for eq in pair_eqs:
+            name = _eq_name(eq)
+            bit = PAIR_EQUATIONS[name]
+            all_bits |= bit
+            d = index[eq.dest]
+            for s in eq.sources:
+                if s not in index:
+                    raise ValueError('equation %s: unknown source array %r'
+                                     % (name, s))
+                prog.eqmask[d][index[s]] |= bit
+            if name == 'MomentumEquation':
+                for k in ('c0', 'alpha', 'beta', 'gx', 'gy', 'gz'):
+                    _set_once(params, k, float(getattr(eq, k)), eq)
+                _set_once(params, 'tensile_correction',
+                          int(bool(eq.tensile_correction)), eq)
+            elif name == 'MonaghanArtificialViscosity':
+                for k in ('alpha', 'beta'):
+                    _set_once(params, k, float(getattr(eq, k)), eq)
+            elif name == 'XSPHCorrection':
+                _set_once(params, 'eps_xsph', float(eq.eps), eq)
+        if (all_bits & _lib.EQ_SUMMATION_DENSITY) and (
+                all_bits & (_lib.EQ_MOMENTUM | _lib.EQ_XSPH |
+                            _lib.EQ_MONAGHAN_AV)):
+            raise NotImplementedError(
+                'B200 backend: SummationDensity (writes rho) cannot share a '
+                'Group with equations that read rho; the reference '
+                'evaluates destinations one after another there '
+                '(mako:20-135) -- use separate Groups')
+        if (all_bits & _lib.EQ_MOMENTUM) and (all_bits & _lib.EQ_MONAGHAN_AV):
+            raise NotImplementedError(
+                'B200 backend: MomentumEquation already contains the '
+                'artificial viscosity; combining it with '
+                'MonaghanArtificialViscosity in one Group is not supported')
+        # NP_DEST = stop_idx replaces size(real=...) (helper:271-278)
+        prog.real_only = real_only if stop is None else 0
+        for k, v in params.items():
+            setattr(prog, k, v)
+        ops.append(('pair', prog))
+    return ops

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), 'libb200sph.so does not export %s' % name
     # and the ctypes table covers exactly the header
     assert set(_lib.SIGNATURES) == declared
-    assert lib.b200sph_abi_version() == 4
+    assert lib.b200sph_abi_version() == 5
 
 
 def test_no_cpu_fallback_without_device():
@@ -107,9 +107,21 @@ def test_program_translation():
         build_program([pb.Group([pb.SummationDensity('fluid', ['fluid']),
                                  pb.XSPHCorrection('fluid', ['fluid'])])],
                       names, 3)
-    with pytest.raises(NotImplementedError):
-        build_program([pb.Group([pb.SummationDensity('fluid', ['fluid'])],
-                                iterate=True)], names, 3)
+    # the loop nest's control features become nested ops (mako:262-363)
+    cond = lambda t, dt: True
+    ops = build_program([pb.Group([pb.SummationDensity('fluid', ['fluid'])],
+                                  iterate=True, min_iterations=2, max_iterations=5,
+                                  condition=cond, start_idx=1, stop_idx='n')],
+                        names, 3, particle_arrays=[
+                            pb.get_particle_array_wcsph(name=n) for n in names])
+    assert ops[0][0] == 'cond' and ops[0][1] is cond
+    it = ops[0][2][0]
+    assert it[0] == 'iterate' and it[1:3] == (2, 5)
+    assert [o[0] for o in it[4]] == ['range', 'pair']
+    assert it[4][0][1][0][:2] == (1, 'n') and it[4][1][1].real_only == 0
+    with pytest.raises(NotImplementedError):     # ranges: the WCSPH pair equations only
+        build_program([pb.Group([pb.TaitEOS('fluid', None, rho0=1., c0=1., gamma=7.)],
+                                stop_idx=3)], names, 3)
     with pytest.raises(NotImplementedError):
         build_program([pb.Group([
             pb.MomentumEquation('fluid', ['fluid'], c0=1.0, alpha=0.1),

@@ -65,7 +65,7 @@ def test_every_entry_point_is_exported(emulated_library):
     lib = _lib.load()
     for name in _lib.SIGNATURES:
         assert hasattr(lib, name), name
-    assert lib.b200sph_abi_version() == 4
+    assert lib.b200sph_abi_version() == 5
 
 
 # ---- the GPU tests of this repository, run against the emulated library --------------------
@@ -116,6 +116,12 @@ FAST = [
     ('test_gpu_mirror', 'test_mirror_errors', {}),
     ('test_gpu_rings_multi', 'test_elastic_halo_and_migration_layout', {}),
     ('test_gpu_rings_multi', 'test_empty_elastic_array_agrees_on_the_message_layout', {}),
+    ('test_gpu_groups', 'test_group_honors_condition', {}),
+    ('test_gpu_groups', 'test_iterated_groups', {}),
+    ('test_gpu_groups', 'test_pre_post_order', {}),
+    ('test_gpu_groups', 'test_start_stop_idx', {'as_str': False}),
+    ('test_gpu_groups', 'test_start_stop_idx', {'as_str': True}),
+    ('test_gpu_groups', 'test_start_stop_idx_three_arrays', {}),
 ]
 FULL = [
     ('test_gpu_parity', 'test_device_resident_dt_is_bitwise_the_host_path', {}),
