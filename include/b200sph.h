@@ -30,6 +30,7 @@ extern "C" {
 #endif
 
 #define B200SPH_MAX_ARRAYS 8
+#define B200SPH_MAX_USER 16    /* user properties of the generic-equation fallback */
 #define B200SPH_MAX_RANKS 16   /* ranks of one node in the peer protocol (b200sph_peer_*) */
 #define B200SPH_ABI_VERSION 5
 
@@ -76,7 +77,10 @@ enum {
     B200SPH_AS00 = 97, B200SPH_AS01, B200SPH_AS02, B200SPH_AS11, B200SPH_AS12, B200SPH_AS22,
     B200SPH_SOLID_PROPS_END = 103,
     /* 32-bit integer props */
-    B200SPH_GID = 64, B200SPH_TAG = 65, B200SPH_PID = 66
+    B200SPH_GID = 64, B200SPH_TAG = 65, B200SPH_PID = 66,
+    /* fp64 properties the pool does not know, created on first use for the generic-equation
+     * fallback (b200sph_user_property): ids B200SPH_USER0 .. B200SPH_USER0 + 15 */
+    B200SPH_USER0 = 110
 };
 
 /* pair-equation bits of one (destination array, source array) loop */
@@ -289,6 +293,26 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog,
  * i.e. what real_only admits); arrays not named keep all their destinations.  One-shot: the
  * pass clears it. */
 int b200sph_set_dest_range(b200sph_ctx *ctx, int arr, int64_t start, int64_t stop);
+
+/* ---- generic-equation fallback -----------------------------------------
+ * Stands where the reference compiles ANY Equation's Python bodies (pysph/sph/equation.py:
+ * 389-420, acceleration_eval_cython.mako:10-155): pysph_b200/codegen.py translates the
+ * initialize / loop / post_loop bodies of equations the library has no hand-written kernel
+ * for into CUDA C, compiles it with NVRTC for sm_100a, and hands the cubin to the library:
+ *   user_property    create (zero-filled) the fp64 property `prop` (B200SPH_USER0 + k) for every
+ *                    array; push_f64 / pull_f64 / device_ptr accept the id afterwards
+ *   generic_load     load a cubin whose kernels take one b200sph_generic_args by value
+ *                    (pysph_b200/csrc/generic_args.h); returns a module handle >= 0
+ *   generic_launch   run phase 0 (initialize) / 1 (loop over the persistent neighbour lists,
+ *                    same accept test as the hand-written pair kernels) / 2 (post_loop) of
+ *                    kernel `kernel` for the destinations of array dest_arr; honours
+ *                    b200sph_set_dest_range; `writes` bit 0: a body stores to x y z h, bit 1:
+ *                    to any other property the packed pair records are made from
+ * One GPU only (the slab decomposition does not carry user properties). */
+int b200sph_user_property(b200sph_ctx *ctx, int prop);
+int b200sph_generic_load(b200sph_ctx *ctx, const void *image, int64_t size);
+int b200sph_generic_launch(b200sph_ctx *ctx, int module, const char *kernel, int dest_arr, int phase,
+                           unsigned src_mask, int real_only, double t, double dt, int writes);
 
 /* The two Groups of EDACScheme._get_internal_flow_equations (wc/edac.py:776-880) in
  * the generated AccelerationEval.compute (acceleration_eval_cython.mako:10-154): group 1 computes

@@ -33,6 +33,7 @@ ELASTIC_PROP_IDS.update(('v%d%d' % (i, j), 82 + 3 * i + j) for i in range(3) for
 ELASTIC_PROP_IDS.update(('r' + k, 91 + i) for i, k in enumerate(_SYM))
 ELASTIC_PROP_IDS.update(('as' + k, 97 + i) for i, k in enumerate(_SYM))
 INT_PROP_IDS = {'gid': 64, 'tag': 65, 'pid': 66}
+USER_PROP0, MAX_USER_PROPS = 110, 16     # B200SPH_USER0, B200SPH_MAX_USER
 F64_DEVICE_PROPS = ('x', 'y', 'z', 'u', 'v', 'w', 'rho', 'h', 'm',
                     'x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'rho0')
 
@@ -140,6 +141,10 @@ SIGNATURES = {
     'b200sph_pair_pass': (C.c_int, [_ctx_p, C.POINTER(PairProgram),
                                     C.POINTER(_i64)]),
     'b200sph_set_dest_range': (C.c_int, [_ctx_p, C.c_int, _i64, _i64]),
+    'b200sph_user_property': (C.c_int, [_ctx_p, C.c_int]),
+    'b200sph_generic_load': (C.c_int, [_ctx_p, C.c_void_p, _i64]),
+    'b200sph_generic_launch': (C.c_int, [_ctx_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_uint,
+                                         C.c_int, C.c_double, C.c_double, C.c_int]),
     'b200sph_tvf_pass': (C.c_int, [_ctx_p, C.POINTER(TvfProgram), C.POINTER(_i64)]),
     'b200sph_stage_tvf': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
     'b200sph_stage_tvf_dev': (C.c_int, [_ctx_p, C.c_int, C.c_int]),

@@ -25,8 +25,15 @@ class B200AccelerationEval(object):
         self.ctx = self.backend.ctx
         self.ctx.call('b200sph_set_kernel', kernel_id(kernel), int(kernel.dim))
         self.equation_groups = equations
+        from . import codegen
+        self._generic_props = codegen.PropertyTable(self.backend.user_props)
         self.ops = build_program(equations, self.backend.names, kernel.dim,
-                                 particle_arrays=self.particle_arrays)
+                                 particle_arrays=self.particle_arrays, kernel=kernel,
+                                 generic=self._generic_props)
+        # properties the generated kernels use beyond the pool's own
+        for name in self._generic_props.user:
+            self.backend.add_user_property(name)
+        self._range = None
         self.nnps = None
         self.count_pairs = False
         self.last_pairs = 0
@@ -78,14 +85,19 @@ class B200AccelerationEval(object):
             elif kind == 'call':
                 op[1]()
             elif kind == 'range':
-                for d, (lo, hi, pa) in op[1].items():
-                    ctx.call('b200sph_set_dest_range', d, index_value(lo, pa),
-                             -1 if hi is None else index_value(hi, pa))
+                # destinations of the NEXT pair / generic op (one-shot in the library too)
+                self._range = dict((d, (index_value(lo, pa), -1 if hi is None else index_value(hi, pa)))
+                                   for d, (lo, hi, pa) in op[1].items())
+            elif kind == 'generic':
+                self._run_generic(op[1], t, dt)
             elif kind == 'eos':
                 ctx.call('b200sph_eos', *op[1:])
             elif kind == 'ferrari':
                 ctx.call('b200sph_ferrari_h', *op[1:])
             elif kind == 'pair':
+                rng, self._range = self._range, None
+                for d, (lo, hi) in (rng or {}).items():
+                    ctx.call('b200sph_set_dest_range', d, lo, hi)
                 if self.count_pairs:
                     ctx.call('b200sph_pair_pass', C.byref(op[1]), C.byref(cnt))
                     self._pairs += cnt.value
@@ -108,3 +120,27 @@ class B200AccelerationEval(object):
                 # mako:139-145: nnps.update_domain(); nnps.update()
                 ctx.call('b200sph_update_domain')
                 ctx.call('b200sph_nnps_update')
+
+    # -- generic-equation fallback (codegen.py) -------------------------------------
+    def _run_generic(self, gg, t, dt):
+        """do_group (acceleration_eval_cython.mako:10-155) for a Group of translated equations:
+        destination after destination -- initialize over its particles, the neighbour loops,
+        post_loop -- each a launch of the Group's run-time compiled kernel."""
+        from . import codegen
+        ctx = self.ctx
+        if getattr(gg, 'module', None) is None:
+            image = codegen.compile_cached(gg.source)
+            buf = C.create_string_buffer(image, len(image))
+            gg.module = ctx.call('b200sph_generic_load', C.cast(buf, C.c_void_p), len(image))
+            w = gg.writes
+            gg.write_flags = (1 if w & {'x', 'y', 'z', 'h'} else 0) | \
+                (2 if w & {'u', 'v', 'w', 'm', 'rho', 'p', 'cs'} else 0)
+        rng, self._range = self._range, None
+        for name, d, has_init, has_loop, has_post, src_mask in gg.kernels:
+            for phase, on in ((0, has_init), (1, has_loop), (2, has_post)):
+                if not on:
+                    continue
+                if rng and d in rng:
+                    ctx.call('b200sph_set_dest_range', d, rng[d][0], rng[d][1])
+                ctx.call('b200sph_generic_launch', gg.module, name.encode(), d, phase, src_mask,
+                         gg.real_only, float(t), float(dt), gg.write_flags)

@@ -72,9 +72,10 @@ class B200Backend(object):
         self.names = [pa.name for pa in particle_arrays]
         self.index = dict((n, i) for i, n in enumerate(self.names))
         # name -> device property id, per array: EDAC arrays evolve p (fp64 PF)
-        self.prop_ids = [EDAC_PROP_IDS if 'ap' in pa.properties else
-                         (ELASTIC_PROP_IDS if 's00' in pa.properties else PROP_IDS)
+        self.prop_ids = [dict(EDAC_PROP_IDS if 'ap' in pa.properties else
+                              (ELASTIC_PROP_IDS if 's00' in pa.properties else PROP_IDS))
                          for pa in particle_arrays]
+        self.user_props = []      # names of the fp64 properties created for generic equations
         for pa in particle_arrays:
             n = pa.get_number_of_particles()
             n_real = pa.get_number_of_particles(real=True)
@@ -85,6 +86,23 @@ class B200Backend(object):
             pa.gpu = B200DeviceHelper(self, i)
         self._dt_cache = None
         self.push_all()
+
+    def add_user_property(self, name):
+        """A property the device pool does not have (generic-equation fallback,
+        pysph_b200/codegen.py): created as a zero-filled fp64 array for every particle
+        array, filled from the host arrays that define it; push / pull carry it from now on."""
+        if name in self.user_props:
+            return _lib.USER_PROP0 + self.user_props.index(name)
+        if len(self.user_props) >= _lib.MAX_USER_PROPS:
+            raise NotImplementedError('at most %d user properties' % _lib.MAX_USER_PROPS)
+        pid = _lib.USER_PROP0 + len(self.user_props)
+        self.user_props.append(name)
+        self.ctx.call('b200sph_user_property', pid)
+        for i, pa in enumerate(self.particle_arrays):
+            self.prop_ids[i][name] = pid
+            if name in pa.properties:
+                self.push(i, [name])
+        return pid
 
     # -- sizes ----------------------------------------------------------------
     def sizes(self, i):

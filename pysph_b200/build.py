@@ -36,7 +36,7 @@ def find_nvcc():
 def sources():
     """b200sph.cu and the kernel files it includes (one translation unit)."""
     d = os.path.dirname(SRC)
-    return [SRC] + sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith('.cuh'))
+    return [SRC] + sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(('.cuh', '.h')))
 
 
 def read_source():
@@ -47,7 +47,7 @@ def read_source():
     out = []
     for line in open(SRC).read().split('\n'):
         name = line[len('#include "'):-1] if line.startswith('#include "') else ''
-        if name.endswith('.cuh') and os.path.exists(os.path.join(d, name)):
+        if name.endswith(('.cuh', '.h')) and os.path.exists(os.path.join(d, name)):
             out.append(open(os.path.join(d, name)).read().rstrip('\n'))
         else:
             out.append(line)

@@ -292,6 +292,9 @@ struct b200sph_ctx {
     // The scalar agreement runs on its own stream: a rank's ghosts only need its two neighbours,
     // the decision needs every rank, and the boundary launch must not wait for the slowest one.
     cudaStream_t red_stream = nullptr;
+    // generic-equation fallback: user properties (fp64, pool-wide) and run-time compiled modules
+    double *user_f64[B200SPH_MAX_USER] = {nullptr};
+    std::vector<void *> gen_modules;             // CUmodule (or, emulated, a dlopen handle)
     // Group(start_idx, stop_idx): one-shot destination ranges of the next pair pass
     int64_t dst_lo[B200SPH_MAX_ARRAYS] = {0}, dst_hi[B200SPH_MAX_ARRAYS] = {0};
     bool dst_ranged = false;
@@ -421,6 +424,7 @@ __device__ __forceinline__ unsigned long long peer_now_ns()
 }
 #endif
 
+#include "generic_args.h"
 #include "pool_kernels.cuh"
 #include "scan.cuh"
 #include "nnps_kernels.cuh"
@@ -435,9 +439,11 @@ __device__ __forceinline__ unsigned long long peer_now_ns()
 // host side
 // --------------------------------------------------------------------------
 static int is_solid_prop(int p) { return p >= B200SPH_S00 && p < B200SPH_SOLID_PROPS_END; }
+static int is_user_prop(int p) { return p >= B200SPH_USER0 && p < B200SPH_USER0 + B200SPH_MAX_USER; }
 static int is_f64_prop(int p)
 {
-    return (p >= 0 && p < N_F64) || (p >= B200SPH_UHAT && p <= B200SPH_PF0) || (p >= B200SPH_S00 && p <= B200SPH_S220);
+    return (p >= 0 && p < N_F64) || (p >= B200SPH_UHAT && p <= B200SPH_PF0) || (p >= B200SPH_S00 && p <= B200SPH_S220) ||
+           is_user_prop(p);
 }
 static int is_f32_prop(int p)
 {
@@ -445,6 +451,7 @@ static int is_f32_prop(int p)
 }
 static double *f64_ptr(b200sph_ctx *ctx, int p)
 {
+    if (is_user_prop(p)) return ctx->user_f64[p - B200SPH_USER0];
     return p < N_F64 ? ctx->f64[p] : (p < B200SPH_S00 ? ctx->f64x[p - B200SPH_UHAT] : ctx->f64s[p - B200SPH_S00]);
 }
 static float *f32_ptr(b200sph_ctx *ctx, int p)
@@ -513,6 +520,18 @@ static int pool_layout(b200sph_ctx *ctx, const int64_t *new_cap)
             if (*r) CU(cudaFree(*r));
             CU(cudaMalloc((void **)r, 16 * (size_t)alloc));
         }
+    }
+    for (int k = 0; k < B200SPH_MAX_USER; k++) {   // user properties move with the pool too
+        if (!ctx->user_f64[k]) continue;
+        double *old = ctx->user_f64[k], *nw = nullptr;
+        CU(cudaMalloc((void **)&nw, 8 * (size_t)alloc));
+        CU(cudaMemsetAsync(nw, 0, 8 * (size_t)alloc, ctx->stream));
+        for (int a = 0; a < ctx->narr; a++)
+            if (ctx->arr[a].n > 0 && ctx->arr[a].cap > 0)
+                CU(cudaMemcpyAsync(nw + new_off[a], old + ctx->arr[a].off, 8 * (size_t)ctx->arr[a].n, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(old));
+        ctx->user_f64[k] = nw;
     }
     if (ctx->ptype) CU(cudaFree(ctx->ptype));
     CU(cudaMalloc((void **)&ctx->ptype, (size_t)alloc));
@@ -701,6 +720,7 @@ extern "C" {
 
 static int eos_flush(b200sph_ctx *ctx, cudaStream_t on_comm_stream = nullptr);
 static void free_peer_pending(b200sph_ctx *ctx);
+static void generic_unload_all(b200sph_ctx *ctx);
 
 int b200sph_abi_version(void) { return B200SPH_ABI_VERSION; }
 
@@ -762,6 +782,8 @@ int b200sph_destroy(b200sph_ctx *ctx)
     for (int k = 0; k < N_F32; k++) cudaFree(ctx->f32[k]);
     for (int k = 0; k < N_U32; k++) cudaFree(ctx->u32[k]);
     for (int k = 0; k < N_F64X; k++) cudaFree(ctx->f64x[k]);
+    for (int k = 0; k < B200SPH_MAX_USER; k++) cudaFree(ctx->user_f64[k]);
+    generic_unload_all(ctx);
     for (int k = 0; k < N_F32X; k++) cudaFree(ctx->f32x[k]);
     cudaFree(ctx->Dv); cudaFree(ctx->PT);
     for (auto &sg : ctx->mirror_segs) cudaFree(sg.idx);
@@ -912,6 +934,18 @@ static int ensure_stage(b200sph_ctx *ctx, int64_t count)
     return 0;
 }
 
+// user properties of the generic-equation fallback: allocated (zeroed) when first named
+static int ensure_user(b200sph_ctx *ctx, int prop)
+{
+    if (!is_user_prop(prop)) return 0;
+    double *&p = ctx->user_f64[prop - B200SPH_USER0];
+    if (p) return 0;
+    const size_t alloc = (size_t)std::max<int64_t>(ctx->pool_cap, 32);
+    CU(cudaMalloc((void **)&p, 8 * alloc));
+    CU(cudaMemsetAsync(p, 0, 8 * alloc, ctx->stream));
+    return 0;
+}
+
 // elastic-dynamics property arrays: allocated (zeroed) the first time anything names them
 static int ensure_solid(b200sph_ctx *ctx)
 {
@@ -939,6 +973,7 @@ int b200sph_push_f64(b200sph_ctx *ctx, int arr, int prop, const double *host, in
     // naming an elastic-dynamics property allocates that pool even for an empty array: every
     // rank of a slab decomposition must agree on the message layout (b200sph_halo_layout)
     if (is_solid_prop(prop) && (rc = ensure_solid(ctx))) return rc;
+    if ((rc = ensure_user(ctx, prop))) return rc;
     if (count == 0) return 0;
     const int64_t o = ctx->arr[arr].off + start;
     if (is_f64_prop(prop)) {
@@ -973,6 +1008,7 @@ int b200sph_pull_f64(b200sph_ctx *ctx, int arr, int prop, double *host, int64_t 
     if (count == 0) return 0;
     const int64_t o = ctx->arr[arr].off + start;
     if (is_solid_prop(prop) && (rc = ensure_solid(ctx))) return rc;
+    if ((rc = ensure_user(ctx, prop))) return rc;
     if (is_f64_prop(prop)) {
         CU(cudaMemcpyAsync(host, f64_ptr(ctx, prop) + o, 8 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
     } else if (is_f32_prop(prop)) {
@@ -1024,6 +1060,7 @@ int b200sph_device_ptr(b200sph_ctx *ctx, int arr, int prop, void **out)
     if (arr < 0 || arr >= ctx->narr) return set_err(ctx, "device_ptr: bad array %d", arr);
     const int64_t o = ctx->arr[arr].off;
     if (is_solid_prop(prop) && (rc = ensure_solid(ctx))) return rc;
+    if ((rc = ensure_user(ctx, prop))) return rc;
     if (is_f64_prop(prop)) *out = f64_ptr(ctx, prop) + o;
     else if (is_f32_prop(prop)) *out = f32_ptr(ctx, prop) + o;
     else if (u32_index(prop) >= 0) *out = ctx->u32[u32_index(prop)] + o;
@@ -1790,6 +1827,161 @@ int b200sph_ferrari_h(b200sph_ctx *ctx, int arr, double hdx, int dim, int real_o
     ctx->domain_valid = false;  // h changed: the next update_domain must re-reduce it
     ctx->h_dirty = true;
     ctx->grid_valid = false, ctx->packed_valid = false;
+    return 0;
+}
+
+// ---- generic-equation fallback (pysph_b200/codegen.py) ---------------------
+// Kernels generated from user Equation bodies and compiled by NVRTC are loaded through the
+// driver API, which is looked up at first use (the library itself links the runtime only, so
+// that it loads -- and fails loudly at the first CUDA call -- on a box without a driver).
+#include <dlfcn.h>
+#ifndef B200SPH_HOST_EMULATION
+struct DriverApi {
+    void *lib = nullptr;
+    int (*ModuleLoadData)(void **, const void *) = nullptr;
+    int (*ModuleGetFunction)(void **, void *, const char *) = nullptr;
+    int (*ModuleUnload)(void *) = nullptr;
+    int (*LaunchKernel)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **) = nullptr;
+    int (*GetErrorString)(int, const char **) = nullptr;
+};
+static DriverApi g_drv;
+static int driver_api(b200sph_ctx *ctx)
+{
+    if (g_drv.lib) return 0;
+    void *lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return set_err(ctx, "generic equations: cannot load libcuda.so.1 (%s)", dlerror());
+    DriverApi d;
+    d.ModuleLoadData = (int (*)(void **, const void *))dlsym(lib, "cuModuleLoadData");
+    d.ModuleGetFunction = (int (*)(void **, void *, const char *))dlsym(lib, "cuModuleGetFunction");
+    d.ModuleUnload = (int (*)(void *))dlsym(lib, "cuModuleUnload");
+    d.LaunchKernel = (int (*)(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **))dlsym(lib, "cuLaunchKernel");
+    d.GetErrorString = (int (*)(int, const char **))dlsym(lib, "cuGetErrorString");
+    if (!d.ModuleLoadData || !d.ModuleGetFunction || !d.ModuleUnload || !d.LaunchKernel)
+        return set_err(ctx, "generic equations: libcuda.so.1 lacks the module API");
+    d.lib = lib;
+    g_drv = d;
+    return 0;
+}
+static const char *drv_err(int e)
+{
+    const char *m = nullptr;
+    if (g_drv.GetErrorString) g_drv.GetErrorString(e, &m);
+    return m ? m : "unknown driver error";
+}
+#endif
+
+static void generic_unload_all(b200sph_ctx *ctx)
+{
+    for (void *m : ctx->gen_modules) {
+        if (!m) continue;
+#ifdef B200SPH_HOST_EMULATION
+        dlclose(m);
+#else
+        if (g_drv.ModuleUnload) g_drv.ModuleUnload(m);
+#endif
+    }
+    ctx->gen_modules.clear();
+}
+
+int b200sph_user_property(b200sph_ctx *ctx, int prop)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!is_user_prop(prop)) return set_err(ctx, "user_property: ids %d..%d", B200SPH_USER0, B200SPH_USER0 + B200SPH_MAX_USER - 1);
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    return ensure_user(ctx, prop);
+}
+
+int b200sph_generic_load(b200sph_ctx *ctx, const void *image, int64_t size)
+{
+    CU(cudaSetDevice(ctx->device));
+    if (!image || size <= 0) return set_err(ctx, "generic_load: empty image");
+    void *mod = nullptr;
+#ifdef B200SPH_HOST_EMULATION
+    // the emulated library runs kernels that a TEST compiled for the host: the "image" is the
+    // path of that shared object
+    mod = dlopen((const char *)image, RTLD_NOW | RTLD_LOCAL);
+    if (!mod) return set_err(ctx, "generic_load: %s", dlerror());
+#else
+    int rc = driver_api(ctx);
+    if (rc) return rc;
+    CU(cudaFree(0));   // the runtime's primary context is current on this thread from here on
+    const int e = g_drv.ModuleLoadData(&mod, image);
+    if (e) return set_err(ctx, "generic_load: cuModuleLoadData: %s", drv_err(e));
+#endif
+    ctx->gen_modules.push_back(mod);
+    return (int)ctx->gen_modules.size() - 1;
+}
+
+// One phase (0 initialize, 1 loop, 2 post_loop) of one destination array of a generated Group
+// kernel.  src_mask: the source arrays of its loop bodies; writes: bit 0 a body stores to
+// x / y / z / h, bit 1 to any other property the packed records are made from.
+int b200sph_generic_launch(b200sph_ctx *ctx, int module, const char *kernel, int dest_arr, int phase, unsigned src_mask,
+                           int real_only, double t, double dt, int writes)
+{
+    if (int rcc = require_confirmed(ctx, "generic_launch")) return rcc;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_pool(ctx);
+    if (rc) return rc;
+    if (module < 0 || module >= (int)ctx->gen_modules.size()) return set_err(ctx, "generic_launch: bad module handle %d", module);
+    if (dest_arr < 0 || dest_arr >= ctx->narr || phase < 0 || phase > 2) return set_err(ctx, "generic_launch: bad destination / phase");
+    if (ctx->peer_box || ctx->comm_pending) return set_err(ctx, "generic equations run on one GPU (no slab decomposition)");
+    if (!ctx->grid_valid) return set_err(ctx, "generic_launch: the NNPS is stale (particles were pushed/resized); call nnps_update first");
+    if ((rc = eos_flush(ctx))) return rc;
+    const bool ranged = ctx->dst_ranged;   // one-shot, as for pair_pass: every launch names its own
+    ctx->dst_ranged = false;
+    const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->n_sorted < (1LL << LIST_JBITS);
+    if (ctx->n_sorted > 0 && !use_lists) return set_err(ctx, "generic equations need the neighbour-list path");
+    if (phase == 1 && use_lists) {
+        unsigned long long want[B200SPH_MAX_ARRAYS];
+        for (int d = 0; d < B200SPH_MAX_ARRAYS; d++) want[d] = 0;
+        for (int sx = 0; sx < ctx->narr; sx++)
+            if ((src_mask >> sx) & 1u) want[dest_arr] |= 0xFFull << (8 * sx);
+        if (ctx->lists_valid && !lists_cover(ctx, want)) ctx->lists_valid = false;
+        if (!ctx->lists_valid) {
+            PhaseTimer pt_build(ctx, 0);
+            if ((rc = build_lists(ctx, want))) return rc;
+        }
+    }
+    b200sph_generic_args ga;
+    memset(&ga, 0, sizeof(ga));
+    for (int k = 0; k < N_F64; k++) ga.f64[k] = ctx->f64[k];
+    for (int k = 0; k < N_F32; k++) ga.f32[k] = ctx->f32[k];
+    for (int k = 0; k < N_U32; k++) ga.u32[k] = ctx->u32[k];
+    for (int k = 0; k < B200SPH_MAX_USER; k++) ga.user[k] = ctx->user_f64[k];
+    ga.AB = ctx->AB; ga.stype = ctx->stype; ga.perm = ctx->perm;
+    ga.cnt = ctx->cnt; ga.lst = ctx->lst; ga.capg = ctx->capg;
+    ga.n = ctx->n_sorted;
+    ga.cellx = (float)ctx->G.cell[0]; ga.celly = (float)ctx->G.cell[1]; ga.cellz = (float)ctx->G.cell[2];
+    ga.k2 = (float)(ctx->radius_scale * ctx->radius_scale);
+    ga.dest_type = dest_arr; ga.real_only = real_only; ga.phase = phase; ga.src_mask = src_mask;
+    ga.t = t; ga.dt = dt;
+    ga.doff = ctx->arr[dest_arr].off;
+    ga.dlo = ranged ? ctx->dst_lo[dest_arr] : 0;
+    ga.dhi = ranged && ctx->dst_hi[dest_arr] >= 0 ? ctx->dst_hi[dest_arr] : (int64_t)1 << 62;
+    if (ctx->n_sorted > 0) {
+        PhaseTimer pt(ctx, phase == 1 ? 1 : 2);
+        const unsigned nb = (unsigned)cdiv(ctx->n_sorted, 128);
+#ifdef B200SPH_HOST_EMULATION
+        void (*fn)(b200sph_generic_args) = (void (*)(b200sph_generic_args))dlsym(ctx->gen_modules[module], kernel);
+        if (!fn) return set_err(ctx, "generic_launch: no kernel '%s' in the module", kernel);
+        emu::launch(nb, 128, emu::SEQ, [&] { fn(ga); });
+#else
+        void *fn = nullptr;
+        int e = g_drv.ModuleGetFunction(&fn, ctx->gen_modules[module], kernel);
+        if (e) return set_err(ctx, "generic_launch: no kernel '%s' in the module: %s", kernel, drv_err(e));
+        void *params[1] = {&ga};
+        e = g_drv.LaunchKernel(fn, nb, 1, 1, 128, 1, 1, 0, (void *)ctx->stream, params, nullptr);
+        if (e) return set_err(ctx, "generic_launch: cuLaunchKernel(%s): %s", kernel, drv_err(e));
+#endif
+        ctx->stats.kernel_launches++;
+    }
+    // what was derived from the properties the bodies stored to is stale
+    if (writes & 1) {
+        ctx->grid_valid = false, ctx->packed_valid = false;
+        ctx->domain_valid = false, ctx->h_dirty = true;
+    }
+    if (writes & 2) ctx->state_packed = false, ctx->spec_records = false;
     return 0;
 }
 

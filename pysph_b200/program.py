@@ -45,6 +45,14 @@ SOLID_GROUP2 = ('ContinuityEquation', 'MomentumEquationWithStress',
                 'XSPHCorrection')
 
 
+# every equation that has a hand-written kernel; a Group made ONLY of others takes the
+# generic-equation fallback (pysph_b200/codegen.py)
+KNOWN_EQUATIONS = set(PAIR_EQUATIONS) | set(NO_SOURCE_EQUATIONS) | set(TVF_GROUP1) | \
+    set(TVF_GROUP2) | set(SOLID_GROUP1) | set(SOLID_GROUP2)
+import itertools
+_generic_uid = itertools.count()
+
+
 def _solid_group_kind(g):
     names = [_eq_name(e) for e in g.equations]
     if any(n in ('IsothermalEOS', 'MonaghanArtificialStress') for n in names):
@@ -311,7 +319,7 @@ def group_equations(equations):
     return [Group(equations=list(equations))]
 
 
-def build_program(groups, array_names, dim, particle_arrays=None):
+def build_program(groups, array_names, dim, particle_arrays=None, kernel=None, generic=None):
     """groups: list of Group objects (ours or PySPH's) -> nested op list, the loop nest of
     acceleration_eval_cython.mako:262-363:
 
@@ -322,9 +330,16 @@ def build_program(groups, array_names, dim, particle_arrays=None):
         ('range', {array: (start, stop)})     Group(start_idx=..., stop_idx=...): destinations
                                               of the NEXT pair op
         ('eos' | 'ferrari' | 'pair' | 'tvf' | 'solid' | 'update_nnps', ...)   device calls
+        ('generic', GenericGroup)             a Group of equations without hand-written kernels:
+                                              their Python bodies, translated and compiled at run
+                                              time (pysph_b200/codegen.py)
+
+    kernel: the smoothing-kernel object (only generic groups need it: WIJ / DWIJ in their bodies);
+    generic: the shared codegen.PropertyTable of the evaluator.
     """
     index = dict((n, i) for i, n in enumerate(array_names))
     arrays = dict((pa.name, pa) for pa in (particle_arrays or []))
+    arrays['__codegen__'] = (kernel, int(dim), generic)
     ops = []
     for g in group_equations(groups):
         ops.extend(_mega_group(g, index, arrays, particle_arrays))
@@ -399,6 +414,23 @@ def _leaf_body(g, index, arrays, particle_arrays):
     ops = []
     start, stop = getattr(g, 'start_idx', 0), getattr(g, 'stop_idx', None)
     ranged = (stop is not None) or (start not in (0, None))
+    from . import codegen
+    if codegen.is_generic_group(g) and not any(
+            _eq_name(e) in KNOWN_EQUATIONS for e in g.equations):
+        kernel, dim, table = arrays.get('__codegen__', (None, 0, None))
+        if kernel is None:
+            raise NotImplementedError(
+                'B200 backend: no CUDA kernel for %s; the generic-equation fallback needs the '
+                'smoothing kernel (build_program(..., kernel=...))'
+                % ', '.join(sorted(set(_eq_name(e) for e in g.equations))))
+        if table is None:
+            table = codegen.PropertyTable()
+        gg = codegen.GenericGroup(g, index, kernel, dim, table, next(_generic_uid))
+        if ranged:
+            ops.append(('range', dict((index[d], (start or 0, stop, arrays.get(d))) for d in gg.dests)))
+            gg.real_only = gg.real_only if stop is None else 0
+        ops.append(('generic', gg))
+        return ops
     kind = _solid_group_kind(g)
     if kind:
         _no_range(g, ranged, 'elastic-dynamics')

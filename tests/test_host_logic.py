@@ -356,3 +356,46 @@ def test_bench_reference_arm_contract(extra):
     assert d['cpu_baseline']['value'] == d['value'] == d['e2e']['value']
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert d['config']['pairs_per_step'] > 0 and 'workload' in d['config']
+
+
+def test_generic_equations_translate_and_compile_with_nvrtc():
+    """The generic-equation fallback without a GPU: user bodies -> CUDA C (codegen.py) -> a
+    cubin for sm_100a through NVRTC (compiling needs no device).  The same sources run on the
+    emulated library in test_library_on_cpu.py and on a B200 in test_gpu_generic.py."""
+    import test_gpu_generic as tg
+    from pysph_b200 import codegen
+    SimpleEquation, MixedTypeEquation, DumbEquation, EqWithTime, KernelSum = tg._equations()
+    MyContinuity, MyMomentum, MyXSPH = tg._generic_wcsph()
+    names = ['fluid', 'boundary']
+    table = codegen.PropertyTable()
+    ops = build_program([
+        pb.Group([SimpleEquation('fluid', ['fluid']), MixedTypeEquation('fluid', ['fluid', 'boundary']),
+                  KernelSum('boundary', ['fluid'])]),
+        pb.Group([MyContinuity('boundary', ['fluid']), MyContinuity('fluid', names),
+                  MyMomentum('fluid', names, c0=10.0, alpha=0.1, beta=0.0, gx=0.0, gy=-9.81, gz=0.0),
+                  MyXSPH('fluid', ['fluid'], eps=0.5)], start_idx=2)],
+        names, 3, kernel=pb.QuinticSpline(dim=3), generic=table)
+    assert [o[0] for o in ops] == ['generic', 'range', 'generic']
+    g1, g2 = ops[0][1], ops[2][1]
+    assert table.user == ['wsum']
+    # destinations in order of first mention, a kernel each; sources as bit masks
+    assert [(k[0], k[1]) for k in g1.kernels] == [('b2g_fluid', 0), ('b2g_boundary', 1)]
+    assert g1.kernels[0][5] == 0b11 and g1.kernels[1][5] == 0b01
+    assert [(k[0], k[1], k[2], k[3], k[4]) for k in g2.kernels] == \
+        [('b2g_boundary', 1, True, True, False), ('b2g_fluid', 0, True, True, True)]
+    assert 'x' not in g2.writes and {'arho', 'au', 'dt_cfl', 'ax'} <= g2.writes
+    assert 'pow(' not in g2.source and 'b2_grad(2, 3,' in g2.source
+    for g in (g1, g2):
+        image = codegen.compile_image(g.source)
+        assert image[:4] == b'\x7fELF' and len(image) > 4000
+    # equations with hand-written kernels never take this path, and a Group that mixes the
+    # two kinds is refused
+    ops = build_program([pb.ContinuityEquation('fluid', ['fluid'])], names, 3,
+                        kernel=pb.CubicSpline(dim=3))
+    assert ops[0][0] == 'pair'
+    with pytest.raises(NotImplementedError):
+        build_program([pb.Group([pb.ContinuityEquation('fluid', ['fluid']),
+                                 SimpleEquation('fluid', ['fluid'])])], names, 3,
+                      kernel=pb.CubicSpline(dim=3))
+    with pytest.raises(NotImplementedError):       # no kernel object, no generated code
+        build_program([SimpleEquation('fluid', ['fluid'])], names, 3)
