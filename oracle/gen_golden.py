@@ -376,6 +376,63 @@ def gen_edac_case(kernels, edac, kernel_name, dim, seed, nfluids=1, alpha=0.0,
                 outputs=arrays)
 
 
+EDAC_WALL_PROPS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'p', 'au', 'av', 'aw',
+                   'V', 'wij', 'ax', 'ay', 'az', 'uf', 'vf', 'wf', 'ug', 'vg', 'wg']
+
+
+def gen_edac_wall_case(kernels, edac, kernel_name, dim, seed, alpha=0.0, nu=0.01, bql=True,
+                       gx=0.0, gy=0.0, tdamp=0.0, t=0.0, moving=False):
+    """One evaluation of EDACScheme(fluids=['fluid'], solids=['wall'], pb != 0).get_equations()
+    (wc/edac.py:776-880 with solids: SourceNumberDensity, VolumeSummation, SolidWallPressureBC,
+    SetWallVelocity in group 1, the average pressure in a group of its own, SolidWallNoSlipBC
+    in group 2) through the reference's own scheme method and equation bodies: a slab of fluid
+    over a two-layer wall, random perturbations, some trailing ghosts in both arrays."""
+    rs = np.random.RandomState(seed)
+    kernel = getattr(kernels, kernel_name)(dim=dim)
+    dx = 0.1
+    rho0, c0 = 1.0, 10.0
+    p0 = rho0 * c0 * c0
+    arrays = {}
+    for name, n, ylo, yhi, props in (('fluid', 80, 0.0, 0.45, EDAC_PROPS),
+                                     ('wall', 45, -0.25, 0.0, EDAC_WALL_PROPS)):
+        ext = np.array([0.5, 1.0, 0.4 if dim == 3 else 0.0])
+        pts = rs.uniform(0.0, 1.0, size=(n, 3)) * ext
+        pts[:, 1] = ylo + (yhi - ylo) * rs.uniform(0.0, 1.0, n)
+        a = dict((q, [0.0] * n) for q in props)
+        a['x'], a['y'], a['z'] = (list(map(float, pts[:, i])) for i in range(3))
+        a['h'] = [float(1.0 * dx)] * n
+        a['m'] = [float(rho0 * dx ** dim)] * n
+        if name == 'fluid':
+            v = rs.normal(size=(n, 3)) * (np.arange(3) < dim)
+            vh = v + 0.05 * rs.normal(size=(n, 3)) * (np.arange(3) < dim)
+            a['uhat'], a['vhat'], a['what'] = (list(map(float, vh[:, i])) for i in range(3))
+            a['p'] = list(map(float, rs.normal(scale=2.0, size=n)))
+            a['_n_real'] = n - 6
+        else:
+            # prescribed wall velocity and acceleration (SetWallVelocity, SolidWallPressureBC)
+            v = (0.3 * rs.normal(size=(n, 3)) if moving else np.zeros((n, 3))) * (np.arange(3) < dim)
+            acc = (0.5 * rs.normal(size=(n, 3)) if moving else np.zeros((n, 3))) * (np.arange(3) < dim)
+            a['au'], a['av'], a['aw'] = (list(map(float, acc[:, i])) for i in range(3))
+            a['rho'] = list(map(float, rho0 * (1.0 + 0.05 * rs.uniform(-1, 1, n))))
+            a['p'] = list(map(float, rs.normal(scale=2.0, size=n)))   # overwritten by the BC
+            a['_n_real'] = n - 4
+        a['u'], a['v'], a['w'] = (list(map(float, v[:, i])) for i in range(3))
+        arrays[name] = a
+    inputs = json.loads(json.dumps(arrays))
+    scheme = edac.EDACScheme(['fluid'], ['wall'], dim=dim, c0=c0, nu=nu, rho0=rho0, pb=p0,
+                             gx=gx, gy=gy, tdamp=tdamp, h=dx, alpha=alpha, bql=bql)
+    eqs = scheme.get_equations()
+    groups = [(g.real, g.equations) for g in eqs]
+    evaluate_reference(kernel, arrays, groups, t=t)
+    params = dict(dim=dim, c0=c0, rho0=rho0, nu=nu, pb=p0, h=dx, alpha=alpha, edac_alpha=0.5,
+                  bql=bql, gx=gx, gy=gy, gz=0.0, tdamp=tdamp, t=t, fluids=['fluid'],
+                  solids=['wall'],
+                  groups=[[type(e).__name__ for e in g.equations] for g in eqs],
+                  group_real=[bool(g.real) for g in eqs],
+                  sources=[[list(e.sources or []) for e in g.equations] for g in eqs])
+    return dict(kernel=kernel_name, dim=dim, params=params, inputs=inputs, outputs=arrays)
+
+
 def gen_edac_stepper(edac):
     rs = np.random.RandomState(12)
     n = 7
@@ -690,7 +747,24 @@ def gen_density_1d(kernels, basic):
     return dict(x=x, h=a['h'], m=a['m'], rho=a['rho'], nbr_counts=counts)
 
 
+def gen_edac_wall_cases(kernels, edac):
+    return [
+        gen_edac_wall_case(kernels, edac, 'QuinticSpline', 2, 401, gy=-1.0),
+        gen_edac_wall_case(kernels, edac, 'QuinticSpline', 3, 402, alpha=0.2, moving=True, gx=0.4),
+        gen_edac_wall_case(kernels, edac, 'CubicSpline', 3, 403, nu=0.0, alpha=0.1, bql=False,
+                           gy=-1.0, tdamp=1.0, t=0.3),
+        gen_edac_wall_case(kernels, edac, 'WendlandQuintic', 2, 404, moving=True),
+    ]
+
+
 def main():
+    if sys.argv[1:] == ['edac_walls']:          # only the file added last
+        kernels, basic, wc, steps, c_kernels = load_reference()
+        tvf, edac = load_reference_edac()
+        with open(os.path.join(GOLD, 'edac_wall_cases.json'), 'w') as f:
+            json.dump(gen_edac_wall_cases(kernels, edac), f)
+        print('wrote edac_wall_cases.json', os.path.getsize(os.path.join(GOLD, 'edac_wall_cases.json')), 'bytes')
+        return
     kernels, basic, wc, steps, c_kernels = load_reference()
     os.makedirs(GOLD, exist_ok=True)
 
@@ -727,6 +801,7 @@ def main():
     ]
     dump('edac_cases.json', ecases)
     dump('edac_stepper.json', gen_edac_stepper(edac))
+    dump('edac_wall_cases.json', gen_edac_wall_cases(kernels, edac))
     solid = load_reference_solid()
     scases = [
         gen_solid_case(kernels, solid, 'CubicSpline', 2, 301),

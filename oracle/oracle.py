@@ -34,12 +34,14 @@ _PTR_FIELDS = ['x', 'y', 'z', 'h', 'm', 'rho', 'u', 'v', 'w', 'p', 'cs',
                'dt_force', 'x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'rho0',
                'uhat', 'vhat', 'what', 'V', 'pavg', 'nnbr', 'auhat', 'avhat',
                'awhat', 'ap', 'p0']
-TVF_PGRAD, TVF_AV, TVF_VISC, TVF_ASTRESS, TVF_EDAC = 1, 2, 4, 8, 16
+TVF_PGRAD, TVF_AV, TVF_VISC, TVF_ASTRESS, TVF_EDAC, TVF_NOSLIP = 1, 2, 4, 8, 16, 32
 # elastic dynamics (solid_mech/basic.py:52-59), in the order of orc_array
 _SYM = ['00', '01', '02', '11', '12', '22']
 _PTR_FIELDS += ['v%d%d' % (i, j) for i in range(3) for j in range(3)] + \
     ['s' + k for k in _SYM] + ['as' + k for k in _SYM] + ['r' + k for k in _SYM] + \
     ['s' + k + '0' for k in _SYM] + ['e', 'e0', 'ae']
+# wall arrays of the EDAC scheme (wc/edac.py:752-753); the C field of 'vg' is 'vgw'
+_PTR_FIELDS += ['wij', 'uf', 'vf', 'wf', 'ug', 'vgw', 'wg']
 
 
 class OrcArray(C.Structure):
@@ -66,7 +68,7 @@ class OrcTvfProgram(C.Structure):
                 ('pb', C.c_double), ('nu', C.c_double), ('edac_nu', C.c_double),
                 ('c0', C.c_double), ('rho0', C.c_double), ('alpha', C.c_double),
                 ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
-                ('tdamp', C.c_double), ('t', C.c_double)]
+                ('tdamp', C.c_double), ('t', C.c_double), ('solid_mask', C.c_uint32)]
 
 
 class OrcSolidProgram(C.Structure):
@@ -118,7 +120,7 @@ def load():
         lib.orc_pair_pass.argtypes = [C.c_void_p, C.POINTER(OrcPairProgram)]
         lib.orc_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         lib.orc_dt_factors.argtypes = [C.c_void_p, C.c_void_p]
-        for f in ('orc_tvf_pass1', 'orc_tvf_pass2'):
+        for f in ('orc_tvf_pass1', 'orc_tvf_pass2', 'orc_tvf_wall', 'orc_tvf_avgp'):
             getattr(lib, f).restype = C.c_int64
             getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(OrcTvfProgram)]
         lib.orc_stage_tvf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
@@ -189,8 +191,9 @@ class Oracle(object):
             oa.n = pa.get_number_of_particles()
             oa.n_real = pa.get_number_of_particles(real=True)
             for f in _PTR_FIELDS:
-                if f in pa.properties:
-                    a = pa.properties[f]
+                name = 'vg' if f == 'vgw' else f
+                if name in pa.properties:
+                    a = pa.properties[name]
                     assert a.dtype == np.float64 and a.flags.c_contiguous
                     setattr(oa, f, a.ctypes.data_as(C.POINTER(C.c_double)))
             self._keep.append(oa)
@@ -285,10 +288,11 @@ class Oracle(object):
     # -- EDAC, transport-velocity branch ---------------------------------------
     def tvf_program(self, fluids, eqbits, bql=True, pb=0.0, nu=0.0, edac_nu=0.0,
                     c0=0.0, rho0=0.0, alpha=0.0, gx=0.0, gy=0.0, gz=0.0,
-                    tdamp=0.0, t=0.0):
+                    tdamp=0.0, t=0.0, solids=()):
         P = OrcTvfProgram()
         P.kernel, P.dim = self.kid, self.dim
         P.fluid_mask = sum(1 << f for f in fluids)
+        P.solid_mask = sum(1 << f for f in solids)
         P.bql, P.eqbits = int(bql), eqbits
         P.pb, P.nu, P.edac_nu, P.c0, P.rho0, P.alpha = pb, nu, edac_nu, c0, rho0, alpha
         P.gx, P.gy, P.gz, P.tdamp, P.t = gx, gy, gz, tdamp, t
@@ -299,6 +303,12 @@ class Oracle(object):
 
     def tvf_pass2(self, P):
         return self.lib.orc_tvf_pass2(self.h, C.byref(P))
+
+    def tvf_wall(self, P):
+        return self.lib.orc_tvf_wall(self.h, C.byref(P))
+
+    def tvf_avgp(self, P):
+        return self.lib.orc_tvf_avgp(self.h, C.byref(P))
 
     def stage_tvf(self, arr, which, dt):
         self.lib.orc_stage_tvf(self.h, arr, which, dt)
@@ -598,13 +608,15 @@ class WCSPHOracleSolver(object):
 
 
 def edac_eqbits(p):
-    """Which equations EDACScheme._get_internal_flow_equations emits for fluids
-    without solids (wc/edac.py:842-878)."""
+    """Which equations EDACScheme._get_internal_flow_equations emits in its second group
+    (wc/edac.py:842-878)."""
     bits = TVF_PGRAD | TVF_ASTRESS | TVF_EDAC
     if p.get('alpha', 0.0) > 0.0:
         bits |= TVF_AV
     if p.get('nu', 0.0) > 0.0:
         bits |= TVF_VISC
+        if p.get('solids'):
+            bits |= TVF_NOSLIP
     return bits
 
 
@@ -663,13 +675,22 @@ class EDACOracleSolver(object):
 
     def evaluate(self, t=None):
         p, o = self.p, self.o
-        fl = list(range(len(self.pas)))
-        P = o.tvf_program(fl, edac_eqbits(p), bql=p.get('bql', True), pb=p['pb'],
+        walls = [i for i, pa in enumerate(self.pas) if pa.name in (p.get('solids') or ())]
+        fl = [i for i in range(len(self.pas)) if i not in walls]
+        bql = p.get('bql', True)
+        P = o.tvf_program(fl, edac_eqbits(p), bql=bql and not walls, pb=p['pb'],
                           nu=p.get('nu', 0.0), edac_nu=edac_nu(p), c0=p['c0'],
                           rho0=p['rho0'], alpha=p.get('alpha', 0.0),
                           gx=p.get('gx', 0.0), gy=p.get('gy', 0.0), gz=p.get('gz', 0.0),
-                          tdamp=p.get('tdamp', 0.0), t=self.t if t is None else t)
+                          tdamp=p.get('tdamp', 0.0), t=self.t if t is None else t,
+                          solids=walls)
         pairs = o.tvf_pass1(P)
+        if walls:
+            # group 1 continues with the wall arrays, then the average pressure has a
+            # group of its own (wc/edac.py:815-842)
+            pairs += o.tvf_wall(P)
+            if bql:
+                pairs += o.tvf_avgp(P)
         pairs += o.tvf_pass2(P)
         self.pairs_last_eval = pairs
         return pairs
@@ -682,15 +703,16 @@ class EDACOracleSolver(object):
     def step(self):
         # PECIntegrator.one_timestep integrator.py:344-361
         self.initialise()
-        n = len(self.pas)
-        for a in range(n):
+        # steppers exist for the fluids only (wc/edac.py:682-687): walls do not move
+        fl = [i for i, pa in enumerate(self.pas) if pa.name not in (self.p.get('solids') or ())]
+        for a in fl:
             self.o.stage_tvf(a, 0, 0.0)
-        for a in range(n):
+        for a in fl:
             self.o.stage_tvf(a, 1, self.dt)
         self.update_domain()
         self.o.nnps_update()
         self.evaluate(self.t)               # a_eval.compute(c_integrator.t, ...) integrator.py:286
-        for a in range(n):
+        for a in fl:
             self.o.stage_tvf(a, 2, self.dt)
         self.update_domain()
         self.t += self.dt

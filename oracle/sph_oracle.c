@@ -783,7 +783,8 @@ int64_t orc_tvf_pass1(orc_ctx *c, const orc_tvf_program *P)
             }
         }
         for (int src = 0; src < c->narr; src++) {
-            if (!(P->fluid_mask >> src & 1u)) continue;
+            /* SummationDensity(dest=fluid, sources=all), wc/edac.py:806 */
+            if (!((P->fluid_mask | P->solid_mask) >> src & 1u)) continue;
             const orc_array *S = &c->arr[src];
             int64_t pairs = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : pairs)
@@ -817,6 +818,104 @@ int64_t orc_tvf_pass1(orc_ctx *c, const orc_tvf_program *P)
     return total;
 }
 
+int64_t orc_tvf_wall(orc_ctx *c, const orc_tvf_program *P)
+{
+    const int kernel = P->kernel, dim = P->dim;
+    const double kfac = k_fac(kernel, dim);
+    int64_t total = 0;
+    double damp = 1.0; /* SolidWallPressureBC takes the body force undamped, wc/edac.py:141-161 */
+    (void)damp;
+    for (int dst = 0; dst < c->narr; dst++) {
+        if (!(P->solid_mask >> dst & 1u)) continue;
+        orc_array *D = &c->arr[dst];
+        const int64_t np = D->n; /* Group(real=False), wc/edac.py:838 */
+        /* initialize: wc/edac.py:148-149, :179-180, :203-206; transport_velocity.py:71-72 */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++) {
+            D->wij[i] = 0.0;
+            D->V[i] = 0.0;
+            D->p[i] = 0.0;
+            D->uf[i] = D->vf[i] = D->wf[i] = 0.0;
+        }
+        for (int src = 0; src < c->narr; src++) {
+            const int is_fluid = (P->fluid_mask >> src) & 1u;
+            if (!((P->fluid_mask | P->solid_mask) >> src & 1u)) continue;
+            const orc_array *S = &c->arr[src];
+            int64_t pairs = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : pairs)
+            for (int64_t d_idx = 0; d_idx < np; d_idx++) {
+                ORC_FOR_NEIGHBORS(c, dst, src, d_idx, s_idx, {
+                    pairs++;
+                    double XIJ[3];
+                    XIJ[0] = D->x[d_idx] - S->x[s_idx];
+                    XIJ[1] = D->y[d_idx] - S->y[s_idx];
+                    XIJ[2] = D->z[d_idx] - S->z[s_idx];
+                    const double RIJ = sqrt(XIJ[0] * XIJ[0] + XIJ[1] * XIJ[1] + XIJ[2] * XIJ[2]);
+                    const double HIJ = 0.5 * (D->h[d_idx] + S->h[s_idx]);
+                    const double WIJ = k_w(kernel, dim, kfac, RIJ, HIJ);
+                    D->V[d_idx] += WIJ;                 /* VolumeSummation, sources = all */
+                    if (is_fluid) {
+                        D->wij[d_idx] += WIJ;           /* SourceNumberDensity            */
+                        /* SolidWallPressureBC.loop wc/edac.py:151-161 */
+                        const double gdotxij = (P->gx - D->au[d_idx]) * XIJ[0] + (P->gy - D->av[d_idx]) * XIJ[1] +
+                                               (P->gz - D->aw[d_idx]) * XIJ[2];
+                        D->p[d_idx] += S->p[s_idx] * WIJ + S->rho[s_idx] * gdotxij * WIJ;
+                        /* SetWallVelocity.loop wc/edac.py:208-214 */
+                        D->uf[d_idx] += S->u[s_idx] * WIJ;
+                        D->vf[d_idx] += S->v[s_idx] * WIJ;
+                        D->wf[d_idx] += S->w[s_idx] * WIJ;
+                    }
+                });
+            }
+            total += pairs;
+        }
+        /* post_loop: wc/edac.py:163-166 and :216-230 */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++) {
+            if (D->wij[i] > 1e-14) D->p[i] /= D->wij[i];
+            if (D->wij[i] > 1e-12) {
+                D->uf[i] /= D->wij[i];
+                D->vf[i] /= D->wij[i];
+                D->wf[i] /= D->wij[i];
+            }
+            D->ug[i] = 2 * D->u[i] - D->uf[i];
+            D->vgw[i] = 2 * D->v[i] - D->vf[i];
+            D->wg[i] = 2 * D->w[i] - D->wf[i];
+        }
+    }
+    return total;
+}
+
+int64_t orc_tvf_avgp(orc_ctx *c, const orc_tvf_program *P)
+{
+    int64_t total = 0;
+    for (int dst = 0; dst < c->narr; dst++) {
+        if (!(P->fluid_mask >> dst & 1u)) continue;
+        orc_array *D = &c->arr[dst];
+        const int64_t np = D->n_real; /* Group(equations=avg_p_group, real=True), wc/edac.py:842 */
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++) D->pavg[i] = D->nnbr[i] = 0.0;
+        for (int src = 0; src < c->narr; src++) {
+            if (!((P->fluid_mask | P->solid_mask) >> src & 1u)) continue;
+            const orc_array *S = &c->arr[src];
+            int64_t pairs = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : pairs)
+            for (int64_t d_idx = 0; d_idx < np; d_idx++) {
+                ORC_FOR_NEIGHBORS(c, dst, src, d_idx, s_idx, {
+                    pairs++;
+                    D->pavg[d_idx] += S->p[s_idx]; /* wc/edac.py:73-75 */
+                    D->nnbr[d_idx] += 1.0;
+                });
+            }
+            total += pairs;
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < np; i++)
+            if (D->nnbr[i] > 0) D->pavg[i] /= D->nnbr[i];
+    }
+    return total;
+}
+
 int64_t orc_tvf_pass2(orc_ctx *c, const orc_tvf_program *P)
 {
     const int kernel = P->kernel, dim = P->dim;
@@ -835,7 +934,12 @@ int64_t orc_tvf_pass2(orc_ctx *c, const orc_tvf_program *P)
             if (bits & ORC_TVF_EDAC) D->ap[i] = 0.0;
         }
         for (int src = 0; src < c->narr; src++) {
-            if (!(P->fluid_mask >> src & 1u)) continue;
+            if (!((P->fluid_mask | P->solid_mask) >> src & 1u)) continue;
+            /* which equations have this source (wc/edac.py:845-878): a wall is a source of the
+             * pressure gradient, the artificial viscosity, the no-slip term and EDAC only */
+            const int wall = (P->solid_mask >> src) & 1u;
+            const uint32_t bits = wall ? (P->eqbits & (ORC_TVF_PGRAD | ORC_TVF_AV | ORC_TVF_NOSLIP | ORC_TVF_EDAC))
+                                       : (P->eqbits & ~(uint32_t)ORC_TVF_NOSLIP);
             const orc_array *S = &c->arr[src];
             int64_t pairs = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : pairs)
@@ -893,6 +997,15 @@ int64_t orc_tvf_pass2(orc_ctx *c, const orc_tvf_program *P)
                         D->au[d_idx] += tmp * VIJ[0];
                         D->av[d_idx] += tmp * VIJ[1];
                         D->aw[d_idx] += tmp * VIJ[2];
+                    }
+                    if (bits & ORC_TVF_NOSLIP) { /* transport_velocity.py:611-638 */
+                        const double etai = P->nu * rhoi, etaj = P->nu * rhoj;
+                        const double etaij = 2 * (etai * etaj) / (etai + etaj);
+                        const double Fij = XIJ[0] * DWIJ[0] + XIJ[1] * DWIJ[1] + XIJ[2] * DWIJ[2];
+                        const double tmp = mi1 * (Vi2 + Vj2) * (etaij * Fij / (R2IJ + EPS));
+                        D->au[d_idx] += tmp * (D->u[d_idx] - S->ug[s_idx]);
+                        D->av[d_idx] += tmp * (D->v[d_idx] - S->vgw[s_idx]);
+                        D->aw[d_idx] += tmp * (D->w[d_idx] - S->wg[s_idx]);
                     }
                     if (bits & ORC_TVF_ASTRESS) { /* transport_velocity.py:473-545 */
                         const double ui = D->u[d_idx], vi = D->v[d_idx], wi = D->w[d_idx];

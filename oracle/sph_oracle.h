@@ -54,6 +54,8 @@ typedef struct {
     /* elastic dynamics (solid_mech/basic.py:52-59); may be NULL.  Symmetric tensors
      * are stored as 00 01 02 11 12 22, the velocity gradient as 00 01 02 10 .. 22 */
     double *vg[9], *s[6], *as[6], *r[6], *s0[6], *e, *e0, *ae;
+    /* wall arrays of the EDAC scheme (TVF_SOLID_PROPS, wc/edac.py:752-753); may be NULL */
+    double *wij, *uf, *vf, *wf, *ug, *vgw, *wg;   /* vgw: the property "vg" (vg[] above is the velocity gradient) */
 } orc_array;
 
 typedef struct {
@@ -82,7 +84,8 @@ enum {
     ORC_TVF_AV      = 2,  /* MomentumEquationArtificialViscosity transport_velocity.py:389-448 */
     ORC_TVF_VISC    = 4,  /* MomentumEquationViscosity         transport_velocity.py:328-386 */
     ORC_TVF_ASTRESS = 8,  /* MomentumEquationArtificialStress  transport_velocity.py:451-545 */
-    ORC_TVF_EDAC    = 16  /* EDACEquation                      wc/edac.py:354-386 */
+    ORC_TVF_EDAC    = 16, /* EDACEquation                      wc/edac.py:354-386 */
+    ORC_TVF_NOSLIP  = 32  /* SolidWallNoSlipBC                 transport_velocity.py:548-638 */
 };
 typedef struct {
     int kernel, dim;
@@ -91,6 +94,9 @@ typedef struct {
     uint32_t eqbits;     /* ORC_TVF_* of the second group */
     double pb, nu, edac_nu, c0, rho0, alpha;
     double gx, gy, gz, tdamp, t;
+    uint32_t solid_mask; /* bit a: array a is a solid wall (EDACScheme(fluids, solids)): a source of
+                          * the pressure gradient, the artificial viscosity, the no-slip term and
+                          * the EDAC equation, and a destination of orc_tvf_wall */
 } orc_tvf_program;
 
 /* ElasticSolidsScheme.get_equations, solid_mech/basic.py:604-651 */
@@ -158,6 +164,14 @@ void orc_dt_factors(orc_ctx *, double out[3]);
 int64_t orc_tvf_pass1(orc_ctx *, const orc_tvf_program *);
 /* group 2 (real=True): the momentum terms and the EDAC pressure evolution */
 int64_t orc_tvf_pass2(orc_ctx *, const orc_tvf_program *);
+/* with solid walls (solid_mask != 0), the wall part of the first group, wc/edac.py:815-822:
+ * SourceNumberDensity (:177-183), VolumeSummation (transport_velocity.py:61-75),
+ * SolidWallPressureBC (wc/edac.py:136-166), SetWallVelocity (:186-230) for every wall array,
+ * all particles (real=False); call AFTER orc_tvf_pass1 (it reads the fluids' new rho) */
+int64_t orc_tvf_wall(orc_ctx *, const orc_tvf_program *);
+/* ComputeAveragePressure as a group of its own, real=True, sources = fluids + walls
+ * (wc/edac.py:840-842: "after the wall pressure is set up") */
+int64_t orc_tvf_avgp(orc_ctx *, const orc_tvf_program *);
 /* EDACTVFStep wc/edac.py:491-540: which = 0 initialize, 1 stage1, 2 stage2 */
 void orc_stage_tvf(orc_ctx *, int arr, int which, double dt);
 

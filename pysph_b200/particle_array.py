@@ -197,6 +197,20 @@ def get_particle_array_edac(constants=None, **props):
     return pa
 
 
+# TVF_SOLID_PROPS of EDACScheme.setup_properties (wc/edac.py:752-753)
+EDAC_WALL_PROPS = ('V', 'wij', 'ax', 'ay', 'az', 'uf', 'vf', 'wf', 'ug', 'vg', 'wg')
+
+
+def get_particle_array_edac_wall(constants=None, **props):
+    """A solid-wall array with the property set ``EDACScheme.setup_properties`` gives the
+    ``solids`` of an internal flow (wc/edac.py:752-762): u v w are the PRESCRIBED wall
+    velocity, au av aw its prescribed acceleration; V, wij, p, uf.., ug.. are computed by
+    the first Group of every evaluation."""
+    pa = get_particle_array(additional_props=EDAC_WALL_PROPS, constants=constants, **props)
+    pa.set_output_arrays(['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'p', 'm', 'h', 'V'])
+    return pa
+
+
 # pysph/sph/solid_mech/basic.py:52-59
 ELASTIC_PROPS = ['cs', 'e', 'v00', 'v01', 'v02', 'v10', 'v11', 'v12', 'v20', 'v21',
                  'v22', 'r00', 'r01', 'r02', 'r11', 'r12', 'r22', 's00', 's01', 's02',

@@ -78,4 +78,18 @@ def edac_arrays_from_dict(d, order=('fluid', 'fluid2')):
     return pas
 
 
+def edac_wall_arrays_from_dict(d):
+    """golden 'inputs' dict of an EDAC case with a solid wall -> [fluid, wall] stand-ins."""
+    from pysph_b200.particle_array import get_particle_array_edac, get_particle_array_edac_wall
+    pas = []
+    for name, factory in (('fluid', get_particle_array_edac), ('wall', get_particle_array_edac_wall)):
+        a = d[name]
+        props = dict((k, np.array(v, dtype=float)) for k, v in a.items() if k[0] != '_')
+        pa = factory(name=name, **props)
+        pa.set_num_real_particles(a.get('_n_real', len(a['x'])))
+        pas.append(pa)
+    return pas
+
+
+EDAC_WALL_FIELDS = ['V', 'wij', 'p', 'uf', 'vf', 'wf', 'ug', 'vg', 'wg']
 EDAC_FIELDS = ['V', 'rho', 'pavg', 'au', 'av', 'aw', 'auhat', 'avhat', 'awhat', 'ap']

@@ -295,6 +295,41 @@ def test_edac_evaluation_matches_reference_bodies(idx):
             assert np.max(np.abs(got - wantv)) <= 5e-12 * scale, (pa.name, f)
 
 
+@pytest.mark.parametrize('idx', range(4))
+def test_edac_solid_wall_evaluation_matches_reference_bodies(idx):
+    """EDACScheme(fluids, solids=['wall']): the reference's own scheme method and the bodies of
+    SourceNumberDensity, VolumeSummation, SolidWallPressureBC, SetWallVelocity,
+    SolidWallNoSlipBC (+ the fluid equations with a wall among their sources)."""
+    from helpers import EDAC_FIELDS, EDAC_WALL_FIELDS, edac_wall_arrays_from_dict
+    case = load_golden('edac_wall_cases.json')[idx]
+    p = case['params']
+    # the Groups, equations and sources the reference emitted are what the oracle driver assumes
+    g1 = ['SummationDensity', 'SourceNumberDensity', 'VolumeSummation', 'SolidWallPressureBC',
+          'SetWallVelocity']
+    g2 = ['MomentumEquationPressureGradient']
+    s2 = [['fluid', 'wall']]
+    if p['alpha'] > 0:
+        g2.append('MomentumEquationArtificialViscosity'); s2.append(['fluid', 'wall'])
+    if p['nu'] > 0:
+        g2 += ['MomentumEquationViscosity', 'SolidWallNoSlipBC']; s2 += [['fluid'], ['wall']]
+    g2 += ['MomentumEquationArtificialStress', 'EDACEquation']; s2 += [['fluid'], ['fluid', 'wall']]
+    want = [g1] + ([['ComputeAveragePressure']] if p['bql'] else []) + [g2]
+    assert p['groups'] == want
+    assert p['group_real'] == [False] + ([True] if p['bql'] else []) + [True]
+    assert p['sources'][0] == [['fluid', 'wall'], ['fluid'], ['fluid', 'wall'], ['fluid'], ['fluid']]
+    assert p['sources'][-1] == s2
+    pas = edac_wall_arrays_from_dict(case['inputs'])
+    s = orc.EDACOracleSolver(pas, dict(p, dt=1e-3), case['kernel'])
+    s.t = p['t']
+    s.evaluate()
+    for pa, fields in zip(pas, (EDAC_FIELDS, EDAC_WALL_FIELDS)):
+        ref = case['outputs'][pa.name]
+        for f in fields:
+            got, wantv = pa.properties[f], np.array(ref[f])
+            scale = max(np.max(np.abs(wantv)), 1e-300)
+            assert np.max(np.abs(got - wantv)) <= 5e-12 * scale, (pa.name, f)
+
+
 def test_edac_tvf_step_matches_reference_bodies():
     from pysph_b200.particle_array import get_particle_array_edac
     g = load_golden('edac_stepper.json')
