@@ -110,20 +110,33 @@ enum {
     B200SPH_TVF_AV = 2,      /* MomentumEquationArtificialViscosity transport_velocity.py:389-448 */
     B200SPH_TVF_VISC = 4,    /* MomentumEquationViscosity          transport_velocity.py:328-386 */
     B200SPH_TVF_ASTRESS = 8, /* MomentumEquationArtificialStress   transport_velocity.py:451-545 */
-    B200SPH_TVF_EDAC = 16    /* EDACEquation                       wc/edac.py:354-386 */
+    B200SPH_TVF_EDAC = 16,   /* EDACEquation                       wc/edac.py:354-386 */
+    B200SPH_TVF_NOSLIP = 32  /* SolidWallNoSlipBC (sources: the walls) transport_velocity.py:548-638 */
 };
 
-/* The two Groups EDACScheme._get_internal_flow_equations (wc/edac.py:776-880) emits
- * for fluids without solids: every fluid array is a destination and a source. */
+/* The Groups EDACScheme._get_internal_flow_equations (wc/edac.py:776-880) emits: every
+ * fluid array is a destination and a source.  With solid walls (solid_mask; :815-822) group 1
+ * continues on the wall arrays -- SourceNumberDensity, VolumeSummation, SolidWallPressureBC,
+ * SetWallVelocity (k_tvf_wall) --, the average pressure becomes a Group of its own behind the
+ * wall pressure (:840-842, passes bit 2) and the walls are sources of the fluids' density,
+ * average pressure, pressure gradient, artificial viscosity, EDAC equation and of
+ * SolidWallNoSlipBC.  A wall array keeps u v w (prescribed velocity) and au av aw (prescribed
+ * acceleration); what the wall equations compute is read back under these property ids:
+ * p -> B200SPH_P, V -> B200SPH_VOL, wij -> B200SPH_PAVG, uf vf wf -> B200SPH_AUHAT.., ug vg wg ->
+ * B200SPH_UHAT.. (the transport-velocity slots a wall does not otherwise use). */
 typedef struct {
     uint32_t fluid_mask; /* bit a: array a is a fluid                           */
     int32_t bql;         /* ComputeAveragePressure (wc/edac.py:62-79) in group 1 */
     uint32_t eqbits;     /* B200SPH_TVF_* of group 2                            */
     int32_t passes;      /* bit 0: group 1 (TVF SummationDensity [+ average p],
-                          * real=False), bit 1: group 2 (real=True)              */
+                          * real=False; + the wall equations), bit 1: group 2
+                          * (real=True), bit 2: the average-pressure Group of a
+                          * scheme with walls (real=True)                         */
     double pb, nu, edac_nu, c0, rho0, alpha;
-    double gx, gy, gz;   /* body force; damped by tdamp at time t (:483-488)     */
+    double gx, gy, gz;   /* body force; damped by tdamp at time t (:483-488); the
+                          * wall pressure takes it undamped (:141-161)            */
     double tdamp, t;
+    uint32_t solid_mask; /* bit a: array a is a solid wall (ABI 5: appended)     */
 } b200sph_tvf_program;
 
 /* The two Groups of ElasticSolidsScheme.get_equations (solid_mech/basic.py:604-651) for

@@ -22,6 +22,7 @@ backend needs the built library and a CUDA device.
 """
 from .particle_array import (ParticleArray, get_particle_array,
                              get_particle_array_wcsph, get_particle_array_edac,
+                             get_particle_array_edac_wall,
                              get_particle_array_elastic_dynamics)
 from .kernels import CubicSpline, WendlandQuintic, QuinticSpline, Gaussian
 from .equations import (Equation, Group, SummationDensity, ContinuityEquation,

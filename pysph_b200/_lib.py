@@ -24,6 +24,12 @@ PROP_IDS.update(uhat=27, vhat=28, what=29, V=32, pavg=33, auhat=34, avhat=35,
 # arrays of the EDAC scheme (they own 'ap') integrate p: it lives in the fp64
 # B200SPH_PF / B200SPH_PF0 instead of the derived fp32 B200SPH_P
 EDAC_PROP_IDS = dict(PROP_IDS, p=30, p0=31)
+# a solid wall of the EDAC scheme (wc/edac.py:752-753): what the wall equations compute is
+# kept in the transport-velocity slots a wall does not otherwise use (include/b200sph.h)
+EDAC_WALL_PROP_IDS = dict(PROP_IDS)
+EDAC_WALL_PROP_IDS.update(ug=27, vg=28, wg=29, V=32, wij=33, uf=34, vf=35, wf=36)
+for _n in ('uhat', 'vhat', 'what', 'pavg', 'auhat', 'avhat', 'awhat', 'ap'):
+    EDAC_WALL_PROP_IDS.pop(_n, None)
 # elastic-dynamics extension (B200SPH_S00 ...); arrays that own 's00' use these
 _SYM = ('00', '01', '02', '11', '12', '22')
 ELASTIC_PROP_IDS = dict(PROP_IDS)
@@ -57,7 +63,7 @@ class PairProgram(C.Structure):
                 ('eps_xsph', C.c_double)]
 
 
-TVF_PGRAD, TVF_AV, TVF_VISC, TVF_ASTRESS, TVF_EDAC = 1, 2, 4, 8, 16
+TVF_PGRAD, TVF_AV, TVF_VISC, TVF_ASTRESS, TVF_EDAC, TVF_NOSLIP = 1, 2, 4, 8, 16, 32
 
 
 class TvfProgram(C.Structure):
@@ -66,7 +72,7 @@ class TvfProgram(C.Structure):
                 ('pb', C.c_double), ('nu', C.c_double), ('edac_nu', C.c_double),
                 ('c0', C.c_double), ('rho0', C.c_double), ('alpha', C.c_double),
                 ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
-                ('tdamp', C.c_double), ('t', C.c_double)]
+                ('tdamp', C.c_double), ('t', C.c_double), ('solid_mask', C.c_uint32)]
 
 
 class SolidProgram(C.Structure):

@@ -12,7 +12,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import PROP_IDS, INT_PROP_IDS, EDAC_PROP_IDS, ELASTIC_PROP_IDS
+from ._lib import (PROP_IDS, INT_PROP_IDS, EDAC_PROP_IDS, EDAC_WALL_PROP_IDS,
+                   ELASTIC_PROP_IDS)
 
 
 def _host_array(pa, name):
@@ -73,7 +74,9 @@ class B200Backend(object):
         self.index = dict((n, i) for i, n in enumerate(self.names))
         # name -> device property id, per array: EDAC arrays evolve p (fp64 PF)
         self.prop_ids = [dict(EDAC_PROP_IDS if 'ap' in pa.properties else
-                              (ELASTIC_PROP_IDS if 's00' in pa.properties else PROP_IDS))
+                              (ELASTIC_PROP_IDS if 's00' in pa.properties else
+                               (EDAC_WALL_PROP_IDS if 'wij' in pa.properties and
+                                'ug' in pa.properties else PROP_IDS)))
                          for pa in particle_arrays]
         self.user_props = []      # names of the fp64 properties created for generic equations
         for pa in particle_arrays:

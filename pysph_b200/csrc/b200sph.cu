@@ -2183,9 +2183,17 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog, int64_t 
     if (rc) return rc;
     if ((rc = eos_flush(ctx))) return rc;
     if (!ctx->grid_valid) return set_err(ctx, "tvf_pass: the NNPS is stale (particles were pushed/resized); call nnps_update first");
-    if (!(prog->passes & 3)) return set_err(ctx, "tvf_pass: passes must select group 1 and/or group 2");
-    if (prog->eqbits > 31u) return set_err(ctx, "tvf_pass: unknown equation bits 0x%x", prog->eqbits);
+    if (!(prog->passes & 7)) return set_err(ctx, "tvf_pass: passes must select group 1, the average-pressure group and/or group 2");
+    if (prog->eqbits > 63u) return set_err(ctx, "tvf_pass: unknown equation bits 0x%x", prog->eqbits);
     if (prog->fluid_mask == 0 || prog->fluid_mask >= (1u << ctx->narr)) return set_err(ctx, "tvf_pass: bad fluid mask 0x%x", prog->fluid_mask);
+    const unsigned solid_mask = prog->solid_mask;
+    if (solid_mask >= (1u << ctx->narr) || (solid_mask & prog->fluid_mask))
+        return set_err(ctx, "tvf_pass: bad solid mask 0x%x (fluids 0x%x)", solid_mask, prog->fluid_mask);
+    if ((prog->eqbits & B200SPH_TVF_NOSLIP) && !solid_mask) return set_err(ctx, "tvf_pass: SolidWallNoSlipBC without a solid wall");
+    if ((prog->passes & 4) && !solid_mask) return set_err(ctx, "tvf_pass: the average pressure has a Group of its own only with solid walls");
+    if ((prog->passes & 1) && solid_mask && prog->bql)
+        return set_err(ctx, "tvf_pass: with solid walls the average pressure is computed after the wall pressure (passes bit 2), not in group 1");
+    if (solid_mask && (ctx->peer_box || ctx->comm_pending)) return set_err(ctx, "tvf_pass: EDAC with solid walls runs on one GPU");
     const bool use_lists = ctx->force_kernel == 0 && ctx->n_sorted > 0 && ctx->n_sorted < (1LL << LIST_JBITS);
     if (ctx->n_sorted == 0) return 0;
     if (!use_lists) return set_err(ctx, "tvf_pass: the EDAC kernels need the neighbour-list path (B200SPH_PAIR_KERNEL=list, < 2^26 particles)");
@@ -2201,7 +2209,7 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog, int64_t 
                                              ctx->f64x[B200SPH_UHAT - B200SPH_UHAT], ctx->f64x[B200SPH_VHAT - B200SPH_UHAT],
                                              ctx->f64x[B200SPH_WHAT - B200SPH_UHAT], ctx->f64x[B200SPH_PF - B200SPH_UHAT],
                                              ctx->f32x[B200SPH_PAVG - B200SPH_VOL], ctx->ptype, ctx->perm, ctx->n_sorted,
-                                             ctx->B, ctx->AB, ctx->C, ctx->Dv, ctx->PT);
+                                             ctx->B, ctx->AB, ctx->C, ctx->Dv, ctx->PT, ctx->f64[B200SPH_RHO], solid_mask);
     LAUNCH_CHECK();
     ctx->state_packed = false;   // B / C no longer hold the WCSPH records
 
@@ -2218,8 +2226,14 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog, int64_t 
     ta.k2 = (float)(ctx->radius_scale * ctx->radius_scale);
     ta.kfac = (float)kernel_fac(ctx->kernel, ctx->dim);
     ta.fluid_mask = prog->fluid_mask;
+    ta.solid_mask = solid_mask;
+    ta.src_mask = prog->fluid_mask | solid_mask;
     ta.eqbits = prog->eqbits;
     ta.bql = prog->bql;
+    ta.wgx = (float)prog->gx; ta.wgy = (float)prog->gy; ta.wgz = (float)prog->gz;
+    ta.p32 = ctx->f32[B200SPH_P - N_F64];
+    ta.ug = ctx->f64x[B200SPH_UHAT - B200SPH_UHAT]; ta.vg = ctx->f64x[B200SPH_VHAT - B200SPH_UHAT];
+    ta.wg = ctx->f64x[B200SPH_WHAT - B200SPH_UHAT];
     ta.pb = (float)prog->pb; ta.nu = (float)prog->nu; ta.edac_nu = (float)prog->edac_nu;
     ta.c0 = (float)prog->c0; ta.alpha = (float)prog->alpha;
     double damp = 1.0;   // wc/edac.py:483-488
@@ -2230,16 +2244,25 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog, int64_t 
         ta.pair_counter = ctx->counter;
     }
     const unsigned nb = (unsigned)cdiv(ctx->n_sorted, LIST_NT);
-    for (int pass = 1; pass <= 2; pass++) {
-        if (pass == 2) {
+    // stages: 1 group 1 (fluids), 2 group 1 (wall arrays), 3 the average-pressure group, 4 group 2
+    for (int stage = 1; stage <= 4; stage++) {
+        const int pass = stage == 4 ? 2 : 1;
+        if (stage == 4) {
             pt.reset();
             pt.reset(new PhaseTimer(ctx, 1));
         }
-        if (!(prog->passes & pass)) continue;
+        if (stage == 1 && !(prog->passes & 1)) continue;
+        if (stage == 2 && !((prog->passes & 1) && solid_mask)) continue;
+        if (stage == 3 && !(prog->passes & 4)) continue;
+        if (stage == 4 && !(prog->passes & 2)) continue;
+        ta.avg_only = stage == 3 ? 1 : 0;
+        if (stage == 3) ta.bql = 1;
         switch (ctx->kernel * 4 + ctx->dim) {
 #define TVF_CASE(K, D)                                                                                   \
     case K * 4 + D:                                                                                      \
-        if (pass == 1) k_tvf_pass1<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg); \
+        if (stage == 2) k_tvf_wall<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg); \
+        else if (pass == 1) k_tvf_pass1<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg); \
+        else if (solid_mask) k_tvf_pass2<K, D, true><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg); \
         else k_tvf_pass2<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg);            \
         break;
             TVF_CASE(0, 1) TVF_CASE(0, 2) TVF_CASE(0, 3) TVF_CASE(1, 2) TVF_CASE(1, 3)
@@ -2248,6 +2271,7 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog, int64_t 
         default: return set_err(ctx, "tvf_pass: unsupported kernel/dim combination");
         }
         LAUNCH_CHECK();
+        if (stage == 3) ta.bql = prog->bql;
         if (pass == 2) ctx->stats.pair_launches++;
     }
     pt.reset();

@@ -20,6 +20,15 @@ struct TvfArgs {
     int bql;
     float pb, nu, edac_nu, c0, alpha, gx, gy, gz;  // gx.. already damped
     unsigned long long *pair_counter;
+    // solid walls (EDACScheme(fluids, solids), wc/edac.py:815-822): sources of the fluids' V,
+    // average pressure, pressure gradient, artificial viscosity, no-slip term and EDAC
+    // equation; destinations of k_tvf_wall.  src_mask = fluid_mask | solid_mask.
+    unsigned solid_mask, src_mask;
+    int avg_only;                 // k_tvf_pass1: only the average pressure, real destinations
+    float wgx, wgy, wgz;          // the UNDAMPED body force of SolidWallPressureBC (:141-161)
+    float *p32;                   // pool p of the wall arrays
+    double *ug, *vg, *wg;         // wall arrays: the slots of uhat vhat what hold ug vg wg,
+    // ... those of auhat avhat awhat hold uf vf wf and pavg holds wij
 };
 
 __global__ void k_pack_tvf(const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
@@ -27,7 +36,8 @@ __global__ void k_pack_tvf(const double *__restrict__ u, const double *__restric
                            const double *__restrict__ wh, const double *__restrict__ pf, const float *__restrict__ pavg,
                            const uint8_t *__restrict__ ptype, const uint32_t *__restrict__ perm, long long n,
                            float4 *__restrict__ B, float4 *__restrict__ AB, float4 *__restrict__ C2,
-                           float4 *__restrict__ Dv, float2 *__restrict__ PT)
+                           float4 *__restrict__ Dv, float2 *__restrict__ PT, const double *__restrict__ rho,
+                           const unsigned solid_mask)
 {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -43,6 +53,12 @@ __global__ void k_pack_tvf(const double *__restrict__ u, const double *__restric
     const float p = (float)pf[g];
     PT[s] = make_float2(p, __int_as_float(t));
     C2[s] = make_float4(0.f, p, 1.f, __int_as_float(t));   // rho, V filled in by pass 1
+    if ((solid_mask >> (t & 7)) & 1u) {
+        // a wall particle: its density is a constant of the run, p / V / the dummy velocity
+        // come from k_tvf_wall
+        C2[s] = make_float4((float)rho[g], 0.f, 1.f, __int_as_float(t));
+        Dv[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 // group 1 (real=False): V_i = sum_j W_ij, rho_i = m_i V_i (transport_velocity.py:52-58) and the
@@ -60,6 +76,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
     if (active) {
         const int ti = __float_as_int(a.PT[s].y);
         if (!((a.fluid_mask >> (ti & 7)) & 1u)) active = false;
+        if (a.avg_only && (ti & PT_GHOST)) active = false;   // that Group is real=True (wc/edac.py:842)
     }
     if (active) {
         ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
@@ -85,7 +102,7 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
             const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
-            if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Pj.y) & 7)) & 1u)) {
+            if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.src_mask >> (__float_as_int(Pj.y) & 7)) & 1u)) {
                 npairs++;
                 const float rij = sqrtf(r2);
                 const float h1 = frcp(0.5f * (Ai.w + Aj.w));
@@ -98,12 +115,14 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
         });
     if (active) {
         const uint32_t g = a.perm[s];
-        const float rho = Bi.w * wsum;
-        a.V[g] = wsum;
-        a.rho[g] = (double)rho;
-        float4 *c2 = a.C2 + s;
-        c2->x = rho;          // .y (p) and .w (type) were written by k_pack_tvf; other
-        c2->z = wsum;         // threads read only those two while this kernel runs
+        if (!a.avg_only) {
+            const float rho = Bi.w * wsum;
+            a.V[g] = wsum;
+            a.rho[g] = (double)rho;
+            float4 *c2 = a.C2 + s;
+            c2->x = rho;          // .y (p) and .w (type) were written by k_pack_tvf; other
+            c2->z = wsum;         // threads read only those two while this kernel runs
+        }
         if (a.bql) {
             const float pv = nn > 0.f ? psum / nn : 0.f;
             a.pavg[g] = pv;
@@ -117,9 +136,105 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_pass1(const TvfArgs a, const
     }
 }
 
-// group 2 (real=True): pressure gradient with the background-pressure term, artificial /
-// physical viscosity, artificial stress and the EDAC pressure evolution, fused
+// group 1, the wall arrays (real=False; wc/edac.py:815-822), after k_tvf_pass1 has put the
+// fluids' new density into their records: SourceNumberDensity (:177-183: wij = sum over the
+// FLUID neighbours of W), VolumeSummation (transport_velocity.py:61-75: V = sum over ALL
+// neighbours), SolidWallPressureBC (:136-166: p = sum_f (p_f + rho_f (g - a_wall) . x_wf) W / wij)
+// and SetWallVelocity (:186-230: uf = sum_f u_f W / wij, ug = 2 u_wall - uf).  Results go to the
+// pool (p; V; wij, uf.., ug.. in the transport-velocity slots a wall does not use) and into the
+// wall particle's own records, from which group 2 reads them as a SOURCE: C2 = (rho, p, V, type),
+// Dv = (ug, vg, wg, -), PT = (p, type).
 template <int K, int DIM>
+__global__ void __launch_bounds__(LIST_NT, 4) k_tvf_wall(const TvfArgs a, const uint32_t *__restrict__ cnt,
+                                                        const uint32_t *__restrict__ lst, const int capg)
+{
+    const int tid = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const long long s = (long long)blockIdx.x * LIST_NT + tid;
+    bool active = s < a.n;
+    float4 Ai = make_float4(0.f, 0.f, 0.f, 0.f), Bi = Ai;
+    int count = 0;
+    int ti = 0;
+    if (active) {
+        ti = __float_as_int(a.PT[s].y);
+        if (!((a.solid_mask >> (ti & 7)) & 1u)) active = false;
+    }
+    uint32_t g = 0;
+    float gax = 0.f, gay = 0.f, gaz = 0.f;
+    if (active) {
+        ld_256(a.AB + 2 * (size_t)s, Ai, Bi);
+        count = (int)cnt[s];
+        g = a.perm[s];
+        // g - a_wall: au av aw of a wall array are its PRESCRIBED acceleration
+        gax = a.wgx - a.au[g]; gay = a.wgy - a.av[g]; gaz = a.wgz - a.aw[g];
+    }
+    int cmax = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, o));
+    const uint32_t *my = lst + ((size_t)(s >> 5) * (size_t)capg) * 32u + (uint32_t)(s & 31);
+    const float hi2 = a.k2 * Ai.w * Ai.w;
+    float vsum = 0.f, wsum = 0.f, psum = 0.f, us = 0.f, vs = 0.f, ws = 0.f;
+    unsigned npairs = 0;
+    struct Rec { float4 A, B, C; };
+    list_walk<Rec>(my, count, cmax,
+        [&](const uint32_t e, Rec &r) {
+            const uint32_t j = LIST_J(e);
+            ld_256(a.AB + 2u * j, r.A, r.B);
+            r.C = a.C2[j];      // a fluid's (rho, p, ., type); of a wall only the type is used
+        },
+        [&](const bool live, const uint32_t e, const Rec &r) {
+            const float4 Aj = r.A, Bj = r.B, Cj = r.C;
+            const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
+            const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
+            const float r2 = xij * xij + yij * yij + zij * zij;
+            const int tj = __float_as_int(Cj.w) & 7;
+            if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.src_mask >> tj) & 1u)) {
+                npairs++;
+                const float rij = sqrtf(r2);
+                const float h1 = frcp(0.5f * (Ai.w + Aj.w));
+                float w, dw;
+                sph_kernel<K>(rij * h1, w, dw);
+                w *= a.kfac * hpow<DIM>(h1);
+                vsum += w;
+                if ((a.fluid_mask >> tj) & 1u) {
+                    wsum += w;
+                    psum += (Cj.y + Cj.x * (gax * xij + gay * yij + gaz * zij)) * w;
+                    us += Bj.x * w; vs += Bj.y * w; ws += Bj.z * w;
+                }
+            }
+        });
+    if (active) {
+        const float pw = wsum > 1e-14f ? psum / wsum : psum;
+        if (wsum > 1e-12f) {
+            const float w1 = 1.0f / wsum;
+            us *= w1; vs *= w1; ws *= w1;
+        }
+        const float ug = 2.0f * Bi.x - us, vg = 2.0f * Bi.y - vs, wg = 2.0f * Bi.z - ws;
+        a.V[g] = vsum;
+        a.p32[g] = pw;
+        a.pavg[g] = wsum;                                      // wij
+        a.auhat[g] = us; a.avhat[g] = vs; a.awhat[g] = ws;     // uf vf wf
+        a.ug[g] = (double)ug; a.vg[g] = (double)vg; a.wg[g] = (double)wg;
+        float4 *c2 = a.C2 + s;
+        c2->y = pw;           // .x (rho) and .w (type) stay; other threads read a wall's .w only
+        c2->z = vsum;
+        a.Dv[s] = make_float4(ug, vg, wg, 0.f);
+        float2 *pt = const_cast<float2 *>(a.PT) + s;
+        pt->x = pw;
+    }
+    if (a.pair_counter) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(FULL, npairs, o);
+        if ((tid & 31) == 0 && npairs) atomicAdd(a.pair_counter, (unsigned long long)npairs);
+    }
+}
+
+// group 2 (real=True): pressure gradient with the background-pressure term, artificial /
+// physical viscosity, artificial stress and the EDAC pressure evolution, fused.  WALLS: solid
+// walls are sources too -- of the pressure gradient, the artificial viscosity, the EDAC
+// equation and (instead of the viscosity) SolidWallNoSlipBC, which takes the dummy velocity
+// from the wall's Dv record; the instantiation without walls is the measured one.
+template <int K, int DIM, bool WALLS = false>
 __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const uint32_t *__restrict__ cnt,
                                                          const uint32_t *__restrict__ lst, const int capg)
 {
@@ -164,7 +279,9 @@ __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const
             const float4 T = list_cell_offset(e, a.cellx, a.celly, a.cellz);
             const float xij = Ai.x - Aj.x + T.x, yij = Ai.y - Aj.y + T.y, zij = Ai.z - Aj.z + T.z;
             const float r2 = xij * xij + yij * yij + zij * zij;
-            if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && ((a.fluid_mask >> (__float_as_int(Cj.w) & 7)) & 1u)) {
+            const int tj = __float_as_int(Cj.w) & 7;
+            const bool wall = WALLS && ((a.solid_mask >> tj) & 1u);
+            if (live && ((r2 < hi2) || (r2 < a.k2 * Aj.w * Aj.w)) && (((WALLS ? a.src_mask : a.fluid_mask) >> tj) & 1u)) {
                 npairs++;
                 const bool far = r2 > 1e-24f;
                 const float rinv = far ? frsqrt(r2) : 0.0f;
@@ -199,14 +316,21 @@ __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const
                 au += fx * xij;
                 av += fx * yij;
                 aw += fx * zij;
-                if (a.eqbits & B200SPH_TVF_VISC) {   // transport_velocity.py:362-386
+                if ((a.eqbits & B200SPH_TVF_VISC) && !wall) {   // transport_velocity.py:362-386
                     const float etaij = 2.0f * a.nu * rhoi * rhoj * rsum1;
                     const float tmp = common * etaij * (gt * r2) * r2e1;
                     au += tmp * uij;
                     av += tmp * vij;
                     aw += tmp * wij;
                 }
-                if (a.eqbits & B200SPH_TVF_ASTRESS) {   // transport_velocity.py:473-545
+                if (WALLS && wall && (a.eqbits & B200SPH_TVF_NOSLIP)) {   // transport_velocity.py:611-638
+                    const float etaij = 2.0f * a.nu * rhoi * rhoj * rsum1;
+                    const float tmp = common * etaij * (gt * r2) * r2e1;
+                    au += tmp * (Bi.x - Dj.x);      // the wall's dummy velocity ug vg wg
+                    av += tmp * (Bi.y - Dj.y);
+                    aw += tmp * (Bi.z - Dj.z);
+                }
+                if ((a.eqbits & B200SPH_TVF_ASTRESS) && !wall) {   // transport_velocity.py:473-545
                     const float si = rhoi * gt * (Di.x * xij + Di.y * yij + Di.z * zij);
                     const float sj = rhoj * gt * (Dj.x * xij + Dj.y * yij + Dj.z * zij);
                     const float c = 0.5f * common;

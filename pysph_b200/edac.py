@@ -1,21 +1,41 @@
-"""EDAC scheme, internal-flow (transport-velocity) branch, for fluids without solids.
+"""EDAC scheme, internal-flow (transport-velocity) branch, with or without solid walls.
 
 Mirrors pysph/sph/wc/edac.py for the Taylor-Green configuration (BASELINE configs[3],
-pysph/examples/taylor_green.py:190-203): ``ComputeAveragePressure`` (:62-79),
-``EDACEquation`` (:354-386), ``MomentumEquationPressureGradient`` (:389-488),
-``EDACTVFStep`` (:491-540) and ``EDACScheme`` (:543-880, ``get_equations`` for
-``pb != 0`` and ``solids == []``).  Everything else of that module (external flows,
-solid walls, inlet/outlet) raises NotImplementedError.
+pysph/examples/taylor_green.py:190-203) and for internal flows between walls (cavity,
+Poiseuille / Couette): ``ComputeAveragePressure`` (:62-79), ``SolidWallPressureBC`` (:136-166),
+``SourceNumberDensity`` (:177-183), ``SetWallVelocity`` (:186-230), ``EDACEquation`` (:354-386),
+``MomentumEquationPressureGradient`` (:389-488), ``EDACTVFStep`` (:491-540) and ``EDACScheme``
+(:543-880, ``get_equations`` for ``pb != 0``).  Everything else of that module (external
+flows, inviscid solids, inlet/outlet, pressure clamping) raises NotImplementedError.
 """
 from .equations import Equation, Group
 from .integrator import IntegratorStep
 from .transport_velocity import (MomentumEquationArtificialStress,
                                  MomentumEquationArtificialViscosity,
-                                 MomentumEquationViscosity, SummationDensity)
+                                 MomentumEquationViscosity, SolidWallNoSlipBC,
+                                 SummationDensity, VolumeSummation)
 
 
 class ComputeAveragePressure(Equation):
     """wc/edac.py:62-79"""
+
+
+class SolidWallPressureBC(Equation):
+    """wc/edac.py:136-166: the fluid pressure extrapolated to a wall particle (Adami, Hu)."""
+
+    def __init__(self, dest, sources, gx=0.0, gy=0.0, gz=0.0):
+        self.gx = gx
+        self.gy = gy
+        self.gz = gz
+        super(SolidWallPressureBC, self).__init__(dest, sources)
+
+
+class SourceNumberDensity(Equation):
+    """wc/edac.py:177-183: wij = sum over the fluid neighbours of W"""
+
+
+class SetWallVelocity(Equation):
+    """wc/edac.py:186-230: uf = the fluid velocity extrapolated to the wall, ug = 2 u - uf"""
 
 
 class EDACEquation(Equation):
@@ -91,15 +111,26 @@ class EDACScheme(object):
     def get_equations(self):                           # wc/edac.py:704-708, :776-880
         if not self.use_tvf:
             raise NotImplementedError('B200 backend: EDAC external-flow branch (pb == 0)')
-        if self.solids or self.inviscid_solids or self.inlet_outlet_manager is not None:
-            raise NotImplementedError('B200 backend: EDAC with solids / inlet-outlet')
+        if self.inviscid_solids or self.inlet_outlet_manager is not None:
+            raise NotImplementedError('B200 backend: EDAC with inviscid solids / inlet-outlet')
+        if self.clamp_p:
+            raise NotImplementedError('B200 backend: EDAC with clamp_p')
         edac_nu = self._get_edac_nu()
-        all_ = self.fluids
-        group1 = []
+        all_ = self.fluids + self.solids
+        has_solids = len(self.solids) > 0
+        group1, avg_p_group = [], []
         for fluid in self.fluids:
             group1.append(SummationDensity(dest=fluid, sources=all_))
             if self.bql:
-                group1.append(ComputeAveragePressure(dest=fluid, sources=all_))
+                eq = ComputeAveragePressure(dest=fluid, sources=all_)
+                (avg_p_group if has_solids else group1).append(eq)
+        for solid in self.solids:                      # :815-822
+            group1.extend([
+                SourceNumberDensity(dest=solid, sources=self.fluids),
+                VolumeSummation(dest=solid, sources=all_),
+                SolidWallPressureBC(dest=solid, sources=self.fluids, gx=self.gx, gy=self.gy,
+                                    gz=self.gz),
+                SetWallVelocity(dest=solid, sources=self.fluids)])
         group2 = []
         for fluid in self.fluids:
             group2.append(MomentumEquationPressureGradient(
@@ -107,12 +138,20 @@ class EDACScheme(object):
                 gz=self.gz, tdamp=self.tdamp))
             if self.alpha > 0.0:
                 group2.append(MomentumEquationArtificialViscosity(
-                    dest=fluid, sources=self.fluids, alpha=self.alpha, c0=self.c0))
+                    dest=fluid, sources=self.fluids + self.solids, alpha=self.alpha,
+                    c0=self.c0))
             if self.nu > 0.0:
                 group2.append(MomentumEquationViscosity(
                     dest=fluid, sources=self.fluids, nu=self.nu))
+            if has_solids and self.nu > 0.0:
+                group2.append(SolidWallNoSlipBC(dest=fluid, sources=self.solids, nu=self.nu))
             group2.extend([
                 MomentumEquationArtificialStress(dest=fluid, sources=self.fluids),
                 EDACEquation(dest=fluid, sources=all_, nu=edac_nu, cs=self.c0,
                              rho0=self.rho0)])
-        return [Group(equations=group1, real=False), Group(equations=group2)]
+        groups = [Group(equations=group1, real=False)]
+        if self.bql and has_solids:
+            # the average pressure *after* the wall pressure is set up (:840-842)
+            groups.append(Group(equations=avg_p_group, real=True))
+        groups.append(Group(equations=group2))
+        return groups

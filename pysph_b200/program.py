@@ -28,12 +28,15 @@ NO_SOURCE_EQUATIONS = ('TaitEOS', 'TaitEOSHGCorrection',
 # EDAC scheme, transport-velocity branch (wc/edac.py:776-880): two Groups that
 # become ('tvf', TvfProgram) ops (merged into one when they follow each other)
 TVF_GROUP1 = ('SummationDensity', 'ComputeAveragePressure')
+# ... continued on the solid walls of an internal flow (wc/edac.py:815-822): k_tvf_wall
+TVF_WALL = ('SourceNumberDensity', 'VolumeSummation', 'SolidWallPressureBC', 'SetWallVelocity')
 TVF_GROUP2 = {
     'MomentumEquationPressureGradient': _lib.TVF_PGRAD,
     'MomentumEquationArtificialViscosity': _lib.TVF_AV,
     'MomentumEquationViscosity': _lib.TVF_VISC,
     'MomentumEquationArtificialStress': _lib.TVF_ASTRESS,
     'EDACEquation': _lib.TVF_EDAC,
+    'SolidWallNoSlipBC': _lib.TVF_NOSLIP,
 }
 
 
@@ -48,7 +51,7 @@ SOLID_GROUP2 = ('ContinuityEquation', 'MomentumEquationWithStress',
 # every equation that has a hand-written kernel; a Group made ONLY of others takes the
 # generic-equation fallback (pysph_b200/codegen.py)
 KNOWN_EQUATIONS = set(PAIR_EQUATIONS) | set(NO_SOURCE_EQUATIONS) | set(TVF_GROUP1) | \
-    set(TVF_GROUP2) | set(SOLID_GROUP1) | set(SOLID_GROUP2)
+    set(TVF_WALL) | set(TVF_GROUP2) | set(SOLID_GROUP1) | set(SOLID_GROUP2)
 import itertools
 _generic_uid = itertools.count()
 
@@ -183,40 +186,71 @@ def _is_tvf_summation(eq):
 
 def _tvf_group_kind(g):
     names = [_eq_name(e) for e in g.equations]
-    if any(n == 'ComputeAveragePressure' for n in names) or \
-            any(_is_tvf_summation(e) for e in g.equations):
+    if any(_is_tvf_summation(e) for e in g.equations) or any(n in TVF_WALL for n in names):
         return 1
+    if any(n == 'ComputeAveragePressure' for n in names):
+        # in group 1 without walls; a Group of its own (real=True) behind the wall pressure
+        return 1 if getattr(g, 'real', True) is False else 3
     if any(n in TVF_GROUP2 for n in names):
         return 2
     return 0
 
 
+def _same(a, b):
+    return sorted(a) == sorted(b)
+
+
 def _build_tvf(g, kind, index):
+    """One Group of EDACScheme._get_internal_flow_equations (wc/edac.py:776-880) -> TvfProgram.
+    The kernels assume exactly the structure that method emits -- which arrays are fluids,
+    which are walls, and who is a source of what -- and everything else is refused here."""
     names = [_eq_name(e) for e in g.equations]
     prog = _lib.TvfProgram()
     params = {}
-    fluids = []
     for eq in g.equations:
         name = _eq_name(eq)
-        ok = (name in TVF_GROUP1 and (name != 'SummationDensity' or
-                                      _is_tvf_summation(eq))) if kind == 1 \
-            else name in TVF_GROUP2
+        ok = {1: name in TVF_WALL or name == 'ComputeAveragePressure' or
+              (name == 'SummationDensity' and _is_tvf_summation(eq)),
+              3: name == 'ComputeAveragePressure', 2: name in TVF_GROUP2}[kind]
         if not ok:
             raise NotImplementedError(
                 'B200 backend: equation %r cannot share a Group with the EDAC '
                 'scheme\'s %s' % (name, names))
-        if eq.dest not in index:
-            raise ValueError('equation %s: unknown destination array %r'
-                             % (name, eq.dest))
-        if eq.dest not in fluids:
-            fluids.append(eq.dest)
-    mask = sum(1 << index[f] for f in fluids)
+        for n in [eq.dest] + list(eq.sources or []):
+            if n not in index:
+                raise ValueError('equation %s: unknown array %r' % (name, n))
+    # fluids: the destinations of the fluid equations; walls: of the wall equations (group 1)
+    # or the sources that are not fluids (the other groups)
+    fluids, walls = [], []
+    for eq in g.equations:
+        where = walls if _eq_name(eq) in TVF_WALL else fluids
+        if eq.dest not in where:
+            where.append(eq.dest)
+    if kind != 1:
+        for eq in g.equations:
+            for s_ in (eq.sources or []):
+                if s_ not in fluids and s_ not in walls:
+                    walls.append(s_)
+    if not fluids or set(fluids) & set(walls):
+        raise NotImplementedError('B200 backend: EDAC Group without fluid destinations, or an '
+                                  'array that is both fluid and wall: %s' % names)
+    all_ = fluids + walls
+    # who may be a source of what (wc/edac.py:806-878)
+    want_sources = {
+        'SummationDensity': all_, 'ComputeAveragePressure': all_,
+        'SourceNumberDensity': fluids, 'VolumeSummation': all_,
+        'SolidWallPressureBC': fluids, 'SetWallVelocity': fluids,
+        'MomentumEquationPressureGradient': all_,
+        'MomentumEquationArtificialViscosity': all_, 'MomentumEquationViscosity': fluids,
+        'SolidWallNoSlipBC': walls, 'MomentumEquationArtificialStress': fluids,
+        'EDACEquation': all_}
     for eq in g.equations:
         name = _eq_name(eq)
-        if sorted(index[s] for s in (eq.sources or [])) != sorted(index[f] for f in fluids):
+        if not _same(eq.sources or [], want_sources[name]):
             raise NotImplementedError(
-                'B200 backend: EDAC kernels take every fluid as a source of every '
-                'fluid (no solids); %s(dest=%r, sources=%r)' % (name, eq.dest, eq.sources))
+                'B200 backend: the EDAC kernels take %s as the sources of %s (wc/edac.py:'
+                '806-878); got %s(dest=%r, sources=%r)'
+                % (want_sources[name], name, name, eq.dest, eq.sources))
         if name == 'MomentumEquationPressureGradient':
             if 'edac' not in eq.__class__.__module__:
                 raise NotImplementedError(
@@ -224,10 +258,13 @@ def _build_tvf(g, kind, index):
                     '(use the EDAC variant, wc/edac.py:389)')
             for k in ('pb', 'gx', 'gy', 'gz', 'tdamp'):
                 _set_once(params, k, float(getattr(eq, k)), eq)
+        elif name == 'SolidWallPressureBC':
+            for k in ('gx', 'gy', 'gz'):
+                _set_once(params, k, float(getattr(eq, k)), eq)
         elif name == 'MomentumEquationArtificialViscosity':
             _set_once(params, 'alpha', float(eq.alpha), eq)
             _set_once(params, 'c0', float(eq.c0), eq)
-        elif name == 'MomentumEquationViscosity':
+        elif name in ('MomentumEquationViscosity', 'SolidWallNoSlipBC'):
             _set_once(params, 'nu', float(eq.nu), eq)
         elif name == 'EDACEquation':
             _set_once(params, 'edac_nu', float(eq.nu), eq)
@@ -239,11 +276,28 @@ def _build_tvf(g, kind, index):
             raise NotImplementedError(
                 'B200 backend: the EDAC density / average-pressure Group must be '
                 'real=False (wc/edac.py:838)')
-        if 'SummationDensity' not in names:
+        if not all(any(_is_tvf_summation(e) and e.dest == f for e in g.equations) for f in fluids):
             raise NotImplementedError(
-                'B200 backend: ComputeAveragePressure without the TVF SummationDensity')
+                'B200 backend: the first EDAC Group needs the TVF SummationDensity of every fluid')
+        for w in walls:
+            mine = [_eq_name(e) for e in g.equations if e.dest == w]
+            if not _same(mine, TVF_WALL):
+                raise NotImplementedError(
+                    'B200 backend: a solid wall needs %s in the first EDAC Group, got %s'
+                    % (list(TVF_WALL), mine))
         prog.bql = int('ComputeAveragePressure' in names)
+        if prog.bql and walls:
+            raise NotImplementedError(
+                'B200 backend: with solid walls ComputeAveragePressure belongs in a Group of '
+                'its own behind the wall pressure (wc/edac.py:840-842)')
         prog.passes = 1
+    elif kind == 3:
+        if not real or not walls:
+            raise NotImplementedError(
+                'B200 backend: a Group of ComputeAveragePressure alone is the one '
+                'EDACScheme emits with solid walls (real=True, wc/edac.py:840-842)')
+        prog.bql = 0          # (bql: the average pressure INSIDE group 1)
+        prog.passes = 4
     else:
         if not real:
             raise NotImplementedError(
@@ -258,22 +312,33 @@ def _build_tvf(g, kind, index):
             bits |= TVF_GROUP2[n]
         prog.eqbits = bits
         prog.passes = 2
-    prog.fluid_mask = mask
+    prog.fluid_mask = sum(1 << index[f] for f in fluids)
+    prog.solid_mask = sum(1 << index[w] for w in walls)
     for k, v in params.items():
         setattr(prog, k, v)
     return prog
 
 
+_TVF_ORDER = {1: 0, 4: 1, 2: 2}      # passes bit -> position in the evaluation
+
+
 def _merge_tvf(ops):
-    """group 1 directly followed by group 2 over the same fluids: one call, one pack."""
+    """The EDAC Groups that follow each other over the same fluids and walls -- group 1,
+    [the average-pressure Group of a scheme with walls], group 2 -- become one call, one pack."""
     out = []
     for op in ops:
-        if out and op[0] == 'tvf' and out[-1][0] == 'tvf' and \
-                out[-1][1].passes == 1 and op[1].passes == 2 and \
-                out[-1][1].fluid_mask == op[1].fluid_mask:
-            op[1].passes = 3
-            op[1].bql = out[-1][1].bql
-            out[-1] = op
+        prev = out[-1][1] if out and out[-1][0] == 'tvf' and op[0] == 'tvf' else None
+        if prev is not None and prev.fluid_mask == op[1].fluid_mask and \
+                prev.solid_mask == op[1].solid_mask and \
+                max(_TVF_ORDER[b] for b in (1, 4, 2) if prev.passes & b) < _TVF_ORDER[op[1].passes]:
+            new = op[1]
+            if prev.passes & 1:
+                new.bql = prev.bql               # what group 1 itself computes
+            if new.passes == 4:                  # (that Group has no parameters of its own)
+                for k in ('gx', 'gy', 'gz'):
+                    setattr(new, k, getattr(prev, k))
+            new.passes |= prev.passes
+            out[-1] = ('tvf', new)
         else:
             out.append(op)
     return out

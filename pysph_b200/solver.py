@@ -157,9 +157,10 @@ class B200Solver(object):
                 'B200 backend: periodic / mirror domains with the slab decomposition')
         if pm is not None:
             from ._lib import EDAC_PROP_IDS
+            # (the per-array tables are copies: compare what an EDAC table maps p to)
             edac = any(s.__class__.__name__ == 'EDACTVFStep'
                        for s in self.integrator.steppers.values()) or \
-                any(ids is EDAC_PROP_IDS for ids in self.backend.prop_ids)
+                any(ids.get('p') == EDAC_PROP_IDS['p'] for ids in self.backend.prop_ids)
             if edac:
                 # uhat vhat what p p0 are in neither the halo nor the migration message
                 raise NotImplementedError(

@@ -28,3 +28,17 @@ class MomentumEquationArtificialViscosity(Equation):
 
 class MomentumEquationArtificialStress(Equation):
     """transport_velocity.py:451-545"""
+
+
+class VolumeSummation(Equation):
+    """V = sum_b W_ab (transport_velocity.py:61-75); the EDAC scheme applies it to its solid
+    walls with every array as a source (wc/edac.py:817)."""
+
+
+class SolidWallNoSlipBC(Equation):
+    """transport_velocity.py:548-638: the viscous force on a fluid from a wall whose dummy
+    velocity ug vg wg SetWallVelocity has extrapolated."""
+
+    def __init__(self, dest, sources, nu):
+        self.nu = nu
+        super(SolidWallNoSlipBC, self).__init__(dest, sources)

@@ -406,7 +406,7 @@ int emul_tvf(const emul_common *c, const b200sph_tvf_program *prog, const double
     std::vector<float4> AB, B((size_t)n), C2((size_t)n), Dv((size_t)n);
     std::vector<float2> PT((size_t)n);
     pack_A(*c, AB);
-    launch(n, 256, [&] { k_pack_tvf(c->u, c->v, c->w, c->m, uh, vh, wh, pf, pavg, c->ptype, perm.data(), n, B.data(), AB.data(), C2.data(), Dv.data(), PT.data()); });
+    launch(n, 256, [&] { k_pack_tvf(c->u, c->v, c->w, c->m, uh, vh, wh, pf, pavg, c->ptype, perm.data(), n, B.data(), AB.data(), C2.data(), Dv.data(), PT.data(), c->rho, 0u); });
     TvfArgs ta;
     memset(&ta, 0, sizeof(ta));
     ta.AB = AB.data(); ta.C2 = C2.data(); ta.Dv = Dv.data(); ta.PT = PT.data(); ta.perm = perm.data();
@@ -416,7 +416,7 @@ int emul_tvf(const emul_common *c, const b200sph_tvf_program *prog, const double
     ta.cellx = ta.celly = ta.cellz = 1.0f;
     ta.k2 = (float)(c->radius_scale * c->radius_scale);
     ta.kfac = (float)c->kfac;
-    ta.fluid_mask = prog->fluid_mask; ta.eqbits = prog->eqbits; ta.bql = prog->bql;
+    ta.fluid_mask = prog->fluid_mask; ta.src_mask = prog->fluid_mask; ta.eqbits = prog->eqbits; ta.bql = prog->bql;
     ta.pb = (float)prog->pb; ta.nu = (float)prog->nu; ta.edac_nu = (float)prog->edac_nu;
     ta.c0 = (float)prog->c0; ta.alpha = (float)prog->alpha;
     double damp = 1.0;

@@ -187,11 +187,148 @@ def test_taylor_green_3d_properties(gpu_device):
     assert np.max(np.abs(b['p'] - a['p'])) <= 2e-3
 
 
+# ---- solid walls (EDACScheme(fluids, solids), wc/edac.py:815-822, :845-878) -----------------
+WALL_TOL = dict(V=2e-5, wij=2e-5, p=2e-5, uf=2e-5, vf=2e-5, wf=2e-5, ug=2e-5, vg=2e-5, wg=2e-5)
+
+
+def _wall_scheme(p):
+    import pysph_b200 as pb
+    return pb.EDACScheme(['fluid'], ['wall'], dim=p['dim'], c0=p['c0'], nu=p['nu'],
+                         rho0=p['rho0'], pb=p['pb'], gx=p.get('gx', 0.0), gy=p.get('gy', 0.0),
+                         gz=p.get('gz', 0.0), tdamp=p.get('tdamp', 0.0), h=p['h'],
+                         alpha=p.get('alpha', 0.0), edac_alpha=p.get('edac_alpha', 0.5),
+                         bql=p.get('bql', True))
+
+
+@pytest.mark.parametrize('idx', range(4))
+def test_edac_solid_wall_evaluation_matches_reference_bodies(gpu_device, idx):
+    """One evaluation of EDACScheme(['fluid'], ['wall']) against the outputs of the reference's
+    own scheme method and equation bodies (tests/golden/edac_wall_cases.json): the wall
+    pressure, number density, volume and dummy velocity on the wall array, every EDAC field on
+    the fluid with the wall among its sources (no-slip term included)."""
+    import pysph_b200 as pb
+    from helpers import EDAC_WALL_FIELDS, edac_wall_arrays_from_dict
+    case = load_golden('edac_wall_cases.json')[idx]
+    p = case['params']
+    pas = edac_wall_arrays_from_dict(case['inputs'])
+    kernel = getattr(pb, case['kernel'])(dim=p['dim'])
+    sch = _wall_scheme(p)
+    groups = sch.get_equations()
+    # our scheme emits the reference's Groups, equations and sources
+    assert [[type(e).__name__ for e in g.equations] for g in groups] == p['groups']
+    assert [bool(g.real) for g in groups] == p['group_real']
+    assert [[list(e.sources or []) for e in g.equations] for g in groups] == p['sources']
+    ae = pb.B200AccelerationEval(pas, groups, kernel)
+    assert [o[0] for o in ae.ops] == ['tvf'] and ae.ops[0][1].passes == (7 if p['bql'] else 3)
+    nn = pb.B200NNPS(p['dim'], pas, backend=ae.backend, kernel=kernel)
+    ae.set_nnps(nn)
+    ae.count_pairs = True
+    ae.compute(p['t'], 1e-3)
+    ae.backend.pull_all()
+    opas = edac_wall_arrays_from_dict(case['inputs'])
+    o = orc.EDACOracleSolver(opas, dict(p, dt=1e-3), case['kernel'])
+    o.t = p['t']
+    assert ae.last_pairs == o.evaluate()
+    fluid, wall = pas
+    ref = case['outputs']['fluid']
+    nr = ref['_n_real']
+    for f in EDAC_FIELDS:
+        want = np.array(ref[f])
+        # group 1 is real=False; the average pressure (with walls) and group 2 are real=True
+        n = len(want) if f in ('V', 'rho') else nr
+        if np.max(np.abs(want[:n])) == 0.0:
+            assert np.max(np.abs(fluid.properties[f][:n])) == 0.0, f
+            continue
+        err = rel_err(fluid.properties[f][:n], want[:n])
+        _record('wall_golden_%d' % idx, f, err)
+        assert err <= TOL[f], ('fluid', f, err)
+    ref = case['outputs']['wall']
+    for f in EDAC_WALL_FIELDS:
+        want = np.array(ref[f])
+        if np.max(np.abs(want)) == 0.0:
+            assert np.max(np.abs(wall.properties[f])) == 0.0, f
+            continue
+        err = rel_err(wall.properties[f], want)
+        _record('wall_golden_%d' % idx, 'wall_' + f, err)
+        assert err <= WALL_TOL[f], ('wall', f, err)
+    # a wall is a destination of group 1 only
+    assert np.allclose(wall.au, case['inputs']['wall']['au'], rtol=1e-6, atol=0.0)   # (fp32 on the device)
+
+
+def _channel(nx=20, ny=12, layers=3):
+    """A 2-D channel: fluid between two three-layer walls, the upper one moving (Couette flow,
+    pysph/examples/couette.py), with a small perturbation of the lattice."""
+    import pysph_b200 as pb
+    dx = 1.0 / ny
+    rho0, c0, nu = 1.0, 10.0, 0.05
+    rs = np.random.RandomState(4)
+    xs = (np.arange(nx) + 0.5) * dx
+    ys = (np.arange(ny) + 0.5) * dx
+    x, y = np.meshgrid(xs, ys, indexing='ij')
+    x = x.ravel() + 0.05 * dx * rs.uniform(-1, 1, nx * ny)
+    y = y.ravel() + 0.05 * dx * rs.uniform(-1, 1, nx * ny)
+    n = x.size
+    fluid = pb.get_particle_array_edac(name='fluid', x=x, y=y, h=np.full(n, dx),
+                                       m=np.full(n, rho0 * dx * dx), rho=np.full(n, rho0))
+    fluid.u[:] = 0.5 * y
+    fluid.uhat[:] = fluid.u
+    yw = np.concatenate([-(np.arange(layers) + 0.5) * dx, 1.0 + (np.arange(layers) + 0.5) * dx])
+    xw, yw = np.meshgrid(xs, yw, indexing='ij')
+    xw, yw = xw.ravel(), yw.ravel()
+    nw = xw.size
+    wall = pb.get_particle_array_edac_wall(name='wall', x=xw, y=yw, h=np.full(nw, dx),
+                                           m=np.full(nw, rho0 * dx * dx), rho=np.full(nw, rho0))
+    wall.u[yw > 0.5] = 0.5          # the moving lid
+    for pa in (fluid, wall):
+        pa.gid[:] = np.arange(pa.get_number_of_particles())
+    p = dict(dim=2, c0=c0, rho0=rho0, nu=nu, pb=rho0 * c0 * c0, h=dx, alpha=0.1, edac_alpha=0.5,
+             bql=True, gx=0.2, gy=0.0, gz=0.0, tdamp=0.0, dt=0.125 * dx / (c0 + 0.5),
+             solids=['wall'])
+    return [fluid, wall], p
+
+
+def test_edac_channel_with_walls_steps_vs_oracle(gpu_device):
+    """Ten PEC steps of a small Couette channel -- walls are sources in every evaluation, the
+    wall pressure and dummy velocity are rebuilt from the moving fluid each time -- against the
+    oracle; the walls themselves must not move."""
+    import pysph_b200 as pb
+    pas, p = _channel()
+    ref, _ = _channel()
+    sch = _wall_scheme(p)
+    s = pb.make_edac_solver(pas, sch, pb.QuinticSpline(dim=2), dt=p['dt'])
+    o = orc.EDACOracleSolver(ref, p, 'QuinticSpline')
+    s.initialise()
+    o.initialise()
+    for _ in range(10):
+        s.step()
+        o.step()
+    s.pull()
+    assert abs(s.t - o.t) <= 1e-12
+    fluid, wall = pas
+    rf, rw = o.pas
+    for f, tol in (('x', 2e-7), ('y', 2e-7), ('u', 5e-6), ('v', 5e-6), ('p', 5e-5), ('rho', 2e-6),
+                   ('uhat', 5e-6)):
+        r = rf.properties[f]
+        scale = max(np.max(np.abs(r)), 1.0 if f in 'xy' else 1e-12)
+        err = np.max(np.abs(fluid.properties[f] - r)) / scale
+        _record('channel_10steps', f, float(err))
+        assert err <= tol, (f, err)
+    for f, tol in (('p', 5e-5), ('ug', 5e-6), ('V', 2e-6)):
+        r = rw.properties[f]
+        err = np.max(np.abs(wall.properties[f] - r)) / max(np.max(np.abs(r)), 1e-12)
+        _record('channel_10steps', 'wall_' + f, float(err))
+        assert err <= tol, ('wall', f, err)
+    w0 = _channel()[0][1]
+    assert np.array_equal(wall.x, w0.x) and np.array_equal(wall.y, w0.y) and np.array_equal(wall.u, w0.u)
+    # the lid drags the fluid: its mean velocity near the moving wall exceeds that near the fixed one
+    assert fluid.u[fluid.y > 0.8].mean() > fluid.u[fluid.y < 0.2].mean()
+
+
 def test_edac_setup_errors(gpu_device):
     import pysph_b200 as pb
     with pytest.raises(NotImplementedError):
-        pb.EDACScheme(['fluid'], ['wall'], dim=2, c0=10., nu=0.01, rho0=1., pb=100.,
-                      h=0.01).get_equations()
+        pb.EDACScheme(['fluid'], [], dim=2, c0=10., nu=0.01, rho0=1., pb=100., h=0.01,
+                      inviscid_solids=['wall']).get_equations()
     with pytest.raises(NotImplementedError):
         pb.EDACScheme(['fluid'], [], dim=2, c0=10., nu=0.01, rho0=1., pb=0.0,
                       h=0.01).get_equations()

@@ -250,9 +250,37 @@ def test_edac_program_and_scheme():
                       ['f1', 'f2'], 2)
     with pytest.raises(NotImplementedError):
         build_program([Group([tv.SummationDensity('f1', ['f1'])], real=True)], ['f1'], 2)
+    # solid walls (wc/edac.py:815-822, :840-842): group 1 + the wall equations, the average
+    # pressure in a Group of its own, group 2 with the no-slip term -> ONE fused op
+    sch = pb.EDACScheme(['f'], ['w1', 'w2'], dim=2, c0=10., nu=0.01, rho0=1., pb=100., h=0.01,
+                        gy=-1.0)
+    groups = sch.get_equations()
+    assert [g.real for g in groups] == [False, True, True]
+    assert [type(e).__name__ for e in groups[0].equations] == ['SummationDensity'] + \
+        ['SourceNumberDensity', 'VolumeSummation', 'SolidWallPressureBC', 'SetWallVelocity'] * 2
+    ops = build_program(groups, ['f', 'w1', 'w2'], 2)
+    assert [o[0] for o in ops] == ['tvf']
+    P = ops[0][1]
+    assert (P.passes, P.fluid_mask, P.solid_mask, P.bql, P.gy) == (7, 1, 6, 0, -1.0)
+    assert P.eqbits == L.TVF_PGRAD | L.TVF_VISC | L.TVF_NOSLIP | L.TVF_ASTRESS | L.TVF_EDAC
+    assert build_program(groups[:1], ['f', 'w1', 'w2'], 2)[0][1].passes == 1
+    assert build_program(groups[:2], ['f', 'w1', 'w2'], 2)[0][1].passes == 5
+    # a wall that lacks one of its four equations, wrong sources, the average pressure inside
+    # group 1 although there are walls: refused
     with pytest.raises(NotImplementedError):
-        pb.EDACScheme(['f'], ['wall'], dim=2, c0=10., nu=0.01, rho0=1., pb=100.,
-                      h=0.01).get_equations()
+        build_program([Group(groups[0].equations[:-1], real=False)], ['f', 'w1', 'w2'], 2)
+    with pytest.raises(NotImplementedError):
+        build_program([Group([tv.SummationDensity('f', ['f', 'w1']),
+                              edac.SourceNumberDensity('w1', ['f', 'w1']),
+                              tv.VolumeSummation('w1', ['f', 'w1']),
+                              edac.SolidWallPressureBC('w1', ['f']),
+                              edac.SetWallVelocity('w1', ['f'])], real=False)], ['f', 'w1'], 2)
+    with pytest.raises(NotImplementedError):
+        build_program([Group(groups[0].equations + [edac.ComputeAveragePressure('f', ['f', 'w1', 'w2'])],
+                             real=False)], ['f', 'w1', 'w2'], 2)
+    with pytest.raises(NotImplementedError):
+        pb.EDACScheme(['f'], [], dim=2, c0=10., nu=0.01, rho0=1., pb=100., h=0.01,
+                      inviscid_solids=['wall']).get_equations()
     # steppers: EDACTVFStep is accepted, unknown ones are not
     pb.PECIntegrator(f1=pb.EDACTVFStep(), f2=pb.EDACTVFStep())
     with pytest.raises(NotImplementedError):
