@@ -72,10 +72,15 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '200'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # its start-up (NVML initialises every GPU of the box) stalls running kernels for
+            # tens of ms: nothing is timed before the first line has arrived
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 15.0 and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -89,7 +94,7 @@ class ClockSampler(object):
         one sampling period."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        time.sleep(0.11)                     # let the sample covering the region's end arrive
+        time.sleep(0.21)                     # let the sample covering the region's end arrive
         if len(self.lines) > first:
             self.lines = self.lines[first:]
         else:
@@ -827,12 +832,18 @@ def run_dam_break(args, rank, local_rank, world):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if pm is not None and getattr(pm, '_prof', None) is not None:
         pm.profile_summary()
+    # the host runs at most one evaluation ahead of the GPU (it reads the list-validity answer
+    # of every evaluation), so a host pause is GPU idle time: no garbage collection in here
+    import gc
+    gc.collect()
+    gc.disable()
     cpu_t0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(K):
         solver.step()
     ev1.record(stream)
     cpu_enqueue_ms = 1e3 * (time.perf_counter() - cpu_t0)
+    gc.enable()
     barrier()
     clocks = sampler.stop(n_s0) if rank == 0 else None
     if os.environ.get('B200SPH_PM_PROFILE') and pm is None:
@@ -1109,6 +1120,9 @@ def run_dam_break(args, rank, local_rank, world):
         'e2e': e2e,
         'gpu_launches': int(st['kernel_launches']),
         'launches_per_step': st['kernel_launches'] / float(K),
+        # wall time of the host loop that enqueued the timed steps (it waits for the GPU once per
+        # evaluation): ~ ms_per_step when the GPU is the bottleneck, larger when the host was
+        'host_loop_ms_per_step': cpu_enqueue_ms / float(K),
         'roofline': roofline,
     }
     if developed:
