@@ -388,7 +388,8 @@ def periodic_ghosts(pas, lo, hi, periodic, cell_size, n_layers=2.0, factory=None
             new = images(ghosts, name, d) + images(props, name, d)
             ghosts = cat([ghosts] + new)
         allp = cat([props, ghosts])
-        q = (factory or get_particle_array_wcsph)(name=pa.name, **allp)
+        fac = factory.get(pa.name) if isinstance(factory, dict) else factory   # per array, by name
+        q = (fac or get_particle_array_wcsph)(name=pa.name, **allp)
         q.set_num_real_particles(nr)
         q.tag[nr:] = 2
         out.append(q)
@@ -655,17 +656,19 @@ class EDACOracleSolver(object):
 
     def _reghost(self):
         lo, hi, per = self.domain
-        from pysph_b200.particle_array import get_particle_array_edac
+        from pysph_b200.particle_array import get_particle_array_edac, get_particle_array_edac_wall
+        walls = self.p.get('solids') or ()
+        fac = dict((pa.name, get_particle_array_edac_wall if pa.name in walls
+                    else get_particle_array_edac) for pa in self.pas)
         real = []
         for pa in self.pas:
             nr = pa.get_number_of_particles(real=True)
-            real.append(get_particle_array_edac(name=pa.name, **dict(
+            real.append(fac[pa.name](name=pa.name, **dict(
                 (k, v[:nr].copy()) for k, v in pa.properties.items())))
         periodic_box_wrap(real, lo, hi, per)
         k = load().orc_kernel_radius_scale(K_IDS[self.kernel])
         hmax = max(float(np.max(q.h)) for q in real if len(q.h))
-        self.pas = periodic_ghosts(real, lo, hi, per, k * hmax,
-                                   factory=get_particle_array_edac)
+        self.pas = periodic_ghosts(real, lo, hi, per, k * hmax, factory=fac)
         self.o = Oracle(self.pas, self.dim, self.kernel, threads=self.threads)
 
     def update_domain(self):

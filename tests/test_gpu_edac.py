@@ -287,6 +287,45 @@ def _channel(nx=20, ny=12, layers=3):
     return [fluid, wall], p
 
 
+def test_edac_periodic_channel_with_walls_vs_oracle(gpu_device):
+    """The usual set-up of a wall-bounded internal flow (pysph/examples/poiseuille.py, couette.py):
+    periodic along the channel, walls across it, a body force -- the periodic cell grid (no
+    materialised images) together with the wall equations, against the oracle, which does
+    materialise the periodic images of fluid AND wall particles."""
+    import pysph_b200 as pb
+    nx, ny = 16, 12
+    pas, p = _channel(nx=nx, ny=ny)
+    ref, _ = _channel(nx=nx, ny=ny)
+    L = nx / float(ny)
+    dm = pb.DomainManager(xmin=0.0, xmax=L, periodic_in_x=True)
+    s = pb.make_edac_solver(pas, _wall_scheme(p), pb.QuinticSpline(dim=2), dt=p['dt'], domain=dm)
+    o = orc.EDACOracleSolver(ref, p, 'QuinticSpline', domain=([0.0, 0.0, 0.0], [L, 0.0, 0.0], [1, 0, 0]))
+    s.initialise()
+    o.initialise()
+    for _ in range(8):
+        s.step()
+        o.step()
+    s.pull()
+    fluid, wall = pas
+    rf, rw = o.pas
+    nf, nw = rf.num_real_particles, rw.num_real_particles
+    assert np.array_equal(rf.gid[:nf], fluid.gid) and np.array_equal(rw.gid[:nw], wall.gid)
+    for f, tol in (('y', 2e-7), ('u', 5e-6), ('v', 5e-6), ('p', 5e-5), ('rho', 2e-6)):
+        r = rf.properties[f][:nf]
+        scale = max(np.max(np.abs(r)), 1.0 if f == 'y' else 1e-12)
+        err = np.max(np.abs(fluid.properties[f] - r)) / scale
+        _record('periodic_channel', f, float(err))
+        assert err <= tol, (f, err)
+    dxp = (fluid.x - rf.x[:nf] + 0.5 * L) % L - 0.5 * L           # positions modulo the period
+    assert np.max(np.abs(dxp)) <= 2e-7
+    for f, tol in (('p', 5e-5), ('ug', 5e-6), ('V', 2e-6), ('wij', 2e-6)):
+        r = rw.properties[f][:nw]
+        err = np.max(np.abs(wall.properties[f] - r)) / max(np.max(np.abs(r)), 1e-12)
+        assert err <= tol, ('wall', f, err)
+    # every wall particle sees fluid on one side through the periodic seam too
+    assert np.min(wall.wij[np.abs(wall.y - 0.5) < 0.5 + 1.01 / ny]) > 0.0
+
+
 def test_edac_channel_with_walls_steps_vs_oracle(gpu_device):
     """Ten PEC steps of a small Couette channel -- walls are sources in every evaluation, the
     wall pressure and dummy velocity are rebuilt from the moving fluid each time -- against the

@@ -119,6 +119,7 @@ FAST = [
     ('test_gpu_edac', 'test_taylor_green_steps_vs_oracle', {'dim': 2, 'nx': 32, 'kernel': 'QuinticSpline'}),
     ('test_gpu_edac', 'test_edac_setup_errors', {}),
     ('test_gpu_edac', 'test_edac_channel_with_walls_steps_vs_oracle', {}),
+    ('test_gpu_edac', 'test_edac_periodic_channel_with_walls_vs_oracle', {}),
 ] + [('test_gpu_edac', 'test_edac_solid_wall_evaluation_matches_reference_bodies', {'idx': i})
      for i in range(4)] + [('test_gpu_solid', 'test_elastic_evaluation_matches_reference_bodies', {'idx': i})
      for i in range(6)] + [
