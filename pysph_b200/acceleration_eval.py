@@ -137,6 +137,9 @@ class B200AccelerationEval(object):
                 (2 if w & {'u', 'v', 'w', 'm', 'rho', 'p', 'cs'} else 0)
         rng, self._range = self._range, None
         for name, d, has_init, has_loop, has_post, src_mask in gg.kernels:
+            py_inits, reduces = gg.host_calls.get(d, ((), ()))
+            for eq in py_inits:          # host side, before anything of the destination (mako:29-40)
+                eq.py_initialize(self.particle_arrays[d], t, dt)
             for phase, on in ((0, has_init), (1, has_loop), (2, has_post)):
                 if not on:
                     continue
@@ -144,3 +147,5 @@ class B200AccelerationEval(object):
                     ctx.call('b200sph_set_dest_range', d, rng[d][0], rng[d][1])
                 ctx.call('b200sph_generic_launch', gg.module, name.encode(), d, phase, src_mask,
                          gg.real_only, float(t), float(dt), gg.write_flags)
+            for eq in reduces:           # host side, after post_loop (mako:127-130)
+                eq.reduce(self.particle_arrays[d], t, dt)

@@ -21,8 +21,13 @@ EDAC / elastic-dynamics paths; a Group made of equations it does NOT know (SURVE
 * properties the device pool does not have are created as fp64 "user" properties
   (``b200sph_user_property``) and travel with push / pull like any other.
 
-Not translated (raises NotImplementedError at set-up): ``reduce``, ``loop_all``,
-``initialize_pair``, ``py_initialize``, array-valued constants, nested function definitions.
+* ``py_initialize(dst, t, dt)`` and ``reduce(dst, t, dt)`` are what they are in the reference:
+  host calls with the destination ParticleArray (whose ``.gpu`` pushes / pulls), before the
+  initialize launch and after the post_loop launch of that destination; the functions an
+  equation lists in ``_get_helpers_()`` become ``__device__`` functions of the module.
+
+Not translated (raises NotImplementedError at set-up): ``loop_all``, ``initialize_pair``,
+array-valued constants, nested function definitions.
 """
 import ast
 import inspect
@@ -57,8 +62,9 @@ ARGS_STRUCT = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csr
 class Translator(ast.NodeVisitor):
     """One method body -> C statements."""
 
-    def __init__(self, eq, method, props, where):
+    def __init__(self, eq, method, props, where, helpers=()):
         self.eq, self.method, self.props, self.where = eq, method, props, where
+        self.helpers = tuple(helpers)          # names of the module's __device__ helper functions
         self.locals = {}          # name -> C declaration
         self.symbols = set()      # pair symbols used
         self.writes = set()       # property names stored to
@@ -153,6 +159,8 @@ class Translator(ast.NodeVisitor):
                         out = '%s(%s, %s)' % (MATH_CALLS[name], out, a)
                     return out
                 return '%s(%s)' % (MATH_CALLS[name], ', '.join(args))
+            if name in self.helpers and isinstance(f, ast.Name) and not n.keywords:
+                return '%s(%s)' % (name, ', '.join('(double)(%s)' % self.expr(a) for a in n.args))
             if name == 'float' and len(n.args) == 1:
                 return '((double)(%s))' % self.expr(n.args[0])
             if name == 'int' and len(n.args) == 1:
@@ -246,6 +254,8 @@ class Translator(ast.NodeVisitor):
             return [p + 'for (%s = %s; %s < %s; %s += %s) {' % (v, lo, v, hi, v, st)] + \
                 self.block(s.body, ind + 1) + [p + '}']
         if isinstance(s, ast.Return):
+            if self.where == 'helper':
+                return [p + 'return %s;' % (self.expr(s.value) if s.value is not None else '0.0')]
             if s.value is not None:
                 self.fail(s, 'return with a value')
             return [p + 'return;']         # the body is a lambda
@@ -296,6 +306,30 @@ class Translator(ast.NodeVisitor):
         body = self.block(node.body, 2)
         decl = ['        ' + d for d in self.locals.values()]
         return ['    [&]() {'] + decl + body + ['    }();']
+
+
+def translate_helper(fn, helpers):
+    """A plain Python function listed by Equation._get_helpers_() -> a __device__ function
+    (double arguments, double result; default values kept)."""
+    try:
+        node = ast.parse(textwrap.dedent(inspect.getsource(fn))).body[0]
+    except (OSError, TypeError):
+        raise NotImplementedError('B200 generic equations: no Python source for helper %r' % fn)
+
+    class _Owner(object):
+        pass
+    t = Translator(_Owner(), fn.__name__, None, 'helper', helpers)
+    t.eq.__class__.__name__ = 'helper'
+    args = [a.arg for a in node.args.args]
+    t.args = args
+    defaults = [None] * (len(args) - len(node.args.defaults)) + list(node.args.defaults)
+    sig = []
+    for a, d in zip(args, defaults):
+        sig.append('double %s%s' % (a, '' if d is None else ' = ' + t.expr(d)))
+    body = t.block(node.body, 1)
+    decl = ['    ' + d for d in t.locals.values()]
+    return '\n'.join(['__device__ static inline double %s(%s)' % (fn.__name__, ', '.join(sig)), '{'] +
+                     decl + body + ['    return 0.0;', '}', ''])
 
 
 def _lit(v):
@@ -406,7 +440,7 @@ class GenericGroup(object):
         self.props = props
         self.uid = uid
         for eq in group.equations:
-            for bad in ('reduce', 'loop_all', 'initialize_pair', 'py_initialize'):
+            for bad in ('loop_all', 'initialize_pair'):
                 if _defines(eq, bad):
                     raise NotImplementedError('B200 generic equations: %s.%s() is not translated' % (
                         eq.__class__.__name__, bad))
@@ -421,12 +455,22 @@ class GenericGroup(object):
             if eq.dest not in self.dests:
                 self.dests.append(eq.dest)
         self.kernels = []          # (name, dest array id, has_init, has_loop, has_post, src_mask)
+        self.host_calls = {}       # dest array id -> (equations with py_initialize, with reduce)
         self.writes = set()
+        # helper functions (Equation._get_helpers_, equation.py:389-420), once each
+        self.helpers = []
+        for eq in group.equations:
+            for fn in (eq._get_helpers_() if hasattr(eq, '_get_helpers_') else []):
+                if fn.__name__ not in [h.__name__ for h in self.helpers]:
+                    self.helpers.append(fn)
         self.source = self._generate()
 
     def _generate(self):
         out = ['/* generated by pysph_b200.codegen for Group %s */' % getattr(self.group, 'name', '?'),
                '#define PT_GHOST 0x08', ARGS_STRUCT, KERNEL_FUNCS]
+        hnames = [h.__name__ for h in self.helpers]
+        for k, h in enumerate(self.helpers):
+            out.append(translate_helper(h, hnames[:k + 1]))
         for d in self.dests:
             eqs = [e for e in self.group.equations if e.dest == d]
             name = 'b2g_%s' % d          # one module per Group: no clash between Groups
@@ -435,14 +479,14 @@ class GenericGroup(object):
             src_mask = 0
             for e in eqs:
                 if _defines(e, 'initialize'):
-                    t = Translator(e, 'initialize', self.props, 'init')
+                    t = Translator(e, 'initialize', self.props, 'init', hnames)
                     init += ['    /* %s.initialize */' % e.__class__.__name__] + t.translate()
                     self.writes |= t.writes
                 if _defines(e, 'loop'):
                     if not e.sources:
                         raise NotImplementedError('B200 generic equations: %s has a loop() but no sources'
                                                   % e.__class__.__name__)
-                    t = Translator(e, 'loop', self.props, 'loop')
+                    t = Translator(e, 'loop', self.props, 'loop', hnames)
                     m = 0
                     for s in e.sources:
                         m |= 1 << self.index[s]
@@ -453,11 +497,13 @@ class GenericGroup(object):
                     symbols |= t.symbols
                     self.writes |= t.writes
                 if _defines(e, 'post_loop'):
-                    t = Translator(e, 'post_loop', self.props, 'post')
+                    t = Translator(e, 'post_loop', self.props, 'post', hnames)
                     post += ['    /* %s.post_loop */' % e.__class__.__name__] + t.translate()
                     self.writes |= t.writes
             out.append(self._kernel(name, init, loop, post, symbols))
             self.kernels.append((name, self.index[d], bool(init), bool(loop), bool(post), src_mask))
+            self.host_calls[self.index[d]] = ([e for e in eqs if _defines(e, 'py_initialize')],
+                                              [e for e in eqs if _defines(e, 'reduce')])
         return '\n'.join(out) + '\n'
 
     def _kernel(self, name, init, loop, post, symbols):
@@ -541,7 +587,8 @@ def _defines(eq, method):
 def is_generic_group(group):
     """A Group every equation of which carries its own Python bodies."""
     eqs = group.equations
-    return len(eqs) > 0 and all(any(_defines(e, m) for m in ('initialize', 'loop', 'post_loop')) for e in eqs)
+    return len(eqs) > 0 and all(any(_defines(e, m) for m in ('initialize', 'loop', 'post_loop', 'reduce',
+                                                             'py_initialize')) for e in eqs)
 
 
 # ---- NVRTC -------------------------------------------------------------------

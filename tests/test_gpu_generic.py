@@ -202,11 +202,11 @@ def test_user_property_and_kernel_symbol(gpu_device):
 def test_untranslatable_bodies_fail_at_setup(gpu_device):
     import pysph_b200 as pb
 
-    class WithReduce(pb.Equation):
+    class WithReduce(pb.Equation):              # (loop_all: the neighbour array itself)
         def initialize(self, d_idx, d_au):
             d_au[d_idx] = 0.0
 
-        def reduce(self, dst, t, dt):
+        def loop_all(self, d_idx, d_au, NBRS, N_NBRS):
             pass
 
     class WithWhile(pb.Equation):
@@ -396,3 +396,60 @@ def test_generic_kernel_symbols_vs_reference_kernels(gpu_device):
             assert np.max(np.abs(g - np.array(c['grad']))) <= 3e-6 * max(scale / c['h'], np.max(np.abs(c['grad']))), (name, dim, c)
             checked += 1
     assert checked >= 20
+
+
+def test_host_callbacks_and_helpers(gpu_device):
+    # test_should_call_py_initialize (:425-445), test_should_run_reduce (:394-406),
+    # test_should_handle_repeated_helper_functions (:482-508)
+    import pysph_b200 as pb
+    from pysph_b200.reduce_array import serial_reduce_array
+
+    class PyInit(pb.Equation):
+        def py_initialize(self, dst, t, dt):
+            self.called_with = t, dt
+            if dst.gpu:
+                dst.gpu.pull('au')
+            dst.au[:] = 1.0
+            if dst.gpu:
+                dst.gpu.push('au')
+
+        def initialize(self, d_idx, d_au):
+            d_au[d_idx] += 1.0
+
+    class SimpleReduction(pb.Equation):
+        def initialize(self, d_idx, d_au):
+            d_au[d_idx] = 0.0
+
+        def reduce(self, dst, t, dt):
+            dst.gpu.pull('m')
+            dst.total_mass[0] = serial_reduce_array(dst.m, op='sum')
+
+    def helper(x=1.0):
+        return x * 1.5
+
+    class SillyEquation2(pb.Equation):
+        def initialize(self, d_idx, d_au, d_m):
+            d_au[d_idx] += helper(d_m[d_idx])
+
+        def _get_helpers_(self):
+            return [helper]
+
+    eq = PyInit(dest='fluid', sources=None)
+    pa, ae, g = make([eq])
+    ae.compute(1.0, 0.1)
+    ae.backend.pull_all(['au'])
+    assert np.all(pa.au == 2.0) and eq.called_with == (1.0, 0.1)
+
+    pa, ae, g = make([SimpleReduction(dest='fluid', sources=['fluid'])])
+    pa.add_constant('total_mass', 0.0)
+    ae.compute(0.1, 0.1)
+    assert abs(pa.total_mass[0] - np.sum(pa.m)) < 1e-14
+
+    pa, ae, g = make([SillyEquation2(dest='fluid', sources=['fluid']),
+                      SillyEquation2(dest='fluid', sources=['fluid'])])
+    pa.au[:] = 0.0
+    ae.backend.push_all()
+    ae.nnps.update()
+    ae.compute(0.1, 0.1)
+    ae.backend.pull_all(['au'])
+    assert list(pa.au) == [3.0] * 10
