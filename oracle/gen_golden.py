@@ -433,6 +433,96 @@ def gen_edac_wall_case(kernels, edac, kernel_name, dim, seed, alpha=0.0, nu=0.01
     return dict(kernel=kernel_name, dim=dim, params=params, inputs=inputs, outputs=arrays)
 
 
+EDAC_EXT_PROPS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'p', 'au', 'av', 'aw', 'ax', 'ay',
+                  'az', 'ap', 'V']
+EDAC_EXT_WALL_PROPS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'p', 'au', 'av', 'aw', 'ap',
+                       'p0', 'V', 'wij', 'ax', 'ay', 'az', 'uf', 'vf', 'wf', 'ug', 'vg', 'wg']
+
+
+def gen_edac_ext_case(kernels, edac, kernel_name, dim, seed, alpha=0.0, nu=0.01, eps=0.5,
+                      clamp_p=False, gy=0.0, tdamp=0.0, t=0.0, moving=False, walls=True,
+                      nfluids=1):
+    """One evaluation of EDACScheme(fluids, solids, pb=0).get_equations(): the EXTERNAL-flow
+    branch (wc/edac.py:882-971) -- SummationDensity, the wall equations [+ ClampWallPressure],
+    then the number-density MomentumEquation (:301-352), [artificial / physical viscosity,
+    no-slip], EDACEquation and XSPHCorrection -- through the reference's own scheme method and
+    equation bodies."""
+    rs = np.random.RandomState(seed)
+    kernel = getattr(kernels, kernel_name)(dim=dim)
+    dx = 0.1
+    rho0, c0 = 1.0, 10.0
+    arrays = {}
+    fluids = ['fluid', 'fluid2'][:nfluids]
+    spec = [(f, 80 if k == 0 else 30, 0.0, 0.45, EDAC_EXT_PROPS) for k, f in enumerate(fluids)]
+    if walls:
+        spec.append(('wall', 45, -0.25, 0.0, EDAC_EXT_WALL_PROPS))
+    for name, n, ylo, yhi, props in spec:
+        ext = np.array([0.5, 1.0, 0.4 if dim == 3 else 0.0])
+        pts = rs.uniform(0.0, 1.0, size=(n, 3)) * ext
+        pts[:, 1] = ylo + (yhi - ylo) * rs.uniform(0.0, 1.0, n)
+        a = dict((q, [0.0] * n) for q in props)
+        a['x'], a['y'], a['z'] = (list(map(float, pts[:, i])) for i in range(3))
+        a['h'] = [float(1.0 * dx)] * n
+        a['m'] = [float(rho0 * dx ** dim * (1.0 + 0.5 * (name == 'fluid2')))] * n
+        a['p'] = list(map(float, rs.normal(scale=2.0, size=n)))
+        if name != 'wall':
+            v = rs.normal(size=(n, 3)) * (np.arange(3) < dim)
+            a['_n_real'] = n - (6 if name == 'fluid' else 0)
+        else:
+            v = (0.3 * rs.normal(size=(n, 3)) if moving else np.zeros((n, 3))) * (np.arange(3) < dim)
+            acc = (0.5 * rs.normal(size=(n, 3)) if moving else np.zeros((n, 3))) * (np.arange(3) < dim)
+            a['au'], a['av'], a['aw'] = (list(map(float, acc[:, i])) for i in range(3))
+            a['rho'] = list(map(float, rho0 * (1.0 + 0.05 * rs.uniform(-1, 1, n))))
+            a['_n_real'] = n - 4
+        a['u'], a['v'], a['w'] = (list(map(float, v[:, i])) for i in range(3))
+        arrays[name] = a
+    inputs = json.loads(json.dumps(arrays))
+    scheme = edac.EDACScheme(fluids, ['wall'] if walls else [], dim=dim, c0=c0, nu=nu, rho0=rho0,
+                             pb=0.0, gy=gy, tdamp=tdamp, h=dx, alpha=alpha, eps=eps,
+                             clamp_p=clamp_p)
+    eqs = scheme.get_equations()
+    groups = [(g.real, g.equations) for g in eqs]
+    evaluate_reference(kernel, arrays, groups, t=t)
+    params = dict(dim=dim, c0=c0, rho0=rho0, nu=nu, pb=0.0, h=dx, alpha=alpha, edac_alpha=0.5,
+                  eps=eps, clamp_p=clamp_p, gx=0.0, gy=gy, gz=0.0, tdamp=tdamp, t=t,
+                  fluids=fluids, solids=['wall'] if walls else [],
+                  groups=[[type(e).__name__ for e in g.equations] for g in eqs],
+                  group_real=[bool(g.real) for g in eqs],
+                  sources=[[list(e.sources or []) for e in g.equations] for g in eqs])
+    return dict(kernel=kernel_name, dim=dim, params=params, inputs=inputs, outputs=arrays)
+
+
+def gen_edac_ext_stepper(edac):
+    """EDACStep (wc/edac.py:82-133) on random data: initialize, stage1, stage2."""
+    rs = np.random.RandomState(13)
+    n = 12
+    names = ['x', 'y', 'z', 'u', 'v', 'w', 'p', 'au', 'av', 'aw', 'ax', 'ay', 'az', 'ap',
+             'x0', 'y0', 'z0', 'u0', 'v0', 'w0', 'p0']
+    st = edac.EDACStep()
+    out = {}
+    dt = 0.013
+    for which in ('initialize', 'stage1', 'stage2'):
+        a = dict((k, list(map(float, rs.normal(size=n)))) for k in names)
+        before = json.loads(json.dumps(a))
+        env = dict(('d_' + k, v) for k, v in a.items())
+        env['dt'] = dt
+        for i in range(n):
+            call(getattr(st, which), dict(env, d_idx=i))
+        out[which] = dict(inputs=before, outputs=a)
+    out['dt'] = dt
+    return out
+
+
+def gen_edac_ext_cases(kernels, edac):
+    return [
+        gen_edac_ext_case(kernels, edac, 'QuinticSpline', 2, 501, gy=-1.0),
+        gen_edac_ext_case(kernels, edac, 'CubicSpline', 3, 502, alpha=0.2, moving=True, clamp_p=True),
+        gen_edac_ext_case(kernels, edac, 'WendlandQuintic', 3, 503, nu=0.0, alpha=0.1, eps=0.0,
+                          gy=-1.0, tdamp=1.0, t=0.3),
+        gen_edac_ext_case(kernels, edac, 'QuinticSpline', 2, 504, walls=False, nfluids=2, eps=0.3),
+    ]
+
+
 def gen_edac_stepper(edac):
     rs = np.random.RandomState(12)
     n = 7
@@ -758,6 +848,16 @@ def gen_edac_wall_cases(kernels, edac):
 
 
 def main():
+    if sys.argv[1:] == ['edac_ext']:            # only the files added last
+        kernels, basic, wc, steps, c_kernels = load_reference()
+        tvf, edac = load_reference_edac()
+        edac.sin, edac.M_PI = math.sin, math.pi
+        for name, obj in (('edac_ext_cases.json', gen_edac_ext_cases(kernels, edac)),
+                          ('edac_ext_stepper.json', gen_edac_ext_stepper(edac))):
+            with open(os.path.join(GOLD, name), 'w') as f:
+                json.dump(obj, f)
+            print('wrote', name, os.path.getsize(os.path.join(GOLD, name)), 'bytes')
+        return
     if sys.argv[1:] == ['edac_walls']:          # only the file added last
         kernels, basic, wc, steps, c_kernels = load_reference()
         tvf, edac = load_reference_edac()
@@ -802,6 +902,8 @@ def main():
     dump('edac_cases.json', ecases)
     dump('edac_stepper.json', gen_edac_stepper(edac))
     dump('edac_wall_cases.json', gen_edac_wall_cases(kernels, edac))
+    dump('edac_ext_cases.json', gen_edac_ext_cases(kernels, edac))
+    dump('edac_ext_stepper.json', gen_edac_ext_stepper(edac))
     solid = load_reference_solid()
     scases = [
         gen_solid_case(kernels, solid, 'CubicSpline', 2, 301),

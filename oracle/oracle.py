@@ -35,6 +35,7 @@ _PTR_FIELDS = ['x', 'y', 'z', 'h', 'm', 'rho', 'u', 'v', 'w', 'p', 'cs',
                'uhat', 'vhat', 'what', 'V', 'pavg', 'nnbr', 'auhat', 'avhat',
                'awhat', 'ap', 'p0']
 TVF_PGRAD, TVF_AV, TVF_VISC, TVF_ASTRESS, TVF_EDAC, TVF_NOSLIP = 1, 2, 4, 8, 16, 32
+TVF_MOM, TVF_XSPH = 64, 128
 # elastic dynamics (solid_mech/basic.py:52-59), in the order of orc_array
 _SYM = ['00', '01', '02', '11', '12', '22']
 _PTR_FIELDS += ['v%d%d' % (i, j) for i in range(3) for j in range(3)] + \
@@ -68,7 +69,8 @@ class OrcTvfProgram(C.Structure):
                 ('pb', C.c_double), ('nu', C.c_double), ('edac_nu', C.c_double),
                 ('c0', C.c_double), ('rho0', C.c_double), ('alpha', C.c_double),
                 ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
-                ('tdamp', C.c_double), ('t', C.c_double), ('solid_mask', C.c_uint32)]
+                ('tdamp', C.c_double), ('t', C.c_double), ('solid_mask', C.c_uint32),
+                ('eps_xsph', C.c_double), ('clamp_p', C.c_int)]
 
 
 class OrcSolidProgram(C.Structure):
@@ -124,6 +126,7 @@ def load():
             getattr(lib, f).restype = C.c_int64
             getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(OrcTvfProgram)]
         lib.orc_stage_tvf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        lib.orc_stage_edac.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         for f in ('orc_solid_group1', 'orc_solid_group2'):
             getattr(lib, f).restype = C.c_int64
             getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(OrcSolidProgram)]
@@ -288,11 +291,12 @@ class Oracle(object):
     # -- EDAC, transport-velocity branch ---------------------------------------
     def tvf_program(self, fluids, eqbits, bql=True, pb=0.0, nu=0.0, edac_nu=0.0,
                     c0=0.0, rho0=0.0, alpha=0.0, gx=0.0, gy=0.0, gz=0.0,
-                    tdamp=0.0, t=0.0, solids=()):
+                    tdamp=0.0, t=0.0, solids=(), eps_xsph=0.0, clamp_p=False):
         P = OrcTvfProgram()
         P.kernel, P.dim = self.kid, self.dim
         P.fluid_mask = sum(1 << f for f in fluids)
         P.solid_mask = sum(1 << f for f in solids)
+        P.eps_xsph, P.clamp_p = eps_xsph, int(clamp_p)
         P.bql, P.eqbits = int(bql), eqbits
         P.pb, P.nu, P.edac_nu, P.c0, P.rho0, P.alpha = pb, nu, edac_nu, c0, rho0, alpha
         P.gx, P.gy, P.gz, P.tdamp, P.t = gx, gy, gz, tdamp, t
@@ -312,6 +316,9 @@ class Oracle(object):
 
     def stage_tvf(self, arr, which, dt):
         self.lib.orc_stage_tvf(self.h, arr, which, dt)
+
+    def stage_edac(self, arr, which, dt):
+        self.lib.orc_stage_edac(self.h, arr, which, dt)
 
     # -- elastic dynamics (oracle only so far) ----------------------------------
     def solid_program(self, elastic, sources, eps=0.3, alpha=1.0, beta=1.0,
@@ -611,7 +618,10 @@ class WCSPHOracleSolver(object):
 def edac_eqbits(p):
     """Which equations EDACScheme._get_internal_flow_equations emits in its second group
     (wc/edac.py:842-878)."""
-    bits = TVF_PGRAD | TVF_ASTRESS | TVF_EDAC
+    if abs(p.get('pb', 0.0)) > 1e-14:       # use_tvf, wc/edac.py:651-655
+        bits = TVF_PGRAD | TVF_ASTRESS | TVF_EDAC
+    else:                                   # external flows, :882-971
+        bits = TVF_MOM | TVF_EDAC | TVF_XSPH
     if p.get('alpha', 0.0) > 0.0:
         bits |= TVF_AV
     if p.get('nu', 0.0) > 0.0:
@@ -680,13 +690,15 @@ class EDACOracleSolver(object):
         p, o = self.p, self.o
         walls = [i for i, pa in enumerate(self.pas) if pa.name in (p.get('solids') or ())]
         fl = [i for i in range(len(self.pas)) if i not in walls]
-        bql = p.get('bql', True)
+        tvf = abs(p.get('pb', 0.0)) > 1e-14
+        bql = p.get('bql', True) and tvf        # the external-flow branch has no average pressure
         P = o.tvf_program(fl, edac_eqbits(p), bql=bql and not walls, pb=p['pb'],
                           nu=p.get('nu', 0.0), edac_nu=edac_nu(p), c0=p['c0'],
                           rho0=p['rho0'], alpha=p.get('alpha', 0.0),
                           gx=p.get('gx', 0.0), gy=p.get('gy', 0.0), gz=p.get('gz', 0.0),
                           tdamp=p.get('tdamp', 0.0), t=self.t if t is None else t,
-                          solids=walls)
+                          solids=walls, eps_xsph=p.get('eps', 0.0),
+                          clamp_p=p.get('clamp_p', False) and not tvf)
         pairs = o.tvf_pass1(P)
         if walls:
             # group 1 continues with the wall arrays, then the average pressure has a
@@ -708,15 +720,17 @@ class EDACOracleSolver(object):
         self.initialise()
         # steppers exist for the fluids only (wc/edac.py:682-687): walls do not move
         fl = [i for i, pa in enumerate(self.pas) if pa.name not in (self.p.get('solids') or ())]
+        # EDACTVFStep with the transport velocity, EDACStep without (wc/edac.py:682)
+        stage = self.o.stage_tvf if abs(self.p.get('pb', 0.0)) > 1e-14 else self.o.stage_edac
         for a in fl:
-            self.o.stage_tvf(a, 0, 0.0)
+            stage(a, 0, 0.0)
         for a in fl:
-            self.o.stage_tvf(a, 1, self.dt)
+            stage(a, 1, self.dt)
         self.update_domain()
         self.o.nnps_update()
         self.evaluate(self.t)               # a_eval.compute(c_integrator.t, ...) integrator.py:286
         for a in fl:
-            self.o.stage_tvf(a, 2, self.dt)
+            stage(a, 2, self.dt)
         self.update_domain()
         self.t += self.dt
         self.count += 1

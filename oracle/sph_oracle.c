@@ -881,6 +881,7 @@ int64_t orc_tvf_wall(orc_ctx *c, const orc_tvf_program *P)
             D->ug[i] = 2 * D->u[i] - D->uf[i];
             D->vgw[i] = 2 * D->v[i] - D->vf[i];
             D->wg[i] = 2 * D->w[i] - D->wf[i];
+            if (P->clamp_p && D->p[i] < 0.0) D->p[i] = 0.0; /* ClampWallPressure wc/edac.py:172-174 */
         }
     }
     return total;
@@ -932,14 +933,17 @@ int64_t orc_tvf_pass2(orc_ctx *c, const orc_tvf_program *P)
             D->au[i] = D->av[i] = D->aw[i] = 0.0;
             if (bits & ORC_TVF_PGRAD) D->auhat[i] = D->avhat[i] = D->awhat[i] = 0.0;
             if (bits & ORC_TVF_EDAC) D->ap[i] = 0.0;
+            if (bits & ORC_TVF_XSPH) D->ax[i] = D->ay[i] = D->az[i] = 0.0; /* basic_equations.py:280-283 */
         }
         for (int src = 0; src < c->narr; src++) {
             if (!((P->fluid_mask | P->solid_mask) >> src & 1u)) continue;
             /* which equations have this source (wc/edac.py:845-878): a wall is a source of the
              * pressure gradient, the artificial viscosity, the no-slip term and EDAC only */
             const int wall = (P->solid_mask >> src) & 1u;
-            const uint32_t bits = wall ? (P->eqbits & (ORC_TVF_PGRAD | ORC_TVF_AV | ORC_TVF_NOSLIP | ORC_TVF_EDAC))
-                                       : (P->eqbits & ~(uint32_t)ORC_TVF_NOSLIP);
+            uint32_t bits_ = wall ? (P->eqbits & (ORC_TVF_PGRAD | ORC_TVF_MOM | ORC_TVF_AV | ORC_TVF_NOSLIP | ORC_TVF_EDAC))
+                                  : (P->eqbits & ~(uint32_t)ORC_TVF_NOSLIP);
+            if (src != dst) bits_ &= ~(uint32_t)ORC_TVF_XSPH; /* XSPHCorrection(dest=fluid, sources=[fluid]) */
+            const uint32_t bits = bits_;
             const orc_array *S = &c->arr[src];
             int64_t pairs = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : pairs)
@@ -975,6 +979,22 @@ int64_t orc_tvf_pass2(orc_ctx *c, const orc_tvf_program *P)
                         D->auhat[d_idx] += tmp * DWIJ[0];
                         D->avhat[d_idx] += tmp * DWIJ[1];
                         D->awhat[d_idx] += tmp * DWIJ[2];
+                    }
+                    if (bits & ORC_TVF_MOM) { /* wc/edac.py:319-341 */
+                        const double pi = D->p[d_idx], pj = S->p[s_idx];
+                        double pij = rhoj * pi + rhoi * pj;
+                        pij /= (rhoj + rhoi);
+                        const double tmp = -pij * mi1 * (Vi2 + Vj2);
+                        D->au[d_idx] += tmp * DWIJ[0];
+                        D->av[d_idx] += tmp * DWIJ[1];
+                        D->aw[d_idx] += tmp * DWIJ[2];
+                    }
+                    if (bits & ORC_TVF_XSPH) { /* basic_equations.py:285-295 */
+                        const double WIJ = k_w(kernel, dim, kfac, RIJ, HIJ);
+                        const double tmp = -P->eps_xsph * S->m[s_idx] * WIJ / (0.5 * (rhoi + rhoj));
+                        D->ax[d_idx] += tmp * VIJ[0];
+                        D->ay[d_idx] += tmp * VIJ[1];
+                        D->az[d_idx] += tmp * VIJ[2];
                     }
                     if (bits & ORC_TVF_AV) { /* transport_velocity.py:432-448 */
                         const double RHOIJ1 = 1.0 / (0.5 * (rhoi + rhoj));
@@ -1038,7 +1058,15 @@ int64_t orc_tvf_pass2(orc_ctx *c, const orc_tvf_program *P)
             }
             total += pairs;
         }
-        if (bits & ORC_TVF_PGRAD) { /* post_loop wc/edac.py:483-488 */
+        if (bits & ORC_TVF_XSPH) { /* post_loop basic_equations.py:297-300 */
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < np; i++) {
+                D->ax[i] += D->u[i];
+                D->ay[i] += D->v[i];
+                D->az[i] += D->w[i];
+            }
+        }
+        if (bits & (ORC_TVF_PGRAD | ORC_TVF_MOM)) { /* post_loop wc/edac.py:483-488, :343-352 */
             double damp = 1.0;
             if (P->t < P->tdamp) damp = 0.5 * (sin((-0.5 + P->t / P->tdamp) * M_PI) + 1.0);
 #pragma omp parallel for schedule(static)
@@ -1086,6 +1114,37 @@ void orc_stage_tvf(orc_ctx *c, int arr, int which, double dt)
     }
 }
 
+
+/* EDACStep wc/edac.py:82-133 (real particles) */
+void orc_stage_edac(orc_ctx *c, int arr, int which, double dt)
+{
+    orc_array *A = &c->arr[arr];
+    const int64_t n = A->n_real;
+    if (which == 0) {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; i++) {
+            A->x0[i] = A->x[i];
+            A->y0[i] = A->y[i];
+            A->z0[i] = A->z[i];
+            A->u0[i] = A->u[i];
+            A->v0[i] = A->v[i];
+            A->w0[i] = A->w[i];
+            A->p0[i] = A->p[i];
+        }
+        return;
+    }
+    const double f = (which == 1) ? 0.5 * dt : dt;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        A->u[i] = A->u0[i] + f * A->au[i];
+        A->v[i] = A->v0[i] + f * A->av[i];
+        A->w[i] = A->w0[i] + f * A->aw[i];
+        A->x[i] = A->x0[i] + f * A->ax[i];
+        A->y[i] = A->y0[i] + f * A->ay[i];
+        A->z[i] = A->z0[i] + f * A->az[i];
+        A->p[i] = A->p0[i] + f * A->ap[i];
+    }
+}
 
 /* ------------------------------------------------------------------------ */
 /* elastic dynamics: oracle only                             */

@@ -85,7 +85,10 @@ enum {
     ORC_TVF_VISC    = 4,  /* MomentumEquationViscosity         transport_velocity.py:328-386 */
     ORC_TVF_ASTRESS = 8,  /* MomentumEquationArtificialStress  transport_velocity.py:451-545 */
     ORC_TVF_EDAC    = 16, /* EDACEquation                      wc/edac.py:354-386 */
-    ORC_TVF_NOSLIP  = 32  /* SolidWallNoSlipBC                 transport_velocity.py:548-638 */
+    ORC_TVF_NOSLIP  = 32, /* SolidWallNoSlipBC                 transport_velocity.py:548-638 */
+    /* the external-flow branch (pb == 0), wc/edac.py:882-971 */
+    ORC_TVF_MOM     = 64, /* edac.MomentumEquation             wc/edac.py:301-352 */
+    ORC_TVF_XSPH    = 128 /* XSPHCorrection(dest=f, sources=[f]) basic_equations.py:260-300 */
 };
 typedef struct {
     int kernel, dim;
@@ -97,6 +100,8 @@ typedef struct {
     uint32_t solid_mask; /* bit a: array a is a solid wall (EDACScheme(fluids, solids)): a source of
                           * the pressure gradient, the artificial viscosity, the no-slip term and
                           * the EDAC equation, and a destination of orc_tvf_wall */
+    double eps_xsph;     /* XSPHCorrection(eps) of the external-flow branch */
+    int clamp_p;         /* ClampWallPressure (wc/edac.py:169-174) behind the wall pressure */
 } orc_tvf_program;
 
 /* ElasticSolidsScheme.get_equations, solid_mech/basic.py:604-651 */
@@ -174,6 +179,8 @@ int64_t orc_tvf_wall(orc_ctx *, const orc_tvf_program *);
 int64_t orc_tvf_avgp(orc_ctx *, const orc_tvf_program *);
 /* EDACTVFStep wc/edac.py:491-540: which = 0 initialize, 1 stage1, 2 stage2 */
 void orc_stage_tvf(orc_ctx *, int arr, int which, double dt);
+/* EDACStep wc/edac.py:82-133 (the external-flow branch: x moves with the XSPH velocity ax) */
+void orc_stage_edac(orc_ctx *, int arr, int which, double dt);
 
 /* elastic dynamics (Gray et al.), SURVEY.md 8f-2 -- ORACLE ONLY so far, no CUDA yet.
  * group 1: IsothermalEOS (solid_mech/basic.py:93-101), VelocityGradient2D/3D

@@ -197,6 +197,18 @@ def get_particle_array_edac(constants=None, **props):
     return pa
 
 
+# EDAC_PROPS (wc/edac.py:30-31): the fluid of an external flow (pb == 0, EDACStep)
+EDAC_EXT_PROPS = ('ap', 'au', 'av', 'aw', 'ax', 'ay', 'az', 'x0', 'y0', 'z0', 'u0', 'v0', 'w0',
+                  'p0', 'V')
+
+
+def get_particle_array_edac_ext(constants=None, **props):
+    """A fluid array of the EDAC scheme WITHOUT transport velocity (wc/edac.py:34-43)."""
+    pa = get_particle_array(additional_props=EDAC_EXT_PROPS, constants=constants, **props)
+    pa.set_output_arrays(['x', 'y', 'z', 'u', 'v', 'w', 'rho', 'p', 'm', 'h', 'V'])
+    return pa
+
+
 # TVF_SOLID_PROPS of EDACScheme.setup_properties (wc/edac.py:752-753)
 EDAC_WALL_PROPS = ('V', 'wij', 'ax', 'ay', 'az', 'uf', 'vf', 'wf', 'ug', 'vg', 'wg')
 

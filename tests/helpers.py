@@ -91,5 +91,22 @@ def edac_wall_arrays_from_dict(d):
     return pas
 
 
+def edac_ext_arrays_from_dict(d):
+    """golden 'inputs' dict of an external-flow EDAC case -> stand-ins (fluids, then the wall)."""
+    from pysph_b200.particle_array import get_particle_array_edac_ext, get_particle_array_edac_wall
+    pas = []
+    for name in ('fluid', 'fluid2', 'wall'):
+        if name not in d:
+            continue
+        a = d[name]
+        props = dict((k, np.array(v, dtype=float)) for k, v in a.items() if k[0] != '_')
+        factory = get_particle_array_edac_wall if name == 'wall' else get_particle_array_edac_ext
+        pa = factory(name=name, **props)
+        pa.set_num_real_particles(a.get('_n_real', len(a['x'])))
+        pas.append(pa)
+    return pas
+
+
+EDAC_EXT_FIELDS = ['V', 'rho', 'au', 'av', 'aw', 'ap', 'ax', 'ay', 'az']
 EDAC_WALL_FIELDS = ['V', 'wij', 'p', 'uf', 'vf', 'wf', 'ug', 'vg', 'wg']
 EDAC_FIELDS = ['V', 'rho', 'pavg', 'au', 'av', 'aw', 'auhat', 'avhat', 'awhat', 'ap']

@@ -330,6 +330,55 @@ def test_edac_solid_wall_evaluation_matches_reference_bodies(idx):
             assert np.max(np.abs(got - wantv)) <= 5e-12 * scale, (pa.name, f)
 
 
+@pytest.mark.parametrize('idx', range(4))
+def test_edac_external_flow_evaluation_matches_reference_bodies(idx):
+    """EDACScheme(..., pb=0): the external-flow branch (wc/edac.py:882-971) -- number-density
+    MomentumEquation, EDACEquation, XSPHCorrection(sources=[the fluid itself]), walls,
+    ClampWallPressure -- through the reference's own scheme method and bodies."""
+    from helpers import EDAC_EXT_FIELDS, EDAC_WALL_FIELDS, edac_ext_arrays_from_dict
+    case = load_golden('edac_ext_cases.json')[idx]
+    p = case['params']
+    fl, walls = p['fluids'], p['solids']
+    g1 = ['SummationDensity'] * len(fl)
+    for w in walls:
+        g1 += ['SourceNumberDensity', 'VolumeSummation', 'SolidWallPressureBC', 'SetWallVelocity']
+        if p['clamp_p']:
+            g1.append('ClampWallPressure')
+    per_fluid = ['MomentumEquation']
+    if p['alpha'] > 0:
+        per_fluid.append('MomentumEquationArtificialViscosity')
+    if p['nu'] > 0:
+        per_fluid.append('MomentumEquationViscosity')
+        if walls:
+            per_fluid.append('SolidWallNoSlipBC')
+    per_fluid += ['EDACEquation', 'XSPHCorrection']
+    assert p['groups'] == [g1, per_fluid * len(fl)] and p['group_real'] == [False, True]
+    # XSPH takes the fluid itself as its only source
+    assert [s_ for s_, n in zip(p['sources'][1], p['groups'][1]) if n == 'XSPHCorrection'] == [[f] for f in fl]
+    pas = edac_ext_arrays_from_dict(case['inputs'])
+    s = orc.EDACOracleSolver(pas, dict(p, dt=1e-3), case['kernel'])
+    s.t = p['t']
+    s.evaluate()
+    for pa in pas:
+        ref = case['outputs'][pa.name]
+        for f in (EDAC_WALL_FIELDS if pa.name in walls else EDAC_EXT_FIELDS):
+            got, wantv = pa.properties[f], np.array(ref[f])
+            scale = max(np.max(np.abs(wantv)), 1e-300)
+            assert np.max(np.abs(got - wantv)) <= 5e-12 * scale, (pa.name, f)
+
+
+def test_edac_step_matches_reference_bodies():
+    from pysph_b200.particle_array import get_particle_array_edac_ext
+    g = load_golden('edac_ext_stepper.json')
+    for which, key in ((0, 'initialize'), (1, 'stage1'), (2, 'stage2')):
+        a = g[key]
+        pa = get_particle_array_edac_ext(name='f', **dict((k, np.array(v)) for k, v in a['inputs'].items()))
+        o = orc.Oracle([pa], 3, 'CubicSpline')
+        o.stage_edac(0, which, g['dt'])
+        for k, v in a['outputs'].items():
+            assert np.max(np.abs(pa.properties[k] - np.array(v))) <= 1e-15 * max(1.0, np.max(np.abs(v))), (key, k)
+
+
 def test_edac_tvf_step_matches_reference_bodies():
     from pysph_b200.particle_array import get_particle_array_edac
     g = load_golden('edac_stepper.json')
