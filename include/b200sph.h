@@ -111,7 +111,10 @@ enum {
     B200SPH_TVF_VISC = 4,    /* MomentumEquationViscosity          transport_velocity.py:328-386 */
     B200SPH_TVF_ASTRESS = 8, /* MomentumEquationArtificialStress   transport_velocity.py:451-545 */
     B200SPH_TVF_EDAC = 16,   /* EDACEquation                       wc/edac.py:354-386 */
-    B200SPH_TVF_NOSLIP = 32  /* SolidWallNoSlipBC (sources: the walls) transport_velocity.py:548-638 */
+    B200SPH_TVF_NOSLIP = 32, /* SolidWallNoSlipBC (sources: the walls) transport_velocity.py:548-638 */
+    /* the external-flow branch (pb == 0, wc/edac.py:882-971) instead of PGRAD + ASTRESS: */
+    B200SPH_TVF_MOM = 64,    /* edac.MomentumEquation (number density)  wc/edac.py:301-352 */
+    B200SPH_TVF_XSPH = 128   /* XSPHCorrection(dest = f, sources = [f]) basic_equations.py:260-300 */
 };
 
 /* The Groups EDACScheme._get_internal_flow_equations (wc/edac.py:776-880) emits: every
@@ -137,6 +140,8 @@ typedef struct {
                           * wall pressure takes it undamped (:141-161)            */
     double tdamp, t;
     uint32_t solid_mask; /* bit a: array a is a solid wall (ABI 5: appended)     */
+    int32_t clamp_p;     /* ClampWallPressure (wc/edac.py:169-174) on the walls   */
+    double eps_xsph;     /* XSPHCorrection(eps) of the external-flow branch       */
 } b200sph_tvf_program;
 
 /* The two Groups of ElasticSolidsScheme.get_equations (solid_mech/basic.py:604-651) for
@@ -338,6 +343,10 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog,
 int b200sph_stage_tvf(b200sph_ctx *ctx, int arr, int which, double dt);
 /* the same with dt read from the device-resident time-control block */
 int b200sph_stage_tvf_dev(b200sph_ctx *ctx, int arr, int which);
+/* EDACStep (wc/edac.py:82-133), the stepper of the scheme WITHOUT transport velocity (pb == 0):
+ * as stage_tvf, but positions move with the XSPH-corrected velocity ax ay az */
+int b200sph_stage_edac(b200sph_ctx *ctx, int arr, int which, double dt);
+int b200sph_stage_edac_dev(b200sph_ctx *ctx, int arr, int which);
 
 /* The elastic-dynamics evaluation (see b200sph_solid_program); same neighbour lists as
  * pair_pass.  NOT YET RUN ON HARDWARE (see the property block above). */

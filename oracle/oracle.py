@@ -721,16 +721,17 @@ class EDACOracleSolver(object):
         # steppers exist for the fluids only (wc/edac.py:682-687): walls do not move
         fl = [i for i, pa in enumerate(self.pas) if pa.name not in (self.p.get('solids') or ())]
         # EDACTVFStep with the transport velocity, EDACStep without (wc/edac.py:682)
-        stage = self.o.stage_tvf if abs(self.p.get('pb', 0.0)) > 1e-14 else self.o.stage_edac
+        # (self.o is replaced by update_domain() in a periodic domain: look the method up each time)
+        name = 'stage_tvf' if abs(self.p.get('pb', 0.0)) > 1e-14 else 'stage_edac'
         for a in fl:
-            stage(a, 0, 0.0)
+            getattr(self.o, name)(a, 0, 0.0)
         for a in fl:
-            stage(a, 1, self.dt)
+            getattr(self.o, name)(a, 1, self.dt)
         self.update_domain()
         self.o.nnps_update()
         self.evaluate(self.t)               # a_eval.compute(c_integrator.t, ...) integrator.py:286
         for a in fl:
-            stage(a, 2, self.dt)
+            getattr(self.o, name)(a, 2, self.dt)
         self.update_domain()
         self.t += self.dt
         self.count += 1

@@ -22,7 +22,7 @@ backend needs the built library and a CUDA device.
 """
 from .particle_array import (ParticleArray, get_particle_array,
                              get_particle_array_wcsph, get_particle_array_edac,
-                             get_particle_array_edac_wall,
+                             get_particle_array_edac_wall, get_particle_array_edac_ext,
                              get_particle_array_elastic_dynamics)
 from .kernels import CubicSpline, WendlandQuintic, QuinticSpline, Gaussian
 from .equations import (Equation, Group, SummationDensity, ContinuityEquation,
@@ -37,7 +37,7 @@ from .acceleration_eval import B200AccelerationEval
 from .integrator import (B200Integrator, PECIntegrator, EPECIntegrator,
                          WCSPHStep)
 from .solver import B200Solver
-from .edac import EDACScheme, EDACTVFStep
+from .edac import EDACScheme, EDACTVFStep, EDACStep
 from .output import dump, load
 from .solid_mech import ElasticSolidsScheme, SolidMechStep
 

@@ -64,6 +64,7 @@ class PairProgram(C.Structure):
 
 
 TVF_PGRAD, TVF_AV, TVF_VISC, TVF_ASTRESS, TVF_EDAC, TVF_NOSLIP = 1, 2, 4, 8, 16, 32
+TVF_MOM, TVF_XSPH = 64, 128
 
 
 class TvfProgram(C.Structure):
@@ -72,7 +73,8 @@ class TvfProgram(C.Structure):
                 ('pb', C.c_double), ('nu', C.c_double), ('edac_nu', C.c_double),
                 ('c0', C.c_double), ('rho0', C.c_double), ('alpha', C.c_double),
                 ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
-                ('tdamp', C.c_double), ('t', C.c_double), ('solid_mask', C.c_uint32)]
+                ('tdamp', C.c_double), ('t', C.c_double), ('solid_mask', C.c_uint32),
+                ('clamp_p', C.c_int32), ('eps_xsph', C.c_double)]
 
 
 class SolidProgram(C.Structure):
@@ -154,6 +156,8 @@ SIGNATURES = {
     'b200sph_tvf_pass': (C.c_int, [_ctx_p, C.POINTER(TvfProgram), C.POINTER(_i64)]),
     'b200sph_stage_tvf': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
     'b200sph_stage_tvf_dev': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
+    'b200sph_stage_edac': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
+    'b200sph_stage_edac_dev': (C.c_int, [_ctx_p, C.c_int, C.c_int]),
     'b200sph_solid_pass': (C.c_int, [_ctx_p, C.POINTER(SolidProgram), C.POINTER(_i64)]),
     'b200sph_stage_solid': (C.c_int, [_ctx_p, C.c_int, C.c_int, C.c_double]),
     'b200sph_stage_solid_dev': (C.c_int, [_ctx_p, C.c_int, C.c_int]),

@@ -73,10 +73,11 @@ class B200Backend(object):
         self.names = [pa.name for pa in particle_arrays]
         self.index = dict((n, i) for i, n in enumerate(self.names))
         # name -> device property id, per array: EDAC arrays evolve p (fp64 PF)
-        self.prop_ids = [dict(EDAC_PROP_IDS if 'ap' in pa.properties else
-                              (ELASTIC_PROP_IDS if 's00' in pa.properties else
-                               (EDAC_WALL_PROP_IDS if 'wij' in pa.properties and
-                                'ug' in pa.properties else PROP_IDS)))
+        # (a wall of the EDAC scheme may carry 'ap' too, wc/edac.py:46-47: walls first)
+        self.prop_ids = [dict(EDAC_WALL_PROP_IDS if 'wij' in pa.properties and
+                              'ug' in pa.properties else
+                              (EDAC_PROP_IDS if 'ap' in pa.properties else
+                               (ELASTIC_PROP_IDS if 's00' in pa.properties else PROP_IDS)))
                          for pa in particle_arrays]
         self.user_props = []      # names of the fp64 properties created for generic equations
         for pa in particle_arrays:

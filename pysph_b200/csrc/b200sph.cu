@@ -2184,12 +2184,17 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog, int64_t 
     if ((rc = eos_flush(ctx))) return rc;
     if (!ctx->grid_valid) return set_err(ctx, "tvf_pass: the NNPS is stale (particles were pushed/resized); call nnps_update first");
     if (!(prog->passes & 7)) return set_err(ctx, "tvf_pass: passes must select group 1, the average-pressure group and/or group 2");
-    if (prog->eqbits > 63u) return set_err(ctx, "tvf_pass: unknown equation bits 0x%x", prog->eqbits);
+    if (prog->eqbits > 255u) return set_err(ctx, "tvf_pass: unknown equation bits 0x%x", prog->eqbits);
+    const bool ext = (prog->eqbits & (B200SPH_TVF_MOM | B200SPH_TVF_XSPH)) != 0;
+    if (ext && (prog->eqbits & (B200SPH_TVF_PGRAD | B200SPH_TVF_ASTRESS)))
+        return set_err(ctx, "tvf_pass: equations of the internal-flow (transport velocity) and of the external-flow branch in one Group");
+    if (prog->clamp_p && !prog->solid_mask) return set_err(ctx, "tvf_pass: ClampWallPressure without a solid wall");
     if (prog->fluid_mask == 0 || prog->fluid_mask >= (1u << ctx->narr)) return set_err(ctx, "tvf_pass: bad fluid mask 0x%x", prog->fluid_mask);
     const unsigned solid_mask = prog->solid_mask;
     if (solid_mask >= (1u << ctx->narr) || (solid_mask & prog->fluid_mask))
         return set_err(ctx, "tvf_pass: bad solid mask 0x%x (fluids 0x%x)", solid_mask, prog->fluid_mask);
     if ((prog->eqbits & B200SPH_TVF_NOSLIP) && !solid_mask) return set_err(ctx, "tvf_pass: SolidWallNoSlipBC without a solid wall");
+    if ((prog->passes & 4) && ext) return set_err(ctx, "tvf_pass: the external-flow branch has no average pressure");
     if ((prog->passes & 4) && !solid_mask) return set_err(ctx, "tvf_pass: the average pressure has a Group of its own only with solid walls");
     if ((prog->passes & 1) && solid_mask && prog->bql)
         return set_err(ctx, "tvf_pass: with solid walls the average pressure is computed after the wall pressure (passes bit 2), not in group 1");
@@ -2231,6 +2236,9 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog, int64_t 
     ta.eqbits = prog->eqbits;
     ta.bql = prog->bql;
     ta.wgx = (float)prog->gx; ta.wgy = (float)prog->gy; ta.wgz = (float)prog->gz;
+    ta.eps_xsph = (float)prog->eps_xsph;
+    ta.clamp_p = prog->clamp_p;
+    ta.ax = ctx->f32[B200SPH_AX - N_F64]; ta.ay = ctx->f32[B200SPH_AY - N_F64]; ta.az = ctx->f32[B200SPH_AZ - N_F64];
     ta.p32 = ctx->f32[B200SPH_P - N_F64];
     ta.ug = ctx->f64x[B200SPH_UHAT - B200SPH_UHAT]; ta.vg = ctx->f64x[B200SPH_VHAT - B200SPH_UHAT];
     ta.wg = ctx->f64x[B200SPH_WHAT - B200SPH_UHAT];
@@ -2262,6 +2270,7 @@ int b200sph_tvf_pass(b200sph_ctx *ctx, const b200sph_tvf_program *prog, int64_t 
     case K * 4 + D:                                                                                      \
         if (stage == 2) k_tvf_wall<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg); \
         else if (pass == 1) k_tvf_pass1<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg); \
+        else if (ext) k_tvf_pass2<K, D, true, true><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg); \
         else if (solid_mask) k_tvf_pass2<K, D, true><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg); \
         else k_tvf_pass2<K, D><<<nb, LIST_NT, 0, ctx->stream>>>(ta, ctx->cnt, ctx->lst, ctx->capg);            \
         break;
@@ -2419,7 +2428,7 @@ int b200sph_stage_solid(b200sph_ctx *ctx, int arr, int which, double dt) { retur
 int b200sph_stage_solid_dev(b200sph_ctx *ctx, int arr, int which) { return stage_solid_impl(ctx, arr, which, 0.0, true); }
 
 static int ensure_tc(b200sph_ctx *ctx);
-static int stage_tvf_impl(b200sph_ctx *ctx, int arr, int which, double dt, bool devdt)
+static int stage_tvf_impl(b200sph_ctx *ctx, int arr, int which, double dt, bool devdt, int ext = 0)
 {
     if (int rcc = require_confirmed(ctx, "stage_tvf")) return rcc;
     CU(cudaSetDevice(ctx->device));
@@ -2445,6 +2454,8 @@ static int stage_tvf_impl(b200sph_ctx *ctx, int arr, int which, double dt, bool 
     sa.arr = arr;
     sa.which = which;
     sa.f = which == 1 ? 0.5 * dt : dt;
+    sa.ext = ext;
+    sa.ax = ctx->f32[B200SPH_AX - N_F64]; sa.ay = ctx->f32[B200SPH_AY - N_F64]; sa.az = ctx->f32[B200SPH_AZ - N_F64];
     if (ctx->pool_end > 0) {
         if (devdt) k_stage_tvf_devdt<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa, ctx->tc);
         else k_stage_tvf<<<(unsigned)cdiv(ctx->pool_end, 256), 256, 0, ctx->stream>>>(sa);
@@ -2458,6 +2469,8 @@ static int stage_tvf_impl(b200sph_ctx *ctx, int arr, int which, double dt, bool 
 }
 int b200sph_stage_tvf(b200sph_ctx *ctx, int arr, int which, double dt) { return stage_tvf_impl(ctx, arr, which, dt, false); }
 int b200sph_stage_tvf_dev(b200sph_ctx *ctx, int arr, int which) { return stage_tvf_impl(ctx, arr, which, 0.0, true); }
+int b200sph_stage_edac(b200sph_ctx *ctx, int arr, int which, double dt) { return stage_tvf_impl(ctx, arr, which, dt, false, 1); }
+int b200sph_stage_edac_dev(b200sph_ctx *ctx, int arr, int which) { return stage_tvf_impl(ctx, arr, which, 0.0, true, 1); }
 
 static int ensure_tc(b200sph_ctx *ctx)
 {

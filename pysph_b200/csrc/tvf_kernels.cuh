@@ -26,6 +26,11 @@ struct TvfArgs {
     unsigned solid_mask, src_mask;
     int avg_only;                 // k_tvf_pass1: only the average pressure, real destinations
     float wgx, wgy, wgz;          // the UNDAMPED body force of SolidWallPressureBC (:141-161)
+    // the external-flow branch (pb == 0, wc/edac.py:882-971): XSPHCorrection(eps) with the fluid
+    // itself as its only source, ClampWallPressure behind the wall pressure
+    float eps_xsph;
+    int clamp_p;
+    float *ax, *ay, *az;
     float *p32;                   // pool p of the wall arrays
     double *ug, *vg, *wg;         // wall arrays: the slots of uhat vhat what hold ug vg wg,
     // ... those of auhat avhat awhat hold uf vf wf and pavg holds wij
@@ -204,7 +209,8 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_wall(const TvfArgs a, const 
             }
         });
     if (active) {
-        const float pw = wsum > 1e-14f ? psum / wsum : psum;
+        float pw = wsum > 1e-14f ? psum / wsum : psum;
+        if (a.clamp_p && pw < 0.f) pw = 0.f;               // ClampWallPressure wc/edac.py:169-174
         if (wsum > 1e-12f) {
             const float w1 = 1.0f / wsum;
             us *= w1; vs *= w1; ws *= w1;
@@ -234,7 +240,10 @@ __global__ void __launch_bounds__(LIST_NT, 4) k_tvf_wall(const TvfArgs a, const 
 // walls are sources too -- of the pressure gradient, the artificial viscosity, the EDAC
 // equation and (instead of the viscosity) SolidWallNoSlipBC, which takes the dummy velocity
 // from the wall's Dv record; the instantiation without walls is the measured one.
-template <int K, int DIM, bool WALLS = false>
+// EXT (implies WALLS): the external-flow branch -- the number-density MomentumEquation
+// (wc/edac.py:301-352: the pressure gradient without average and background pressure) and
+// XSPHCorrection (basic_equations.py:260-300) over the destination's own array.
+template <int K, int DIM, bool WALLS = false, bool EXT = false>
 __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const uint32_t *__restrict__ cnt,
                                                          const uint32_t *__restrict__ lst, const int capg)
 {
@@ -265,6 +274,8 @@ __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const
     const float mi1 = frcp(Bi.w);
     const float cs2 = a.c0 * a.c0;
     float au = 0.f, av = 0.f, aw = 0.f, auh = 0.f, avh = 0.f, awh = 0.f, ap = 0.f;
+    float xs = 0.f, ys = 0.f, zs = 0.f;          // XSPH sums (EXT)
+    const int ti7 = __float_as_int(Ci.w) & 7;
     unsigned npairs = 0;
     struct Rec { float4 A, B, C, D; };
     list_walk<Rec>(my, count, cmax,
@@ -300,6 +311,14 @@ __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const
                 const float rsum1 = frcp(rhoi + rhoj);
                 const float r2e1 = frcp(r2 + eps);
                 float fx = 0.f;   // multiplies XIJ in au
+                if (EXT && (a.eqbits & B200SPH_TVF_MOM)) {   // wc/edac.py:319-341
+                    const float pij = (rhoj * pi + rhoi * pj) * rsum1;
+                    fx += -pij * common * gt;
+                }
+                if (EXT && (a.eqbits & B200SPH_TVF_XSPH) && tj == ti7) {   // basic_equations.py:285-295
+                    const float t_ = -a.eps_xsph * Bj.w * (w * a.kfac * hpow<DIM>(h1)) * (2.0f * rsum1);
+                    xs += t_ * uij; ys += t_ * vij; zs += t_ * wij;
+                }
                 if (a.eqbits & B200SPH_TVF_PGRAD) {   // wc/edac.py:447-481
                     const float pij = (rhoj * (pi - pavg) + rhoi * (pj - pavg)) * rsum1;
                     fx += -pij * common * gt;
@@ -351,6 +370,12 @@ __global__ void __launch_bounds__(LIST_NT, 6) k_tvf_pass2(const TvfArgs a, const
             au += a.gx; av += a.gy; aw += a.gz;
             a.auhat[g] = auh; a.avhat[g] = avh; a.awhat[g] = awh;
         }
+        if (EXT && (a.eqbits & B200SPH_TVF_MOM)) {   // post_loop wc/edac.py:343-352
+            au += a.gx; av += a.gy; aw += a.gz;
+        }
+        if (EXT && (a.eqbits & B200SPH_TVF_XSPH)) {  // post_loop basic_equations.py:297-300
+            a.ax[g] = xs + Bi.x; a.ay[g] = ys + Bi.y; a.az[g] = zs + Bi.z;
+        }
         a.au[g] = au; a.av[g] = av; a.aw[g] = aw;
         if (a.eqbits & B200SPH_TVF_EDAC) a.ap[g] = ap;
     }
@@ -369,8 +394,12 @@ struct StageTvfArgs {
     long long pool_end;
     int arr, which;
     double f;
+    // EDACStep (wc/edac.py:82-133, the scheme without transport velocity): positions move with
+    // the XSPH-corrected velocity ax ay az, there is no uhat
+    int ext;
+    const float *ax, *ay, *az;
 };
-// EDACTVFStep wc/edac.py:491-540 (real particles)
+// EDACTVFStep wc/edac.py:491-540 / EDACStep :82-133 (real particles)
 __device__ __forceinline__ void stage_tvf_body(const StageTvfArgs &a)
 {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -388,14 +417,20 @@ __device__ __forceinline__ void stage_tvf_body(const StageTvfArgs &a)
     const double u = a.u0[g] + f * (double)a.au[g];
     const double v = a.v0[g] + f * (double)a.av[g];
     const double w = a.w0[g] + f * (double)a.aw[g];
-    const double uh = u + f * (double)a.auh[g];
-    const double vh = v + f * (double)a.avh[g];
-    const double wh = w + f * (double)a.awh[g];
     a.u[g] = u; a.v[g] = v; a.w[g] = w;
-    a.uh[g] = uh; a.vh[g] = vh; a.wh[g] = wh;
-    a.x[g] = a.x0[g] + f * uh;
-    a.y[g] = a.y0[g] + f * vh;
-    a.z[g] = a.z0[g] + f * wh;
+    if (a.ext) {
+        a.x[g] = a.x0[g] + f * (double)a.ax[g];
+        a.y[g] = a.y0[g] + f * (double)a.ay[g];
+        a.z[g] = a.z0[g] + f * (double)a.az[g];
+    } else {
+        const double uh = u + f * (double)a.auh[g];
+        const double vh = v + f * (double)a.avh[g];
+        const double wh = w + f * (double)a.awh[g];
+        a.uh[g] = uh; a.vh[g] = vh; a.wh[g] = wh;
+        a.x[g] = a.x0[g] + f * uh;
+        a.y[g] = a.y0[g] + f * vh;
+        a.z[g] = a.z0[g] + f * wh;
+    }
     a.pf[g] = a.pf0[g] + f * (double)a.ap[g];
 }
 __global__ void k_stage_tvf(StageTvfArgs a) { stage_tvf_body(a); }

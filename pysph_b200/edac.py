@@ -5,10 +5,12 @@ pysph/examples/taylor_green.py:190-203) and for internal flows between walls (ca
 Poiseuille / Couette): ``ComputeAveragePressure`` (:62-79), ``SolidWallPressureBC`` (:136-166),
 ``SourceNumberDensity`` (:177-183), ``SetWallVelocity`` (:186-230), ``EDACEquation`` (:354-386),
 ``MomentumEquationPressureGradient`` (:389-488), ``EDACTVFStep`` (:491-540) and ``EDACScheme``
-(:543-880, ``get_equations`` for ``pb != 0``).  Everything else of that module (external
-flows, inviscid solids, inlet/outlet, pressure clamping) raises NotImplementedError.
+(:543-971, ``get_equations`` for ``pb != 0`` -- internal flows with the transport velocity -- and
+for ``pb == 0`` -- the external-flow branch :882-971 with ``EDACStep`` (:82-133), the
+number-density ``MomentumEquation`` (:301-352), ``XSPHCorrection`` and ``ClampWallPressure``
+(:169-174)).  Inviscid solids and inlet / outlet raise NotImplementedError.
 """
-from .equations import Equation, Group
+from .equations import Equation, Group, XSPHCorrection
 from .integrator import IntegratorStep
 from .transport_velocity import (MomentumEquationArtificialStress,
                                  MomentumEquationArtificialViscosity,
@@ -28,6 +30,23 @@ class SolidWallPressureBC(Equation):
         self.gy = gy
         self.gz = gz
         super(SolidWallPressureBC, self).__init__(dest, sources)
+
+
+class ClampWallPressure(Equation):
+    """wc/edac.py:169-174: p = max(p, 0) on a wall, behind SolidWallPressureBC"""
+
+
+class MomentumEquation(Equation):
+    """wc/edac.py:301-352: the pressure gradient in the number-density form of Hu and Adams
+    (NOT wc/basic.py's MomentumEquation: recognised by its module)"""
+
+    def __init__(self, dest, sources, c0, gx=0.0, gy=0.0, gz=0.0, tdamp=0.0):
+        self.gx = gx
+        self.gy = gy
+        self.gz = gz
+        self.c0 = c0
+        self.tdamp = tdamp
+        super(MomentumEquation, self).__init__(dest, sources)
 
 
 class SourceNumberDensity(Equation):
@@ -62,6 +81,10 @@ class MomentumEquationPressureGradient(Equation):
 
 class EDACTVFStep(IntegratorStep):
     """wc/edac.py:491-540 (device kernel: k_stage_tvf)"""
+
+
+class EDACStep(IntegratorStep):
+    """wc/edac.py:82-133: the stepper without transport velocity (device kernel: k_stage_tvf, ext)"""
 
 
 class EDACScheme(object):
@@ -105,16 +128,15 @@ class EDACScheme(object):
     def _get_edac_nu(self):                            # wc/edac.py:766-774
         return self.art_nu if self.art_nu > 0 else self.nu
 
-    def get_steppers(self):
-        return dict((f, EDACTVFStep()) for f in self.fluids)
+    def get_steppers(self):                            # wc/edac.py:682-687
+        cls = EDACTVFStep if self.use_tvf else EDACStep
+        return dict((f, cls()) for f in self.fluids)
 
     def get_equations(self):                           # wc/edac.py:704-708, :776-880
-        if not self.use_tvf:
-            raise NotImplementedError('B200 backend: EDAC external-flow branch (pb == 0)')
         if self.inviscid_solids or self.inlet_outlet_manager is not None:
             raise NotImplementedError('B200 backend: EDAC with inviscid solids / inlet-outlet')
-        if self.clamp_p:
-            raise NotImplementedError('B200 backend: EDAC with clamp_p')
+        if not self.use_tvf:
+            return self._get_external_flow_equations()
         edac_nu = self._get_edac_nu()
         all_ = self.fluids + self.solids
         has_solids = len(self.solids) > 0
@@ -155,3 +177,35 @@ class EDACScheme(object):
             groups.append(Group(equations=avg_p_group, real=True))
         groups.append(Group(equations=group2))
         return groups
+
+    def _get_external_flow_equations(self):            # wc/edac.py:882-971
+        edac_nu = self._get_edac_nu()
+        all_ = self.fluids + self.solids
+        group1 = [SummationDensity(dest=fluid, sources=all_) for fluid in self.fluids]
+        for solid in self.solids:
+            group1.extend([
+                SourceNumberDensity(dest=solid, sources=self.fluids),
+                VolumeSummation(dest=solid, sources=all_),
+                SolidWallPressureBC(dest=solid, sources=self.fluids, gx=self.gx, gy=self.gy,
+                                    gz=self.gz),
+                SetWallVelocity(dest=solid, sources=self.fluids)])
+            if self.clamp_p:
+                group1.append(ClampWallPressure(dest=solid, sources=None))
+        group2 = []
+        for fluid in self.fluids:
+            group2.append(MomentumEquation(dest=fluid, sources=all_, gx=self.gx, gy=self.gy,
+                                           gz=self.gz, c0=self.c0, tdamp=self.tdamp))
+            if self.alpha > 0.0:
+                group2.append(MomentumEquationArtificialViscosity(
+                    dest=fluid, sources=self.fluids + self.solids, alpha=self.alpha,
+                    c0=self.c0))
+            if self.nu > 0.0:
+                group2.append(MomentumEquationViscosity(
+                    dest=fluid, sources=self.fluids, nu=self.nu))
+            if len(self.solids) > 0 and self.nu > 0.0:
+                group2.append(SolidWallNoSlipBC(dest=fluid, sources=self.solids, nu=self.nu))
+            group2.extend([
+                EDACEquation(dest=fluid, sources=all_, nu=edac_nu, cs=self.c0,
+                             rho0=self.rho0),
+                XSPHCorrection(dest=fluid, sources=[fluid], eps=self.eps)])
+        return [Group(equations=group1, real=False), Group(equations=group2)]

@@ -29,6 +29,7 @@ class WCSPHStep(IntegratorStep):
 _SUPPORTED_STEPPERS = {
     'WCSPHStep': ('b200sph_stage', 'b200sph_stage_dev'),
     'EDACTVFStep': ('b200sph_stage_tvf', 'b200sph_stage_tvf_dev'),   # wc/edac.py:491-540
+    'EDACStep': ('b200sph_stage_edac', 'b200sph_stage_edac_dev'),    # wc/edac.py:82-133
     'SolidMechStep': ('b200sph_stage_solid', 'b200sph_stage_solid_dev'),   # integrator_step.py:173-252
 }
 

@@ -30,6 +30,7 @@ NO_SOURCE_EQUATIONS = ('TaitEOS', 'TaitEOSHGCorrection',
 TVF_GROUP1 = ('SummationDensity', 'ComputeAveragePressure')
 # ... continued on the solid walls of an internal flow (wc/edac.py:815-822): k_tvf_wall
 TVF_WALL = ('SourceNumberDensity', 'VolumeSummation', 'SolidWallPressureBC', 'SetWallVelocity')
+TVF_WALL_OPTIONAL = ('ClampWallPressure',)      # the external-flow branch with clamp_p
 TVF_GROUP2 = {
     'MomentumEquationPressureGradient': _lib.TVF_PGRAD,
     'MomentumEquationArtificialViscosity': _lib.TVF_AV,
@@ -37,6 +38,10 @@ TVF_GROUP2 = {
     'MomentumEquationArtificialStress': _lib.TVF_ASTRESS,
     'EDACEquation': _lib.TVF_EDAC,
     'SolidWallNoSlipBC': _lib.TVF_NOSLIP,
+    # the external-flow branch (pb == 0, wc/edac.py:882-971); both names also exist in the WCSPH
+    # scheme: inside an EDAC Group (one that has an EDACEquation) they are these
+    'MomentumEquation': _lib.TVF_MOM,
+    'XSPHCorrection': _lib.TVF_XSPH,
 }
 
 
@@ -51,7 +56,7 @@ SOLID_GROUP2 = ('ContinuityEquation', 'MomentumEquationWithStress',
 # every equation that has a hand-written kernel; a Group made ONLY of others takes the
 # generic-equation fallback (pysph_b200/codegen.py)
 KNOWN_EQUATIONS = set(PAIR_EQUATIONS) | set(NO_SOURCE_EQUATIONS) | set(TVF_GROUP1) | \
-    set(TVF_WALL) | set(TVF_GROUP2) | set(SOLID_GROUP1) | set(SOLID_GROUP2)
+    set(TVF_WALL) | set(TVF_WALL_OPTIONAL) | set(TVF_GROUP2) | set(SOLID_GROUP1) | set(SOLID_GROUP2)
 import itertools
 _generic_uid = itertools.count()
 
@@ -188,10 +193,13 @@ def _tvf_group_kind(g):
     names = [_eq_name(e) for e in g.equations]
     if any(_is_tvf_summation(e) for e in g.equations) or any(n in TVF_WALL for n in names):
         return 1
+    if 'MomentumEquationWithStress' in names:
+        return 0                      # (elastic dynamics share XSPHCorrection / the viscosity)
     if any(n == 'ComputeAveragePressure' for n in names):
         # in group 1 without walls; a Group of its own (real=True) behind the wall pressure
         return 1 if getattr(g, 'real', True) is False else 3
-    if any(n in TVF_GROUP2 for n in names):
+    if 'EDACEquation' in names or 'MomentumEquationPressureGradient' in names or \
+            any(n in TVF_GROUP2 and n not in ('MomentumEquation', 'XSPHCorrection') for n in names):
         return 2
     return 0
 
@@ -209,7 +217,7 @@ def _build_tvf(g, kind, index):
     params = {}
     for eq in g.equations:
         name = _eq_name(eq)
-        ok = {1: name in TVF_WALL or name == 'ComputeAveragePressure' or
+        ok = {1: name in TVF_WALL or name in TVF_WALL_OPTIONAL or name == 'ComputeAveragePressure' or
               (name == 'SummationDensity' and _is_tvf_summation(eq)),
               3: name == 'ComputeAveragePressure', 2: name in TVF_GROUP2}[kind]
         if not ok:
@@ -223,7 +231,7 @@ def _build_tvf(g, kind, index):
     # or the sources that are not fluids (the other groups)
     fluids, walls = [], []
     for eq in g.equations:
-        where = walls if _eq_name(eq) in TVF_WALL else fluids
+        where = walls if _eq_name(eq) in TVF_WALL + TVF_WALL_OPTIONAL else fluids
         if eq.dest not in where:
             where.append(eq.dest)
     if kind != 1:
@@ -243,14 +251,15 @@ def _build_tvf(g, kind, index):
         'MomentumEquationPressureGradient': all_,
         'MomentumEquationArtificialViscosity': all_, 'MomentumEquationViscosity': fluids,
         'SolidWallNoSlipBC': walls, 'MomentumEquationArtificialStress': fluids,
-        'EDACEquation': all_}
+        'EDACEquation': all_, 'MomentumEquation': all_, 'ClampWallPressure': []}
     for eq in g.equations:
         name = _eq_name(eq)
-        if not _same(eq.sources or [], want_sources[name]):
+        want = [eq.dest] if name == 'XSPHCorrection' else want_sources[name]   # the fluid itself
+        if not _same(eq.sources or [], want):
             raise NotImplementedError(
                 'B200 backend: the EDAC kernels take %s as the sources of %s (wc/edac.py:'
-                '806-878); got %s(dest=%r, sources=%r)'
-                % (want_sources[name], name, name, eq.dest, eq.sources))
+                '806-878, :905-966); got %s(dest=%r, sources=%r)'
+                % (want, name, name, eq.dest, eq.sources))
         if name == 'MomentumEquationPressureGradient':
             if 'edac' not in eq.__class__.__module__:
                 raise NotImplementedError(
@@ -261,6 +270,18 @@ def _build_tvf(g, kind, index):
         elif name == 'SolidWallPressureBC':
             for k in ('gx', 'gy', 'gz'):
                 _set_once(params, k, float(getattr(eq, k)), eq)
+        elif name == 'MomentumEquation':
+            if 'edac' not in eq.__class__.__module__:
+                raise NotImplementedError(
+                    'B200 backend: wc/basic.py\'s MomentumEquation in an EDAC Group (the '
+                    'external-flow branch uses wc/edac.py:301)')
+            for k in ('gx', 'gy', 'gz', 'tdamp'):
+                _set_once(params, k, float(getattr(eq, k)), eq)
+            _set_once(params, 'c0', float(eq.c0), eq)
+        elif name == 'XSPHCorrection':
+            _set_once(params, 'eps_xsph', float(eq.eps), eq)
+        elif name == 'ClampWallPressure':
+            params['clamp_p'] = 1
         elif name == 'MomentumEquationArtificialViscosity':
             _set_once(params, 'alpha', float(eq.alpha), eq)
             _set_once(params, 'c0', float(eq.c0), eq)
@@ -280,7 +301,8 @@ def _build_tvf(g, kind, index):
             raise NotImplementedError(
                 'B200 backend: the first EDAC Group needs the TVF SummationDensity of every fluid')
         for w in walls:
-            mine = [_eq_name(e) for e in g.equations if e.dest == w]
+            mine = [_eq_name(e) for e in g.equations if e.dest == w and
+                    _eq_name(e) not in TVF_WALL_OPTIONAL]
             if not _same(mine, TVF_WALL):
                 raise NotImplementedError(
                     'B200 backend: a solid wall needs %s in the first EDAC Group, got %s'
@@ -334,6 +356,7 @@ def _merge_tvf(ops):
             new = op[1]
             if prev.passes & 1:
                 new.bql = prev.bql               # what group 1 itself computes
+                new.clamp_p = prev.clamp_p
             if new.passes == 4:                  # (that Group has no parameters of its own)
                 for k in ('gx', 'gy', 'gz'):
                     setattr(new, k, getattr(prev, k))

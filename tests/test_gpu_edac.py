@@ -255,6 +255,110 @@ def test_edac_solid_wall_evaluation_matches_reference_bodies(gpu_device, idx):
     assert np.allclose(wall.au, case['inputs']['wall']['au'], rtol=1e-6, atol=0.0)   # (fp32 on the device)
 
 
+# ---- the external-flow branch: EDACScheme(..., pb=0), wc/edac.py:882-971 ----------------------
+def _ext_scheme(p):
+    import pysph_b200 as pb
+    return pb.EDACScheme(p['fluids'], p['solids'], dim=p['dim'], c0=p['c0'], nu=p['nu'],
+                         rho0=p['rho0'], pb=0.0, gx=p.get('gx', 0.0), gy=p.get('gy', 0.0),
+                         gz=p.get('gz', 0.0), tdamp=p.get('tdamp', 0.0), h=p['h'],
+                         alpha=p.get('alpha', 0.0), edac_alpha=p.get('edac_alpha', 0.5),
+                         eps=p.get('eps', 0.0), clamp_p=p.get('clamp_p', False))
+
+
+EXT_TOL = dict(V=2e-5, rho=2e-5, au=2e-5, av=2e-5, aw=2e-5, ap=5e-5, ax=2e-5, ay=2e-5, az=2e-5)
+
+
+@pytest.mark.parametrize('idx', range(4))
+def test_edac_external_flow_evaluation_matches_reference_bodies(gpu_device, idx):
+    """One evaluation of EDACScheme(fluids, solids, pb=0) -- number-density MomentumEquation,
+    EDACEquation, XSPHCorrection over the fluid itself, walls [+ ClampWallPressure] -- against the
+    outputs of the reference's scheme method and bodies (tests/golden/edac_ext_cases.json)."""
+    import pysph_b200 as pb
+    from helpers import EDAC_EXT_FIELDS, EDAC_WALL_FIELDS, edac_ext_arrays_from_dict
+    case = load_golden('edac_ext_cases.json')[idx]
+    p = case['params']
+    pas = edac_ext_arrays_from_dict(case['inputs'])
+    kernel = getattr(pb, case['kernel'])(dim=p['dim'])
+    sch = _ext_scheme(p)
+    groups = sch.get_equations()
+    assert [[type(e).__name__ for e in g.equations] for g in groups] == p['groups']
+    assert [[list(e.sources or []) for e in g.equations] for g in groups] == p['sources']
+    assert set(type(s_).__name__ for s_ in sch.get_steppers().values()) == {'EDACStep'}
+    ae = pb.B200AccelerationEval(pas, groups, kernel)
+    assert [o[0] for o in ae.ops] == ['tvf'] and ae.ops[0][1].passes == 3
+    nn = pb.B200NNPS(p['dim'], pas, backend=ae.backend, kernel=kernel)
+    ae.set_nnps(nn)
+    ae.count_pairs = True
+    ae.compute(p['t'], 1e-3)
+    ae.backend.pull_all()
+    opas = edac_ext_arrays_from_dict(case['inputs'])
+    o = orc.EDACOracleSolver(opas, dict(p, dt=1e-3), case['kernel'])
+    o.t = p['t']
+    assert ae.last_pairs == o.evaluate()
+    for pa in pas:
+        ref = case['outputs'][pa.name]
+        nr = ref['_n_real']
+        wall = pa.name in p['solids']
+        for f in (EDAC_WALL_FIELDS if wall else EDAC_EXT_FIELDS):
+            want = np.array(ref[f])
+            n = len(want) if (wall or f in ('V', 'rho')) else nr
+            if np.max(np.abs(want[:n])) == 0.0:
+                assert np.max(np.abs(pa.properties[f][:n])) == 0.0, (pa.name, f)
+                continue
+            err = rel_err(pa.properties[f][:n], want[:n])
+            _record('ext_golden_%d' % idx, pa.name + '_' + f, err)
+            assert err <= (WALL_TOL if wall else EXT_TOL)[f], (pa.name, f, err)
+        if wall and p['clamp_p']:
+            assert np.min(pa.p) >= 0.0 and np.any(pa.p == 0.0)
+
+
+def test_edac_step_matches_reference_bodies(gpu_device):
+    import pysph_b200 as pb
+    g = load_golden('edac_ext_stepper.json')
+    for which, key in ((0, 'initialize'), (1, 'stage1'), (2, 'stage2')):
+        a = g[key]
+        pa = pb.get_particle_array_edac_ext(name='f', **dict((k, np.array(v)) for k, v in a['inputs'].items()))
+        be = pb.B200Backend([pa])
+        be.ctx.call('b200sph_stage_edac', 0, which, g['dt'])
+        be.pull_all()
+        for k, v in a['outputs'].items():
+            # accelerations live in fp32 on the device: their rounding (6e-8) times dt
+            tol = 1e-15 if which == 0 or k in ('au', 'av', 'aw', 'ax', 'ay', 'az', 'ap') else 2e-8
+            if k in ('au', 'av', 'aw', 'ax', 'ay', 'az', 'ap'):
+                tol = 1e-7
+            assert np.max(np.abs(pa.properties[k] - np.array(v))) <= tol * max(1.0, np.max(np.abs(v))), (key, k)
+
+
+def test_edac_external_flow_steps_vs_oracle(gpu_device):
+    """Ten PEC steps of a small tank (fluid over a wall, gravity, pb = 0: EDACStep, XSPH) against
+    the oracle."""
+    import pysph_b200 as pb
+    pas, p = _channel()
+    ref, _ = _channel()
+    for arrs in (pas, ref):          # the same particles as external-flow arrays
+        f = arrs[0]
+        arrs[0] = pb.get_particle_array_edac_ext(name='fluid', **dict(
+            (k, f.properties[k]) for k in ('x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'gid')))
+    p = dict(p, pb=0.0, eps=0.5, gx=0.0, gy=-1.0, fluids=['fluid'], alpha=0.1)
+    s = pb.make_edac_solver(pas, _ext_scheme(p), pb.QuinticSpline(dim=2), dt=p['dt'])
+    o = orc.EDACOracleSolver(ref, p, 'QuinticSpline')
+    s.initialise()
+    o.initialise()
+    for _ in range(10):
+        s.step()
+        o.step()
+    s.pull()
+    fluid, wall = pas
+    rf, rw = o.pas
+    for f, tol in (('x', 2e-7), ('y', 2e-7), ('u', 5e-6), ('v', 5e-6), ('p', 5e-5), ('rho', 2e-6)):
+        r = rf.properties[f]
+        scale = max(np.max(np.abs(r)), 1.0 if f in 'xy' else 1e-12)
+        err = np.max(np.abs(fluid.properties[f] - r)) / scale
+        _record('ext_10steps', f, float(err))
+        assert err <= tol, (f, err)
+    assert np.max(np.abs(wall.p - rw.p)) <= 5e-5 * max(np.max(np.abs(rw.p)), 1e-12)
+
+
 def _channel(nx=20, ny=12, layers=3):
     """A 2-D channel: fluid between two three-layer walls, the upper one moving (Couette flow,
     pysph/examples/couette.py), with a small perturbation of the lattice."""
@@ -369,5 +473,5 @@ def test_edac_setup_errors(gpu_device):
         pb.EDACScheme(['fluid'], [], dim=2, c0=10., nu=0.01, rho0=1., pb=100., h=0.01,
                       inviscid_solids=['wall']).get_equations()
     with pytest.raises(NotImplementedError):
-        pb.EDACScheme(['fluid'], [], dim=2, c0=10., nu=0.01, rho0=1., pb=0.0,
-                      h=0.01).get_equations()
+        pb.EDACScheme(['fluid'], [], dim=2, c0=10., nu=0.01, rho0=1., pb=0.0, h=0.01,
+                      inlet_outlet_manager=object()).get_equations()

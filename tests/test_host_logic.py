@@ -281,6 +281,27 @@ def test_edac_program_and_scheme():
     with pytest.raises(NotImplementedError):
         pb.EDACScheme(['f'], [], dim=2, c0=10., nu=0.01, rho0=1., pb=100., h=0.01,
                       inviscid_solids=['wall']).get_equations()
+    # the external-flow branch (pb == 0, wc/edac.py:882-971): EDACStep, the number-density
+    # MomentumEquation and XSPHCorrection -- names the WCSPH scheme has too; inside an EDAC
+    # Group they are the EDAC kernels' equations
+    sch = pb.EDACScheme(['f'], ['w1'], dim=2, c0=10., nu=0.01, rho0=1., pb=0.0, h=0.01,
+                        alpha=0.2, eps=0.4, clamp_p=True, gy=-1.0, tdamp=0.5)
+    assert [type(s_).__name__ for s_ in sch.get_steppers().values()] == ['EDACStep']
+    ops = build_program(sch.get_equations(), ['f', 'w1'], 2)
+    assert [o[0] for o in ops] == ['tvf']
+    P = ops[0][1]
+    assert (P.passes, P.fluid_mask, P.solid_mask, P.bql, P.clamp_p) == (3, 1, 2, 0, 1)
+    assert P.eqbits == L.TVF_MOM | L.TVF_AV | L.TVF_VISC | L.TVF_NOSLIP | L.TVF_EDAC | L.TVF_XSPH
+    assert (P.eps_xsph, P.gy, P.tdamp, P.c0, P.pb) == (0.4, -1.0, 0.5, 10.0, 0.0)
+    with pytest.raises(NotImplementedError):     # XSPH over another array than the fluid itself
+        g2 = sch.get_equations()[1]
+        g2.equations[-1].sources = ['f', 'w1']
+        build_program([g2], ['f', 'w1'], 2)
+    # the WCSPH Group with the same two names still goes to the pair kernel
+    ops = build_program([pb.Group([pb.MomentumEquation('f', ['f'], c0=1.0, alpha=0.1),
+                                   pb.XSPHCorrection('f', ['f'])])], ['f'], 2)
+    assert ops[0][0] == 'pair'
+    pb.PECIntegrator(f=pb.EDACStep())
     # steppers: EDACTVFStep is accepted, unknown ones are not
     pb.PECIntegrator(f1=pb.EDACTVFStep(), f2=pb.EDACTVFStep())
     with pytest.raises(NotImplementedError):

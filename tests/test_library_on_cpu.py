@@ -120,6 +120,10 @@ FAST = [
     ('test_gpu_edac', 'test_edac_setup_errors', {}),
     ('test_gpu_edac', 'test_edac_channel_with_walls_steps_vs_oracle', {}),
     ('test_gpu_edac', 'test_edac_periodic_channel_with_walls_vs_oracle', {}),
+    ('test_gpu_edac', 'test_edac_step_matches_reference_bodies', {}),
+    ('test_gpu_edac', 'test_edac_external_flow_steps_vs_oracle', {}),
+] + [('test_gpu_edac', 'test_edac_external_flow_evaluation_matches_reference_bodies', {'idx': i})
+     for i in range(4)] + [
 ] + [('test_gpu_edac', 'test_edac_solid_wall_evaluation_matches_reference_bodies', {'idx': i})
      for i in range(4)] + [('test_gpu_solid', 'test_elastic_evaluation_matches_reference_bodies', {'idx': i})
      for i in range(6)] + [
