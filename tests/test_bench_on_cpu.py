@@ -198,3 +198,5 @@ def test_bench_two_ranks_on_the_emulated_library(emulated_library, argv):  # noq
         dev = d['developed']
         assert dev['value'] > 0 and dev['full_builds'] >= 1, dev
         assert d['launches_per_step'] > 0
+        # the disturbed-run guard: the keys exist; on a quiet run nothing was taken again
+        assert d['host_loop_ms_per_step'] > 0 and 'remeasured' in d
