@@ -89,7 +89,8 @@ enum {
     B200SPH_EQ_CONTINUITY = 2,        /* basic_equations.py:180-192 */
     B200SPH_EQ_MOMENTUM = 4,          /* wc/basic.py:129-269        */
     B200SPH_EQ_XSPH = 8,              /* basic_equations.py:260-300 */
-    B200SPH_EQ_MONAGHAN_AV = 16       /* basic_equations.py:195-257 */
+    B200SPH_EQ_MONAGHAN_AV = 16,      /* basic_equations.py:195-257 */
+    B200SPH_EQ_LAMINAR = 32           /* LaminarViscosity wc/viscosity.py:5-27: WCSPHScheme(nu != 0), scheme.py:486-496 */
 };
 
 /* One Group's pair loops (acceleration_eval_cython.mako:10-154) after the
@@ -102,6 +103,7 @@ typedef struct {
     double c0, alpha, beta;     /* MomentumEquation / MonaghanArtificialViscosity */
     double gx, gy, gz;          /* MomentumEquation body force               */
     double eps_xsph;            /* XSPHCorrection(eps=...)                   */
+    double nu, eta;             /* LaminarViscosity(nu, eta = 0.01) (ABI 5: appended) */
 } b200sph_pair_program;
 
 /* pair-equation bits of the EDAC scheme's momentum group */

@@ -294,6 +294,32 @@ def gen_wcsph_case(kernels, basic, wc, kernel_name, dim, seed, hvar=0.0,
                 outputs=arrays)
 
 
+def gen_laminar_case(kernels, basic, wc, kernel_name, dim, seed, nu=0.05, hvar=0.0):
+    """WCSPHScheme(nu != 0) (scheme.py:486-496): the WCSPH Group with LaminarViscosity
+    (wc/viscosity.py:5-27) inserted before XSPHCorrection, through the reference's bodies."""
+    visc = _load('pysph.sph.wc.viscosity', os.path.join(REF, 'pysph/sph/wc/viscosity.py'))
+    case = gen_wcsph_case(kernels, basic, wc, kernel_name, dim, seed, hvar=hvar)
+    arrays = json.loads(json.dumps(case['inputs']))
+    kernel = getattr(kernels, kernel_name)(dim=dim)
+    p = case['params']
+    fluids, solids = ['fluid'], ['boundary', 'obstacle']
+    all_ = fluids + solids
+    g1 = [wc.TaitEOS(dest=f, sources=None, rho0=p['rho0'], c0=p['c0'], gamma=p['gamma']) for f in fluids]
+    g1 += [wc.TaitEOSHGCorrection(dest=s_, sources=None, rho0=p['rho0'], c0=p['c0'],
+                                  gamma=p['gamma']) for s_ in solids]
+    g2 = [basic.ContinuityEquation(dest=s_, sources=fluids) for s_ in solids]
+    for f in fluids:
+        g2.append(basic.ContinuityEquation(dest=f, sources=all_))
+        g2.append(wc.MomentumEquation(dest=f, sources=all_, c0=p['c0'], alpha=p['alpha'],
+                                      beta=p['beta'], gx=p['gx'], gy=p['gy'], gz=p['gz'],
+                                      tensile_correction=False))
+        g2.append(visc.LaminarViscosity(dest=f, sources=all_, nu=nu))
+        g2.append(basic.XSPHCorrection(dest=f, sources=[f]))
+    evaluate_reference(kernel, arrays, [(False, g1), (True, g2)])
+    params = dict(p, nu=nu, eta=0.01)
+    return dict(kernel=kernel_name, dim=dim, params=params, inputs=case['inputs'], outputs=arrays)
+
+
 def gen_monaghan_av_case(kernels, basic, wc, kernel_name, dim, seed, hvar=0.0):
     """The stand-alone artificial viscosity (basic_equations.py:195-257): a Group in which
     the fluid's velocity change comes from MonaghanArtificialViscosity alone (no
@@ -837,6 +863,11 @@ def gen_density_1d(kernels, basic):
     return dict(x=x, h=a['h'], m=a['m'], rho=a['rho'], nbr_counts=counts)
 
 
+def gen_laminar_cases(kernels, basic, wc):
+    return [gen_laminar_case(kernels, basic, wc, 'CubicSpline', 3, 121),
+            gen_laminar_case(kernels, basic, wc, 'WendlandQuintic', 2, 122, nu=0.2, hvar=0.1)]
+
+
 def gen_edac_wall_cases(kernels, edac):
     return [
         gen_edac_wall_case(kernels, edac, 'QuinticSpline', 2, 401, gy=-1.0),
@@ -848,6 +879,12 @@ def gen_edac_wall_cases(kernels, edac):
 
 
 def main():
+    if sys.argv[1:] == ['laminar']:
+        kernels, basic, wc, steps, c_kernels = load_reference()
+        with open(os.path.join(GOLD, 'laminar_cases.json'), 'w') as f:
+            json.dump(gen_laminar_cases(kernels, basic, wc), f)
+        print('wrote laminar_cases.json', os.path.getsize(os.path.join(GOLD, 'laminar_cases.json')), 'bytes')
+        return
     if sys.argv[1:] == ['edac_ext']:            # only the files added last
         kernels, basic, wc, steps, c_kernels = load_reference()
         tvf, edac = load_reference_edac()
@@ -887,6 +924,7 @@ def main():
         gen_wcsph_case(kernels, basic, wc, 'Gaussian', 3, 106),
     ]
     dump('wcsph_cases.json', cases)
+    dump('laminar_cases.json', gen_laminar_cases(kernels, basic, wc))
     dump('monaghan_av_cases.json', [
         gen_monaghan_av_case(kernels, basic, wc, 'CubicSpline', 3, 111),
         gen_monaghan_av_case(kernels, basic, wc, 'WendlandQuintic', 2, 112, hvar=0.1),

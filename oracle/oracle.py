@@ -27,7 +27,7 @@ LIB = os.path.join(HERE, 'liboracle.so')
 MAX_ARRAYS = 8
 K_IDS = {'CubicSpline': 0, 'WendlandQuintic': 1, 'QuinticSpline': 2,
          'Gaussian': 3}
-EQ_SUMDENS, EQ_CONT, EQ_MOM, EQ_XSPH, EQ_AV = 1, 2, 4, 8, 16
+EQ_SUMDENS, EQ_CONT, EQ_MOM, EQ_XSPH, EQ_AV, EQ_LAMINAR = 1, 2, 4, 8, 16, 32
 
 _PTR_FIELDS = ['x', 'y', 'z', 'h', 'm', 'rho', 'u', 'v', 'w', 'p', 'cs',
                'arho', 'au', 'av', 'aw', 'ax', 'ay', 'az', 'dt_cfl',
@@ -59,7 +59,8 @@ class OrcPairProgram(C.Structure):
                 ('real_only', C.c_int),
                 ('eqmask', (C.c_uint32 * MAX_ARRAYS) * MAX_ARRAYS),
                 ('src_order', (C.c_int * MAX_ARRAYS) * MAX_ARRAYS),
-                ('dest_order', C.c_int * MAX_ARRAYS)]
+                ('dest_order', C.c_int * MAX_ARRAYS),
+                ('nu', C.c_double), ('eta', C.c_double)]
 
 
 class OrcTvfProgram(C.Structure):
@@ -256,9 +257,10 @@ class Oracle(object):
 
     def pair_pass(self, eqs, real_only=True, c0=0.0, alpha=0.0, beta=0.0,
                   gx=0.0, gy=0.0, gz=0.0, tensile_correction=False,
-                  eps_xsph=0.5):
+                  eps_xsph=0.5, nu=0.0, eta=0.01):
         """eqs: list of (bit, dest_index, [source indices]) in user order."""
         P = OrcPairProgram()
+        P.nu, P.eta = nu, eta
         P.kernel, P.dim = self.kid, self.dim
         P.c0, P.alpha, P.beta = c0, alpha, beta
         P.gx, P.gy, P.gz = gx, gy, gz
@@ -533,12 +535,15 @@ class WCSPHOracleSolver(object):
             if not p.get('summation_density', False):
                 eqs.append((EQ_CONT, f, self.all))
             eqs.append((EQ_MOM, f, self.all))
+            if abs(p.get('nu', 0.0)) > 1e-14:        # scheme.py:486-496: before XSPH
+                eqs.append((EQ_LAMINAR, f, self.all))
             eqs.append((EQ_XSPH, f, [f]))
         pairs += o.pair_pass(
             eqs, real_only=True, c0=p['c0'], alpha=p.get('alpha', 0.1),
             beta=p.get('beta', 0.0), gx=p.get('gx', 0.0), gy=p.get('gy', 0.0),
             gz=p.get('gz', 0.0),
-            tensile_correction=p.get('tensile_correction', False), eps_xsph=0.5)
+            tensile_correction=p.get('tensile_correction', False), eps_xsph=0.5,
+            nu=p.get('nu', 0.0))
         if p.get('update_h', False):
             for f in self.fluids:
                 o.ferrari_h(f, p['hdx'], self.dim, real_only=False)

@@ -590,7 +590,7 @@ int64_t orc_pair_pass(orc_ctx *c, const orc_pair_program *P)
                     double RIJ = sqrt(R2IJ);
                     double HIJ = 0.5 * (D->h[d_idx] + S->h[s_idx]);
                     double WIJ = 0.0, RHOIJ1 = 0.0, EPS = 0.01 * HIJ * HIJ;
-                    if (bits & (ORC_EQ_CONT | ORC_EQ_MOM | ORC_EQ_XSPH | ORC_EQ_AV)) {
+                    if (bits & (ORC_EQ_CONT | ORC_EQ_MOM | ORC_EQ_XSPH | ORC_EQ_AV | ORC_EQ_LAMINAR)) {
                         VIJ[0] = D->u[d_idx] - S->u[s_idx];
                         VIJ[1] = D->v[d_idx] - S->v[s_idx];
                         VIJ[2] = D->w[d_idx] - S->w[s_idx];
@@ -601,7 +601,7 @@ int64_t orc_pair_pass(orc_ctx *c, const orc_pair_program *P)
                     }
                     if (bits & (ORC_EQ_SUMDENS | ORC_EQ_MOM | ORC_EQ_XSPH))
                         WIJ = k_w(kernel, dim, kfac, RIJ, HIJ);
-                    if (bits & (ORC_EQ_CONT | ORC_EQ_MOM | ORC_EQ_AV))
+                    if (bits & (ORC_EQ_CONT | ORC_EQ_MOM | ORC_EQ_AV | ORC_EQ_LAMINAR))
                         k_grad(kernel, dim, kfac, XIJ, RIJ, HIJ, DWIJ);
 
                     /* equations in user order (scheme.py:452-483: Continuity,
@@ -666,6 +666,15 @@ int64_t orc_pair_pass(orc_ctx *c, const orc_pair_program *P)
                         D->au[d_idx] += -S->m[s_idx] * piij * DWIJ[0];
                         D->av[d_idx] += -S->m[s_idx] * piij * DWIJ[1];
                         D->aw[d_idx] += -S->m[s_idx] * piij * DWIJ[2];
+                    }
+                    if (bits & ORC_EQ_LAMINAR) {
+                        /* wc/viscosity.py:12-27 (inserted before XSPH, scheme.py:496) */
+                        const double rhoa = D->rho[d_idx], rhob = S->rho[s_idx];
+                        const double Fij = DWIJ[0] * XIJ[0] + DWIJ[1] * XIJ[1] + DWIJ[2] * XIJ[2];
+                        const double tmp = S->m[s_idx] * 4 * P->nu * Fij / ((rhoa + rhob) * (R2IJ + P->eta * HIJ * HIJ));
+                        D->au[d_idx] += tmp * VIJ[0];
+                        D->av[d_idx] += tmp * VIJ[1];
+                        D->aw[d_idx] += tmp * VIJ[2];
                     }
                     if (bits & ORC_EQ_XSPH) {
                         /* basic_equations.py:290-295 */

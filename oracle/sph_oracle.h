@@ -37,7 +37,8 @@ enum {
     ORC_EQ_CONT    = 2,   /* ContinuityEquation        basic_equations.py:180-192 */
     ORC_EQ_MOM     = 4,   /* MomentumEquation          wc/basic.py:129-269        */
     ORC_EQ_XSPH    = 8,   /* XSPHCorrection            basic_equations.py:260-300 */
-    ORC_EQ_AV      = 16   /* MonaghanArtificialViscosity basic_equations.py:195-257 */
+    ORC_EQ_AV      = 16,  /* MonaghanArtificialViscosity basic_equations.py:195-257 */
+    ORC_EQ_LAMINAR = 32   /* LaminarViscosity          wc/viscosity.py:5-27 (WCSPHScheme(nu != 0), scheme.py:486-496) */
 };
 
 /* borrowed host pointers to one ParticleArray's fp64 SoA properties
@@ -75,6 +76,8 @@ typedef struct {
     int src_order[ORC_MAX_ARRAYS][ORC_MAX_ARRAYS];
     /* dest_order[k]: k-th destination array; -1 terminates */
     int dest_order[ORC_MAX_ARRAYS];
+    /* LaminarViscosity(nu, eta) */
+    double nu, eta;
 } orc_pair_program;
 
 /* EDAC scheme, internal-flow (transport velocity) branch for fluid arrays without

@@ -25,7 +25,7 @@ from .particle_array import (ParticleArray, get_particle_array,
                              get_particle_array_edac_wall, get_particle_array_edac_ext,
                              get_particle_array_elastic_dynamics)
 from .kernels import CubicSpline, WendlandQuintic, QuinticSpline, Gaussian
-from .equations import (Equation, Group, SummationDensity, ContinuityEquation,
+from .equations import (Equation, Group, SummationDensity, ContinuityEquation, LaminarViscosity,
                         MonaghanArtificialViscosity, XSPHCorrection, TaitEOS,
                         TaitEOSHGCorrection, MomentumEquation,
                         UpdateSmoothingLengthFerrari)

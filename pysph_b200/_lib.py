@@ -48,6 +48,7 @@ EQ_CONTINUITY = 2
 EQ_MOMENTUM = 4
 EQ_XSPH = 8
 EQ_MONAGHAN_AV = 16
+EQ_LAMINAR = 32
 
 HALO_FIELDS = 9
 MIGRATE_FIELDS = 17
@@ -60,7 +61,7 @@ class PairProgram(C.Structure):
                 ('tensile_correction', C.c_int32),
                 ('c0', C.c_double), ('alpha', C.c_double), ('beta', C.c_double),
                 ('gx', C.c_double), ('gy', C.c_double), ('gz', C.c_double),
-                ('eps_xsph', C.c_double)]
+                ('eps_xsph', C.c_double), ('nu', C.c_double), ('eta', C.c_double)]
 
 
 TVF_PGRAD, TVF_AV, TVF_VISC, TVF_ASTRESS, TVF_EDAC, TVF_NOSLIP = 1, 2, 4, 8, 16, 32

@@ -2085,6 +2085,7 @@ int b200sph_pair_pass(b200sph_ctx *ctx, const b200sph_pair_program *prog, int64_
     pa.c0 = (float)prog->c0; pa.alpha = (float)prog->alpha; pa.beta = (float)prog->beta;
     pa.gx = (float)prog->gx; pa.gy = (float)prog->gy; pa.gz = (float)prog->gz;
     pa.eps_xsph = (float)prog->eps_xsph;
+    pa.nu4 = (float)(4.0 * prog->nu); pa.eta = (float)prog->eta;
     pa.tensile = prog->tensile_correction;
     pa.real_only = prog->real_only;
     // the WCSPH scheme's Group (continuity + momentum + XSPH, no tensile correction) has a

@@ -19,6 +19,7 @@ struct PairArgs {
     float deltap;
     unsigned long long emask[B200SPH_MAX_ARRAYS];  // per dest type: 8 bits per source type
     float c0, alpha, beta, gx, gy, gz, eps_xsph;
+    float nu4, eta;             // LaminarViscosity: 4 nu, eta
     int tensile, real_only;
     unsigned long long *pair_counter;  // may be null
     // Group(start_idx, stop_idx): destinations [dlo, dhi) of every array, as indices INTO the
@@ -72,7 +73,7 @@ __device__ __forceinline__ void pair_body(const PairArgs &a, const float4 qv, co
     if (bits & B200SPH_EQ_SUMMATION_DENSITY) acc.rsum += mj * wij;  // basic_equations.py:28-29
     if (bits & B200SPH_EQ_CONTINUITY)                              // basic_equations.py:190-192
         acc.arho += mj * gt * vdotx;
-    if (bits & (B200SPH_EQ_MOMENTUM | B200SPH_EQ_MONAGHAN_AV | B200SPH_EQ_XSPH)) {
+    if (bits & (B200SPH_EQ_MOMENTUM | B200SPH_EQ_MONAGHAN_AV | B200SPH_EQ_XSPH | (EQS & B200SPH_EQ_LAMINAR))) {
         const float rhoij1 = frcp(0.5f * (Ci.x + Cj.x));
         // wc/basic.py:215-222, basic_equations.py:245-252 (vdotx < 0 only); branch-free: in a
         // warp some lane almost always takes it, and a select is cheaper than a
@@ -105,6 +106,13 @@ __device__ __forceinline__ void pair_body(const PairArgs &a, const float4 qv, co
             acc.au += f * xij;
             acc.av += f * yij;
             acc.aw += f * zij;
+        }
+        if ((EQS & B200SPH_EQ_LAMINAR) && (bits & B200SPH_EQ_LAMINAR)) {  // wc/viscosity.py:12-27
+            // Fij = DWIJ . XIJ = gt r^2
+            const float f = mj * a.nu4 * (gt * r2) * frcp((Ci.x + Cj.x) * (r2 + a.eta * hij * hij));
+            acc.au += f * uij;
+            acc.av += f * vij;
+            acc.aw += f * wwij;
         }
         if (bits & B200SPH_EQ_XSPH) {  // basic_equations.py:290-295
             const float f = -a.eps_xsph * mj * wij * rhoij1;
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(const PairArgs a)
                 a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
                 a.dt_cfl[g] = acc.cfl;
                 a.dt_force[g] = fu * fu + fv * fv + fw * fw;
-            } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
+            } else if (all_bits & (B200SPH_EQ_MONAGHAN_AV | B200SPH_EQ_LAMINAR)) {
                 a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
             }
             if (all_bits & B200SPH_EQ_XSPH) {

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(LIST_NT, MINB) k_pair_list(const PairArgs a, c
             a.au[g] = fu; a.av[g] = fv; a.aw[g] = fw;
             a.dt_cfl[g] = acc.cfl;
             a.dt_force[g] = fu * fu + fv * fv + fw * fw;
-        } else if (all_bits & B200SPH_EQ_MONAGHAN_AV) {
+        } else if (all_bits & (B200SPH_EQ_MONAGHAN_AV | B200SPH_EQ_LAMINAR)) {
             a.au[g] = acc.au; a.av[g] = acc.av; a.aw[g] = acc.aw;
         }
         if (all_bits & B200SPH_EQ_XSPH) {

@@ -83,6 +83,15 @@ class XSPHCorrection(Equation):
         super(XSPHCorrection, self).__init__(dest, sources)
 
 
+class LaminarViscosity(Equation):
+    """pysph/sph/wc/viscosity.py:5-27 (WCSPHScheme(nu != 0), scheme.py:486-496)"""
+
+    def __init__(self, dest, sources, nu, eta=0.01):
+        self.nu = nu
+        self.eta = eta
+        super(LaminarViscosity, self).__init__(dest, sources)
+
+
 class TaitEOS(Equation):
     """pysph/sph/wc/basic.py:9-65"""
 

@@ -21,6 +21,7 @@ PAIR_EQUATIONS = {
     'MomentumEquation': _lib.EQ_MOMENTUM,
     'XSPHCorrection': _lib.EQ_XSPH,
     'MonaghanArtificialViscosity': _lib.EQ_MONAGHAN_AV,
+    'LaminarViscosity': _lib.EQ_LAMINAR,          # WCSPHScheme(nu != 0), scheme.py:486-496
 }
 NO_SOURCE_EQUATIONS = ('TaitEOS', 'TaitEOSHGCorrection',
                        'UpdateSmoothingLengthFerrari')
@@ -598,9 +599,12 @@ def _leaf_body(g, index, arrays, particle_arrays):
                     _set_once(params, k, float(getattr(eq, k)), eq)
             elif name == 'XSPHCorrection':
                 _set_once(params, 'eps_xsph', float(eq.eps), eq)
+            elif name == 'LaminarViscosity':
+                _set_once(params, 'nu', float(eq.nu), eq)
+                _set_once(params, 'eta', float(getattr(eq, 'eta', 0.01)), eq)
         if (all_bits & _lib.EQ_SUMMATION_DENSITY) and (
                 all_bits & (_lib.EQ_MOMENTUM | _lib.EQ_XSPH |
-                            _lib.EQ_MONAGHAN_AV)):
+                            _lib.EQ_MONAGHAN_AV | _lib.EQ_LAMINAR)):
             raise NotImplementedError(
                 'B200 backend: SummationDensity (writes rho) cannot share a '
                 'Group with equations that read rho; the reference '

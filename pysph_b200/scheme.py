@@ -3,12 +3,12 @@
 Restates the equation assembly of pysph/sph/scheme.py:388-506
 (``WCSPHScheme.get_equations``) for the options the hot path covers
 (``hg_correction``, ``update_h``, ``summation_density``,
-``tensile_correction``); ``delta_sph`` and ``nu != 0`` belong to equation
-families outside SURVEY.md section 8 and raise.
+``tensile_correction``, ``nu != 0`` -> ``LaminarViscosity``); ``delta_sph`` (gradient
+correction + density diffusion) has no kernels and raises.
 """
 from .equations import (Group, SummationDensity, TaitEOS, TaitEOSHGCorrection,
                         ContinuityEquation, MomentumEquation, XSPHCorrection,
-                        UpdateSmoothingLengthFerrari)
+                        LaminarViscosity, UpdateSmoothingLengthFerrari)
 
 
 class WCSPHScheme(object):
@@ -16,10 +16,11 @@ class WCSPHScheme(object):
                  gx=0.0, gy=0.0, gz=0.0, alpha=0.1, beta=0.0, delta=0.1,
                  nu=0.0, tensile_correction=False, hg_correction=False,
                  update_h=False, delta_sph=False, summation_density=False):
-        if delta_sph or abs(nu) > 1e-14:
+        if delta_sph:
             raise NotImplementedError(
-                'B200 backend: delta_sph / laminar viscosity are outside the '
-                'WCSPH hot path (SURVEY.md section 8)')
+                'B200 backend: delta_sph (gradient correction + density diffusion, '
+                'scheme.py:431-447) has no kernels')
+        self.nu = nu
         self.fluids = list(fluids)
         self.solids = list(solids)
         self.dim = dim
@@ -65,6 +66,8 @@ class WCSPHScheme(object):
                 beta=self.beta, gx=self.gx, gy=self.gy, gz=self.gz,
                 tensile_correction=self.tensile_correction))
             g2.append(XSPHCorrection(dest=f, sources=[f]))
+            if abs(self.nu) > 1e-14:            # scheme.py:486-496: g2.insert(-1, eq)
+                g2.insert(-1, LaminarViscosity(dest=f, sources=all_, nu=self.nu))
         equations.append(Group(g2))
 
         if self.update_h:

@@ -552,6 +552,41 @@ def test_device_resident_dt_is_bitwise_the_host_path(gpu_device):
 
 
 @pytest.mark.parametrize('idx', range(2))
+def test_laminar_viscosity_vs_reference_bodies(gpu_device, idx):
+    """WCSPHScheme(nu != 0): the WCSPH Group with LaminarViscosity (wc/viscosity.py:5-27,
+    scheme.py:486-496) against the outputs of the reference's bodies (laminar_cases.json)."""
+    import pysph_b200 as pb
+    case = load_golden('laminar_cases.json')[idx]
+    p = wcsph_params_from_case(case)
+    pas = arrays_from_dict(case['inputs'])
+    s = make_solver(pas, dict(scheme_params(p), nu=p['nu']), case['kernel'])
+    names = [type(e).__name__ for e in s.a_eval.equation_groups[-1].equations]
+    assert names[-2:] == ['LaminarViscosity', 'XSPHCorrection']      # inserted before XSPH
+    s.a_eval.count_pairs = True
+    s.a_eval.compute(0.0, 0.0)
+    s.pull()
+    opas = arrays_from_dict(case['inputs'])
+    osol = orc.WCSPHOracleSolver(opas, p, case['kernel'])
+    assert s.a_eval.last_pairs == osol.evaluate()
+    visc_seen = False
+    for pa, opa in zip(pas, opas):
+        ref = case['outputs'][pa.name]
+        nr = ref['_n_real']
+        for f in ACC_FIELDS:
+            want = np.array(ref[f])[:nr]
+            got = pa.properties[f][:nr]
+            if np.max(np.abs(want)) == 0.0:
+                assert np.max(np.abs(got)) == 0.0, (pa.name, f)
+                continue
+            assert rel_err(got, want) <= TOL_EVAL, (pa.name, f, rel_err(got, want))
+    # the viscous term is not lost in the tolerance: without it au differs by far more
+    inv = load_golden('wcsph_cases.json')[0 if idx == 0 else 2]
+    if idx == 0:
+        d = np.array(case['outputs']['fluid']['au']) - np.array(inv['outputs']['fluid']['au'])
+        assert np.max(np.abs(d)) > 1e-3 * np.max(np.abs(case['outputs']['fluid']['au']))
+
+
+@pytest.mark.parametrize('idx', range(2))
 def test_monaghan_av_vs_reference_bodies(gpu_device, idx):
     """The B200SPH_EQ_MONAGHAN_AV branch of pair_body: a Group with ContinuityEquation,
     stand-alone MonaghanArtificialViscosity (basic_equations.py:195-257) and

@@ -53,7 +53,8 @@ def test_product_does_not_import_oracle():
 
 def test_struct_layouts_match_header():
     # sizes implied by include/b200sph.h (x86-64 SysV)
-    assert C.sizeof(_lib.PairProgram) == 8 * 8 * 4 + 2 * 4 + 7 * 8
+    assert C.sizeof(_lib.PairProgram) == 8 * 8 * 4 + 2 * 4 + 9 * 8
+    assert C.sizeof(_lib.TvfProgram) == 4 * 4 + 11 * 8 + 2 * 4 + 8
     assert C.sizeof(_lib.GridInfo) == 8 + 8 + 24 + 24 + 12 + 4 + 8 + 8
     assert C.sizeof(_lib.Stats) == 3 * 8 + 17 * 8
     ids = _lib.PROP_IDS
@@ -78,6 +79,16 @@ def test_wcsph_scheme_equations_order():
         ('ContinuityEquation', 'fluid', ['fluid', 'boundary', 'obstacle']),
         ('MomentumEquation', 'fluid', ['fluid', 'boundary', 'obstacle']),
         ('XSPHCorrection', 'fluid', ['fluid'])]
+    # nu != 0: LaminarViscosity inserted before XSPH (scheme.py:486-496); delta_sph has no kernels
+    s = pb.WCSPHScheme(['fluid'], ['boundary'], dim=3, rho0=1000.0, c0=32.85, h0=0.026, hdx=1.3,
+                       nu=1e-3)
+    g2 = [(e.name, e.sources) for e in s.get_equations()[1].equations]
+    assert g2[-2:] == [('LaminarViscosity', ['fluid', 'boundary']), ('XSPHCorrection', ['fluid'])]
+    ops = build_program(s.get_equations(), ['fluid', 'boundary'], 3)
+    prog = [o for o in ops if o[0] == 'pair'][0][1]
+    assert prog.eqmask[0][1] & _lib.EQ_LAMINAR and prog.nu == 1e-3 and prog.eta == 0.01
+    with pytest.raises(NotImplementedError):
+        pb.WCSPHScheme(['fluid'], [], dim=3, rho0=1000.0, c0=32.85, h0=0.026, hdx=1.3, delta_sph=True)
     with pytest.raises(NotImplementedError):
         pb.WCSPHScheme(['f'], [], dim=2, rho0=1, c0=1, h0=1, hdx=1, delta_sph=True)
 

@@ -107,6 +107,7 @@ FAST = [
     ('test_gpu_parity', 'test_push_pull_roundtrip_and_errors', {}),
 ] + [('test_gpu_parity', 'test_wcsph_evaluation_vs_reference_bodies', {'idx': i}) for i in range(6)] + [
     ('test_gpu_parity', 'test_monaghan_av_vs_reference_bodies', {'idx': i}) for i in range(2)] + [
+    ('test_gpu_parity', 'test_laminar_viscosity_vs_reference_bodies', {'idx': i}) for i in range(2)] + [
     ('test_gpu_periodic', 'test_periodic_lattice_density', {'dim': d, 'n': n, 'shift': sh})
     for d, n in ((1, 20), (2, 10), (3, 5)) for sh in (0.0, 0.35)
 ] + [
