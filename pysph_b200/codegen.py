@@ -262,24 +262,30 @@ class Translator(ast.NodeVisitor):
         self.fail(s, 'statement %s' % type(s).__name__)
 
     def declare(self, s, t, v):
-        if not (isinstance(t, ast.Name) and v.args and isinstance(v.args[0], ast.Constant)):
+        """``x = declare('matrix(3)')``, ``i, j = declare('int', 2)`` (equation.py: the
+        reference's type declarations for its C translation)."""
+        if isinstance(t, ast.Tuple) and all(isinstance(e, ast.Name) for e in t.elts):
+            names = [e.id for e in t.elts]
+        elif isinstance(t, ast.Name):
+            names = [t.id]
+        else:
+            self.fail(s, 'declare(...) target')
+        if not (v.args and isinstance(v.args[0], ast.Constant) and isinstance(v.args[0].value, str)):
             self.fail(s, 'declare(...)')
         kind = v.args[0].value.replace(' ', '')
-        names = [t.id]
-        if kind.startswith('matrix('):
-            dims = kind[len('matrix('):-1].strip('()').split(',')
-            size = 1
-            for d in dims:
-                if d:
-                    size *= int(d)
-            for nme in names:
+        for nme in names:
+            if kind.startswith('matrix('):
+                size = 1
+                for d in kind[len('matrix('):-1].strip('()').split(','):
+                    if d:
+                        size *= int(d)
                 self.locals[nme] = 'double %s[%d] = {0.0};' % (nme, size)
-        elif kind in ('double', 'float'):
-            self.locals[t.id] = 'double %s = 0.0;' % t.id
-        elif kind in ('int', 'long', 'unsignedint'):
-            self.locals[t.id] = 'long long %s = 0;' % t.id
-        else:
-            self.fail(s, 'declare(%r)' % kind)
+            elif kind in ('double', 'float'):
+                self.locals[nme] = 'double %s = 0.0;' % nme
+            elif kind in ('int', 'long', 'unsignedint'):
+                self.locals[nme] = 'long long %s = 0;' % nme
+            else:
+                self.fail(s, 'declare(%r)' % kind)
         return []
 
     def translate(self):
@@ -316,10 +322,9 @@ def translate_helper(fn, helpers):
     except (OSError, TypeError):
         raise NotImplementedError('B200 generic equations: no Python source for helper %r' % fn)
 
-    class _Owner(object):
+    class helper(object):           # (names the function in the translator's error messages)
         pass
-    t = Translator(_Owner(), fn.__name__, None, 'helper', helpers)
-    t.eq.__class__.__name__ = 'helper'
+    t = Translator(helper(), fn.__name__, None, 'helper', helpers)
     args = [a.arg for a in node.args.args]
     t.args = args
     defaults = [None] * (len(args) - len(node.args.defaults)) + list(node.args.defaults)

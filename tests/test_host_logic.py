@@ -459,3 +459,18 @@ def test_generic_equations_translate_and_compile_with_nvrtc():
                       kernel=pb.CubicSpline(dim=3))
     with pytest.raises(NotImplementedError):       # no kernel object, no generated code
         build_program([SimpleEquation('fluid', ['fluid'])], names, 3)
+    # the reference's type declarations, several names at once
+    ops = build_program([_Declares('fluid', ['fluid'])], names, 3, kernel=pb.CubicSpline(dim=3))
+    src = ops[0][1].source
+    assert 'long long i = 0;' in src and 'long long j = 0;' in src and 'double acc[3] = {0.0};' in src
+    assert codegen.compile_image(src)[:4] == b'\x7fELF'
+
+
+class _Declares(pb.Equation):
+    def loop(self, d_idx, s_idx, d_au, s_m, XIJ):
+        i, j = declare('int', 2)
+        acc = declare('matrix(3)')
+        for i in range(3):
+            for j in range(3):
+                acc[i] += XIJ[j] * s_m[s_idx]
+        d_au[d_idx] += acc[0] + acc[1] + acc[2]
