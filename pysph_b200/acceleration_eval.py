@@ -30,6 +30,19 @@ class B200AccelerationEval(object):
         self.ops = build_program(equations, self.backend.names, kernel.dim,
                                  particle_arrays=self.particle_arrays, kernel=kernel,
                                  generic=self._generic_props)
+        # generated kernels address properties by NAME through the base table (x .. dt_force) and
+        # the user properties: an array whose scheme keeps a name elsewhere (the EDAC fluids'
+        # evolved p, a wall's ug ...) or a scheme-owned extension property would be aliased
+        from ._lib import PROP_IDS
+        base = set(codegen.F64_NAMES) | set(codegen.F32_NAMES) | set(codegen.U32_NAMES)
+        for name in sorted(self._generic_props.used):
+            for i, ids in enumerate(self.backend.prop_ids):
+                if name in ids and name not in self.backend.user_props and \
+                        (name not in base or ids[name] != PROP_IDS[name]):
+                    raise NotImplementedError(
+                        'B200 generic equations: property %r of array %r belongs to a hand-written '
+                        'scheme (device id %d); generated kernels can only use the WCSPH base '
+                        'properties and their own' % (name, self.backend.names[i], ids[name]))
         # properties the generated kernels use beyond the pool's own
         for name in self._generic_props.user:
             self.backend.add_user_property(name)

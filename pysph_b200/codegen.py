@@ -352,8 +352,10 @@ class PropertyTable(object):
 
     def __init__(self, user_names=None):
         self.user = list(user_names or [])
+        self.used = set()          # every property name a generated body mentions
 
     def pointer(self, name):
+        self.used.add(name)
         if name in F64_NAMES:
             return 'a.f64[%d]' % F64_NAMES.index(name)
         if name in F32_NAMES:

@@ -504,7 +504,10 @@ def _leaf_body(g, index, arrays, particle_arrays):
     start, stop = getattr(g, 'start_idx', 0), getattr(g, 'stop_idx', None)
     ranged = (stop is not None) or (start not in (0, None))
     from . import codegen
-    if codegen.is_generic_group(g) and not any(
+    # a Group with at least one equation the library has no kernel for, all of whose equations
+    # carry Python bodies (the reference's own objects always do; this package's descriptors of
+    # the hand-written equations do not): the whole Group is translated
+    if codegen.is_generic_group(g) and not all(
             _eq_name(e) in KNOWN_EQUATIONS for e in g.equations):
         kernel, dim, table = arrays.get('__codegen__', (None, 0, None))
         if kernel is None:

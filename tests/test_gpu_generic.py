@@ -453,3 +453,41 @@ def test_host_callbacks_and_helpers(gpu_device):
     ae.compute(0.1, 0.1)
     ae.backend.pull_all(['au'])
     assert list(pa.au) == [3.0] * 10
+
+
+def test_mixed_and_aliased_groups(gpu_device):
+    """A Group that mixes an equation the library knows BY NAME with an unknown one is translated
+    as a whole when every equation carries its Python body (the reference's objects do); a
+    generated kernel may not touch a property that a hand-written scheme keeps elsewhere."""
+    import pysph_b200 as pb
+    SimpleEquation = _equations()[0]
+
+    class SummationDensity(pb.Equation):          # a name the library has a kernel for, with a body
+        def initialize(self, d_idx, d_rho):
+            d_rho[d_idx] = 0.0
+
+        def loop(self, d_idx, d_rho, s_idx, s_m, WIJ):
+            d_rho[d_idx] += s_m[s_idx] * WIJ
+
+    pa, ae, g = make([pb.Group(equations=[SummationDensity(dest='fluid', sources=['fluid']),
+                                          SimpleEquation(dest='fluid', sources=['fluid'])])])
+    assert [o[0] for o in ae.ops] == ['generic']
+    ae.compute(0.1, 0.1)
+    ae.backend.pull_all(['rho', 'u'])
+    assert np.allclose(pa.rho, g['rho'], rtol=1e-6) and list(pa.u) == list(EXPECT)
+    # this package's descriptor of the same equation has no body: the mix is refused
+    with pytest.raises(NotImplementedError):
+        make([pb.Group(equations=[pb.SummationDensity(dest='fluid', sources=['fluid']),
+                                  SimpleEquation(dest='fluid', sources=['fluid'])])])
+
+    class TouchesPressure(pb.Equation):
+        def initialize(self, d_idx, d_p):
+            d_p[d_idx] = 1.0
+
+    # on an EDAC fluid p is the EVOLVED pressure (a different device array): refused at set-up
+    n = 10
+    fl = pb.get_particle_array_edac(name='fluid', x=np.linspace(0, 1, n), h=np.full(n, 0.12),
+                                    m=np.ones(n))
+    with pytest.raises(NotImplementedError):
+        pb.B200AccelerationEval([fl], [TouchesPressure(dest='fluid', sources=None)],
+                                pb.CubicSpline(dim=1))

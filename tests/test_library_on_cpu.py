@@ -165,6 +165,7 @@ FAST = [
     ('test_gpu_generic', 'test_untranslatable_bodies_fail_at_setup', {}),
     ('test_gpu_generic', 'test_generic_kernel_symbols_vs_reference_kernels', {}),
     ('test_gpu_generic', 'test_host_callbacks_and_helpers', {}),
+    ('test_gpu_generic', 'test_mixed_and_aliased_groups', {}),
 ] + [('test_gpu_generic', 'test_generic_wcsph_group_equals_golden', {'idx': i}) for i in (0, 1, 2, 5)]
 FULL = [
     ('test_gpu_parity', 'test_device_resident_dt_is_bitwise_the_host_path', {}),
