@@ -99,6 +99,13 @@ class B200Backend(object):
             return _lib.USER_PROP0 + self.user_props.index(name)
         if len(self.user_props) >= _lib.MAX_USER_PROPS:
             raise NotImplementedError('at most %d user properties' % _lib.MAX_USER_PROPS)
+        for pa in self.particle_arrays:
+            if name in pa.properties and \
+                    len(pa.properties[name]) != pa.get_number_of_particles():
+                raise NotImplementedError(
+                    'B200 generic equations: property %r of %r has a stride (%d values for %d '
+                    'particles); user properties hold one value per particle'
+                    % (name, pa.name, len(pa.properties[name]), pa.get_number_of_particles()))
         pid = _lib.USER_PROP0 + len(self.user_props)
         self.user_props.append(name)
         self.ctx.call('b200sph_user_property', pid)
